@@ -1,0 +1,66 @@
+"""Oracle-side mirror of mia_main.c main() (lines 759-976) built from the
+restated pieces in oracle/mia_oracle.c.  Test infrastructure."""
+import numpy as np
+
+
+class OracleRun:
+    def __init__(self, o, ref_raw, sm, circular=1, k=0, soft_mask=0, cons_code=1, distant_ref=0):
+        self.o, self.sm, self.circular, self.cons_code = o, np.ascontiguousarray(sm, np.int32), circular, cons_code
+        self.smr = o.revcom_pssm(self.sm)
+        self.ctx = o.ctx_new(ref_raw, circular, self.sm, with_rc=1, k=k, soft_mask=soft_mask, distant_ref=distant_ref)
+        self.seq_len = len(ref_raw)
+        self.wrap_len = o.lib.orc_ctx_wrap_len(self.ctx)
+        self.cur_ref = o.ctx_seq(self.ctx)[: self.seq_len]
+        self.asm = o.asm_new()
+        o.asm_begin_round(self.asm, self.seq_len, self.wrap_len)
+        self.fsdb = []
+        self.iter = 0
+        self.cons = None
+
+    def pass1(self, read, want_masks=False):
+        p = self.o.pass1(self.ctx, read, want_masks)
+        if p["added"]:
+            seq = self.o.revcom(read) if (p["rc"] and p["strand_known"]) else read      # fsdb.c:209-227
+            end = p["b_end"] if p["split"] else p["end"]
+            f, b = self.o.asm_add(self.asm, p["f_ref"] + p["b_ref"], p["f_frag"] + p["b_frag"], p["start"], end, p["rc"], p["score"])
+            self.fsdb.append(dict(seq=seq, seq_len=len(read), score=p["score"], rc=p["rc"], as_=p["as_"], ae=p["ae"],
+                                  strand_known=p["strand_known"], front=f, back=-1 if b is None else b))   # mia.c:1626-1642
+        return p
+
+    def _arrays(self):
+        g = lambda k: np.array([f[k] for f in self.fsdb], np.int32)
+        return g("front"), g("back"), g("seq_len"), g("score")
+
+    def end_pass1(self):
+        fr, bk, sl, sc = self._arrays()
+        self.o.asm_pop_smp(self.asm, fr, bk)
+        self.o.asm_cull(self.asm, fr, bk, sl, sc)
+        self.fsdb = [f for f in self.fsdb if f["score"] > 0]                             # clean_FSDB mia.c:400-406
+        self.iter = 1
+        self.last = self.cur_ref
+
+    def iterate(self):
+        o = self.o
+        if self.cons is not None:
+            self.iter += 1
+            self.last = self.cons
+        ref = self.last
+        ctx = o.ctx_new(ref, self.circular, self.sm, with_rc=0, k=0)
+        self.seq_len = len(ref)
+        self.wrap_len = o.lib.orc_ctx_wrap_len(ctx)
+        o.asm_begin_round(self.asm, self.seq_len, self.wrap_len)
+        for f in self.fsdb:
+            if not f["strand_known"]:
+                continue
+            r = o.realign(ctx, f["seq"], f["rc"], f["as_"], f["ae"])
+            f["as_"], f["ae"], f["score"] = r["as_"], r["ae"], r["score"]
+            fs, bs = o.asm_add(self.asm, r["ref_gapped"], r["read_gapped"], r["as_"], r["ae"], f["rc"], r["score"])
+            f["front"] = fs
+            if bs is not None:
+                f["back"] = bs          # otherwise the old back slot id stays: mia_main.c:273-276
+        o.ctx_free(ctx)
+        fr, bk, sl, sc = self._arrays()
+        o.asm_pop_smp(self.asm, fr, bk)
+        o.asm_cull(self.asm, fr, bk, sl, sc)
+        self.cons = o.asm_consensus(self.asm, self.sm, self.smr, self.cons_code, self.seq_len)
+        return self.cons, self.cons == self.last
