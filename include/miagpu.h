@@ -1,0 +1,212 @@
+/* miagpu.h -- C ABI of the B200-native hot path for the Mapping Iterative
+ * Assembler (MIA).  Plain C, no CUDA / torch types in any signature.
+ *
+ * Every entry point sits at a call site of the reference's own C host code
+ * (citations are /root/reference/src/<file>:<line>); INTEGRATION.md shows the
+ * stubs a maintainer of the reference would add.  Conventions follow the
+ * reference: functions return 1 on success and 0 on
+ * failure, never throw; the message of the last failure is available from
+ * miagpu_last_error().  There is NO CPU fallback: without a CUDA device every
+ * compute call fails loudly.
+ *
+ * Compile-time limits are the reference's (params.h): reads <= 256 bases
+ * (INIT_ALN_SEQ_LEN), alignment strings <= 512 columns, k <= 14
+ * (MAX_KMER_LEN), <= 128 positions per k-mer (MAX_KMER_POS), saturation at 128
+ * hits (KMER_SATURATE), mask buffer 10 (ALIGN_MASK_BUFFER), realign buffer 50
+ * (REALIGN_BUFFER), GOP 1000, GEP 200, PSSM depth 15, first-round cutoff 2000.
+ */
+#ifndef MIAGPU_H
+#define MIAGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MIAGPU_MAX_READ      256      /* INIT_ALN_SEQ_LEN, params.h:71 */
+#define MIAGPU_PSSM_INTS     775      /* int sm[31][5][5], types.h:155-158 */
+#define MIAGPU_MAX_RUNS      24       /* alignment runs returned per read */
+#define MIAGPU_COUNTS_PER_COL 10      /* As,Cs,Gs,Ts,gaps,cov,scoreA,scoreC,scoreG,scoreT (types.h:198-211) */
+
+/* Alignment run: (type << 14) | length, in 5'->3' order of the stored read.
+ *   type 0  M  read base aligned to reference base (both strings advance)
+ *   type 1  I  read bases against '-' in the reference string (mia.c:1466-1476)
+ *   type 2  D  reference bases against '-' in the read string   (mia.c:1477-1487)
+ * The pair of gapped strings populate_pwaln_to_begin builds (mia.c:1440-1497)
+ * is exactly the expansion of these runs starting at reference column `as`
+ * and read row `abr`. */
+#define MIAGPU_RUN_M 0
+#define MIAGPU_RUN_I 1
+#define MIAGPU_RUN_D 2
+#define MIAGPU_RUN_TYPE(x) ((x) >> 14)
+#define MIAGPU_RUN_LEN(x)  ((x) & 0x3fff)
+
+/* per-read status bits (status[] outputs) */
+#define MIAGPU_ST_OK          0
+#define MIAGPU_ST_RUNS_OVERFLOW 1     /* more than MIAGPU_MAX_RUNS runs: n_runs = -1 */
+#define MIAGPU_ST_SKIPPED     2       /* pass 1: no k-mer hit, read not aligned (mia_main.c:781) */
+#define MIAGPU_ST_STR_OVERFLOW 4      /* alignment longer than the reference's 512-column buffers */
+
+typedef struct miagpu_ctx miagpu_ctx;
+
+/* ---- lifetime.  Replaces init_alignment x2 + init_kpa (mia_main.c:659-690). */
+int         miagpu_device_count( void );
+int         miagpu_create( miagpu_ctx** out, int device );
+void        miagpu_destroy( miagpu_ctx* ctx );
+const char* miagpu_last_error( void );
+const char* miagpu_version( void );
+
+/* ---- a1. Scoring matrices.  fwd is PSSM.sm as read_pssm / init_flatsubmat
+ * fill it (io.c:408-503, pssm.c:96-126); the strand-reversed copy
+ * (revcom_submat, pssm.c:53-93) is derived inside.  Entries must satisfy
+ * |x| <= 4000 (the packed-key DP needs scores below 2^20). */
+int miagpu_set_pssm( miagpu_ctx* ctx, const int32_t* fwd );
+int miagpu_get_pssm( miagpu_ctx* ctx, int32_t* fwd, int32_t* rev );
+
+/* ---- reference / current consensus.  seq is what read_fasta_ref left in
+ * RefSeq.seq (case preserved, so that -M soft masking still works); the
+ * library appends the circular wrap (add_ref_wrap, mia.c:657-689), builds the
+ * reverse complement when with_rc (make_reverse_complement, io.c:388-398) and
+ * upper-cases both (make_ref_upper, mia.c:642-648).  Called once before pass 1
+ * (mia_main.c:637-733) and once per iteration with the new consensus
+ * (reiterate_assembly, mia_main.c:43-78; with_rc = 0 there). */
+int miagpu_set_reference( miagpu_ctx* ctx, const char* seq, int seq_len,
+                          int circular, int with_rc );
+int miagpu_ref_wrap_len( miagpu_ctx* ctx );
+
+/* ---- a2. k-mer tables of both strands over the wrapped, NOT yet upper-cased
+ * reference (populate_kpa, kmer.c:153-168; call site mia_main.c:659-672).
+ * k <= 0 disables the filter (all masks ones, new_kmer_filter kmer.c:251-255). */
+int miagpu_build_kmers( miagpu_ctx* ctx, int k, int soft_mask );
+
+/* ---- reads.  bases = all reads concatenated, upper-case ASCII as read_fasta /
+ * read_fastq store them (io.c:102, 251); offsets[n+1].  The batch stays
+ * resident in HBM until the next upload.  store_rc (nullable): 1 = replace the
+ * read by its reverse complement on upload (what add_virgin_fs2fsdb does once
+ * the strand is known, fsdb.c:209-227). */
+int miagpu_upload_reads( miagpu_ctx* ctx, int64_t n, const uint8_t* bases,
+                         const int64_t* offsets );
+
+/* ---- a3+a5..a8. Pass 1 over the resident reads: k-mer filter, both-strand
+ * whole-reference DP with the forward matrix, strand pick, traceback and the
+ * coordinate fix-ups of sg_align (mia_main.c:781-796; mia.c:1500-1610).
+ * Outputs (host arrays of n, any may be NULL):
+ *   hits      return value of new_kmer_filter (0 => skipped)
+ *   score     best_score of the chosen strand; fw_score / rc_score both strands
+ *   rc        1 if the reverse strand won (ties go to rc, mia.c:1549-1554)
+ *   as, ae    FragSeq.as / ae after mia.c:1587-1604
+ *   start,end PWAlnFrag start / end after the "end > seq_len" fix (mia.c:1606-1610)
+ *   abr       first aligned read row (soft clip), in the orientation aligned
+ *   n_runs, runs[n*MIAGPU_MAX_RUNS]  alignment of the chosen strand, already
+ *             reverse-complemented for rc (revcom_PWAF), i.e. in forward
+ *             reference orientation starting at `start`
+ * The accept / strand_known / split decisions (mia.c:1614-1658) are pure
+ * functions of these and stay in the host code. */
+int miagpu_pass1( miagpu_ctx* ctx, int32_t* hits, int32_t* score,
+                  int32_t* fw_score, int32_t* rc_score, uint8_t* rc,
+                  int32_t* as, int32_t* ae, int32_t* start, int32_t* end,
+                  int32_t* abr, int32_t* n_runs, uint16_t* runs,
+                  uint8_t* status );
+
+/* After pass 1 the host tells the device which resident reads to keep and in
+ * which orientation (sg_align's accept test + add_virgin_fs2fsdb + clean_FSDB):
+ * keep[i] in {0,1}; revcomp[i] = 1 stores the reverse complement.  Reads are
+ * compacted in order; returns the new count through n_out. */
+int miagpu_compact_reads( miagpu_ctx* ctx, const uint8_t* keep,
+                          const uint8_t* revcomp, int64_t* n_out );
+
+/* ---- a9 (+a5..a7). One round of reiterate_assembly's per-read body
+ * (mia_main.c:178-257) over the resident reads against the current reference:
+ * window [max(0,as-50), ae+50) with the clamp at mia_main.c:197-212, matrix by
+ * strand (179-184), sg5 = 1, unmasked DP, first-max end cell, traceback.
+ * Inputs (host, n each): rc, as, ae.  Outputs (host, n each, nullable):
+ *   score, as_out, ae_out (absolute), abr, n_runs, runs[n*MIAGPU_MAX_RUNS],
+ *   status.  Results are in input order. */
+int miagpu_realign( miagpu_ctx* ctx, const uint8_t* rc, const int32_t* as,
+                    const int32_t* ae, int32_t* score, int32_t* as_out,
+                    int32_t* ae_out, int32_t* abr, int32_t* n_runs,
+                    uint16_t* runs, uint8_t* status );
+
+/* Convenience form used by the end-to-end benchmark: upload + realign +
+ * download in one call with host buffers only. */
+int miagpu_realign_host( miagpu_ctx* ctx, int64_t n, const uint8_t* bases,
+                         const int64_t* offsets, const uint8_t* rc,
+                         const int32_t* as, const int32_t* ae, int32_t* score,
+                         int32_t* as_out, int32_t* ae_out, int32_t* abr,
+                         int32_t* n_runs, uint16_t* runs, uint8_t* status );
+
+/* ---- a10..a13. Column accumulation and base calling over the alignments the
+ * last miagpu_pass1 / miagpu_realign left on the device.
+ *
+ * The host keeps the reference's own bookkeeping (FragSeq.front_asp/back_asp,
+ * AlnSeq.dropped; H10 and the stale back pointer of mia_main.c:273-276) and
+ * describes the culled AlnSeq list to the device as `entries`:
+ *   entry e = { read index, segment (0 = whole/front, 1 = back), flags,
+ *               smp parameters }  -- see miagpu_entry below.
+ * The device derives AlnSeq.seq / ins / smp on the fly from the run lists
+ * (merge_pwaln_into_maln map_align.c:866-954, split_pwaln mia.c:1376-1438,
+ * pop_smp_from_FSDB fsdb.c:542-619), takes the per-position maximum insert
+ * length (ref->gaps, mia.c:486-504), adds every covered column into the
+ * BaseCounts accumulators (add_base map_align.c:229-263) and calls bases
+ * (find_consensus map_align.c:294-391; consensus_assembly_string mia.c:515-603).
+ */
+typedef struct {
+  int32_t read;       /* index into the resident reads */
+  uint8_t segment;    /* 0: the part with ref pos < seq_len ('a' or 'f'); 1: the wrapped part ('b') */
+  uint8_t dropped;    /* AlnSeq.dropped: excluded from base columns, NOT from insert columns */
+  uint8_t back_formula; /* pop_smp formula: 0 = front loop (fsdb.c:563-584), 1 = back loop (588-614) */
+  uint8_t reserved;
+  int32_t front_len;  /* asp_len(front_asp) of the read that owns the pointer (fsdb.c:553) */
+  int32_t total_len;  /* front_seq_len + back_seq_len (fsdb.c:554-559) */
+  int32_t act0;       /* act_seq_pos on entry to this segment's loop */
+} miagpu_entry;
+
+/* per-read segment geometry the host needs to fill miagpu_entry (asp_len etc.):
+ * for segment s in {0,1}: cols[s] = covered reference columns, ins[s] = inserted
+ * bases, bases[s] = non-gap read bases; split = alignment crosses seq_len. */
+typedef struct {
+  int32_t cols[2], ins[2], bases[2];
+  int32_t split;
+  int32_t start, end;   /* PWAlnFrag start / end after the end > seq_len fix */
+} miagpu_geom;
+
+int miagpu_geometry( miagpu_ctx* ctx, miagpu_geom* geom /* n */ );
+
+/* Accumulate + call.  gaps_out[wrap_len+1] (nullable) = ref->gaps;
+ * counts_out[seq_len*10] (nullable) = BaseCounts of every base column;
+ * cons_out must hold seq_len + sum(gaps) + 1 chars; *cons_len its strlen. */
+int miagpu_consensus( miagpu_ctx* ctx, int64_t n_entries,
+                      const miagpu_entry* entries, int cons_code,
+                      int32_t* gaps_out, int32_t* counts_out, char* cons_out,
+                      int32_t* cons_len );
+
+/* Multi-GPU: split miagpu_consensus in two so that the caller can
+ * all-reduce between them.  After _accumulate the device buffers
+ *   gaps   int32[wrap_len+1]                       (reduce with MAX)
+ *   counts int32[(seq_len + n_ins_cols) * 10]      (reduce with SUM)
+ * are exposed as raw device pointers; the insert-column layout is a function
+ * of the reduced gaps only, so the caller reduces gaps first
+ * (_accumulate_gaps -> allreduce(max) -> _accumulate_counts -> allreduce(sum)
+ * -> _call). */
+int miagpu_accumulate_gaps( miagpu_ctx* ctx, int64_t n_entries,
+                            const miagpu_entry* entries, void** dev_gaps,
+                            int64_t* n_gaps );
+int miagpu_accumulate_counts( miagpu_ctx* ctx, void** dev_counts,
+                              int64_t* n_counts );
+int miagpu_call( miagpu_ctx* ctx, int cons_code, int32_t* gaps_out,
+                 int32_t* counts_out, char* cons_out, int32_t* cons_len );
+
+/* ---- measurement helpers (bench.py) */
+/* device time in ms of the kernels launched by the last call, per phase */
+int miagpu_last_timing( miagpu_ctx* ctx, float* ms_kernels, float* ms_h2d,
+                        float* ms_d2h, int64_t* dp_cells, int32_t* launches );
+/* dependent-free INT32 ALU micro-benchmark; returns achieved ops/s (IADD3 /
+ * IMNMX / SEL mix) so the roofline can quote a measured integer peak */
+int miagpu_int32_peak( miagpu_ctx* ctx, double* ops_per_s );
+void* miagpu_stream( miagpu_ctx* ctx );   /* cudaStream_t the library launches on */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,202 @@
+"""ctypes binding of libmiagpu.so (include/miagpu.h) -- the host-side mirror of the
+reference's call sites.  Python is plumbing only: every compute call goes through
+the C ABI into hand-written sm_100a kernels; there is no CPU fallback and this
+module raises if the library is missing or a call fails.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmiagpu.so")
+MAX_RUNS = 24
+RUN_M, RUN_I, RUN_D = 0, 1, 2
+
+_i32p = C.POINTER(C.c_int32)
+_u8p = C.POINTER(C.c_uint8)
+_u16p = C.POINTER(C.c_uint16)
+_i64p = C.POINTER(C.c_int64)
+
+
+class MiaGpuError(RuntimeError):
+    pass
+
+
+class Entry(C.Structure):
+    _fields_ = [("read", C.c_int32), ("segment", C.c_uint8), ("dropped", C.c_uint8), ("back_formula", C.c_uint8),
+                ("reserved", C.c_uint8), ("front_len", C.c_int32), ("total_len", C.c_int32), ("act0", C.c_int32)]
+
+
+class Geom(C.Structure):
+    _fields_ = [("cols", C.c_int32 * 2), ("ins", C.c_int32 * 2), ("bases", C.c_int32 * 2), ("split", C.c_int32),
+                ("start", C.c_int32), ("end", C.c_int32)]
+
+
+ENTRY_DTYPE = np.dtype([("read", np.int32), ("segment", np.uint8), ("dropped", np.uint8), ("back_formula", np.uint8),
+                        ("reserved", np.uint8), ("front_len", np.int32), ("total_len", np.int32), ("act0", np.int32)])
+GEOM_DTYPE = np.dtype([("cols", np.int32, 2), ("ins", np.int32, 2), ("bases", np.int32, 2), ("split", np.int32),
+                       ("start", np.int32), ("end", np.int32)])
+
+_lib = None
+
+
+def load_library():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MiaGpuError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    L.miagpu_last_error.restype = C.c_char_p
+    L.miagpu_version.restype = C.c_char_p
+    L.miagpu_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+    L.miagpu_destroy.argtypes = [C.c_void_p]
+    L.miagpu_destroy.restype = None
+    L.miagpu_set_pssm.argtypes = [C.c_void_p, _i32p]
+    L.miagpu_get_pssm.argtypes = [C.c_void_p, _i32p, _i32p]
+    L.miagpu_set_reference.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_int]
+    L.miagpu_ref_wrap_len.argtypes = [C.c_void_p]
+    L.miagpu_build_kmers.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.miagpu_upload_reads.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    L.miagpu_pass1.argtypes = [C.c_void_p] + [C.c_void_p] * 13
+    L.miagpu_compact_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, _i64p]
+    L.miagpu_realign.argtypes = [C.c_void_p] + [C.c_void_p] * 10
+    L.miagpu_realign_host.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 12
+    L.miagpu_geometry.argtypes = [C.c_void_p, C.c_void_p]
+    L.miagpu_consensus.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, _i32p]
+    L.miagpu_accumulate_gaps.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_void_p), _i64p]
+    L.miagpu_accumulate_counts.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), _i64p]
+    L.miagpu_call.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, _i32p]
+    L.miagpu_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), _i64p, _i32p]
+    L.miagpu_int32_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    L.miagpu_stream.restype = C.c_void_p
+    L.miagpu_stream.argtypes = [C.c_void_p]
+    _lib = L
+    return L
+
+
+EXPORTS = ["miagpu_device_count", "miagpu_create", "miagpu_destroy", "miagpu_last_error", "miagpu_version", "miagpu_set_pssm",
+           "miagpu_get_pssm", "miagpu_set_reference", "miagpu_ref_wrap_len", "miagpu_build_kmers", "miagpu_upload_reads",
+           "miagpu_pass1", "miagpu_compact_reads", "miagpu_realign", "miagpu_realign_host", "miagpu_geometry",
+           "miagpu_consensus", "miagpu_accumulate_gaps", "miagpu_accumulate_counts", "miagpu_call", "miagpu_last_timing",
+           "miagpu_int32_peak", "miagpu_stream"]
+
+
+def _ptr(a):
+    """Raw address of a numpy array / torch tensor / None."""
+    if a is None:
+        return None
+    if hasattr(a, "data_ptr"):
+        return C.c_void_p(a.data_ptr())
+    return C.c_void_p(a.ctypes.data)
+
+
+class MiaGpu:
+    """One context = one GPU = one stream."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        if not self.lib.miagpu_create(C.byref(h), device):
+            raise MiaGpuError(self.lib.miagpu_last_error().decode())
+        self.h = h
+        self.n = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.miagpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, ok):
+        if not ok:
+            raise MiaGpuError(self.lib.miagpu_last_error().decode())
+
+    # -- setup
+    def set_pssm(self, sm):
+        sm = np.ascontiguousarray(sm, np.int32)
+        assert sm.size == 775
+        self._ck(self.lib.miagpu_set_pssm(self.h, sm.ctypes.data_as(_i32p)))
+
+    def get_pssm(self):
+        f, r = np.zeros(775, np.int32), np.zeros(775, np.int32)
+        self._ck(self.lib.miagpu_get_pssm(self.h, f.ctypes.data_as(_i32p), r.ctypes.data_as(_i32p)))
+        return f, r
+
+    def set_reference(self, seq, circular=1, with_rc=0):
+        b = seq if isinstance(seq, bytes) else seq.encode()
+        self._ck(self.lib.miagpu_set_reference(self.h, b, len(b), int(circular), int(with_rc)))
+        self.seq_len = len(b)
+        self.wrap_len = self.lib.miagpu_ref_wrap_len(self.h)
+
+    def build_kmers(self, k, soft_mask=0):
+        self._ck(self.lib.miagpu_build_kmers(self.h, int(k), int(soft_mask)))
+
+    def upload_reads(self, bases, offsets):
+        n = len(offsets) - 1
+        self._ck(self.lib.miagpu_upload_reads(self.h, n, _ptr(bases), _ptr(offsets)))
+        self.n = n
+
+    # -- iteration regime
+    @staticmethod
+    def alloc_realign_outputs(n, pinned=False):
+        def mk(shape, dt):
+            if pinned:
+                import torch
+                return torch.empty(shape, dtype=getattr(torch, dt), pin_memory=True)
+            return np.empty(shape, dtype=dt)
+        return dict(score=mk(n, "int32"), as_out=mk(n, "int32"), ae_out=mk(n, "int32"), abr=mk(n, "int32"),
+                    n_runs=mk(n, "int32"), runs=mk((n, MAX_RUNS), "int16" if pinned else "uint16"), status=mk(n, "uint8"))
+
+    def realign(self, rc, as_, ae, out=None):
+        """reiterate_assembly's per-read body over the resident reads (mia_main.c:178-257)."""
+        n = self.n
+        out = out or self.alloc_realign_outputs(n)
+        self._ck(self.lib.miagpu_realign(self.h, _ptr(rc), _ptr(as_), _ptr(ae), _ptr(out["score"]), _ptr(out["as_out"]),
+                                         _ptr(out["ae_out"]), _ptr(out["abr"]), _ptr(out["n_runs"]), _ptr(out["runs"]),
+                                         _ptr(out["status"])))
+        return out
+
+    def realign_host(self, bases, offsets, rc, as_, ae, out=None):
+        n = len(offsets) - 1
+        out = out or self.alloc_realign_outputs(n)
+        self._ck(self.lib.miagpu_realign_host(self.h, n, _ptr(bases), _ptr(offsets), _ptr(rc), _ptr(as_), _ptr(ae),
+                                              _ptr(out["score"]), _ptr(out["as_out"]), _ptr(out["ae_out"]), _ptr(out["abr"]),
+                                              _ptr(out["n_runs"]), _ptr(out["runs"]), _ptr(out["status"])))
+        self.n = n
+        return out
+
+    def last_timing(self):
+        k, h, d = C.c_float(), C.c_float(), C.c_float()
+        cells, launches = C.c_int64(), C.c_int32()
+        self._ck(self.lib.miagpu_last_timing(self.h, C.byref(k), C.byref(h), C.byref(d), C.byref(cells), C.byref(launches)))
+        return dict(ms_kernels=k.value, ms_h2d=h.value, ms_d2h=d.value, dp_cells=cells.value, launches=launches.value)
+
+    def int32_peak(self):
+        v = C.c_double()
+        self._ck(self.lib.miagpu_int32_peak(self.h, C.byref(v)))
+        return v.value
+
+
+def expand_runs(ref, read, start, abr, runs, n_runs):
+    """Gapped strings (PWAlnFrag.ref_seq / frag_seq, mia.c:1440-1497) from a run list.
+    ref must be indexable at reference coordinates (wrapped); start = first ref column."""
+    rg, fg = [], []
+    c, r = start, abr
+    for x in runs[:n_runs]:
+        x = int(x) & 0xFFFF
+        t, ln = x >> 14, x & 0x3FFF
+        if t == RUN_M:
+            rg.append(ref[c:c + ln]); fg.append(read[r:r + ln]); c += ln; r += ln
+        elif t == RUN_I:
+            rg.append("-" * ln); fg.append(read[r:r + ln]); r += ln
+        else:
+            rg.append(ref[c:c + ln]); fg.append("-" * ln); c += ln
+    return "".join(rg), "".join(fg)

@@ -1,0 +1,462 @@
+// miagpu.cu -- C ABI (include/miagpu.h) + host orchestration for libmiagpu.so.
+// sm_100a only; no CPU fallback: every compute entry point needs a CUDA device.
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "realign.cuh"
+
+namespace miagpu {
+
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// ------------------------------------------------------------------ buffers
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t n) {
+    if (n <= cap) return 1;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = n + n / 8 + 64;
+    MIAGPU_CUDA(cudaMalloc(&p, want * sizeof(T)));
+    cap = want;
+    return 1;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+constexpr int NBUCKET = 8;                                   // 7 register-tiled widths + "big"
+static const int BUCKET_K[NBUCKET] = {2, 4, 6, 8, 10, 12, 16, 0};
+
+}  // namespace miagpu
+
+using namespace miagpu;
+
+struct miagpu_ctx {
+  int device = 0;
+  int num_sms = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[6] = {};
+  // scoring
+  bool have_pssm = false;
+  int32_t sm_f[MIAGPU_PSSM_INTS], sm_r[MIAGPU_PSSM_INTS];
+  DevBuf<int32_t> d_prof;
+  // reference
+  bool have_ref = false;
+  std::string raw_wrapped, raw_rc_wrapped;     // case preserved (k-mer soft mask)
+  int seq_len = 0, wrap_len = 0, circular = 0, with_rc = 0;
+  DevBuf<uint8_t> d_ref, d_rcref;              // codes 0..4, padded to 16 B
+  int ref_bytes = 0;
+  // reads
+  int64_t n = 0, total_bases = 0;
+  DevBuf<uint8_t> d_bases;
+  DevBuf<int64_t> d_off;
+  // per-read
+  DevBuf<uint8_t> d_rc, d_status;
+  DevBuf<int32_t> d_as, d_ae, d_score, d_as_out, d_ae_out, d_abr, d_nruns, d_win_start, d_win_len, d_lists;
+  DevBuf<uint16_t> d_runs;
+  DevBuf<int32_t> d_meta;                      // bucket counts[8], work counters[8], max L[8], cells(2 x int32 -> int64)
+  DevBuf<uint32_t> d_scratch;
+  // timing of the last call
+  float ms_kernels = 0, ms_h2d = 0, ms_d2h = 0;
+  int64_t dp_cells = 0;
+  int launches = 0;
+};
+
+// -------------------------------------------------------------------- misc
+extern "C" const char* miagpu_last_error(void) { return g_err; }
+extern "C" const char* miagpu_version(void) { return "miagpu 0.1 (sm_100a)"; }
+
+extern "C" int miagpu_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+extern "C" int miagpu_create(miagpu_ctx** out, int device) {
+  if (!out) { set_error("miagpu_create: out is NULL"); return 0; }
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    set_error("miagpu_create: no CUDA device (%s); this library has no CPU fallback", e == cudaSuccess ? "count = 0" : cudaGetErrorString(e));
+    return 0;
+  }
+  if (device < 0 || device >= n) { set_error("miagpu_create: device %d out of range (0..%d)", device, n - 1); return 0; }
+  MIAGPU_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  MIAGPU_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) { set_error("miagpu_create: device %d is sm_%d%d; this build is sm_100a only", device, prop.major, prop.minor); return 0; }
+  miagpu_ctx* c = new miagpu_ctx();
+  c->device = device;
+  c->num_sms = prop.multiProcessorCount;
+  MIAGPU_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  for (auto& ev : c->ev) MIAGPU_CUDA(cudaEventCreate(&ev));
+  *out = c;
+  return 1;
+}
+
+extern "C" void miagpu_destroy(miagpu_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  c->d_prof.release(); c->d_ref.release(); c->d_rcref.release(); c->d_bases.release(); c->d_off.release();
+  c->d_rc.release(); c->d_status.release(); c->d_as.release(); c->d_ae.release(); c->d_score.release();
+  c->d_as_out.release(); c->d_ae_out.release(); c->d_abr.release(); c->d_nruns.release(); c->d_win_start.release();
+  c->d_win_len.release(); c->d_lists.release(); c->d_runs.release(); c->d_meta.release(); c->d_scratch.release();
+  for (auto& ev : c->ev) cudaEventDestroy(ev);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+extern "C" void* miagpu_stream(miagpu_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+// -------------------------------------------------------------------- PSSM
+static void revcom_pssm(const int32_t* in, int32_t* out) {      // pssm.c:53-93
+  for (int d = 0; d < NMAT; d++)
+    for (int i = 0; i < 5; i++)
+      for (int j = 0; j < 5; j++) {
+        int ci = i < 4 ? 3 - i : 4, cj = j < 4 ? 3 - j : 4;
+        out[((NMAT - 1 - d) * 5 + i) * 5 + j] = in[(d * 5 + ci) * 5 + cj];
+      }
+}
+
+extern "C" int miagpu_set_pssm(miagpu_ctx* c, const int32_t* fwd) {
+  if (!c || !fwd) { set_error("miagpu_set_pssm: NULL argument"); return 0; }
+  for (int i = 0; i < MIAGPU_PSSM_INTS; i++)
+    if (fwd[i] > PSSM_ABS_LIMIT || fwd[i] < -PSSM_ABS_LIMIT) {
+      set_error("miagpu_set_pssm: entry %d = %d exceeds the supported magnitude %d", i, fwd[i], PSSM_ABS_LIMIT);
+      return 0;
+    }
+  MIAGPU_CUDA(cudaSetDevice(c->device));
+  memcpy(c->sm_f, fwd, sizeof(c->sm_f));
+  revcom_pssm(c->sm_f, c->sm_r);
+  std::vector<int32_t> prof(PROF_INTS, 0);
+  for (int s = 0; s < 2; s++)
+    for (int d = 0; d < NMAT; d++)
+      for (int rb = 0; rb < 5; rb++)
+        for (int fb = 0; fb < 5; fb++)   // sm[depth][ref_base][read_base]
+          prof[prof_row_index(s, d, rb) + fb] = (s ? c->sm_r : c->sm_f)[(d * 5 + fb) * 5 + rb];
+  if (!c->d_prof.reserve(PROF_INTS)) return 0;
+  MIAGPU_CUDA(cudaMemcpyAsync(c->d_prof.p, prof.data(), PROF_INTS * 4, cudaMemcpyHostToDevice, c->stream));
+  MIAGPU_CUDA(cudaStreamSynchronize(c->stream));
+  c->have_pssm = true;
+  return 1;
+}
+
+extern "C" int miagpu_get_pssm(miagpu_ctx* c, int32_t* fwd, int32_t* rev) {
+  if (!c || !c->have_pssm) { set_error("miagpu_get_pssm: no matrices set"); return 0; }
+  if (fwd) memcpy(fwd, c->sm_f, sizeof(c->sm_f));
+  if (rev) memcpy(rev, c->sm_r, sizeof(c->sm_r));
+  return 1;
+}
+
+// --------------------------------------------------------------- reference
+static char revcom_char(char b) {                                // map_align.c:418-431
+  static const char* from = "ABCDGHKMNRSTUVWXY";
+  static const char* to = "TVGHCDMKNYSAABWXR";
+  if (b == '-') return '-';
+  bool lower = b >= 'a' && b <= 'z';
+  char u = lower ? (char)(b - 32) : b;
+  const char* q = (u >= 'A' && u <= 'Z') ? strchr(from, u) : nullptr;
+  if (!q || !*q) return 'N';
+  return lower ? (char)(to[q - from] + 32) : to[q - from];
+}
+
+static int upload_codes(miagpu_ctx* c, const std::string& s, DevBuf<uint8_t>& dst) {
+  int padded = ((int)s.size() + 15) / 16 * 16 + 16;
+  std::vector<uint8_t> codes(padded, 4);
+  for (size_t i = 0; i < s.size(); i++) {
+    char u = s[i];
+    if (u >= 'a' && u <= 'z') u = (char)(u - 32);               // make_ref_upper, mia.c:642-648
+    codes[i] = (uint8_t)base_code((uint8_t)u);
+  }
+  if (!dst.reserve(padded)) return 0;
+  MIAGPU_CUDA(cudaMemcpyAsync(dst.p, codes.data(), padded, cudaMemcpyHostToDevice, c->stream));
+  MIAGPU_CUDA(cudaStreamSynchronize(c->stream));
+  c->ref_bytes = padded;
+  return 1;
+}
+
+extern "C" int miagpu_set_reference(miagpu_ctx* c, const char* seq, int seq_len, int circular, int with_rc) {
+  if (!c || !seq || seq_len <= 0) { set_error("miagpu_set_reference: bad argument"); return 0; }
+  MIAGPU_CUDA(cudaSetDevice(c->device));
+  int wrap = circular ? std::min(seq_len, MAX_READ) : 0;         // add_ref_wrap, mia.c:657-689
+  c->seq_len = seq_len;
+  c->wrap_len = seq_len + wrap;
+  c->circular = circular;
+  c->with_rc = with_rc;
+  c->raw_wrapped.assign(seq, seq_len);
+  c->raw_wrapped.append(seq, wrap);
+  if (!upload_codes(c, c->raw_wrapped, c->d_ref)) return 0;
+  c->raw_rc_wrapped.clear();
+  if (with_rc) {                                                 // io.c:388-398, then the same wrap
+    std::string rcs(seq_len, 'N');
+    for (int i = 0; i < seq_len; i++) rcs[i] = revcom_char(seq[seq_len - 1 - i]);
+    c->raw_rc_wrapped = rcs;
+    c->raw_rc_wrapped.append(rcs, 0, wrap);
+    if (!upload_codes(c, c->raw_rc_wrapped, c->d_rcref)) return 0;
+  }
+  c->have_ref = true;
+  return 1;
+}
+
+extern "C" int miagpu_ref_wrap_len(miagpu_ctx* c) { return c ? c->wrap_len : 0; }
+
+// ------------------------------------------------------------------- reads
+static int reserve_per_read(miagpu_ctx* c, int64_t n) {
+  return c->d_rc.reserve(n) && c->d_status.reserve(n) && c->d_as.reserve(n) && c->d_ae.reserve(n) && c->d_score.reserve(n) &&
+         c->d_as_out.reserve(n) && c->d_ae_out.reserve(n) && c->d_abr.reserve(n) && c->d_nruns.reserve(n) &&
+         c->d_win_start.reserve(n) && c->d_win_len.reserve(n) && c->d_lists.reserve(n * NBUCKET) &&
+         c->d_runs.reserve(n * MAX_RUNS) && c->d_meta.reserve(64);
+}
+
+extern "C" int miagpu_upload_reads(miagpu_ctx* c, int64_t n, const uint8_t* bases, const int64_t* offsets) {
+  if (!c || n < 0 || (n > 0 && (!bases || !offsets))) { set_error("miagpu_upload_reads: bad argument"); return 0; }
+  MIAGPU_CUDA(cudaSetDevice(c->device));
+  if (n > 0x7fffffffLL / NBUCKET) { set_error("miagpu_upload_reads: at most %lld reads per batch", 0x7fffffffLL / NBUCKET); return 0; }
+  int64_t total = n ? offsets[n] : 0;
+  if (n && offsets[0] != 0) { set_error("miagpu_upload_reads: offsets[0] must be 0"); return 0; }
+  if (!c->d_bases.reserve(total + 16) || !c->d_off.reserve(n + 1) || !reserve_per_read(c, n)) return 0;
+  MIAGPU_CUDA(cudaEventRecord(c->ev[0], c->stream));
+  if (n) {
+    MIAGPU_CUDA(cudaMemcpyAsync(c->d_bases.p, bases, total, cudaMemcpyHostToDevice, c->stream));
+    MIAGPU_CUDA(cudaMemcpyAsync(c->d_off.p, offsets, (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+  }
+  MIAGPU_CUDA(cudaEventRecord(c->ev[1], c->stream));
+  MIAGPU_CUDA(cudaStreamSynchronize(c->stream));
+  MIAGPU_CUDA(cudaEventElapsedTime(&c->ms_h2d, c->ev[0], c->ev[1]));
+  c->n = n;
+  c->total_bases = total;
+  return 1;
+}
+
+// ----------------------------------------------------------------- realign
+// Window rule of reiterate_assembly (mia_main.c:190-212) + width bucket.
+__global__ void classify_kernel(int64_t n, const int64_t* off, const int32_t* as, const int32_t* ae, int wrap_len,
+                                int32_t* win_start, int32_t* win_len, int32_t* lists, int32_t* meta) {
+  __shared__ int s_cnt[NBUCKET], s_base[NBUCKET], s_maxL[NBUCKET];
+  __shared__ unsigned long long s_cells;
+  if (threadIdx.x < NBUCKET) { s_cnt[threadIdx.x] = 0; s_maxL[threadIdx.x] = 0; }
+  if (threadIdx.x == 0) s_cells = 0;
+  __syncthreads();
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int b = -1, slot = 0, L = 0;
+  if (i < n) {
+    L = (int)(off[i + 1] - off[i]);
+    int rs = as[i] - REALIGN_BUFFER < 0 ? 0 : as[i] - REALIGN_BUFFER;
+    int re = (ae[i] + REALIGN_BUFFER + 1 > wrap_len) ? wrap_len : ae[i] + REALIGN_BUFFER;
+    if (rs + L > re) { rs = 0; re = wrap_len; }
+    int len1 = re - rs;
+    win_start[i] = rs;
+    win_len[i] = len1;
+    b = len1 <= 64 ? 0 : len1 <= 128 ? 1 : len1 <= 192 ? 2 : len1 <= 256 ? 3 : len1 <= 320 ? 4 : len1 <= 384 ? 5 : len1 <= 512 ? 6 : 7;
+    if (L <= 0 || L > MAX_READ) b = 7;
+    slot = atomicAdd(&s_cnt[b], 1);
+    atomicMax(&s_maxL[b], L);
+    atomicAdd(&s_cells, (unsigned long long)L * (unsigned long long)len1);
+  }
+  __syncthreads();
+  if (threadIdx.x < NBUCKET) {
+    s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd(&meta[threadIdx.x], s_cnt[threadIdx.x]) : 0;
+    if (s_maxL[threadIdx.x]) atomicMax(&meta[16 + threadIdx.x], s_maxL[threadIdx.x]);
+  }
+  if (threadIdx.x == 0) atomicAdd(reinterpret_cast<unsigned long long*>(meta + 32), s_cells);
+  __syncthreads();
+  if (b >= 0) lists[(int64_t)b * n + s_base[b] + slot] = (int32_t)i;
+}
+
+__global__ void flag_big_kernel(const int32_t* list, int n_list, int32_t* score, int32_t* n_runs, uint8_t* status) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_list) { int rd = list[i]; score[rd] = INT_MIN; n_runs[rd] = -1; status[rd] = 0x80; }
+}
+
+template <int K>
+static int launch_bucket(miagpu_ctx* c, RealignParams p, int maxL) {
+  using TL = TraceLayout<K>;
+  bool ref_in_smem = c->ref_bytes <= 160 * 1024;
+  size_t smem = PROF_INTS * 4 + WARPS_PER_BLOCK * MAX_READ * 2 + (ref_in_smem ? c->ref_bytes : 0);
+  MIAGPU_CUDA(cudaFuncSetAttribute(realign_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  MIAGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, realign_kernel<K>, WARPS_PER_BLOCK * 32, smem));
+  if (per_sm < 1) { set_error("realign_kernel<%d> does not fit on an SM (smem %zu)", K, smem); return 0; }
+  per_sm = std::min(per_sm, 6);                            // 24 warps/SM: enough ILP, keeps trace scratch L2-resident
+  int blocks = c->num_sms * per_sm;
+  blocks = std::min(blocks, (p.n_list + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+  if (blocks < 1) return 1;
+  int64_t words = (int64_t)std::max(maxL - 1, 1) * TL::ROW_WORDS;
+  if (!c->d_scratch.reserve((size_t)words * blocks * WARPS_PER_BLOCK)) return 0;
+  p.scratch = c->d_scratch.p;
+  p.scratch_words_per_warp = words;
+  p.ref_in_smem = ref_in_smem;
+  realign_kernel<K><<<blocks, WARPS_PER_BLOCK * 32, smem, c->stream>>>(p);
+  MIAGPU_CUDA(cudaGetLastError());
+  c->launches++;
+  return 1;
+}
+
+static int realign_device(miagpu_ctx* c) {
+  const int64_t n = c->n;
+  c->launches = 0;
+  c->dp_cells = 0;
+  if (n == 0) return 1;
+  MIAGPU_CUDA(cudaMemsetAsync(c->d_meta.p, 0, 64 * sizeof(int32_t), c->stream));
+  classify_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, c->d_off.p, c->d_as.p, c->d_ae.p, c->wrap_len,
+                                                                     c->d_win_start.p, c->d_win_len.p, c->d_lists.p, c->d_meta.p);
+  MIAGPU_CUDA(cudaGetLastError());
+  c->launches++;
+  int32_t meta[64];
+  MIAGPU_CUDA(cudaMemcpyAsync(meta, c->d_meta.p, sizeof(meta), cudaMemcpyDeviceToHost, c->stream));
+  MIAGPU_CUDA(cudaStreamSynchronize(c->stream));
+  memcpy(&c->dp_cells, meta + 32, sizeof(int64_t));
+  for (int b = 0; b < NBUCKET; b++) {
+    if (!meta[b]) continue;
+    RealignParams p{};
+    p.bases = c->d_bases.p; p.off = c->d_off.p; p.rc = c->d_rc.p;
+    p.win_start = c->d_win_start.p; p.win_len = c->d_win_len.p;
+    p.list = c->d_lists.p + (int64_t)b * n; p.n_list = meta[b]; p.counter = c->d_meta.p + 8 + b;
+    p.ref_codes = c->d_ref.p; p.ref_bytes = c->ref_bytes; p.prof = c->d_prof.p; p.sg5 = 1;
+    p.score = c->d_score.p; p.as_out = c->d_as_out.p; p.ae_out = c->d_ae_out.p; p.abr = c->d_abr.p;
+    p.n_runs = c->d_nruns.p; p.runs = c->d_runs.p; p.status = c->d_status.p;
+    int ok = 1, maxL = meta[16 + b];
+    switch (BUCKET_K[b]) {
+      case 2: ok = launch_bucket<2>(c, p, maxL); break;
+      case 4: ok = launch_bucket<4>(c, p, maxL); break;
+      case 6: ok = launch_bucket<6>(c, p, maxL); break;
+      case 8: ok = launch_bucket<8>(c, p, maxL); break;
+      case 10: ok = launch_bucket<10>(c, p, maxL); break;
+      case 12: ok = launch_bucket<12>(c, p, maxL); break;
+      case 16: ok = launch_bucket<16>(c, p, maxL); break;
+      default:
+        flag_big_kernel<<<(meta[b] + 255) / 256, 256, 0, c->stream>>>(p.list, p.n_list, p.score, p.n_runs, p.status);
+        MIAGPU_CUDA(cudaGetLastError());
+        c->launches++;
+    }
+    if (!ok) return 0;
+  }
+  return 1;
+}
+
+static int realign_common(miagpu_ctx* c, const uint8_t* rc, const int32_t* as, const int32_t* ae, int32_t* score,
+                          int32_t* as_out, int32_t* ae_out, int32_t* abr, int32_t* n_runs, uint16_t* runs, uint8_t* status,
+                          bool time_h2d_from_upload) {
+  if (!c || !c->have_pssm || !c->have_ref) { set_error("miagpu_realign: set_pssm and set_reference first"); return 0; }
+  if (c->n && (!rc || !as || !ae)) { set_error("miagpu_realign: rc/as/ae are required"); return 0; }
+  MIAGPU_CUDA(cudaSetDevice(c->device));
+  const int64_t n = c->n;
+  MIAGPU_CUDA(cudaEventRecord(c->ev[0], c->stream));
+  if (n) {
+    MIAGPU_CUDA(cudaMemcpyAsync(c->d_rc.p, rc, n, cudaMemcpyHostToDevice, c->stream));
+    MIAGPU_CUDA(cudaMemcpyAsync(c->d_as.p, as, n * 4, cudaMemcpyHostToDevice, c->stream));
+    MIAGPU_CUDA(cudaMemcpyAsync(c->d_ae.p, ae, n * 4, cudaMemcpyHostToDevice, c->stream));
+  }
+  MIAGPU_CUDA(cudaEventRecord(c->ev[1], c->stream));
+  if (!realign_device(c)) return 0;
+  MIAGPU_CUDA(cudaEventRecord(c->ev[2], c->stream));
+  if (n) {
+    if (score) MIAGPU_CUDA(cudaMemcpyAsync(score, c->d_score.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (as_out) MIAGPU_CUDA(cudaMemcpyAsync(as_out, c->d_as_out.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (ae_out) MIAGPU_CUDA(cudaMemcpyAsync(ae_out, c->d_ae_out.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (abr) MIAGPU_CUDA(cudaMemcpyAsync(abr, c->d_abr.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (n_runs) MIAGPU_CUDA(cudaMemcpyAsync(n_runs, c->d_nruns.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (runs) MIAGPU_CUDA(cudaMemcpyAsync(runs, c->d_runs.p, n * MAX_RUNS * 2, cudaMemcpyDeviceToHost, c->stream));
+    if (status) MIAGPU_CUDA(cudaMemcpyAsync(status, c->d_status.p, n, cudaMemcpyDeviceToHost, c->stream));
+  }
+  MIAGPU_CUDA(cudaEventRecord(c->ev[3], c->stream));
+  MIAGPU_CUDA(cudaStreamSynchronize(c->stream));
+  float h2d = 0;
+  MIAGPU_CUDA(cudaEventElapsedTime(&h2d, c->ev[0], c->ev[1]));
+  c->ms_h2d = time_h2d_from_upload ? c->ms_h2d + h2d : h2d;
+  MIAGPU_CUDA(cudaEventElapsedTime(&c->ms_kernels, c->ev[1], c->ev[2]));
+  MIAGPU_CUDA(cudaEventElapsedTime(&c->ms_d2h, c->ev[2], c->ev[3]));
+  return 1;
+}
+
+extern "C" int miagpu_realign(miagpu_ctx* c, const uint8_t* rc, const int32_t* as, const int32_t* ae, int32_t* score,
+                              int32_t* as_out, int32_t* ae_out, int32_t* abr, int32_t* n_runs, uint16_t* runs, uint8_t* status) {
+  return realign_common(c, rc, as, ae, score, as_out, ae_out, abr, n_runs, runs, status, false);
+}
+
+extern "C" int miagpu_realign_host(miagpu_ctx* c, int64_t n, const uint8_t* bases, const int64_t* offsets, const uint8_t* rc,
+                                   const int32_t* as, const int32_t* ae, int32_t* score, int32_t* as_out, int32_t* ae_out,
+                                   int32_t* abr, int32_t* n_runs, uint16_t* runs, uint8_t* status) {
+  if (!miagpu_upload_reads(c, n, bases, offsets)) return 0;
+  return realign_common(c, rc, as, ae, score, as_out, ae_out, abr, n_runs, runs, status, true);
+}
+
+extern "C" int miagpu_last_timing(miagpu_ctx* c, float* ms_kernels, float* ms_h2d, float* ms_d2h, int64_t* dp_cells, int32_t* launches) {
+  if (!c) { set_error("miagpu_last_timing: NULL ctx"); return 0; }
+  if (ms_kernels) *ms_kernels = c->ms_kernels;
+  if (ms_h2d) *ms_h2d = c->ms_h2d;
+  if (ms_d2h) *ms_d2h = c->ms_d2h;
+  if (dp_cells) *dp_cells = c->dp_cells;
+  if (launches) *launches = c->launches;
+  return 1;
+}
+
+// ------------------------------------------------ integer peak micro-benchmark
+// 8 independent chains per thread of IADD3 / IMNMX / SEL-style ops, no memory.
+__global__ void int_peak_kernel(int* out, int iters, int seed) {
+  int a[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) a[i] = seed + threadIdx.x * (i + 1);
+  int b = seed ^ 0x5bd1e995, c = seed + 77;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      a[i] = a[i] + b + it;               // IADD3
+      a[i] = max(a[i], c - i);            // IMNMX
+      a[i] = (a[i] > b) ? a[i] - c : a[i] + 3;   // ISETP + SEL(+IADD)
+      a[i] = min(a[i], 0x3fffffff);
+    }
+  }
+  int s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s ^= a[i];
+  if (s == 0x7fffffff) out[0] = s;
+}
+
+extern "C" int miagpu_int32_peak(miagpu_ctx* c, double* ops_per_s) {
+  if (!c || !ops_per_s) { set_error("miagpu_int32_peak: NULL argument"); return 0; }
+  MIAGPU_CUDA(cudaSetDevice(c->device));
+  if (!c->d_meta.reserve(64)) return 0;
+  const int iters = 4096, threads = 256, blocks = c->num_sms * 8;
+  // ops per inner statement group: IADD3(1) + IMNMX(1) + ISETP/SEL/IADD(3) + IMNMX(1) = 6 per chain element
+  for (int rep = 0; rep < 2; rep++) {
+    MIAGPU_CUDA(cudaEventRecord(c->ev[4], c->stream));
+    int_peak_kernel<<<blocks, threads, 0, c->stream>>>(c->d_meta.p + 48, iters, 12345);
+    MIAGPU_CUDA(cudaEventRecord(c->ev[5], c->stream));
+    MIAGPU_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  float ms = 0;
+  MIAGPU_CUDA(cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]));
+  *ops_per_s = (double)blocks * threads * iters * 8.0 * 6.0 / (ms * 1e-3);
+  return 1;
+}
+
+// ------------------------------------------------------------ not yet built
+extern "C" int miagpu_build_kmers(miagpu_ctx*, int, int) { set_error("miagpu_build_kmers: not implemented yet"); return 0; }
+extern "C" int miagpu_pass1(miagpu_ctx*, int32_t*, int32_t*, int32_t*, int32_t*, uint8_t*, int32_t*, int32_t*, int32_t*, int32_t*,
+                            int32_t*, int32_t*, uint16_t*, uint8_t*) { set_error("miagpu_pass1: not implemented yet"); return 0; }
+extern "C" int miagpu_compact_reads(miagpu_ctx*, const uint8_t*, const uint8_t*, int64_t*) { set_error("miagpu_compact_reads: not implemented yet"); return 0; }
+extern "C" int miagpu_geometry(miagpu_ctx*, miagpu_geom*) { set_error("miagpu_geometry: not implemented yet"); return 0; }
+extern "C" int miagpu_consensus(miagpu_ctx*, int64_t, const miagpu_entry*, int, int32_t*, int32_t*, char*, int32_t*) { set_error("miagpu_consensus: not implemented yet"); return 0; }
+extern "C" int miagpu_accumulate_gaps(miagpu_ctx*, int64_t, const miagpu_entry*, void**, int64_t*) { set_error("miagpu_accumulate_gaps: not implemented yet"); return 0; }
+extern "C" int miagpu_accumulate_counts(miagpu_ctx*, void**, int64_t*) { set_error("miagpu_accumulate_counts: not implemented yet"); return 0; }
+extern "C" int miagpu_call(miagpu_ctx*, int, int32_t*, int32_t*, char*, int32_t*) { set_error("miagpu_call: not implemented yet"); return 0; }

@@ -1,0 +1,325 @@
+// realign.cuh -- windowed PSSM semi-global DP + on-device traceback (sm_100a).
+//
+// Replaces, for a whole batch of reads, the per-read body of reiterate_assembly
+// (mia_main.c:178-257): pop_s2c_in_a / pop_s1c_in_a (mia.c:1243, 1054),
+// dyn_prog (mia.c:740-981), max_sg_score (mia.c:1278-1302), find_align_begin
+// (mia.c:612-637) and populate_pwaln_to_begin (mia.c:1440-1497).
+//
+// Parallelisation.  dyn_prog's cell (r,c) reads only rows < r:
+//     D   = S[r-1][c-1]
+//     G_c = max_{k<=c-2} S[r-1][k] - P(c-k-1)      (best_gap_col, running arg-max along row r-1)
+//     G_r = max_{j<=r-2} S[j][c-1] - P(r-j-1)      (best_gap_row[c-1], running arg-max down column c-1)
+// so a whole row is computed at once: ONE WARP PER READ, lane l owns K consecutive
+// columns [l*K, l*K+K) for every row, all state in registers.  There is no
+// anti-diagonal skew and no fill/drain loss; the only cross-lane traffic per row
+// is 3 shuffles for the left neighbours and a 5-step warp max-scan that turns the
+// per-lane arg-max of (S[r-1][k] + GEP*k) into the running prefix the reference
+// keeps in best_gap_col.  Both arg-maxes are carried as single packed 32-bit keys
+// (common.cuh) so "value then earliest index" is one IMNMX.
+//
+// Traceback.  Every cell stores a 16-bit trace word (the low 16 bits of the
+// winning key: 2-bit move marker + 9-bit jump target) into a per-warp scratch
+// matrix in global memory, written with one coalesced 128-bit (or 64-bit) store
+// per lane per row.  Scratch is re-used by the persistent warp for every read it
+// processes and sized to stay L2-resident.  The walk back reproduces the
+// reference's quirks: a jump target of 0 is indistinguishable from "diagonal"
+// (trace == 0, H2), the walk stops in row 0 / column 0 / at a start-new cell.
+#pragma once
+#include "common.cuh"
+
+namespace miagpu {
+
+struct RealignParams {
+  // resident reads
+  const uint8_t* bases;
+  const int64_t* off;
+  // per read inputs
+  const uint8_t* rc;
+  const int32_t* win_start;
+  const int32_t* win_len;
+  // work list of this bucket
+  const int32_t* list;
+  int32_t n_list;
+  int32_t* counter;          // dynamic work fetch
+  // reference codes (0..4), padded to 16 B
+  const uint8_t* ref_codes;
+  int32_t ref_bytes;         // padded length (multiple of 16)
+  int32_t ref_in_smem;
+  const int32_t* prof;       // PROF_INTS
+  int32_t sg5;
+  // outputs
+  int32_t* score;
+  int32_t* as_out;
+  int32_t* ae_out;
+  int32_t* abr;
+  int32_t* n_runs;
+  uint16_t* runs;
+  uint8_t* status;
+  // trace scratch
+  uint32_t* scratch;
+  int64_t scratch_words_per_warp;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ int lds_s32(uint32_t addr) {
+  int v;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+
+// TMA-style bulk copy global -> shared with mbarrier completion (UBLKCP in SASS)
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(phase)
+      : "memory");
+}
+
+template <int K>
+struct TraceLayout {
+  static constexpr int W = K / 2;                                  // 32-bit words of trace per lane per row
+  static constexpr int WP = (W <= 2) ? 2 : (W <= 4) ? 4 : 8;       // padded to a vector store
+  static constexpr int ROW_WORDS = 32 * WP;
+};
+
+constexpr int WARPS_PER_BLOCK = 4;
+
+// dynamic shared memory: [prof PROF_INTS ints][rowoff WARPS*256 u16][ref codes]
+template <int K>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) realign_kernel(RealignParams p) {
+  static_assert(K % 2 == 0 && K >= 2 && K <= 16, "K must be even");
+  using TL = TraceLayout<K>;
+  extern __shared__ __align__(16) uint8_t smem[];
+  __shared__ __align__(8) uint64_t ref_bar;
+  int32_t* s_prof = reinterpret_cast<int32_t*>(smem);
+  uint16_t* s_rowoff = reinterpret_cast<uint16_t*>(smem + PROF_INTS * 4);
+  uint8_t* s_ref = smem + PROF_INTS * 4 + WARPS_PER_BLOCK * MAX_READ * 2;
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+
+  // ---- stage the scoring profile and (if it fits) the whole reference once per block
+  if (p.ref_in_smem) {
+    if (tid == 0) {
+      mbar_init(&ref_bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+      mbar_expect_tx(&ref_bar, (uint32_t)p.ref_bytes);
+      // bulk copies are limited only by the tx counter (2^20-1 bytes); chunk anyway
+      for (int o = 0; o < p.ref_bytes; o += 32768) {
+        int n = min(32768, p.ref_bytes - o);
+        bulk_g2s(s_ref + o, p.ref_codes + o, (uint32_t)n, &ref_bar);
+      }
+    }
+  }
+  for (int i = tid; i < PROF_INTS; i += blockDim.x) s_prof[i] = p.prof[i];
+  if (p.ref_in_smem) mbar_wait(&ref_bar, 0);
+  __syncthreads();
+
+  uint16_t* my_rowoff = s_rowoff + warp * MAX_READ;
+  const uint32_t prof_base = smem_u32(s_prof);
+  const int64_t gwarp = (int64_t)blockIdx.x * WARPS_PER_BLOCK + warp;
+  uint32_t* trace = p.scratch + gwarp * p.scratch_words_per_warp;
+
+  // per-lane column constants
+  int constP[K];
+#pragma unroll
+  for (int j = 0; j < K; j++) {
+    int c = lane * K + j;
+    constP[j] = (GEP * c) * KEY_MUL + (MARK_COL << 9) + (KEY_IDX_MASK - c);
+  }
+  const int gcBase = -(GOP - GEP) - GEP * (lane * K);     // G_c = A - 800 - 200*c
+
+  for (;;) {
+    int item = 0;
+    if (lane == 0) item = atomicAdd(p.counter, 1);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= p.n_list) break;
+    const int rd = p.list[item];
+    const int64_t o0 = p.off[rd];
+    const int L = (int)(p.off[rd + 1] - o0);
+    const int ws = p.win_start[rd];
+    const int len1 = p.win_len[rd];
+    const int strand = p.rc[rd] ? 1 : 0;
+
+    // ---- read -> per-row profile offsets (pop_s2c_in_a + find_sm_depth), lanes in parallel
+    __syncwarp();
+    for (int r = lane; r < L; r += 32) {
+      int code = base_code(p.bases[o0 + r]);
+      my_rowoff[r] = (uint16_t)(prof_row_index(strand, sm_depth(r, L), code) * 4);
+    }
+    // ---- reference window -> per-column code*4 (pop_s1c_in_a)
+    int code4[K];
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+      int c = lane * K + j;
+      int code = 4;
+      if (c < len1) code = p.ref_in_smem ? s_ref[ws + c] : p.ref_codes[ws + c];
+      code4[j] = code * 4;
+    }
+    __syncwarp();
+
+    // ---- row 0 (mia.c:769-785): plain substitution scores, no trace
+    int Sp[K], R[K];
+    {
+      uint32_t pa = prof_base + my_rowoff[0];
+#pragma unroll
+      for (int j = 0; j < K; j++) {
+        Sp[j] = lds_s32(pa + code4[j]);
+        R[j] = NEG_KEY;
+      }
+    }
+
+    for (int r = 1; r < L; r++) {
+      const uint32_t pa = prof_base + my_rowoff[r];
+      const int N = p.sg5 ? -(GOP + GEP * (r + 1)) : 0;                       // mia.c:877-880
+      const int grc = -(GOP - GEP) - GEP * r;                                 // G_r = B - 800 - 200*r
+      const int rowKey = (GEP * (r - 1)) * KEY_MUL + (MARK_ROW << 9) + (KEY_IDX_MASK - (r - 1));
+
+      // candidate keys of row r-1: column k becomes a best_gap_col candidate at column k+2
+      int cand[K];
+      {
+        int pk_a = Sp[K - 2] * KEY_MUL + constP[K - 2];
+        int pk_b = Sp[K - 1] * KEY_MUL + constP[K - 1];
+        int l2 = __shfl_up_sync(0xffffffffu, pk_a, 1);
+        int l1 = __shfl_up_sync(0xffffffffu, pk_b, 1);
+        cand[0] = lane ? l2 : NEG_KEY;
+        if (K > 1) cand[1] = lane ? l1 : NEG_KEY;
+#pragma unroll
+        for (int j = 2; j < K; j++) cand[j] = Sp[j - 2] * KEY_MUL + constP[j - 2];
+      }
+      int dleft = __shfl_up_sync(0xffffffffu, Sp[K - 1], 1);
+      if (lane == 0) dleft = N;          // column 0: S = sub + N, trace 0 (mia.c:805-822)
+
+      // lane total, then exclusive warp max-scan = best_gap_col state entering this lane
+      int t = cand[0];
+#pragma unroll
+      for (int j = 1; j < K; j++) t = max(t, cand[j]);
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        int v = __shfl_up_sync(0xffffffffu, t, d);
+        if (lane >= d) t = max(t, v);
+      }
+      int P = __shfl_up_sync(0xffffffffu, t, 1);
+      if (lane == 0) P = NEG_KEY;
+
+      int D = dleft;
+      uint32_t tw[K];
+#pragma unroll
+      for (int j = 0; j < K; j++) {
+        P = max(P, cand[j]);
+        const int sub = lds_s32(pa + code4[j]);
+        const int Gc = (P >> KEY_SHIFT) + (gcBase - GEP * j);
+        const int Gr = (R[j] >> KEY_SHIFT) + grc;
+        const bool pC = Gc >= Gr;                       // mia.c:933
+        const int m1 = pC ? Gc : Gr;
+        const bool pD = D >= m1;                        // mia.c:922-923
+        const int m = pD ? D : m1;
+        const bool pS = N > m;                          // mia.c:910-912 (strict)
+        const int S = pS ? N : sub + m;
+        int w = pC ? P : R[j];
+        w = pD ? (MARK_DIAG << 9) : w;
+        w = pS ? (MARK_START << 9) : w;
+        tw[j] = (uint32_t)w;
+        R[j] = max(R[j], D * KEY_MUL + rowKey);         // row r-1 joins best_gap_row[c-1] for row r+1
+        D = Sp[j];
+        Sp[j] = S;
+      }
+      if (lane == 0) R[0] = NEG_KEY;                    // there is no column -1
+
+      // ---- one vector store of this lane's K trace words (row r stored at r-1)
+      uint32_t* trow = trace + (int64_t)(r - 1) * TL::ROW_WORDS + lane * TL::WP;
+      uint32_t wv[TL::WP];
+#pragma unroll
+      for (int w = 0; w < TL::WP; w++) wv[w] = (w < TL::W) ? __byte_perm(tw[2 * w], tw[2 * w + 1], 0x5410) : 0u;
+      if (TL::WP == 2) {
+        *reinterpret_cast<uint2*>(trow) = make_uint2(wv[0], wv[1]);
+      } else {
+#pragma unroll
+        for (int w = 0; w < TL::WP; w += 4) *reinterpret_cast<uint4*>(trow + w) = make_uint4(wv[w], wv[w + 1], wv[w + 2], wv[w + 3]);
+      }
+    }
+
+    // ---- max_sg_score (mia.c:1278-1302): first maximum of the last row
+    int best = INT_MIN;
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+      int c = lane * K + j;
+      int key = (c < len1) ? Sp[j] * 512 + (KEY_IDX_MASK - c) : INT_MIN;
+      best = max(best, key);
+    }
+    best = __reduce_max_sync(0xffffffffu, best);
+    const int score = best >> 9;
+    const int aec = KEY_IDX_MASK - (best & KEY_IDX_MASK);
+
+    // ---- find_align_begin + populate_pwaln_to_begin, executed uniformly by the warp
+    __syncwarp();   // trace stores of all lanes visible (same warp, global memory)
+    int row = L - 1, col = aec, nrun = 0, curM = 0, ncols = 0;
+    uint16_t* my_runs = p.runs + (int64_t)rd * MAX_RUNS;
+    const uint16_t* t16 = reinterpret_cast<const uint16_t*>(trace);
+    auto push = [&](int type, int len) {
+      if (nrun < MAX_RUNS && lane == 0) my_runs[nrun] = (uint16_t)((type << 14) | len);
+      nrun++;
+      ncols += len;
+    };
+    while (row > 0 && col > 0) {
+      const int tl = col / K, tj = col - tl * K;
+      const uint32_t w16 = __ldcg(t16 + ((int64_t)(row - 1) * TL::ROW_WORDS + tl * TL::WP) * 2 + tj);
+      const int mk = (w16 >> 9) & 3;
+      const int idx = KEY_IDX_MASK - (int)(w16 & KEY_IDX_MASK);
+      if (mk == MARK_START) break;
+      curM++;
+      if (mk == MARK_DIAG || idx == 0) {          // idx 0: trace == 0 reads as diagonal (H2)
+        row--; col--;
+      } else if (mk == MARK_ROW) {                // mia.c:1466-1476
+        push(MIAGPU_RUN_M, curM); curM = 0;
+        push(MIAGPU_RUN_I, row - 1 - idx);
+        row = idx; col--;
+      } else {                                    // mia.c:1477-1487
+        push(MIAGPU_RUN_M, curM); curM = 0;
+        push(MIAGPU_RUN_D, col - 1 - idx);
+        col = idx; row--;
+      }
+    }
+    push(MIAGPU_RUN_M, curM + 1);
+    if (lane == 0) {
+      uint8_t st = MIAGPU_ST_OK;
+      if (nrun > MAX_RUNS) { st |= MIAGPU_ST_RUNS_OVERFLOW; nrun = -1; }
+      if (ncols > 2 * MAX_READ) st |= MIAGPU_ST_STR_OVERFLOW;
+      for (int a = 0, b = nrun - 1; a < b; a++, b--) {       // runs were produced 3'->5'
+        uint16_t x = my_runs[a]; my_runs[a] = my_runs[b]; my_runs[b] = x;
+      }
+      p.score[rd] = score;
+      p.as_out[rd] = col + ws;                    // mia_main.c:250-255
+      p.ae_out[rd] = aec + ws;
+      p.abr[rd] = row;
+      p.n_runs[rd] = nrun;
+      p.status[rd] = st;
+    }
+  }
+}
+
+}  // namespace miagpu

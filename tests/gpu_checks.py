@@ -1,0 +1,71 @@
+"""Parity checks of the CUDA path against the CPU oracle, shared by tests/ and smoke().
+Everything goes through the C ABI (mia_b200.api)."""
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def load_pssm(name="onepass"):
+    return np.load(os.path.join(ROOT, "tests", "golden", "pssm.npz"))[name]
+
+
+def make_case(n_reads, ref_len, seed, divergence=0.02, indel_rate=0.004, min_len=35, max_len=75, n_rate=0.002):
+    import _pkg
+    _pkg.load()
+    from mia_b200 import synth
+    ref = synth.random_reference(ref_len, seed=seed)
+    genome = synth.diverge(ref, divergence, seed=seed + 1, indel_rate=indel_rate)
+    bases, off, truth = synth.make_reads(genome, n_reads, min_len, max_len, seed=seed + 2, n_rate=n_rate)
+    # stored orientation: reverse-strand reads are kept reverse-complemented (fsdb.c:209-227)
+    rc = truth["strand"].astype(np.uint8)
+    out = bases.copy()
+    for i in np.flatnonzero(rc):
+        out[off[i]:off[i + 1]] = synth.revcomp_bytes(bases[off[i]:off[i + 1]])
+    # as/ae guesses: true start on the sample genome +- a few bases (indels shift them)
+    rng = np.random.default_rng(seed + 3)
+    as_ = (truth["start"] + rng.integers(-6, 7, n_reads)).astype(np.int32)
+    as_ = np.clip(as_, 0, ref_len - 1)
+    ae = (as_ + truth["length"] - 1 + rng.integers(-3, 4, n_reads)).astype(np.int32)
+    return ref, out, off, rc, as_, ae
+
+
+def check_realign(gpu, oracle, ref, bases, off, rc, as_, ae, sm, circular=1, sample=None):
+    """GPU realign vs oracle realign, read by read: score, as, ae, abr, gapped strings."""
+    from mia_b200 import api
+    gpu.set_pssm(sm)
+    gpu.set_reference(ref, circular=circular, with_rc=0)
+    out = gpu.realign_host(bases, off, rc, as_, ae)
+    ctx = oracle.ctx_new(ref, circular, sm, with_rc=0, k=0)
+    wref = oracle.ctx_seq(ctx)
+    n = len(off) - 1
+    idx = range(n) if sample is None else sample
+    bad = []
+    for i in idx:
+        read = bases[off[i]:off[i + 1]].tobytes().decode()
+        o = oracle.realign(ctx, read, int(rc[i]), int(as_[i]), int(ae[i]))
+        st = int(out["status"][i])
+        if st & 0x80:
+            bad.append((i, "unsupported window", st))
+            continue
+        rg, fg = api.expand_runs(wref, read, int(out["as_out"][i]), int(out["abr"][i]), out["runs"][i], int(out["n_runs"][i]))
+        got = (int(out["score"][i]), int(out["as_out"][i]), int(out["ae_out"][i]), int(out["abr"][i]), rg, fg)
+        exp = (o["score"], o["as_"], o["ae"], o["abr"], o["ref_gapped"], o["read_gapped"])
+        if got != exp:
+            bad.append((i, got, exp))
+    oracle.ctx_free(ctx)
+    return bad, out
+
+
+def check_realign_small(n_reads=2000, ref_len=3000, seed=7):
+    import _pkg
+    _pkg.load()
+    from mia_b200 import api
+    from oracle.pyoracle import Oracle
+    o = Oracle()
+    g = api.MiaGpu(0)
+    ref, bases, off, rc, as_, ae = make_case(n_reads, ref_len, seed)
+    bad, _ = check_realign(g, o, ref, bases, off, rc, as_, ae, load_pssm("onepass"))
+    g.close()
+    assert not bad, f"{len(bad)} of {n_reads} reads differ from the oracle; first: {bad[0]}"
