@@ -47,6 +47,7 @@ extern "C" {
 #define MIAGPU_ST_RUNS_OVERFLOW 1     /* more than MIAGPU_MAX_RUNS runs: n_runs = -1 */
 #define MIAGPU_ST_SKIPPED     2       /* pass 1: no k-mer hit, read not aligned (mia_main.c:781) */
 #define MIAGPU_ST_STR_OVERFLOW 4      /* alignment longer than the reference's 512-column buffers */
+#define MIAGPU_ST_UNSUPPORTED  0x80    /* window wider than the register-tiled kernels handle (reported, never silent) */
 
 typedef struct miagpu_ctx miagpu_ctx;
 
@@ -60,7 +61,7 @@ const char* miagpu_version( void );
 /* ---- a1. Scoring matrices.  fwd is PSSM.sm as read_pssm / init_flatsubmat
  * fill it (io.c:408-503, pssm.c:96-126); the strand-reversed copy
  * (revcom_submat, pssm.c:53-93) is derived inside.  Entries must satisfy
- * |x| <= 4000 (the packed-key DP needs scores below 2^20). */
+ * |x| <= 2000 (the packed-key DP needs 256*|x| + 200*511 < 2^20). */
 int miagpu_set_pssm( miagpu_ctx* ctx, const int32_t* fwd );
 int miagpu_get_pssm( miagpu_ctx* ctx, int32_t* fwd, int32_t* rev );
 
@@ -139,56 +140,63 @@ int miagpu_realign_host( miagpu_ctx* ctx, int64_t n, const uint8_t* bases,
 /* ---- a10..a13. Column accumulation and base calling over the alignments the
  * last miagpu_pass1 / miagpu_realign left on the device.
  *
- * The host keeps the reference's own bookkeeping (FragSeq.front_asp/back_asp,
- * AlnSeq.dropped; H10 and the stale back pointer of mia_main.c:273-276) and
- * describes the culled AlnSeq list to the device as `entries`:
- *   entry e = { read index, segment (0 = whole/front, 1 = back), flags,
- *               smp parameters }  -- see miagpu_entry below.
+ * The host keeps the reference's own bookkeeping -- which AlnSeq slot belongs
+ * to which read (FragSeq.front_asp / back_asp), the sticky AlnSeq.dropped flag
+ * (H10), the back pointer that reiterate_assembly never clears
+ * (mia_main.c:273-276) -- and describes culled_maln->AlnSeqArray to the device
+ * as a list of entries, one per AlnSeq in the list (duplicates allowed).
  * The device derives AlnSeq.seq / ins / smp on the fly from the run lists
  * (merge_pwaln_into_maln map_align.c:866-954, split_pwaln mia.c:1376-1438,
  * pop_smp_from_FSDB fsdb.c:542-619), takes the per-position maximum insert
- * length (ref->gaps, mia.c:486-504), adds every covered column into the
- * BaseCounts accumulators (add_base map_align.c:229-263) and calls bases
- * (find_consensus map_align.c:294-391; consensus_assembly_string mia.c:515-603).
+ * length (ref->gaps as left by cull_maln_from_fsdb, mia.c:486-504), adds every
+ * covered column into the BaseCounts accumulators (add_base
+ * map_align.c:229-263, find_ins_cons 444-510) and calls bases (find_consensus
+ * map_align.c:294-391; consensus_assembly_string mia.c:515-603).
+ *
+ * An alignment is a sequence of reference columns (M and D runs) numbered from
+ * 0 at its first column; an entry covers columns [col_begin, col_begin +
+ * col_count) and places the first of them at reference position ref_pos
+ * (AlnSeq.start).  Inserted bases belong to the column that follows them
+ * (AlnSeq.ins[], map_align.c:906-927).  For a whole alignment: col_begin = 0,
+ * ref_pos = start; for a wrap-split one the 'f' entry ends at seq_len-1 and the
+ * 'b' entry has ref_pos = 0 (mia.c:1419-1422).
+ * smp (fsdb.c:563-614): with act = act_bias + (read bases consumed before the
+ * column, inserted ones included),
+ *     dist_front = back_formula ? front_len + act : act
+ *     dist_back  = total_len - act - 1
+ *     depth = dist_front <= 15 ? dist_front : dist_back < 15 ? 30 - dist_back : 15
  */
 typedef struct {
-  int32_t read;       /* index into the resident reads */
-  uint8_t segment;    /* 0: the part with ref pos < seq_len ('a' or 'f'); 1: the wrapped part ('b') */
-  uint8_t dropped;    /* AlnSeq.dropped: excluded from base columns, NOT from insert columns */
-  uint8_t back_formula; /* pop_smp formula: 0 = front loop (fsdb.c:563-584), 1 = back loop (588-614) */
-  uint8_t reserved;
-  int32_t front_len;  /* asp_len(front_asp) of the read that owns the pointer (fsdb.c:553) */
-  int32_t total_len;  /* front_seq_len + back_seq_len (fsdb.c:554-559) */
-  int32_t act0;       /* act_seq_pos on entry to this segment's loop */
+  int32_t read;         /* index into the resident reads */
+  int32_t col_begin;
+  int32_t col_count;
+  int32_t ref_pos;      /* AlnSeq.start */
+  int32_t front_len;    /* asp_len(front_asp) of the read that holds the pointer (fsdb.c:553) */
+  int32_t total_len;    /* front_seq_len + back_seq_len (fsdb.c:554-559) */
+  int32_t act_bias;     /* 0 for a read's own segments */
+  uint8_t dropped;      /* AlnSeq.dropped: excluded from base columns, NOT from insert columns */
+  uint8_t back_formula; /* 0 = front loop (fsdb.c:563-584), 1 = back loop (588-614) */
+  uint8_t reserved[2];
 } miagpu_entry;
 
-/* per-read segment geometry the host needs to fill miagpu_entry (asp_len etc.):
- * for segment s in {0,1}: cols[s] = covered reference columns, ins[s] = inserted
- * bases, bases[s] = non-gap read bases; split = alignment crosses seq_len. */
-typedef struct {
-  int32_t cols[2], ins[2], bases[2];
-  int32_t split;
-  int32_t start, end;   /* PWAlnFrag start / end after the end > seq_len fix */
-} miagpu_geom;
-
-int miagpu_geometry( miagpu_ctx* ctx, miagpu_geom* geom /* n */ );
-
-/* Accumulate + call.  gaps_out[wrap_len+1] (nullable) = ref->gaps;
- * counts_out[seq_len*10] (nullable) = BaseCounts of every base column;
- * cons_out must hold seq_len + sum(gaps) + 1 chars; *cons_len its strlen. */
+/* Accumulate + call in one step (single GPU).  Outputs are host arrays, any may
+ * be NULL: gaps_out[seq_len] = ref->gaps for positions < seq_len;
+ * counts_out[seq_len*10] = BaseCounts of every base column (MIAGPU_COUNTS_PER_COL
+ * order); cons_out must hold seq_len + sum(gaps) + 1 chars; *cons_len its strlen. */
 int miagpu_consensus( miagpu_ctx* ctx, int64_t n_entries,
                       const miagpu_entry* entries, int cons_code,
                       int32_t* gaps_out, int32_t* counts_out, char* cons_out,
                       int32_t* cons_len );
 
-/* Multi-GPU: split miagpu_consensus in two so that the caller can
- * all-reduce between them.  After _accumulate the device buffers
- *   gaps   int32[wrap_len+1]                       (reduce with MAX)
- *   counts int32[(seq_len + n_ins_cols) * 10]      (reduce with SUM)
- * are exposed as raw device pointers; the insert-column layout is a function
- * of the reduced gaps only, so the caller reduces gaps first
- * (_accumulate_gaps -> allreduce(max) -> _accumulate_counts -> allreduce(sum)
- * -> _call). */
+/* Multi-GPU: the same in three steps so that the caller can
+ * all-reduce between them (reads are sharded, the reference is replicated):
+ *   _accumulate_gaps   -> device int32 gaps[seq_len]          reduce with MAX
+ *   _accumulate_counts -> device int32 counts[10][n_cols]      reduce with SUM
+ *                         (n_cols = seq_len + sum(gaps); plane-major)
+ *   _call              -> consensus from the reduced buffers
+ * The insert-column layout is a function of the reduced gaps only, so every
+ * rank derives the same layout.  Integer sums: bit-identical for any number
+ * of GPUs and any order. */
 int miagpu_accumulate_gaps( miagpu_ctx* ctx, int64_t n_entries,
                             const miagpu_entry* entries, void** dev_gaps,
                             int64_t* n_gaps );

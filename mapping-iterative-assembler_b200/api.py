@@ -23,20 +23,10 @@ class MiaGpuError(RuntimeError):
     pass
 
 
-class Entry(C.Structure):
-    _fields_ = [("read", C.c_int32), ("segment", C.c_uint8), ("dropped", C.c_uint8), ("back_formula", C.c_uint8),
-                ("reserved", C.c_uint8), ("front_len", C.c_int32), ("total_len", C.c_int32), ("act0", C.c_int32)]
-
-
-class Geom(C.Structure):
-    _fields_ = [("cols", C.c_int32 * 2), ("ins", C.c_int32 * 2), ("bases", C.c_int32 * 2), ("split", C.c_int32),
-                ("start", C.c_int32), ("end", C.c_int32)]
-
-
-ENTRY_DTYPE = np.dtype([("read", np.int32), ("segment", np.uint8), ("dropped", np.uint8), ("back_formula", np.uint8),
-                        ("reserved", np.uint8), ("front_len", np.int32), ("total_len", np.int32), ("act0", np.int32)])
-GEOM_DTYPE = np.dtype([("cols", np.int32, 2), ("ins", np.int32, 2), ("bases", np.int32, 2), ("split", np.int32),
-                       ("start", np.int32), ("end", np.int32)])
+ENTRY_DTYPE = np.dtype([("read", np.int32), ("col_begin", np.int32), ("col_count", np.int32), ("ref_pos", np.int32),
+                        ("front_len", np.int32), ("total_len", np.int32), ("act_bias", np.int32), ("dropped", np.uint8),
+                        ("back_formula", np.uint8), ("reserved", np.uint8, 2)])
+assert ENTRY_DTYPE.itemsize == 32
 
 _lib = None
 
@@ -64,7 +54,6 @@ def load_library():
     L.miagpu_compact_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, _i64p]
     L.miagpu_realign.argtypes = [C.c_void_p] + [C.c_void_p] * 10
     L.miagpu_realign_host.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 12
-    L.miagpu_geometry.argtypes = [C.c_void_p, C.c_void_p]
     L.miagpu_consensus.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, _i32p]
     L.miagpu_accumulate_gaps.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_void_p), _i64p]
     L.miagpu_accumulate_counts.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), _i64p]
@@ -79,7 +68,7 @@ def load_library():
 
 EXPORTS = ["miagpu_device_count", "miagpu_create", "miagpu_destroy", "miagpu_last_error", "miagpu_version", "miagpu_set_pssm",
            "miagpu_get_pssm", "miagpu_set_reference", "miagpu_ref_wrap_len", "miagpu_build_kmers", "miagpu_upload_reads",
-           "miagpu_pass1", "miagpu_compact_reads", "miagpu_realign", "miagpu_realign_host", "miagpu_geometry",
+           "miagpu_pass1", "miagpu_compact_reads", "miagpu_realign", "miagpu_realign_host",
            "miagpu_consensus", "miagpu_accumulate_gaps", "miagpu_accumulate_counts", "miagpu_call", "miagpu_last_timing",
            "miagpu_int32_peak", "miagpu_stream"]
 
@@ -172,6 +161,37 @@ class MiaGpu:
                                               _ptr(out["n_runs"]), _ptr(out["runs"]), _ptr(out["status"])))
         self.n = n
         return out
+
+    # -- consensus
+    def consensus(self, entries, cons_code=1, want_counts=False):
+        """consensus_assembly_string over the culled entry list (mia.c:515-603).
+        Returns (consensus, gaps[seq_len], counts[seq_len,10] or None)."""
+        entries = np.ascontiguousarray(entries, ENTRY_DTYPE)
+        gaps = np.zeros(self.seq_len, np.int32)
+        counts = np.zeros((self.seq_len, 10), np.int32) if want_counts else None
+        buf = C.create_string_buffer(self.seq_len * 2 + 1024 + len(entries) * 4)
+        n = C.c_int32()
+        self._ck(self.lib.miagpu_consensus(self.h, len(entries), _ptr(entries), cons_code, _ptr(gaps), _ptr(counts), buf, C.byref(n)))
+        return buf.value.decode(), gaps, counts
+
+    def accumulate_gaps(self, entries):
+        entries = np.ascontiguousarray(entries, ENTRY_DTYPE)
+        ptr, n = C.c_void_p(), C.c_int64()
+        self._ck(self.lib.miagpu_accumulate_gaps(self.h, len(entries), _ptr(entries), C.byref(ptr), C.byref(n)))
+        return ptr.value, n.value
+
+    def accumulate_counts(self):
+        ptr, n = C.c_void_p(), C.c_int64()
+        self._ck(self.lib.miagpu_accumulate_counts(self.h, C.byref(ptr), C.byref(n)))
+        return ptr.value, n.value
+
+    def call(self, cons_code=1, want_counts=False, max_len=None):
+        gaps = np.zeros(self.seq_len, np.int32)
+        counts = np.zeros((self.seq_len, 10), np.int32) if want_counts else None
+        buf = C.create_string_buffer(max_len or (self.seq_len * 4 + 4096))
+        n = C.c_int32()
+        self._ck(self.lib.miagpu_call(self.h, cons_code, _ptr(gaps), _ptr(counts), buf, C.byref(n)))
+        return buf.value.decode(), gaps, counts
 
     def last_timing(self):
         k, h, d = C.c_float(), C.c_float(), C.c_float()

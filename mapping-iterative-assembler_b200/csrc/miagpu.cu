@@ -8,6 +8,8 @@
 
 #include "common.cuh"
 #include "realign.cuh"
+#include "consensus.cuh"
+#include <cub/device/device_scan.cuh>
 
 namespace miagpu {
 
@@ -73,6 +75,14 @@ struct miagpu_ctx {
   DevBuf<uint16_t> d_runs;
   DevBuf<int32_t> d_meta;                      // bucket counts[8], work counters[8], max L[8], cells(2 x int32 -> int64)
   DevBuf<uint32_t> d_scratch;
+  // consensus
+  DevBuf<miagpu_entry> d_entries;
+  int64_t n_entries = 0;
+  DevBuf<int32_t> d_sm, d_gaps, d_ins_off, d_acc;
+  DevBuf<uint8_t> d_cub;
+  DevBuf<char> d_called;
+  int64_t n_cols = 0;
+  int cons_stage = 0;                          // 0 none, 1 gaps done, 2 counts done
   // timing of the last call
   float ms_kernels = 0, ms_h2d = 0, ms_d2h = 0;
   int64_t dp_cells = 0;
@@ -120,6 +130,7 @@ extern "C" void miagpu_destroy(miagpu_ctx* c) {
   c->d_rc.release(); c->d_status.release(); c->d_as.release(); c->d_ae.release(); c->d_score.release();
   c->d_as_out.release(); c->d_ae_out.release(); c->d_abr.release(); c->d_nruns.release(); c->d_win_start.release();
   c->d_win_len.release(); c->d_lists.release(); c->d_runs.release(); c->d_meta.release(); c->d_scratch.release();
+  c->d_entries.release(); c->d_sm.release(); c->d_gaps.release(); c->d_ins_off.release(); c->d_acc.release(); c->d_cub.release(); c->d_called.release();
   for (auto& ev : c->ev) cudaEventDestroy(ev);
   cudaStreamDestroy(c->stream);
   delete c;
@@ -153,8 +164,10 @@ extern "C" int miagpu_set_pssm(miagpu_ctx* c, const int32_t* fwd) {
       for (int rb = 0; rb < 5; rb++)
         for (int fb = 0; fb < 5; fb++)   // sm[depth][ref_base][read_base]
           prof[prof_row_index(s, d, rb) + fb] = (s ? c->sm_r : c->sm_f)[(d * 5 + fb) * 5 + rb];
-  if (!c->d_prof.reserve(PROF_INTS)) return 0;
+  if (!c->d_prof.reserve(PROF_INTS) || !c->d_sm.reserve(2 * MIAGPU_PSSM_INTS)) return 0;
   MIAGPU_CUDA(cudaMemcpyAsync(c->d_prof.p, prof.data(), PROF_INTS * 4, cudaMemcpyHostToDevice, c->stream));
+  MIAGPU_CUDA(cudaMemcpyAsync(c->d_sm.p, c->sm_f, sizeof(c->sm_f), cudaMemcpyHostToDevice, c->stream));
+  MIAGPU_CUDA(cudaMemcpyAsync(c->d_sm.p + MIAGPU_PSSM_INTS, c->sm_r, sizeof(c->sm_r), cudaMemcpyHostToDevice, c->stream));
   MIAGPU_CUDA(cudaStreamSynchronize(c->stream));
   c->have_pssm = true;
   return 1;
@@ -450,13 +463,127 @@ extern "C" int miagpu_int32_peak(miagpu_ctx* c, double* ops_per_s) {
   return 1;
 }
 
+// --------------------------------------------------------------- consensus
+static ConsParams cons_params(miagpu_ctx* c) {
+  ConsParams p{};
+  p.entries = c->d_entries.p; p.n_entries = c->n_entries;
+  p.bases = c->d_bases.p; p.off = c->d_off.p; p.rc = c->d_rc.p; p.abr = c->d_abr.p;
+  p.n_runs = c->d_nruns.p; p.runs = c->d_runs.p; p.sm = c->d_sm.p; p.seq_len = c->seq_len;
+  p.gaps = c->d_gaps.p; p.ins_off = c->d_ins_off.p; p.acc = c->d_acc.p; p.n_cols = c->n_cols;
+  return p;
+}
+
+extern "C" int miagpu_accumulate_gaps(miagpu_ctx* c, int64_t n_entries, const miagpu_entry* entries, void** dev_gaps, int64_t* n_gaps) {
+  if (!c || !c->have_ref || !c->have_pssm) { set_error("miagpu_accumulate_gaps: set_pssm / set_reference / realign first"); return 0; }
+  if (n_entries < 0 || (n_entries && !entries)) { set_error("miagpu_accumulate_gaps: bad entries"); return 0; }
+  MIAGPU_CUDA(cudaSetDevice(c->device));
+  for (int64_t i = 0; i < n_entries; i++)
+    if (entries[i].read < 0 || entries[i].read >= c->n) { set_error("miagpu_accumulate_gaps: entry %lld names read %d of %lld", (long long)i, entries[i].read, (long long)c->n); return 0; }
+  c->launches = 0;
+  if (!c->d_entries.reserve(n_entries) || !c->d_gaps.reserve(c->seq_len + 2) || !c->d_ins_off.reserve(c->seq_len + 2)) return 0;
+  MIAGPU_CUDA(cudaEventRecord(c->ev[0], c->stream));
+  if (n_entries) MIAGPU_CUDA(cudaMemcpyAsync(c->d_entries.p, entries, n_entries * sizeof(miagpu_entry), cudaMemcpyHostToDevice, c->stream));
+  MIAGPU_CUDA(cudaEventRecord(c->ev[1], c->stream));
+  c->n_entries = n_entries;
+  MIAGPU_CUDA(cudaMemsetAsync(c->d_gaps.p, 0, (c->seq_len + 2) * sizeof(int32_t), c->stream));
+  if (n_entries) {
+    ConsParams p = cons_params(c);
+    entry_kernel<0><<<(unsigned)((n_entries * 32 + 255) / 256), 256, 0, c->stream>>>(p);
+    MIAGPU_CUDA(cudaGetLastError());
+    c->launches++;
+  }
+  MIAGPU_CUDA(cudaEventRecord(c->ev[2], c->stream));
+  MIAGPU_CUDA(cudaStreamSynchronize(c->stream));
+  MIAGPU_CUDA(cudaEventElapsedTime(&c->ms_h2d, c->ev[0], c->ev[1]));
+  MIAGPU_CUDA(cudaEventElapsedTime(&c->ms_kernels, c->ev[1], c->ev[2]));
+  c->ms_d2h = 0;
+  c->cons_stage = 1;
+  if (dev_gaps) *dev_gaps = c->d_gaps.p;
+  if (n_gaps) *n_gaps = c->seq_len;
+  return 1;
+}
+
+extern "C" int miagpu_accumulate_counts(miagpu_ctx* c, void** dev_counts, int64_t* n_counts) {
+  if (!c || c->cons_stage < 1) { set_error("miagpu_accumulate_counts: call miagpu_accumulate_gaps first"); return 0; }
+  MIAGPU_CUDA(cudaSetDevice(c->device));
+  MIAGPU_CUDA(cudaEventRecord(c->ev[1], c->stream));
+  // insert-column layout: exclusive scan of gaps[0..seq_len] (gaps[seq_len] = 0 pad)
+  size_t tmp = 0;
+  MIAGPU_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, c->d_gaps.p, c->d_ins_off.p, c->seq_len + 1, c->stream));
+  if (!c->d_cub.reserve(tmp + 16)) return 0;
+  MIAGPU_CUDA(cub::DeviceScan::ExclusiveSum(c->d_cub.p, tmp, c->d_gaps.p, c->d_ins_off.p, c->seq_len + 1, c->stream));
+  int32_t total_ins = 0;
+  MIAGPU_CUDA(cudaMemcpyAsync(&total_ins, c->d_ins_off.p + c->seq_len, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  MIAGPU_CUDA(cudaStreamSynchronize(c->stream));
+  c->n_cols = (int64_t)c->seq_len + total_ins;
+  if (!c->d_acc.reserve(c->n_cols * NPLANE) || !c->d_called.reserve(c->n_cols + 16)) return 0;
+  MIAGPU_CUDA(cudaMemsetAsync(c->d_acc.p, 0, c->n_cols * NPLANE * sizeof(int32_t), c->stream));
+  if (c->n_entries) {
+    ConsParams p = cons_params(c);
+    entry_kernel<1><<<(unsigned)((c->n_entries * 32 + 255) / 256), 256, 0, c->stream>>>(p);
+    MIAGPU_CUDA(cudaGetLastError());
+    c->launches += 2;
+  }
+  MIAGPU_CUDA(cudaEventRecord(c->ev[2], c->stream));
+  MIAGPU_CUDA(cudaStreamSynchronize(c->stream));
+  float ms = 0;
+  MIAGPU_CUDA(cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]));
+  c->ms_kernels += ms;
+  c->cons_stage = 2;
+  if (dev_counts) *dev_counts = c->d_acc.p;
+  if (n_counts) *n_counts = c->n_cols * NPLANE;
+  return 1;
+}
+
+extern "C" int miagpu_call(miagpu_ctx* c, int cons_code, int32_t* gaps_out, int32_t* counts_out, char* cons_out, int32_t* cons_len) {
+  if (!c || c->cons_stage < 2) { set_error("miagpu_call: call miagpu_accumulate_counts first"); return 0; }
+  MIAGPU_CUDA(cudaSetDevice(c->device));
+  const int64_t nc = c->n_cols;
+  MIAGPU_CUDA(cudaEventRecord(c->ev[1], c->stream));
+  call_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, c->stream>>>(c->d_acc.p, nc, cons_code, c->d_called.p);
+  MIAGPU_CUDA(cudaGetLastError());
+  c->launches++;
+  MIAGPU_CUDA(cudaEventRecord(c->ev[2], c->stream));
+  std::vector<char> called(nc);
+  std::vector<int32_t> gaps(c->seq_len), ins_off(c->seq_len + 1), acc;
+  MIAGPU_CUDA(cudaMemcpyAsync(called.data(), c->d_called.p, nc, cudaMemcpyDeviceToHost, c->stream));
+  MIAGPU_CUDA(cudaMemcpyAsync(gaps.data(), c->d_gaps.p, c->seq_len * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  if (counts_out) {
+    acc.resize(nc * NPLANE);
+    MIAGPU_CUDA(cudaMemcpyAsync(ins_off.data(), c->d_ins_off.p, (c->seq_len + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    MIAGPU_CUDA(cudaMemcpyAsync(acc.data(), c->d_acc.p, nc * NPLANE * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  }
+  MIAGPU_CUDA(cudaEventRecord(c->ev[3], c->stream));
+  MIAGPU_CUDA(cudaStreamSynchronize(c->stream));
+  float ms = 0;
+  MIAGPU_CUDA(cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]));
+  c->ms_kernels += ms;
+  MIAGPU_CUDA(cudaEventElapsedTime(&c->ms_d2h, c->ev[2], c->ev[3]));
+  if (gaps_out) memcpy(gaps_out, gaps.data(), c->seq_len * sizeof(int32_t));
+  if (counts_out)
+    for (int pos = 0; pos < c->seq_len; pos++)
+      for (int pl = 0; pl < NPLANE; pl++) counts_out[(int64_t)pos * NPLANE + pl] = acc[(int64_t)pl * nc + pos + ins_off[pos + 1]];
+  // consensus string: columns in layout order, gap calls dropped (mia.c:562-570, 600-601)
+  int32_t n = 0;
+  for (int64_t i = 0; i < nc; i++)
+    if (called[i] != '-' && called[i] != ' ') { if (cons_out) cons_out[n] = called[i]; n++; }
+  if (cons_out) cons_out[n] = 0;
+  if (cons_len) *cons_len = n;
+  return 1;
+}
+
+extern "C" int miagpu_consensus(miagpu_ctx* c, int64_t n_entries, const miagpu_entry* entries, int cons_code, int32_t* gaps_out,
+                                int32_t* counts_out, char* cons_out, int32_t* cons_len) {
+  if (!miagpu_accumulate_gaps(c, n_entries, entries, nullptr, nullptr)) return 0;
+  float h2d = c->ms_h2d;
+  if (!miagpu_accumulate_counts(c, nullptr, nullptr)) return 0;
+  if (!miagpu_call(c, cons_code, gaps_out, counts_out, cons_out, cons_len)) return 0;
+  c->ms_h2d = h2d;
+  return 1;
+}
+
 // ------------------------------------------------------------ not yet built
 extern "C" int miagpu_build_kmers(miagpu_ctx*, int, int) { set_error("miagpu_build_kmers: not implemented yet"); return 0; }
 extern "C" int miagpu_pass1(miagpu_ctx*, int32_t*, int32_t*, int32_t*, int32_t*, uint8_t*, int32_t*, int32_t*, int32_t*, int32_t*,
                             int32_t*, int32_t*, uint16_t*, uint8_t*) { set_error("miagpu_pass1: not implemented yet"); return 0; }
 extern "C" int miagpu_compact_reads(miagpu_ctx*, const uint8_t*, const uint8_t*, int64_t*) { set_error("miagpu_compact_reads: not implemented yet"); return 0; }
-extern "C" int miagpu_geometry(miagpu_ctx*, miagpu_geom*) { set_error("miagpu_geometry: not implemented yet"); return 0; }
-extern "C" int miagpu_consensus(miagpu_ctx*, int64_t, const miagpu_entry*, int, int32_t*, int32_t*, char*, int32_t*) { set_error("miagpu_consensus: not implemented yet"); return 0; }
-extern "C" int miagpu_accumulate_gaps(miagpu_ctx*, int64_t, const miagpu_entry*, void**, int64_t*) { set_error("miagpu_accumulate_gaps: not implemented yet"); return 0; }
-extern "C" int miagpu_accumulate_counts(miagpu_ctx*, void**, int64_t*) { set_error("miagpu_accumulate_counts: not implemented yet"); return 0; }
-extern "C" int miagpu_call(miagpu_ctx*, int, int32_t*, int32_t*, char*, int32_t*) { set_error("miagpu_call: not implemented yet"); return 0; }

@@ -69,3 +69,68 @@ def check_realign_small(n_reads=2000, ref_len=3000, seed=7):
     bad, _ = check_realign(g, o, ref, bases, off, rc, as_, ae, load_pssm("onepass"))
     g.close()
     assert not bad, f"{len(bad)} of {n_reads} reads differ from the oracle; first: {bad[0]}"
+
+
+def oracle_round(oracle, ref, bases, off, rc, res, sm, circular, dropped_by_read=None, cons_code=1):
+    """Oracle assembly of one round from per-read realign results (natural pointers):
+    returns (consensus, gaps, counts, entries-as-slots)."""
+    import numpy as np
+    smr = oracle.revcom_pssm(sm)
+    ctx = oracle.ctx_new(ref, circular, sm, with_rc=0, k=0)
+    wrap = oracle.lib.orc_ctx_wrap_len(ctx)
+    a = oracle.asm_new()
+    oracle.asm_begin_round(a, len(ref), wrap)
+    n = len(off) - 1
+    front, back = np.full(n, -1, np.int32), np.full(n, -1, np.int32)
+    for i in range(n):
+        r = res[i]
+        if r is None:
+            continue
+        f, b = oracle.asm_add(a, r["ref_gapped"], r["read_gapped"], r["as_"], r["ae"], int(rc[i]), r["score"])
+        front[i] = f
+        back[i] = -1 if b is None else b
+    oracle.asm_pop_smp(a, front, back)
+    seq_len = np.diff(off).astype(np.int32)
+    if dropped_by_read is None:
+        score = np.array([0 if r is None else r["score"] for r in res], np.int32)
+        oracle.asm_cull(a, front, back, seq_len, score)
+    else:
+        # force the flags: score 1 / 0 against a hard cut of 1
+        score = np.where(np.asarray(dropped_by_read) > 0, 0, 1).astype(np.int32)
+        oracle.asm_cull(a, front, back, seq_len, score, hard_cut=1)
+    cons, counts = oracle.asm_consensus(a, sm, smr, cons_code, len(ref), counts=True)
+    gaps = oracle.asm_gaps(a, wrap)
+    ent = oracle.asm_entries(a)
+    oracle.asm_free(a)
+    oracle.ctx_free(ctx)
+    return cons, gaps, counts, ent
+
+
+def check_consensus(gpu, oracle, ref, bases, off, rc, as_, ae, sm, circular=1, cons_code=1, drop_frac=0.1, seed=0):
+    """GPU realign + consensus vs the oracle's round on the same inputs."""
+    import numpy as np
+    from mia_b200 import entries as E
+    gpu.set_pssm(sm)
+    gpu.set_reference(ref, circular=circular, with_rc=0)
+    out = gpu.realign_host(bases, off, rc, as_, ae)
+    n = len(off) - 1
+    ctx = oracle.ctx_new(ref, circular, sm, with_rc=0, k=0)
+    res = []
+    for i in range(n):
+        read = bases[off[i]:off[i + 1]].tobytes().decode()
+        res.append(oracle.realign(ctx, read, int(rc[i]), int(as_[i]), int(ae[i])))
+    oracle.ctx_free(ctx)
+    rng = np.random.default_rng(seed)
+    dropped = (rng.random(n) < drop_frac).astype(np.uint8)
+    cons, gaps, counts, _ = oracle_round(oracle, ref, bases, off, rc, res, sm, circular, dropped, cons_code)
+    ent, split, _ = E.natural_entries(out["as_out"], out["ae_out"], out["n_runs"], out["runs"], len(ref), dropped, dropped)
+    gcons, ggaps, gcounts = gpu.consensus(ent, cons_code, want_counts=True)
+    problems = []
+    if not (ggaps == gaps[:len(ref)]).all():
+        problems.append(("gaps", np.flatnonzero(ggaps != gaps[:len(ref)])[:5].tolist()))
+    if not (gcounts == counts).all():
+        w = np.argwhere(gcounts != counts)[:5].tolist()
+        problems.append(("counts", w, [(gcounts[r].tolist(), counts[r].tolist()) for r, _ in w[:2]]))
+    if gcons != cons:
+        problems.append(("consensus", len(gcons), len(cons)))
+    return problems, dict(n_split=int(split.sum()), n_ins_cols=int(ggaps.sum()), cons_len=len(gcons))

@@ -1,0 +1,23 @@
+"""-m gpu: column accumulation + base calling (C ABI) vs the CPU oracle, bit-exact."""
+import pytest
+
+import gpu_checks
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("cons_code", [1, 2])
+def test_consensus_matches_oracle(gpu, oracle, cons_code):
+    ref, bases, off, rc, as_, ae = gpu_checks.make_case(3000, 2500, seed=51, divergence=0.03, indel_rate=0.01)
+    problems, info = gpu_checks.check_consensus(gpu, oracle, ref, bases, off, rc, as_, ae, gpu_checks.load_pssm("onepass"),
+                                                cons_code=cons_code)
+    assert not problems, problems
+    assert info["n_split"] > 0 and info["n_ins_cols"] > 0      # the case must exercise wrap splits and insert columns
+
+
+def test_consensus_low_coverage_linear(gpu, oracle):
+    # coverage ~1x: N calls, ties, uncovered columns; linear reference: no splits
+    ref, bases, off, rc, as_, ae = gpu_checks.make_case(60, 3000, seed=61, divergence=0.05, indel_rate=0.01)
+    problems, _ = gpu_checks.check_consensus(gpu, oracle, ref, bases, off, rc, as_, ae, gpu_checks.load_pssm("ancient"),
+                                             circular=0, drop_frac=0.3)
+    assert not problems, problems
