@@ -1,0 +1,398 @@
+#!/usr/bin/env python
+"""bench.py -- MIA per-iteration hot path on B200 (BASELINE.json metric/config).
+
+A "step" is ONE ITERATION of the hot path over one batch of synthetic aDNA reads:
+windowed PSSM semi-global DP + on-device traceback of every read against the current
+consensus (reiterate_assembly, mia_main.c:178-257), then per-column accumulation and base
+calling (consensus_assembly_string, mia.c:515-603).  Workload at N=1 is BASELINE.json
+configs[1]: 1 M synthetic 35-75 bp aDNA-damaged reads vs a 16,569 bp circular reference,
+ancient.submat.solexa.onepass, single iteration.  Reads shard across ranks (weak scaling:
+1 M reads per GPU, consensus replicated, gaps all-reduced with MAX and the column planes
+with SUM over NCCL).
+
+  value : reads/s, whole job, inputs resident in HBM, device time (CUDA events on the
+          library's stream), max over ranks.
+  e2e   : the same through the C ABI with HOST buffers: H2D of reads + rc/as/ae from pinned
+          memory, realign, D2H of per-read results, host score cut (a12), H2D of the dropped
+          flags, consensus, D2H of the consensus -- wall clock around the calls.
+  --impl reference : the unmodified reference (oracle/_ref, built from /root/reference/src)
+          running its own per-read realign sequence on the host cores, one process per core
+          on disjoint shards (the reference itself is single-threaded).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "aligned reads/sec per iteration (windowed PSSM DP + traceback + consensus)"
+UNIT = "reads/s"
+REF_LEN = 16569
+INT_OPS_PER_CELL = 15          # minimum straight-line INT32 work per DP cell
+
+
+def load_pssm(name="onepass"):
+    return np.load(os.path.join(ROOT, "tests", "golden", "pssm.npz"))[name]
+
+
+def make_workload(n_reads, seed):
+    import _pkg
+    _pkg.load()
+    from mia_b200 import synth
+    ref = synth.random_reference(REF_LEN, seed=1)
+    genome = synth.diverge(ref, 0.005, seed=2)
+    bases, off, truth = synth.make_reads(genome, n_reads, 35, 75, seed=seed)
+    rc = truth["strand"].astype(np.uint8)
+    # stored orientation: reverse-strand reads are kept reverse-complemented (fsdb.c:209-227)
+    comp = np.zeros(256, np.uint8)
+    for a, b in zip(b"ACGTN", b"TGCAN"):
+        comp[a] = b
+    rid = np.repeat(np.arange(n_reads), np.diff(off))
+    pos = np.arange(len(bases)) - off[rid]
+    src = np.where(rc[rid] == 1, off[rid] + (off[rid + 1] - off[rid]) - 1 - pos, np.arange(len(bases)))
+    stored = np.where(rc[rid] == 1, comp[bases[src]], bases)
+    as_ = truth["start"].astype(np.int32)
+    ae = (as_ + truth["length"] - 1).astype(np.int32)
+    return ref, np.ascontiguousarray(stored, np.uint8), off, rc, as_, ae
+
+
+def windows(off, as_, ae, wrap_len):
+    """mia_main.c:190-212"""
+    L = np.diff(off).astype(np.int64)
+    rs = np.maximum(as_.astype(np.int64) - 50, 0)
+    re = np.where(ae.astype(np.int64) + 51 > wrap_len, wrap_len, ae.astype(np.int64) + 50)
+    whole = rs + L > re
+    rs = np.where(whole, 0, rs)
+    re = np.where(whole, wrap_len, re)
+    return rs.astype(np.int32), (re - rs).astype(np.int32)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import _pkg
+    _pkg.load()
+    from mia_b200 import api
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n = args.reads
+    ref, bases, off, rc, as_, ae = make_workload(n, seed=1000 + rank)
+    sm = load_pssm("onepass")
+    g = api.MiaGpu(local)
+    g.set_pssm(sm)
+    g.set_reference(ref, circular=1, with_rc=0)
+    lib_stream = torch.cuda.ExternalStream(g.lib.miagpu_stream(g.h), device=torch.device("cuda", local))
+    seq_len = np.diff(off).astype(np.int32)
+
+    class Raw:
+        def __init__(self, ptr, count):
+            self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<i4", "data": (ptr, False), "version": 3}
+
+    def consensus_step(drop_f=None, drop_b=None):
+        """accumulate -> (all-reduce) -> call; returns the consensus string"""
+        if world == 1:
+            return g.consensus_natural(drop_f, drop_b, 1, want_gaps=False)[0]
+        ptr, cnt = g.accumulate_gaps_natural(drop_f, drop_b)
+        t = torch.as_tensor(Raw(ptr, cnt), device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        torch.cuda.synchronize()
+        ptr, cnt = g.accumulate_counts()
+        t = torch.as_tensor(Raw(ptr, cnt), device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        torch.cuda.synchronize()
+        return g.call(1)[0]
+
+    launches = {"n": 0}
+
+    def step_resident():
+        g.realign_resident()
+        launches["n"] += g.last_timing()["launches"]
+        cons = consensus_step()
+        launches["n"] += g.last_timing()["launches"]
+        return cons
+
+    # pinned host buffers for the end-to-end path
+    def pin(a):
+        t = torch.from_numpy(a).pin_memory()
+        return t
+    h_bases, h_off, h_rc, h_as, h_ae = pin(bases), pin(off), pin(rc), pin(as_), pin(ae)
+    h_out = api.MiaGpu.alloc_realign_outputs(n, pinned=True)
+    below = torch.zeros(n, dtype=torch.uint8).pin_memory()
+
+    def step_e2e():
+        out = g.realign_host(h_bases, h_off, h_rc, h_as, h_ae, h_out)
+        score = out["score"].numpy()
+        if world > 1:       # the regression runs over all reads of the job (FSDB order = rank order)
+            sc = torch.from_numpy(score).cuda(non_blocking=True)
+            sl = torch.from_numpy(seq_len).cuda(non_blocking=True)
+            all_sc = torch.empty(world * n, dtype=torch.int32, device="cuda")
+            all_sl = torch.empty(world * n, dtype=torch.int32, device="cuda")
+            dist.all_gather_into_tensor(all_sc, sc)
+            dist.all_gather_into_tensor(all_sl, sl)
+            slope, icpt = api.score_cut(all_sl.cpu().numpy(), all_sc.cpu().numpy())
+            api.cull_flags(seq_len, score, None, 0, 1, slope, icpt, out=below.numpy())
+        else:
+            api.cull_flags(seq_len, score, out=below.numpy())
+        return consensus_step(below, below)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- resident arm: device time per step via events on the library's stream
+    g.upload_reads(bases, off)
+    g.set_alignment_inputs(rc, as_, ae)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for _ in range(max(args.warmup, 3)):
+        cons = step_resident()
+    tim = g.last_timing()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches["n"] = 0
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for k in range(args.steps):
+        flush.zero_()                       # L2 flush between timed iterations (outside the timed events)
+        barrier()
+        ev[k][0].record(lib_stream)
+        cons = step_resident()
+        ev[k][1].record(lib_stream)
+        torch.cuda.synchronize()
+    barrier()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = float(sum(step_ms))
+    # one more resident realign just to read the per-bucket kernel times (same launches as the timed ones)
+    g.realign_resident()
+    buckets = g.last_buckets()
+    tim_realign = g.last_timing()
+    dom = max(buckets, key=lambda x: x["cells"])
+    int_peak = g.int32_peak()
+
+    # ---- end-to-end arm
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    e2e_times = []
+    for k in range(args.steps):
+        flush.zero_()
+        barrier()
+        t0 = time.perf_counter()
+        cons_e2e = step_e2e()
+        torch.cuda.synchronize()
+        e2e_times.append(time.perf_counter() - t0)
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    e2e_total = float(sum(e2e_times))
+
+    if world > 1:
+        t = torch.tensor([total_ms, e2e_total], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_total = t.tolist()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    ms_per_step = total_ms / args.steps
+    value = world * n / (ms_per_step * 1e-3)
+    cells = tim_realign["dp_cells"]
+    gcups = world * cells / (ms_per_step * 1e-3) / 1e9
+    h2d = int(len(bases) + off.nbytes + rc.nbytes + as_.nbytes + ae.nbytes + 2 * n)
+    d2h = int(sum(v.numel() * v.element_size() for v in h_out.values()) + len(cons_e2e))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    # algorithmic bytes of the dominant realign launch: read bases + offset(8) + rc/as/ae(9) in,
+    # score/as/ae/abr/n_runs/status(21) + one run word(2) out, per read
+    frac_reads = dom["reads"] / n
+    alg_bytes = frac_reads * (len(bases) + n * (8 + 9 + 21 + 2))
+    dom_s = dom["ms"] * 1e-3
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+        "data": "synthetic",
+        "config": {"workload": "BASELINE configs[1]: 1M synthetic 35-75 bp aDNA-damaged reads per GPU vs 16,569 bp circular "
+                               "R-rand reference, ancient.submat.solexa.onepass, single iteration (realign + consensus)",
+                   "reads_per_gpu": n, "ref_len": REF_LEN, "l2": "256 MiB buffer written between timed steps",
+                   "parallelism": f"reads sharded x{world}, consensus replicated, allreduce(max gaps, sum planes)"},
+        "gcups": gcups, "dp_cells_per_step": world * cells,
+        "e2e": {"value": world * n / (e2e_total / args.steps), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_total / args.steps * 1e3},
+        "gpu_launches": launches["n"],
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": alg_bytes / dom_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": alg_bytes / dom_s / 1e9 / hbm_peak, "traffic": None,
+                     "kernel": f"realign_kernel<{dom['K']}>", "kernel_ms": dom["ms"], "kernel_share_of_step": dom["ms"] / ms_per_step,
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst)" if peaks else "fallback 6650 GB/s",
+                     "note": "integer-issue bound, not HBM bound: see roofline_int32"},
+        "roofline_int32": {"bound": "int32 issue", "achieved": INT_OPS_PER_CELL * dom["cells"] / dom_s / 1e12,
+                           "peak": int_peak / 1e12, "unit": "Tops/s", "frac": INT_OPS_PER_CELL * dom["cells"] / dom_s / int_peak,
+                           "ops_per_cell": INT_OPS_PER_CELL, "kernel_gcups": dom["cells"] / dom_s / 1e9,
+                           "peak_source": "miagpu_int32_peak micro-benchmark, same run"},
+        "buckets": buckets,
+        "consensus_matches_e2e": bool(cons == cons_e2e) if world == 1 else None,
+    }
+    # ---- CPU baseline: the reference's own realign sequence on a bounded sample, 1 thread
+    if world == 1 and not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline(ref, bases, off, rc, as_, ae, sm, args.cpu_sample)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(ref, bases, off, rc, as_, ae, sm, sample):
+    from oracle.pyoracle import Oracle, Ref, have_ref
+    o = Oracle()
+    wrap = ref + ref[:256]
+    s = min(sample, len(off) - 1)
+    ws, wl = windows(off[: s + 1], as_[:s], ae[:s], len(wrap))
+    smr = o.revcom_pssm(sm)
+    if have_ref():
+        r = Ref()
+        t, cells, _ = r.time_realign(wrap, bases, off[: s + 1], ws, wl, rc[:s], sm, smr)
+        kind = "reference"
+    else:
+        ctx = o.ctx_new(ref, 1, sm, with_rc=0, k=0)
+        t0 = time.perf_counter()
+        cells = 0
+        for i in range(s):
+            o.realign(ctx, bases[off[i]:off[i + 1]].tobytes(), int(rc[i]), int(as_[i]), int(ae[i]))
+            cells += int(off[i + 1] - off[i]) * int(wl[i])
+        t = time.perf_counter() - t0
+        kind = "port"
+    return {"value": s / t, "unit": UNIT, "cores": 1, "kind": kind, "gcups": cells / t / 1e9,
+            "sample": f"first {s} reads of the same workload, realign sequence only (pop_s1c/pop_s2c/dyn_prog/max_sg_score/"
+                      f"find_align_begin/populate_pwaln_to_begin), {t:.1f} s wall; the O(ref_len x N) consensus scan is NOT included"}
+
+
+def _ref_worker(q, ref, bases, off, rc, as_, ae, sm, smr, lo, hi, steps, warmup):
+    from oracle.pyoracle import Ref
+    r = Ref()
+    wrap = ref + ref[:256]
+    o = off[lo:hi + 1] - off[lo]
+    b = bases[off[lo]:off[hi]]
+    ws, wl = windows(off[lo:hi + 1], as_[lo:hi], ae[lo:hi], len(wrap))
+    for _ in range(warmup):
+        r.time_realign(wrap, b, o, ws[: max(1, (hi - lo) // 8)], wl, rc[lo:hi], sm, smr)
+    ts, cells = [], 0
+    for _ in range(steps):
+        t, cells, _ = r.time_realign(wrap, b, o, ws, wl, rc[lo:hi], sm, smr)
+        ts.append(t)
+    q.put((ts, cells))
+
+
+def run_reference(args):
+    """The reference's CPU implementation of the path, all host cores (one process per core)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    from oracle.pyoracle import Oracle, have_ref
+    if not have_ref():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libmia_ref.so missing (reference sources not on this box)"}))
+        return
+    cores = os.cpu_count() or 1
+    per_core = args.ref_reads_per_core
+    n = cores * per_core
+    ref, bases, off, rc, as_, ae = make_workload(n, seed=1000)
+    sm = load_pssm("onepass")
+    smr = Oracle().revcom_pssm(sm)
+    q = mp.Queue()
+    procs = [mp.Process(target=_ref_worker, args=(q, ref, bases, off, rc, as_, ae, sm, smr, i * per_core, (i + 1) * per_core,
+                                                  args.steps, min(args.warmup, 1))) for i in range(cores)]
+    t0 = time.perf_counter()
+    for p in procs:
+        p.start()
+    res = [q.get() for _ in procs]
+    for p in procs:
+        p.join()
+    wall = time.perf_counter() - t0
+    step_t = [max(r[0][k] for r in res) for k in range(args.steps)]       # slowest shard per step
+    cells = sum(r[1] for r in res)
+    ms = float(np.mean(step_t)) * 1e3
+    value = n / (ms * 1e-3)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int32", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[1] (same generator), bounded sample per step", "reads_per_step": n,
+                   "ref_len": REF_LEN},
+        "gcups": cells / (ms * 1e-3) / 1e9,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
+                         "sample": f"{per_core} reads per core x {cores} processes per step; unmodified reference realign sequence "
+                                   f"(dyn_prog + traceback), consensus scan not included; total wall {wall:.1f} s"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reads", type=int, default=1_000_000, help="reads per GPU")
+    ap.add_argument("--cpu-sample", type=int, default=60000)
+    ap.add_argument("--ref-reads-per-core", type=int, default=4000)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

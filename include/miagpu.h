@@ -205,7 +205,42 @@ int miagpu_accumulate_counts( miagpu_ctx* ctx, void** dev_counts,
 int miagpu_call( miagpu_ctx* ctx, int cons_code, int32_t* gaps_out,
                  int32_t* counts_out, char* cons_out, int32_t* cons_len );
 
+/* The same with the entry list built ON THE DEVICE from the resident alignments:
+ * every read contributes its own fresh segment(s) (no stale AlnSeq pointers to
+ * describe).  dropped_front / dropped_back: host arrays of n flags for the
+ * read's whole-or-front and back AlnSeq (nullable = nothing dropped). */
+int miagpu_consensus_natural( miagpu_ctx* ctx, const uint8_t* dropped_front,
+                              const uint8_t* dropped_back, int cons_code,
+                              int32_t* gaps_out, int32_t* counts_out,
+                              char* cons_out, int32_t* cons_len );
+
+int miagpu_accumulate_gaps_natural( miagpu_ctx* ctx, const uint8_t* dropped_front,
+                                    const uint8_t* dropped_back, void** dev_gaps,
+                                    int64_t* n_gaps );
+
+/* ---- a12, host policy kept on the host (H8): the score/length regression of
+ * find_fsdb_score_cut (fsdb.c:269-383, double sums in FSDB order) and the
+ * per-read test of cull_maln_from_fsdb (mia.c:418-479): below[i] = 1 iff
+ * score[i] < (hard_cut > 0 ? hard_cut : intercept + slope*seq_len[i]).  The
+ * caller ORs below[] into its sticky per-slot dropped flags (H10). */
+int miagpu_score_cut( int64_t n, const int32_t* seq_len, const int32_t* score,
+                      const uint8_t* unique_best, double* slope,
+                      double* intercept );
+int miagpu_cull_flags( int64_t n, const int32_t* seq_len, const int32_t* score,
+                       const uint8_t* unique_best, int hard_cut,
+                       int score_cut_set, double slope, double intercept,
+                       uint8_t* below );
+
+/* Device-resident round (reads, rc, as, ae stay in HBM between calls): */
+int miagpu_set_alignment_inputs( miagpu_ctx* ctx, const uint8_t* rc,
+                                 const int32_t* as, const int32_t* ae );
+int miagpu_realign_resident( miagpu_ctx* ctx );
+
 /* ---- measurement helpers (bench.py) */
+/* per width bucket of the last realign: columns-per-lane K (0 = too wide),
+ * reads, DP cells, kernel ms (CUDA events on the library's stream); 8 entries */
+int miagpu_last_buckets( miagpu_ctx* ctx, int32_t* k, int32_t* reads,
+                         int64_t* cells, float* ms );
 /* device time in ms of the kernels launched by the last call, per phase */
 int miagpu_last_timing( miagpu_ctx* ctx, float* ms_kernels, float* ms_h2d,
                         float* ms_d2h, int64_t* dp_cells, int32_t* launches );

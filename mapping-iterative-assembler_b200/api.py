@@ -58,6 +58,13 @@ def load_library():
     L.miagpu_accumulate_gaps.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_void_p), _i64p]
     L.miagpu_accumulate_counts.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), _i64p]
     L.miagpu_call.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, _i32p]
+    L.miagpu_consensus_natural.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, _i32p]
+    L.miagpu_accumulate_gaps_natural.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), _i64p]
+    L.miagpu_score_cut.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.miagpu_cull_flags.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p]
+    L.miagpu_set_alignment_inputs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.miagpu_realign_resident.argtypes = [C.c_void_p]
+    L.miagpu_last_buckets.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.miagpu_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), _i64p, _i32p]
     L.miagpu_int32_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.miagpu_stream.restype = C.c_void_p
@@ -69,7 +76,9 @@ def load_library():
 EXPORTS = ["miagpu_device_count", "miagpu_create", "miagpu_destroy", "miagpu_last_error", "miagpu_version", "miagpu_set_pssm",
            "miagpu_get_pssm", "miagpu_set_reference", "miagpu_ref_wrap_len", "miagpu_build_kmers", "miagpu_upload_reads",
            "miagpu_pass1", "miagpu_compact_reads", "miagpu_realign", "miagpu_realign_host",
-           "miagpu_consensus", "miagpu_accumulate_gaps", "miagpu_accumulate_counts", "miagpu_call", "miagpu_last_timing",
+           "miagpu_consensus", "miagpu_accumulate_gaps", "miagpu_accumulate_counts", "miagpu_call", "miagpu_consensus_natural", "miagpu_accumulate_gaps_natural",
+           "miagpu_score_cut", "miagpu_cull_flags",
+           "miagpu_set_alignment_inputs", "miagpu_realign_resident", "miagpu_last_buckets", "miagpu_last_timing",
            "miagpu_int32_peak", "miagpu_stream"]
 
 
@@ -174,6 +183,32 @@ class MiaGpu:
         self._ck(self.lib.miagpu_consensus(self.h, len(entries), _ptr(entries), cons_code, _ptr(gaps), _ptr(counts), buf, C.byref(n)))
         return buf.value.decode(), gaps, counts
 
+    def consensus_natural(self, dropped_front=None, dropped_back=None, cons_code=1, want_counts=False, want_gaps=True):
+        gaps = np.zeros(self.seq_len, np.int32) if want_gaps else None
+        counts = np.zeros((self.seq_len, 10), np.int32) if want_counts else None
+        if not hasattr(self, "_consbuf") or len(self._consbuf) < self.seq_len * 4 + 4096:
+            self._consbuf = C.create_string_buffer(self.seq_len * 4 + 4096)
+        n = C.c_int32()
+        self._ck(self.lib.miagpu_consensus_natural(self.h, _ptr(dropped_front), _ptr(dropped_back), cons_code, _ptr(gaps),
+                                                   _ptr(counts), self._consbuf, C.byref(n)))
+        return self._consbuf.value.decode(), gaps, counts
+
+    def accumulate_gaps_natural(self, dropped_front=None, dropped_back=None):
+        ptr, n = C.c_void_p(), C.c_int64()
+        self._ck(self.lib.miagpu_accumulate_gaps_natural(self.h, _ptr(dropped_front), _ptr(dropped_back), C.byref(ptr), C.byref(n)))
+        return ptr.value, n.value
+
+    def set_alignment_inputs(self, rc, as_, ae):
+        self._ck(self.lib.miagpu_set_alignment_inputs(self.h, _ptr(rc), _ptr(as_), _ptr(ae)))
+
+    def realign_resident(self):
+        self._ck(self.lib.miagpu_realign_resident(self.h))
+
+    def last_buckets(self):
+        k, r, cells, ms = np.zeros(8, np.int32), np.zeros(8, np.int32), np.zeros(8, np.int64), np.zeros(8, np.float32)
+        self._ck(self.lib.miagpu_last_buckets(self.h, _ptr(k), _ptr(r), _ptr(cells), _ptr(ms)))
+        return [dict(K=int(k[i]), reads=int(r[i]), cells=int(cells[i]), ms=float(ms[i])) for i in range(8) if r[i]]
+
     def accumulate_gaps(self, entries):
         entries = np.ascontiguousarray(entries, ENTRY_DTYPE)
         ptr, n = C.c_void_p(), C.c_int64()
@@ -220,3 +255,23 @@ def expand_runs(ref, read, start, abr, runs, n_runs):
         else:
             rg.append(ref[c:c + ln]); fg.append("-" * ln); c += ln
     return "".join(rg), "".join(fg)
+
+
+def score_cut(seq_len, score, unique_best=None):
+    """find_fsdb_score_cut (fsdb.c:269-383) -> (slope, intercept)."""
+    L = load_library()
+    sl, sc = np.ascontiguousarray(seq_len, np.int32), np.ascontiguousarray(score, np.int32)
+    s, i = C.c_double(), C.c_double()
+    if not L.miagpu_score_cut(len(sl), _ptr(sl), _ptr(sc), _ptr(unique_best), C.byref(s), C.byref(i)):
+        raise MiaGpuError(L.miagpu_last_error().decode())
+    return s.value, i.value
+
+
+def cull_flags(seq_len, score, unique_best=None, hard_cut=0, score_cut_set=0, slope=200.0, intercept=0.0, out=None):
+    """Per-read `score < min_score_for_len` of cull_maln_from_fsdb (mia.c:418-479)."""
+    L = load_library()
+    n = len(seq_len)
+    out = np.zeros(n, np.uint8) if out is None else out
+    if not L.miagpu_cull_flags(n, _ptr(seq_len), _ptr(score), _ptr(unique_best), hard_cut, score_cut_set, slope, intercept, _ptr(out)):
+        raise MiaGpuError(L.miagpu_last_error().decode())
+    return out

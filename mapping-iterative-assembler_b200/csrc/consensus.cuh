@@ -64,6 +64,7 @@ __global__ void __launch_bounds__(256) entry_kernel(ConsParams p) {
   const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (w >= p.n_entries) return;
   const miagpu_entry e = p.entries[w];
+  if (e.col_count <= 0) return;
   const int rd = e.read;
   const int nr = p.n_runs[rd];
   if (nr <= 0) return;
@@ -131,6 +132,45 @@ __global__ void call_kernel(const int32_t* acc, int64_t n_cols, int cons_code, c
     else r = top >= -399 ? base : 'N';                                              // MIN_SCORE_CONS
   }
   out[c] = r;
+}
+
+// Device-side construction of the "natural" entry list: read i owns entries 2i (whole
+// alignment or front part) and 2i+1 (wrapped back part, col_count = 0 when not split).
+// Mirrors mia_main.c:259-276 (end fix, split test), split_pwaln (mia.c:1376-1438) and
+// asp_len (fsdb.c:518-530); used when the host has no stale AlnSeq pointers to describe.
+__global__ void natural_entries_kernel(int64_t n, const int32_t* as_out, const int32_t* ae_out, const int32_t* n_runs,
+                                       const uint16_t* runs, const uint8_t* status, int seq_len, const uint8_t* dropped_front,
+                                       const uint8_t* dropped_back, miagpu_entry* out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  miagpu_entry f{}, b{};
+  f.read = b.read = (int32_t)i;
+  const int nr = n_runs[i];
+  if (nr > 0 && !(status[i] & MIAGPU_ST_UNSUPPORTED)) {
+    const int start = as_out[i];
+    int end = ae_out[i];
+    if (end > seq_len) end -= seq_len;
+    const bool split = start > end;
+    const int cf = split ? seq_len - start : 0x7fffffff;     // alignment columns that stay in front
+    int cols = 0, ins = 0, fins = 0;
+    const uint16_t* r = runs + i * MAX_RUNS;
+    for (int k = 0; k < nr; k++) {
+      const int x = r[k], t = x >> 14, len = x & 0x3fff;
+      if (t == MIAGPU_RUN_I) { ins += len; if (cols < cf) fins += len; }
+      else cols += len;
+    }
+    const int fcols = split ? cf : cols;
+    const int fl = fcols + fins, bl = split ? (cols - fcols) + (ins - fins) : 0;
+    f.col_begin = 0; f.col_count = fcols; f.ref_pos = start; f.front_len = fl; f.total_len = fl + bl;
+    f.dropped = dropped_front ? dropped_front[i] : 0;
+    if (split) {
+      b = f;
+      b.col_begin = fcols; b.col_count = cols - fcols; b.ref_pos = 0; b.back_formula = 1;
+      b.dropped = dropped_back ? dropped_back[i] : f.dropped;
+    }
+  }
+  out[2 * i] = f;
+  out[2 * i + 1] = b;
 }
 
 // gaps[0] is ignored by the consensus (mia.c:557 "ref_pos > 0"); force it to 0 so the scan

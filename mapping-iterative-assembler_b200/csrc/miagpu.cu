@@ -55,6 +55,10 @@ struct miagpu_ctx {
   int num_sms = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[6] = {};
+  cudaEvent_t bev[2 * 8] = {};                 // per width-bucket start/stop
+  float bucket_ms[8] = {};
+  int64_t bucket_cells[8] = {};
+  int32_t bucket_reads[8] = {};
   // scoring
   bool have_pssm = false;
   int32_t sm_f[MIAGPU_PSSM_INTS], sm_r[MIAGPU_PSSM_INTS];
@@ -79,7 +83,7 @@ struct miagpu_ctx {
   DevBuf<miagpu_entry> d_entries;
   int64_t n_entries = 0;
   DevBuf<int32_t> d_sm, d_gaps, d_ins_off, d_acc;
-  DevBuf<uint8_t> d_cub;
+  DevBuf<uint8_t> d_cub, d_dropf, d_dropb;
   DevBuf<char> d_called;
   int64_t n_cols = 0;
   int cons_stage = 0;                          // 0 none, 1 gaps done, 2 counts done
@@ -118,6 +122,7 @@ extern "C" int miagpu_create(miagpu_ctx** out, int device) {
   c->num_sms = prop.multiProcessorCount;
   MIAGPU_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   for (auto& ev : c->ev) MIAGPU_CUDA(cudaEventCreate(&ev));
+  for (auto& ev : c->bev) MIAGPU_CUDA(cudaEventCreate(&ev));
   *out = c;
   return 1;
 }
@@ -130,8 +135,9 @@ extern "C" void miagpu_destroy(miagpu_ctx* c) {
   c->d_rc.release(); c->d_status.release(); c->d_as.release(); c->d_ae.release(); c->d_score.release();
   c->d_as_out.release(); c->d_ae_out.release(); c->d_abr.release(); c->d_nruns.release(); c->d_win_start.release();
   c->d_win_len.release(); c->d_lists.release(); c->d_runs.release(); c->d_meta.release(); c->d_scratch.release();
-  c->d_entries.release(); c->d_sm.release(); c->d_gaps.release(); c->d_ins_off.release(); c->d_acc.release(); c->d_cub.release(); c->d_called.release();
+  c->d_entries.release(); c->d_sm.release(); c->d_gaps.release(); c->d_ins_off.release(); c->d_acc.release(); c->d_cub.release(); c->d_called.release(); c->d_dropf.release(); c->d_dropb.release();
   for (auto& ev : c->ev) cudaEventDestroy(ev);
+  for (auto& ev : c->bev) cudaEventDestroy(ev);
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -265,9 +271,9 @@ extern "C" int miagpu_upload_reads(miagpu_ctx* c, int64_t n, const uint8_t* base
 __global__ void classify_kernel(int64_t n, const int64_t* off, const int32_t* as, const int32_t* ae, int wrap_len,
                                 int32_t* win_start, int32_t* win_len, int32_t* lists, int32_t* meta) {
   __shared__ int s_cnt[NBUCKET], s_base[NBUCKET], s_maxL[NBUCKET];
-  __shared__ unsigned long long s_cells;
+  __shared__ unsigned long long s_cells[NBUCKET];
   if (threadIdx.x < NBUCKET) { s_cnt[threadIdx.x] = 0; s_maxL[threadIdx.x] = 0; }
-  if (threadIdx.x == 0) s_cells = 0;
+  if (threadIdx.x < NBUCKET) s_cells[threadIdx.x] = 0;
   __syncthreads();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int b = -1, slot = 0, L = 0;
@@ -283,14 +289,14 @@ __global__ void classify_kernel(int64_t n, const int64_t* off, const int32_t* as
     if (L <= 0 || L > MAX_READ) b = 7;
     slot = atomicAdd(&s_cnt[b], 1);
     atomicMax(&s_maxL[b], L);
-    atomicAdd(&s_cells, (unsigned long long)L * (unsigned long long)len1);
+    atomicAdd(&s_cells[b], (unsigned long long)L * (unsigned long long)len1);
   }
   __syncthreads();
   if (threadIdx.x < NBUCKET) {
     s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd(&meta[threadIdx.x], s_cnt[threadIdx.x]) : 0;
     if (s_maxL[threadIdx.x]) atomicMax(&meta[16 + threadIdx.x], s_maxL[threadIdx.x]);
   }
-  if (threadIdx.x == 0) atomicAdd(reinterpret_cast<unsigned long long*>(meta + 32), s_cells);
+  if (threadIdx.x < NBUCKET && s_cells[threadIdx.x]) atomicAdd(reinterpret_cast<unsigned long long*>(meta + 32) + threadIdx.x, s_cells[threadIdx.x]);
   __syncthreads();
   if (b >= 0) lists[(int64_t)b * n + s_base[b] + slot] = (int32_t)i;
 }
@@ -335,11 +341,14 @@ static int realign_device(miagpu_ctx* c) {
   MIAGPU_CUDA(cudaGetLastError());
   c->launches++;
   int32_t meta[64];
+  static_assert(32 + 2 * NBUCKET <= 64, "meta layout");
   MIAGPU_CUDA(cudaMemcpyAsync(meta, c->d_meta.p, sizeof(meta), cudaMemcpyDeviceToHost, c->stream));
   MIAGPU_CUDA(cudaStreamSynchronize(c->stream));
-  memcpy(&c->dp_cells, meta + 32, sizeof(int64_t));
+  memcpy(c->bucket_cells, meta + 32, sizeof(c->bucket_cells));
+  for (int b = 0; b < NBUCKET; b++) { c->dp_cells += c->bucket_cells[b]; c->bucket_reads[b] = meta[b]; c->bucket_ms[b] = 0; }
   for (int b = 0; b < NBUCKET; b++) {
     if (!meta[b]) continue;
+    MIAGPU_CUDA(cudaEventRecord(c->bev[2 * b], c->stream));
     RealignParams p{};
     p.bases = c->d_bases.p; p.off = c->d_off.p; p.rc = c->d_rc.p;
     p.win_start = c->d_win_start.p; p.win_len = c->d_win_len.p;
@@ -362,7 +371,14 @@ static int realign_device(miagpu_ctx* c) {
         c->launches++;
     }
     if (!ok) return 0;
+    MIAGPU_CUDA(cudaEventRecord(c->bev[2 * b + 1], c->stream));
   }
+  return 1;
+}
+
+static int realign_bucket_times(miagpu_ctx* c) {
+  for (int b = 0; b < NBUCKET; b++)
+    if (c->bucket_reads[b]) MIAGPU_CUDA(cudaEventElapsedTime(&c->bucket_ms[b], c->bev[2 * b], c->bev[2 * b + 1]));
   return 1;
 }
 
@@ -398,7 +414,7 @@ static int realign_common(miagpu_ctx* c, const uint8_t* rc, const int32_t* as, c
   c->ms_h2d = time_h2d_from_upload ? c->ms_h2d + h2d : h2d;
   MIAGPU_CUDA(cudaEventElapsedTime(&c->ms_kernels, c->ev[1], c->ev[2]));
   MIAGPU_CUDA(cudaEventElapsedTime(&c->ms_d2h, c->ev[2], c->ev[3]));
-  return 1;
+  return realign_bucket_times(c);
 }
 
 extern "C" int miagpu_realign(miagpu_ctx* c, const uint8_t* rc, const int32_t* as, const int32_t* ae, int32_t* score,
@@ -421,6 +437,43 @@ extern "C" int miagpu_last_timing(miagpu_ctx* c, float* ms_kernels, float* ms_h2
   if (dp_cells) *dp_cells = c->dp_cells;
   if (launches) *launches = c->launches;
   return 1;
+}
+
+extern "C" int miagpu_last_buckets(miagpu_ctx* c, int32_t* k, int32_t* reads, int64_t* cells, float* ms) {
+  if (!c) { set_error("miagpu_last_buckets: NULL ctx"); return 0; }
+  for (int b = 0; b < NBUCKET; b++) {
+    if (k) k[b] = BUCKET_K[b];
+    if (reads) reads[b] = c->bucket_reads[b];
+    if (cells) cells[b] = c->bucket_cells[b];
+    if (ms) ms[b] = c->bucket_ms[b];
+  }
+  return 1;
+}
+
+// Device-resident round: rc/as/ae already on the device (from miagpu_realign / _set_alignment_inputs);
+// nothing crosses PCIe except the consensus string.
+extern "C" int miagpu_set_alignment_inputs(miagpu_ctx* c, const uint8_t* rc, const int32_t* as, const int32_t* ae) {
+  if (!c || (c->n && (!rc || !as || !ae))) { set_error("miagpu_set_alignment_inputs: bad argument"); return 0; }
+  MIAGPU_CUDA(cudaSetDevice(c->device));
+  if (c->n) {
+    MIAGPU_CUDA(cudaMemcpyAsync(c->d_rc.p, rc, c->n, cudaMemcpyHostToDevice, c->stream));
+    MIAGPU_CUDA(cudaMemcpyAsync(c->d_as.p, as, c->n * 4, cudaMemcpyHostToDevice, c->stream));
+    MIAGPU_CUDA(cudaMemcpyAsync(c->d_ae.p, ae, c->n * 4, cudaMemcpyHostToDevice, c->stream));
+  }
+  MIAGPU_CUDA(cudaStreamSynchronize(c->stream));
+  return 1;
+}
+
+extern "C" int miagpu_realign_resident(miagpu_ctx* c) {
+  if (!c || !c->have_pssm || !c->have_ref) { set_error("miagpu_realign_resident: set_pssm and set_reference first"); return 0; }
+  MIAGPU_CUDA(cudaSetDevice(c->device));
+  MIAGPU_CUDA(cudaEventRecord(c->ev[1], c->stream));
+  if (!realign_device(c)) return 0;
+  MIAGPU_CUDA(cudaEventRecord(c->ev[2], c->stream));
+  MIAGPU_CUDA(cudaStreamSynchronize(c->stream));
+  MIAGPU_CUDA(cudaEventElapsedTime(&c->ms_kernels, c->ev[1], c->ev[2]));
+  c->ms_h2d = c->ms_d2h = 0;
+  return realign_bucket_times(c);
 }
 
 // ------------------------------------------------ integer peak micro-benchmark
@@ -569,6 +622,92 @@ extern "C" int miagpu_call(miagpu_ctx* c, int cons_code, int32_t* gaps_out, int3
     if (called[i] != '-' && called[i] != ' ') { if (cons_out) cons_out[n] = called[i]; n++; }
   if (cons_out) cons_out[n] = 0;
   if (cons_len) *cons_len = n;
+  return 1;
+}
+
+// Entries built on the device from the resident alignments (every read points at its own
+// fresh segments).  dropped_front/back: host arrays of n (nullable = nothing dropped).
+extern "C" int miagpu_accumulate_gaps_natural(miagpu_ctx* c, const uint8_t* dropped_front, const uint8_t* dropped_back,
+                                              void** dev_gaps, int64_t* n_gaps) {
+  if (!c || !c->have_ref || !c->have_pssm) { set_error("miagpu_accumulate_gaps_natural: set_pssm / set_reference / realign first"); return 0; }
+  MIAGPU_CUDA(cudaSetDevice(c->device));
+  const int64_t n = c->n;
+  c->launches = 0;
+  if (!c->d_entries.reserve(2 * n + 2) || !c->d_gaps.reserve(c->seq_len + 2) || !c->d_ins_off.reserve(c->seq_len + 2) ||
+      !c->d_dropf.reserve(n + 1) || !c->d_dropb.reserve(n + 1)) return 0;
+  MIAGPU_CUDA(cudaEventRecord(c->ev[0], c->stream));
+  if (n && dropped_front) MIAGPU_CUDA(cudaMemcpyAsync(c->d_dropf.p, dropped_front, n, cudaMemcpyHostToDevice, c->stream));
+  if (n && dropped_back) MIAGPU_CUDA(cudaMemcpyAsync(c->d_dropb.p, dropped_back, n, cudaMemcpyHostToDevice, c->stream));
+  MIAGPU_CUDA(cudaEventRecord(c->ev[1], c->stream));
+  c->n_entries = 2 * n;
+  MIAGPU_CUDA(cudaMemsetAsync(c->d_gaps.p, 0, (c->seq_len + 2) * sizeof(int32_t), c->stream));
+  if (n) {
+    natural_entries_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(
+        n, c->d_as_out.p, c->d_ae_out.p, c->d_nruns.p, c->d_runs.p, c->d_status.p, c->seq_len, dropped_front ? c->d_dropf.p : nullptr,
+        dropped_back ? c->d_dropb.p : nullptr, c->d_entries.p);
+    MIAGPU_CUDA(cudaGetLastError());
+    ConsParams p = cons_params(c);
+    entry_kernel<0><<<(unsigned)((c->n_entries * 32 + 255) / 256), 256, 0, c->stream>>>(p);
+    MIAGPU_CUDA(cudaGetLastError());
+    c->launches += 2;
+  }
+  MIAGPU_CUDA(cudaEventRecord(c->ev[2], c->stream));
+  MIAGPU_CUDA(cudaStreamSynchronize(c->stream));
+  MIAGPU_CUDA(cudaEventElapsedTime(&c->ms_h2d, c->ev[0], c->ev[1]));
+  MIAGPU_CUDA(cudaEventElapsedTime(&c->ms_kernels, c->ev[1], c->ev[2]));
+  c->ms_d2h = 0;
+  c->cons_stage = 1;
+  if (dev_gaps) *dev_gaps = c->d_gaps.p;
+  if (n_gaps) *n_gaps = c->seq_len;
+  return 1;
+}
+
+extern "C" int miagpu_consensus_natural(miagpu_ctx* c, const uint8_t* dropped_front, const uint8_t* dropped_back, int cons_code,
+                                        int32_t* gaps_out, int32_t* counts_out, char* cons_out, int32_t* cons_len) {
+  if (!miagpu_accumulate_gaps_natural(c, dropped_front, dropped_back, nullptr, nullptr)) return 0;
+  float h2d = c->ms_h2d;
+  if (!miagpu_accumulate_counts(c, nullptr, nullptr)) return 0;
+  if (!miagpu_call(c, cons_code, gaps_out, counts_out, cons_out, cons_len)) return 0;
+  c->ms_h2d = h2d;
+  return 1;
+}
+
+// ------------------------------------------------------- host policy (a12)
+// find_fsdb_score_cut (fsdb.c:269-383): double-precision sums in FSDB order.
+extern "C" int miagpu_score_cut(int64_t n, const int32_t* seq_len, const int32_t* score, const uint8_t* unique_best,
+                                double* slope, double* intercept) {
+  if (n < 0 || !seq_len || !score || !slope || !intercept) { set_error("miagpu_score_cut: bad argument"); return 0; }
+  double xbar = 0, ybar = 0, ssxy = 0, ssxx = 0, max_delta = 0;
+  int64_t j = 0;
+  auto use = [&](int64_t i) { return (!unique_best || unique_best[i]) && score[i] >= FIRST_ROUND_SCORE_CUTOFF; };
+  for (int64_t i = 0; i < n; i++) if (use(i)) { xbar += seq_len[i]; ybar += score[i]; j++; }
+  xbar /= j; ybar /= j;
+  for (int64_t i = 0; i < n; i++) if (use(i)) {
+    ssxy += (seq_len[i] - xbar) * (score[i] - ybar);
+    ssxx += (seq_len[i] - xbar) * (seq_len[i] - xbar);
+  }
+  const double bf = ssxy / ssxx, ib = ybar - bf * xbar;
+  for (int64_t i = 0; i < n; i++) if (use(i)) {
+    double d = (score[i] - ((bf * seq_len[i]) + ib)) / seq_len[i];
+    if (d > max_delta) max_delta = d;
+  }
+  *intercept = ib;
+  if ((bf - max_delta) > 0) *slope = bf - (max_delta * 2.0);
+  else *slope = (double)(bf * (80 / 100.0));                     // SCORE_CUTOFF_BUFFER, params.h:24
+  return 1;
+}
+
+// The per-read test of cull_maln_from_fsdb (mia.c:418-479): below[i] = score < min_score_for_len.
+extern "C" int miagpu_cull_flags(int64_t n, const int32_t* seq_len, const int32_t* score, const uint8_t* unique_best, int hard_cut,
+                                 int score_cut_set, double slope_in, double intercept_in, uint8_t* below) {
+  if (n < 0 || !seq_len || !score || !below) { set_error("miagpu_cull_flags: bad argument"); return 0; }
+  double slope = slope_in, intercept = intercept_in;
+  if (!score_cut_set && !miagpu_score_cut(n, seq_len, score, unique_best, &slope, &intercept)) return 0;
+  if (slope <= 0) slope = 100.0;
+  for (int64_t i = 0; i < n; i++) {
+    const double min_score = hard_cut > 0 ? (double)hard_cut : (double)(intercept + (slope * seq_len[i]));
+    below[i] = score[i] < min_score;
+  }
   return 1;
 }
 
