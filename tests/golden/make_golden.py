@@ -1,8 +1,11 @@
 """Generates tests/golden/*.npz by running the UNMODIFIED reference (oracle/_ref, built from
 /root/reference/src by oracle/Makefile).  Run here, in the build container; the GPU box only
 reads the committed outputs.   python tests/golden/make_golden.py"""
+import json
 import os
+import random
 import sys
+import tempfile
 
 import numpy as np
 
@@ -10,8 +13,87 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 from oracle.pyoracle import Ref  # noqa: E402
+import _pkg  # noqa: E402
+
+_pkg.load()
+from mia_b200 import synth  # noqa: E402
 
 REFROOT = "/root/reference"
+
+
+def fuzz_align_cases(n, seed):
+    rng = random.Random(seed)
+    cases = []
+    for _ in range(n):
+        n1 = rng.randint(5, 200)
+        ref = "".join(rng.choice("ACGT" if rng.random() < 0.97 else "N") for _ in range(n1))
+        n2 = rng.randint(1, 90)
+        if rng.random() < 0.7 and n1 > n2:
+            s = rng.randint(0, n1 - n2)
+            rd = list(ref[s:s + n2])
+            for i in range(len(rd)):
+                x = rng.random()
+                if x < 0.05:
+                    rd[i] = rng.choice("ACGT")
+                elif x < 0.07:
+                    rd[i] = ""
+                elif x < 0.09:
+                    rd[i] = rd[i] + rng.choice("ACGT")
+                elif x < 0.095:
+                    rd[i] = "N"
+            rd = "".join(rd)[:256] or "A"
+        else:
+            rd = "".join(rng.choice("ACGT") for _ in range(n2))
+        mask = None
+        if rng.random() < 0.5:
+            mask = [0] * n1
+            for _ in range(rng.randint(1, 3)):
+                a = rng.randint(0, n1 - 1)
+                b = rng.randint(a, min(n1 - 1, a + rng.randint(0, 90)))
+                for i in range(a, b + 1):
+                    mask[i] = 1
+        cases.append(dict(ref=ref, read=rd, mask=mask, sg5=rng.randint(0, 1), mat=rng.choice(["flat", "ancient", "ancient_rc", "onepass"])))
+    return cases
+
+
+def read_fixture_reads(path):
+    reads, ids = [], []
+    for line in open(path):
+        line = line.strip()
+        if line.startswith(">"):
+            ids.append(line[1:].split()[0])
+            reads.append("")
+        elif reads:
+            reads[-1] += line.upper()
+    return ids, [r[:256] for r in reads]
+
+
+def session(r, ref, reads, sm, circular, k, soft_mask, max_iter=30):
+    with tempfile.NamedTemporaryFile("w", suffix=".fa", delete=False) as f:
+        f.write(">ref\n" + ref + "\n")
+        path = f.name
+    s = r.sess_new(path, circular, sm, k=k, soft_mask=soft_mask)
+    p1 = []
+    for i, rd in enumerate(reads):
+        if not rd:
+            p1.append(None)
+            continue
+        d = r.sess_pass1(s, "r%d" % i, rd)
+        p1.append({k2: d[k2] for k2 in ("hits", "added", "score", "rc", "as_", "ae", "strand_known", "fw_score", "rc_score",
+                                       "start", "end", "split", "b_start", "b_end", "f_ref", "f_frag", "b_ref", "b_frag")})
+    r.sess_end_pass1(s)
+    iters = []
+    for _ in range(max_iter):
+        cons, conv = r.sess_iterate(s, sort=0)
+        rd = r.sess_reads(s)
+        slots = r.sess_slots(s)
+        iters.append(dict(cons=cons, converged=conv, reads=[[x["score"], x["as_"], x["ae"], x["rc"]] for x in rd],
+                          slots=[[x["start"], x["end"], x["dropped"], x["segment"], x["seq"], x["smp"], x["ins"]] for x in slots],
+                          gaps=np.flatnonzero(r.sess_gaps(s)).tolist()))
+        if conv:
+            break
+    os.unlink(path)
+    return dict(ref=ref, reads=reads, circular=circular, k=k, soft_mask=soft_mask, pass1=p1, iters=iters)
 
 
 def main():
@@ -23,7 +105,31 @@ def main():
     for k in list(m):
         m[k + "_rc"] = r.revcom_pssm(m[k])
     np.savez_compressed(os.path.join(HERE, "pssm.npz"), **m)
-    print("wrote pssm.npz")
+    # matrix text of one file, to pin the oracle's parser
+    open(os.path.join(HERE, "onepass_matrix_fixture.json"), "w").write(json.dumps(
+        {"text": open(f"{REFROOT}/matrices/ancient.submat.solexa.onepass.txt").read()}))
+
+    # a5-a7: the reference's answers on fuzzed alignments
+    cases = fuzz_align_cases(400, seed=17)
+    for c in cases:
+        mask = None if c["mask"] is None else np.array(c["mask"], np.uint8)
+        a = r.align(c["ref"], c["read"], m[c["mat"]], c["sg5"], mask)
+        c["out"] = [a["score"], a["abr"], a["abc"], a["aer"], a["aec"], a["ref_gapped"], a["read_gapped"]]
+    json.dump(cases, open(os.path.join(HERE, "align_cases.json"), "w"))
+
+    # sessions: the reference's own fixtures + a small synthetic circular case
+    tr1 = "".join(open(f"{REFROOT}/test/tr1.fna").read().split("\n")[1:])
+    _, tf = read_fixture_reads(f"{REFROOT}/test/tf.fna")
+    sess = {"tr1_tf_c": session(r, tr1, tf, m["ancient"], 1, 0, 0),
+            "tr1_tf_lin": session(r, tr1, tf, m["ancient"], 0, 0, 0),
+            "tr1_tf_c_k8_M": session(r, tr1, tf, m["ancient"], 1, 8, 1)}
+    ref = synth.random_reference(2000, seed=1)
+    g = synth.diverge(ref, 0.02, seed=3, indel_rate=0.003)
+    b, off, _ = synth.make_reads(g, 250, 35, 75, seed=4)
+    reads = [synth.read_str(b, off, i) for i in range(250)]
+    sess["synth2k_c_k10"] = session(r, ref, reads, m["onepass"], 1, 10, 0)
+    json.dump(sess, open(os.path.join(HERE, "sessions.json"), "w"))
+    print("wrote pssm.npz, align_cases.json, sessions.json")
 
 
 if __name__ == "__main__":

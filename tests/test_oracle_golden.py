@@ -1,0 +1,91 @@
+"""CPU: the oracle restatement against golden vectors produced by the UNMODIFIED reference
+(tests/golden/make_golden.py).  These run everywhere, including the GPU box where
+/root/reference does not exist."""
+import json
+import os
+
+import numpy as np
+
+from oracle_driver import OracleRun
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_pssm_parser_flat_and_revcom(oracle, golden):
+    text = json.load(open(os.path.join(G, "onepass_matrix_fixture.json")))["text"]
+    assert (oracle.parse_pssm(text) == golden["onepass"]).all()
+    assert (oracle.flat_pssm() == golden["flat"]).all()
+    for k in ("ancient", "onepass", "pe", "flat"):
+        assert (oracle.revcom_pssm(golden[k]) == golden[k + "_rc"]).all()
+        assert (oracle.revcom_pssm(golden[k + "_rc"]) == golden[k]).all()       # involution
+
+
+def test_sm_depth_rule(oracle):
+    # pssm.c:36-46: 5' depth wins over 3' depth for short reads
+    assert [oracle.sm_depth(r, 40) for r in (0, 14, 15, 24, 25, 26, 39)] == [0, 14, 15, 15, 16, 17, 30]
+    assert [oracle.sm_depth(r, 10) for r in range(10)] == list(range(10))
+    assert oracle.sm_depth(15, 16) == 30 and oracle.sm_depth(15, 30) == 16
+
+
+def test_align_matches_reference_golden(oracle, golden):
+    cases = json.load(open(os.path.join(G, "align_cases.json")))
+    assert len(cases) >= 400
+    for i, c in enumerate(cases):
+        mask = None if c["mask"] is None else np.array(c["mask"], np.uint8)
+        a = oracle.align(c["ref"], c["read"], golden[c["mat"]], c["sg5"], mask)
+        got = [a["score"], a["abr"], a["abc"], a["aer"], a["aec"], a["ref_gapped"], a["read_gapped"]]
+        assert got == c["out"], f"case {i}"
+
+
+def _run_session(oracle, golden, name, matrix):
+    s = json.load(open(os.path.join(G, "sessions.json")))[name]
+    R = OracleRun(oracle, s["ref"], golden[matrix], s["circular"], s["k"], s["soft_mask"])
+    for i, (rd, exp) in enumerate(zip(s["reads"], s["pass1"])):
+        if exp is None:
+            continue
+        p = R.pass1(rd)
+        for key, v in exp.items():
+            if not exp["hits"] and key not in ("hits", "added"):
+                continue
+            assert p[key] == v, f"{name}: pass1 read {i} field {key}"
+    R.end_pass1()
+    for it, exp in enumerate(s["iters"]):
+        cons, conv = R.iterate()
+        assert [[f["score"], f["as_"], f["ae"], f["rc"]] for f in R.fsdb] == exp["reads"], f"{name}: iteration {it} reads"
+        slots = [[x["start"], x["end"], x["dropped"], x["segment"], x["seq"], x["smp"], x["ins"]] for x in oracle.asm_entries(R.asm)]
+        assert slots == exp["slots"], f"{name}: iteration {it} AlnSeq list"
+        assert np.flatnonzero(oracle.asm_gaps(R.asm, R.wrap_len)).tolist() == exp["gaps"]
+        assert cons == exp["cons"], f"{name}: iteration {it} consensus"
+        assert conv == exp["converged"]
+    return len(s["iters"])
+
+
+def test_session_reference_fixtures_circular(oracle, golden):
+    assert _run_session(oracle, golden, "tr1_tf_c", "ancient") == 3
+
+
+def test_session_reference_fixtures_linear(oracle, golden):
+    _run_session(oracle, golden, "tr1_tf_lin", "ancient")
+
+
+def test_session_reference_fixtures_kmer_softmask(oracle, golden):
+    # exercises the k-mer filter with -M and the stale back-pointer behaviour (5 stale slots)
+    _run_session(oracle, golden, "tr1_tf_c_k8_M", "ancient")
+
+
+def test_session_synthetic_circular_kmer(oracle, golden):
+    _run_session(oracle, golden, "synth2k_c_k10", "onepass")
+
+
+def test_find_consensus_rules(oracle):
+    # map_align.c:294-391: cov 0 -> N; gaps/cov >= 0.5 -> '-'; '>=' lets the later base win ties
+    f = oracle.find_consensus
+    assert f([0] * 10) == "N"
+    assert f([1, 0, 0, 0, 1, 2, 100, 0, 0, 0]) == "-"
+    assert f([1, 0, 0, 0, 1, 3, 100, 0, 0, 0]) == "A"
+    assert f([1, 1, 1, 1, 0, 4, 50, 50, 50, 50]) == "T"
+    assert f([1, 1, 0, 0, 0, 2, 50, 50, 40, 40]) == "C"
+    assert f([1, 0, 0, 0, 0, 1, -400, -500, -500, -500]) == "N"      # MIN_SCORE_CONS = -399
+    assert f([1, 0, 0, 0, 0, 1, -399, -500, -500, -500]) == "A"
+    assert f([1, 0, 0, 0, 0, 1, -1, -2401, -3000, -3000], 2) == "N"  # cons_code 2: diff must EXCEED 2400
+    assert f([1, 0, 0, 0, 0, 1, -1, -2402, -3000, -3000], 2) == "A"
