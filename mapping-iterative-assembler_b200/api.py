@@ -142,6 +142,26 @@ class MiaGpu:
         self._ck(self.lib.miagpu_upload_reads(self.h, n, _ptr(bases), _ptr(offsets)))
         self.n = n
 
+    # -- pass 1
+    def pass1(self):
+        """new_kmer_filter + sg_align's compute over the resident reads (mia_main.c:781-796)."""
+        n = self.n
+        o = dict(hits=np.zeros(n, np.int32), score=np.zeros(n, np.int32), fw_score=np.zeros(n, np.int32),
+                 rc_score=np.zeros(n, np.int32), rc=np.zeros(n, np.uint8), as_=np.zeros(n, np.int32), ae=np.zeros(n, np.int32),
+                 start=np.zeros(n, np.int32), end=np.zeros(n, np.int32), abr=np.zeros(n, np.int32), n_runs=np.zeros(n, np.int32),
+                 runs=np.zeros((n, MAX_RUNS), np.uint16), status=np.zeros(n, np.uint8))
+        self._ck(self.lib.miagpu_pass1(self.h, *[_ptr(o[k]) for k in ("hits", "score", "fw_score", "rc_score", "rc", "as_", "ae",
+                                                                     "start", "end", "abr", "n_runs", "runs", "status")]))
+        return o
+
+    def compact_reads(self, keep, revcomp=None):
+        keep = np.ascontiguousarray(keep, np.uint8)
+        rv = None if revcomp is None else np.ascontiguousarray(revcomp, np.uint8)
+        n = C.c_int64()
+        self._ck(self.lib.miagpu_compact_reads(self.h, _ptr(keep), _ptr(rv), C.byref(n)))
+        self.n = n.value
+        return self.n
+
     # -- iteration regime
     @staticmethod
     def alloc_realign_outputs(n, pinned=False):

@@ -9,6 +9,7 @@
 #include "common.cuh"
 #include "realign.cuh"
 #include "consensus.cuh"
+#include "strip.cuh"
 #include <cub/device/device_scan.cuh>
 
 namespace miagpu {
@@ -79,6 +80,18 @@ struct miagpu_ctx {
   DevBuf<uint16_t> d_runs;
   DevBuf<int32_t> d_meta;                      // bucket counts[8], work counters[8], max L[8], cells(2 x int32 -> int64)
   DevBuf<uint32_t> d_scratch;
+  // pass 1 / wide windows
+  int kmer_k = 0;
+  DevBuf<int32_t> d_kb[2], d_kp[2];
+  DevBuf<uint32_t> d_kk[2];
+  int kmer_shift[2] = {0, 0};
+  int max_read_len = 0;
+  DevBuf<uint32_t> d_smask;
+  DevBuf<int4> d_ckpt;
+  DevBuf<int32_t> d_chunk_ids, d_strace, d_hits, d_fw, d_rcs, d_start, d_end;
+  DevBuf<uint8_t> d_rc_out, d_bases2;
+  DevBuf<int64_t> d_off2;
+  DevBuf<int32_t> d_src;
   // consensus
   DevBuf<miagpu_entry> d_entries;
   int64_t n_entries = 0;
@@ -135,6 +148,9 @@ extern "C" void miagpu_destroy(miagpu_ctx* c) {
   c->d_rc.release(); c->d_status.release(); c->d_as.release(); c->d_ae.release(); c->d_score.release();
   c->d_as_out.release(); c->d_ae_out.release(); c->d_abr.release(); c->d_nruns.release(); c->d_win_start.release();
   c->d_win_len.release(); c->d_lists.release(); c->d_runs.release(); c->d_meta.release(); c->d_scratch.release();
+  for (int t = 0; t < 2; t++) { c->d_kb[t].release(); c->d_kp[t].release(); c->d_kk[t].release(); }
+  c->d_smask.release(); c->d_ckpt.release(); c->d_chunk_ids.release(); c->d_strace.release(); c->d_hits.release(); c->d_fw.release();
+  c->d_rcs.release(); c->d_start.release(); c->d_end.release(); c->d_rc_out.release(); c->d_bases2.release(); c->d_off2.release(); c->d_src.release();
   c->d_entries.release(); c->d_sm.release(); c->d_gaps.release(); c->d_ins_off.release(); c->d_acc.release(); c->d_cub.release(); c->d_called.release(); c->d_dropf.release(); c->d_dropb.release();
   for (auto& ev : c->ev) cudaEventDestroy(ev);
   for (auto& ev : c->bev) cudaEventDestroy(ev);
@@ -263,6 +279,8 @@ extern "C" int miagpu_upload_reads(miagpu_ctx* c, int64_t n, const uint8_t* base
   MIAGPU_CUDA(cudaEventElapsedTime(&c->ms_h2d, c->ev[0], c->ev[1]));
   c->n = n;
   c->total_bases = total;
+  c->max_read_len = 0;
+  for (int64_t i = 0; i < n; i++) c->max_read_len = std::max<int64_t>(c->max_read_len, offsets[i + 1] - offsets[i]);
   return 1;
 }
 
@@ -304,6 +322,44 @@ __global__ void classify_kernel(int64_t n, const int64_t* off, const int32_t* as
 __global__ void flag_big_kernel(const int32_t* list, int n_list, int32_t* score, int32_t* n_runs, uint8_t* status) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_list) { int rd = list[i]; score[rd] = INT_MIN; n_runs[rd] = -1; status[rd] = 0x80; }
+}
+
+// ------------------------------------------------ chunked kernel (pass 1, wide windows)
+static int launch_strip(miagpu_ctx* c, int mode, const int32_t* list, int n_list, int32_t* counter) {
+  const int len1 = c->circular ? c->wrap_len : c->seq_len;                 // mia_main.c:721-728
+  const int n_chunks = (len1 + CW - 1) / CW;
+  const int Lmax = std::min(std::max(c->max_read_len, 1), MAX_READ);
+  const int mask_words = n_chunks * (CW / 32);
+  const size_t smem = PROF_INTS * 4 + WARPS_PER_BLOCK * MAX_READ * 2;
+  int per_sm = 0;
+  MIAGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, strip_kernel, WARPS_PER_BLOCK * 32, smem));
+  if (per_sm < 1) { set_error("strip_kernel does not fit on an SM"); return 0; }
+  const int64_t total = mode == 0 ? c->n : n_list;
+  if (total == 0) return 1;
+  // per-warp scratch: keep the total under ~6 GB
+  const size_t per_warp = (size_t)2 * mask_words * 4 + (size_t)2 * (n_chunks + 1) * Lmax * 16 + (size_t)2 * n_chunks * 4 + (size_t)Lmax * CW * 4;
+  per_sm = std::min(per_sm, 4);
+  while (per_sm > 1 && per_warp * c->num_sms * per_sm * WARPS_PER_BLOCK > ((size_t)6 << 30)) per_sm--;
+  int blocks = (int)std::min<int64_t>((int64_t)c->num_sms * per_sm, (total + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+  const size_t warps = (size_t)blocks * WARPS_PER_BLOCK;
+  if (!c->d_smask.reserve(warps * 2 * mask_words) || !c->d_ckpt.reserve(warps * 2 * (n_chunks + 1) * Lmax) ||
+      !c->d_chunk_ids.reserve(warps * 2 * n_chunks) || !c->d_strace.reserve(warps * Lmax * CW)) return 0;
+  StripParams p{};
+  p.bases = c->d_bases.p; p.off = c->d_off.p; p.n = c->n; p.counter = counter; p.mode = mode;
+  p.list = list; p.n_list = n_list; p.rc_in = c->d_rc.p;
+  p.ref_codes[0] = c->d_ref.p; p.ref_codes[1] = c->with_rc ? c->d_rcref.p : c->d_ref.p;
+  p.len1 = len1; p.seq_len = c->seq_len; p.prof = c->d_prof.p;
+  p.k = mode == 0 ? c->kmer_k : 0;
+  for (int t = 0; t < 2; t++) p.kt[t] = KmerTable{c->d_kb[t].p, c->d_kk[t].p, c->d_kp[t].p, c->kmer_shift[t]};
+  p.mask = c->d_smask.p; p.mask_words = mask_words; p.ckpt = c->d_ckpt.p; p.chunk_ids = c->d_chunk_ids.p;
+  p.max_chunks = n_chunks; p.Lmax = Lmax; p.trace = c->d_strace.p;
+  p.hits = mode == 0 ? c->d_hits.p : nullptr; p.score = c->d_score.p; p.fw_score = c->d_fw.p; p.rc_score = c->d_rcs.p;
+  p.as_out = c->d_as_out.p; p.ae_out = c->d_ae_out.p; p.start = c->d_start.p; p.end = c->d_end.p; p.abr = c->d_abr.p;
+  p.n_runs = c->d_nruns.p; p.rc_out = c->d_rc_out.p; p.runs = c->d_runs.p; p.status = c->d_status.p;
+  strip_kernel<<<blocks, WARPS_PER_BLOCK * 32, smem, c->stream>>>(p);
+  MIAGPU_CUDA(cudaGetLastError());
+  c->launches++;
+  return 1;
 }
 
 template <int K>
@@ -366,9 +422,7 @@ static int realign_device(miagpu_ctx* c) {
       case 12: ok = launch_bucket<12>(c, p, maxL); break;
       case 16: ok = launch_bucket<16>(c, p, maxL); break;
       default:
-        flag_big_kernel<<<(meta[b] + 255) / 256, 256, 0, c->stream>>>(p.list, p.n_list, p.score, p.n_runs, p.status);
-        MIAGPU_CUDA(cudaGetLastError());
-        c->launches++;
+        ok = launch_strip(c, 1, p.list, p.n_list, c->d_meta.p + 8 + b);
     }
     if (!ok) return 0;
     MIAGPU_CUDA(cudaEventRecord(c->bev[2 * b + 1], c->stream));
@@ -721,8 +775,147 @@ extern "C" int miagpu_consensus(miagpu_ctx* c, int64_t n_entries, const miagpu_e
   return 1;
 }
 
-// ------------------------------------------------------------ not yet built
-extern "C" int miagpu_build_kmers(miagpu_ctx*, int, int) { set_error("miagpu_build_kmers: not implemented yet"); return 0; }
-extern "C" int miagpu_pass1(miagpu_ctx*, int32_t*, int32_t*, int32_t*, int32_t*, uint8_t*, int32_t*, int32_t*, int32_t*, int32_t*,
-                            int32_t*, int32_t*, uint16_t*, uint8_t*) { set_error("miagpu_pass1: not implemented yet"); return 0; }
-extern "C" int miagpu_compact_reads(miagpu_ctx*, const uint8_t*, const uint8_t*, int64_t*) { set_error("miagpu_compact_reads: not implemented yet"); return 0; }
+// ------------------------------------------------------------------ pass 1
+// populate_kpa / add_kmer (kmer.c:63-85, 153-168) as a bucketed, sorted (k-mer, position) table
+static int build_kmer_strand(miagpu_ctx* c, int t, const std::string& seq, int k, int soft_mask) {
+  std::vector<uint64_t> all;
+  all.reserve(seq.size());
+  for (size_t i = 0; i + k <= seq.size(); i++) {
+    bool ok = true;
+    uint64_t inx = 0;
+    for (int j = 0; j < k && ok; j++) {
+      char ch = seq[i + j];
+      if (soft_mask && ch >= 'a' && ch <= 'z') ok = false;                  // all_upper, kmer.c:140-148
+      if (ch >= 'a' && ch <= 'z') ch = (char)(ch - 32);                     // kmer2inx upper-cases, kmer.c:27
+      int code = ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'T' ? 3 : -1;
+      if (code < 0) ok = false;
+      inx = (inx << 2) | (uint64_t)(code & 3);
+    }
+    if (ok) all.push_back((inx << 32) | (uint64_t)i);
+  }
+  std::sort(all.begin(), all.end());
+  const int bucket_bits = std::min(2 * k, 16);
+  const int shift = 2 * k - bucket_bits;
+  const int nb = 1 << bucket_bits;
+  std::vector<int32_t> bstart(nb + 1, 0), pos;
+  std::vector<uint32_t> km;
+  int run = 0;
+  for (size_t i = 0; i < all.size(); i++) {
+    run = (i > 0 && (all[i] >> 32) == (all[i - 1] >> 32)) ? run + 1 : 0;
+    if (run >= MAX_KMER_POS) continue;                                      // add_kmer keeps the first 128 positions
+    km.push_back((uint32_t)(all[i] >> 32));
+    pos.push_back((int32_t)(all[i] & 0xffffffffu));
+    bstart[(km.back() >> shift) + 1]++;
+  }
+  for (int b = 0; b < nb; b++) bstart[b + 1] += bstart[b];
+  if (!c->d_kb[t].reserve(nb + 1) || !c->d_kk[t].reserve(km.size() + 1) || !c->d_kp[t].reserve(pos.size() + 1)) return 0;
+  MIAGPU_CUDA(cudaMemcpyAsync(c->d_kb[t].p, bstart.data(), (nb + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+  if (!km.empty()) {
+    MIAGPU_CUDA(cudaMemcpyAsync(c->d_kk[t].p, km.data(), km.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    MIAGPU_CUDA(cudaMemcpyAsync(c->d_kp[t].p, pos.data(), pos.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  }
+  MIAGPU_CUDA(cudaStreamSynchronize(c->stream));
+  c->kmer_shift[t] = shift;
+  return 1;
+}
+
+extern "C" int miagpu_build_kmers(miagpu_ctx* c, int k, int soft_mask) {
+  if (!c || !c->have_ref) { set_error("miagpu_build_kmers: set_reference first"); return 0; }
+  if (k > 14) { set_error("Cannot use kmer length greater than 14"); return 0; }   // init_kpa, kmer.c:93-97
+  MIAGPU_CUDA(cudaSetDevice(c->device));
+  if (k <= 0) { c->kmer_k = 0; return 1; }
+  if (!c->with_rc) { set_error("miagpu_build_kmers: the reference was set without its reverse complement"); return 0; }
+  if ((int)c->raw_wrapped.size() < k) { set_error("miagpu_build_kmers: reference shorter than k"); return 0; }
+  if (!build_kmer_strand(c, 0, c->raw_wrapped, k, soft_mask) || !build_kmer_strand(c, 1, c->raw_rc_wrapped, k, soft_mask)) return 0;
+  c->kmer_k = k;
+  return 1;
+}
+
+extern "C" int miagpu_pass1(miagpu_ctx* c, int32_t* hits, int32_t* score, int32_t* fw_score, int32_t* rc_score, uint8_t* rc, int32_t* as,
+                            int32_t* ae, int32_t* start, int32_t* end, int32_t* abr, int32_t* n_runs, uint16_t* runs, uint8_t* status) {
+  if (!c || !c->have_pssm || !c->have_ref || !c->with_rc) { set_error("miagpu_pass1: set_pssm and set_reference(with_rc=1) first"); return 0; }
+  MIAGPU_CUDA(cudaSetDevice(c->device));
+  const int64_t n = c->n;
+  c->launches = 0;
+  if (!c->d_hits.reserve(n + 1) || !c->d_fw.reserve(n + 1) || !c->d_rcs.reserve(n + 1) || !c->d_start.reserve(n + 1) ||
+      !c->d_end.reserve(n + 1) || !c->d_rc_out.reserve(n + 1)) return 0;
+  MIAGPU_CUDA(cudaMemsetAsync(c->d_meta.p, 0, 64 * sizeof(int32_t), c->stream));
+  MIAGPU_CUDA(cudaEventRecord(c->ev[1], c->stream));
+  if (!launch_strip(c, 0, nullptr, 0, c->d_meta.p + 8)) return 0;
+  MIAGPU_CUDA(cudaEventRecord(c->ev[2], c->stream));
+  if (n) {
+    auto dl = [&](void* h, const void* d, size_t bytes) { return h ? cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, c->stream) : cudaSuccess; };
+    MIAGPU_CUDA(dl(hits, c->d_hits.p, n * 4)); MIAGPU_CUDA(dl(score, c->d_score.p, n * 4)); MIAGPU_CUDA(dl(fw_score, c->d_fw.p, n * 4));
+    MIAGPU_CUDA(dl(rc_score, c->d_rcs.p, n * 4)); MIAGPU_CUDA(dl(rc, c->d_rc_out.p, n)); MIAGPU_CUDA(dl(as, c->d_as_out.p, n * 4));
+    MIAGPU_CUDA(dl(ae, c->d_ae_out.p, n * 4)); MIAGPU_CUDA(dl(start, c->d_start.p, n * 4)); MIAGPU_CUDA(dl(end, c->d_end.p, n * 4));
+    MIAGPU_CUDA(dl(abr, c->d_abr.p, n * 4)); MIAGPU_CUDA(dl(n_runs, c->d_nruns.p, n * 4)); MIAGPU_CUDA(dl(runs, c->d_runs.p, n * MAX_RUNS * 2));
+    MIAGPU_CUDA(dl(status, c->d_status.p, n));
+  }
+  MIAGPU_CUDA(cudaEventRecord(c->ev[3], c->stream));
+  MIAGPU_CUDA(cudaStreamSynchronize(c->stream));
+  MIAGPU_CUDA(cudaEventElapsedTime(&c->ms_kernels, c->ev[1], c->ev[2]));
+  MIAGPU_CUDA(cudaEventElapsedTime(&c->ms_d2h, c->ev[2], c->ev[3]));
+  c->ms_h2d = 0;
+  const int len1 = c->circular ? c->wrap_len : c->seq_len;
+  c->dp_cells = 2 * (int64_t)len1 * c->total_bases;                        // nominal cells
+  return 1;
+}
+
+// keep / reverse-complement the resident reads in place (sg_align's accept + add_virgin_fs2fsdb + clean_FSDB)
+__global__ void compact_kernel(int64_t n_new, const int32_t* src, const uint8_t* revcomp, const int64_t* off_old, const uint8_t* bases_old,
+                               const int64_t* off_new, uint8_t* bases_new) {
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= n_new) return;
+  const int i = src[w];
+  const int64_t o = off_old[i], L = off_old[i + 1] - o, d = off_new[w];
+  const bool rcv = revcomp[w];
+  for (int64_t j = lane; j < L; j += 32) {
+    uint8_t b = rcv ? bases_old[o + L - 1 - j] : bases_old[o + j];
+    if (rcv) {                                                             // revcom_char, map_align.c:418-431
+      const char* from = "ABCDGHKMNRSTUVWXY";
+      const char* to = "TVGHCDMKNYSAABWXR";
+      uint8_t r = 'N';
+      for (int q = 0; q < 17; q++) if (from[q] == b) r = to[q];
+      b = b == '-' ? '-' : r;
+    }
+    bases_new[d + j] = b;
+  }
+}
+
+extern "C" int miagpu_compact_reads(miagpu_ctx* c, const uint8_t* keep, const uint8_t* revcomp, int64_t* n_out) {
+  if (!c || (c->n && !keep)) { set_error("miagpu_compact_reads: bad argument"); return 0; }
+  MIAGPU_CUDA(cudaSetDevice(c->device));
+  std::vector<int64_t> off_old(c->n + 1), off_new(1, 0);
+  if (c->n) MIAGPU_CUDA(cudaMemcpy(off_old.data(), c->d_off.p, (c->n + 1) * 8, cudaMemcpyDeviceToHost));
+  std::vector<int32_t> src;
+  std::vector<uint8_t> rcv;
+  int maxL = 0;
+  for (int64_t i = 0; i < c->n; i++)
+    if (keep[i]) {
+      src.push_back((int32_t)i);
+      rcv.push_back(revcomp ? revcomp[i] : 0);
+      off_new.push_back(off_new.back() + off_old[i + 1] - off_old[i]);
+      maxL = std::max<int64_t>(maxL, off_old[i + 1] - off_old[i]);
+    }
+  const int64_t m = (int64_t)src.size();
+  if (!c->d_bases2.reserve(off_new.back() + 16) || !c->d_off2.reserve(m + 1) || !c->d_src.reserve(m + 1) || !c->d_dropf.reserve(m + 1)) return 0;
+  if (m) {
+    MIAGPU_CUDA(cudaMemcpyAsync(c->d_src.p, src.data(), m * 4, cudaMemcpyHostToDevice, c->stream));
+    MIAGPU_CUDA(cudaMemcpyAsync(c->d_dropf.p, rcv.data(), m, cudaMemcpyHostToDevice, c->stream));
+    MIAGPU_CUDA(cudaMemcpyAsync(c->d_off2.p, off_new.data(), (m + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    compact_kernel<<<(unsigned)((m * 32 + 255) / 256), 256, 0, c->stream>>>(m, c->d_src.p, c->d_dropf.p, c->d_off.p, c->d_bases.p, c->d_off2.p, c->d_bases2.p);
+    MIAGPU_CUDA(cudaGetLastError());
+  } else {
+    MIAGPU_CUDA(cudaMemcpyAsync(c->d_off2.p, off_new.data(), 8, cudaMemcpyHostToDevice, c->stream));
+  }
+  MIAGPU_CUDA(cudaStreamSynchronize(c->stream));
+  std::swap(c->d_bases, c->d_bases2);
+  std::swap(c->d_off, c->d_off2);
+  c->n = m;
+  c->total_bases = off_new.back();
+  c->max_read_len = maxL;
+  if (n_out) *n_out = m;
+  return 1;
+}
+

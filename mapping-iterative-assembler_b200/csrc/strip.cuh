@@ -1,0 +1,390 @@
+// strip.cuh -- general (chunked, maskable) PSSM DP for pass 1 and for windows wider than the
+// register-tiled kernels of realign.cuh (sm_100a).
+//
+// Replaces new_kmer_filter (kmer.c:239-331) + sg_align's compute (mia.c:1500-1610): both
+// strands x whole wrapped reference with the forward matrix, masked by the k-mer filter,
+// strand pick, traceback, coordinate fix-ups; and the whole-reference fallback of
+// reiterate_assembly (mia_main.c:209-212).
+//
+// Same row-parallel scheme as realign.cuh (a row has no internal dependency), but the columns
+// are processed in CHUNKS of CW = 32*K columns: for each chunk the warp runs all L rows, and
+// per row hands the next chunk {S[r][last], S[r][last-1], best_gap_col state} through a
+// checkpoint array in global memory.  Fully masked chunks are skipped (best_gap_col persists
+// across them, exactly like the reference's running variable, H3).  The forward sweep keeps
+// no trace; the traceback re-runs only the chunk(s) the path crosses from their checkpoints
+// with a full int32 trace (the reference's own encoding, so the trace==0 collision H2 is
+// reproduced by construction).  Arg-maxes are (value, index) pairs in plain int32 with the real
+// HIM = INT_MIN/2 sentinel: no packing limits, any reference length.
+#pragma once
+#include "common.cuh"
+#include "realign.cuh"
+
+namespace miagpu {
+
+constexpr int SK = 8;                 // columns per lane
+constexpr int CW = 32 * SK;           // chunk width
+constexpr int KMER_SATURATE = 128;    // params.h:85
+constexpr int MAX_KMER_POS = 128;     // params.h:83
+constexpr int ALIGN_MASK_BUFFER = 10; // params.h:86
+
+struct KmerTable {                    // one strand; sorted (kmer, pos), <= 128 positions per k-mer
+  const int32_t* bucket_start;        // [nbuckets+1]
+  const uint32_t* kmer;               // full k-mer index of entry
+  const int32_t* pos;
+  int32_t bucket_shift;               // bucket = kmer >> bucket_shift
+};
+
+struct StripParams {
+  const uint8_t* bases;
+  const int64_t* off;
+  int64_t n;
+  int32_t* counter;
+  // mode 0: pass 1 (both strands, forward matrix, k-mer masks).  mode 1: single strand, unmasked,
+  // explicit work list + per-read strand matrix (wide realign)
+  int32_t mode;
+  const int32_t* list;
+  int32_t n_list;
+  const uint8_t* rc_in;
+  const uint8_t* ref_codes[2];        // forward / reverse-complement strand, wrapped
+  int32_t len1;                       // columns (wrap_len if circular else seq_len)
+  int32_t seq_len;
+  const int32_t* prof;
+  int32_t k;                          // k-mer length, <= 0: no filter
+  KmerTable kt[2];
+  // per-warp scratch
+  uint32_t* mask;                     // [warp][2][mask_words]
+  int32_t mask_words;
+  int4* ckpt;                         // [warp][2][(max_chunks+1)][Lmax]
+  int32_t* chunk_ids;                 // [warp][2][max_chunks]
+  int32_t max_chunks;
+  int32_t Lmax;
+  int32_t* trace;                     // [warp][(Lmax)][CW]
+  // outputs
+  int32_t *hits, *score, *fw_score, *rc_score, *as_out, *ae_out, *start, *end, *abr, *n_runs;
+  uint8_t* rc_out;
+  uint16_t* runs;
+  uint8_t* status;
+};
+
+struct PV { int v, i; };
+__device__ __forceinline__ PV pv_better(PV a, PV b) { return (b.v > a.v) ? b : a; }   // strict '>' keeps the earlier
+
+// One chunk, all rows.  TRACE: also write trace ints for rows 1..L-1 into trace[(r)*CW + cc].
+// ck_in: checkpoint of this chunk (per row {S1,S2,PV,PI}); adjacent: S1/S2 valid (previous chunk is c0-CW).
+// ck_out: written for the next processed chunk.  Returns via best/best_col the running first-max of the last row.
+template <bool TRACE>
+__device__ void strip_chunk(const int L, const int len1, const int c0, const uint8_t* __restrict__ ref, const uint32_t* __restrict__ mask,
+                            const uint16_t* rowoff, const uint32_t prof_base, const int4* ck_in, const bool adjacent, const bool have_in,
+                            int4* ck_out, int32_t* trace, int& best, int& best_col) {
+  const int lane = threadIdx.x & 31;
+  const int cbase = c0 + lane * SK;
+  int code4[SK];
+  bool mb[SK];
+  {
+    const uint32_t mword = mask ? __ldcg(mask + (cbase >> 5)) : 0xffffffffu;       // SK = 8 divides 32: one word per lane
+#pragma unroll
+    for (int j = 0; j < SK; j++) {
+      const int c = cbase + j;
+      code4[j] = (c < len1 ? ref[c] : 4) * 4;
+      mb[j] = c < len1 && ((mword >> ((cbase & 31) + j)) & 1u);
+    }
+  }
+  int Sp[SK], RV[SK], RI[SK];
+  {
+    const uint32_t pa = prof_base + rowoff[0];
+#pragma unroll
+    for (int j = 0; j < SK; j++) {
+      Sp[j] = mb[j] ? lds_s32(pa + code4[j]) : HIM;                     // mia.c:769-785
+      RV[j] = INT_MIN; RI[j] = 0;
+    }
+  }
+  if (ck_out && lane == 31) ck_out[0] = make_int4(Sp[SK - 1], Sp[SK - 2], 0, 0);
+  for (int r = 1; r < L; r++) {
+    const uint32_t pa = prof_base + rowoff[r];
+    const int N = -(GOP + GEP * (r + 1));                                // sg5 = 1 on every path that reaches here
+    // left neighbours of this lane's first column in row r-1
+    int l1 = __shfl_up_sync(0xffffffffu, Sp[SK - 1], 1);
+    int l2 = __shfl_up_sync(0xffffffffu, Sp[SK - 2], 1);
+    PV seed;
+    if (lane == 0) {
+      int4 ci = have_in ? ck_in[r - 1] : make_int4(HIM, HIM, 0, 0);
+      l1 = adjacent ? ci.x : HIM;
+      l2 = adjacent ? ci.y : HIM;
+      // best_gap_col entering this chunk at row r: the previous processed chunk's state, or the row-start
+      // state bgc = 0 (mia.c:825) = (S[r-1][0], 0)
+      if (c0 == 0) seed = PV{Sp[0], 0};
+      else if (have_in) { int4 cr = ck_in[r]; seed = PV{cr.z, cr.w}; }
+      else seed = PV{HIM, 0};
+    }
+    // candidates: column k = c-2 joins when column c is unmasked and c >= 2 (mia.c:827-843)
+    PV cand[SK];
+#pragma unroll
+    for (int j = 0; j < SK; j++) {
+      const int c = cbase + j, k = c - 2;
+      const int s = j == 0 ? l2 : j == 1 ? l1 : Sp[j - 2];
+      cand[j] = (mb[j] && k >= 0) ? PV{s + GEP * k, k} : PV{INT_MIN, 0};
+    }
+    PV t = cand[0];
+#pragma unroll
+    for (int j = 1; j < SK; j++) t = pv_better(t, cand[j]);
+    if (lane == 0) t = pv_better(seed, t);                              // seed is earlier than every candidate
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      PV o{__shfl_up_sync(0xffffffffu, t.v, d), __shfl_up_sync(0xffffffffu, t.i, d)};
+      if (lane >= d) t = pv_better(o, t);
+    }
+    PV P{__shfl_up_sync(0xffffffffu, t.v, 1), __shfl_up_sync(0xffffffffu, t.i, 1)};
+    if (lane == 0) P = seed;
+    if (ck_out && lane == 31) ck_out[r] = make_int4(0, 0, t.v, t.i);    // S1/S2 patched below
+
+    int D = l1;
+    int tr[SK];
+#pragma unroll
+    for (int j = 0; j < SK; j++) {
+      const int c = cbase + j;
+      P = pv_better(P, cand[j]);
+      int S = HIM, trace_v = 0;
+      if (mb[j]) {
+        const int sub = lds_s32(pa + code4[j]);
+        if (c == 0) {
+          S = sub + N;                                                   // mia.c:805-822
+        } else {
+          const int Gc = c >= 2 ? P.v - (GOP - GEP) - GEP * c : HIM;     // mia.c:838-850
+          const int Gr = r >= 2 ? RV[j] - (GOP - GEP) - GEP * r : HIM;   // mia.c:856-868
+          if (N > D && N > Gc && N > Gr) { S = N; trace_v = c; }         // mia.c:910-918
+          else if (D >= Gc && D >= Gr) { S = sub + D; trace_v = 0; }
+          else if (Gc >= Gr) { S = sub + Gc; trace_v = P.i; }
+          else { S = sub + Gr; trace_v = -RI[j]; }
+          // row r-1 joins best_gap_row[c-1] (used from row r+1 on)
+          const int cv = D + GEP * (r - 1);
+          if (cv > RV[j]) { RV[j] = cv; RI[j] = r - 1; }
+        }
+      }
+      tr[j] = trace_v;
+      D = Sp[j];
+      Sp[j] = S;
+    }
+    if (ck_out && lane == 31) { ck_out[r].x = Sp[SK - 1]; ck_out[r].y = Sp[SK - 2]; }
+    if (TRACE) {
+      int4* trow = reinterpret_cast<int4*>(trace + (int64_t)r * CW + lane * SK);
+      trow[0] = make_int4(tr[0], tr[1], tr[2], tr[3]);
+      trow[1] = make_int4(tr[4], tr[5], tr[6], tr[7]);
+    }
+  }
+  // max_sg_score over this chunk's columns (mia.c:1293-1299): strict '>' in column order
+  int lb = INT_MIN, lc = 0;
+#pragma unroll
+  for (int j = 0; j < SK; j++) {
+    const int c = cbase + j;
+    if (c < len1 && Sp[j] > lb) { lb = Sp[j]; lc = c; }
+  }
+  const int wb = __reduce_max_sync(0xffffffffu, lb);
+  const int wc = __reduce_min_sync(0xffffffffu, lb == wb ? lc : 0x7fffffff);
+  if (wb > best) { best = wb; best_col = wc; }
+}
+
+__device__ __forceinline__ int kmer_code(uint8_t b) {                   // kmer2inx upper-cases (kmer.c:27)
+  if (b >= 'a' && b <= 'z') b -= 32;
+  return b == 'A' ? 0 : b == 'C' ? 1 : b == 'G' ? 2 : b == 'T' ? 3 : -1;
+}
+
+// new_kmer_filter for one strand: sets mask bits, returns the hit count (kmer.c:275-327)
+__device__ int seed_strand(const KmerTable& kt, const int k, const uint8_t* read, const int L, const int len1, const int strand,
+                           uint32_t* mask, const int mask_words) {
+  const int lane = threadIdx.x & 31;
+  int hits = 0;
+  for (int p = lane; p + k <= L; p += 32) {
+    uint32_t inx = 0;
+    bool ok = true;
+    for (int i = 0; i < k; i++) {
+      const int c = kmer_code(read[p + i]);
+      if (c < 0) { ok = false; break; }
+      inx = (inx << 2) | (uint32_t)c;
+    }
+    if (!ok) continue;
+    const int b = (int)(inx >> kt.bucket_shift);
+    for (int e = kt.bucket_start[b]; e < kt.bucket_start[b + 1]; e++) {
+      if (kt.kmer[e] != inx) continue;
+      hits++;
+      const int q = kt.pos[e];
+      int lo = q - p - ALIGN_MASK_BUFFER;
+      int hi = q + (L - p) + ALIGN_MASK_BUFFER - strand;                // rc bound is one shorter: kmer.c:294 vs 319
+      if (lo < 0) lo = 0;
+      if (hi >= len1) hi = len1 - 1;
+      for (int w = lo >> 5; w <= (hi >> 5); w++) {
+        const int a = max(lo, w << 5) & 31, z = min(hi, (w << 5) + 31) & 31;
+        atomicOr(mask + w, (0xffffffffu >> (31 - z)) & (0xffffffffu << a));
+      }
+    }
+  }
+  hits = __reduce_add_sync(0xffffffffu, hits);
+  if (hits >= KMER_SATURATE) {                                           // kmer.c:283-285
+    __syncwarp();
+    for (int w = lane; w < mask_words; w += 32) mask[w] = 0xffffffffu;
+  }
+  return hits;
+}
+
+// dynamic smem: [prof PROF_INTS ints][rowoff WARPS*256 u16]
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) strip_kernel(StripParams p) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  int32_t* s_prof = reinterpret_cast<int32_t*>(smem);
+  uint16_t* s_rowoff = reinterpret_cast<uint16_t*>(smem + PROF_INTS * 4);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < PROF_INTS; i += blockDim.x) s_prof[i] = p.prof[i];
+  __syncthreads();
+  uint16_t* rowoff = s_rowoff + warp * MAX_READ;
+  const uint32_t prof_base = smem_u32(s_prof);
+  const int64_t gw = (int64_t)blockIdx.x * WARPS_PER_BLOCK + warp;
+  uint32_t* mask0 = p.mask + gw * 2 * p.mask_words;
+  int4* ck0 = p.ckpt + gw * 2 * (int64_t)(p.max_chunks + 1) * p.Lmax;
+  int32_t* ids0 = p.chunk_ids + gw * 2 * p.max_chunks;
+  int32_t* trace = p.trace + gw * (int64_t)p.Lmax * CW;
+  const int total = p.mode == 0 ? (int)p.n : p.n_list;
+  const int len1 = p.len1;
+
+  for (;;) {
+    int item = 0;
+    if (lane == 0) item = atomicAdd(p.counter, 1);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= total) break;
+    const int rd = p.mode == 0 ? item : p.list[item];
+    const int64_t o0 = p.off[rd];
+    const int L = (int)(p.off[rd + 1] - o0);
+    const uint8_t* read = p.bases + o0;
+    if (L <= 0 || L > MAX_READ) {
+      if (lane == 0) { p.status[rd] = MIAGPU_ST_UNSUPPORTED; p.n_runs[rd] = -1; p.score[rd] = INT_MIN; if (p.hits) p.hits[rd] = 0; }
+      continue;
+    }
+    const int nstrand = p.mode == 0 ? 2 : 1;
+    const int mat = p.mode == 0 ? 0 : (p.rc_in[rd] ? 1 : 0);             // pass 1 scores BOTH strands with the forward matrix (H5)
+    __syncwarp();
+    for (int r = lane; r < L; r += 32) rowoff[r] = (uint16_t)(prof_row_index(mat, sm_depth(r, L), base_code(read[r])) * 4);
+    // ---- k-mer filter
+    int hits[2] = {1, 0};
+    const bool masked = p.mode == 0 && p.k > 0;
+    if (masked) {
+      for (int w = lane; w < 2 * p.mask_words; w += 32) mask0[w] = 0;
+      __syncwarp();
+      hits[0] = hits[1] = 0;
+      if (L >= p.k) {
+        hits[0] = seed_strand(p.kt[0], p.k, read, L, len1, 0, mask0, p.mask_words);
+        hits[1] = seed_strand(p.kt[1], p.k, read, L, len1, 1, mask0 + p.mask_words, p.mask_words);
+      }
+      __syncwarp();
+    }
+    if (p.hits && lane == 0) p.hits[rd] = hits[0] + hits[1];
+    if (masked && hits[0] + hits[1] == 0) {                              // mia_main.c:781: the read is not aligned at all
+      if (lane == 0) { p.status[rd] = MIAGPU_ST_SKIPPED; p.n_runs[rd] = 0; p.score[rd] = INT_MIN; }
+      continue;
+    }
+    // ---- forward sweeps
+    int best[2] = {INT_MIN, INT_MIN}, bcol[2] = {0, 0}, nch[2] = {0, 0};
+    const int n_chunks_all = (len1 + CW - 1) / CW;
+    for (int s = 0; s < nstrand; s++) {
+      const uint32_t* mask = masked ? mask0 + s * p.mask_words : nullptr;
+      int32_t* ids = ids0 + s * p.max_chunks;
+      int4* ck = ck0 + (int64_t)s * (p.max_chunks + 1) * p.Lmax;
+      // chunk list: chunks with at least one unmasked column
+      int n = 0;
+      for (int base = 0; base < n_chunks_all; base += 32) {
+        const int ch = base + lane;
+        bool any = false;
+        if (ch < n_chunks_all) {
+          if (!mask) any = true;
+          else for (int w = 0; w < CW / 32; w++) { const int wi = ch * (CW / 32) + w; if (wi < p.mask_words && __ldcg(mask + wi)) any = true; }
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, any);
+        if (any) ids[n + __popc(bal & ((1u << lane) - 1))] = ch;
+        n += __popc(bal);
+      }
+      __syncwarp();
+      nch[s] = n;
+      // the reference's scan starts at column 0: S[L-1][0] (HIM if masked) is the first incumbent
+      best[s] = HIM; bcol[s] = 0;
+      int prev = -2;
+      for (int q = 0; q < n; q++) {
+        const int ch = ids[q];
+        strip_chunk<false>(L, len1, ch * CW, p.ref_codes[s], mask, rowoff, prof_base, ck + (int64_t)q * p.Lmax, prev == ch - 1, q > 0,
+                           ck + (int64_t)(q + 1) * p.Lmax, nullptr, best[s], bcol[s]);
+        prev = ch;
+        __syncwarp();
+      }
+    }
+    // ---- strand pick: fw only if strictly better (mia.c:1549-1554)
+    const int s = (nstrand == 2 && !(best[0] > best[1])) ? 1 : 0;
+    const int score = best[s];
+    const int aec = bcol[s];
+    // ---- traceback: re-run the chunks the path crosses, with trace
+    const uint32_t* mask = masked ? mask0 + s * p.mask_words : nullptr;
+    const int32_t* ids = ids0 + s * p.max_chunks;
+    const int4* ck = ck0 + (int64_t)s * (p.max_chunks + 1) * p.Lmax;
+    int row = L - 1, col = aec, nrun = 0, curM = 0, ncols = 0, loaded = -1;
+    uint16_t* my_runs = p.runs + (int64_t)rd * MAX_RUNS;
+    auto push = [&](int type, int len) {
+      while (len > 0) {                                                  // a run longer than 14 bits is split
+        const int l = min(len, 0x3fff);
+        if (nrun < MAX_RUNS && lane == 0) my_runs[nrun] = (uint16_t)((type << 14) | l);
+        nrun++; len -= l;
+      }
+    };
+    bool lost = false;
+    while (row > 0 && col > 0) {
+      const int ch = col / CW;
+      if (ch != loaded) {
+        int q = -1;                                                      // position of chunk ch in the processed list
+        for (int base = 0; base < nch[s]; base += 32) {
+          const bool hit = base + lane < nch[s] && ids[base + lane] == ch;
+          const unsigned bal = __ballot_sync(0xffffffffu, hit);
+          if (bal) { q = base + __ffs(bal) - 1; break; }
+        }
+        if (q < 0) { lost = true; break; }                               // cannot happen: the path only visits unmasked cells
+        int dummy_b = INT_MIN, dummy_c = 0;
+        __syncwarp();
+        strip_chunk<true>(L, len1, ch * CW, p.ref_codes[s], mask, rowoff, prof_base, ck + (int64_t)q * p.Lmax,
+                          q > 0 && ids[q - 1] == ch - 1, q > 0, nullptr, trace, dummy_b, dummy_c);
+        __syncwarp();
+        loaded = ch;
+      }
+      const int t = __ldcg(trace + (int64_t)row * CW + (col - ch * CW));
+      if (t == col || t == -row) break;                                  // mia.c:617-618
+      curM++;
+      if (t == 0) { row--; col--; }
+      else if (t < 0) { push(MIAGPU_RUN_M, curM); ncols += curM; curM = 0; push(MIAGPU_RUN_I, row - 1 + t); ncols += row - 1 + t; row = -t; col--; }
+      else { push(MIAGPU_RUN_M, curM); ncols += curM; curM = 0; push(MIAGPU_RUN_D, col - 1 - t); ncols += col - 1 - t; col = t; row--; }
+    }
+    push(MIAGPU_RUN_M, curM + 1); ncols += curM + 1;
+    if (lane == 0) {
+      uint8_t st = lost ? MIAGPU_ST_UNSUPPORTED : MIAGPU_ST_OK;
+      if (nrun > MAX_RUNS) { st |= MIAGPU_ST_RUNS_OVERFLOW; nrun = -1; }
+      if (ncols > 2 * MAX_READ) st |= MIAGPU_ST_STR_OVERFLOW;
+      const int abc = col, abr = row;
+      if (p.mode == 0) {
+        // sg_align's coordinates (mia.c:1568-1610); runs go out in forward-reference orientation
+        int start = abc, end = aec;
+        if (s == 1) {                                                     // c2rcc, mia.c:26-30; revcom_PWAF reverses the columns
+          start = p.seq_len - (aec % p.seq_len) - 1;
+          end = p.seq_len - (abc % p.seq_len) - 1;
+        } else {
+          for (int a = 0, b = nrun - 1; a < b; a++, b--) { uint16_t x = my_runs[a]; my_runs[a] = my_runs[b]; my_runs[b] = x; }
+        }
+        int as = start, ae = end;
+        if (as > ae) ae = p.seq_len + as;                                 // mia.c:1600-1604
+        if (end > p.seq_len) end -= p.seq_len;                            // mia.c:1606-1610
+        p.as_out[rd] = as; p.ae_out[rd] = ae; p.start[rd] = start; p.end[rd] = end;
+        p.rc_out[rd] = (uint8_t)s;
+        p.fw_score[rd] = best[0]; p.rc_score[rd] = best[1];
+        p.abr[rd] = s == 1 ? 0 : abr;                                     // row of the returned runs' first base in the STORED orientation
+      } else {
+        for (int a = 0, b = nrun - 1; a < b; a++, b--) { uint16_t x = my_runs[a]; my_runs[a] = my_runs[b]; my_runs[b] = x; }
+        p.as_out[rd] = abc; p.ae_out[rd] = aec;                           // window starts at 0: mia_main.c:209-212, 250-255
+        p.abr[rd] = abr;
+      }
+      p.score[rd] = score;
+      p.n_runs[rd] = nrun;
+      p.status[rd] = st;
+    }
+  }
+}
+
+}  // namespace miagpu

@@ -134,3 +134,41 @@ def check_consensus(gpu, oracle, ref, bases, off, rc, as_, ae, sm, circular=1, c
     if gcons != cons:
         problems.append(("consensus", len(gcons), len(cons)))
     return problems, dict(n_split=int(split.sum()), n_ins_cols=int(ggaps.sum()), cons_len=len(gcons))
+
+
+def check_pass1(gpu, oracle, ref, reads, sm, circular=1, k=0, soft_mask=0):
+    """GPU pass 1 (k-mer filter + both-strand DP + strand pick + traceback + coordinates) vs oracle."""
+    import numpy as np
+    from mia_b200 import api
+    gpu.set_pssm(sm)
+    gpu.set_reference(ref, circular=circular, with_rc=1)
+    gpu.build_kmers(k, soft_mask)
+    off = np.zeros(len(reads) + 1, np.int64)
+    np.cumsum([len(r) for r in reads], out=off[1:])
+    bases = np.frombuffer("".join(reads).encode(), np.uint8)
+    gpu.upload_reads(bases, off)
+    out = gpu.pass1()
+    ctx = oracle.ctx_new(ref, circular, sm, with_rc=1, k=k, soft_mask=soft_mask)
+    wref = oracle.ctx_seq(ctx)
+    bad = []
+    for i, rd in enumerate(reads):
+        o = oracle.pass1(ctx, rd)
+        if int(out["hits"][i]) != o["hits"]:
+            bad.append((i, "hits", int(out["hits"][i]), o["hits"]))
+            continue
+        if not o["hits"]:
+            if not (int(out["status"][i]) & 2):
+                bad.append((i, "not flagged skipped"))
+            continue
+        got = tuple(int(out[k2][i]) for k2 in ("score", "fw_score", "rc_score", "rc", "as_", "ae", "start", "end"))
+        exp = (o["score"], o["fw_score"], o["rc_score"], o["rc"], o["as_"], o["ae"], o["start"], o["end"] if not o["split"] else o["b_end"])
+        if got != exp:
+            bad.append((i, got, exp))
+            continue
+        # gapped strings in forward-reference orientation: the stored read is revcomp'd for rc
+        stored = oracle.revcom(rd) if o["rc"] else rd
+        rg, fg = api.expand_runs(wref, stored, int(out["start"][i]), int(out["abr"][i]), out["runs"][i], int(out["n_runs"][i]))
+        if (rg, fg) != (o["f_ref"] + o["b_ref"], o["f_frag"] + o["b_frag"]):
+            bad.append((i, "strings", rg, fg, o["f_ref"] + o["b_ref"], o["f_frag"] + o["b_frag"]))
+    oracle.ctx_free(ctx)
+    return bad, out
