@@ -25,22 +25,29 @@ constexpr int FIRST_ROUND_SCORE_CUTOFF = 2000;
 // given depth) is 8 consecutive ints = 32 B, so a DP row needs ONE uniform
 // offset and every lane adds its column's ref_code*4.
 constexpr int PROF_ROW_INTS = 8;
-constexpr int PROF_INTS = 2 * NMAT * 5 * PROF_ROW_INTS;       // 2480 ints = 9920 B
+constexpr int PROF_INTS = 2 * NMAT * 5 * PROF_ROW_INTS;       // 2480 ints = 9920 B (plain); a second copy * 2048 follows
 __host__ __device__ inline int prof_row_index(int strand, int depth, int read_code) {
   return ((strand * NMAT + depth) * 5 + read_code) * PROF_ROW_INTS;
 }
 
-// ---- packed arg-max keys (windowed kernel).
-// key = value * 2048 + (marker << 9) + (511 - index);  max() over keys picks the
-// larger value and, on equal values, the SMALLER index -- which is the
-// reference's strict-'>' "earliest candidate wins" rule (mia.c:839-843, 857-861).
-// value needs |value| < 2^20; index < 512.
+// ---- packed keys (windowed kernel).
+// key = value * 2048 + (marker << 9) + (511 - index).  max() over keys picks the larger value;
+// on equal values the larger marker, then the SMALLER index.  That single ordering carries
+// every tie rule of dyn_prog (mia.c:838-965):
+//   * candidates for best_gap_col / best_gap_row share one marker, so "earliest index wins"
+//     is the reference's strict-'>' replacement (839-843, 857-861);
+//   * between move types DIAG(3) > COL(2) > ROW(1) reproduces "diag if >= both, else col if >= row";
+//   * START(0) with index bits 0 loses every tie, i.e. start-new needs strictly-greater (910-915).
+// Scores themselves live in "diagonal key" form Sd = S*2048 + (DIAG<<9) so that no conversion is
+// needed between a cell's result and the next row's operands.  |value| < 2^20, index < 512.
 constexpr int KEY_SHIFT = 11;
 constexpr int KEY_MUL = 1 << KEY_SHIFT;
+constexpr int KEY_LOW_MASK = KEY_MUL - 1;
 constexpr int KEY_IDX_MASK = 511;
-constexpr int MARK_DIAG = 0, MARK_START = 1, MARK_COL = 2, MARK_ROW = 3;
-constexpr int NEG_VALUE = -1000000;                  // "-infinity" that still packs
-constexpr int NEG_KEY = NEG_VALUE * KEY_MUL;         // -2,048,000,000 > INT_MIN
+constexpr int MARK_START = 0, MARK_ROW = 1, MARK_COL = 2, MARK_DIAG = 3;
+constexpr int DIAG_BITS = MARK_DIAG << 9;
+constexpr int NEG_VALUE = -900000;                   // "-infinity" that still packs after -(800+200*511)
+constexpr int NEG_KEY = NEG_VALUE * KEY_MUL;         // -1,843,200,000
 constexpr int PSSM_ABS_LIMIT = 2000;                 // keeps 256*|x| + 200*511 below 2^20
 
 __host__ __device__ inline int base_code(uint8_t b) {   // mia.c:1054-1082

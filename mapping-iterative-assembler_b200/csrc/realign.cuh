@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) realign_kernel(RealignPa
       }
     }
   }
-  for (int i = tid; i < PROF_INTS; i += blockDim.x) s_prof[i] = p.prof[i];
+  for (int i = tid; i < PROF_INTS; i += blockDim.x) s_prof[i] = p.prof[i] * KEY_MUL;   // pre-multiplied: sub lands in the key's value field
   if (p.ref_in_smem) mbar_wait(&ref_bar, 0);
   __syncthreads();
 
@@ -144,14 +144,17 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) realign_kernel(RealignPa
   const int64_t gwarp = (int64_t)blockIdx.x * WARPS_PER_BLOCK + warp;
   uint32_t* trace = p.scratch + gwarp * p.scratch_words_per_warp;
 
-  // per-lane column constants
-  int constP[K];
+  // per-lane column constants.  Scores are kept in "diagonal key" form Sd = S*2048 + (DIAG<<9).
+  // candP[j] turns the Sd of column c into its best_gap_col candidate key: value S + GEP*c, marker COL, index c
+  int candP[K];
 #pragma unroll
   for (int j = 0; j < K; j++) {
-    int c = lane * K + j;
-    constP[j] = (GEP * c) * KEY_MUL + (MARK_COL << 9) + (KEY_IDX_MASK - c);
+    const int c = lane * K + j;
+    candP[j] = (GEP * c) * KEY_MUL + ((MARK_COL - MARK_DIAG) << 9) + (KEY_IDX_MASK - c);
   }
-  const int gcBase = -(GOP - GEP) - GEP * (lane * K);     // G_c = A - 800 - 200*c
+  const int candL2 = candP[0] - 2 * (GEP * KEY_MUL - 1);      // columns lane*K-2 and lane*K-1 (held by the left lane)
+  const int candL1 = candP[0] - 1 * (GEP * KEY_MUL - 1);
+  const int gcLane = -((GOP - GEP) + GEP * (lane * K)) * KEY_MUL;   // key(G_c) = P - (800 + 200*c)*2048
 
   for (;;) {
     int item = 0;
@@ -188,7 +191,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) realign_kernel(RealignPa
       uint32_t pa = prof_base + my_rowoff[0];
 #pragma unroll
       for (int j = 0; j < K; j++) {
-        Sp[j] = lds_s32(pa + code4[j]);
+        Sp[j] = lds_s32(pa + code4[j]) + DIAG_BITS;          // profile is pre-multiplied by 2048
         R[j] = NEG_KEY;
       }
     }
@@ -196,23 +199,20 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) realign_kernel(RealignPa
     for (int r = 1; r < L; r++) {
       const uint32_t pa = prof_base + my_rowoff[r];
       const int N = p.sg5 ? -(GOP + GEP * (r + 1)) : 0;                       // mia.c:877-880
-      const int grc = -(GOP - GEP) - GEP * r;                                 // G_r = B - 800 - 200*r
-      const int rowKey = (GEP * (r - 1)) * KEY_MUL + (MARK_ROW << 9) + (KEY_IDX_MASK - (r - 1));
+      const int keyN = N * KEY_MUL;                                           // START: marker 0, loses every tie
+      const int NdKey = keyN + DIAG_BITS;                                     // the cell's value if it starts here
+      const int grK = -((GOP - GEP) + GEP * r) * KEY_MUL;                     // key(G_r) = R - (800 + 200*r)*2048
+      const int rowK = (GEP * (r - 1)) * KEY_MUL + ((MARK_ROW - MARK_DIAG) << 9) + (KEY_IDX_MASK - (r - 1));
 
       // candidate keys of row r-1: column k becomes a best_gap_col candidate at column k+2
       int cand[K];
-      {
-        int pk_a = Sp[K - 2] * KEY_MUL + constP[K - 2];
-        int pk_b = Sp[K - 1] * KEY_MUL + constP[K - 1];
-        int l2 = __shfl_up_sync(0xffffffffu, pk_a, 1);
-        int l1 = __shfl_up_sync(0xffffffffu, pk_b, 1);
-        cand[0] = lane ? l2 : NEG_KEY;
-        if (K > 1) cand[1] = lane ? l1 : NEG_KEY;
+      int l2 = __shfl_up_sync(0xffffffffu, Sp[K - 2], 1);
+      int l1 = __shfl_up_sync(0xffffffffu, Sp[K - 1], 1);
+      cand[0] = lane ? l2 + candL2 : NEG_KEY;
+      if (K > 1) cand[1] = lane ? l1 + candL1 : NEG_KEY;
 #pragma unroll
-        for (int j = 2; j < K; j++) cand[j] = Sp[j - 2] * KEY_MUL + constP[j - 2];
-      }
-      int dleft = __shfl_up_sync(0xffffffffu, Sp[K - 1], 1);
-      if (lane == 0) dleft = N;          // column 0: S = sub + N, trace 0 (mia.c:805-822)
+      for (int j = 2; j < K; j++) cand[j] = Sp[j - 2] + candP[j - 2];
+      int D = lane ? l1 : NdKey;         // column 0: S = sub + N, trace 0 (mia.c:805-822)
 
       // lane total, then exclusive warp max-scan = best_gap_col state entering this lane
       int t = cand[0];
@@ -226,27 +226,20 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) realign_kernel(RealignPa
       int P = __shfl_up_sync(0xffffffffu, t, 1);
       if (lane == 0) P = NEG_KEY;
 
-      int D = dleft;
       uint32_t tw[K];
 #pragma unroll
       for (int j = 0; j < K; j++) {
         P = max(P, cand[j]);
-        const int sub = lds_s32(pa + code4[j]);
-        const int Gc = (P >> KEY_SHIFT) + (gcBase - GEP * j);
-        const int Gr = (R[j] >> KEY_SHIFT) + grc;
-        const bool pC = Gc >= Gr;                       // mia.c:933
-        const int m1 = pC ? Gc : Gr;
-        const bool pD = D >= m1;                        // mia.c:922-923
-        const int m = pD ? D : m1;
-        const bool pS = N > m;                          // mia.c:910-912 (strict)
-        const int S = pS ? N : sub + m;
-        int w = pC ? P : R[j];
-        w = pD ? (MARK_DIAG << 9) : w;
-        w = pS ? (MARK_START << 9) : w;
-        tw[j] = (uint32_t)w;
-        R[j] = max(R[j], D * KEY_MUL + rowKey);         // row r-1 joins best_gap_row[c-1] for row r+1
+        const int subK = lds_s32(pa + code4[j]);
+        const int kGc = P + (gcLane - GEP * KEY_MUL * j);
+        const int kGr = R[j] + grK;
+        const int best3 = max(max(D, kGc), kGr);        // DIAG > COL > ROW on ties (mia.c:922-948)
+        const bool pS = keyN > best3;                   // strictly better than all three (mia.c:910-915)
+        tw[j] = (uint32_t)(pS ? 0 : best3);             // low 16 bits: marker + jump target
+        const int cont = ((best3 + subK) & ~KEY_LOW_MASK) | DIAG_BITS;
+        R[j] = max(R[j], D + rowK);                     // row r-1 joins best_gap_row[c-1] for row r+1
         D = Sp[j];
-        Sp[j] = S;
+        Sp[j] = pS ? NdKey : cont;                      // start-new does NOT add the substitution score
       }
       if (lane == 0) R[0] = NEG_KEY;                    // there is no column -1
 
@@ -268,11 +261,11 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) realign_kernel(RealignPa
 #pragma unroll
     for (int j = 0; j < K; j++) {
       int c = lane * K + j;
-      int key = (c < len1) ? Sp[j] * 512 + (KEY_IDX_MASK - c) : INT_MIN;
+      int key = (c < len1) ? (Sp[j] - DIAG_BITS) + (KEY_IDX_MASK - c) : INT_MIN;
       best = max(best, key);
     }
     best = __reduce_max_sync(0xffffffffu, best);
-    const int score = best >> 9;
+    const int score = best >> KEY_SHIFT;
     const int aec = KEY_IDX_MASK - (best & KEY_IDX_MASK);
 
     // ---- find_align_begin + populate_pwaln_to_begin, executed uniformly by the warp
