@@ -27,6 +27,7 @@ extern "C" {
 #define MIAGPU_MAX_READ      256      /* INIT_ALN_SEQ_LEN, params.h:71 */
 #define MIAGPU_PSSM_INTS     775      /* int sm[31][5][5], types.h:155-158 */
 #define MIAGPU_MAX_RUNS      24       /* alignment runs returned per read */
+#define MIAGPU_NBUCKET       10       /* window-width buckets of the realign kernels */
 #define MIAGPU_COUNTS_PER_COL 10      /* As,Cs,Gs,Ts,gaps,cov,scoreA,scoreC,scoreG,scoreT (types.h:198-211) */
 
 /* Alignment run: (type << 14) | length, in 5'->3' order of the stored read.
@@ -238,7 +239,7 @@ int miagpu_realign_resident( miagpu_ctx* ctx );
 
 /* ---- measurement helpers (bench.py) */
 /* per width bucket of the last realign: columns-per-lane K (0 = too wide),
- * reads, DP cells, kernel ms (CUDA events on the library's stream); 8 entries */
+ * reads, DP cells, kernel ms (CUDA events on the library's stream); MIAGPU_NBUCKET entries */
 int miagpu_last_buckets( miagpu_ctx* ctx, int32_t* k, int32_t* reads,
                          int64_t* cells, float* ms );
 /* device time in ms of the kernels launched by the last call, per phase */

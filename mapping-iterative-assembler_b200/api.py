@@ -225,9 +225,9 @@ class MiaGpu:
         self._ck(self.lib.miagpu_realign_resident(self.h))
 
     def last_buckets(self):
-        k, r, cells, ms = np.zeros(8, np.int32), np.zeros(8, np.int32), np.zeros(8, np.int64), np.zeros(8, np.float32)
+        k, r, cells, ms = np.zeros(10, np.int32), np.zeros(10, np.int32), np.zeros(10, np.int64), np.zeros(10, np.float32)
         self._ck(self.lib.miagpu_last_buckets(self.h, _ptr(k), _ptr(r), _ptr(cells), _ptr(ms)))
-        return [dict(K=int(k[i]), reads=int(r[i]), cells=int(cells[i]), ms=float(ms[i])) for i in range(8) if r[i]]
+        return [dict(K=int(k[i]), reads=int(r[i]), cells=int(cells[i]), ms=float(ms[i])) for i in range(10) if r[i]]
 
     def accumulate_gaps(self, entries):
         entries = np.ascontiguousarray(entries, ENTRY_DTYPE)

@@ -2,6 +2,7 @@
 // sm_100a only; no CPU fallback: every compute entry point needs a CUDA device.
 #include <stdarg.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <vector>
@@ -44,8 +45,8 @@ struct DevBuf {
   }
 };
 
-constexpr int NBUCKET = 8;                                   // 7 register-tiled widths + "big"
-static const int BUCKET_K[NBUCKET] = {2, 4, 6, 8, 10, 12, 16, 0};
+constexpr int NBUCKET = 10;                                  // 9 register-tiled widths + "big"
+static const int BUCKET_K[NBUCKET] = {2, 4, 5, 6, 7, 8, 10, 12, 16, 0};
 
 }  // namespace miagpu
 
@@ -56,10 +57,10 @@ struct miagpu_ctx {
   int num_sms = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[6] = {};
-  cudaEvent_t bev[2 * 8] = {};                 // per width-bucket start/stop
-  float bucket_ms[8] = {};
-  int64_t bucket_cells[8] = {};
-  int32_t bucket_reads[8] = {};
+  cudaEvent_t bev[2 * NBUCKET] = {};           // per width-bucket start/stop
+  float bucket_ms[NBUCKET] = {};
+  int64_t bucket_cells[NBUCKET] = {};
+  int32_t bucket_reads[NBUCKET] = {};
   // scoring
   bool have_pssm = false;
   int32_t sm_f[MIAGPU_PSSM_INTS], sm_r[MIAGPU_PSSM_INTS];
@@ -259,7 +260,7 @@ static int reserve_per_read(miagpu_ctx* c, int64_t n) {
   return c->d_rc.reserve(n) && c->d_status.reserve(n) && c->d_as.reserve(n) && c->d_ae.reserve(n) && c->d_score.reserve(n) &&
          c->d_as_out.reserve(n) && c->d_ae_out.reserve(n) && c->d_abr.reserve(n) && c->d_nruns.reserve(n) &&
          c->d_win_start.reserve(n) && c->d_win_len.reserve(n) && c->d_lists.reserve(n * NBUCKET) &&
-         c->d_runs.reserve(n * MAX_RUNS) && c->d_meta.reserve(64);
+         c->d_runs.reserve(n * MAX_RUNS) && c->d_meta.reserve(128);
 }
 
 extern "C" int miagpu_upload_reads(miagpu_ctx* c, int64_t n, const uint8_t* bases, const int64_t* offsets) {
@@ -303,8 +304,8 @@ __global__ void classify_kernel(int64_t n, const int64_t* off, const int32_t* as
     int len1 = re - rs;
     win_start[i] = rs;
     win_len[i] = len1;
-    b = len1 <= 64 ? 0 : len1 <= 128 ? 1 : len1 <= 192 ? 2 : len1 <= 256 ? 3 : len1 <= 320 ? 4 : len1 <= 384 ? 5 : len1 <= 512 ? 6 : 7;
-    if (L <= 0 || L > MAX_READ) b = 7;
+    b = len1 <= 64 ? 0 : len1 <= 128 ? 1 : len1 <= 160 ? 2 : len1 <= 192 ? 3 : len1 <= 224 ? 4 : len1 <= 256 ? 5 : len1 <= 320 ? 6 : len1 <= 384 ? 7 : len1 <= 512 ? 8 : 9;
+    if (L <= 0 || L > MAX_READ) b = NBUCKET - 1;
     slot = atomicAdd(&s_cnt[b], 1);
     atomicMax(&s_maxL[b], L);
     atomicAdd(&s_cells[b], (unsigned long long)L * (unsigned long long)len1);
@@ -312,9 +313,9 @@ __global__ void classify_kernel(int64_t n, const int64_t* off, const int32_t* as
   __syncthreads();
   if (threadIdx.x < NBUCKET) {
     s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd(&meta[threadIdx.x], s_cnt[threadIdx.x]) : 0;
-    if (s_maxL[threadIdx.x]) atomicMax(&meta[16 + threadIdx.x], s_maxL[threadIdx.x]);
+    if (s_maxL[threadIdx.x]) atomicMax(&meta[32 + threadIdx.x], s_maxL[threadIdx.x]);
   }
-  if (threadIdx.x < NBUCKET && s_cells[threadIdx.x]) atomicAdd(reinterpret_cast<unsigned long long*>(meta + 32) + threadIdx.x, s_cells[threadIdx.x]);
+  if (threadIdx.x < NBUCKET && s_cells[threadIdx.x]) atomicAdd(reinterpret_cast<unsigned long long*>(meta + 48) + threadIdx.x, s_cells[threadIdx.x]);
   __syncthreads();
   if (b >= 0) lists[(int64_t)b * n + s_base[b] + slot] = (int32_t)i;
 }
@@ -371,7 +372,9 @@ static int launch_bucket(miagpu_ctx* c, RealignParams p, int maxL) {
   int per_sm = 0;
   MIAGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, realign_kernel<K>, WARPS_PER_BLOCK * 32, smem));
   if (per_sm < 1) { set_error("realign_kernel<%d> does not fit on an SM (smem %zu)", K, smem); return 0; }
-  per_sm = std::min(per_sm, 6);                            // 24 warps/SM: enough ILP, keeps trace scratch L2-resident
+  int cap = 6;                                             // 24 warps/SM: enough ILP, bounds the trace scratch
+  if (const char* e = getenv("MIAGPU_BLOCKS_PER_SM")) cap = std::max(1, atoi(e));
+  per_sm = std::min(per_sm, cap);
   int blocks = c->num_sms * per_sm;
   blocks = std::min(blocks, (p.n_list + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
   if (blocks < 1) return 1;
@@ -391,16 +394,16 @@ static int realign_device(miagpu_ctx* c) {
   c->launches = 0;
   c->dp_cells = 0;
   if (n == 0) return 1;
-  MIAGPU_CUDA(cudaMemsetAsync(c->d_meta.p, 0, 64 * sizeof(int32_t), c->stream));
+  MIAGPU_CUDA(cudaMemsetAsync(c->d_meta.p, 0, 128 * sizeof(int32_t), c->stream));
   classify_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, c->d_off.p, c->d_as.p, c->d_ae.p, c->wrap_len,
                                                                      c->d_win_start.p, c->d_win_len.p, c->d_lists.p, c->d_meta.p);
   MIAGPU_CUDA(cudaGetLastError());
   c->launches++;
-  int32_t meta[64];
-  static_assert(32 + 2 * NBUCKET <= 64, "meta layout");
+  int32_t meta[96];
+  static_assert(NBUCKET <= 16 && 48 + 2 * NBUCKET <= 96, "meta layout");
   MIAGPU_CUDA(cudaMemcpyAsync(meta, c->d_meta.p, sizeof(meta), cudaMemcpyDeviceToHost, c->stream));
   MIAGPU_CUDA(cudaStreamSynchronize(c->stream));
-  memcpy(c->bucket_cells, meta + 32, sizeof(c->bucket_cells));
+  memcpy(c->bucket_cells, meta + 48, sizeof(c->bucket_cells));
   for (int b = 0; b < NBUCKET; b++) { c->dp_cells += c->bucket_cells[b]; c->bucket_reads[b] = meta[b]; c->bucket_ms[b] = 0; }
   for (int b = 0; b < NBUCKET; b++) {
     if (!meta[b]) continue;
@@ -408,21 +411,23 @@ static int realign_device(miagpu_ctx* c) {
     RealignParams p{};
     p.bases = c->d_bases.p; p.off = c->d_off.p; p.rc = c->d_rc.p;
     p.win_start = c->d_win_start.p; p.win_len = c->d_win_len.p;
-    p.list = c->d_lists.p + (int64_t)b * n; p.n_list = meta[b]; p.counter = c->d_meta.p + 8 + b;
+    p.list = c->d_lists.p + (int64_t)b * n; p.n_list = meta[b]; p.counter = c->d_meta.p + 16 + b;
     p.ref_codes = c->d_ref.p; p.ref_bytes = c->ref_bytes; p.prof = c->d_prof.p; p.sg5 = 1;
     p.score = c->d_score.p; p.as_out = c->d_as_out.p; p.ae_out = c->d_ae_out.p; p.abr = c->d_abr.p;
     p.n_runs = c->d_nruns.p; p.runs = c->d_runs.p; p.status = c->d_status.p;
-    int ok = 1, maxL = meta[16 + b];
+    int ok = 1, maxL = meta[32 + b];
     switch (BUCKET_K[b]) {
       case 2: ok = launch_bucket<2>(c, p, maxL); break;
       case 4: ok = launch_bucket<4>(c, p, maxL); break;
+      case 5: ok = launch_bucket<5>(c, p, maxL); break;
       case 6: ok = launch_bucket<6>(c, p, maxL); break;
+      case 7: ok = launch_bucket<7>(c, p, maxL); break;
       case 8: ok = launch_bucket<8>(c, p, maxL); break;
       case 10: ok = launch_bucket<10>(c, p, maxL); break;
       case 12: ok = launch_bucket<12>(c, p, maxL); break;
       case 16: ok = launch_bucket<16>(c, p, maxL); break;
       default:
-        ok = launch_strip(c, 1, p.list, p.n_list, c->d_meta.p + 8 + b);
+        ok = launch_strip(c, 1, p.list, p.n_list, c->d_meta.p + 16 + b);
     }
     if (!ok) return 0;
     MIAGPU_CUDA(cudaEventRecord(c->bev[2 * b + 1], c->stream));
@@ -555,7 +560,7 @@ __global__ void int_peak_kernel(int* out, int iters, int seed) {
 extern "C" int miagpu_int32_peak(miagpu_ctx* c, double* ops_per_s) {
   if (!c || !ops_per_s) { set_error("miagpu_int32_peak: NULL argument"); return 0; }
   MIAGPU_CUDA(cudaSetDevice(c->device));
-  if (!c->d_meta.reserve(64)) return 0;
+  if (!c->d_meta.reserve(128)) return 0;
   const int iters = 4096, threads = 256, blocks = c->num_sms * 8;
   // ops per inner statement group: IADD3(1) + IMNMX(1) + ISETP/SEL/IADD(3) + IMNMX(1) = 6 per chain element
   for (int rep = 0; rep < 2; rep++) {
@@ -839,9 +844,9 @@ extern "C" int miagpu_pass1(miagpu_ctx* c, int32_t* hits, int32_t* score, int32_
   c->launches = 0;
   if (!c->d_hits.reserve(n + 1) || !c->d_fw.reserve(n + 1) || !c->d_rcs.reserve(n + 1) || !c->d_start.reserve(n + 1) ||
       !c->d_end.reserve(n + 1) || !c->d_rc_out.reserve(n + 1)) return 0;
-  MIAGPU_CUDA(cudaMemsetAsync(c->d_meta.p, 0, 64 * sizeof(int32_t), c->stream));
+  MIAGPU_CUDA(cudaMemsetAsync(c->d_meta.p, 0, 128 * sizeof(int32_t), c->stream));
   MIAGPU_CUDA(cudaEventRecord(c->ev[1], c->stream));
-  if (!launch_strip(c, 0, nullptr, 0, c->d_meta.p + 8)) return 0;
+  if (!launch_strip(c, 0, nullptr, 0, c->d_meta.p + 16)) return 0;
   MIAGPU_CUDA(cudaEventRecord(c->ev[2], c->stream));
   if (n) {
     auto dl = [&](void* h, const void* d, size_t bytes) { return h ? cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, c->stream) : cudaSuccess; };

@@ -63,6 +63,12 @@ struct RealignParams {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+// (a & b) | c in ONE LOP3 (b in a register so that ptxas does not split two immediates)
+__device__ __forceinline__ int and_or(int a, int b, int c) {
+  int d;
+  asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
 __device__ __forceinline__ int lds_s32(uint32_t addr) {
   int v;
   asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
@@ -97,7 +103,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
 
 template <int K>
 struct TraceLayout {
-  static constexpr int W = K / 2;                                  // 32-bit words of trace per lane per row
+  static constexpr int W = (K + 1) / 2;                            // 32-bit words of trace per lane per row
   static constexpr int WP = (W <= 2) ? 2 : (W <= 4) ? 4 : 8;       // padded to a vector store
   static constexpr int ROW_WORDS = 32 * WP;
 };
@@ -107,7 +113,7 @@ constexpr int WARPS_PER_BLOCK = 4;
 // dynamic shared memory: [prof PROF_INTS ints][rowoff WARPS*256 u16][ref codes]
 template <int K>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) realign_kernel(RealignParams p) {
-  static_assert(K % 2 == 0 && K >= 2 && K <= 16, "K must be even");
+  static_assert(K >= 2 && K <= 16, "columns per lane");
   using TL = TraceLayout<K>;
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ __align__(8) uint64_t ref_bar;
@@ -155,6 +161,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) realign_kernel(RealignPa
   const int candL2 = candP[0] - 2 * (GEP * KEY_MUL - 1);      // columns lane*K-2 and lane*K-1 (held by the left lane)
   const int candL1 = candP[0] - 1 * (GEP * KEY_MUL - 1);
   const int gcLane = -((GOP - GEP) + GEP * (lane * K)) * KEY_MUL;   // key(G_c) = P - (800 + 200*c)*2048
+  int value_mask = ~KEY_LOW_MASK;
+  asm volatile("" : "+r"(value_mask));                            // keep it in a register
 
   for (;;) {
     int item = 0;
@@ -236,7 +244,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) realign_kernel(RealignPa
         const int best3 = max(max(D, kGc), kGr);        // DIAG > COL > ROW on ties (mia.c:922-948)
         const bool pS = keyN > best3;                   // strictly better than all three (mia.c:910-915)
         tw[j] = (uint32_t)(pS ? 0 : best3);             // low 16 bits: marker + jump target
-        const int cont = ((best3 + subK) & ~KEY_LOW_MASK) | DIAG_BITS;
+        const int cont = and_or(best3 + subK, value_mask, DIAG_BITS);
         R[j] = max(R[j], D + rowK);                     // row r-1 joins best_gap_row[c-1] for row r+1
         D = Sp[j];
         Sp[j] = pS ? NdKey : cont;                      // start-new does NOT add the substitution score
@@ -247,7 +255,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) realign_kernel(RealignPa
       uint32_t* trow = trace + (int64_t)(r - 1) * TL::ROW_WORDS + lane * TL::WP;
       uint32_t wv[TL::WP];
 #pragma unroll
-      for (int w = 0; w < TL::WP; w++) wv[w] = (w < TL::W) ? __byte_perm(tw[2 * w], tw[2 * w + 1], 0x5410) : 0u;
+      for (int w = 0; w < TL::WP; w++) wv[w] = (w < TL::W) ? __byte_perm(tw[2 * w], (2 * w + 1 < K) ? tw[(2 * w + 1 < K) ? 2 * w + 1 : 0] : 0u, 0x5410) : 0u;
       if (TL::WP == 2) {
         *reinterpret_cast<uint2*>(trow) = make_uint2(wv[0], wv[1]);
       } else {
@@ -278,20 +286,31 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) realign_kernel(RealignPa
       nrun++;
       ncols += len;
     };
-    while (row > 0 && col > 0) {
-      const int tl = col / K, tj = col - tl * K;
-      const uint32_t w16 = __ldcg(t16 + ((int64_t)(row - 1) * TL::ROW_WORDS + tl * TL::WP) * 2 + tj);
-      const int mk = (w16 >> 9) & 3;
-      const int idx = KEY_IDX_MASK - (int)(w16 & KEY_IDX_MASK);
+    // Lanes fetch the next 32 cells of the DIAGONAL through (row,col) in one round trip; the walk then
+    // consumes the leading run of plain diagonal moves at once and handles the first other cell.
+    for (;;) {
+      const int tr_ = row - lane, tc_ = col - lane;
+      uint32_t w16 = MARK_START << 9;                        // off-matrix: never consumed
+      if (tr_ > 0 && tc_ > 0) {
+        const int tl = tc_ / K, tj = tc_ - tl * K;
+        w16 = __ldcg(t16 + ((int64_t)(tr_ - 1) * TL::ROW_WORDS + tl * TL::WP) * 2 + tj);
+      }
+      const int mk_l = (w16 >> 9) & 3;
+      const int idx_l = KEY_IDX_MASK - (int)(w16 & KEY_IDX_MASK);
+      const bool diag_l = tr_ > 0 && tc_ > 0 && (mk_l == MARK_DIAG || (mk_l != MARK_START && idx_l == 0));   // idx 0: trace == 0 reads as diagonal (H2)
+      const unsigned nd = __ballot_sync(0xffffffffu, !diag_l);
+      const int n = nd ? __ffs(nd) - 1 : 32;                 // leading diagonal moves
+      curM += n; row -= n; col -= n;
+      if (n == 32) continue;
+      if (row <= 0 || col <= 0) break;                       // row 0 / column 0: trace 0 == -row or == col (mia.c:617-618)
+      const int mk = __shfl_sync(0xffffffffu, mk_l, n), idx = __shfl_sync(0xffffffffu, idx_l, n);
       if (mk == MARK_START) break;
       curM++;
-      if (mk == MARK_DIAG || idx == 0) {          // idx 0: trace == 0 reads as diagonal (H2)
-        row--; col--;
-      } else if (mk == MARK_ROW) {                // mia.c:1466-1476
+      if (mk == MARK_ROW) {                                  // mia.c:1466-1476
         push(MIAGPU_RUN_M, curM); curM = 0;
         push(MIAGPU_RUN_I, row - 1 - idx);
         row = idx; col--;
-      } else {                                    // mia.c:1477-1487
+      } else {                                               // mia.c:1477-1487
         push(MIAGPU_RUN_M, curM); curM = 0;
         push(MIAGPU_RUN_D, col - 1 - idx);
         col = idx; row--;

@@ -1,0 +1,202 @@
+"""Host-side mirror of mia_main.c's control flow (lines 759-976) on top of the C ABI.
+
+The reference's host code stays what it is -- one pass over the reads, then
+"reiterate_assembly -> pop_smp -> cull -> consensus" until the consensus stops changing.
+This module is that loop with the hot calls replaced by libmiagpu entry points, plus the
+reference's own bookkeeping that decides WHAT is fed to the consensus:
+
+  * AlnSeq slots are numbered in merge order, 1 per read, 2 per wrap-split read
+    (merge_pwaln_into_maln, map_align.c:866-954);
+  * AlnSeq.dropped is sticky per slot (H10: cull only sets it, mia.c:471-478; merge copies
+    every field except it, map_align.c:885-893);
+  * FragSeq.back_asp is never cleared by reiterate_assembly (mia_main.c:273-276): a read that
+    was split once keeps pointing at its old back slot; pop_smp, cull and the consensus follow
+    that pointer.  A stale pointer to a slot that is live this round is described to the
+    device as an extra entry on the owner's segment (with the smp parameters of whichever
+    pointer pop_smp visits last); a stale pointer to a slot beyond this round's slot count
+    (content from an older round) is not reproduced and is reported in `self.ghosts`.
+
+Used by tests and bench; a C host would make the same calls.
+"""
+import numpy as np
+
+from . import api
+from .api import ENTRY_DTYPE, MAX_RUNS
+
+FIRST_ROUND_SCORE_CUTOFF = 2000
+MAX_ITER = 30
+
+
+def _geom(runs_i, n, cut=None):
+    """(cols, ins, dels) of the alignment columns [0,cut) and [cut, end) (cut=None: everything in the first)."""
+    g = [[0, 0, 0], [0, 0, 0]]
+    col = 0
+    for x in runs_i[:n]:
+        x = int(x)
+        t, ln = x >> 14, x & 0x3FFF
+        if t == 1:
+            g[0 if (cut is None or col < cut) else 1][1] += ln
+            continue
+        for _ in range(ln):                      # rare path (split reads only): per-column is fine
+            s = 0 if (cut is None or col < cut) else 1
+            g[s][0] += 1
+            if t == 2:
+                g[s][2] += 1
+            col += 1
+    return g
+
+
+class Assembler:
+    def __init__(self, gpu, ref, sm, circular=1, k=0, soft_mask=0, cons_code=1):
+        self.g, self.sm, self.circular, self.k, self.soft_mask, self.cons_code = gpu, sm, circular, k, soft_mask, cons_code
+        self.ref0 = ref
+        self.ghosts = 0
+        gpu.set_pssm(sm)
+
+    # ------------------------------------------------------------------ pass 1
+    def pass1(self, bases, off):
+        g = self.g
+        g.set_reference(self.ref0, self.circular, with_rc=1)
+        g.build_kmers(self.k, self.soft_mask)
+        g.upload_reads(bases, off)
+        p = g.pass1()
+        self.p1 = p
+        n = len(off) - 1
+        seq_len = np.diff(off).astype(np.int32)
+        aligned = p["hits"] > 0
+        keep = aligned & (p["score"] >= FIRST_ROUND_SCORE_CUTOFF)                   # mia.c:1614
+        strand_known = keep & (p["score"] > FIRST_ROUND_SCORE_CUTOFF)               # mia.c:1653
+        idx = np.flatnonzero(keep)
+        # pass-1 AlnSeq slots, in merge order (mia.c:1619-1643); back_asp = NULL unless split
+        split = p["start"][idx] > p["end"][idx]
+        nsl = 1 + split.astype(np.int64)
+        first = np.concatenate([[0], np.cumsum(nsl)[:-1]]) if len(idx) else np.zeros(0, np.int64)
+        self.dropped_slot = np.zeros(int(nsl.sum()) + 16, np.uint8)
+        self.seq_len = seq_len[idx]
+        self.score = p["score"][idx].copy()
+        self.rc = p["rc"][idx].copy()
+        self.as_ = p["as_"][idx].copy()
+        self.ae = p["ae"][idx].copy()
+        self.strand_known = strand_known[idx]
+        self.front = first.astype(np.int64)
+        self.back = np.where(split, first + 1, -1).astype(np.int64)
+        # pass-1 cull (mia_main.c:848): only its dropped flags survive
+        self._cull()
+        # clean_FSDB (mia.c:400-406) and stored orientation (fsdb.c:209-227)
+        ok = self.score > 0
+        keep_dev = np.zeros(n, np.uint8)
+        keep_dev[idx[ok]] = 1
+        rev = np.zeros(n, np.uint8)
+        rev[idx] = (self.rc == 1) & self.strand_known
+        g.compact_reads(keep_dev, rev)
+        for name in ("seq_len", "score", "rc", "as_", "ae", "strand_known", "front", "back"):
+            setattr(self, name, getattr(self, name)[ok])
+        if not self.strand_known.all():
+            raise NotImplementedError("reads with score == 2000 keep strand_known = 0 and are never realigned (mia.c:1653)")
+        self.iter = 0
+        self.cons = None
+        self.last = self.ref0.upper()
+        return p
+
+    def _cull(self):
+        below = api.cull_flags(self.seq_len, self.score)
+        need = int(max(self.front.max(initial=0), self.back.max(initial=0))) + 2
+        if need > len(self.dropped_slot):
+            self.dropped_slot = np.concatenate([self.dropped_slot, np.zeros(need, np.uint8)])
+        f = self.front[below > 0]
+        self.dropped_slot[f] = 1
+        b = self.back[(below > 0) & (self.back >= 0)]
+        self.dropped_slot[b] = 1
+
+    # --------------------------------------------------------------- one round
+    def iterate(self):
+        """mia_main.c:878-900 / 918-963: realign everything against the current consensus, cull, call."""
+        g = self.g
+        if self.cons is not None:
+            self.last = self.cons
+        self.iter += 1
+        ref = self.last
+        g.set_reference(ref, self.circular, with_rc=0)
+        out = g.realign(self.rc, self.as_, self.ae)
+        self.out = out
+        if (out["status"] != 0).any():
+            raise api.MiaGpuError(f"realign status bits set on {(out['status'] != 0).sum()} reads")
+        self.as_, self.ae, self.score = out["as_out"].copy(), out["ae_out"].copy(), out["score"].copy()
+        n, L = len(self.as_), len(ref)
+        runs = out["runs"].view(np.uint16).reshape(-1, MAX_RUNS)
+        end = np.where(self.ae > L, self.ae - L, self.ae)
+        split = self.as_ > end
+        nsl = 1 + split.astype(np.int64)
+        first = np.concatenate([[0], np.cumsum(nsl)[:-1]])
+        n_slots = int(nsl.sum())
+        self.front = first
+        self.back = np.where(split, first + 1, self.back)              # NOT cleared when not split: mia_main.c:273-276
+        self._cull()
+        # ---- natural entries (vectorised), then the alias fix-ups
+        from .entries import natural_entries
+        ent, _, _ = natural_entries(self.as_, self.ae, out["n_runs"], runs, L)
+        slot_entry = np.arange(n_slots)                                # natural entry index of slot k == k
+        ent["dropped"] = self.dropped_slot[:n_slots]
+        stale = np.flatnonzero(~split & (self.back >= 0))
+        extra = []
+        if len(stale):
+            owner = np.repeat(np.arange(n), nsl)                       # slot -> owning read
+            last_holder = {}
+            for i in stale:
+                kslot = int(self.back[i])
+                if kslot >= n_slots:
+                    self.ghosts += 1
+                    continue
+                j = int(owner[kslot])
+                seg = kslot - int(first[j])
+                e_own = ent[slot_entry[kslot]]
+                gi = _geom(runs[i], int(out["n_runs"][i]))[0]
+                fl_i = gi[0] + gi[1]
+                bases_f_i = gi[0] - gi[2] + gi[1]
+                bl = int(e_own["col_count"]) + self._slot_ins(runs[j], int(out["n_runs"][j]), int(e_own["col_begin"]), int(e_own["col_count"]))
+                # the holder's own front AlnSeq sees back_seq_len = asp_len(stale slot) (fsdb.c:554-559)
+                ent["total_len"][slot_entry[first[i]]] = fl_i + bl
+                rb = 0
+                if seg == 1:
+                    gj = _geom(runs[j], int(out["n_runs"][j]), int(e_own["col_begin"]))[0]
+                    rb = gj[0] - gj[2] + gj[1]
+                x = e_own.copy()
+                x["back_formula"], x["front_len"], x["total_len"], x["act_bias"] = 1, fl_i, fl_i + bl, bases_f_i - rb
+                extra.append((kslot, i, x))
+                if i > j and i > last_holder.get(kslot, (-1,))[0]:
+                    last_holder[kslot] = (i, x)
+            for kslot, (_, x) in last_holder.items():                  # pop_smp visits this pointer last: its smp sticks
+                for fld in ("back_formula", "front_len", "total_len", "act_bias"):
+                    ent[fld][slot_entry[kslot]] = x[fld]
+            add = []
+            for kslot, i, x in extra:                                  # every pointer is one list entry; same AlnSeq => same smp
+                y = ent[slot_entry[kslot]].copy()
+                add.append(y)
+            if add:
+                ent = np.concatenate([ent, np.array(add, ENTRY_DTYPE)])
+        self.entries = ent
+        cons, gaps, _ = g.consensus(ent, self.cons_code)
+        self.gaps = gaps
+        self.cons = cons
+        return cons, cons == self.last
+
+    @staticmethod
+    def _slot_ins(runs_i, n, cb, cc):
+        """inserted bases attached to alignment columns [cb, cb+cc) (asp_len's second term)"""
+        col, tot = 0, 0
+        for x in runs_i[:n]:
+            x = int(x)
+            t, ln = x >> 14, x & 0x3FFF
+            if t == 1:
+                if cb <= col < cb + cc:
+                    tot += ln
+            else:
+                col += ln
+        return tot
+
+    def run(self, bases, off, max_iter=MAX_ITER):
+        self.pass1(bases, off)
+        conv = False
+        while not conv and self.iter < max_iter:
+            _, conv = self.iterate()
+        return self.cons, self.iter, conv
