@@ -167,10 +167,14 @@ def run_ours(args):
         return t
     h_bases, h_off, h_rc, h_as, h_ae = pin(bases), pin(off), pin(rc), pin(as_), pin(ae)
     h_out = api.MiaGpu.alloc_realign_outputs(n, pinned=True)
+    del h_out["runs"]                                   # run lists come back packed (sum(n_runs) words, not n*24)
+    h_packed = torch.empty(4 * n, dtype=torch.int16).pin_memory()
     below = torch.zeros(n, dtype=torch.uint8).pin_memory()
+    packed_total = {"n": 0}
 
     def step_e2e():
         out = g.realign_host(h_bases, h_off, h_rc, h_as, h_ae, h_out)
+        packed_total["n"] = g.get_runs_packed(None, h_packed)[0]      # offsets = cumsum(n_runs) on the host if needed
         score = out["score"].numpy()
         if world > 1:       # the regression runs over all reads of the job (FSDB order = rank order)
             sc = torch.from_numpy(score).cuda(non_blocking=True)
@@ -248,7 +252,7 @@ def run_ours(args):
     cells = tim_realign["dp_cells"]
     gcups = world * cells / (ms_per_step * 1e-3) / 1e9
     h2d = int(len(bases) + off.nbytes + rc.nbytes + as_.nbytes + ae.nbytes + 2 * n)
-    d2h = int(sum(v.numel() * v.element_size() for v in h_out.values()) + len(cons_e2e))
+    d2h = int(sum(v.numel() * v.element_size() for v in h_out.values()) + 2 * packed_total["n"] + len(cons_e2e))
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

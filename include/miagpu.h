@@ -130,6 +130,12 @@ int miagpu_realign( miagpu_ctx* ctx, const uint8_t* rc, const int32_t* as,
                     int32_t* ae_out, int32_t* abr, int32_t* n_runs,
                     uint16_t* runs, uint8_t* status );
 
+/* The run lists of the last realign / pass 1 in packed form: the n_runs[i] valid runs
+ * of every read concatenated in read order (run_off[n+1], nullable; packed nullable
+ * = only report *total).  Moves sum(n_runs)*2 bytes instead of n*MIAGPU_MAX_RUNS*2. */
+int miagpu_get_runs_packed( miagpu_ctx* ctx, int64_t* run_off, uint16_t* packed,
+                            int64_t capacity, int64_t* total );
+
 /* Convenience form used by the end-to-end benchmark: upload + realign +
  * download in one call with host buffers only. */
 int miagpu_realign_host( miagpu_ctx* ctx, int64_t n, const uint8_t* bases,

@@ -53,6 +53,7 @@ def load_library():
     L.miagpu_pass1.argtypes = [C.c_void_p] + [C.c_void_p] * 13
     L.miagpu_compact_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, _i64p]
     L.miagpu_realign.argtypes = [C.c_void_p] + [C.c_void_p] * 10
+    L.miagpu_get_runs_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, _i64p]
     L.miagpu_realign_host.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 12
     L.miagpu_consensus.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, _i32p]
     L.miagpu_accumulate_gaps.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_void_p), _i64p]
@@ -75,7 +76,7 @@ def load_library():
 
 EXPORTS = ["miagpu_device_count", "miagpu_create", "miagpu_destroy", "miagpu_last_error", "miagpu_version", "miagpu_set_pssm",
            "miagpu_get_pssm", "miagpu_set_reference", "miagpu_ref_wrap_len", "miagpu_build_kmers", "miagpu_upload_reads",
-           "miagpu_pass1", "miagpu_compact_reads", "miagpu_realign", "miagpu_realign_host",
+           "miagpu_pass1", "miagpu_compact_reads", "miagpu_realign", "miagpu_realign_host", "miagpu_get_runs_packed",
            "miagpu_consensus", "miagpu_accumulate_gaps", "miagpu_accumulate_counts", "miagpu_call", "miagpu_consensus_natural", "miagpu_accumulate_gaps_natural",
            "miagpu_score_cut", "miagpu_cull_flags",
            "miagpu_set_alignment_inputs", "miagpu_realign_resident", "miagpu_last_buckets", "miagpu_last_timing",
@@ -182,12 +183,19 @@ class MiaGpu:
                                          _ptr(out["status"])))
         return out
 
+    def get_runs_packed(self, run_off=None, packed=None):
+        """(total, run_off, packed): packed run lists of the last realign / pass 1."""
+        tot = C.c_int64()
+        cap = 0 if packed is None else (packed.numel() if hasattr(packed, "numel") else packed.size)
+        self._ck(self.lib.miagpu_get_runs_packed(self.h, _ptr(run_off), _ptr(packed), cap, C.byref(tot)))
+        return tot.value, run_off, packed
+
     def realign_host(self, bases, offsets, rc, as_, ae, out=None):
         n = len(offsets) - 1
         out = out or self.alloc_realign_outputs(n)
         self._ck(self.lib.miagpu_realign_host(self.h, n, _ptr(bases), _ptr(offsets), _ptr(rc), _ptr(as_), _ptr(ae),
                                               _ptr(out["score"]), _ptr(out["as_out"]), _ptr(out["ae_out"]), _ptr(out["abr"]),
-                                              _ptr(out["n_runs"]), _ptr(out["runs"]), _ptr(out["status"])))
+                                              _ptr(out["n_runs"]), _ptr(out.get("runs")), _ptr(out["status"])))
         self.n = n
         return out
 

@@ -91,6 +91,7 @@ struct miagpu_ctx {
   DevBuf<int4> d_ckpt;
   DevBuf<int32_t> d_chunk_ids, d_strace, d_hits, d_fw, d_rcs, d_start, d_end;
   DevBuf<uint8_t> d_rc_out, d_bases2;
+  DevBuf<uint16_t> d_packed;
   DevBuf<int64_t> d_off2;
   DevBuf<int32_t> d_src;
   // consensus
@@ -151,7 +152,7 @@ extern "C" void miagpu_destroy(miagpu_ctx* c) {
   c->d_win_len.release(); c->d_lists.release(); c->d_runs.release(); c->d_meta.release(); c->d_scratch.release();
   for (int t = 0; t < 2; t++) { c->d_kb[t].release(); c->d_kp[t].release(); c->d_kk[t].release(); }
   c->d_smask.release(); c->d_ckpt.release(); c->d_chunk_ids.release(); c->d_strace.release(); c->d_hits.release(); c->d_fw.release();
-  c->d_rcs.release(); c->d_start.release(); c->d_end.release(); c->d_rc_out.release(); c->d_bases2.release(); c->d_off2.release(); c->d_src.release();
+  c->d_rcs.release(); c->d_start.release(); c->d_end.release(); c->d_rc_out.release(); c->d_bases2.release(); c->d_packed.release(); c->d_off2.release(); c->d_src.release();
   c->d_entries.release(); c->d_sm.release(); c->d_gaps.release(); c->d_ins_off.release(); c->d_acc.release(); c->d_cub.release(); c->d_called.release(); c->d_dropf.release(); c->d_dropb.release();
   for (auto& ev : c->ev) cudaEventDestroy(ev);
   for (auto& ev : c->bev) cudaEventDestroy(ev);
@@ -372,7 +373,7 @@ static int launch_bucket(miagpu_ctx* c, RealignParams p, int maxL) {
   int per_sm = 0;
   MIAGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, realign_kernel<K>, WARPS_PER_BLOCK * 32, smem));
   if (per_sm < 1) { set_error("realign_kernel<%d> does not fit on an SM (smem %zu)", K, smem); return 0; }
-  int cap = 6;                                             // 24 warps/SM: enough ILP, bounds the trace scratch
+  int cap = 8;                                             // 32 warps/SM (measured best on B200); bounds the trace scratch
   if (const char* e = getenv("MIAGPU_BLOCKS_PER_SM")) cap = std::max(1, atoi(e));
   per_sm = std::min(per_sm, cap);
   int blocks = c->num_sms * per_sm;
@@ -533,6 +534,52 @@ extern "C" int miagpu_realign_resident(miagpu_ctx* c) {
   MIAGPU_CUDA(cudaEventElapsedTime(&c->ms_kernels, c->ev[1], c->ev[2]));
   c->ms_h2d = c->ms_d2h = 0;
   return realign_bucket_times(c);
+}
+
+// Packed run lists: the n_runs[i] valid runs of every read, concatenated in read order.
+__global__ void pack_runs_kernel(int64_t n, const int32_t* n_runs, const int64_t* run_off, const uint16_t* runs, uint16_t* packed) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int k = n_runs[i] > 0 ? n_runs[i] : 0;
+  const int64_t o = run_off[i];
+  for (int j = 0; j < k; j++) packed[o + j] = runs[i * MAX_RUNS + j];
+}
+__global__ void clamp_runs_kernel(int64_t n, const int32_t* n_runs, int64_t* cnt) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) cnt[i] = n_runs[i] > 0 ? n_runs[i] : 0;
+  if (i == n) cnt[i] = 0;
+}
+
+extern "C" int miagpu_get_runs_packed(miagpu_ctx* c, int64_t* run_off, uint16_t* packed, int64_t capacity, int64_t* total) {
+  if (!c || !total) { set_error("miagpu_get_runs_packed: bad argument"); return 0; }
+  MIAGPU_CUDA(cudaSetDevice(c->device));
+  const int64_t n = c->n;
+  if (!c->d_off2.reserve(2 * (n + 2))) return 0;
+  int64_t* cnt = c->d_off2.p;
+  int64_t* offs = c->d_off2.p + (n + 2);
+  MIAGPU_CUDA(cudaEventRecord(c->ev[1], c->stream));
+  clamp_runs_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, c->stream>>>(n, c->d_nruns.p, cnt);
+  size_t tmp = 0;
+  MIAGPU_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, cnt, offs, n + 1, c->stream));
+  if (!c->d_cub.reserve(tmp + 16)) return 0;
+  MIAGPU_CUDA(cub::DeviceScan::ExclusiveSum(c->d_cub.p, tmp, cnt, offs, n + 1, c->stream));
+  int64_t tot = 0;
+  MIAGPU_CUDA(cudaMemcpyAsync(&tot, offs + n, 8, cudaMemcpyDeviceToHost, c->stream));
+  MIAGPU_CUDA(cudaStreamSynchronize(c->stream));
+  *total = tot;
+  if (packed && tot > capacity) { set_error("miagpu_get_runs_packed: %lld runs, capacity %lld", (long long)tot, (long long)capacity); return 0; }
+  if (!c->d_packed.reserve(tot + 1)) return 0;
+  if (n) pack_runs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, c->d_nruns.p, offs, c->d_runs.p, c->d_packed.p);
+  MIAGPU_CUDA(cudaGetLastError());
+  MIAGPU_CUDA(cudaEventRecord(c->ev[2], c->stream));
+  if (run_off) MIAGPU_CUDA(cudaMemcpyAsync(run_off, offs, (n + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (packed && tot) MIAGPU_CUDA(cudaMemcpyAsync(packed, c->d_packed.p, tot * 2, cudaMemcpyDeviceToHost, c->stream));
+  MIAGPU_CUDA(cudaEventRecord(c->ev[3], c->stream));
+  MIAGPU_CUDA(cudaStreamSynchronize(c->stream));
+  MIAGPU_CUDA(cudaEventElapsedTime(&c->ms_kernels, c->ev[1], c->ev[2]));
+  MIAGPU_CUDA(cudaEventElapsedTime(&c->ms_d2h, c->ev[2], c->ev[3]));
+  c->launches = 4;
+  return 1;
 }
 
 // ------------------------------------------------ integer peak micro-benchmark

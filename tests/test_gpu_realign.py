@@ -42,3 +42,18 @@ def test_empty_batch(gpu):
     out = gpu.realign_host(np.zeros(0, np.uint8), np.zeros(1, np.int64), np.zeros(0, np.uint8), np.zeros(0, np.int32),
                            np.zeros(0, np.int32))
     assert len(out["score"]) == 0
+
+
+def test_packed_runs_equal_strided_runs(gpu, oracle):
+    ref, bases, off, rc, as_, ae = gpu_checks.make_case(2000, 3000, seed=91, divergence=0.04, indel_rate=0.02)
+    gpu.set_pssm(gpu_checks.load_pssm("onepass"))
+    gpu.set_reference(ref, circular=1)
+    out = gpu.realign_host(bases, off, rc, as_, ae)
+    n = len(off) - 1
+    total, _, _ = gpu.get_runs_packed()
+    assert total == int(np.maximum(out["n_runs"], 0).sum())
+    run_off, packed = np.zeros(n + 1, np.int64), np.zeros(total, np.uint16)
+    gpu.get_runs_packed(run_off, packed)
+    assert (np.diff(run_off) == out["n_runs"]).all()
+    for i in range(0, n, 7):
+        assert (packed[run_off[i]:run_off[i + 1]] == out["runs"][i, :out["n_runs"][i]]).all()
