@@ -289,12 +289,42 @@ def run_ours(args):
         "buckets": buckets,
         "consensus_matches_e2e": bool(cons == cons_e2e) if world == 1 else None,
     }
+    # ---- pass 1 (k-mer seeding + whole-reference both-strand DP), reported beside the headline
+    if world == 1 and not args.no_pass1:
+        line["pass1"] = pass1_numbers(g, ref, bases, off, rc, args)
     # ---- CPU baseline: the reference's own realign sequence on a bounded sample, 1 thread
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(ref, bases, off, rc, as_, ae, sm, args.cpu_sample)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def pass1_numbers(g, ref, stored, off, rc, args):
+    """Pass 1 on the original (un-revcomped) reads: (a) k = 12 filter on all reads, (b) no filter on a prefix."""
+    comp = np.zeros(256, np.uint8)
+    for a, b in zip(b"ACGTN", b"TGCAN"):
+        comp[a] = b
+    n = len(off) - 1
+    rid = np.repeat(np.arange(n), np.diff(off))
+    pos = np.arange(len(stored)) - off[rid]
+    src = np.where(rc[rid] == 1, off[rid] + (off[rid + 1] - off[rid]) - 1 - pos, np.arange(len(stored)))
+    orig = np.ascontiguousarray(np.where(rc[rid] == 1, comp[stored[src]], stored), np.uint8)
+    g.set_reference(ref, circular=1, with_rc=1)
+    res = {}
+    for tag, k, m in (("k12", 12, n), ("unmasked", 0, min(n, args.pass1_unmasked_reads))):
+        g.build_kmers(k)
+        g.upload_reads(orig[: off[m]], off[: m + 1])
+        g.pass1()                                   # warm-up
+        out = g.pass1()
+        t = g.last_timing()
+        nominal = t["dp_cells"]
+        res[tag] = {"reads": m, "kernel_ms": t["ms_kernels"], "reads_per_s": m / (t["ms_kernels"] * 1e-3),
+                    "nominal_gcups": nominal / (t["ms_kernels"] * 1e-3) / 1e9,
+                    "accepted": int((out["score"] >= 2000).sum()), "rc_fraction": float(out["rc"].mean()),
+                    "skipped_by_filter": int(((out["status"] & 2) != 0).sum())}
+    g.build_kmers(0)
+    return res
 
 
 def cpu_baseline(ref, bases, off, rc, as_, ae, sm, sample):
@@ -391,6 +421,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=60000)
     ap.add_argument("--ref-reads-per-core", type=int, default=4000)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-pass1", action="store_true")
+    ap.add_argument("--pass1-unmasked-reads", type=int, default=100000)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
