@@ -179,7 +179,7 @@ class MiaGpu:
         n = self.n
         out = out or self.alloc_realign_outputs(n)
         self._ck(self.lib.miagpu_realign(self.h, _ptr(rc), _ptr(as_), _ptr(ae), _ptr(out["score"]), _ptr(out["as_out"]),
-                                         _ptr(out["ae_out"]), _ptr(out["abr"]), _ptr(out["n_runs"]), _ptr(out["runs"]),
+                                         _ptr(out["ae_out"]), _ptr(out["abr"]), _ptr(out["n_runs"]), _ptr(out.get("runs")),
                                          _ptr(out["status"])))
         return out
 

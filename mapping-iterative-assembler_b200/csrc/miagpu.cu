@@ -281,8 +281,7 @@ extern "C" int miagpu_upload_reads(miagpu_ctx* c, int64_t n, const uint8_t* base
   MIAGPU_CUDA(cudaEventElapsedTime(&c->ms_h2d, c->ev[0], c->ev[1]));
   c->n = n;
   c->total_bases = total;
-  c->max_read_len = 0;
-  for (int64_t i = 0; i < n; i++) c->max_read_len = std::max<int64_t>(c->max_read_len, offsets[i + 1] - offsets[i]);
+  c->max_read_len = -1;                      // computed on demand (device reduction) by the chunked kernel's launcher
   return 1;
 }
 
@@ -327,7 +326,28 @@ __global__ void flag_big_kernel(const int32_t* list, int n_list, int32_t* score,
 }
 
 // ------------------------------------------------ chunked kernel (pass 1, wide windows)
+__global__ void max_len_kernel(int64_t n, const int64_t* off, int32_t* out) {
+  int m = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) m = max(m, (int)(off[i + 1] - off[i]));
+  m = __reduce_max_sync(0xffffffffu, m);
+  if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+
+static int ensure_max_read_len(miagpu_ctx* c) {
+  if (c->max_read_len >= 0) return 1;
+  int32_t m = 0;
+  if (c->n) {
+    MIAGPU_CUDA(cudaMemsetAsync(c->d_meta.p + 100, 0, 4, c->stream));
+    max_len_kernel<<<256, 256, 0, c->stream>>>(c->n, c->d_off.p, c->d_meta.p + 100);
+    MIAGPU_CUDA(cudaMemcpyAsync(&m, c->d_meta.p + 100, 4, cudaMemcpyDeviceToHost, c->stream));
+    MIAGPU_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  c->max_read_len = m;
+  return 1;
+}
+
 static int launch_strip(miagpu_ctx* c, int mode, const int32_t* list, int n_list, int32_t* counter) {
+  if (!ensure_max_read_len(c)) return 0;
   const int len1 = c->circular ? c->wrap_len : c->seq_len;                 // mia_main.c:721-728
   const int n_chunks = (len1 + CW - 1) / CW;
   const int Lmax = std::min(std::max(c->max_read_len, 1), MAX_READ);
@@ -783,20 +803,36 @@ extern "C" int miagpu_consensus_natural(miagpu_ctx* c, const uint8_t* dropped_fr
 extern "C" int miagpu_score_cut(int64_t n, const int32_t* seq_len, const int32_t* score, const uint8_t* unique_best,
                                 double* slope, double* intercept) {
   if (n < 0 || !seq_len || !score || !slope || !intercept) { set_error("miagpu_score_cut: bad argument"); return 0; }
-  double xbar = 0, ybar = 0, ssxy = 0, ssxx = 0, max_delta = 0;
-  int64_t j = 0;
-  auto use = [&](int64_t i) { return (!unique_best || unique_best[i]) && score[i] >= FIRST_ROUND_SCORE_CUTOFF; };
-  for (int64_t i = 0; i < n; i++) if (use(i)) { xbar += seq_len[i]; ybar += score[i]; j++; }
+  // xbar / ybar are sums of integers: exact in double in any order (< 2^53), so they are taken in int64.
+  // ssxy / ssxx are rounded at every step: those two chains keep the reference's FSDB order.
+  // max slope_delta: for a fixed length the quotient is monotone in the score, so the maximum over reads
+  // is the maximum over lengths of the quotient at that length's best score (same doubles, same result).
+  int64_t sx = 0, sy = 0, j = 0;
+  std::vector<int32_t> sel;
+  sel.reserve((size_t)n);
+  int32_t best_at_len[MAX_READ + 1];
+  for (int l = 0; l <= MAX_READ; l++) best_at_len[l] = INT_MIN;
+  for (int64_t i = 0; i < n; i++)
+    if ((!unique_best || unique_best[i]) && score[i] >= FIRST_ROUND_SCORE_CUTOFF) {
+      const int l = seq_len[i];
+      if (l < 0 || l > MAX_READ) { set_error("miagpu_score_cut: seq_len[%lld] = %d out of range", (long long)i, l); return 0; }
+      sx += l; sy += score[i]; sel.push_back((int32_t)i);
+      if (score[i] > best_at_len[l]) best_at_len[l] = score[i];
+    }
+  j = (int64_t)sel.size();
+  double xbar = (double)sx, ybar = (double)sy, ssxy = 0, ssxx = 0, max_delta = 0;
   xbar /= j; ybar /= j;
-  for (int64_t i = 0; i < n; i++) if (use(i)) {
-    ssxy += (seq_len[i] - xbar) * (score[i] - ybar);
-    ssxx += (seq_len[i] - xbar) * (seq_len[i] - xbar);
+  for (int32_t i : sel) {
+    const double dx = seq_len[i] - xbar;
+    ssxy += dx * (score[i] - ybar);
+    ssxx += dx * dx;
   }
   const double bf = ssxy / ssxx, ib = ybar - bf * xbar;
-  for (int64_t i = 0; i < n; i++) if (use(i)) {
-    double d = (score[i] - ((bf * seq_len[i]) + ib)) / seq_len[i];
-    if (d > max_delta) max_delta = d;
-  }
+  for (int l = 0; l <= MAX_READ; l++)
+    if (best_at_len[l] != INT_MIN) {
+      double d = (best_at_len[l] - ((bf * l) + ib)) / l;
+      if (d > max_delta) max_delta = d;
+    }
   *intercept = ib;
   if ((bf - max_delta) > 0) *slope = bf - (max_delta * 2.0);
   else *slope = (double)(bf * (80 / 100.0));                     // SCORE_CUTOFF_BUFFER, params.h:24
@@ -810,9 +846,12 @@ extern "C" int miagpu_cull_flags(int64_t n, const int32_t* seq_len, const int32_
   double slope = slope_in, intercept = intercept_in;
   if (!score_cut_set && !miagpu_score_cut(n, seq_len, score, unique_best, &slope, &intercept)) return 0;
   if (slope <= 0) slope = 100.0;
+  double min_score[MAX_READ + 1];                                  // the threshold depends on the length only
+  for (int l = 0; l <= MAX_READ; l++) min_score[l] = hard_cut > 0 ? (double)hard_cut : (double)(intercept + (slope * l));
   for (int64_t i = 0; i < n; i++) {
-    const double min_score = hard_cut > 0 ? (double)hard_cut : (double)(intercept + (slope * seq_len[i]));
-    below[i] = score[i] < min_score;
+    const int l = seq_len[i];
+    if (l < 0 || l > MAX_READ) { set_error("miagpu_cull_flags: seq_len[%lld] = %d out of range", (long long)i, l); return 0; }
+    below[i] = score[i] < min_score[l];
   }
   return 1;
 }
