@@ -66,6 +66,7 @@ def load_library():
     L.miagpu_set_alignment_inputs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.miagpu_realign_resident.argtypes = [C.c_void_p]
     L.miagpu_last_buckets.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.miagpu_last_pair_buckets.argtypes = [C.c_void_p] + [C.c_void_p] * 5 + [_i32p, _i32p]
     L.miagpu_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), _i64p, _i32p]
     L.miagpu_int32_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.miagpu_stream.restype = C.c_void_p
@@ -79,7 +80,7 @@ EXPORTS = ["miagpu_device_count", "miagpu_create", "miagpu_destroy", "miagpu_las
            "miagpu_pass1", "miagpu_compact_reads", "miagpu_realign", "miagpu_realign_host", "miagpu_get_runs_packed",
            "miagpu_consensus", "miagpu_accumulate_gaps", "miagpu_accumulate_counts", "miagpu_call", "miagpu_consensus_natural", "miagpu_accumulate_gaps_natural",
            "miagpu_score_cut", "miagpu_cull_flags",
-           "miagpu_set_alignment_inputs", "miagpu_realign_resident", "miagpu_last_buckets", "miagpu_last_timing",
+           "miagpu_set_alignment_inputs", "miagpu_realign_resident", "miagpu_last_buckets", "miagpu_last_pair_buckets", "miagpu_last_timing",
            "miagpu_int32_peak", "miagpu_stream"]
 
 
@@ -236,6 +237,15 @@ class MiaGpu:
         k, r, cells, ms = np.zeros(10, np.int32), np.zeros(10, np.int32), np.zeros(10, np.int64), np.zeros(10, np.float32)
         self._ck(self.lib.miagpu_last_buckets(self.h, _ptr(k), _ptr(r), _ptr(cells), _ptr(ms)))
         return [dict(K=int(k[i]), reads=int(r[i]), cells=int(cells[i]), ms=float(ms[i])) for i in range(10) if r[i]]
+
+    def last_pair_buckets(self):
+        """16-bit pair kernels of the last realign: (list of per-class dicts, reads handed to the 32-bit kernels, max read length)."""
+        k, r, pr = np.zeros(4, np.int32), np.zeros(4, np.int32), np.zeros(4, np.int32)
+        cells, ms = np.zeros(4, np.int64), np.zeros(4, np.float32)
+        fb, ml = C.c_int32(), C.c_int32()
+        self._ck(self.lib.miagpu_last_pair_buckets(self.h, _ptr(k), _ptr(r), _ptr(pr), _ptr(cells), _ptr(ms), C.byref(fb), C.byref(ml)))
+        return ([dict(K=int(k[i]), reads=int(r[i]), pairs=int(pr[i]), cells=int(cells[i]), ms=float(ms[i])) for i in range(4) if r[i]],
+                fb.value, ml.value)
 
     def accumulate_gaps(self, entries):
         entries = np.ascontiguousarray(entries, ENTRY_DTYPE)

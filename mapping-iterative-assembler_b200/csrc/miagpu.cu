@@ -9,6 +9,7 @@
 
 #include "common.cuh"
 #include "realign.cuh"
+#include "pair16.cuh"
 #include "consensus.cuh"
 #include "strip.cuh"
 #include <cub/device/device_scan.cuh>
@@ -47,6 +48,26 @@ struct DevBuf {
 
 constexpr int NBUCKET = 10;                                  // 9 register-tiled widths + "big"
 static const int BUCKET_K[NBUCKET] = {2, 4, 5, 6, 7, 8, 10, 12, 16, 0};
+static const int P16_K[P16_NKB] = {4, 5, 6, 8};
+
+// d_meta layout (int32 words)
+constexpr int META_COUNT = 0;        // [16] fill counters of the 32-bit work lists
+constexpr int META_WORK = 16;        // [16] dynamic work-fetch counters of the 32-bit kernels
+constexpr int META_MAXL = 32;        // [16] longest read per width class (all reads of the class)
+constexpr int META_CELLS = 48;       // [16] int64 DP cells per width class (all reads of the class)
+constexpr int META_POP = 80;         // [16] reads per width class (direct + pair-eligible)
+constexpr int META_NPAIRS = 96;      // [4]  pairs per pair class
+constexpr int META_MAXLEN = 100;     // scratch of max_len_kernel
+constexpr int META_PWORK = 104;      // [4]  work-fetch counters of the pair kernels
+constexpr int META_NFALL = 108;      // reads handed from the pair kernels to the 32-bit kernels
+constexpr int META_PREADS = 112;     // [4]  eligible reads per pair class
+constexpr int META_PCELLS = 120;     // [4]  int64 cells of the eligible reads
+constexpr int META_HOST = 128;       // words copied to the host after classification
+constexpr int P16_KEYS = P16_NKB * (P16_MAXL + 1);
+constexpr int META_HIST = 256;       // [P16_KEYS] eligible reads per (pair class, read length)
+constexpr int META_PSTART = 1024;    // [P16_KEYS] first pair of the key
+constexpr int META_CURSOR = 2048;    // [P16_KEYS] scatter cursors
+constexpr int META_WORDS = 3072;
 
 }  // namespace miagpu
 
@@ -79,8 +100,18 @@ struct miagpu_ctx {
   DevBuf<uint8_t> d_rc, d_status;
   DevBuf<int32_t> d_as, d_ae, d_score, d_as_out, d_ae_out, d_abr, d_nruns, d_win_start, d_win_len, d_lists;
   DevBuf<uint16_t> d_runs;
-  DevBuf<int32_t> d_meta;                      // bucket counts[8], work counters[8], max L[8], cells(2 x int32 -> int64)
+  DevBuf<int32_t> d_meta;                      // META_* layout below
   DevBuf<uint32_t> d_scratch;
+  // 16-bit SIMD pair kernel (pair16.cuh)
+  DevBuf<int16_t> d_prof16;
+  DevBuf<uint8_t> d_kind;
+  DevBuf<int32_t> d_pairs;
+  int pssm_min = 0, pssm_max = 0, lmax16 = 0;
+  cudaEvent_t pev[2 * P16_NKB] = {};
+  float pair_ms[P16_NKB] = {};
+  int32_t pair_reads[P16_NKB] = {}, pair_pairs[P16_NKB] = {};
+  int64_t pair_cells[P16_NKB] = {};
+  int32_t n_fallback = 0;
   // pass 1 / wide windows
   int kmer_k = 0;
   DevBuf<int32_t> d_kb[2], d_kp[2];
@@ -107,6 +138,8 @@ struct miagpu_ctx {
   int64_t dp_cells = 0;
   int launches = 0;
 };
+
+static void pair16_limits(const miagpu_ctx* c, int K, int* off16, int* lmax);
 
 // -------------------------------------------------------------------- misc
 extern "C" const char* miagpu_last_error(void) { return g_err; }
@@ -138,6 +171,7 @@ extern "C" int miagpu_create(miagpu_ctx** out, int device) {
   MIAGPU_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   for (auto& ev : c->ev) MIAGPU_CUDA(cudaEventCreate(&ev));
   for (auto& ev : c->bev) MIAGPU_CUDA(cudaEventCreate(&ev));
+  for (auto& ev : c->pev) MIAGPU_CUDA(cudaEventCreate(&ev));
   *out = c;
   return 1;
 }
@@ -156,6 +190,8 @@ extern "C" void miagpu_destroy(miagpu_ctx* c) {
   c->d_entries.release(); c->d_sm.release(); c->d_gaps.release(); c->d_ins_off.release(); c->d_acc.release(); c->d_cub.release(); c->d_called.release(); c->d_dropf.release(); c->d_dropb.release();
   for (auto& ev : c->ev) cudaEventDestroy(ev);
   for (auto& ev : c->bev) cudaEventDestroy(ev);
+  for (auto& ev : c->pev) cudaEventDestroy(ev);
+  c->d_prof16.release(); c->d_kind.release(); c->d_pairs.release();
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -192,7 +228,18 @@ extern "C" int miagpu_set_pssm(miagpu_ctx* c, const int32_t* fwd) {
   MIAGPU_CUDA(cudaMemcpyAsync(c->d_prof.p, prof.data(), PROF_INTS * 4, cudaMemcpyHostToDevice, c->stream));
   MIAGPU_CUDA(cudaMemcpyAsync(c->d_sm.p, c->sm_f, sizeof(c->sm_f), cudaMemcpyHostToDevice, c->stream));
   MIAGPU_CUDA(cudaMemcpyAsync(c->d_sm.p + MIAGPU_PSSM_INTS, c->sm_r, sizeof(c->sm_r), cudaMemcpyHostToDevice, c->stream));
+  // 16-bit profile of the pair kernel: sub + GEP (row-frame shift), entry PROF16_N = GEP (start-new addend)
+  std::vector<int16_t> prof16(PROF16_N + 8, 0);
+  for (int i = 0; i < PROF16_N; i++) prof16[i] = (int16_t)(prof[i] + GEP);
+  prof16[PROF16_N] = (int16_t)GEP;
+  if (!c->d_prof16.reserve(PROF16_N + 8)) return 0;
+  MIAGPU_CUDA(cudaMemcpyAsync(c->d_prof16.p, prof16.data(), (PROF16_N + 8) * 2, cudaMemcpyHostToDevice, c->stream));
   MIAGPU_CUDA(cudaStreamSynchronize(c->stream));
+  c->pssm_min = *std::min_element(fwd, fwd + MIAGPU_PSSM_INTS);
+  c->pssm_max = *std::max_element(fwd, fwd + MIAGPU_PSSM_INTS);
+  int off16 = 0;
+  pair16_limits(c, 8, &off16, &c->lmax16);            // widest class: the most conservative OFF
+  if (c->pssm_max + GEP <= 0 || off16 < 4 * (GOP + GEP)) c->lmax16 = 0;   // degenerate matrices: 32-bit kernels only
   c->have_pssm = true;
   return 1;
 }
@@ -261,7 +308,8 @@ static int reserve_per_read(miagpu_ctx* c, int64_t n) {
   return c->d_rc.reserve(n) && c->d_status.reserve(n) && c->d_as.reserve(n) && c->d_ae.reserve(n) && c->d_score.reserve(n) &&
          c->d_as_out.reserve(n) && c->d_ae_out.reserve(n) && c->d_abr.reserve(n) && c->d_nruns.reserve(n) &&
          c->d_win_start.reserve(n) && c->d_win_len.reserve(n) && c->d_lists.reserve(n * NBUCKET) &&
-         c->d_runs.reserve(n * MAX_RUNS) && c->d_meta.reserve(128);
+         c->d_runs.reserve(n * MAX_RUNS) && c->d_meta.reserve(META_WORDS) && c->d_kind.reserve(n + 1) &&
+         c->d_pairs.reserve(n + 2 * P16_KEYS + 64);
 }
 
 extern "C" int miagpu_upload_reads(miagpu_ctx* c, int64_t n, const uint8_t* bases, const int64_t* offsets) {
@@ -286,38 +334,104 @@ extern "C" int miagpu_upload_reads(miagpu_ctx* c, int64_t n, const uint8_t* base
 }
 
 // ----------------------------------------------------------------- realign
-// Window rule of reiterate_assembly (mia_main.c:190-212) + width bucket.
-__global__ void classify_kernel(int64_t n, const int64_t* off, const int32_t* as, const int32_t* ae, int wrap_len,
-                                int32_t* win_start, int32_t* win_len, int32_t* lists, int32_t* meta) {
-  __shared__ int s_cnt[NBUCKET], s_base[NBUCKET], s_maxL[NBUCKET];
+// Window rule of reiterate_assembly (mia_main.c:190-212) + width class.  A read goes either to the
+// work list of its 32-bit width bucket or, when the 16-bit pair kernel can take it (lmax16 > 0:
+// short enough for the 16-bit frame, window = [as-50, ...) so that the expected diagonal is 50,
+// at most 256 columns), into the (pair class, read length) histogram that pairs reads of equal length.
+__global__ void classify_kernel(int64_t n, const int64_t* off, const int32_t* as, const int32_t* ae, int wrap_len, int lmax16,
+                                int32_t* win_start, int32_t* win_len, int32_t* lists, uint8_t* kind, int32_t* meta) {
+  __shared__ int s_cnt[NBUCKET], s_base[NBUCKET], s_maxL[NBUCKET], s_pop[NBUCKET];
   __shared__ unsigned long long s_cells[NBUCKET];
-  if (threadIdx.x < NBUCKET) { s_cnt[threadIdx.x] = 0; s_maxL[threadIdx.x] = 0; }
-  if (threadIdx.x < NBUCKET) s_cells[threadIdx.x] = 0;
+  __shared__ int s_hist[P16_KEYS];
+  __shared__ int s_preads[P16_NKB];
+  __shared__ unsigned long long s_pcells[P16_NKB];
+  if (threadIdx.x < NBUCKET) { s_cnt[threadIdx.x] = 0; s_maxL[threadIdx.x] = 0; s_pop[threadIdx.x] = 0; s_cells[threadIdx.x] = 0; }
+  if (threadIdx.x < P16_NKB) { s_preads[threadIdx.x] = 0; s_pcells[threadIdx.x] = 0; }
+  if (lmax16 > 0) for (int i = threadIdx.x; i < P16_KEYS; i += blockDim.x) s_hist[i] = 0;
   __syncthreads();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int b = -1, slot = 0, L = 0;
+  bool direct = false;
   if (i < n) {
     L = (int)(off[i + 1] - off[i]);
     int rs = as[i] - REALIGN_BUFFER < 0 ? 0 : as[i] - REALIGN_BUFFER;
     int re = (ae[i] + REALIGN_BUFFER + 1 > wrap_len) ? wrap_len : ae[i] + REALIGN_BUFFER;
-    if (rs + L > re) { rs = 0; re = wrap_len; }
+    bool whole = rs + L > re;
+    if (whole) { rs = 0; re = wrap_len; }
     int len1 = re - rs;
     win_start[i] = rs;
     win_len[i] = len1;
-    b = len1 <= 64 ? 0 : len1 <= 128 ? 1 : len1 <= 160 ? 2 : len1 <= 192 ? 3 : len1 <= 224 ? 4 : len1 <= 256 ? 5 : len1 <= 320 ? 6 : len1 <= 384 ? 7 : len1 <= 512 ? 8 : 9;
+    b = bucket32_of(len1);
     if (L <= 0 || L > MAX_READ) b = NBUCKET - 1;
-    slot = atomicAdd(&s_cnt[b], 1);
+    const int kb = p16_class(len1);
+    const bool elig = lmax16 > 0 && b != NBUCKET - 1 && kb >= 0 && !whole && L <= lmax16 && L <= P16_MAXL && as[i] - rs == P16_DIAG0;
+    atomicAdd(&s_pop[b], 1);
     atomicMax(&s_maxL[b], L);
     atomicAdd(&s_cells[b], (unsigned long long)L * (unsigned long long)len1);
+    if (elig) {
+      kind[i] = (uint8_t)(16 + kb);
+      atomicAdd(&s_hist[kb * (P16_MAXL + 1) + L], 1);
+      atomicAdd(&s_preads[kb], 1);
+      atomicAdd(&s_pcells[kb], (unsigned long long)L * (unsigned long long)len1);
+    } else {
+      kind[i] = (uint8_t)b;
+      direct = true;
+      slot = atomicAdd(&s_cnt[b], 1);
+    }
   }
   __syncthreads();
   if (threadIdx.x < NBUCKET) {
-    s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd(&meta[threadIdx.x], s_cnt[threadIdx.x]) : 0;
-    if (s_maxL[threadIdx.x]) atomicMax(&meta[32 + threadIdx.x], s_maxL[threadIdx.x]);
+    const int t = threadIdx.x;
+    s_base[t] = s_cnt[t] ? atomicAdd(&meta[META_COUNT + t], s_cnt[t]) : 0;
+    if (s_maxL[t]) atomicMax(&meta[META_MAXL + t], s_maxL[t]);
+    if (s_pop[t]) atomicAdd(&meta[META_POP + t], s_pop[t]);
+    if (s_cells[t]) atomicAdd(reinterpret_cast<unsigned long long*>(meta + META_CELLS) + t, s_cells[t]);
   }
-  if (threadIdx.x < NBUCKET && s_cells[threadIdx.x]) atomicAdd(reinterpret_cast<unsigned long long*>(meta + 48) + threadIdx.x, s_cells[threadIdx.x]);
+  if (threadIdx.x < P16_NKB && s_preads[threadIdx.x]) {
+    atomicAdd(&meta[META_PREADS + threadIdx.x], s_preads[threadIdx.x]);
+    atomicAdd(reinterpret_cast<unsigned long long*>(meta + META_PCELLS) + threadIdx.x, s_pcells[threadIdx.x]);
+  }
+  if (lmax16 > 0)
+    for (int k = threadIdx.x; k < P16_KEYS; k += blockDim.x)
+      if (s_hist[k]) atomicAdd(&meta[META_HIST + k], s_hist[k]);
   __syncthreads();
-  if (b >= 0) lists[(int64_t)b * n + s_base[b] + slot] = (int32_t)i;
+  if (direct) lists[(int64_t)b * n + s_base[b] + slot] = (int32_t)i;
+}
+
+// Pairs per (class, length) key: ceil(count / 2), laid out class after class.
+__global__ void pair_layout_kernel(int32_t* meta) {
+  if (threadIdx.x || blockIdx.x) return;
+  int run = 0;
+  for (int kb = 0; kb < P16_NKB; kb++) {
+    const int first = run;
+    for (int L = 0; L <= P16_MAXL; L++) {
+      const int k = kb * (P16_MAXL + 1) + L;
+      meta[META_PSTART + k] = run;
+      run += (meta[META_HIST + k] + 1) >> 1;
+    }
+    meta[META_NPAIRS + kb] = run - first;
+  }
+}
+
+// Eligible reads take the next free slot of their key: slot s is member s&1 of pair pstart + s/2.
+__global__ void pair_scatter_kernel(int64_t n, const int64_t* off, const uint8_t* kind, int32_t* meta, int32_t* pairs) {
+  __shared__ int s_cnt[P16_KEYS], s_base[P16_KEYS];
+  for (int i = threadIdx.x; i < P16_KEYS; i += blockDim.x) s_cnt[i] = 0;
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int key = -1, slot = 0;
+  if (i < n && kind[i] >= 16) {
+    key = (kind[i] - 16) * (P16_MAXL + 1) + (int)(off[i + 1] - off[i]);
+    slot = atomicAdd(&s_cnt[key], 1);
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < P16_KEYS; k += blockDim.x)
+    if (s_cnt[k]) s_base[k] = atomicAdd(&meta[META_CURSOR + k], s_cnt[k]);
+  __syncthreads();
+  if (key >= 0) {
+    const int g = s_base[key] + slot;
+    pairs[2 * (int64_t)(meta[META_PSTART + key] + (g >> 1)) + (g & 1)] = (int32_t)i;
+  }
 }
 
 __global__ void flag_big_kernel(const int32_t* list, int n_list, int32_t* score, int32_t* n_runs, uint8_t* status) {
@@ -337,9 +451,9 @@ static int ensure_max_read_len(miagpu_ctx* c) {
   if (c->max_read_len >= 0) return 1;
   int32_t m = 0;
   if (c->n) {
-    MIAGPU_CUDA(cudaMemsetAsync(c->d_meta.p + 100, 0, 4, c->stream));
-    max_len_kernel<<<256, 256, 0, c->stream>>>(c->n, c->d_off.p, c->d_meta.p + 100);
-    MIAGPU_CUDA(cudaMemcpyAsync(&m, c->d_meta.p + 100, 4, cudaMemcpyDeviceToHost, c->stream));
+    MIAGPU_CUDA(cudaMemsetAsync(c->d_meta.p + META_MAXLEN, 0, 4, c->stream));
+    max_len_kernel<<<256, 256, 0, c->stream>>>(c->n, c->d_off.p, c->d_meta.p + META_MAXLEN);
+    MIAGPU_CUDA(cudaMemcpyAsync(&m, c->d_meta.p + META_MAXLEN, 4, cudaMemcpyDeviceToHost, c->stream));
     MIAGPU_CUDA(cudaStreamSynchronize(c->stream));
   }
   c->max_read_len = m;
@@ -410,33 +524,125 @@ static int launch_bucket(miagpu_ctx* c, RealignParams p, int maxL) {
   return 1;
 }
 
+// OFF of the 16-bit row frame and the longest read it can hold, from the extreme matrix entries
+// (same formulas as tests/model/pair16_model.c:p16_limits, which is checked against the oracle).
+static void pair16_limits(const miagpu_ctx* c, int K, int* off16, int* lmax) {
+  const int mn = std::min(c->pssm_min, 0), mx = std::max(c->pssm_max, 0);
+  const int a = 32768 - 2 * (GOP + GEP) - GEP * (K - 1) + mn;
+  const int b = 32768 - (GOP + 2 * GEP) - GEP * K - GEP - 1;
+  const int off = std::min(a, b) - 32;
+  const int inc = mx + GEP;
+  int lm = 1 + (32767 + off - mx) / inc;
+  *off16 = off;
+  *lmax = std::min(lm, P16_MAXL);
+}
+
+template <int K>
+static int launch_pair16(miagpu_ctx* c, Pair16Params p, int n_pairs, int maxL) {
+  using BL = BandLayout<K>;
+  bool ref_in_smem = c->ref_bytes <= 160 * 1024;
+  size_t smem = (PROF16_N + 8) * 2 + WARPS_PER_BLOCK * 2 * P16_MAXL * 2 + (ref_in_smem ? c->ref_bytes : 0);
+  MIAGPU_CUDA(cudaFuncSetAttribute(pair16_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  MIAGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pair16_kernel<K>, WARPS_PER_BLOCK * 32, smem));
+  if (per_sm < 1) { set_error("pair16_kernel<%d> does not fit on an SM (smem %zu)", K, smem); return 0; }
+  int cap = 8;
+  if (const char* e = getenv("MIAGPU_PAIR_BLOCKS_PER_SM")) cap = std::max(1, atoi(e));
+  per_sm = std::min(per_sm, cap);
+  int blocks = std::min(c->num_sms * per_sm, (n_pairs + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+  if (blocks < 1) return 1;
+  int64_t words = (int64_t)std::max(maxL, 1) * BL::WORDS_PER_ROW;
+  words = (words + 31) / 32 * 32;                                // 128-byte aligned per warp
+  if (!c->d_scratch.reserve((size_t)words * blocks * WARPS_PER_BLOCK)) return 0;
+  int lm = 0;
+  pair16_limits(c, K, &p.off16, &lm);
+  p.scratch = c->d_scratch.p;
+  p.scratch_words_per_warp = words;
+  p.ref_in_smem = ref_in_smem;
+  pair16_kernel<K><<<blocks, WARPS_PER_BLOCK * 32, smem, c->stream>>>(p);
+  MIAGPU_CUDA(cudaGetLastError());
+  c->launches++;
+  return 1;
+}
+
 static int realign_device(miagpu_ctx* c) {
   const int64_t n = c->n;
   c->launches = 0;
   c->dp_cells = 0;
+  c->n_fallback = 0;
+  for (int kb = 0; kb < P16_NKB; kb++) { c->pair_ms[kb] = 0; c->pair_reads[kb] = 0; c->pair_pairs[kb] = 0; c->pair_cells[kb] = 0; }
+  for (int b = 0; b < NBUCKET; b++) { c->bucket_ms[b] = 0; c->bucket_reads[b] = 0; c->bucket_cells[b] = 0; }
   if (n == 0) return 1;
-  MIAGPU_CUDA(cudaMemsetAsync(c->d_meta.p, 0, 128 * sizeof(int32_t), c->stream));
-  classify_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, c->d_off.p, c->d_as.p, c->d_ae.p, c->wrap_len,
-                                                                     c->d_win_start.p, c->d_win_len.p, c->d_lists.p, c->d_meta.p);
+  int lmax16 = c->lmax16;
+  if (const char* e = getenv("MIAGPU_PAIR16")) if (atoi(e) == 0) lmax16 = 0;
+  MIAGPU_CUDA(cudaMemsetAsync(c->d_meta.p, 0, META_WORDS * sizeof(int32_t), c->stream));
+  classify_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, c->d_off.p, c->d_as.p, c->d_ae.p, c->wrap_len, lmax16,
+                                                                     c->d_win_start.p, c->d_win_len.p, c->d_lists.p, c->d_kind.p, c->d_meta.p);
   MIAGPU_CUDA(cudaGetLastError());
   c->launches++;
-  int32_t meta[96];
-  static_assert(NBUCKET <= 16 && 48 + 2 * NBUCKET <= 96, "meta layout");
+  if (lmax16 > 0) {
+    pair_layout_kernel<<<1, 32, 0, c->stream>>>(c->d_meta.p);
+    MIAGPU_CUDA(cudaGetLastError());
+    c->launches++;
+  }
+  int32_t meta[META_HOST];
   MIAGPU_CUDA(cudaMemcpyAsync(meta, c->d_meta.p, sizeof(meta), cudaMemcpyDeviceToHost, c->stream));
   MIAGPU_CUDA(cudaStreamSynchronize(c->stream));
-  memcpy(c->bucket_cells, meta + 48, sizeof(c->bucket_cells));
-  for (int b = 0; b < NBUCKET; b++) { c->dp_cells += c->bucket_cells[b]; c->bucket_reads[b] = meta[b]; c->bucket_ms[b] = 0; }
+  memcpy(c->bucket_cells, meta + META_CELLS, sizeof(int64_t) * NBUCKET);
+  memcpy(c->pair_cells, meta + META_PCELLS, sizeof(int64_t) * P16_NKB);
+  for (int b = 0; b < NBUCKET; b++) c->dp_cells += c->bucket_cells[b];
+  int total_pairs = 0;
+  for (int kb = 0; kb < P16_NKB; kb++) { c->pair_pairs[kb] = meta[META_NPAIRS + kb]; c->pair_reads[kb] = meta[META_PREADS + kb]; total_pairs += c->pair_pairs[kb]; }
+
+  // ---- 16-bit pair kernels first: the reads they cannot finish join the 32-bit lists
+  if (total_pairs) {
+    MIAGPU_CUDA(cudaMemsetAsync(c->d_pairs.p, 0xff, (size_t)2 * total_pairs * sizeof(int32_t), c->stream));
+    pair_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, c->d_off.p, c->d_kind.p, c->d_meta.p, c->d_pairs.p);
+    MIAGPU_CUDA(cudaGetLastError());
+    c->launches++;
+    int base = 0;
+    for (int kb = 0; kb < P16_NKB; kb++) {
+      const int np = c->pair_pairs[kb];
+      if (!np) continue;
+      MIAGPU_CUDA(cudaEventRecord(c->pev[2 * kb], c->stream));
+      Pair16Params p{};
+      p.bases = c->d_bases.p; p.off = c->d_off.p; p.rc = c->d_rc.p; p.win_start = c->d_win_start.p; p.win_len = c->d_win_len.p;
+      p.pairs = c->d_pairs.p + 2 * (int64_t)base; p.n_pairs = c->d_meta.p + META_NPAIRS + kb; p.counter = c->d_meta.p + META_PWORK + kb;
+      p.ref_codes = c->d_ref.p; p.ref_bytes = c->ref_bytes; p.prof16 = c->d_prof16.p;
+      p.score = c->d_score.p; p.as_out = c->d_as_out.p; p.ae_out = c->d_ae_out.p; p.abr = c->d_abr.p;
+      p.n_runs = c->d_nruns.p; p.runs = c->d_runs.p; p.status = c->d_status.p;
+      p.lists = c->d_lists.p; p.list_counts = c->d_meta.p + META_COUNT; p.n_reads = n; p.n_fallback = c->d_meta.p + META_NFALL;
+      int maxL = 0;                                     // longest read among the 32-bit classes this pair class draws from
+      for (int b = 0; b < NBUCKET - 1; b++) if (p16_class(BUCKET_K[b] * 32) == kb) maxL = std::max(maxL, meta[META_MAXL + b]);
+      maxL = std::min(maxL, P16_MAXL);
+      int ok = 1;
+      switch (P16_K[kb]) {
+        case 4: ok = launch_pair16<4>(c, p, np, maxL); break;
+        case 5: ok = launch_pair16<5>(c, p, np, maxL); break;
+        case 6: ok = launch_pair16<6>(c, p, np, maxL); break;
+        default: ok = launch_pair16<8>(c, p, np, maxL); break;
+      }
+      if (!ok) return 0;
+      MIAGPU_CUDA(cudaEventRecord(c->pev[2 * kb + 1], c->stream));
+      base += np;
+    }
+  }
+
+  // ---- 32-bit kernels over the direct lists plus whatever the pair kernels appended
   for (int b = 0; b < NBUCKET; b++) {
-    if (!meta[b]) continue;
+    const int pop = meta[META_POP + b];               // upper bound of the final list length
+    if (!pop) continue;
+    if (!total_pairs && !meta[META_COUNT + b]) continue;
     MIAGPU_CUDA(cudaEventRecord(c->bev[2 * b], c->stream));
     RealignParams p{};
     p.bases = c->d_bases.p; p.off = c->d_off.p; p.rc = c->d_rc.p;
     p.win_start = c->d_win_start.p; p.win_len = c->d_win_len.p;
-    p.list = c->d_lists.p + (int64_t)b * n; p.n_list = meta[b]; p.counter = c->d_meta.p + 16 + b;
+    p.list = c->d_lists.p + (int64_t)b * n; p.n_list = total_pairs ? pop : meta[META_COUNT + b];
+    p.n_list_ptr = c->d_meta.p + META_COUNT + b; p.counter = c->d_meta.p + META_WORK + b;
     p.ref_codes = c->d_ref.p; p.ref_bytes = c->ref_bytes; p.prof = c->d_prof.p; p.sg5 = 1;
     p.score = c->d_score.p; p.as_out = c->d_as_out.p; p.ae_out = c->d_ae_out.p; p.abr = c->d_abr.p;
     p.n_runs = c->d_nruns.p; p.runs = c->d_runs.p; p.status = c->d_status.p;
-    int ok = 1, maxL = meta[32 + b];
+    int ok = 1, maxL = meta[META_MAXL + b];
     switch (BUCKET_K[b]) {
       case 2: ok = launch_bucket<2>(c, p, maxL); break;
       case 4: ok = launch_bucket<4>(c, p, maxL); break;
@@ -448,17 +654,28 @@ static int realign_device(miagpu_ctx* c) {
       case 12: ok = launch_bucket<12>(c, p, maxL); break;
       case 16: ok = launch_bucket<16>(c, p, maxL); break;
       default:
-        ok = launch_strip(c, 1, p.list, p.n_list, c->d_meta.p + 16 + b);
+        ok = launch_strip(c, 1, p.list, meta[META_COUNT + b], c->d_meta.p + META_WORK + b);   // too wide for either kernel: never pair-eligible
     }
     if (!ok) return 0;
     MIAGPU_CUDA(cudaEventRecord(c->bev[2 * b + 1], c->stream));
+    c->bucket_reads[b] = -1;                         // launched; the final list length is read back with the timings
   }
   return 1;
 }
 
 static int realign_bucket_times(miagpu_ctx* c) {
+  if (c->n == 0) return 1;
+  int32_t meta[META_HOST];
+  MIAGPU_CUDA(cudaMemcpyAsync(meta, c->d_meta.p, sizeof(meta), cudaMemcpyDeviceToHost, c->stream));
+  MIAGPU_CUDA(cudaStreamSynchronize(c->stream));
+  c->n_fallback = meta[META_NFALL];
   for (int b = 0; b < NBUCKET; b++)
-    if (c->bucket_reads[b]) MIAGPU_CUDA(cudaEventElapsedTime(&c->bucket_ms[b], c->bev[2 * b], c->bev[2 * b + 1]));
+    if (c->bucket_reads[b]) {
+      c->bucket_reads[b] = meta[META_COUNT + b];
+      MIAGPU_CUDA(cudaEventElapsedTime(&c->bucket_ms[b], c->bev[2 * b], c->bev[2 * b + 1]));
+    }
+  for (int kb = 0; kb < P16_NKB; kb++)
+    if (c->pair_pairs[kb]) MIAGPU_CUDA(cudaEventElapsedTime(&c->pair_ms[kb], c->pev[2 * kb], c->pev[2 * kb + 1]));
   return 1;
 }
 
@@ -527,6 +744,20 @@ extern "C" int miagpu_last_buckets(miagpu_ctx* c, int32_t* k, int32_t* reads, in
     if (cells) cells[b] = c->bucket_cells[b];
     if (ms) ms[b] = c->bucket_ms[b];
   }
+  return 1;
+}
+
+extern "C" int miagpu_last_pair_buckets(miagpu_ctx* c, int32_t* k, int32_t* reads, int32_t* pairs, int64_t* cells, float* ms, int32_t* fallback_reads, int32_t* max_len16) {
+  if (!c) { set_error("miagpu_last_pair_buckets: NULL ctx"); return 0; }
+  for (int kb = 0; kb < P16_NKB; kb++) {
+    if (k) k[kb] = P16_K[kb];
+    if (reads) reads[kb] = c->pair_reads[kb];
+    if (pairs) pairs[kb] = c->pair_pairs[kb];
+    if (cells) cells[kb] = c->pair_cells[kb];
+    if (ms) ms[kb] = c->pair_ms[kb];
+  }
+  if (fallback_reads) *fallback_reads = c->n_fallback;
+  if (max_len16) *max_len16 = c->lmax16;
   return 1;
 }
 
@@ -627,12 +858,12 @@ __global__ void int_peak_kernel(int* out, int iters, int seed) {
 extern "C" int miagpu_int32_peak(miagpu_ctx* c, double* ops_per_s) {
   if (!c || !ops_per_s) { set_error("miagpu_int32_peak: NULL argument"); return 0; }
   MIAGPU_CUDA(cudaSetDevice(c->device));
-  if (!c->d_meta.reserve(128)) return 0;
+  if (!c->d_meta.reserve(META_WORDS)) return 0;
   const int iters = 4096, threads = 256, blocks = c->num_sms * 8;
   // ops per inner statement group: IADD3(1) + IMNMX(1) + ISETP/SEL/IADD(3) + IMNMX(1) = 6 per chain element
   for (int rep = 0; rep < 2; rep++) {
     MIAGPU_CUDA(cudaEventRecord(c->ev[4], c->stream));
-    int_peak_kernel<<<blocks, threads, 0, c->stream>>>(c->d_meta.p + 48, iters, 12345);
+    int_peak_kernel<<<blocks, threads, 0, c->stream>>>(c->d_meta.p + META_WORDS - 4, iters, 12345);
     MIAGPU_CUDA(cudaEventRecord(c->ev[5], c->stream));
     MIAGPU_CUDA(cudaStreamSynchronize(c->stream));
   }

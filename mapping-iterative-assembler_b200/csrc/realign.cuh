@@ -39,7 +39,8 @@ struct RealignParams {
   const int32_t* win_len;
   // work list of this bucket
   const int32_t* list;
-  int32_t n_list;
+  int32_t n_list;            // upper bound used to size the grid
+  const int32_t* n_list_ptr; // device-side length of the list (the pair kernel appends to it before this launch)
   int32_t* counter;          // dynamic work fetch
   // reference codes (0..4), padded to 16 B
   const uint8_t* ref_codes;
@@ -164,11 +165,12 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) realign_kernel(RealignPa
   int value_mask = ~KEY_LOW_MASK;
   asm volatile("" : "+r"(value_mask));                            // keep it in a register
 
+  const int n_list = *p.n_list_ptr;
   for (;;) {
     int item = 0;
     if (lane == 0) item = atomicAdd(p.counter, 1);
     item = __shfl_sync(0xffffffffu, item, 0);
-    if (item >= p.n_list) break;
+    if (item >= n_list) break;
     const int rd = p.list[item];
     const int64_t o0 = p.off[rd];
     const int L = (int)(p.off[rd + 1] - o0);
