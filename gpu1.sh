@@ -1,4 +1,6 @@
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -q -x 2>&1 | tail -15
-python bench.py --steps 5 --warmup 3 --no-cpu --no-pass1 > gpurun_out/bench_p16.log 2>&1; tail -1 gpurun_out/bench_p16.log | python -c "
-import json,sys; d=json.loads(sys.stdin.read()); print({k:d[k] for k in ('value','ms_per_step','gcups')}, d['e2e'], d['buckets'], d['pair16'], d['consensus_matches_e2e'])" || tail -20 gpurun_out/bench_p16.log
+python -m pytest tests -m gpu -q -x 2>&1 | tail -5
+for G in 16 32; do
+MIAGPU_PAIR_G=$G python bench.py --steps 5 --warmup 3 --no-cpu --no-pass1 > gpurun_out/bench_p16_$G.log 2>&1; tail -1 gpurun_out/bench_p16_$G.log | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print($G, {k:d[k] for k in ('value','ms_per_step','gcups')}, d['e2e']['ms_per_step'], [(b['kernel'],round(b['ms'],3)) for b in d['buckets']], d['pair16'], d['consensus_matches_e2e'])" || tail -20 gpurun_out/bench_p16_$G.log
+done

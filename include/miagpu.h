@@ -238,6 +238,23 @@ int miagpu_cull_flags( int64_t n, const int32_t* seq_len, const int32_t* score,
                        int score_cut_set, double slope, double intercept,
                        uint8_t* below );
 
+/* ---- a9..a13 in one call for a batch that lives in host memory: one iteration of
+ * mia_main.c:931-963.  Equivalent to miagpu_realign_host + miagpu_get_runs_packed +
+ * miagpu_cull_flags (dropped[i] |= below[i], sticky as in H10) + miagpu_consensus_natural
+ * (every read owns its fresh AlnSeq segments; dropped[] serves the front and the back
+ * segment), but the host-side score cut overlaps the downloads and the insert-maxima
+ * pass.  seq_len / unique_best / hard_cut / score_cut_set / slope / intercept as in
+ * miagpu_cull_flags; packed_runs (nullable) as in miagpu_get_runs_packed. */
+int miagpu_iterate_host( miagpu_ctx* ctx, int64_t n, const uint8_t* bases,
+                         const int64_t* offsets, const uint8_t* rc, const int32_t* as,
+                         const int32_t* ae, int32_t* score, int32_t* as_out,
+                         int32_t* ae_out, int32_t* abr, int32_t* n_runs, uint8_t* status,
+                         uint16_t* packed_runs, int64_t capacity, int64_t* total_runs,
+                         const int32_t* seq_len, const uint8_t* unique_best, int hard_cut,
+                         int score_cut_set, double slope, double intercept,
+                         uint8_t* dropped, int cons_code, int32_t* gaps_out,
+                         char* cons_out, int32_t* cons_len );
+
 /* Device-resident round (reads, rc, as, ae stay in HBM between calls): */
 int miagpu_set_alignment_inputs( miagpu_ctx* ctx, const uint8_t* rc,
                                  const int32_t* as, const int32_t* ae );

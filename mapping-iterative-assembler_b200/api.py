@@ -66,6 +66,8 @@ def load_library():
     L.miagpu_set_alignment_inputs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.miagpu_realign_resident.argtypes = [C.c_void_p]
     L.miagpu_last_buckets.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.miagpu_iterate_host.argtypes = ([C.c_void_p, C.c_int64] + [C.c_void_p] * 12 + [C.c_int64, _i64p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                      C.c_double, C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_char_p, _i32p])
     L.miagpu_last_pair_buckets.argtypes = [C.c_void_p] + [C.c_void_p] * 5 + [_i32p, _i32p]
     L.miagpu_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), _i64p, _i32p]
     L.miagpu_int32_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
@@ -77,7 +79,7 @@ def load_library():
 
 EXPORTS = ["miagpu_device_count", "miagpu_create", "miagpu_destroy", "miagpu_last_error", "miagpu_version", "miagpu_set_pssm",
            "miagpu_get_pssm", "miagpu_set_reference", "miagpu_ref_wrap_len", "miagpu_build_kmers", "miagpu_upload_reads",
-           "miagpu_pass1", "miagpu_compact_reads", "miagpu_realign", "miagpu_realign_host", "miagpu_get_runs_packed",
+           "miagpu_pass1", "miagpu_compact_reads", "miagpu_realign", "miagpu_realign_host", "miagpu_iterate_host", "miagpu_get_runs_packed",
            "miagpu_consensus", "miagpu_accumulate_gaps", "miagpu_accumulate_counts", "miagpu_call", "miagpu_consensus_natural", "miagpu_accumulate_gaps_natural",
            "miagpu_score_cut", "miagpu_cull_flags",
            "miagpu_set_alignment_inputs", "miagpu_realign_resident", "miagpu_last_buckets", "miagpu_last_pair_buckets", "miagpu_last_timing",
@@ -199,6 +201,26 @@ class MiaGpu:
                                               _ptr(out["n_runs"]), _ptr(out.get("runs")), _ptr(out["status"])))
         self.n = n
         return out
+
+    def iterate_host(self, bases, offsets, rc, as_, ae, seq_len, dropped, out=None, packed=None, cons_code=1, unique_best=None,
+                     hard_cut=0, score_cut=None, want_gaps=False):
+        """One whole iteration for a host-resident batch (miagpu_iterate_host).  `dropped` is updated in place (sticky).
+        Returns (consensus, out, total_runs, gaps)."""
+        n = len(offsets) - 1
+        out = out or self.alloc_realign_outputs(n)
+        if not hasattr(self, "_consbuf") or len(self._consbuf) < self.seq_len * 4 + 4096:
+            self._consbuf = C.create_string_buffer(self.seq_len * 4 + 4096)
+        cap = 0 if packed is None else (packed.numel() if hasattr(packed, "numel") else packed.size)
+        tot, cl = C.c_int64(), C.c_int32()
+        gaps = np.zeros(self.seq_len, np.int32) if want_gaps else None
+        slope, icpt = score_cut if score_cut is not None else (0.0, 0.0)
+        self._ck(self.lib.miagpu_iterate_host(self.h, n, _ptr(bases), _ptr(offsets), _ptr(rc), _ptr(as_), _ptr(ae), _ptr(out["score"]),
+                                              _ptr(out["as_out"]), _ptr(out["ae_out"]), _ptr(out["abr"]), _ptr(out["n_runs"]),
+                                              _ptr(out["status"]), _ptr(packed), cap, C.byref(tot), _ptr(seq_len), _ptr(unique_best),
+                                              hard_cut, 0 if score_cut is None else 1, slope, icpt, _ptr(dropped), cons_code,
+                                              _ptr(gaps), self._consbuf, C.byref(cl)))
+        self.n = n
+        return self._consbuf.value.decode(), out, tot.value, gaps
 
     # -- consensus
     def consensus(self, entries, cons_code=1, want_counts=False):

@@ -5,6 +5,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -48,7 +49,7 @@ struct DevBuf {
 
 constexpr int NBUCKET = 10;                                  // 9 register-tiled widths + "big"
 static const int BUCKET_K[NBUCKET] = {2, 4, 5, 6, 7, 8, 10, 12, 16, 0};
-static const int P16_K[P16_NKB] = {4, 5, 6, 8};
+static const int P16_COLS[P16_NKB] = {128, 160, 192, 256};   // columns of the pair kernels' width classes
 
 // d_meta layout (int32 words)
 constexpr int META_COUNT = 0;        // [16] fill counters of the 32-bit work lists
@@ -112,6 +113,7 @@ struct miagpu_ctx {
   int32_t pair_reads[P16_NKB] = {}, pair_pairs[P16_NKB] = {};
   int64_t pair_cells[P16_NKB] = {};
   int32_t n_fallback = 0;
+  int pair_g = 16;
   // pass 1 / wide windows
   int kmer_k = 0;
   DevBuf<int32_t> d_kb[2], d_kp[2];
@@ -238,7 +240,7 @@ extern "C" int miagpu_set_pssm(miagpu_ctx* c, const int32_t* fwd) {
   c->pssm_min = *std::min_element(fwd, fwd + MIAGPU_PSSM_INTS);
   c->pssm_max = *std::max_element(fwd, fwd + MIAGPU_PSSM_INTS);
   int off16 = 0;
-  pair16_limits(c, 8, &off16, &c->lmax16);            // widest class: the most conservative OFF
+  pair16_limits(c, 16, &off16, &c->lmax16);           // most columns per lane: the most conservative OFF
   if (c->pssm_max + GEP <= 0 || off16 < 4 * (GOP + GEP)) c->lmax16 = 0;   // degenerate matrices: 32-bit kernels only
   c->have_pssm = true;
   return 1;
@@ -309,7 +311,7 @@ static int reserve_per_read(miagpu_ctx* c, int64_t n) {
          c->d_as_out.reserve(n) && c->d_ae_out.reserve(n) && c->d_abr.reserve(n) && c->d_nruns.reserve(n) &&
          c->d_win_start.reserve(n) && c->d_win_len.reserve(n) && c->d_lists.reserve(n * NBUCKET) &&
          c->d_runs.reserve(n * MAX_RUNS) && c->d_meta.reserve(META_WORDS) && c->d_kind.reserve(n + 1) &&
-         c->d_pairs.reserve(n + 2 * P16_KEYS + 64);
+         c->d_pairs.reserve(n + 4 * P16_KEYS + 64);
 }
 
 extern "C" int miagpu_upload_reads(miagpu_ctx* c, int64_t n, const uint8_t* bases, const int64_t* offsets) {
@@ -398,8 +400,9 @@ __global__ void classify_kernel(int64_t n, const int64_t* off, const int32_t* as
   if (direct) lists[(int64_t)b * n + s_base[b] + slot] = (int32_t)i;
 }
 
-// Pairs per (class, length) key: ceil(count / 2), laid out class after class.
-__global__ void pair_layout_kernel(int32_t* meta) {
+// Pairs per (class, length) key: ceil(count / 2), rounded up to whole work items of np pairs (a warp's reads all
+// have one length), laid out class after class.  META_PSTART is in pairs, META_NPAIRS in work items.
+__global__ void pair_layout_kernel(int32_t* meta, int np) {
   if (threadIdx.x || blockIdx.x) return;
   int run = 0;
   for (int kb = 0; kb < P16_NKB; kb++) {
@@ -407,9 +410,10 @@ __global__ void pair_layout_kernel(int32_t* meta) {
     for (int L = 0; L <= P16_MAXL; L++) {
       const int k = kb * (P16_MAXL + 1) + L;
       meta[META_PSTART + k] = run;
-      run += (meta[META_HIST + k] + 1) >> 1;
+      const int pairs = (meta[META_HIST + k] + 1) >> 1;
+      run += (pairs + np - 1) / np * np;
     }
-    meta[META_NPAIRS + kb] = run - first;
+    meta[META_NPAIRS + kb] = (run - first) / np;
   }
 }
 
@@ -537,15 +541,15 @@ static void pair16_limits(const miagpu_ctx* c, int K, int* off16, int* lmax) {
   *lmax = std::min(lm, P16_MAXL);
 }
 
-template <int K>
+template <int K, int G>
 static int launch_pair16(miagpu_ctx* c, Pair16Params p, int n_pairs, int maxL) {
   using BL = BandLayout<K>;
   bool ref_in_smem = c->ref_bytes <= 160 * 1024;
-  size_t smem = (PROF16_N + 8) * 2 + WARPS_PER_BLOCK * 2 * P16_MAXL * 2 + (ref_in_smem ? c->ref_bytes : 0);
-  MIAGPU_CUDA(cudaFuncSetAttribute(pair16_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  size_t smem = (PROF16_N + 8) * 2 + WARPS_PER_BLOCK * (32 / G) * 2 * P16_MAXL * 2 + (ref_in_smem ? c->ref_bytes : 0);
+  MIAGPU_CUDA(cudaFuncSetAttribute((pair16_kernel<K, G>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
-  MIAGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pair16_kernel<K>, WARPS_PER_BLOCK * 32, smem));
-  if (per_sm < 1) { set_error("pair16_kernel<%d> does not fit on an SM (smem %zu)", K, smem); return 0; }
+  MIAGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (pair16_kernel<K, G>), WARPS_PER_BLOCK * 32, smem));
+  if (per_sm < 1) { set_error("pair16_kernel<%d,%d> does not fit on an SM (smem %zu)", K, G, smem); return 0; }
   int cap = 8;
   if (const char* e = getenv("MIAGPU_PAIR_BLOCKS_PER_SM")) cap = std::max(1, atoi(e));
   per_sm = std::min(per_sm, cap);
@@ -559,7 +563,7 @@ static int launch_pair16(miagpu_ctx* c, Pair16Params p, int n_pairs, int maxL) {
   p.scratch = c->d_scratch.p;
   p.scratch_words_per_warp = words;
   p.ref_in_smem = ref_in_smem;
-  pair16_kernel<K><<<blocks, WARPS_PER_BLOCK * 32, smem, c->stream>>>(p);
+  pair16_kernel<K, G><<<blocks, WARPS_PER_BLOCK * 32, smem, c->stream>>>(p);
   MIAGPU_CUDA(cudaGetLastError());
   c->launches++;
   return 1;
@@ -580,8 +584,12 @@ static int realign_device(miagpu_ctx* c) {
                                                                      c->d_win_start.p, c->d_win_len.p, c->d_lists.p, c->d_kind.p, c->d_meta.p);
   MIAGPU_CUDA(cudaGetLastError());
   c->launches++;
+  int pair_g = 16;                                   // lanes per pair: 16 = two pairs per warp
+  if (const char* e = getenv("MIAGPU_PAIR_G")) pair_g = atoi(e) == 32 ? 32 : 16;
+  const int np = 32 / pair_g;
+  c->pair_g = pair_g;
   if (lmax16 > 0) {
-    pair_layout_kernel<<<1, 32, 0, c->stream>>>(c->d_meta.p);
+    pair_layout_kernel<<<1, 32, 0, c->stream>>>(c->d_meta.p, np);
     MIAGPU_CUDA(cudaGetLastError());
     c->launches++;
   }
@@ -591,23 +599,23 @@ static int realign_device(miagpu_ctx* c) {
   memcpy(c->bucket_cells, meta + META_CELLS, sizeof(int64_t) * NBUCKET);
   memcpy(c->pair_cells, meta + META_PCELLS, sizeof(int64_t) * P16_NKB);
   for (int b = 0; b < NBUCKET; b++) c->dp_cells += c->bucket_cells[b];
-  int total_pairs = 0;
+  int total_pairs = 0;                               // in work items (np pairs each)
   for (int kb = 0; kb < P16_NKB; kb++) { c->pair_pairs[kb] = meta[META_NPAIRS + kb]; c->pair_reads[kb] = meta[META_PREADS + kb]; total_pairs += c->pair_pairs[kb]; }
 
   // ---- 16-bit pair kernels first: the reads they cannot finish join the 32-bit lists
   if (total_pairs) {
-    MIAGPU_CUDA(cudaMemsetAsync(c->d_pairs.p, 0xff, (size_t)2 * total_pairs * sizeof(int32_t), c->stream));
+    MIAGPU_CUDA(cudaMemsetAsync(c->d_pairs.p, 0xff, (size_t)2 * np * total_pairs * sizeof(int32_t), c->stream));
     pair_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, c->d_off.p, c->d_kind.p, c->d_meta.p, c->d_pairs.p);
     MIAGPU_CUDA(cudaGetLastError());
     c->launches++;
     int base = 0;
     for (int kb = 0; kb < P16_NKB; kb++) {
-      const int np = c->pair_pairs[kb];
-      if (!np) continue;
+      const int ni = c->pair_pairs[kb];
+      if (!ni) continue;
       MIAGPU_CUDA(cudaEventRecord(c->pev[2 * kb], c->stream));
       Pair16Params p{};
       p.bases = c->d_bases.p; p.off = c->d_off.p; p.rc = c->d_rc.p; p.win_start = c->d_win_start.p; p.win_len = c->d_win_len.p;
-      p.pairs = c->d_pairs.p + 2 * (int64_t)base; p.n_pairs = c->d_meta.p + META_NPAIRS + kb; p.counter = c->d_meta.p + META_PWORK + kb;
+      p.pairs = c->d_pairs.p + 2 * (int64_t)np * base; p.n_items = c->d_meta.p + META_NPAIRS + kb; p.counter = c->d_meta.p + META_PWORK + kb;
       p.ref_codes = c->d_ref.p; p.ref_bytes = c->ref_bytes; p.prof16 = c->d_prof16.p;
       p.score = c->d_score.p; p.as_out = c->d_as_out.p; p.ae_out = c->d_ae_out.p; p.abr = c->d_abr.p;
       p.n_runs = c->d_nruns.p; p.runs = c->d_runs.p; p.status = c->d_status.p;
@@ -616,15 +624,24 @@ static int realign_device(miagpu_ctx* c) {
       for (int b = 0; b < NBUCKET - 1; b++) if (p16_class(BUCKET_K[b] * 32) == kb) maxL = std::max(maxL, meta[META_MAXL + b]);
       maxL = std::min(maxL, P16_MAXL);
       int ok = 1;
-      switch (P16_K[kb]) {
-        case 4: ok = launch_pair16<4>(c, p, np, maxL); break;
-        case 5: ok = launch_pair16<5>(c, p, np, maxL); break;
-        case 6: ok = launch_pair16<6>(c, p, np, maxL); break;
-        default: ok = launch_pair16<8>(c, p, np, maxL); break;
+      if (pair_g == 32) {
+        switch (kb) {
+          case 0: ok = launch_pair16<4, 32>(c, p, ni, maxL); break;
+          case 1: ok = launch_pair16<5, 32>(c, p, ni, maxL); break;
+          case 2: ok = launch_pair16<6, 32>(c, p, ni, maxL); break;
+          default: ok = launch_pair16<8, 32>(c, p, ni, maxL); break;
+        }
+      } else {
+        switch (kb) {
+          case 0: ok = launch_pair16<8, 16>(c, p, ni, maxL); break;
+          case 1: ok = launch_pair16<10, 16>(c, p, ni, maxL); break;
+          case 2: ok = launch_pair16<12, 16>(c, p, ni, maxL); break;
+          default: ok = launch_pair16<16, 16>(c, p, ni, maxL); break;
+        }
       }
       if (!ok) return 0;
       MIAGPU_CUDA(cudaEventRecord(c->pev[2 * kb + 1], c->stream));
-      base += np;
+      base += ni;
     }
   }
 
@@ -750,7 +767,7 @@ extern "C" int miagpu_last_buckets(miagpu_ctx* c, int32_t* k, int32_t* reads, in
 extern "C" int miagpu_last_pair_buckets(miagpu_ctx* c, int32_t* k, int32_t* reads, int32_t* pairs, int64_t* cells, float* ms, int32_t* fallback_reads, int32_t* max_len16) {
   if (!c) { set_error("miagpu_last_pair_buckets: NULL ctx"); return 0; }
   for (int kb = 0; kb < P16_NKB; kb++) {
-    if (k) k[kb] = P16_K[kb];
+    if (k) k[kb] = P16_COLS[kb] / c->pair_g;
     if (reads) reads[kb] = c->pair_reads[kb];
     if (pairs) pairs[kb] = c->pair_pairs[kb];
     if (cells) cells[kb] = c->pair_cells[kb];
@@ -1031,6 +1048,22 @@ extern "C" int miagpu_consensus_natural(miagpu_ctx* c, const uint8_t* dropped_fr
 
 // ------------------------------------------------------- host policy (a12)
 // find_fsdb_score_cut (fsdb.c:269-383): double-precision sums in FSDB order.
+// The order-independent parts (integer sums, per-length maxima, the final per-read test) run on a few
+// host threads; the two rounded chains ssxy / ssxx run on one thread in the reference's order.
+static int host_threads(int64_t n) {
+  int t = (int)std::thread::hardware_concurrency();
+  t = std::max(1, std::min(t, 8));
+  if (const char* e = getenv("MIAGPU_HOST_THREADS")) t = std::max(1, atoi(e));
+  return (int)std::min<int64_t>(t, std::max<int64_t>(1, n / 65536));
+}
+template <typename F>
+static void parallel_chunks(int64_t n, int T, F f) {
+  if (T <= 1) { f(0, 0, n); return; }
+  std::vector<std::thread> th;
+  for (int t = 0; t < T; t++) th.emplace_back(f, t, n * t / T, n * (t + 1) / T);
+  for (auto& x : th) x.join();
+}
+
 extern "C" int miagpu_score_cut(int64_t n, const int32_t* seq_len, const int32_t* score, const uint8_t* unique_best,
                                 double* slope, double* intercept) {
   if (n < 0 || !seq_len || !score || !slope || !intercept) { set_error("miagpu_score_cut: bad argument"); return 0; }
@@ -1038,26 +1071,38 @@ extern "C" int miagpu_score_cut(int64_t n, const int32_t* seq_len, const int32_t
   // ssxy / ssxx are rounded at every step: those two chains keep the reference's FSDB order.
   // max slope_delta: for a fixed length the quotient is monotone in the score, so the maximum over reads
   // is the maximum over lengths of the quotient at that length's best score (same doubles, same result).
+  const int T = host_threads(n);
+  struct Part { int64_t sx = 0, sy = 0, cnt = 0, bad = -1; int32_t best[MAX_READ + 1]; };
+  std::vector<Part> parts(T);
+  parallel_chunks(n, T, [&](int t, int64_t lo, int64_t hi) {
+    Part& q = parts[t];
+    for (int l = 0; l <= MAX_READ; l++) q.best[l] = INT_MIN;
+    for (int64_t i = lo; i < hi; i++)
+      if ((!unique_best || unique_best[i]) && score[i] >= FIRST_ROUND_SCORE_CUTOFF) {
+        const int l = seq_len[i];
+        if (l < 0 || l > MAX_READ) { q.bad = i; return; }
+        q.sx += l; q.sy += score[i]; q.cnt++;
+        if (score[i] > q.best[l]) q.best[l] = score[i];
+      }
+  });
   int64_t sx = 0, sy = 0, j = 0;
-  std::vector<int32_t> sel;
-  sel.reserve((size_t)n);
   int32_t best_at_len[MAX_READ + 1];
   for (int l = 0; l <= MAX_READ; l++) best_at_len[l] = INT_MIN;
+  for (const Part& q : parts) {
+    if (q.bad >= 0) { set_error("miagpu_score_cut: seq_len[%lld] = %d out of range", (long long)q.bad, seq_len[q.bad]); return 0; }
+    sx += q.sx; sy += q.sy; j += q.cnt;
+    for (int l = 0; l <= MAX_READ; l++) best_at_len[l] = std::max(best_at_len[l], q.best[l]);
+  }
+  double xbar = (double)sx, ybar = (double)sy, ssxy = 0, ssxx = 0, max_delta = 0;
+  xbar /= j; ybar /= j;
+  double dx_of[MAX_READ + 1], dx2_of[MAX_READ + 1];                 // the same doubles the reference forms per read
+  for (int l = 0; l <= MAX_READ; l++) { dx_of[l] = l - xbar; dx2_of[l] = dx_of[l] * dx_of[l]; }
   for (int64_t i = 0; i < n; i++)
     if ((!unique_best || unique_best[i]) && score[i] >= FIRST_ROUND_SCORE_CUTOFF) {
       const int l = seq_len[i];
-      if (l < 0 || l > MAX_READ) { set_error("miagpu_score_cut: seq_len[%lld] = %d out of range", (long long)i, l); return 0; }
-      sx += l; sy += score[i]; sel.push_back((int32_t)i);
-      if (score[i] > best_at_len[l]) best_at_len[l] = score[i];
+      ssxy += dx_of[l] * (score[i] - ybar);
+      ssxx += dx2_of[l];
     }
-  j = (int64_t)sel.size();
-  double xbar = (double)sx, ybar = (double)sy, ssxy = 0, ssxx = 0, max_delta = 0;
-  xbar /= j; ybar /= j;
-  for (int32_t i : sel) {
-    const double dx = seq_len[i] - xbar;
-    ssxy += dx * (score[i] - ybar);
-    ssxx += dx * dx;
-  }
   const double bf = ssxy / ssxx, ib = ybar - bf * xbar;
   for (int l = 0; l <= MAX_READ; l++)
     if (best_at_len[l] != INT_MIN) {
@@ -1079,11 +1124,17 @@ extern "C" int miagpu_cull_flags(int64_t n, const int32_t* seq_len, const int32_
   if (slope <= 0) slope = 100.0;
   double min_score[MAX_READ + 1];                                  // the threshold depends on the length only
   for (int l = 0; l <= MAX_READ; l++) min_score[l] = hard_cut > 0 ? (double)hard_cut : (double)(intercept + (slope * l));
-  for (int64_t i = 0; i < n; i++) {
-    const int l = seq_len[i];
-    if (l < 0 || l > MAX_READ) { set_error("miagpu_cull_flags: seq_len[%lld] = %d out of range", (long long)i, l); return 0; }
-    below[i] = score[i] < min_score[l];
-  }
+  const int T = host_threads(n);
+  std::vector<int64_t> bad(T, -1);
+  parallel_chunks(n, T, [&](int t, int64_t lo, int64_t hi) {
+    for (int64_t i = lo; i < hi; i++) {
+      const int l = seq_len[i];
+      if (l < 0 || l > MAX_READ) { bad[t] = i; return; }
+      below[i] = score[i] < min_score[l];
+    }
+  });
+  for (int64_t x : bad)
+    if (x >= 0) { set_error("miagpu_cull_flags: seq_len[%lld] = %d out of range", (long long)x, seq_len[x]); return 0; }
   return 1;
 }
 
@@ -1095,6 +1146,123 @@ extern "C" int miagpu_consensus(miagpu_ctx* c, int64_t n_entries, const miagpu_e
   if (!miagpu_call(c, cons_code, gaps_out, counts_out, cons_out, cons_len)) return 0;
   c->ms_h2d = h2d;
   return 1;
+}
+
+// ---------------------------------------------------- one whole round, host buffers in and out
+__global__ void set_dropped_kernel(int64_t n, const uint8_t* flags, miagpu_entry* entries) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  entries[2 * i].dropped = flags[i];
+  entries[2 * i + 1].dropped = flags[i];
+}
+
+// One iteration of mia_main.c:931-963 for a batch that arrives in host memory: upload, realign every read
+// (reiterate_assembly), score cut (cull_maln_from_fsdb, host policy), column accumulation and base calling
+// (consensus_assembly_string).  Same results as miagpu_realign_host + miagpu_get_runs_packed +
+// miagpu_cull_flags + miagpu_consensus_natural called one after the other; here the host-side score cut runs
+// on a helper thread as soon as the scores have arrived while the stream keeps downloading the other
+// per-read outputs, packs the run lists and takes the per-position insert maxima (which ignore `dropped`).
+extern "C" int miagpu_iterate_host(miagpu_ctx* c, int64_t n, const uint8_t* bases, const int64_t* offsets, const uint8_t* rc,
+                                   const int32_t* as, const int32_t* ae, int32_t* score, int32_t* as_out, int32_t* ae_out,
+                                   int32_t* abr, int32_t* n_runs, uint8_t* status, uint16_t* packed_runs, int64_t capacity,
+                                   int64_t* total_runs, const int32_t* seq_len, const uint8_t* unique_best, int hard_cut,
+                                   int score_cut_set, double slope, double intercept, uint8_t* dropped, int cons_code,
+                                   int32_t* gaps_out, char* cons_out, int32_t* cons_len) {
+  if (!c || !c->have_pssm || !c->have_ref) { set_error("miagpu_iterate_host: set_pssm and set_reference first"); return 0; }
+  if (n <= 0 || !bases || !offsets || !rc || !as || !ae || !score || !seq_len || !dropped) { set_error("miagpu_iterate_host: bad argument"); return 0; }
+  MIAGPU_CUDA(cudaSetDevice(c->device));
+  if (n > 0x7fffffffLL / NBUCKET) { set_error("miagpu_iterate_host: at most %lld reads per batch", 0x7fffffffLL / NBUCKET); return 0; }
+  const int64_t total = offsets[n];
+  if (!c->d_bases.reserve(total + 16) || !c->d_off.reserve(n + 1) || !reserve_per_read(c, n)) return 0;
+  if (!c->d_entries.reserve(2 * n + 2) || !c->d_gaps.reserve(c->seq_len + 2) || !c->d_ins_off.reserve(c->seq_len + 2) ||
+      !c->d_dropf.reserve(n + 1) || !c->d_off2.reserve(2 * (n + 2))) return 0;
+  // ---- upload + realign
+  MIAGPU_CUDA(cudaEventRecord(c->ev[0], c->stream));
+  MIAGPU_CUDA(cudaMemcpyAsync(c->d_bases.p, bases, total, cudaMemcpyHostToDevice, c->stream));
+  MIAGPU_CUDA(cudaMemcpyAsync(c->d_off.p, offsets, (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+  MIAGPU_CUDA(cudaMemcpyAsync(c->d_rc.p, rc, n, cudaMemcpyHostToDevice, c->stream));
+  MIAGPU_CUDA(cudaMemcpyAsync(c->d_as.p, as, n * 4, cudaMemcpyHostToDevice, c->stream));
+  MIAGPU_CUDA(cudaMemcpyAsync(c->d_ae.p, ae, n * 4, cudaMemcpyHostToDevice, c->stream));
+  c->n = n; c->total_bases = total; c->max_read_len = -1;
+  MIAGPU_CUDA(cudaEventRecord(c->ev[1], c->stream));
+  if (!realign_device(c)) return 0;
+  const int launches_realign = c->launches;
+  MIAGPU_CUDA(cudaEventRecord(c->ev[2], c->stream));
+  // ---- scores first: the host policy starts as soon as they are here
+  MIAGPU_CUDA(cudaMemcpyAsync(score, c->d_score.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+  MIAGPU_CUDA(cudaEventRecord(c->ev[4], c->stream));
+  std::vector<uint8_t> below(n);
+  int cut_ok = 0;
+  char cut_err[256] = "";
+  std::thread cut([&] {
+    cudaSetDevice(c->device);
+    if (cudaEventSynchronize(c->ev[4]) != cudaSuccess) { snprintf(cut_err, sizeof(cut_err), "miagpu_iterate_host: waiting for the scores failed"); return; }
+    cut_ok = miagpu_cull_flags(n, seq_len, score, unique_best, hard_cut, score_cut_set, slope, intercept, below.data());
+    if (!cut_ok) snprintf(cut_err, sizeof(cut_err), "%s", miagpu_last_error());
+    else for (int64_t i = 0; i < n; i++) dropped[i] |= below[i];           // sticky (H10)
+  });
+  auto fail = [&](const char* what, cudaError_t e) { cut.join(); set_error("miagpu_iterate_host: %s: %s", what, cudaGetErrorString(e)); return 0; };
+#define IT_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(#call, e_); } while (0)
+  if (as_out) IT_CUDA(cudaMemcpyAsync(as_out, c->d_as_out.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (ae_out) IT_CUDA(cudaMemcpyAsync(ae_out, c->d_ae_out.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (abr) IT_CUDA(cudaMemcpyAsync(abr, c->d_abr.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (n_runs) IT_CUDA(cudaMemcpyAsync(n_runs, c->d_nruns.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (status) IT_CUDA(cudaMemcpyAsync(status, c->d_status.p, n, cudaMemcpyDeviceToHost, c->stream));
+  // ---- packed run lists + entries + per-position insert maxima, one host sync for the two totals
+  int64_t* cnt = c->d_off2.p;
+  int64_t* offs = c->d_off2.p + (n + 2);
+  clamp_runs_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, c->stream>>>(n, c->d_nruns.p, cnt);
+  size_t tmp = 0, tmp2 = 0;
+  IT_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, cnt, offs, n + 1, c->stream));
+  IT_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp2, c->d_gaps.p, c->d_ins_off.p, c->seq_len + 1, c->stream));
+  if (!c->d_cub.reserve(std::max(tmp, tmp2) + 16)) { cut.join(); return 0; }
+  IT_CUDA(cub::DeviceScan::ExclusiveSum(c->d_cub.p, tmp, cnt, offs, n + 1, c->stream));
+  int64_t tot = 0;
+  IT_CUDA(cudaMemcpyAsync(&tot, offs + n, 8, cudaMemcpyDeviceToHost, c->stream));
+  c->n_entries = 2 * n;
+  IT_CUDA(cudaMemsetAsync(c->d_gaps.p, 0, (c->seq_len + 2) * sizeof(int32_t), c->stream));
+  natural_entries_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, c->d_as_out.p, c->d_ae_out.p, c->d_nruns.p, c->d_runs.p,
+                                                                             c->d_status.p, c->seq_len, nullptr, nullptr, c->d_entries.p);
+  {
+    ConsParams p = cons_params(c);
+    entry_kernel<0><<<(unsigned)((c->n_entries * 32 + 255) / 256), 256, 0, c->stream>>>(p);
+  }
+  IT_CUDA(cub::DeviceScan::ExclusiveSum(c->d_cub.p, tmp2, c->d_gaps.p, c->d_ins_off.p, c->seq_len + 1, c->stream));
+  int32_t total_ins = 0;
+  IT_CUDA(cudaMemcpyAsync(&total_ins, c->d_ins_off.p + c->seq_len, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  IT_CUDA(cudaStreamSynchronize(c->stream));
+  float ms_h2d = 0, ms_k = 0;
+  IT_CUDA(cudaEventElapsedTime(&ms_h2d, c->ev[0], c->ev[1]));
+  IT_CUDA(cudaEventElapsedTime(&ms_k, c->ev[1], c->ev[2]));
+  if (total_runs) *total_runs = tot;
+  if (packed_runs && tot > capacity) { cut.join(); set_error("miagpu_iterate_host: %lld runs, capacity %lld", (long long)tot, (long long)capacity); return 0; }
+  if (!c->d_packed.reserve(tot + 1)) { cut.join(); return 0; }
+  c->n_cols = (int64_t)c->seq_len + total_ins;
+  if (!c->d_acc.reserve(c->n_cols * NPLANE) || !c->d_called.reserve(c->n_cols + 16)) { cut.join(); return 0; }
+  if (packed_runs) {
+    pack_runs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, c->d_nruns.p, offs, c->d_runs.p, c->d_packed.p);
+    if (tot) IT_CUDA(cudaMemcpyAsync(packed_runs, c->d_packed.p, tot * 2, cudaMemcpyDeviceToHost, c->stream));
+  }
+  IT_CUDA(cudaMemsetAsync(c->d_acc.p, 0, c->n_cols * NPLANE * sizeof(int32_t), c->stream));
+  // ---- the flags are needed from here on
+  cut.join();
+  if (!cut_ok) { set_error("%s", cut_err); return 0; }
+#undef IT_CUDA
+  MIAGPU_CUDA(cudaMemcpyAsync(c->d_dropf.p, dropped, n, cudaMemcpyHostToDevice, c->stream));
+  set_dropped_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, c->d_dropf.p, c->d_entries.p);
+  {
+    ConsParams p = cons_params(c);
+    entry_kernel<1><<<(unsigned)((c->n_entries * 32 + 255) / 256), 256, 0, c->stream>>>(p);
+  }
+  MIAGPU_CUDA(cudaGetLastError());
+  c->launches = launches_realign + 9;
+  c->cons_stage = 2;
+  MIAGPU_CUDA(cudaEventRecord(c->ev[3], c->stream));
+  if (!miagpu_call(c, cons_code, gaps_out, nullptr, cons_out, cons_len)) return 0;
+  c->launches = launches_realign + 10;
+  c->ms_h2d = ms_h2d;
+  c->ms_kernels = ms_k;
+  return realign_bucket_times(c);
 }
 
 // ------------------------------------------------------------------ pass 1

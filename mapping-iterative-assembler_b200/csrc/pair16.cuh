@@ -7,9 +7,11 @@
 // diagonal near the expected one.  Everything else is handed, read by read, to the 32-bit
 // kernel of realign.cuh through its work list -- never approximated.
 //
-// 1. Two reads of equal length share a warp: every 32-bit register holds the same DP cell of
-//    read A (low half) and read B (high half), so one VIADDMNMX.S16x2 / VIMNMX3.S16x2 /
-//    VIADD.16x2 does two cells.  Lane l owns columns [l*K, l*K+K) as in realign.cuh.
+// 1. Two reads of equal length share a group of G lanes: every 32-bit register holds the same DP
+//    cell of read A (low half) and read B (high half), so one VIADDMNMX.S16x2 / VIMNMX3.S16x2 /
+//    VIADD.16x2 does two cells.  Lane l of the group owns columns [l*K, l*K+K) as in realign.cuh.
+//    G = 16: a warp carries two such pairs (four reads of equal length), which halves the
+//    per-row cost of the cross-lane scan, the neighbour shuffles and the loop itself per cell.
 //
 // 2. Row frame.  Scores are kept as  V(r,c) = S(r,c) + GEP*r - OFF.  In this frame
 //      * the start-new candidate N_r = -(GOP + GEP*(r+1)) (mia.c:877-880) is the CONSTANT
@@ -59,8 +61,8 @@ struct Pair16Params {
   const uint8_t* rc;
   const int32_t* win_start;
   const int32_t* win_len;
-  const int32_t* pairs;          // [n_pairs][2] read ids, second = -1 for an unpaired read
-  const int32_t* n_pairs;        // device counter (layout kernel wrote it)
+  const int32_t* pairs;          // [n_items][32/G][2] read ids; -1 = empty slot (a work item's first slot is never empty)
+  const int32_t* n_items;        // device counter (layout kernel wrote it)
   int32_t* counter;
   const uint8_t* ref_codes;
   int32_t ref_bytes;
@@ -82,11 +84,15 @@ struct Pair16Params {
   int64_t scratch_words_per_warp;
 };
 
+// Band scratch of one warp: plane 0 = W0/4 uint4s [row][lane] (the lane's first W0 columns), plane 1 = KR
+// words [row][lane] (the remaining K % 4 columns).  Only the lanes whose columns intersect the band are ever written, so the
+// footprint that lives in L2 is ~(2*BAND+K)*4 B per row although the address range is the full matrix.
 template <int K>
 struct BandLayout {
-  static constexpr int NLS = (2 * P16_BAND) / K + 2;          // lane slots stored per row
-  static constexpr int KR = K <= 4 ? 0 : K <= 5 ? 1 : K <= 6 ? 2 : 4;   // words of the second plane per slot
-  static constexpr int WORDS_PER_ROW = NLS * (4 + KR);
+  static constexpr int REM = K % 4;
+  static constexpr int KR = REM == 0 ? 0 : REM == 1 ? 1 : REM == 2 ? 2 : 4;   // words of the second plane per lane
+  static constexpr int W0 = REM == 0 ? K : K - REM;                           // words of the first plane (uint4s)
+  static constexpr int WORDS_PER_ROW = 32 * (W0 + KR);
 };
 
 __device__ __forceinline__ uint32_t pack2(int v) { return ((uint32_t)v & 0xffffu) | ((uint32_t)v << 16); }
@@ -124,21 +130,25 @@ __device__ __forceinline__ uint32_t mad16(uint32_t hi, uint32_t lo) {   // hi * 
   return r;
 }
 
-// dynamic shared memory: [prof16 (PROF16_N + 8) int16][rowoff WARPS*2*P16_MAXL u16][ref codes]
-template <int K>
+// dynamic shared memory: [prof16 (PROF16_N + 8) int16][rowoff WARPS*(32/G)*2*P16_MAXL u16][ref codes]
+template <int K, int G>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) pair16_kernel(Pair16Params p) {
-  static_assert(K >= 4 && K <= 8, "columns per lane");
+  static_assert(K >= 4 && K <= 16 && (G == 16 || G == 32), "columns per lane / lanes per pair");
   using BL = BandLayout<K>;
+  constexpr int NP = 32 / G;                         // pairs per warp
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ __align__(8) uint64_t ref_bar;
   int16_t* s_prof = reinterpret_cast<int16_t*>(smem);
   constexpr int PROF_BYTES = (PROF16_N + 8) * 2;
   uint16_t* s_rowoff = reinterpret_cast<uint16_t*>(smem + PROF_BYTES);
-  uint8_t* s_ref = smem + PROF_BYTES + WARPS_PER_BLOCK * 2 * P16_MAXL * 2;
+  uint8_t* s_ref = smem + PROF_BYTES + WARPS_PER_BLOCK * NP * 2 * P16_MAXL * 2;
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
+  const int sub = lane & (G - 1);                    // lane within the pair's group
+  const int hw = lane / G;                           // which pair of the warp
+  const unsigned gmask = G == 32 ? 0xffffffffu : (0xffffu << (hw * 16));
 
   if (p.ref_in_smem) {
     if (tid == 0) {
@@ -155,8 +165,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) pair16_kernel(Pair16Para
   if (p.ref_in_smem) mbar_wait(&ref_bar, 0);
   __syncthreads();
 
-  uint16_t* rowA = s_rowoff + (warp * 2 + 0) * P16_MAXL;
-  uint16_t* rowB = s_rowoff + (warp * 2 + 1) * P16_MAXL;
+  uint16_t* rowA = s_rowoff + ((warp * NP + hw) * 2 + 0) * P16_MAXL;
+  uint16_t* rowB = s_rowoff + ((warp * NP + hw) * 2 + 1) * P16_MAXL;
   const uint32_t prof_base = smem_u32(s_prof);
   const uint32_t addr_gep = prof_base + PROF16_N * 2;
   const int64_t gwarp = (int64_t)blockIdx.x * WARPS_PER_BLOCK + warp;
@@ -172,25 +182,27 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) pair16_kernel(Pair16Para
   constexpr uint32_t SENT2 = ((uint32_t)(-32768 + GEP * K + GEP) & 0xffffu) * 0x10001u;
   constexpr uint32_t CLK2 = ((uint32_t)(-32768 + GEP * K) & 0xffffu) * 0x10001u;
   constexpr uint32_t NEG2 = 0x80008000u;
-  const int n_pairs = *p.n_pairs;
+  const int n_items = *p.n_items;
 
   for (;;) {
     int item = 0;
     if (lane == 0) item = atomicAdd(p.counter, 1);
     item = __shfl_sync(0xffffffffu, item, 0);
-    if (item >= n_pairs) break;
-    const int rdA = p.pairs[2 * item];
-    int rdB = p.pairs[2 * item + 1];
-    const bool hasB = rdB >= 0;
-    if (!hasB) rdB = rdA;
+    if (item >= n_items) break;
+    int rdA = p.pairs[2 * (item * NP + hw)];
+    int rdB = p.pairs[2 * (item * NP + hw) + 1];
+    const bool hasA = rdA >= 0;                       // an empty pair slot recomputes the warp's first pair and writes nothing
+    if (!hasA) rdA = p.pairs[2 * (item * NP)];
+    const bool hasB = hasA && rdB >= 0;
+    if (rdB < 0 || !hasA) rdB = rdA;
     const int64_t oA = p.off[rdA], oB = p.off[rdB];
-    const int L = (int)(p.off[rdA + 1] - oA);
+    const int L = (int)(p.off[rdA + 1] - oA);         // the same for every read of the work item
     const int wsA = p.win_start[rdA], wsB = p.win_start[rdB];
     const int lenA = p.win_len[rdA], lenB = p.win_len[rdB];
     const int sA = p.rc[rdA] ? 1 : 0, sB = p.rc[rdB] ? 1 : 0;
 
     __syncwarp();
-    for (int r = lane; r < L; r += 32) {
+    for (int r = sub; r < L; r += G) {
       const int d = sm_depth(r, L);
       rowA[r] = (uint16_t)(prof_row_index(sA, d, base_code(p.bases[oA + r])) * 2);
       rowB[r] = (uint16_t)(prof_row_index(sB, d, base_code(p.bases[oB + r])) * 2);
@@ -198,7 +210,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) pair16_kernel(Pair16Para
     uint32_t cA[K], cB[K];
 #pragma unroll
     for (int j = 0; j < K; j++) {
-      const int c = lane * K + j;
+      const int c = sub * K + j;
       int a = 4, b = 4;
       if (c < lenA) a = p.ref_in_smem ? s_ref[wsA + c] : p.ref_codes[wsA + c];
       if (c < lenB) b = p.ref_in_smem ? s_ref[wsB + c] : p.ref_codes[wsB + c];
@@ -207,17 +219,20 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) pair16_kernel(Pair16Para
     }
     __syncwarp();
 
-    // band bookkeeping: lanes [lane_lo(r), lane_lo(r) + NLS) hold the diagonals 50 +- BAND of row r
+    // band bookkeeping: row r keeps the lanes that own a column c with c - r in [DIAG0 - BAND, DIAG0 + BAND]:
+    // sub*K + K-1 >= r + DIAG0 - BAND  and  sub*K <= r + DIAG0 + BAND
     uint4* plane0 = reinterpret_cast<uint4*>(band);
-    uint32_t* plane1 = band + (size_t)L * BL::NLS * 4;
+    uint32_t* plane1 = band + (size_t)L * 32 * BL::W0;
     auto store_row = [&](int r, const uint32_t* W) {
-      const int slot = lane - (r + P16_DIAG0 - P16_BAND) / K;
-      if ((unsigned)slot < (unsigned)BL::NLS) {
-        const int e = r * BL::NLS + slot;
-        plane0[e] = make_uint4(W[0], W[1], W[2], W[3]);
-        if (BL::KR == 1) plane1[e] = W[4];
-        if (BL::KR == 2) *reinterpret_cast<uint2*>(plane1 + 2 * e) = make_uint2(W[4], W[5 < K ? 5 : 0]);
-        if (BL::KR == 4) *reinterpret_cast<uint4*>(plane1 + 4 * e) = make_uint4(W[4], W[5 < K ? 5 : 0], W[6 < K ? 6 : 0], W[7 < K ? 7 : 0]);
+      const int u = sub * K + (K - 1) - (P16_DIAG0 - P16_BAND) - r;
+      if ((unsigned)u <= (unsigned)(2 * P16_BAND + K - 1)) {
+        const int e = r * 32 + lane;
+#pragma unroll
+        for (int q = 0; q < BL::W0 / 4; q++) plane0[e * (BL::W0 / 4) + q] = make_uint4(W[4 * q], W[4 * q + 1], W[4 * q + 2], W[4 * q + 3]);
+        constexpr int B1 = BL::W0;                    // first column of the second plane
+        if (BL::KR == 1) plane1[e] = W[B1 < K ? B1 : 0];
+        if (BL::KR == 2) *reinterpret_cast<uint2*>(plane1 + 2 * e) = make_uint2(W[B1 < K ? B1 : 0], W[B1 + 1 < K ? B1 + 1 : 0]);
+        if (BL::KR == 4) *reinterpret_cast<uint4*>(plane1 + 4 * e) = make_uint4(W[B1 < K ? B1 : 0], W[B1 + 1 < K ? B1 + 1 : 0], W[B1 + 2 < K ? B1 + 2 : 0], W[B1 + 3 < K ? B1 + 3 : 0]);
       }
     };
 
@@ -235,29 +250,28 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) pair16_kernel(Pair16Para
 
     for (int r = 1; r < L; r++) {
       const uint32_t pa = prof_base + rowA[r], pb = prof_base + rowB[r];
-      const uint32_t l2 = __shfl_up_sync(0xffffffffu, W[K - 2], 1);
-      const uint32_t l1 = __shfl_up_sync(0xffffffffu, W[K - 1], 1);
+      const uint32_t l2 = __shfl_up_sync(0xffffffffu, W[K - 2], 1, G);
+      const uint32_t l1 = __shfl_up_sync(0xffffffffu, W[K - 1], 1, G);
       // per-lane chain of column-gap candidates (incoming prefix taken as -inf)
       uint32_t T[K];
-      T[0] = lane ? __vadd2(l2, M_OPEN) : SENT2;
-      T[1] = __viaddmax_s16x2(T[0], M_GEP, lane ? __vadd2(l1, M_OPEN) : SENT2);
+      T[0] = sub ? __vadd2(l2, M_OPEN) : SENT2;
+      T[1] = __viaddmax_s16x2(T[0], M_GEP, sub ? __vadd2(l1, M_OPEN) : SENT2);
 #pragma unroll
       for (int j = 2; j < K; j++) T[j] = __viaddmax_s16x2(T[j - 1], M_GEP, __vadd2(W[j - 2], M_OPEN));
       // inclusive cross-lane scan of the lane totals, decay GEP*K per lane, clamped so nothing wraps
       uint32_t X = T[K - 1];
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t y = __shfl_up_sync(0xffffffffu, X, d);
+      for (int d = 1; d < G; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, X, d, G);
         const uint32_t cl = ((uint32_t)(-32768 + GEP * K * d) & 0xffffu) * 0x10001u;
         const uint32_t dec = ((uint32_t)(-GEP * K * d) & 0xffffu) * 0x10001u;
-        const uint32_t z = __viaddmax_s16x2(__vmaxs2(y, cl), dec, X);
-        if (lane >= d) X = z;
+        X = __viaddmax_s16x2(__vmaxs2(y, cl), dec, X);    // lanes < d get their own X back from the shuffle: max(X, max(X,cl)-dec) = X
       }
-      uint32_t qin = __shfl_up_sync(0xffffffffu, X, 1);
-      if (lane == 0) qin = SENT2;
+      uint32_t qin = __shfl_up_sync(0xffffffffu, X, 1, G);
+      if (sub == 0) qin = SENT2;
       qin = __vmaxs2(qin, CLK2);
 
-      uint32_t D = lane ? l1 : NCMP2;           // column 0: S = sub + N, never start-new (mia.c:805-822)
+      uint32_t D = sub ? l1 : NCMP2;            // column 0: S = sub + N, never start-new (mia.c:805-822)
 #pragma unroll
       for (int j = 0; j < K; j++) {
         const uint32_t mj = ((uint32_t)(-GEP * (j + 1)) & 0xffffu) * 0x10001u;
@@ -272,9 +286,11 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) pair16_kernel(Pair16Para
       store_row(r, W);
     }
 
-    // ---- max_sg_score + in-band diagonal traceback, one read (half) at a time
+    // ---- max_sg_score + in-band diagonal traceback, one read (half) at a time, each group for its own pair
     __syncwarp();
-    for (int h = 0; h < (hasB ? 2 : 1); h++) {
+#pragma unroll 1
+    for (int h = 0; h < 2; h++) {
+      const bool live = h ? hasB : hasA;              // uniform within the group
       const int rd = h ? rdB : rdA;
       const int ws = h ? wsB : wsA;
       const int len1 = h ? lenB : lenA;
@@ -282,12 +298,12 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) pair16_kernel(Pair16Para
       int best = INT_MIN;
 #pragma unroll
       for (int j = 0; j < K; j++) {
-        const int c = lane * K + j;
+        const int c = sub * K + j;
         const int v = h ? ((int)W[j] >> 16) : (int)(short)(W[j] & 0xffffu);
         const int key = (c < len1) ? v * 512 + (KEY_IDX_MASK - c) : INT_MIN;
         best = max(best, key);
       }
-      best = __reduce_max_sync(0xffffffffu, best);
+      best = __reduce_max_sync(gmask, best);
       const int aec = KEY_IDX_MASK - (best & KEY_IDX_MASK);
       const int score = (best >> 9) + OFF - GEP * (L - 1);
       const int nsteps = min(L - 1, aec);
@@ -295,23 +311,23 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) pair16_kernel(Pair16Para
       bool ok = dg >= P16_DIAG0 - P16_BAND && dg <= P16_DIAG0 + P16_BAND;
       auto cell = [&](int r, int c) -> int {
         const int lc = c / K, j = c - lc * K;
-        const int e = r * BL::NLS + (lc - (r + P16_DIAG0 - P16_BAND) / K);
-        const uint32_t w = j < 4 ? __ldcg(band + 4 * e + j) : __ldcg(plane1 + BL::KR * e + (j - 4));
+        const int e = r * 32 + hw * G + lc;
+        const uint32_t w = j < BL::W0 ? __ldcg(band + BL::W0 * e + j) : __ldcg(plane1 + BL::KR * e + (j - BL::W0));
         return h ? ((int)w >> 16) : (int)(short)(w & 0xffffu);
       };
-      for (int t0 = 0; ok && t0 < nsteps; t0 += 32) {
-        const int t = t0 + lane;
+      for (int t0 = 0; ok && t0 < nsteps; t0 += G) {
+        const int t = t0 + sub;
         bool good = true;
         if (t < nsteps) {
           const int r = L - 1 - t, c = aec - t;
           const int v = cell(r, c), dv = cell(r - 1, c - 1);
           const int code = p.ref_in_smem ? s_ref[ws + c] : p.ref_codes[ws + c];
-          const int sub = lds_s16(prof_base + rowX[r] + code * 2);      // sub + GEP; V(r) = V(r-1) + sub + GEP on a diagonal move
-          good = (v - sub == dv) && (dv >= NCMP);
+          const int sb = lds_s16(prof_base + rowX[r] + code * 2);       // sub + GEP; V(r) = V(r-1) + sub + GEP on a diagonal move
+          good = (v - sb == dv) && (dv >= NCMP);
         }
-        ok = __all_sync(0xffffffffu, good);
+        ok = __all_sync(gmask, good);
       }
-      if (lane == 0) {
+      if (sub == 0 && live) {
         if (ok) {
           p.score[rd] = score;
           p.as_out[rd] = aec - nsteps + ws;

@@ -36,9 +36,11 @@ def _mutate(rng, s, sub, indel):
     return "".join(out)
 
 
-@pytest.mark.parametrize("matrix,K,lens", [("onepass", 5, (20, 75)), ("ancient", 6, (60, 92)), ("onepass", 8, (100, 134)), ("flat", 4, (1, 28))])
-def test_model_matches_oracle(model, oracle, matrix, K, lens):
-    rng = np.random.default_rng(1000 * K + len(matrix))
+@pytest.mark.parametrize("matrix,K,G,lens", [("onepass", 5, 32, (20, 75)), ("ancient", 6, 32, (60, 92)), ("onepass", 8, 32, (100, 134)),
+                                             ("flat", 4, 32, (1, 28)), ("onepass", 10, 16, (20, 75)), ("ancient", 12, 16, (60, 92)),
+                                             ("onepass", 16, 16, (100, 131)), ("flat", 8, 16, (1, 28))])
+def test_model_matches_oracle(model, oracle, matrix, K, G, lens):
+    rng = np.random.default_rng(1000 * K + len(matrix) + G)
     if matrix == "flat":
         sm = oracle.flat_pssm()
     else:
@@ -63,12 +65,12 @@ def test_model_matches_oracle(model, oracle, matrix, K, lens):
             frag = "".join("ACGT"[i] for i in rng.integers(0, 4, L))          # unrelated read: start-new everywhere
         frag = frag[:L] if frag else "A"
         L = len(frag)
-        len1 = min(L + 100, 32 * K)
+        len1 = min(L + 100, G * K)
         ref = genome[:len1]
         m = smr if it % 2 else sm
         o = oracle.align(ref, frag, m, sg5=1)
         out = (C.c_int * 6)()
-        ok = model.p16_model(ref.encode(), len1, frag.encode(), L, np.ascontiguousarray(m).ctypes.data_as(ip), K, 32, 16, 50, out)
+        ok = model.p16_model(ref.encode(), len1, frag.encode(), L, np.ascontiguousarray(m).ctypes.data_as(ip), K, G, 16, 50, out)
         assert ok
         assert out[5] == 0, f"16-bit wrap in case {it} (L={L})"
         assert (out[0], out[1]) == (o["score"], o["aec"]), (it, L, list(out), o["score"], o["aec"])
