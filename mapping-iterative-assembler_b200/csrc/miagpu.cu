@@ -141,7 +141,6 @@ struct miagpu_ctx {
   int launches = 0;
 };
 
-static void pair16_limits(const miagpu_ctx* c, int K, int* off16, int* lmax);
 
 // -------------------------------------------------------------------- misc
 extern "C" const char* miagpu_last_error(void) { return g_err; }
@@ -230,18 +229,16 @@ extern "C" int miagpu_set_pssm(miagpu_ctx* c, const int32_t* fwd) {
   MIAGPU_CUDA(cudaMemcpyAsync(c->d_prof.p, prof.data(), PROF_INTS * 4, cudaMemcpyHostToDevice, c->stream));
   MIAGPU_CUDA(cudaMemcpyAsync(c->d_sm.p, c->sm_f, sizeof(c->sm_f), cudaMemcpyHostToDevice, c->stream));
   MIAGPU_CUDA(cudaMemcpyAsync(c->d_sm.p + MIAGPU_PSSM_INTS, c->sm_r, sizeof(c->sm_r), cudaMemcpyHostToDevice, c->stream));
-  // 16-bit profile of the pair kernel: sub + GEP (row-frame shift), entry PROF16_N = GEP (start-new addend)
+  // 16-bit profile of the pair kernel
   std::vector<int16_t> prof16(PROF16_N + 8, 0);
-  for (int i = 0; i < PROF16_N; i++) prof16[i] = (int16_t)(prof[i] + GEP);
-  prof16[PROF16_N] = (int16_t)GEP;
+  for (int i = 0; i < PROF16_N; i++) prof16[i] = (int16_t)prof[i];
   if (!c->d_prof16.reserve(PROF16_N + 8)) return 0;
   MIAGPU_CUDA(cudaMemcpyAsync(c->d_prof16.p, prof16.data(), (PROF16_N + 8) * 2, cudaMemcpyHostToDevice, c->stream));
   MIAGPU_CUDA(cudaStreamSynchronize(c->stream));
   c->pssm_min = *std::min_element(fwd, fwd + MIAGPU_PSSM_INTS);
   c->pssm_max = *std::max_element(fwd, fwd + MIAGPU_PSSM_INTS);
-  int off16 = 0;
-  pair16_limits(c, 16, &off16, &c->lmax16);           // most columns per lane: the most conservative OFF
-  if (c->pssm_max + GEP <= 0 || off16 < 4 * (GOP + GEP)) c->lmax16 = 0;   // degenerate matrices: 32-bit kernels only
+  c->lmax16 = std::min(p16_lmax(4, c->pssm_max), P16_MAXL);   // longest read any pair class holds (fewest columns per lane)
+  if (c->pssm_max + GEP <= 0) c->lmax16 = 0;                   // degenerate matrices: 32-bit kernels only
   c->have_pssm = true;
   return 1;
 }
@@ -337,11 +334,13 @@ extern "C" int miagpu_upload_reads(miagpu_ctx* c, int64_t n, const uint8_t* base
 
 // ----------------------------------------------------------------- realign
 // Window rule of reiterate_assembly (mia_main.c:190-212) + width class.  A read goes either to the
-// work list of its 32-bit width bucket or, when the 16-bit pair kernel can take it (lmax16 > 0:
-// short enough for the 16-bit frame, window = [as-50, ...) so that the expected diagonal is 50,
-// at most 256 columns), into the (pair class, read length) histogram that pairs reads of equal length.
-__global__ void classify_kernel(int64_t n, const int64_t* off, const int32_t* as, const int32_t* ae, int wrap_len, int lmax16,
+// work list of its 32-bit width bucket or, when the 16-bit pair kernel can take it (short enough for
+// the 16-bit frame of its width class, at most 256 columns), into the (pair class, read length)
+// histogram that pairs reads of equal length.
+struct PairLmax { int v[P16_NKB]; };                 // longest read each pair class takes (0 = pair kernels off)
+__global__ void classify_kernel(int64_t n, const int64_t* off, const int32_t* as, const int32_t* ae, int wrap_len, PairLmax lm,
                                 int32_t* win_start, int32_t* win_len, int32_t* lists, uint8_t* kind, int32_t* meta) {
+  const int lmax16 = max(max(lm.v[0], lm.v[1]), max(lm.v[2], lm.v[3]));
   __shared__ int s_cnt[NBUCKET], s_base[NBUCKET], s_maxL[NBUCKET], s_pop[NBUCKET];
   __shared__ unsigned long long s_cells[NBUCKET];
   __shared__ int s_hist[P16_KEYS];
@@ -366,7 +365,7 @@ __global__ void classify_kernel(int64_t n, const int64_t* off, const int32_t* as
     b = bucket32_of(len1);
     if (L <= 0 || L > MAX_READ) b = NBUCKET - 1;
     const int kb = p16_class(len1);
-    const bool elig = lmax16 > 0 && b != NBUCKET - 1 && kb >= 0 && !whole && L <= lmax16 && L <= P16_MAXL && as[i] - rs == P16_DIAG0;
+    const bool elig = b != NBUCKET - 1 && kb >= 0 && !whole && L <= lm.v[kb < 0 ? 0 : kb];
     atomicAdd(&s_pop[b], 1);
     atomicMax(&s_maxL[b], L);
     atomicAdd(&s_cells[b], (unsigned long long)L * (unsigned long long)len1);
@@ -528,24 +527,10 @@ static int launch_bucket(miagpu_ctx* c, RealignParams p, int maxL) {
   return 1;
 }
 
-// OFF of the 16-bit row frame and the longest read it can hold, from the extreme matrix entries
-// (same formulas as tests/model/pair16_model.c:p16_limits, which is checked against the oracle).
-static void pair16_limits(const miagpu_ctx* c, int K, int* off16, int* lmax) {
-  const int mn = std::min(c->pssm_min, 0), mx = std::max(c->pssm_max, 0);
-  const int a = 32768 - 2 * (GOP + GEP) - GEP * (K - 1) + mn;
-  const int b = 32768 - (GOP + 2 * GEP) - GEP * K - GEP - 1;
-  const int off = std::min(a, b) - 32;
-  const int inc = mx + GEP;
-  int lm = 1 + (32767 + off - mx) / inc;
-  *off16 = off;
-  *lmax = std::min(lm, P16_MAXL);
-}
-
 template <int K, int G>
 static int launch_pair16(miagpu_ctx* c, Pair16Params p, int n_pairs, int maxL) {
-  using BL = BandLayout<K>;
   bool ref_in_smem = c->ref_bytes <= 160 * 1024;
-  size_t smem = (PROF16_N + 8) * 2 + WARPS_PER_BLOCK * (32 / G) * 2 * P16_MAXL * 2 + (ref_in_smem ? c->ref_bytes : 0);
+  size_t smem = p16_smem_fixed<G>() + (ref_in_smem ? c->ref_bytes : 0);
   MIAGPU_CUDA(cudaFuncSetAttribute((pair16_kernel<K, G>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   MIAGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (pair16_kernel<K, G>), WARPS_PER_BLOCK * 32, smem));
@@ -555,14 +540,9 @@ static int launch_pair16(miagpu_ctx* c, Pair16Params p, int n_pairs, int maxL) {
   per_sm = std::min(per_sm, cap);
   int blocks = std::min(c->num_sms * per_sm, (n_pairs + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
   if (blocks < 1) return 1;
-  int64_t words = (int64_t)std::max(maxL, 1) * BL::WORDS_PER_ROW;
-  words = (words + 31) / 32 * 32;                                // 128-byte aligned per warp
-  if (!c->d_scratch.reserve((size_t)words * blocks * WARPS_PER_BLOCK)) return 0;
-  int lm = 0;
-  pair16_limits(c, K, &p.off16, &lm);
-  p.scratch = c->d_scratch.p;
-  p.scratch_words_per_warp = words;
+  (void)maxL;
   p.ref_in_smem = ref_in_smem;
+  p.gep2 = K2(2 * GEP);
   pair16_kernel<K, G><<<blocks, WARPS_PER_BLOCK * 32, smem, c->stream>>>(p);
   MIAGPU_CUDA(cudaGetLastError());
   c->launches++;
@@ -579,15 +559,17 @@ static int realign_device(miagpu_ctx* c) {
   if (n == 0) return 1;
   int lmax16 = c->lmax16;
   if (const char* e = getenv("MIAGPU_PAIR16")) if (atoi(e) == 0) lmax16 = 0;
-  MIAGPU_CUDA(cudaMemsetAsync(c->d_meta.p, 0, META_WORDS * sizeof(int32_t), c->stream));
-  classify_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, c->d_off.p, c->d_as.p, c->d_ae.p, c->wrap_len, lmax16,
-                                                                     c->d_win_start.p, c->d_win_len.p, c->d_lists.p, c->d_kind.p, c->d_meta.p);
-  MIAGPU_CUDA(cudaGetLastError());
-  c->launches++;
   int pair_g = 16;                                   // lanes per pair: 16 = two pairs per warp
   if (const char* e = getenv("MIAGPU_PAIR_G")) pair_g = atoi(e) == 32 ? 32 : 16;
   const int np = 32 / pair_g;
   c->pair_g = pair_g;
+  PairLmax lm{};
+  for (int kb = 0; kb < P16_NKB; kb++) lm.v[kb] = lmax16 > 0 ? std::min(p16_lmax(P16_COLS[kb] / pair_g, c->pssm_max), P16_MAXL) : 0;
+  MIAGPU_CUDA(cudaMemsetAsync(c->d_meta.p, 0, META_WORDS * sizeof(int32_t), c->stream));
+  classify_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, c->d_off.p, c->d_as.p, c->d_ae.p, c->wrap_len, lm,
+                                                                     c->d_win_start.p, c->d_win_len.p, c->d_lists.p, c->d_kind.p, c->d_meta.p);
+  MIAGPU_CUDA(cudaGetLastError());
+  c->launches++;
   if (lmax16 > 0) {
     pair_layout_kernel<<<1, 32, 0, c->stream>>>(c->d_meta.p, np);
     MIAGPU_CUDA(cudaGetLastError());

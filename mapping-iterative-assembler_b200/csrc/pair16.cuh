@@ -1,55 +1,66 @@
-// pair16.cuh -- windowed PSSM semi-global DP in packed 16-bit SIMD (s16x2), TWO READS PER WARP,
-// with an in-band diagonal traceback (sm_100a).
+// pair16.cuh -- windowed PSSM semi-global DP in packed 16-bit SIMD (u16x2), TWO READS PER REGISTER,
+// with the pure-diagonal traceback folded into the forward pass (sm_100a).
 //
 // Same contract as realign.cuh (reiterate_assembly's per-read body, mia_main.c:178-257:
 // dyn_prog mia.c:740-981, max_sg_score 1278-1302, find_align_begin 612-637,
 // populate_pwaln_to_begin 1440-1497), for the common case: short reads whose path is a plain
-// diagonal near the expected one.  Everything else is handed, read by read, to the 32-bit
-// kernel of realign.cuh through its work list -- never approximated.
+// diagonal.  Everything else is handed, read by read, to the 32-bit kernel of realign.cuh through
+// its work list -- never approximated.
 //
 // 1. Two reads of equal length share a group of G lanes: every 32-bit register holds the same DP
-//    cell of read A (low half) and read B (high half), so one VIADDMNMX.S16x2 / VIMNMX3.S16x2 /
-//    VIADD.16x2 does two cells.  Lane l of the group owns columns [l*K, l*K+K) as in realign.cuh.
-//    G = 16: a warp carries two such pairs (four reads of equal length), which halves the
-//    per-row cost of the cross-lane scan, the neighbour shuffles and the loop itself per cell.
+//    cell of read A (low half) and read B (high half), so one VIADDMNMX.U16x2 / VIMNMX3.U16x2 does
+//    two cells.  Lane l of the group owns columns [l*K, l*K+K) as in realign.cuh.  G = 16: a warp
+//    carries two such pairs (four reads of equal length).
 //
-// 2. Row frame.  Scores are kept as  V(r,c) = S(r,c) + GEP*r - OFF.  In this frame
-//      * the start-new candidate N_r = -(GOP + GEP*(r+1)) (mia.c:877-880) is the CONSTANT
-//        NCMP = -(GOP+2*GEP) - OFF when compared in row r-1's frame, and a start-new cell is the
-//        constant NCMP + GEP;
-//      * the row-gap candidate max_j S[j][c-1] - P(r-j-1) (mia.c:856-868) is  max_j V(j,c-1) - GOP:
-//        a plain running maximum, no per-row decay;
-//      * the column-gap candidate keeps its GEP decay per column (mia.c:838-850):
-//        Q(c) = max(Q(c-1) - GEP, V(r-1,c-2) - (GOP+GEP)), evaluated as a per-lane chain T plus a
-//        5-step cross-lane max-scan with decay GEP*K per lane.
-//    A gap candidate below NCMP can never be chosen nor change the start-new test, so the scan
-//    clamps from below before subtracting its decay: no 16-bit operation wraps (checked lane
-//    for lane against the oracle by tests/model/pair16_model.c).  OFF and the longest read the
-//    frame can hold follow from the matrices' extreme entries (pair16_limits in miagpu.cu).
+// 2. Lane frame (checked lane for lane against the oracle by tests/model/pair16_model.c).  A cell of
+//    column c = l*K + j is held as  V(r,c) = S(r,c) + GEP*r + GEP*j - OFF  (stored biased, V + 32768,
+//    so that the halves order as unsigned numbers); a value taken from another lane is converted by
+//    -GEP*K per lane of distance.  In this frame none of dyn_prog's candidates decays:
+//      diagonal    V(r-1,c-1)                    + 2*GEP
+//      column gap  max_{k<=c-2} V(r-1,k) - GOP   + 2*GEP      (mia.c:838-850: a plain running maximum,
+//                                                              per-lane chain seeded by a cross-lane scan)
+//      row gap     max_{i<=r-2} V(i,c-1) - GOP   + 2*GEP      (mia.c:856-868: a plain running maximum)
+//    and the start-new candidate N_r (mia.c:877-880) is the per-column constant NCMP_j + 2*GEP.
+//    A candidate below NCMP_j can never be chosen nor change the start-new test, so the scan clamps
+//    from below before converting: no 16-bit operation wraps.  OFF and the longest read the frame
+//    holds follow from the matrices' extreme entries (pair16_limits in miagpu.cu).
 //
-// 3. Only scores are computed: no arg-max indices, no trace words.  The start-new rule "S = N,
-//    substitution score NOT added" is a predicated move of the profile address (the cell reads
-//    the constant GEP instead of its substitution score), not a select on the result.
+// 3. One table read per cell pair, adds on the FMA pipe.  The substitution scores of a DP row depend
+//    on the column only through the two reference codes (a of read A's window, b of read B's), so each
+//    group keeps a 25-entry table of 64-bit entries  tab[a*5+b] = { (int32) subA(r,a), subB(r,b) << 16 }
+//    for the current row in shared memory (double-buffered, built for row r+1 while row r is
+//    computed): one LDS.64 per cell pair.  Because the halves are biased-unsigned and never leave
+//    [0, 65535], plain 32-bit adds (IMAD, FMA pipe -- the 16x2 min/max unit is the busy one) add each
+//    half exactly: the sign extension of the low entry cancels its borrow.  The start-new rule
+//    "S = N, substitution score NOT added" (mia.c:910-915) is the predicate on those two adds; the
+//    predicates come out of the VIMNMX.U16x2 that applies the floor NCMP_j.
 //
-// 4. Traceback.  Cells within +-P16_BAND diagonals of the expected one (window start = as - 50)
-//    are stored (16 bit per cell, a few lanes per row) in a per-warp scratch that stays in L2.
-//    From the first maximum of the last row the warp checks, 32 rows at a time, that every cell
-//    up to row 0 / column 0 satisfies  V(r,c) - sub(r,c) == V(r-1,c-1)  and  V(r-1,c-1) >= N_r:
-//    exactly the condition under which dyn_prog stores trace 0 there.  If it holds the alignment
-//    is one M run; if not (gap, start-new cell, jump stored as 0, path outside the band) the read
-//    is appended to the 32-bit kernel's list.
+// 4. Traceback without a trace.  find_align_begin walks a plain diagonal exactly when every cell on it
+//    (rows and columns >= 1) stored trace 0, i.e. max(D, Gc, Gr, NCMP_j) == D there.  The kernel ORs
+//    bad(r,c) = max(...) ^ D down the diagonals (acc(r,c) = acc(r-1,c-1) | bad(r,c), one LOP3 per cell
+//    pair, the carry moving with the diagonal operand): acc == 0 in the first-maximum cell of the last
+//    row means the alignment is one M run from (abr, abc) = (L-1-n, aec-n), n = min(L-1, aec).
+//    Otherwise (gap, start-new cell on the path, jump stored as trace 0) the read is appended to the
+//    32-bit kernel's list.  No trace matrix, no band, no scratch memory.
 #pragma once
 #include "common.cuh"
 #include "realign.cuh"
 
 namespace miagpu {
 
-constexpr int P16_BAND = 16;
-constexpr int P16_DIAG0 = REALIGN_BUFFER;
 constexpr int P16_MAXL = 144;                       // rows the shared row-offset arrays hold
-constexpr int PROF16_N = 2 * NMAT * 5 * PROF_ROW_INTS;   // int16 entries (sub + GEP); entry PROF16_N holds GEP
-constexpr int P16_NKB = 4;                          // width classes K = 4, 5, 6, 8 (128 / 160 / 192 / 256 columns)
+constexpr int PROF16_N = 2 * NMAT * 5 * PROF_ROW_INTS;   // int16 entries
+constexpr int P16_NKB = 4;                          // width classes: 128 / 160 / 192 / 256 columns
+constexpr int P16_TAB_WORDS = 64;                   // 25 64-bit entries, padded to 32
 
+// OFF of the lane frame: the lowest intermediate, (lowest cell = -OFF-GOP-GEP+min entry) converted to the next lane
+// (-GEP*K) minus GOP, must stay above -32768 for every matrix set_pssm accepts (|entry| <= PSSM_ABS_LIMIT).
+__host__ __device__ constexpr int p16_off(int K) { return 32768 - 2 * GOP - GEP - PSSM_ABS_LIMIT - GEP * K - 32; }
+// longest read the frame holds: L*max_entry + GEP*(L-1) + GEP*(K-1) - OFF <= 32767
+__host__ __device__ inline int p16_lmax(int K, int max_entry) {
+  const int inc = max_entry + GEP;
+  return inc > 0 ? (32767 + p16_off(K) - GEP * (K - 2)) / inc : MAX_READ;
+}
 __host__ __device__ inline int p16_class(int len1) { return len1 <= 128 ? 0 : len1 <= 160 ? 1 : len1 <= 192 ? 2 : len1 <= 256 ? 3 : -1; }
 __host__ __device__ inline int bucket32_of(int len1) {
   return len1 <= 64 ? 0 : len1 <= 128 ? 1 : len1 <= 160 ? 2 : len1 <= 192 ? 3 : len1 <= 224 ? 4 : len1 <= 256 ? 5 : len1 <= 320 ? 6 : len1 <= 384 ? 7 : len1 <= 512 ? 8 : 9;
@@ -68,7 +79,6 @@ struct Pair16Params {
   int32_t ref_bytes;
   int32_t ref_in_smem;
   const int16_t* prof16;
-  int32_t off16;
   int32_t* score;
   int32_t* as_out;
   int32_t* ae_out;
@@ -80,68 +90,62 @@ struct Pair16Params {
   int32_t* list_counts;          // their fill counters
   int64_t n_reads;
   int32_t* n_fallback;           // statistics
-  uint32_t* scratch;
-  int64_t scratch_words_per_warp;
+  uint32_t gep2;                 // K2(2*GEP), passed as data so that ptxas keeps this add an IMAD (FMA pipe) instead of folding it into a VIADD
 };
 
-// Band scratch of one warp: plane 0 = W0/4 uint4s [row][lane] (the lane's first W0 columns), plane 1 = KR
-// words [row][lane] (the remaining K % 4 columns).  Only the lanes whose columns intersect the band are ever written, so the
-// footprint that lives in L2 is ~(2*BAND+K)*4 B per row although the address range is the full matrix.
-template <int K>
-struct BandLayout {
-  static constexpr int REM = K % 4;
-  static constexpr int KR = REM == 0 ? 0 : REM == 1 ? 1 : REM == 2 ? 2 : 4;   // words of the second plane per lane
-  static constexpr int W0 = REM == 0 ? K : K - REM;                           // words of the first plane (uint4s)
-  static constexpr int WORDS_PER_ROW = 32 * (W0 + KR);
-};
+// packed constants: B2(v) = the cell value v in both halves (biased), K2(k) = the addend k in both halves
+__host__ __device__ constexpr uint32_t B2(int v) { return ((uint32_t)(v + 32768) & 0xffffu) * 0x10001u; }
+__host__ __device__ constexpr uint32_t K2(int k) { return ((uint32_t)k & 0xffffu) * 0x10001u; }
 
-__device__ __forceinline__ uint32_t pack2(int v) { return ((uint32_t)v & 0xffffu) | ((uint32_t)v << 16); }
-__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
-  uint32_t v;
-  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
-  return v;
-}
 __device__ __forceinline__ int lds_s16(uint32_t addr) {
   int v;
   asm volatile("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(addr));
   return v;
 }
-// max(best, ncmp) per half; where a half of `best` is below ncmp (start-new) the matching profile
-// address is replaced by the address of the constant GEP.  The setp.eq pattern is the one ptxas
-// folds into VIMNMX.S16x2 with two predicate outputs; the moves stay predicated (FMA-pipe IMAD.MOV).
-__device__ __forceinline__ uint32_t vmax_start(uint32_t best, uint32_t ncmp, uint32_t& addr_lo, uint32_t& addr_hi, uint32_t addr_gep) {
-  uint32_t r;
-  asm("{.reg .pred pu, pv;\n\t"
-      ".reg .s16 h0, h1, h2, h3;\n\t"
-      "max.s16x2 %0, %3, %4;\n\t"
-      "mov.b32 {h0, h1}, %0;\n\t"
-      "mov.b32 {h2, h3}, %3;\n\t"
-      "setp.eq.s16 pv, h0, h2;\n\t"
-      "setp.eq.s16 pu, h1, h3;\n\t"
-      "@!pv mov.b32 %1, %5;\n\t"
-      "@!pu mov.b32 %2, %5;}\n\t"
-      : "=r"(r), "+r"(addr_lo), "+r"(addr_hi)
-      : "r"(best), "r"(ncmp), "r"(addr_gep));
-  return r;
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
 }
-__device__ __forceinline__ uint32_t mad16(uint32_t hi, uint32_t lo) {   // hi * 65536 + lo on the FMA pipe
-  uint32_t r;
-  asm("mad.lo.u32 %0, %1, 65536, %2;" : "=r"(r) : "r"(hi), "r"(lo));
-  return r;
+// One DP cell pair.  bp = max(best, ncmp) per half; w = bp + 2*GEP + (start-new ? 0 : sub) per half, as 32-bit adds
+// (exact, see 3. above).  The setp.eq pattern is the one ptxas folds into VIMNMX.U16x2 with two predicate
+// outputs; mad.lo keeps the adds on the FMA pipe.
+__device__ __forceinline__ uint32_t cell_pair(uint32_t best, uint32_t ncmp, uint32_t ea, uint32_t eb, uint32_t gep2, uint32_t& bp) {
+  uint32_t w;
+  asm("{.reg .pred pu, pv;\n\t"
+      ".reg .u16 h0, h1, h2, h3;\n\t"
+      "max.u16x2 %1, %2, %3;\n\t"
+      "mov.b32 {h0, h1}, %1;\n\t"
+      "mov.b32 {h2, h3}, %2;\n\t"
+      "setp.eq.u16 pv, h0, h2;\n\t"
+      "setp.eq.u16 pu, h1, h3;\n\t"
+      "mad.lo.u32 %0, %1, 1, %6;\n\t"
+      "@pv mad.lo.u32 %0, %4, 1, %0;\n\t"
+      "@pu mad.lo.u32 %0, %5, 1, %0;}\n\t"
+      : "=&r"(w), "=&r"(bp)
+      : "r"(best), "r"(ncmp), "r"(ea), "r"(eb), "r"(gep2));
+  return w;
 }
 
-// dynamic shared memory: [prof16 (PROF16_N + 8) int16][rowoff WARPS*(32/G)*2*P16_MAXL u16][ref codes]
+// dynamic shared memory: [prof16 (PROF16_N + 8) int16][rowoff WARPS*(32/G)*2*P16_MAXL u16][tab WARPS*(32/G)*2*32 u32][ref codes]
+template <int G>
+__host__ __device__ constexpr int p16_smem_fixed() {
+  return (PROF16_N + 8) * 2 + WARPS_PER_BLOCK * (32 / G) * 2 * P16_MAXL * 2 + WARPS_PER_BLOCK * (32 / G) * 2 * P16_TAB_WORDS * 4;
+}
+
 template <int K, int G>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) pair16_kernel(Pair16Params p) {
   static_assert(K >= 4 && K <= 16 && (G == 16 || G == 32), "columns per lane / lanes per pair");
-  using BL = BandLayout<K>;
   constexpr int NP = 32 / G;                         // pairs per warp
+  constexpr int NE = (25 + G - 1) / G;               // table entries a lane builds per row
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ __align__(8) uint64_t ref_bar;
   int16_t* s_prof = reinterpret_cast<int16_t*>(smem);
   constexpr int PROF_BYTES = (PROF16_N + 8) * 2;
+  constexpr int ROWOFF_BYTES = WARPS_PER_BLOCK * NP * 2 * P16_MAXL * 2;
   uint16_t* s_rowoff = reinterpret_cast<uint16_t*>(smem + PROF_BYTES);
-  uint8_t* s_ref = smem + PROF_BYTES + WARPS_PER_BLOCK * NP * 2 * P16_MAXL * 2;
+  uint32_t* s_tab = reinterpret_cast<uint32_t*>(smem + PROF_BYTES + ROWOFF_BYTES);
+  uint8_t* s_ref = smem + p16_smem_fixed<G>();
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -167,22 +171,31 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) pair16_kernel(Pair16Para
 
   uint16_t* rowA = s_rowoff + ((warp * NP + hw) * 2 + 0) * P16_MAXL;
   uint16_t* rowB = s_rowoff + ((warp * NP + hw) * 2 + 1) * P16_MAXL;
+  uint32_t* tab = s_tab + (warp * NP + hw) * 2 * P16_TAB_WORDS;     // two buffers of P16_TAB_WORDS
   const uint32_t prof_base = smem_u32(s_prof);
-  const uint32_t addr_gep = prof_base + PROF16_N * 2;
-  const int64_t gwarp = (int64_t)blockIdx.x * WARPS_PER_BLOCK + warp;
-  uint32_t* band = p.scratch + gwarp * p.scratch_words_per_warp;
 
-  const int OFF = p.off16;
-  const int NCMP = -(GOP + 2 * GEP) - OFF;
-  uint32_t NCMP2 = pack2(NCMP);
-  const uint32_t SEED2 = pack2(-OFF - GEP);
-  constexpr uint32_t M_OPEN = ((uint32_t)(-(GOP + GEP)) & 0xffffu) * 0x10001u;     // -(GOP+GEP) in both halves
-  constexpr uint32_t M_GEP = ((uint32_t)(-GEP) & 0xffffu) * 0x10001u;
-  constexpr uint32_t M_GOP = ((uint32_t)(-GOP) & 0xffffu) * 0x10001u;
-  constexpr uint32_t SENT2 = ((uint32_t)(-32768 + GEP * K + GEP) & 0xffffu) * 0x10001u;
-  constexpr uint32_t CLK2 = ((uint32_t)(-32768 + GEP * K) & 0xffffu) * 0x10001u;
-  constexpr uint32_t NEG2 = 0x80008000u;
+  constexpr int OFF = p16_off(K);
+  constexpr int CONV = GEP * K;                      // frame shift per lane of distance
+  constexpr int SENT = -32768 + GOP;                 // "-infinity" that survives one -GOP
   const int n_items = *p.n_items;
+  const uint32_t gep2 = p.gep2;
+
+  // table entries this lane builds every row: e = sub + G*t -> (a, b) = (e / 5, e % 5)
+  uint32_t eoa[NE], eob[NE];
+#pragma unroll
+  for (int t = 0; t < NE; t++) {
+    const int e = min(sub + G * t, 24);
+    eoa[t] = (e / 5) * 2;
+    eob[t] = (e % 5) * 2;
+  }
+  auto build_table = [&](int r, uint32_t* dst) {
+    const uint32_t pa = prof_base + rowA[r], pb = prof_base + rowB[r];
+#pragma unroll
+    for (int t = 0; t < NE; t++) {
+      const uint2 v = make_uint2((uint32_t)lds_s16(pa + eoa[t]), lds_u16(pb + eob[t]) << 16);
+      if (sub + G * t < 25) reinterpret_cast<uint2*>(dst)[sub + G * t] = v;
+    }
+  };
 
   for (;;) {
     int item = 0;
@@ -207,126 +220,103 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) pair16_kernel(Pair16Para
       rowA[r] = (uint16_t)(prof_row_index(sA, d, base_code(p.bases[oA + r])) * 2);
       rowB[r] = (uint16_t)(prof_row_index(sB, d, base_code(p.bases[oB + r])) * 2);
     }
-    uint32_t cA[K], cB[K];
+    uint32_t comb[K];                                 // byte offset of the column's (a, b) entry
 #pragma unroll
     for (int j = 0; j < K; j++) {
       const int c = sub * K + j;
       int a = 4, b = 4;
       if (c < lenA) a = p.ref_in_smem ? s_ref[wsA + c] : p.ref_codes[wsA + c];
       if (c < lenB) b = p.ref_in_smem ? s_ref[wsB + c] : p.ref_codes[wsB + c];
-      cA[j] = a * 2;
-      cB[j] = b * 2;
+      comb[j] = (uint32_t)(a * 5 + b) * 8;
     }
     __syncwarp();
+    build_table(0, tab);
+    __syncwarp();
 
-    // band bookkeeping: row r keeps the lanes that own a column c with c - r in [DIAG0 - BAND, DIAG0 + BAND]:
-    // sub*K + K-1 >= r + DIAG0 - BAND  and  sub*K <= r + DIAG0 + BAND
-    uint4* plane0 = reinterpret_cast<uint4*>(band);
-    uint32_t* plane1 = band + (size_t)L * 32 * BL::W0;
-    auto store_row = [&](int r, const uint32_t* W) {
-      const int u = sub * K + (K - 1) - (P16_DIAG0 - P16_BAND) - r;
-      if ((unsigned)u <= (unsigned)(2 * P16_BAND + K - 1)) {
-        const int e = r * 32 + lane;
-#pragma unroll
-        for (int q = 0; q < BL::W0 / 4; q++) plane0[e * (BL::W0 / 4) + q] = make_uint4(W[4 * q], W[4 * q + 1], W[4 * q + 2], W[4 * q + 3]);
-        constexpr int B1 = BL::W0;                    // first column of the second plane
-        if (BL::KR == 1) plane1[e] = W[B1 < K ? B1 : 0];
-        if (BL::KR == 2) *reinterpret_cast<uint2*>(plane1 + 2 * e) = make_uint2(W[B1 < K ? B1 : 0], W[B1 + 1 < K ? B1 + 1 : 0]);
-        if (BL::KR == 4) *reinterpret_cast<uint4*>(plane1 + 4 * e) = make_uint4(W[B1 < K ? B1 : 0], W[B1 + 1 < K ? B1 + 1 : 0], W[B1 + 2 < K ? B1 + 2 : 0], W[B1 + 3 < K ? B1 + 3 : 0]);
-      }
-    };
-
-    // ---- row 0 (mia.c:769-785): V = sub - OFF
-    uint32_t W[K], Rg[K];
+    // ---- row 0 (mia.c:769-785): V = sub + GEP*j - OFF
+    uint32_t W[K], Rg[K], acc[K];
     {
-      const uint32_t pa = prof_base + rowA[0], pb = prof_base + rowB[0];
+      if (L > 1) build_table(1, tab + P16_TAB_WORDS);
 #pragma unroll
       for (int j = 0; j < K; j++) {
-        W[j] = __vadd2(mad16(lds_u16(pb + cB[j]), lds_u16(pa + cA[j])), SEED2);
-        Rg[j] = NEG2;
+        const uint2 e = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(tab) + comb[j]);
+        W[j] = B2(GEP * j - OFF) + e.x + e.y;         // biased seed + entries: 32-bit adds, as in cell_pair
+        Rg[j] = B2(-32768);
+        acc[j] = 0;
       }
+      __syncwarp();
     }
-    store_row(0, W);
 
     for (int r = 1; r < L; r++) {
-      const uint32_t pa = prof_base + rowA[r], pb = prof_base + rowB[r];
-      const uint32_t l2 = __shfl_up_sync(0xffffffffu, W[K - 2], 1, G);
-      const uint32_t l1 = __shfl_up_sync(0xffffffffu, W[K - 1], 1, G);
-      // per-lane chain of column-gap candidates (incoming prefix taken as -inf)
-      uint32_t T[K];
-      T[0] = sub ? __vadd2(l2, M_OPEN) : SENT2;
-      T[1] = __viaddmax_s16x2(T[0], M_GEP, sub ? __vadd2(l1, M_OPEN) : SENT2);
+      const uint32_t* cur = tab + (r & 1) * P16_TAB_WORDS;
+      if (r + 1 < L) build_table(r + 1, tab + ((r + 1) & 1) * P16_TAB_WORDS);
+      uint32_t l2 = __shfl_up_sync(0xffffffffu, W[K - 2], 1, G);
+      uint32_t l1 = __shfl_up_sync(0xffffffffu, W[K - 1], 1, G);
+      uint32_t ain = __shfl_up_sync(0xffffffffu, acc[K - 1], 1, G);
+      l2 = sub ? __vadd2(l2, K2(-CONV)) : B2(SENT);
+      l1 = sub ? __vadd2(l1, K2(-CONV)) : B2(SENT);
+      if (sub == 0) ain = 0;
+      // lane total of the column-gap candidates E = {l2, l1, W[0..K-3]}
+      uint32_t X = __vimax3_u16x2(l2, l1, W[0]);
 #pragma unroll
-      for (int j = 2; j < K; j++) T[j] = __viaddmax_s16x2(T[j - 1], M_GEP, __vadd2(W[j - 2], M_OPEN));
-      // inclusive cross-lane scan of the lane totals, decay GEP*K per lane, clamped so nothing wraps
-      uint32_t X = T[K - 1];
+      for (int j = 1; j + 1 < K - 2; j += 2) X = __vimax3_u16x2(X, W[j], W[j + 1]);
+      if ((K - 3) & 1) X = __vmaxu2(X, W[K - 3]);
+      X = __vadd2(X, K2(-GOP));
+      // inclusive cross-lane scan, converting by CONV per lane, clamped so nothing wraps
 #pragma unroll
       for (int d = 1; d < G; d <<= 1) {
         const uint32_t y = __shfl_up_sync(0xffffffffu, X, d, G);
-        const uint32_t cl = ((uint32_t)(-32768 + GEP * K * d) & 0xffffu) * 0x10001u;
-        const uint32_t dec = ((uint32_t)(-GEP * K * d) & 0xffffu) * 0x10001u;
-        X = __viaddmax_s16x2(__vmaxs2(y, cl), dec, X);    // lanes < d get their own X back from the shuffle: max(X, max(X,cl)-dec) = X
+        X = __viaddmax_u16x2(__vmaxu2(y, B2(-32768 + CONV * d)), K2(-CONV * d), X);    // lanes < d get their own X back: max(X, max(X,cl)-dec) = X
       }
-      uint32_t qin = __shfl_up_sync(0xffffffffu, X, 1, G);
-      if (sub == 0) qin = SENT2;
-      qin = __vmaxs2(qin, CLK2);
-
-      uint32_t D = sub ? l1 : NCMP2;            // column 0: S = sub + N, never start-new (mia.c:805-822)
+      uint32_t q = __shfl_up_sync(0xffffffffu, X, 1, G);
+      q = sub ? __vadd2(__vmaxu2(q, B2(-32768 + CONV)), K2(-CONV)) : B2(-32768);
+      // column-gap chain (mia.c:838-850): Q[j] = max over columns <= c-2 of V - GOP
+      uint32_t Q[K];
+      Q[0] = __viaddmax_u16x2(l2, K2(-GOP), q);
+      Q[1] = __viaddmax_u16x2(l1, K2(-GOP), Q[0]);
 #pragma unroll
-      for (int j = 0; j < K; j++) {
-        const uint32_t mj = ((uint32_t)(-GEP * (j + 1)) & 0xffffu) * 0x10001u;
-        const uint32_t Q = __viaddmax_s16x2(qin, mj, T[j]);
-        const uint32_t best = __vimax3_s16x2(D, Q, Rg[j]);
-        Rg[j] = __viaddmax_s16x2(D, M_GOP, Rg[j]);          // row r-1 joins the row-gap candidates of column c-1
-        uint32_t aA = pa + cA[j], aB = pb + cB[j];
-        const uint32_t bp = vmax_start(best, NCMP2, aA, aB, addr_gep);
-        D = W[j];
-        W[j] = __vadd2(bp, mad16(lds_u16(aB), lds_u16(aA)));
+      for (int j = 2; j < K; j++) Q[j] = __viaddmax_u16x2(W[j - 2], K2(-GOP), Q[j - 1]);
+      // cells, right to left so that W[j-1] and acc[j-1] are still row r-1's
+#pragma unroll
+      for (int j = K - 1; j >= 0; j--) {
+        const uint32_t ncmpj = B2(-(GOP + 3 * GEP) - OFF) + K2(GEP * j);     // NCMP_j: compile-time after unrolling
+        uint32_t D, ad;
+        if (j > 0) { D = W[j - 1]; ad = acc[j - 1]; }
+        else { D = sub ? l1 : ncmpj; ad = ain; }       // column 0: S = sub + N, never start-new (mia.c:805-822)
+        const uint32_t best = __vimax3_u16x2(D, Q[j], Rg[j]);
+        Rg[j] = __viaddmax_u16x2(D, K2(-GOP), Rg[j]);          // row r-1 joins the row-gap candidates of column c-1
+        const uint2 e = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(cur) + comb[j]);
+        uint32_t bp;
+        W[j] = cell_pair(best, ncmpj, e.x, e.y, gep2, bp);
+        acc[j] = ad | (bp ^ D);
       }
-      store_row(r, W);
+      __syncwarp();
     }
 
-    // ---- max_sg_score + in-band diagonal traceback, one read (half) at a time, each group for its own pair
-    __syncwarp();
+    // ---- max_sg_score (first maximum of the last row) + the diagonal verdict, one read (half) at a time
 #pragma unroll 1
     for (int h = 0; h < 2; h++) {
       const bool live = h ? hasB : hasA;              // uniform within the group
       const int rd = h ? rdB : rdA;
       const int ws = h ? wsB : wsA;
       const int len1 = h ? lenB : lenA;
-      const uint16_t* rowX = h ? rowB : rowA;
       int best = INT_MIN;
 #pragma unroll
       for (int j = 0; j < K; j++) {
         const int c = sub * K + j;
-        const int v = h ? ((int)W[j] >> 16) : (int)(short)(W[j] & 0xffffu);
+        const int v = (int)(h ? (W[j] >> 16) : (W[j] & 0xffffu)) - 32768 - GEP * j;
         const int key = (c < len1) ? v * 512 + (KEY_IDX_MASK - c) : INT_MIN;
         best = max(best, key);
       }
       best = __reduce_max_sync(gmask, best);
       const int aec = KEY_IDX_MASK - (best & KEY_IDX_MASK);
       const int score = (best >> 9) + OFF - GEP * (L - 1);
+      bool bad = false;
+#pragma unroll
+      for (int j = 0; j < K; j++)
+        if (sub * K + j == aec) bad = (h ? (acc[j] >> 16) : (acc[j] & 0xffffu)) != 0;
+      const bool ok = !__any_sync(gmask, bad);
       const int nsteps = min(L - 1, aec);
-      const int dg = aec - (L - 1);
-      bool ok = dg >= P16_DIAG0 - P16_BAND && dg <= P16_DIAG0 + P16_BAND;
-      auto cell = [&](int r, int c) -> int {
-        const int lc = c / K, j = c - lc * K;
-        const int e = r * 32 + hw * G + lc;
-        const uint32_t w = j < BL::W0 ? __ldcg(band + BL::W0 * e + j) : __ldcg(plane1 + BL::KR * e + (j - BL::W0));
-        return h ? ((int)w >> 16) : (int)(short)(w & 0xffffu);
-      };
-      for (int t0 = 0; ok && t0 < nsteps; t0 += G) {
-        const int t = t0 + sub;
-        bool good = true;
-        if (t < nsteps) {
-          const int r = L - 1 - t, c = aec - t;
-          const int v = cell(r, c), dv = cell(r - 1, c - 1);
-          const int code = p.ref_in_smem ? s_ref[ws + c] : p.ref_codes[ws + c];
-          const int sb = lds_s16(prof_base + rowX[r] + code * 2);       // sub + GEP; V(r) = V(r-1) + sub + GEP on a diagonal move
-          good = (v - sb == dv) && (dv >= NCMP);
-        }
-        ok = __all_sync(gmask, good);
-      }
       if (sub == 0 && live) {
         if (ok) {
           p.score[rd] = score;

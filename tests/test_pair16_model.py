@@ -1,4 +1,4 @@
-"""The 16-bit V-frame arithmetic of the SIMD realign kernel (csrc/pair16.cuh), modelled on the CPU
+"""The 16-bit lane-frame arithmetic of the SIMD realign kernel (csrc/pair16.cuh), modelled on the CPU
 (tests/model/pair16_model.c), against the oracle's dyn_prog restatement: scores, end cells and
 pure-diagonal tracebacks must agree and no 16-bit operation may wrap."""
 import ctypes as C
@@ -19,7 +19,7 @@ def model():
         subprocess.run(["gcc", "-O2", "-shared", "-fPIC", "-o", so, src], check=True)
     lib = C.CDLL(so)
     ip = C.POINTER(C.c_int)
-    lib.p16_model.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, ip, C.c_int, C.c_int, C.c_int, C.c_int, ip]
+    lib.p16_model.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, ip, C.c_int, C.c_int, ip]
     lib.p16_limits.argtypes = [ip, C.c_int, ip, ip]
     return lib
 
@@ -36,9 +36,9 @@ def _mutate(rng, s, sub, indel):
     return "".join(out)
 
 
-@pytest.mark.parametrize("matrix,K,G,lens", [("onepass", 5, 32, (20, 75)), ("ancient", 6, 32, (60, 92)), ("onepass", 8, 32, (100, 134)),
+@pytest.mark.parametrize("matrix,K,G,lens", [("onepass", 5, 32, (20, 75)), ("ancient", 6, 32, (60, 92)), ("onepass", 8, 32, (100, 130)),
                                              ("flat", 4, 32, (1, 28)), ("onepass", 10, 16, (20, 75)), ("ancient", 12, 16, (60, 92)),
-                                             ("onepass", 16, 16, (100, 131)), ("flat", 8, 16, (1, 28))])
+                                             ("onepass", 16, 16, (100, 122)), ("flat", 8, 16, (1, 28))])
 def test_model_matches_oracle(model, oracle, matrix, K, G, lens):
     rng = np.random.default_rng(1000 * K + len(matrix) + G)
     if matrix == "flat":
@@ -70,7 +70,7 @@ def test_model_matches_oracle(model, oracle, matrix, K, G, lens):
         m = smr if it % 2 else sm
         o = oracle.align(ref, frag, m, sg5=1)
         out = (C.c_int * 6)()
-        ok = model.p16_model(ref.encode(), len1, frag.encode(), L, np.ascontiguousarray(m).ctypes.data_as(ip), K, G, 16, 50, out)
+        ok = model.p16_model(ref.encode(), len1, frag.encode(), L, np.ascontiguousarray(m).ctypes.data_as(ip), K, G, out)
         assert ok
         assert out[5] == 0, f"16-bit wrap in case {it} (L={L})"
         assert (out[0], out[1]) == (o["score"], o["aec"]), (it, L, list(out), o["score"], o["aec"])
@@ -80,9 +80,8 @@ def test_model_matches_oracle(model, oracle, matrix, K, G, lens):
             assert pure_ref and (out[3], out[4]) == (o["abr"], o["abc"]), (it, list(out), o)
         else:
             n_gap += 1
-            # giving up is always safe (the 32-bit kernel redoes the read); it should be rare for plain in-band
+            # giving up is always safe (the 32-bit kernel redoes the read); it should be rare for plain
             # diagonals -- it still happens when a jump to row/column 0 is stored as trace 0 and READ as a diagonal
             # move by find_align_begin (mia.c:619, H2): the strings show no gap but the scores do
-            d = o["aec"] - (L - 1)
-            n_spurious += pure_ref and abs(d - 50) <= 16
+            n_spurious += pure_ref
     assert n_pure > 20 and n_gap > 5 and n_spurious * 20 < n_pure, (n_pure, n_gap, n_spurious)
