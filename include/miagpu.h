@@ -265,11 +265,11 @@ int miagpu_realign_resident( miagpu_ctx* ctx );
  * reads, DP cells, kernel ms (CUDA events on the library's stream); MIAGPU_NBUCKET entries */
 int miagpu_last_buckets( miagpu_ctx* ctx, int32_t* k, int32_t* reads,
                          int64_t* cells, float* ms );
-/* the 16-bit SIMD pair kernels of the last realign (csrc/pair16.cuh): per width class (4 entries)
+/* the 16-bit SIMD pair kernels of the last realign (csrc/pair16.cuh): per width class (MIAGPU_NPAIRCLASS entries)
  * columns-per-lane K, reads taken, pairs formed, DP cells of those reads, kernel ms; plus the number
  * of reads the pair kernels handed on to the 32-bit kernels (counted in miagpu_last_buckets as well)
  * and the longest read the 16-bit frame holds with the current matrices (0 = pair kernels off) */
-#define MIAGPU_NPAIRCLASS 4
+#define MIAGPU_NPAIRCLASS 8
 int miagpu_last_pair_buckets( miagpu_ctx* ctx, int32_t* k, int32_t* reads, int32_t* pairs,
                               int64_t* cells, float* ms, int32_t* fallback_reads,
                               int32_t* max_len16 );

@@ -262,11 +262,11 @@ class MiaGpu:
 
     def last_pair_buckets(self):
         """16-bit pair kernels of the last realign: (list of per-class dicts, reads handed to the 32-bit kernels, max read length)."""
-        k, r, pr = np.zeros(4, np.int32), np.zeros(4, np.int32), np.zeros(4, np.int32)
-        cells, ms = np.zeros(4, np.int64), np.zeros(4, np.float32)
+        k, r, pr = np.zeros(8, np.int32), np.zeros(8, np.int32), np.zeros(8, np.int32)       # MIAGPU_NPAIRCLASS
+        cells, ms = np.zeros(8, np.int64), np.zeros(8, np.float32)
         fb, ml = C.c_int32(), C.c_int32()
         self._ck(self.lib.miagpu_last_pair_buckets(self.h, _ptr(k), _ptr(r), _ptr(pr), _ptr(cells), _ptr(ms), C.byref(fb), C.byref(ml)))
-        return ([dict(K=int(k[i]), reads=int(r[i]), pairs=int(pr[i]), cells=int(cells[i]), ms=float(ms[i])) for i in range(4) if r[i]],
+        return ([dict(K=int(k[i]), reads=int(r[i]), pairs=int(pr[i]), cells=int(cells[i]), ms=float(ms[i])) for i in range(8) if r[i]],
                 fb.value, ml.value)
 
     def accumulate_gaps(self, entries):

@@ -49,7 +49,7 @@ struct DevBuf {
 
 constexpr int NBUCKET = 10;                                  // 9 register-tiled widths + "big"
 static const int BUCKET_K[NBUCKET] = {2, 4, 5, 6, 7, 8, 10, 12, 16, 0};
-static const int P16_COLS[P16_NKB] = {128, 160, 192, 256};   // columns of the pair kernels' width classes
+static const int P16_COLS[P16_NKB] = {128, 144, 160, 176, 192, 208, 224, 256};   // columns of the pair kernels' width classes
 
 // d_meta layout (int32 words)
 constexpr int META_COUNT = 0;        // [16] fill counters of the 32-bit work lists
@@ -57,18 +57,19 @@ constexpr int META_WORK = 16;        // [16] dynamic work-fetch counters of the 
 constexpr int META_MAXL = 32;        // [16] longest read per width class (all reads of the class)
 constexpr int META_CELLS = 48;       // [16] int64 DP cells per width class (all reads of the class)
 constexpr int META_POP = 80;         // [16] reads per width class (direct + pair-eligible)
-constexpr int META_NPAIRS = 96;      // [4]  pairs per pair class
-constexpr int META_MAXLEN = 100;     // scratch of max_len_kernel
-constexpr int META_PWORK = 104;      // [4]  work-fetch counters of the pair kernels
-constexpr int META_NFALL = 108;      // reads handed from the pair kernels to the 32-bit kernels
-constexpr int META_PREADS = 112;     // [4]  eligible reads per pair class
-constexpr int META_PCELLS = 120;     // [4]  int64 cells of the eligible reads
-constexpr int META_HOST = 128;       // words copied to the host after classification
+constexpr int META_NPAIRS = 96;      // [8]  work items per pair class
+constexpr int META_PWORK = 104;      // [8]  work-fetch counters of the pair kernels
+constexpr int META_PREADS = 112;     // [8]  eligible reads per pair class
+constexpr int META_PCELLS = 120;     // [8]  int64 cells of the eligible reads
+constexpr int META_MAXLEN = 136;     // scratch of max_len_kernel
+constexpr int META_NFALL = 137;      // reads handed from the pair kernels to the 32-bit kernels
+constexpr int META_HOST = 144;       // words copied to the host after classification
 constexpr int P16_KEYS = P16_NKB * (P16_MAXL + 1);
 constexpr int META_HIST = 256;       // [P16_KEYS] eligible reads per (pair class, read length)
-constexpr int META_PSTART = 1024;    // [P16_KEYS] first pair of the key
-constexpr int META_CURSOR = 2048;    // [P16_KEYS] scatter cursors
-constexpr int META_WORDS = 3072;
+constexpr int META_PSTART = META_HIST + 1280;    // [P16_KEYS] first pair of the key
+constexpr int META_CURSOR = META_PSTART + 1280;  // [P16_KEYS] scatter cursors
+constexpr int META_WORDS = META_CURSOR + 1280;
+static_assert(P16_KEYS <= 1280 && P16_NKB == 8, "meta layout");
 
 }  // namespace miagpu
 
@@ -340,7 +341,8 @@ extern "C" int miagpu_upload_reads(miagpu_ctx* c, int64_t n, const uint8_t* base
 struct PairLmax { int v[P16_NKB]; };                 // longest read each pair class takes (0 = pair kernels off)
 __global__ void classify_kernel(int64_t n, const int64_t* off, const int32_t* as, const int32_t* ae, int wrap_len, PairLmax lm,
                                 int32_t* win_start, int32_t* win_len, int32_t* lists, uint8_t* kind, int32_t* meta) {
-  const int lmax16 = max(max(lm.v[0], lm.v[1]), max(lm.v[2], lm.v[3]));
+  int lmax16 = 0;
+  for (int k = 0; k < P16_NKB; k++) lmax16 = max(lmax16, lm.v[k]);
   __shared__ int s_cnt[NBUCKET], s_base[NBUCKET], s_maxL[NBUCKET], s_pop[NBUCKET];
   __shared__ unsigned long long s_cells[NBUCKET];
   __shared__ int s_hist[P16_KEYS];
@@ -559,8 +561,7 @@ static int realign_device(miagpu_ctx* c) {
   if (n == 0) return 1;
   int lmax16 = c->lmax16;
   if (const char* e = getenv("MIAGPU_PAIR16")) if (atoi(e) == 0) lmax16 = 0;
-  int pair_g = 16;                                   // lanes per pair: 16 = two pairs per warp
-  if (const char* e = getenv("MIAGPU_PAIR_G")) pair_g = atoi(e) == 32 ? 32 : 16;
+  const int pair_g = 16;                             // lanes per pair: two pairs per warp
   const int np = 32 / pair_g;
   c->pair_g = pair_g;
   PairLmax lm{};
@@ -602,24 +603,17 @@ static int realign_device(miagpu_ctx* c) {
       p.score = c->d_score.p; p.as_out = c->d_as_out.p; p.ae_out = c->d_ae_out.p; p.abr = c->d_abr.p;
       p.n_runs = c->d_nruns.p; p.runs = c->d_runs.p; p.status = c->d_status.p;
       p.lists = c->d_lists.p; p.list_counts = c->d_meta.p + META_COUNT; p.n_reads = n; p.n_fallback = c->d_meta.p + META_NFALL;
-      int maxL = 0;                                     // longest read among the 32-bit classes this pair class draws from
-      for (int b = 0; b < NBUCKET - 1; b++) if (p16_class(BUCKET_K[b] * 32) == kb) maxL = std::max(maxL, meta[META_MAXL + b]);
-      maxL = std::min(maxL, P16_MAXL);
+      const int maxL = P16_MAXL;
       int ok = 1;
-      if (pair_g == 32) {
-        switch (kb) {
-          case 0: ok = launch_pair16<4, 32>(c, p, ni, maxL); break;
-          case 1: ok = launch_pair16<5, 32>(c, p, ni, maxL); break;
-          case 2: ok = launch_pair16<6, 32>(c, p, ni, maxL); break;
-          default: ok = launch_pair16<8, 32>(c, p, ni, maxL); break;
-        }
-      } else {
-        switch (kb) {
-          case 0: ok = launch_pair16<8, 16>(c, p, ni, maxL); break;
-          case 1: ok = launch_pair16<10, 16>(c, p, ni, maxL); break;
-          case 2: ok = launch_pair16<12, 16>(c, p, ni, maxL); break;
-          default: ok = launch_pair16<16, 16>(c, p, ni, maxL); break;
-        }
+      switch (kb) {
+        case 0: ok = launch_pair16<8, 16>(c, p, ni, maxL); break;
+        case 1: ok = launch_pair16<9, 16>(c, p, ni, maxL); break;
+        case 2: ok = launch_pair16<10, 16>(c, p, ni, maxL); break;
+        case 3: ok = launch_pair16<11, 16>(c, p, ni, maxL); break;
+        case 4: ok = launch_pair16<12, 16>(c, p, ni, maxL); break;
+        case 5: ok = launch_pair16<13, 16>(c, p, ni, maxL); break;
+        case 6: ok = launch_pair16<14, 16>(c, p, ni, maxL); break;
+        default: ok = launch_pair16<16, 16>(c, p, ni, maxL); break;
       }
       if (!ok) return 0;
       MIAGPU_CUDA(cudaEventRecord(c->pev[2 * kb + 1], c->stream));

@@ -45,12 +45,13 @@
 #pragma once
 #include "common.cuh"
 #include "realign.cuh"
+#include <type_traits>
 
 namespace miagpu {
 
 constexpr int P16_MAXL = 144;                       // rows the shared row-offset arrays hold
 constexpr int PROF16_N = 2 * NMAT * 5 * PROF_ROW_INTS;   // int16 entries
-constexpr int P16_NKB = 4;                          // width classes: 128 / 160 / 192 / 256 columns
+constexpr int P16_NKB = 8;                          // width classes: 128 / 144 / 160 / 176 / 192 / 208 / 224 / 256 columns (K = columns / 16)
 constexpr int P16_TAB_WORDS = 64;                   // 25 64-bit entries, padded to 32
 
 // OFF of the lane frame: the lowest intermediate, (lowest cell = -OFF-GOP-GEP+min entry) converted to the next lane
@@ -61,7 +62,9 @@ __host__ __device__ inline int p16_lmax(int K, int max_entry) {
   const int inc = max_entry + GEP;
   return inc > 0 ? (32767 + p16_off(K) - GEP * (K - 2)) / inc : MAX_READ;
 }
-__host__ __device__ inline int p16_class(int len1) { return len1 <= 128 ? 0 : len1 <= 160 ? 1 : len1 <= 192 ? 2 : len1 <= 256 ? 3 : -1; }
+__host__ __device__ inline int p16_class(int len1) {
+  return len1 <= 128 ? 0 : len1 <= 144 ? 1 : len1 <= 160 ? 2 : len1 <= 176 ? 3 : len1 <= 192 ? 4 : len1 <= 208 ? 5 : len1 <= 224 ? 6 : len1 <= 256 ? 7 : -1;
+}
 __host__ __device__ inline int bucket32_of(int len1) {
   return len1 <= 64 ? 0 : len1 <= 128 ? 1 : len1 <= 160 ? 2 : len1 <= 192 ? 3 : len1 <= 224 ? 4 : len1 <= 256 ? 5 : len1 <= 320 ? 6 : len1 <= 384 ? 7 : len1 <= 512 ? 8 : 9;
 }
@@ -107,6 +110,18 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
   asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
   return v;
 }
+__device__ __forceinline__ uint32_t and_or(uint32_t a, uint32_t b, uint32_t c) {   // (a & b) | c in one LOP3
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+// table entry {eA, eB} at a shared address plus a compile-time offset (the table buffer)
+template <int OFS>
+__device__ __forceinline__ uint2 lds_entry(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2+%3];" : "=r"(v.x), "=r"(v.y) : "r"(addr), "n"(OFS));
+  return v;
+}
 // One DP cell pair.  bp = max(best, ncmp) per half; w = bp + 2*GEP + (start-new ? 0 : sub) per half, as 32-bit adds
 // (exact, see 3. above).  The setp.eq pattern is the one ptxas folds into VIMNMX.U16x2 with two predicate
 // outputs; mad.lo keeps the adds on the FMA pipe.
@@ -134,8 +149,8 @@ __host__ __device__ constexpr int p16_smem_fixed() {
 }
 
 template <int K, int G>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) pair16_kernel(Pair16Params p) {
-  static_assert(K >= 4 && K <= 16 && (G == 16 || G == 32), "columns per lane / lanes per pair");
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, (K <= 12 ? 5 : 4)) pair16_kernel(Pair16Params p) {
+  static_assert(K >= 4 && K <= 16 && G == 16, "columns per lane / lanes per pair");
   constexpr int NP = 32 / G;                         // pairs per warp
   constexpr int NE = (25 + G - 1) / G;               // table entries a lane builds per row
   extern __shared__ __align__(16) uint8_t smem[];
@@ -173,12 +188,16 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) pair16_kernel(Pair16Para
   uint16_t* rowB = s_rowoff + ((warp * NP + hw) * 2 + 1) * P16_MAXL;
   uint32_t* tab = s_tab + (warp * NP + hw) * 2 * P16_TAB_WORDS;     // two buffers of P16_TAB_WORDS
   const uint32_t prof_base = smem_u32(s_prof);
+  const uint32_t tab_addr = smem_u32(tab);
 
   constexpr int OFF = p16_off(K);
   constexpr int CONV = GEP * K;                      // frame shift per lane of distance
   constexpr int SENT = -32768 + GOP;                 // "-infinity" that survives one -GOP
   const int n_items = *p.n_items;
   const uint32_t gep2 = p.gep2;
+  const uint32_t keep = sub ? 0xffffffffu : 0u;      // lane masks for the group's first lane (one LOP3 instead of a select)
+  const uint32_t sentm = sub ? 0u : B2(SENT);
+  const uint32_t ncmp0m = sub ? 0u : B2(-(GOP + 3 * GEP) - OFF);
 
   // table entries this lane builds every row: e = sub + G*t -> (a, b) = (e / 5, e % 5)
   uint32_t eoa[NE], eob[NE];
@@ -220,14 +239,14 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) pair16_kernel(Pair16Para
       rowA[r] = (uint16_t)(prof_row_index(sA, d, base_code(p.bases[oA + r])) * 2);
       rowB[r] = (uint16_t)(prof_row_index(sB, d, base_code(p.bases[oB + r])) * 2);
     }
-    uint32_t comb[K];                                 // byte offset of the column's (a, b) entry
+    uint32_t comb[K];                                 // shared address of the column's (a, b) entry in table buffer 0
 #pragma unroll
     for (int j = 0; j < K; j++) {
       const int c = sub * K + j;
       int a = 4, b = 4;
       if (c < lenA) a = p.ref_in_smem ? s_ref[wsA + c] : p.ref_codes[wsA + c];
       if (c < lenB) b = p.ref_in_smem ? s_ref[wsB + c] : p.ref_codes[wsB + c];
-      comb[j] = (uint32_t)(a * 5 + b) * 8;
+      comb[j] = tab_addr + (uint32_t)(a * 5 + b) * 8;
     }
     __syncwarp();
     build_table(0, tab);
@@ -239,7 +258,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) pair16_kernel(Pair16Para
       if (L > 1) build_table(1, tab + P16_TAB_WORDS);
 #pragma unroll
       for (int j = 0; j < K; j++) {
-        const uint2 e = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(tab) + comb[j]);
+        const uint2 e = lds_entry<0>(comb[j]);
         W[j] = B2(GEP * j - OFF) + e.x + e.y;         // biased seed + entries: 32-bit adds, as in cell_pair
         Rg[j] = B2(-32768);
         acc[j] = 0;
@@ -247,15 +266,19 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) pair16_kernel(Pair16Para
       __syncwarp();
     }
 
-    for (int r = 1; r < L; r++) {
-      const uint32_t* cur = tab + (r & 1) * P16_TAB_WORDS;
-      if (r + 1 < L) build_table(r + 1, tab + ((r + 1) & 1) * P16_TAB_WORDS);
+    // One DP row: row r-1 in W / acc -> row r in Wn / accn (Rg in place).  PAR = r & 1 selects the table buffer at
+    // compile time (an immediate offset of the LDS), so the row loop below is unrolled by two and ping-pongs
+    // between two register sets (no moves at the back edge).
+    auto dp_row = [&](int r, auto par, const uint32_t (&W)[K], const uint32_t (&acc)[K], uint32_t (&Wn)[K], uint32_t (&accn)[K]) {
+      constexpr int PAR = decltype(par)::value;
+      if (r + 1 < L) build_table(r + 1, tab + (PAR ^ 1) * P16_TAB_WORDS);
       uint32_t l2 = __shfl_up_sync(0xffffffffu, W[K - 2], 1, G);
       uint32_t l1 = __shfl_up_sync(0xffffffffu, W[K - 1], 1, G);
       uint32_t ain = __shfl_up_sync(0xffffffffu, acc[K - 1], 1, G);
-      l2 = sub ? __vadd2(l2, K2(-CONV)) : B2(SENT);
-      l1 = sub ? __vadd2(l1, K2(-CONV)) : B2(SENT);
-      if (sub == 0) ain = 0;
+      l2 = and_or(__vadd2(l2, K2(-CONV)), keep, sentm);          // first lane of the group: no left neighbour
+      const uint32_t l1c = __vadd2(l1, K2(-CONV));
+      l1 = and_or(l1c, keep, sentm);
+      ain &= keep;
       // lane total of the column-gap candidates E = {l2, l1, W[0..K-3]}
       uint32_t X = __vimax3_u16x2(l2, l1, W[0]);
 #pragma unroll
@@ -269,28 +292,40 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) pair16_kernel(Pair16Para
         X = __viaddmax_u16x2(__vmaxu2(y, B2(-32768 + CONV * d)), K2(-CONV * d), X);    // lanes < d get their own X back: max(X, max(X,cl)-dec) = X
       }
       uint32_t q = __shfl_up_sync(0xffffffffu, X, 1, G);
-      q = sub ? __vadd2(__vmaxu2(q, B2(-32768 + CONV)), K2(-CONV)) : B2(-32768);
+      q = __vadd2(__vmaxu2(q, B2(-32768 + CONV)), K2(-CONV)) & keep;      // B2(-32768) = 0
       // column-gap chain (mia.c:838-850): Q[j] = max over columns <= c-2 of V - GOP
       uint32_t Q[K];
       Q[0] = __viaddmax_u16x2(l2, K2(-GOP), q);
       Q[1] = __viaddmax_u16x2(l1, K2(-GOP), Q[0]);
 #pragma unroll
       for (int j = 2; j < K; j++) Q[j] = __viaddmax_u16x2(W[j - 2], K2(-GOP), Q[j - 1]);
-      // cells, right to left so that W[j-1] and acc[j-1] are still row r-1's
 #pragma unroll
-      for (int j = K - 1; j >= 0; j--) {
+      for (int j = 0; j < K; j++) {
         const uint32_t ncmpj = B2(-(GOP + 3 * GEP) - OFF) + K2(GEP * j);     // NCMP_j: compile-time after unrolling
         uint32_t D, ad;
         if (j > 0) { D = W[j - 1]; ad = acc[j - 1]; }
-        else { D = sub ? l1 : ncmpj; ad = ain; }       // column 0: S = sub + N, never start-new (mia.c:805-822)
+        else { D = and_or(l1c, keep, ncmp0m); ad = ain; }   // column 0: S = sub + N, never start-new (mia.c:805-822)
         const uint32_t best = __vimax3_u16x2(D, Q[j], Rg[j]);
         Rg[j] = __viaddmax_u16x2(D, K2(-GOP), Rg[j]);          // row r-1 joins the row-gap candidates of column c-1
-        const uint2 e = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(cur) + comb[j]);
+        const uint2 e = lds_entry<PAR * P16_TAB_WORDS * 4>(comb[j]);
         uint32_t bp;
-        W[j] = cell_pair(best, ncmpj, e.x, e.y, gep2, bp);
-        acc[j] = ad | (bp ^ D);
+        Wn[j] = cell_pair(best, ncmpj, e.x, e.y, gep2, bp);
+        accn[j] = ad | (bp ^ D);
       }
       __syncwarp();
+    };
+    {
+      uint32_t W1[K], acc1[K];
+      int r = 1;
+      for (; r + 1 < L; r += 2) {
+        dp_row(r, std::integral_constant<int, 1>{}, W, acc, W1, acc1);
+        dp_row(r + 1, std::integral_constant<int, 0>{}, W1, acc1, W, acc);
+      }
+      if (r < L) {
+        dp_row(r, std::integral_constant<int, 1>{}, W, acc, W1, acc1);
+#pragma unroll
+        for (int j = 0; j < K; j++) { W[j] = W1[j]; acc[j] = acc1[j]; }
+      }
     }
 
     // ---- max_sg_score (first maximum of the last row) + the diagonal verdict, one read (half) at a time
