@@ -43,27 +43,45 @@ __device__ __forceinline__ int smp_depth(const miagpu_entry& e, int act) {   // 
   return dfront <= PSSM_DEPTH ? dfront : (dback < PSSM_DEPTH ? 2 * PSSM_DEPTH - dback : PSSM_DEPTH);
 }
 
-// add_base (map_align.c:229-263) into column `col` of the plane-major accumulators
-__device__ __forceinline__ void add_base_dev(int32_t* acc, int64_t n_cols, int64_t col, int ch_code /*0..4, 5 = '-'*/,
-                                             const int32_t* sm_strand, int depth) {
-  atomicAdd(acc + PL_COV * n_cols + col, 1);
-  if (ch_code == 5) { atomicAdd(acc + PL_GAPS * n_cols + col, 1); return; }
-  if (ch_code < 4) atomicAdd(acc + ch_code * n_cols + col, 1);
+// add_base (map_align.c:229-263) into column `col` of the plane-major accumulators.
+// GlobalAdder: RED.ADD straight into the global planes (coalesced: lane i -> address base+i).
+struct GlobalAdder {
+  int32_t* acc;
+  int64_t n_cols;
+  __device__ __forceinline__ void add(int plane, int64_t col, int v) const { atomicAdd(acc + plane * n_cols + col, v); }
+};
+// TileAdder: a block owns the padded columns [c0, c0 + TILE_COLS) in shared memory; whatever an entry
+// adds outside that window (its tail past the tile, at most a read length) goes to the global planes.
+constexpr int TILE_POS = 1792;                  // reference positions per tile
+constexpr int TILE_COLS = 2304;                 // padded columns a tile holds in shared memory (positions + overhang + inserts)
+struct TileAdder {
+  int32_t* s_acc;                               // [NPLANE][TILE_COLS]
+  int64_t c0;
+  int32_t* acc;
+  int64_t n_cols;
+  __device__ __forceinline__ void add(int plane, int64_t col, int v) const {
+    const int64_t d = col - c0;
+    if ((uint64_t)d < (uint64_t)TILE_COLS) atomicAdd(s_acc + plane * TILE_COLS + (int)d, v);
+    else atomicAdd(acc + plane * n_cols + col, v);
+  }
+};
+template <typename Adder>
+__device__ __forceinline__ void add_base_dev(const Adder& A, int64_t col, int ch_code /*0..4, 5 = '-'*/, const int32_t* sm_strand, int depth) {
+  A.add(PL_COV, col, 1);
+  if (ch_code == 5) { A.add(PL_GAPS, col, 1); return; }
+  if (ch_code < 4) A.add(ch_code, col, 1);
   const int32_t* m = sm_strand + depth * 25 + ch_code;          // sm[depth][X][b]
 #pragma unroll
-  for (int x = 0; x < 4; x++) atomicAdd(acc + (PL_SCORE + x) * n_cols + col, m[x * 5]);
+  for (int x = 0; x < 4; x++) A.add(PL_SCORE + x, col, m[x * 5]);
 }
 
+// One entry, walked by a whole warp (lanes take consecutive reference columns).
 // MODE 0: ref->gaps = max insert length per position over the culled list (mia.c:486-504;
 //         positions with start < pos <= end only, so an insert in front of an entry's first
 //         column never counts)
 // MODE 1: base columns + insert columns
-template <int MODE>
-__global__ void __launch_bounds__(256) entry_kernel(ConsParams p) {
-  const int lane = threadIdx.x & 31;
-  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (w >= p.n_entries) return;
-  const miagpu_entry e = p.entries[w];
+template <int MODE, typename Adder>
+__device__ __forceinline__ void walk_entry(const ConsParams& p, const miagpu_entry& e, int lane, const Adder& A) {
   if (e.col_count <= 0) return;
   const int rd = e.read;
   const int nr = p.n_runs[rd];
@@ -96,12 +114,12 @@ __global__ void __launch_bounds__(256) entry_kernel(ConsParams p) {
         const int depth = smp_depth(e, act);
         if (!e.dropped) {
           const int ch = isM ? base_code(read[row]) : 5;
-          add_base_dev(p.acc, p.n_cols, pos + p.ins_off[pos + 1], ch, sm_strand, depth);   // base column sits after its insert columns
+          add_base_dev(A, pos + p.ins_off[pos + 1], ch, sm_strand, depth);   // base column sits after its insert columns
         }
         const int g = (i > cb && pos > 0) ? p.gaps[pos] : 0; // find_ins_cons: start < pos <= end, dropped NOT checked
         for (int j = 0; j < g; j++) {
           const int ch = j < q ? base_code(read[row - q + j]) : 5;
-          add_base_dev(p.acc, p.n_cols, pos + p.ins_off[pos] + j, ch, sm_strand, depth);
+          add_base_dev(A, pos + p.ins_off[pos] + j, ch, sm_strand, depth);
         }
       }
     }
@@ -109,6 +127,132 @@ __global__ void __launch_bounds__(256) entry_kernel(ConsParams p) {
     if (type == MIAGPU_RUN_M) rpos += len;
     pend = 0;
   }
+}
+
+// MODE 0 / 1 over the whole entry list, accumulators in global memory: one warp per entry.
+template <int MODE>
+__global__ void __launch_bounds__(256) entry_kernel(ConsParams p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= p.n_entries) return;
+  const miagpu_entry e = p.entries[w];
+  walk_entry<MODE>(p, e, lane, GlobalAdder{p.acc, p.n_cols});
+}
+
+// MODE 0 with a cheap filter in front: a lane looks at one entry, only entries whose alignment has more
+// than one run (an insert needs at least M I M) are walked by the warp.
+__global__ void __launch_bounds__(256) gaps_kernel(ConsParams p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32;
+  const int64_t idx = w0 + lane;
+  bool want = false;
+  if (idx < p.n_entries) {
+    const int32_t rd = p.entries[idx].read;
+    want = p.entries[idx].col_count > 0 && p.n_runs[rd] > 2;
+  }
+  unsigned m = __ballot_sync(0xffffffffu, want);
+  while (m) {
+    const int b = __ffs(m) - 1;
+    m &= m - 1;
+    const miagpu_entry e = p.entries[w0 + b];
+    walk_entry<0>(p, e, lane, GlobalAdder{p.acc, p.n_cols});
+  }
+}
+
+// MODE 1 with the accumulators of one reference tile private to the block (shared-memory atomics), flushed
+// once at the end.  grid = (slices, tiles): block (s, t) scans slice s of ent_pos[] (start position of every
+// entry, -1 = empty) and walks the entries that start inside tile t.  Used when the reference is short enough
+// for every tile to be scanned by many blocks (high coverage per column = the case where global atomics
+// contend); integer sums, so the result does not depend on the path taken.
+// Shared memory: [NPLANE][TILE_COLS] accumulators, ins_off[t0 .. t0+TILE_COLS], both PSSMs.
+// A lane first loads the metadata of "its" entry (32 independent loads in flight), then the warp walks the
+// flagged entries one by one; the common alignment -- a single M run -- takes a loop that touches global
+// memory only for the read bases.
+constexpr int TILE_THREADS = 512;
+constexpr int TILE_SMEM_INTS = NPLANE * TILE_COLS + (TILE_COLS + 1) + 2 * MIAGPU_PSSM_INTS;
+__global__ void __launch_bounds__(TILE_THREADS) tile_kernel(ConsParams p, const int32_t* __restrict__ ent_pos) {
+  extern __shared__ int32_t s_acc[];                       // [NPLANE][TILE_COLS]
+  int32_t* s_ins = s_acc + NPLANE * TILE_COLS;             // ins_off[t0 + i], i <= TILE_COLS
+  int32_t* s_sm = s_ins + TILE_COLS + 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int t0 = blockIdx.y * TILE_POS, t1 = min(t0 + TILE_POS, p.seq_len);
+  const int64_t c0 = (int64_t)t0 + p.ins_off[t0];
+  for (int i = threadIdx.x; i < NPLANE * TILE_COLS; i += blockDim.x) s_acc[i] = 0;
+  for (int i = threadIdx.x; i <= TILE_COLS; i += blockDim.x) s_ins[i] = p.ins_off[min(t0 + i, p.seq_len)];
+  for (int i = threadIdx.x; i < 2 * MIAGPU_PSSM_INTS; i += blockDim.x) s_sm[i] = p.sm[i];
+  __syncthreads();
+  const TileAdder A{s_acc, c0, p.acc, p.n_cols};
+  const int64_t per = (p.n_entries + gridDim.x - 1) / gridDim.x;
+  const int64_t lo = per * blockIdx.x, hi = min(lo + per, p.n_entries);
+  for (int64_t base = lo + warp * 32; base < hi; base += nwarps * 32) {
+    const int64_t idx = base + lane;
+    int pos0 = -1;
+    if (idx < hi) pos0 = ent_pos[idx];
+    const bool mine = pos0 >= t0 && pos0 < t1;
+    miagpu_entry e{};
+    int nr = 0, ab = 0, strand = 0, run0 = 0;
+    int64_t o = 0;
+    if (mine) {
+      e = p.entries[idx];
+      nr = p.n_runs[e.read];
+      ab = p.abr[e.read];
+      strand = p.rc[e.read] ? 1 : 0;
+      o = p.off[e.read];
+      run0 = p.runs[(int64_t)e.read * MAX_RUNS];
+    }
+    unsigned m = __ballot_sync(0xffffffffu, mine);
+    while (m) {
+      const int b = __ffs(m) - 1;
+      m &= m - 1;
+      const int b_nr = __shfl_sync(0xffffffffu, nr, b);
+      const int b_run0 = __shfl_sync(0xffffffffu, run0, b);
+      if (b_nr != 1 || (b_run0 >> 14) != MIAGPU_RUN_M) {   // gaps in the alignment: the general walk
+        const miagpu_entry eb = p.entries[base + b];
+        walk_entry<1>(p, eb, lane, A);
+        continue;
+      }
+      const int cb = __shfl_sync(0xffffffffu, e.col_begin, b), cc = __shfl_sync(0xffffffffu, e.col_count, b);
+      const int rp = __shfl_sync(0xffffffffu, e.ref_pos, b), fl = __shfl_sync(0xffffffffu, e.front_len, b);
+      const int tl = __shfl_sync(0xffffffffu, e.total_len, b), bias = __shfl_sync(0xffffffffu, e.act_bias, b);
+      const int flags = __shfl_sync(0xffffffffu, (int)e.dropped | ((int)e.back_formula << 8), b);
+      const int b_ab = __shfl_sync(0xffffffffu, ab, b), b_strand = __shfl_sync(0xffffffffu, strand, b);
+      const int64_t b_o = __shfl_sync(0xffffffffu, o, b);
+      const int len = b_run0 & 0x3fff;
+      const bool dropped = flags & 0xff, backf = (flags >> 8) != 0;
+      const int32_t* sms = s_sm + b_strand * MIAGPU_PSSM_INTS;
+      const uint8_t* read = p.bases + b_o + b_ab;
+      const int hi_col = min(len, cb + cc);
+      for (int i = cb + lane; i < hi_col; i += 32) {
+        const int pos = rp + (i - cb);
+        if (pos >= p.seq_len) continue;
+        const int act = bias + i;
+        const int dfront = backf ? fl + act : act, dback = tl - act - 1;
+        const int depth = dfront <= PSSM_DEPTH ? dfront : (dback < PSSM_DEPTH ? 2 * PSSM_DEPTH - dback : PSSM_DEPTH);
+        const int d = pos - t0;
+        int io0, io1;
+        if (d < TILE_COLS) { io0 = s_ins[d]; io1 = s_ins[d + 1]; }
+        else { io0 = p.ins_off[pos]; io1 = p.ins_off[pos + 1]; }
+        if (!dropped) add_base_dev(A, (int64_t)pos + io1, base_code(read[i]), sms, depth);
+        if (i > cb && pos > 0)                               // find_ins_cons: start < pos <= end, dropped NOT checked
+          for (int j = io0; j < io1; j++) add_base_dev(A, (int64_t)pos + j, 5, sms, depth);
+      }
+    }
+  }
+  __syncthreads();
+  const int64_t room = min((int64_t)TILE_COLS, p.n_cols - c0);
+  for (int i = threadIdx.x; i < NPLANE * TILE_COLS; i += blockDim.x) {
+    const int pl = i / TILE_COLS, d = i - pl * TILE_COLS;
+    const int v = s_acc[i];
+    if (v != 0 && d < room) atomicAdd(p.acc + pl * p.n_cols + c0 + d, v);
+  }
+}
+
+// start position of every entry for tile_kernel's scan (-1 = nothing to add)
+__global__ void ent_pos_kernel(int64_t n_entries, const miagpu_entry* entries, const int32_t* n_runs, int32_t* ent_pos) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_entries) return;
+  const miagpu_entry e = entries[i];
+  ent_pos[i] = (e.col_count > 0 && n_runs[e.read] > 0) ? e.ref_pos : -1;
 }
 
 // find_consensus (map_align.c:294-391) for every column of the padded layout.

@@ -130,6 +130,7 @@ struct miagpu_ctx {
   DevBuf<int32_t> d_src;
   // consensus
   DevBuf<miagpu_entry> d_entries;
+  DevBuf<int32_t> d_ent_pos;                   // start position per entry (tile_kernel's scan list)
   int64_t n_entries = 0;
   DevBuf<int32_t> d_sm, d_gaps, d_ins_off, d_acc;
   DevBuf<uint8_t> d_cub, d_dropf, d_dropb;
@@ -189,7 +190,7 @@ extern "C" void miagpu_destroy(miagpu_ctx* c) {
   for (int t = 0; t < 2; t++) { c->d_kb[t].release(); c->d_kp[t].release(); c->d_kk[t].release(); }
   c->d_smask.release(); c->d_ckpt.release(); c->d_chunk_ids.release(); c->d_strace.release(); c->d_hits.release(); c->d_fw.release();
   c->d_rcs.release(); c->d_start.release(); c->d_end.release(); c->d_rc_out.release(); c->d_bases2.release(); c->d_packed.release(); c->d_off2.release(); c->d_src.release();
-  c->d_entries.release(); c->d_sm.release(); c->d_gaps.release(); c->d_ins_off.release(); c->d_acc.release(); c->d_cub.release(); c->d_called.release(); c->d_dropf.release(); c->d_dropb.release();
+  c->d_entries.release(); c->d_ent_pos.release(); c->d_sm.release(); c->d_gaps.release(); c->d_ins_off.release(); c->d_acc.release(); c->d_cub.release(); c->d_called.release(); c->d_dropf.release(); c->d_dropb.release();
   for (auto& ev : c->ev) cudaEventDestroy(ev);
   for (auto& ev : c->bev) cudaEventDestroy(ev);
   for (auto& ev : c->pev) cudaEventDestroy(ev);
@@ -876,6 +877,42 @@ static ConsParams cons_params(miagpu_ctx* c) {
   return p;
 }
 
+// MODE 0 (per-position insert maxima) over the current entry list
+static int launch_gaps(miagpu_ctx* c) {
+  if (!c->n_entries) return 1;
+  ConsParams p = cons_params(c);
+  gaps_kernel<<<(unsigned)((c->n_entries + 255) / 256), 256, 0, c->stream>>>(p);          // a warp filters 32 entries
+  MIAGPU_CUDA(cudaGetLastError());
+  c->launches++;
+  return 1;
+}
+
+// MODE 1 (base + insert columns) over the current entry list: tile-private shared-memory accumulators when the
+// reference is short (many reads per column), global REDs otherwise.
+static int launch_accumulate(miagpu_ctx* c) {
+  if (!c->n_entries) return 1;
+  ConsParams p = cons_params(c);
+  const int n_tiles = (c->seq_len + TILE_POS - 1) / TILE_POS;
+  bool tiles = n_tiles <= 64 && c->n_entries >= 4096;
+  if (const char* e = getenv("MIAGPU_CONS_TILES")) tiles = atoi(e) != 0;
+  if (tiles) {
+    if (!c->d_ent_pos.reserve(c->n_entries + 1)) return 0;
+    ent_pos_kernel<<<(unsigned)((c->n_entries + 255) / 256), 256, 0, c->stream>>>(c->n_entries, c->d_entries.p, c->d_nruns.p, c->d_ent_pos.p);
+    MIAGPU_CUDA(cudaGetLastError());
+    const size_t smem = (size_t)TILE_SMEM_INTS * sizeof(int32_t);
+    MIAGPU_CUDA(cudaFuncSetAttribute(tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int slices = std::max(1, (2 * c->num_sms + n_tiles - 1) / n_tiles);
+    tile_kernel<<<dim3(slices, n_tiles), TILE_THREADS, smem, c->stream>>>(p, c->d_ent_pos.p);
+    MIAGPU_CUDA(cudaGetLastError());
+    c->launches += 2;
+  } else {
+    entry_kernel<1><<<(unsigned)((c->n_entries * 32 + 255) / 256), 256, 0, c->stream>>>(p);
+    MIAGPU_CUDA(cudaGetLastError());
+    c->launches++;
+  }
+  return 1;
+}
+
 extern "C" int miagpu_accumulate_gaps(miagpu_ctx* c, int64_t n_entries, const miagpu_entry* entries, void** dev_gaps, int64_t* n_gaps) {
   if (!c || !c->have_ref || !c->have_pssm) { set_error("miagpu_accumulate_gaps: set_pssm / set_reference / realign first"); return 0; }
   if (n_entries < 0 || (n_entries && !entries)) { set_error("miagpu_accumulate_gaps: bad entries"); return 0; }
@@ -889,12 +926,7 @@ extern "C" int miagpu_accumulate_gaps(miagpu_ctx* c, int64_t n_entries, const mi
   MIAGPU_CUDA(cudaEventRecord(c->ev[1], c->stream));
   c->n_entries = n_entries;
   MIAGPU_CUDA(cudaMemsetAsync(c->d_gaps.p, 0, (c->seq_len + 2) * sizeof(int32_t), c->stream));
-  if (n_entries) {
-    ConsParams p = cons_params(c);
-    entry_kernel<0><<<(unsigned)((n_entries * 32 + 255) / 256), 256, 0, c->stream>>>(p);
-    MIAGPU_CUDA(cudaGetLastError());
-    c->launches++;
-  }
+  if (!launch_gaps(c)) return 0;
   MIAGPU_CUDA(cudaEventRecord(c->ev[2], c->stream));
   MIAGPU_CUDA(cudaStreamSynchronize(c->stream));
   MIAGPU_CUDA(cudaEventElapsedTime(&c->ms_h2d, c->ev[0], c->ev[1]));
@@ -921,12 +953,8 @@ extern "C" int miagpu_accumulate_counts(miagpu_ctx* c, void** dev_counts, int64_
   c->n_cols = (int64_t)c->seq_len + total_ins;
   if (!c->d_acc.reserve(c->n_cols * NPLANE) || !c->d_called.reserve(c->n_cols + 16)) return 0;
   MIAGPU_CUDA(cudaMemsetAsync(c->d_acc.p, 0, c->n_cols * NPLANE * sizeof(int32_t), c->stream));
-  if (c->n_entries) {
-    ConsParams p = cons_params(c);
-    entry_kernel<1><<<(unsigned)((c->n_entries * 32 + 255) / 256), 256, 0, c->stream>>>(p);
-    MIAGPU_CUDA(cudaGetLastError());
-    c->launches += 2;
-  }
+  if (!launch_accumulate(c)) return 0;
+  c->launches++;                                     // the scan
   MIAGPU_CUDA(cudaEventRecord(c->ev[2], c->stream));
   MIAGPU_CUDA(cudaStreamSynchronize(c->stream));
   float ms = 0;
@@ -996,10 +1024,8 @@ extern "C" int miagpu_accumulate_gaps_natural(miagpu_ctx* c, const uint8_t* drop
         n, c->d_as_out.p, c->d_ae_out.p, c->d_nruns.p, c->d_runs.p, c->d_status.p, c->seq_len, dropped_front ? c->d_dropf.p : nullptr,
         dropped_back ? c->d_dropb.p : nullptr, c->d_entries.p);
     MIAGPU_CUDA(cudaGetLastError());
-    ConsParams p = cons_params(c);
-    entry_kernel<0><<<(unsigned)((c->n_entries * 32 + 255) / 256), 256, 0, c->stream>>>(p);
-    MIAGPU_CUDA(cudaGetLastError());
-    c->launches += 2;
+    c->launches++;
+    if (!launch_gaps(c)) return 0;
   }
   MIAGPU_CUDA(cudaEventRecord(c->ev[2], c->stream));
   MIAGPU_CUDA(cudaStreamSynchronize(c->stream));
@@ -1199,10 +1225,7 @@ extern "C" int miagpu_iterate_host(miagpu_ctx* c, int64_t n, const uint8_t* base
   IT_CUDA(cudaMemsetAsync(c->d_gaps.p, 0, (c->seq_len + 2) * sizeof(int32_t), c->stream));
   natural_entries_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, c->d_as_out.p, c->d_ae_out.p, c->d_nruns.p, c->d_runs.p,
                                                                              c->d_status.p, c->seq_len, nullptr, nullptr, c->d_entries.p);
-  {
-    ConsParams p = cons_params(c);
-    entry_kernel<0><<<(unsigned)((c->n_entries * 32 + 255) / 256), 256, 0, c->stream>>>(p);
-  }
+  if (!launch_gaps(c)) { cut.join(); return 0; }
   IT_CUDA(cub::DeviceScan::ExclusiveSum(c->d_cub.p, tmp2, c->d_gaps.p, c->d_ins_off.p, c->seq_len + 1, c->stream));
   int32_t total_ins = 0;
   IT_CUDA(cudaMemcpyAsync(&total_ins, c->d_ins_off.p + c->seq_len, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
@@ -1226,16 +1249,13 @@ extern "C" int miagpu_iterate_host(miagpu_ctx* c, int64_t n, const uint8_t* base
 #undef IT_CUDA
   MIAGPU_CUDA(cudaMemcpyAsync(c->d_dropf.p, dropped, n, cudaMemcpyHostToDevice, c->stream));
   set_dropped_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, c->d_dropf.p, c->d_entries.p);
-  {
-    ConsParams p = cons_params(c);
-    entry_kernel<1><<<(unsigned)((c->n_entries * 32 + 255) / 256), 256, 0, c->stream>>>(p);
-  }
+  if (!launch_accumulate(c)) return 0;
   MIAGPU_CUDA(cudaGetLastError());
-  c->launches = launches_realign + 9;
+  c->launches = launches_realign + 10;
   c->cons_stage = 2;
   MIAGPU_CUDA(cudaEventRecord(c->ev[3], c->stream));
   if (!miagpu_call(c, cons_code, gaps_out, nullptr, cons_out, cons_len)) return 0;
-  c->launches = launches_realign + 10;
+  c->launches = launches_realign + 11;
   c->ms_h2d = ms_h2d;
   c->ms_kernels = ms_k;
   return realign_bucket_times(c);
