@@ -340,6 +340,8 @@ extern "C" int miagpu_upload_reads(miagpu_ctx* c, int64_t n, const uint8_t* base
 // the 16-bit frame of its width class, at most 256 columns), into the (pair class, read length)
 // histogram that pairs reads of equal length.
 struct PairLmax { int v[P16_NKB]; };                 // longest read each pair class takes (0 = pair kernels off)
+// Block-level statistics go through shared-memory counters; lanes of a warp that hit the same counter are
+// merged first (match.any + redux), so a counter sees one atomic per warp instead of up to 32.
 __global__ void classify_kernel(int64_t n, const int64_t* off, const int32_t* as, const int32_t* ae, int wrap_len, PairLmax lm,
                                 int32_t* win_start, int32_t* win_len, int32_t* lists, uint8_t* kind, int32_t* meta) {
   int lmax16 = 0;
@@ -354,7 +356,10 @@ __global__ void classify_kernel(int64_t n, const int64_t* off, const int32_t* as
   if (lmax16 > 0) for (int i = threadIdx.x; i < P16_KEYS; i += blockDim.x) s_hist[i] = 0;
   __syncthreads();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int b = -1, slot = 0, L = 0;
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1;
+  int b = -1, slot = 0, L = 0, key = -1, kb = -1;
+  unsigned cells = 0;
   bool direct = false;
   if (i < n) {
     L = (int)(off[i + 1] - off[i]);
@@ -367,21 +372,40 @@ __global__ void classify_kernel(int64_t n, const int64_t* off, const int32_t* as
     win_len[i] = len1;
     b = bucket32_of(len1);
     if (L <= 0 || L > MAX_READ) b = NBUCKET - 1;
-    const int kb = p16_class(len1);
+    kb = p16_class(len1);
     const bool elig = b != NBUCKET - 1 && kb >= 0 && !whole && L <= lm.v[kb < 0 ? 0 : kb];
-    atomicAdd(&s_pop[b], 1);
-    atomicMax(&s_maxL[b], L);
-    atomicAdd(&s_cells[b], (unsigned long long)L * (unsigned long long)len1);
-    if (elig) {
-      kind[i] = (uint8_t)(16 + kb);
-      atomicAdd(&s_hist[kb * (P16_MAXL + 1) + L], 1);
-      atomicAdd(&s_preads[kb], 1);
-      atomicAdd(&s_pcells[kb], (unsigned long long)L * (unsigned long long)len1);
-    } else {
-      kind[i] = (uint8_t)b;
-      direct = true;
-      slot = atomicAdd(&s_cnt[b], 1);
+    cells = (unsigned)max(L, 0) * (unsigned)len1;                       // <= 256 * wrap_len: a warp's sum fits 32 bits up to 500 kb windows
+    if (elig) { kind[i] = (uint8_t)(16 + kb); key = kb * (P16_MAXL + 1) + L; }
+    else { kind[i] = (uint8_t)b; direct = true; kb = -1; }
+  }
+  // per width bucket: population, longest read, cells
+  {
+    const unsigned peers = __match_any_sync(0xffffffffu, b);
+    const int mx = __reduce_max_sync(peers, L);
+    const unsigned long long cs = (unsigned long long)__reduce_add_sync(peers, cells & 0xffffu) +
+                                  ((unsigned long long)__reduce_add_sync(peers, cells >> 16) << 16);
+    if (b >= 0 && (peers & lt) == 0) {
+      atomicAdd(&s_pop[b], __popc(peers));
+      atomicMax(&s_maxL[b], mx);
+      atomicAdd(&s_cells[b], cs);
     }
+  }
+  // pair-eligible reads: histogram per (class, length), reads and cells per class
+  if (lmax16 > 0) {
+    const unsigned pk = __match_any_sync(0xffffffffu, key);
+    if (key >= 0 && (pk & lt) == 0) atomicAdd(&s_hist[key], __popc(pk));
+    const unsigned pc = __match_any_sync(0xffffffffu, kb);
+    const unsigned long long cs = (unsigned long long)__reduce_add_sync(pc, cells & 0xffffu) + ((unsigned long long)__reduce_add_sync(pc, cells >> 16) << 16);
+    if (kb >= 0 && (pc & lt) == 0) { atomicAdd(&s_preads[kb], __popc(pc)); atomicAdd(&s_pcells[kb], cs); }
+  }
+  // reads that go straight to a 32-bit list take consecutive slots
+  {
+    const int db = direct ? b : -1;
+    const unsigned pd = __match_any_sync(0xffffffffu, db);
+    int base = 0;
+    if (direct && (pd & lt) == 0) base = atomicAdd(&s_cnt[b], __popc(pd));
+    base = __shfl_sync(0xffffffffu, base, __ffs(pd) - 1);
+    slot = base + __popc(pd & lt);
   }
   __syncthreads();
   if (threadIdx.x < NBUCKET) {
@@ -404,19 +428,39 @@ __global__ void classify_kernel(int64_t n, const int64_t* off, const int32_t* as
 
 // Pairs per (class, length) key: ceil(count / 2), rounded up to whole work items of np pairs (a warp's reads all
 // have one length), laid out class after class.  META_PSTART is in pairs, META_NPAIRS in work items.
-__global__ void pair_layout_kernel(int32_t* meta, int np) {
-  if (threadIdx.x || blockIdx.x) return;
-  int run = 0;
-  for (int kb = 0; kb < P16_NKB; kb++) {
-    const int first = run;
-    for (int L = 0; L <= P16_MAXL; L++) {
-      const int k = kb * (P16_MAXL + 1) + L;
-      meta[META_PSTART + k] = run;
-      const int pairs = (meta[META_HIST + k] + 1) >> 1;
-      run += (pairs + np - 1) / np * np;
-    }
-    meta[META_NPAIRS + kb] = (run - first) / np;
+// One block: a thread takes LAYOUT_PER consecutive keys, the block scans the per-thread totals.
+constexpr int LAYOUT_THREADS = 256;
+constexpr int LAYOUT_PER = (P16_KEYS + LAYOUT_THREADS - 1) / LAYOUT_THREADS;
+__global__ void __launch_bounds__(LAYOUT_THREADS) pair_layout_kernel(int32_t* meta, int np) {
+  __shared__ int s_tot[LAYOUT_THREADS];
+  __shared__ int s_start[P16_KEYS + 1];
+  const int t = threadIdx.x;
+  int items[LAYOUT_PER], sum = 0;
+#pragma unroll
+  for (int q = 0; q < LAYOUT_PER; q++) {
+    const int k = t * LAYOUT_PER + q;
+    const int pairs = k < P16_KEYS ? (meta[META_HIST + k] + 1) >> 1 : 0;
+    items[q] = (pairs + np - 1) / np * np;
+    sum += items[q];
   }
+  s_tot[t] = sum;
+  __syncthreads();
+  for (int d = 1; d < LAYOUT_THREADS; d <<= 1) {           // Hillis-Steele inclusive scan
+    const int v = t >= d ? s_tot[t - d] : 0;
+    __syncthreads();
+    s_tot[t] += v;
+    __syncthreads();
+  }
+  int run = s_tot[t] - sum;
+#pragma unroll
+  for (int q = 0; q < LAYOUT_PER; q++) {
+    const int k = t * LAYOUT_PER + q;
+    if (k < P16_KEYS) { meta[META_PSTART + k] = run; s_start[k] = run; }
+    run += items[q];
+  }
+  if (t == LAYOUT_THREADS - 1) s_start[P16_KEYS] = s_tot[t];
+  __syncthreads();
+  if (t < P16_NKB) meta[META_NPAIRS + t] = (s_start[(t + 1) * (P16_MAXL + 1)] - s_start[t * (P16_MAXL + 1)]) / np;
 }
 
 // Eligible reads take the next free slot of their key: slot s is member s&1 of pair pstart + s/2.
@@ -573,7 +617,7 @@ static int realign_device(miagpu_ctx* c) {
   MIAGPU_CUDA(cudaGetLastError());
   c->launches++;
   if (lmax16 > 0) {
-    pair_layout_kernel<<<1, 32, 0, c->stream>>>(c->d_meta.p, np);
+    pair_layout_kernel<<<1, LAYOUT_THREADS, 0, c->stream>>>(c->d_meta.p, np);
     MIAGPU_CUDA(cudaGetLastError());
     c->launches++;
   }

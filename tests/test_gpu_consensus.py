@@ -6,9 +6,11 @@ import gpu_checks
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("cons_code", [1, 2])
-def test_consensus_matches_oracle(gpu, oracle, cons_code):
-    ref, bases, off, rc, as_, ae = gpu_checks.make_case(3000, 2500, seed=51, divergence=0.03, indel_rate=0.01)
+@pytest.mark.parametrize("cons_code,tiles", [(1, "1"), (2, "1"), (1, "0")])
+def test_consensus_matches_oracle(gpu, oracle, cons_code, tiles, monkeypatch):
+    # tiles: "1" = tile-private shared-memory accumulators (tile_kernel), "0" = global REDs (entry_kernel<1>)
+    monkeypatch.setenv("MIAGPU_CONS_TILES", tiles)
+    ref, bases, off, rc, as_, ae = gpu_checks.make_case(3000, 4100, seed=51, divergence=0.03, indel_rate=0.01)
     problems, info = gpu_checks.check_consensus(gpu, oracle, ref, bases, off, rc, as_, ae, gpu_checks.load_pssm("onepass"),
                                                 cons_code=cons_code)
     assert not problems, problems
