@@ -5,6 +5,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <chrono>
 #include <thread>
 #include <vector>
 
@@ -13,6 +14,7 @@
 #include "pair16.cuh"
 #include "consensus.cuh"
 #include "strip.cuh"
+#include "scorecut.hpp"
 #include <cub/device/device_scan.cuh>
 
 namespace miagpu {
@@ -69,6 +71,7 @@ constexpr int META_HIST = 256;       // [P16_KEYS] eligible reads per (pair clas
 constexpr int META_PSTART = META_HIST + 1280;    // [P16_KEYS] first pair of the key
 constexpr int META_CURSOR = META_PSTART + 1280;  // [P16_KEYS] scatter cursors
 constexpr int META_WORDS = META_CURSOR + 1280;
+constexpr int MAX_CHUNKS = 16;
 static_assert(P16_KEYS <= 1280 && P16_NKB == 8, "meta layout");
 
 }  // namespace miagpu
@@ -115,6 +118,13 @@ struct miagpu_ctx {
   int64_t pair_cells[P16_NKB] = {};
   int32_t n_fallback = 0;
   int pair_g = 16;
+  // chunked pipeline of miagpu_iterate_host: upload / download streams, per-chunk events, pinned meta copies
+  cudaStream_t s_up = nullptr, s_down = nullptr;
+  cudaEvent_t cev[4 * 16] = {};                 // [MAX_CHUNKS][4]: classified, realigned, scores on host, spare
+  cudaEvent_t xev[4] = {};
+  int32_t* h_meta = nullptr;                    // pinned, MAX_CHUNKS * META_HOST
+  uint8_t* h_newly = nullptr;                   // pinned, flags of the reads dropped in this round
+  int64_t h_newly_cap = 0;
   // pass 1 / wide windows
   int kmer_k = 0;
   DevBuf<int32_t> d_kb[2], d_kp[2];
@@ -175,6 +185,11 @@ extern "C" int miagpu_create(miagpu_ctx** out, int device) {
   for (auto& ev : c->ev) MIAGPU_CUDA(cudaEventCreate(&ev));
   for (auto& ev : c->bev) MIAGPU_CUDA(cudaEventCreate(&ev));
   for (auto& ev : c->pev) MIAGPU_CUDA(cudaEventCreate(&ev));
+  MIAGPU_CUDA(cudaStreamCreateWithFlags(&c->s_up, cudaStreamNonBlocking));
+  MIAGPU_CUDA(cudaStreamCreateWithFlags(&c->s_down, cudaStreamNonBlocking));
+  for (auto& ev : c->cev) MIAGPU_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  for (auto& ev : c->xev) MIAGPU_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  MIAGPU_CUDA(cudaMallocHost(&c->h_meta, sizeof(int32_t) * MAX_CHUNKS * META_HOST));
   *out = c;
   return 1;
 }
@@ -195,6 +210,12 @@ extern "C" void miagpu_destroy(miagpu_ctx* c) {
   for (auto& ev : c->bev) cudaEventDestroy(ev);
   for (auto& ev : c->pev) cudaEventDestroy(ev);
   c->d_prof16.release(); c->d_kind.release(); c->d_pairs.release();
+  for (auto& ev : c->cev) cudaEventDestroy(ev);
+  for (auto& ev : c->xev) cudaEventDestroy(ev);
+  cudaStreamDestroy(c->s_up);
+  cudaStreamDestroy(c->s_down);
+  cudaFreeHost(c->h_meta);
+  if (c->h_newly) cudaFreeHost(c->h_newly);
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -309,8 +330,8 @@ static int reserve_per_read(miagpu_ctx* c, int64_t n) {
   return c->d_rc.reserve(n) && c->d_status.reserve(n) && c->d_as.reserve(n) && c->d_ae.reserve(n) && c->d_score.reserve(n) &&
          c->d_as_out.reserve(n) && c->d_ae_out.reserve(n) && c->d_abr.reserve(n) && c->d_nruns.reserve(n) &&
          c->d_win_start.reserve(n) && c->d_win_len.reserve(n) && c->d_lists.reserve(n * NBUCKET) &&
-         c->d_runs.reserve(n * MAX_RUNS) && c->d_meta.reserve(META_WORDS) && c->d_kind.reserve(n + 1) &&
-         c->d_pairs.reserve(n + 4 * P16_KEYS + 64);
+         c->d_runs.reserve(n * MAX_RUNS) && c->d_meta.reserve(META_WORDS * MAX_CHUNKS) && c->d_kind.reserve(n + 1) &&
+         c->d_pairs.reserve(n + MAX_CHUNKS * (4 * P16_KEYS + 64));
 }
 
 extern "C" int miagpu_upload_reads(miagpu_ctx* c, int64_t n, const uint8_t* bases, const int64_t* offsets) {
@@ -510,7 +531,7 @@ static int ensure_max_read_len(miagpu_ctx* c) {
   return 1;
 }
 
-static int launch_strip(miagpu_ctx* c, int mode, const int32_t* list, int n_list, int32_t* counter) {
+static int launch_strip(miagpu_ctx* c, int mode, const int32_t* list, int n_list, int32_t* counter, int64_t lo = 0) {
   if (!ensure_max_read_len(c)) return 0;
   const int len1 = c->circular ? c->wrap_len : c->seq_len;                 // mia_main.c:721-728
   const int n_chunks = (len1 + CW - 1) / CW;
@@ -542,6 +563,10 @@ static int launch_strip(miagpu_ctx* c, int mode, const int32_t* list, int n_list
   p.hits = mode == 0 ? c->d_hits.p : nullptr; p.score = c->d_score.p; p.fw_score = c->d_fw.p; p.rc_score = c->d_rcs.p;
   p.as_out = c->d_as_out.p; p.ae_out = c->d_ae_out.p; p.start = c->d_start.p; p.end = c->d_end.p; p.abr = c->d_abr.p;
   p.n_runs = c->d_nruns.p; p.rc_out = c->d_rc_out.p; p.runs = c->d_runs.p; p.status = c->d_status.p;
+  if (mode == 1 && lo) {                       // a chunk of the batch: list entries count from read `lo`
+    p.off += lo; p.rc_in += lo; p.score += lo; p.as_out += lo; p.ae_out += lo; p.abr += lo; p.n_runs += lo;
+    p.runs += lo * MAX_RUNS; p.status += lo;
+  }
   strip_kernel<<<blocks, WARPS_PER_BLOCK * 32, smem, c->stream>>>(p);
   MIAGPU_CUDA(cudaGetLastError());
   c->launches++;
@@ -596,58 +621,89 @@ static int launch_pair16(miagpu_ctx* c, Pair16Params p, int n_pairs, int maxL) {
   return 1;
 }
 
-static int realign_device(miagpu_ctx* c) {
-  const int64_t n = c->n;
+// One realign job = reads [lo, lo + n) of the resident batch with their own meta block, work lists and pair
+// table, so that several jobs (the chunks of miagpu_iterate_host's pipeline) can be in flight.
+struct RealignJob {
+  int64_t lo = 0, n = 0;
+  int32_t* d_meta = nullptr;     // META_WORDS
+  int32_t* d_lists = nullptr;    // NBUCKET * n
+  int32_t* d_pairs = nullptr;    // n + 4 * P16_KEYS + 64
+  int32_t* h_meta = nullptr;     // META_HOST words on the host (pinned for an asynchronous copy)
+  bool timed = false;            // per-class events (the whole-batch path)
+};
+
+static PairLmax pair_lmax(miagpu_ctx* c) {
+  int lmax16 = c->lmax16;
+  if (const char* e = getenv("MIAGPU_PAIR16")) if (atoi(e) == 0) lmax16 = 0;
+  c->pair_g = 16;                                    // lanes per pair: two pairs per warp
+  PairLmax lm{};
+  for (int kb = 0; kb < P16_NKB; kb++) lm.v[kb] = lmax16 > 0 ? std::min(p16_lmax(P16_COLS[kb] / c->pair_g, c->pssm_max), P16_MAXL) : 0;
+  return lm;
+}
+
+static void realign_reset_stats(miagpu_ctx* c) {
   c->launches = 0;
   c->dp_cells = 0;
   c->n_fallback = 0;
   for (int kb = 0; kb < P16_NKB; kb++) { c->pair_ms[kb] = 0; c->pair_reads[kb] = 0; c->pair_pairs[kb] = 0; c->pair_cells[kb] = 0; }
   for (int b = 0; b < NBUCKET; b++) { c->bucket_ms[b] = 0; c->bucket_reads[b] = 0; c->bucket_cells[b] = 0; }
-  if (n == 0) return 1;
-  int lmax16 = c->lmax16;
-  if (const char* e = getenv("MIAGPU_PAIR16")) if (atoi(e) == 0) lmax16 = 0;
-  const int pair_g = 16;                             // lanes per pair: two pairs per warp
-  const int np = 32 / pair_g;
-  c->pair_g = pair_g;
-  PairLmax lm{};
-  for (int kb = 0; kb < P16_NKB; kb++) lm.v[kb] = lmax16 > 0 ? std::min(p16_lmax(P16_COLS[kb] / pair_g, c->pssm_max), P16_MAXL) : 0;
-  MIAGPU_CUDA(cudaMemsetAsync(c->d_meta.p, 0, META_WORDS * sizeof(int32_t), c->stream));
-  classify_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, c->d_off.p, c->d_as.p, c->d_ae.p, c->wrap_len, lm,
-                                                                     c->d_win_start.p, c->d_win_len.p, c->d_lists.p, c->d_kind.p, c->d_meta.p);
+}
+
+// window rule + width classes + pair layout of one job on stream st; the meta block is copied to j.h_meta
+static int realign_classify(miagpu_ctx* c, const RealignJob& j, cudaStream_t st) {
+  if (j.n == 0) return 1;
+  const PairLmax lm = pair_lmax(c);
+  const int np = 32 / c->pair_g;
+  MIAGPU_CUDA(cudaMemsetAsync(j.d_meta, 0, META_WORDS * sizeof(int32_t), st));
+  classify_kernel<<<(unsigned)((j.n + 255) / 256), 256, 0, st>>>(j.n, c->d_off.p + j.lo, c->d_as.p + j.lo, c->d_ae.p + j.lo, c->wrap_len, lm,
+                                                                c->d_win_start.p + j.lo, c->d_win_len.p + j.lo, j.d_lists, c->d_kind.p + j.lo, j.d_meta);
   MIAGPU_CUDA(cudaGetLastError());
   c->launches++;
-  if (lmax16 > 0) {
-    pair_layout_kernel<<<1, LAYOUT_THREADS, 0, c->stream>>>(c->d_meta.p, np);
+  if (lm.v[0] > 0) {
+    pair_layout_kernel<<<1, LAYOUT_THREADS, 0, st>>>(j.d_meta, np);
     MIAGPU_CUDA(cudaGetLastError());
     c->launches++;
   }
-  int32_t meta[META_HOST];
-  MIAGPU_CUDA(cudaMemcpyAsync(meta, c->d_meta.p, sizeof(meta), cudaMemcpyDeviceToHost, c->stream));
-  MIAGPU_CUDA(cudaStreamSynchronize(c->stream));
-  memcpy(c->bucket_cells, meta + META_CELLS, sizeof(int64_t) * NBUCKET);
-  memcpy(c->pair_cells, meta + META_PCELLS, sizeof(int64_t) * P16_NKB);
-  for (int b = 0; b < NBUCKET; b++) c->dp_cells += c->bucket_cells[b];
+  MIAGPU_CUDA(cudaMemcpyAsync(j.h_meta, j.d_meta, sizeof(int32_t) * META_HOST, cudaMemcpyDeviceToHost, st));
+  return 1;
+}
+
+// the DP kernels of one job on c->stream; j.h_meta must have arrived
+static int realign_launch(miagpu_ctx* c, const RealignJob& j) {
+  const int64_t n = j.n, lo = j.lo;
+  if (n == 0) return 1;
+  const int32_t* meta = j.h_meta;
+  const int np = 32 / c->pair_g;
+  int64_t cells[NBUCKET], pcells[P16_NKB];
+  memcpy(cells, meta + META_CELLS, sizeof(cells));
+  memcpy(pcells, meta + META_PCELLS, sizeof(pcells));
+  for (int b = 0; b < NBUCKET; b++) { c->bucket_cells[b] += cells[b]; c->dp_cells += cells[b]; }
+  int pair_items[P16_NKB];
   int total_pairs = 0;                               // in work items (np pairs each)
-  for (int kb = 0; kb < P16_NKB; kb++) { c->pair_pairs[kb] = meta[META_NPAIRS + kb]; c->pair_reads[kb] = meta[META_PREADS + kb]; total_pairs += c->pair_pairs[kb]; }
+  for (int kb = 0; kb < P16_NKB; kb++) {
+    pair_items[kb] = meta[META_NPAIRS + kb];
+    c->pair_pairs[kb] += pair_items[kb]; c->pair_reads[kb] += meta[META_PREADS + kb]; c->pair_cells[kb] += pcells[kb];
+    total_pairs += pair_items[kb];
+  }
 
   // ---- 16-bit pair kernels first: the reads they cannot finish join the 32-bit lists
   if (total_pairs) {
-    MIAGPU_CUDA(cudaMemsetAsync(c->d_pairs.p, 0xff, (size_t)2 * np * total_pairs * sizeof(int32_t), c->stream));
-    pair_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, c->d_off.p, c->d_kind.p, c->d_meta.p, c->d_pairs.p);
+    MIAGPU_CUDA(cudaMemsetAsync(j.d_pairs, 0xff, (size_t)2 * np * total_pairs * sizeof(int32_t), c->stream));
+    pair_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, c->d_off.p + lo, c->d_kind.p + lo, j.d_meta, j.d_pairs);
     MIAGPU_CUDA(cudaGetLastError());
     c->launches++;
     int base = 0;
     for (int kb = 0; kb < P16_NKB; kb++) {
-      const int ni = c->pair_pairs[kb];
+      const int ni = pair_items[kb];
       if (!ni) continue;
-      MIAGPU_CUDA(cudaEventRecord(c->pev[2 * kb], c->stream));
+      if (j.timed) MIAGPU_CUDA(cudaEventRecord(c->pev[2 * kb], c->stream));
       Pair16Params p{};
-      p.bases = c->d_bases.p; p.off = c->d_off.p; p.rc = c->d_rc.p; p.win_start = c->d_win_start.p; p.win_len = c->d_win_len.p;
-      p.pairs = c->d_pairs.p + 2 * (int64_t)np * base; p.n_items = c->d_meta.p + META_NPAIRS + kb; p.counter = c->d_meta.p + META_PWORK + kb;
+      p.bases = c->d_bases.p; p.off = c->d_off.p + lo; p.rc = c->d_rc.p + lo; p.win_start = c->d_win_start.p + lo; p.win_len = c->d_win_len.p + lo;
+      p.pairs = j.d_pairs + 2 * (int64_t)np * base; p.n_items = j.d_meta + META_NPAIRS + kb; p.counter = j.d_meta + META_PWORK + kb;
       p.ref_codes = c->d_ref.p; p.ref_bytes = c->ref_bytes; p.prof16 = c->d_prof16.p;
-      p.score = c->d_score.p; p.as_out = c->d_as_out.p; p.ae_out = c->d_ae_out.p; p.abr = c->d_abr.p;
-      p.n_runs = c->d_nruns.p; p.runs = c->d_runs.p; p.status = c->d_status.p;
-      p.lists = c->d_lists.p; p.list_counts = c->d_meta.p + META_COUNT; p.n_reads = n; p.n_fallback = c->d_meta.p + META_NFALL;
+      p.score = c->d_score.p + lo; p.as_out = c->d_as_out.p + lo; p.ae_out = c->d_ae_out.p + lo; p.abr = c->d_abr.p + lo;
+      p.n_runs = c->d_nruns.p + lo; p.runs = c->d_runs.p + lo * MAX_RUNS; p.status = c->d_status.p + lo;
+      p.lists = j.d_lists; p.list_counts = j.d_meta + META_COUNT; p.n_reads = n; p.n_fallback = j.d_meta + META_NFALL;
       const int maxL = P16_MAXL;
       int ok = 1;
       switch (kb) {
@@ -661,7 +717,7 @@ static int realign_device(miagpu_ctx* c) {
         default: ok = launch_pair16<16, 16>(c, p, ni, maxL); break;
       }
       if (!ok) return 0;
-      MIAGPU_CUDA(cudaEventRecord(c->pev[2 * kb + 1], c->stream));
+      if (j.timed) MIAGPU_CUDA(cudaEventRecord(c->pev[2 * kb + 1], c->stream));
       base += ni;
     }
   }
@@ -671,15 +727,15 @@ static int realign_device(miagpu_ctx* c) {
     const int pop = meta[META_POP + b];               // upper bound of the final list length
     if (!pop) continue;
     if (!total_pairs && !meta[META_COUNT + b]) continue;
-    MIAGPU_CUDA(cudaEventRecord(c->bev[2 * b], c->stream));
+    if (j.timed) MIAGPU_CUDA(cudaEventRecord(c->bev[2 * b], c->stream));
     RealignParams p{};
-    p.bases = c->d_bases.p; p.off = c->d_off.p; p.rc = c->d_rc.p;
-    p.win_start = c->d_win_start.p; p.win_len = c->d_win_len.p;
-    p.list = c->d_lists.p + (int64_t)b * n; p.n_list = total_pairs ? pop : meta[META_COUNT + b];
-    p.n_list_ptr = c->d_meta.p + META_COUNT + b; p.counter = c->d_meta.p + META_WORK + b;
+    p.bases = c->d_bases.p; p.off = c->d_off.p + lo; p.rc = c->d_rc.p + lo;
+    p.win_start = c->d_win_start.p + lo; p.win_len = c->d_win_len.p + lo;
+    p.list = j.d_lists + (int64_t)b * n; p.n_list = total_pairs ? pop : meta[META_COUNT + b];
+    p.n_list_ptr = j.d_meta + META_COUNT + b; p.counter = j.d_meta + META_WORK + b;
     p.ref_codes = c->d_ref.p; p.ref_bytes = c->ref_bytes; p.prof = c->d_prof.p; p.sg5 = 1;
-    p.score = c->d_score.p; p.as_out = c->d_as_out.p; p.ae_out = c->d_ae_out.p; p.abr = c->d_abr.p;
-    p.n_runs = c->d_nruns.p; p.runs = c->d_runs.p; p.status = c->d_status.p;
+    p.score = c->d_score.p + lo; p.as_out = c->d_as_out.p + lo; p.ae_out = c->d_ae_out.p + lo; p.abr = c->d_abr.p + lo;
+    p.n_runs = c->d_nruns.p + lo; p.runs = c->d_runs.p + lo * MAX_RUNS; p.status = c->d_status.p + lo;
     int ok = 1, maxL = meta[META_MAXL + b];
     switch (BUCKET_K[b]) {
       case 2: ok = launch_bucket<2>(c, p, maxL); break;
@@ -692,13 +748,28 @@ static int realign_device(miagpu_ctx* c) {
       case 12: ok = launch_bucket<12>(c, p, maxL); break;
       case 16: ok = launch_bucket<16>(c, p, maxL); break;
       default:
-        ok = launch_strip(c, 1, p.list, meta[META_COUNT + b], c->d_meta.p + META_WORK + b);   // too wide for either kernel: never pair-eligible
+        ok = launch_strip(c, 1, p.list, meta[META_COUNT + b], j.d_meta + META_WORK + b, lo);   // too wide for either kernel: never pair-eligible
     }
     if (!ok) return 0;
-    MIAGPU_CUDA(cudaEventRecord(c->bev[2 * b + 1], c->stream));
-    c->bucket_reads[b] = -1;                         // launched; the final list length is read back with the timings
+    if (j.timed) MIAGPU_CUDA(cudaEventRecord(c->bev[2 * b + 1], c->stream));
+    if (j.timed) c->bucket_reads[b] = -1;            // launched; the final list length is read back with the timings
   }
   return 1;
+}
+
+static RealignJob whole_batch_job(miagpu_ctx* c) {
+  RealignJob j;
+  j.lo = 0; j.n = c->n; j.d_meta = c->d_meta.p; j.d_lists = c->d_lists.p; j.d_pairs = c->d_pairs.p; j.h_meta = c->h_meta; j.timed = true;
+  return j;
+}
+
+static int realign_device(miagpu_ctx* c) {
+  realign_reset_stats(c);
+  if (c->n == 0) return 1;
+  const RealignJob j = whole_batch_job(c);
+  if (!realign_classify(c, j, c->stream)) return 0;
+  MIAGPU_CUDA(cudaStreamSynchronize(c->stream));
+  return realign_launch(c, j);
 }
 
 static int realign_bucket_times(miagpu_ctx* c) {
@@ -1093,66 +1164,54 @@ extern "C" int miagpu_consensus_natural(miagpu_ctx* c, const uint8_t* dropped_fr
 }
 
 // ------------------------------------------------------- host policy (a12)
-// find_fsdb_score_cut (fsdb.c:269-383): double-precision sums in FSDB order.
-// The order-independent parts (integer sums, per-length maxima, the final per-read test) run on a few
-// host threads; the two rounded chains ssxy / ssxx run on one thread in the reference's order.
+// find_fsdb_score_cut (fsdb.c:269-383): double-precision sums in FSDB order (scorecut.hpp explains how the two
+// rounded chains are evaluated block-wise without changing a bit of the result).
 static int host_threads(int64_t n) {
   int t = (int)std::thread::hardware_concurrency();
   t = std::max(1, std::min(t, 8));
   if (const char* e = getenv("MIAGPU_HOST_THREADS")) t = std::max(1, atoi(e));
   return (int)std::min<int64_t>(t, std::max<int64_t>(1, n / 65536));
 }
-template <typename F>
-static void parallel_chunks(int64_t n, int T, F f) {
-  if (T <= 1) { f(0, 0, n); return; }
-  std::vector<std::thread> th;
-  for (int t = 0; t < T; t++) th.emplace_back(f, t, n * t / T, n * (t + 1) / T);
-  for (auto& x : th) x.join();
-}
 
-extern "C" int miagpu_score_cut(int64_t n, const int32_t* seq_len, const int32_t* score, const uint8_t* unique_best,
-                                double* slope, double* intercept) {
-  if (n < 0 || !seq_len || !score || !slope || !intercept) { set_error("miagpu_score_cut: bad argument"); return 0; }
-  // xbar / ybar are sums of integers: exact in double in any order (< 2^53), so they are taken in int64.
-  // ssxy / ssxx are rounded at every step: those two chains keep the reference's FSDB order.
-  // max slope_delta: for a fixed length the quotient is monotone in the score, so the maximum over reads
-  // is the maximum over lengths of the quotient at that length's best score (same doubles, same result).
-  const int T = host_threads(n);
-  struct Part { int64_t sx = 0, sy = 0, cnt = 0, bad = -1; int32_t best[MAX_READ + 1]; };
-  std::vector<Part> parts(T);
-  parallel_chunks(n, T, [&](int t, int64_t lo, int64_t hi) {
-    Part& q = parts[t];
-    for (int l = 0; l <= MAX_READ; l++) q.best[l] = INT_MIN;
+// order-independent part of the regression, mergeable across slices (and across the chunks of a pipeline)
+struct CutSums {
+  int64_t sx = 0, sy = 0, cnt = 0, bad = -1;
+  int32_t best[MAX_READ + 1];
+  CutSums() { for (int l = 0; l <= MAX_READ; l++) best[l] = INT_MIN; }
+  void scan(const int32_t* seq_len, const int32_t* score, const uint8_t* unique_best, int64_t lo, int64_t hi) {
+    // xbar / ybar are sums of integers: exact in double in any order (< 2^53), so they are taken in int64.
+    // max slope_delta: for a fixed length the quotient is monotone in the score, so the maximum over reads
+    // is the maximum over lengths of the quotient at that length's best score (same doubles, same result).
     for (int64_t i = lo; i < hi; i++)
       if ((!unique_best || unique_best[i]) && score[i] >= FIRST_ROUND_SCORE_CUTOFF) {
         const int l = seq_len[i];
-        if (l < 0 || l > MAX_READ) { q.bad = i; return; }
-        q.sx += l; q.sy += score[i]; q.cnt++;
-        if (score[i] > q.best[l]) q.best[l] = score[i];
+        if (l < 0 || l > MAX_READ) { bad = i; return; }
+        sx += l; sy += score[i]; cnt++;
+        if (score[i] > best[l]) best[l] = score[i];
       }
-  });
-  int64_t sx = 0, sy = 0, j = 0;
-  int32_t best_at_len[MAX_READ + 1];
-  for (int l = 0; l <= MAX_READ; l++) best_at_len[l] = INT_MIN;
-  for (const Part& q : parts) {
-    if (q.bad >= 0) { set_error("miagpu_score_cut: seq_len[%lld] = %d out of range", (long long)q.bad, seq_len[q.bad]); return 0; }
-    sx += q.sx; sy += q.sy; j += q.cnt;
-    for (int l = 0; l <= MAX_READ; l++) best_at_len[l] = std::max(best_at_len[l], q.best[l]);
   }
-  double xbar = (double)sx, ybar = (double)sy, ssxy = 0, ssxx = 0, max_delta = 0;
-  xbar /= j; ybar /= j;
+  void merge(const CutSums& q) {
+    if (q.bad >= 0 && bad < 0) bad = q.bad;
+    sx += q.sx; sy += q.sy; cnt += q.cnt;
+    for (int l = 0; l <= MAX_READ; l++) best[l] = std::max(best[l], q.best[l]);
+  }
+};
+
+// slope / intercept from the merged sums plus the two rounded chains over all reads in order
+static int score_cut_finish(int64_t n, const int32_t* seq_len, const int32_t* score, const uint8_t* unique_best, const CutSums& S,
+                            HostTeam& team, double* slope, double* intercept) {
+  if (S.bad >= 0) { set_error("miagpu_score_cut: seq_len[%lld] = %d out of range", (long long)S.bad, seq_len[S.bad]); return 0; }
+  double xbar = (double)S.sx, ybar = (double)S.sy, max_delta = 0;
+  xbar /= S.cnt; ybar /= S.cnt;
   double dx_of[MAX_READ + 1], dx2_of[MAX_READ + 1];                 // the same doubles the reference forms per read
   for (int l = 0; l <= MAX_READ; l++) { dx_of[l] = l - xbar; dx2_of[l] = dx_of[l] * dx_of[l]; }
-  for (int64_t i = 0; i < n; i++)
-    if ((!unique_best || unique_best[i]) && score[i] >= FIRST_ROUND_SCORE_CUTOFF) {
-      const int l = seq_len[i];
-      ssxy += dx_of[l] * (score[i] - ybar);
-      ssxx += dx2_of[l];
-    }
+  auto used = [&](int64_t i) { return (!unique_best || unique_best[i]) && score[i] >= FIRST_ROUND_SCORE_CUTOFF; };
+  const double ssxy = chained_sum(n, [&](int64_t i) { return used(i) ? dx_of[seq_len[i]] * (score[i] - ybar) : 0.0; }, team);
+  const double ssxx = chained_sum(n, [&](int64_t i) { return used(i) ? dx2_of[seq_len[i]] : 0.0; }, team);
   const double bf = ssxy / ssxx, ib = ybar - bf * xbar;
   for (int l = 0; l <= MAX_READ; l++)
-    if (best_at_len[l] != INT_MIN) {
-      double d = (best_at_len[l] - ((bf * l) + ib)) / l;
+    if (S.best[l] != INT_MIN) {
+      double d = (S.best[l] - ((bf * l) + ib)) / l;
       if (d > max_delta) max_delta = d;
     }
   *intercept = ib;
@@ -1161,27 +1220,53 @@ extern "C" int miagpu_score_cut(int64_t n, const int32_t* seq_len, const int32_t
   return 1;
 }
 
+static int score_cut_team(int64_t n, const int32_t* seq_len, const int32_t* score, const uint8_t* unique_best, HostTeam& team,
+                          double* slope, double* intercept) {
+  std::vector<CutSums> parts(team.size());
+  team.chunks(n, [&](int t, int64_t lo, int64_t hi) { parts[t].scan(seq_len, score, unique_best, lo, hi); });
+  CutSums S;
+  for (const CutSums& q : parts) S.merge(q);
+  return score_cut_finish(n, seq_len, score, unique_best, S, team, slope, intercept);
+}
+
+extern "C" int miagpu_score_cut(int64_t n, const int32_t* seq_len, const int32_t* score, const uint8_t* unique_best,
+                                double* slope, double* intercept) {
+  if (n < 0 || !seq_len || !score || !slope || !intercept) { set_error("miagpu_score_cut: bad argument"); return 0; }
+  HostTeam team(host_threads(n));
+  return score_cut_team(n, seq_len, score, unique_best, team, slope, intercept);
+}
+
 // The per-read test of cull_maln_from_fsdb (mia.c:418-479): below[i] = score < min_score_for_len.
-extern "C" int miagpu_cull_flags(int64_t n, const int32_t* seq_len, const int32_t* score, const uint8_t* unique_best, int hard_cut,
-                                 int score_cut_set, double slope_in, double intercept_in, uint8_t* below) {
-  if (n < 0 || !seq_len || !score || !below) { set_error("miagpu_cull_flags: bad argument"); return 0; }
-  double slope = slope_in, intercept = intercept_in;
-  if (!score_cut_set && !miagpu_score_cut(n, seq_len, score, unique_best, &slope, &intercept)) return 0;
+// sticky (nullable): the caller's dropped flags, updated in place (dropped |= below, H10); newly (nullable):
+// below & !dropped-before.
+static int cull_flags_team(int64_t n, const int32_t* seq_len, const int32_t* score, int hard_cut, double slope, double intercept,
+                           HostTeam& team, uint8_t* below, uint8_t* sticky, uint8_t* newly) {
   if (slope <= 0) slope = 100.0;
   double min_score[MAX_READ + 1];                                  // the threshold depends on the length only
   for (int l = 0; l <= MAX_READ; l++) min_score[l] = hard_cut > 0 ? (double)hard_cut : (double)(intercept + (slope * l));
-  const int T = host_threads(n);
-  std::vector<int64_t> bad(T, -1);
-  parallel_chunks(n, T, [&](int t, int64_t lo, int64_t hi) {
+  std::vector<int64_t> bad(team.size(), -1);
+  team.chunks(n, [&](int t, int64_t lo, int64_t hi) {
     for (int64_t i = lo; i < hi; i++) {
       const int l = seq_len[i];
       if (l < 0 || l > MAX_READ) { bad[t] = i; return; }
-      below[i] = score[i] < min_score[l];
+      const uint8_t b = score[i] < min_score[l];
+      if (below) below[i] = b;
+      if (newly) newly[i] = b & !sticky[i];
+      if (sticky) sticky[i] |= b;
     }
   });
   for (int64_t x : bad)
     if (x >= 0) { set_error("miagpu_cull_flags: seq_len[%lld] = %d out of range", (long long)x, seq_len[x]); return 0; }
   return 1;
+}
+
+extern "C" int miagpu_cull_flags(int64_t n, const int32_t* seq_len, const int32_t* score, const uint8_t* unique_best, int hard_cut,
+                                 int score_cut_set, double slope_in, double intercept_in, uint8_t* below) {
+  if (n < 0 || !seq_len || !score || !below) { set_error("miagpu_cull_flags: bad argument"); return 0; }
+  double slope = slope_in, intercept = intercept_in;
+  HostTeam team(host_threads(n));
+  if (!score_cut_set && !score_cut_team(n, seq_len, score, unique_best, team, &slope, &intercept)) return 0;
+  return cull_flags_team(n, seq_len, score, hard_cut, slope, intercept, team, below, nullptr, nullptr);
 }
 
 extern "C" int miagpu_consensus(miagpu_ctx* c, int64_t n_entries, const miagpu_entry* entries, int cons_code, int32_t* gaps_out,
@@ -1205,9 +1290,28 @@ __global__ void set_dropped_kernel(int64_t n, const uint8_t* flags, miagpu_entry
 // One iteration of mia_main.c:931-963 for a batch that arrives in host memory: upload, realign every read
 // (reiterate_assembly), score cut (cull_maln_from_fsdb, host policy), column accumulation and base calling
 // (consensus_assembly_string).  Same results as miagpu_realign_host + miagpu_get_runs_packed +
-// miagpu_cull_flags + miagpu_consensus_natural called one after the other; here the host-side score cut runs
-// on a helper thread as soon as the scores have arrived while the stream keeps downloading the other
-// per-read outputs, packs the run lists and takes the per-position insert maxima (which ignore `dropped`).
+// miagpu_cull_flags + miagpu_consensus_natural called one after the other, as a pipeline over three streams:
+//   upload stream   chunk k's reads + rc/as/ae, then its classification (window rule, width classes, pairs)
+//   compute stream  chunk k's DP kernels as soon as chunk k is classified; afterwards entries, insert maxima,
+//                   column accumulation with the flags of EARLIER rounds (known on entry), base calling
+//   download stream chunk k's scores (first) and the other per-read outputs while chunk k+1 computes
+// The host-side score cut runs on a helper thread once the last scores have arrived, concurrently with the
+// column accumulation; the base columns of the reads it drops are then taken back out (integer sums: the
+// accumulators are exactly those of an accumulation that knew the flags).
+struct Trace {                                       // MIAGPU_TRACE=1: host-side timeline of one miagpu_iterate_host call on stderr
+  bool on = getenv("MIAGPU_TRACE") != nullptr;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  void mark(const char* what) const {
+    if (on) fprintf(stderr, "[miagpu trace] %8.3f ms  %s\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(), what);
+  }
+};
+
+static int pick_chunks(int64_t n) {
+  int ch = (int)std::min<int64_t>(8, std::max<int64_t>(1, (n + 125000) / 250000));
+  if (const char* e = getenv("MIAGPU_CHUNKS")) ch = std::max(1, std::min(MAX_CHUNKS, atoi(e)));
+  return (int)std::min<int64_t>(ch, std::max<int64_t>(1, n));
+}
+
 extern "C" int miagpu_iterate_host(miagpu_ctx* c, int64_t n, const uint8_t* bases, const int64_t* offsets, const uint8_t* rc,
                                    const int32_t* as, const int32_t* ae, int32_t* score, int32_t* as_out, int32_t* ae_out,
                                    int32_t* abr, int32_t* n_runs, uint8_t* status, uint16_t* packed_runs, int64_t capacity,
@@ -1218,91 +1322,161 @@ extern "C" int miagpu_iterate_host(miagpu_ctx* c, int64_t n, const uint8_t* base
   if (n <= 0 || !bases || !offsets || !rc || !as || !ae || !score || !seq_len || !dropped) { set_error("miagpu_iterate_host: bad argument"); return 0; }
   MIAGPU_CUDA(cudaSetDevice(c->device));
   if (n > 0x7fffffffLL / NBUCKET) { set_error("miagpu_iterate_host: at most %lld reads per batch", 0x7fffffffLL / NBUCKET); return 0; }
+  if (offsets[0] != 0) { set_error("miagpu_iterate_host: offsets[0] must be 0"); return 0; }
   const int64_t total = offsets[n];
   if (!c->d_bases.reserve(total + 16) || !c->d_off.reserve(n + 1) || !reserve_per_read(c, n)) return 0;
   if (!c->d_entries.reserve(2 * n + 2) || !c->d_gaps.reserve(c->seq_len + 2) || !c->d_ins_off.reserve(c->seq_len + 2) ||
-      !c->d_dropf.reserve(n + 1) || !c->d_off2.reserve(2 * (n + 2))) return 0;
-  // ---- upload + realign
-  MIAGPU_CUDA(cudaEventRecord(c->ev[0], c->stream));
-  MIAGPU_CUDA(cudaMemcpyAsync(c->d_bases.p, bases, total, cudaMemcpyHostToDevice, c->stream));
-  MIAGPU_CUDA(cudaMemcpyAsync(c->d_off.p, offsets, (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
-  MIAGPU_CUDA(cudaMemcpyAsync(c->d_rc.p, rc, n, cudaMemcpyHostToDevice, c->stream));
-  MIAGPU_CUDA(cudaMemcpyAsync(c->d_as.p, as, n * 4, cudaMemcpyHostToDevice, c->stream));
-  MIAGPU_CUDA(cudaMemcpyAsync(c->d_ae.p, ae, n * 4, cudaMemcpyHostToDevice, c->stream));
-  c->n = n; c->total_bases = total; c->max_read_len = -1;
-  MIAGPU_CUDA(cudaEventRecord(c->ev[1], c->stream));
-  if (!realign_device(c)) return 0;
+      !c->d_dropf.reserve(n + 1) || !c->d_dropb.reserve(n + 1) || !c->d_off2.reserve(2 * (n + 2))) return 0;
+  if (c->h_newly_cap < n) {
+    if (c->h_newly) cudaFreeHost(c->h_newly);
+    c->h_newly = nullptr; c->h_newly_cap = 0;
+    MIAGPU_CUDA(cudaMallocHost(&c->h_newly, n + 64));
+    c->h_newly_cap = n;
+  }
+  cudaStream_t main = c->stream, up = c->s_up, down = c->s_down;
+  const int C = pick_chunks(n);
+  HostTeam team(host_threads(n));                     // started now: the threads are waiting by the time the scores arrive
+  const Trace tr;
+  tr.mark("buffers reserved");
+  realign_reset_stats(c);
+  c->n = n; c->total_bases = total;
+  c->max_read_len = C > 1 ? MAX_READ : -1;            // chunked: the longest read is not known before the last upload
+  // the side streams start after whatever the compute stream still has queued
+  MIAGPU_CUDA(cudaEventRecord(c->ev[0], main));
+  MIAGPU_CUDA(cudaStreamWaitEvent(up, c->ev[0], 0));
+  MIAGPU_CUDA(cudaStreamWaitEvent(down, c->ev[0], 0));
+  // ---- upload stream: every chunk's inputs and classification, then the flags of earlier rounds
+  RealignJob jobs[MAX_CHUNKS];
+  for (int k = 0; k < C; k++) {
+    const int64_t lo = n * k / C, hi = n * (k + 1) / C;
+    RealignJob& j = jobs[k];
+    j.lo = lo; j.n = hi - lo; j.d_meta = c->d_meta.p + (size_t)META_WORDS * k; j.d_lists = c->d_lists.p + (size_t)NBUCKET * lo;
+    j.d_pairs = c->d_pairs.p + lo + (size_t)k * (4 * P16_KEYS + 64); j.h_meta = c->h_meta + (size_t)META_HOST * k; j.timed = false;
+    MIAGPU_CUDA(cudaMemcpyAsync(c->d_bases.p + offsets[lo], bases + offsets[lo], offsets[hi] - offsets[lo], cudaMemcpyHostToDevice, up));
+    if (k == 0) MIAGPU_CUDA(cudaMemcpyAsync(c->d_off.p, offsets, sizeof(int64_t), cudaMemcpyHostToDevice, up));
+    MIAGPU_CUDA(cudaMemcpyAsync(c->d_off.p + lo + 1, offsets + lo + 1, (hi - lo) * sizeof(int64_t), cudaMemcpyHostToDevice, up));   // every element once
+    MIAGPU_CUDA(cudaMemcpyAsync(c->d_rc.p + lo, rc + lo, hi - lo, cudaMemcpyHostToDevice, up));
+    MIAGPU_CUDA(cudaMemcpyAsync(c->d_as.p + lo, as + lo, (hi - lo) * 4, cudaMemcpyHostToDevice, up));
+    MIAGPU_CUDA(cudaMemcpyAsync(c->d_ae.p + lo, ae + lo, (hi - lo) * 4, cudaMemcpyHostToDevice, up));
+    if (!realign_classify(c, j, up)) return 0;
+    MIAGPU_CUDA(cudaEventRecord(c->cev[4 * k], up));
+  }
+  MIAGPU_CUDA(cudaMemcpyAsync(c->d_dropf.p, dropped, n, cudaMemcpyHostToDevice, up));       // sticky flags of earlier rounds (H10)
+  MIAGPU_CUDA(cudaEventRecord(c->xev[1], up));
+  tr.mark("uploads + classification enqueued");
+  // ---- compute + download streams, chunk by chunk
+  for (int k = 0; k < C; k++) {
+    const RealignJob& j = jobs[k];
+    MIAGPU_CUDA(cudaEventSynchronize(c->cev[4 * k]));           // the chunk's meta block is on the host
+    tr.mark("chunk classified");
+    MIAGPU_CUDA(cudaStreamWaitEvent(main, c->cev[4 * k], 0));
+    if (!realign_launch(c, j)) return 0;
+    MIAGPU_CUDA(cudaEventRecord(c->cev[4 * k + 1], main));
+    MIAGPU_CUDA(cudaStreamWaitEvent(down, c->cev[4 * k + 1], 0));
+    MIAGPU_CUDA(cudaMemcpyAsync(score + j.lo, c->d_score.p + j.lo, j.n * 4, cudaMemcpyDeviceToHost, down));
+    MIAGPU_CUDA(cudaEventRecord(c->cev[4 * k + 2], down));            // this chunk's scores: the host policy scans them as they arrive
+    if (as_out) MIAGPU_CUDA(cudaMemcpyAsync(as_out + j.lo, c->d_as_out.p + j.lo, j.n * 4, cudaMemcpyDeviceToHost, down));
+    if (ae_out) MIAGPU_CUDA(cudaMemcpyAsync(ae_out + j.lo, c->d_ae_out.p + j.lo, j.n * 4, cudaMemcpyDeviceToHost, down));
+    if (abr) MIAGPU_CUDA(cudaMemcpyAsync(abr + j.lo, c->d_abr.p + j.lo, j.n * 4, cudaMemcpyDeviceToHost, down));
+    if (n_runs) MIAGPU_CUDA(cudaMemcpyAsync(n_runs + j.lo, c->d_nruns.p + j.lo, j.n * 4, cudaMemcpyDeviceToHost, down));
+    if (status) MIAGPU_CUDA(cudaMemcpyAsync(status + j.lo, c->d_status.p + j.lo, j.n, cudaMemcpyDeviceToHost, down));
+  }
   const int launches_realign = c->launches;
-  MIAGPU_CUDA(cudaEventRecord(c->ev[2], c->stream));
-  // ---- scores first: the host policy starts as soon as they are here
-  MIAGPU_CUDA(cudaMemcpyAsync(score, c->d_score.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
-  MIAGPU_CUDA(cudaEventRecord(c->ev[4], c->stream));
-  std::vector<uint8_t> below(n);
+  tr.mark("DP + downloads enqueued");
+  // ---- host policy on a helper thread (+ its team): newly[i] = below & !sticky, dropped |= below
+  uint8_t* newly = c->h_newly;
   int cut_ok = 0;
   char cut_err[256] = "";
   std::thread cut([&] {
     cudaSetDevice(c->device);
-    if (cudaEventSynchronize(c->ev[4]) != cudaSuccess) { snprintf(cut_err, sizeof(cut_err), "miagpu_iterate_host: waiting for the scores failed"); return; }
-    cut_ok = miagpu_cull_flags(n, seq_len, score, unique_best, hard_cut, score_cut_set, slope, intercept, below.data());
+    CutSums sums;
+    for (int k = 0; k < C && !score_cut_set; k++) {             // order-independent sums, chunk by chunk as the scores land
+      if (cudaEventSynchronize(c->cev[4 * k + 2]) != cudaSuccess) { snprintf(cut_err, sizeof(cut_err), "miagpu_iterate_host: waiting for the scores failed"); return; }
+      std::vector<CutSums> parts(team.size());
+      const int64_t lo = jobs[k].lo;
+      team.chunks(jobs[k].n, [&](int t, int64_t a, int64_t b) { parts[t].scan(seq_len, score, unique_best, lo + a, lo + b); });
+      for (const CutSums& q : parts) sums.merge(q);
+    }
+    if (cudaEventSynchronize(c->cev[4 * (C - 1) + 2]) != cudaSuccess || cudaEventSynchronize(c->xev[1]) != cudaSuccess) {
+      snprintf(cut_err, sizeof(cut_err), "miagpu_iterate_host: waiting for the scores failed");
+      return;
+    }
+    tr.mark("  [cut thread] scores on host");
+    double sl = slope, ic = intercept;
+    cut_ok = score_cut_set ? 1 : score_cut_finish(n, seq_len, score, unique_best, sums, team, &sl, &ic);
+    tr.mark("  [cut thread] regression done");
+    if (cut_ok) cut_ok = cull_flags_team(n, seq_len, score, hard_cut, sl, ic, team, nullptr, dropped, newly);      // sticky (H10)
     if (!cut_ok) snprintf(cut_err, sizeof(cut_err), "%s", miagpu_last_error());
-    else for (int64_t i = 0; i < n; i++) dropped[i] |= below[i];           // sticky (H10)
+    tr.mark("  [cut thread] flags computed");
   });
   auto fail = [&](const char* what, cudaError_t e) { cut.join(); set_error("miagpu_iterate_host: %s: %s", what, cudaGetErrorString(e)); return 0; };
 #define IT_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(#call, e_); } while (0)
-  if (as_out) IT_CUDA(cudaMemcpyAsync(as_out, c->d_as_out.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
-  if (ae_out) IT_CUDA(cudaMemcpyAsync(ae_out, c->d_ae_out.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
-  if (abr) IT_CUDA(cudaMemcpyAsync(abr, c->d_abr.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
-  if (n_runs) IT_CUDA(cudaMemcpyAsync(n_runs, c->d_nruns.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
-  if (status) IT_CUDA(cudaMemcpyAsync(status, c->d_status.p, n, cudaMemcpyDeviceToHost, c->stream));
-  // ---- packed run lists + entries + per-position insert maxima, one host sync for the two totals
+  // ---- compute stream: packed run lists + entries + per-position insert maxima, one host sync for the two totals
   int64_t* cnt = c->d_off2.p;
   int64_t* offs = c->d_off2.p + (n + 2);
-  clamp_runs_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, c->stream>>>(n, c->d_nruns.p, cnt);
   size_t tmp = 0, tmp2 = 0;
-  IT_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, cnt, offs, n + 1, c->stream));
-  IT_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp2, c->d_gaps.p, c->d_ins_off.p, c->seq_len + 1, c->stream));
-  if (!c->d_cub.reserve(std::max(tmp, tmp2) + 16)) { cut.join(); return 0; }
-  IT_CUDA(cub::DeviceScan::ExclusiveSum(c->d_cub.p, tmp, cnt, offs, n + 1, c->stream));
   int64_t tot = 0;
-  IT_CUDA(cudaMemcpyAsync(&tot, offs + n, 8, cudaMemcpyDeviceToHost, c->stream));
+  if (packed_runs || total_runs) {
+    clamp_runs_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, main>>>(n, c->d_nruns.p, cnt);
+    IT_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, cnt, offs, n + 1, main));
+  }
+  IT_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp2, c->d_gaps.p, c->d_ins_off.p, c->seq_len + 1, main));
+  if (!c->d_cub.reserve(std::max(tmp, tmp2) + 16)) { cut.join(); return 0; }
+  if (packed_runs || total_runs) {
+    IT_CUDA(cub::DeviceScan::ExclusiveSum(c->d_cub.p, tmp, cnt, offs, n + 1, main));
+    IT_CUDA(cudaMemcpyAsync(&tot, offs + n, 8, cudaMemcpyDeviceToHost, main));
+  }
   c->n_entries = 2 * n;
-  IT_CUDA(cudaMemsetAsync(c->d_gaps.p, 0, (c->seq_len + 2) * sizeof(int32_t), c->stream));
-  natural_entries_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, c->d_as_out.p, c->d_ae_out.p, c->d_nruns.p, c->d_runs.p,
-                                                                             c->d_status.p, c->seq_len, nullptr, nullptr, c->d_entries.p);
+  IT_CUDA(cudaMemsetAsync(c->d_gaps.p, 0, (c->seq_len + 2) * sizeof(int32_t), main));
+  IT_CUDA(cudaStreamWaitEvent(main, c->xev[1], 0));             // the earlier rounds' flags
+  natural_entries_kernel<<<(unsigned)((n + 255) / 256), 256, 0, main>>>(n, c->d_as_out.p, c->d_ae_out.p, c->d_nruns.p, c->d_runs.p,
+                                                                        c->d_status.p, c->seq_len, c->d_dropf.p, c->d_dropf.p, c->d_entries.p);
   if (!launch_gaps(c)) { cut.join(); return 0; }
-  IT_CUDA(cub::DeviceScan::ExclusiveSum(c->d_cub.p, tmp2, c->d_gaps.p, c->d_ins_off.p, c->seq_len + 1, c->stream));
+  IT_CUDA(cub::DeviceScan::ExclusiveSum(c->d_cub.p, tmp2, c->d_gaps.p, c->d_ins_off.p, c->seq_len + 1, main));
   int32_t total_ins = 0;
-  IT_CUDA(cudaMemcpyAsync(&total_ins, c->d_ins_off.p + c->seq_len, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-  IT_CUDA(cudaStreamSynchronize(c->stream));
-  float ms_h2d = 0, ms_k = 0;
-  IT_CUDA(cudaEventElapsedTime(&ms_h2d, c->ev[0], c->ev[1]));
-  IT_CUDA(cudaEventElapsedTime(&ms_k, c->ev[1], c->ev[2]));
+  IT_CUDA(cudaMemcpyAsync(&total_ins, c->d_ins_off.p + c->seq_len, sizeof(int32_t), cudaMemcpyDeviceToHost, main));
+  tr.mark("entries + insert maxima enqueued");
+  IT_CUDA(cudaStreamSynchronize(main));
+  tr.mark("compute stream drained (DP, entries, insert maxima)");
   if (total_runs) *total_runs = tot;
   if (packed_runs && tot > capacity) { cut.join(); set_error("miagpu_iterate_host: %lld runs, capacity %lld", (long long)tot, (long long)capacity); return 0; }
   if (!c->d_packed.reserve(tot + 1)) { cut.join(); return 0; }
   c->n_cols = (int64_t)c->seq_len + total_ins;
   if (!c->d_acc.reserve(c->n_cols * NPLANE) || !c->d_called.reserve(c->n_cols + 16)) { cut.join(); return 0; }
   if (packed_runs) {
-    pack_runs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, c->d_nruns.p, offs, c->d_runs.p, c->d_packed.p);
-    if (tot) IT_CUDA(cudaMemcpyAsync(packed_runs, c->d_packed.p, tot * 2, cudaMemcpyDeviceToHost, c->stream));
+    pack_runs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, main>>>(n, c->d_nruns.p, offs, c->d_runs.p, c->d_packed.p);
+    IT_CUDA(cudaEventRecord(c->xev[3], main));
+    IT_CUDA(cudaStreamWaitEvent(down, c->xev[3], 0));
+    if (tot) IT_CUDA(cudaMemcpyAsync(packed_runs, c->d_packed.p, tot * 2, cudaMemcpyDeviceToHost, down));
   }
-  IT_CUDA(cudaMemsetAsync(c->d_acc.p, 0, c->n_cols * NPLANE * sizeof(int32_t), c->stream));
-  // ---- the flags are needed from here on
+  IT_CUDA(cudaMemsetAsync(c->d_acc.p, 0, c->n_cols * NPLANE * sizeof(int32_t), main));
+  if (!launch_accumulate(c)) { cut.join(); return 0; }          // every read not dropped in an earlier round
+  // ---- the flags of this round: take the newly dropped reads' base columns back out
+  tr.mark("accumulation enqueued");
   cut.join();
+  tr.mark("cut thread joined");
   if (!cut_ok) { set_error("%s", cut_err); return 0; }
 #undef IT_CUDA
-  MIAGPU_CUDA(cudaMemcpyAsync(c->d_dropf.p, dropped, n, cudaMemcpyHostToDevice, c->stream));
-  set_dropped_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, c->d_dropf.p, c->d_entries.p);
-  if (!launch_accumulate(c)) return 0;
-  MIAGPU_CUDA(cudaGetLastError());
-  c->launches = launches_realign + 10;
+  MIAGPU_CUDA(cudaMemcpyAsync(c->d_dropb.p, newly, n, cudaMemcpyHostToDevice, main));
+  {
+    ConsParams p = cons_params(c);
+    undo_kernel<<<(unsigned)((n + 255) / 256), 256, 0, main>>>(p, n, c->d_dropb.p, c->d_entries.p);
+    MIAGPU_CUDA(cudaGetLastError());
+  }
   c->cons_stage = 2;
-  MIAGPU_CUDA(cudaEventRecord(c->ev[3], c->stream));
   if (!miagpu_call(c, cons_code, gaps_out, nullptr, cons_out, cons_len)) return 0;
-  c->launches = launches_realign + 11;
-  c->ms_h2d = ms_h2d;
-  c->ms_kernels = ms_k;
-  return realign_bucket_times(c);
+  tr.mark("consensus called and downloaded");
+  MIAGPU_CUDA(cudaStreamSynchronize(down));
+  tr.mark("download stream drained");
+  c->launches = launches_realign + 12;
+  c->ms_h2d = 0; c->ms_kernels = 0; c->ms_d2h = 0;   // the phases overlap: only the caller's wall clock means something
+  // statistics of the chunks
+  for (int k = 0; k < C; k++) {
+    int32_t nf = 0;
+    MIAGPU_CUDA(cudaMemcpy(&nf, jobs[k].d_meta + META_NFALL, 4, cudaMemcpyDeviceToHost));
+    c->n_fallback += nf;
+  }
+  return 1;
 }
 
 // ------------------------------------------------------------------ pass 1
