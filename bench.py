@@ -6,15 +6,16 @@ windowed PSSM semi-global DP + on-device traceback of every read against the cur
 consensus (reiterate_assembly, mia_main.c:178-257), then per-column accumulation and base
 calling (consensus_assembly_string, mia.c:515-603).  Workload at N=1 is BASELINE.json
 configs[1]: 1 M synthetic 35-75 bp aDNA-damaged reads vs a 16,569 bp circular reference,
-ancient.submat.solexa.onepass, single iteration.  Reads shard across ranks (weak scaling:
+ancient.submat.solexa.onepass, single iteration.  At N=1 the step also holds the iteration's score cut
+(cull_maln_from_fsdb / find_fsdb_score_cut, mia.c:418-479, fsdb.c:269-383) between the two.  Reads shard across ranks (weak scaling:
 1 M reads per GPU, consensus replicated, gaps all-reduced with MAX and the column planes
 with SUM over NCCL).
 
   value : reads/s, whole job, inputs resident in HBM, device time (CUDA events on the
           library's stream), max over ranks.
-  e2e   : the same through the C ABI with HOST buffers: H2D of reads + rc/as/ae from pinned
-          memory, realign, D2H of per-read results, host score cut (a12), H2D of the dropped
-          flags, consensus, D2H of the consensus -- wall clock around the calls.
+  e2e   : the same through the C ABI with HOST buffers (miagpu_iterate_host): H2D of reads +
+          rc/as/ae/seq_len/flags from pinned memory, realign, score cut, consensus, D2H of the
+          per-read results, packed run lists, flags and consensus -- wall clock around the call.
   --impl reference : the unmodified reference (oracle/_ref, built from /root/reference/src)
           running its own per-read realign sequence on the host cores, one process per core
           on disjoint shards (the reference itself is single-threaded).
@@ -33,7 +34,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-METRIC = "aligned reads/sec per iteration (windowed PSSM DP + traceback + consensus)"
+METRIC = "aligned reads/sec per iteration (windowed PSSM DP + traceback + score cut + consensus)"
 UNIT = "reads/s"
 REF_LEN = 16569
 INT_OPS_PER_CELL = 15          # minimum straight-line INT32 work per DP cell
@@ -155,6 +156,11 @@ def run_ours(args):
     launches = {"n": 0}
 
     def step_resident():
+        if world == 1:      # the whole round on resident inputs: realign, score cut (device), consensus
+            g.reset_dropped()                               # every timed step starts from the same state
+            cons = g.iterate_resident()[0]
+            launches["n"] += g.last_timing()["launches"]
+            return cons
         g.realign_resident()
         launches["n"] += g.last_timing()["launches"]
         cons = consensus_step()
@@ -206,6 +212,7 @@ def run_ours(args):
     # ---- resident arm: device time per step via events on the library's stream
     g.upload_reads(bases, off)
     g.set_alignment_inputs(rc, as_, ae)
+    g.set_cut_inputs(seq_len)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     for _ in range(max(args.warmup, 3)):
         cons = step_resident()
@@ -261,8 +268,8 @@ def run_ours(args):
     value = world * n / (ms_per_step * 1e-3)
     cells = tim_realign["dp_cells"]
     gcups = world * cells / (ms_per_step * 1e-3) / 1e9
-    h2d = int(len(bases) + off.nbytes + rc.nbytes + as_.nbytes + ae.nbytes + (n if world == 1 else 2 * n))
-    d2h = int(sum(v.numel() * v.element_size() for v in h_out.values()) + 2 * packed_total["n"] + len(cons_e2e))
+    h2d = int(len(bases) + off.nbytes + rc.nbytes + as_.nbytes + ae.nbytes + (seq_len.nbytes + n if world == 1 else 2 * n))
+    d2h = int(sum(v.numel() * v.element_size() for v in h_out.values()) + 2 * packed_total["n"] + len(cons_e2e) + (n if world == 1 else 0))
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -279,7 +286,7 @@ def run_ours(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
         "data": "synthetic",
         "config": {"workload": "BASELINE configs[1]: 1M synthetic 35-75 bp aDNA-damaged reads per GPU vs 16,569 bp circular "
-                               "R-rand reference, ancient.submat.solexa.onepass, single iteration (realign + consensus)",
+                               "R-rand reference, ancient.submat.solexa.onepass, single iteration (realign + score cut + consensus)",
                    "reads_per_gpu": n, "ref_len": REF_LEN, "l2": "256 MiB buffer written between timed steps",
                    "parallelism": f"reads sharded x{world}, consensus replicated, allreduce(max gaps, sum planes)"},
         "gcups": gcups, "dp_cells_per_step": world * cells,

@@ -225,7 +225,8 @@ int miagpu_accumulate_gaps_natural( miagpu_ctx* ctx, const uint8_t* dropped_fron
                                     const uint8_t* dropped_back, void** dev_gaps,
                                     int64_t* n_gaps );
 
-/* ---- a12, host policy kept on the host (H8): the score/length regression of
+/* ---- a12 on the host (H8; scores in host memory, e.g. gathered from several
+ * GPUs): the score/length regression of
  * find_fsdb_score_cut (fsdb.c:269-383, double sums in FSDB order) and the
  * per-read test of cull_maln_from_fsdb (mia.c:418-479): below[i] = 1 iff
  * score[i] < (hard_cut > 0 ? hard_cut : intercept + slope*seq_len[i]).  The
@@ -242,8 +243,13 @@ int miagpu_cull_flags( int64_t n, const int32_t* seq_len, const int32_t* score,
  * mia_main.c:931-963.  Equivalent to miagpu_realign_host + miagpu_get_runs_packed +
  * miagpu_cull_flags (dropped[i] |= below[i], sticky as in H10) + miagpu_consensus_natural
  * (every read owns its fresh AlnSeq segments; dropped[] serves the front and the back
- * segment), but the host-side score cut overlaps the downloads and the insert-maxima
- * pass.  seq_len / unique_best / hard_cut / score_cut_set / slope / intercept as in
+ * segment), pipelined over upload / compute / download streams.  The score cut runs
+ * on the device over the scores where they are (csrc/scorecut.cuh): integer sums,
+ * then the two double-precision chains of find_fsdb_score_cut block by block with
+ * a proof per block that the block-wise result equals the reference's read-by-read
+ * rounding; blocks without a proof are summed read by read on the host.  Slope,
+ * intercept and flags are bit-identical to miagpu_score_cut / miagpu_cull_flags.
+ * seq_len / unique_best / hard_cut / score_cut_set / slope / intercept as in
  * miagpu_cull_flags; packed_runs (nullable) as in miagpu_get_runs_packed. */
 int miagpu_iterate_host( miagpu_ctx* ctx, int64_t n, const uint8_t* bases,
                          const int64_t* offsets, const uint8_t* rc, const int32_t* as,
@@ -254,6 +260,24 @@ int miagpu_iterate_host( miagpu_ctx* ctx, int64_t n, const uint8_t* bases,
                          int score_cut_set, double slope, double intercept,
                          uint8_t* dropped, int cons_code, int32_t* gaps_out,
                          char* cons_out, int32_t* cons_len );
+
+/* The same round with everything resident in HBM (reads from miagpu_upload_reads,
+ * rc/as/ae from miagpu_set_alignment_inputs, and the score cut's per-read inputs
+ * from miagpu_set_cut_inputs: FragSeq.seq_len, unique_best (nullable = all 1),
+ * the sticky AlnSeq.dropped flags of earlier rounds (nullable = none)).  The
+ * sticky flags stay on the device and keep accumulating from round to round
+ * (H10); miagpu_reset_dropped clears them.  Outputs are nullable host arrays:
+ * slope_out / intercept_out (the fit, or the values passed in when
+ * score_cut_set), dropped[n] (sticky flags after this round), gaps_out[seq_len],
+ * cons_out / cons_len as in miagpu_consensus. */
+int miagpu_set_cut_inputs( miagpu_ctx* ctx, const int32_t* seq_len,
+                           const uint8_t* unique_best, const uint8_t* dropped );
+int miagpu_reset_dropped( miagpu_ctx* ctx );
+int miagpu_iterate_resident( miagpu_ctx* ctx, int hard_cut, int score_cut_set,
+                             double slope, double intercept, int cons_code,
+                             double* slope_out, double* intercept_out,
+                             uint8_t* dropped, int32_t* gaps_out, char* cons_out,
+                             int32_t* cons_len );
 
 /* Device-resident round (reads, rc, as, ae stay in HBM between calls): */
 int miagpu_set_alignment_inputs( miagpu_ctx* ctx, const uint8_t* rc,

@@ -65,6 +65,10 @@ def load_library():
     L.miagpu_cull_flags.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p]
     L.miagpu_set_alignment_inputs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.miagpu_realign_resident.argtypes = [C.c_void_p]
+    L.miagpu_set_cut_inputs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.miagpu_reset_dropped.argtypes = [C.c_void_p]
+    L.miagpu_iterate_resident.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.POINTER(C.c_double),
+                                          C.POINTER(C.c_double), C.c_void_p, C.c_void_p, C.c_void_p, _i32p]
     L.miagpu_last_buckets.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.miagpu_iterate_host.argtypes = ([C.c_void_p, C.c_int64] + [C.c_void_p] * 12 + [C.c_int64, _i64p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                       C.c_double, C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_char_p, _i32p])
@@ -82,7 +86,7 @@ EXPORTS = ["miagpu_device_count", "miagpu_create", "miagpu_destroy", "miagpu_las
            "miagpu_pass1", "miagpu_compact_reads", "miagpu_realign", "miagpu_realign_host", "miagpu_iterate_host", "miagpu_get_runs_packed",
            "miagpu_consensus", "miagpu_accumulate_gaps", "miagpu_accumulate_counts", "miagpu_call", "miagpu_consensus_natural", "miagpu_accumulate_gaps_natural",
            "miagpu_score_cut", "miagpu_cull_flags",
-           "miagpu_set_alignment_inputs", "miagpu_realign_resident", "miagpu_last_buckets", "miagpu_last_pair_buckets", "miagpu_last_timing",
+           "miagpu_set_alignment_inputs", "miagpu_realign_resident", "miagpu_set_cut_inputs", "miagpu_reset_dropped", "miagpu_iterate_resident", "miagpu_last_buckets", "miagpu_last_pair_buckets", "miagpu_last_timing",
            "miagpu_int32_peak", "miagpu_stream"]
 
 
@@ -221,6 +225,26 @@ class MiaGpu:
                                               _ptr(gaps), self._consbuf, C.byref(cl)))
         self.n = n
         return self._consbuf.value.decode(), out, tot.value, gaps
+
+    def set_cut_inputs(self, seq_len, unique_best=None, dropped=None):
+        """Per-read inputs of the score cut, resident from here on (miagpu_set_cut_inputs)."""
+        self._ck(self.lib.miagpu_set_cut_inputs(self.h, _ptr(np.ascontiguousarray(seq_len, np.int32)), _ptr(unique_best), _ptr(dropped)))
+
+    def reset_dropped(self):
+        self._ck(self.lib.miagpu_reset_dropped(self.h))
+
+    def iterate_resident(self, cons_code=1, hard_cut=0, score_cut=None, dropped=None, want_gaps=False):
+        """One whole iteration over resident inputs (miagpu_iterate_resident).
+        Returns (consensus, (slope, intercept), gaps); `dropped` (uint8[n], optional) receives the sticky flags."""
+        if not hasattr(self, "_consbuf") or len(self._consbuf) < self.seq_len * 4 + 4096:
+            self._consbuf = C.create_string_buffer(self.seq_len * 4 + 4096)
+        cl = C.c_int32()
+        gaps = np.zeros(self.seq_len, np.int32) if want_gaps else None
+        slope, icpt = score_cut if score_cut is not None else (0.0, 0.0)
+        so, io = C.c_double(), C.c_double()
+        self._ck(self.lib.miagpu_iterate_resident(self.h, hard_cut, 0 if score_cut is None else 1, slope, icpt, cons_code, C.byref(so),
+                                                  C.byref(io), _ptr(dropped), _ptr(gaps), self._consbuf, C.byref(cl)))
+        return self._consbuf.value.decode(), (so.value, io.value), gaps
 
     # -- consensus
     def consensus(self, entries, cons_code=1, want_counts=False):

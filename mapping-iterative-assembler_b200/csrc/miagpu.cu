@@ -15,6 +15,7 @@
 #include "consensus.cuh"
 #include "strip.cuh"
 #include "scorecut.hpp"
+#include "scorecut.cuh"
 #include <cub/device/device_scan.cuh>
 
 namespace miagpu {
@@ -123,8 +124,22 @@ struct miagpu_ctx {
   cudaEvent_t cev[4 * 16] = {};                 // [MAX_CHUNKS][4]: classified, realigned, scores on host, spare
   cudaEvent_t xev[4] = {};
   int32_t* h_meta = nullptr;                    // pinned, MAX_CHUNKS * META_HOST
-  uint8_t* h_newly = nullptr;                   // pinned, flags of the reads dropped in this round
-  int64_t h_newly_cap = 0;
+  // device score cut (scorecut.cuh): seq_len / unique_best copies, integer sums, tables, thresholds, chain blocks
+  DevBuf<int32_t> d_seqlen;
+  DevBuf<uint8_t> d_unique;
+  DevBuf<CutStatsDev> d_cstats;
+  DevBuf<CutTables> d_ctab;
+  DevBuf<double> d_thr;
+  DevBuf<CutBlockDev> d_cblk;
+  struct CutHost* h_cut = nullptr;              // pinned
+  CutBlockDev* h_cblk = nullptr;                // pinned
+  int64_t h_cblk_cap = 0;
+  int32_t* h_score = nullptr;                   // pinned copy of the scores (resident rounds)
+  int64_t h_score_cap = 0;
+  std::vector<int32_t> h_seqlen;                // host copies for the chains' unproven blocks (resident rounds)
+  std::vector<uint8_t> h_unique;
+  int64_t cut_inputs_n = -1;
+  int64_t cut_serial_blocks = 0;                // chain blocks the last round summed read by read on the host
   // pass 1 / wide windows
   int kmer_k = 0;
   DevBuf<int32_t> d_kb[2], d_kp[2];
@@ -215,7 +230,10 @@ extern "C" void miagpu_destroy(miagpu_ctx* c) {
   cudaStreamDestroy(c->s_up);
   cudaStreamDestroy(c->s_down);
   cudaFreeHost(c->h_meta);
-  if (c->h_newly) cudaFreeHost(c->h_newly);
+  if (c->h_cut) cudaFreeHost(c->h_cut);
+  if (c->h_cblk) cudaFreeHost(c->h_cblk);
+  if (c->h_score) cudaFreeHost(c->h_score);
+  c->d_seqlen.release(); c->d_unique.release(); c->d_cstats.release(); c->d_ctab.release(); c->d_thr.release(); c->d_cblk.release();
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -351,6 +369,7 @@ extern "C" int miagpu_upload_reads(miagpu_ctx* c, int64_t n, const uint8_t* base
   MIAGPU_CUDA(cudaEventElapsedTime(&c->ms_h2d, c->ev[0], c->ev[1]));
   c->n = n;
   c->total_bases = total;
+  c->cut_inputs_n = -1;
   c->max_read_len = -1;                      // computed on demand (device reduction) by the chunked kernel's launcher
   return 1;
 }
@@ -1197,18 +1216,17 @@ struct CutSums {
   }
 };
 
-// slope / intercept from the merged sums plus the two rounded chains over all reads in order
-static int score_cut_finish(int64_t n, const int32_t* seq_len, const int32_t* score, const uint8_t* unique_best, const CutSums& S,
-                            HostTeam& team, double* slope, double* intercept) {
-  if (S.bad >= 0) { set_error("miagpu_score_cut: seq_len[%lld] = %d out of range", (long long)S.bad, seq_len[S.bad]); return 0; }
-  double xbar = (double)S.sx, ybar = (double)S.sy, max_delta = 0;
-  xbar /= S.cnt; ybar /= S.cnt;
-  double dx_of[MAX_READ + 1], dx2_of[MAX_READ + 1];                 // the same doubles the reference forms per read
-  for (int l = 0; l <= MAX_READ; l++) { dx_of[l] = l - xbar; dx2_of[l] = dx_of[l] * dx_of[l]; }
-  auto used = [&](int64_t i) { return (!unique_best || unique_best[i]) && score[i] >= FIRST_ROUND_SCORE_CUTOFF; };
-  const double ssxy = chained_sum(n, [&](int64_t i) { return used(i) ? dx_of[seq_len[i]] * (score[i] - ybar) : 0.0; }, team);
-  const double ssxx = chained_sum(n, [&](int64_t i) { return used(i) ? dx2_of[seq_len[i]] : 0.0; }, team);
-  const double bf = ssxy / ssxx, ib = ybar - bf * xbar;
+// xbar / ybar and the per-length tables: the same doubles the reference forms per read (fsdb.c:296-316)
+struct CutFit { double xbar, ybar; double dx_of[MAX_READ + 1], dx2_of[MAX_READ + 1]; };
+static void cut_fit_tables(const CutSums& S, CutFit& F) {
+  F.xbar = (double)S.sx; F.ybar = (double)S.sy;
+  F.xbar /= S.cnt; F.ybar /= S.cnt;
+  for (int l = 0; l <= MAX_READ; l++) { F.dx_of[l] = l - F.xbar; F.dx2_of[l] = F.dx_of[l] * F.dx_of[l]; }
+}
+// slope / intercept from the two chains (fsdb.c:318-383)
+static void cut_fit_slope(const CutSums& S, const CutFit& F, double ssxy, double ssxx, double* slope, double* intercept) {
+  double max_delta = 0;
+  const double bf = ssxy / ssxx, ib = F.ybar - bf * F.xbar;
   for (int l = 0; l <= MAX_READ; l++)
     if (S.best[l] != INT_MIN) {
       double d = (S.best[l] - ((bf * l) + ib)) / l;
@@ -1217,6 +1235,23 @@ static int score_cut_finish(int64_t n, const int32_t* seq_len, const int32_t* sc
   *intercept = ib;
   if ((bf - max_delta) > 0) *slope = bf - (max_delta * 2.0);
   else *slope = (double)(bf * (80 / 100.0));                     // SCORE_CUTOFF_BUFFER, params.h:24
+}
+// min_score_for_len of cull_maln_from_fsdb (mia.c:452-470): the threshold depends on the length only
+static void cut_thresholds(int hard_cut, double slope, double intercept, double* min_score) {
+  if (slope <= 0) slope = 100.0;
+  for (int l = 0; l <= MAX_READ; l++) min_score[l] = hard_cut > 0 ? (double)hard_cut : (double)(intercept + (slope * l));
+}
+
+// slope / intercept from the merged sums plus the two rounded chains over all reads in order
+static int score_cut_finish(int64_t n, const int32_t* seq_len, const int32_t* score, const uint8_t* unique_best, const CutSums& S,
+                            HostTeam& team, double* slope, double* intercept) {
+  if (S.bad >= 0) { set_error("miagpu_score_cut: seq_len[%lld] = %d out of range", (long long)S.bad, seq_len[S.bad]); return 0; }
+  CutFit F;
+  cut_fit_tables(S, F);
+  auto used = [&](int64_t i) { return (!unique_best || unique_best[i]) && score[i] >= FIRST_ROUND_SCORE_CUTOFF; };
+  const double ssxy = chained_sum(n, [&](int64_t i) { return used(i) ? F.dx_of[seq_len[i]] * (score[i] - F.ybar) : 0.0; }, team);
+  const double ssxx = chained_sum(n, [&](int64_t i) { return used(i) ? F.dx2_of[seq_len[i]] : 0.0; }, team);
+  cut_fit_slope(S, F, ssxy, ssxx, slope, intercept);
   return 1;
 }
 
@@ -1241,9 +1276,8 @@ extern "C" int miagpu_score_cut(int64_t n, const int32_t* seq_len, const int32_t
 // below & !dropped-before.
 static int cull_flags_team(int64_t n, const int32_t* seq_len, const int32_t* score, int hard_cut, double slope, double intercept,
                            HostTeam& team, uint8_t* below, uint8_t* sticky, uint8_t* newly) {
-  if (slope <= 0) slope = 100.0;
-  double min_score[MAX_READ + 1];                                  // the threshold depends on the length only
-  for (int l = 0; l <= MAX_READ; l++) min_score[l] = hard_cut > 0 ? (double)hard_cut : (double)(intercept + (slope * l));
+  double min_score[MAX_READ + 1];
+  cut_thresholds(hard_cut, slope, intercept, min_score);
   std::vector<int64_t> bad(team.size(), -1);
   team.chunks(n, [&](int t, int64_t lo, int64_t hi) {
     for (int64_t i = lo; i < hi; i++) {
@@ -1279,26 +1313,8 @@ extern "C" int miagpu_consensus(miagpu_ctx* c, int64_t n_entries, const miagpu_e
   return 1;
 }
 
-// ---------------------------------------------------- one whole round, host buffers in and out
-__global__ void set_dropped_kernel(int64_t n, const uint8_t* flags, miagpu_entry* entries) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  entries[2 * i].dropped = flags[i];
-  entries[2 * i + 1].dropped = flags[i];
-}
-
-// One iteration of mia_main.c:931-963 for a batch that arrives in host memory: upload, realign every read
-// (reiterate_assembly), score cut (cull_maln_from_fsdb, host policy), column accumulation and base calling
-// (consensus_assembly_string).  Same results as miagpu_realign_host + miagpu_get_runs_packed +
-// miagpu_cull_flags + miagpu_consensus_natural called one after the other, as a pipeline over three streams:
-//   upload stream   chunk k's reads + rc/as/ae, then its classification (window rule, width classes, pairs)
-//   compute stream  chunk k's DP kernels as soon as chunk k is classified; afterwards entries, insert maxima,
-//                   column accumulation with the flags of EARLIER rounds (known on entry), base calling
-//   download stream chunk k's scores (first) and the other per-read outputs while chunk k+1 computes
-// The host-side score cut runs on a helper thread once the last scores have arrived, concurrently with the
-// column accumulation; the base columns of the reads it drops are then taken back out (integer sums: the
-// accumulators are exactly those of an accumulation that knew the flags).
-struct Trace {                                       // MIAGPU_TRACE=1: host-side timeline of one miagpu_iterate_host call on stderr
+// ---------------------------------------------------- one whole round (a9..a13), score cut on the device
+struct Trace {                                       // MIAGPU_TRACE=1: host-side timeline of one iteration call on stderr
   bool on = getenv("MIAGPU_TRACE") != nullptr;
   std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
   void mark(const char* what) const {
@@ -1312,6 +1328,181 @@ static int pick_chunks(int64_t n) {
   return (int)std::min<int64_t>(ch, std::max<int64_t>(1, n));
 }
 
+// pinned staging of the device score cut
+struct CutHost {
+  CutStatsDev stats;
+  CutTables tab;
+  double thr[MAX_READ + 1];
+  int64_t tot_runs;
+  int32_t total_ins;
+  long long bad_after;
+};
+
+static int cut_reserve(miagpu_ctx* c, int64_t n) {
+  const int64_t nb = (n + CUT_BLOCK - 1) / CUT_BLOCK;
+  if (!c->d_cstats.reserve(1) || !c->d_ctab.reserve(1) || !c->d_thr.reserve(MAX_READ + 1) || !c->d_cblk.reserve(nb + 1)) return 0;
+  if (!c->h_cut) MIAGPU_CUDA(cudaMallocHost(&c->h_cut, sizeof(CutHost)));
+  if (c->h_cblk_cap < nb) {
+    if (c->h_cblk) cudaFreeHost(c->h_cblk);
+    c->h_cblk = nullptr; c->h_cblk_cap = 0;
+    MIAGPU_CUDA(cudaMallocHost(&c->h_cblk, sizeof(CutBlockDev) * (nb + nb / 8 + 16)));
+    c->h_cblk_cap = nb + nb / 8 + 16;
+  }
+  return 1;
+}
+
+// integer sums + per-length maxima of the reads [lo, hi) on the compute stream (after their DP)
+static int cut_launch_stats(miagpu_ctx* c, int64_t lo, int64_t hi, bool has_unique) {
+  if (hi <= lo) return 1;
+  const unsigned grid = (unsigned)std::min<int64_t>(4 * c->num_sms, (hi - lo + CUT_THREADS * 4 - 1) / (CUT_THREADS * 4));
+  cut_stats_kernel<<<grid, CUT_THREADS, 0, c->stream>>>(lo, hi, c->d_seqlen.p, c->d_score.p, has_unique ? c->d_unique.p : nullptr, c->d_cstats.p);
+  MIAGPU_CUDA(cudaGetLastError());
+  c->launches++;
+  return 1;
+}
+
+struct IterTail {
+  // what the host knows about the reads (fallback blocks of the chains are summed on the host, read by read)
+  const int32_t* h_seq_len; const uint8_t* h_unique; const int32_t* h_score; cudaEvent_t scores_on_host;
+  bool wait_old_flags;                               // c->xev[1]: the earlier rounds' flags are on the device
+  int hard_cut, score_cut_set; double slope, intercept; int cons_code;
+  // outputs (host, nullable)
+  uint16_t* packed_runs; int64_t capacity; int64_t* total_runs; uint8_t* dropped; int32_t* gaps_out; char* cons_out; int32_t* cons_len;
+  double* slope_out; double* intercept_out;
+};
+
+// Everything after the DP of one round: score cut (stats kernels already enqueued per chunk), entries, insert maxima,
+// column accumulation, base calling.  Compute stream throughout; two short host waits (the integer sums, the blocks).
+static int iterate_tail(miagpu_ctx* c, const IterTail& a, const Trace& tr) {
+  cudaStream_t main = c->stream, down = c->s_down;
+  const int64_t n = c->n;
+  const bool fit = !a.score_cut_set && a.hard_cut <= 0;
+  const bool has_unique = a.h_unique != nullptr;
+  CutHost* H = c->h_cut;
+  const int64_t nb = (n + CUT_BLOCK - 1) / CUT_BLOCK;
+  if (fit) {
+    MIAGPU_CUDA(cudaMemcpyAsync(&H->stats, c->d_cstats.p, sizeof(CutStatsDev), cudaMemcpyDeviceToHost, main));
+    MIAGPU_CUDA(cudaEventRecord(c->xev[0], main));
+  }
+  // ---- packed run lists + entries + per-position insert maxima: none of it depends on this round's flags
+  int64_t* cnt = c->d_off2.p;
+  int64_t* offs = c->d_off2.p + (n + 2);
+  size_t tmp = 0, tmp2 = 0;
+  const bool want_packed = a.packed_runs || a.total_runs;
+  if (want_packed) MIAGPU_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, cnt, offs, n + 1, main));
+  MIAGPU_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp2, c->d_gaps.p, c->d_ins_off.p, c->seq_len + 1, main));
+  if (!c->d_cub.reserve(std::max(tmp, tmp2) + 16)) return 0;
+  H->tot_runs = 0;
+  if (want_packed) {
+    clamp_runs_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, main>>>(n, c->d_nruns.p, cnt);
+    MIAGPU_CUDA(cub::DeviceScan::ExclusiveSum(c->d_cub.p, tmp, cnt, offs, n + 1, main));
+    MIAGPU_CUDA(cudaMemcpyAsync(&H->tot_runs, offs + n, 8, cudaMemcpyDeviceToHost, main));
+    c->launches += 3;
+  }
+  c->n_entries = 2 * n;
+  MIAGPU_CUDA(cudaMemsetAsync(c->d_gaps.p, 0, (c->seq_len + 2) * sizeof(int32_t), main));
+  natural_entries_kernel<<<(unsigned)((n + 255) / 256), 256, 0, main>>>(n, c->d_as_out.p, c->d_ae_out.p, c->d_nruns.p, c->d_runs.p,
+                                                                        c->d_status.p, c->seq_len, nullptr, nullptr, c->d_entries.p);
+  MIAGPU_CUDA(cudaGetLastError());
+  c->launches++;
+  if (!launch_gaps(c)) return 0;
+  MIAGPU_CUDA(cub::DeviceScan::ExclusiveSum(c->d_cub.p, tmp2, c->d_gaps.p, c->d_ins_off.p, c->seq_len + 1, main));
+  MIAGPU_CUDA(cudaMemcpyAsync(&H->total_ins, c->d_ins_off.p + c->seq_len, sizeof(int32_t), cudaMemcpyDeviceToHost, main));
+  c->launches += 2;
+  tr.mark("entries + insert maxima enqueued");
+  // ---- regression: integer sums -> tables -> block kernels -> stitch (find_fsdb_score_cut, fsdb.c:269-383)
+  CutSums S;
+  CutFit F;
+  if (fit) {
+    MIAGPU_CUDA(cudaEventSynchronize(c->xev[0]));
+    tr.mark("integer sums on host");
+    S.sx = H->stats.sx; S.sy = H->stats.sy; S.cnt = H->stats.cnt; S.bad = H->stats.bad == LLONG_MAX ? -1 : H->stats.bad;
+    memcpy(S.best, H->stats.best, sizeof(S.best));
+    if (S.bad >= 0) { cudaStreamSynchronize(main); set_error("miagpu_score_cut: seq_len[%lld] = %d out of range", (long long)S.bad, a.h_seq_len[S.bad]); return 0; }
+    cut_fit_tables(S, F);
+    H->tab.ybar = F.ybar;
+    memcpy(H->tab.dx, F.dx_of, sizeof(F.dx_of));
+    memcpy(H->tab.dx2, F.dx2_of, sizeof(F.dx2_of));
+    MIAGPU_CUDA(cudaMemcpyAsync(c->d_ctab.p, &H->tab, sizeof(CutTables), cudaMemcpyHostToDevice, main));
+    const uint8_t* du = has_unique ? c->d_unique.p : nullptr;
+    cut_approx_kernel<<<(unsigned)nb, CUT_THREADS, 0, main>>>(n, c->d_seqlen.p, c->d_score.p, du, c->d_ctab.p, c->d_cblk.p);
+    cut_exact_kernel<<<(unsigned)nb, CUT_THREADS, 0, main>>>(n, c->d_seqlen.p, c->d_score.p, du, c->d_ctab.p, c->d_cblk.p);
+    MIAGPU_CUDA(cudaGetLastError());
+    MIAGPU_CUDA(cudaMemcpyAsync(c->h_cblk, c->d_cblk.p, sizeof(CutBlockDev) * nb, cudaMemcpyDeviceToHost, main));
+    c->launches += 2;
+  }
+  MIAGPU_CUDA(cudaStreamSynchronize(main));
+  tr.mark("compute stream drained (DP, entries, insert maxima, chain blocks)");
+  double slope = a.slope, intercept = a.intercept;
+  if (fit) {
+    MIAGPU_CUDA(cudaEventSynchronize(a.scores_on_host));
+    std::vector<ChainBlock> bxy(nb), bxx(nb);
+    for (int64_t b = 0; b < nb; b++) {
+      const CutBlockDev& B = c->h_cblk[b];
+      bxy[b] = ChainBlock{B.approx[0], B.T[0], B.A[0], B.e[0], B.ok[0] != 0};
+      bxx[b] = ChainBlock{B.approx[1], B.T[1], B.A[1], B.e[1], B.ok[1] != 0};
+    }
+    const int32_t* seq_len = a.h_seq_len; const int32_t* score = a.h_score; const uint8_t* ub = a.h_unique;
+    auto used = [&](int64_t i) { return (!ub || ub[i]) && score[i] >= FIRST_ROUND_SCORE_CUTOFF; };
+    int64_t ser0 = 0, ser1 = 0;
+    const double ssxy = chain_stitch(n, [&](int64_t i) { return used(i) ? F.dx_of[seq_len[i]] * (score[i] - F.ybar) : 0.0; }, bxy.data(), nb, &ser0);
+    const double ssxx = chain_stitch(n, [&](int64_t i) { return used(i) ? F.dx2_of[seq_len[i]] : 0.0; }, bxx.data(), nb, &ser1);
+    c->cut_serial_blocks = ser0 + ser1;
+    cut_fit_slope(S, F, ssxy, ssxx, &slope, &intercept);
+    tr.mark("chains stitched, slope / intercept known");
+  }
+  if (a.slope_out) *a.slope_out = slope;
+  if (a.intercept_out) *a.intercept_out = intercept;
+  // ---- this round's flags (cull_maln_from_fsdb, mia.c:452-470), sticky (H10)
+  cut_thresholds(a.hard_cut, slope, intercept, H->thr);
+  MIAGPU_CUDA(cudaMemcpyAsync(c->d_thr.p, H->thr, sizeof(H->thr), cudaMemcpyHostToDevice, main));
+  if (a.wait_old_flags) MIAGPU_CUDA(cudaStreamWaitEvent(main, c->xev[1], 0));
+  cut_flags_kernel<<<(unsigned)((n + 255) / 256), 256, 0, main>>>(n, c->d_seqlen.p, c->d_score.p, c->d_thr.p, c->d_dropf.p, c->d_entries.p, c->d_cstats.p);
+  MIAGPU_CUDA(cudaGetLastError());
+  c->launches++;
+  MIAGPU_CUDA(cudaMemcpyAsync(&H->bad_after, &c->d_cstats.p->bad, sizeof(long long), cudaMemcpyDeviceToHost, main));
+  MIAGPU_CUDA(cudaEventRecord(c->xev[2], main));
+  if (a.dropped) {
+    MIAGPU_CUDA(cudaStreamWaitEvent(down, c->xev[2], 0));
+    MIAGPU_CUDA(cudaMemcpyAsync(a.dropped, c->d_dropf.p, n, cudaMemcpyDeviceToHost, down));
+  }
+  // ---- packed run lists out, column accumulation, base calling
+  const int64_t tot = H->tot_runs;
+  if (a.total_runs) *a.total_runs = tot;
+  if (a.packed_runs && tot > a.capacity) { cudaStreamSynchronize(main); set_error("miagpu_iterate: %lld runs, capacity %lld", (long long)tot, (long long)a.capacity); return 0; }
+  if (!c->d_packed.reserve(tot + 1)) return 0;
+  c->n_cols = (int64_t)c->seq_len + H->total_ins;
+  if (!c->d_acc.reserve(c->n_cols * NPLANE) || !c->d_called.reserve(c->n_cols + 16)) return 0;
+  if (a.packed_runs) {
+    pack_runs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, main>>>(n, c->d_nruns.p, offs, c->d_runs.p, c->d_packed.p);
+    MIAGPU_CUDA(cudaEventRecord(c->xev[3], main));
+    MIAGPU_CUDA(cudaStreamWaitEvent(down, c->xev[3], 0));
+    if (tot) MIAGPU_CUDA(cudaMemcpyAsync(a.packed_runs, c->d_packed.p, tot * 2, cudaMemcpyDeviceToHost, down));
+    c->launches++;
+  }
+  MIAGPU_CUDA(cudaMemsetAsync(c->d_acc.p, 0, c->n_cols * NPLANE * sizeof(int32_t), main));
+  if (!launch_accumulate(c)) return 0;
+  tr.mark("flags + accumulation enqueued");
+  c->cons_stage = 2;
+  const int launches = c->launches;
+  if (!miagpu_call(c, a.cons_code, a.gaps_out, nullptr, a.cons_out, a.cons_len)) return 0;
+  c->launches = launches + 1;
+  tr.mark("consensus called and downloaded");
+  if (H->bad_after != LLONG_MAX) { set_error("miagpu_cull_flags: seq_len[%lld] = %d out of range", H->bad_after, a.h_seq_len[H->bad_after]); return 0; }
+  MIAGPU_CUDA(cudaStreamSynchronize(down));
+  tr.mark("download stream drained");
+  return 1;
+}
+
+// One iteration of mia_main.c:931-963 for a batch that arrives in host memory: upload, realign every read
+// (reiterate_assembly), score cut (cull_maln_from_fsdb), column accumulation and base calling
+// (consensus_assembly_string).  Same results as miagpu_realign_host + miagpu_get_runs_packed +
+// miagpu_cull_flags + miagpu_consensus_natural called one after the other, as a pipeline over three streams:
+//   upload stream   chunk k's reads + rc/as/ae/seq_len, then its classification (window rule, width classes, pairs)
+//   compute stream  chunk k's DP kernels as soon as chunk k is classified, then its share of the regression's
+//                   integer sums; afterwards entries, insert maxima, the regression's block kernels, flags,
+//                   column accumulation, base calling
+//   download stream chunk k's scores (first) and the other per-read outputs while chunk k+1 computes
 extern "C" int miagpu_iterate_host(miagpu_ctx* c, int64_t n, const uint8_t* bases, const int64_t* offsets, const uint8_t* rc,
                                    const int32_t* as, const int32_t* ae, int32_t* score, int32_t* as_out, int32_t* ae_out,
                                    int32_t* abr, int32_t* n_runs, uint8_t* status, uint16_t* packed_runs, int64_t capacity,
@@ -1326,22 +1517,19 @@ extern "C" int miagpu_iterate_host(miagpu_ctx* c, int64_t n, const uint8_t* base
   const int64_t total = offsets[n];
   if (!c->d_bases.reserve(total + 16) || !c->d_off.reserve(n + 1) || !reserve_per_read(c, n)) return 0;
   if (!c->d_entries.reserve(2 * n + 2) || !c->d_gaps.reserve(c->seq_len + 2) || !c->d_ins_off.reserve(c->seq_len + 2) ||
-      !c->d_dropf.reserve(n + 1) || !c->d_dropb.reserve(n + 1) || !c->d_off2.reserve(2 * (n + 2))) return 0;
-  if (c->h_newly_cap < n) {
-    if (c->h_newly) cudaFreeHost(c->h_newly);
-    c->h_newly = nullptr; c->h_newly_cap = 0;
-    MIAGPU_CUDA(cudaMallocHost(&c->h_newly, n + 64));
-    c->h_newly_cap = n;
-  }
+      !c->d_dropf.reserve(n + 1) || !c->d_off2.reserve(2 * (n + 2)) || !c->d_seqlen.reserve(n + 1) || !c->d_unique.reserve(n + 1) ||
+      !cut_reserve(c, n)) return 0;
   cudaStream_t main = c->stream, up = c->s_up, down = c->s_down;
   const int C = pick_chunks(n);
-  HostTeam team(host_threads(n));                     // started now: the threads are waiting by the time the scores arrive
+  const bool fit = !score_cut_set && hard_cut <= 0;
   const Trace tr;
   tr.mark("buffers reserved");
   realign_reset_stats(c);
-  c->n = n; c->total_bases = total;
+  c->n = n; c->total_bases = total; c->cut_inputs_n = -1;
   c->max_read_len = C > 1 ? MAX_READ : -1;            // chunked: the longest read is not known before the last upload
   // the side streams start after whatever the compute stream still has queued
+  cut_init_kernel<<<1, 256, 0, main>>>(c->d_cstats.p);
+  MIAGPU_CUDA(cudaGetLastError());
   MIAGPU_CUDA(cudaEventRecord(c->ev[0], main));
   MIAGPU_CUDA(cudaStreamWaitEvent(up, c->ev[0], 0));
   MIAGPU_CUDA(cudaStreamWaitEvent(down, c->ev[0], 0));
@@ -1358,6 +1546,8 @@ extern "C" int miagpu_iterate_host(miagpu_ctx* c, int64_t n, const uint8_t* base
     MIAGPU_CUDA(cudaMemcpyAsync(c->d_rc.p + lo, rc + lo, hi - lo, cudaMemcpyHostToDevice, up));
     MIAGPU_CUDA(cudaMemcpyAsync(c->d_as.p + lo, as + lo, (hi - lo) * 4, cudaMemcpyHostToDevice, up));
     MIAGPU_CUDA(cudaMemcpyAsync(c->d_ae.p + lo, ae + lo, (hi - lo) * 4, cudaMemcpyHostToDevice, up));
+    MIAGPU_CUDA(cudaMemcpyAsync(c->d_seqlen.p + lo, seq_len + lo, (hi - lo) * 4, cudaMemcpyHostToDevice, up));
+    if (unique_best) MIAGPU_CUDA(cudaMemcpyAsync(c->d_unique.p + lo, unique_best + lo, hi - lo, cudaMemcpyHostToDevice, up));
     if (!realign_classify(c, j, up)) return 0;
     MIAGPU_CUDA(cudaEventRecord(c->cev[4 * k], up));
   }
@@ -1372,103 +1562,24 @@ extern "C" int miagpu_iterate_host(miagpu_ctx* c, int64_t n, const uint8_t* base
     MIAGPU_CUDA(cudaStreamWaitEvent(main, c->cev[4 * k], 0));
     if (!realign_launch(c, j)) return 0;
     MIAGPU_CUDA(cudaEventRecord(c->cev[4 * k + 1], main));
+    if (fit && !cut_launch_stats(c, j.lo, j.lo + j.n, unique_best != nullptr)) return 0;
     MIAGPU_CUDA(cudaStreamWaitEvent(down, c->cev[4 * k + 1], 0));
     MIAGPU_CUDA(cudaMemcpyAsync(score + j.lo, c->d_score.p + j.lo, j.n * 4, cudaMemcpyDeviceToHost, down));
-    MIAGPU_CUDA(cudaEventRecord(c->cev[4 * k + 2], down));            // this chunk's scores: the host policy scans them as they arrive
+    MIAGPU_CUDA(cudaEventRecord(c->cev[4 * k + 2], down));            // this chunk's scores
     if (as_out) MIAGPU_CUDA(cudaMemcpyAsync(as_out + j.lo, c->d_as_out.p + j.lo, j.n * 4, cudaMemcpyDeviceToHost, down));
     if (ae_out) MIAGPU_CUDA(cudaMemcpyAsync(ae_out + j.lo, c->d_ae_out.p + j.lo, j.n * 4, cudaMemcpyDeviceToHost, down));
     if (abr) MIAGPU_CUDA(cudaMemcpyAsync(abr + j.lo, c->d_abr.p + j.lo, j.n * 4, cudaMemcpyDeviceToHost, down));
     if (n_runs) MIAGPU_CUDA(cudaMemcpyAsync(n_runs + j.lo, c->d_nruns.p + j.lo, j.n * 4, cudaMemcpyDeviceToHost, down));
     if (status) MIAGPU_CUDA(cudaMemcpyAsync(status + j.lo, c->d_status.p + j.lo, j.n, cudaMemcpyDeviceToHost, down));
   }
-  const int launches_realign = c->launches;
   tr.mark("DP + downloads enqueued");
-  // ---- host policy on a helper thread (+ its team): newly[i] = below & !sticky, dropped |= below
-  uint8_t* newly = c->h_newly;
-  int cut_ok = 0;
-  char cut_err[256] = "";
-  std::thread cut([&] {
-    cudaSetDevice(c->device);
-    CutSums sums;
-    for (int k = 0; k < C && !score_cut_set; k++) {             // order-independent sums, chunk by chunk as the scores land
-      if (cudaEventSynchronize(c->cev[4 * k + 2]) != cudaSuccess) { snprintf(cut_err, sizeof(cut_err), "miagpu_iterate_host: waiting for the scores failed"); return; }
-      std::vector<CutSums> parts(team.size());
-      const int64_t lo = jobs[k].lo;
-      team.chunks(jobs[k].n, [&](int t, int64_t a, int64_t b) { parts[t].scan(seq_len, score, unique_best, lo + a, lo + b); });
-      for (const CutSums& q : parts) sums.merge(q);
-    }
-    if (cudaEventSynchronize(c->cev[4 * (C - 1) + 2]) != cudaSuccess || cudaEventSynchronize(c->xev[1]) != cudaSuccess) {
-      snprintf(cut_err, sizeof(cut_err), "miagpu_iterate_host: waiting for the scores failed");
-      return;
-    }
-    tr.mark("  [cut thread] scores on host");
-    double sl = slope, ic = intercept;
-    cut_ok = score_cut_set ? 1 : score_cut_finish(n, seq_len, score, unique_best, sums, team, &sl, &ic);
-    tr.mark("  [cut thread] regression done");
-    if (cut_ok) cut_ok = cull_flags_team(n, seq_len, score, hard_cut, sl, ic, team, nullptr, dropped, newly);      // sticky (H10)
-    if (!cut_ok) snprintf(cut_err, sizeof(cut_err), "%s", miagpu_last_error());
-    tr.mark("  [cut thread] flags computed");
-  });
-  auto fail = [&](const char* what, cudaError_t e) { cut.join(); set_error("miagpu_iterate_host: %s: %s", what, cudaGetErrorString(e)); return 0; };
-#define IT_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(#call, e_); } while (0)
-  // ---- compute stream: packed run lists + entries + per-position insert maxima, one host sync for the two totals
-  int64_t* cnt = c->d_off2.p;
-  int64_t* offs = c->d_off2.p + (n + 2);
-  size_t tmp = 0, tmp2 = 0;
-  int64_t tot = 0;
-  if (packed_runs || total_runs) {
-    clamp_runs_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, main>>>(n, c->d_nruns.p, cnt);
-    IT_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, cnt, offs, n + 1, main));
-  }
-  IT_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp2, c->d_gaps.p, c->d_ins_off.p, c->seq_len + 1, main));
-  if (!c->d_cub.reserve(std::max(tmp, tmp2) + 16)) { cut.join(); return 0; }
-  if (packed_runs || total_runs) {
-    IT_CUDA(cub::DeviceScan::ExclusiveSum(c->d_cub.p, tmp, cnt, offs, n + 1, main));
-    IT_CUDA(cudaMemcpyAsync(&tot, offs + n, 8, cudaMemcpyDeviceToHost, main));
-  }
-  c->n_entries = 2 * n;
-  IT_CUDA(cudaMemsetAsync(c->d_gaps.p, 0, (c->seq_len + 2) * sizeof(int32_t), main));
-  IT_CUDA(cudaStreamWaitEvent(main, c->xev[1], 0));             // the earlier rounds' flags
-  natural_entries_kernel<<<(unsigned)((n + 255) / 256), 256, 0, main>>>(n, c->d_as_out.p, c->d_ae_out.p, c->d_nruns.p, c->d_runs.p,
-                                                                        c->d_status.p, c->seq_len, c->d_dropf.p, c->d_dropf.p, c->d_entries.p);
-  if (!launch_gaps(c)) { cut.join(); return 0; }
-  IT_CUDA(cub::DeviceScan::ExclusiveSum(c->d_cub.p, tmp2, c->d_gaps.p, c->d_ins_off.p, c->seq_len + 1, main));
-  int32_t total_ins = 0;
-  IT_CUDA(cudaMemcpyAsync(&total_ins, c->d_ins_off.p + c->seq_len, sizeof(int32_t), cudaMemcpyDeviceToHost, main));
-  tr.mark("entries + insert maxima enqueued");
-  IT_CUDA(cudaStreamSynchronize(main));
-  tr.mark("compute stream drained (DP, entries, insert maxima)");
-  if (total_runs) *total_runs = tot;
-  if (packed_runs && tot > capacity) { cut.join(); set_error("miagpu_iterate_host: %lld runs, capacity %lld", (long long)tot, (long long)capacity); return 0; }
-  if (!c->d_packed.reserve(tot + 1)) { cut.join(); return 0; }
-  c->n_cols = (int64_t)c->seq_len + total_ins;
-  if (!c->d_acc.reserve(c->n_cols * NPLANE) || !c->d_called.reserve(c->n_cols + 16)) { cut.join(); return 0; }
-  if (packed_runs) {
-    pack_runs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, main>>>(n, c->d_nruns.p, offs, c->d_runs.p, c->d_packed.p);
-    IT_CUDA(cudaEventRecord(c->xev[3], main));
-    IT_CUDA(cudaStreamWaitEvent(down, c->xev[3], 0));
-    if (tot) IT_CUDA(cudaMemcpyAsync(packed_runs, c->d_packed.p, tot * 2, cudaMemcpyDeviceToHost, down));
-  }
-  IT_CUDA(cudaMemsetAsync(c->d_acc.p, 0, c->n_cols * NPLANE * sizeof(int32_t), main));
-  if (!launch_accumulate(c)) { cut.join(); return 0; }          // every read not dropped in an earlier round
-  // ---- the flags of this round: take the newly dropped reads' base columns back out
-  tr.mark("accumulation enqueued");
-  cut.join();
-  tr.mark("cut thread joined");
-  if (!cut_ok) { set_error("%s", cut_err); return 0; }
-#undef IT_CUDA
-  MIAGPU_CUDA(cudaMemcpyAsync(c->d_dropb.p, newly, n, cudaMemcpyHostToDevice, main));
-  {
-    ConsParams p = cons_params(c);
-    undo_kernel<<<(unsigned)((n + 255) / 256), 256, 0, main>>>(p, n, c->d_dropb.p, c->d_entries.p);
-    MIAGPU_CUDA(cudaGetLastError());
-  }
-  c->cons_stage = 2;
-  if (!miagpu_call(c, cons_code, gaps_out, nullptr, cons_out, cons_len)) return 0;
-  tr.mark("consensus called and downloaded");
-  MIAGPU_CUDA(cudaStreamSynchronize(down));
-  tr.mark("download stream drained");
-  c->launches = launches_realign + 12;
+  IterTail t{};
+  t.h_seq_len = seq_len; t.h_unique = unique_best; t.h_score = score; t.scores_on_host = c->cev[4 * (C - 1) + 2];
+  t.wait_old_flags = true;
+  t.hard_cut = hard_cut; t.score_cut_set = score_cut_set; t.slope = slope; t.intercept = intercept; t.cons_code = cons_code;
+  t.packed_runs = packed_runs; t.capacity = capacity; t.total_runs = total_runs; t.dropped = dropped;
+  t.gaps_out = gaps_out; t.cons_out = cons_out; t.cons_len = cons_len;
+  if (!iterate_tail(c, t, tr)) { cudaStreamSynchronize(down); cudaStreamSynchronize(up); return 0; }
   c->ms_h2d = 0; c->ms_kernels = 0; c->ms_d2h = 0;   // the phases overlap: only the caller's wall clock means something
   // statistics of the chunks
   for (int k = 0; k < C; k++) {
@@ -1476,6 +1587,78 @@ extern "C" int miagpu_iterate_host(miagpu_ctx* c, int64_t n, const uint8_t* base
     MIAGPU_CUDA(cudaMemcpy(&nf, jobs[k].d_meta + META_NFALL, 4, cudaMemcpyDeviceToHost));
     c->n_fallback += nf;
   }
+  return 1;
+}
+
+// The same round over reads, rc/as/ae, seq_len / unique_best and sticky flags that are already resident:
+extern "C" int miagpu_set_cut_inputs(miagpu_ctx* c, const int32_t* seq_len, const uint8_t* unique_best, const uint8_t* dropped) {
+  if (!c || (c->n && !seq_len)) { set_error("miagpu_set_cut_inputs: bad argument"); return 0; }
+  MIAGPU_CUDA(cudaSetDevice(c->device));
+  const int64_t n = c->n;
+  if (!c->d_seqlen.reserve(n + 1) || !c->d_unique.reserve(n + 1) || !c->d_dropf.reserve(n + 1)) return 0;
+  c->h_seqlen.assign(seq_len, seq_len + n);
+  c->h_unique.clear();
+  if (unique_best) c->h_unique.assign(unique_best, unique_best + n);
+  if (n) {
+    MIAGPU_CUDA(cudaMemcpyAsync(c->d_seqlen.p, seq_len, n * 4, cudaMemcpyHostToDevice, c->stream));
+    if (unique_best) MIAGPU_CUDA(cudaMemcpyAsync(c->d_unique.p, unique_best, n, cudaMemcpyHostToDevice, c->stream));
+    if (dropped) MIAGPU_CUDA(cudaMemcpyAsync(c->d_dropf.p, dropped, n, cudaMemcpyHostToDevice, c->stream));
+    else MIAGPU_CUDA(cudaMemsetAsync(c->d_dropf.p, 0, n, c->stream));
+  }
+  MIAGPU_CUDA(cudaStreamSynchronize(c->stream));
+  c->cut_inputs_n = n;
+  return 1;
+}
+
+extern "C" int miagpu_reset_dropped(miagpu_ctx* c) {
+  if (!c || c->cut_inputs_n != c->n) { set_error("miagpu_reset_dropped: call miagpu_set_cut_inputs first"); return 0; }
+  MIAGPU_CUDA(cudaSetDevice(c->device));
+  if (c->n) MIAGPU_CUDA(cudaMemsetAsync(c->d_dropf.p, 0, c->n, c->stream));
+  return 1;
+}
+
+extern "C" int miagpu_iterate_resident(miagpu_ctx* c, int hard_cut, int score_cut_set, double slope, double intercept, int cons_code,
+                                       double* slope_out, double* intercept_out, uint8_t* dropped, int32_t* gaps_out, char* cons_out,
+                                       int32_t* cons_len) {
+  if (!c || !c->have_pssm || !c->have_ref) { set_error("miagpu_iterate_resident: set_pssm and set_reference first"); return 0; }
+  if (c->n <= 0 || c->cut_inputs_n != c->n) { set_error("miagpu_iterate_resident: upload reads, alignment inputs and cut inputs first"); return 0; }
+  MIAGPU_CUDA(cudaSetDevice(c->device));
+  const int64_t n = c->n;
+  if (!c->d_entries.reserve(2 * n + 2) || !c->d_gaps.reserve(c->seq_len + 2) || !c->d_ins_off.reserve(c->seq_len + 2) ||
+      !c->d_off2.reserve(2 * (n + 2)) || !cut_reserve(c, n)) return 0;
+  if (c->h_score_cap < n) {
+    if (c->h_score) cudaFreeHost(c->h_score);
+    c->h_score = nullptr; c->h_score_cap = 0;
+    MIAGPU_CUDA(cudaMallocHost(&c->h_score, sizeof(int32_t) * (n + 64)));
+    c->h_score_cap = n;
+  }
+  const bool fit = !score_cut_set && hard_cut <= 0;
+  const Trace tr;
+  cudaStream_t main = c->stream, down = c->s_down;
+  MIAGPU_CUDA(cudaEventRecord(c->ev[1], main));
+  cut_init_kernel<<<1, 256, 0, main>>>(c->d_cstats.p);
+  MIAGPU_CUDA(cudaGetLastError());
+  if (!realign_device(c)) return 0;
+  MIAGPU_CUDA(cudaEventRecord(c->ev[2], main));
+  if (fit) {
+    MIAGPU_CUDA(cudaStreamWaitEvent(down, c->ev[2], 0));
+    MIAGPU_CUDA(cudaMemcpyAsync(c->h_score, c->d_score.p, n * 4, cudaMemcpyDeviceToHost, down));    // only the chains' unproven blocks read them
+    MIAGPU_CUDA(cudaEventRecord(c->cev[2], down));
+    if (!cut_launch_stats(c, 0, n, !c->h_unique.empty())) return 0;
+  }
+  tr.mark("DP enqueued");
+  IterTail t{};
+  t.h_seq_len = c->h_seqlen.data(); t.h_unique = c->h_unique.empty() ? nullptr : c->h_unique.data(); t.h_score = c->h_score;
+  t.scores_on_host = c->cev[2]; t.wait_old_flags = false;
+  t.hard_cut = hard_cut; t.score_cut_set = score_cut_set; t.slope = slope; t.intercept = intercept; t.cons_code = cons_code;
+  t.dropped = dropped; t.gaps_out = gaps_out; t.cons_out = cons_out; t.cons_len = cons_len;
+  t.slope_out = slope_out; t.intercept_out = intercept_out;
+  if (!iterate_tail(c, t, tr)) { cudaStreamSynchronize(down); return 0; }
+  MIAGPU_CUDA(cudaEventElapsedTime(&c->ms_kernels, c->ev[1], c->ev[2]));
+  c->ms_h2d = c->ms_d2h = 0;
+  const int launches = c->launches;
+  if (!realign_bucket_times(c)) return 0;
+  c->launches = launches;
   return 1;
 }
 
@@ -1616,7 +1799,7 @@ extern "C" int miagpu_compact_reads(miagpu_ctx* c, const uint8_t* keep, const ui
   MIAGPU_CUDA(cudaStreamSynchronize(c->stream));
   std::swap(c->d_bases, c->d_bases2);
   std::swap(c->d_off, c->d_off2);
-  c->n = m;
+  c->n = m; c->cut_inputs_n = -1;
   c->total_bases = off_new.back();
   c->max_read_len = maxL;
   if (n_out) *n_out = m;

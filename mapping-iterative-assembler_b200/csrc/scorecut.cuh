@@ -1,0 +1,209 @@
+// scorecut.cuh -- device side of an iteration's score cut (a12): find_fsdb_score_cut (fsdb.c:269-383) and the
+// per-read test of cull_maln_from_fsdb (mia.c:418-479) over scores that are already in HBM.
+//
+// The regression's two double-precision chains (scorecut.hpp explains why they can be taken block-wise without
+// changing a bit) are split like this:
+//   cut_stats_kernel   integer sums (sum len, sum score, count) and the best score per read length   [per DP chunk]
+//   -- host: xbar, ybar, the 257-entry tables (len - xbar), (len - xbar)^2 -- the same doubles the reference forms
+//   cut_approx_kernel  plain block sums of both chains (predict the binade of the running sum at every block start)
+//   cut_exact_kernel   per block: T = sum rint(a_i / ulp), A = sum |rint(a_i / ulp)|, tie / range flags
+//   -- host: chain_stitch (in order; unproven blocks read by read), slope / intercept, threshold per length
+//   cut_flags_kernel   below = score < threshold[len]; sticky |= below (H10); entry flags for the accumulation
+// Every addend is formed with __dmul_rn / __dsub_rn / __dadd_rn: IEEE operations that nvcc never contracts into an
+// FMA, so a_i, a_i / ulp and the magic-constant rounding are bit for bit what the host code computes.
+#pragma once
+#include <limits.h>
+
+#include "common.cuh"
+
+namespace miagpu {
+
+constexpr int CUT_BLOCK = 2048;                      // = CHAIN_BLOCK of scorecut.hpp
+constexpr int CUT_THREADS = 256;
+constexpr int CUT_PER_THREAD = CUT_BLOCK / CUT_THREADS;
+
+struct CutStatsDev {
+  long long sx, sy, cnt, bad;                        // bad = smallest index whose seq_len is outside [0, MAX_READ] (LLONG_MAX = none)
+  int best[MAX_READ + 1];
+  int pad;
+};
+struct CutTables {                                   // host-made, the same doubles the reference forms per read
+  double ybar;
+  double dx[MAX_READ + 1];
+  double dx2[MAX_READ + 1];
+};
+struct CutBlockDev {                                 // chain 0 = ssxy, chain 1 = ssxx
+  double approx[2], T[2], A[2];
+  int e[2], ok[2];
+};
+
+__global__ void cut_init_kernel(CutStatsDev* st) {
+  const int t = threadIdx.x;
+  if (t == 0) { st->sx = 0; st->sy = 0; st->cnt = 0; st->bad = LLONG_MAX; st->pad = 0; }
+  for (int l = t; l <= MAX_READ; l += blockDim.x) st->best[l] = INT_MIN;
+}
+
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+#pragma unroll
+  for (int d = 16; d; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int d = 16; d; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+  return v;
+}
+
+// reads [lo, hi): used = unique_best && score >= FIRST_ROUND_SCORE_CUTOFF (fsdb.c:283-293)
+__global__ void __launch_bounds__(CUT_THREADS) cut_stats_kernel(int64_t lo, int64_t hi, const int32_t* __restrict__ seq_len,
+                                                                const int32_t* __restrict__ score, const uint8_t* __restrict__ unique_best,
+                                                                CutStatsDev* st) {
+  __shared__ int s_best[MAX_READ + 1];
+  __shared__ long long s_sum[3];
+  for (int l = threadIdx.x; l <= MAX_READ; l += blockDim.x) s_best[l] = INT_MIN;
+  if (threadIdx.x < 3) s_sum[threadIdx.x] = 0;
+  __syncthreads();
+  long long sx = 0, sy = 0, cnt = 0;
+  for (int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (int64_t)gridDim.x * blockDim.x) {
+    const int l = seq_len[i];
+    if (l < 0 || l > MAX_READ) { atomicMin(&st->bad, (long long)i); continue; }
+    const int sc = score[i];
+    if ((!unique_best || unique_best[i]) && sc >= FIRST_ROUND_SCORE_CUTOFF) {
+      sx += l; sy += sc; cnt++;
+      if (sc > s_best[l]) atomicMax(&s_best[l], sc);
+    }
+  }
+  sx = warp_sum_ll(sx); sy = warp_sum_ll(sy); cnt = warp_sum_ll(cnt);
+  if ((threadIdx.x & 31) == 0 && cnt) {
+    atomicAdd((unsigned long long*)&s_sum[0], (unsigned long long)sx);
+    atomicAdd((unsigned long long*)&s_sum[1], (unsigned long long)sy);
+    atomicAdd((unsigned long long*)&s_sum[2], (unsigned long long)cnt);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && s_sum[2]) {
+    atomicAdd((unsigned long long*)&st->sx, (unsigned long long)s_sum[0]);
+    atomicAdd((unsigned long long*)&st->sy, (unsigned long long)s_sum[1]);
+    atomicAdd((unsigned long long*)&st->cnt, (unsigned long long)s_sum[2]);
+  }
+  for (int l = threadIdx.x; l <= MAX_READ; l += blockDim.x)
+    if (s_best[l] != INT_MIN) atomicMax(&st->best[l], s_best[l]);
+}
+
+// the two addends of read i: (len - xbar) * (score - ybar) and (len - xbar)^2, 0 for a read the fit does not use
+__device__ __forceinline__ void cut_addends(int64_t i, const int32_t* seq_len, const int32_t* score, const uint8_t* unique_best,
+                                            const CutTables* __restrict__ t, double& axy, double& axx) {
+  const int sc = score[i];
+  axy = 0.0; axx = 0.0;
+  if ((!unique_best || unique_best[i]) && sc >= FIRST_ROUND_SCORE_CUTOFF) {
+    const int l = min(max(seq_len[i], 0), MAX_READ);
+    axy = __dmul_rn(t->dx[l], __dsub_rn((double)sc, t->ybar));
+    axx = t->dx2[l];
+  }
+}
+
+// block-wide sum of two doubles, result valid in every thread
+__device__ __forceinline__ void block_sum2(double& a, double& b, double* s_red) {
+  a = warp_sum_d(a); b = warp_sum_d(b);
+  const int w = threadIdx.x >> 5;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) { s_red[2 * w] = a; s_red[2 * w + 1] = b; }
+  __syncthreads();
+  a = 0; b = 0;
+#pragma unroll
+  for (int k = 0; k < CUT_THREADS / 32; k++) { a += s_red[2 * k]; b += s_red[2 * k + 1]; }
+}
+
+__global__ void __launch_bounds__(CUT_THREADS) cut_approx_kernel(int64_t n, const int32_t* __restrict__ seq_len, const int32_t* __restrict__ score,
+                                                                 const uint8_t* __restrict__ unique_best, const CutTables* __restrict__ t,
+                                                                 CutBlockDev* blk) {
+  __shared__ double s_red[2 * CUT_THREADS / 32];
+  const int64_t i0 = (int64_t)blockIdx.x * CUT_BLOCK;
+  double s0 = 0, s1 = 0;
+#pragma unroll
+  for (int k = 0; k < CUT_PER_THREAD; k++) {
+    const int64_t i = i0 + k * CUT_THREADS + threadIdx.x;
+    if (i < n) {
+      double axy, axx;
+      cut_addends(i, seq_len, score, unique_best, t, axy, axx);
+      s0 += axy; s1 += axx;
+    }
+  }
+  block_sum2(s0, s1, s_red);
+  if (threadIdx.x == 0) { blk[blockIdx.x].approx[0] = s0; blk[blockIdx.x].approx[1] = s1; }
+}
+
+__global__ void __launch_bounds__(CUT_THREADS) cut_exact_kernel(int64_t n, const int32_t* __restrict__ seq_len, const int32_t* __restrict__ score,
+                                                                const uint8_t* __restrict__ unique_best, const CutTables* __restrict__ t,
+                                                                CutBlockDev* blk) {
+  __shared__ double s_red[2 * CUT_THREADS / 32];
+  __shared__ int s_bad[2];
+  const int b = blockIdx.x;
+  // approximate running sums at the block start (any order: it only predicts the binade, chain_stitch verifies it)
+  double run0 = 0, run1 = 0;
+  for (int j = threadIdx.x; j < b; j += CUT_THREADS) { run0 += blk[j].approx[0]; run1 += blk[j].approx[1]; }
+  if (threadIdx.x < 2) s_bad[threadIdx.x] = 0;
+  block_sum2(run0, run1, s_red);
+  const double run[2] = {run0, run1};
+  bool valid[2];
+  double inv[2];
+  int e[2];
+#pragma unroll
+  for (int ch = 0; ch < 2; ch++) {
+    const double s = run[ch];
+    valid[ch] = s > 0 && isfinite(s);
+    int e2 = 0;
+    const double f = valid[ch] ? frexp(s, &e2) : 0.75;
+    if (f < 0.5 + 1e-6 || f > 1 - 1e-6) valid[ch] = false;          // too close to a binade boundary to predict
+    e[ch] = e2 - 1;
+    if (e[ch] < -900 || e[ch] > 900) valid[ch] = false;
+    inv[ch] = valid[ch] ? ldexp(1.0, 52 - e[ch]) : 1.0;             // 1 / ulp
+  }
+  constexpr double MAGIC = 6755399441055744.0;                      // 1.5 * 2^52
+  constexpr double LIM = 1125899906842624.0;                        // 2^50
+  const int64_t i0 = (int64_t)b * CUT_BLOCK;
+  double T[2] = {0, 0}, A[2] = {0, 0};
+  bool bad[2] = {false, false};
+#pragma unroll
+  for (int k = 0; k < CUT_PER_THREAD; k++) {
+    const int64_t i = i0 + k * CUT_THREADS + threadIdx.x;
+    if (i < n) {
+      double a[2];
+      cut_addends(i, seq_len, score, unique_best, t, a[0], a[1]);
+#pragma unroll
+      for (int ch = 0; ch < 2; ch++) {
+        const double x = __dmul_rn(a[ch], inv[ch]);
+        const double m = __dsub_rn(__dadd_rn(x, MAGIC), MAGIC);
+        bad[ch] |= !(fabs(x) < LIM) | (fabs(__dsub_rn(x, m)) == 0.5);       // exact ties round by the parity of the running sum
+        T[ch] += m; A[ch] += fabs(m);
+      }
+    }
+  }
+  if (bad[0]) s_bad[0] = 1;                                         // benign race: every writer stores 1 (after block_sum2's barriers)
+  if (bad[1]) s_bad[1] = 1;
+  block_sum2(T[0], A[0], s_red);
+  block_sum2(T[1], A[1], s_red);
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    const int ch = threadIdx.x;
+    const double Tc = ch ? T[1] : T[0], Ac = ch ? A[1] : A[0];
+    blk[b].T[ch] = Tc;
+    blk[b].A[ch] = Ac;
+    blk[b].e[ch] = ch ? e[1] : e[0];
+    blk[b].ok[ch] = (ch ? valid[1] : valid[0]) && !s_bad[ch] && Ac < 4503599627370496.0;   // 2^52: all partial integer sums exact
+  }
+}
+
+// below = score < threshold(len) (mia.c:452-470); sticky |= below (H10); the natural entries (2i, 2i+1) of the read
+// take the sticky flag (nullable)
+__global__ void cut_flags_kernel(int64_t n, const int32_t* __restrict__ seq_len, const int32_t* __restrict__ score,
+                                 const double* __restrict__ thr, uint8_t* sticky, miagpu_entry* entries, CutStatsDev* st) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int l = seq_len[i];
+  if (l < 0 || l > MAX_READ) { atomicMin(&st->bad, (long long)i); return; }
+  const uint8_t s = sticky[i] | (uint8_t)((double)score[i] < thr[l]);
+  sticky[i] = s;
+  if (entries) { entries[2 * i].dropped = s; entries[2 * i + 1].dropped = s; }
+}
+
+}  // namespace miagpu

@@ -81,6 +81,35 @@ class HostTeam {
 
 constexpr int64_t CHAIN_BLOCK = 2048;
 
+// What phases 1 and 2 know about one block of CHAIN_BLOCK consecutive addends: the binade e the running sum is
+// predicted to be in when the block starts, T = sum(rint(a_i / ulp_e)), A = sum(|rint(a_i / ulp_e)|), and ok =
+// every quotient was far from a tie and all partial integer sums were exact.  The host team below fills these,
+// and so do the device kernels of scorecut.cuh (same arithmetic, IEEE double, no contraction).
+struct ChainBlock { double approx, T, A; int e; bool ok; };
+
+// phase 3: stitch the blocks in order; whatever cannot be proven goes read by read, exactly as the reference adds
+template <typename Addend>
+double chain_stitch(int64_t n, const Addend& a, const ChainBlock* blk, int64_t nb, int64_t* n_serial = nullptr) {
+  double S = 0;
+  int64_t serial = 0;
+  for (int64_t b = 0; b < nb; b++) {
+    const ChainBlock& B = blk[b];
+    if (B.ok && S > 0 && std::ilogb(S) == B.e) {
+      const double inv = std::ldexp(1.0, 52 - B.e), ulp = std::ldexp(1.0, B.e - 52);
+      const double N0 = S * inv;                      // integer in [2^52, 2^53)
+      if (N0 - B.A >= 4503599627370497.0 && N0 + B.A <= 9007199254740990.0) {
+        S = (N0 + B.T) * ulp;
+        continue;
+      }
+    }
+    const int64_t i1 = std::min(n, (b + 1) * CHAIN_BLOCK);
+    for (int64_t i = b * CHAIN_BLOCK; i < i1; i++) S += a(i);
+    serial++;
+  }
+  if (n_serial) *n_serial = serial;
+  return S;
+}
+
 // (((0 + a(0)) + a(1)) + ... + a(n-1)) with a rounding after every addition, bit-identical to the plain loop.
 template <typename Addend>
 double chained_sum(int64_t n, const Addend& a, HostTeam& team) {
@@ -90,8 +119,7 @@ double chained_sum(int64_t n, const Addend& a, HostTeam& team) {
     for (int64_t i = 0; i < n; i++) s += a(i);
     return s;
   }
-  struct Block { double approx, T, A; int e; bool ok; };
-  std::vector<Block> blk(nb);
+  std::vector<ChainBlock> blk(nb);
   // phase 1: plain block sums -> approximate running sum at every block start (predicts the binade)
   team.chunks(nb, [&](int, int64_t b0, int64_t b1) {
     for (int64_t b = b0; b < b1; b++) {
@@ -109,7 +137,7 @@ double chained_sum(int64_t n, const Addend& a, HostTeam& team) {
   constexpr double MAGIC = 6755399441055744.0;       // 1.5 * 2^52: (x + MAGIC) - MAGIC = x rounded to nearest-even for |x| < 2^51
   team.chunks(nb, [&](int, int64_t b0, int64_t b1) {
     for (int64_t b = b0; b < b1; b++) {
-      Block& B = blk[b];
+      ChainBlock& B = blk[b];
       B.ok = false;
       const double s = B.approx;
       if (!(s > 0) || !std::isfinite(s)) continue;
@@ -141,22 +169,7 @@ double chained_sum(int64_t n, const Addend& a, HostTeam& team) {
       B.ok = !bad && B.A < 4503599627370496.0;        // 2^52: all partial integer sums were exact
     }
   });
-  // phase 3: stitch in order; whatever cannot be proven goes read by read
-  double S = 0;
-  for (int64_t b = 0; b < nb; b++) {
-    const Block& B = blk[b];
-    if (B.ok && S > 0 && std::ilogb(S) == B.e) {
-      const double inv = std::ldexp(1.0, 52 - B.e), ulp = std::ldexp(1.0, B.e - 52);
-      const double N0 = S * inv;                      // integer in [2^52, 2^53)
-      if (N0 - B.A >= 4503599627370497.0 && N0 + B.A <= 9007199254740990.0) {
-        S = (N0 + B.T) * ulp;
-        continue;
-      }
-    }
-    const int64_t i1 = std::min(n, (b + 1) * CHAIN_BLOCK);
-    for (int64_t i = b * CHAIN_BLOCK; i < i1; i++) S += a(i);
-  }
-  return S;
+  return chain_stitch(n, a, blk.data(), nb);
 }
 
 }  // namespace miagpu
