@@ -107,7 +107,11 @@ struct miagpu_ctx {
   DevBuf<int32_t> d_as, d_ae, d_score, d_as_out, d_ae_out, d_abr, d_nruns, d_win_start, d_win_len, d_lists;
   DevBuf<uint16_t> d_runs;
   DevBuf<int32_t> d_meta;                      // META_* layout below
-  DevBuf<uint32_t> d_scratch;
+  DevBuf<uint32_t> d_scratch[4];               // trace scratch of the 32-bit kernels, one per launch stream
+  cudaStream_t s_aux[4] = {};                  // [0] = stream; [1..3] side streams of the concurrent DP launches
+  cudaEvent_t aev[8] = {};                     // fork / join events of those
+  cudaStream_t launch_stream = nullptr;        // where launch_bucket / launch_pair16 / launch_strip put their kernel
+  int launch_slot = 0;
   // 16-bit SIMD pair kernel (pair16.cuh)
   DevBuf<int16_t> d_prof16;
   DevBuf<uint8_t> d_kind;
@@ -200,7 +204,14 @@ extern "C" int miagpu_create(miagpu_ctx** out, int device) {
   for (auto& ev : c->ev) MIAGPU_CUDA(cudaEventCreate(&ev));
   for (auto& ev : c->bev) MIAGPU_CUDA(cudaEventCreate(&ev));
   for (auto& ev : c->pev) MIAGPU_CUDA(cudaEventCreate(&ev));
-  MIAGPU_CUDA(cudaStreamCreateWithFlags(&c->s_up, cudaStreamNonBlocking));
+  c->s_aux[0] = c->stream; c->launch_stream = c->stream;
+  for (int i = 1; i < 4; i++) MIAGPU_CUDA(cudaStreamCreateWithFlags(&c->s_aux[i], cudaStreamNonBlocking));
+  for (auto& ev : c->aev) MIAGPU_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  // the upload stream also classifies the next chunk while this chunk's persistent DP blocks hold every SM slot:
+  // highest priority, so that its few blocks are placed first whenever a DP class drains
+  int prio_lo = 0, prio_hi = 0;
+  MIAGPU_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  MIAGPU_CUDA(cudaStreamCreateWithPriority(&c->s_up, cudaStreamNonBlocking, prio_hi));
   MIAGPU_CUDA(cudaStreamCreateWithFlags(&c->s_down, cudaStreamNonBlocking));
   for (auto& ev : c->cev) MIAGPU_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   for (auto& ev : c->xev) MIAGPU_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -216,7 +227,10 @@ extern "C" void miagpu_destroy(miagpu_ctx* c) {
   c->d_prof.release(); c->d_ref.release(); c->d_rcref.release(); c->d_bases.release(); c->d_off.release();
   c->d_rc.release(); c->d_status.release(); c->d_as.release(); c->d_ae.release(); c->d_score.release();
   c->d_as_out.release(); c->d_ae_out.release(); c->d_abr.release(); c->d_nruns.release(); c->d_win_start.release();
-  c->d_win_len.release(); c->d_lists.release(); c->d_runs.release(); c->d_meta.release(); c->d_scratch.release();
+  c->d_win_len.release(); c->d_lists.release(); c->d_runs.release(); c->d_meta.release();
+  for (auto& b : c->d_scratch) b.release();
+  for (int i = 1; i < 4; i++) cudaStreamDestroy(c->s_aux[i]);
+  for (auto& ev : c->aev) cudaEventDestroy(ev);
   for (int t = 0; t < 2; t++) { c->d_kb[t].release(); c->d_kp[t].release(); c->d_kk[t].release(); }
   c->d_smask.release(); c->d_ckpt.release(); c->d_chunk_ids.release(); c->d_strace.release(); c->d_hits.release(); c->d_fw.release();
   c->d_rcs.release(); c->d_start.release(); c->d_end.release(); c->d_rc_out.release(); c->d_bases2.release(); c->d_packed.release(); c->d_off2.release(); c->d_src.release();
@@ -586,7 +600,7 @@ static int launch_strip(miagpu_ctx* c, int mode, const int32_t* list, int n_list
     p.off += lo; p.rc_in += lo; p.score += lo; p.as_out += lo; p.ae_out += lo; p.abr += lo; p.n_runs += lo;
     p.runs += lo * MAX_RUNS; p.status += lo;
   }
-  strip_kernel<<<blocks, WARPS_PER_BLOCK * 32, smem, c->stream>>>(p);
+  strip_kernel<<<blocks, WARPS_PER_BLOCK * 32, smem, c->launch_stream>>>(p);
   MIAGPU_CUDA(cudaGetLastError());
   c->launches++;
   return 1;
@@ -597,9 +611,14 @@ static int launch_bucket(miagpu_ctx* c, RealignParams p, int maxL) {
   using TL = TraceLayout<K>;
   bool ref_in_smem = c->ref_bytes <= 160 * 1024;
   size_t smem = PROF_INTS * 4 + WARPS_PER_BLOCK * MAX_READ * 2 + (ref_in_smem ? c->ref_bytes : 0);
-  MIAGPU_CUDA(cudaFuncSetAttribute(realign_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int per_sm = 0;
-  MIAGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, realign_kernel<K>, WARPS_PER_BLOCK * 32, smem));
+  static size_t cached_smem = ~(size_t)0;            // per instantiation: the attribute / occupancy calls cost more than the launch
+  static int cached_per_sm = 0;
+  if (cached_smem != smem) {
+    MIAGPU_CUDA(cudaFuncSetAttribute(realign_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MIAGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cached_per_sm, realign_kernel<K>, WARPS_PER_BLOCK * 32, smem));
+    cached_smem = smem;
+  }
+  int per_sm = cached_per_sm;
   if (per_sm < 1) { set_error("realign_kernel<%d> does not fit on an SM (smem %zu)", K, smem); return 0; }
   int cap = 8;                                             // 32 warps/SM (measured best on B200); bounds the trace scratch
   if (const char* e = getenv("MIAGPU_BLOCKS_PER_SM")) cap = std::max(1, atoi(e));
@@ -608,11 +627,12 @@ static int launch_bucket(miagpu_ctx* c, RealignParams p, int maxL) {
   blocks = std::min(blocks, (p.n_list + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
   if (blocks < 1) return 1;
   int64_t words = (int64_t)std::max(maxL - 1, 1) * TL::ROW_WORDS;
-  if (!c->d_scratch.reserve((size_t)words * blocks * WARPS_PER_BLOCK)) return 0;
-  p.scratch = c->d_scratch.p;
+  DevBuf<uint32_t>& scratch = c->d_scratch[c->launch_slot];
+  if (!scratch.reserve((size_t)words * blocks * WARPS_PER_BLOCK)) return 0;
+  p.scratch = scratch.p;
   p.scratch_words_per_warp = words;
   p.ref_in_smem = ref_in_smem;
-  realign_kernel<K><<<blocks, WARPS_PER_BLOCK * 32, smem, c->stream>>>(p);
+  realign_kernel<K><<<blocks, WARPS_PER_BLOCK * 32, smem, c->launch_stream>>>(p);
   MIAGPU_CUDA(cudaGetLastError());
   c->launches++;
   return 1;
@@ -622,9 +642,14 @@ template <int K, int G>
 static int launch_pair16(miagpu_ctx* c, Pair16Params p, int n_pairs, int maxL) {
   bool ref_in_smem = c->ref_bytes <= 160 * 1024;
   size_t smem = p16_smem_fixed<G>() + (ref_in_smem ? c->ref_bytes : 0);
-  MIAGPU_CUDA(cudaFuncSetAttribute((pair16_kernel<K, G>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int per_sm = 0;
-  MIAGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (pair16_kernel<K, G>), WARPS_PER_BLOCK * 32, smem));
+  static size_t cached_smem = ~(size_t)0;
+  static int cached_per_sm = 0;
+  if (cached_smem != smem) {
+    MIAGPU_CUDA(cudaFuncSetAttribute((pair16_kernel<K, G>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MIAGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cached_per_sm, (pair16_kernel<K, G>), WARPS_PER_BLOCK * 32, smem));
+    cached_smem = smem;
+  }
+  int per_sm = cached_per_sm;
   if (per_sm < 1) { set_error("pair16_kernel<%d,%d> does not fit on an SM (smem %zu)", K, G, smem); return 0; }
   int cap = 8;
   if (const char* e = getenv("MIAGPU_PAIR_BLOCKS_PER_SM")) cap = std::max(1, atoi(e));
@@ -634,7 +659,7 @@ static int launch_pair16(miagpu_ctx* c, Pair16Params p, int n_pairs, int maxL) {
   (void)maxL;
   p.ref_in_smem = ref_in_smem;
   p.gep2 = K2(2 * GEP);
-  pair16_kernel<K, G><<<blocks, WARPS_PER_BLOCK * 32, smem, c->stream>>>(p);
+  pair16_kernel<K, G><<<blocks, WARPS_PER_BLOCK * 32, smem, c->launch_stream>>>(p);
   MIAGPU_CUDA(cudaGetLastError());
   c->launches++;
   return 1;
@@ -648,8 +673,28 @@ struct RealignJob {
   int32_t* d_lists = nullptr;    // NBUCKET * n
   int32_t* d_pairs = nullptr;    // n + 4 * P16_KEYS + 64
   int32_t* h_meta = nullptr;     // META_HOST words on the host (pinned for an asynchronous copy)
-  bool timed = false;            // per-class events (the whole-batch path)
+  bool timed = false;            // per-class events, one kernel after the other (the measurement path)
 };
+
+// Untimed jobs spread their DP kernels over four streams: the kernels are persistent (every block fetches work
+// until its class runs dry), so the next class's blocks move in as the previous class's tail drains.
+static int fork_streams(miagpu_ctx* c, int ev) {
+  MIAGPU_CUDA(cudaEventRecord(c->aev[ev], c->stream));
+  for (int i = 1; i < 4; i++) MIAGPU_CUDA(cudaStreamWaitEvent(c->s_aux[i], c->aev[ev], 0));
+  return 1;
+}
+static int join_streams(miagpu_ctx* c, int ev) {
+  for (int i = 1; i < 4; i++) {
+    MIAGPU_CUDA(cudaEventRecord(c->aev[ev + i], c->s_aux[i]));
+    MIAGPU_CUDA(cudaStreamWaitEvent(c->stream, c->aev[ev + i], 0));
+  }
+  c->launch_stream = c->stream; c->launch_slot = 0;
+  return 1;
+}
+static void pick_stream(miagpu_ctx* c, bool concurrent, int& rr) {
+  c->launch_slot = concurrent ? (rr++ & 3) : 0;
+  c->launch_stream = c->s_aux[c->launch_slot];
+}
 
 static PairLmax pair_lmax(miagpu_ctx* c) {
   int lmax16 = c->lmax16;
@@ -693,6 +738,8 @@ static int realign_launch(miagpu_ctx* c, const RealignJob& j) {
   if (n == 0) return 1;
   const int32_t* meta = j.h_meta;
   const int np = 32 / c->pair_g;
+  const bool concurrent = !j.timed && !getenv("MIAGPU_SERIAL_LAUNCH");
+  int rr = 0;
   int64_t cells[NBUCKET], pcells[P16_NKB];
   memcpy(cells, meta + META_CELLS, sizeof(cells));
   memcpy(pcells, meta + META_PCELLS, sizeof(pcells));
@@ -711,10 +758,18 @@ static int realign_launch(miagpu_ctx* c, const RealignJob& j) {
     pair_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, c->d_off.p + lo, c->d_kind.p + lo, j.d_meta, j.d_pairs);
     MIAGPU_CUDA(cudaGetLastError());
     c->launches++;
-    int base = 0;
-    for (int kb = 0; kb < P16_NKB; kb++) {
+    int base_of[P16_NKB], base = 0, order[P16_NKB];
+    for (int kb = 0; kb < P16_NKB; kb++) { base_of[kb] = base; base += pair_items[kb]; order[kb] = kb; }
+    if (concurrent) {                                 // biggest class first: the small ones fill its tail
+      std::sort(order, order + P16_NKB, [&](int a, int b) { return pcells[a] > pcells[b]; });
+      if (!fork_streams(c, 0)) return 0;
+    }
+    for (int oi = 0; oi < P16_NKB; oi++) {
+      const int kb = order[oi];
       const int ni = pair_items[kb];
       if (!ni) continue;
+      const int base = base_of[kb];
+      pick_stream(c, concurrent, rr);
       if (j.timed) MIAGPU_CUDA(cudaEventRecord(c->pev[2 * kb], c->stream));
       Pair16Params p{};
       p.bases = c->d_bases.p; p.off = c->d_off.p + lo; p.rc = c->d_rc.p + lo; p.win_start = c->d_win_start.p + lo; p.win_len = c->d_win_len.p + lo;
@@ -737,15 +792,17 @@ static int realign_launch(miagpu_ctx* c, const RealignJob& j) {
       }
       if (!ok) return 0;
       if (j.timed) MIAGPU_CUDA(cudaEventRecord(c->pev[2 * kb + 1], c->stream));
-      base += ni;
     }
+    if (concurrent && !join_streams(c, 0)) return 0;
   }
 
   // ---- 32-bit kernels over the direct lists plus whatever the pair kernels appended
+  if (concurrent && !fork_streams(c, 4)) return 0;
   for (int b = 0; b < NBUCKET; b++) {
     const int pop = meta[META_POP + b];               // upper bound of the final list length
     if (!pop) continue;
     if (!total_pairs && !meta[META_COUNT + b]) continue;
+    pick_stream(c, concurrent, rr);
     if (j.timed) MIAGPU_CUDA(cudaEventRecord(c->bev[2 * b], c->stream));
     RealignParams p{};
     p.bases = c->d_bases.p; p.off = c->d_off.p + lo; p.rc = c->d_rc.p + lo;
@@ -773,6 +830,7 @@ static int realign_launch(miagpu_ctx* c, const RealignJob& j) {
     if (j.timed) MIAGPU_CUDA(cudaEventRecord(c->bev[2 * b + 1], c->stream));
     if (j.timed) c->bucket_reads[b] = -1;            // launched; the final list length is read back with the timings
   }
+  if (concurrent && !join_streams(c, 4)) return 0;
   return 1;
 }
 
@@ -782,10 +840,11 @@ static RealignJob whole_batch_job(miagpu_ctx* c) {
   return j;
 }
 
-static int realign_device(miagpu_ctx* c) {
+static int realign_device(miagpu_ctx* c, bool timed = true) {
   realign_reset_stats(c);
   if (c->n == 0) return 1;
-  const RealignJob j = whole_batch_job(c);
+  RealignJob j = whole_batch_job(c);
+  j.timed = timed;
   if (!realign_classify(c, j, c->stream)) return 0;
   MIAGPU_CUDA(cudaStreamSynchronize(c->stream));
   return realign_launch(c, j);
@@ -1638,7 +1697,7 @@ extern "C" int miagpu_iterate_resident(miagpu_ctx* c, int hard_cut, int score_cu
   MIAGPU_CUDA(cudaEventRecord(c->ev[1], main));
   cut_init_kernel<<<1, 256, 0, main>>>(c->d_cstats.p);
   MIAGPU_CUDA(cudaGetLastError());
-  if (!realign_device(c)) return 0;
+  if (!realign_device(c, false)) return 0;
   MIAGPU_CUDA(cudaEventRecord(c->ev[2], main));
   if (fit) {
     MIAGPU_CUDA(cudaStreamWaitEvent(down, c->ev[2], 0));
@@ -1656,9 +1715,7 @@ extern "C" int miagpu_iterate_resident(miagpu_ctx* c, int hard_cut, int score_cu
   if (!iterate_tail(c, t, tr)) { cudaStreamSynchronize(down); return 0; }
   MIAGPU_CUDA(cudaEventElapsedTime(&c->ms_kernels, c->ev[1], c->ev[2]));
   c->ms_h2d = c->ms_d2h = 0;
-  const int launches = c->launches;
-  if (!realign_bucket_times(c)) return 0;
-  c->launches = launches;
+  MIAGPU_CUDA(cudaMemcpy(&c->n_fallback, c->d_meta.p + META_NFALL, 4, cudaMemcpyDeviceToHost));
   return 1;
 }
 
