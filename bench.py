@@ -340,7 +340,8 @@ def pass1_numbers(g, ref, stored, off, rc, args):
         res[tag] = {"reads": m, "kernel_ms": t["ms_kernels"], "reads_per_s": m / (t["ms_kernels"] * 1e-3),
                     "nominal_gcups": nominal / (t["ms_kernels"] * 1e-3) / 1e9,
                     "accepted": int((out["score"] >= 2000).sum()), "rc_fraction": float(out["rc"].mean()),
-                    "skipped_by_filter": int(((out["status"] & 2) != 0).sum())}
+                    "skipped_by_filter": int(((out["status"] & 2) != 0).sum()),
+                    "reads_windowed_pair_kernels": g.last_pass1_stats()[0], "reads_general_kernel": g.last_pass1_stats()[1]}
     g.build_kmers(0)
     return res
 

@@ -111,6 +111,12 @@ int miagpu_pass1( miagpu_ctx* ctx, int32_t* hits, int32_t* score,
                   int32_t* abr, int32_t* n_runs, uint16_t* runs,
                   uint8_t* status );
 
+/* How the last miagpu_pass1 was computed: reads finished by the windowed 16-bit
+ * pair kernels (k-mer filter on, all hits of a strand on neighbouring diagonals:
+ * csrc/pass1.cuh), reads the general chunked kernel took, reads without a hit. */
+int miagpu_last_pass1_stats( miagpu_ctx* ctx, int64_t* fast_reads,
+                             int64_t* general_reads, int64_t* skipped_reads );
+
 /* After pass 1 the host tells the device which resident reads to keep and in
  * which orientation (sg_align's accept test + add_virgin_fs2fsdb + clean_FSDB):
  * keep[i] in {0,1}; revcomp[i] = 1 stores the reverse complement.  Reads are

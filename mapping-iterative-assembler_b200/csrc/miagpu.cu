@@ -14,6 +14,7 @@
 #include "pair16.cuh"
 #include "consensus.cuh"
 #include "strip.cuh"
+#include "pass1.cuh"
 #include "scorecut.hpp"
 #include "scorecut.cuh"
 #include <cub/device/device_scan.cuh>
@@ -54,26 +55,7 @@ constexpr int NBUCKET = 10;                                  // 9 register-tiled
 static const int BUCKET_K[NBUCKET] = {2, 4, 5, 6, 7, 8, 10, 12, 16, 0};
 static const int P16_COLS[P16_NKB] = {128, 144, 160, 176, 192, 208, 224, 256};   // columns of the pair kernels' width classes
 
-// d_meta layout (int32 words)
-constexpr int META_COUNT = 0;        // [16] fill counters of the 32-bit work lists
-constexpr int META_WORK = 16;        // [16] dynamic work-fetch counters of the 32-bit kernels
-constexpr int META_MAXL = 32;        // [16] longest read per width class (all reads of the class)
-constexpr int META_CELLS = 48;       // [16] int64 DP cells per width class (all reads of the class)
-constexpr int META_POP = 80;         // [16] reads per width class (direct + pair-eligible)
-constexpr int META_NPAIRS = 96;      // [8]  work items per pair class
-constexpr int META_PWORK = 104;      // [8]  work-fetch counters of the pair kernels
-constexpr int META_PREADS = 112;     // [8]  eligible reads per pair class
-constexpr int META_PCELLS = 120;     // [8]  int64 cells of the eligible reads
-constexpr int META_MAXLEN = 136;     // scratch of max_len_kernel
-constexpr int META_NFALL = 137;      // reads handed from the pair kernels to the 32-bit kernels
-constexpr int META_HOST = 144;       // words copied to the host after classification
-constexpr int P16_KEYS = P16_NKB * (P16_MAXL + 1);
-constexpr int META_HIST = 256;       // [P16_KEYS] eligible reads per (pair class, read length)
-constexpr int META_PSTART = META_HIST + 1280;    // [P16_KEYS] first pair of the key
-constexpr int META_CURSOR = META_PSTART + 1280;  // [P16_KEYS] scatter cursors
-constexpr int META_WORDS = META_CURSOR + 1280;
 constexpr int MAX_CHUNKS = 16;
-static_assert(P16_KEYS <= 1280 && P16_NKB == 8, "meta layout");
 
 }  // namespace miagpu
 
@@ -96,7 +78,7 @@ struct miagpu_ctx {
   bool have_ref = false;
   std::string raw_wrapped, raw_rc_wrapped;     // case preserved (k-mer soft mask)
   int seq_len = 0, wrap_len = 0, circular = 0, with_rc = 0;
-  DevBuf<uint8_t> d_ref, d_rcref;              // codes 0..4, padded to 16 B
+  DevBuf<uint8_t> d_ref, d_rcref, d_ref2;      // codes 0..4, padded to 16 B; d_ref2 = both strands back to back
   int ref_bytes = 0;
   // reads
   int64_t n = 0, total_bases = 0;
@@ -154,6 +136,10 @@ struct miagpu_ctx {
   DevBuf<int4> d_ckpt;
   DevBuf<int32_t> d_chunk_ids, d_strace, d_hits, d_fw, d_rcs, d_start, d_end;
   DevBuf<uint8_t> d_rc_out, d_bases2;
+  // pass-1 fast path (pass1.cuh): per job (2 * read + strand) inputs / outputs, per read route, general-kernel list
+  DevBuf<uint8_t> d_jkind, d_jstatus, d_route;
+  DevBuf<int32_t> d_jws, d_jwl, d_jscore, d_jabc, d_jaec, d_jabr, d_p1list, d_p1meta, d_jpairs;
+  int64_t p1_fast = 0, p1_general = 0, p1_skipped = 0;
   DevBuf<uint16_t> d_packed;
   DevBuf<int64_t> d_off2;
   DevBuf<int32_t> d_src;
@@ -224,7 +210,9 @@ extern "C" void miagpu_destroy(miagpu_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  c->d_prof.release(); c->d_ref.release(); c->d_rcref.release(); c->d_bases.release(); c->d_off.release();
+  c->d_jkind.release(); c->d_jstatus.release(); c->d_route.release(); c->d_jws.release(); c->d_jwl.release(); c->d_jscore.release();
+  c->d_jabc.release(); c->d_jaec.release(); c->d_jabr.release(); c->d_p1list.release(); c->d_p1meta.release(); c->d_jpairs.release();
+  c->d_prof.release(); c->d_ref.release(); c->d_rcref.release(); c->d_ref2.release(); c->d_bases.release(); c->d_off.release();
   c->d_rc.release(); c->d_status.release(); c->d_as.release(); c->d_ae.release(); c->d_score.release();
   c->d_as_out.release(); c->d_ae_out.release(); c->d_abr.release(); c->d_nruns.release(); c->d_win_start.release();
   c->d_win_len.release(); c->d_lists.release(); c->d_runs.release(); c->d_meta.release();
@@ -350,6 +338,11 @@ extern "C" int miagpu_set_reference(miagpu_ctx* c, const char* seq, int seq_len,
     c->raw_rc_wrapped = rcs;
     c->raw_rc_wrapped.append(rcs, 0, wrap);
     if (!upload_codes(c, c->raw_rc_wrapped, c->d_rcref)) return 0;
+    // both strands back to back for the pass-1 pair kernels (a job's window start carries the strand)
+    if (!c->d_ref2.reserve(2 * (size_t)c->ref_bytes)) return 0;
+    MIAGPU_CUDA(cudaMemcpyAsync(c->d_ref2.p, c->d_ref.p, c->ref_bytes, cudaMemcpyDeviceToDevice, c->stream));
+    MIAGPU_CUDA(cudaMemcpyAsync(c->d_ref2.p + c->ref_bytes, c->d_rcref.p, c->ref_bytes, cudaMemcpyDeviceToDevice, c->stream));
+    MIAGPU_CUDA(cudaStreamSynchronize(c->stream));
   }
   c->have_ref = true;
   return 1;
@@ -393,7 +386,6 @@ extern "C" int miagpu_upload_reads(miagpu_ctx* c, int64_t n, const uint8_t* base
 // work list of its 32-bit width bucket or, when the 16-bit pair kernel can take it (short enough for
 // the 16-bit frame of its width class, at most 256 columns), into the (pair class, read length)
 // histogram that pairs reads of equal length.
-struct PairLmax { int v[P16_NKB]; };                 // longest read each pair class takes (0 = pair kernels off)
 // Block-level statistics go through shared-memory counters; lanes of a warp that hit the same counter are
 // merged first (match.any + redux), so a counter sees one atomic per warp instead of up to 32.
 __global__ void classify_kernel(int64_t n, const int64_t* off, const int32_t* as, const int32_t* ae, int wrap_len, PairLmax lm,
@@ -518,14 +510,15 @@ __global__ void __launch_bounds__(LAYOUT_THREADS) pair_layout_kernel(int32_t* me
 }
 
 // Eligible reads take the next free slot of their key: slot s is member s&1 of pair pstart + s/2.
-__global__ void pair_scatter_kernel(int64_t n, const int64_t* off, const uint8_t* kind, int32_t* meta, int32_t* pairs) {
+// shift = 1: the items are pass-1 jobs (2 * read + strand) and off[] is per read.
+__global__ void pair_scatter_kernel(int64_t n, const int64_t* off, const uint8_t* kind, int32_t* meta, int32_t* pairs, int shift = 0) {
   __shared__ int s_cnt[P16_KEYS], s_base[P16_KEYS];
   for (int i = threadIdx.x; i < P16_KEYS; i += blockDim.x) s_cnt[i] = 0;
   __syncthreads();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int key = -1, slot = 0;
   if (i < n && kind[i] >= 16) {
-    key = (kind[i] - 16) * (P16_MAXL + 1) + (int)(off[i + 1] - off[i]);
+    key = (kind[i] - 16) * (P16_MAXL + 1) + (int)(off[(i >> shift) + 1] - off[i >> shift]);
     slot = atomicAdd(&s_cnt[key], 1);
   }
   __syncthreads();
@@ -564,7 +557,9 @@ static int ensure_max_read_len(miagpu_ctx* c) {
   return 1;
 }
 
-static int launch_strip(miagpu_ctx* c, int mode, const int32_t* list, int n_list, int32_t* counter, int64_t lo = 0) {
+// mode 0 with a list: pass 1 over the listed reads only; n_list is then an upper bound and n_list_ptr the list's
+// length on the device (the seeding / merge kernels of pass1.cuh fill it).
+static int launch_strip(miagpu_ctx* c, int mode, const int32_t* list, int n_list, int32_t* counter, int64_t lo = 0, const int32_t* n_list_ptr = nullptr) {
   if (!ensure_max_read_len(c)) return 0;
   const int len1 = c->circular ? c->wrap_len : c->seq_len;                 // mia_main.c:721-728
   const int n_chunks = (len1 + CW - 1) / CW;
@@ -574,7 +569,7 @@ static int launch_strip(miagpu_ctx* c, int mode, const int32_t* list, int n_list
   int per_sm = 0;
   MIAGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, strip_kernel, WARPS_PER_BLOCK * 32, smem));
   if (per_sm < 1) { set_error("strip_kernel does not fit on an SM"); return 0; }
-  const int64_t total = mode == 0 ? c->n : n_list;
+  const int64_t total = (mode == 0 && !list) ? c->n : n_list;
   if (total == 0) return 1;
   // per-warp scratch: keep the total under ~6 GB
   const size_t per_warp = (size_t)2 * mask_words * 4 + (size_t)2 * (n_chunks + 1) * Lmax * 16 + (size_t)2 * n_chunks * 4 + (size_t)Lmax * CW * 4;
@@ -586,7 +581,7 @@ static int launch_strip(miagpu_ctx* c, int mode, const int32_t* list, int n_list
       !c->d_chunk_ids.reserve(warps * 2 * n_chunks) || !c->d_strace.reserve(warps * Lmax * CW)) return 0;
   StripParams p{};
   p.bases = c->d_bases.p; p.off = c->d_off.p; p.n = c->n; p.counter = counter; p.mode = mode;
-  p.list = list; p.n_list = n_list; p.rc_in = c->d_rc.p;
+  p.list = list; p.n_list = n_list; p.n_list_ptr = n_list_ptr; p.rc_in = c->d_rc.p;
   p.ref_codes[0] = c->d_ref.p; p.ref_codes[1] = c->with_rc ? c->d_rcref.p : c->d_ref.p;
   p.len1 = len1; p.seq_len = c->seq_len; p.prof = c->d_prof.p;
   p.k = mode == 0 ? c->kmer_k : 0;
@@ -638,15 +633,15 @@ static int launch_bucket(miagpu_ctx* c, RealignParams p, int maxL) {
   return 1;
 }
 
-template <int K, int G>
+template <int K, int G, bool JOB = false>
 static int launch_pair16(miagpu_ctx* c, Pair16Params p, int n_pairs, int maxL) {
-  bool ref_in_smem = c->ref_bytes <= 160 * 1024;
-  size_t smem = p16_smem_fixed<G>() + (ref_in_smem ? c->ref_bytes : 0);
+  bool ref_in_smem = p.ref_bytes <= 160 * 1024;
+  size_t smem = p16_smem_fixed<G>() + (ref_in_smem ? p.ref_bytes : 0);
   static size_t cached_smem = ~(size_t)0;
   static int cached_per_sm = 0;
   if (cached_smem != smem) {
-    MIAGPU_CUDA(cudaFuncSetAttribute((pair16_kernel<K, G>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MIAGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cached_per_sm, (pair16_kernel<K, G>), WARPS_PER_BLOCK * 32, smem));
+    MIAGPU_CUDA(cudaFuncSetAttribute((pair16_kernel<K, G, JOB>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MIAGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cached_per_sm, (pair16_kernel<K, G, JOB>), WARPS_PER_BLOCK * 32, smem));
     cached_smem = smem;
   }
   int per_sm = cached_per_sm;
@@ -659,7 +654,7 @@ static int launch_pair16(miagpu_ctx* c, Pair16Params p, int n_pairs, int maxL) {
   (void)maxL;
   p.ref_in_smem = ref_in_smem;
   p.gep2 = K2(2 * GEP);
-  pair16_kernel<K, G><<<blocks, WARPS_PER_BLOCK * 32, smem, c->launch_stream>>>(p);
+  pair16_kernel<K, G, JOB><<<blocks, WARPS_PER_BLOCK * 32, smem, c->launch_stream>>>(p);
   MIAGPU_CUDA(cudaGetLastError());
   c->launches++;
   return 1;
@@ -1775,6 +1770,85 @@ extern "C" int miagpu_build_kmers(miagpu_ctx* c, int k, int soft_mask) {
   return 1;
 }
 
+// Pass 1 with the k-mer filter on (pass1.cuh): seed every read, run the single-stretch strands through the pair
+// kernels, merge, and leave the rest to the general kernel.
+static int pass1_fast(miagpu_ctx* c, const PairLmax& lm) {
+  const int64_t n = c->n, nj = 2 * n;
+  const int np = 32 / c->pair_g;
+  if (n > 0x3fffffffLL) { set_error("miagpu_pass1: at most %d reads per batch", 0x3fffffff); return 0; }
+  if (!c->d_jkind.reserve(nj + 1) || !c->d_jstatus.reserve(nj + 1) || !c->d_route.reserve(n + 1) || !c->d_jws.reserve(nj + 1) ||
+      !c->d_jwl.reserve(nj + 1) || !c->d_jscore.reserve(nj + 1) || !c->d_jabc.reserve(nj + 1) || !c->d_jaec.reserve(nj + 1) ||
+      !c->d_jabr.reserve(nj + 1) || !c->d_p1list.reserve(n + 1) || !c->d_p1meta.reserve(META_WORDS) ||
+      !c->d_jpairs.reserve(nj + 4 * P16_KEYS + 64)) return 0;
+  cudaStream_t st = c->stream;
+  int32_t* meta = c->d_p1meta.p;
+  const int len1 = c->circular ? c->wrap_len : c->seq_len;
+  MIAGPU_CUDA(cudaMemsetAsync(meta, 0, META_WORDS * sizeof(int32_t), st));
+  P1SeedParams sp{};
+  sp.bases = c->d_bases.p; sp.off = c->d_off.p; sp.n = n; sp.k = c->kmer_k; sp.len1 = len1; sp.strand_stride = c->ref_bytes;
+  for (int t = 0; t < 2; t++) sp.kt[t] = KmerTable{c->d_kb[t].p, c->d_kk[t].p, c->d_kp[t].p, c->kmer_shift[t]};
+  sp.lm = lm;
+  sp.jkind = c->d_jkind.p; sp.jws = c->d_jws.p; sp.jwl = c->d_jwl.p; sp.hits = c->d_hits.p; sp.route = c->d_route.p;
+  sp.general_list = c->d_p1list.p; sp.score = c->d_score.p; sp.n_runs = c->d_nruns.p; sp.status = c->d_status.p; sp.meta = meta;
+  const unsigned seed_blocks = (unsigned)std::min<int64_t>((int64_t)c->num_sms * 8, (n + 7) / 8);
+  p1_seed_kernel<<<seed_blocks, 256, 0, st>>>(sp);
+  MIAGPU_CUDA(cudaGetLastError());
+  pair_layout_kernel<<<1, LAYOUT_THREADS, 0, st>>>(meta, np);
+  MIAGPU_CUDA(cudaGetLastError());
+  MIAGPU_CUDA(cudaMemcpyAsync(c->h_meta, meta, sizeof(int32_t) * META_HOST, cudaMemcpyDeviceToHost, st));
+  MIAGPU_CUDA(cudaStreamSynchronize(st));
+  c->launches += 2;
+  int pair_items[P16_NKB], total_pairs = 0;
+  for (int kb = 0; kb < P16_NKB; kb++) { pair_items[kb] = c->h_meta[META_NPAIRS + kb]; total_pairs += pair_items[kb]; }
+  if (total_pairs) {
+    MIAGPU_CUDA(cudaMemsetAsync(c->d_jpairs.p, 0xff, (size_t)2 * np * total_pairs * sizeof(int32_t), st));
+    pair_scatter_kernel<<<(unsigned)((nj + 255) / 256), 256, 0, st>>>(nj, c->d_off.p, c->d_jkind.p, meta, c->d_jpairs.p, 1);
+    MIAGPU_CUDA(cudaGetLastError());
+    c->launches++;
+    int base = 0;
+    c->launch_stream = st; c->launch_slot = 0;
+    for (int kb = 0; kb < P16_NKB; kb++) {
+      const int ni = pair_items[kb];
+      if (!ni) continue;
+      Pair16Params p{};
+      p.bases = c->d_bases.p; p.off = c->d_off.p; p.rc = nullptr; p.win_start = c->d_jws.p; p.win_len = c->d_jwl.p;
+      p.pairs = c->d_jpairs.p + 2 * (int64_t)np * base; p.n_items = meta + META_NPAIRS + kb; p.counter = meta + META_PWORK + kb;
+      p.ref_codes = c->d_ref2.p; p.ref_bytes = 2 * c->ref_bytes; p.strand_stride = c->ref_bytes; p.prof16 = c->d_prof16.p;
+      p.score = c->d_jscore.p; p.as_out = c->d_jabc.p; p.ae_out = c->d_jaec.p; p.abr = c->d_jabr.p; p.status = c->d_jstatus.p;
+      p.n_reads = nj;
+      int ok = 1;
+      switch (kb) {
+        case 0: ok = launch_pair16<8, 16, true>(c, p, ni, P16_MAXL); break;
+        case 1: ok = launch_pair16<9, 16, true>(c, p, ni, P16_MAXL); break;
+        case 2: ok = launch_pair16<10, 16, true>(c, p, ni, P16_MAXL); break;
+        case 3: ok = launch_pair16<11, 16, true>(c, p, ni, P16_MAXL); break;
+        case 4: ok = launch_pair16<12, 16, true>(c, p, ni, P16_MAXL); break;
+        case 5: ok = launch_pair16<13, 16, true>(c, p, ni, P16_MAXL); break;
+        case 6: ok = launch_pair16<14, 16, true>(c, p, ni, P16_MAXL); break;
+        default: ok = launch_pair16<16, 16, true>(c, p, ni, P16_MAXL); break;
+      }
+      if (!ok) return 0;
+      base += ni;
+    }
+  }
+  P1MergeParams mp{};
+  mp.n = n; mp.off = c->d_off.p; mp.seq_len = c->seq_len; mp.route = c->d_route.p; mp.jkind = c->d_jkind.p; mp.jstatus = c->d_jstatus.p;
+  mp.jscore = c->d_jscore.p; mp.jabc = c->d_jabc.p; mp.jaec = c->d_jaec.p; mp.jabr = c->d_jabr.p; mp.general_list = c->d_p1list.p; mp.meta = meta;
+  mp.score = c->d_score.p; mp.fw_score = c->d_fw.p; mp.rc_score = c->d_rcs.p; mp.as_out = c->d_as_out.p; mp.ae_out = c->d_ae_out.p;
+  mp.start = c->d_start.p; mp.end = c->d_end.p; mp.abr = c->d_abr.p; mp.n_runs = c->d_nruns.p; mp.rc_out = c->d_rc_out.p;
+  mp.runs = c->d_runs.p; mp.status = c->d_status.p;
+  p1_merge_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(mp);
+  MIAGPU_CUDA(cudaGetLastError());
+  c->launches++;
+  // the general kernel over whatever is left (list length read on the device; the grid is sized for the seeding's share)
+  MIAGPU_CUDA(cudaMemcpyAsync(c->h_meta, meta, sizeof(int32_t) * META_HOST, cudaMemcpyDeviceToHost, st));
+  MIAGPU_CUDA(cudaStreamSynchronize(st));
+  const int n_general = c->h_meta[P1_NGENERAL];
+  c->p1_general = n_general; c->p1_fast = c->h_meta[P1_NFAST]; c->p1_skipped = c->h_meta[P1_NSKIPPED];
+  if (n_general && !launch_strip(c, 0, c->d_p1list.p, n_general, meta + P1_WORK, 0, meta + P1_NGENERAL)) return 0;
+  return 1;
+}
+
 extern "C" int miagpu_pass1(miagpu_ctx* c, int32_t* hits, int32_t* score, int32_t* fw_score, int32_t* rc_score, uint8_t* rc, int32_t* as,
                             int32_t* ae, int32_t* start, int32_t* end, int32_t* abr, int32_t* n_runs, uint16_t* runs, uint8_t* status) {
   if (!c || !c->have_pssm || !c->have_ref || !c->with_rc) { set_error("miagpu_pass1: set_pssm and set_reference(with_rc=1) first"); return 0; }
@@ -1785,7 +1859,16 @@ extern "C" int miagpu_pass1(miagpu_ctx* c, int32_t* hits, int32_t* score, int32_
       !c->d_end.reserve(n + 1) || !c->d_rc_out.reserve(n + 1)) return 0;
   MIAGPU_CUDA(cudaMemsetAsync(c->d_meta.p, 0, 128 * sizeof(int32_t), c->stream));
   MIAGPU_CUDA(cudaEventRecord(c->ev[1], c->stream));
-  if (!launch_strip(c, 0, nullptr, 0, c->d_meta.p + 16)) return 0;
+  const PairLmax lm = pair_lmax(c);
+  bool fast = c->kmer_k > 0 && lm.v[0] > 0 && n > 0;
+  if (const char* e = getenv("MIAGPU_PASS1_FAST")) fast = fast && atoi(e) != 0;
+  c->p1_fast = c->p1_general = c->p1_skipped = 0;
+  if (!fast) {
+    if (!launch_strip(c, 0, nullptr, 0, c->d_meta.p + 16)) return 0;
+    c->p1_general = n;
+  } else if (!pass1_fast(c, lm)) {
+    return 0;
+  }
   MIAGPU_CUDA(cudaEventRecord(c->ev[2], c->stream));
   if (n) {
     auto dl = [&](void* h, const void* d, size_t bytes) { return h ? cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, c->stream) : cudaSuccess; };
@@ -1802,6 +1885,14 @@ extern "C" int miagpu_pass1(miagpu_ctx* c, int32_t* hits, int32_t* score, int32_
   c->ms_h2d = 0;
   const int len1 = c->circular ? c->wrap_len : c->seq_len;
   c->dp_cells = 2 * (int64_t)len1 * c->total_bases;                        // nominal cells
+  return 1;
+}
+
+extern "C" int miagpu_last_pass1_stats(miagpu_ctx* c, int64_t* fast_reads, int64_t* general_reads, int64_t* skipped_reads) {
+  if (!c) { set_error("miagpu_last_pass1_stats: bad argument"); return 0; }
+  if (fast_reads) *fast_reads = c->p1_fast;
+  if (general_reads) *general_reads = c->p1_general;
+  if (skipped_reads) *skipped_reads = c->p1_skipped;
   return 1;
 }
 

@@ -69,6 +69,28 @@ __host__ __device__ inline int bucket32_of(int len1) {
   return len1 <= 64 ? 0 : len1 <= 128 ? 1 : len1 <= 160 ? 2 : len1 <= 192 ? 3 : len1 <= 224 ? 4 : len1 <= 256 ? 5 : len1 <= 320 ? 6 : len1 <= 384 ? 7 : len1 <= 512 ? 8 : 9;
 }
 
+struct PairLmax { int v[P16_NKB]; };                 // longest read each pair class takes (0 = pair kernels off)
+
+// Meta block of a realign / pass-1 job (int32 words): classification counters, pair layout, work-fetch counters
+constexpr int META_COUNT = 0;        // [16] fill counters of the 32-bit work lists
+constexpr int META_WORK = 16;        // [16] dynamic work-fetch counters of the 32-bit kernels
+constexpr int META_MAXL = 32;        // [16] longest read per width class (all reads of the class)
+constexpr int META_CELLS = 48;       // [16] int64 DP cells per width class (all reads of the class)
+constexpr int META_POP = 80;         // [16] reads per width class (direct + pair-eligible)
+constexpr int META_NPAIRS = 96;      // [8]  work items per pair class
+constexpr int META_PWORK = 104;      // [8]  work-fetch counters of the pair kernels
+constexpr int META_PREADS = 112;     // [8]  eligible reads per pair class
+constexpr int META_PCELLS = 120;     // [8]  int64 cells of the eligible reads
+constexpr int META_MAXLEN = 136;     // scratch of max_len_kernel
+constexpr int META_NFALL = 137;      // reads handed from the pair kernels to the 32-bit kernels
+constexpr int META_HOST = 144;       // words copied to the host after classification
+constexpr int P16_KEYS = P16_NKB * (P16_MAXL + 1);
+constexpr int META_HIST = 256;       // [P16_KEYS] eligible reads per (pair class, read length)
+constexpr int META_PSTART = META_HIST + 1280;    // [P16_KEYS] first pair of the key
+constexpr int META_CURSOR = META_PSTART + 1280;  // [P16_KEYS] scatter cursors
+constexpr int META_WORDS = META_CURSOR + 1280;
+static_assert(P16_NKB * (P16_MAXL + 1) <= 1280 && P16_NKB == 8, "meta layout");
+
 struct Pair16Params {
   const uint8_t* bases;
   const int64_t* off;
@@ -94,7 +116,10 @@ struct Pair16Params {
   int64_t n_reads;
   int32_t* n_fallback;           // statistics
   uint32_t gep2;                 // K2(2*GEP), passed as data so that ptxas keeps this add an IMAD (FMA pipe) instead of folding it into a VIADD
+  int32_t strand_stride;         // JOB kernels: bytes between the forward and the reverse-complement codes in ref_codes
 };
+
+constexpr uint8_t P16_ST_GENERAL = 0x40;   // JOB kernels: the alignment is not one plain diagonal, the general kernel takes the read
 
 // packed constants: B2(v) = the cell value v in both halves (biased), K2(k) = the addend k in both halves
 __host__ __device__ constexpr uint32_t B2(int v) { return ((uint32_t)(v + 32768) & 0xffffu) * 0x10001u; }
@@ -148,7 +173,15 @@ __host__ __device__ constexpr int p16_smem_fixed() {
   return (PROF16_N + 8) * 2 + WARPS_PER_BLOCK * (32 / G) * 2 * P16_MAXL * 2 + WARPS_PER_BLOCK * (32 / G) * 2 * P16_TAB_WORDS * 4;
 }
 
-template <int K, int G>
+// JOB = false: a work item names reads (reiterate_assembly's windows, matrix by strand).
+// JOB = true : pass 1 with the k-mer filter (sg_align, mia.c:1500-1610).  A work item names jobs, job = 2 * read + strand:
+//   the read against the ONE stretch of columns its k-mer hits unmasked on that strand (new_kmer_filter, kmer.c:239-331),
+//   always with the forward matrix (H5).  The masked matrix differs from a window in one place: when the stretch does
+//   not begin at column 0 its first column has a masked left neighbour, so there dyn_prog starts a new alignment
+//   (S = N, substitution score not added, mia.c:910-915) instead of applying the column-0 rule (mia.c:805-822).
+//   Everything to the left / right of the stretch is HIM and can neither be chosen nor become the best end cell.
+//   Outputs are per job, in strand coordinates: as_out = abc, ae_out = aec.
+template <int K, int G, bool JOB>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, (K <= 12 ? 5 : 4)) pair16_kernel(Pair16Params p) {
   static_assert(K >= 4 && K <= 16 && G == 16, "columns per lane / lanes per pair");
   constexpr int NP = 32 / G;                         // pairs per warp
@@ -197,7 +230,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, (K <= 12 ? 5 : 4)) pair1
   const uint32_t gep2 = p.gep2;
   const uint32_t keep = sub ? 0xffffffffu : 0u;      // lane masks for the group's first lane (one LOP3 instead of a select)
   const uint32_t sentm = sub ? 0u : B2(SENT);
-  const uint32_t ncmp0m = sub ? 0u : B2(-(GOP + 3 * GEP) - OFF);
+  uint32_t ncmp0m = sub ? 0u : B2(-(GOP + 3 * GEP) - OFF);
 
   // table entries this lane builds every row: e = sub + G*t -> (a, b) = (e / 5, e % 5)
   uint32_t eoa[NE], eob[NE];
@@ -227,11 +260,17 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, (K <= 12 ? 5 : 4)) pair1
     if (!hasA) rdA = p.pairs[2 * (item * NP)];
     const bool hasB = hasA && rdB >= 0;
     if (rdB < 0 || !hasA) rdB = rdA;
-    const int64_t oA = p.off[rdA], oB = p.off[rdB];
-    const int L = (int)(p.off[rdA + 1] - oA);         // the same for every read of the work item
+    const int rrA = JOB ? rdA >> 1 : rdA, rrB = JOB ? rdB >> 1 : rdB;      // the reads behind the jobs
+    const int64_t oA = p.off[rrA], oB = p.off[rrB];
+    const int L = (int)(p.off[rrA + 1] - oA);         // the same for every read of the work item
     const int wsA = p.win_start[rdA], wsB = p.win_start[rdB];
     const int lenA = p.win_len[rdA], lenB = p.win_len[rdB];
-    const int sA = p.rc[rdA] ? 1 : 0, sB = p.rc[rdB] ? 1 : 0;
+    const int sA = JOB ? 0 : (p.rc[rdA] ? 1 : 0), sB = JOB ? 0 : (p.rc[rdB] ? 1 : 0);
+    if (JOB) {                                        // first column: column 0 of the matrix, or a column with a masked left neighbour
+      const bool mlA = wsA - (rdA & 1) * p.strand_stride > 0, mlB = wsB - (rdB & 1) * p.strand_stride > 0;
+      const uint32_t real = B2(-(GOP + 3 * GEP) - OFF), cut = B2(SENT);
+      ncmp0m = sub ? 0u : (((mlA ? cut : real) & 0xffffu) | ((mlB ? cut : real) & 0xffff0000u));
+    }
 
     __syncwarp();
     for (int r = sub; r < L; r += G) {
@@ -310,7 +349,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, (K <= 12 ? 5 : 4)) pair1
         const uint2 e = lds_entry<PAR * P16_TAB_WORDS * 4>(comb[j]);
         uint32_t bp;
         Wn[j] = cell_pair(best, ncmpj, e.x, e.y, gep2, bp);
-        accn[j] = ad | (bp ^ D);
+        if (JOB && j == 0) accn[j] = and_or(bp ^ D, keep, ad);   // a start-new cell in the stretch's first column ends the walk like column 0 does
+        else accn[j] = ad | (bp ^ D);
       }
       __syncwarp();
     };
@@ -352,7 +392,20 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, (K <= 12 ? 5 : 4)) pair1
         if (sub * K + j == aec) bad = (h ? (acc[j] >> 16) : (acc[j] & 0xffffu)) != 0;
       const bool ok = !__any_sync(gmask, bad);
       const int nsteps = min(L - 1, aec);
-      if (sub == 0 && live) {
+      if (JOB) {
+        if (sub == 0 && live) {
+          const int lo = ws - (rd & 1) * p.strand_stride;
+          if (ok) {
+            p.score[rd] = score;
+            p.as_out[rd] = aec - nsteps + lo;           // abc
+            p.ae_out[rd] = aec + lo;                    // aec
+            p.abr[rd] = L - 1 - nsteps;
+            p.status[rd] = MIAGPU_ST_OK;
+          } else {
+            p.status[rd] = P16_ST_GENERAL;
+          }
+        }
+      } else if (sub == 0 && live) {
         if (ok) {
           p.score[rd] = score;
           p.as_out[rd] = aec - nsteps + ws;

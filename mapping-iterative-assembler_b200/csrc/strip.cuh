@@ -44,6 +44,7 @@ struct StripParams {
   int32_t mode;
   const int32_t* list;
   int32_t n_list;
+  const int32_t* n_list_ptr;          // nullable: the list's length on the device (mode 0 with a list)
   const uint8_t* rc_in;
   const uint8_t* ref_codes[2];        // forward / reverse-complement strand, wrapped
   int32_t len1;                       // columns (wrap_len if circular else seq_len)
@@ -240,7 +241,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) strip_kernel(StripParams
   int4* ck0 = p.ckpt + gw * 2 * (int64_t)(p.max_chunks + 1) * p.Lmax;
   int32_t* ids0 = p.chunk_ids + gw * 2 * p.max_chunks;
   int32_t* trace = p.trace + gw * (int64_t)p.Lmax * CW;
-  const int total = p.mode == 0 ? (int)p.n : p.n_list;
+  const int total = p.n_list_ptr ? *p.n_list_ptr : (p.mode == 0 && !p.list) ? (int)p.n : p.n_list;
   const int len1 = p.len1;
 
   for (;;) {
@@ -248,7 +249,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) strip_kernel(StripParams
     if (lane == 0) item = atomicAdd(p.counter, 1);
     item = __shfl_sync(0xffffffffu, item, 0);
     if (item >= total) break;
-    const int rd = p.mode == 0 ? item : p.list[item];
+    const int rd = p.list ? p.list[item] : item;
     const int64_t o0 = p.off[rd];
     const int L = (int)(p.off[rd + 1] - o0);
     const uint8_t* read = p.bases + o0;

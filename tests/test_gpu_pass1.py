@@ -49,3 +49,47 @@ def test_pass1_long_reads(gpu, oracle):
     ref, reads = _reads(200, 2500, seed=111, min_len=100, max_len=256, divergence=0.04, indel_rate=0.01)
     bad, _ = gpu_checks.check_pass1(gpu, oracle, ref, reads, gpu_checks.load_pssm("pe"), 1, 10)
     assert not bad, f"{len(bad)} reads differ; first {bad[0]}"
+
+
+def test_pass1_fast_path_vs_oracle(gpu, oracle):
+    # k = 12 on a 5 kb circular reference: nearly every read is one stretch on one strand -> windowed pair kernels;
+    # reads near position 0 (real column 0) and in the wrap (stretch clipped at the last column) included
+    ref, reads = _reads(3000, 5000, seed=211, divergence=0.01, indel_rate=0.002)
+    bad, out = gpu_checks.check_pass1(gpu, oracle, ref, reads, gpu_checks.load_pssm("onepass"), 1, 12)
+    assert not bad, f"{len(bad)} reads differ; first {bad[0]}"
+    fast, general, skipped = gpu.last_pass1_stats()
+    assert fast > 2400 and fast + general + skipped == len(reads), (fast, general, skipped)
+
+
+def test_pass1_fast_path_linear_short_k(gpu, oracle):
+    # linear reference, k = 10: more spurious hits (second stretches, hits on both strands)
+    ref, reads = _reads(1500, 4000, seed=223, divergence=0.03, indel_rate=0.006)
+    bad, out = gpu_checks.check_pass1(gpu, oracle, ref, reads, gpu_checks.load_pssm("ancient"), 0, 10)
+    assert not bad, f"{len(bad)} reads differ; first {bad[0]}"
+    fast, general, skipped = gpu.last_pass1_stats()
+    assert fast > 500 and general > 0, (fast, general, skipped)
+
+
+def test_pass1_fast_equals_general_large(gpu, monkeypatch):
+    # size-independent property at bench scale: the windowed fast path and the general chunked kernel agree read by read
+    import _pkg
+    _pkg.load()
+    from mia_b200 import synth
+    ref = synth.random_reference(16569, seed=1)
+    g = synth.diverge(ref, 0.005, seed=2, indel_rate=0.001)
+    b, off, _ = synth.make_reads(g, 60000, 35, 75, seed=77)
+    gpu.set_pssm(gpu_checks.load_pssm("onepass"))
+    gpu.set_reference(ref, circular=1, with_rc=1)
+    gpu.build_kmers(12)
+    gpu.upload_reads(b, off)
+    a = gpu.pass1()
+    fast, general, skipped = gpu.last_pass1_stats()
+    assert fast > 50000
+    monkeypatch.setenv("MIAGPU_PASS1_FAST", "0")
+    z = gpu.pass1()
+    assert gpu.last_pass1_stats()[0] == 0
+    for k in ("hits", "score", "fw_score", "rc_score", "rc", "as_", "ae", "start", "end", "abr", "n_runs", "status"):
+        assert (a[k] == z[k]).all(), (k, int((a[k] != z[k]).sum()))
+    nr = np.maximum(a["n_runs"], 0)
+    m = np.arange(a["runs"].shape[1])[None, :] < nr[:, None]
+    assert (np.where(m, a["runs"], 0) == np.where(m, z["runs"], 0)).all()
