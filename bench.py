@@ -6,10 +6,11 @@ windowed PSSM semi-global DP + on-device traceback of every read against the cur
 consensus (reiterate_assembly, mia_main.c:178-257), then per-column accumulation and base
 calling (consensus_assembly_string, mia.c:515-603).  Workload at N=1 is BASELINE.json
 configs[1]: 1 M synthetic 35-75 bp aDNA-damaged reads vs a 16,569 bp circular reference,
-ancient.submat.solexa.onepass, single iteration.  At N=1 the step also holds the iteration's score cut
-(cull_maln_from_fsdb / find_fsdb_score_cut, mia.c:418-479, fsdb.c:269-383) between the two.  Reads shard across ranks (weak scaling:
-1 M reads per GPU, consensus replicated, gaps all-reduced with MAX and the column planes
-with SUM over NCCL).
+ancient.submat.solexa.onepass, single iteration.  The step also holds the iteration's score cut
+(cull_maln_from_fsdb / find_fsdb_score_cut, mia.c:418-479, fsdb.c:269-383) between the two, at every N.
+Reads shard across ranks (weak scaling: 1 M reads per GPU, consensus replicated; per round one
+all-gather of the regression keys, one all-reduce MAX of the insert maxima and one all-reduce SUM of
+the column planes over NCCL, enqueued on the library's stream: mia_b200/shard.py).
 
   value : reads/s, whole job, inputs resident in HBM, device time (CUDA events on the
           library's stream), max over ranks.
@@ -135,35 +136,16 @@ def run_ours(args):
     lib_stream = torch.cuda.ExternalStream(g.lib.miagpu_stream(g.h), device=torch.device("cuda", local))
     seq_len = np.diff(off).astype(np.int32)
 
-    class Raw:
-        def __init__(self, ptr, count):
-            self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<i4", "data": (ptr, False), "version": 3}
-
-    def consensus_step(drop_f=None, drop_b=None):
-        """accumulate -> (all-reduce) -> call; returns the consensus string"""
-        if world == 1:
-            return g.consensus_natural(drop_f, drop_b, 1, want_gaps=False)[0]
-        ptr, cnt = g.accumulate_gaps_natural(drop_f, drop_b)
-        t = torch.as_tensor(Raw(ptr, cnt), device=f"cuda:{local}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        torch.cuda.synchronize()
-        ptr, cnt = g.accumulate_counts()
-        t = torch.as_tensor(Raw(ptr, cnt), device=f"cuda:{local}")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        torch.cuda.synchronize()
-        return g.call(1)[0]
+    from mia_b200 import shard
+    S = shard.ShardedRounds(g, local, world, rank, n) if world > 1 else None     # weak scaling: n reads on every rank
 
     launches = {"n": 0}
 
     def step_resident():
-        if world == 1:      # the whole round on resident inputs: realign, score cut (device), consensus
-            g.reset_dropped()                               # every timed step starts from the same state
-            cons = g.iterate_resident()[0]
-            launches["n"] += g.last_timing()["launches"]
-            return cons
-        g.realign_resident()
-        launches["n"] += g.last_timing()["launches"]
-        cons = consensus_step()
+        """the whole round on resident inputs: realign, score cut, consensus (N > 1: the sharded protocol,
+        all-gather + 2 all-reduces over NCCL on the library's stream; same work per read at every N)"""
+        g.reset_dropped()                               # every timed step starts from the same state
+        cons = g.iterate_resident()[0] if world == 1 else S.resident()[0]
         launches["n"] += g.last_timing()["launches"]
         return cons
 
@@ -175,33 +157,20 @@ def run_ours(args):
     h_out = api.MiaGpu.alloc_realign_outputs(n, pinned=True)
     del h_out["runs"]                                   # run lists come back packed (sum(n_runs) words, not n*24)
     h_packed = torch.empty(4 * n, dtype=torch.int16).pin_memory()
-    below = torch.zeros(n, dtype=torch.uint8).pin_memory()
     packed_total = {"n": 0}
 
     h_seq_len = pin(seq_len)
     dropped = torch.zeros(n, dtype=torch.uint8).pin_memory()
 
     def step_e2e():
-        if world == 1:      # one C-ABI call: upload, realign, host score cut (overlapped), consensus
-            dropped.zero_()                                 # every timed step starts from the same state
+        """one call sequence through the C ABI with host buffers: upload, realign, score cut, consensus, downloads"""
+        dropped.zero_()                                 # every timed step starts from the same state
+        if world == 1:
             cons, _, tot, _ = g.iterate_host(h_bases, h_off, h_rc, h_as, h_ae, h_seq_len, dropped, h_out, h_packed)
-            packed_total["n"] = tot
-            return cons
-        out = g.realign_host(h_bases, h_off, h_rc, h_as, h_ae, h_out)
-        packed_total["n"] = g.get_runs_packed(None, h_packed)[0]      # offsets = cumsum(n_runs) on the host if needed
-        score = out["score"].numpy()
-        if world > 1:       # the regression runs over all reads of the job (FSDB order = rank order)
-            sc = torch.from_numpy(score).cuda(non_blocking=True)
-            sl = torch.from_numpy(seq_len).cuda(non_blocking=True)
-            all_sc = torch.empty(world * n, dtype=torch.int32, device="cuda")
-            all_sl = torch.empty(world * n, dtype=torch.int32, device="cuda")
-            dist.all_gather_into_tensor(all_sc, sc)
-            dist.all_gather_into_tensor(all_sl, sl)
-            slope, icpt = api.score_cut(all_sl.cpu().numpy(), all_sc.cpu().numpy())
-            api.cull_flags(seq_len, score, None, 0, 1, slope, icpt, out=below.numpy())
         else:
-            api.cull_flags(seq_len, score, out=below.numpy())
-        return consensus_step(below, below)
+            cons, _, tot, _ = S.host(h_bases, h_off, h_rc, h_as, h_ae, h_seq_len, dropped, h_out, h_packed)
+        packed_total["n"] = tot
+        return cons
 
     def barrier():
         torch.cuda.synchronize()
@@ -268,8 +237,8 @@ def run_ours(args):
     value = world * n / (ms_per_step * 1e-3)
     cells = tim_realign["dp_cells"]
     gcups = world * cells / (ms_per_step * 1e-3) / 1e9
-    h2d = int(len(bases) + off.nbytes + rc.nbytes + as_.nbytes + ae.nbytes + (seq_len.nbytes + n if world == 1 else 2 * n))
-    d2h = int(sum(v.numel() * v.element_size() for v in h_out.values()) + 2 * packed_total["n"] + len(cons_e2e) + (n if world == 1 else 0))
+    h2d = world * int(len(bases) + off.nbytes + rc.nbytes + as_.nbytes + ae.nbytes + seq_len.nbytes + n)
+    d2h = world * int(sum(v.numel() * v.element_size() for v in h_out.values()) + 2 * packed_total["n"] + len(cons_e2e) + n)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -288,7 +257,8 @@ def run_ours(args):
         "config": {"workload": "BASELINE configs[1]: 1M synthetic 35-75 bp aDNA-damaged reads per GPU vs 16,569 bp circular "
                                "R-rand reference, ancient.submat.solexa.onepass, single iteration (realign + score cut + consensus)",
                    "reads_per_gpu": n, "ref_len": REF_LEN, "l2": "256 MiB buffer written between timed steps",
-                   "parallelism": f"reads sharded x{world}, consensus replicated, allreduce(max gaps, sum planes)"},
+                   "parallelism": f"reads sharded x{world}, consensus replicated; per round 1 all-gather (regression keys, 4 B/read) + "
+                                  f"all-reduce MAX (insert maxima) + all-reduce SUM (column planes) over NCCL on the library stream"},
         "gcups": gcups, "dp_cells_per_step": world * cells,
         "e2e": {"value": world * n / (e2e_total / args.steps), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_total / args.steps * 1e3},
@@ -305,7 +275,8 @@ def run_ours(args):
                            "peak_source": "miagpu_int32_peak micro-benchmark, same run"},
         "buckets": pbuckets + buckets,
         "pair16": {"reads_handed_to_32bit_kernels": n_fallback, "max_read_len": lmax16},
-        "consensus_matches_e2e": bool(cons == cons_e2e) if world == 1 else None,
+        "consensus_matches_e2e": bool(cons == cons_e2e),
+        "score_cut": g.last_cut_stats(),
     }
     # ---- pass 1 (k-mer seeding + whole-reference both-strand DP), reported beside the headline
     if world == 1 and not args.no_pass1:

@@ -285,6 +285,50 @@ int miagpu_iterate_resident( miagpu_ctx* ctx, int hard_cut, int score_cut_set,
                              uint8_t* dropped, int32_t* gaps_out, char* cons_out,
                              int32_t* cons_len );
 
+/* ---- 8e. The same round with the reads sharded over `world` GPUs of one box: one context (one process) per GPU,
+ * reads partitioned contiguously in FSDB order (rank 0 holds the first reads), reference, matrices and k-mer
+ * tables replicated.  The library links no communication library; between the phases the caller runs ONE
+ * collective each, on miagpu_stream(), over device buffers the library hands out (ncclAllGather /
+ * ncclAllReduce in C, torch.distributed in bench.py; INTEGRATION.md shows both):
+ *
+ *   miagpu_shard_begin       realign the resident local reads (inputs as for miagpu_iterate_resident); or
+ *   miagpu_shard_begin_host  the same for a local batch in host memory (arguments as for miagpu_iterate_host)
+ *        -> all-gather  gather_send (gather_words uint32) into gather_recv (world * gather_words, rank order)
+ *        -> all-reduce  MAX, int32, max_words words at max_buf
+ *   miagpu_shard_cut         find_fsdb_score_cut over the reads of ALL ranks in rank order (fsdb.c:269-383: every
+ *                            rank evaluates the same two exact chains and gets the same slope / intercept, bit for
+ *                            bit what one GPU computes over the concatenated reads), cull flags of the local reads
+ *                            (mia.c:452-470, sticky as in H10), insert-column layout, column accumulation
+ *        -> all-reduce  SUM, int32, sum_words words at sum_buf
+ *   miagpu_shard_finish      base calling (identical on every rank) and downloads: dropped[n] = the local reads'
+ *                            sticky flags, packed_runs / total_runs as in miagpu_get_runs_packed, gaps_out /
+ *                            cons_out / cons_len as in miagpu_consensus.  All nullable.
+ *
+ * n_max = the largest local read count of any rank (the same value on every rank).  hard_cut / score_cut_set /
+ * slope / intercept as in miagpu_cull_flags.  world = 1 needs no collectives (gather_recv must still receive a
+ * copy of gather_send) and equals miagpu_iterate_resident / miagpu_iterate_host. */
+int miagpu_shard_begin( miagpu_ctx* ctx, int world, int rank, int64_t n_max, int hard_cut,
+                        int score_cut_set, double slope, double intercept,
+                        void** gather_send, void** gather_recv, int64_t* gather_words,
+                        void** max_buf, int64_t* max_words );
+int miagpu_shard_begin_host( miagpu_ctx* ctx, int world, int rank, int64_t n_max, int64_t n,
+                             const uint8_t* bases, const int64_t* offsets, const uint8_t* rc,
+                             const int32_t* as, const int32_t* ae, int32_t* score,
+                             int32_t* as_out, int32_t* ae_out, int32_t* abr, int32_t* n_runs,
+                             uint8_t* status, const int32_t* seq_len, const uint8_t* unique_best,
+                             const uint8_t* dropped, int hard_cut, int score_cut_set,
+                             double slope, double intercept, void** gather_send,
+                             void** gather_recv, int64_t* gather_words, void** max_buf,
+                             int64_t* max_words );
+int miagpu_shard_cut( miagpu_ctx* ctx, double* slope_out, double* intercept_out,
+                      void** sum_buf, int64_t* sum_words );
+int miagpu_shard_finish( miagpu_ctx* ctx, int cons_code, uint8_t* dropped,
+                         uint16_t* packed_runs, int64_t capacity, int64_t* total_runs,
+                         int32_t* gaps_out, char* cons_out, int32_t* cons_len );
+/* chain blocks of the last round's regression that were summed read by read on the host, and how many of
+ * those needed an extra device fetch (sharded rounds prefetch the likely ones with the block records) */
+int miagpu_last_cut_stats( miagpu_ctx* ctx, int64_t* serial_blocks, int64_t* fetched_blocks );
+
 /* Device-resident round (reads, rc, as, ae stay in HBM between calls): */
 int miagpu_set_alignment_inputs( miagpu_ctx* ctx, const uint8_t* rc,
                                  const int32_t* as, const int32_t* ae );

@@ -73,6 +73,13 @@ def load_library():
     L.miagpu_last_buckets.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.miagpu_iterate_host.argtypes = ([C.c_void_p, C.c_int64] + [C.c_void_p] * 12 + [C.c_int64, _i64p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                       C.c_double, C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_char_p, _i32p])
+    _vpp = C.POINTER(C.c_void_p)
+    L.miagpu_shard_begin.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_double, _vpp, _vpp, _i64p, _vpp, _i64p]
+    L.miagpu_shard_begin_host.argtypes = ([C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int64] + [C.c_void_p] * 14 +
+                                          [C.c_int, C.c_int, C.c_double, C.c_double, _vpp, _vpp, _i64p, _vpp, _i64p])
+    L.miagpu_shard_cut.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), _vpp, _i64p]
+    L.miagpu_shard_finish.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, _i64p, C.c_void_p, C.c_char_p, _i32p]
+    L.miagpu_last_cut_stats.argtypes = [C.c_void_p, _i64p, _i64p]
     L.miagpu_last_pair_buckets.argtypes = [C.c_void_p] + [C.c_void_p] * 5 + [_i32p, _i32p]
     L.miagpu_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), _i64p, _i32p]
     L.miagpu_int32_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
@@ -88,7 +95,8 @@ EXPORTS = ["miagpu_device_count", "miagpu_create", "miagpu_destroy", "miagpu_las
            "miagpu_consensus", "miagpu_accumulate_gaps", "miagpu_accumulate_counts", "miagpu_call", "miagpu_consensus_natural", "miagpu_accumulate_gaps_natural",
            "miagpu_score_cut", "miagpu_cull_flags",
            "miagpu_set_alignment_inputs", "miagpu_realign_resident", "miagpu_set_cut_inputs", "miagpu_reset_dropped", "miagpu_iterate_resident", "miagpu_last_buckets", "miagpu_last_pair_buckets", "miagpu_last_timing",
-           "miagpu_int32_peak", "miagpu_stream"]
+           "miagpu_int32_peak", "miagpu_stream", "miagpu_shard_begin", "miagpu_shard_begin_host", "miagpu_shard_cut", "miagpu_shard_finish",
+           "miagpu_last_cut_stats"]
 
 
 def _ptr(a):
@@ -252,6 +260,53 @@ class MiaGpu:
         self._ck(self.lib.miagpu_iterate_resident(self.h, hard_cut, 0 if score_cut is None else 1, slope, icpt, cons_code, C.byref(so),
                                                   C.byref(io), _ptr(dropped), _ptr(gaps), self._consbuf, C.byref(cl)))
         return self._consbuf.value.decode(), (so.value, io.value), gaps
+
+    # -- sharded rounds: three phases with one collective after each of the first two (see shard.py)
+    def shard_begin(self, world, rank, n_max, hard_cut=0, score_cut=None):
+        """-> dict(send=(ptr, words), recv=(ptr, world * words), max=(ptr, words)): device buffers to all-gather / MAX-reduce"""
+        gs, gr, mb = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        gw, mw = C.c_int64(), C.c_int64()
+        slope, icpt = score_cut if score_cut is not None else (0.0, 0.0)
+        self._ck(self.lib.miagpu_shard_begin(self.h, world, rank, n_max, hard_cut, 0 if score_cut is None else 1, slope, icpt,
+                                             C.byref(gs), C.byref(gr), C.byref(gw), C.byref(mb), C.byref(mw)))
+        return dict(send=(gs.value, gw.value), recv=(gr.value, world * gw.value), max=(mb.value, mw.value))
+
+    def shard_begin_host(self, world, rank, n_max, bases, offsets, rc, as_, ae, seq_len, dropped, out, unique_best=None, hard_cut=0,
+                         score_cut=None):
+        n = len(offsets) - 1
+        gs, gr, mb = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        gw, mw = C.c_int64(), C.c_int64()
+        slope, icpt = score_cut if score_cut is not None else (0.0, 0.0)
+        self._ck(self.lib.miagpu_shard_begin_host(self.h, world, rank, n_max, n, _ptr(bases), _ptr(offsets), _ptr(rc), _ptr(as_), _ptr(ae),
+                                                  _ptr(out["score"]), _ptr(out["as_out"]), _ptr(out["ae_out"]), _ptr(out["abr"]),
+                                                  _ptr(out["n_runs"]), _ptr(out["status"]), _ptr(seq_len), _ptr(unique_best), _ptr(dropped),
+                                                  hard_cut, 0 if score_cut is None else 1, slope, icpt,
+                                                  C.byref(gs), C.byref(gr), C.byref(gw), C.byref(mb), C.byref(mw)))
+        self.n = n
+        return dict(send=(gs.value, gw.value), recv=(gr.value, world * gw.value), max=(mb.value, mw.value))
+
+    def shard_cut(self):
+        """-> ((slope, intercept), (ptr, words) of the column planes to SUM-reduce)"""
+        so, io, sb, sw = C.c_double(), C.c_double(), C.c_void_p(), C.c_int64()
+        self._ck(self.lib.miagpu_shard_cut(self.h, C.byref(so), C.byref(io), C.byref(sb), C.byref(sw)))
+        return (so.value, io.value), (sb.value, sw.value)
+
+    def shard_finish(self, cons_code=1, dropped=None, packed=None, want_gaps=False, want_total_runs=False):
+        """-> (consensus, gaps or None, total_runs or None)"""
+        if not hasattr(self, "_consbuf") or len(self._consbuf) < self.seq_len * 4 + 4096:
+            self._consbuf = C.create_string_buffer(self.seq_len * 4 + 4096)
+        cl, tot = C.c_int32(), C.c_int64()
+        gaps = np.zeros(self.seq_len, np.int32) if want_gaps else None
+        cap = 0 if packed is None else (packed.numel() if hasattr(packed, "numel") else packed.size)
+        want_tot = want_total_runs or packed is not None
+        self._ck(self.lib.miagpu_shard_finish(self.h, cons_code, _ptr(dropped), _ptr(packed), cap, C.byref(tot) if want_tot else None,
+                                              _ptr(gaps), self._consbuf, C.byref(cl)))
+        return self._consbuf.value.decode(), gaps, (tot.value if want_tot else None)
+
+    def last_cut_stats(self):
+        a, b = C.c_int64(), C.c_int64()
+        self._ck(self.lib.miagpu_last_cut_stats(self.h, C.byref(a), C.byref(b)))
+        return dict(serial_blocks=a.value, fetched_blocks=b.value)
 
     # -- consensus
     def consensus(self, entries, cons_code=1, want_counts=False):

@@ -126,6 +126,15 @@ struct miagpu_ctx {
   std::vector<uint8_t> h_unique;
   int64_t cut_inputs_n = -1;
   int64_t cut_serial_blocks = 0;                // chain blocks the last round summed read by read on the host
+  // sharded rounds: this rank's part of the all-gather, what came back, prefetched chain blocks
+  int sh_world = 0, sh_rank = 0, sh_phase = 0, sh_hard_cut = 0, sh_cut_set = 0, sh_chunks = 0;
+  int64_t sh_nmax = 0, sh_stride = 0, sh_fetched = 0;
+  bool sh_fit = false, sh_host = false, sh_want_packed = false;
+  double sh_slope = 0, sh_icpt = 0;
+  DevBuf<uint32_t> d_sh_send, d_sh_recv, d_sh_pf;
+  DevBuf<int32_t> d_sh_pfid;
+  uint32_t* h_sh_pf = nullptr;                  // pinned: SHARD_PF_SLOTS blocks of keys
+  int32_t* h_sh_pfid = nullptr;                 // pinned: count + block ids
   // pass 1 / wide windows
   int kmer_k = 0;
   DevBuf<int32_t> d_kb[2], d_kp[2];
@@ -235,6 +244,9 @@ extern "C" void miagpu_destroy(miagpu_ctx* c) {
   if (c->h_cut) cudaFreeHost(c->h_cut);
   if (c->h_cblk) cudaFreeHost(c->h_cblk);
   if (c->h_score) cudaFreeHost(c->h_score);
+  if (c->h_sh_pf) cudaFreeHost(c->h_sh_pf);
+  if (c->h_sh_pfid) cudaFreeHost(c->h_sh_pfid);
+  c->d_sh_send.release(); c->d_sh_recv.release(); c->d_sh_pf.release(); c->d_sh_pfid.release();
   c->d_seqlen.release(); c->d_unique.release(); c->d_cstats.release(); c->d_ctab.release(); c->d_thr.release(); c->d_cblk.release();
   cudaStreamDestroy(c->stream);
   delete c;
@@ -1479,8 +1491,10 @@ static int iterate_tail(miagpu_ctx* c, const IterTail& a, const Trace& tr) {
     memcpy(H->tab.dx2, F.dx2_of, sizeof(F.dx2_of));
     MIAGPU_CUDA(cudaMemcpyAsync(c->d_ctab.p, &H->tab, sizeof(CutTables), cudaMemcpyHostToDevice, main));
     const uint8_t* du = has_unique ? c->d_unique.p : nullptr;
-    cut_approx_kernel<<<(unsigned)nb, CUT_THREADS, 0, main>>>(n, c->d_seqlen.p, c->d_score.p, du, c->d_ctab.p, c->d_cblk.p);
-    cut_exact_kernel<<<(unsigned)nb, CUT_THREADS, 0, main>>>(n, c->d_seqlen.p, c->d_score.p, du, c->d_ctab.p, c->d_cblk.p);
+    CutSrc src{};
+    src.seq_len = c->d_seqlen.p; src.score = c->d_score.p; src.unique_best = du;
+    cut_approx_kernel<false><<<(unsigned)nb, CUT_THREADS, 0, main>>>(n, src, c->d_ctab.p, c->d_cblk.p);
+    cut_exact_kernel<false><<<(unsigned)nb, CUT_THREADS, 0, main>>>(n, src, c->d_ctab.p, c->d_cblk.p, nullptr, nullptr);
     MIAGPU_CUDA(cudaGetLastError());
     MIAGPU_CUDA(cudaMemcpyAsync(c->h_cblk, c->d_cblk.p, sizeof(CutBlockDev) * nb, cudaMemcpyDeviceToHost, main));
     c->launches += 2;
@@ -1557,26 +1571,25 @@ static int iterate_tail(miagpu_ctx* c, const IterTail& a, const Trace& tr) {
 //                   integer sums; afterwards entries, insert maxima, the regression's block kernels, flags,
 //                   column accumulation, base calling
 //   download stream chunk k's scores (first) and the other per-read outputs while chunk k+1 computes
-extern "C" int miagpu_iterate_host(miagpu_ctx* c, int64_t n, const uint8_t* bases, const int64_t* offsets, const uint8_t* rc,
-                                   const int32_t* as, const int32_t* ae, int32_t* score, int32_t* as_out, int32_t* ae_out,
-                                   int32_t* abr, int32_t* n_runs, uint8_t* status, uint16_t* packed_runs, int64_t capacity,
-                                   int64_t* total_runs, const int32_t* seq_len, const uint8_t* unique_best, int hard_cut,
-                                   int score_cut_set, double slope, double intercept, uint8_t* dropped, int cons_code,
-                                   int32_t* gaps_out, char* cons_out, int32_t* cons_len) {
-  if (!c || !c->have_pssm || !c->have_ref) { set_error("miagpu_iterate_host: set_pssm and set_reference first"); return 0; }
-  if (n <= 0 || !bases || !offsets || !rc || !as || !ae || !score || !seq_len || !dropped) { set_error("miagpu_iterate_host: bad argument"); return 0; }
+// upload, per-chunk classification + DP + downloads of a host-resident batch (the front half of a round); returns the
+// number of chunks through *chunks (the last chunk's "scores on host" event is c->cev[4 * (C - 1) + 2])
+static int host_round_front(miagpu_ctx* c, const char* who, int64_t n, const uint8_t* bases, const int64_t* offsets, const uint8_t* rc,
+                            const int32_t* as, const int32_t* ae, int32_t* score, int32_t* as_out, int32_t* ae_out, int32_t* abr,
+                            int32_t* n_runs, uint8_t* status, const int32_t* seq_len, const uint8_t* unique_best, bool stats,
+                            const uint8_t* dropped, const Trace& tr, int* chunks) {
+  if (!c || !c->have_pssm || !c->have_ref) { set_error("%s: set_pssm and set_reference first", who); return 0; }
+  if (n <= 0 || !bases || !offsets || !rc || !as || !ae || !score || !seq_len || !dropped) { set_error("%s: bad argument", who); return 0; }
   MIAGPU_CUDA(cudaSetDevice(c->device));
-  if (n > 0x7fffffffLL / NBUCKET) { set_error("miagpu_iterate_host: at most %lld reads per batch", 0x7fffffffLL / NBUCKET); return 0; }
-  if (offsets[0] != 0) { set_error("miagpu_iterate_host: offsets[0] must be 0"); return 0; }
+  if (n > 0x7fffffffLL / NBUCKET) { set_error("%s: at most %lld reads per batch", who, 0x7fffffffLL / NBUCKET); return 0; }
+  if (offsets[0] != 0) { set_error("%s: offsets[0] must be 0", who); return 0; }
   const int64_t total = offsets[n];
   if (!c->d_bases.reserve(total + 16) || !c->d_off.reserve(n + 1) || !reserve_per_read(c, n)) return 0;
-  if (!c->d_entries.reserve(2 * n + 2) || !c->d_gaps.reserve(c->seq_len + 2) || !c->d_ins_off.reserve(c->seq_len + 2) ||
+  if (!c->d_entries.reserve(2 * n + 2) || !c->d_gaps.reserve(c->seq_len + 2 + MAX_READ + 8) || !c->d_ins_off.reserve(c->seq_len + 2) ||
       !c->d_dropf.reserve(n + 1) || !c->d_off2.reserve(2 * (n + 2)) || !c->d_seqlen.reserve(n + 1) || !c->d_unique.reserve(n + 1) ||
       !cut_reserve(c, n)) return 0;
   cudaStream_t main = c->stream, up = c->s_up, down = c->s_down;
   const int C = pick_chunks(n);
-  const bool fit = !score_cut_set && hard_cut <= 0;
-  const Trace tr;
+  *chunks = C;
   tr.mark("buffers reserved");
   realign_reset_stats(c);
   c->n = n; c->total_bases = total; c->cut_inputs_n = -1;
@@ -1616,7 +1629,7 @@ extern "C" int miagpu_iterate_host(miagpu_ctx* c, int64_t n, const uint8_t* base
     MIAGPU_CUDA(cudaStreamWaitEvent(main, c->cev[4 * k], 0));
     if (!realign_launch(c, j)) return 0;
     MIAGPU_CUDA(cudaEventRecord(c->cev[4 * k + 1], main));
-    if (fit && !cut_launch_stats(c, j.lo, j.lo + j.n, unique_best != nullptr)) return 0;
+    if (stats && !cut_launch_stats(c, j.lo, j.lo + j.n, unique_best != nullptr)) return 0;
     MIAGPU_CUDA(cudaStreamWaitEvent(down, c->cev[4 * k + 1], 0));
     MIAGPU_CUDA(cudaMemcpyAsync(score + j.lo, c->d_score.p + j.lo, j.n * 4, cudaMemcpyDeviceToHost, down));
     MIAGPU_CUDA(cudaEventRecord(c->cev[4 * k + 2], down));            // this chunk's scores
@@ -1627,6 +1640,34 @@ extern "C" int miagpu_iterate_host(miagpu_ctx* c, int64_t n, const uint8_t* base
     if (status) MIAGPU_CUDA(cudaMemcpyAsync(status + j.lo, c->d_status.p + j.lo, j.n, cudaMemcpyDeviceToHost, down));
   }
   tr.mark("DP + downloads enqueued");
+  return 1;
+}
+// the chunks' statistics after a round that went through host_round_front
+static int host_round_stats(miagpu_ctx* c, int C) {
+  c->ms_h2d = 0; c->ms_kernels = 0; c->ms_d2h = 0;   // the phases overlap: only the caller's wall clock means something
+  for (int k = 0; k < C; k++) {
+    int32_t nf = 0;
+    MIAGPU_CUDA(cudaMemcpy(&nf, c->d_meta.p + (size_t)META_WORDS * k + META_NFALL, 4, cudaMemcpyDeviceToHost));
+    c->n_fallback += nf;
+  }
+  return 1;
+}
+
+extern "C" int miagpu_iterate_host(miagpu_ctx* c, int64_t n, const uint8_t* bases, const int64_t* offsets, const uint8_t* rc,
+                                   const int32_t* as, const int32_t* ae, int32_t* score, int32_t* as_out, int32_t* ae_out,
+                                   int32_t* abr, int32_t* n_runs, uint8_t* status, uint16_t* packed_runs, int64_t capacity,
+                                   int64_t* total_runs, const int32_t* seq_len, const uint8_t* unique_best, int hard_cut,
+                                   int score_cut_set, double slope, double intercept, uint8_t* dropped, int cons_code,
+                                   int32_t* gaps_out, char* cons_out, int32_t* cons_len) {
+  const bool fit = !score_cut_set && hard_cut <= 0;
+  const Trace tr;
+  int C = 1;
+  if (!host_round_front(c, "miagpu_iterate_host", n, bases, offsets, rc, as, ae, score, as_out, ae_out, abr, n_runs, status, seq_len,
+                        unique_best, fit, dropped, tr, &C)) {
+    if (c && c->s_up) { cudaStreamSynchronize(c->s_down); cudaStreamSynchronize(c->s_up); }
+    return 0;
+  }
+  cudaStream_t down = c->s_down, up = c->s_up;
   IterTail t{};
   t.h_seq_len = seq_len; t.h_unique = unique_best; t.h_score = score; t.scores_on_host = c->cev[4 * (C - 1) + 2];
   t.wait_old_flags = true;
@@ -1634,14 +1675,7 @@ extern "C" int miagpu_iterate_host(miagpu_ctx* c, int64_t n, const uint8_t* base
   t.packed_runs = packed_runs; t.capacity = capacity; t.total_runs = total_runs; t.dropped = dropped;
   t.gaps_out = gaps_out; t.cons_out = cons_out; t.cons_len = cons_len;
   if (!iterate_tail(c, t, tr)) { cudaStreamSynchronize(down); cudaStreamSynchronize(up); return 0; }
-  c->ms_h2d = 0; c->ms_kernels = 0; c->ms_d2h = 0;   // the phases overlap: only the caller's wall clock means something
-  // statistics of the chunks
-  for (int k = 0; k < C; k++) {
-    int32_t nf = 0;
-    MIAGPU_CUDA(cudaMemcpy(&nf, jobs[k].d_meta + META_NFALL, 4, cudaMemcpyDeviceToHost));
-    c->n_fallback += nf;
-  }
-  return 1;
+  return host_round_stats(c, C);
 }
 
 // The same round over reads, rc/as/ae, seq_len / unique_best and sticky flags that are already resident:
@@ -1682,6 +1716,9 @@ extern "C" int miagpu_iterate_resident(miagpu_ctx* c, int hard_cut, int score_cu
       !c->d_off2.reserve(2 * (n + 2)) || !cut_reserve(c, n)) return 0;
   if (c->h_score_cap < n) {
     if (c->h_score) cudaFreeHost(c->h_score);
+  if (c->h_sh_pf) cudaFreeHost(c->h_sh_pf);
+  if (c->h_sh_pfid) cudaFreeHost(c->h_sh_pfid);
+  c->d_sh_send.release(); c->d_sh_recv.release(); c->d_sh_pf.release(); c->d_sh_pfid.release();
     c->h_score = nullptr; c->h_score_cap = 0;
     MIAGPU_CUDA(cudaMallocHost(&c->h_score, sizeof(int32_t) * (n + 64)));
     c->h_score_cap = n;
@@ -1711,6 +1748,268 @@ extern "C" int miagpu_iterate_resident(miagpu_ctx* c, int hard_cut, int score_cu
   MIAGPU_CUDA(cudaEventElapsedTime(&c->ms_kernels, c->ev[1], c->ev[2]));
   c->ms_h2d = c->ms_d2h = 0;
   MIAGPU_CUDA(cudaMemcpy(&c->n_fallback, c->d_meta.p + META_NFALL, 4, cudaMemcpyDeviceToHost));
+  return 1;
+}
+
+// ------------------------------------------------------------------ sharded rounds
+// One round of mia_main.c:931-963 with the reads sharded over `world` GPUs, one context (one process) per GPU,
+// the consensus replicated.  The library does not link a communication library: between the three phases the
+// caller runs one collective each on the buffers the library hands out, on miagpu_stream (NCCL in bench.py and
+// driver.py; INTEGRATION.md shows the C calls):
+//   miagpu_shard_begin[_host]   DP of the local reads; integer sums + per-length maxima of the regression; the local
+//                               reads' keys; entries; per-position insert maxima
+//       -> all-gather  gather_send -> gather_recv   (stride words per rank)
+//       -> all-reduce  MAX over max_buf             (insert maxima + per-length best scores)
+//   miagpu_shard_cut            the regression over the gathered keys of every rank in rank order = FSDB order (the
+//                               same block-wise exact chains as a single-GPU round, evaluated redundantly on every
+//                               rank: identical slope / intercept everywhere), flags of the local reads, insert-column
+//                               layout from the reduced maxima, column accumulation of the local reads
+//       -> all-reduce  SUM over sum_buf             (the column planes)
+//   miagpu_shard_finish         base calling (every rank calls the same bases), downloads
+// Integer sums and maxima commute and the chains are evaluated exactly: the results are bit-identical to a
+// single-GPU round over the concatenated reads for any number of ranks.
+static int shard_reserve(miagpu_ctx* c, int world, int64_t n_max) {
+  const int64_t stride = (n_max + SHARD_HDR_WORDS + CUT_BLOCK - 1) / CUT_BLOCK * CUT_BLOCK;
+  c->sh_stride = stride;
+  const int64_t nb = (int64_t)world * stride / CUT_BLOCK;
+  if (!c->d_sh_send.reserve(stride) || !c->d_sh_recv.reserve((size_t)world * stride) || !c->d_sh_pf.reserve((size_t)SHARD_PF_SLOTS * CUT_BLOCK) ||
+      !c->d_sh_pfid.reserve(SHARD_PF_SLOTS + 8) || !cut_reserve(c, nb * CUT_BLOCK)) return 0;
+  if (!c->h_sh_pf) MIAGPU_CUDA(cudaMallocHost(&c->h_sh_pf, sizeof(uint32_t) * SHARD_PF_SLOTS * CUT_BLOCK));
+  if (!c->h_sh_pfid) MIAGPU_CUDA(cudaMallocHost(&c->h_sh_pfid, sizeof(int32_t) * (SHARD_PF_SLOTS + 8)));
+  return 1;
+}
+
+// after the DP: what this rank contributes to the collectives, and the flag-independent part of the consensus
+static int shard_after_dp(miagpu_ctx* c, bool stats_done, bool has_unique, void** gather_send, void** gather_recv, int64_t* gather_words,
+                          void** max_buf, int64_t* max_words) {
+  cudaStream_t main = c->stream;
+  const int64_t n = c->n, stride = c->sh_stride;
+  if (!stats_done && !cut_launch_stats(c, 0, n, has_unique)) return 0;
+  shard_pack_kernel<<<(unsigned)((stride + 255) / 256), 256, 0, main>>>(n, stride, c->d_seqlen.p, c->d_score.p, has_unique ? c->d_unique.p : nullptr,
+                                                                       c->d_sh_send.p);
+  MIAGPU_CUDA(cudaMemsetAsync(c->d_gaps.p, 0, (c->seq_len + 2) * sizeof(int32_t), main));
+  shard_hdr_kernel<<<1, 256, 0, main>>>(c->d_cstats.p, c->d_sh_send.p, stride, c->d_gaps.p + c->seq_len + 2);
+  MIAGPU_CUDA(cudaGetLastError());
+  c->launches += 2;
+  c->n_entries = 2 * n;
+  if (n) {
+    natural_entries_kernel<<<(unsigned)((n + 255) / 256), 256, 0, main>>>(n, c->d_as_out.p, c->d_ae_out.p, c->d_nruns.p, c->d_runs.p,
+                                                                          c->d_status.p, c->seq_len, nullptr, nullptr, c->d_entries.p);
+    MIAGPU_CUDA(cudaGetLastError());
+    c->launches++;
+    if (!launch_gaps(c)) return 0;
+  }
+  if (gather_send) *gather_send = c->d_sh_send.p;
+  if (gather_recv) *gather_recv = c->d_sh_recv.p;
+  if (gather_words) *gather_words = stride;
+  if (max_buf) *max_buf = c->d_gaps.p;
+  if (max_words) *max_words = c->seq_len + 2 + MAX_READ + 1;
+  c->sh_phase = 1;
+  return 1;
+}
+
+static int shard_args(miagpu_ctx* c, const char* who, int world, int rank, int64_t n_max, int64_t n) {
+  if (!c || !c->have_pssm || !c->have_ref) { set_error("%s: set_pssm and set_reference first", who); return 0; }
+  if (world < 1 || rank < 0 || rank >= world || n_max < n || n_max < 1) { set_error("%s: bad world / rank / n_max (n_max must be the largest read count of any rank)", who); return 0; }
+  if ((int64_t)world * (n_max + SHARD_HDR_WORDS + CUT_BLOCK) > 0x7fffffffLL * 64) { set_error("%s: too many reads", who); return 0; }
+  return 1;
+}
+
+extern "C" int miagpu_shard_begin(miagpu_ctx* c, int world, int rank, int64_t n_max, int hard_cut, int score_cut_set, double slope,
+                                  double intercept, void** gather_send, void** gather_recv, int64_t* gather_words, void** max_buf,
+                                  int64_t* max_words) {
+  if (!shard_args(c, "miagpu_shard_begin", world, rank, n_max, c ? c->n : 0)) return 0;
+  if (c->cut_inputs_n != c->n) { set_error("miagpu_shard_begin: upload reads, alignment inputs and cut inputs first"); return 0; }
+  MIAGPU_CUDA(cudaSetDevice(c->device));
+  const int64_t n = c->n;
+  if (!c->d_entries.reserve(2 * n + 2) || !c->d_gaps.reserve(c->seq_len + 2 + MAX_READ + 8) || !c->d_ins_off.reserve(c->seq_len + 2) ||
+      !c->d_off2.reserve(2 * (n + 2)) || !c->d_seqlen.reserve(n + 1) || !c->d_score.reserve(n + 1) || !shard_reserve(c, world, n_max)) return 0;
+  c->sh_world = world; c->sh_rank = rank; c->sh_nmax = n_max; c->sh_hard_cut = hard_cut; c->sh_cut_set = score_cut_set;
+  c->sh_slope = slope; c->sh_icpt = intercept; c->sh_fit = !score_cut_set && hard_cut <= 0; c->sh_host = false; c->sh_want_packed = false;
+  c->sh_phase = 0;
+  MIAGPU_CUDA(cudaEventRecord(c->ev[1], c->stream));
+  cut_init_kernel<<<1, 256, 0, c->stream>>>(c->d_cstats.p);
+  MIAGPU_CUDA(cudaGetLastError());
+  if (!realign_device(c, false)) return 0;
+  MIAGPU_CUDA(cudaEventRecord(c->ev[2], c->stream));
+  return shard_after_dp(c, false, !c->h_unique.empty(), gather_send, gather_recv, gather_words, max_buf, max_words);
+}
+
+extern "C" int miagpu_shard_begin_host(miagpu_ctx* c, int world, int rank, int64_t n_max, int64_t n, const uint8_t* bases,
+                                       const int64_t* offsets, const uint8_t* rc, const int32_t* as, const int32_t* ae, int32_t* score,
+                                       int32_t* as_out, int32_t* ae_out, int32_t* abr, int32_t* n_runs, uint8_t* status,
+                                       const int32_t* seq_len, const uint8_t* unique_best, const uint8_t* dropped, int hard_cut,
+                                       int score_cut_set, double slope, double intercept, void** gather_send, void** gather_recv,
+                                       int64_t* gather_words, void** max_buf, int64_t* max_words) {
+  if (!shard_args(c, "miagpu_shard_begin_host", world, rank, n_max, n)) return 0;
+  const Trace tr;
+  int C = 1;
+  c->sh_phase = 0;
+  if (!host_round_front(c, "miagpu_shard_begin_host", n, bases, offsets, rc, as, ae, score, as_out, ae_out, abr, n_runs, status, seq_len,
+                        unique_best, true, dropped, tr, &C)) {
+    if (c->s_up) { cudaStreamSynchronize(c->s_down); cudaStreamSynchronize(c->s_up); }
+    return 0;
+  }
+  if (!shard_reserve(c, world, n_max)) return 0;
+  c->sh_world = world; c->sh_rank = rank; c->sh_nmax = n_max; c->sh_hard_cut = hard_cut; c->sh_cut_set = score_cut_set;
+  c->sh_slope = slope; c->sh_icpt = intercept; c->sh_fit = !score_cut_set && hard_cut <= 0; c->sh_host = true; c->sh_chunks = C;
+  return shard_after_dp(c, true, unique_best != nullptr, gather_send, gather_recv, gather_words, max_buf, max_words);
+}
+
+extern "C" int miagpu_shard_cut(miagpu_ctx* c, double* slope_out, double* intercept_out, void** sum_buf, int64_t* sum_words) {
+  if (!c || c->sh_phase != 1) { set_error("miagpu_shard_cut: call miagpu_shard_begin first"); return 0; }
+  MIAGPU_CUDA(cudaSetDevice(c->device));
+  cudaStream_t main = c->stream;
+  const int64_t n = c->n, stride = c->sh_stride;
+  const int world = c->sh_world;
+  const int64_t ntot = (int64_t)world * stride, nb = ntot / CUT_BLOCK;
+  const bool fit = c->sh_fit;
+  CutHost* H = c->h_cut;
+  // insert-column layout from the reduced maxima
+  size_t tmp = 0;
+  MIAGPU_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, c->d_gaps.p, c->d_ins_off.p, c->seq_len + 1, main));
+  if (!c->d_cub.reserve(tmp + 16)) return 0;
+  if (fit) {
+    shard_merge_kernel<<<1, 256, 0, main>>>(world, stride, c->d_sh_recv.p, c->d_gaps.p + c->seq_len + 2, c->d_cstats.p, c->d_sh_pfid.p);
+    MIAGPU_CUDA(cudaGetLastError());
+    MIAGPU_CUDA(cudaMemcpyAsync(&H->stats, c->d_cstats.p, sizeof(CutStatsDev), cudaMemcpyDeviceToHost, main));
+    MIAGPU_CUDA(cudaEventRecord(c->xev[0], main));
+    c->launches++;
+  }
+  MIAGPU_CUDA(cub::DeviceScan::ExclusiveSum(c->d_cub.p, tmp, c->d_gaps.p, c->d_ins_off.p, c->seq_len + 1, main));
+  MIAGPU_CUDA(cudaMemcpyAsync(&H->total_ins, c->d_ins_off.p + c->seq_len, sizeof(int32_t), cudaMemcpyDeviceToHost, main));
+  c->launches += 2;
+  CutSums S;
+  CutFit F;
+  if (fit) {
+    MIAGPU_CUDA(cudaEventSynchronize(c->xev[0]));
+    S.sx = H->stats.sx; S.sy = H->stats.sy; S.cnt = H->stats.cnt; S.bad = H->stats.bad == LLONG_MAX ? -1 : H->stats.bad;
+    memcpy(S.best, H->stats.best, sizeof(S.best));
+    if (S.bad >= 0) { cudaStreamSynchronize(main); set_error("miagpu_shard_cut: seq_len of local read %lld out of range", (long long)S.bad); return 0; }
+    if (S.cnt > 0) {
+      cut_fit_tables(S, F);
+      H->tab.ybar = F.ybar;
+      memcpy(H->tab.dx, F.dx_of, sizeof(F.dx_of));
+      memcpy(H->tab.dx2, F.dx2_of, sizeof(F.dx2_of));
+      MIAGPU_CUDA(cudaMemcpyAsync(c->d_ctab.p, &H->tab, sizeof(CutTables), cudaMemcpyHostToDevice, main));
+      CutSrc src{};
+      src.keys = c->d_sh_recv.p; src.n_max = c->sh_nmax; src.stride = stride;
+      cut_approx_kernel<true><<<(unsigned)nb, CUT_THREADS, 0, main>>>(ntot, src, c->d_ctab.p, c->d_cblk.p);
+      cut_exact_kernel<true><<<(unsigned)nb, CUT_THREADS, 0, main>>>(ntot, src, c->d_ctab.p, c->d_cblk.p, c->d_sh_pf.p, c->d_sh_pfid.p);
+      MIAGPU_CUDA(cudaGetLastError());
+      MIAGPU_CUDA(cudaMemcpyAsync(c->h_cblk, c->d_cblk.p, sizeof(CutBlockDev) * nb, cudaMemcpyDeviceToHost, main));
+      MIAGPU_CUDA(cudaMemcpyAsync(c->h_sh_pfid, c->d_sh_pfid.p, sizeof(int32_t) * (SHARD_PF_SLOTS + 1), cudaMemcpyDeviceToHost, main));
+      MIAGPU_CUDA(cudaMemcpyAsync(c->h_sh_pf, c->d_sh_pf.p, sizeof(uint32_t) * SHARD_PF_SLOTS * CUT_BLOCK, cudaMemcpyDeviceToHost, main));
+      c->launches += 2;
+    }
+  }
+  MIAGPU_CUDA(cudaStreamSynchronize(main));
+  double slope = c->sh_slope, intercept = c->sh_icpt;
+  if (fit) {
+    if (S.cnt <= 0) { set_error("miagpu_shard_cut: no read of any rank scores >= %d: nothing to fit", FIRST_ROUND_SCORE_CUTOFF); return 0; }
+    std::vector<ChainBlock> bxy(nb), bxx(nb);
+    for (int64_t b = 0; b < nb; b++) {
+      const CutBlockDev& B = c->h_cblk[b];
+      bxy[b] = ChainBlock{B.approx[0], B.T[0], B.A[0], B.e[0], B.ok[0] != 0};
+      bxx[b] = ChainBlock{B.approx[1], B.T[1], B.A[1], B.e[1], B.ok[1] != 0};
+    }
+    // keys of a block the stitch cannot prove: prefetched with the records, else fetched now
+    const int npf = std::min<int>(c->h_sh_pfid[0], SHARD_PF_SLOTS);
+    std::vector<std::pair<int64_t, std::vector<uint32_t>>> fetched;
+    int64_t n_fetched = 0;
+    int fetch_failed = 0;
+    auto block_keys = [&](int64_t b) -> const uint32_t* {
+      for (int k = 0; k < npf; k++)
+        if (c->h_sh_pfid[1 + k] == b) return c->h_sh_pf + (size_t)k * CUT_BLOCK;
+      for (auto& f : fetched)
+        if (f.first == b) return f.second.data();
+      fetched.emplace_back(b, std::vector<uint32_t>(CUT_BLOCK));
+      if (cudaMemcpy(fetched.back().second.data(), c->d_sh_recv.p + b * CUT_BLOCK, sizeof(uint32_t) * CUT_BLOCK, cudaMemcpyDeviceToHost) != cudaSuccess) fetch_failed = 1;
+      const int64_t l0 = b * CUT_BLOCK % stride;
+      for (int k = 0; k < CUT_BLOCK; k++)
+        if (l0 + k >= c->sh_nmax) fetched.back().second[k] = CUT_KEY_UNUSED;
+      n_fetched++;
+      return fetched.back().second.data();
+    };
+    int64_t ser0 = 0, ser1 = 0;
+    const double ssxy = chain_stitch_blocks(bxy.data(), nb, [&](int64_t b, double Sum) {
+      const uint32_t* k = block_keys(b);
+      for (int i = 0; i < CUT_BLOCK; i++) Sum += k[i] == CUT_KEY_UNUSED ? 0.0 : F.dx_of[k[i] & 511] * ((double)(int)(k[i] >> 9) - F.ybar);
+      return Sum;
+    }, &ser0);
+    const double ssxx = chain_stitch_blocks(bxx.data(), nb, [&](int64_t b, double Sum) {
+      const uint32_t* k = block_keys(b);
+      for (int i = 0; i < CUT_BLOCK; i++) Sum += k[i] == CUT_KEY_UNUSED ? 0.0 : F.dx2_of[k[i] & 511];
+      return Sum;
+    }, &ser1);
+    if (fetch_failed) { set_error("miagpu_shard_cut: device copy failed"); return 0; }
+    c->cut_serial_blocks = ser0 + ser1;
+    c->sh_fetched = n_fetched;
+    cut_fit_slope(S, F, ssxy, ssxx, &slope, &intercept);
+  }
+  if (slope_out) *slope_out = slope;
+  if (intercept_out) *intercept_out = intercept;
+  c->sh_slope = slope; c->sh_icpt = intercept;
+  // ---- flags of the local reads (cull_maln_from_fsdb, mia.c:452-470), sticky (H10)
+  cut_thresholds(c->sh_hard_cut, slope, intercept, H->thr);
+  MIAGPU_CUDA(cudaMemcpyAsync(c->d_thr.p, H->thr, sizeof(H->thr), cudaMemcpyHostToDevice, main));
+  if (c->sh_host) MIAGPU_CUDA(cudaStreamWaitEvent(main, c->xev[1], 0));
+  if (n) {
+    cut_flags_kernel<<<(unsigned)((n + 255) / 256), 256, 0, main>>>(n, c->d_seqlen.p, c->d_score.p, c->d_thr.p, c->d_dropf.p, c->d_entries.p, c->d_cstats.p);
+    MIAGPU_CUDA(cudaGetLastError());
+    c->launches++;
+  }
+  MIAGPU_CUDA(cudaEventRecord(c->xev[2], main));
+  // ---- column accumulation of the local reads into planes laid out by the reduced insert maxima
+  c->n_cols = (int64_t)c->seq_len + H->total_ins;
+  if (!c->d_acc.reserve(c->n_cols * NPLANE) || !c->d_called.reserve(c->n_cols + 16)) return 0;
+  MIAGPU_CUDA(cudaMemsetAsync(c->d_acc.p, 0, c->n_cols * NPLANE * sizeof(int32_t), main));
+  if (!launch_accumulate(c)) return 0;
+  if (sum_buf) *sum_buf = c->d_acc.p;
+  if (sum_words) *sum_words = c->n_cols * NPLANE;
+  c->sh_phase = 2;
+  return 1;
+}
+
+extern "C" int miagpu_shard_finish(miagpu_ctx* c, int cons_code, uint8_t* dropped, uint16_t* packed_runs, int64_t capacity,
+                                   int64_t* total_runs, int32_t* gaps_out, char* cons_out, int32_t* cons_len) {
+  if (!c || c->sh_phase != 2) { set_error("miagpu_shard_finish: call miagpu_shard_cut first"); return 0; }
+  MIAGPU_CUDA(cudaSetDevice(c->device));
+  cudaStream_t down = c->s_down;
+  const int64_t n = c->n;
+  c->sh_phase = 0;
+  if (dropped && n) {
+    MIAGPU_CUDA(cudaStreamWaitEvent(down, c->xev[2], 0));
+    MIAGPU_CUDA(cudaMemcpyAsync(dropped, c->d_dropf.p, n, cudaMemcpyDeviceToHost, down));
+  }
+  c->cons_stage = 2;
+  const int launches = c->launches;
+  if (!miagpu_call(c, cons_code, gaps_out, nullptr, cons_out, cons_len)) { cudaStreamSynchronize(down); return 0; }
+  c->launches = launches + 1;
+  float ms_dp = 0;
+  if (!c->sh_host) MIAGPU_CUDA(cudaEventElapsedTime(&ms_dp, c->ev[1], c->ev[2]));
+  if (packed_runs || total_runs) {
+    int64_t tot = 0;
+    const int l2 = c->launches;
+    if (!miagpu_get_runs_packed(c, nullptr, packed_runs, capacity, &tot)) { cudaStreamSynchronize(down); return 0; }
+    c->launches = l2 + 4;
+    if (total_runs) *total_runs = tot;
+  }
+  MIAGPU_CUDA(cudaStreamSynchronize(down));
+  if (c->sh_host) {
+    MIAGPU_CUDA(cudaStreamSynchronize(c->s_up));
+    return host_round_stats(c, c->sh_chunks);
+  }
+  c->ms_kernels = ms_dp;
+  c->ms_h2d = c->ms_d2h = 0;
+  MIAGPU_CUDA(cudaMemcpy(&c->n_fallback, c->d_meta.p + META_NFALL, 4, cudaMemcpyDeviceToHost));
+  return 1;
+}
+
+extern "C" int miagpu_last_cut_stats(miagpu_ctx* c, int64_t* serial_blocks, int64_t* fetched_blocks) {
+  if (!c) { set_error("miagpu_last_cut_stats: no context"); return 0; }
+  if (serial_blocks) *serial_blocks = c->cut_serial_blocks;
+  if (fetched_blocks) *fetched_blocks = c->sh_fetched;
   return 1;
 }
 

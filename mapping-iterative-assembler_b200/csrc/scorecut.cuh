@@ -89,15 +89,41 @@ __global__ void __launch_bounds__(CUT_THREADS) cut_stats_kernel(int64_t lo, int6
     if (s_best[l] != INT_MIN) atomicMax(&st->best[l], s_best[l]);
 }
 
+// Where the chains' per-read inputs come from: the resident arrays of one GPU, or (sharded rounds)
+// the all-gathered keys of every rank: key = score << 9 | seq_len for a read the fit uses, CUT_KEY_UNUSED otherwise.
+// The gathered space is world * stride words, stride a multiple of CUT_BLOCK; words at local index >= n_max
+// (padding and the rank's header) count as unused reads: a 0.0 addend leaves a rounded chain unchanged.
+constexpr uint32_t CUT_KEY_UNUSED = 0xffffffffu;
+constexpr int SHARD_HDR_WORDS = 8;                   // tail of a rank's stride: sum len, sum score, count (int64 each), 2 spare
+constexpr int SHARD_PF_SLOTS = 64;                   // chain blocks whose keys travel to the host with the block records
+
+struct CutSrc {
+  const int32_t* seq_len; const int32_t* score; const uint8_t* unique_best;       // KEYS = false
+  const uint32_t* keys; int64_t n_max, stride;                                    // KEYS = true
+};
+
+__device__ __forceinline__ uint32_t cut_key(int l, int sc, bool unique) {
+  return (unique && sc >= FIRST_ROUND_SCORE_CUTOFF) ? ((uint32_t)sc << 9) | (uint32_t)min(max(l, 0), MAX_READ) : CUT_KEY_UNUSED;
+}
+
 // the two addends of read i: (len - xbar) * (score - ybar) and (len - xbar)^2, 0 for a read the fit does not use
-__device__ __forceinline__ void cut_addends(int64_t i, const int32_t* seq_len, const int32_t* score, const uint8_t* unique_best,
-                                            const CutTables* __restrict__ t, double& axy, double& axx) {
-  const int sc = score[i];
+template <bool KEYS>
+__device__ __forceinline__ void cut_addends(int64_t i, int64_t local, const CutSrc& s, const CutTables* __restrict__ t, double& axy, double& axx) {
   axy = 0.0; axx = 0.0;
-  if ((!unique_best || unique_best[i]) && sc >= FIRST_ROUND_SCORE_CUTOFF) {
-    const int l = min(max(seq_len[i], 0), MAX_READ);
+  if (KEYS) {
+    if (local >= s.n_max) return;
+    const uint32_t key = s.keys[i];
+    if (key == CUT_KEY_UNUSED) return;
+    const int l = key & 511, sc = (int)(key >> 9);
     axy = __dmul_rn(t->dx[l], __dsub_rn((double)sc, t->ybar));
     axx = t->dx2[l];
+  } else {
+    const int sc = s.score[i];
+    if ((!s.unique_best || s.unique_best[i]) && sc >= FIRST_ROUND_SCORE_CUTOFF) {
+      const int l = min(max(s.seq_len[i], 0), MAX_READ);
+      axy = __dmul_rn(t->dx[l], __dsub_rn((double)sc, t->ybar));
+      axx = t->dx2[l];
+    }
   }
 }
 
@@ -113,18 +139,18 @@ __device__ __forceinline__ void block_sum2(double& a, double& b, double* s_red) 
   for (int k = 0; k < CUT_THREADS / 32; k++) { a += s_red[2 * k]; b += s_red[2 * k + 1]; }
 }
 
-__global__ void __launch_bounds__(CUT_THREADS) cut_approx_kernel(int64_t n, const int32_t* __restrict__ seq_len, const int32_t* __restrict__ score,
-                                                                 const uint8_t* __restrict__ unique_best, const CutTables* __restrict__ t,
-                                                                 CutBlockDev* blk) {
+template <bool KEYS>
+__global__ void __launch_bounds__(CUT_THREADS) cut_approx_kernel(int64_t n, CutSrc src, const CutTables* __restrict__ t, CutBlockDev* blk) {
   __shared__ double s_red[2 * CUT_THREADS / 32];
   const int64_t i0 = (int64_t)blockIdx.x * CUT_BLOCK;
+  const int64_t l0 = KEYS ? i0 % src.stride : 0;                    // a block never straddles two ranks' strides
   double s0 = 0, s1 = 0;
 #pragma unroll
   for (int k = 0; k < CUT_PER_THREAD; k++) {
     const int64_t i = i0 + k * CUT_THREADS + threadIdx.x;
     if (i < n) {
       double axy, axx;
-      cut_addends(i, seq_len, score, unique_best, t, axy, axx);
+      cut_addends<KEYS>(i, l0 + k * CUT_THREADS + threadIdx.x, src, t, axy, axx);
       s0 += axy; s1 += axx;
     }
   }
@@ -132,11 +158,15 @@ __global__ void __launch_bounds__(CUT_THREADS) cut_approx_kernel(int64_t n, cons
   if (threadIdx.x == 0) { blk[blockIdx.x].approx[0] = s0; blk[blockIdx.x].approx[1] = s1; }
 }
 
-__global__ void __launch_bounds__(CUT_THREADS) cut_exact_kernel(int64_t n, const int32_t* __restrict__ seq_len, const int32_t* __restrict__ score,
-                                                                const uint8_t* __restrict__ unique_best, const CutTables* __restrict__ t,
-                                                                CutBlockDev* blk) {
+// KEYS: blocks the stitch will probably have to add read by read (no proof, or the predicted running sum too close
+// to the edge of its binade for the block's increments) also copy their keys to one of SHARD_PF_SLOTS slots
+// (pf_ids[0] = number of such blocks, pf_ids[1 + slot] = block), so that the host has them without another round trip.
+template <bool KEYS>
+__global__ void __launch_bounds__(CUT_THREADS) cut_exact_kernel(int64_t n, CutSrc src, const CutTables* __restrict__ t, CutBlockDev* blk,
+                                                                uint32_t* pf_keys, int32_t* pf_ids) {
   __shared__ double s_red[2 * CUT_THREADS / 32];
   __shared__ int s_bad[2];
+  __shared__ int s_slot;
   const int b = blockIdx.x;
   // approximate running sums at the block start (any order: it only predicts the binade, chain_stitch verifies it)
   double run0 = 0, run1 = 0;
@@ -161,6 +191,7 @@ __global__ void __launch_bounds__(CUT_THREADS) cut_exact_kernel(int64_t n, const
   constexpr double MAGIC = 6755399441055744.0;                      // 1.5 * 2^52
   constexpr double LIM = 1125899906842624.0;                        // 2^50
   const int64_t i0 = (int64_t)b * CUT_BLOCK;
+  const int64_t l0 = KEYS ? i0 % src.stride : 0;
   double T[2] = {0, 0}, A[2] = {0, 0};
   bool bad[2] = {false, false};
 #pragma unroll
@@ -168,7 +199,7 @@ __global__ void __launch_bounds__(CUT_THREADS) cut_exact_kernel(int64_t n, const
     const int64_t i = i0 + k * CUT_THREADS + threadIdx.x;
     if (i < n) {
       double a[2];
-      cut_addends(i, seq_len, score, unique_best, t, a[0], a[1]);
+      cut_addends<KEYS>(i, l0 + k * CUT_THREADS + threadIdx.x, src, t, a[0], a[1]);
 #pragma unroll
       for (int ch = 0; ch < 2; ch++) {
         const double x = __dmul_rn(a[ch], inv[ch]);
@@ -191,6 +222,57 @@ __global__ void __launch_bounds__(CUT_THREADS) cut_exact_kernel(int64_t n, const
     blk[b].e[ch] = ch ? e[1] : e[0];
     blk[b].ok[ch] = (ch ? valid[1] : valid[0]) && !s_bad[ch] && Ac < 4503599627370496.0;   // 2^52: all partial integer sums exact
   }
+  if (KEYS && pf_keys) {
+    if (threadIdx.x == 0) {
+      bool suspect = false;
+#pragma unroll
+      for (int ch = 0; ch < 2; ch++) {
+        const double N0 = run[ch] * inv[ch];                          // ~ the running sum in ulps, [2^52, 2^53) when the prediction holds
+        const bool ok = valid[ch] && !s_bad[ch] && A[ch] < 4503599627370496.0;
+        suspect |= !ok || !(N0 * (1 - 4e-6) - A[ch] >= 4503599627370497.0) || !(N0 * (1 + 4e-6) + A[ch] <= 9007199254740990.0);
+      }
+      int slot = -1;
+      if (suspect) { slot = atomicAdd(&pf_ids[0], 1); if (slot >= SHARD_PF_SLOTS) slot = -1; else pf_ids[1 + slot] = b; }
+      s_slot = slot;
+    }
+    __syncthreads();
+    const int slot = s_slot;
+    if (slot >= 0)
+      for (int k = threadIdx.x; k < CUT_BLOCK; k += CUT_THREADS) {
+        const int64_t i = i0 + k;
+        pf_keys[(size_t)slot * CUT_BLOCK + k] = (i < n && l0 + k < src.n_max) ? src.keys[i] : CUT_KEY_UNUSED;
+      }
+  }
+}
+
+// ---- sharded rounds: what a rank contributes to the all-gather / all-reduce(MAX), and the merge of what came back
+__global__ void shard_pack_kernel(int64_t n, int64_t stride, const int32_t* __restrict__ seq_len, const int32_t* __restrict__ score,
+                                  const uint8_t* __restrict__ unique_best, uint32_t* send) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= stride - SHARD_HDR_WORDS) return;
+  send[i] = i < n ? cut_key(seq_len[i], score[i], !unique_best || unique_best[i]) : CUT_KEY_UNUSED;
+}
+// after cut_stats_kernel: integer sums into the stride's tail, per-length maxima behind the insert maxima (MAX-reduced together)
+__global__ void shard_hdr_kernel(const CutStatsDev* st, uint32_t* send, int64_t stride, int32_t* max_best) {
+  const int t = threadIdx.x;
+  if (t == 0) {
+    long long* h = (long long*)(send + stride - SHARD_HDR_WORDS);    // 8-byte aligned: stride and SHARD_HDR_WORDS are even
+    h[0] = st->sx; h[1] = st->sy; h[2] = st->cnt; h[3] = 0;
+  }
+  for (int l = t; l <= MAX_READ; l += blockDim.x) max_best[l] = st->best[l];
+}
+__global__ void shard_merge_kernel(int world, int64_t stride, const uint32_t* recv, const int32_t* max_best, CutStatsDev* st, int32_t* pf_ids) {
+  const int t = threadIdx.x;
+  if (t == 0) {
+    long long sx = 0, sy = 0, cnt = 0;
+    for (int r = 0; r < world; r++) {
+      const long long* h = (const long long*)(recv + (int64_t)(r + 1) * stride - SHARD_HDR_WORDS);
+      sx += h[0]; sy += h[1]; cnt += h[2];
+    }
+    st->sx = sx; st->sy = sy; st->cnt = cnt;
+    pf_ids[0] = 0;
+  }
+  for (int l = t; l <= MAX_READ; l += blockDim.x) st->best[l] = max_best[l];
 }
 
 // below = score < threshold(len) (mia.c:452-470); sticky |= below (H10); the natural entries (2i, 2i+1) of the read

@@ -87,11 +87,12 @@ constexpr int64_t CHAIN_BLOCK = 2048;
 // and so do the device kernels of scorecut.cuh (same arithmetic, IEEE double, no contraction).
 struct ChainBlock { double approx, T, A; int e; bool ok; };
 
-// phase 3: stitch the blocks in order; whatever cannot be proven goes read by read, exactly as the reference adds
-template <typename Addend>
-double chain_stitch(int64_t n, const Addend& a, const ChainBlock* blk, int64_t nb, int64_t* n_serial = nullptr) {
+// phase 3: stitch the blocks in order; whatever cannot be proven goes read by read, exactly as the reference adds.
+// serial(b, S) returns S after the addends of block b have been added one at a time.
+template <typename Serial>
+double chain_stitch_blocks(const ChainBlock* blk, int64_t nb, const Serial& serial, int64_t* n_serial = nullptr) {
   double S = 0;
-  int64_t serial = 0;
+  int64_t count = 0;
   for (int64_t b = 0; b < nb; b++) {
     const ChainBlock& B = blk[b];
     if (B.ok && S > 0 && std::ilogb(S) == B.e) {
@@ -102,12 +103,19 @@ double chain_stitch(int64_t n, const Addend& a, const ChainBlock* blk, int64_t n
         continue;
       }
     }
+    S = serial(b, S);
+    count++;
+  }
+  if (n_serial) *n_serial = count;
+  return S;
+}
+template <typename Addend>
+double chain_stitch(int64_t n, const Addend& a, const ChainBlock* blk, int64_t nb, int64_t* n_serial = nullptr) {
+  return chain_stitch_blocks(blk, nb, [&](int64_t b, double S) {
     const int64_t i1 = std::min(n, (b + 1) * CHAIN_BLOCK);
     for (int64_t i = b * CHAIN_BLOCK; i < i1; i++) S += a(i);
-    serial++;
-  }
-  if (n_serial) *n_serial = serial;
-  return S;
+    return S;
+  }, n_serial);
 }
 
 // (((0 + a(0)) + a(1)) + ... + a(n-1)) with a rounding after every addition, bit-identical to the plain loop.
