@@ -200,7 +200,9 @@ def run_ours(args):
     barrier()
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = float(sum(step_ms))
-    # one more resident realign just to read the per-bucket kernel times (same launches as the timed ones)
+    # resident realigns on the measurement path (one width class after the other, events around each) just to read the
+    # per-class kernel times; the first call only sizes that path's scratch buffers
+    g.realign_resident()
     g.realign_resident()
     buckets = [dict(b, kernel=f"realign_kernel<{b['K']}>") for b in g.last_buckets()]
     pbuckets, n_fallback, lmax16 = g.last_pair_buckets()
@@ -273,6 +275,14 @@ def run_ours(args):
                            "peak": int_peak / 1e12, "unit": "Tops/s", "frac": INT_OPS_PER_CELL * dom["cells"] / dom_s / int_peak,
                            "ops_per_cell": INT_OPS_PER_CELL, "kernel_gcups": dom["cells"] / dom_s / 1e9,
                            "peak_source": "miagpu_int32_peak micro-benchmark, same run"},
+        # the pair kernels compute two 16-bit cells per 32-bit SIMD op, so the 15-ops-per-cell figure can exceed the INT32 peak;
+        # what bounds them is the issue slot: SASS warp instructions per cell (ncu smsp__inst_executed.sum / cells of the
+        # committed capture profiles/r01c_ncu_pair16_full.md) x cells/s against 4 schedulers x 148 SMs x SM clock
+        "roofline_issue": (lambda ipc, clk: {"bound": "issue slots", "warp_inst_per_cell": ipc, "achieved": ipc * dom["cells"] / dom_s / 1e9,
+                                             "peak": 4 * 148 * clk / 1e3, "unit": "G warp-inst/s",
+                                             "frac": ipc * dom["cells"] / dom_s / 1e9 / (4 * 148 * clk / 1e3),
+                                             "source": "905,288,115 inst / 3.19e9 cells, ncu --set full of pair16_kernel<10,16> (profiles/)"})(
+            905288115 / 3189673284, (clocks or {}).get("sm_mhz") or 1965.0) if dom["kernel"].startswith("pair16") else None,
         "buckets": pbuckets + buckets,
         "pair16": {"reads_handed_to_32bit_kernels": n_fallback, "max_read_len": lmax16},
         "consensus_matches_e2e": bool(cons == cons_e2e),

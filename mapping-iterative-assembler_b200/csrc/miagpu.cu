@@ -145,9 +145,10 @@ struct miagpu_ctx {
   DevBuf<int4> d_ckpt;
   DevBuf<int32_t> d_chunk_ids, d_strace, d_hits, d_fw, d_rcs, d_start, d_end;
   DevBuf<uint8_t> d_rc_out, d_bases2;
-  // pass-1 fast path (pass1.cuh): per job (2 * read + strand) inputs / outputs, per read route, general-kernel list
+  // pass-1 fast path (pass1.cuh): per job (8 slots per read: strand x stretch) inputs / outputs, per read route, general-kernel list
   DevBuf<uint8_t> d_jkind, d_jstatus, d_route;
-  DevBuf<int32_t> d_jws, d_jwl, d_jscore, d_jabc, d_jaec, d_jabr, d_p1list, d_p1meta, d_jpairs;
+  DevBuf<int32_t> d_jws, d_jwl, d_jscore, d_jabc, d_jaec, d_jabr, d_p1list, d_p1meta, d_jpairs, d_jread, d_jfirst;
+  DevBuf<uint16_t> d_jcount;
   int64_t p1_fast = 0, p1_general = 0, p1_skipped = 0;
   DevBuf<uint16_t> d_packed;
   DevBuf<int64_t> d_off2;
@@ -221,6 +222,7 @@ extern "C" void miagpu_destroy(miagpu_ctx* c) {
   cudaStreamSynchronize(c->stream);
   c->d_jkind.release(); c->d_jstatus.release(); c->d_route.release(); c->d_jws.release(); c->d_jwl.release(); c->d_jscore.release();
   c->d_jabc.release(); c->d_jaec.release(); c->d_jabr.release(); c->d_p1list.release(); c->d_p1meta.release(); c->d_jpairs.release();
+  c->d_jread.release(); c->d_jfirst.release(); c->d_jcount.release();
   c->d_prof.release(); c->d_ref.release(); c->d_rcref.release(); c->d_ref2.release(); c->d_bases.release(); c->d_off.release();
   c->d_rc.release(); c->d_status.release(); c->d_as.release(); c->d_ae.release(); c->d_score.release();
   c->d_as_out.release(); c->d_ae_out.release(); c->d_abr.release(); c->d_nruns.release(); c->d_win_start.release();
@@ -522,15 +524,17 @@ __global__ void __launch_bounds__(LAYOUT_THREADS) pair_layout_kernel(int32_t* me
 }
 
 // Eligible reads take the next free slot of their key: slot s is member s&1 of pair pstart + s/2.
-// shift = 1: the items are pass-1 jobs (2 * read + strand) and off[] is per read.
-__global__ void pair_scatter_kernel(int64_t n, const int64_t* off, const uint8_t* kind, int32_t* meta, int32_t* pairs, int shift = 0) {
+// item_read (nullable): the items are pass-1 jobs, item_read[i] & 0x7fffffff is the job's read and off[] is per read.
+__global__ void pair_scatter_kernel(int64_t n, const int64_t* off, const uint8_t* kind, int32_t* meta, int32_t* pairs,
+                                    const int32_t* item_read = nullptr) {
   __shared__ int s_cnt[P16_KEYS], s_base[P16_KEYS];
   for (int i = threadIdx.x; i < P16_KEYS; i += blockDim.x) s_cnt[i] = 0;
   __syncthreads();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int key = -1, slot = 0;
   if (i < n && kind[i] >= 16) {
-    key = (kind[i] - 16) * (P16_MAXL + 1) + (int)(off[(i >> shift) + 1] - off[i >> shift]);
+    const int64_t rd = item_read ? (int64_t)(item_read[i] & 0x7fffffff) : i;
+    key = (kind[i] - 16) * (P16_MAXL + 1) + (int)(off[rd + 1] - off[rd]);
     slot = atomicAdd(&s_cnt[key], 1);
   }
   __syncthreads();
@@ -2069,12 +2073,13 @@ extern "C" int miagpu_build_kmers(miagpu_ctx* c, int k, int soft_mask) {
   return 1;
 }
 
-// Pass 1 with the k-mer filter on (pass1.cuh): seed every read, run the single-stretch strands through the pair
+// Pass 1 with the k-mer filter on (pass1.cuh): seed every read, run the strands' separate stretches through the pair
 // kernels, merge, and leave the rest to the general kernel.
 static int pass1_fast(miagpu_ctx* c, const PairLmax& lm) {
-  const int64_t n = c->n, nj = 2 * n;
+  const int64_t n = c->n, nj = 10 * n + 4096;          // job capacity; reads whose jobs do not fit go to the general kernel
   const int np = 32 / c->pair_g;
-  if (n > 0x3fffffffLL) { set_error("miagpu_pass1: at most %d reads per batch", 0x3fffffff); return 0; }
+  if (n > 0x7fffffffLL / 8) { set_error("miagpu_pass1: at most %d reads per batch", 0x7fffffff / 8); return 0; }
+  if (!c->d_jread.reserve(nj + 1) || !c->d_jfirst.reserve(n + 1) || !c->d_jcount.reserve(n + 1)) return 0;
   if (!c->d_jkind.reserve(nj + 1) || !c->d_jstatus.reserve(nj + 1) || !c->d_route.reserve(n + 1) || !c->d_jws.reserve(nj + 1) ||
       !c->d_jwl.reserve(nj + 1) || !c->d_jscore.reserve(nj + 1) || !c->d_jabc.reserve(nj + 1) || !c->d_jaec.reserve(nj + 1) ||
       !c->d_jabr.reserve(nj + 1) || !c->d_p1list.reserve(n + 1) || !c->d_p1meta.reserve(META_WORDS) ||
@@ -2083,10 +2088,12 @@ static int pass1_fast(miagpu_ctx* c, const PairLmax& lm) {
   int32_t* meta = c->d_p1meta.p;
   const int len1 = c->circular ? c->wrap_len : c->seq_len;
   MIAGPU_CUDA(cudaMemsetAsync(meta, 0, META_WORDS * sizeof(int32_t), st));
+  MIAGPU_CUDA(cudaMemsetAsync(c->d_jkind.p, 0, nj, st));
   P1SeedParams sp{};
-  sp.bases = c->d_bases.p; sp.off = c->d_off.p; sp.n = n; sp.k = c->kmer_k; sp.len1 = len1; sp.strand_stride = c->ref_bytes;
+  sp.bases = c->d_bases.p; sp.off = c->d_off.p; sp.n = n; sp.k = c->kmer_k; sp.len1 = len1; sp.strand_stride = c->ref_bytes; sp.pssm_max = c->pssm_max;
   for (int t = 0; t < 2; t++) sp.kt[t] = KmerTable{c->d_kb[t].p, c->d_kk[t].p, c->d_kp[t].p, c->kmer_shift[t]};
   sp.lm = lm;
+  sp.job_cap = nj; sp.jread = c->d_jread.p; sp.jfirst = c->d_jfirst.p; sp.jcount = c->d_jcount.p;
   sp.jkind = c->d_jkind.p; sp.jws = c->d_jws.p; sp.jwl = c->d_jwl.p; sp.hits = c->d_hits.p; sp.route = c->d_route.p;
   sp.general_list = c->d_p1list.p; sp.score = c->d_score.p; sp.n_runs = c->d_nruns.p; sp.status = c->d_status.p; sp.meta = meta;
   const unsigned seed_blocks = (unsigned)std::min<int64_t>((int64_t)c->num_sms * 8, (n + 7) / 8);
@@ -2101,7 +2108,8 @@ static int pass1_fast(miagpu_ctx* c, const PairLmax& lm) {
   for (int kb = 0; kb < P16_NKB; kb++) { pair_items[kb] = c->h_meta[META_NPAIRS + kb]; total_pairs += pair_items[kb]; }
   if (total_pairs) {
     MIAGPU_CUDA(cudaMemsetAsync(c->d_jpairs.p, 0xff, (size_t)2 * np * total_pairs * sizeof(int32_t), st));
-    pair_scatter_kernel<<<(unsigned)((nj + 255) / 256), 256, 0, st>>>(nj, c->d_off.p, c->d_jkind.p, meta, c->d_jpairs.p, 1);
+    const int64_t njobs = std::min<int64_t>(nj, (uint32_t)c->h_meta[P1_NJOBS]);
+    pair_scatter_kernel<<<(unsigned)((njobs + 255) / 256), 256, 0, st>>>(njobs, c->d_off.p, c->d_jkind.p, meta, c->d_jpairs.p, c->d_jread.p);
     MIAGPU_CUDA(cudaGetLastError());
     c->launches++;
     int base = 0;
@@ -2112,7 +2120,7 @@ static int pass1_fast(miagpu_ctx* c, const PairLmax& lm) {
       Pair16Params p{};
       p.bases = c->d_bases.p; p.off = c->d_off.p; p.rc = nullptr; p.win_start = c->d_jws.p; p.win_len = c->d_jwl.p;
       p.pairs = c->d_jpairs.p + 2 * (int64_t)np * base; p.n_items = meta + META_NPAIRS + kb; p.counter = meta + META_PWORK + kb;
-      p.ref_codes = c->d_ref2.p; p.ref_bytes = 2 * c->ref_bytes; p.strand_stride = c->ref_bytes; p.prof16 = c->d_prof16.p;
+      p.ref_codes = c->d_ref2.p; p.ref_bytes = 2 * c->ref_bytes; p.strand_stride = c->ref_bytes; p.prof16 = c->d_prof16.p; p.job_read = c->d_jread.p;
       p.score = c->d_jscore.p; p.as_out = c->d_jabc.p; p.ae_out = c->d_jaec.p; p.abr = c->d_jabr.p; p.status = c->d_jstatus.p;
       p.n_reads = nj;
       int ok = 1;
@@ -2131,7 +2139,7 @@ static int pass1_fast(miagpu_ctx* c, const PairLmax& lm) {
     }
   }
   P1MergeParams mp{};
-  mp.n = n; mp.off = c->d_off.p; mp.seq_len = c->seq_len; mp.route = c->d_route.p; mp.jkind = c->d_jkind.p; mp.jstatus = c->d_jstatus.p;
+  mp.n = n; mp.off = c->d_off.p; mp.seq_len = c->seq_len; mp.route = c->d_route.p; mp.jfirst = c->d_jfirst.p; mp.jcount = c->d_jcount.p; mp.jkind = c->d_jkind.p; mp.jstatus = c->d_jstatus.p;
   mp.jscore = c->d_jscore.p; mp.jabc = c->d_jabc.p; mp.jaec = c->d_jaec.p; mp.jabr = c->d_jabr.p; mp.general_list = c->d_p1list.p; mp.meta = meta;
   mp.score = c->d_score.p; mp.fw_score = c->d_fw.p; mp.rc_score = c->d_rcs.p; mp.as_out = c->d_as_out.p; mp.ae_out = c->d_ae_out.p;
   mp.start = c->d_start.p; mp.end = c->d_end.p; mp.abr = c->d_abr.p; mp.n_runs = c->d_nruns.p; mp.rc_out = c->d_rc_out.p;

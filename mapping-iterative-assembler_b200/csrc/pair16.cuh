@@ -117,6 +117,7 @@ struct Pair16Params {
   int32_t* n_fallback;           // statistics
   uint32_t gep2;                 // K2(2*GEP), passed as data so that ptxas keeps this add an IMAD (FMA pipe) instead of folding it into a VIADD
   int32_t strand_stride;         // JOB kernels: bytes between the forward and the reverse-complement codes in ref_codes
+  const int32_t* job_read;       // JOB kernels: read of a job, bit 31 = reverse strand
 };
 
 constexpr uint8_t P16_ST_GENERAL = 0x40;   // JOB kernels: the alignment is not one plain diagonal, the general kernel takes the read
@@ -174,8 +175,8 @@ __host__ __device__ constexpr int p16_smem_fixed() {
 }
 
 // JOB = false: a work item names reads (reiterate_assembly's windows, matrix by strand).
-// JOB = true : pass 1 with the k-mer filter (sg_align, mia.c:1500-1610).  A work item names jobs, job = 2 * read + strand:
-//   the read against the ONE stretch of columns its k-mer hits unmasked on that strand (new_kmer_filter, kmer.c:239-331),
+// JOB = true : pass 1 with the k-mer filter (sg_align, mia.c:1500-1610).  A work item names jobs (pass1.cuh;
+//   job_read[job] = read, bit 31 = strand): the read against ONE stretch of columns its k-mer hits unmasked on that strand (new_kmer_filter, kmer.c:239-331),
 //   always with the forward matrix (H5).  The masked matrix differs from a window in one place: when the stretch does
 //   not begin at column 0 its first column has a masked left neighbour, so there dyn_prog starts a new alignment
 //   (S = N, substitution score not added, mia.c:910-915) instead of applying the column-0 rule (mia.c:805-822).
@@ -260,14 +261,15 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, (K <= 12 ? 5 : 4)) pair1
     if (!hasA) rdA = p.pairs[2 * (item * NP)];
     const bool hasB = hasA && rdB >= 0;
     if (rdB < 0 || !hasA) rdB = rdA;
-    const int rrA = JOB ? rdA >> 1 : rdA, rrB = JOB ? rdB >> 1 : rdB;      // the reads behind the jobs
+    const int jrA = JOB ? p.job_read[rdA] : 0, jrB = JOB ? p.job_read[rdB] : 0;
+    const int rrA = JOB ? jrA & 0x7fffffff : rdA, rrB = JOB ? jrB & 0x7fffffff : rdB;      // the reads behind the jobs
     const int64_t oA = p.off[rrA], oB = p.off[rrB];
     const int L = (int)(p.off[rrA + 1] - oA);         // the same for every read of the work item
     const int wsA = p.win_start[rdA], wsB = p.win_start[rdB];
     const int lenA = p.win_len[rdA], lenB = p.win_len[rdB];
     const int sA = JOB ? 0 : (p.rc[rdA] ? 1 : 0), sB = JOB ? 0 : (p.rc[rdB] ? 1 : 0);
     if (JOB) {                                        // first column: column 0 of the matrix, or a column with a masked left neighbour
-      const bool mlA = wsA - (rdA & 1) * p.strand_stride > 0, mlB = wsB - (rdB & 1) * p.strand_stride > 0;
+      const bool mlA = wsA - (jrA < 0 ? p.strand_stride : 0) > 0, mlB = wsB - (jrB < 0 ? p.strand_stride : 0) > 0;
       const uint32_t real = B2(-(GOP + 3 * GEP) - OFF), cut = B2(SENT);
       ncmp0m = sub ? 0u : (((mlA ? cut : real) & 0xffffu) | ((mlB ? cut : real) & 0xffff0000u));
     }
@@ -394,9 +396,9 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, (K <= 12 ? 5 : 4)) pair1
       const int nsteps = min(L - 1, aec);
       if (JOB) {
         if (sub == 0 && live) {
-          const int lo = ws - (rd & 1) * p.strand_stride;
+          const int lo = ws - ((h ? jrB : jrA) < 0 ? p.strand_stride : 0);
+          p.score[rd] = score;                          // exact whatever the path looks like: a losing job needs no more
           if (ok) {
-            p.score[rd] = score;
             p.as_out[rd] = aec - nsteps + lo;           // abc
             p.ae_out[rd] = aec + lo;                    // aec
             p.abr[rd] = L - 1 - nsteps;

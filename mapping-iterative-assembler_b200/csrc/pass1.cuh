@@ -5,16 +5,24 @@
 // runs dyn_prog over both whole strands, where masked cells are HIM.  For a read whose hits on a strand all lie on
 // neighbouring diagonals the unmasked columns form ONE stretch of about L+20 columns, and the masked DP over the
 // whole strand equals a DP over that stretch alone (pair16.cuh, JOB kernels, explains the one cell rule that
-// differs).  So:
-//   p1_seed_kernel   warp per read: k-mer lookups on both strands -> hits, lowest / highest hit diagonal per strand;
-//                    a strand with hits becomes a job (2*read + strand) when its stretch is one piece, at most 256
-//                    columns wide and the read fits the 16-bit frame; a read whose strands with hits are all jobs
-//                    goes to the pair kernels, a read without hits is skipped (mia_main.c:781), everything else
-//                    (several stretches, saturated strand, long read) goes to the general kernel (strip.cuh)
+// differs).  Several stretches on one strand (chance k-mer hits elsewhere, the rule on a long reference) are
+// independent DPs as well when enough masked columns lie between them: the only state dyn_prog carries across masked
+// columns is best_gap_col (H3), a candidate worth at most S - P(g) = r*max(sm) - GOP - GEP*g in row r after g masked
+// columns, and a column-gap candidate below the start-new value N(r) = -P(r+1) can never be chosen nor change which
+// other candidate is (mia.c:910-965: every branch compares against N first).  So with
+//     GEP*g > (L-1)*(max(sm) + GEP) + GEP          [`need` in p1_seed_kernel]
+// every stretch is its own job, and max_sg_score's first maximum of the last row is the first maximum over the
+// jobs in column order.  So:
+//   p1_seed_kernel   warp per read: k-mer lookups on both strands -> hits and their diagonals, chained into stretches;
+//                    a strand becomes up to P1_JPS jobs (allocated from one counter, a read's jobs are contiguous) when every stretch is
+//                    at most 256 columns wide, the stretches are far enough apart and the read fits the 16-bit
+//                    frame; a read whose strands with hits are all jobs goes to the pair kernels, a read without hits
+//                    is skipped (mia_main.c:781), everything else (close stretches, saturated strand, long read)
+//                    goes to the general kernel (strip.cuh)
 //   pair16_kernel<K, G, true>   the jobs, two per register
-//   p1_merge_kernel  strand pick (forward only if strictly better, mia.c:1549-1554), sg_align's coordinates
-//                    (c2rcc, as / ae / start / end fix-ups, mia.c:1568-1610), or hand-over to the general kernel
-//                    when a job's alignment was not one plain diagonal
+//   p1_merge_kernel  first best job per strand, strand pick (forward only if strictly better, mia.c:1549-1554),
+//                    sg_align's coordinates (c2rcc, as / ae / start / end fix-ups, mia.c:1568-1610), or hand-over to
+//                    the general kernel when the winning job's alignment was not one plain diagonal
 #pragma once
 #include "common.cuh"
 #include "pair16.cuh"
@@ -28,12 +36,20 @@ constexpr int P1_NFAST = 139;        // reads finished by the pair kernels
 constexpr int P1_NSKIPPED = 140;     // reads without a k-mer hit
 constexpr int P1_WORK = 141;         // work-fetch counter of the general kernel
 
-struct SeedRange { int hits, dmin, dmax; };
+constexpr int P1_NJOBS = 142;        // jobs allocated (may exceed the capacity: reads that did not fit go to the general kernel)
+constexpr int P1_JPS = 12;           // stretches per strand that become jobs
+constexpr int P1_MAXD = 128;         // diagonals kept per strand: KMER_SATURATE hits unmask the whole strand anyway
 
-// new_kmer_filter's hit loop for one strand (kmer.c:275-327) without the mask: hit count and diagonal range
-__device__ __forceinline__ SeedRange seed_range(const KmerTable& kt, const int k, const uint8_t* __restrict__ read, const int L) {
+struct Stretches { int hits, n; int lo[P1_JPS], hi[P1_JPS]; };   // n > P1_JPS: too many
+
+// new_kmer_filter's hit loop for one strand (kmer.c:275-327) without the mask: hit count and the hit diagonals
+// (reference position - read offset) chained into stretches: two hits belong to one stretch when their unmasked
+// intervals [d - 10, d + span - 10] overlap or adjoin, i.e. their diagonals differ by at most span + 1.
+__device__ __forceinline__ Stretches seed_stretches(const KmerTable& kt, const int k, const uint8_t* __restrict__ read, const int L,
+                                                    const int span, int* s_diag, int* s_n) {
   const int lane = threadIdx.x & 31;
-  int hits = 0, dmin = INT_MAX, dmax = INT_MIN;
+  if (lane == 0) *s_n = 0;
+  __syncwarp();
   for (int p = lane; p + k <= L; p += 32) {
     uint32_t inx = 0;
     bool ok = true;
@@ -47,15 +63,44 @@ __device__ __forceinline__ SeedRange seed_range(const KmerTable& kt, const int k
     const int e1 = __ldg(kt.bucket_start + b + 1);
     for (int e = __ldg(kt.bucket_start + b); e < e1; e++) {
       if (__ldg(kt.kmer + e) != inx) continue;
-      hits++;
-      const int d = __ldg(kt.pos + e) - p;
-      dmin = min(dmin, d); dmax = max(dmax, d);
+      const int slot = atomicAdd(s_n, 1);
+      if (slot < P1_MAXD) s_diag[slot] = __ldg(kt.pos + e) - p;
     }
   }
-  SeedRange r;
-  r.hits = __reduce_add_sync(0xffffffffu, hits);
-  r.dmin = __reduce_min_sync(0xffffffffu, dmin);
-  r.dmax = __reduce_max_sync(0xffffffffu, dmax);
+  __syncwarp();
+  Stretches r;
+  r.hits = *s_n;
+  r.n = 0;
+  __syncwarp();                                        // everybody has read the count before the next strand resets it
+  if (r.hits == 0 || r.hits >= KMER_SATURATE) return r;
+  int v[P1_MAXD / 32];
+#pragma unroll
+  for (int i = 0; i < P1_MAXD / 32; i++) v[i] = lane + 32 * i < r.hits ? s_diag[lane + 32 * i] : INT_MAX;
+  int lo = INT_MAX;
+#pragma unroll
+  for (int i = 0; i < P1_MAXD / 32; i++) lo = min(lo, v[i]);
+  lo = __reduce_min_sync(0xffffffffu, lo);
+  while (lo != INT_MAX) {
+    int hi = lo;
+    for (;;) {                                        // extend the stretch while some diagonal is within reach
+      int m = hi;
+#pragma unroll
+      for (int i = 0; i < P1_MAXD / 32; i++)
+        if (v[i] != INT_MAX && v[i] > hi && v[i] <= hi + span + 1) m = max(m, v[i]);
+      m = __reduce_max_sync(0xffffffffu, m);
+      if (m == hi) break;
+      hi = m;
+    }
+    if (r.n < P1_JPS) { r.lo[r.n] = lo; r.hi[r.n] = hi; }
+    r.n++;
+    if (r.n > P1_JPS) break;
+    int nx = INT_MAX;
+#pragma unroll
+    for (int i = 0; i < P1_MAXD / 32; i++)
+      if (v[i] != INT_MAX && v[i] > hi) nx = min(nx, v[i]);
+    lo = __reduce_min_sync(0xffffffffu, nx);
+  }
+  __syncwarp();
   return r;
 }
 
@@ -63,14 +108,18 @@ struct P1SeedParams {
   const uint8_t* bases;
   const int64_t* off;
   int64_t n;
-  int32_t k, len1, strand_stride;
+  int32_t k, len1, strand_stride, pssm_max;
   KmerTable kt[2];
   PairLmax lm;
-  // per job (2n)
+  // per job (zeroed jkind: a slot nobody filled is no job)
+  int64_t job_cap;
   uint8_t* jkind;                // 16 + pair class, 0 = no job
   int32_t* jws;                  // first column of the stretch, as an index into the concatenated codes
   int32_t* jwl;                  // columns
+  int32_t* jread;                // read, bit 31 = reverse strand
   // per read
+  int32_t* jfirst;               // first job of the read; its forward stretches in column order, then the reverse ones
+  uint16_t* jcount;              // forward | reverse << 8
   int32_t* hits;
   uint8_t* route;                // 0 skipped, 1 pair kernels, 2 general kernel
   int32_t* general_list;
@@ -83,62 +132,81 @@ __global__ void __launch_bounds__(256) p1_seed_kernel(P1SeedParams p) {
   __shared__ int s_preads[P16_NKB];
   __shared__ unsigned long long s_pcells[P16_NKB];
   __shared__ int s_counts[3];
+  __shared__ int s_diag[8][P1_MAXD];
+  __shared__ int s_nd[8];
   for (int i = threadIdx.x; i < P16_KEYS; i += blockDim.x) s_hist[i] = 0;
   if (threadIdx.x < P16_NKB) { s_preads[threadIdx.x] = 0; s_pcells[threadIdx.x] = 0; }
   if (threadIdx.x < 3) s_counts[threadIdx.x] = 0;
   __syncthreads();
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
-  for (int64_t rd = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); rd < p.n; rd += warps) {
+  for (int64_t rd = (int64_t)blockIdx.x * (blockDim.x >> 5) + w; rd < p.n; rd += warps) {
     const int64_t o = p.off[rd];
     const int L = (int)(p.off[rd + 1] - o);
     if (L <= 0 || L > MAX_READ) {                                        // the general kernel reports it
-      if (lane == 0) { p.route[rd] = 2; p.jkind[2 * rd] = 0; p.jkind[2 * rd + 1] = 0; p.general_list[atomicAdd(p.meta + P1_NGENERAL, 1)] = (int32_t)rd; }
+      if (lane == 0) { p.route[rd] = 2; p.jcount[rd] = 0; p.general_list[atomicAdd(p.meta + P1_NGENERAL, 1)] = (int32_t)rd; }
       continue;
     }
-    SeedRange sr[2] = {{0, 0, 0}, {0, 0, 0}};
+    Stretches st[2];
+    st[0].hits = st[1].hits = 0; st[0].n = st[1].n = 0;
     if (L >= p.k) {
-      sr[0] = seed_range(p.kt[0], p.k, p.bases + o, L);
-      sr[1] = seed_range(p.kt[1], p.k, p.bases + o, L);
+      // every hit unmasks [d - 10, d + L + 10 - s] (kmer.c:294, 319)
+      st[0] = seed_stretches(p.kt[0], p.k, p.bases + o, L, L + 2 * ALIGN_MASK_BUFFER, s_diag[w], &s_nd[w]);
+      st[1] = seed_stretches(p.kt[1], p.k, p.bases + o, L, L + 2 * ALIGN_MASK_BUFFER - 1, s_diag[w], &s_nd[w]);
     }
     if (lane != 0) continue;
-    const int total = sr[0].hits + sr[1].hits;
+    const int total = st[0].hits + st[1].hits;
     p.hits[rd] = total;
-    int kb[2] = {-1, -1}, lo[2] = {0, 0}, wl[2] = {0, 0};
     bool fast = total > 0;
-    for (int s = 0; s < 2; s++) {
-      if (!sr[s].hits) continue;
-      // every hit unmasks [d - 10, d + L + 10 - s] (kmer.c:294, 319): one stretch when the diagonals are close enough
-      const int span = L + 2 * ALIGN_MASK_BUFFER - s;                    // last column of a hit's stretch minus its first
-      int a = sr[s].dmin - ALIGN_MASK_BUFFER, z = sr[s].dmax + span - ALIGN_MASK_BUFFER;
-      if (a < 0) a = 0;
-      if (z >= p.len1) z = p.len1 - 1;
-      const bool one_piece = sr[s].dmax - sr[s].dmin <= span + 1;
-      lo[s] = a; wl[s] = z - a + 1;
-      kb[s] = p16_class(wl[s]);
-      if (sr[s].hits >= KMER_SATURATE || !one_piece || z < a || kb[s] < 0 || L > p.lm.v[kb[s] < 0 ? 0 : kb[s]]) fast = false;
+    // masked columns needed between two stretches so that no column-gap candidate crosses (see the header)
+    const int need = (L - 1) * (max(p.pssm_max, 0) + GEP) + GEP;
+    for (int s = 0; s < 2 && fast; s++) {
+      if (!st[s].hits) continue;
+      if (st[s].hits >= KMER_SATURATE || st[s].n > P1_JPS) { fast = false; break; }
+      const int span = L + 2 * ALIGN_MASK_BUFFER - s;                    // last column of a hit's interval minus its first
+      int prev_z = -1;
+      for (int t = 0; t < st[s].n; t++) {
+        int a = st[s].lo[t] - ALIGN_MASK_BUFFER, z = st[s].hi[t] + span - ALIGN_MASK_BUFFER;
+        if (a < 0) a = 0;
+        if (z >= p.len1) z = p.len1 - 1;
+        const int kb = z < a ? -1 : p16_class(z - a + 1);
+        if (kb < 0 || L > p.lm.v[kb]) { fast = false; break; }
+        if (t > 0 && !(GEP * (a - prev_z - 1) > need)) { fast = false; break; }
+        prev_z = z;
+        st[s].lo[t] = a; st[s].hi[t] = z;                                // from here on: first / last unmasked column
+      }
+    }
+    int64_t first = 0;
+    if (fast) {
+      first = atomicAdd(reinterpret_cast<unsigned int*>(p.meta + P1_NJOBS), (unsigned)(st[0].n + st[1].n));
+      if (first + st[0].n + st[1].n > p.job_cap) fast = false;           // no room: the slots stay "no job"
     }
     if (!total) {
       p.route[rd] = 0;
       p.status[rd] = MIAGPU_ST_SKIPPED; p.n_runs[rd] = 0; p.score[rd] = INT_MIN;      // mia_main.c:781: not aligned at all
-      p.jkind[2 * rd] = 0; p.jkind[2 * rd + 1] = 0;
+      p.jcount[rd] = 0;
       atomicAdd(&s_counts[0], 1);
     } else if (!fast) {
       p.route[rd] = 2;
-      p.jkind[2 * rd] = 0; p.jkind[2 * rd + 1] = 0;
+      p.jcount[rd] = 0;
       p.general_list[atomicAdd(p.meta + P1_NGENERAL, 1)] = (int32_t)rd;
     } else {
       p.route[rd] = 1;
-      for (int s = 0; s < 2; s++) {
-        const int64_t j = 2 * rd + s;
-        if (!sr[s].hits) { p.jkind[j] = 0; continue; }
-        p.jkind[j] = (uint8_t)(16 + kb[s]);
-        p.jws[j] = s * p.strand_stride + lo[s];
-        p.jwl[j] = wl[s];
-        atomicAdd(&s_hist[kb[s] * (P16_MAXL + 1) + L], 1);
-        atomicAdd(&s_preads[kb[s]], 1);
-        atomicAdd(&s_pcells[kb[s]], (unsigned long long)L * wl[s]);
-      }
+      p.jfirst[rd] = (int32_t)first;
+      p.jcount[rd] = (uint16_t)(st[0].n | (st[1].n << 8));
+      int64_t job = first;
+      for (int s = 0; s < 2; s++)
+        for (int t = 0; t < st[s].n; t++, job++) {
+          const int a = st[s].lo[t], wl = st[s].hi[t] - a + 1;
+          const int kb = p16_class(wl);
+          p.jkind[job] = (uint8_t)(16 + kb);
+          p.jws[job] = s * p.strand_stride + a;
+          p.jwl[job] = wl;
+          p.jread[job] = (int32_t)((uint32_t)rd | ((uint32_t)s << 31));
+          atomicAdd(&s_hist[kb * (P16_MAXL + 1) + L], 1);
+          atomicAdd(&s_preads[kb], 1);
+          atomicAdd(&s_pcells[kb], (unsigned long long)L * wl);
+        }
     }
   }
   __syncthreads();
@@ -156,6 +224,7 @@ struct P1MergeParams {
   const int64_t* off;
   int32_t seq_len;
   const uint8_t* route;
+  const int32_t* jfirst; const uint16_t* jcount;
   const uint8_t* jkind; const uint8_t* jstatus;
   const int32_t* jscore; const int32_t* jabc; const int32_t* jaec; const int32_t* jabr;
   int32_t* general_list;
@@ -170,20 +239,19 @@ __global__ void p1_merge_kernel(P1MergeParams p) {
   const int64_t rd = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (rd >= p.n || p.route[rd] != 1) return;
   int best[2] = {HIM, HIM};                         // a strand without a hit is masked everywhere: max_sg_score finds HIM in column 0
-  bool general = false;
-  for (int s = 0; s < 2; s++) {
-    const int64_t j = 2 * rd + s;
-    if (!p.jkind[j]) continue;
-    if (p.jstatus[j] != MIAGPU_ST_OK) general = true;
-    else best[s] = p.jscore[j];
-  }
-  if (general) {
+  int64_t bj[2] = {-1, -1};
+  int64_t j0 = p.jfirst[rd];
+  const int cnt[2] = {p.jcount[rd] & 0xff, p.jcount[rd] >> 8};
+  for (int s = 0; s < 2; s++)
+    for (int t = 0; t < cnt[s]; t++, j0++)          // stretches in column order: the first maximum wins (mia.c:1278-1302)
+      if (p.jscore[j0] > best[s]) { best[s] = p.jscore[j0]; bj[s] = j0; }
+  const int s = !(best[0] > best[1]) ? 1 : 0;       // forward only if strictly better (mia.c:1549-1554)
+  const int64_t j = bj[s];
+  if (j < 0 || p.jstatus[j] != MIAGPU_ST_OK) {      // the winner's path is not one plain diagonal: the general kernel traces it
     p.general_list[atomicAdd(p.meta + P1_NGENERAL, 1)] = (int32_t)rd;
     return;
   }
   atomicAdd(p.meta + P1_NFAST, 1);
-  const int s = !(best[0] > best[1]) ? 1 : 0;       // forward only if strictly better (mia.c:1549-1554)
-  const int64_t j = 2 * rd + s;
   const int L = (int)(p.off[rd + 1] - p.off[rd]);
   const int abc = p.jabc[j], aec = p.jaec[j], abr = p.jabr[j];
   int start = abc, end = aec;

@@ -93,3 +93,41 @@ def test_pass1_fast_equals_general_large(gpu, monkeypatch):
     nr = np.maximum(a["n_runs"], 0)
     m = np.arange(a["runs"].shape[1])[None, :] < nr[:, None]
     assert (np.where(m, a["runs"], 0) == np.where(m, z["runs"], 0)).all()
+
+
+@pytest.mark.parametrize("circular,k", [(0, 10), (1, 12)])
+def test_pass1_multi_stretch_repeats_and_ties(gpu, oracle, circular, k):
+    # exact and near-exact repeats far apart: several stretches per strand with equal / competing scores -> every
+    # stretch is its own windowed job, the first maximum in column order wins (mia.c:1278-1302), ties between the
+    # strands go to the reverse strand (palindromic repeat unit)
+    import _pkg
+    _pkg.load()
+    from mia_b200 import synth
+    rng = np.random.default_rng(77)
+    ref = list(synth.random_reference(9000, seed=70))
+    unit = ref[500:700]
+    ref[4000:4200] = unit                                   # exact copy
+    near = list(unit)
+    near[40], near[120] = ("A" if near[40] != "A" else "C"), ("G" if near[120] != "G" else "T")
+    ref[6500:6700] = near                                   # two mismatches
+    rcu = list(synth.revcomp_bytes(np.frombuffer("".join(unit).encode(), np.uint8)).tobytes().decode())
+    ref[8000:8200] = rcu                                    # the unit's reverse complement: hits on both strands
+    ref = "".join(ref)
+    reads = []
+    for _ in range(400):
+        L = int(rng.integers(35, 76))
+        p = int(rng.integers(500, 700 - L))
+        r = ref[p:p + L]
+        if rng.random() < 0.5:
+            r = synth.revcomp_bytes(np.frombuffer(r.encode(), np.uint8)).tobytes().decode()
+        if rng.random() < 0.3:                              # a substitution: breaks some ties
+            q = int(rng.integers(0, L))
+            r = r[:q] + "ACGT"[(("ACGT".index(r[q])) + 1) % 4] + r[q + 1:]
+        reads.append(r)
+    g = synth.diverge(ref, 0.01, seed=71, indel_rate=0.002)
+    b, off, _ = synth.make_reads(g, 600, 35, 75, seed=72, circular=bool(circular))
+    reads += [synth.read_str(b, off, i) for i in range(600)]
+    bad, out = gpu_checks.check_pass1(gpu, oracle, ref, reads, gpu_checks.load_pssm("onepass"), circular, k)
+    assert not bad, f"{len(bad)} reads differ; first {bad[0]}"
+    fast, general, skipped = gpu.last_pass1_stats()
+    assert fast > 700, (fast, general, skipped)             # the repeat reads (3-4 stretches) stay on the fast path
