@@ -249,6 +249,16 @@ def run_ours(args):
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     # algorithmic bytes of the dominant realign launch: read bases + offset(8) + rc/as/ae(9) in,
     # score/as/ae/abr/n_runs/status(21) + one run word(2) out, per read
+    # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture, scaled by DP cells to this launch
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        ent = next((v for k, v in tj.items() if dom["kernel"].split("<")[0] == k.split("<")[0]), None)
+        if ent:
+            traffic = ent["dram_bytes_per_launch"] / ent["cells_per_launch"] * dom["cells"]
+            traffic_src = ent["source"]
+    except Exception:
+        pass
     frac_reads = dom["reads"] / n
     alg_bytes = frac_reads * (len(bases) + n * (8 + 9 + 21 + 2))
     dom_s = dom["ms"] * 1e-3
@@ -267,7 +277,7 @@ def run_ours(args):
         "gpu_launches": launches["n"],
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": alg_bytes / dom_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": alg_bytes / dom_s / 1e9 / hbm_peak, "traffic": None,
+                     "frac": alg_bytes / dom_s / 1e9 / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
                      "kernel": dom["kernel"], "kernel_ms": dom["ms"], "kernel_share_of_step": dom["ms"] / ms_per_step,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst)" if peaks else "fallback 6650 GB/s",
                      "note": "integer-issue bound, not HBM bound: see roofline_int32"},

@@ -116,6 +116,9 @@ int miagpu_pass1( miagpu_ctx* ctx, int32_t* hits, int32_t* score,
  * csrc/pass1.cuh), reads the general chunked kernel took, reads without a hit. */
 int miagpu_last_pass1_stats( miagpu_ctx* ctx, int64_t* fast_reads,
                              int64_t* general_reads, int64_t* skipped_reads );
+/* per read of the last miagpu_pass1: 0 no k-mer hit, 1 finished by the pair kernels, 2 general kernel
+ * (decided while seeding), 3 general kernel (the winning job's path was not a plain diagonal) */
+int miagpu_last_pass1_route( miagpu_ctx* ctx, uint8_t* route );
 
 /* After pass 1 the host tells the device which resident reads to keep and in
  * which orientation (sg_align's accept test + add_virgin_fs2fsdb + clean_FSDB):

@@ -52,6 +52,7 @@ def load_library():
     L.miagpu_upload_reads.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     L.miagpu_pass1.argtypes = [C.c_void_p] + [C.c_void_p] * 13
     L.miagpu_last_pass1_stats.argtypes = [C.c_void_p, _i64p, _i64p, _i64p]
+    L.miagpu_last_pass1_route.argtypes = [C.c_void_p, C.c_void_p]
     L.miagpu_compact_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, _i64p]
     L.miagpu_realign.argtypes = [C.c_void_p] + [C.c_void_p] * 10
     L.miagpu_get_runs_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, _i64p]
@@ -91,7 +92,7 @@ def load_library():
 
 EXPORTS = ["miagpu_device_count", "miagpu_create", "miagpu_destroy", "miagpu_last_error", "miagpu_version", "miagpu_set_pssm",
            "miagpu_get_pssm", "miagpu_set_reference", "miagpu_ref_wrap_len", "miagpu_build_kmers", "miagpu_upload_reads",
-           "miagpu_pass1", "miagpu_last_pass1_stats", "miagpu_compact_reads", "miagpu_realign", "miagpu_realign_host", "miagpu_iterate_host", "miagpu_get_runs_packed",
+           "miagpu_pass1", "miagpu_last_pass1_stats", "miagpu_last_pass1_route", "miagpu_compact_reads", "miagpu_realign", "miagpu_realign_host", "miagpu_iterate_host", "miagpu_get_runs_packed",
            "miagpu_consensus", "miagpu_accumulate_gaps", "miagpu_accumulate_counts", "miagpu_call", "miagpu_consensus_natural", "miagpu_accumulate_gaps_natural",
            "miagpu_score_cut", "miagpu_cull_flags",
            "miagpu_set_alignment_inputs", "miagpu_realign_resident", "miagpu_set_cut_inputs", "miagpu_reset_dropped", "miagpu_iterate_resident", "miagpu_last_buckets", "miagpu_last_pair_buckets", "miagpu_last_timing",
@@ -176,6 +177,11 @@ class MiaGpu:
         f, g, k = C.c_int64(), C.c_int64(), C.c_int64()
         self._ck(self.lib.miagpu_last_pass1_stats(self.h, C.byref(f), C.byref(g), C.byref(k)))
         return f.value, g.value, k.value
+
+    def last_pass1_route(self):
+        r = np.zeros(self.n, np.uint8)
+        self._ck(self.lib.miagpu_last_pass1_route(self.h, _ptr(r)))
+        return r
 
     def compact_reads(self, keep, revcomp=None):
         keep = np.ascontiguousarray(keep, np.uint8)

@@ -2106,6 +2106,18 @@ static int pass1_fast(miagpu_ctx* c, const PairLmax& lm) {
   c->launches += 2;
   int pair_items[P16_NKB], total_pairs = 0;
   for (int kb = 0; kb < P16_NKB; kb++) { pair_items[kb] = c->h_meta[META_NPAIRS + kb]; total_pairs += pair_items[kb]; }
+  // The reads the seeding already sent to the general kernel (saturated strands above all: a whole strand on one
+  // warp, milliseconds per read) start first, on a side stream, and run beside the pair kernels.
+  const int n_general0 = c->h_meta[P1_NGENERAL];
+  if (n_general0) {
+    MIAGPU_CUDA(cudaEventRecord(c->aev[0], st));
+    MIAGPU_CUDA(cudaStreamWaitEvent(c->s_aux[1], c->aev[0], 0));
+    c->launch_stream = c->s_aux[1];
+    const int ok = launch_strip(c, 0, c->d_p1list.p, n_general0, meta + P1_WORK, 0, nullptr);
+    c->launch_stream = st;
+    if (!ok) return 0;
+    MIAGPU_CUDA(cudaEventRecord(c->aev[1], c->s_aux[1]));
+  }
   if (total_pairs) {
     MIAGPU_CUDA(cudaMemsetAsync(c->d_jpairs.p, 0xff, (size_t)2 * np * total_pairs * sizeof(int32_t), st));
     const int64_t njobs = std::min<int64_t>(nj, (uint32_t)c->h_meta[P1_NJOBS]);
@@ -2152,7 +2164,9 @@ static int pass1_fast(miagpu_ctx* c, const PairLmax& lm) {
   MIAGPU_CUDA(cudaStreamSynchronize(st));
   const int n_general = c->h_meta[P1_NGENERAL];
   c->p1_general = n_general; c->p1_fast = c->h_meta[P1_NFAST]; c->p1_skipped = c->h_meta[P1_NSKIPPED];
-  if (n_general && !launch_strip(c, 0, c->d_p1list.p, n_general, meta + P1_WORK, 0, meta + P1_NGENERAL)) return 0;
+  if (n_general0) MIAGPU_CUDA(cudaStreamWaitEvent(st, c->aev[1], 0));      // the two general launches share their scratch
+  if (n_general > n_general0 &&
+      !launch_strip(c, 0, c->d_p1list.p + n_general0, n_general - n_general0, meta + P1_WORK2, 0, nullptr)) return 0;
   return 1;
 }
 
@@ -2192,6 +2206,14 @@ extern "C" int miagpu_pass1(miagpu_ctx* c, int32_t* hits, int32_t* score, int32_
   c->ms_h2d = 0;
   const int len1 = c->circular ? c->wrap_len : c->seq_len;
   c->dp_cells = 2 * (int64_t)len1 * c->total_bases;                        // nominal cells
+  return 1;
+}
+
+extern "C" int miagpu_last_pass1_route(miagpu_ctx* c, uint8_t* route) {
+  if (!c || !route) { set_error("miagpu_last_pass1_route: bad argument"); return 0; }
+  if (c->p1_fast + c->p1_skipped == 0 && c->p1_general == c->n) { memset(route, 2, c->n); return 1; }   // the fast path was off
+  MIAGPU_CUDA(cudaSetDevice(c->device));
+  MIAGPU_CUDA(cudaMemcpy(route, c->d_route.p, c->n, cudaMemcpyDeviceToHost));
   return 1;
 }
 

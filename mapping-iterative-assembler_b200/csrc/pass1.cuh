@@ -36,6 +36,7 @@ constexpr int P1_NFAST = 139;        // reads finished by the pair kernels
 constexpr int P1_NSKIPPED = 140;     // reads without a k-mer hit
 constexpr int P1_WORK = 141;         // work-fetch counter of the general kernel
 
+constexpr int P1_WORK2 = 143;        // work-fetch counter of the general kernel's second launch (reads the merge handed over)
 constexpr int P1_NJOBS = 142;        // jobs allocated (may exceed the capacity: reads that did not fit go to the general kernel)
 constexpr int P1_JPS = 12;           // stretches per strand that become jobs
 constexpr int P1_MAXD = 128;         // diagonals kept per strand: KMER_SATURATE hits unmask the whole strand anyway
@@ -134,30 +135,31 @@ __global__ void __launch_bounds__(256) p1_seed_kernel(P1SeedParams p) {
   __shared__ int s_counts[3];
   __shared__ int s_diag[8][P1_MAXD];
   __shared__ int s_nd[8];
+  __shared__ int s_need[8];
+  __shared__ long long s_first[8];
   for (int i = threadIdx.x; i < P16_KEYS; i += blockDim.x) s_hist[i] = 0;
   if (threadIdx.x < P16_NKB) { s_preads[threadIdx.x] = 0; s_pcells[threadIdx.x] = 0; }
   if (threadIdx.x < 3) s_counts[threadIdx.x] = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
-  for (int64_t rd = (int64_t)blockIdx.x * (blockDim.x >> 5) + w; rd < p.n; rd += warps) {
-    const int64_t o = p.off[rd];
-    const int L = (int)(p.off[rd + 1] - o);
-    if (L <= 0 || L > MAX_READ) {                                        // the general kernel reports it
-      if (lane == 0) { p.route[rd] = 2; p.jcount[rd] = 0; p.general_list[atomicAdd(p.meta + P1_NGENERAL, 1)] = (int32_t)rd; }
-      continue;
-    }
+  // block-uniform rounds of 8 reads: the jobs of a round are allocated with ONE atomic on the global counter
+  for (int64_t rd0 = (int64_t)blockIdx.x * (blockDim.x >> 5); rd0 < p.n; rd0 += warps) {
+    const int64_t rd = rd0 + w;
+    const bool live = rd < p.n;
+    const int64_t o = live ? p.off[rd] : 0;
+    const int L = live ? (int)(p.off[rd + 1] - o) : 0;
+    const bool odd = live && (L <= 0 || L > MAX_READ);                    // the general kernel reports it
     Stretches st[2];
     st[0].hits = st[1].hits = 0; st[0].n = st[1].n = 0;
-    if (L >= p.k) {
+    if (live && !odd && L >= p.k) {
       // every hit unmasks [d - 10, d + L + 10 - s] (kmer.c:294, 319)
       st[0] = seed_stretches(p.kt[0], p.k, p.bases + o, L, L + 2 * ALIGN_MASK_BUFFER, s_diag[w], &s_nd[w]);
       st[1] = seed_stretches(p.kt[1], p.k, p.bases + o, L, L + 2 * ALIGN_MASK_BUFFER - 1, s_diag[w], &s_nd[w]);
     }
-    if (lane != 0) continue;
     const int total = st[0].hits + st[1].hits;
-    p.hits[rd] = total;
-    bool fast = total > 0;
+    if (live && lane == 0) p.hits[rd] = odd ? 0 : total;
+    bool fast = live && !odd && total > 0;
     // masked columns needed between two stretches so that no column-gap candidate crosses (see the header)
     const int need = (L - 1) * (max(p.pssm_max, 0) + GEP) + GEP;
     for (int s = 0; s < 2 && fast; s++) {
@@ -176,12 +178,21 @@ __global__ void __launch_bounds__(256) p1_seed_kernel(P1SeedParams p) {
         st[s].lo[t] = a; st[s].hi[t] = z;                                // from here on: first / last unmasked column
       }
     }
-    int64_t first = 0;
-    if (fast) {
-      first = atomicAdd(reinterpret_cast<unsigned int*>(p.meta + P1_NJOBS), (unsigned)(st[0].n + st[1].n));
-      if (first + st[0].n + st[1].n > p.job_cap) fast = false;           // no room: the slots stay "no job"
+    if (lane == 0) s_need[w] = fast ? st[0].n + st[1].n : 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int i = 0; i < 8; i++) tot += s_need[i];
+      long long base = tot ? (long long)atomicAdd(reinterpret_cast<unsigned int*>(p.meta + P1_NJOBS), (unsigned)tot) : 0;
+      for (int i = 0; i < 8; i++) { s_first[i] = base; base += s_need[i]; }
     }
-    if (!total) {
+    __syncthreads();
+    if (lane != 0 || !live) continue;
+    const int64_t first = s_first[w];
+    if (fast && first + st[0].n + st[1].n > p.job_cap) fast = false;     // no room: the slots stay "no job"
+    if (odd) {
+      p.route[rd] = 2; p.jcount[rd] = 0; p.general_list[atomicAdd(p.meta + P1_NGENERAL, 1)] = (int32_t)rd;
+    } else if (!total) {
       p.route[rd] = 0;
       p.status[rd] = MIAGPU_ST_SKIPPED; p.n_runs[rd] = 0; p.score[rd] = INT_MIN;      // mia_main.c:781: not aligned at all
       p.jcount[rd] = 0;
@@ -223,7 +234,7 @@ struct P1MergeParams {
   int64_t n;
   const int64_t* off;
   int32_t seq_len;
-  const uint8_t* route;
+  uint8_t* route;                // 3 = handed to the general kernel by the merge
   const int32_t* jfirst; const uint16_t* jcount;
   const uint8_t* jkind; const uint8_t* jstatus;
   const int32_t* jscore; const int32_t* jabc; const int32_t* jaec; const int32_t* jabr;
@@ -249,6 +260,7 @@ __global__ void p1_merge_kernel(P1MergeParams p) {
   const int64_t j = bj[s];
   if (j < 0 || p.jstatus[j] != MIAGPU_ST_OK) {      // the winner's path is not one plain diagonal: the general kernel traces it
     p.general_list[atomicAdd(p.meta + P1_NGENERAL, 1)] = (int32_t)rd;
+    p.route[rd] = 3;
     return;
   }
   atomicAdd(p.meta + P1_NFAST, 1);

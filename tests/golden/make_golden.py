@@ -128,6 +128,18 @@ def main():
     b, off, _ = synth.make_reads(g, 250, 35, 75, seed=4)
     reads = [synth.read_str(b, off, i) for i in range(250)]
     sess["synth2k_c_k10"] = session(r, ref, reads, m["onepass"], 1, 10, 0)
+    # BASELINE configs[3] in small: k-mer filter + a starting reference 10 % (+ indels) away from the sample -> many rounds
+    ref = synth.random_reference(3000, seed=11)
+    g = synth.diverge(ref, 0.10, seed=12, indel_rate=0.005)
+    b, off, _ = synth.make_reads(g, 500, 35, 75, seed=13)
+    reads = [synth.read_str(b, off, i) for i in range(500)]
+    sess["synth3k_div10_c_k12"] = session(r, ref, reads, m["ancient"], 1, 12, 0)
+    # BASELINE configs[2] in small: merged paired-end reads (30-140 bp), ancient.submat.solexa.pe, to convergence
+    ref = synth.random_reference(2500, seed=21)
+    g = synth.diverge(ref, 0.03, seed=22, indel_rate=0.004)
+    b, off, _ = synth.make_reads(g, 300, 30, 140, seed=23)
+    reads = [synth.read_str(b, off, i) for i in range(300)]
+    sess["synth2k5_pe_long_c_k12"] = session(r, ref, reads, m["pe"], 1, 12, 0)
     json.dump(sess, open(os.path.join(HERE, "sessions.json"), "w"))
     print("wrote pssm.npz, align_cases.json, sessions.json")
 

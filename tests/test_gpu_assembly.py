@@ -53,3 +53,13 @@ def test_reference_fixtures_kmer_softmask_stale_back_pointers(gpu, golden):
 
 def test_synthetic_circular_kmer(gpu, golden):
     _run(gpu, golden, "synth2k_c_k10", "onepass")
+
+
+def test_divergent_seed_kmer(gpu, golden):
+    # BASELINE configs[3] in small: starting reference 10 % + indels away from the sample, k = 12
+    _run(gpu, golden, "synth3k_div10_c_k12", "ancient")
+
+
+def test_merged_pe_long_reads(gpu, golden):
+    # BASELINE configs[2] in small: 30-140 bp reads (16-bit pair kernels up to their frame limit, 32-bit beyond), pe matrix
+    _run(gpu, golden, "synth2k5_pe_long_c_k12", "pe")

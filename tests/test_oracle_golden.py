@@ -77,6 +77,16 @@ def test_session_synthetic_circular_kmer(oracle, golden):
     _run_session(oracle, golden, "synth2k_c_k10", "onepass")
 
 
+def test_session_divergent_seed_kmer(oracle, golden):
+    # BASELINE configs[3] in small: starting reference 10 % + indels away from the sample, k = 12
+    _run_session(oracle, golden, "synth3k_div10_c_k12", "ancient")
+
+
+def test_session_merged_pe_long_reads(oracle, golden):
+    # BASELINE configs[2] in small: 30-140 bp reads, ancient.submat.solexa.pe
+    _run_session(oracle, golden, "synth2k5_pe_long_c_k12", "pe")
+
+
 def test_find_consensus_rules(oracle):
     # map_align.c:294-391: cov 0 -> N; gaps/cov >= 0.5 -> '-'; '>=' lets the later base win ties
     f = oracle.find_consensus
