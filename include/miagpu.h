@@ -336,6 +336,9 @@ int miagpu_last_cut_stats( miagpu_ctx* ctx, int64_t* serial_blocks, int64_t* fet
 int miagpu_set_alignment_inputs( miagpu_ctx* ctx, const uint8_t* rc,
                                  const int32_t* as, const int32_t* ae );
 int miagpu_realign_resident( miagpu_ctx* ctx );
+/* The last round's as_out / ae_out become the resident as / ae of the next round (fs->as, fs->ae:
+ * mia_main.c:252-256); score / as / ae (nullable host arrays of n) receive this round's values. */
+int miagpu_adopt_alignment( miagpu_ctx* ctx, int32_t* score, int32_t* as, int32_t* ae );
 
 /* ---- measurement helpers (bench.py) */
 /* per width bucket of the last realign: columns-per-lane K (0 = too wide),

@@ -67,6 +67,7 @@ def load_library():
     L.miagpu_cull_flags.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p]
     L.miagpu_set_alignment_inputs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.miagpu_realign_resident.argtypes = [C.c_void_p]
+    L.miagpu_adopt_alignment.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.miagpu_set_cut_inputs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.miagpu_reset_dropped.argtypes = [C.c_void_p]
     L.miagpu_iterate_resident.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.POINTER(C.c_double),
@@ -95,7 +96,7 @@ EXPORTS = ["miagpu_device_count", "miagpu_create", "miagpu_destroy", "miagpu_las
            "miagpu_pass1", "miagpu_last_pass1_stats", "miagpu_last_pass1_route", "miagpu_compact_reads", "miagpu_realign", "miagpu_realign_host", "miagpu_iterate_host", "miagpu_get_runs_packed",
            "miagpu_consensus", "miagpu_accumulate_gaps", "miagpu_accumulate_counts", "miagpu_call", "miagpu_consensus_natural", "miagpu_accumulate_gaps_natural",
            "miagpu_score_cut", "miagpu_cull_flags",
-           "miagpu_set_alignment_inputs", "miagpu_realign_resident", "miagpu_set_cut_inputs", "miagpu_reset_dropped", "miagpu_iterate_resident", "miagpu_last_buckets", "miagpu_last_pair_buckets", "miagpu_last_timing",
+           "miagpu_set_alignment_inputs", "miagpu_realign_resident", "miagpu_adopt_alignment", "miagpu_set_cut_inputs", "miagpu_reset_dropped", "miagpu_iterate_resident", "miagpu_last_buckets", "miagpu_last_pair_buckets", "miagpu_last_timing",
            "miagpu_int32_peak", "miagpu_stream", "miagpu_shard_begin", "miagpu_shard_begin_host", "miagpu_shard_cut", "miagpu_shard_finish",
            "miagpu_last_cut_stats"]
 
@@ -343,6 +344,15 @@ class MiaGpu:
 
     def set_alignment_inputs(self, rc, as_, ae):
         self._ck(self.lib.miagpu_set_alignment_inputs(self.h, _ptr(rc), _ptr(as_), _ptr(ae)))
+
+    def adopt_alignment(self, want=True):
+        """this round's as / ae become the next round's inputs; -> (score, as, ae) of this round if want"""
+        if not want:
+            self._ck(self.lib.miagpu_adopt_alignment(self.h, None, None, None))
+            return None
+        sc, a, e = np.zeros(self.n, np.int32), np.zeros(self.n, np.int32), np.zeros(self.n, np.int32)
+        self._ck(self.lib.miagpu_adopt_alignment(self.h, _ptr(sc), _ptr(a), _ptr(e)))
+        return sc, a, e
 
     def realign_resident(self):
         self._ck(self.lib.miagpu_realign_resident(self.h))

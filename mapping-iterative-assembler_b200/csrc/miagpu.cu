@@ -120,6 +120,8 @@ struct miagpu_ctx {
   struct CutHost* h_cut = nullptr;              // pinned
   CutBlockDev* h_cblk = nullptr;                // pinned
   int64_t h_cblk_cap = 0;
+  char* h_call = nullptr;                       // pinned staging of miagpu_call
+  size_t h_call_cap = 0;
   int32_t* h_score = nullptr;                   // pinned copy of the scores (resident rounds)
   int64_t h_score_cap = 0;
   std::vector<int32_t> h_seqlen;                // host copies for the chains' unproven blocks (resident rounds)
@@ -246,6 +248,7 @@ extern "C" void miagpu_destroy(miagpu_ctx* c) {
   if (c->h_cut) cudaFreeHost(c->h_cut);
   if (c->h_cblk) cudaFreeHost(c->h_cblk);
   if (c->h_score) cudaFreeHost(c->h_score);
+  if (c->h_call) cudaFreeHost(c->h_call);
   if (c->h_sh_pf) cudaFreeHost(c->h_sh_pf);
   if (c->h_sh_pfid) cudaFreeHost(c->h_sh_pfid);
   c->d_sh_send.release(); c->d_sh_recv.release(); c->d_sh_pf.release(); c->d_sh_pfid.release();
@@ -973,6 +976,22 @@ extern "C" int miagpu_set_alignment_inputs(miagpu_ctx* c, const uint8_t* rc, con
   return 1;
 }
 
+// fs->as / fs->ae / fs->score of the next round are this round's results (mia_main.c:252-256)
+extern "C" int miagpu_adopt_alignment(miagpu_ctx* c, int32_t* score, int32_t* as, int32_t* ae) {
+  if (!c) { set_error("miagpu_adopt_alignment: no context"); return 0; }
+  MIAGPU_CUDA(cudaSetDevice(c->device));
+  const int64_t n = c->n;
+  if (n) {
+    MIAGPU_CUDA(cudaMemcpyAsync(c->d_as.p, c->d_as_out.p, n * 4, cudaMemcpyDeviceToDevice, c->stream));
+    MIAGPU_CUDA(cudaMemcpyAsync(c->d_ae.p, c->d_ae_out.p, n * 4, cudaMemcpyDeviceToDevice, c->stream));
+    if (score) MIAGPU_CUDA(cudaMemcpyAsync(score, c->d_score.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (as) MIAGPU_CUDA(cudaMemcpyAsync(as, c->d_as_out.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (ae) MIAGPU_CUDA(cudaMemcpyAsync(ae, c->d_ae_out.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+  }
+  MIAGPU_CUDA(cudaStreamSynchronize(c->stream));
+  return 1;
+}
+
 extern "C" int miagpu_realign_resident(miagpu_ctx* c) {
   if (!c || !c->have_pssm || !c->have_ref) { set_error("miagpu_realign_resident: set_pssm and set_reference first"); return 0; }
   MIAGPU_CUDA(cudaSetDevice(c->device));
@@ -1179,12 +1198,22 @@ extern "C" int miagpu_call(miagpu_ctx* c, int cons_code, int32_t* gaps_out, int3
   MIAGPU_CUDA(cudaGetLastError());
   c->launches++;
   MIAGPU_CUDA(cudaEventRecord(c->ev[2], c->stream));
-  std::vector<char> called(nc);
-  std::vector<int32_t> gaps(c->seq_len), ins_off(c->seq_len + 1), acc;
-  MIAGPU_CUDA(cudaMemcpyAsync(called.data(), c->d_called.p, nc, cudaMemcpyDeviceToHost, c->stream));
-  MIAGPU_CUDA(cudaMemcpyAsync(gaps.data(), c->d_gaps.p, c->seq_len * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  // pinned staging: the called columns (and the gaps when asked for) come back at full PCIe speed
+  const size_t need = (size_t)nc + 16 + (size_t)c->seq_len * sizeof(int32_t);
+  if (c->h_call_cap < need) {
+    if (c->h_call) cudaFreeHost(c->h_call);
+    c->h_call = nullptr; c->h_call_cap = 0;
+    MIAGPU_CUDA(cudaMallocHost(&c->h_call, need + need / 8));
+    c->h_call_cap = need + need / 8;
+  }
+  char* called = c->h_call;
+  int32_t* gaps = reinterpret_cast<int32_t*>(c->h_call + ((nc + 15) / 16) * 16);
+  std::vector<int32_t> ins_off, acc;
+  MIAGPU_CUDA(cudaMemcpyAsync(called, c->d_called.p, nc, cudaMemcpyDeviceToHost, c->stream));
+  if (gaps_out) MIAGPU_CUDA(cudaMemcpyAsync(gaps, c->d_gaps.p, c->seq_len * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
   if (counts_out) {
     acc.resize(nc * NPLANE);
+    ins_off.resize(c->seq_len + 1);
     MIAGPU_CUDA(cudaMemcpyAsync(ins_off.data(), c->d_ins_off.p, (c->seq_len + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
     MIAGPU_CUDA(cudaMemcpyAsync(acc.data(), c->d_acc.p, nc * NPLANE * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
   }
@@ -1194,7 +1223,7 @@ extern "C" int miagpu_call(miagpu_ctx* c, int cons_code, int32_t* gaps_out, int3
   MIAGPU_CUDA(cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]));
   c->ms_kernels += ms;
   MIAGPU_CUDA(cudaEventElapsedTime(&c->ms_d2h, c->ev[2], c->ev[3]));
-  if (gaps_out) memcpy(gaps_out, gaps.data(), c->seq_len * sizeof(int32_t));
+  if (gaps_out) memcpy(gaps_out, gaps, c->seq_len * sizeof(int32_t));
   if (counts_out)
     for (int pos = 0; pos < c->seq_len; pos++)
       for (int pl = 0; pl < NPLANE; pl++) counts_out[(int64_t)pos * NPLANE + pl] = acc[(int64_t)pl * nc + pos + ins_off[pos + 1]];
@@ -1720,9 +1749,6 @@ extern "C" int miagpu_iterate_resident(miagpu_ctx* c, int hard_cut, int score_cu
       !c->d_off2.reserve(2 * (n + 2)) || !cut_reserve(c, n)) return 0;
   if (c->h_score_cap < n) {
     if (c->h_score) cudaFreeHost(c->h_score);
-  if (c->h_sh_pf) cudaFreeHost(c->h_sh_pf);
-  if (c->h_sh_pfid) cudaFreeHost(c->h_sh_pfid);
-  c->d_sh_send.release(); c->d_sh_recv.release(); c->d_sh_pf.release(); c->d_sh_pfid.release();
     c->h_score = nullptr; c->h_score_cap = 0;
     MIAGPU_CUDA(cudaMallocHost(&c->h_score, sizeof(int32_t) * (n + 64)));
     c->h_score_cap = n;

@@ -200,3 +200,97 @@ class Assembler:
         while not conv and self.iter < max_iter:
             _, conv = self.iterate()
         return self.cons, self.iter, conv
+
+
+class ResidentAssembler:
+    """The same loop with everything resident in HBM and one library call per round (miagpu_iterate_resident, or the
+    sharded protocol when `world` > 1): the path for large read sets (BASELINE configs[2]..[4]).
+
+    Every read owns its fresh AlnSeq segments and carries one sticky dropped flag, so this equals the reference as long
+    as no read changes between wrap-split and whole from one round to the next (then the reference's slot-indexed
+    flags and never-cleared back pointers, H10 / mia_main.c:273-276, shift to OTHER reads; `Assembler` above reproduces
+    that, this class reports `split_changes` instead).
+
+    `exchange`: None for one GPU; otherwise an object with
+        all_gather_host(np_array) -> concatenation over ranks in rank order
+        rounds                    -> shard.ShardedRounds (or anything with .resident(...))
+    """
+
+    def __init__(self, gpu, ref, sm, circular=1, k=0, soft_mask=0, cons_code=1, exchange=None):
+        self.g, self.sm, self.circular, self.k, self.soft_mask, self.cons_code = gpu, sm, circular, k, soft_mask, cons_code
+        self.ref0, self.x = ref, exchange
+        self.split_changes = 0
+        gpu.set_pssm(sm)
+
+    def _gather(self, a):
+        return a if self.x is None else self.x.all_gather_host(a)
+
+    def pass1(self, bases, off, defer_cull=False):
+        g = self.g
+        g.set_reference(self.ref0, self.circular, with_rc=1)
+        g.build_kmers(self.k, self.soft_mask)
+        g.upload_reads(bases, off)
+        p = g.pass1()
+        self.p1 = p
+        seq_len = np.diff(off).astype(np.int32)
+        keep = (p["hits"] > 0) & (p["score"] >= FIRST_ROUND_SCORE_CUTOFF)            # mia.c:1614
+        if (keep & (p["score"] == FIRST_ROUND_SCORE_CUTOFF)).any():
+            raise NotImplementedError("reads with score == 2000 keep strand_known = 0 and are never realigned (mia.c:1653)")
+        idx = np.flatnonzero(keep)
+        self._idx, self._n_all = idx, len(seq_len)
+        self.seq_len, self.score = seq_len[idx], p["score"][idx].copy()
+        self.rc, self.as_, self.ae = p["rc"][idx].copy(), p["as_"][idx].copy(), p["ae"][idx].copy()
+        self.split = p["start"][idx] > p["end"][idx]                                 # mia.c:1619
+        if self.x is not None or not defer_cull:
+            self.pass1_cull(self._gather(self.seq_len), self._gather(self.score))
+        return p
+
+    def pass1_cull(self, all_seq_len, all_score):
+        """pass-1 cull (mia_main.c:848) with the fit over the reads of ALL ranks in FSDB order: only its dropped flags survive"""
+        g, idx = self.g, self._idx
+        fit = api.score_cut(all_seq_len, all_score)
+        dropped = api.cull_flags(self.seq_len, self.score, None, 0, 1, fit[0], fit[1])
+        ok = self.score > 0                                                          # clean_FSDB (mia.c:400-406)
+        keep_dev = np.zeros(self._n_all, np.uint8)
+        keep_dev[idx[ok]] = 1
+        rev = np.zeros(self._n_all, np.uint8)
+        rev[idx] = self.rc == 1                                                      # stored orientation (fsdb.c:209-227)
+        g.compact_reads(keep_dev, rev)
+        for name in ("seq_len", "score", "rc", "as_", "ae", "split"):
+            setattr(self, name, getattr(self, name)[ok])
+        self.dropped = np.ascontiguousarray(dropped[ok], np.uint8)
+        g.set_alignment_inputs(self.rc, self.as_, self.ae)
+        g.set_cut_inputs(self.seq_len, None, self.dropped)
+        self.iter, self.cons, self.last = 0, None, self.ref0.upper()
+
+    def begin_round(self):
+        if self.cons is not None:
+            self.last = self.cons
+        self.iter += 1
+        self.g.set_reference(self.last, self.circular, with_rc=0)
+
+    def iterate(self, want_gaps=False):
+        g = self.g
+        self.begin_round()
+        if self.x is None:
+            res = g.iterate_resident(self.cons_code, dropped=self.dropped, want_gaps=want_gaps)
+        else:
+            res = self.x.rounds.resident(self.cons_code, dropped=self.dropped, want_gaps=want_gaps)
+        return self.end_round(*res)
+
+    def end_round(self, cons, fit, gaps):
+        self.fit, self.gaps = fit, gaps
+        self.score, self.as_, self.ae = self.g.adopt_alignment()
+        L = len(self.last)
+        split = self.as_ > np.where(self.ae > L, self.ae - L, self.ae)
+        self.split_changes += int((split != self.split).sum())
+        self.split = split
+        self.cons = cons
+        return cons, cons == self.last
+
+    def run(self, bases, off, max_iter=MAX_ITER):
+        self.pass1(bases, off)
+        conv = False
+        while not conv and self.iter < max_iter:
+            _, conv = self.iterate()
+        return self.cons, self.iter, conv

@@ -63,3 +63,66 @@ def test_divergent_seed_kmer(gpu, golden):
 def test_merged_pe_long_reads(gpu, golden):
     # BASELINE configs[2] in small: 30-140 bp reads (16-bit pair kernels up to their frame limit, 32-bit beyond), pe matrix
     _run(gpu, golden, "synth2k5_pe_long_c_k12", "pe")
+
+
+def _session_inputs(name):
+    s = json.load(open(os.path.join(G, "sessions.json")))[name]
+    reads = [r for r in s["reads"] if r]
+    off = np.zeros(len(reads) + 1, np.int64)
+    np.cumsum([len(r) for r in reads], out=off[1:])
+    bases = np.frombuffer("".join(reads).encode(), np.uint8)
+    return s, bases, off
+
+
+@pytest.mark.parametrize("name,matrix", [("synth2k_c_k10", "onepass"), ("synth3k_div10_c_k12", "ancient"), ("synth2k5_pe_long_c_k12", "pe"),
+                                         ("tr1_tf_lin", "ancient")])
+def test_resident_rounds_reproduce_reference_sessions(gpu, golden, name, matrix):
+    # everything resident, one library call per round (score cut on the device): the reference's consensus of every round
+    import _pkg
+    _pkg.load()
+    from mia_b200 import driver
+    s, bases, off = _session_inputs(name)
+    A = driver.ResidentAssembler(gpu, s["ref"], golden[matrix], s["circular"], s["k"], s["soft_mask"])
+    A.pass1(bases, off)
+    for it, e in enumerate(s["iters"]):
+        cons, conv = A.iterate(want_gaps=True)
+        got = np.stack([A.score, A.as_, A.ae, A.rc.astype(np.int32)], 1).tolist()
+        assert got == e["reads"], f"{name}: iteration {it + 1} per-read score/as/ae"
+        assert cons == e["cons"], f"{name}: iteration {it + 1} consensus"
+        assert conv == e["converged"]
+    assert A.split_changes == 0
+
+
+@pytest.mark.parametrize("name,matrix,parts", [("synth3k_div10_c_k12", "ancient", 2), ("synth2k5_pe_long_c_k12", "pe", 3)])
+def test_sharded_assembly_to_convergence(gpu, golden, name, matrix, parts):
+    # BASELINE configs[2] / [3] in small: pass 1 and every round with the reads sharded (contexts of one process, collectives
+    # emulated by device copies) -- the reference's consensus of every round on every shard
+    import _pkg
+    _pkg.load()
+    from mia_b200 import api, driver, shard
+    s, bases, off = _session_inputs(name)
+    n = len(off) - 1
+    ctxs = [api.MiaGpu(0) for _ in range(parts)]
+    try:
+        asms = [driver.ResidentAssembler(g, s["ref"], golden[matrix], s["circular"], s["k"], s["soft_mask"]) for g in ctxs]
+        for r, a in enumerate(asms):
+            lo, hi = n * r // parts, n * (r + 1) // parts
+            a.pass1(np.ascontiguousarray(bases[off[lo]:off[hi]]), np.ascontiguousarray(off[lo:hi + 1] - off[lo]), defer_cull=True)
+        all_sl = np.concatenate([a.seq_len for a in asms])
+        all_sc = np.concatenate([a.score for a in asms])
+        for a in asms:
+            a.pass1_cull(all_sl, all_sc)
+        L = shard.LocalShards(ctxs)
+        for it, e in enumerate(s["iters"]):
+            for a in asms:
+                a.begin_round()
+            res = L.resident(max(len(a.seq_len) for a in asms), dropped=[a.dropped for a in asms])
+            outs = [a.end_round(*r) for a, r in zip(asms, res)]
+            for cons, conv in outs:
+                assert cons == e["cons"], f"{name}: iteration {it + 1} consensus"
+                assert conv == e["converged"]
+            got = np.concatenate([np.stack([a.score, a.as_, a.ae, a.rc.astype(np.int32)], 1) for a in asms]).tolist()
+            assert got == e["reads"], f"{name}: iteration {it + 1} per-read score/as/ae"
+    finally:
+        for g in ctxs:
+            g.close()
