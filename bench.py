@@ -83,10 +83,10 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.rows, self.proc = [], None
+        self.rows, self.proc, self.start = [], None, 0
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -96,6 +96,10 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
+    def mark(self):
+        """samples before this point (start-up, warm-up) are dropped"""
+        self.start = len(self.rows)
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -104,6 +108,7 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        self.rows = self.rows[self.start:]
         sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -183,11 +188,17 @@ def run_ours(args):
     g.set_alignment_inputs(rc, as_, ae)
     g.set_cut_inputs(seq_len)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    sampler = ClockSampler(local) if rank == 0 else None      # nvidia-smi needs a few hundred ms to start: launched before the warm-up
     for _ in range(max(args.warmup, 3)):
         cons = step_resident()
     tim = g.last_timing()
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        t_wait = time.perf_counter()
+        while not sampler.rows and time.perf_counter() - t_wait < 3.0:      # first sample in: the sampling loop is running
+            time.sleep(0.01)
+        sampler.mark()
+    barrier()
     launches["n"] = 0
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for k in range(args.steps):
@@ -424,7 +435,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reads", type=int, default=1_000_000, help="reads per GPU")
