@@ -66,6 +66,8 @@ struct miagpu_ctx {
   int num_sms = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[6] = {};
+  cudaEvent_t p1ev[3] = {};                    // pass-1 fast path: after seeding, after the pair kernels, after the merge
+  bool p1ev_valid = false;
   cudaEvent_t bev[2 * NBUCKET] = {};           // per width-bucket start/stop
   float bucket_ms[NBUCKET] = {};
   int64_t bucket_cells[NBUCKET] = {};
@@ -200,6 +202,7 @@ extern "C" int miagpu_create(miagpu_ctx** out, int device) {
   c->num_sms = prop.multiProcessorCount;
   MIAGPU_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   for (auto& ev : c->ev) MIAGPU_CUDA(cudaEventCreate(&ev));
+  for (auto& ev : c->p1ev) MIAGPU_CUDA(cudaEventCreate(&ev));
   for (auto& ev : c->bev) MIAGPU_CUDA(cudaEventCreate(&ev));
   for (auto& ev : c->pev) MIAGPU_CUDA(cudaEventCreate(&ev));
   c->s_aux[0] = c->stream; c->launch_stream = c->stream;
@@ -237,6 +240,7 @@ extern "C" void miagpu_destroy(miagpu_ctx* c) {
   c->d_rcs.release(); c->d_start.release(); c->d_end.release(); c->d_rc_out.release(); c->d_bases2.release(); c->d_packed.release(); c->d_off2.release(); c->d_src.release();
   c->d_entries.release(); c->d_ent_pos.release(); c->d_sm.release(); c->d_gaps.release(); c->d_ins_off.release(); c->d_acc.release(); c->d_cub.release(); c->d_called.release(); c->d_dropf.release(); c->d_dropb.release();
   for (auto& ev : c->ev) cudaEventDestroy(ev);
+  for (auto& ev : c->p1ev) cudaEventDestroy(ev);
   for (auto& ev : c->bev) cudaEventDestroy(ev);
   for (auto& ev : c->pev) cudaEventDestroy(ev);
   c->d_prof16.release(); c->d_kind.release(); c->d_pairs.release();
@@ -584,18 +588,28 @@ static int launch_strip(miagpu_ctx* c, int mode, const int32_t* list, int n_list
   const int n_chunks = (len1 + CW - 1) / CW;
   const int Lmax = std::min(std::max(c->max_read_len, 1), MAX_READ);
   const int mask_words = n_chunks * (CW / 32);
-  const size_t smem = PROF_INTS * 4 + WARPS_PER_BLOCK * MAX_READ * 2;
-  int per_sm = 0;
-  MIAGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, strip_kernel, WARPS_PER_BLOCK * 32, smem));
-  if (per_sm < 1) { set_error("strip_kernel does not fit on an SM"); return 0; }
   const int64_t total = (mode == 0 && !list) ? c->n : n_list;
   if (total == 0) return 1;
-  // per-warp scratch: keep the total under ~6 GB
+  // few reads: a team of warps per read (strip_team_kernel), else a warp per read
+  bool team = total <= (int64_t)2 * c->num_sms * 4;
+  if (const char* e = getenv("MIAGPU_STRIP_TEAM")) team = atoi(e) != 0;
+  const size_t smem = team ? PROF_INTS * 4 + MAX_READ * 2 + (size_t)n_chunks * 4 : PROF_INTS * 4 + WARPS_PER_BLOCK * MAX_READ * 2;
+  if (team && smem > 200 * 1024) team = false;
+  int per_sm = 0;
+  if (team) {
+    if (smem > 48 * 1024) MIAGPU_CUDA(cudaFuncSetAttribute(strip_team_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MIAGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, strip_team_kernel, TEAM_WARPS * 32, smem));
+  } else {
+    MIAGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, strip_kernel, WARPS_PER_BLOCK * 32, smem));
+  }
+  if (per_sm < 1) { set_error("strip_kernel does not fit on an SM"); return 0; }
+  // per-warp (per-team) scratch: keep the total under ~6 GB
   const size_t per_warp = (size_t)2 * mask_words * 4 + (size_t)2 * (n_chunks + 1) * Lmax * 16 + (size_t)2 * n_chunks * 4 + (size_t)Lmax * CW * 4;
+  const int units_per_block = team ? 1 : WARPS_PER_BLOCK;
   per_sm = std::min(per_sm, 4);
-  while (per_sm > 1 && per_warp * c->num_sms * per_sm * WARPS_PER_BLOCK > ((size_t)6 << 30)) per_sm--;
-  int blocks = (int)std::min<int64_t>((int64_t)c->num_sms * per_sm, (total + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
-  const size_t warps = (size_t)blocks * WARPS_PER_BLOCK;
+  while (per_sm > 1 && per_warp * c->num_sms * per_sm * units_per_block > ((size_t)6 << 30)) per_sm--;
+  int blocks = (int)std::min<int64_t>((int64_t)c->num_sms * per_sm, (total + units_per_block - 1) / units_per_block);
+  const size_t warps = (size_t)blocks * units_per_block;
   if (!c->d_smask.reserve(warps * 2 * mask_words) || !c->d_ckpt.reserve(warps * 2 * (n_chunks + 1) * Lmax) ||
       !c->d_chunk_ids.reserve(warps * 2 * n_chunks) || !c->d_strace.reserve(warps * Lmax * CW)) return 0;
   StripParams p{};
@@ -614,7 +628,8 @@ static int launch_strip(miagpu_ctx* c, int mode, const int32_t* list, int n_list
     p.off += lo; p.rc_in += lo; p.score += lo; p.as_out += lo; p.ae_out += lo; p.abr += lo; p.n_runs += lo;
     p.runs += lo * MAX_RUNS; p.status += lo;
   }
-  strip_kernel<<<blocks, WARPS_PER_BLOCK * 32, smem, c->launch_stream>>>(p);
+  if (team) strip_team_kernel<<<blocks, TEAM_WARPS * 32, smem, c->launch_stream>>>(p);
+  else strip_kernel<<<blocks, WARPS_PER_BLOCK * 32, smem, c->launch_stream>>>(p);
   MIAGPU_CUDA(cudaGetLastError());
   c->launches++;
   return 1;
@@ -2127,6 +2142,7 @@ static int pass1_fast(miagpu_ctx* c, const PairLmax& lm) {
   MIAGPU_CUDA(cudaGetLastError());
   pair_layout_kernel<<<1, LAYOUT_THREADS, 0, st>>>(meta, np);
   MIAGPU_CUDA(cudaGetLastError());
+  MIAGPU_CUDA(cudaEventRecord(c->p1ev[0], st));
   MIAGPU_CUDA(cudaMemcpyAsync(c->h_meta, meta, sizeof(int32_t) * META_HOST, cudaMemcpyDeviceToHost, st));
   MIAGPU_CUDA(cudaStreamSynchronize(st));
   c->launches += 2;
@@ -2176,6 +2192,7 @@ static int pass1_fast(miagpu_ctx* c, const PairLmax& lm) {
       base += ni;
     }
   }
+  MIAGPU_CUDA(cudaEventRecord(c->p1ev[1], st));
   P1MergeParams mp{};
   mp.n = n; mp.off = c->d_off.p; mp.seq_len = c->seq_len; mp.route = c->d_route.p; mp.jfirst = c->d_jfirst.p; mp.jcount = c->d_jcount.p; mp.jkind = c->d_jkind.p; mp.jstatus = c->d_jstatus.p;
   mp.jscore = c->d_jscore.p; mp.jabc = c->d_jabc.p; mp.jaec = c->d_jaec.p; mp.jabr = c->d_jabr.p; mp.general_list = c->d_p1list.p; mp.meta = meta;
@@ -2184,6 +2201,7 @@ static int pass1_fast(miagpu_ctx* c, const PairLmax& lm) {
   mp.runs = c->d_runs.p; mp.status = c->d_status.p;
   p1_merge_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(mp);
   MIAGPU_CUDA(cudaGetLastError());
+  MIAGPU_CUDA(cudaEventRecord(c->p1ev[2], st));
   c->launches++;
   // the general kernel over whatever is left (list length read on the device; the grid is sized for the seeding's share)
   MIAGPU_CUDA(cudaMemcpyAsync(c->h_meta, meta, sizeof(int32_t) * META_HOST, cudaMemcpyDeviceToHost, st));
@@ -2210,6 +2228,7 @@ extern "C" int miagpu_pass1(miagpu_ctx* c, int32_t* hits, int32_t* score, int32_
   bool fast = c->kmer_k > 0 && lm.v[0] > 0 && n > 0;
   if (const char* e = getenv("MIAGPU_PASS1_FAST")) fast = fast && atoi(e) != 0;
   c->p1_fast = c->p1_general = c->p1_skipped = 0;
+  c->p1ev_valid = fast;
   if (!fast) {
     if (!launch_strip(c, 0, nullptr, 0, c->d_meta.p + 16)) return 0;
     c->p1_general = n;
@@ -2230,6 +2249,12 @@ extern "C" int miagpu_pass1(miagpu_ctx* c, int32_t* hits, int32_t* score, int32_
   MIAGPU_CUDA(cudaEventElapsedTime(&c->ms_kernels, c->ev[1], c->ev[2]));
   MIAGPU_CUDA(cudaEventElapsedTime(&c->ms_d2h, c->ev[2], c->ev[3]));
   c->ms_h2d = 0;
+  if (c->p1ev_valid && getenv("MIAGPU_TRACE")) {
+    float a = 0, b = 0, d = 0, e = 0;
+    cudaEventElapsedTime(&a, c->ev[1], c->p1ev[0]); cudaEventElapsedTime(&b, c->p1ev[0], c->p1ev[1]);
+    cudaEventElapsedTime(&d, c->p1ev[1], c->p1ev[2]); cudaEventElapsedTime(&e, c->p1ev[2], c->ev[2]);
+    fprintf(stderr, "[miagpu trace] pass 1: seeding %.3f ms, pair kernels (+ host sync) %.3f ms, merge %.3f ms, general tail %.3f ms\n", a, b, d, e);
+  }
   const int len1 = c->circular ? c->wrap_len : c->seq_len;
   c->dp_cells = 2 * (int64_t)len1 * c->total_bases;                        // nominal cells
   return 1;

@@ -43,36 +43,58 @@ constexpr int P1_MAXD = 128;         // diagonals kept per strand: KMER_SATURATE
 
 struct Stretches { int hits, n; int lo[P1_JPS], hi[P1_JPS]; };   // n > P1_JPS: too many
 
-// new_kmer_filter's hit loop for one strand (kmer.c:275-327) without the mask: hit count and the hit diagonals
-// (reference position - read offset) chained into stretches: two hits belong to one stretch when their unmasked
-// intervals [d - 10, d + span - 10] overlap or adjoin, i.e. their diagonals differ by at most span + 1.
-__device__ __forceinline__ Stretches seed_stretches(const KmerTable& kt, const int k, const uint8_t* __restrict__ read, const int L,
-                                                    const int span, int* s_diag, int* s_n) {
+// The read as 2-bit codes, 16 bases per 32-bit word, first base in the top bits (so that a k-mer's index -- first base
+// most significant, kmer2inx kmer.c:18-48 -- is a funnel shift away), plus one validity bit per base (A/C/G/T after
+// upper-casing, kmer.c:27), 32 bases per word.  Lane l packs bases [8l, 8l+8).  s_code: 17 words, s_valid: 9 words.
+__device__ __forceinline__ void pack_read(const uint8_t* __restrict__ read, const int L, uint32_t* s_code, uint32_t* s_valid) {
   const int lane = threadIdx.x & 31;
-  if (lane == 0) *s_n = 0;
+  uint32_t code = 0, valid = 0;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const int i = lane * 8 + j;
+    const int c = i < L ? kmer_code(read[i]) : -1;
+    code = (code << 2) | (uint32_t)(c & 3);
+    valid = (valid << 1) | (c >= 0 ? 1u : 0u);
+  }
+  reinterpret_cast<uint16_t*>(s_code)[lane ^ 1] = (uint16_t)code;      // word = (even lane << 16) | odd lane
+  reinterpret_cast<uint8_t*>(s_valid)[lane ^ 3] = (uint8_t)valid;      // word = lanes 4j .. 4j+3, first in the top byte
+  if (lane == 0) { s_code[16] = 0; s_valid[8] = 0; }
   __syncwarp();
+}
+
+// new_kmer_filter's hit loop (kmer.c:275-327) without the mask, both strands in one pass over the read's k-mers:
+// the hit diagonals (reference position - read offset) of strand t go to s_diag[t] (the first P1_MAXD), s_n[t] counts.
+__device__ __forceinline__ void seed_hits(const KmerTable (&kt)[2], const int k, const int L, const uint32_t* s_code, const uint32_t* s_valid,
+                                          int (*s_diag)[P1_MAXD], int* s_n) {
+  const int lane = threadIdx.x & 31;
+  if (lane < 2) s_n[lane] = 0;
+  __syncwarp();
+  const uint32_t full = (1u << k) - 1;
   for (int p = lane; p + k <= L; p += 32) {
-    uint32_t inx = 0;
-    bool ok = true;
-    for (int i = 0; i < k; i++) {
-      const int c = kmer_code(read[p + i]);
-      if (c < 0) { ok = false; break; }
-      inx = (inx << 2) | (uint32_t)c;
-    }
-    if (!ok) continue;
-    const int b = (int)(inx >> kt.bucket_shift);
-    const int e1 = __ldg(kt.bucket_start + b + 1);
-    for (int e = __ldg(kt.bucket_start + b); e < e1; e++) {
-      if (__ldg(kt.kmer + e) != inx) continue;
-      const int slot = atomicAdd(s_n, 1);
-      if (slot < P1_MAXD) s_diag[slot] = __ldg(kt.pos + e) - p;
+    const uint32_t v = __funnelshift_l(s_valid[(p >> 5) + 1], s_valid[p >> 5], p & 31) >> (32 - k);
+    if (v != full) continue;                                             // a base other than A/C/G/T: kmer2inx fails
+    const uint32_t inx = __funnelshift_l(s_code[(p >> 4) + 1], s_code[p >> 4], 2 * (p & 15)) >> (32 - 2 * k);
+#pragma unroll
+    for (int t = 0; t < 2; t++) {
+      const int b = (int)(inx >> kt[t].bucket_shift);
+      const int e0 = __ldg(kt[t].bucket_start + b), e1 = __ldg(kt[t].bucket_start + b + 1);
+      for (int e = e0; e < e1; e++) {
+        if (__ldg(kt[t].kmer + e) != inx) continue;
+        const int slot = atomicAdd(&s_n[t], 1);
+        if (slot < P1_MAXD) s_diag[t][slot] = __ldg(kt[t].pos + e) - p;
+      }
     }
   }
   __syncwarp();
+}
+
+// The hit diagonals of one strand chained into stretches: two hits belong to one stretch when their unmasked
+// intervals [d - 10, d + span - 10] overlap or adjoin, i.e. their diagonals differ by at most span + 1.
+__device__ __forceinline__ Stretches chain_stretches(const int hits, const int* s_diag, const int span) {
+  const int lane = threadIdx.x & 31;
   Stretches r;
-  r.hits = *s_n;
+  r.hits = hits;
   r.n = 0;
-  __syncwarp();                                        // everybody has read the count before the next strand resets it
   if (r.hits == 0 || r.hits >= KMER_SATURATE) return r;
   int v[P1_MAXD / 32];
 #pragma unroll
@@ -101,7 +123,6 @@ __device__ __forceinline__ Stretches seed_stretches(const KmerTable& kt, const i
       if (v[i] != INT_MAX && v[i] > hi) nx = min(nx, v[i]);
     lo = __reduce_min_sync(0xffffffffu, nx);
   }
-  __syncwarp();
   return r;
 }
 
@@ -133,8 +154,9 @@ __global__ void __launch_bounds__(256) p1_seed_kernel(P1SeedParams p) {
   __shared__ int s_preads[P16_NKB];
   __shared__ unsigned long long s_pcells[P16_NKB];
   __shared__ int s_counts[3];
-  __shared__ int s_diag[8][P1_MAXD];
-  __shared__ int s_nd[8];
+  __shared__ int s_diag[8][2][P1_MAXD];
+  __shared__ int s_nd[8][2];
+  __shared__ uint32_t s_code[8][17], s_valid[8][9];
   __shared__ int s_need[8];
   __shared__ long long s_first[8];
   for (int i = threadIdx.x; i < P16_KEYS; i += blockDim.x) s_hist[i] = 0;
@@ -153,9 +175,12 @@ __global__ void __launch_bounds__(256) p1_seed_kernel(P1SeedParams p) {
     Stretches st[2];
     st[0].hits = st[1].hits = 0; st[0].n = st[1].n = 0;
     if (live && !odd && L >= p.k) {
+      pack_read(p.bases + o, L, s_code[w], s_valid[w]);
+      seed_hits(p.kt, p.k, L, s_code[w], s_valid[w], s_diag[w], s_nd[w]);
       // every hit unmasks [d - 10, d + L + 10 - s] (kmer.c:294, 319)
-      st[0] = seed_stretches(p.kt[0], p.k, p.bases + o, L, L + 2 * ALIGN_MASK_BUFFER, s_diag[w], &s_nd[w]);
-      st[1] = seed_stretches(p.kt[1], p.k, p.bases + o, L, L + 2 * ALIGN_MASK_BUFFER - 1, s_diag[w], &s_nd[w]);
+      st[0] = chain_stretches(s_nd[w][0], s_diag[w][0], L + 2 * ALIGN_MASK_BUFFER);
+      st[1] = chain_stretches(s_nd[w][1], s_diag[w][1], L + 2 * ALIGN_MASK_BUFFER - 1);
+      __syncwarp();                                                        // everybody is done with the shared lists
     }
     const int total = st[0].hits + st[1].hits;
     if (live && lane == 0) p.hits[rd] = odd ? 0 : total;

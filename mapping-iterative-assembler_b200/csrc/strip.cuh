@@ -73,10 +73,14 @@ __device__ __forceinline__ PV pv_better(PV a, PV b) { return (b.v > a.v) ? b : a
 // One chunk, all rows.  TRACE: also write trace ints for rows 1..L-1 into trace[(r)*CW + cc].
 // ck_in: checkpoint of this chunk (per row {S1,S2,PV,PI}); adjacent: S1/S2 valid (previous chunk is c0-CW).
 // ck_out: written for the next processed chunk.  Returns via best/best_col the running first-max of the last row.
-template <bool TRACE>
+// PIPE (strip_team_kernel): the previous processed chunk is swept by ANOTHER warp of the block at the same time, one row
+// ahead: row r waits until *flag_prev > r (that warp has written its row r candidate state and its row r-1 scores) and
+// announces its own progress through *flag_mine.
+template <bool TRACE, bool PIPE = false>
 __device__ void strip_chunk(const int L, const int len1, const int c0, const uint8_t* __restrict__ ref, const uint32_t* __restrict__ mask,
                             const uint16_t* rowoff, const uint32_t prof_base, const int4* ck_in, const bool adjacent, const bool have_in,
-                            int4* ck_out, int32_t* trace, int& best, int& best_col) {
+                            int4* ck_out, int32_t* trace, int& best, int& best_col, volatile int* flag_prev = nullptr,
+                            volatile int* flag_mine = nullptr) {
   const int lane = threadIdx.x & 31;
   const int cbase = c0 + lane * SK;
   int code4[SK];
@@ -108,13 +112,17 @@ __device__ void strip_chunk(const int L, const int len1, const int c0, const uin
     int l2 = __shfl_up_sync(0xffffffffu, Sp[SK - 2], 1);
     PV seed;
     if (lane == 0) {
-      int4 ci = have_in ? ck_in[r - 1] : make_int4(HIM, HIM, 0, 0);
+      if (PIPE && have_in) {
+        while (*flag_prev <= r) {}
+        __threadfence_block();
+      }
+      int4 ci = have_in ? (PIPE ? __ldcg(ck_in + r - 1) : ck_in[r - 1]) : make_int4(HIM, HIM, 0, 0);
       l1 = adjacent ? ci.x : HIM;
       l2 = adjacent ? ci.y : HIM;
       // best_gap_col entering this chunk at row r: the previous processed chunk's state, or the row-start
       // state bgc = 0 (mia.c:825) = (S[r-1][0], 0)
       if (c0 == 0) seed = PV{Sp[0], 0};
-      else if (have_in) { int4 cr = ck_in[r]; seed = PV{cr.z, cr.w}; }
+      else if (have_in) { int4 cr = PIPE ? __ldcg(ck_in + r) : ck_in[r]; seed = PV{cr.z, cr.w}; }
       else seed = PV{HIM, 0};
     }
     // candidates: column k = c-2 joins when column c is unmasked and c >= 2 (mia.c:827-843)
@@ -136,7 +144,10 @@ __device__ void strip_chunk(const int L, const int len1, const int c0, const uin
     }
     PV P{__shfl_up_sync(0xffffffffu, t.v, 1), __shfl_up_sync(0xffffffffu, t.i, 1)};
     if (lane == 0) P = seed;
-    if (ck_out && lane == 31) ck_out[r] = make_int4(0, 0, t.v, t.i);    // S1/S2 patched below
+    if (ck_out && lane == 31) {
+      ck_out[r] = make_int4(0, 0, t.v, t.i);                            // S1/S2 patched below
+      if (PIPE) { __threadfence_block(); *flag_mine = r + 1; }          // row r-1's scores went out before (program order)
+    }
 
     int D = l1;
     int tr[SK];
@@ -226,6 +237,87 @@ __device__ int seed_strand(const KmerTable& kt, const int k, const uint8_t* read
   return hits;
 }
 
+// One warp: strand pick, traceback (re-running the chunks the path crosses from their checkpoints) and the outputs of read rd.
+__device__ void strip_finish(const StripParams& p, const int rd, const int L, const int nstrand, const bool masked, const int (&best)[2],
+                             const int (&bcol)[2], const int (&nch)[2], const uint32_t* mask0, const int32_t* ids0, const int4* ck0,
+                             int32_t* trace, const uint16_t* rowoff, const uint32_t prof_base) {
+  const int lane = threadIdx.x & 31;
+  const int len1 = p.len1;
+  // ---- strand pick: fw only if strictly better (mia.c:1549-1554)
+  const int s = (nstrand == 2 && !(best[0] > best[1])) ? 1 : 0;
+  const int score = best[s];
+  const int aec = bcol[s];
+  // ---- traceback: re-run the chunks the path crosses, with trace
+  const uint32_t* mask = masked ? mask0 + s * p.mask_words : nullptr;
+  const int32_t* ids = ids0 + s * p.max_chunks;
+  const int4* ck = ck0 + (int64_t)s * (p.max_chunks + 1) * p.Lmax;
+  int row = L - 1, col = aec, nrun = 0, curM = 0, ncols = 0, loaded = -1;
+  uint16_t* my_runs = p.runs + (int64_t)rd * MAX_RUNS;
+  auto push = [&](int type, int len) {
+    while (len > 0) {                                                  // a run longer than 14 bits is split
+      const int l = min(len, 0x3fff);
+      if (nrun < MAX_RUNS && lane == 0) my_runs[nrun] = (uint16_t)((type << 14) | l);
+      nrun++; len -= l;
+    }
+  };
+  bool lost = false;
+  while (row > 0 && col > 0) {
+    const int ch = col / CW;
+    if (ch != loaded) {
+      int q = -1;                                                      // position of chunk ch in the processed list
+      for (int base = 0; base < nch[s]; base += 32) {
+        const bool hit = base + lane < nch[s] && ids[base + lane] == ch;
+        const unsigned bal = __ballot_sync(0xffffffffu, hit);
+        if (bal) { q = base + __ffs(bal) - 1; break; }
+      }
+      if (q < 0) { lost = true; break; }                               // cannot happen: the path only visits unmasked cells
+      int dummy_b = INT_MIN, dummy_c = 0;
+      __syncwarp();
+      strip_chunk<true>(L, len1, ch * CW, p.ref_codes[s], mask, rowoff, prof_base, ck + (int64_t)q * p.Lmax,
+                        q > 0 && ids[q - 1] == ch - 1, q > 0, nullptr, trace, dummy_b, dummy_c);
+      __syncwarp();
+      loaded = ch;
+    }
+    const int t = __ldcg(trace + (int64_t)row * CW + (col - ch * CW));
+    if (t == col || t == -row) break;                                  // mia.c:617-618
+    curM++;
+    if (t == 0) { row--; col--; }
+    else if (t < 0) { push(MIAGPU_RUN_M, curM); ncols += curM; curM = 0; push(MIAGPU_RUN_I, row - 1 + t); ncols += row - 1 + t; row = -t; col--; }
+    else { push(MIAGPU_RUN_M, curM); ncols += curM; curM = 0; push(MIAGPU_RUN_D, col - 1 - t); ncols += col - 1 - t; col = t; row--; }
+  }
+  push(MIAGPU_RUN_M, curM + 1); ncols += curM + 1;
+  if (lane == 0) {
+    uint8_t st = lost ? MIAGPU_ST_UNSUPPORTED : MIAGPU_ST_OK;
+    if (nrun > MAX_RUNS) { st |= MIAGPU_ST_RUNS_OVERFLOW; nrun = -1; }
+    if (ncols > 2 * MAX_READ) st |= MIAGPU_ST_STR_OVERFLOW;
+    const int abc = col, abr = row;
+    if (p.mode == 0) {
+      // sg_align's coordinates (mia.c:1568-1610); runs go out in forward-reference orientation
+      int start = abc, end = aec;
+      if (s == 1) {                                                     // c2rcc, mia.c:26-30; revcom_PWAF reverses the columns
+        start = p.seq_len - (aec % p.seq_len) - 1;
+        end = p.seq_len - (abc % p.seq_len) - 1;
+      } else {
+        for (int a = 0, b = nrun - 1; a < b; a++, b--) { uint16_t x = my_runs[a]; my_runs[a] = my_runs[b]; my_runs[b] = x; }
+      }
+      int as = start, ae = end;
+      if (as > ae) ae = p.seq_len + as;                                 // mia.c:1600-1604
+      if (end > p.seq_len) end -= p.seq_len;                            // mia.c:1606-1610
+      p.as_out[rd] = as; p.ae_out[rd] = ae; p.start[rd] = start; p.end[rd] = end;
+      p.rc_out[rd] = (uint8_t)s;
+      p.fw_score[rd] = best[0]; p.rc_score[rd] = best[1];
+      p.abr[rd] = s == 1 ? 0 : abr;                                     // row of the returned runs' first base in the STORED orientation
+    } else {
+      for (int a = 0, b = nrun - 1; a < b; a++, b--) { uint16_t x = my_runs[a]; my_runs[a] = my_runs[b]; my_runs[b] = x; }
+      p.as_out[rd] = abc; p.ae_out[rd] = aec;                           // window starts at 0: mia_main.c:209-212, 250-255
+      p.abr[rd] = abr;
+    }
+    p.score[rd] = score;
+    p.n_runs[rd] = nrun;
+    p.status[rd] = st;
+  }
+}
+
 // dynamic smem: [prof PROF_INTS ints][rowoff WARPS*256 u16]
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) strip_kernel(StripParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
@@ -312,79 +404,114 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) strip_kernel(StripParams
         __syncwarp();
       }
     }
-    // ---- strand pick: fw only if strictly better (mia.c:1549-1554)
-    const int s = (nstrand == 2 && !(best[0] > best[1])) ? 1 : 0;
-    const int score = best[s];
-    const int aec = bcol[s];
-    // ---- traceback: re-run the chunks the path crosses, with trace
-    const uint32_t* mask = masked ? mask0 + s * p.mask_words : nullptr;
-    const int32_t* ids = ids0 + s * p.max_chunks;
-    const int4* ck = ck0 + (int64_t)s * (p.max_chunks + 1) * p.Lmax;
-    int row = L - 1, col = aec, nrun = 0, curM = 0, ncols = 0, loaded = -1;
-    uint16_t* my_runs = p.runs + (int64_t)rd * MAX_RUNS;
-    auto push = [&](int type, int len) {
-      while (len > 0) {                                                  // a run longer than 14 bits is split
-        const int l = min(len, 0x3fff);
-        if (nrun < MAX_RUNS && lane == 0) my_runs[nrun] = (uint16_t)((type << 14) | l);
-        nrun++; len -= l;
-      }
-    };
-    bool lost = false;
-    while (row > 0 && col > 0) {
-      const int ch = col / CW;
-      if (ch != loaded) {
-        int q = -1;                                                      // position of chunk ch in the processed list
-        for (int base = 0; base < nch[s]; base += 32) {
-          const bool hit = base + lane < nch[s] && ids[base + lane] == ch;
-          const unsigned bal = __ballot_sync(0xffffffffu, hit);
-          if (bal) { q = base + __ffs(bal) - 1; break; }
-        }
-        if (q < 0) { lost = true; break; }                               // cannot happen: the path only visits unmasked cells
-        int dummy_b = INT_MIN, dummy_c = 0;
-        __syncwarp();
-        strip_chunk<true>(L, len1, ch * CW, p.ref_codes[s], mask, rowoff, prof_base, ck + (int64_t)q * p.Lmax,
-                          q > 0 && ids[q - 1] == ch - 1, q > 0, nullptr, trace, dummy_b, dummy_c);
-        __syncwarp();
-        loaded = ch;
-      }
-      const int t = __ldcg(trace + (int64_t)row * CW + (col - ch * CW));
-      if (t == col || t == -row) break;                                  // mia.c:617-618
-      curM++;
-      if (t == 0) { row--; col--; }
-      else if (t < 0) { push(MIAGPU_RUN_M, curM); ncols += curM; curM = 0; push(MIAGPU_RUN_I, row - 1 + t); ncols += row - 1 + t; row = -t; col--; }
-      else { push(MIAGPU_RUN_M, curM); ncols += curM; curM = 0; push(MIAGPU_RUN_D, col - 1 - t); ncols += col - 1 - t; col = t; row--; }
+    strip_finish(p, rd, L, nstrand, masked, best, bcol, nch, mask0, ids0, ck0, trace, rowoff, prof_base);
+  }
+}
+
+// The same for FEW reads with MANY chunks to sweep (a strand the k-mer filter saturated, an unmasked strand, a wide
+// realign window): a block of TEAM_WARPS warps takes one read; warp w sweeps processed chunks w, w + TEAM_WARPS, ...,
+// each one row behind the warp that holds the chunk to its left (strip_chunk's PIPE mode: row r of a chunk needs only
+// row r-1 / the row-r candidate state of the chunks before it).  L + chunks/TEAM_WARPS row steps instead of L * chunks.
+// dynamic smem: [prof PROF_INTS ints][rowoff 256 u16][flags max_chunks ints]
+constexpr int TEAM_WARPS = 16;
+__global__ void __launch_bounds__(TEAM_WARPS * 32) strip_team_kernel(StripParams p) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  int32_t* s_prof = reinterpret_cast<int32_t*>(smem);
+  uint16_t* rowoff = reinterpret_cast<uint16_t*>(smem + PROF_INTS * 4);
+  volatile int* s_flag = reinterpret_cast<volatile int*>(smem + PROF_INTS * 4 + MAX_READ * 2);
+  __shared__ int s_item, s_hits[2], s_n, s_wb[TEAM_WARPS], s_wc[TEAM_WARPS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < PROF_INTS; i += blockDim.x) s_prof[i] = p.prof[i];
+  __syncthreads();
+  const uint32_t prof_base = smem_u32(s_prof);
+  const int64_t gw = blockIdx.x;
+  uint32_t* mask0 = p.mask + gw * 2 * p.mask_words;
+  int4* ck0 = p.ckpt + gw * 2 * (int64_t)(p.max_chunks + 1) * p.Lmax;
+  int32_t* ids0 = p.chunk_ids + gw * 2 * p.max_chunks;
+  int32_t* trace = p.trace + gw * (int64_t)p.Lmax * CW;
+  const int total = p.n_list_ptr ? *p.n_list_ptr : (p.mode == 0 && !p.list) ? (int)p.n : p.n_list;
+  const int len1 = p.len1;
+  const int n_chunks_all = (len1 + CW - 1) / CW;
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_item = atomicAdd(p.counter, 1);
+    __syncthreads();
+    const int item = s_item;
+    if (item >= total) break;
+    const int rd = p.list ? p.list[item] : item;
+    const int64_t o0 = p.off[rd];
+    const int L = (int)(p.off[rd + 1] - o0);
+    const uint8_t* read = p.bases + o0;
+    if (L <= 0 || L > MAX_READ) {
+      if (tid == 0) { p.status[rd] = MIAGPU_ST_UNSUPPORTED; p.n_runs[rd] = -1; p.score[rd] = INT_MIN; if (p.hits) p.hits[rd] = 0; }
+      continue;
     }
-    push(MIAGPU_RUN_M, curM + 1); ncols += curM + 1;
-    if (lane == 0) {
-      uint8_t st = lost ? MIAGPU_ST_UNSUPPORTED : MIAGPU_ST_OK;
-      if (nrun > MAX_RUNS) { st |= MIAGPU_ST_RUNS_OVERFLOW; nrun = -1; }
-      if (ncols > 2 * MAX_READ) st |= MIAGPU_ST_STR_OVERFLOW;
-      const int abc = col, abr = row;
-      if (p.mode == 0) {
-        // sg_align's coordinates (mia.c:1568-1610); runs go out in forward-reference orientation
-        int start = abc, end = aec;
-        if (s == 1) {                                                     // c2rcc, mia.c:26-30; revcom_PWAF reverses the columns
-          start = p.seq_len - (aec % p.seq_len) - 1;
-          end = p.seq_len - (abc % p.seq_len) - 1;
-        } else {
-          for (int a = 0, b = nrun - 1; a < b; a++, b--) { uint16_t x = my_runs[a]; my_runs[a] = my_runs[b]; my_runs[b] = x; }
+    const int nstrand = p.mode == 0 ? 2 : 1;
+    const int mat = p.mode == 0 ? 0 : (p.rc_in[rd] ? 1 : 0);             // pass 1 scores BOTH strands with the forward matrix (H5)
+    for (int r = tid; r < L; r += blockDim.x) rowoff[r] = (uint16_t)(prof_row_index(mat, sm_depth(r, L), base_code(read[r])) * 4);
+    const bool masked = p.mode == 0 && p.k > 0;
+    if (masked) {
+      for (int w = tid; w < 2 * p.mask_words; w += blockDim.x) mask0[w] = 0;
+      __syncthreads();
+      if (warp == 0) {
+        int h0 = 0, h1 = 0;
+        if (L >= p.k) {
+          h0 = seed_strand(p.kt[0], p.k, read, L, len1, 0, mask0, p.mask_words);
+          h1 = seed_strand(p.kt[1], p.k, read, L, len1, 1, mask0 + p.mask_words, p.mask_words);
         }
-        int as = start, ae = end;
-        if (as > ae) ae = p.seq_len + as;                                 // mia.c:1600-1604
-        if (end > p.seq_len) end -= p.seq_len;                            // mia.c:1606-1610
-        p.as_out[rd] = as; p.ae_out[rd] = ae; p.start[rd] = start; p.end[rd] = end;
-        p.rc_out[rd] = (uint8_t)s;
-        p.fw_score[rd] = best[0]; p.rc_score[rd] = best[1];
-        p.abr[rd] = s == 1 ? 0 : abr;                                     // row of the returned runs' first base in the STORED orientation
-      } else {
-        for (int a = 0, b = nrun - 1; a < b; a++, b--) { uint16_t x = my_runs[a]; my_runs[a] = my_runs[b]; my_runs[b] = x; }
-        p.as_out[rd] = abc; p.ae_out[rd] = aec;                           // window starts at 0: mia_main.c:209-212, 250-255
-        p.abr[rd] = abr;
+        if (lane == 0) { s_hits[0] = h0; s_hits[1] = h1; }
       }
-      p.score[rd] = score;
-      p.n_runs[rd] = nrun;
-      p.status[rd] = st;
+    } else if (tid == 0) { s_hits[0] = 1; s_hits[1] = 0; }
+    __syncthreads();
+    const int hits[2] = {s_hits[0], s_hits[1]};
+    if (p.hits && tid == 0) p.hits[rd] = hits[0] + hits[1];
+    if (masked && hits[0] + hits[1] == 0) {                              // mia_main.c:781: the read is not aligned at all
+      if (tid == 0) { p.status[rd] = MIAGPU_ST_SKIPPED; p.n_runs[rd] = 0; p.score[rd] = INT_MIN; }
+      continue;
     }
+    int best[2] = {INT_MIN, INT_MIN}, bcol[2] = {0, 0}, nch[2] = {0, 0};
+    for (int s = 0; s < nstrand; s++) {
+      const uint32_t* mask = masked ? mask0 + s * p.mask_words : nullptr;
+      int32_t* ids = ids0 + s * p.max_chunks;
+      int4* ck = ck0 + (int64_t)s * (p.max_chunks + 1) * p.Lmax;
+      if (warp == 0) {                                                   // chunk list: chunks with at least one unmasked column
+        int n = 0;
+        for (int base = 0; base < n_chunks_all; base += 32) {
+          const int ch = base + lane;
+          bool any = false;
+          if (ch < n_chunks_all) {
+            if (!mask) any = true;
+            else for (int w = 0; w < CW / 32; w++) { const int wi = ch * (CW / 32) + w; if (wi < p.mask_words && __ldcg(mask + wi)) any = true; }
+          }
+          const unsigned bal = __ballot_sync(0xffffffffu, any);
+          if (any) ids[n + __popc(bal & ((1u << lane) - 1))] = ch;
+          n += __popc(bal);
+        }
+        if (lane == 0) s_n = n;
+      }
+      for (int q = tid; q < n_chunks_all; q += blockDim.x) s_flag[q] = 0;
+      __syncthreads();
+      const int n = s_n;
+      nch[s] = n;
+      int wb = INT_MIN, wc = 0x7fffffff;
+      for (int q = warp; q < n; q += TEAM_WARPS) {
+        const int ch = ids[q];
+        strip_chunk<false, true>(L, len1, ch * CW, p.ref_codes[s], mask, rowoff, prof_base, ck + (int64_t)q * p.Lmax,
+                                 q > 0 && ids[q - 1] == ch - 1, q > 0, ck + (int64_t)(q + 1) * p.Lmax, nullptr, wb, wc,
+                                 q > 0 ? s_flag + (q - 1) : nullptr, s_flag + q);
+        __syncwarp();
+      }
+      if (lane == 0) { s_wb[warp] = wb; s_wc[warp] = wc; }
+      __syncthreads();
+      // the reference's scan starts at column 0: S[L-1][0] (HIM if masked) is the first incumbent; first maximum in column order
+      int b = HIM, bc = 0;
+      for (int w = 0; w < TEAM_WARPS; w++)
+        if (s_wb[w] > b || (s_wb[w] == b && s_wc[w] < bc)) { b = s_wb[w]; bc = s_wc[w]; }
+      best[s] = b; bcol[s] = bc;
+      __syncthreads();
+    }
+    if (warp == 0) strip_finish(p, rd, L, nstrand, masked, best, bcol, nch, mask0, ids0, ck0, trace, rowoff, prof_base);
   }
 }
 

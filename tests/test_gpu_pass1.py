@@ -131,3 +131,29 @@ def test_pass1_multi_stretch_repeats_and_ties(gpu, oracle, circular, k):
     assert not bad, f"{len(bad)} reads differ; first {bad[0]}"
     fast, general, skipped = gpu.last_pass1_stats()
     assert fast > 700, (fast, general, skipped)             # the repeat reads (3-4 stretches) stay on the fast path
+
+
+@pytest.mark.parametrize("k", [0, 9])
+def test_strip_team_kernel_equals_warp_kernel(gpu, monkeypatch, k):
+    # the general kernel's two schedules (a warp per read / a team of 16 warps per read, chunks pipelined one row apart)
+    # must agree field for field; low-complexity reads saturate the filter (whole strand unmasked)
+    import _pkg
+    _pkg.load()
+    from mia_b200 import synth
+    ref = synth.random_reference(5000, seed=31) + "AC" * 200 + synth.random_reference(3000, seed=32)
+    g = synth.diverge(ref, 0.03, seed=33, indel_rate=0.006)
+    b, off, _ = synth.make_reads(g, 500, 30, 140, seed=34)
+    gpu.set_pssm(gpu_checks.load_pssm("ancient"))
+    gpu.set_reference(ref, circular=1, with_rc=1)
+    gpu.build_kmers(k)
+    gpu.upload_reads(b, off)
+    monkeypatch.setenv("MIAGPU_PASS1_FAST", "0")
+    monkeypatch.setenv("MIAGPU_STRIP_TEAM", "0")
+    a = gpu.pass1()
+    monkeypatch.setenv("MIAGPU_STRIP_TEAM", "1")
+    z = gpu.pass1()
+    for key in ("hits", "score", "fw_score", "rc_score", "rc", "as_", "ae", "start", "end", "abr", "n_runs", "status"):
+        assert (a[key] == z[key]).all(), (key, int((a[key] != z[key]).sum()))
+    nr = np.maximum(a["n_runs"], 0)
+    m = np.arange(a["runs"].shape[1])[None, :] < nr[:, None]
+    assert (np.where(m, a["runs"], 0) == np.where(m, z["runs"], 0)).all()
