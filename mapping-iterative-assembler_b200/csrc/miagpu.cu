@@ -53,7 +53,7 @@ struct DevBuf {
 
 constexpr int NBUCKET = 10;                                  // 9 register-tiled widths + "big"
 static const int BUCKET_K[NBUCKET] = {2, 4, 5, 6, 7, 8, 10, 12, 16, 0};
-static const int P16_COLS[P16_NKB] = {128, 144, 160, 176, 192, 208, 224, 256};   // columns of the pair kernels' width classes
+static const int P16_COLS[P16_NKB] = {128, 144, 160, 176, 192, 208, 224, 256, 64, 80, 96, 112};   // columns of the pair kernels' width classes
 
 constexpr int MAX_CHUNKS = 16;
 
@@ -593,16 +593,17 @@ static int launch_strip(miagpu_ctx* c, int mode, const int32_t* list, int n_list
   // few reads: a team of warps per read (strip_team_kernel), else a warp per read
   bool team = total <= (int64_t)2 * c->num_sms * 4;
   if (const char* e = getenv("MIAGPU_STRIP_TEAM")) team = atoi(e) != 0;
-  const size_t smem = team ? PROF_INTS * 4 + MAX_READ * 2 + (size_t)n_chunks * 4 : PROF_INTS * 4 + WARPS_PER_BLOCK * MAX_READ * 2;
+  const size_t smem = team ? PROF_INTS * 4 + MAX_READ * 2 + (size_t)((n_chunks + 3) & ~3) * 4 + (size_t)2 * TEAM_WARPS * Lmax * 16
+                           : PROF_INTS * 4 + WARPS_PER_BLOCK * MAX_READ * 2;
   if (team && smem > 200 * 1024) team = false;
   int per_sm = 0;
   if (team) {
-    if (smem > 48 * 1024) MIAGPU_CUDA(cudaFuncSetAttribute(strip_team_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 40 * 1024) MIAGPU_CUDA(cudaFuncSetAttribute(strip_team_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // + static
     MIAGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, strip_team_kernel, TEAM_WARPS * 32, smem));
   } else {
     MIAGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, strip_kernel, WARPS_PER_BLOCK * 32, smem));
   }
-  if (per_sm < 1) { set_error("strip_kernel does not fit on an SM"); return 0; }
+  if (per_sm < 1) { set_error("strip_kernel does not fit on an SM (team %d, %zu bytes of shared memory, Lmax %d, %d chunks)", (int)team, smem, Lmax, n_chunks); return 0; }
   // per-warp (per-team) scratch: keep the total under ~6 GB
   const size_t per_warp = (size_t)2 * mask_words * 4 + (size_t)2 * (n_chunks + 1) * Lmax * 16 + (size_t)2 * n_chunks * 4 + (size_t)Lmax * CW * 4;
   const int units_per_block = team ? 1 : WARPS_PER_BLOCK;
@@ -817,7 +818,8 @@ static int realign_launch(miagpu_ctx* c, const RealignJob& j) {
         case 4: ok = launch_pair16<12, 16>(c, p, ni, maxL); break;
         case 5: ok = launch_pair16<13, 16>(c, p, ni, maxL); break;
         case 6: ok = launch_pair16<14, 16>(c, p, ni, maxL); break;
-        default: ok = launch_pair16<16, 16>(c, p, ni, maxL); break;
+        case 7: ok = launch_pair16<16, 16>(c, p, ni, maxL); break;
+        default: set_error("pair class %d holds no realign window", kb); ok = 0; break;
       }
       if (!ok) return 0;
       if (j.timed) MIAGPU_CUDA(cudaEventRecord(c->pev[2 * kb + 1], c->stream));
@@ -965,7 +967,7 @@ extern "C" int miagpu_last_buckets(miagpu_ctx* c, int32_t* k, int32_t* reads, in
 
 extern "C" int miagpu_last_pair_buckets(miagpu_ctx* c, int32_t* k, int32_t* reads, int32_t* pairs, int64_t* cells, float* ms, int32_t* fallback_reads, int32_t* max_len16) {
   if (!c) { set_error("miagpu_last_pair_buckets: NULL ctx"); return 0; }
-  for (int kb = 0; kb < P16_NKB; kb++) {
+  for (int kb = 0; kb < P16_NKB_WIDE; kb++) {            // MIAGPU_NPAIRCLASS slots: the classes realign windows use
     if (k) k[kb] = P16_COLS[kb] / c->pair_g;
     if (reads) reads[kb] = c->pair_reads[kb];
     if (pairs) pairs[kb] = c->pair_pairs[kb];
@@ -2186,7 +2188,11 @@ static int pass1_fast(miagpu_ctx* c, const PairLmax& lm) {
         case 4: ok = launch_pair16<12, 16, true>(c, p, ni, P16_MAXL); break;
         case 5: ok = launch_pair16<13, 16, true>(c, p, ni, P16_MAXL); break;
         case 6: ok = launch_pair16<14, 16, true>(c, p, ni, P16_MAXL); break;
-        default: ok = launch_pair16<16, 16, true>(c, p, ni, P16_MAXL); break;
+        case 7: ok = launch_pair16<16, 16, true>(c, p, ni, P16_MAXL); break;
+        case 8: ok = launch_pair16<4, 16, true>(c, p, ni, P16_MAXL); break;
+        case 9: ok = launch_pair16<5, 16, true>(c, p, ni, P16_MAXL); break;
+        case 10: ok = launch_pair16<6, 16, true>(c, p, ni, P16_MAXL); break;
+        default: ok = launch_pair16<7, 16, true>(c, p, ni, P16_MAXL); break;
       }
       if (!ok) return 0;
       base += ni;

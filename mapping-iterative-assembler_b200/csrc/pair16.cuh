@@ -51,7 +51,9 @@ namespace miagpu {
 
 constexpr int P16_MAXL = 144;                       // rows the shared row-offset arrays hold
 constexpr int PROF16_N = 2 * NMAT * 5 * PROF_ROW_INTS;   // int16 entries
-constexpr int P16_NKB = 8;                          // width classes: 128 / 144 / 160 / 176 / 192 / 208 / 224 / 256 columns (K = columns / 16)
+constexpr int P16_NKB = 12;                         // width classes: 128 / 144 / 160 / 176 / 192 / 208 / 224 / 256 columns (K = columns / 16),
+                                                    // then the narrow classes of pass-1 jobs: 64 / 80 / 96 / 112 (K = 4 .. 7)
+constexpr int P16_NKB_WIDE = 8;                     // classes reiterate_assembly's windows use (a window is at least 100 columns + the read)
 constexpr int P16_TAB_WORDS = 64;                   // 25 64-bit entries, padded to 32
 
 // OFF of the lane frame: the lowest intermediate, (lowest cell = -OFF-GOP-GEP+min entry) converted to the next lane
@@ -65,6 +67,10 @@ __host__ __device__ inline int p16_lmax(int K, int max_entry) {
 __host__ __device__ inline int p16_class(int len1) {
   return len1 <= 128 ? 0 : len1 <= 144 ? 1 : len1 <= 160 ? 2 : len1 <= 176 ? 3 : len1 <= 192 ? 4 : len1 <= 208 ? 5 : len1 <= 224 ? 6 : len1 <= 256 ? 7 : -1;
 }
+// pass-1 jobs (a stretch is about L + 20 columns): the narrow classes first
+__host__ __device__ inline int p16_job_class(int len1) {
+  return len1 <= 64 ? 8 : len1 <= 80 ? 9 : len1 <= 96 ? 10 : len1 <= 112 ? 11 : p16_class(len1);
+}
 __host__ __device__ inline int bucket32_of(int len1) {
   return len1 <= 64 ? 0 : len1 <= 128 ? 1 : len1 <= 160 ? 2 : len1 <= 192 ? 3 : len1 <= 224 ? 4 : len1 <= 256 ? 5 : len1 <= 320 ? 6 : len1 <= 384 ? 7 : len1 <= 512 ? 8 : 9;
 }
@@ -77,19 +83,21 @@ constexpr int META_WORK = 16;        // [16] dynamic work-fetch counters of the 
 constexpr int META_MAXL = 32;        // [16] longest read per width class (all reads of the class)
 constexpr int META_CELLS = 48;       // [16] int64 DP cells per width class (all reads of the class)
 constexpr int META_POP = 80;         // [16] reads per width class (direct + pair-eligible)
-constexpr int META_NPAIRS = 96;      // [8]  work items per pair class
-constexpr int META_PWORK = 104;      // [8]  work-fetch counters of the pair kernels
-constexpr int META_PREADS = 112;     // [8]  eligible reads per pair class
-constexpr int META_PCELLS = 120;     // [8]  int64 cells of the eligible reads
-constexpr int META_MAXLEN = 136;     // scratch of max_len_kernel
-constexpr int META_NFALL = 137;      // reads handed from the pair kernels to the 32-bit kernels
-constexpr int META_HOST = 144;       // words copied to the host after classification
+constexpr int META_NPAIRS = 96;      // [12] work items per pair class
+constexpr int META_PWORK = 108;      // [12] work-fetch counters of the pair kernels
+constexpr int META_PREADS = 120;     // [12] eligible reads per pair class
+constexpr int META_PCELLS = 132;     // [12] int64 cells of the eligible reads
+constexpr int META_MAXLEN = 156;     // scratch of max_len_kernel
+constexpr int META_NFALL = 157;      // reads handed from the pair kernels to the 32-bit kernels
+constexpr int META_P1 = 158;         // [6]  pass-1 counters (pass1.cuh)
+constexpr int META_HOST = 168;       // words copied to the host after classification
 constexpr int P16_KEYS = P16_NKB * (P16_MAXL + 1);
+constexpr int META_KEYS = 1792;      // room per key table
 constexpr int META_HIST = 256;       // [P16_KEYS] eligible reads per (pair class, read length)
-constexpr int META_PSTART = META_HIST + 1280;    // [P16_KEYS] first pair of the key
-constexpr int META_CURSOR = META_PSTART + 1280;  // [P16_KEYS] scatter cursors
-constexpr int META_WORDS = META_CURSOR + 1280;
-static_assert(P16_NKB * (P16_MAXL + 1) <= 1280 && P16_NKB == 8, "meta layout");
+constexpr int META_PSTART = META_HIST + META_KEYS;    // [P16_KEYS] first pair of the key
+constexpr int META_CURSOR = META_PSTART + META_KEYS;  // [P16_KEYS] scatter cursors
+constexpr int META_WORDS = META_CURSOR + META_KEYS;
+static_assert(P16_KEYS <= META_KEYS && P16_NKB == 12 && META_PCELLS % 2 == 0, "meta layout");
 
 struct Pair16Params {
   const uint8_t* bases;
@@ -183,7 +191,7 @@ __host__ __device__ constexpr int p16_smem_fixed() {
 //   Everything to the left / right of the stretch is HIM and can neither be chosen nor become the best end cell.
 //   Outputs are per job, in strand coordinates: as_out = abc, ae_out = aec.
 template <int K, int G, bool JOB>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, (K <= 12 ? 5 : 4)) pair16_kernel(Pair16Params p) {
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, (K <= 5 ? 8 : K <= 7 ? 6 : K <= 12 ? 5 : 4)) pair16_kernel(Pair16Params p) {
   static_assert(K >= 4 && K <= 16 && G == 16, "columns per lane / lanes per pair");
   constexpr int NP = 32 / G;                         // pairs per warp
   constexpr int NE = (25 + G - 1) / G;               // table entries a lane builds per row

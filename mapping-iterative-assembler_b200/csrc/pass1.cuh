@@ -31,13 +31,13 @@
 namespace miagpu {
 
 // p1 meta block (int32 words) -- laid out like the realign meta block where pair_layout / pair_scatter read it
-constexpr int P1_NGENERAL = 138;     // reads handed to the general kernel (list fill counter)
-constexpr int P1_NFAST = 139;        // reads finished by the pair kernels
-constexpr int P1_NSKIPPED = 140;     // reads without a k-mer hit
-constexpr int P1_WORK = 141;         // work-fetch counter of the general kernel
+constexpr int P1_NGENERAL = META_P1;      // reads handed to the general kernel (list fill counter)
+constexpr int P1_NFAST = META_P1 + 1;     // reads finished by the pair kernels
+constexpr int P1_NSKIPPED = META_P1 + 2;  // reads without a k-mer hit
+constexpr int P1_WORK = META_P1 + 3;      // work-fetch counter of the general kernel
 
-constexpr int P1_WORK2 = 143;        // work-fetch counter of the general kernel's second launch (reads the merge handed over)
-constexpr int P1_NJOBS = 142;        // jobs allocated (may exceed the capacity: reads that did not fit go to the general kernel)
+constexpr int P1_WORK2 = META_P1 + 5;       // work-fetch counter of the general kernel's second launch (reads the merge handed over)
+constexpr int P1_NJOBS = META_P1 + 4;       // jobs allocated (may exceed the capacity: reads that did not fit go to the general kernel)
 constexpr int P1_JPS = 12;           // stretches per strand that become jobs
 constexpr int P1_MAXD = 128;         // diagonals kept per strand: KMER_SATURATE hits unmask the whole strand anyway
 
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(256) p1_seed_kernel(P1SeedParams p) {
         int a = st[s].lo[t] - ALIGN_MASK_BUFFER, z = st[s].hi[t] + span - ALIGN_MASK_BUFFER;
         if (a < 0) a = 0;
         if (z >= p.len1) z = p.len1 - 1;
-        const int kb = z < a ? -1 : p16_class(z - a + 1);
+        const int kb = z < a ? -1 : p16_job_class(z - a + 1);
         if (kb < 0 || L > p.lm.v[kb]) { fast = false; break; }
         if (t > 0 && !(GEP * (a - prev_z - 1) > need)) { fast = false; break; }
         prev_z = z;
@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(256) p1_seed_kernel(P1SeedParams p) {
       for (int s = 0; s < 2; s++)
         for (int t = 0; t < st[s].n; t++, job++) {
           const int a = st[s].lo[t], wl = st[s].hi[t] - a + 1;
-          const int kb = p16_class(wl);
+          const int kb = p16_job_class(wl);
           p.jkind[job] = (uint8_t)(16 + kb);
           p.jws[job] = s * p.strand_stride + a;
           p.jwl[job] = wl;

@@ -75,12 +75,13 @@ __device__ __forceinline__ PV pv_better(PV a, PV b) { return (b.v > a.v) ? b : a
 // ck_out: written for the next processed chunk.  Returns via best/best_col the running first-max of the last row.
 // PIPE (strip_team_kernel): the previous processed chunk is swept by ANOTHER warp of the block at the same time, one row
 // ahead: row r waits until *flag_prev > r (that warp has written its row r candidate state and its row r-1 scores) and
-// announces its own progress through *flag_mine.
+// announces its own progress through *flag_mine.  The hand-over goes through shared memory (ring_in = that warp's
+// per-row {S1, S2, PV, PI}, ring_out = mine); the global checkpoints are still written, for the traceback.
 template <bool TRACE, bool PIPE = false>
 __device__ void strip_chunk(const int L, const int len1, const int c0, const uint8_t* __restrict__ ref, const uint32_t* __restrict__ mask,
                             const uint16_t* rowoff, const uint32_t prof_base, const int4* ck_in, const bool adjacent, const bool have_in,
                             int4* ck_out, int32_t* trace, int& best, int& best_col, volatile int* flag_prev = nullptr,
-                            volatile int* flag_mine = nullptr) {
+                            volatile int* flag_mine = nullptr, volatile int* ring_in = nullptr, volatile int* ring_out = nullptr) {
   const int lane = threadIdx.x & 31;
   const int cbase = c0 + lane * SK;
   int code4[SK];
@@ -103,7 +104,10 @@ __device__ void strip_chunk(const int L, const int len1, const int c0, const uin
       RV[j] = INT_MIN; RI[j] = 0;
     }
   }
-  if (ck_out && lane == 31) ck_out[0] = make_int4(Sp[SK - 1], Sp[SK - 2], 0, 0);
+  if (ck_out && lane == 31) {
+    ck_out[0] = make_int4(Sp[SK - 1], Sp[SK - 2], 0, 0);
+    if (PIPE) { ring_out[0] = Sp[SK - 1]; ring_out[1] = Sp[SK - 2]; }
+  }
   for (int r = 1; r < L; r++) {
     const uint32_t pa = prof_base + rowoff[r];
     const int N = -(GOP + GEP * (r + 1));                                // sg5 = 1 on every path that reaches here
@@ -116,13 +120,20 @@ __device__ void strip_chunk(const int L, const int len1, const int c0, const uin
         while (*flag_prev <= r) {}
         __threadfence_block();
       }
-      int4 ci = have_in ? (PIPE ? __ldcg(ck_in + r - 1) : ck_in[r - 1]) : make_int4(HIM, HIM, 0, 0);
+      int4 ci = make_int4(HIM, HIM, 0, 0);
+      if (have_in) {
+        if (PIPE) { ci.x = ring_in[4 * (r - 1)]; ci.y = ring_in[4 * (r - 1) + 1]; }
+        else ci = ck_in[r - 1];
+      }
       l1 = adjacent ? ci.x : HIM;
       l2 = adjacent ? ci.y : HIM;
       // best_gap_col entering this chunk at row r: the previous processed chunk's state, or the row-start
       // state bgc = 0 (mia.c:825) = (S[r-1][0], 0)
       if (c0 == 0) seed = PV{Sp[0], 0};
-      else if (have_in) { int4 cr = PIPE ? __ldcg(ck_in + r) : ck_in[r]; seed = PV{cr.z, cr.w}; }
+      else if (have_in) {
+        if (PIPE) seed = PV{ring_in[4 * r + 2], ring_in[4 * r + 3]};
+        else { int4 cr = ck_in[r]; seed = PV{cr.z, cr.w}; }
+      }
       else seed = PV{HIM, 0};
     }
     // candidates: column k = c-2 joins when column c is unmasked and c >= 2 (mia.c:827-843)
@@ -146,7 +157,11 @@ __device__ void strip_chunk(const int L, const int len1, const int c0, const uin
     if (lane == 0) P = seed;
     if (ck_out && lane == 31) {
       ck_out[r] = make_int4(0, 0, t.v, t.i);                            // S1/S2 patched below
-      if (PIPE) { __threadfence_block(); *flag_mine = r + 1; }          // row r-1's scores went out before (program order)
+      if (PIPE) {
+        ring_out[4 * r + 2] = t.v; ring_out[4 * r + 3] = t.i;
+        __threadfence_block();
+        *flag_mine = r + 1;                                             // row r-1's scores went out before (program order)
+      }
     }
 
     int D = l1;
@@ -176,7 +191,10 @@ __device__ void strip_chunk(const int L, const int len1, const int c0, const uin
       D = Sp[j];
       Sp[j] = S;
     }
-    if (ck_out && lane == 31) { ck_out[r].x = Sp[SK - 1]; ck_out[r].y = Sp[SK - 2]; }
+    if (ck_out && lane == 31) {
+      ck_out[r].x = Sp[SK - 1]; ck_out[r].y = Sp[SK - 2];
+      if (PIPE) { ring_out[4 * r] = Sp[SK - 1]; ring_out[4 * r + 1] = Sp[SK - 2]; }
+    }
     if (TRACE) {
       int4* trow = reinterpret_cast<int4*>(trace + (int64_t)r * CW + lane * SK);
       trow[0] = make_int4(tr[0], tr[1], tr[2], tr[3]);
@@ -412,13 +430,17 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) strip_kernel(StripParams
 // realign window): a block of TEAM_WARPS warps takes one read; warp w sweeps processed chunks w, w + TEAM_WARPS, ...,
 // each one row behind the warp that holds the chunk to its left (strip_chunk's PIPE mode: row r of a chunk needs only
 // row r-1 / the row-r candidate state of the chunks before it).  L + chunks/TEAM_WARPS row steps instead of L * chunks.
-// dynamic smem: [prof PROF_INTS ints][rowoff 256 u16][flags max_chunks ints]
+// A warp alternates between two rings from one of its chunks to the next: when it re-uses a ring (two chunks later, 2 *
+// TEAM_WARPS chunks further right) its own previous chunk is finished, hence -- every chunk trails its left neighbour --
+// so is the reader of the ring's old content, which the next warp swept before ITS previous chunk.
+// dynamic smem: [prof PROF_INTS ints][rowoff 256 u16][flags max_chunks ints][rings 2 x TEAM_WARPS x Lmax x 4 ints]
 constexpr int TEAM_WARPS = 16;
 __global__ void __launch_bounds__(TEAM_WARPS * 32) strip_team_kernel(StripParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   int32_t* s_prof = reinterpret_cast<int32_t*>(smem);
   uint16_t* rowoff = reinterpret_cast<uint16_t*>(smem + PROF_INTS * 4);
   volatile int* s_flag = reinterpret_cast<volatile int*>(smem + PROF_INTS * 4 + MAX_READ * 2);
+  volatile int* s_ring = s_flag + ((p.max_chunks + 3) & ~3);
   __shared__ int s_item, s_hits[2], s_n, s_wb[TEAM_WARPS], s_wc[TEAM_WARPS];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < PROF_INTS; i += blockDim.x) s_prof[i] = p.prof[i];
@@ -499,7 +521,9 @@ __global__ void __launch_bounds__(TEAM_WARPS * 32) strip_team_kernel(StripParams
         const int ch = ids[q];
         strip_chunk<false, true>(L, len1, ch * CW, p.ref_codes[s], mask, rowoff, prof_base, ck + (int64_t)q * p.Lmax,
                                  q > 0 && ids[q - 1] == ch - 1, q > 0, ck + (int64_t)(q + 1) * p.Lmax, nullptr, wb, wc,
-                                 q > 0 ? s_flag + (q - 1) : nullptr, s_flag + q);
+                                 q > 0 ? s_flag + (q - 1) : nullptr, s_flag + q,
+                                 s_ring + (size_t)((((q - 1) / TEAM_WARPS) & 1) * TEAM_WARPS + (q + TEAM_WARPS - 1) % TEAM_WARPS) * p.Lmax * 4,
+                                 s_ring + (size_t)(((q / TEAM_WARPS) & 1) * TEAM_WARPS + warp) * p.Lmax * 4);
         __syncwarp();
       }
       if (lane == 0) { s_wb[warp] = wb; s_wc[warp] = wc; }
