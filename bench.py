@@ -45,11 +45,11 @@ def load_pssm(name="onepass"):
     return np.load(os.path.join(ROOT, "tests", "golden", "pssm.npz"))[name]
 
 
-def make_workload(n_reads, seed):
+def make_workload(n_reads, seed, ref=None):
     import _pkg
     _pkg.load()
     from mia_b200 import synth
-    ref = synth.random_reference(REF_LEN, seed=1)
+    ref = ref or synth.random_reference(REF_LEN, seed=1)
     genome = synth.diverge(ref, 0.005, seed=2)
     bases, off, truth = synth.make_reads(genome, n_reads, 35, 75, seed=seed)
     rc = truth["strand"].astype(np.uint8)
@@ -309,6 +309,9 @@ def run_ours(args):
         "consensus_matches_e2e": bool(cons == cons_e2e),
         "score_cut": g.last_cut_stats(),
     }
+    # ---- the same round on R-mt (the reference's mt311 consensus, real composition and low-complexity stretches)
+    if world == 1 and not args.no_rmt:
+        line["r_mt"] = rmt_numbers(g, args, flush, lib_stream)
     # ---- pass 1 (k-mer seeding + whole-reference both-strand DP), reported beside the headline
     if world == 1 and not args.no_pass1:
         line["pass1"] = pass1_numbers(g, ref, bases, off, rc, args)
@@ -320,7 +323,44 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def pass1_numbers(g, ref, stored, off, rc, args):
+def rmt_numbers(g, args, flush, lib_stream):
+    """Resident rounds + k = 12 pass 1 with R-mt as the reference (derived from the reference's mt311 consensus by
+    oracle/pyoracle.write_r_mt at build time, where /root/reference exists; a data file, nothing of oracle/ is executed)."""
+    import torch
+    path = os.path.join(ROOT, "oracle", "_ref", "r_mt.fa")
+    if not os.path.exists(path):
+        return {"unavailable": "oracle/_ref/r_mt.fa was not generated (no /root/reference at build time)"}
+    rmt = "".join(l.strip() for l in open(path) if not l.startswith(">"))
+    n = args.reads
+    ref, bases, off, rc, as_, ae = make_workload(n, seed=2000, ref=rmt)
+    g.set_reference(ref, circular=1, with_rc=0)
+    g.upload_reads(bases, off)
+    g.set_alignment_inputs(rc, as_, ae)
+    g.set_cut_inputs(np.diff(off).astype(np.int32))
+    for _ in range(3):
+        g.reset_dropped()
+        g.iterate_resident()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for k in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        ev[k][0].record(lib_stream)
+        g.reset_dropped()
+        g.iterate_resident()
+        ev[k][1].record(lib_stream)
+        torch.cuda.synchronize()
+    ms = float(sum(a.elapsed_time(b) for a, b in ev)) / args.steps
+    g.realign_resident()
+    cells = g.last_timing()["dp_cells"]
+    _, n_fallback, _ = g.last_pair_buckets()
+    res = {"ref_len": len(ref), "reads": n, "value": n / (ms * 1e-3), "ms_per_step": ms, "gcups": cells / (ms * 1e-3) / 1e9,
+           "reads_handed_to_32bit_kernels": n_fallback}
+    if not args.no_pass1:
+        res["pass1_k12"] = pass1_numbers(g, ref, bases, off, rc, args, only_k12=True)["k12"]
+    return res
+
+
+def pass1_numbers(g, ref, stored, off, rc, args, only_k12=False):
     """Pass 1 on the original (un-revcomped) reads: (a) k = 12 filter on all reads, (b) no filter on a prefix."""
     comp = np.zeros(256, np.uint8)
     for a, b in zip(b"ACGTN", b"TGCAN"):
@@ -332,7 +372,7 @@ def pass1_numbers(g, ref, stored, off, rc, args):
     orig = np.ascontiguousarray(np.where(rc[rid] == 1, comp[stored[src]], stored), np.uint8)
     g.set_reference(ref, circular=1, with_rc=1)
     res = {}
-    for tag, k, m in (("k12", 12, n), ("unmasked", 0, min(n, args.pass1_unmasked_reads))):
+    for tag, k, m in (("k12", 12, n), ("unmasked", 0, min(n, args.pass1_unmasked_reads)))[: 1 if only_k12 else 2]:
         g.build_kmers(k)
         g.upload_reads(orig[: off[m]], off[: m + 1])
         g.pass1()                                   # warm-up
@@ -443,6 +483,7 @@ def main():
     ap.add_argument("--ref-reads-per-core", type=int, default=4000)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-pass1", action="store_true")
+    ap.add_argument("--no-rmt", action="store_true")
     ap.add_argument("--pass1-unmasked-reads", type=int, default=100000)
     args = ap.parse_args()
     if args.impl == "reference":

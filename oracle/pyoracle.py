@@ -28,6 +28,29 @@ def build(ref=True):
     subprocess.run(["make", "-s", "-C", HERE, "oracle"], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     if ref and os.path.exists(os.path.join(REFERENCE_ROOT, "src", "mia.c")):
         subprocess.run(["make", "-s", "-C", HERE, "ref"], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        write_r_mt()
+
+
+R_MT = os.path.join(HERE, "_ref", "r_mt.fa")
+
+
+def write_r_mt():
+    """R-mt of SURVEY.md 8d: the reference's built-in mt311 consensus (src/mt311.c) with the optional (lower-case) bases
+    removed and every IUPAC code replaced by its alphabetically first base -> 16,517 bp with a real mitochondrial
+    composition and real low-complexity stretches.  Derived here, where /root/reference exists; the file lives in the
+    git-ignored oracle/_ref/ and travels to the GPU box with the other built artefacts."""
+    import re
+    src = open(os.path.join(REFERENCE_ROOT, "src", "mt311.c")).read()
+    seq = "".join(re.findall(r'"([A-Za-z]+)"', src[src.index("mt311_sequence"):]))
+    first = dict(R="A", Y="C", S="C", W="A", K="G", M="A", B="C", D="A", H="A", V="A", N="A")
+    out = "".join(first.get(ch, ch) for ch in seq if not ch.islower())
+    assert set(out) <= set("ACGT"), sorted(set(out))
+    os.makedirs(os.path.dirname(R_MT), exist_ok=True)
+    with open(R_MT, "w") as f:
+        f.write(">R-mt mt311 consensus, lower-case removed, IUPAC -> first base\n")
+        for i in range(0, len(out), 60):
+            f.write(out[i:i + 60] + "\n")
+    return len(out)
 
 
 def have_ref():
