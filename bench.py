@@ -484,7 +484,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-pass1", action="store_true")
     ap.add_argument("--no-rmt", action="store_true")
-    ap.add_argument("--pass1-unmasked-reads", type=int, default=100000)
+    ap.add_argument("--pass1-unmasked-reads", type=int, default=1000000)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -15,6 +15,7 @@
 #include "consensus.cuh"
 #include "strip.cuh"
 #include "pass1.cuh"
+#include "sweep16.cuh"
 #include "scorecut.hpp"
 #include "scorecut.cuh"
 #include <cub/device/device_scan.cuh>
@@ -2220,6 +2221,86 @@ static int pass1_fast(miagpu_ctx* c, const PairLmax& lm) {
   return 1;
 }
 
+// Pass 1 without the k-mer filter (sweep16.cuh): both whole strands of every read in one 16-bit sweep, two reads per warp;
+// the merge kernel of the fast path finishes the reads whose winning path is a plain diagonal, the general kernel the rest.
+static int pass1_sweep(miagpu_ctx* c, const PairLmax& lm) {
+  const int64_t n = c->n, nj = 2 * n;
+  if (n > 0x3fffffffLL) { set_error("miagpu_pass1: at most %d reads per batch", 0x3fffffff); return 0; }
+  if (!c->d_jfirst.reserve(n + 1) || !c->d_jcount.reserve(n + 1) || !c->d_jkind.reserve(nj + 1) || !c->d_jstatus.reserve(nj + 1) ||
+      !c->d_route.reserve(n + 1) || !c->d_jscore.reserve(nj + 1) || !c->d_jabc.reserve(nj + 1) || !c->d_jaec.reserve(nj + 1) ||
+      !c->d_jabr.reserve(nj + 1) || !c->d_p1list.reserve(n + 1) || !c->d_p1meta.reserve(META_WORDS) || !c->d_kind.reserve(n + 1) ||
+      !c->d_jpairs.reserve(n + 4 * P16_KEYS + 64)) return 0;
+  cudaStream_t st = c->stream;
+  int32_t* meta = c->d_p1meta.p;
+  const int len1 = c->circular ? c->wrap_len : c->seq_len;
+  MIAGPU_CUDA(cudaMemsetAsync(meta, 0, META_WORDS * sizeof(int32_t), st));
+  SweepPrepParams pp{};
+  pp.n = n; pp.off = c->d_off.p; pp.lmax = lm.v[SW_CLASS]; pp.kind = c->d_kind.p; pp.route = c->d_route.p; pp.jfirst = c->d_jfirst.p;
+  pp.jcount = c->d_jcount.p; pp.jkind = c->d_jkind.p; pp.hits = c->d_hits.p; pp.general_list = c->d_p1list.p; pp.meta = meta;
+  sweep_prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pp, P1_NGENERAL);
+  MIAGPU_CUDA(cudaGetLastError());
+  pair_layout_kernel<<<1, LAYOUT_THREADS, 0, st>>>(meta, 1);
+  MIAGPU_CUDA(cudaGetLastError());
+  MIAGPU_CUDA(cudaEventRecord(c->p1ev[0], st));
+  MIAGPU_CUDA(cudaMemcpyAsync(c->h_meta, meta, sizeof(int32_t) * META_HOST, cudaMemcpyDeviceToHost, st));
+  MIAGPU_CUDA(cudaStreamSynchronize(st));
+  c->launches += 2;
+  int n_pairs = 0, base = 0;
+  for (int kb = 0; kb < P16_NKB; kb++) { if (kb < SW_CLASS) base += c->h_meta[META_NPAIRS + kb]; n_pairs += c->h_meta[META_NPAIRS + kb]; }
+  const int n_items = c->h_meta[META_NPAIRS + SW_CLASS];
+  const int n_general0 = c->h_meta[P1_NGENERAL];
+  if (n_general0) {                                   // reads beyond the 16-bit frame: the general kernel, beside the sweep
+    MIAGPU_CUDA(cudaEventRecord(c->aev[0], st));
+    MIAGPU_CUDA(cudaStreamWaitEvent(c->s_aux[1], c->aev[0], 0));
+    c->launch_stream = c->s_aux[1];
+    const int ok = launch_strip(c, 0, c->d_p1list.p, n_general0, meta + P1_WORK, 0, nullptr);
+    c->launch_stream = st;
+    if (!ok) return 0;
+    MIAGPU_CUDA(cudaEventRecord(c->aev[1], c->s_aux[1]));
+  }
+  if (n_items) {
+    MIAGPU_CUDA(cudaMemsetAsync(c->d_jpairs.p, 0xff, (size_t)2 * n_pairs * sizeof(int32_t), st));
+    pair_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, c->d_off.p, c->d_kind.p, meta, c->d_jpairs.p);
+    MIAGPU_CUDA(cudaGetLastError());
+    Sweep16Params sp{};
+    sp.bases = c->d_bases.p; sp.off = c->d_off.p; sp.pairs = c->d_jpairs.p + 2 * (int64_t)base; sp.n_items = meta + META_NPAIRS + SW_CLASS;
+    sp.counter = meta + META_PWORK + SW_CLASS; sp.ref_fw = c->d_ref.p; sp.ref_rc = c->d_rcref.p; sp.len1 = len1; sp.prof16 = c->d_prof16.p;
+    sp.gep2 = K2(2 * GEP);
+    sp.jscore = c->d_jscore.p; sp.jabc = c->d_jabc.p; sp.jaec = c->d_jaec.p; sp.jabr = c->d_jabr.p; sp.jstatus = c->d_jstatus.p;
+    const size_t smem = sw_smem();
+    static int per_sm = -1;
+    if (per_sm < 0) {
+      MIAGPU_CUDA(cudaFuncSetAttribute(sweep16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      MIAGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep16_kernel, WARPS_PER_BLOCK * 32, smem));
+    }
+    if (per_sm < 1) { set_error("sweep16_kernel does not fit on an SM (smem %zu)", smem); return 0; }
+    const int blocks = std::min(c->num_sms * per_sm, (n_items + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+    sweep16_kernel<<<blocks, WARPS_PER_BLOCK * 32, smem, st>>>(sp);
+    MIAGPU_CUDA(cudaGetLastError());
+    c->launches += 2;
+  }
+  MIAGPU_CUDA(cudaEventRecord(c->p1ev[1], st));
+  P1MergeParams mp{};
+  mp.n = n; mp.off = c->d_off.p; mp.seq_len = c->seq_len; mp.route = c->d_route.p; mp.jfirst = c->d_jfirst.p; mp.jcount = c->d_jcount.p;
+  mp.jkind = c->d_jkind.p; mp.jstatus = c->d_jstatus.p;
+  mp.jscore = c->d_jscore.p; mp.jabc = c->d_jabc.p; mp.jaec = c->d_jaec.p; mp.jabr = c->d_jabr.p; mp.general_list = c->d_p1list.p; mp.meta = meta;
+  mp.score = c->d_score.p; mp.fw_score = c->d_fw.p; mp.rc_score = c->d_rcs.p; mp.as_out = c->d_as_out.p; mp.ae_out = c->d_ae_out.p;
+  mp.start = c->d_start.p; mp.end = c->d_end.p; mp.abr = c->d_abr.p; mp.n_runs = c->d_nruns.p; mp.rc_out = c->d_rc_out.p;
+  mp.runs = c->d_runs.p; mp.status = c->d_status.p;
+  p1_merge_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(mp);
+  MIAGPU_CUDA(cudaGetLastError());
+  MIAGPU_CUDA(cudaEventRecord(c->p1ev[2], st));
+  c->launches++;
+  MIAGPU_CUDA(cudaMemcpyAsync(c->h_meta, meta, sizeof(int32_t) * META_HOST, cudaMemcpyDeviceToHost, st));
+  MIAGPU_CUDA(cudaStreamSynchronize(st));
+  const int n_general = c->h_meta[P1_NGENERAL];
+  c->p1_general = n_general; c->p1_fast = c->h_meta[P1_NFAST]; c->p1_skipped = 0;
+  if (n_general0) MIAGPU_CUDA(cudaStreamWaitEvent(st, c->aev[1], 0));
+  if (n_general > n_general0 &&
+      !launch_strip(c, 0, c->d_p1list.p + n_general0, n_general - n_general0, meta + P1_WORK2, 0, nullptr)) return 0;
+  return 1;
+}
+
 extern "C" int miagpu_pass1(miagpu_ctx* c, int32_t* hits, int32_t* score, int32_t* fw_score, int32_t* rc_score, uint8_t* rc, int32_t* as,
                             int32_t* ae, int32_t* start, int32_t* end, int32_t* abr, int32_t* n_runs, uint16_t* runs, uint8_t* status) {
   if (!c || !c->have_pssm || !c->have_ref || !c->with_rc) { set_error("miagpu_pass1: set_pssm and set_reference(with_rc=1) first"); return 0; }
@@ -2233,9 +2314,13 @@ extern "C" int miagpu_pass1(miagpu_ctx* c, int32_t* hits, int32_t* score, int32_
   const PairLmax lm = pair_lmax(c);
   bool fast = c->kmer_k > 0 && lm.v[0] > 0 && n > 0;
   if (const char* e = getenv("MIAGPU_PASS1_FAST")) fast = fast && atoi(e) != 0;
+  bool sweep = c->kmer_k <= 0 && lm.v[SW_CLASS] > 0 && n > 0;
+  if (const char* e = getenv("MIAGPU_PASS1_FAST")) sweep = sweep && atoi(e) != 0;
   c->p1_fast = c->p1_general = c->p1_skipped = 0;
-  c->p1ev_valid = fast;
-  if (!fast) {
+  c->p1ev_valid = fast || sweep;
+  if (sweep) {
+    if (!pass1_sweep(c, lm)) return 0;
+  } else if (!fast) {
     if (!launch_strip(c, 0, nullptr, 0, c->d_meta.p + 16)) return 0;
     c->p1_general = n;
   } else if (!pass1_fast(c, lm)) {

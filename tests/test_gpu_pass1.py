@@ -157,3 +157,29 @@ def test_strip_team_kernel_equals_warp_kernel(gpu, monkeypatch, k):
     nr = np.maximum(a["n_runs"], 0)
     m = np.arange(a["runs"].shape[1])[None, :] < nr[:, None]
     assert (np.where(m, a["runs"], 0) == np.where(m, z["runs"], 0)).all()
+
+
+def test_unmasked_sweep16_equals_general_kernel(gpu, monkeypatch):
+    # no k-mer filter: both whole strands in one 16-bit sweep (sweep16.cuh) vs the general chunked kernel, field for field;
+    # circular wrap, indels (winner not a plain diagonal -> handed over), reads longer than the 16-bit frame (never swept)
+    import _pkg
+    _pkg.load()
+    from mia_b200 import synth
+    ref = synth.random_reference(16569, seed=1)
+    g = synth.diverge(ref, 0.02, seed=41, indel_rate=0.004)
+    b, off, _ = synth.make_reads(g, 6000, 30, 140, seed=42, n_rate=0.002)
+    gpu.set_pssm(gpu_checks.load_pssm("onepass"))
+    gpu.set_reference(ref, circular=1, with_rc=1)
+    gpu.build_kmers(0)
+    gpu.upload_reads(b, off)
+    a = gpu.pass1()
+    fast, general, skipped = gpu.last_pass1_stats()
+    assert fast > 3000 and general > 100 and fast + general == 6000, (fast, general, skipped)
+    monkeypatch.setenv("MIAGPU_PASS1_FAST", "0")
+    z = gpu.pass1()
+    assert gpu.last_pass1_stats()[0] == 0
+    for key in ("hits", "score", "fw_score", "rc_score", "rc", "as_", "ae", "start", "end", "abr", "n_runs", "status"):
+        assert (a[key] == z[key]).all(), (key, int((a[key] != z[key]).sum()), np.flatnonzero(a[key] != z[key])[:5])
+    nr = np.maximum(a["n_runs"], 0)
+    m = np.arange(a["runs"].shape[1])[None, :] < nr[:, None]
+    assert (np.where(m, a["runs"], 0) == np.where(m, z["runs"], 0)).all()
