@@ -2170,10 +2170,18 @@ static int pass1_fast(miagpu_ctx* c, const PairLmax& lm) {
     MIAGPU_CUDA(cudaGetLastError());
     c->launches++;
     int base = 0;
-    c->launch_stream = st; c->launch_slot = 0;
+    // the classes' kernels are persistent (blocks fetch work until the class runs dry): spread over three streams, the next
+    // class's blocks move in as the previous class's tail drains (s_aux[1] belongs to the general kernel)
+    cudaStream_t lanes3[3] = {st, c->s_aux[2], c->s_aux[3]};
+    MIAGPU_CUDA(cudaEventRecord(c->aev[2], st));
+    MIAGPU_CUDA(cudaStreamWaitEvent(c->s_aux[2], c->aev[2], 0));
+    MIAGPU_CUDA(cudaStreamWaitEvent(c->s_aux[3], c->aev[2], 0));
+    int rr = 0;
+    c->launch_slot = 0;
     for (int kb = 0; kb < P16_NKB; kb++) {
       const int ni = pair_items[kb];
       if (!ni) continue;
+      c->launch_stream = lanes3[rr++ % 3];
       Pair16Params p{};
       p.bases = c->d_bases.p; p.off = c->d_off.p; p.rc = nullptr; p.win_start = c->d_jws.p; p.win_len = c->d_jwl.p;
       p.pairs = c->d_jpairs.p + 2 * (int64_t)np * base; p.n_items = meta + META_NPAIRS + kb; p.counter = meta + META_PWORK + kb;
@@ -2195,8 +2203,13 @@ static int pass1_fast(miagpu_ctx* c, const PairLmax& lm) {
         case 10: ok = launch_pair16<6, 16, true>(c, p, ni, P16_MAXL); break;
         default: ok = launch_pair16<7, 16, true>(c, p, ni, P16_MAXL); break;
       }
-      if (!ok) return 0;
+      if (!ok) { c->launch_stream = st; return 0; }
       base += ni;
+    }
+    c->launch_stream = st;
+    for (int i = 2; i < 4; i++) {
+      MIAGPU_CUDA(cudaEventRecord(c->aev[1 + i], c->s_aux[i]));
+      MIAGPU_CUDA(cudaStreamWaitEvent(st, c->aev[1 + i], 0));
     }
   }
   MIAGPU_CUDA(cudaEventRecord(c->p1ev[1], st));
