@@ -183,3 +183,27 @@ def test_unmasked_sweep16_equals_general_kernel(gpu, monkeypatch):
     nr = np.maximum(a["n_runs"], 0)
     m = np.arange(a["runs"].shape[1])[None, :] < nr[:, None]
     assert (np.where(m, a["runs"], 0) == np.where(m, z["runs"], 0)).all()
+
+
+@pytest.mark.parametrize("circular,matrix", [(0, "ancient"), (1, "flat")])
+def test_unmasked_sweep16_edge_reads_vs_oracle(gpu, oracle, circular, matrix):
+    # 1-bp to 12-bp reads, reads of N, reads hanging over either end of a linear reference, a reference whose width is
+    # not a multiple of the 256-column chunk, ties between the strands (palindromes) -- all without the k-mer filter
+    import _pkg
+    _pkg.load()
+    from mia_b200 import synth
+    rng = np.random.default_rng(5)
+    ref = synth.random_reference(1337, seed=51)
+    reads = []
+    for L in list(range(1, 13)) + [20, 33, 64, 100, 121]:
+        p = int(rng.integers(0, len(ref) - L))
+        reads.append(ref[p:p + L])
+        reads.append(synth.revcomp_bytes(np.frombuffer(ref[p:p + L].encode(), np.uint8)).tobytes().decode())
+    reads += ["N" * 30, "ACGT" * 10, "AATT" * 8, ref[:40], ref[-40:], "GG" + ref[:30], ref[-30:] + "TTT", ref[600:640] + "NNN" + ref[643:670]]
+    g = synth.diverge(ref, 0.05, seed=52, indel_rate=0.01)
+    b, off, _ = synth.make_reads(g, 150, 25, 110, seed=53, circular=bool(circular), n_rate=0.01)
+    reads += [synth.read_str(b, off, i) for i in range(150)]
+    bad, out = gpu_checks.check_pass1(gpu, oracle, ref, reads, gpu_checks.load_pssm(matrix), circular, 0)
+    assert not bad, f"{len(bad)} reads differ; first {bad[0]}"
+    fast, general, skipped = gpu.last_pass1_stats()
+    assert fast > 100, (fast, general, skipped)
