@@ -65,8 +65,13 @@ struct TileAdder {
     else atomicAdd(acc + plane * n_cols + col, v);
   }
 };
-template <typename Adder>
-__device__ __forceinline__ void add_base_dev(const Adder& A, int64_t col, int ch_code /*0..4, 5 = '-'*/, const int32_t* sm_strand, int depth) {
+// LocalAdder: every column of the entry lies inside the tile's shared window: plain 32-bit indices, no range test
+struct LocalAdder {
+  int32_t* s_acc;
+  __device__ __forceinline__ void add(int plane, int col, int v) const { atomicAdd(s_acc + plane * TILE_COLS + col, v); }
+};
+template <typename Adder, typename Col>
+__device__ __forceinline__ void add_base_dev(const Adder& A, Col col, int ch_code /*0..4, 5 = '-'*/, const int32_t* sm_strand, int depth) {
   A.add(PL_COV, col, 1);
   if (ch_code == 5) { A.add(PL_GAPS, col, 1); return; }
   if (ch_code < 4) A.add(ch_code, col, 1);
@@ -222,6 +227,26 @@ __global__ void __launch_bounds__(TILE_THREADS) tile_kernel(ConsParams p, const 
       const int32_t* sms = s_sm + b_strand * MIAGPU_PSSM_INTS;
       const uint8_t* read = p.bases + b_o + b_ab;
       const int hi_col = min(len, cb + cc);
+      // the entry's last column inside the shared window => all of them are (positions and insert offsets grow together)
+      const int d_last = min(rp + (hi_col - 1 - cb), p.seq_len - 1) - t0;
+      const bool inside = hi_col > cb && d_last >= 0 && d_last < TILE_COLS && d_last + (s_ins[min(d_last + 1, TILE_COLS)] - s_ins[0]) < TILE_COLS;
+      if (inside) {
+        const LocalAdder LA{s_acc};
+        const int ins0 = s_ins[0];
+        for (int i = cb + lane; i < hi_col; i += 32) {
+          const int pos = rp + (i - cb);
+          if (pos >= p.seq_len) continue;
+          const int act = bias + i;
+          const int dfront = backf ? fl + act : act, dback = tl - act - 1;
+          const int depth = dfront <= PSSM_DEPTH ? dfront : (dback < PSSM_DEPTH ? 2 * PSSM_DEPTH - dback : PSSM_DEPTH);
+          const int d = pos - t0;
+          const int io0 = s_ins[d] - ins0, io1 = s_ins[d + 1] - ins0;
+          if (!dropped) add_base_dev(LA, d + io1, base_code(read[i]), sms, depth);
+          if (i > cb && pos > 0)                             // find_ins_cons: start < pos <= end, dropped NOT checked
+            for (int j = io0; j < io1; j++) add_base_dev(LA, d + j, 5, sms, depth);
+        }
+        continue;
+      }
       for (int i = cb + lane; i < hi_col; i += 32) {
         const int pos = rp + (i - cb);
         if (pos >= p.seq_len) continue;
