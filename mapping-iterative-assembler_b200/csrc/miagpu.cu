@@ -55,6 +55,13 @@ struct DevBuf {
 constexpr int NBUCKET = 10;                                  // 9 register-tiled widths + "big"
 static const int BUCKET_K[NBUCKET] = {2, 4, 5, 6, 7, 8, 10, 12, 16, 0};
 static const int P16_COLS[P16_NKB] = {128, 144, 160, 176, 192, 208, 224, 256, 64, 80, 96, 112};   // columns of the pair kernels' width classes
+// Lanes per pair in reiterate_assembly's windows with MIAGPU_PAIR_G=8: 8 lanes x 16..22 columns for the classes up to 176
+// columns (four pairs per warp, rows updated in place; the per-row scan and table build are shared by twice the cells:
+// 18 % fewer instructions per cell), 16 lanes beyond.  Measured on B200 it LOSES -- 1.47 vs 1.15 ms for the 160-column
+// class: 128 registers with spills and 16 warps per SM -- so the default is 16 lanes everywhere; the variant stays
+// selectable and tested (tests/test_gpu_pair16.py) as the starting point for a version with the table in registers.
+static const int P16_G_REALIGN[P16_NKB] = {8, 8, 8, 8, 16, 16, 16, 16, 16, 16, 16, 16};
+struct PairNp { int v[P16_NKB]; };                           // pairs per work item (= per warp) of every class
 
 constexpr int MAX_CHUNKS = 16;
 
@@ -378,7 +385,7 @@ static int reserve_per_read(miagpu_ctx* c, int64_t n) {
          c->d_as_out.reserve(n) && c->d_ae_out.reserve(n) && c->d_abr.reserve(n) && c->d_nruns.reserve(n) &&
          c->d_win_start.reserve(n) && c->d_win_len.reserve(n) && c->d_lists.reserve(n * NBUCKET) &&
          c->d_runs.reserve(n * MAX_RUNS) && c->d_meta.reserve(META_WORDS * MAX_CHUNKS) && c->d_kind.reserve(n + 1) &&
-         c->d_pairs.reserve(n + MAX_CHUNKS * (4 * P16_KEYS + 64));
+         c->d_pairs.reserve(n + MAX_CHUNKS * (8 * P16_KEYS + 64));
 }
 
 extern "C" int miagpu_upload_reads(miagpu_ctx* c, int64_t n, const uint8_t* bases, const int64_t* offsets) {
@@ -499,7 +506,7 @@ __global__ void classify_kernel(int64_t n, const int64_t* off, const int32_t* as
 // One block: a thread takes LAYOUT_PER consecutive keys, the block scans the per-thread totals.
 constexpr int LAYOUT_THREADS = 256;
 constexpr int LAYOUT_PER = (P16_KEYS + LAYOUT_THREADS - 1) / LAYOUT_THREADS;
-__global__ void __launch_bounds__(LAYOUT_THREADS) pair_layout_kernel(int32_t* meta, int np) {
+__global__ void __launch_bounds__(LAYOUT_THREADS) pair_layout_kernel(int32_t* meta, PairNp npk) {
   __shared__ int s_tot[LAYOUT_THREADS];
   __shared__ int s_start[P16_KEYS + 1];
   const int t = threadIdx.x;
@@ -508,6 +515,7 @@ __global__ void __launch_bounds__(LAYOUT_THREADS) pair_layout_kernel(int32_t* me
   for (int q = 0; q < LAYOUT_PER; q++) {
     const int k = t * LAYOUT_PER + q;
     const int pairs = k < P16_KEYS ? (meta[META_HIST + k] + 1) >> 1 : 0;
+    const int np = npk.v[min(k / (P16_MAXL + 1), P16_NKB - 1)];
     items[q] = (pairs + np - 1) / np * np;
     sum += items[q];
   }
@@ -528,7 +536,7 @@ __global__ void __launch_bounds__(LAYOUT_THREADS) pair_layout_kernel(int32_t* me
   }
   if (t == LAYOUT_THREADS - 1) s_start[P16_KEYS] = s_tot[t];
   __syncthreads();
-  if (t < P16_NKB) meta[META_NPAIRS + t] = (s_start[(t + 1) * (P16_MAXL + 1)] - s_start[t * (P16_MAXL + 1)]) / np;
+  if (t < P16_NKB) meta[META_NPAIRS + t] = (s_start[(t + 1) * (P16_MAXL + 1)] - s_start[t * (P16_MAXL + 1)]) / npk.v[t];
 }
 
 // Eligible reads take the next free slot of their key: slot s is member s&1 of pair pstart + s/2.
@@ -727,12 +735,21 @@ static void pick_stream(miagpu_ctx* c, bool concurrent, int& rr) {
   c->launch_stream = c->s_aux[c->launch_slot];
 }
 
+static int realign_g(int kb) {
+  const char* e = getenv("MIAGPU_PAIR_G");
+  return (e && atoi(e) == 8) ? P16_G_REALIGN[kb] : 16;
+}
+static PairNp realign_np() {
+  PairNp r;
+  for (int kb = 0; kb < P16_NKB; kb++) r.v[kb] = 32 / realign_g(kb);
+  return r;
+}
 static PairLmax pair_lmax(miagpu_ctx* c) {
   int lmax16 = c->lmax16;
   if (const char* e = getenv("MIAGPU_PAIR16")) if (atoi(e) == 0) lmax16 = 0;
-  c->pair_g = 16;                                    // lanes per pair: two pairs per warp
+  c->pair_g = 16;                                    // lanes per pair of the pass-1 job kernels
   PairLmax lm{};
-  for (int kb = 0; kb < P16_NKB; kb++) lm.v[kb] = lmax16 > 0 ? std::min(p16_lmax(P16_COLS[kb] / c->pair_g, c->pssm_max), P16_MAXL) : 0;
+  for (int kb = 0; kb < P16_NKB; kb++) lm.v[kb] = lmax16 > 0 ? std::min(p16_lmax(P16_COLS[kb] / realign_g(kb), c->pssm_max), P16_MAXL) : 0;
   return lm;
 }
 
@@ -748,14 +765,13 @@ static void realign_reset_stats(miagpu_ctx* c) {
 static int realign_classify(miagpu_ctx* c, const RealignJob& j, cudaStream_t st) {
   if (j.n == 0) return 1;
   const PairLmax lm = pair_lmax(c);
-  const int np = 32 / c->pair_g;
   MIAGPU_CUDA(cudaMemsetAsync(j.d_meta, 0, META_WORDS * sizeof(int32_t), st));
   classify_kernel<<<(unsigned)((j.n + 255) / 256), 256, 0, st>>>(j.n, c->d_off.p + j.lo, c->d_as.p + j.lo, c->d_ae.p + j.lo, c->wrap_len, lm,
                                                                 c->d_win_start.p + j.lo, c->d_win_len.p + j.lo, j.d_lists, c->d_kind.p + j.lo, j.d_meta);
   MIAGPU_CUDA(cudaGetLastError());
   c->launches++;
   if (lm.v[0] > 0) {
-    pair_layout_kernel<<<1, LAYOUT_THREADS, 0, st>>>(j.d_meta, np);
+    pair_layout_kernel<<<1, LAYOUT_THREADS, 0, st>>>(j.d_meta, realign_np());
     MIAGPU_CUDA(cudaGetLastError());
     c->launches++;
   }
@@ -768,7 +784,7 @@ static int realign_launch(miagpu_ctx* c, const RealignJob& j) {
   const int64_t n = j.n, lo = j.lo;
   if (n == 0) return 1;
   const int32_t* meta = j.h_meta;
-  const int np = 32 / c->pair_g;
+  const PairNp npk = realign_np();
   const bool concurrent = !j.timed && !getenv("MIAGPU_SERIAL_LAUNCH");
   int rr = 0;
   int64_t cells[NBUCKET], pcells[P16_NKB];
@@ -776,21 +792,21 @@ static int realign_launch(miagpu_ctx* c, const RealignJob& j) {
   memcpy(pcells, meta + META_PCELLS, sizeof(pcells));
   for (int b = 0; b < NBUCKET; b++) { c->bucket_cells[b] += cells[b]; c->dp_cells += cells[b]; }
   int pair_items[P16_NKB];
-  int total_pairs = 0;                               // in work items (np pairs each)
+  int total_pairs = 0;                               // pair slots of all classes (a work item holds npk.v[class] pairs)
   for (int kb = 0; kb < P16_NKB; kb++) {
     pair_items[kb] = meta[META_NPAIRS + kb];
     c->pair_pairs[kb] += pair_items[kb]; c->pair_reads[kb] += meta[META_PREADS + kb]; c->pair_cells[kb] += pcells[kb];
-    total_pairs += pair_items[kb];
+    total_pairs += pair_items[kb] * npk.v[kb];
   }
 
   // ---- 16-bit pair kernels first: the reads they cannot finish join the 32-bit lists
   if (total_pairs) {
-    MIAGPU_CUDA(cudaMemsetAsync(j.d_pairs, 0xff, (size_t)2 * np * total_pairs * sizeof(int32_t), c->stream));
+    MIAGPU_CUDA(cudaMemsetAsync(j.d_pairs, 0xff, (size_t)2 * total_pairs * sizeof(int32_t), c->stream));
     pair_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, c->d_off.p + lo, c->d_kind.p + lo, j.d_meta, j.d_pairs);
     MIAGPU_CUDA(cudaGetLastError());
     c->launches++;
     int base_of[P16_NKB], base = 0, order[P16_NKB];
-    for (int kb = 0; kb < P16_NKB; kb++) { base_of[kb] = base; base += pair_items[kb]; order[kb] = kb; }
+    for (int kb = 0; kb < P16_NKB; kb++) { base_of[kb] = base; base += pair_items[kb] * npk.v[kb]; order[kb] = kb; }   // in pair slots
     if (concurrent) {                                 // biggest class first: the small ones fill its tail
       std::sort(order, order + P16_NKB, [&](int a, int b) { return pcells[a] > pcells[b]; });
       if (!fork_streams(c, 0)) return 0;
@@ -804,14 +820,18 @@ static int realign_launch(miagpu_ctx* c, const RealignJob& j) {
       if (j.timed) MIAGPU_CUDA(cudaEventRecord(c->pev[2 * kb], c->stream));
       Pair16Params p{};
       p.bases = c->d_bases.p; p.off = c->d_off.p + lo; p.rc = c->d_rc.p + lo; p.win_start = c->d_win_start.p + lo; p.win_len = c->d_win_len.p + lo;
-      p.pairs = j.d_pairs + 2 * (int64_t)np * base; p.n_items = j.d_meta + META_NPAIRS + kb; p.counter = j.d_meta + META_PWORK + kb;
+      p.pairs = j.d_pairs + 2 * (int64_t)base; p.n_items = j.d_meta + META_NPAIRS + kb; p.counter = j.d_meta + META_PWORK + kb;
       p.ref_codes = c->d_ref.p; p.ref_bytes = c->ref_bytes; p.prof16 = c->d_prof16.p;
       p.score = c->d_score.p + lo; p.as_out = c->d_as_out.p + lo; p.ae_out = c->d_ae_out.p + lo; p.abr = c->d_abr.p + lo;
       p.n_runs = c->d_nruns.p + lo; p.runs = c->d_runs.p + lo * MAX_RUNS; p.status = c->d_status.p + lo;
       p.lists = j.d_lists; p.list_counts = j.d_meta + META_COUNT; p.n_reads = n; p.n_fallback = j.d_meta + META_NFALL;
       const int maxL = P16_MAXL;
       int ok = 1;
-      switch (kb) {
+      switch (realign_g(kb) == 8 ? 100 + kb : kb) {
+        case 100: ok = launch_pair16<16, 8>(c, p, ni, maxL); break;
+        case 101: ok = launch_pair16<18, 8>(c, p, ni, maxL); break;
+        case 102: ok = launch_pair16<20, 8>(c, p, ni, maxL); break;
+        case 103: ok = launch_pair16<22, 8>(c, p, ni, maxL); break;
         case 0: ok = launch_pair16<8, 16>(c, p, ni, maxL); break;
         case 1: ok = launch_pair16<9, 16>(c, p, ni, maxL); break;
         case 2: ok = launch_pair16<10, 16>(c, p, ni, maxL); break;
@@ -969,7 +989,7 @@ extern "C" int miagpu_last_buckets(miagpu_ctx* c, int32_t* k, int32_t* reads, in
 extern "C" int miagpu_last_pair_buckets(miagpu_ctx* c, int32_t* k, int32_t* reads, int32_t* pairs, int64_t* cells, float* ms, int32_t* fallback_reads, int32_t* max_len16) {
   if (!c) { set_error("miagpu_last_pair_buckets: NULL ctx"); return 0; }
   for (int kb = 0; kb < P16_NKB_WIDE; kb++) {            // MIAGPU_NPAIRCLASS slots: the classes realign windows use
-    if (k) k[kb] = P16_COLS[kb] / c->pair_g;
+    if (k) k[kb] = P16_COLS[kb] / realign_g(kb);
     if (reads) reads[kb] = c->pair_reads[kb];
     if (pairs) pairs[kb] = c->pair_pairs[kb];
     if (cells) cells[kb] = c->pair_cells[kb];
@@ -1657,7 +1677,7 @@ static int host_round_front(miagpu_ctx* c, const char* who, int64_t n, const uin
     const int64_t lo = n * k / C, hi = n * (k + 1) / C;
     RealignJob& j = jobs[k];
     j.lo = lo; j.n = hi - lo; j.d_meta = c->d_meta.p + (size_t)META_WORDS * k; j.d_lists = c->d_lists.p + (size_t)NBUCKET * lo;
-    j.d_pairs = c->d_pairs.p + lo + (size_t)k * (4 * P16_KEYS + 64); j.h_meta = c->h_meta + (size_t)META_HOST * k; j.timed = false;
+    j.d_pairs = c->d_pairs.p + lo + (size_t)k * (8 * P16_KEYS + 64); j.h_meta = c->h_meta + (size_t)META_HOST * k; j.timed = false;
     MIAGPU_CUDA(cudaMemcpyAsync(c->d_bases.p + offsets[lo], bases + offsets[lo], offsets[hi] - offsets[lo], cudaMemcpyHostToDevice, up));
     if (k == 0) MIAGPU_CUDA(cudaMemcpyAsync(c->d_off.p, offsets, sizeof(int64_t), cudaMemcpyHostToDevice, up));
     MIAGPU_CUDA(cudaMemcpyAsync(c->d_off.p + lo + 1, offsets + lo + 1, (hi - lo) * sizeof(int64_t), cudaMemcpyHostToDevice, up));   // every element once
@@ -2143,7 +2163,8 @@ static int pass1_fast(miagpu_ctx* c, const PairLmax& lm) {
   const unsigned seed_blocks = (unsigned)std::min<int64_t>((int64_t)c->num_sms * 8, (n + 7) / 8);
   p1_seed_kernel<<<seed_blocks, 256, 0, st>>>(sp);
   MIAGPU_CUDA(cudaGetLastError());
-  pair_layout_kernel<<<1, LAYOUT_THREADS, 0, st>>>(meta, np);
+  PairNp npj; for (int kb = 0; kb < P16_NKB; kb++) npj.v[kb] = np;
+  pair_layout_kernel<<<1, LAYOUT_THREADS, 0, st>>>(meta, npj);
   MIAGPU_CUDA(cudaGetLastError());
   MIAGPU_CUDA(cudaEventRecord(c->p1ev[0], st));
   MIAGPU_CUDA(cudaMemcpyAsync(c->h_meta, meta, sizeof(int32_t) * META_HOST, cudaMemcpyDeviceToHost, st));
@@ -2252,7 +2273,8 @@ static int pass1_sweep(miagpu_ctx* c, const PairLmax& lm) {
   pp.jcount = c->d_jcount.p; pp.jkind = c->d_jkind.p; pp.hits = c->d_hits.p; pp.general_list = c->d_p1list.p; pp.meta = meta;
   sweep_prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pp, P1_NGENERAL);
   MIAGPU_CUDA(cudaGetLastError());
-  pair_layout_kernel<<<1, LAYOUT_THREADS, 0, st>>>(meta, 1);
+  PairNp np1; for (int kb = 0; kb < P16_NKB; kb++) np1.v[kb] = 1;
+  pair_layout_kernel<<<1, LAYOUT_THREADS, 0, st>>>(meta, np1);
   MIAGPU_CUDA(cudaGetLastError());
   MIAGPU_CUDA(cudaEventRecord(c->p1ev[0], st));
   MIAGPU_CUDA(cudaMemcpyAsync(c->h_meta, meta, sizeof(int32_t) * META_HOST, cudaMemcpyDeviceToHost, st));

@@ -192,7 +192,7 @@ __host__ __device__ constexpr int p16_smem_fixed() {
 //   Outputs are per job, in strand coordinates: as_out = abc, ae_out = aec.
 template <int K, int G, bool JOB>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, (K <= 5 ? 8 : K <= 7 ? 6 : K <= 12 ? 5 : 4)) pair16_kernel(Pair16Params p) {
-  static_assert(K >= 4 && K <= 16 && G == 16, "columns per lane / lanes per pair");
+  static_assert(K >= 4 && ((G == 16 && K <= 16) || (G == 8 && K <= 24)), "columns per lane / lanes per pair");
   constexpr int NP = 32 / G;                         // pairs per warp
   constexpr int NE = (25 + G - 1) / G;               // table entries a lane builds per row
   extern __shared__ __align__(16) uint8_t smem[];
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, (K <= 5 ? 8 : K <= 7 ? 6
   const int warp = tid >> 5;
   const int sub = lane & (G - 1);                    // lane within the pair's group
   const int hw = lane / G;                           // which pair of the warp
-  const unsigned gmask = G == 32 ? 0xffffffffu : (0xffffu << (hw * 16));
+  const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (hw * G));
 
   if (p.ref_in_smem) {
     if (tid == 0) {
@@ -364,7 +364,57 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, (K <= 5 ? 8 : K <= 7 ? 6
       }
       __syncwarp();
     };
-    {
+    // The same row, updated IN PLACE (G = 8: twice the columns per lane, no room for a second register set): the column-gap
+    // chain and the diagonal operand read row r-1's cells just before they are overwritten, two rotating registers deep.
+    auto dp_row_inplace = [&](int r, auto par, uint32_t (&W)[K], uint32_t (&acc)[K]) {
+      constexpr int PAR = decltype(par)::value;
+      if (r + 1 < L) build_table(r + 1, tab + (PAR ^ 1) * P16_TAB_WORDS);
+      uint32_t l2 = __shfl_up_sync(0xffffffffu, W[K - 2], 1, G);
+      uint32_t l1 = __shfl_up_sync(0xffffffffu, W[K - 1], 1, G);
+      uint32_t ain = __shfl_up_sync(0xffffffffu, acc[K - 1], 1, G);
+      l2 = and_or(__vadd2(l2, K2(-CONV)), keep, sentm);
+      const uint32_t l1c = __vadd2(l1, K2(-CONV));
+      l1 = and_or(l1c, keep, sentm);
+      ain &= keep;
+      uint32_t X = __vimax3_u16x2(l2, l1, W[0]);
+#pragma unroll
+      for (int j = 1; j + 1 < K - 2; j += 2) X = __vimax3_u16x2(X, W[j], W[j + 1]);
+      if ((K - 3) & 1) X = __vmaxu2(X, W[K - 3]);
+      X = __vadd2(X, K2(-GOP));
+#pragma unroll
+      for (int d = 1; d < G; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, X, d, G);
+        X = __viaddmax_u16x2(__vmaxu2(y, B2(-32768 + CONV * d)), K2(-CONV * d), X);
+      }
+      uint32_t q = __shfl_up_sync(0xffffffffu, X, 1, G);
+      q = __vadd2(__vmaxu2(q, B2(-32768 + CONV)), K2(-CONV)) & keep;
+      uint32_t o2 = l2, o1 = l1, oa = ain;            // row r-1: cells j-2, j-1 and the verdict carry of cell j-1
+#pragma unroll
+      for (int j = 0; j < K; j++) {
+        const uint32_t ncmpj = B2(-(GOP + 3 * GEP) - OFF) + K2(GEP * j);
+        q = __viaddmax_u16x2(o2, K2(-GOP), q);        // Q[j]: max over columns <= c-2 of V - GOP
+        const uint32_t D = j > 0 ? o1 : and_or(l1c, keep, ncmp0m);
+        const uint32_t ad = oa;
+        const uint32_t best = __vimax3_u16x2(D, q, Rg[j]);
+        Rg[j] = __viaddmax_u16x2(D, K2(-GOP), Rg[j]);
+        const uint2 e = lds_entry<PAR * P16_TAB_WORDS * 4>(comb[j]);
+        uint32_t bp;
+        const uint32_t wn = cell_pair(best, ncmpj, e.x, e.y, gep2, bp);
+        const uint32_t an = (JOB && j == 0) ? and_or(bp ^ D, keep, ad) : (ad | (bp ^ D));
+        o2 = j > 0 ? o1 : l1;                         // row r-1's cell j-1 (the converted neighbour for j = 0)
+        o1 = W[j]; oa = acc[j];
+        W[j] = wn; acc[j] = an;
+      }
+      __syncwarp();
+    };
+    if (G == 8) {
+      int r = 1;
+      for (; r + 1 < L; r += 2) {
+        dp_row_inplace(r, std::integral_constant<int, 1>{}, W, acc);
+        dp_row_inplace(r + 1, std::integral_constant<int, 0>{}, W, acc);
+      }
+      if (r < L) dp_row_inplace(r, std::integral_constant<int, 1>{}, W, acc);
+    } else {
       uint32_t W1[K], acc1[K];
       int r = 1;
       for (; r + 1 < L; r += 2) {
