@@ -190,8 +190,14 @@ __host__ __device__ constexpr int p16_smem_fixed() {
 //   (S = N, substitution score not added, mia.c:910-915) instead of applying the column-0 rule (mia.c:805-822).
 //   Everything to the left / right of the stretch is HIM and can neither be chosen nor become the best end cell.
 //   Outputs are per job, in strand coordinates: as_out = abc, ae_out = aec.
+#ifndef P16_INPLACE
+#define P16_INPLACE 0
+#endif
+#ifndef P16_SIX_BLOCKS_K
+#define P16_SIX_BLOCKS_K 7
+#endif
 template <int K, int G, bool JOB>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, (K <= 5 ? 8 : K <= 7 ? 6 : K <= 12 ? 5 : 4)) pair16_kernel(Pair16Params p) {
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, (K <= 5 ? 8 : K <= P16_SIX_BLOCKS_K ? 6 : K <= 12 ? 5 : 4)) pair16_kernel(Pair16Params p) {
   static_assert(K >= 4 && ((G == 16 && K <= 16) || (G == 8 && K <= 24)), "columns per lane / lanes per pair");
   constexpr int NP = 32 / G;                         // pairs per warp
   constexpr int NE = (25 + G - 1) / G;               // table entries a lane builds per row
@@ -407,7 +413,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, (K <= 5 ? 8 : K <= 7 ? 6
       }
       __syncwarp();
     };
-    if (G == 8) {
+    if (G == 8 || (P16_INPLACE && !JOB)) {
       int r = 1;
       for (; r + 1 < L; r += 2) {
         dp_row_inplace(r, std::integral_constant<int, 1>{}, W, acc);
