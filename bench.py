@@ -284,7 +284,9 @@ def run_ours(args):
                                   f"all-reduce MAX (insert maxima) + all-reduce SUM (column planes) over NCCL on the library stream"},
         "gcups": gcups, "dp_cells_per_step": world * cells,
         "e2e": {"value": world * n / (e2e_total / args.steps), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_total / args.steps * 1e3},
+                "ms_per_step": e2e_total / args.steps * 1e3,
+                "ms_min_median_max": [round(float(np.min(e2e_times)) * 1e3, 3), round(float(np.median(e2e_times)) * 1e3, 3),
+                                      round(float(np.max(e2e_times)) * 1e3, 3)]},
         "gpu_launches": launches["n"],
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": alg_bytes / dom_s / 1e9, "peak": hbm_peak, "unit": "GB/s",

@@ -1673,8 +1673,11 @@ static int host_round_front(miagpu_ctx* c, const char* who, int64_t n, const uin
   MIAGPU_CUDA(cudaStreamWaitEvent(down, c->ev[0], 0));
   // ---- upload stream: every chunk's inputs and classification, then the flags of earlier rounds
   RealignJob jobs[MAX_CHUNKS];
+  // the first chunk is half the size of the others: the DP starts after its upload, and from then on the uploads (about
+  // twice as fast as the DP) stay ahead
+  auto bound = [&](int k) { return k <= 0 ? (int64_t)0 : k >= C ? n : n * (2 * k - 1) / (2 * C - 1); };
   for (int k = 0; k < C; k++) {
-    const int64_t lo = n * k / C, hi = n * (k + 1) / C;
+    const int64_t lo = bound(k), hi = bound(k + 1);
     RealignJob& j = jobs[k];
     j.lo = lo; j.n = hi - lo; j.d_meta = c->d_meta.p + (size_t)META_WORDS * k; j.d_lists = c->d_lists.p + (size_t)NBUCKET * lo;
     j.d_pairs = c->d_pairs.p + lo + (size_t)k * (8 * P16_KEYS + 64); j.h_meta = c->h_meta + (size_t)META_HOST * k; j.timed = false;

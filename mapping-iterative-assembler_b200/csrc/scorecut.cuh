@@ -18,7 +18,7 @@
 
 namespace miagpu {
 
-constexpr int CUT_BLOCK = 2048;                      // = CHAIN_BLOCK of scorecut.hpp
+constexpr int CUT_BLOCK = 512;                       // = CHAIN_BLOCK of scorecut.hpp
 constexpr int CUT_THREADS = 256;
 constexpr int CUT_PER_THREAD = CUT_BLOCK / CUT_THREADS;
 
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(CUT_THREADS) cut_stats_kernel(int64_t lo, int6
 // (padding and the rank's header) count as unused reads: a 0.0 addend leaves a rounded chain unchanged.
 constexpr uint32_t CUT_KEY_UNUSED = 0xffffffffu;
 constexpr int SHARD_HDR_WORDS = 8;                   // tail of a rank's stride: sum len, sum score, count (int64 each), 2 spare
-constexpr int SHARD_PF_SLOTS = 64;                   // chain blocks whose keys travel to the host with the block records
+constexpr int SHARD_PF_SLOTS = 256;                  // chain blocks whose keys travel to the host with the block records
 
 struct CutSrc {
   const int32_t* seq_len; const int32_t* score; const uint8_t* unique_best;       // KEYS = false

@@ -16,6 +16,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <climits>
 #include <cmath>
 #include <condition_variable>
 #include <functional>
@@ -79,7 +80,9 @@ class HostTeam {
   bool stop_ = false;
 };
 
-constexpr int64_t CHAIN_BLOCK = 2048;
+// 512: a block the stitch cannot prove costs 512 dependent additions on the host (about 25 such blocks per chain and million
+// reads: the first one and the binade crossings); smaller blocks would only add records
+constexpr int64_t CHAIN_BLOCK = 512;
 
 // What phases 1 and 2 know about one block of CHAIN_BLOCK consecutive addends: the binade e the running sum is
 // predicted to be in when the block starts, T = sum(rint(a_i / ulp_e)), A = sum(|rint(a_i / ulp_e)|), and ok =
@@ -93,14 +96,22 @@ template <typename Serial>
 double chain_stitch_blocks(const ChainBlock* blk, int64_t nb, const Serial& serial, int64_t* n_serial = nullptr) {
   double S = 0;
   int64_t count = 0;
+  int e_cached = INT32_MIN;                           // the scale factors change only when the running sum changes binade
+  double inv = 0, ulp = 0, lo = 0, hi = 0;            // lo <= S < hi: S is in binade e_cached
   for (int64_t b = 0; b < nb; b++) {
     const ChainBlock& B = blk[b];
-    if (B.ok && S > 0 && std::ilogb(S) == B.e) {
-      const double inv = std::ldexp(1.0, 52 - B.e), ulp = std::ldexp(1.0, B.e - 52);
-      const double N0 = S * inv;                      // integer in [2^52, 2^53)
-      if (N0 - B.A >= 4503599627370497.0 && N0 + B.A <= 9007199254740990.0) {
-        S = (N0 + B.T) * ulp;
-        continue;
+    if (B.ok && S > 0) {
+      if (!(S >= lo && S < hi)) {
+        e_cached = std::ilogb(S);
+        inv = std::ldexp(1.0, 52 - e_cached); ulp = std::ldexp(1.0, e_cached - 52);
+        lo = std::ldexp(1.0, e_cached); hi = std::ldexp(1.0, e_cached + 1);
+      }
+      if (e_cached == B.e) {
+        const double N0 = S * inv;                    // integer in [2^52, 2^53)
+        if (N0 - B.A >= 4503599627370497.0 && N0 + B.A <= 9007199254740990.0) {
+          S = (N0 + B.T) * ulp;
+          continue;
+        }
       }
     }
     S = serial(b, S);
