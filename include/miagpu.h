@@ -340,6 +340,20 @@ int miagpu_realign_resident( miagpu_ctx* ctx );
  * mia_main.c:252-256); score / as / ae (nullable host arrays of n) receive this round's values. */
 int miagpu_adopt_alignment( miagpu_ctx* ctx, int32_t* score, int32_t* as, int32_t* ae );
 
+/* ---- 8f1. The repeat filter (-u / -U): sort_fsdb / sort_fsdb_qscore (fsdb.c:13-88, 90-180,
+ * 240-252) + set_uniq_in_fsdb (fsdb.c:440-508) at the call sites mia_main.c:827-844, 883-890,
+ * 938-945.  Inputs are host arrays of n in FSDB order: FragSeq.rc / as / ae, key4 = FragSeq.score
+ * (-u) or FragSeq.qual_sum (-U), trimmed (nullable).  Outputs: order[k] (nullable) = input index of
+ * the FragSeq that stands at position k of fsdb->fss after the sort (a stable sort, as glibc's
+ * qsort is while its merge buffer fits: equal reads keep their order); unique_best[i] by INPUT
+ * index.  Coordinates must lie in [0, 2^21), key4 in [-2^20, 2^20).  Sort and flags run on the
+ * device (64-bit keys, LSD radix sort); with tolerance > 0 (-C) the greedy grouping of
+ * set_uniq_in_fsdb runs on the host over the device-sorted order. */
+int miagpu_repeat_filter( miagpu_ctx* ctx, int64_t n, const uint8_t* rc, const int32_t* as,
+                          const int32_t* ae, const int32_t* key4, const uint8_t* trimmed,
+                          int just_outer_coords, int tolerance, int64_t* order,
+                          uint8_t* unique_best );
+
 /* ---- measurement helpers (bench.py) */
 /* per width bucket of the last realign: columns-per-lane K (0 = too wide),
  * reads, DP cells, kernel ms (CUDA events on the library's stream); MIAGPU_NBUCKET entries */

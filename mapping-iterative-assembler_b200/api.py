@@ -82,6 +82,7 @@ def load_library():
     L.miagpu_shard_cut.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), _vpp, _i64p]
     L.miagpu_shard_finish.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, _i64p, C.c_void_p, C.c_char_p, _i32p]
     L.miagpu_last_cut_stats.argtypes = [C.c_void_p, _i64p, _i64p]
+    L.miagpu_repeat_filter.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 5 + [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     L.miagpu_last_pair_buckets.argtypes = [C.c_void_p] + [C.c_void_p] * 5 + [_i32p, _i32p]
     L.miagpu_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), _i64p, _i32p]
     L.miagpu_int32_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
@@ -98,7 +99,7 @@ EXPORTS = ["miagpu_device_count", "miagpu_create", "miagpu_destroy", "miagpu_las
            "miagpu_score_cut", "miagpu_cull_flags",
            "miagpu_set_alignment_inputs", "miagpu_realign_resident", "miagpu_adopt_alignment", "miagpu_set_cut_inputs", "miagpu_reset_dropped", "miagpu_iterate_resident", "miagpu_last_buckets", "miagpu_last_pair_buckets", "miagpu_last_timing",
            "miagpu_int32_peak", "miagpu_stream", "miagpu_shard_begin", "miagpu_shard_begin_host", "miagpu_shard_cut", "miagpu_shard_finish",
-           "miagpu_last_cut_stats"]
+           "miagpu_last_cut_stats", "miagpu_repeat_filter"]
 
 
 def _ptr(a):
@@ -314,6 +315,19 @@ class MiaGpu:
         a, b = C.c_int64(), C.c_int64()
         self._ck(self.lib.miagpu_last_cut_stats(self.h, C.byref(a), C.byref(b)))
         return dict(serial_blocks=a.value, fetched_blocks=b.value)
+
+    # -- repeat filter (8f1)
+    def repeat_filter(self, rc, as_, ae, key4, trimmed=None, just_outer_coords=1, tolerance=0, want_order=True):
+        """sort_fsdb[_qscore] + set_uniq_in_fsdb: -> (order int64[n] or None, unique_best uint8[n] by input index)"""
+        n = len(rc)
+        rc = np.ascontiguousarray(rc, np.uint8); as_ = np.ascontiguousarray(as_, np.int32); ae = np.ascontiguousarray(ae, np.int32)
+        key4 = np.ascontiguousarray(key4, np.int32)
+        tr = None if trimmed is None else np.ascontiguousarray(trimmed, np.uint8)
+        order = np.zeros(n, np.int64) if want_order else None
+        uniq = np.zeros(n, np.uint8)
+        self._ck(self.lib.miagpu_repeat_filter(self.h, n, _ptr(rc), _ptr(as_), _ptr(ae), _ptr(key4), _ptr(tr), int(just_outer_coords),
+                                               int(tolerance), _ptr(order), _ptr(uniq)))
+        return order, uniq
 
     # -- consensus
     def consensus(self, entries, cons_code=1, want_counts=False):

@@ -5,6 +5,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <functional>
 #include <chrono>
 #include <thread>
 #include <vector>
@@ -18,7 +19,9 @@
 #include "sweep16.cuh"
 #include "scorecut.hpp"
 #include "scorecut.cuh"
+#include "repeat.cuh"
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_radix_sort.cuh>
 
 namespace miagpu {
 
@@ -138,6 +141,12 @@ struct miagpu_ctx {
   std::vector<uint8_t> h_unique;
   int64_t cut_inputs_n = -1;
   int64_t cut_serial_blocks = 0;                // chain blocks the last round summed read by read on the host
+  // repeat filter (repeat.cuh)
+  DevBuf<uint8_t> rf_rc, rf_tr, rf_uq, rf_tmp;
+  DevBuf<int32_t> rf_as, rf_ae, rf_k4, rf_idx, rf_idx2;
+  DevBuf<uint64_t> rf_key, rf_key2;
+  DevBuf<int64_t> rf_ord;
+  DevBuf<int> rf_bad;
   // sharded rounds: this rank's part of the all-gather, what came back, prefetched chain blocks
   int sh_world = 0, sh_rank = 0, sh_phase = 0, sh_hard_cut = 0, sh_cut_set = 0, sh_chunks = 0;
   int64_t sh_nmax = 0, sh_stride = 0, sh_fetched = 0;
@@ -264,6 +273,8 @@ extern "C" void miagpu_destroy(miagpu_ctx* c) {
   if (c->h_sh_pf) cudaFreeHost(c->h_sh_pf);
   if (c->h_sh_pfid) cudaFreeHost(c->h_sh_pfid);
   c->d_sh_send.release(); c->d_sh_recv.release(); c->d_sh_pf.release(); c->d_sh_pfid.release();
+  c->rf_rc.release(); c->rf_tr.release(); c->rf_uq.release(); c->rf_tmp.release(); c->rf_as.release(); c->rf_ae.release(); c->rf_k4.release();
+  c->rf_idx.release(); c->rf_idx2.release(); c->rf_key.release(); c->rf_key2.release(); c->rf_ord.release(); c->rf_bad.release();
   c->d_seqlen.release(); c->d_unique.release(); c->d_cstats.release(); c->d_ctab.release(); c->d_thr.release(); c->d_cblk.release();
   cudaStreamDestroy(c->stream);
   delete c;
@@ -2081,6 +2092,79 @@ extern "C" int miagpu_last_cut_stats(miagpu_ctx* c, int64_t* serial_blocks, int6
   if (!c) { set_error("miagpu_last_cut_stats: no context"); return 0; }
   if (serial_blocks) *serial_blocks = c->cut_serial_blocks;
   if (fetched_blocks) *fetched_blocks = c->sh_fetched;
+  return 1;
+}
+
+// ------------------------------------------------------------------ repeat filter (8f1)
+extern "C" int miagpu_repeat_filter(miagpu_ctx* c, int64_t n, const uint8_t* rc, const int32_t* as, const int32_t* ae, const int32_t* key4,
+                                    const uint8_t* trimmed, int just_outer_coords, int tolerance, int64_t* order, uint8_t* unique_best) {
+  if (!c || n < 0 || (n && (!rc || !as || !ae || !key4 || !unique_best)) || tolerance < 0) { set_error("miagpu_repeat_filter: bad argument"); return 0; }
+  if (n > 0x7fffffffLL) { set_error("miagpu_repeat_filter: at most %d reads", 0x7fffffff); return 0; }
+  if (n == 0) return 1;
+  MIAGPU_CUDA(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  // scratch of the filter stays with the context (the call comes once per iteration)
+  DevBuf<uint8_t>&d_rc = c->rf_rc, &d_tr = c->rf_tr, &d_uq = c->rf_uq, &d_tmp = c->rf_tmp;
+  DevBuf<int32_t>&d_as = c->rf_as, &d_ae = c->rf_ae, &d_k4 = c->rf_k4, &d_idx = c->rf_idx, &d_idx2 = c->rf_idx2;
+  DevBuf<uint64_t>&d_key = c->rf_key, &d_key2 = c->rf_key2;
+  DevBuf<int64_t>& d_ord = c->rf_ord;
+  DevBuf<int>& d_bad = c->rf_bad;
+  if (!d_rc.reserve(n) || !d_as.reserve(n) || !d_ae.reserve(n) || !d_k4.reserve(n) || !d_idx.reserve(n) || !d_idx2.reserve(n) ||
+      !d_key.reserve(n) || !d_key2.reserve(n) || !d_uq.reserve(n) || !d_bad.reserve(1) || (trimmed && !d_tr.reserve(n)) ||
+      (order && !d_ord.reserve(n))) return 0;
+  MIAGPU_CUDA(cudaEventRecord(c->ev[0], st));
+  MIAGPU_CUDA(cudaMemcpyAsync(d_rc.p, rc, n, cudaMemcpyHostToDevice, st));
+  MIAGPU_CUDA(cudaMemcpyAsync(d_as.p, as, n * 4, cudaMemcpyHostToDevice, st));
+  MIAGPU_CUDA(cudaMemcpyAsync(d_ae.p, ae, n * 4, cudaMemcpyHostToDevice, st));
+  MIAGPU_CUDA(cudaMemcpyAsync(d_k4.p, key4, n * 4, cudaMemcpyHostToDevice, st));
+  if (trimmed) MIAGPU_CUDA(cudaMemcpyAsync(d_tr.p, trimmed, n, cudaMemcpyHostToDevice, st));
+  MIAGPU_CUDA(cudaMemsetAsync(d_bad.p, 0, sizeof(int), st));
+  MIAGPU_CUDA(cudaEventRecord(c->ev[1], st));
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  rf_key_kernel<<<grid, 256, 0, st>>>(n, d_rc.p, d_as.p, d_ae.p, d_k4.p, d_key.p, d_idx.p, d_bad.p);
+  MIAGPU_CUDA(cudaGetLastError());
+  size_t tmp = 0;
+  MIAGPU_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, d_key.p, d_key2.p, d_idx.p, d_idx2.p, (int)n, 0, 64, st));
+  if (!d_tmp.reserve(tmp + 16)) return 0;
+  MIAGPU_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp.p, tmp, d_key.p, d_key2.p, d_idx.p, d_idx2.p, (int)n, 0, 64, st));
+  int bad = 0;
+  MIAGPU_CUDA(cudaMemcpyAsync(&bad, d_bad.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  c->launches = 2;
+  if (tolerance == 0) {
+    rf_unique_kernel<<<grid, 256, 0, st>>>(n, d_idx2.p, d_rc.p, d_as.p, d_ae.p, trimmed ? d_tr.p : nullptr, just_outer_coords, d_uq.p);
+    MIAGPU_CUDA(cudaGetLastError());
+    c->launches++;
+  }
+  if (order) {
+    rf_widen_kernel<<<grid, 256, 0, st>>>(n, d_idx2.p, d_ord.p);
+    MIAGPU_CUDA(cudaGetLastError());
+    c->launches++;
+  }
+  MIAGPU_CUDA(cudaEventRecord(c->ev[2], st));
+  std::vector<int32_t> h_idx;
+  if (tolerance == 0) MIAGPU_CUDA(cudaMemcpyAsync(unique_best, d_uq.p, n, cudaMemcpyDeviceToHost, st));
+  else { h_idx.resize(n); MIAGPU_CUDA(cudaMemcpyAsync(h_idx.data(), d_idx2.p, n * 4, cudaMemcpyDeviceToHost, st)); }
+  if (order) MIAGPU_CUDA(cudaMemcpyAsync(order, d_ord.p, n * 8, cudaMemcpyDeviceToHost, st));
+  MIAGPU_CUDA(cudaEventRecord(c->ev[3], st));
+  MIAGPU_CUDA(cudaStreamSynchronize(st));
+  MIAGPU_CUDA(cudaEventElapsedTime(&c->ms_h2d, c->ev[0], c->ev[1]));
+  MIAGPU_CUDA(cudaEventElapsedTime(&c->ms_kernels, c->ev[1], c->ev[2]));
+  MIAGPU_CUDA(cudaEventElapsedTime(&c->ms_d2h, c->ev[2], c->ev[3]));
+  if (bad) { set_error("miagpu_repeat_filter: coordinates must lie in [0, %d] and the fourth key in [%d, %d)", RF_COORD_MAX, -RF_KEY4_HALF, RF_KEY4_HALF); return 0; }
+  if (tolerance > 0) {                                 // set_uniq_in_fsdb's greedy grouping (fsdb.c:452-506) over the sorted order
+    int64_t f = h_idx[0];
+    int curr_rc = rc[f] != 0, curr_as = as[f], curr_ae = ae[f];
+    unique_best[f] = 1;
+    for (int64_t k = 1; k < n; k++) {
+      f = h_idx[k];
+      const int frc = rc[f] != 0;
+      if (frc == curr_rc && abs(as[f] - curr_as) <= tolerance && abs(ae[f] - curr_ae) <= tolerance) { unique_best[f] = 0; continue; }
+      if (just_outer_coords) unique_best[f] = 1;
+      else if (!frc) unique_best[f] = as[f] == curr_as ? (trimmed && trimmed[f] ? 1 : 0) : 1;
+      else unique_best[f] = ae[f] == curr_ae ? (trimmed && trimmed[f] ? 1 : 0) : 1;
+      curr_rc = frc; curr_as = as[f]; curr_ae = ae[f];
+    }
+  }
   return 1;
 }
 

@@ -673,3 +673,58 @@ void orc_asm_slot( const orc_asm* a, int i, int* out7, char* seq, char* smp, cha
   *p = '\0';
   out7[6] = n;
 }
+
+/* ---- f1: repeat filter (fsdb.c:13-88 fs_comp, 90-180 fs_comp_qscore, 440-508 set_uniq_in_fsdb) */
+typedef struct { const unsigned char* rc; const int* as; const int* ae; const int* k4; } orc_rf;
+static int orc_rf_comp( const orc_rf* d, long long a, long long b ) {
+  const int ra = d->rc[a] != 0, rb = d->rc[b] != 0;
+  if ( ra && !rb ) return -1;                        /* reverse strand first */
+  if ( !ra && rb ) return 1;
+  if ( !ra ) {                                       /* forward: as ascending, ae descending, key4 descending */
+    if ( d->as[a] != d->as[b] ) return d->as[a] < d->as[b] ? -1 : 1;
+    if ( d->ae[a] != d->ae[b] ) return d->ae[a] < d->ae[b] ? 1 : -1;
+  } else {                                           /* reverse: ae descending, as ascending, key4 descending */
+    if ( d->ae[a] != d->ae[b] ) return d->ae[a] < d->ae[b] ? 1 : -1;
+    if ( d->as[a] != d->as[b] ) return d->as[a] < d->as[b] ? -1 : 1;
+  }
+  if ( d->k4[a] != d->k4[b] ) return d->k4[a] < d->k4[b] ? 1 : -1;
+  return 0;
+}
+void orc_repeat_filter( long long n, const unsigned char* rc, const int* as, const int* ae, const int* key4,
+                        const unsigned char* trimmed, int just_outer_coords, int tolerance,
+                        long long* order, unsigned char* unique ) {
+  orc_rf d;
+  long long i, w, *tmp;
+  int curr_rc, curr_as, curr_ae;
+  if ( n <= 0 ) return;
+  d.rc = rc; d.as = as; d.ae = ae; d.k4 = key4;
+  tmp = (long long*)malloc( (size_t)n * sizeof(long long) );
+  for ( i = 0; i < n; i++ ) order[i] = i;
+  for ( w = 1; w < n; w *= 2 ) {                     /* bottom-up merge sort: stable */
+    long long lo;
+    for ( lo = 0; lo < n; lo += 2 * w ) {
+      long long mid = lo + w < n ? lo + w : n, hi = lo + 2 * w < n ? lo + 2 * w : n;
+      long long a = lo, b = mid, k = lo;
+      while ( a < mid && b < hi ) tmp[k++] = orc_rf_comp( &d, order[b], order[a] ) < 0 ? order[b++] : order[a++];
+      while ( a < mid ) tmp[k++] = order[a++];
+      while ( b < hi ) tmp[k++] = order[b++];
+    }
+    memcpy( order, tmp, (size_t)n * sizeof(long long) );
+  }
+  free( tmp );
+  /* set_uniq_in_fsdb */
+  curr_rc = rc[order[0]] != 0; curr_as = as[order[0]]; curr_ae = ae[order[0]];
+  unique[order[0]] = 1;
+  for ( i = 1; i < n; i++ ) {
+    const long long f = order[i];
+    const int frc = rc[f] != 0;
+    if ( frc == curr_rc && abs( as[f] - curr_as ) <= tolerance && abs( ae[f] - curr_ae ) <= tolerance ) {
+      unique[f] = 0;                                 /* curr stays */
+      continue;
+    }
+    if ( just_outer_coords ) unique[f] = 1;
+    else if ( !frc ) unique[f] = ( as[f] == curr_as ) ? ( trimmed && trimmed[f] ? 1 : 0 ) : 1;
+    else unique[f] = ( ae[f] == curr_ae ) ? ( trimmed && trimmed[f] ? 1 : 0 ) : 1;
+    curr_rc = frc; curr_as = as[f]; curr_ae = ae[f];
+  }
+}

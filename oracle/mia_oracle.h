@@ -121,6 +121,14 @@ void orc_asm_gaps( const orc_asm* a, int* out );           /* wrap_len+1 ints */
 void orc_asm_slot( const orc_asm* a, int i, int* out7, char* seq, char* smp,
                    char* ins );
 int  orc_find_consensus( const int* in10, int cons_code ); /* map_align.c:294-391 */
+/* f1: sort_fsdb / sort_fsdb_qscore (fsdb.c:13-88, 90-180, 240-252; key4 = score or
+ * qual_sum) as a STABLE sort -- what glibc's qsort is while its merge buffer fits --
+ * then set_uniq_in_fsdb (fsdb.c:440-508).  order[k] = input index at sorted
+ * position k, unique[i] = unique_best by input index. */
+void orc_repeat_filter( long long n, const unsigned char* rc, const int* as,
+                        const int* ae, const int* key4,
+                        const unsigned char* trimmed, int just_outer_coords,
+                        int tolerance, long long* order, unsigned char* unique );
 
 #ifdef __cplusplus
 }

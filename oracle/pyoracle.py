@@ -265,6 +265,20 @@ class Oracle(_AlignMixin):
         """The culled list (= culled_maln->AlnSeqArray before sort_aln_frags)."""
         return [self.asm_slot(a, self.lib.orc_asm_entry(a, i)) for i in range(self.lib.orc_asm_num_entries(a))]
 
+    def repeat_filter(self, rc, as_, ae, key4, trimmed=None, just_outer_coords=1, tolerance=0):
+        """f1: (order int64[n], unique uint8[n] by input index)"""
+        n = len(rc)
+        rc = np.ascontiguousarray(rc, np.uint8); as_ = np.ascontiguousarray(as_, np.int32); ae = np.ascontiguousarray(ae, np.int32)
+        key4 = np.ascontiguousarray(key4, np.int32)
+        tr = None if trimmed is None else np.ascontiguousarray(trimmed, np.uint8)
+        order, uniq = np.zeros(n, np.int64), np.zeros(n, np.uint8)
+        f = self.lib.orc_repeat_filter
+        f.argtypes = [C.c_longlong] + [C.c_void_p] * 5 + [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        f.restype = None
+        f(n, rc.ctypes.data, as_.ctypes.data, ae.ctypes.data, key4.ctypes.data, None if tr is None else tr.ctypes.data,
+          int(just_outer_coords), int(tolerance), order.ctypes.data, uniq.ctypes.data)
+        return order, uniq
+
     def find_consensus(self, counts10, cons_code=1):
         c = np.ascontiguousarray(counts10, np.int32)
         return chr(self.lib.orc_find_consensus(_ip(c), cons_code))
@@ -449,6 +463,21 @@ class Ref(_AlignMixin):
 
     def sess_write_ma(self, s, path):
         return self.lib.refh_sess_write_ma(s, _b(path))
+
+    def repeat_filter(self, rc, as_, ae, key4, trimmed=None, just_outer_coords=1, tolerance=0, use_qscore=0):
+        """the reference's sort_fsdb[_qscore] + set_uniq_in_fsdb: (order int64[n], unique uint8[n] by input index)"""
+        n = len(rc)
+        rc = np.ascontiguousarray(rc, np.uint8); as_ = np.ascontiguousarray(as_, np.int32); ae = np.ascontiguousarray(ae, np.int32)
+        key4 = np.ascontiguousarray(key4, np.int32)
+        tr = None if trimmed is None else np.ascontiguousarray(trimmed, np.uint8)
+        order, uniq = np.zeros(n, np.int64), np.zeros(n, np.uint8)
+        f = self.lib.refh_repeat_filter
+        f.argtypes = [C.c_longlong] + [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        f.restype = None
+        f(n, rc.ctypes.data, as_.ctypes.data, ae.ctypes.data, None if use_qscore else key4.ctypes.data,
+          key4.ctypes.data if use_qscore else None, None if tr is None else tr.ctypes.data, int(use_qscore), int(just_outer_coords),
+          int(tolerance), order.ctypes.data, uniq.ctypes.data)
+        return order, uniq
 
     def find_consensus(self, counts10, cons_code=1):
         c = np.ascontiguousarray(counts10, np.int32)

@@ -412,3 +412,33 @@ int refh_find_consensus( const int* in10, int cons_code ) {
   b.cov = in10[5]; b.scoreA = in10[6]; b.scoreC = in10[7]; b.scoreG = in10[8]; b.scoreT = in10[9];
   return find_consensus( &b, cons_code );
 }
+
+/* f1: the repeat filter -- sort_fsdb / sort_fsdb_qscore (fsdb.c:240-252) followed by set_uniq_in_fsdb
+   (fsdb.c:440-508) on n FragSeqs that carry only the fields those functions read.  order[k] = input
+   index of the FragSeq at position k afterwards; unique[i] = its unique_best, by INPUT index. */
+void refh_repeat_filter( long long n, const unsigned char* rc, const int* as, const int* ae,
+                         const int* score, const int* qual_sum, const unsigned char* trimmed,
+                         int use_qscore, int just_outer_coords, int tolerance,
+                         long long* order, unsigned char* unique ) {
+  long long i;
+  FragSeq* all;
+  FragSeqDB db;
+  if ( n <= 0 ) return;
+  all = (FragSeq*)calloc( (size_t)n, sizeof(FragSeq) );
+  db.fss = (FragSeqP*)malloc( (size_t)n * sizeof(FragSeqP) );
+  db.size = db.num_fss = (size_t)n;
+  db.trim_sort = 0;
+  for ( i = 0; i < n; i++ ) {
+    all[i].rc = rc[i]; all[i].as = as[i]; all[i].ae = ae[i];
+    all[i].score = score ? score[i] : 0; all[i].qual_sum = qual_sum ? qual_sum[i] : 0;
+    all[i].trimmed = trimmed ? trimmed[i] : 0;
+    db.fss[i] = &all[i];
+  }
+  if ( use_qscore ) sort_fsdb_qscore( &db ); else sort_fsdb( &db );
+  set_uniq_in_fsdb( &db, just_outer_coords, (unsigned short)tolerance );
+  for ( i = 0; i < n; i++ ) {
+    order[i] = (long long)( db.fss[i] - all );
+    unique[ order[i] ] = (unsigned char)db.fss[i]->unique_best;
+  }
+  free( db.fss ); free( all );
+}

@@ -141,7 +141,20 @@ def main():
     reads = [synth.read_str(b, off, i) for i in range(300)]
     sess["synth2k5_pe_long_c_k12"] = session(r, ref, reads, m["pe"], 1, 12, 0)
     json.dump(sess, open(os.path.join(HERE, "sessions.json"), "w"))
-    print("wrote pssm.npz, align_cases.json, sessions.json")
+    # f1: the reference's sort_fsdb[_qscore] + set_uniq_in_fsdb on small FSDBs full of ties
+    rng = np.random.default_rng(7)
+    rep = []
+    for n in (1, 2, 9, 60, 400):
+        for use_q in (0, 1):
+            for jo in (0, 1):
+                for tol in (0, 2):
+                    rc = rng.integers(0, 2, n); as_ = rng.integers(0, 12, n); ae = as_ + rng.integers(30, 34, n)
+                    k4 = rng.integers(2000, 2004, n); tr = rng.integers(0, 2, n)
+                    order, uniq = r.repeat_filter(rc, as_, ae, k4, tr, jo, tol, use_qscore=use_q)
+                    rep.append(dict(rc=rc.tolist(), as_=as_.tolist(), ae=ae.tolist(), key4=k4.tolist(), trimmed=tr.tolist(), use_qscore=use_q,
+                                    just_outer=jo, tolerance=tol, order=order.tolist(), unique=uniq.tolist()))
+    json.dump(rep, open(os.path.join(HERE, "repeat_cases.json"), "w"))
+    print("wrote pssm.npz, align_cases.json, sessions.json, repeat_cases.json")
 
 
 if __name__ == "__main__":

@@ -99,3 +99,13 @@ def test_find_consensus_rules(oracle):
     assert f([1, 0, 0, 0, 0, 1, -399, -500, -500, -500]) == "A"
     assert f([1, 0, 0, 0, 0, 1, -1, -2401, -3000, -3000], 2) == "N"  # cons_code 2: diff must EXCEED 2400
     assert f([1, 0, 0, 0, 0, 1, -1, -2402, -3000, -3000], 2) == "A"
+
+
+def test_repeat_filter_matches_reference_golden(oracle):
+    # f1: the oracle's stable sort + set_uniq_in_fsdb against what the reference's own functions returned
+    cases = json.load(open(os.path.join(G, "repeat_cases.json")))
+    assert len(cases) == 40
+    for i, c in enumerate(cases):
+        order, uniq = oracle.repeat_filter(np.array(c["rc"], np.uint8), np.array(c["as_"], np.int32), np.array(c["ae"], np.int32),
+                                           np.array(c["key4"], np.int32), np.array(c["trimmed"], np.uint8), c["just_outer"], c["tolerance"])
+        assert order.tolist() == c["order"] and uniq.tolist() == c["unique"], i

@@ -135,3 +135,22 @@ def test_score_cut_matches_reference_regression(oracle, ref):
         s, i = oracle.score_cut(sl, sc)
         s = 100.0 if s <= 0 else s
         assert (below == (sc < (i + s * sl))).all()
+
+
+def test_repeat_filter_oracle_equals_reference(oracle, ref):
+    # f1: sort_fsdb / sort_fsdb_qscore + set_uniq_in_fsdb (fsdb.c:240-252, 440-508) on FSDBs full of ties, both sort keys,
+    # both just_outer_coords settings, with and without a tolerance
+    rng = np.random.default_rng(1)
+    for trial in range(25):
+        n = int(rng.integers(1, 3000))
+        rc = rng.integers(0, 2, n).astype(np.uint8)
+        as_ = rng.integers(0, 60, n).astype(np.int32)
+        ae = (as_ + rng.integers(30, 40, n)).astype(np.int32)
+        k4 = rng.integers(2000, 2010, n).astype(np.int32)
+        tr = rng.integers(0, 2, n).astype(np.uint8)
+        for uq in (0, 1):
+            for jo in (0, 1):
+                for tol in (0, 2):
+                    a = oracle.repeat_filter(rc, as_, ae, k4, tr, jo, tol)
+                    b = ref.repeat_filter(rc, as_, ae, k4, tr, jo, tol, use_qscore=uq)
+                    assert (a[0] == b[0]).all() and (a[1] == b[1]).all(), (trial, uq, jo, tol)
