@@ -224,7 +224,9 @@ int miagpu_call( miagpu_ctx* ctx, int cons_code, int32_t* gaps_out,
 /* The same with the entry list built ON THE DEVICE from the resident alignments:
  * every read contributes its own fresh segment(s) (no stale AlnSeq pointers to
  * describe).  dropped_front / dropped_back: host arrays of n flags for the
- * read's whole-or-front and back AlnSeq (nullable = nothing dropped). */
+ * read's whole-or-front and back AlnSeq (nullable = nothing dropped): 0 = in the
+ * culled list, 1 = AlnSeq.dropped, 2 (in dropped_front) = the read is not
+ * unique_best and therefore not in the culled list at all (mia.c:466). */
 int miagpu_consensus_natural( miagpu_ctx* ctx, const uint8_t* dropped_front,
                               const uint8_t* dropped_back, int cons_code,
                               int32_t* gaps_out, int32_t* counts_out,
@@ -259,7 +261,9 @@ int miagpu_cull_flags( int64_t n, const int32_t* seq_len, const int32_t* score,
  * rounding; blocks without a proof are summed read by read on the host.  Slope,
  * intercept and flags are bit-identical to miagpu_score_cut / miagpu_cull_flags.
  * seq_len / unique_best / hard_cut / score_cut_set / slope / intercept as in
- * miagpu_cull_flags; packed_runs (nullable) as in miagpu_get_runs_packed. */
+ * miagpu_cull_flags; a read that is not unique_best is left out of the fit, is not
+ * tested against the cut and is absent from the consensus (mia.c:466).
+ * packed_runs (nullable) as in miagpu_get_runs_packed. */
 int miagpu_iterate_host( miagpu_ctx* ctx, int64_t n, const uint8_t* bases,
                          const int64_t* offsets, const uint8_t* rc, const int32_t* as,
                          const int32_t* ae, int32_t* score, int32_t* as_out,

@@ -307,15 +307,18 @@ __global__ void call_kernel(const int32_t* acc, int64_t n_cols, int cons_code, c
 // alignment or front part) and 2i+1 (wrapped back part, col_count = 0 when not split).
 // Mirrors mia_main.c:259-276 (end fix, split test), split_pwaln (mia.c:1376-1438) and
 // asp_len (fsdb.c:518-530); used when the host has no stale AlnSeq pointers to describe.
+// A read that is not unique_best (-u / -U) is not in the culled list at all (mia.c:466): flag value 2 in dropped_front /
+// dropped_back, or unique[i] == 0, leaves its entries empty.
 __global__ void natural_entries_kernel(int64_t n, const int32_t* as_out, const int32_t* ae_out, const int32_t* n_runs,
                                        const uint16_t* runs, const uint8_t* status, int seq_len, const uint8_t* dropped_front,
-                                       const uint8_t* dropped_back, miagpu_entry* out) {
+                                       const uint8_t* dropped_back, miagpu_entry* out, const uint8_t* unique = nullptr) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   miagpu_entry f{}, b{};
   f.read = b.read = (int32_t)i;
   const int nr = n_runs[i];
-  if (nr > 0 && !(status[i] & MIAGPU_ST_UNSUPPORTED)) {
+  const bool absent = (unique && !unique[i]) || (dropped_front && dropped_front[i] == 2);
+  if (nr > 0 && !(status[i] & MIAGPU_ST_UNSUPPORTED) && !absent) {
     const int start = as_out[i];
     int end = ae_out[i];
     if (end > seq_len) end -= seq_len;
@@ -331,11 +334,11 @@ __global__ void natural_entries_kernel(int64_t n, const int32_t* as_out, const i
     const int fcols = split ? cf : cols;
     const int fl = fcols + fins, bl = split ? (cols - fcols) + (ins - fins) : 0;
     f.col_begin = 0; f.col_count = fcols; f.ref_pos = start; f.front_len = fl; f.total_len = fl + bl;
-    f.dropped = dropped_front ? dropped_front[i] : 0;
+    f.dropped = dropped_front ? (dropped_front[i] != 0) : 0;
     if (split) {
       b = f;
       b.col_begin = fcols; b.col_count = cols - fcols; b.ref_pos = 0; b.back_formula = 1;
-      b.dropped = dropped_back ? dropped_back[i] : f.dropped;
+      b.dropped = dropped_back ? (dropped_back[i] != 0) : f.dropped;
     }
   }
   out[2 * i] = f;

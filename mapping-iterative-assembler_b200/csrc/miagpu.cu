@@ -150,7 +150,7 @@ struct miagpu_ctx {
   // sharded rounds: this rank's part of the all-gather, what came back, prefetched chain blocks
   int sh_world = 0, sh_rank = 0, sh_phase = 0, sh_hard_cut = 0, sh_cut_set = 0, sh_chunks = 0;
   int64_t sh_nmax = 0, sh_stride = 0, sh_fetched = 0;
-  bool sh_fit = false, sh_host = false, sh_want_packed = false;
+  bool sh_fit = false, sh_host = false, sh_want_packed = false, sh_has_unique = false;
   double sh_slope = 0, sh_icpt = 0;
   DevBuf<uint32_t> d_sh_send, d_sh_recv, d_sh_pf;
   DevBuf<int32_t> d_sh_pfid;
@@ -1550,7 +1550,8 @@ static int iterate_tail(miagpu_ctx* c, const IterTail& a, const Trace& tr) {
   c->n_entries = 2 * n;
   MIAGPU_CUDA(cudaMemsetAsync(c->d_gaps.p, 0, (c->seq_len + 2) * sizeof(int32_t), main));
   natural_entries_kernel<<<(unsigned)((n + 255) / 256), 256, 0, main>>>(n, c->d_as_out.p, c->d_ae_out.p, c->d_nruns.p, c->d_runs.p,
-                                                                        c->d_status.p, c->seq_len, nullptr, nullptr, c->d_entries.p);
+                                                                        c->d_status.p, c->seq_len, nullptr, nullptr, c->d_entries.p,
+                                                                        has_unique ? c->d_unique.p : nullptr);
   MIAGPU_CUDA(cudaGetLastError());
   c->launches++;
   if (!launch_gaps(c)) return 0;
@@ -1607,7 +1608,8 @@ static int iterate_tail(miagpu_ctx* c, const IterTail& a, const Trace& tr) {
   cut_thresholds(a.hard_cut, slope, intercept, H->thr);
   MIAGPU_CUDA(cudaMemcpyAsync(c->d_thr.p, H->thr, sizeof(H->thr), cudaMemcpyHostToDevice, main));
   if (a.wait_old_flags) MIAGPU_CUDA(cudaStreamWaitEvent(main, c->xev[1], 0));
-  cut_flags_kernel<<<(unsigned)((n + 255) / 256), 256, 0, main>>>(n, c->d_seqlen.p, c->d_score.p, c->d_thr.p, c->d_dropf.p, c->d_entries.p, c->d_cstats.p);
+  cut_flags_kernel<<<(unsigned)((n + 255) / 256), 256, 0, main>>>(n, c->d_seqlen.p, c->d_score.p, c->d_thr.p, c->d_dropf.p, c->d_entries.p, c->d_cstats.p,
+                                                                  has_unique ? c->d_unique.p : nullptr);
   MIAGPU_CUDA(cudaGetLastError());
   c->launches++;
   MIAGPU_CUDA(cudaMemcpyAsync(&H->bad_after, &c->d_cstats.p->bad, sizeof(long long), cudaMemcpyDeviceToHost, main));
@@ -1866,6 +1868,7 @@ static int shard_after_dp(miagpu_ctx* c, bool stats_done, bool has_unique, void*
                           void** max_buf, int64_t* max_words) {
   cudaStream_t main = c->stream;
   const int64_t n = c->n, stride = c->sh_stride;
+  c->sh_has_unique = has_unique;
   if (!stats_done && !cut_launch_stats(c, 0, n, has_unique)) return 0;
   shard_pack_kernel<<<(unsigned)((stride + 255) / 256), 256, 0, main>>>(n, stride, c->d_seqlen.p, c->d_score.p, has_unique ? c->d_unique.p : nullptr,
                                                                        c->d_sh_send.p);
@@ -1876,7 +1879,8 @@ static int shard_after_dp(miagpu_ctx* c, bool stats_done, bool has_unique, void*
   c->n_entries = 2 * n;
   if (n) {
     natural_entries_kernel<<<(unsigned)((n + 255) / 256), 256, 0, main>>>(n, c->d_as_out.p, c->d_ae_out.p, c->d_nruns.p, c->d_runs.p,
-                                                                          c->d_status.p, c->seq_len, nullptr, nullptr, c->d_entries.p);
+                                                                          c->d_status.p, c->seq_len, nullptr, nullptr, c->d_entries.p,
+                                                                          has_unique ? c->d_unique.p : nullptr);
     MIAGPU_CUDA(cudaGetLastError());
     c->launches++;
     if (!launch_gaps(c)) return 0;
@@ -2037,7 +2041,8 @@ extern "C" int miagpu_shard_cut(miagpu_ctx* c, double* slope_out, double* interc
   MIAGPU_CUDA(cudaMemcpyAsync(c->d_thr.p, H->thr, sizeof(H->thr), cudaMemcpyHostToDevice, main));
   if (c->sh_host) MIAGPU_CUDA(cudaStreamWaitEvent(main, c->xev[1], 0));
   if (n) {
-    cut_flags_kernel<<<(unsigned)((n + 255) / 256), 256, 0, main>>>(n, c->d_seqlen.p, c->d_score.p, c->d_thr.p, c->d_dropf.p, c->d_entries.p, c->d_cstats.p);
+    cut_flags_kernel<<<(unsigned)((n + 255) / 256), 256, 0, main>>>(n, c->d_seqlen.p, c->d_score.p, c->d_thr.p, c->d_dropf.p, c->d_entries.p, c->d_cstats.p,
+                                                                    c->sh_has_unique ? c->d_unique.p : nullptr);
     MIAGPU_CUDA(cudaGetLastError());
     c->launches++;
   }

@@ -294,3 +294,99 @@ class ResidentAssembler:
         while not conv and self.iter < max_iter:
             _, conv = self.iterate()
         return self.cons, self.iter, conv
+
+
+class RepeatFilterAssembler:
+    """mia -u / -U on the device: every round re-sorts the FSDB (sort_fsdb, fsdb.c:240-252), marks the first of every group
+    of reads with the same strand, start and end as unique_best (set_uniq_in_fsdb, fsdb.c:440-508) and leaves the others
+    out of the regression and of the consensus (mia.c:466).  Reads, alignments and the DP stay resident; the filter is
+    miagpu_repeat_filter; the host keeps what the reference keeps per FSDB POSITION rather than per read:
+
+      * the FSDB order itself (the next sort's ties are resolved by it);
+      * AlnSeq slots are numbered in FSDB order at every merge, and AlnSeq.dropped is sticky per slot (H10): a flag set
+        for the read at position k stays with position k when the next sort puts another read there.
+
+    Stale back pointers (a read that was wrap-split in an earlier round, mia_main.c:273-276) are counted in
+    `split_changes`, not reproduced (driver.Assembler does that, without the filter)."""
+
+    def __init__(self, gpu, ref, sm, circular=1, k=0, soft_mask=0, cons_code=1, just_outer_coords=1, key="score"):
+        self.g, self.sm, self.circular, self.k, self.soft_mask, self.cons_code = gpu, sm, circular, k, soft_mask, cons_code
+        self.just_outer_coords, self.ref0 = just_outer_coords, ref
+        self.split_changes = 0
+        if key != "score":
+            raise NotImplementedError("-U needs FragSeq.qual_sum from the FASTQ parser (host side); pass it as key4 to miagpu_repeat_filter")
+        gpu.set_pssm(sm)
+
+    def _filter_and_cull(self, split):
+        """sort + unique flags + cull over the current FSDB; returns per-read flags for miagpu_consensus_natural"""
+        g, fo = self.g, self.order
+        order, uniq = g.repeat_filter(self.rc[fo], self.as_[fo], self.ae[fo], self.score[fo], None, self.just_outer_coords, 0)
+        # slots were numbered in the FSDB order the merges ran in (BEFORE this sort)
+        nsl = 1 + split.astype(np.int64)
+        first = np.zeros(len(nsl), np.int64)
+        first[fo] = np.cumsum(nsl[fo]) - nsl[fo]
+        need = int(nsl.sum()) + 2
+        if need > len(self.dropped_slot):
+            self.dropped_slot = np.concatenate([self.dropped_slot, np.zeros(need - len(self.dropped_slot) + 64, np.uint8)])
+        self.unique = np.zeros(len(fo), np.uint8)
+        self.unique[fo] = uniq
+        self.order = fo[order]                                                       # the sort's effect on fsdb->fss
+        fo = self.order
+        fit = api.score_cut(self.seq_len[fo], self.score[fo], self.unique[fo])       # sums run in FSDB order (H8)
+        below = api.cull_flags(self.seq_len, self.score, None, 0, 1, fit[0], fit[1]).astype(bool) & (self.unique > 0)
+        self.dropped_slot[first[below]] = 1
+        self.dropped_slot[first[below & split] + 1] = 1
+        df = np.where(self.unique > 0, self.dropped_slot[first], 2).astype(np.uint8)
+        db = np.where(self.unique > 0, self.dropped_slot[np.minimum(first + 1, len(self.dropped_slot) - 1)], 2).astype(np.uint8)
+        self.fit = fit
+        return df, db
+
+    def pass1(self, bases, off):
+        g = self.g
+        g.set_reference(self.ref0, self.circular, with_rc=1)
+        g.build_kmers(self.k, self.soft_mask)
+        g.upload_reads(bases, off)
+        p = g.pass1()
+        seq_len = np.diff(off).astype(np.int32)
+        keep = (p["hits"] > 0) & (p["score"] >= FIRST_ROUND_SCORE_CUTOFF)            # mia.c:1614
+        if (keep & (p["score"] == FIRST_ROUND_SCORE_CUTOFF)).any():
+            raise NotImplementedError("reads with score == 2000 keep strand_known = 0 and are never realigned (mia.c:1653)")
+        idx = np.flatnonzero(keep)
+        self.ids = idx.copy()                                                        # input index of every FSDB read
+        self.seq_len, self.score = seq_len[idx], p["score"][idx].copy()
+        self.rc, self.as_, self.ae = p["rc"][idx].copy(), p["as_"][idx].copy(), p["ae"][idx].copy()
+        split = p["start"][idx] > p["end"][idx]                                      # mia.c:1619
+        self.order = np.arange(len(idx))
+        self.dropped_slot = np.zeros(2 * len(idx) + 64, np.uint8)
+        self._filter_and_cull(split)                                                 # mia_main.c:827-848: only the flags survive
+        ok = self.score > 0                                                          # clean_FSDB (mia.c:400-406)
+        keep_dev = np.zeros(len(seq_len), np.uint8)
+        keep_dev[idx[ok]] = 1
+        rev = np.zeros(len(seq_len), np.uint8)
+        rev[idx] = self.rc == 1
+        g.compact_reads(keep_dev, rev)
+        newpos = np.cumsum(ok) - 1
+        self.order = newpos[self.order[ok[self.order]]]
+        for name in ("seq_len", "score", "rc", "as_", "ae", "ids"):
+            setattr(self, name, getattr(self, name)[ok])
+        self.split = split[ok]
+        g.set_alignment_inputs(self.rc, self.as_, self.ae)
+        self.iter, self.cons, self.last = 0, None, self.ref0.upper()
+        return p
+
+    def iterate(self):
+        g = self.g
+        if self.cons is not None:
+            self.last = self.cons
+        self.iter += 1
+        g.set_reference(self.last, self.circular, with_rc=0)
+        g.realign_resident()
+        self.score, self.as_, self.ae = g.adopt_alignment()
+        L = len(self.last)
+        split = self.as_ > np.where(self.ae > L, self.ae - L, self.ae)
+        self.split_changes += int((split != self.split).sum())
+        self.split = split
+        df, db = self._filter_and_cull(split)
+        cons, self.gaps, _ = g.consensus_natural(df, db, self.cons_code)
+        self.cons = cons
+        return cons, cons == self.last

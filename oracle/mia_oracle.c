@@ -563,13 +563,19 @@ void orc_score_cut( long long n, const int* seq_len, const int* score,
 void orc_asm_cull( orc_asm* a, long long n_reads, const int* front, const int* back,
                    const int* seq_len, const int* score,
                    int hard_cut, int score_cut_set, double s, double n ) {   /* mia.c:418-506 */
+  orc_asm_cull_u( a, n_reads, front, back, seq_len, score, NULL, hard_cut, score_cut_set, s, n );
+}
+void orc_asm_cull_u( orc_asm* a, long long n_reads, const int* front, const int* back,
+                     const int* seq_len, const int* score, const unsigned char* unique_best,
+                     int hard_cut, int score_cut_set, double s, double n ) {
   double slope, intercept;
   if ( score_cut_set ) { slope = s; intercept = n; }
-  else orc_score_cut( n_reads, seq_len, score, NULL, &slope, &intercept );
+  else orc_score_cut( n_reads, seq_len, score, unique_best, &slope, &intercept );
   if ( slope <= 0 ) slope = 100.0;
   a->ne = 0;
   for ( long long r = 0; r < n_reads; r++ ) {
     if ( front[r] < 0 ) continue;
+    if ( unique_best && !unique_best[r] ) continue;   /* mia.c:466: not in the culled list at all */
     double min_score = hard_cut > 0 ? (double)hard_cut : (double)( intercept + ( slope * seq_len[r] ) );
     int drop = ( score[r] < min_score );
     int ids[2] = { front[r], back[r] };

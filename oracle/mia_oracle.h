@@ -107,6 +107,12 @@ void orc_asm_cull( orc_asm* a, long long n_reads, const int* front,
                    const int* back, const int* seq_len, const int* score,
                    int hard_cut, int score_cut_set, double slope,
                    double intercept );
+/* the same with FragSeq.unique_best (nullable = all 1; -u / -U): a read that is not
+ * unique_best is left out of the culled list and of the regression */
+void orc_asm_cull_u( orc_asm* a, long long n_reads, const int* front,
+                     const int* back, const int* seq_len, const int* score,
+                     const unsigned char* unique_best, int hard_cut,
+                     int score_cut_set, double slope, double intercept );
 /* a13: mia.c:515-603 over the culled entry list.  cons must hold
  * seq_len + sum(gaps) + 1 chars.  counts (nullable): 10 ints per base column:
  * As,Cs,Gs,Ts,gaps,cov,sA,sC,sG,sT */

@@ -237,10 +237,17 @@ class Oracle(_AlignMixin):
         self.lib.orc_score_cut(len(sl), _ip(sl), _ip(sc), None, C.byref(s), C.byref(n))
         return s.value, n.value
 
-    def asm_cull(self, a, front, back, seq_len, score, hard_cut=0, score_cut_set=0, slope=200.0, intercept=0.0):
+    def asm_cull(self, a, front, back, seq_len, score, hard_cut=0, score_cut_set=0, slope=200.0, intercept=0.0, unique_best=None):
         f, b = np.ascontiguousarray(front, np.int32), np.ascontiguousarray(back, np.int32)
         sl, sc = np.ascontiguousarray(seq_len, np.int32), np.ascontiguousarray(score, np.int32)
-        self.lib.orc_asm_cull(a, len(sl), _ip(f), _ip(b), _ip(sl), _ip(sc), hard_cut, score_cut_set, slope, intercept)
+        if unique_best is None:
+            self.lib.orc_asm_cull(a, len(sl), _ip(f), _ip(b), _ip(sl), _ip(sc), hard_cut, score_cut_set, slope, intercept)
+            return
+        uq = np.ascontiguousarray(unique_best, np.uint8)
+        fn = self.lib.orc_asm_cull_u
+        fn.argtypes = [C.c_void_p, C.c_longlong] + [C.c_void_p] * 5 + [C.c_int, C.c_int, C.c_double, C.c_double]
+        fn.restype = None
+        fn(a, len(sl), f.ctypes.data, b.ctypes.data, sl.ctypes.data, sc.ctypes.data, uq.ctypes.data, hard_cut, score_cut_set, slope, intercept)
 
     def asm_consensus(self, a, sm_fwd, sm_rc, cons_code, seq_len, max_extra=1 << 20, counts=False):
         buf = C.create_string_buffer(seq_len + max_extra + 1)
@@ -331,6 +338,10 @@ class Ref(_AlignMixin):
         L.refh_sess_num_fs.restype = C.c_longlong
         L.refh_sess_num_fs.argtypes = [C.c_void_p]
         L.refh_sess_fs.argtypes = [C.c_void_p, C.c_longlong, c_int_p, C.c_char_p]
+        L.refh_sess_fs_id.argtypes = [C.c_void_p, C.c_longlong, C.c_char_p]
+        L.refh_sess_fs_id.restype = None
+        L.refh_sess_set_repeat.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.refh_sess_set_repeat.restype = None
         L.refh_sess_aln.argtypes = [C.c_void_p, C.c_int, c_int_p] + [C.c_char_p] * 4
         L.refh_sess_column.argtypes = [C.c_void_p, C.c_int, c_int_p]
         L.refh_find_consensus.argtypes = [c_int_p, C.c_int]
@@ -407,6 +418,9 @@ class Ref(_AlignMixin):
             raise RuntimeError("reference session failed to read " + ref_fasta_path)
         return s
 
+    def sess_set_repeat(self, s, repeat_filt=1, just_outer_coords=1):
+        self.lib.refh_sess_set_repeat(s, int(repeat_filt), int(just_outer_coords))
+
     def sess_pass1(self, s, rid, read, want_masks=False):
         out = np.zeros(18, np.int32)
         bufs = [C.create_string_buffer(520) for _ in range(4)]
@@ -440,8 +454,11 @@ class Ref(_AlignMixin):
             o = np.zeros(8, np.int32)
             seq = C.create_string_buffer(260)
             self.lib.refh_sess_fs(s, i, _ip(o), seq)
+            rid = C.create_string_buffer(128)
+            self.lib.refh_sess_fs_id(s, C.c_longlong(i), rid)
             res.append(dict(seq_len=int(o[0]), score=int(o[1]), rc=int(o[2]), as_=int(o[3]), ae=int(o[4]),
-                            strand_known=int(o[5]), unique_best=int(o[6]), has_back=int(o[7]), seq=seq.value.decode()))
+                            strand_known=int(o[5]), unique_best=int(o[6]), has_back=int(o[7]), seq=seq.value.decode(),
+                            id=rid.value.decode()))
         return res
 
     def sess_slots(self, s):

@@ -200,6 +200,7 @@ typedef struct {
   char *last_cons, *cons;
   int hard_cut, score_cut_set;
   double slope, intercept;
+  int repeat_filt, just_outer_coords;      /* -u, -A */
 } Sess;
 
 /* mia_main.c:618-757 with the getopt results passed in */
@@ -238,6 +239,7 @@ void* refh_sess_new( const char* ref_fasta, int circular, int k, int soft_mask,
   s->front = (PWAlnFragP)calloc( 1, sizeof(PWAlnFrag) );
   s->back  = (PWAlnFragP)calloc( 1, sizeof(PWAlnFrag) );
   s->slope = DEF_S; s->intercept = DEF_N;
+  s->just_outer_coords = 1;                /* mia_main.c:420 */
   return s;
 }
 
@@ -246,6 +248,19 @@ void refh_sess_set_cut( void* s_, int hard_cut, int score_cut_set, double slope,
   s->hard_cut = hard_cut; s->score_cut_set = score_cut_set;
   s->slope = slope; s->intercept = intercept;
 }
+
+/* -u (repeat_filt) and -A (just_outer_coords = 0): mia_main.c:500-505 */
+void refh_sess_set_repeat( void* s_, int repeat_filt, int just_outer_coords ) {
+  Sess* s = (Sess*)s_;
+  s->repeat_filt = repeat_filt; s->just_outer_coords = just_outer_coords;
+}
+static void sess_repeat_filter( Sess* s ) {            /* mia_main.c:827-834, 883-886, 938-941 */
+  if ( s->repeat_filt && s->fsdb->num_fss > 0 ) {
+    sort_fsdb( s->fsdb );
+    set_uniq_in_fsdb( s->fsdb, s->just_outer_coords, 0 );
+  }
+}
+void refh_sess_fs_id( void* s_, long long i, char* id ) { strcpy( id, ((Sess*)s_)->fsdb->fss[i]->id ); }
 
 /* One read through mia_main.c:759-797 (no -T, no -I).
    out[0]=kmer hits (return of new_kmer_filter)  out[1]=added to fsdb (0/1)
@@ -306,6 +321,7 @@ void refh_sess_end_pass1( void* s_ ) {
   pop_smp_from_FSDB( s->fsdb, PSSM_DEPTH );
   s->iter = 1;
   s->culled = init_culled_map_alignment( s->maln );
+  sess_repeat_filter( s );
   cull_maln_from_fsdb( s->culled, s->fsdb, s->hard_cut, s->score_cut_set, s->slope, s->intercept );
   s->culled->fpsm = s->anc;
   s->culled->rpsm = s->rcanc;
@@ -340,6 +356,7 @@ const char* refh_sess_iterate( void* s_, int sort, int* converged ) {
   reiterate_assembly( ref_for_round, s->iter, s->maln, s->fsdb, s->fw,
                       s->front, s->back, s->anc, s->rcanc );
   pop_smp_from_FSDB( s->fsdb, PSSM_DEPTH );
+  sess_repeat_filter( s );
   cull_maln_from_fsdb( s->culled, s->fsdb, s->hard_cut, s->score_cut_set, s->slope, s->intercept );
   s->culled->fpsm = s->anc;
   s->culled->rpsm = s->rcanc;

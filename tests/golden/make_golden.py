@@ -68,11 +68,13 @@ def read_fixture_reads(path):
     return ids, [r[:256] for r in reads]
 
 
-def session(r, ref, reads, sm, circular, k, soft_mask, max_iter=30):
+def session(r, ref, reads, sm, circular, k, soft_mask, max_iter=30, repeat_filt=0, just_outer_coords=1):
     with tempfile.NamedTemporaryFile("w", suffix=".fa", delete=False) as f:
         f.write(">ref\n" + ref + "\n")
         path = f.name
     s = r.sess_new(path, circular, sm, k=k, soft_mask=soft_mask)
+    if repeat_filt:
+        r.sess_set_repeat(s, repeat_filt, just_outer_coords)
     p1 = []
     for i, rd in enumerate(reads):
         if not rd:
@@ -88,12 +90,14 @@ def session(r, ref, reads, sm, circular, k, soft_mask, max_iter=30):
         rd = r.sess_reads(s)
         slots = r.sess_slots(s)
         iters.append(dict(cons=cons, converged=conv, reads=[[x["score"], x["as_"], x["ae"], x["rc"]] for x in rd],
+                          ids=[int(x["id"][1:]) for x in rd], unique=[x["unique_best"] for x in rd],
                           slots=[[x["start"], x["end"], x["dropped"], x["segment"], x["seq"], x["smp"], x["ins"]] for x in slots],
                           gaps=np.flatnonzero(r.sess_gaps(s)).tolist()))
         if conv:
             break
     os.unlink(path)
-    return dict(ref=ref, reads=reads, circular=circular, k=k, soft_mask=soft_mask, pass1=p1, iters=iters)
+    return dict(ref=ref, reads=reads, circular=circular, k=k, soft_mask=soft_mask, pass1=p1, iters=iters, repeat_filt=repeat_filt,
+                just_outer_coords=just_outer_coords)
 
 
 def main():
@@ -140,6 +144,22 @@ def main():
     b, off, _ = synth.make_reads(g, 300, 30, 140, seed=23)
     reads = [synth.read_str(b, off, i) for i in range(300)]
     sess["synth2k5_pe_long_c_k12"] = session(r, ref, reads, m["pe"], 1, 12, 0)
+    # -u (repeat filter): a small genome at high coverage with PCR-style duplicates, some of them with a sequencing error
+    ref = synth.random_reference(1500, seed=31)
+    g = synth.diverge(ref, 0.03, seed=32, indel_rate=0.003)
+    b, off, _ = synth.make_reads(g, 260, 35, 75, seed=33)
+    reads = [synth.read_str(b, off, i) for i in range(260)]
+    rng = np.random.default_rng(34)
+    for _ in range(140):                                   # duplicates: same molecule, sometimes one base changed
+        rd = reads[int(rng.integers(0, 260))]
+        if rng.random() < 0.4:
+            q = int(rng.integers(0, len(rd)))
+            rd = rd[:q] + "ACGT"[("ACGT".index(rd[q]) + 1) % 4 if rd[q] in "ACGT" else 0] + rd[q + 1:]
+        reads.append(rd)
+    order = rng.permutation(len(reads))
+    reads = [reads[i] for i in order]
+    sess["synth1k5_dups_c_k10_u"] = session(r, ref, reads, m["onepass"], 1, 10, 0, repeat_filt=1)
+    sess["synth1k5_dups_lin_k10_uA"] = session(r, ref, reads, m["onepass"], 0, 10, 0, repeat_filt=1, just_outer_coords=0)
     json.dump(sess, open(os.path.join(HERE, "sessions.json"), "w"))
     # f1: the reference's sort_fsdb[_qscore] + set_uniq_in_fsdb on small FSDBs full of ties
     rng = np.random.default_rng(7)

@@ -4,8 +4,9 @@ import numpy as np
 
 
 class OracleRun:
-    def __init__(self, o, ref_raw, sm, circular=1, k=0, soft_mask=0, cons_code=1, distant_ref=0):
+    def __init__(self, o, ref_raw, sm, circular=1, k=0, soft_mask=0, cons_code=1, distant_ref=0, repeat_filt=0, just_outer_coords=1):
         self.o, self.sm, self.circular, self.cons_code = o, np.ascontiguousarray(sm, np.int32), circular, cons_code
+        self.repeat_filt, self.just_outer_coords = repeat_filt, just_outer_coords
         self.smr = o.revcom_pssm(self.sm)
         self.ctx = o.ctx_new(ref_raw, circular, self.sm, with_rc=1, k=k, soft_mask=soft_mask, distant_ref=distant_ref)
         self.seq_len = len(ref_raw)
@@ -23,7 +24,7 @@ class OracleRun:
             seq = self.o.revcom(read) if (p["rc"] and p["strand_known"]) else read      # fsdb.c:209-227
             end = p["b_end"] if p["split"] else p["end"]
             f, b = self.o.asm_add(self.asm, p["f_ref"] + p["b_ref"], p["f_frag"] + p["b_frag"], p["start"], end, p["rc"], p["score"])
-            self.fsdb.append(dict(seq=seq, seq_len=len(read), score=p["score"], rc=p["rc"], as_=p["as_"], ae=p["ae"],
+            self.fsdb.append(dict(rid=len(self.fsdb), unique_best=1, seq=seq, seq_len=len(read), score=p["score"], rc=p["rc"], as_=p["as_"], ae=p["ae"],
                                   strand_known=p["strand_known"], front=f, back=-1 if b is None else b))   # mia.c:1626-1642
         return p
 
@@ -31,10 +32,23 @@ class OracleRun:
         g = lambda k: np.array([f[k] for f in self.fsdb], np.int32)
         return g("front"), g("back"), g("seq_len"), g("score")
 
+    def _repeat_filter(self):
+        """-u: sort_fsdb + set_uniq_in_fsdb (mia_main.c:827-834, 883-886, 938-941): the FSDB itself is re-ordered"""
+        if not self.repeat_filt or not self.fsdb:
+            return None
+        g = lambda k: np.array([f[k] for f in self.fsdb], np.int32)
+        order, uniq = self.o.repeat_filter(g("rc").astype(np.uint8), g("as_"), g("ae"), g("score"), None, self.just_outer_coords, 0)
+        for f, u in zip(self.fsdb, uniq):
+            f["unique_best"] = int(u)
+        self.fsdb = [self.fsdb[k] for k in order]
+        return np.array([f["unique_best"] for f in self.fsdb], np.uint8)
+
     def end_pass1(self):
         fr, bk, sl, sc = self._arrays()
         self.o.asm_pop_smp(self.asm, fr, bk)
-        self.o.asm_cull(self.asm, fr, bk, sl, sc)
+        uq = self._repeat_filter()
+        fr, bk, sl, sc = self._arrays()
+        self.o.asm_cull(self.asm, fr, bk, sl, sc, unique_best=uq)
         self.fsdb = [f for f in self.fsdb if f["score"] > 0]                             # clean_FSDB mia.c:400-406
         self.iter = 1
         self.last = self.cur_ref
@@ -53,7 +67,7 @@ class OracleRun:
             if not f["strand_known"]:
                 continue
             r = o.realign(ctx, f["seq"], f["rc"], f["as_"], f["ae"])
-            f["as_"], f["ae"], f["score"] = r["as_"], r["ae"], r["score"]
+            f["as_"], f["ae"], f["score"], f["unique_best"] = r["as_"], r["ae"], r["score"], 1          # mia_main.c:254
             fs, bs = o.asm_add(self.asm, r["ref_gapped"], r["read_gapped"], r["as_"], r["ae"], f["rc"], r["score"])
             f["front"] = fs
             if bs is not None:
@@ -61,6 +75,8 @@ class OracleRun:
         o.ctx_free(ctx)
         fr, bk, sl, sc = self._arrays()
         o.asm_pop_smp(self.asm, fr, bk)
-        o.asm_cull(self.asm, fr, bk, sl, sc)
+        uq = self._repeat_filter()
+        fr, bk, sl, sc = self._arrays()
+        o.asm_cull(self.asm, fr, bk, sl, sc, unique_best=uq)
         self.cons = o.asm_consensus(self.asm, self.sm, self.smr, self.cons_code, self.seq_len)
         return self.cons, self.cons == self.last

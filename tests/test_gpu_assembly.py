@@ -126,3 +126,25 @@ def test_sharded_assembly_to_convergence(gpu, golden, name, matrix, parts):
     finally:
         for g in ctxs:
             g.close()
+
+
+@pytest.mark.parametrize("name", ["synth1k5_dups_c_k10_u", "synth1k5_dups_lin_k10_uA"])
+def test_repeat_filter_sessions_reproduce_reference(gpu, golden, name):
+    # mia -u (and -u -A): the FSDB is re-sorted every round, duplicates are left out, sticky flags stay with FSDB positions --
+    # per round: the reads in the reference's FSDB order, their unique_best flags, the consensus
+    import _pkg
+    _pkg.load()
+    from mia_b200 import driver
+    s, bases, off = _session_inputs(name)
+    A = driver.RepeatFilterAssembler(gpu, s["ref"], golden["onepass"], s["circular"], s["k"], s["soft_mask"],
+                                     just_outer_coords=s["just_outer_coords"])
+    A.pass1(bases, off)
+    for it, e in enumerate(s["iters"]):
+        cons, conv = A.iterate()
+        fo = A.order
+        assert A.ids[fo].tolist() == e["ids"], f"{name}: iteration {it + 1} FSDB order"
+        got = np.stack([A.score[fo], A.as_[fo], A.ae[fo], A.rc[fo].astype(np.int32)], 1).tolist()
+        assert got == e["reads"], f"{name}: iteration {it + 1} per-read score/as/ae"
+        assert A.unique[fo].tolist() == e["unique"], f"{name}: iteration {it + 1} unique_best"
+        assert cons == e["cons"], f"{name}: iteration {it + 1} consensus"
+        assert conv == e["converged"]

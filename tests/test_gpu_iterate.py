@@ -22,8 +22,10 @@ def _separate(gpu, api, bases, off, rc, as_, ae, seq_len, sticky, unique_best=No
     else:
         fit = score_cut
         below = api.cull_flags(seq_len, out["score"], unique_best, hard_cut, 1, fit[0], fit[1])
-    drop = (sticky | below).astype(np.uint8)
-    cons, gaps, _ = gpu.consensus_natural(drop, drop, 1)
+    tested = np.ones(len(sticky), bool) if unique_best is None else unique_best.astype(bool)
+    drop = (sticky | (below & tested)).astype(np.uint8)             # a read that is not unique_best is not tested (mia.c:466)
+    flags = np.where(tested, drop, 2).astype(np.uint8)              # ... and not in the culled list at all
+    cons, gaps, _ = gpu.consensus_natural(flags, flags, 1)
     return out, fit, drop, cons, gaps
 
 

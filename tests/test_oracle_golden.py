@@ -39,7 +39,8 @@ def test_align_matches_reference_golden(oracle, golden):
 
 def _run_session(oracle, golden, name, matrix):
     s = json.load(open(os.path.join(G, "sessions.json")))[name]
-    R = OracleRun(oracle, s["ref"], golden[matrix], s["circular"], s["k"], s["soft_mask"])
+    R = OracleRun(oracle, s["ref"], golden[matrix], s["circular"], s["k"], s["soft_mask"], repeat_filt=s.get("repeat_filt", 0),
+                  just_outer_coords=s.get("just_outer_coords", 1))
     for i, (rd, exp) in enumerate(zip(s["reads"], s["pass1"])):
         if exp is None:
             continue
@@ -52,6 +53,8 @@ def _run_session(oracle, golden, name, matrix):
     for it, exp in enumerate(s["iters"]):
         cons, conv = R.iterate()
         assert [[f["score"], f["as_"], f["ae"], f["rc"]] for f in R.fsdb] == exp["reads"], f"{name}: iteration {it} reads"
+        if s.get("repeat_filt"):
+            assert [f["unique_best"] for f in R.fsdb] == exp["unique"], f"{name}: iteration {it} unique_best"
         slots = [[x["start"], x["end"], x["dropped"], x["segment"], x["seq"], x["smp"], x["ins"]] for x in oracle.asm_entries(R.asm)]
         assert slots == exp["slots"], f"{name}: iteration {it} AlnSeq list"
         assert np.flatnonzero(oracle.asm_gaps(R.asm, R.wrap_len)).tolist() == exp["gaps"]
@@ -99,6 +102,12 @@ def test_find_consensus_rules(oracle):
     assert f([1, 0, 0, 0, 0, 1, -399, -500, -500, -500]) == "A"
     assert f([1, 0, 0, 0, 0, 1, -1, -2401, -3000, -3000], 2) == "N"  # cons_code 2: diff must EXCEED 2400
     assert f([1, 0, 0, 0, 0, 1, -1, -2402, -3000, -3000], 2) == "A"
+
+
+def test_session_repeat_filter(oracle, golden):
+    # -u: sort_fsdb + set_uniq_in_fsdb every round (the FSDB order itself changes), circular; -u -A, linear
+    _run_session(oracle, golden, "synth1k5_dups_c_k10_u", "onepass")
+    _run_session(oracle, golden, "synth1k5_dups_lin_k10_uA", "onepass")
 
 
 def test_repeat_filter_matches_reference_golden(oracle):
