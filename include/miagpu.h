@@ -344,6 +344,16 @@ int miagpu_realign_resident( miagpu_ctx* ctx );
  * mia_main.c:252-256); score / as / ae (nullable host arrays of n) receive this round's values. */
 int miagpu_adopt_alignment( miagpu_ctx* ctx, int32_t* score, int32_t* as, int32_t* ae );
 
+/* ---- 8f4. Adapter trimming (-T): trim_frag (mia.c:1318-1368) for every read of a batch in
+ * host memory (call site mia_main.c:773-777; set-up 692-713): dyn_prog of the adapter (rows)
+ * against the read (columns) with the flat matrix (init_flatsubmat, pssm.c:96-126), sg5 = 1, the
+ * first maximum of the last column, find_align_begin.  Outputs (host arrays of n, nullable):
+ * max_score, abr, abc, aer as trim_frag leaves them in the Alignment; trimmed / trim_point =
+ * FragSeq.trimmed / trim_point (trim_point 0 when not trimmed).  No homopolymer discount (-h). */
+int miagpu_trim( miagpu_ctx* ctx, int64_t n, const uint8_t* bases, const int64_t* offsets,
+                 const char* adapter, int adapter_len, int32_t* max_score, int32_t* abr,
+                 int32_t* abc, int32_t* aer, uint8_t* trimmed, int32_t* trim_point );
+
 /* ---- 8f1. The repeat filter (-u / -U): sort_fsdb / sort_fsdb_qscore (fsdb.c:13-88, 90-180,
  * 240-252) + set_uniq_in_fsdb (fsdb.c:440-508) at the call sites mia_main.c:827-844, 883-890,
  * 938-945.  Inputs are host arrays of n in FSDB order: FragSeq.rc / as / ae, key4 = FragSeq.score

@@ -82,6 +82,7 @@ def load_library():
     L.miagpu_shard_cut.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), _vpp, _i64p]
     L.miagpu_shard_finish.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, _i64p, C.c_void_p, C.c_char_p, _i32p]
     L.miagpu_last_cut_stats.argtypes = [C.c_void_p, _i64p, _i64p]
+    L.miagpu_trim.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_char_p, C.c_int] + [C.c_void_p] * 6
     L.miagpu_repeat_filter.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 5 + [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     L.miagpu_last_pair_buckets.argtypes = [C.c_void_p] + [C.c_void_p] * 5 + [_i32p, _i32p]
     L.miagpu_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), _i64p, _i32p]
@@ -99,7 +100,7 @@ EXPORTS = ["miagpu_device_count", "miagpu_create", "miagpu_destroy", "miagpu_las
            "miagpu_score_cut", "miagpu_cull_flags",
            "miagpu_set_alignment_inputs", "miagpu_realign_resident", "miagpu_adopt_alignment", "miagpu_set_cut_inputs", "miagpu_reset_dropped", "miagpu_iterate_resident", "miagpu_last_buckets", "miagpu_last_pair_buckets", "miagpu_last_timing",
            "miagpu_int32_peak", "miagpu_stream", "miagpu_shard_begin", "miagpu_shard_begin_host", "miagpu_shard_cut", "miagpu_shard_finish",
-           "miagpu_last_cut_stats", "miagpu_repeat_filter"]
+           "miagpu_last_cut_stats", "miagpu_repeat_filter", "miagpu_trim"]
 
 
 def _ptr(a):
@@ -315,6 +316,17 @@ class MiaGpu:
         a, b = C.c_int64(), C.c_int64()
         self._ck(self.lib.miagpu_last_cut_stats(self.h, C.byref(a), C.byref(b)))
         return dict(serial_blocks=a.value, fetched_blocks=b.value)
+
+    # -- adapter trimming (8f4)
+    def trim(self, bases, offsets, adapter):
+        """trim_frag for a batch: -> dict(score, abr, abc, aer, trimmed, trim_point) of numpy arrays"""
+        n = len(offsets) - 1
+        o = dict(score=np.zeros(n, np.int32), abr=np.zeros(n, np.int32), abc=np.zeros(n, np.int32), aer=np.zeros(n, np.int32),
+                 trimmed=np.zeros(n, np.uint8), trim_point=np.zeros(n, np.int32))
+        ad = adapter if isinstance(adapter, bytes) else adapter.encode()
+        self._ck(self.lib.miagpu_trim(self.h, n, _ptr(bases), _ptr(offsets), ad, len(ad), _ptr(o["score"]), _ptr(o["abr"]), _ptr(o["abc"]),
+                                      _ptr(o["aer"]), _ptr(o["trimmed"]), _ptr(o["trim_point"])))
+        return o
 
     # -- repeat filter (8f1)
     def repeat_filter(self, rc, as_, ae, key4, trimmed=None, just_outer_coords=1, tolerance=0, want_order=True):

@@ -19,6 +19,11 @@ constexpr int REALIGN_BUFFER = 50;   // params.h:34
 constexpr int MAX_RUNS = MIAGPU_MAX_RUNS;
 constexpr int HIM = -1073741824;     // INT_MIN/2, mia.c:751
 constexpr int FIRST_ROUND_SCORE_CUTOFF = 2000;
+constexpr int FLAT_MATCH = 200;      // params.h:28
+constexpr int FLAT_MISMATCH = -600;  // params.h:29
+constexpr int N_SCORE_FLAT = -100;   // params.h:30 N_SCORE
+constexpr int NR_SCORE_FLAT = -10;   // params.h:31 NR_SCORE
+constexpr int TRIM_SCORE_CUT = 1000; // params.h:32
 
 // ---- kernel-side PSSM layout: prof[strand][depth][read_base][ref_code padded to 8]
 // One "profile row" (the 5 scores a read base can get against A,C,G,T,other at a

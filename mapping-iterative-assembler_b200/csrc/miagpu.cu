@@ -141,6 +141,9 @@ struct miagpu_ctx {
   std::vector<uint8_t> h_unique;
   int64_t cut_inputs_n = -1;
   int64_t cut_serial_blocks = 0;                // chain blocks the last round summed read by read on the host
+  // adapter trimming
+  DevBuf<int32_t> tr_prof, tr_ws, tr_wl, tr_out, tr_cnt;
+  DevBuf<uint8_t> tr_codes, tr_ad, tr_st;
   // repeat filter (repeat.cuh)
   DevBuf<uint8_t> rf_rc, rf_tr, rf_uq, rf_tmp;
   DevBuf<int32_t> rf_as, rf_ae, rf_k4, rf_idx, rf_idx2;
@@ -273,6 +276,8 @@ extern "C" void miagpu_destroy(miagpu_ctx* c) {
   if (c->h_sh_pf) cudaFreeHost(c->h_sh_pf);
   if (c->h_sh_pfid) cudaFreeHost(c->h_sh_pfid);
   c->d_sh_send.release(); c->d_sh_recv.release(); c->d_sh_pf.release(); c->d_sh_pfid.release();
+  c->tr_prof.release(); c->tr_ws.release(); c->tr_wl.release(); c->tr_out.release(); c->tr_cnt.release(); c->tr_codes.release();
+  c->tr_ad.release(); c->tr_st.release();
   c->rf_rc.release(); c->rf_tr.release(); c->rf_uq.release(); c->rf_tmp.release(); c->rf_as.release(); c->rf_ae.release(); c->rf_k4.release();
   c->rf_idx.release(); c->rf_idx2.release(); c->rf_key.release(); c->rf_key2.release(); c->rf_ord.release(); c->rf_bad.release();
   c->d_seqlen.release(); c->d_unique.release(); c->d_cstats.release(); c->d_ctab.release(); c->d_thr.release(); c->d_cblk.release();
@@ -2097,6 +2102,103 @@ extern "C" int miagpu_last_cut_stats(miagpu_ctx* c, int64_t* serial_blocks, int6
   if (!c) { set_error("miagpu_last_cut_stats: no context"); return 0; }
   if (serial_blocks) *serial_blocks = c->cut_serial_blocks;
   if (fetched_blocks) *fetched_blocks = c->sh_fetched;
+  return 1;
+}
+
+// ------------------------------------------------------------------ adapter trimming (8f4)
+template <int K>
+static int launch_trim(miagpu_ctx* c, RealignParams p, int maxL, int n) {
+  using TL = TraceLayout<K>;
+  const size_t smem = PROF_INTS * 4 + WARPS_PER_BLOCK * MAX_READ * 2;
+  int per_sm = 0;
+  MIAGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (realign_kernel<K, true>), WARPS_PER_BLOCK * 32, smem));
+  if (per_sm < 1) { set_error("realign_kernel<%d, trim> does not fit on an SM", K); return 0; }
+  per_sm = std::min(per_sm, 8);
+  const int blocks = std::min(c->num_sms * per_sm, (n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+  const int64_t words = (int64_t)std::max(maxL - 1, 1) * TL::ROW_WORDS;
+  DevBuf<uint32_t>& scratch = c->d_scratch[0];
+  if (!scratch.reserve((size_t)words * blocks * WARPS_PER_BLOCK)) return 0;
+  p.scratch = scratch.p; p.scratch_words_per_warp = words; p.ref_in_smem = 0;
+  realign_kernel<K, true><<<blocks, WARPS_PER_BLOCK * 32, smem, c->stream>>>(p);
+  MIAGPU_CUDA(cudaGetLastError());
+  c->launches++;
+  return 1;
+}
+
+extern "C" int miagpu_trim(miagpu_ctx* c, int64_t n, const uint8_t* bases, const int64_t* offsets, const char* adapter, int adapter_len,
+                           int32_t* max_score, int32_t* abr, int32_t* abc, int32_t* aer, uint8_t* trimmed, int32_t* trim_point) {
+  if (!c || n < 0 || (n && (!bases || !offsets)) || !adapter || adapter_len < 1 || adapter_len > 127) {   // mia_main.c:559: "That adapter is too big!"
+    set_error("miagpu_trim: bad argument (the adapter holds 1..127 bases)");
+    return 0;
+  }
+  if (n == 0) return 1;
+  if (n > 0x7fffffffLL || offsets[n] > 0x7fffffffLL) { set_error("miagpu_trim: batch too large"); return 0; }
+  MIAGPU_CUDA(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  // flat matrix (init_flatsubmat, pssm.c:96-126) as a scoring profile: prof[depth][row base][column code]
+  int32_t flat[MIAGPU_PSSM_INTS];
+  for (int d = 0; d < NMAT; d++)
+    for (int a = 0; a < 5; a++)
+      for (int b = 0; b < 5; b++) flat[(d * 5 + a) * 5 + b] = a == 4 ? NR_SCORE_FLAT : b == 4 ? N_SCORE_FLAT : a == b ? FLAT_MATCH : FLAT_MISMATCH;
+  std::vector<int32_t> prof(PROF_INTS, 0);
+  for (int d = 0; d < NMAT; d++)
+    for (int rb = 0; rb < 5; rb++)
+      for (int fb = 0; fb < 5; fb++) prof[prof_row_index(0, d, rb) + fb] = flat[(d * 5 + fb) * 5 + rb];
+  const int64_t total = offsets[n];
+  int maxL = 0;
+  std::vector<int32_t> ws(n), wl(n);
+  for (int64_t i = 0; i < n; i++) {
+    const int64_t l = offsets[i + 1] - offsets[i];
+    if (l < 1 || l > MAX_READ) { set_error("miagpu_trim: read %lld has %lld bases (1..%d)", (long long)i, (long long)l, MAX_READ); return 0; }
+    ws[i] = (int32_t)offsets[i]; wl[i] = (int32_t)l;
+    maxL = std::max(maxL, (int)l);
+  }
+  std::vector<uint8_t> codes(total + 16, 4), ad(adapter_len);
+  for (int64_t i = 0; i < total; i++) codes[i] = (uint8_t)base_code(bases[i]);
+  for (int i = 0; i < adapter_len; i++) ad[i] = (uint8_t)adapter[i];
+  DevBuf<int32_t>&d_prof = c->tr_prof, &d_ws = c->tr_ws, &d_wl = c->tr_wl, &d_out = c->tr_out, &d_cnt = c->tr_cnt;
+  DevBuf<uint8_t>&d_codes = c->tr_codes, &d_ad = c->tr_ad, &d_st = c->tr_st;
+  if (!d_prof.reserve(PROF_INTS) || !d_ws.reserve(n) || !d_wl.reserve(n) || !d_out.reserve(5 * n) || !d_cnt.reserve(4) ||
+      !d_codes.reserve(total + 16) || !d_ad.reserve(adapter_len + 16) || !d_st.reserve(n)) return 0;
+  MIAGPU_CUDA(cudaEventRecord(c->ev[0], st));
+  MIAGPU_CUDA(cudaMemcpyAsync(d_prof.p, prof.data(), PROF_INTS * 4, cudaMemcpyHostToDevice, st));
+  MIAGPU_CUDA(cudaMemcpyAsync(d_ws.p, ws.data(), n * 4, cudaMemcpyHostToDevice, st));
+  MIAGPU_CUDA(cudaMemcpyAsync(d_wl.p, wl.data(), n * 4, cudaMemcpyHostToDevice, st));
+  MIAGPU_CUDA(cudaMemcpyAsync(d_codes.p, codes.data(), total + 16, cudaMemcpyHostToDevice, st));
+  MIAGPU_CUDA(cudaMemcpyAsync(d_ad.p, ad.data(), adapter_len, cudaMemcpyHostToDevice, st));
+  MIAGPU_CUDA(cudaMemsetAsync(d_cnt.p, 0, 16, st));
+  MIAGPU_CUDA(cudaEventRecord(c->ev[1], st));
+  RealignParams p{};
+  p.bases = d_ad.p; p.off = nullptr; p.rc = nullptr; p.win_start = d_ws.p; p.win_len = d_wl.p; p.list = nullptr; p.n_list = (int)n;
+  p.n_list_ptr = nullptr; p.counter = d_cnt.p; p.ref_codes = d_codes.p; p.ref_bytes = 0; p.prof = d_prof.p; p.sg5 = 1;   // mia_main.c:711-712
+  p.score = d_out.p; p.as_out = d_out.p + n; p.ae_out = d_out.p + 2 * n; p.abr = d_out.p + 3 * n; p.aer_out = d_out.p + 4 * n;
+  p.n_runs = nullptr; p.runs = nullptr; p.status = d_st.p; p.shared_rows = adapter_len;
+  c->launches = 0;
+  const int K = (maxL + 31) / 32;
+  int ok;
+  if (K <= 2) ok = launch_trim<2>(c, p, adapter_len, (int)n);
+  else if (K <= 4) ok = launch_trim<4>(c, p, adapter_len, (int)n);
+  else ok = launch_trim<8>(c, p, adapter_len, (int)n);
+  if (!ok) return 0;
+  MIAGPU_CUDA(cudaEventRecord(c->ev[2], st));
+  std::vector<int32_t> out(5 * n);
+  MIAGPU_CUDA(cudaMemcpyAsync(out.data(), d_out.p, 5 * n * 4, cudaMemcpyDeviceToHost, st));
+  MIAGPU_CUDA(cudaEventRecord(c->ev[3], st));
+  MIAGPU_CUDA(cudaStreamSynchronize(st));
+  MIAGPU_CUDA(cudaEventElapsedTime(&c->ms_h2d, c->ev[0], c->ev[1]));
+  MIAGPU_CUDA(cudaEventElapsedTime(&c->ms_kernels, c->ev[1], c->ev[2]));
+  MIAGPU_CUDA(cudaEventElapsedTime(&c->ms_d2h, c->ev[2], c->ev[3]));
+  c->dp_cells = total * adapter_len;
+  for (int64_t i = 0; i < n; i++) {
+    const int sc = out[i], col = out[n + i], row = out[3 * n + i], er = out[4 * n + i];
+    const int t = (sc >= TRIM_SCORE_CUT) || (sc >= (er - row + 1) * FLAT_MATCH);       // mia.c:1358-1366
+    if (max_score) max_score[i] = sc;
+    if (abr) abr[i] = row;
+    if (abc) abc[i] = col;
+    if (aer) aer[i] = er;
+    if (trimmed) trimmed[i] = (uint8_t)t;
+    if (trim_point) trim_point[i] = t ? col - 1 : 0;
+  }
   return 1;
 }
 

@@ -59,6 +59,11 @@ struct RealignParams {
   // trace scratch
   uint32_t* scratch;
   int64_t scratch_words_per_warp;
+  // TRIM (trim_frag, mia.c:1318-1368): every work item has the SAME rows (the adapter: bases[0 .. shared_rows)), item i is
+  // read i, whose bases are the matrix columns (ref_codes + win_start[i], win_len[i] columns); the end cell is the first
+  // maximum of the LAST COLUMN in row order; as_out / ae_out are matrix columns (abc, aec), aer_out the end row
+  int32_t shared_rows;
+  int32_t* aer_out;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -112,7 +117,7 @@ struct TraceLayout {
 constexpr int WARPS_PER_BLOCK = 4;
 
 // dynamic shared memory: [prof PROF_INTS ints][rowoff WARPS*256 u16][ref codes]
-template <int K>
+template <int K, bool TRIM = false>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) realign_kernel(RealignParams p) {
   static_assert(K >= 2 && K <= 16, "columns per lane");
   using TL = TraceLayout<K>;
@@ -165,18 +170,21 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) realign_kernel(RealignPa
   int value_mask = ~KEY_LOW_MASK;
   asm volatile("" : "+r"(value_mask));                            // keep it in a register
 
-  const int n_list = *p.n_list_ptr;
+  const int n_list = p.n_list_ptr ? *p.n_list_ptr : p.n_list;
   for (;;) {
     int item = 0;
     if (lane == 0) item = atomicAdd(p.counter, 1);
     item = __shfl_sync(0xffffffffu, item, 0);
     if (item >= n_list) break;
-    const int rd = p.list[item];
-    const int64_t o0 = p.off[rd];
-    const int L = (int)(p.off[rd + 1] - o0);
+    const int rd = TRIM ? item : p.list[item];
+    const int64_t o0 = TRIM ? 0 : p.off[rd];
+    const int L = TRIM ? p.shared_rows : (int)(p.off[rd + 1] - o0);
     const int ws = p.win_start[rd];
     const int len1 = p.win_len[rd];
-    const int strand = p.rc[rd] ? 1 : 0;
+    const int strand = TRIM ? 0 : (p.rc[rd] ? 1 : 0);
+    // TRIM: the lane / register that hold the last column, its running first maximum over the rows
+    const int lcl = TRIM ? (len1 - 1) / K : 0, lcj = TRIM ? (len1 - 1) - lcl * K : 0;
+    int lc_best = INT_MIN, lc_row = 0;
 
     // ---- read -> per-row profile offsets (pop_s2c_in_a + find_sm_depth), lanes in parallel
     __syncwarp();
@@ -204,6 +212,10 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) realign_kernel(RealignPa
         Sp[j] = lds_s32(pa + code4[j]) + DIAG_BITS;          // profile is pre-multiplied by 2048
         R[j] = NEG_KEY;
       }
+    }
+    if (TRIM && lane == lcl) {
+#pragma unroll
+      for (int j = 0; j < K; j++) if (j == lcj) lc_best = Sp[j];
     }
 
     for (int r = 1; r < L; r++) {
@@ -252,6 +264,12 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) realign_kernel(RealignPa
         Sp[j] = pS ? NdKey : cont;                      // start-new does NOT add the substitution score
       }
       if (lane == 0) R[0] = NEG_KEY;                    // there is no column -1
+      if (TRIM && lane == lcl) {                        // mia.c:1345-1352: strict '>' in row order
+        int v = INT_MIN;
+#pragma unroll
+        for (int j = 0; j < K; j++) if (j == lcj) v = Sp[j];
+        if (v > lc_best) { lc_best = v; lc_row = r; }
+      }
 
       // ---- one vector store of this lane's K trace words (row r stored at r-1)
       uint32_t* trow = trace + (int64_t)(r - 1) * TL::ROW_WORDS + lane * TL::WP;
@@ -275,16 +293,22 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) realign_kernel(RealignPa
       best = max(best, key);
     }
     best = __reduce_max_sync(0xffffffffu, best);
-    const int score = best >> KEY_SHIFT;
-    const int aec = KEY_IDX_MASK - (best & KEY_IDX_MASK);
+    int score = best >> KEY_SHIFT;
+    int aec = KEY_IDX_MASK - (best & KEY_IDX_MASK);
+    int aer = L - 1;
+    if (TRIM) {
+      score = (__shfl_sync(0xffffffffu, lc_best, lcl) - DIAG_BITS) >> KEY_SHIFT;
+      aer = __shfl_sync(0xffffffffu, lc_row, lcl);
+      aec = len1 - 1;
+    }
 
     // ---- find_align_begin + populate_pwaln_to_begin, executed uniformly by the warp
     __syncwarp();   // trace stores of all lanes visible (same warp, global memory)
-    int row = L - 1, col = aec, nrun = 0, curM = 0, ncols = 0;
-    uint16_t* my_runs = p.runs + (int64_t)rd * MAX_RUNS;
+    int row = aer, col = aec, nrun = 0, curM = 0, ncols = 0;
+    uint16_t* my_runs = p.runs ? p.runs + (int64_t)rd * MAX_RUNS : nullptr;
     const uint16_t* t16 = reinterpret_cast<const uint16_t*>(trace);
     auto push = [&](int type, int len) {
-      if (nrun < MAX_RUNS && lane == 0) my_runs[nrun] = (uint16_t)((type << 14) | len);
+      if (my_runs && nrun < MAX_RUNS && lane == 0) my_runs[nrun] = (uint16_t)((type << 14) | len);
       nrun++;
       ncols += len;
     };
@@ -323,14 +347,16 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) realign_kernel(RealignPa
       uint8_t st = MIAGPU_ST_OK;
       if (nrun > MAX_RUNS) { st |= MIAGPU_ST_RUNS_OVERFLOW; nrun = -1; }
       if (ncols > 2 * MAX_READ) st |= MIAGPU_ST_STR_OVERFLOW;
-      for (int a = 0, b = nrun - 1; a < b; a++, b--) {       // runs were produced 3'->5'
-        uint16_t x = my_runs[a]; my_runs[a] = my_runs[b]; my_runs[b] = x;
-      }
+      if (my_runs)
+        for (int a = 0, b = nrun - 1; a < b; a++, b--) {     // runs were produced 3'->5'
+          uint16_t x = my_runs[a]; my_runs[a] = my_runs[b]; my_runs[b] = x;
+        }
       p.score[rd] = score;
-      p.as_out[rd] = col + ws;                    // mia_main.c:250-255
-      p.ae_out[rd] = aec + ws;
+      p.as_out[rd] = TRIM ? col : col + ws;       // mia_main.c:250-255
+      p.ae_out[rd] = TRIM ? aec : aec + ws;
       p.abr[rd] = row;
-      p.n_runs[rd] = nrun;
+      if (TRIM) p.aer_out[rd] = aer;
+      if (p.n_runs) p.n_runs[rd] = nrun;
       p.status[rd] = st;
     }
   }

@@ -734,3 +734,31 @@ void orc_repeat_filter( long long n, const unsigned char* rc, const int* as, con
     curr_rc = frc; curr_as = as[f]; curr_ae = ae[f];
   }
 }
+
+/* ---- f4: trim_frag (mia.c:1318-1368) */
+int orc_trim( const char* read, int read_len, const char* adapter, int adapter_len, int* out6 ) {
+  int sm[775], o5[5];
+  char rg[2*ORC_MAX_READ + 2], fg[2*ORC_MAX_READ + 2];
+  if ( read_len <= 0 || adapter_len <= 0 || adapter_len > ORC_MAX_READ ) return 0;
+  int* S = (int*)malloc( sizeof(int) * (size_t)read_len * adapter_len );
+  int* T = (int*)malloc( sizeof(int) * (size_t)read_len * adapter_len );
+  orc_flat_pssm( sm );
+  if ( !orc_align( read, read_len, adapter, adapter_len, NULL, sm, 1, o5, rg, fg, S, T ) ) { free( S ); free( T ); return 0; }
+  /* the last column, rows in order, strict '>' (mia.c:1345-1352) */
+  int col = read_len - 1, best = INT_MIN, aer = 0;
+  for ( int r = 0; r < adapter_len; r++ )
+    if ( S[(size_t)r * read_len + col] > best ) { best = S[(size_t)r * read_len + col]; aer = r; }
+  /* find_align_begin (mia.c:612-637) */
+  int row = aer;
+  for (;;) {
+    int t = T[(size_t)row * read_len + col];
+    if ( t == col || t == -row ) break;
+    if ( t == 0 ) { row--; col--; }
+    else if ( t < 0 ) { row = -t; col--; }
+    else { col = t; row--; }
+  }
+  int trimmed = ( best >= 1000 ) || ( best >= ( aer - row + 1 ) * 200 );   /* TRIM_SCORE_CUT, FLAT_MATCH: params.h:28,32 */
+  out6[0] = trimmed; out6[1] = trimmed ? col - 1 : 0; out6[2] = best; out6[3] = row; out6[4] = col; out6[5] = aer;
+  free( S ); free( T );
+  return 1;
+}

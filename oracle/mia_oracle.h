@@ -127,6 +127,11 @@ void orc_asm_gaps( const orc_asm* a, int* out );           /* wrap_len+1 ints */
 void orc_asm_slot( const orc_asm* a, int i, int* out7, char* seq, char* smp,
                    char* ins );
 int  orc_find_consensus( const int* in10, int cons_code ); /* map_align.c:294-391 */
+/* f4: trim_frag (mia.c:1318-1368; set-up mia_main.c:692-713): dyn_prog of the adapter
+ * (rows) against the read (columns) with the flat matrix and sg5 = 1, the first
+ * maximum of the LAST COLUMN in row order, find_align_begin from there.
+ * out6: trimmed, trim_point (0 if not trimmed), that maximum, abr, abc, aer. */
+int orc_trim( const char* read, int read_len, const char* adapter, int adapter_len, int* out6 );
 /* f1: sort_fsdb / sort_fsdb_qscore (fsdb.c:13-88, 90-180, 240-252; key4 = score or
  * qual_sum) as a STABLE sort -- what glibc's qsort is while its merge buffer fits --
  * then set_uniq_in_fsdb (fsdb.c:440-508).  order[k] = input index at sorted

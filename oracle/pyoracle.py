@@ -272,6 +272,15 @@ class Oracle(_AlignMixin):
         """The culled list (= culled_maln->AlnSeqArray before sort_aln_frags)."""
         return [self.asm_slot(a, self.lib.orc_asm_entry(a, i)) for i in range(self.lib.orc_asm_num_entries(a))]
 
+    def trim(self, read, adapter):
+        """f4: trim_frag -> dict(trimmed, trim_point, score, abr, abc, aer)"""
+        out = np.zeros(6, np.int32)
+        f = self.lib.orc_trim
+        f.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, c_int_p]
+        ok = f(_b(read), len(read), _b(adapter), len(adapter), _ip(out))
+        assert ok
+        return dict(zip(("trimmed", "trim_point", "score", "abr", "abc", "aer"), map(int, out)))
+
     def repeat_filter(self, rc, as_, ae, key4, trimmed=None, just_outer_coords=1, tolerance=0):
         """f1: (order int64[n], unique uint8[n] by input index)"""
         n = len(rc)
@@ -480,6 +489,15 @@ class Ref(_AlignMixin):
 
     def sess_write_ma(self, s, path):
         return self.lib.refh_sess_write_ma(s, _b(path))
+
+    def trim(self, read, adapter):
+        """the reference's trim_frag -> dict(trimmed, trim_point, score, abr, abc, aer)"""
+        out = np.zeros(6, np.int32)
+        f = self.lib.refh_trim
+        f.argtypes = [C.c_char_p, C.c_char_p, c_int_p]
+        f.restype = None
+        f(_b(read), _b(adapter), _ip(out))
+        return dict(zip(("trimmed", "trim_point", "score", "abr", "abc", "aer"), map(int, out)))
 
     def repeat_filter(self, rc, as_, ae, key4, trimmed=None, just_outer_coords=1, tolerance=0, use_qscore=0):
         """the reference's sort_fsdb[_qscore] + set_uniq_in_fsdb: (order int64[n], unique uint8[n] by input index)"""

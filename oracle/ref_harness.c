@@ -459,3 +459,29 @@ void refh_repeat_filter( long long n, const unsigned char* rc, const int* as, co
   }
   free( db.fss ); free( all );
 }
+
+/* f4: trim_frag (mia.c:1318-1368) as main() sets it up (mia_main.c:692-713): adapter rows x read columns, flat matrix,
+   sg5 = 1, sg3 = 0, no homopolymer discount.  out6: trimmed, trim_point, best score of the last column, abr, abc, aer */
+void refh_trim( const char* read, const char* adapter, int* out6 ) {
+  static AlignmentP a = NULL;
+  static PSSMP flat = NULL;
+  static char adapt[INIT_ALN_SEQ_LEN + 1];
+  FragSeq fs;
+  if ( a == NULL ) {
+    a = init_alignment( INIT_ALN_SEQ_LEN, INIT_ALN_SEQ_LEN, 0, 0 );
+    flat = init_flatsubmat();
+    a->submat = flat;
+    a->sg5 = 1; a->sg3 = 0;
+  }
+  strncpy( adapt, adapter, INIT_ALN_SEQ_LEN ); adapt[INIT_ALN_SEQ_LEN] = '\0';
+  a->seq2 = adapt;
+  a->len2 = strlen( adapt );
+  pop_s2c_in_a( a );
+  memset( &fs, 0, sizeof(fs) );
+  strncpy( fs.seq, read, INIT_ALN_SEQ_LEN );
+  fs.seq_len = strlen( fs.seq );
+  trim_frag( &fs, adapt, a );
+  out6[0] = fs.trimmed; out6[1] = fs.trimmed ? fs.trim_point : 0;
+  out6[2] = a->m->mat[a->aer][a->aec].score;
+  out6[3] = a->abr; out6[4] = a->abc; out6[5] = a->aer;
+}

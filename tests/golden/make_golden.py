@@ -174,7 +174,27 @@ def main():
                     rep.append(dict(rc=rc.tolist(), as_=as_.tolist(), ae=ae.tolist(), key4=k4.tolist(), trimmed=tr.tolist(), use_qscore=use_q,
                                     just_outer=jo, tolerance=tol, order=order.tolist(), unique=uniq.tolist()))
     json.dump(rep, open(os.path.join(HERE, "repeat_cases.json"), "w"))
-    print("wrote pssm.npz, align_cases.json, sessions.json, repeat_cases.json")
+    # f4: the reference's trim_frag on reads with (damaged) adapter prefixes at the 3' end
+    import random as _r
+    rg = _r.Random(11)
+    trims = []
+    for adapter in ("GTCAGACACGCAACAGGGGATAGGCAAGGCACACAGGGGATAGG", "ACGTTGCA"):
+        for _ in range(150):
+            L = rg.randint(1, 90)
+            rd = "".join(rg.choice("ACGT") for _ in range(L))
+            if rg.random() < 0.7:
+                frag = list(adapter[: rg.randint(1, len(adapter))])
+                for i in range(len(frag)):
+                    y = rg.random()
+                    if y < 0.06:
+                        frag[i] = rg.choice("ACGTN")
+                    elif y < 0.08:
+                        frag[i] = ""
+                rd = rd + "".join(frag)
+            t = r.trim(rd, adapter)
+            trims.append(dict(read=rd, adapter=adapter, out=[t[k] for k in ("trimmed", "trim_point", "score", "abr", "abc", "aer")]))
+    json.dump(trims, open(os.path.join(HERE, "trim_cases.json"), "w"))
+    print("wrote pssm.npz, align_cases.json, sessions.json, repeat_cases.json, trim_cases.json")
 
 
 if __name__ == "__main__":

@@ -118,3 +118,12 @@ def test_repeat_filter_matches_reference_golden(oracle):
         order, uniq = oracle.repeat_filter(np.array(c["rc"], np.uint8), np.array(c["as_"], np.int32), np.array(c["ae"], np.int32),
                                            np.array(c["key4"], np.int32), np.array(c["trimmed"], np.uint8), c["just_outer"], c["tolerance"])
         assert order.tolist() == c["order"] and uniq.tolist() == c["unique"], i
+
+
+def test_trim_matches_reference_golden(oracle):
+    # f4: the oracle's trim_frag against what the reference's own function returned
+    cases = json.load(open(os.path.join(G, "trim_cases.json")))
+    assert len(cases) == 300
+    for i, c in enumerate(cases):
+        t = oracle.trim(c["read"], c["adapter"])
+        assert [t[k] for k in ("trimmed", "trim_point", "score", "abr", "abc", "aer")] == c["out"], (i, c["read"])

@@ -154,3 +154,27 @@ def test_repeat_filter_oracle_equals_reference(oracle, ref):
                     a = oracle.repeat_filter(rc, as_, ae, k4, tr, jo, tol)
                     b = ref.repeat_filter(rc, as_, ae, k4, tr, jo, tol, use_qscore=uq)
                     assert (a[0] == b[0]).all() and (a[1] == b[1]).all(), (trial, uq, jo, tol)
+
+
+def test_trim_oracle_equals_reference(oracle, ref):
+    # f4: trim_frag (mia.c:1318-1368) on reads with damaged adapter prefixes, adapters of 1 .. 44 bases, reads with N
+    rng = random.Random(3)
+    adapters = ["GTCAGACACGCAACAGGGGATAGGCAAGGCACACAGGGGATAGG", "CTGAGACACGCAACAGGGGATAGGCAAGGCACACAGGGGATAGG", "ACGTTGCA", "A"]
+    for t in range(1500):
+        ad = rng.choice(adapters)
+        rd = "".join(rng.choice("ACGT") for _ in range(rng.randint(1, 120)))
+        if rng.random() < 0.6:
+            frag = list(ad[: rng.randint(1, len(ad))])
+            for i in range(len(frag)):
+                y = rng.random()
+                if y < 0.05:
+                    frag[i] = rng.choice("ACGT")
+                elif y < 0.07:
+                    frag[i] = ""
+                elif y < 0.09:
+                    frag[i] += rng.choice("ACGT")
+            rd = (rd + "".join(frag))[:256]
+        if rng.random() < 0.05:
+            rd = rd[: len(rd) // 2] + "N" + rd[len(rd) // 2 + 1:]
+        rd = rd or "A"
+        assert oracle.trim(rd, ad) == ref.trim(rd, ad), (t, rd, ad)
