@@ -164,16 +164,16 @@ class MiaGpu:
         self.n = n
 
     # -- pass 1
-    def pass1(self):
-        """new_kmer_filter + sg_align's compute over the resident reads (mia_main.c:781-796)."""
+    def pass1(self, fields=None):
+        """new_kmer_filter + sg_align's compute over the resident reads (mia_main.c:781-796).
+        fields: the outputs wanted (default: all); the others are not downloaded."""
         n = self.n
-        o = dict(hits=np.zeros(n, np.int32), score=np.zeros(n, np.int32), fw_score=np.zeros(n, np.int32),
-                 rc_score=np.zeros(n, np.int32), rc=np.zeros(n, np.uint8), as_=np.zeros(n, np.int32), ae=np.zeros(n, np.int32),
-                 start=np.zeros(n, np.int32), end=np.zeros(n, np.int32), abr=np.zeros(n, np.int32), n_runs=np.zeros(n, np.int32),
-                 runs=np.zeros((n, MAX_RUNS), np.uint16), status=np.zeros(n, np.uint8))
+        spec = dict(hits=np.int32, score=np.int32, fw_score=np.int32, rc_score=np.int32, rc=np.uint8, as_=np.int32, ae=np.int32,
+                    start=np.int32, end=np.int32, abr=np.int32, n_runs=np.int32, runs=np.uint16, status=np.uint8)
+        o = {k: (np.zeros((n, MAX_RUNS) if k == "runs" else n, dt) if (fields is None or k in fields) else None) for k, dt in spec.items()}
         self._ck(self.lib.miagpu_pass1(self.h, *[_ptr(o[k]) for k in ("hits", "score", "fw_score", "rc_score", "rc", "as_", "ae",
                                                                      "start", "end", "abr", "n_runs", "runs", "status")]))
-        return o
+        return {k: v for k, v in o.items() if v is not None}
 
     def last_pass1_stats(self):
         """(reads finished by the windowed pair kernels, reads the general kernel took, reads without a k-mer hit)"""

@@ -2106,6 +2106,18 @@ extern "C" int miagpu_last_cut_stats(miagpu_ctx* c, int64_t* serial_blocks, int6
 }
 
 // ------------------------------------------------------------------ adapter trimming (8f4)
+__global__ void trim_codes_kernel(int64_t total, uint8_t* bases_to_codes) {          // pop_s1c_in_a: ASCII -> 0..4, in place
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < total) bases_to_codes[i] = (uint8_t)base_code(bases_to_codes[i]);
+}
+__global__ void trim_windows_kernel(int64_t n, const int64_t* off, int32_t* ws, int32_t* wl, int* bad) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t l = off[i + 1] - off[i];
+  if (l < 1 || l > MAX_READ) atomicMin(bad, (int)i);
+  ws[i] = (int32_t)off[i]; wl[i] = (int32_t)min(max(l, (int64_t)1), (int64_t)MAX_READ);
+}
+
 template <int K>
 static int launch_trim(miagpu_ctx* c, RealignParams p, int maxL, int n) {
   using TL = TraceLayout<K>;
@@ -2145,29 +2157,30 @@ extern "C" int miagpu_trim(miagpu_ctx* c, int64_t n, const uint8_t* bases, const
     for (int rb = 0; rb < 5; rb++)
       for (int fb = 0; fb < 5; fb++) prof[prof_row_index(0, d, rb) + fb] = flat[(d * 5 + fb) * 5 + rb];
   const int64_t total = offsets[n];
-  int maxL = 0;
-  std::vector<int32_t> ws(n), wl(n);
-  for (int64_t i = 0; i < n; i++) {
-    const int64_t l = offsets[i + 1] - offsets[i];
-    if (l < 1 || l > MAX_READ) { set_error("miagpu_trim: read %lld has %lld bases (1..%d)", (long long)i, (long long)l, MAX_READ); return 0; }
-    ws[i] = (int32_t)offsets[i]; wl[i] = (int32_t)l;
-    maxL = std::max(maxL, (int)l);
-  }
-  std::vector<uint8_t> codes(total + 16, 4), ad(adapter_len);
-  for (int64_t i = 0; i < total; i++) codes[i] = (uint8_t)base_code(bases[i]);
+  std::vector<uint8_t> ad(adapter_len);
   for (int i = 0; i < adapter_len; i++) ad[i] = (uint8_t)adapter[i];
   DevBuf<int32_t>&d_prof = c->tr_prof, &d_ws = c->tr_ws, &d_wl = c->tr_wl, &d_out = c->tr_out, &d_cnt = c->tr_cnt;
   DevBuf<uint8_t>&d_codes = c->tr_codes, &d_ad = c->tr_ad, &d_st = c->tr_st;
   if (!d_prof.reserve(PROF_INTS) || !d_ws.reserve(n) || !d_wl.reserve(n) || !d_out.reserve(5 * n) || !d_cnt.reserve(4) ||
-      !d_codes.reserve(total + 16) || !d_ad.reserve(adapter_len + 16) || !d_st.reserve(n)) return 0;
+      !d_codes.reserve(total + 16) || !d_ad.reserve(adapter_len + 16) || !d_st.reserve(n) || !c->d_off2.reserve(n + 2)) return 0;
   MIAGPU_CUDA(cudaEventRecord(c->ev[0], st));
   MIAGPU_CUDA(cudaMemcpyAsync(d_prof.p, prof.data(), PROF_INTS * 4, cudaMemcpyHostToDevice, st));
-  MIAGPU_CUDA(cudaMemcpyAsync(d_ws.p, ws.data(), n * 4, cudaMemcpyHostToDevice, st));
-  MIAGPU_CUDA(cudaMemcpyAsync(d_wl.p, wl.data(), n * 4, cudaMemcpyHostToDevice, st));
-  MIAGPU_CUDA(cudaMemcpyAsync(d_codes.p, codes.data(), total + 16, cudaMemcpyHostToDevice, st));
+  MIAGPU_CUDA(cudaMemcpyAsync(c->d_off2.p, offsets, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+  MIAGPU_CUDA(cudaMemcpyAsync(d_codes.p, bases, total, cudaMemcpyHostToDevice, st));
   MIAGPU_CUDA(cudaMemcpyAsync(d_ad.p, ad.data(), adapter_len, cudaMemcpyHostToDevice, st));
   MIAGPU_CUDA(cudaMemsetAsync(d_cnt.p, 0, 16, st));
+  int bad_read = 0x7fffffff, maxL = 0;
+  MIAGPU_CUDA(cudaMemcpyAsync(d_cnt.p + 1, &bad_read, 4, cudaMemcpyHostToDevice, st));
   MIAGPU_CUDA(cudaEventRecord(c->ev[1], st));
+  trim_codes_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(total, d_codes.p);
+  trim_windows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, c->d_off2.p, d_ws.p, d_wl.p, d_cnt.p + 1);
+  max_len_kernel<<<256, 256, 0, st>>>(n, c->d_off2.p, d_cnt.p + 2);
+  MIAGPU_CUDA(cudaGetLastError());
+  int chk[2] = {0, 0};
+  MIAGPU_CUDA(cudaMemcpyAsync(chk, d_cnt.p + 1, 8, cudaMemcpyDeviceToHost, st));
+  MIAGPU_CUDA(cudaStreamSynchronize(st));
+  if (chk[0] != 0x7fffffff) { set_error("miagpu_trim: read %d has %lld bases (1..%d)", chk[0], (long long)(offsets[chk[0] + 1] - offsets[chk[0]]), MAX_READ); return 0; }
+  maxL = std::min(chk[1], MAX_READ);
   RealignParams p{};
   p.bases = d_ad.p; p.off = nullptr; p.rc = nullptr; p.win_start = d_ws.p; p.win_len = d_wl.p; p.list = nullptr; p.n_list = (int)n;
   p.n_list_ptr = nullptr; p.counter = d_cnt.p; p.ref_codes = d_codes.p; p.ref_bytes = 0; p.prof = d_prof.p; p.sg5 = 1;   // mia_main.c:711-712

@@ -230,7 +230,7 @@ class ResidentAssembler:
         g.set_reference(self.ref0, self.circular, with_rc=1)
         g.build_kmers(self.k, self.soft_mask)
         g.upload_reads(bases, off)
-        p = g.pass1()
+        p = g.pass1(fields=("hits", "score", "rc", "as_", "ae", "start", "end"))
         self.p1 = p
         seq_len = np.diff(off).astype(np.int32)
         keep = (p["hits"] > 0) & (p["score"] >= FIRST_ROUND_SCORE_CUTOFF)            # mia.c:1614
