@@ -89,3 +89,19 @@ def test_one_megabase_properties(gpu, monkeypatch):
     assert (below == d).all() and s2 == fit
     cons2, gaps2, _ = gpu.consensus_natural(below, below, 1)
     assert cons2 == cons and (gaps2 == gaps).all()
+
+
+def test_unmasked_pass1_200kb_vs_oracle(gpu, oracle):
+    # no k-mer filter on a reference of 782 chunks: the 16-bit whole-strand sweep (and the general kernel for the gapped
+    # winners) against the oracle's full both-strand DP
+    import _pkg
+    _pkg.load()
+    from mia_b200 import synth
+    ref = synth.random_reference(200_000, seed=331)
+    g = synth.diverge(ref, 0.03, seed=332, indel_rate=0.01)
+    b, off, _ = synth.make_reads(g, 10, 35, 75, seed=333)
+    reads = [synth.read_str(b, off, i) for i in range(10)]
+    bad, out = gpu_checks.check_pass1(gpu, oracle, ref, reads, gpu_checks.load_pssm("onepass"), 1, 0)
+    assert not bad, f"{len(bad)} reads differ; first {bad[0]}"
+    fast, general, skipped = gpu.last_pass1_stats()
+    assert fast + general == 10 and fast >= 3, (fast, general, skipped)
