@@ -50,6 +50,13 @@ struct GlobalAdder {
   int64_t n_cols;
   __device__ __forceinline__ void add(int plane, int64_t col, int v) const { atomicAdd(acc + plane * n_cols + col, v); }
 };
+// NegGlobalAdder: takes a contribution back out of the global planes (one-call rounds accumulate every read while the host
+// still stitches the score cut's chains, then remove the base columns of the reads this round's cut dropped)
+struct NegGlobalAdder {
+  int32_t* acc;
+  int64_t n_cols;
+  __device__ __forceinline__ void add(int plane, int64_t col, int v) const { atomicAdd(acc + plane * n_cols + col, -v); }
+};
 // TileAdder: a block owns the padded columns [c0, c0 + TILE_COLS) in shared memory; whatever an entry
 // adds outside that window (its tail past the tile, at most a read length) goes to the global planes.
 constexpr int TILE_POS = 1792;                  // reference positions per tile
@@ -85,6 +92,7 @@ __device__ __forceinline__ void add_base_dev(const Adder& A, Col col, int ch_cod
 //         positions with start < pos <= end only, so an insert in front of an entry's first
 //         column never counts)
 // MODE 1: base columns + insert columns
+// MODE 2: base columns only (what AlnSeq.dropped decides, mia.c:571-579; insert columns count dropped reads too)
 template <int MODE, typename Adder>
 __device__ __forceinline__ void walk_entry(const ConsParams& p, const miagpu_entry& e, int lane, const Adder& A) {
   if (e.col_count <= 0) return;
@@ -121,6 +129,7 @@ __device__ __forceinline__ void walk_entry(const ConsParams& p, const miagpu_ent
           const int ch = isM ? base_code(read[row]) : 5;
           add_base_dev(A, pos + p.ins_off[pos + 1], ch, sm_strand, depth);   // base column sits after its insert columns
         }
+        if (MODE == 2) continue;
         const int g = (i > cb && pos > 0) ? p.gaps[pos] : 0; // find_ins_cons: start < pos <= end, dropped NOT checked
         for (int j = 0; j < g; j++) {
           const int ch = j < q ? base_code(read[row - q + j]) : 5;
@@ -269,6 +278,27 @@ __global__ void __launch_bounds__(TILE_THREADS) tile_kernel(ConsParams p, const 
     const int pl = i / TILE_COLS, d = i - pl * TILE_COLS;
     const int v = s_acc[i];
     if (v != 0 && d < room) atomicAdd(p.acc + pl * p.n_cols + c0 + d, v);
+  }
+}
+
+// The reads this round's cut dropped (newly[i] = below the cut now, not dropped before): their base columns come back out
+// of the planes and their entries take the flag.  A lane looks at one read, the warp walks the flagged ones.
+__global__ void __launch_bounds__(256) undo_kernel(ConsParams p, int64_t n_reads, const uint8_t* __restrict__ newly, miagpu_entry* entries) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32;
+  const int64_t i = w0 + lane;
+  unsigned m = __ballot_sync(0xffffffffu, i < n_reads && newly[i]);
+  while (m) {
+    const int b = __ffs(m) - 1;
+    m &= m - 1;
+    for (int h = 0; h < 2; h++) {
+      const int64_t idx = 2 * (w0 + b) + h;
+      const miagpu_entry e = entries[idx];
+      if (e.dropped) continue;
+      walk_entry<2>(p, e, lane, NegGlobalAdder{p.acc, p.n_cols});
+      __syncwarp();
+      if (lane == 0) entries[idx].dropped = 1;
+    }
   }
 }
 

@@ -182,7 +182,7 @@ struct miagpu_ctx {
   DevBuf<int32_t> d_ent_pos;                   // start position per entry (tile_kernel's scan list)
   int64_t n_entries = 0;
   DevBuf<int32_t> d_sm, d_gaps, d_ins_off, d_acc;
-  DevBuf<uint8_t> d_cub, d_dropf, d_dropb;
+  DevBuf<uint8_t> d_cub, d_dropf, d_dropb, d_newly;
   DevBuf<char> d_called;
   int64_t n_cols = 0;
   int cons_stage = 0;                          // 0 none, 1 gaps done, 2 counts done
@@ -258,7 +258,7 @@ extern "C" void miagpu_destroy(miagpu_ctx* c) {
   for (int t = 0; t < 2; t++) { c->d_kb[t].release(); c->d_kp[t].release(); c->d_kk[t].release(); }
   c->d_smask.release(); c->d_ckpt.release(); c->d_chunk_ids.release(); c->d_strace.release(); c->d_hits.release(); c->d_fw.release();
   c->d_rcs.release(); c->d_start.release(); c->d_end.release(); c->d_rc_out.release(); c->d_bases2.release(); c->d_packed.release(); c->d_off2.release(); c->d_src.release();
-  c->d_entries.release(); c->d_ent_pos.release(); c->d_sm.release(); c->d_gaps.release(); c->d_ins_off.release(); c->d_acc.release(); c->d_cub.release(); c->d_called.release(); c->d_dropf.release(); c->d_dropb.release();
+  c->d_entries.release(); c->d_ent_pos.release(); c->d_sm.release(); c->d_gaps.release(); c->d_ins_off.release(); c->d_acc.release(); c->d_cub.release(); c->d_called.release(); c->d_dropf.release(); c->d_dropb.release(); c->d_newly.release();
   for (auto& ev : c->ev) cudaEventDestroy(ev);
   for (auto& ev : c->p1ev) cudaEventDestroy(ev);
   for (auto& ev : c->bev) cudaEventDestroy(ev);
@@ -1527,17 +1527,20 @@ struct IterTail {
 // Everything after the DP of one round: score cut (stats kernels already enqueued per chunk), entries, insert maxima,
 // column accumulation, base calling.  Compute stream throughout; two short host waits (the integer sums, the blocks).
 static int iterate_tail(miagpu_ctx* c, const IterTail& a, const Trace& tr) {
-  cudaStream_t main = c->stream, down = c->s_down;
+  cudaStream_t main = c->stream, down = c->s_down, side = c->s_aux[2];
   const int64_t n = c->n;
   const bool fit = !a.score_cut_set && a.hard_cut <= 0;
   const bool has_unique = a.h_unique != nullptr;
   CutHost* H = c->h_cut;
   const int64_t nb = (n + CUT_BLOCK - 1) / CUT_BLOCK;
+  if (!c->d_newly.reserve(n + 1)) return 0;
   if (fit) {
     MIAGPU_CUDA(cudaMemcpyAsync(&H->stats, c->d_cstats.p, sizeof(CutStatsDev), cudaMemcpyDeviceToHost, main));
     MIAGPU_CUDA(cudaEventRecord(c->xev[0], main));
   }
-  // ---- packed run lists + entries + per-position insert maxima: none of it depends on this round's flags
+  // ---- packed run lists + entries + per-position insert maxima: none of it depends on this round's cut.  The entries take
+  // the sticky flags of EARLIER rounds; the reads this round drops are taken back out of the planes afterwards (undo_kernel),
+  // so that the column accumulation runs while the host stitches the regression's chains.
   int64_t* cnt = c->d_off2.p;
   int64_t* offs = c->d_off2.p + (n + 2);
   size_t tmp = 0, tmp2 = 0;
@@ -1554,17 +1557,19 @@ static int iterate_tail(miagpu_ctx* c, const IterTail& a, const Trace& tr) {
   }
   c->n_entries = 2 * n;
   MIAGPU_CUDA(cudaMemsetAsync(c->d_gaps.p, 0, (c->seq_len + 2) * sizeof(int32_t), main));
+  if (a.wait_old_flags) MIAGPU_CUDA(cudaStreamWaitEvent(main, c->xev[1], 0));          // the earlier rounds' flags are on the device
   natural_entries_kernel<<<(unsigned)((n + 255) / 256), 256, 0, main>>>(n, c->d_as_out.p, c->d_ae_out.p, c->d_nruns.p, c->d_runs.p,
-                                                                        c->d_status.p, c->seq_len, nullptr, nullptr, c->d_entries.p,
+                                                                        c->d_status.p, c->seq_len, c->d_dropf.p, c->d_dropf.p, c->d_entries.p,
                                                                         has_unique ? c->d_unique.p : nullptr);
   MIAGPU_CUDA(cudaGetLastError());
   c->launches++;
   if (!launch_gaps(c)) return 0;
   MIAGPU_CUDA(cub::DeviceScan::ExclusiveSum(c->d_cub.p, tmp2, c->d_gaps.p, c->d_ins_off.p, c->seq_len + 1, main));
   MIAGPU_CUDA(cudaMemcpyAsync(&H->total_ins, c->d_ins_off.p + c->seq_len, sizeof(int32_t), cudaMemcpyDeviceToHost, main));
+  MIAGPU_CUDA(cudaEventRecord(c->aev[6], main));
   c->launches += 2;
   tr.mark("entries + insert maxima enqueued");
-  // ---- regression: integer sums -> tables -> block kernels -> stitch (find_fsdb_score_cut, fsdb.c:269-383)
+  // ---- regression: integer sums -> tables -> block kernels (side stream) -> stitch (find_fsdb_score_cut, fsdb.c:269-383)
   CutSums S;
   CutFit F;
   if (fit) {
@@ -1577,21 +1582,41 @@ static int iterate_tail(miagpu_ctx* c, const IterTail& a, const Trace& tr) {
     H->tab.ybar = F.ybar;
     memcpy(H->tab.dx, F.dx_of, sizeof(F.dx_of));
     memcpy(H->tab.dx2, F.dx2_of, sizeof(F.dx2_of));
-    MIAGPU_CUDA(cudaMemcpyAsync(c->d_ctab.p, &H->tab, sizeof(CutTables), cudaMemcpyHostToDevice, main));
+    MIAGPU_CUDA(cudaStreamWaitEvent(side, c->xev[0], 0));                              // the scores are final
+    MIAGPU_CUDA(cudaMemcpyAsync(c->d_ctab.p, &H->tab, sizeof(CutTables), cudaMemcpyHostToDevice, side));
     const uint8_t* du = has_unique ? c->d_unique.p : nullptr;
     CutSrc src{};
     src.seq_len = c->d_seqlen.p; src.score = c->d_score.p; src.unique_best = du;
-    cut_approx_kernel<false><<<(unsigned)nb, CUT_THREADS, 0, main>>>(n, src, c->d_ctab.p, c->d_cblk.p);
-    cut_exact_kernel<false><<<(unsigned)nb, CUT_THREADS, 0, main>>>(n, src, c->d_ctab.p, c->d_cblk.p, nullptr, nullptr);
+    cut_approx_kernel<false><<<(unsigned)nb, CUT_THREADS, 0, side>>>(n, src, c->d_ctab.p, c->d_cblk.p);
+    cut_exact_kernel<false><<<(unsigned)nb, CUT_THREADS, 0, side>>>(n, src, c->d_ctab.p, c->d_cblk.p, nullptr, nullptr);
     MIAGPU_CUDA(cudaGetLastError());
-    MIAGPU_CUDA(cudaMemcpyAsync(c->h_cblk, c->d_cblk.p, sizeof(CutBlockDev) * nb, cudaMemcpyDeviceToHost, main));
+    MIAGPU_CUDA(cudaMemcpyAsync(c->h_cblk, c->d_cblk.p, sizeof(CutBlockDev) * nb, cudaMemcpyDeviceToHost, side));
+    MIAGPU_CUDA(cudaEventRecord(c->aev[7], side));
     c->launches += 2;
   }
-  MIAGPU_CUDA(cudaStreamSynchronize(main));
-  tr.mark("compute stream drained (DP, entries, insert maxima, chain blocks)");
+  // ---- column accumulation of every read that is not yet dropped (needs the insert-column layout: one short wait)
+  MIAGPU_CUDA(cudaEventSynchronize(c->aev[6]));
+  const int64_t tot = H->tot_runs;
+  if (a.total_runs) *a.total_runs = tot;
+  if (a.packed_runs && tot > a.capacity) { cudaStreamSynchronize(main); cudaStreamSynchronize(side); set_error("miagpu_iterate: %lld runs, capacity %lld", (long long)tot, (long long)a.capacity); return 0; }
+  if (!c->d_packed.reserve(tot + 1)) return 0;
+  c->n_cols = (int64_t)c->seq_len + H->total_ins;
+  if (!c->d_acc.reserve(c->n_cols * NPLANE) || !c->d_called.reserve(c->n_cols + 16)) return 0;
+  MIAGPU_CUDA(cudaMemsetAsync(c->d_acc.p, 0, c->n_cols * NPLANE * sizeof(int32_t), main));
+  if (!launch_accumulate(c)) return 0;
+  if (a.packed_runs) {
+    pack_runs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, main>>>(n, c->d_nruns.p, offs, c->d_runs.p, c->d_packed.p);
+    MIAGPU_CUDA(cudaEventRecord(c->xev[3], main));
+    MIAGPU_CUDA(cudaStreamWaitEvent(down, c->xev[3], 0));
+    if (tot) MIAGPU_CUDA(cudaMemcpyAsync(a.packed_runs, c->d_packed.p, tot * 2, cudaMemcpyDeviceToHost, down));
+    c->launches++;
+  }
+  tr.mark("accumulation enqueued");
   double slope = a.slope, intercept = a.intercept;
   if (fit) {
+    MIAGPU_CUDA(cudaEventSynchronize(c->aev[7]));
     MIAGPU_CUDA(cudaEventSynchronize(a.scores_on_host));
+    tr.mark("chain blocks on host");
     std::vector<ChainBlock> bxy(nb), bxx(nb);
     for (int64_t b = 0; b < nb; b++) {
       const CutBlockDev& B = c->h_cblk[b];
@@ -1609,37 +1634,21 @@ static int iterate_tail(miagpu_ctx* c, const IterTail& a, const Trace& tr) {
   }
   if (a.slope_out) *a.slope_out = slope;
   if (a.intercept_out) *a.intercept_out = intercept;
-  // ---- this round's flags (cull_maln_from_fsdb, mia.c:452-470), sticky (H10)
+  // ---- this round's flags (cull_maln_from_fsdb, mia.c:452-470), sticky (H10); the newly dropped reads leave the base columns
   cut_thresholds(a.hard_cut, slope, intercept, H->thr);
   MIAGPU_CUDA(cudaMemcpyAsync(c->d_thr.p, H->thr, sizeof(H->thr), cudaMemcpyHostToDevice, main));
-  if (a.wait_old_flags) MIAGPU_CUDA(cudaStreamWaitEvent(main, c->xev[1], 0));
-  cut_flags_kernel<<<(unsigned)((n + 255) / 256), 256, 0, main>>>(n, c->d_seqlen.p, c->d_score.p, c->d_thr.p, c->d_dropf.p, c->d_entries.p, c->d_cstats.p,
-                                                                  has_unique ? c->d_unique.p : nullptr);
+  cut_flags_kernel<<<(unsigned)((n + 255) / 256), 256, 0, main>>>(n, c->d_seqlen.p, c->d_score.p, c->d_thr.p, c->d_dropf.p, nullptr, c->d_cstats.p,
+                                                                  has_unique ? c->d_unique.p : nullptr, c->d_newly.p);
+  undo_kernel<<<(unsigned)((n + 255) / 256), 256, 0, main>>>(cons_params(c), n, c->d_newly.p, c->d_entries.p);
   MIAGPU_CUDA(cudaGetLastError());
-  c->launches++;
+  c->launches += 2;
   MIAGPU_CUDA(cudaMemcpyAsync(&H->bad_after, &c->d_cstats.p->bad, sizeof(long long), cudaMemcpyDeviceToHost, main));
   MIAGPU_CUDA(cudaEventRecord(c->xev[2], main));
   if (a.dropped) {
     MIAGPU_CUDA(cudaStreamWaitEvent(down, c->xev[2], 0));
     MIAGPU_CUDA(cudaMemcpyAsync(a.dropped, c->d_dropf.p, n, cudaMemcpyDeviceToHost, down));
   }
-  // ---- packed run lists out, column accumulation, base calling
-  const int64_t tot = H->tot_runs;
-  if (a.total_runs) *a.total_runs = tot;
-  if (a.packed_runs && tot > a.capacity) { cudaStreamSynchronize(main); set_error("miagpu_iterate: %lld runs, capacity %lld", (long long)tot, (long long)a.capacity); return 0; }
-  if (!c->d_packed.reserve(tot + 1)) return 0;
-  c->n_cols = (int64_t)c->seq_len + H->total_ins;
-  if (!c->d_acc.reserve(c->n_cols * NPLANE) || !c->d_called.reserve(c->n_cols + 16)) return 0;
-  if (a.packed_runs) {
-    pack_runs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, main>>>(n, c->d_nruns.p, offs, c->d_runs.p, c->d_packed.p);
-    MIAGPU_CUDA(cudaEventRecord(c->xev[3], main));
-    MIAGPU_CUDA(cudaStreamWaitEvent(down, c->xev[3], 0));
-    if (tot) MIAGPU_CUDA(cudaMemcpyAsync(a.packed_runs, c->d_packed.p, tot * 2, cudaMemcpyDeviceToHost, down));
-    c->launches++;
-  }
-  MIAGPU_CUDA(cudaMemsetAsync(c->d_acc.p, 0, c->n_cols * NPLANE * sizeof(int32_t), main));
-  if (!launch_accumulate(c)) return 0;
-  tr.mark("flags + accumulation enqueued");
+  tr.mark("flags + undo enqueued");
   c->cons_stage = 2;
   const int launches = c->launches;
   if (!miagpu_call(c, a.cons_code, a.gaps_out, nullptr, a.cons_out, a.cons_len)) return 0;
@@ -1657,8 +1666,10 @@ static int iterate_tail(miagpu_ctx* c, const IterTail& a, const Trace& tr) {
 // miagpu_cull_flags + miagpu_consensus_natural called one after the other, as a pipeline over three streams:
 //   upload stream   chunk k's reads + rc/as/ae/seq_len, then its classification (window rule, width classes, pairs)
 //   compute stream  chunk k's DP kernels as soon as chunk k is classified, then its share of the regression's
-//                   integer sums; afterwards entries, insert maxima, the regression's block kernels, flags,
-//                   column accumulation, base calling
+//                   integer sums; afterwards entries, insert maxima, column accumulation of every read not yet
+//                   dropped, this round's flags, the newly dropped reads taken back out, base calling
+//   side stream     the regression's block kernels + their records to the host (the host stitches the chains while the
+//                   compute stream accumulates)
 //   download stream chunk k's scores (first) and the other per-read outputs while chunk k+1 computes
 // upload, per-chunk classification + DP + downloads of a host-resident batch (the front half of a round); returns the
 // number of chunks through *chunks (the last chunk's "scores on host" event is c->cev[4 * (C - 1) + 2])

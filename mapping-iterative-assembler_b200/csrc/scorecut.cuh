@@ -277,16 +277,18 @@ __global__ void shard_merge_kernel(int world, int64_t stride, const uint32_t* re
 
 // below = score < threshold(len) (mia.c:452-470); sticky |= below (H10); the natural entries (2i, 2i+1) of the read
 // take the sticky flag (nullable)
-// a read that is not unique_best is not tested (mia.c:466) and keeps its flag
+// a read that is not unique_best is not tested (mia.c:466) and keeps its flag; newly (nullable): dropped by this round
 __global__ void cut_flags_kernel(int64_t n, const int32_t* __restrict__ seq_len, const int32_t* __restrict__ score,
                                  const double* __restrict__ thr, uint8_t* sticky, miagpu_entry* entries, CutStatsDev* st,
-                                 const uint8_t* __restrict__ unique = nullptr) {
+                                 const uint8_t* __restrict__ unique = nullptr, uint8_t* newly = nullptr) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int l = seq_len[i];
-  if (l < 0 || l > MAX_READ) { atomicMin(&st->bad, (long long)i); return; }
+  if (l < 0 || l > MAX_READ) { atomicMin(&st->bad, (long long)i); if (newly) newly[i] = 0; return; }
   const bool tested = !unique || unique[i];
-  const uint8_t s = sticky[i] | (uint8_t)(tested && (double)score[i] < thr[l]);
+  const uint8_t old = sticky[i];
+  const uint8_t s = old | (uint8_t)(tested && (double)score[i] < thr[l]);
+  if (newly) newly[i] = s & !old;
   sticky[i] = s;
   if (entries) { entries[2 * i].dropped = s; entries[2 * i + 1].dropped = s; }
 }
