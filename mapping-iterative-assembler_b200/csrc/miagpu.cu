@@ -1588,6 +1588,7 @@ static int iterate_tail(miagpu_ctx* c, const IterTail& a, const Trace& tr) {
     CutSrc src{};
     src.seq_len = c->d_seqlen.p; src.score = c->d_score.p; src.unique_best = du;
     cut_approx_kernel<false><<<(unsigned)nb, CUT_THREADS, 0, side>>>(n, src, c->d_ctab.p, c->d_cblk.p);
+    cut_prefix_kernel<<<1, CUT_PREFIX_THREADS, 0, side>>>(nb, c->d_cblk.p);
     cut_exact_kernel<false><<<(unsigned)nb, CUT_THREADS, 0, side>>>(n, src, c->d_ctab.p, c->d_cblk.p, nullptr, nullptr);
     MIAGPU_CUDA(cudaGetLastError());
     MIAGPU_CUDA(cudaMemcpyAsync(c->h_cblk, c->d_cblk.p, sizeof(CutBlockDev) * nb, cudaMemcpyDeviceToHost, side));
@@ -1997,6 +1998,7 @@ extern "C" int miagpu_shard_cut(miagpu_ctx* c, double* slope_out, double* interc
       CutSrc src{};
       src.keys = c->d_sh_recv.p; src.n_max = c->sh_nmax; src.stride = stride;
       cut_approx_kernel<true><<<(unsigned)nb, CUT_THREADS, 0, main>>>(ntot, src, c->d_ctab.p, c->d_cblk.p);
+      cut_prefix_kernel<<<1, CUT_PREFIX_THREADS, 0, main>>>(nb, c->d_cblk.p);
       cut_exact_kernel<true><<<(unsigned)nb, CUT_THREADS, 0, main>>>(ntot, src, c->d_ctab.p, c->d_cblk.p, c->d_sh_pf.p, c->d_sh_pfid.p);
       MIAGPU_CUDA(cudaGetLastError());
       MIAGPU_CUDA(cudaMemcpyAsync(c->h_cblk, c->d_cblk.p, sizeof(CutBlockDev) * nb, cudaMemcpyDeviceToHost, main));

@@ -35,6 +35,7 @@ struct CutTables {                                   // host-made, the same doub
 struct CutBlockDev {                                 // chain 0 = ssxy, chain 1 = ssxx
   double approx[2], T[2], A[2];
   int e[2], ok[2];
+  double run[2];                                     // approximate running sums at the block start (cut_prefix_kernel)
 };
 
 __global__ void cut_init_kernel(CutStatsDev* st) {
@@ -158,6 +159,30 @@ __global__ void __launch_bounds__(CUT_THREADS) cut_approx_kernel(int64_t n, CutS
   if (threadIdx.x == 0) { blk[blockIdx.x].approx[0] = s0; blk[blockIdx.x].approx[1] = s1; }
 }
 
+// exclusive prefix of the blocks' plain sums: one block, a contiguous run of chain blocks per thread
+constexpr int CUT_PREFIX_THREADS = 1024;
+__global__ void __launch_bounds__(CUT_PREFIX_THREADS) cut_prefix_kernel(int64_t nb, CutBlockDev* blk) {
+  __shared__ double s_tot[2][CUT_PREFIX_THREADS];
+  const int t = threadIdx.x;
+  const int64_t per = (nb + CUT_PREFIX_THREADS - 1) / CUT_PREFIX_THREADS;
+  const int64_t lo = min(nb, per * t), hi = min(nb, lo + per);
+  double a0 = 0, a1 = 0;
+  for (int64_t j = lo; j < hi; j++) { a0 += blk[j].approx[0]; a1 += blk[j].approx[1]; }
+  s_tot[0][t] = a0; s_tot[1][t] = a1;
+  __syncthreads();
+  for (int d = 1; d < CUT_PREFIX_THREADS; d <<= 1) {       // Hillis-Steele inclusive scan
+    const double v0 = t >= d ? s_tot[0][t - d] : 0.0, v1 = t >= d ? s_tot[1][t - d] : 0.0;
+    __syncthreads();
+    s_tot[0][t] += v0; s_tot[1][t] += v1;
+    __syncthreads();
+  }
+  double r0 = s_tot[0][t] - a0, r1 = s_tot[1][t] - a1;
+  for (int64_t j = lo; j < hi; j++) {
+    blk[j].run[0] = r0; blk[j].run[1] = r1;
+    r0 += blk[j].approx[0]; r1 += blk[j].approx[1];
+  }
+}
+
 // KEYS: blocks the stitch will probably have to add read by read (no proof, or the predicted running sum too close
 // to the edge of its binade for the block's increments) also copy their keys to one of SHARD_PF_SLOTS slots
 // (pf_ids[0] = number of such blocks, pf_ids[1 + slot] = block), so that the host has them without another round trip.
@@ -169,10 +194,9 @@ __global__ void __launch_bounds__(CUT_THREADS) cut_exact_kernel(int64_t n, CutSr
   __shared__ int s_slot;
   const int b = blockIdx.x;
   // approximate running sums at the block start (any order: it only predicts the binade, chain_stitch verifies it)
-  double run0 = 0, run1 = 0;
-  for (int j = threadIdx.x; j < b; j += CUT_THREADS) { run0 += blk[j].approx[0]; run1 += blk[j].approx[1]; }
+  const double run0 = blk[b].run[0], run1 = blk[b].run[1];
   if (threadIdx.x < 2) s_bad[threadIdx.x] = 0;
-  block_sum2(run0, run1, s_red);
+  __syncthreads();
   const double run[2] = {run0, run1};
   bool valid[2];
   double inv[2];

@@ -4,7 +4,7 @@ echo "GPUs: $NG"
 for N in 1 2 4 8; do
   if [ "$N" -le "$NG" ]; then
     if [ "$N" -eq 1 ]; then
-      python bench.py --gpus 1 --steps 5 --warmup 3 --no-cpu --no-pass1 > gpurun_out/scale_n$N.log 2>&1
+      python bench.py --gpus 1 --steps 5 --warmup 3 --no-cpu --no-pass1 --no-rmt --no-extras > gpurun_out/scale_n$N.log 2>&1
     else
       python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2961$N bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/scale_n$N.log 2>&1
     fi
