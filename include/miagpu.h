@@ -344,6 +344,11 @@ int miagpu_realign_resident( miagpu_ctx* ctx );
  * mia_main.c:252-256); score / as / ae (nullable host arrays of n) receive this round's values. */
 int miagpu_adopt_alignment( miagpu_ctx* ctx, int32_t* score, int32_t* as, int32_t* ae );
 
+/* The alignment the last round left on the device, as miagpu_realign returns it (host arrays of n, all nullable):
+ * after miagpu_iterate_resident / miagpu_shard_finish this plus miagpu_get_runs_packed is what miagpu_write_maln takes. */
+int miagpu_get_alignment( miagpu_ctx* ctx, int32_t* score, int32_t* as_out, int32_t* ae_out,
+                          int32_t* abr, int32_t* n_runs, uint8_t* status );
+
 /* ---- 8f4. Adapter trimming (-T): trim_frag (mia.c:1318-1368) for every read of a batch in
  * host memory (call site mia_main.c:773-777; set-up 692-713): dyn_prog of the adapter (rows)
  * against the read (columns) with the flat matrix (init_flatsubmat, pssm.c:96-126), sg5 = 1, the
@@ -367,6 +372,79 @@ int miagpu_repeat_filter( miagpu_ctx* ctx, int64_t n, const uint8_t* rc, const i
                           const int32_t* ae, const int32_t* key4, const uint8_t* trimmed,
                           int just_outer_coords, int tolerance, int64_t* order,
                           uint8_t* unique_best );
+
+/* ---- 8f2. Streaming FASTA / FASTQ record reader: find_input_type (io.c:11-25), read_fastq
+ * (io.c:46-167) and read_fasta (io.c:190-281) as mia_main.c:746-759 drives them, over a
+ * memory-mapped file, filling batch arrays that go straight into miagpu_upload_reads /
+ * miagpu_trim / miagpu_write_maln.  Host only (no device work).  Record rules are the reference's:
+ * ids end at the first blank or after 100 characters (the character that ends an over-long id is
+ * consumed and starts the description), descriptions are cut at 128, FASTA descriptions repeat
+ * their first character (the ungetc at io.c:224), bases are upper-cased and cut at 256 per read,
+ * qual_sum = sum(q - 33); the input ends at the first record that does not start with '@' / '>',
+ * at a FASTQ record whose quality line differs in length from its sequence, or at end of file.
+ *   miagpu_fastx_next  parses up to max_reads records into the handle's batch (replacing the
+ *                      previous batch); *n_out = records parsed, 0 at the end of the input.
+ *   miagpu_fastx_batch borrows the batch arrays (valid until the next _next / _close):
+ *                      bases (ASCII), offsets[n+1], ids / descs as NUL-terminated strings
+ *                      back to back with id_off[n+1] / desc_off[n+1], qual_sum[n]. */
+typedef struct miagpu_fastx miagpu_fastx;
+int  miagpu_fastx_open( miagpu_fastx** out, const char* path );
+int  miagpu_fastx_open_memory( miagpu_fastx** out, const void* text, int64_t len );  /* text is borrowed */
+int  miagpu_fastx_format( miagpu_fastx* h );            /* 0 FASTA, 1 FASTQ (seq_code, io.c:11-25) */
+int  miagpu_fastx_next( miagpu_fastx* h, int64_t max_reads, int64_t* n_out );
+int  miagpu_fastx_batch( miagpu_fastx* h, const uint8_t** bases, const int64_t** offsets,
+                         const char** ids, const int64_t** id_off, const char** descs,
+                         const int64_t** desc_off, const int32_t** qual_sum );
+void miagpu_fastx_close( miagpu_fastx* h );
+
+/* ---- 8f3. write_ma (map_alignment.c:283-382) fed from the device's per-read results, at the call
+ * sites mia_main.c:905, 958, 974.  The AlnSeq list is rebuilt on the host from the packed run
+ * lists: AlnSeq.seq / ins as merge_pwaln_into_maln (map_align.c:866-954) and split_pwaln
+ * (mia.c:1376-1438, "_f" / "_b" ids) make them, AlnSeq.smp as pop_smp_from_FSDB (fsdb.c:542-619),
+ * list order = FSDB order of the unique_best reads, front before back (cull_maln_from_fsdb
+ * mia.c:463-476), then sort_aln_frags by (start, end) (map_alignment.c:630; stable, as glibc's
+ * merge-sort qsort).  The file is byte-identical to the reference's after line 1 (its time stamp).
+ * Every read owns its fresh AlnSeqs here (the model of miagpu_iterate_resident); the reference's
+ * never-cleared back pointers (mia_main.c:273-276) are not reproduced. */
+typedef struct {
+  const char*    ref_id;      /* maln->ref->id: the input's id in round 1, "ConsAssem.<iter>" later (mia_main.c:47, 62-65) */
+  const char*    ref_desc;    /* "iteration assembly" from round 2 on */
+  const char*    ref_seq;     /* the reference of THIS round (ref_len characters) */
+  int32_t        ref_len;
+  int32_t        circular;
+  int32_t        ref_size;    /* RefSeq.size; 0 = derive with miagpu_maln_ref_size */
+  int32_t        maln_size;   /* culled_maln->size = number of AlnSeqs after pass 1 (mia.c:54) */
+  int32_t        cons_code;
+  const int32_t* gaps;        /* ref->gaps after the cull (gaps output of miagpu_call / _iterate_*), ref_len entries */
+  const int32_t* fpsm;        /* int sm[31][5][5] x 2, as miagpu_get_pssm returns them */
+  const int32_t* rpsm;
+} miagpu_maln_header;
+
+typedef struct {
+  int64_t        n;           /* FragSeqs in FSDB order */
+  const uint8_t* bases;       /* STORED orientation (fsdb.c:209-227: rc reads are kept reverse-complemented), ASCII */
+  const int64_t* offsets;     /* n+1 */
+  const char*    ids;         /* NUL-terminated strings back to back (the layout miagpu_fastx_batch returns) */
+  const int64_t* id_off;      /* n+1 */
+  const char*    descs;       /* nullable */
+  const int64_t* desc_off;
+  const uint8_t* rc;
+  const uint8_t* trimmed;     /* nullable = 0 */
+  const int32_t* num_inputs;  /* nullable = 1 */
+  const int32_t* score;       /* outputs of miagpu_realign / miagpu_iterate_*: */
+  const int32_t* as;          /*   as_out (absolute)                           */
+  const int32_t* ae;          /*   ae_out (absolute, may exceed ref_len)       */
+  const int32_t* abr;         /*   first aligned read row (soft clip)          */
+  const int64_t* run_off;     /* n+1, miagpu_get_runs_packed                   */
+  const uint16_t* packed;
+  const uint8_t* unique_best;   /* nullable = all 1 */
+  const uint8_t* dropped_front; /* AlnSeq.dropped of the front / only segment; nullable = 0 */
+  const uint8_t* dropped_back;  /* nullable = dropped_front */
+} miagpu_maln_reads;
+
+int miagpu_maln_ref_size( int ref_len, int circular );   /* mia_main.c:67 + add_ref_wrap mia.c:669-675 */
+int miagpu_write_maln( const char* path, const miagpu_maln_header* hd,
+                       const miagpu_maln_reads* rd, int64_t* n_alnseqs_out );
 
 /* ---- measurement helpers (bench.py) */
 /* per width bucket of the last realign: columns-per-lane K (0 = too wide),

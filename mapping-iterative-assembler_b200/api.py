@@ -87,6 +87,16 @@ def load_library():
     L.miagpu_last_pair_buckets.argtypes = [C.c_void_p] + [C.c_void_p] * 5 + [_i32p, _i32p]
     L.miagpu_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), _i64p, _i32p]
     L.miagpu_int32_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    L.miagpu_get_alignment.argtypes = [C.c_void_p] + [C.c_void_p] * 6
+    L.miagpu_fastx_open.argtypes = [_vpp, C.c_char_p]
+    L.miagpu_fastx_open_memory.argtypes = [_vpp, C.c_void_p, C.c_int64]
+    L.miagpu_fastx_format.argtypes = [C.c_void_p]
+    L.miagpu_fastx_next.argtypes = [C.c_void_p, C.c_int64, _i64p]
+    L.miagpu_fastx_batch.argtypes = [C.c_void_p] + [_vpp] * 7
+    L.miagpu_fastx_close.argtypes = [C.c_void_p]
+    L.miagpu_fastx_close.restype = None
+    L.miagpu_maln_ref_size.argtypes = [C.c_int, C.c_int]
+    L.miagpu_write_maln.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, _i64p]
     L.miagpu_stream.restype = C.c_void_p
     L.miagpu_stream.argtypes = [C.c_void_p]
     _lib = L
@@ -100,7 +110,9 @@ EXPORTS = ["miagpu_device_count", "miagpu_create", "miagpu_destroy", "miagpu_las
            "miagpu_score_cut", "miagpu_cull_flags",
            "miagpu_set_alignment_inputs", "miagpu_realign_resident", "miagpu_adopt_alignment", "miagpu_set_cut_inputs", "miagpu_reset_dropped", "miagpu_iterate_resident", "miagpu_last_buckets", "miagpu_last_pair_buckets", "miagpu_last_timing",
            "miagpu_int32_peak", "miagpu_stream", "miagpu_shard_begin", "miagpu_shard_begin_host", "miagpu_shard_cut", "miagpu_shard_finish",
-           "miagpu_last_cut_stats", "miagpu_repeat_filter", "miagpu_trim"]
+           "miagpu_last_cut_stats", "miagpu_repeat_filter", "miagpu_trim", "miagpu_get_alignment",
+           "miagpu_fastx_open", "miagpu_fastx_open_memory", "miagpu_fastx_format", "miagpu_fastx_next", "miagpu_fastx_batch", "miagpu_fastx_close",
+           "miagpu_maln_ref_size", "miagpu_write_maln"]
 
 
 def _ptr(a):
@@ -380,6 +392,13 @@ class MiaGpu:
         self._ck(self.lib.miagpu_adopt_alignment(self.h, _ptr(sc), _ptr(a), _ptr(e)))
         return sc, a, e
 
+    def get_alignment(self):
+        """the alignment the last round left on the device (miagpu_get_alignment) -> dict like realign's, without runs"""
+        out = {k: np.zeros(self.n, np.int32) for k in ("score", "as_out", "ae_out", "abr", "n_runs")}
+        out["status"] = np.zeros(self.n, np.uint8)
+        self._ck(self.lib.miagpu_get_alignment(self.h, *[_ptr(out[k]) for k in ("score", "as_out", "ae_out", "abr", "n_runs", "status")]))
+        return out
+
     def realign_resident(self):
         self._ck(self.lib.miagpu_realign_resident(self.h))
 
@@ -463,3 +482,108 @@ def cull_flags(seq_len, score, unique_best=None, hard_cut=0, score_cut_set=0, sl
     if not L.miagpu_cull_flags(n, _ptr(seq_len), _ptr(score), _ptr(unique_best), hard_cut, score_cut_set, slope, intercept, _ptr(out)):
         raise MiaGpuError(L.miagpu_last_error().decode())
     return out
+
+
+# ---------------------------------------------------------------- host formats either side of the path
+class FastxReader:
+    """find_input_type + read_fasta / read_fastq (io.c:11-281) as mia_main.c:746-759 drives them: batches of records
+    ready for upload_reads (miagpu_fastx_*).  Host only."""
+
+    def __init__(self, path=None, text=None):
+        self.lib = load_library()
+        self.h = C.c_void_p()
+        if path is not None:
+            ok = self.lib.miagpu_fastx_open(C.byref(self.h), os.fsencode(path))
+        else:
+            self._text = text if isinstance(text, bytes) else text.encode("latin-1")
+            ok = self.lib.miagpu_fastx_open_memory(C.byref(self.h), self._text, len(self._text))
+        if not ok:
+            raise MiaGpuError(self.lib.miagpu_last_error().decode())
+        self.format = self.lib.miagpu_fastx_format(self.h)
+
+    def close(self):
+        if self.h:
+            self.lib.miagpu_fastx_close(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def next(self, max_reads=1 << 20):
+        """-> dict(n, bases uint8, offsets int64[n+1], ids bytes, id_off, descs bytes, desc_off, qual_sum) (copies) or None at the end"""
+        n = C.c_int64()
+        if not self.lib.miagpu_fastx_next(self.h, max_reads, C.byref(n)):
+            raise MiaGpuError(self.lib.miagpu_last_error().decode())
+        n = n.value
+        if n == 0:
+            return None
+        p = [C.c_void_p() for _ in range(7)]
+        self.lib.miagpu_fastx_batch(self.h, *[C.byref(x) for x in p])
+
+        def arr(ptr, count, dt):
+            if count == 0:
+                return np.zeros(0, dt)
+            nbytes = count * np.dtype(dt).itemsize
+            return np.frombuffer(C.string_at(ptr.value, nbytes), dt).copy()
+        off = arr(p[1], n + 1, np.int64)
+        id_off = arr(p[3], n + 1, np.int64)
+        desc_off = arr(p[5], n + 1, np.int64)
+        return dict(n=n, bases=arr(p[0], int(off[-1]), np.uint8), offsets=off, ids=C.string_at(p[2].value, int(id_off[-1])), id_off=id_off,
+                    descs=C.string_at(p[4].value, int(desc_off[-1])), desc_off=desc_off, qual_sum=arr(p[6], n, np.int32))
+
+    @staticmethod
+    def strings(blob, off):
+        return [blob[off[i]:off[i + 1] - 1].decode("latin-1") for i in range(len(off) - 1)]
+
+
+class _MalnHeader(C.Structure):
+    _fields_ = [("ref_id", C.c_char_p), ("ref_desc", C.c_char_p), ("ref_seq", C.c_char_p), ("ref_len", C.c_int32), ("circular", C.c_int32),
+                ("ref_size", C.c_int32), ("maln_size", C.c_int32), ("cons_code", C.c_int32), ("gaps", C.c_void_p), ("fpsm", C.c_void_p),
+                ("rpsm", C.c_void_p)]
+
+
+class _MalnReads(C.Structure):
+    _fields_ = [("n", C.c_int64)] + [(k, C.c_void_p) for k in
+                                     ("bases", "offsets", "ids", "id_off", "descs", "desc_off", "rc", "trimmed", "num_inputs", "score", "as_",
+                                      "ae", "abr", "run_off", "packed", "unique_best", "dropped_front", "dropped_back")]
+
+
+def maln_ref_size(ref_len, circular):
+    return load_library().miagpu_maln_ref_size(ref_len, circular)
+
+
+def write_maln(path, ref_id, ref_desc, ref_seq, circular, maln_size, cons_code, gaps, fpsm, rpsm, reads):
+    """write_ma (map_alignment.c:283-382) from per-read device results (miagpu_write_maln).  `reads`: dict with bases (STORED
+    orientation), offsets, ids (bytes blob), id_off, descs, desc_off, rc, score, as_, ae, abr, run_off, packed and optionally
+    trimmed, num_inputs, unique_best, dropped_front, dropped_back.  -> number of AlnSeqs written."""
+    L = load_library()
+    keep = []
+
+    def a(x, dt):
+        if x is None:
+            return None
+        x = np.ascontiguousarray(x, dt)
+        keep.append(x)
+        return x.ctypes.data
+
+    def blob(x):
+        if x is None:
+            return None
+        b = C.create_string_buffer(bytes(x), len(x))
+        keep.append(b)
+        return C.addressof(b)
+    hd = _MalnHeader(ref_id.encode(), ref_desc.encode(), ref_seq.encode(), len(ref_seq), int(circular), 0, int(maln_size), int(cons_code),
+                     a(gaps, np.int32), a(fpsm, np.int32), a(rpsm, np.int32))
+    r = reads
+    rd = _MalnReads(len(r["offsets"]) - 1, a(r["bases"], np.uint8), a(r["offsets"], np.int64), blob(r["ids"]), a(r["id_off"], np.int64),
+                    blob(r.get("descs")), a(r.get("desc_off"), np.int64), a(r["rc"], np.uint8), a(r.get("trimmed"), np.uint8),
+                    a(r.get("num_inputs"), np.int32), a(r["score"], np.int32), a(r["as_"], np.int32), a(r["ae"], np.int32),
+                    a(r["abr"], np.int32), a(r["run_off"], np.int64), a(r["packed"], np.uint16), a(r.get("unique_best"), np.uint8),
+                    a(r.get("dropped_front"), np.uint8), a(r.get("dropped_back"), np.uint8))
+    n_out = C.c_int64()
+    if not L.miagpu_write_maln(os.fsencode(path), C.byref(hd), C.byref(rd), C.byref(n_out)):
+        raise MiaGpuError(L.miagpu_last_error().decode())
+    return n_out.value

@@ -1,0 +1,412 @@
+// hostio.hpp -- host-side data formats either side of the hot path. Plain C++17, no CUDA.
+//
+//   f2  miagpu_fastx_*   : the reference's FASTA / FASTQ record readers (io.c:11-25 find_input_type,
+//                          io.c:46-167 read_fastq, io.c:190-281 read_fasta) restated as a cursor over a memory-mapped
+//                          file that fills batch arrays (bases + offsets + ids + descs + qual_sum) ready for
+//                          miagpu_upload_reads -- quirks included, because they decide which reads exist:
+//                          ids cut at 100 chars with the cut character going to the description, FASTA
+//                          descriptions that repeat their first character (ungetc at io.c:224), reads cut at
+//                          256 bases, a record that does not start with '@' / '>' ends the input.
+//   f3  miagpu_write_maln: write_ma (map_alignment.c:283-382) fed from what the device returns -- per read
+//                          score / as / ae / abr and the packed run lists -- materialising each AlnSeq's
+//                          seq / ins (merge_pwaln_into_maln map_align.c:866-954, split_pwaln mia.c:1376-1438),
+//                          smp (pop_smp_from_FSDB fsdb.c:542-619), the list order of cull_maln_from_fsdb
+//                          (mia.c:463-476) and sort_aln_frags (map_alignment.c:630, glibc's stable merge sort).
+//                          Output is byte-identical to the reference's file after line 1 (a time stamp).
+#pragma once
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <time.h>
+#include <fcntl.h>
+#include <unistd.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/miagpu.h"
+
+namespace miagpu { void set_error(const char* fmt, ...); }
+using miagpu::set_error;
+
+namespace hostio {
+
+constexpr int kMaxId = 100;     // MAX_ID_LEN   params.h:17
+constexpr int kMaxDesc = 128;   // MAX_DESC_LEN params.h:18
+constexpr int kMaxRead = 256;   // INIT_ALN_SEQ_LEN params.h:68
+constexpr int kDepth = 15;      // PSSM_DEPTH
+
+inline bool c_space(int c) { return c == ' ' || (c >= '\t' && c <= '\r'); }
+inline int c_upper(int c) { return (c >= 'a' && c <= 'z') ? c - 32 : c; }
+
+// ------------------------------------------------------------------------------------------------ f2
+struct Fastx {
+  const unsigned char* buf = nullptr;
+  size_t len = 0, pos = 0;
+  int fd = -1;
+  bool mapped = false;
+  int format = 0;            // 0 fasta, 1 fastq (find_input_type io.c:11-25)
+  bool done = false;
+  int last_qual_sum = 0;     // FragSeq is reused by the caller's loop: a record without '+' keeps the previous sum
+  // current batch
+  std::vector<uint8_t> bases;
+  std::vector<int64_t> off;
+  std::vector<char> ids, descs;
+  std::vector<int64_t> id_off, desc_off;
+  std::vector<int32_t> qual_sum;
+  int64_t records_total = 0;
+
+  // the reference keeps what fgetc returned in a `char`: end of input and byte 0xFF are both -1
+  int get() { return pos < len ? (int)(signed char)buf[pos++] : (pos++, -1); }
+  void unget() { if (pos > 0) pos--; }
+
+  void clear_batch() {
+    bases.clear(); off.assign(1, 0); ids.clear(); descs.clear(); id_off.assign(1, 0); desc_off.assign(1, 0); qual_sum.clear();
+  }
+
+  void push(const char* id, int idn, const char* desc, int dn, const unsigned char* seq, int sn, int qs) {
+    ids.insert(ids.end(), id, id + idn); ids.push_back('\0'); id_off.push_back((int64_t)ids.size());
+    descs.insert(descs.end(), desc, desc + dn); descs.push_back('\0'); desc_off.push_back((int64_t)descs.size());
+    bases.insert(bases.end(), seq, seq + sn); off.push_back((int64_t)bases.size());
+    qual_sum.push_back(qs);
+    records_total++;
+  }
+
+  // header line shared by both formats (io.c:58-91 / 203-232). Returns false at end of input inside the id.
+  bool header(char* id, int& idn, char* desc, int& dn, bool fasta) {
+    int c;
+    idn = 0;
+    for (;;) {
+      c = get();
+      if (c_space(c) || idn >= kMaxId) break;          // the character that ends an over-long id is consumed here
+      if (c == -1) return false;
+      id[idn++] = (char)c;
+    }
+    dn = 0;
+    if (c == '\n') return true;
+    while (c != '\n' && c_space(c)) c = get();
+    if (fasta) unget();                                // io.c:224: the pushed-back character is stored, then read again
+    while (c != '\n' && dn < kMaxDesc) { desc[dn++] = (char)c; c = get(); }
+    return true;                                       // a description cut at 128 leaves the rest of its line unread
+  }
+
+  // one FASTQ record; 0 = stop, 1 = record stored
+  int next_fastq() {
+    int c = get();
+    if (c == -1 || c != '@') return 0;
+    char id[kMaxId + 1], desc[kMaxDesc + 1];
+    unsigned char seq[kMaxRead + 1];
+    int idn, dn, sn = 0;
+    if (!header(id, idn, desc, dn, false)) return 0;
+    c = get();
+    while (c != '\n' && c != -1 && sn < kMaxRead) { if (!c_space(c)) seq[sn++] = (unsigned char)c_upper(c); c = get(); }
+    if (sn == kMaxRead) while (c != '\n' && c != -1) c = get();
+    c = get();
+    if (c != '+') { push(id, idn, desc, dn, seq, sn, last_qual_sum); return 1; }   // io.c:121-124: accepted as it is
+    do c = get(); while (c != '\n' && c != -1);
+    c = get();
+    int qn = 0, qs = 0;
+    while (c != '\n' && c != -1 && qn < kMaxRead) { if (!c_space(c)) { qs += c - 33; qn++; } c = get(); }
+    last_qual_sum = qs;
+    if (qn == kMaxRead) while (c != '\n' && c != -1) c = get();
+    if (qn != sn) return 0;                                                        // io.c:162-166
+    push(id, idn, desc, dn, seq, sn, qs);
+    return 1;
+  }
+
+  int next_fasta() {
+    int c = get();
+    if (c == -1 || c != '>') return 0;
+    char id[kMaxId + 1], desc[kMaxDesc + 1];
+    unsigned char seq[kMaxRead + 1];
+    int idn, dn, sn = 0;
+    if (!header(id, idn, desc, dn, true)) return 0;
+    c = get();
+    while (c != '>' && c != -1 && sn < kMaxRead) { if (!c_space(c)) seq[sn++] = (unsigned char)c_upper(c); c = get(); }
+    if (c != '>' && sn == kMaxRead) while (c != '>' && c != -1) c = get();
+    if (c == '>') unget();
+    push(id, idn, desc, dn, seq, sn, 0);
+    return 1;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------ f3
+struct Out {
+  FILE* f;
+  std::vector<char> b;
+  explicit Out(FILE* f_) : f(f_) { b.reserve(1 << 22); }
+  void flush() { if (!b.empty()) { fwrite(b.data(), 1, b.size(), f); b.clear(); } }
+  void room() { if (b.size() > (1u << 22) - 4096) flush(); }
+  void s(const char* p) { size_t n = strlen(p); if (n > 2048) flush(); b.insert(b.end(), p, p + n); room(); }
+  void s(const char* p, size_t n) { if (n > 2048) flush(); b.insert(b.end(), p, p + n); room(); }
+  void ch(char c) { b.push_back(c); }
+  void i(long v) {
+    char t[24]; int n = 0; bool neg = v < 0; unsigned long u = neg ? 0ul - (unsigned long)v : (unsigned long)v;
+    do { t[n++] = (char)('0' + u % 10); u /= 10; } while (u);
+    if (neg) b.push_back('-');
+    while (n) b.push_back(t[--n]);
+    room();
+  }
+  void kv(const char* k, long v) { s(k); i(v); ch('\n'); }
+};
+
+struct Seg {                  // one AlnSeq of the list
+  int64_t read;
+  int32_t start, end;
+  int32_t col0, ncol;         // slice of the read's alignment columns
+  char seg;
+  uint8_t dropped;
+};
+
+inline char smp_code(int from_front, int from_back) {
+  if (from_front <= kDepth) return (char)('A' + from_front);
+  if (from_back < kDepth) return (char)('A' + 2 * kDepth - from_back);
+  return (char)('A' + kDepth);
+}
+
+}  // namespace hostio
+
+struct miagpu_fastx { hostio::Fastx x; };
+
+extern "C" int miagpu_fastx_open(miagpu_fastx** out, const char* path) {
+  if (!out || !path) { set_error("miagpu_fastx_open: NULL argument"); return 0; }
+  int fd = open(path, O_RDONLY);
+  if (fd < 0) { set_error("miagpu_fastx_open: cannot open %s", path); return 0; }
+  struct stat st;
+  if (fstat(fd, &st) != 0) { close(fd); set_error("miagpu_fastx_open: cannot stat %s", path); return 0; }
+  miagpu_fastx* h = new miagpu_fastx();
+  h->x.fd = fd;
+  h->x.len = (size_t)st.st_size;
+  if (h->x.len) {
+    void* p = mmap(nullptr, h->x.len, PROT_READ, MAP_PRIVATE, fd, 0);
+    if (p == MAP_FAILED) { close(fd); delete h; set_error("miagpu_fastx_open: mmap of %s failed", path); return 0; }
+    madvise(p, h->x.len, MADV_SEQUENTIAL);
+    h->x.buf = (const unsigned char*)p;
+    h->x.mapped = true;
+  }
+  h->x.format = (h->x.len && h->x.buf[0] == '@') ? 1 : 0;
+  h->x.clear_batch();
+  *out = h;
+  return 1;
+}
+
+extern "C" int miagpu_fastx_open_memory(miagpu_fastx** out, const void* text, int64_t len) {
+  if (!out || (!text && len) || len < 0) { set_error("miagpu_fastx_open_memory: bad argument"); return 0; }
+  miagpu_fastx* h = new miagpu_fastx();
+  h->x.buf = (const unsigned char*)text;
+  h->x.len = (size_t)len;
+  h->x.format = (len && h->x.buf[0] == '@') ? 1 : 0;
+  h->x.clear_batch();
+  *out = h;
+  return 1;
+}
+
+extern "C" void miagpu_fastx_close(miagpu_fastx* h) {
+  if (!h) return;
+  if (h->x.mapped) munmap((void*)h->x.buf, h->x.len);
+  if (h->x.fd >= 0) close(h->x.fd);
+  delete h;
+}
+
+extern "C" int miagpu_fastx_format(miagpu_fastx* h) { return h ? h->x.format : -1; }
+
+extern "C" int miagpu_fastx_next(miagpu_fastx* h, int64_t max_reads, int64_t* n_out) {
+  if (!h || !n_out || max_reads < 0) { set_error("miagpu_fastx_next: bad argument"); return 0; }
+  hostio::Fastx& x = h->x;
+  x.clear_batch();
+  int64_t n = 0;
+  while (!x.done && n < max_reads) {
+    int r = x.format ? x.next_fastq() : x.next_fasta();
+    if (!r) { x.done = true; break; }
+    n++;
+  }
+  *n_out = n;
+  return 1;
+}
+
+extern "C" int miagpu_fastx_batch(miagpu_fastx* h, const uint8_t** bases, const int64_t** offsets, const char** ids,
+                                  const int64_t** id_off, const char** descs, const int64_t** desc_off, const int32_t** qual_sum) {
+  if (!h) { set_error("miagpu_fastx_batch: NULL handle"); return 0; }
+  hostio::Fastx& x = h->x;
+  if (bases) *bases = x.bases.data();
+  if (offsets) *offsets = x.off.data();
+  if (ids) *ids = x.ids.data();
+  if (id_off) *id_off = x.id_off.data();
+  if (descs) *descs = x.descs.data();
+  if (desc_off) *desc_off = x.desc_off.data();
+  if (qual_sum) *qual_sum = x.qual_sum.data();
+  return 1;
+}
+
+extern "C" int miagpu_maln_ref_size(int ref_len, int circular) {
+  // reiterate_assembly sets size = len + 1 (mia_main.c:67), add_ref_wrap doubles it until the wrap fits (mia.c:669-675)
+  long size = (long)ref_len + 1;
+  if (circular) {
+    int wrap = ref_len < hostio::kMaxRead ? ref_len : hostio::kMaxRead;
+    while ((long)ref_len + wrap >= size) size *= 2;
+  }
+  return (int)size;
+}
+
+extern "C" int miagpu_write_maln(const char* path, const miagpu_maln_header* hd, const miagpu_maln_reads* rd, int64_t* n_alnseqs_out) {
+  using namespace hostio;
+  if (!path || !hd || !rd) { set_error("miagpu_write_maln: NULL argument"); return 0; }
+  if (!hd->ref_seq || hd->ref_len <= 0 || !hd->gaps || !hd->fpsm || !hd->rpsm || !hd->ref_id || !hd->ref_desc) {
+    set_error("miagpu_write_maln: incomplete header"); return 0;
+  }
+  const int64_t n = rd->n;
+  if (n < 0 || (n && (!rd->bases || !rd->offsets || !rd->rc || !rd->score || !rd->as || !rd->ae || !rd->abr || !rd->run_off || !rd->packed ||
+                      !rd->ids || !rd->id_off))) {
+    set_error("miagpu_write_maln: incomplete read arrays"); return 0;
+  }
+  const int L = hd->ref_len;
+  // ---- the AlnSeq list in FSDB order (cull_maln_from_fsdb mia.c:463-476), then sort_aln_frags
+  std::vector<Seg> segs;
+  segs.reserve((size_t)n + 16);
+  for (int64_t i = 0; i < n; i++) {
+    if (rd->unique_best && !rd->unique_best[i]) continue;
+    int start = rd->as[i];
+    int end = rd->ae[i] > L ? rd->ae[i] - L : rd->ae[i];                           // mia_main.c:259-263
+    int ncol = 0;
+    for (int64_t r = rd->run_off[i]; r < rd->run_off[i + 1]; r++) {
+      unsigned x = rd->packed[r];
+      if (MIAGPU_RUN_TYPE(x) != MIAGPU_RUN_I) ncol += (int)MIAGPU_RUN_LEN(x);
+    }
+    uint8_t df = rd->dropped_front ? rd->dropped_front[i] : 0, db = rd->dropped_back ? rd->dropped_back[i] : df;
+    if (start > end) {                                                             // split_pwaln at seq_len
+      int nf = L - start;
+      if (nf < 0) nf = 0;
+      if (nf > ncol) nf = ncol;
+      segs.push_back({i, start, L - 1, 0, nf, 'f', (uint8_t)(df != 0)});
+      segs.push_back({i, 0, end, nf, ncol - nf, 'b', (uint8_t)(db != 0)});
+    } else {
+      segs.push_back({i, start, end, 0, ncol, 'a', (uint8_t)(df != 0)});
+    }
+  }
+  std::vector<uint32_t> order(segs.size());
+  for (size_t k = 0; k < order.size(); k++) order[k] = (uint32_t)k;
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+    if (segs[a].start != segs[b].start) return segs[a].start < segs[b].start;
+    return segs[a].end < segs[b].end;
+  });
+
+  FILE* f = fopen(path, "w");
+  if (!f) { set_error("miagpu_write_maln: cannot open %s for writing", path); return 0; }
+  Out o(f);
+  time_t t = time(nullptr);
+  char stamp[64];
+  struct tm tmv;
+  localtime_r(&t, &tmv);
+  asctime_r(&tmv, stamp);
+  o.s("/* map_alignment [V1.0] */ "); o.s(stamp);
+  o.kv("MALN_NAS ", (long)segs.size());
+  o.kv("MALN_SIZ ", hd->maln_size);
+  o.kv("MALN_COC ", hd->cons_code);
+  o.s("__REFERENCE__\n");
+  o.s("ID "); o.s(hd->ref_id); o.ch('\n');
+  o.s("DESC "); o.s(hd->ref_desc); o.ch('\n');
+  o.kv("LEN ", L);
+  o.kv("SIZE ", hd->ref_size > 0 ? hd->ref_size : miagpu_maln_ref_size(L, hd->circular));
+  o.s("SEQ "); o.s(hd->ref_seq, (size_t)L); o.ch('\n');
+  o.s("GAPS");
+  for (int i = 0; i < L; i++) { o.ch(' '); o.i(hd->gaps[i]); }
+  o.ch('\n');
+  o.s("__PSSM__\n");
+  o.kv("DEPTH ", kDepth);
+  for (int which = 0; which < 2; which++) {
+    const int32_t* sm = which ? hd->rpsm : hd->fpsm;
+    o.s(which ? "RPSM:\n" : "FPSM:\n");
+    for (int d = 0; d <= 2 * kDepth; d++) {
+      for (int row = 0; row < 5; row++) {
+        for (int col = 0; col < 5; col++) { if (col) o.ch(' '); o.i(sm[(d * 5 + row) * 5 + col]); }
+        o.ch('\n');
+      }
+      o.ch('\n');
+    }
+  }
+  o.s("__ALNSEQS__\n");
+
+  // ---- per AlnSeq: columns, inserts, smp from the run list
+  std::vector<char> colc, smp;                 // per alignment column of the read: AlnSeq.seq character
+  std::vector<int32_t> ins_at, ins_len;        // per column: read row and length of the insert in front of it
+  std::string idbuf;
+  int64_t cached = -1;
+  int front_total = 0, back_total = 0, nfront = 0;
+  for (uint32_t k : order) {
+    const Seg& sg = segs[k];
+    const int64_t i = sg.read;
+    const uint8_t* read = rd->bases + rd->offsets[i];
+    const int rlen = (int)(rd->offsets[i + 1] - rd->offsets[i]);
+    if (cached != i) {
+      cached = i;
+      colc.clear(); ins_at.clear(); ins_len.clear();
+      int row = rd->abr[i], pend_at = 0, pend_len = 0;
+      for (int64_t r = rd->run_off[i]; r < rd->run_off[i + 1]; r++) {
+        unsigned x = rd->packed[r];
+        int ty = (int)MIAGPU_RUN_TYPE(x), ln = (int)MIAGPU_RUN_LEN(x);
+        if (ty == MIAGPU_RUN_I) {
+          if (!pend_len) pend_at = row;
+          pend_len += ln; row += ln;
+          continue;
+        }
+        for (int q = 0; q < ln; q++) {
+          ins_at.push_back(pend_at); ins_len.push_back(pend_len); pend_len = 0;
+          if (ty == MIAGPU_RUN_M) { colc.push_back(row < rlen ? (char)read[row] : '?'); row++; }
+          else colc.push_back('-');
+        }
+      }
+      if (row > rlen) { o.flush(); fclose(f); set_error("miagpu_write_maln: runs of read %lld overrun its %d bases", (long long)i, rlen); return 0; }
+      // asp_len of the front and back AlnSeq (fsdb.c:518-530): columns + inserted bases (deletions count as sequence)
+      int tot = (int)colc.size();
+      int s0 = rd->as[i], e0 = rd->ae[i] > L ? rd->ae[i] - L : rd->ae[i];
+      nfront = tot;
+      if (s0 > e0) { nfront = L - s0; if (nfront < 0) nfront = 0; if (nfront > tot) nfront = tot; }
+      front_total = nfront; back_total = tot - nfront;
+      for (int c = 0; c < tot; c++) (c < nfront ? front_total : back_total) += ins_len[c];
+      // smp over front then back with one running position (fsdb.c:556-616)
+      smp.resize(colc.size());
+      int act = 0;
+      for (int c = 0; c < tot; c++) {
+        act += ins_len[c];
+        int from_front = (c < nfront) ? act : front_total + act;      // fsdb.c:596: the back segment adds the front's length again
+        int from_back = front_total + back_total - act - 1;
+        smp[c] = smp_code(from_front, from_back);
+        if (colc[c] != '-') act++;
+      }
+    }
+    // id, with split_pwaln's suffix rule (mia.c:1389-1398)
+    const char* id = rd->ids + rd->id_off[i];
+    idbuf.assign(id);
+    if (sg.seg != 'a') {
+      size_t cut = std::min<size_t>(idbuf.size(), (size_t)kMaxId - 1);
+      idbuf.resize(cut);
+      idbuf += (sg.seg == 'f') ? "_f" : "_b";
+    }
+    o.s("ID "); o.s(idbuf.c_str()); o.ch('\n');
+    o.s("DESC "); if (rd->descs && rd->desc_off) o.s(rd->descs + rd->desc_off[i]); o.ch('\n');
+    o.kv("SCORE ", rd->score[i]);
+    o.kv("NUM_INPUTS ", rd->num_inputs ? rd->num_inputs[i] : 1);
+    o.kv("START ", sg.start);
+    o.kv("END ", sg.end);
+    o.kv("RC ", rd->rc[i] ? 1 : 0);
+    o.kv("TR ", (rd->trimmed && rd->trimmed[i]) ? 1 : 0);
+    o.kv("DR ", sg.dropped);
+    o.s("SEG "); o.ch(sg.seg); o.ch('\n');
+    o.s("SEQ "); o.s(colc.data() + sg.col0, (size_t)sg.ncol); o.ch('\n');
+    o.s("SMP "); o.s(smp.data() + sg.col0, (size_t)sg.ncol); o.ch('\n');
+    o.s("INS_POS");
+    for (int c = 0; c < sg.ncol; c++) {
+      int g = sg.col0 + c;
+      if (ins_len[g]) { o.ch(' '); o.i(c); o.ch(' '); o.s((const char*)read + ins_at[g], (size_t)ins_len[g]); }
+    }
+    o.ch('\n');
+  }
+  o.flush();
+  bool ok = !ferror(f);
+  if (fclose(f) != 0) ok = false;
+  if (!ok) { set_error("miagpu_write_maln: write to %s failed", path); return 0; }
+  if (n_alnseqs_out) *n_alnseqs_out = (int64_t)segs.size();
+  return 1;
+}

@@ -1046,6 +1046,25 @@ extern "C" int miagpu_adopt_alignment(miagpu_ctx* c, int32_t* score, int32_t* as
   return 1;
 }
 
+// The resident alignment of the last round as miagpu_realign would have returned it (all outputs nullable): what
+// miagpu_write_maln needs beside the packed run lists after a one-call round.
+extern "C" int miagpu_get_alignment(miagpu_ctx* c, int32_t* score, int32_t* as_out, int32_t* ae_out, int32_t* abr, int32_t* n_runs,
+                                    uint8_t* status) {
+  if (!c) { set_error("miagpu_get_alignment: no context"); return 0; }
+  MIAGPU_CUDA(cudaSetDevice(c->device));
+  const int64_t n = c->n;
+  if (n) {
+    if (score) MIAGPU_CUDA(cudaMemcpyAsync(score, c->d_score.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (as_out) MIAGPU_CUDA(cudaMemcpyAsync(as_out, c->d_as_out.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (ae_out) MIAGPU_CUDA(cudaMemcpyAsync(ae_out, c->d_ae_out.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (abr) MIAGPU_CUDA(cudaMemcpyAsync(abr, c->d_abr.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (n_runs) MIAGPU_CUDA(cudaMemcpyAsync(n_runs, c->d_nruns.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (status) MIAGPU_CUDA(cudaMemcpyAsync(status, c->d_status.p, n, cudaMemcpyDeviceToHost, c->stream));
+  }
+  MIAGPU_CUDA(cudaStreamSynchronize(c->stream));
+  return 1;
+}
+
 extern "C" int miagpu_realign_resident(miagpu_ctx* c) {
   if (!c || !c->have_pssm || !c->have_ref) { set_error("miagpu_realign_resident: set_pssm and set_reference first"); return 0; }
   MIAGPU_CUDA(cudaSetDevice(c->device));
@@ -2680,3 +2699,6 @@ extern "C" int miagpu_compact_reads(miagpu_ctx* c, const uint8_t* keep, const ui
   return 1;
 }
 
+
+// host-side formats either side of the path: FASTA / FASTQ reader, .maln writer
+#include "hostio.hpp"

@@ -241,6 +241,7 @@ class ResidentAssembler:
         self.seq_len, self.score = seq_len[idx], p["score"][idx].copy()
         self.rc, self.as_, self.ae = p["rc"][idx].copy(), p["as_"][idx].copy(), p["ae"][idx].copy()
         self.split = p["start"][idx] > p["end"][idx]                                 # mia.c:1619
+        self.maln_size = int(len(idx) + self.split.sum())                            # culled_maln->size (mia.c:54): AlnSeqs of pass 1
         if self.x is not None or not defer_cull:
             self.pass1_cull(self._gather(self.seq_len), self._gather(self.score))
         return p
@@ -256,6 +257,7 @@ class ResidentAssembler:
         rev = np.zeros(self._n_all, np.uint8)
         rev[idx] = self.rc == 1                                                      # stored orientation (fsdb.c:209-227)
         g.compact_reads(keep_dev, rev)
+        self.fsdb_idx = idx[ok]                                                      # input index of every FSDB read
         for name in ("seq_len", "score", "rc", "as_", "ae", "split"):
             setattr(self, name, getattr(self, name)[ok])
         self.dropped = np.ascontiguousarray(dropped[ok], np.uint8)
@@ -287,6 +289,36 @@ class ResidentAssembler:
         self.split = split
         self.cons = cons
         return cons, cons == self.last
+
+    def write_maln(self, path, batch, ref_id, ref_desc=""):
+        """write_ma of this round's culled_maln (mia_main.c:905 / 958) from the device's results: `batch` is the FastxReader batch
+        (or any dict with bases / offsets / ids / id_off / descs / desc_off) the reads came from, in input order; call after
+        iterate(want_gaps=True).  Reference id / desc follow mia_main.c:47, 62-65."""
+        from .synth import revcomp_bytes
+        g = self.g
+        al = g.get_alignment()
+        tot, _, _ = g.get_runs_packed()
+        run_off, packed = np.zeros(len(self.rc) + 1, np.int64), np.zeros(max(tot, 1), np.uint16)
+        g.get_runs_packed(run_off, packed)
+        off, bases = np.asarray(batch["offsets"]), np.asarray(batch["bases"])
+        stored, ids, descs = [], [], []
+        idb, ido = batch["ids"], batch["id_off"]
+        dsb, dso = batch.get("descs"), batch.get("desc_off")
+        for j, i in enumerate(self.fsdb_idx):                                        # stored orientation: fsdb.c:209-227
+            r = bases[off[i]:off[i + 1]]
+            stored.append(revcomp_bytes(r) if self.rc[j] else r)
+            ids.append(idb[ido[i]:ido[i + 1]])
+            descs.append(dsb[dso[i]:dso[i + 1]] if dsb is not None else b"\0")
+        so = np.zeros(len(stored) + 1, np.int64)
+        np.cumsum([len(x) for x in stored], out=so[1:])
+        cum = lambda xs: np.concatenate([[0], np.cumsum([len(x) for x in xs])]).astype(np.int64)
+        fpsm, rpsm = g.get_pssm()
+        if self.iter > 1:
+            ref_id, ref_desc = f"ConsAssem.{self.iter}", "iteration assembly"
+        rd = dict(bases=np.concatenate(stored) if stored else np.zeros(0, np.uint8), offsets=so, ids=b"".join(ids), id_off=cum(ids),
+                  descs=b"".join(descs), desc_off=cum(descs), rc=self.rc, score=al["score"], as_=al["as_out"], ae=al["ae_out"], abr=al["abr"],
+                  run_off=run_off, packed=packed, dropped_front=self.dropped, dropped_back=self.dropped)
+        return api.write_maln(path, ref_id, ref_desc, self.last, self.circular, self.maln_size, self.cons_code, self.gaps, fpsm, rpsm, rd)
 
     def run(self, bases, off, max_iter=MAX_ITER):
         self.pass1(bases, off)

@@ -485,3 +485,26 @@ void refh_trim( const char* read, const char* adapter, int* out6 ) {
   out6[2] = a->m->mat[a->aer][a->aec].score;
   out6[3] = a->abr; out6[4] = a->abc; out6[5] = a->aer;
 }
+
+/* ---------------------------------------------------- FASTA / FASTQ reader
+   mia_main.c:746-759: find_input_type, then read_next_seq into ONE reused FragSeq until it
+   returns 0.  Every record is dumped as id \t desc \t seq \t qual_sum \n (ids and descs with
+   their bytes as they are; tabs inside a description are kept -- the dump is split on the first
+   and the last two tabs).  Returns the number of records, -1 if a file cannot be opened. */
+long long refh_read_seqs( const char* in_fn, const char* out_fn ) {
+  FILE* FF = fopen( in_fn, "r" );
+  FILE* OUT = fopen( out_fn, "w" );
+  FragSeqP fs = (FragSeqP)calloc( 1, sizeof(FragSeq) );
+  long long n = 0;
+  int code;
+  if ( FF == NULL || OUT == NULL ) return -1;
+  code = find_input_type( FF );
+  while ( read_next_seq( FF, fs, code ) ) {
+    fprintf( OUT, "%s\t%s\t%s\t%d\n", fs->id, fs->desc, fs->seq, code ? fs->qual_sum : 0 );
+    n++;
+  }
+  fclose( FF );
+  fclose( OUT );
+  free( fs );
+  return n;
+}
