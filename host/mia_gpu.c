@@ -1,0 +1,203 @@
+/* mia_gpu.c -- a plain-C host for libmiagpu.so: the call sequence INTEGRATION.md gives a maintainer of the reference,
+ * compiled and run.  It is NOT the reference's CLI (out of scope): it covers the default assembly mode only
+ *
+ *     mia_gpu -r ref.fa -f reads.fq -s matrix.txt -m out [-c] [-k K] [-p 1|2] [-H cut] [-F]
+ *
+ * and exists to show (and test, tests/test_gpu_host_c.py) that the C ABI alone -- no Python, no torch -- reproduces
+ * the reference's `.maln` files: reader (miagpu_fastx_*), matrices (miagpu_read_pssm), pass 1, score cut, one library
+ * call per round with everything resident, writer (miagpu_write_maln).  The host keeps what mia_main.c keeps: which
+ * reads enter the FSDB (mia.c:1614), their strand, the convergence test (mia_main.c:909-976), the file names.
+ * Reads that score exactly 2000 (strand_known = 0, mia.c:1653), -D, -u/-U, -T, -h, -C, -I are not handled here.
+ * There is no CPU fallback: without a CUDA device miagpu_create fails and so does this program. */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <ctype.h>
+#include "miagpu.h"
+
+#define FIRST_ROUND_SCORE_CUTOFF 2000   /* params.h */
+#define MAX_ITER 30
+
+static void die( const char* what ) {
+  fprintf( stderr, "mia_gpu: %s: %s\n", what, miagpu_last_error() );
+  exit( 1 );
+}
+#define CK( call ) do { if ( !( call ) ) die( #call ); } while ( 0 )
+
+static void* xmalloc( size_t n ) {
+  void* p = calloc( n ? n : 1, 1 );
+  if ( !p ) { fprintf( stderr, "mia_gpu: out of memory\n" ); exit( 1 ); }
+  return p;
+}
+
+/* first record of a FASTA file: id = up to the first blank, desc = rest of the line after ONE blank, sequence with
+ * white space removed, case kept (read_fasta_ref io.c:288-386; the -M soft mask needs the case) */
+static char* read_reference( const char* fn, char* id, char* desc, int* len_out ) {
+  FILE* f = fopen( fn, "r" );
+  size_t cap = 1 << 16, n = 0;
+  char* seq = (char*)xmalloc( cap );
+  int c, k = 0;
+  if ( !f || fgetc( f ) != '>' ) { fprintf( stderr, "mia_gpu: cannot read reference %s\n", fn ); exit( 1 ); }
+  while ( ( c = fgetc( f ) ) != EOF && !isspace( c ) && k < 100 ) id[k++] = (char)c;
+  id[k] = 0;
+  k = 0;
+  if ( c != '\n' && c != EOF )
+    while ( ( c = fgetc( f ) ) != EOF && c != '\n' && k < 128 ) desc[k++] = (char)c;
+  desc[k] = 0;
+  while ( c != '\n' && c != EOF ) c = fgetc( f );
+  while ( ( c = fgetc( f ) ) != EOF && c != '>' ) {
+    if ( isspace( c ) ) continue;
+    if ( n + 2 > cap ) { cap *= 2; seq = (char*)realloc( seq, cap ); if ( !seq ) exit( 1 ); }
+    seq[n++] = (char)c;
+  }
+  seq[n] = 0;
+  fclose( f );
+  *len_out = (int)n;
+  return seq;
+}
+
+static unsigned char comp[256];
+static void init_comp( void ) {
+  const char* a = "ACGTRYKMBDHVNSWacgtrykmbdhvnsw-";
+  const char* b = "TGCAYRMKVHDBNSWtgcayrmkvhdbnsw-";
+  int i;
+  for ( i = 0; i < 256; i++ ) comp[i] = 'N';
+  for ( i = 0; a[i]; i++ ) comp[(unsigned char)a[i]] = (unsigned char)b[i];
+}
+
+int main( int argc, char** argv ) {
+  const char *ref_fn = NULL, *frag_fn = NULL, *mat_fn = NULL, *root = "assembly.maln.iter";
+  int circular = 0, k = -1, cons_code = 1, hard_cut = 0, final_only = 0, i;
+  for ( i = 1; i < argc; i++ ) {
+    if ( !strcmp( argv[i], "-c" ) ) circular = 1;
+    else if ( !strcmp( argv[i], "-F" ) ) final_only = 1;
+    else if ( !strcmp( argv[i], "-i" ) ) ;
+    else if ( i + 1 < argc && !strcmp( argv[i], "-r" ) ) ref_fn = argv[++i];
+    else if ( i + 1 < argc && !strcmp( argv[i], "-f" ) ) frag_fn = argv[++i];
+    else if ( i + 1 < argc && !strcmp( argv[i], "-s" ) ) mat_fn = argv[++i];
+    else if ( i + 1 < argc && !strcmp( argv[i], "-m" ) ) root = argv[++i];
+    else if ( i + 1 < argc && !strcmp( argv[i], "-k" ) ) k = atoi( argv[++i] );
+    else if ( i + 1 < argc && !strcmp( argv[i], "-p" ) ) cons_code = atoi( argv[++i] );
+    else if ( i + 1 < argc && !strcmp( argv[i], "-H" ) ) hard_cut = atoi( argv[++i] );
+    else { fprintf( stderr, "mia_gpu: option %s is not handled by this host (see the header of host/mia_gpu.c)\n", argv[i] ); return 2; }
+  }
+  if ( !ref_fn || !frag_fn || !mat_fn ) {
+    fprintf( stderr, "usage: mia_gpu -r ref.fa -f reads.fa|fq -s matrix.txt [-m root] [-c] [-k K] [-p code] [-H cut] [-F]\n" );
+    return 2;
+  }
+  init_comp();
+
+  /* ---- set-up: mia_main.c:299-335 (matrices), 618-733 (reference, k-mer tables) */
+  static int32_t fwd[MIAGPU_PSSM_INTS], fpsm[MIAGPU_PSSM_INTS], rpsm[MIAGPU_PSSM_INTS];
+  char ref_id[128], ref_desc[160];
+  int ref_len;
+  char* ref = read_reference( ref_fn, ref_id, ref_desc, &ref_len );
+  miagpu_ctx* g;
+  CK( miagpu_read_pssm( mat_fn, fwd ) );
+  CK( miagpu_create( &g, 0 ) );
+  CK( miagpu_set_pssm( g, fwd ) );
+  CK( miagpu_get_pssm( g, fpsm, rpsm ) );
+  CK( miagpu_set_reference( g, ref, ref_len, circular, 1 ) );
+  CK( miagpu_build_kmers( g, k, 0 ) );
+
+  /* ---- pass 1 over the whole file (mia_main.c:746-805), one batch */
+  miagpu_fastx* fx;
+  int64_t n = 0, j, m = 0;
+  const uint8_t* bases; const int64_t *off, *id_off, *desc_off; const char *ids, *descs; const int32_t* qual_sum;
+  CK( miagpu_fastx_open( &fx, frag_fn ) );
+  CK( miagpu_fastx_next( fx, (int64_t)1 << 40, &n ) );
+  CK( miagpu_fastx_batch( fx, &bases, &off, &ids, &id_off, &descs, &desc_off, &qual_sum ) );
+  CK( miagpu_upload_reads( g, n, bases, off ) );
+  int32_t *hits = xmalloc( n * 4 ), *score = xmalloc( n * 4 ), *as = xmalloc( n * 4 ), *ae = xmalloc( n * 4 ), *start = xmalloc( n * 4 ),
+          *end = xmalloc( n * 4 );
+  uint8_t *rc = xmalloc( n ), *keep = xmalloc( n );
+  CK( miagpu_pass1( g, hits, score, NULL, NULL, rc, as, ae, start, end, NULL, NULL, NULL, NULL ) );
+
+  /* sg_align's accept test (mia.c:1614), the FSDB in input order, the number of AlnSeqs pass 1 merges (mia.c:1619-1643) */
+  int64_t* src = xmalloc( n * 8 );
+  int32_t maln_size = 0;
+  for ( j = 0; j < n; j++ ) {
+    keep[j] = ( hits[j] > 0 && score[j] >= FIRST_ROUND_SCORE_CUTOFF );
+    if ( !keep[j] ) continue;
+    if ( score[j] == FIRST_ROUND_SCORE_CUTOFF ) { fprintf( stderr, "mia_gpu: a read scores exactly 2000 (strand_known = 0): not handled\n" ); return 3; }
+    maln_size += 1 + ( start[j] > end[j] );
+    src[m++] = j;
+  }
+  int32_t *f_len = xmalloc( m * 4 ), *f_score = xmalloc( m * 4 ), *f_as = xmalloc( m * 4 ), *f_ae = xmalloc( m * 4 ), *abr = xmalloc( m * 4 );
+  uint8_t *f_rc = xmalloc( m ), *dropped = xmalloc( m );
+  int64_t *s_off = xmalloc( ( m + 1 ) * 8 ), *f_id_off = xmalloc( ( m + 1 ) * 8 ), *f_desc_off = xmalloc( ( m + 1 ) * 8 );
+  for ( j = 0; j < m; j++ ) {
+    int64_t q = src[j];
+    f_len[j] = (int32_t)( off[q + 1] - off[q] ); f_score[j] = score[q]; f_as[j] = as[q]; f_ae[j] = ae[q]; f_rc[j] = rc[q];
+    s_off[j + 1] = s_off[j] + f_len[j];
+    f_id_off[j + 1] = f_id_off[j] + ( id_off[q + 1] - id_off[q] );
+    f_desc_off[j + 1] = f_desc_off[j] + ( desc_off[q + 1] - desc_off[q] );
+  }
+  /* host copy of the FSDB: stored orientation (fsdb.c:209-227), ids, descriptions -- what the writer needs */
+  uint8_t* stored = xmalloc( (size_t)s_off[m] + 1 );
+  char *f_ids = xmalloc( (size_t)f_id_off[m] + 1 ), *f_descs = xmalloc( (size_t)f_desc_off[m] + 1 );
+  for ( j = 0; j < m; j++ ) {
+    int64_t q = src[j], L = f_len[j], t;
+    for ( t = 0; t < L; t++ ) stored[s_off[j] + t] = f_rc[j] ? comp[bases[off[q] + L - 1 - t]] : bases[off[q] + t];
+    memcpy( f_ids + f_id_off[j], ids + id_off[q], (size_t)( id_off[q + 1] - id_off[q] ) );
+    memcpy( f_descs + f_desc_off[j], descs + desc_off[q], (size_t)( desc_off[q + 1] - desc_off[q] ) );
+  }
+  /* pass-1 cull (mia_main.c:848): only its sticky flags survive */
+  double slope = 0, icpt = 0;
+  if ( hard_cut > 0 ) CK( miagpu_cull_flags( m, f_len, f_score, NULL, hard_cut, 0, 0.0, 0.0, dropped ) );
+  else {
+    CK( miagpu_score_cut( m, f_len, f_score, NULL, &slope, &icpt ) );
+    CK( miagpu_cull_flags( m, f_len, f_score, NULL, 0, 1, slope, icpt, dropped ) );
+  }
+  int64_t n_kept = 0;
+  CK( miagpu_compact_reads( g, keep, rc, &n_kept ) );
+  if ( n_kept != m ) { fprintf( stderr, "mia_gpu: compact_reads kept %lld of %lld\n", (long long)n_kept, (long long)m ); return 3; }
+  CK( miagpu_set_alignment_inputs( g, f_rc, f_as, f_ae ) );
+  CK( miagpu_set_cut_inputs( g, f_len, NULL, dropped ) );
+  miagpu_fastx_close( fx );
+  fprintf( stderr, "mia_gpu: %lld reads read, %lld aligned in pass 1\n", (long long)n, (long long)m );
+
+  /* ---- rounds (mia_main.c:878-976): one library call each */
+  size_t cons_cap = (size_t)ref_len * 4 + 4096;
+  char *last = xmalloc( cons_cap ), *cons = xmalloc( cons_cap ), fn[4096], iter_id[64];
+  int32_t* gaps = xmalloc( cons_cap * 4 );
+  int64_t *run_off = xmalloc( ( m + 1 ) * 8 ), total = 0, cap = 0, n_aln = 0;
+  uint16_t* packed = NULL;
+  int iter = 0, converged = 0;
+  for ( j = 0; j < ref_len; j++ ) last[j] = (char)toupper( (unsigned char)ref[j] );      /* make_ref_upper mia.c:642-648 */
+  last[ref_len] = 0;
+  while ( !converged && iter < MAX_ITER ) {
+    int32_t cons_len = 0, L = (int32_t)strlen( last );
+    iter++;
+    CK( miagpu_set_reference( g, last, L, circular, 0 ) );
+    CK( miagpu_iterate_resident( g, hard_cut, 0, 0.0, 0.0, cons_code, &slope, &icpt, dropped, gaps, cons, &cons_len ) );
+    CK( miagpu_adopt_alignment( g, f_score, f_as, f_ae ) );
+    cons[cons_len] = 0;
+    converged = !strcmp( cons, last );
+    if ( !final_only || converged || iter == MAX_ITER ) {
+      miagpu_maln_header hd;
+      miagpu_maln_reads rd;
+      CK( miagpu_get_alignment( g, NULL, NULL, NULL, abr, NULL, NULL ) );
+      CK( miagpu_get_runs_packed( g, NULL, NULL, 0, &total ) );
+      if ( total > cap ) { free( packed ); cap = total + total / 4 + 16; packed = xmalloc( (size_t)cap * 2 ); }
+      CK( miagpu_get_runs_packed( g, run_off, packed, cap, &total ) );
+      memset( &hd, 0, sizeof hd );
+      memset( &rd, 0, sizeof rd );
+      snprintf( iter_id, sizeof iter_id, "ConsAssem.%d", iter );
+      hd.ref_id = iter > 1 ? iter_id : ref_id;                                           /* mia_main.c:47, 62-65 */
+      hd.ref_desc = iter > 1 ? "iteration assembly" : ref_desc;
+      hd.ref_seq = last; hd.ref_len = L; hd.circular = circular; hd.maln_size = maln_size; hd.cons_code = cons_code;
+      hd.gaps = gaps; hd.fpsm = fpsm; hd.rpsm = rpsm;
+      rd.n = m; rd.bases = stored; rd.offsets = s_off; rd.ids = f_ids; rd.id_off = f_id_off; rd.descs = f_descs; rd.desc_off = f_desc_off;
+      rd.rc = f_rc; rd.score = f_score; rd.as = f_as; rd.ae = f_ae; rd.abr = abr; rd.run_off = run_off; rd.packed = packed;
+      rd.dropped_front = dropped; rd.dropped_back = dropped;
+      snprintf( fn, sizeof fn, "%s.%d", root, iter );
+      CK( miagpu_write_maln( fn, &hd, &rd, &n_aln ) );
+      fprintf( stderr, "mia_gpu: iteration %d: %lld AlnSeqs -> %s\n", iter, (long long)n_aln, fn );
+    }
+    { char* t = last; last = cons; cons = t; }
+  }
+  fprintf( stderr, converged ? "Assembly convergence after %d rounds\n" : "Assembly did not converge after %d rounds, quitting\n", iter );
+  miagpu_destroy( g );
+  return 0;
+}

@@ -65,6 +65,9 @@ const char* miagpu_version( void );
  * |x| <= 2000 (the packed-key DP needs 256*|x| + 200*511 < 2^20). */
 int miagpu_set_pssm( miagpu_ctx* ctx, const int32_t* fwd );
 int miagpu_get_pssm( miagpu_ctx* ctx, int32_t* fwd, int32_t* rev );
+/* read_pssm (io.c:408-503; call site mia_main.c:299-335): the matrix file -> int fwd[31][5][5] for miagpu_set_pssm, with the
+ * reference's N column (-100) and non-ACGT reference row (-10).  Host only.  A malformed file returns 0 (the reference exits). */
+int miagpu_read_pssm( const char* path, int32_t* fwd );
 
 /* ---- reference / current consensus.  seq is what read_fasta_ref left in
  * RefSeq.seq (case preserved, so that -M soft masking still works); the

@@ -96,6 +96,7 @@ def load_library():
     L.miagpu_fastx_close.argtypes = [C.c_void_p]
     L.miagpu_fastx_close.restype = None
     L.miagpu_maln_ref_size.argtypes = [C.c_int, C.c_int]
+    L.miagpu_read_pssm.argtypes = [C.c_char_p, _i32p]
     L.miagpu_write_maln.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, _i64p]
     L.miagpu_stream.restype = C.c_void_p
     L.miagpu_stream.argtypes = [C.c_void_p]
@@ -112,7 +113,7 @@ EXPORTS = ["miagpu_device_count", "miagpu_create", "miagpu_destroy", "miagpu_las
            "miagpu_int32_peak", "miagpu_stream", "miagpu_shard_begin", "miagpu_shard_begin_host", "miagpu_shard_cut", "miagpu_shard_finish",
            "miagpu_last_cut_stats", "miagpu_repeat_filter", "miagpu_trim", "miagpu_get_alignment",
            "miagpu_fastx_open", "miagpu_fastx_open_memory", "miagpu_fastx_format", "miagpu_fastx_next", "miagpu_fastx_batch", "miagpu_fastx_close",
-           "miagpu_maln_ref_size", "miagpu_write_maln"]
+           "miagpu_maln_ref_size", "miagpu_write_maln", "miagpu_read_pssm"]
 
 
 def _ptr(a):
@@ -549,6 +550,15 @@ class _MalnReads(C.Structure):
     _fields_ = [("n", C.c_int64)] + [(k, C.c_void_p) for k in
                                      ("bases", "offsets", "ids", "id_off", "descs", "desc_off", "rc", "trimmed", "num_inputs", "score", "as_",
                                       "ae", "abr", "run_off", "packed", "unique_best", "dropped_front", "dropped_back")]
+
+
+def read_pssm(path):
+    """read_pssm (io.c:408-503) -> int32[31, 5, 5]"""
+    L = load_library()
+    sm = np.zeros(775, np.int32)
+    if not L.miagpu_read_pssm(os.fsencode(path), sm.ctypes.data_as(_i32p)):
+        raise MiaGpuError(L.miagpu_last_error().decode())
+    return sm.reshape(31, 5, 5)
 
 
 def maln_ref_size(ref_len, circular):

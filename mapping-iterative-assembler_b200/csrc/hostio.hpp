@@ -240,6 +240,40 @@ extern "C" int miagpu_fastx_batch(miagpu_fastx* h, const uint8_t** bases, const 
   return 1;
 }
 
+// a1: read_pssm (io.c:408-503).  31 blocks of "# Matrix for position ..." + four rows of four tab-separated integers + one
+// more line; the block after the 15th must say MIDDLE.  Column 4 (read base not ACGT) = N_SCORE -100, row 4 (reference base
+// not ACGT) = NR_SCORE -10 (params.h:30-31).  The reference exits on a malformed file; here: return 0 with the message.
+extern "C" int miagpu_read_pssm(const char* path, int32_t* fwd) {
+  using namespace hostio;
+  if (!path || !fwd) { set_error("miagpu_read_pssm: NULL argument"); return 0; }
+  FILE* f = fopen(path, "r");
+  if (!f) { set_error("miagpu_read_pssm: cannot open %s", path); return 0; }
+  char line[4096];
+  for (int d = 0; d <= 2 * kDepth; d++) {
+    const char* want = (d == kDepth) ? "# Matrix for position: MIDDLE" : (d < kDepth ? "# Matrix for position" : "# Matrix for position:");
+    if (!fgets(line, sizeof line, f) || !strstr(line, want)) {
+      fclose(f);
+      set_error("miagpu_read_pssm: %s: block %d does not start with \"%s\"", path, d + 1, want);
+      return 0;
+    }
+    int32_t* m = fwd + d * 25;
+    for (int row = 0; row < 4; row++) {
+      int v[4] = {0, 0, 0, 0};
+      if (!fgets(line, sizeof line, f) || sscanf(line, "%d\t%d\t%d\t%d", &v[0], &v[1], &v[2], &v[3]) != 4) {
+        fclose(f);
+        set_error("miagpu_read_pssm: %s: block %d row %d is not four integers", path, d + 1, row + 1);
+        return 0;
+      }
+      for (int col = 0; col < 4; col++) m[row * 5 + col] = v[col];
+      m[row * 5 + 4] = -100;
+    }
+    for (int col = 0; col < 5; col++) m[4 * 5 + col] = -10;
+    if (!fgets(line, sizeof line, f)) line[0] = 0;      // the line after a block is skipped whatever it holds
+  }
+  fclose(f);
+  return 1;
+}
+
 extern "C" int miagpu_maln_ref_size(int ref_len, int circular) {
   // reiterate_assembly sets size = len + 1 (mia_main.c:67), add_ref_wrap doubles it until the wrap fits (mia.c:669-675)
   long size = (long)ref_len + 1;

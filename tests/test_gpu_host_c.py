@@ -1,0 +1,32 @@
+"""-m gpu: the plain-C host (host/mia_gpu.c, gcc, linked against libmiagpu.so only) run as a program on the inputs the
+UNMODIFIED reference binary was run on (tests/golden/maln_session.json.gz): same FASTA, FASTQ, matrix file and flags ->
+the same number of `.maln` files, each byte-identical after line 1."""
+import gzip
+import json
+import os
+import subprocess
+
+import pytest
+
+from test_host_c import HOST, matrix_text
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.mark.parametrize("name,matrix", [("circ_k10", "ancient"), ("lin_pe", "pe")])
+def test_c_host_writes_the_reference_maln_files(golden, name, matrix, tmp_path):
+    s = json.load(gzip.open(os.path.join(HERE, "golden", "maln_session.json.gz"), "rt"))["sessions"][name]
+    (tmp_path / "ref.fa").write_text(f">{s['ref_id']} {s['ref_desc']}\n{s['ref']}\n")
+    (tmp_path / "reads.fq").write_text(s["fastq"])
+    (tmp_path / "m.txt").write_text(matrix_text(golden[matrix]))
+    r = subprocess.run([HOST, "-r", "ref.fa", "-f", "reads.fq", "-s", "m.txt", "-m", "out"] + s["flags"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    for it, body in enumerate(s["malns"]):
+        got = open(tmp_path / f"out.{it + 1}").read().split("\n", 1)[1]
+        if got != body:
+            for ln, (x, y) in enumerate(zip(got.split("\n"), body.split("\n"))):
+                assert x == y, f"{name} iteration {it + 1}: line {ln + 2}: {x[:160]!r} != {y[:160]!r}"
+            assert len(got) == len(body)
+    assert not os.path.exists(tmp_path / f"out.{len(s['malns']) + 1}")
+    assert "Assembly convergence" in r.stderr

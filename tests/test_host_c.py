@@ -1,0 +1,76 @@
+"""CPU: the C side of the boundary -- include/miagpu.h is plain C99, miagpu_read_pssm equals the reference's read_pssm
+(the golden matrices in tests/golden/pssm.npz came out of the reference's own reader), and the plain-C host
+(host/mia_gpu.c) fails loudly without a GPU instead of falling back to anything."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "host", "mia_gpu")
+
+
+def matrix_text(sm):
+    """the reference's matrix file layout (matrices/*.txt) for an int[31][5][5]"""
+    sm = np.asarray(sm).reshape(31, 5, 5)
+    out = []
+    for d in range(31):
+        name = "MIDDLE" if d == 15 else (str(d + 1) if d < 15 else str(d - 31))
+        out.append(f"# Matrix for position: {name}\n")
+        for r in range(4):
+            out.append("\t".join(str(int(x)) for x in sm[d, r, :4]) + "\t\n")
+        out.append("\n")
+    return "".join(out)
+
+
+def _api():
+    import _pkg
+    _pkg.load()
+    from mia_b200 import api
+    return api
+
+
+def test_header_is_plain_c99(tmp_path):
+    src = tmp_path / "t.c"
+    src.write_text('#include "miagpu.h"\nint main(void) { miagpu_maln_header h; miagpu_maln_reads r; (void)h; (void)r; return MIAGPU_MAX_READ == 256 ? 0 : 1; }\n')
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-I" + os.path.join(ROOT, "include"), str(src)], check=True)
+
+
+@pytest.mark.parametrize("name", ["ancient", "onepass", "pe", "ancient_rc"])
+def test_read_pssm_equals_reference(golden, name, tmp_path):
+    api = _api()
+    p = tmp_path / "m.txt"
+    p.write_text(matrix_text(golden[name]))
+    got = api.read_pssm(str(p)).reshape(-1)
+    want = np.asarray(golden[name]).reshape(31, 5, 5).copy()
+    want[:, :4, 4] = -100                                  # io.c:443-448: N column / non-ACGT reference row are constants
+    want[:, 4, :] = -10
+    assert (got == want.reshape(-1)).all()
+
+
+def test_read_pssm_shipped_files_and_errors(golden, tmp_path):
+    api = _api()
+    d = "/root/reference/matrices"
+    if os.path.isdir(d):
+        for fn, key in (("ancient.submat.txt", "ancient"), ("ancient.submat.solexa.onepass.txt", "onepass"), ("ancient.submat.solexa.pe.txt", "pe")):
+            assert (api.read_pssm(os.path.join(d, fn)).reshape(-1) == golden[key]).all(), fn
+    bad = tmp_path / "bad.txt"
+    bad.write_text(matrix_text(golden["ancient"]).replace("MIDDLE", "16"))
+    with pytest.raises(api.MiaGpuError, match="MIDDLE"):
+        api.read_pssm(str(bad))
+    with pytest.raises(api.MiaGpuError, match="cannot open"):
+        api.read_pssm(str(tmp_path / "none.txt"))
+
+
+def test_c_host_has_no_cpu_fallback(golden, tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    assert os.path.exists(HOST), "host/mia_gpu is missing: run __graft_entry__.build()"
+    (tmp_path / "m.txt").write_text(matrix_text(golden["ancient"]))
+    (tmp_path / "r.fa").write_text(">r\nACGTACGTACGTACGTACGT\n")
+    (tmp_path / "q.fq").write_text("@a\nACGTACGTAC\n+\nIIIIIIIIII\n")
+    r = subprocess.run([HOST, "-r", "r.fa", "-f", "q.fq", "-s", "m.txt", "-m", "out"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 1 and "no CUDA device" in r.stderr and "no CPU fallback" in r.stderr
+    assert not os.path.exists(tmp_path / "out.1")
