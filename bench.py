@@ -433,7 +433,72 @@ def pass1_numbers(g, ref, stored, off, rc, args, only_k12=False):
                     "skipped_by_filter": int(((out["status"] & 2) != 0).sum()),
                     "reads_windowed_pair_kernels": g.last_pass1_stats()[0], "reads_general_kernel": g.last_pass1_stats()[1]}
     g.build_kmers(0)
+    res["files"] = file_to_file(ref, orig, off)
     return res
+
+
+def file_to_file(ref, orig, off, ref_sample=5000):
+    """SURVEY 8 f2 / f3 and the plain-C host: FASTQ file -> reader -> pass 1 (k = 12) -> rounds -> `.maln` file, as a PROGRAM
+    (host/mia_gpu, C, linked against libmiagpu.so only), wall clock with its own phase timing; the reader alone; and the
+    unmodified reference binary (oracle/_ref/mia, 1 thread) on the first `ref_sample` reads of the same file with the same
+    flags, whose final `.maln` must equal ours byte for byte after line 1 (checked here, reported as maln_identical)."""
+    import ctypes as C
+    import re
+    import subprocess
+    import tempfile
+    from mia_b200 import api, synth
+    root = os.path.dirname(os.path.abspath(__file__))
+    host = os.path.join(root, "host", "mia_gpu")
+    out = {}
+    if not os.path.exists(host):
+        return {"skipped": "host/mia_gpu not built"}
+    n = len(off) - 1
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "ref.fa"), "w").write(">ref synthetic\n" + ref + "\n")
+        open(os.path.join(d, "m.txt"), "w").write(synth.matrix_text(load_pssm()))
+        open(os.path.join(d, "all.fq"), "wb").write(synth.fastq_text(orig, off))
+        open(os.path.join(d, "part.fq"), "wb").write(synth.fastq_text(orig, off, 0, min(ref_sample, n)))
+        fq_bytes = os.path.getsize(os.path.join(d, "all.fq"))
+        # the reader alone (miagpu_fastx_open + _next over the whole file), second pass = page cache warm
+        L = api.load_library()
+        for _ in range(2):
+            h, cnt = C.c_void_p(), C.c_int64()
+            t0 = time.perf_counter()
+            L.miagpu_fastx_open(C.byref(h), os.path.join(d, "all.fq").encode())
+            L.miagpu_fastx_next(h, 1 << 40, C.byref(cnt))
+            t = time.perf_counter() - t0
+            L.miagpu_fastx_close(h)
+        out["reader"] = {"reads": cnt.value, "file_mb": fq_bytes / 1e6, "wall_ms": t * 1e3, "mb_per_s": fq_bytes / 1e6 / t, "reads_per_s": cnt.value / t}
+
+        def run(cmd):
+            t0 = time.perf_counter()
+            r = subprocess.run(cmd, cwd=d, capture_output=True, text=True)
+            return time.perf_counter() - t0, r
+        flags = ["-s", "m.txt", "-c", "-k", "12", "-F"]
+        t, r = run([host, "-r", "ref.fa", "-f", "all.fq", "-m", "ours_all"] + flags)
+        if r.returncode != 0:
+            return {"error": r.stderr[-300:]}
+        ph = re.search(r"timing ms: init ([\d.]+) parse ([\d.]+) pass1 ([\d.]+) rounds ([\d.]+) write ([\d.]+) total ([\d.]+)", r.stderr)
+        rounds = int(re.search(r"after (\d+) rounds", r.stderr).group(1))
+        final = os.path.join(d, f"ours_all.{rounds}")
+        out["program"] = {"reads": n, "rounds": rounds, "wall_s": t, "reads_per_s": n / t, "maln_mb": os.path.getsize(final) / 1e6,
+                          "phases_ms": dict(zip(("init", "parse", "pass1", "rounds", "write", "total"), map(float, ph.groups()))) if ph else None,
+                          "note": "host/mia_gpu -c -k 12 -F: process start to exit incl. CUDA context creation, FASTQ parse, pass 1, all rounds, "
+                                  "final .maln written to a tmpfs/overlay file"}
+        t_o, r_o = run([host, "-r", "ref.fa", "-f", "part.fq", "-m", "ours_part"] + flags)
+        mia = os.path.join(root, "oracle", "_ref", "mia")
+        if os.path.exists(mia) and r_o.returncode == 0:
+            t_r, r_r = run([mia, "-r", "ref.fa", "-f", "part.fq", "-m", "ref_part"] + flags)
+            ro = int(re.search(r"after (\d+) rounds", r_o.stderr).group(1))
+            ours = open(os.path.join(d, f"ours_part.{ro}")).read().split("\n", 1)[1]
+            refs = sorted(f for f in os.listdir(d) if f.startswith("ref_part."))
+            theirs = open(os.path.join(d, refs[-1])).read().split("\n", 1)[1] if refs else ""
+            out["vs_reference_binary"] = {"reads": min(ref_sample, n), "ours_wall_s": t_o, "reference_wall_s": t_r, "reference_cores": 1,
+                                          "speedup_wall": t_r / t_o, "rounds": ro, "reference_final_file": refs[-1] if refs else None,
+                                          "maln_identical": bool(refs) and ours == theirs,
+                                          "note": "oracle/_ref/mia = the unmodified reference compiled with gcc -O2; same FASTA / FASTQ / matrix / flags; "
+                                                  "ours includes ~0.3-0.5 s of CUDA context creation per process"}
+    return out
 
 
 def cpu_baseline(ref, bases, off, rc, as_, ae, sm, sample):

@@ -9,10 +9,12 @@
  * reads enter the FSDB (mia.c:1614), their strand, the convergence test (mia_main.c:909-976), the file names.
  * Reads that score exactly 2000 (strand_known = 0, mia.c:1653), -D, -u/-U, -T, -h, -C, -I are not handled here.
  * There is no CPU fallback: without a CUDA device miagpu_create fails and so does this program. */
+#define _POSIX_C_SOURCE 199309L
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <ctype.h>
+#include <time.h>
 #include "miagpu.h"
 
 #define FIRST_ROUND_SCORE_CUTOFF 2000   /* params.h */
@@ -23,6 +25,12 @@ static void die( const char* what ) {
   exit( 1 );
 }
 #define CK( call ) do { if ( !( call ) ) die( #call ); } while ( 0 )
+
+static double now_ms( void ) {
+  struct timespec t;
+  clock_gettime( CLOCK_MONOTONIC, &t );
+  return t.tv_sec * 1e3 + t.tv_nsec * 1e-6;
+}
 
 static void* xmalloc( size_t n ) {
   void* p = calloc( n ? n : 1, 1 );
@@ -93,12 +101,14 @@ int main( int argc, char** argv ) {
   int ref_len;
   char* ref = read_reference( ref_fn, ref_id, ref_desc, &ref_len );
   miagpu_ctx* g;
+  double t0 = now_ms(), t_init, t_parse, t_pass1, t_rounds = 0, t_write = 0, t1;
   CK( miagpu_read_pssm( mat_fn, fwd ) );
   CK( miagpu_create( &g, 0 ) );
   CK( miagpu_set_pssm( g, fwd ) );
   CK( miagpu_get_pssm( g, fpsm, rpsm ) );
   CK( miagpu_set_reference( g, ref, ref_len, circular, 1 ) );
   CK( miagpu_build_kmers( g, k, 0 ) );
+  t_init = now_ms() - t0;
 
   /* ---- pass 1 over the whole file (mia_main.c:746-805), one batch */
   miagpu_fastx* fx;
@@ -107,6 +117,7 @@ int main( int argc, char** argv ) {
   CK( miagpu_fastx_open( &fx, frag_fn ) );
   CK( miagpu_fastx_next( fx, (int64_t)1 << 40, &n ) );
   CK( miagpu_fastx_batch( fx, &bases, &off, &ids, &id_off, &descs, &desc_off, &qual_sum ) );
+  t_parse = now_ms() - t0 - t_init;
   CK( miagpu_upload_reads( g, n, bases, off ) );
   int32_t *hits = xmalloc( n * 4 ), *score = xmalloc( n * 4 ), *as = xmalloc( n * 4 ), *ae = xmalloc( n * 4 ), *start = xmalloc( n * 4 ),
           *end = xmalloc( n * 4 );
@@ -156,6 +167,7 @@ int main( int argc, char** argv ) {
   CK( miagpu_set_cut_inputs( g, f_len, NULL, dropped ) );
   miagpu_fastx_close( fx );
   fprintf( stderr, "mia_gpu: %lld reads read, %lld aligned in pass 1\n", (long long)n, (long long)m );
+  t_pass1 = now_ms() - t0 - t_init - t_parse;
 
   /* ---- rounds (mia_main.c:878-976): one library call each */
   size_t cons_cap = (size_t)ref_len * 4 + 4096;
@@ -169,11 +181,14 @@ int main( int argc, char** argv ) {
   while ( !converged && iter < MAX_ITER ) {
     int32_t cons_len = 0, L = (int32_t)strlen( last );
     iter++;
+    t1 = now_ms();
     CK( miagpu_set_reference( g, last, L, circular, 0 ) );
     CK( miagpu_iterate_resident( g, hard_cut, 0, 0.0, 0.0, cons_code, &slope, &icpt, dropped, gaps, cons, &cons_len ) );
     CK( miagpu_adopt_alignment( g, f_score, f_as, f_ae ) );
     cons[cons_len] = 0;
     converged = !strcmp( cons, last );
+    t_rounds += now_ms() - t1;
+    t1 = now_ms();
     if ( !final_only || converged || iter == MAX_ITER ) {
       miagpu_maln_header hd;
       miagpu_maln_reads rd;
@@ -195,9 +210,12 @@ int main( int argc, char** argv ) {
       CK( miagpu_write_maln( fn, &hd, &rd, &n_aln ) );
       fprintf( stderr, "mia_gpu: iteration %d: %lld AlnSeqs -> %s\n", iter, (long long)n_aln, fn );
     }
+    t_write += now_ms() - t1;
     { char* t = last; last = cons; cons = t; }
   }
   fprintf( stderr, converged ? "Assembly convergence after %d rounds\n" : "Assembly did not converge after %d rounds, quitting\n", iter );
+  fprintf( stderr, "mia_gpu: timing ms: init %.1f parse %.1f pass1 %.1f rounds %.1f write %.1f total %.1f\n", t_init, t_parse, t_pass1,
+           t_rounds, t_write, now_ms() - t0 );
   miagpu_destroy( g );
   return 0;
 }

@@ -89,3 +89,27 @@ def read_str(bases, off, i):
 
 def revcomp_bytes(a):
     return _COMP[a[::-1]]
+
+
+def matrix_text(sm):
+    """the layout of the reference's matrix files (matrices/*.txt; read_pssm io.c:408-503) for an int[31][5][5]"""
+    sm = np.asarray(sm).reshape(31, 5, 5)
+    out = []
+    for d in range(31):
+        name = "MIDDLE" if d == 15 else (str(d + 1) if d < 15 else str(d - 31))
+        out.append(f"# Matrix for position: {name}\n")
+        for r in range(4):
+            out.append("\t".join(str(int(x)) for x in sm[d, r, :4]) + "\t\n")
+        out.append("\n")
+    return "".join(out)
+
+
+def fastq_text(bases, off, lo=0, hi=None, qual="I"):
+    """reads lo..hi as FASTQ text (ids r0000000...), constant quality"""
+    hi = len(off) - 1 if hi is None else hi
+    b = bases.tobytes()
+    parts = []
+    for i in range(lo, hi):
+        s = b[off[i]:off[i + 1]]
+        parts.append(b"@r%07d\n%s\n+\n%s\n" % (i, s, qual.encode() * len(s)))
+    return b"".join(parts)

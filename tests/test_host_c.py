@@ -11,17 +11,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HOST = os.path.join(ROOT, "host", "mia_gpu")
 
 
-def matrix_text(sm):
-    """the reference's matrix file layout (matrices/*.txt) for an int[31][5][5]"""
-    sm = np.asarray(sm).reshape(31, 5, 5)
-    out = []
-    for d in range(31):
-        name = "MIDDLE" if d == 15 else (str(d + 1) if d < 15 else str(d - 31))
-        out.append(f"# Matrix for position: {name}\n")
-        for r in range(4):
-            out.append("\t".join(str(int(x)) for x in sm[d, r, :4]) + "\t\n")
-        out.append("\n")
-    return "".join(out)
+import _pkg  # noqa: E402
+
+_pkg.load()
+from mia_b200.synth import matrix_text  # noqa: E402,F401
 
 
 def _api():
