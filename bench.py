@@ -405,6 +405,7 @@ def extras(g, ref, stored, off, rc, as_, ae, sm):
                        "note": "driver.ResidentAssembler: pass 1 (k = 12) + rounds to convergence, everything resident; wall clock incl. "
                                "the host-side numpy bookkeeping between the library calls"}
     g.build_kmers(0)
+    res["files"] = file_to_file(ref, orig, off)
     return res
 
 
@@ -433,7 +434,6 @@ def pass1_numbers(g, ref, stored, off, rc, args, only_k12=False):
                     "skipped_by_filter": int(((out["status"] & 2) != 0).sum()),
                     "reads_windowed_pair_kernels": g.last_pass1_stats()[0], "reads_general_kernel": g.last_pass1_stats()[1]}
     g.build_kmers(0)
-    res["files"] = file_to_file(ref, orig, off)
     return res
 
 

@@ -16,6 +16,7 @@
 #pragma once
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <time.h>
 #include <fcntl.h>
@@ -23,6 +24,9 @@
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <algorithm>
+#include <atomic>
+#include <functional>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -136,11 +140,11 @@ struct Fastx {
 struct Out {
   FILE* f;
   std::vector<char> b;
-  explicit Out(FILE* f_) : f(f_) { b.reserve(1 << 22); }
-  void flush() { if (!b.empty()) { fwrite(b.data(), 1, b.size(), f); b.clear(); } }
-  void room() { if (b.size() > (1u << 22) - 4096) flush(); }
-  void s(const char* p) { size_t n = strlen(p); if (n > 2048) flush(); b.insert(b.end(), p, p + n); room(); }
-  void s(const char* p, size_t n) { if (n > 2048) flush(); b.insert(b.end(), p, p + n); room(); }
+  explicit Out(FILE* f_) : f(f_) { if (f) b.reserve(1 << 22); }
+  void flush() { if (f && !b.empty()) { fwrite(b.data(), 1, b.size(), f); b.clear(); } }   // f == nullptr: a memory buffer
+  void room() { if (f && b.size() > (1u << 22) - 4096) flush(); }
+  void s(const char* p) { size_t n = strlen(p); b.insert(b.end(), p, p + n); room(); }
+  void s(const char* p, size_t n) { b.insert(b.end(), p, p + n); room(); }
   void ch(char c) { b.push_back(c); }
   void i(long v) {
     char t[24]; int n = 0; bool neg = v < 0; unsigned long u = neg ? 0ul - (unsigned long)v : (unsigned long)v;
@@ -363,13 +367,17 @@ extern "C" int miagpu_write_maln(const char* path, const miagpu_maln_header* hd,
   o.s("__ALNSEQS__\n");
 
   // ---- per AlnSeq: columns, inserts, smp from the run list
+  // Formatting is the expensive part (about 1.3 us per AlnSeq on one core): ranges of the sorted list are formatted into memory
+  // buffers by worker threads, wave after wave, and written in order.
+  std::atomic<long long> bad_read{-1};
+  auto format_range = [&](size_t lo, size_t hi, Out& o) {
   std::vector<char> colc, smp;                 // per alignment column of the read: AlnSeq.seq character
   std::vector<int32_t> ins_at, ins_len;        // per column: read row and length of the insert in front of it
   std::string idbuf;
   int64_t cached = -1;
   int front_total = 0, back_total = 0, nfront = 0;
-  for (uint32_t k : order) {
-    const Seg& sg = segs[k];
+  for (size_t kk = lo; kk < hi; kk++) {
+    const Seg& sg = segs[order[kk]];
     const int64_t i = sg.read;
     const uint8_t* read = rd->bases + rd->offsets[i];
     const int rlen = (int)(rd->offsets[i + 1] - rd->offsets[i]);
@@ -391,7 +399,7 @@ extern "C" int miagpu_write_maln(const char* path, const miagpu_maln_header* hd,
           else colc.push_back('-');
         }
       }
-      if (row > rlen) { o.flush(); fclose(f); set_error("miagpu_write_maln: runs of read %lld overrun its %d bases", (long long)i, rlen); return 0; }
+      if (row > rlen) { bad_read.store((long long)i); return; }
       // asp_len of the front and back AlnSeq (fsdb.c:518-530): columns + inserted bases (deletions count as sequence)
       int tot = (int)colc.size();
       int s0 = rd->as[i], e0 = rd->ae[i] > L ? rd->ae[i] - L : rd->ae[i];
@@ -436,6 +444,30 @@ extern "C" int miagpu_write_maln(const char* path, const miagpu_maln_header* hd,
       if (ins_len[g]) { o.ch(' '); o.i(c); o.ch(' '); o.s((const char*)read + ins_at[g], (size_t)ins_len[g]); }
     }
     o.ch('\n');
+  }
+  };
+  const size_t total = order.size();
+  unsigned hw = std::thread::hardware_concurrency();
+  size_t T = std::max<size_t>(1, std::min<size_t>({(size_t)(hw ? hw : 1), (size_t)16, (total + 1023) / 1024}));
+  if (const char* e = getenv("MIAGPU_MALN_THREADS")) T = std::max(1, atoi(e));              // tests: 1 = everything on the caller's thread
+  const size_t per = std::max<size_t>(1, std::min<size_t>(32768, (total + T - 1) / T));
+  o.flush();
+  std::vector<Out> bufs;
+  for (size_t t = 0; t < T; t++) bufs.emplace_back((FILE*)nullptr);
+  for (size_t base = 0; base < total && bad_read.load() < 0; base += T * per) {
+    std::vector<std::thread> th;
+    for (size_t t = 0; t < T; t++) {
+      size_t lo = std::min(total, base + t * per), hi = std::min(total, lo + per);
+      bufs[t].b.clear();
+      if (lo < hi) th.emplace_back(format_range, lo, hi, std::ref(bufs[t]));
+    }
+    for (auto& x : th) x.join();
+    for (size_t t = 0; t < T; t++) if (!bufs[t].b.empty()) fwrite(bufs[t].b.data(), 1, bufs[t].b.size(), f);
+  }
+  if (bad_read.load() >= 0) {
+    fclose(f);
+    set_error("miagpu_write_maln: the runs of read %lld overrun its bases", bad_read.load());
+    return 0;
   }
   o.flush();
   bool ok = !ferror(f);

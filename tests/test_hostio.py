@@ -173,3 +173,23 @@ def test_write_maln_rejects_bad_input(api, tmp_path):
                        dict(bases=np.zeros(0, np.uint8), offsets=np.zeros(1, np.int64), ids=b"", id_off=np.zeros(1, np.int64), rc=np.zeros(0, np.uint8),
                             score=np.zeros(0, np.int32), as_=np.zeros(0, np.int32), ae=np.zeros(0, np.int32), abr=np.zeros(0, np.int32),
                             run_off=np.zeros(1, np.int64), packed=np.zeros(0, np.uint16)))
+
+
+def test_write_maln_threads_do_not_change_the_file(api, gold, tmp_path, monkeypatch):
+    # 30 x the golden reads (about 12,000 AlnSeqs): worker threads format ranges of the sorted list; the file must not depend on them
+    s = gold["sessions"]["circ_k10"]
+    h, seqs = parse_maln(s["malns"][1])
+    reads = reads_from_alnseqs(h, seqs)
+    big = [dict(r, id=f"{r['id']}x{rep}") for rep in range(30) for r in reads]
+    outs = []
+    for threads in ("1", "3", "16"):
+        monkeypatch.setenv("MIAGPU_MALN_THREADS", threads)
+        p = str(tmp_path / f"t{threads}")
+        n = write_from_reads(api, h, big, p, 1)
+        assert n == 30 * h["nas"]
+        outs.append(open(p).read().split("\n", 1)[1])
+    assert outs[0] == outs[1] == outs[2]
+    monkeypatch.delenv("MIAGPU_MALN_THREADS")
+    p = str(tmp_path / "auto")
+    write_from_reads(api, h, big, p, 1)
+    assert open(p).read().split("\n", 1)[1] == outs[0]
