@@ -347,6 +347,19 @@ int miagpu_realign_resident( miagpu_ctx* ctx );
  * mia_main.c:252-256); score / as / ae (nullable host arrays of n) receive this round's values. */
 int miagpu_adopt_alignment( miagpu_ctx* ctx, int32_t* score, int32_t* as, int32_t* ae );
 
+/* ---- 8f4 (second client). The bare alignment sequence that ccheck runs per read (ccheck.cc:571-603: pop_s1c_in_a,
+ * pop_s2c_in_a, dyn_prog, max_sg_score, find_align_begin, populate_pwaln_to_begin) and that reiterate_assembly runs after
+ * its window rule: every resident read against its own stretch [win_start, win_start + win_len) of the resident reference
+ * (for ccheck: the lifted-over consensus pieces back to back, set with miagpu_set_reference( circular = 0 ); matrix =
+ * init_flatsubmat through miagpu_set_pssm), unmasked, sg5 as given, rc[i] picks the strand-reversed matrix.  No window rule,
+ * no fall-back to the whole reference; a window may be shorter than its read.  Outputs as miagpu_realign (as_out / ae_out are
+ * reference coordinates: abc + win_start, aec + win_start).  Overwrites the resident as / ae of
+ * miagpu_set_alignment_inputs. */
+int miagpu_align_windows( miagpu_ctx* ctx, const uint8_t* rc, const int32_t* win_start,
+                          const int32_t* win_len, int sg5, int32_t* score, int32_t* as_out,
+                          int32_t* ae_out, int32_t* abr, int32_t* n_runs, uint16_t* runs,
+                          uint8_t* status );
+
 /* The alignment the last round left on the device, as miagpu_realign returns it (host arrays of n, all nullable):
  * after miagpu_iterate_resident / miagpu_shard_finish this plus miagpu_get_runs_packed is what miagpu_write_maln takes. */
 int miagpu_get_alignment( miagpu_ctx* ctx, int32_t* score, int32_t* as_out, int32_t* ae_out,

@@ -88,6 +88,7 @@ def load_library():
     L.miagpu_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), _i64p, _i32p]
     L.miagpu_int32_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.miagpu_get_alignment.argtypes = [C.c_void_p] + [C.c_void_p] * 6
+    L.miagpu_align_windows.argtypes = [C.c_void_p] + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 7
     L.miagpu_fastx_open.argtypes = [_vpp, C.c_char_p]
     L.miagpu_fastx_open_memory.argtypes = [_vpp, C.c_void_p, C.c_int64]
     L.miagpu_fastx_format.argtypes = [C.c_void_p]
@@ -113,7 +114,7 @@ EXPORTS = ["miagpu_device_count", "miagpu_create", "miagpu_destroy", "miagpu_las
            "miagpu_int32_peak", "miagpu_stream", "miagpu_shard_begin", "miagpu_shard_begin_host", "miagpu_shard_cut", "miagpu_shard_finish",
            "miagpu_last_cut_stats", "miagpu_repeat_filter", "miagpu_trim", "miagpu_get_alignment",
            "miagpu_fastx_open", "miagpu_fastx_open_memory", "miagpu_fastx_format", "miagpu_fastx_next", "miagpu_fastx_batch", "miagpu_fastx_close",
-           "miagpu_maln_ref_size", "miagpu_write_maln", "miagpu_read_pssm"]
+           "miagpu_maln_ref_size", "miagpu_write_maln", "miagpu_read_pssm", "miagpu_align_windows"]
 
 
 def _ptr(a):
@@ -225,6 +226,15 @@ class MiaGpu:
         self._ck(self.lib.miagpu_realign(self.h, _ptr(rc), _ptr(as_), _ptr(ae), _ptr(out["score"]), _ptr(out["as_out"]),
                                          _ptr(out["ae_out"]), _ptr(out["abr"]), _ptr(out["n_runs"]), _ptr(out.get("runs")),
                                          _ptr(out["status"])))
+        return out
+
+    def align_windows(self, rc, win_start, win_len, sg5=1, out=None):
+        """the bare dyn_prog client sequence (ccheck.cc:571-603) of every resident read against its own reference stretch"""
+        out = out or self.alloc_realign_outputs(self.n)
+        rc, ws, wl = np.ascontiguousarray(rc, np.uint8), np.ascontiguousarray(win_start, np.int32), np.ascontiguousarray(win_len, np.int32)
+        self._ck(self.lib.miagpu_align_windows(self.h, _ptr(rc), _ptr(ws), _ptr(wl), int(sg5), _ptr(out["score"]), _ptr(out["as_out"]),
+                                               _ptr(out["ae_out"]), _ptr(out["abr"]), _ptr(out["n_runs"]), _ptr(out.get("runs")),
+                                               _ptr(out["status"])))
         return out
 
     def get_runs_packed(self, run_off=None, packed=None):

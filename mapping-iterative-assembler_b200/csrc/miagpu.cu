@@ -91,6 +91,8 @@ struct miagpu_ctx {
   bool have_ref = false;
   std::string raw_wrapped, raw_rc_wrapped;     // case preserved (k-mer soft mask)
   int seq_len = 0, wrap_len = 0, circular = 0, with_rc = 0;
+  bool explicit_windows = false;   // miagpu_align_windows: d_as / d_ae hold [start, end) of every read's window, no window rule
+  int explicit_sg5 = 1;
   DevBuf<uint8_t> d_ref, d_rcref, d_ref2;      // codes 0..4, padded to 16 B; d_ref2 = both strands back to back
   int ref_bytes = 0;
   // reads
@@ -434,7 +436,7 @@ extern "C" int miagpu_upload_reads(miagpu_ctx* c, int64_t n, const uint8_t* base
 // Block-level statistics go through shared-memory counters; lanes of a warp that hit the same counter are
 // merged first (match.any + redux), so a counter sees one atomic per warp instead of up to 32.
 __global__ void classify_kernel(int64_t n, const int64_t* off, const int32_t* as, const int32_t* ae, int wrap_len, PairLmax lm,
-                                int32_t* win_start, int32_t* win_len, int32_t* lists, uint8_t* kind, int32_t* meta) {
+                                int32_t* win_start, int32_t* win_len, int32_t* lists, uint8_t* kind, int32_t* meta, int explicit_win = 0) {
   int lmax16 = 0;
   for (int k = 0; k < P16_NKB; k++) lmax16 = max(lmax16, lm.v[k]);
   __shared__ int s_cnt[NBUCKET], s_base[NBUCKET], s_maxL[NBUCKET], s_pop[NBUCKET];
@@ -458,6 +460,7 @@ __global__ void classify_kernel(int64_t n, const int64_t* off, const int32_t* as
     int re = (ae[i] + REALIGN_BUFFER + 1 > wrap_len) ? wrap_len : ae[i] + REALIGN_BUFFER;
     bool whole = rs + L > re;
     if (whole) { rs = 0; re = wrap_len; }
+    if (explicit_win) { rs = as[i]; re = ae[i]; whole = true; }          // caller's window as it is; 32-bit kernels only (whole => not pair-eligible)
     int len1 = re - rs;
     win_start[i] = rs;
     win_len[i] = len1;
@@ -783,7 +786,8 @@ static int realign_classify(miagpu_ctx* c, const RealignJob& j, cudaStream_t st)
   const PairLmax lm = pair_lmax(c);
   MIAGPU_CUDA(cudaMemsetAsync(j.d_meta, 0, META_WORDS * sizeof(int32_t), st));
   classify_kernel<<<(unsigned)((j.n + 255) / 256), 256, 0, st>>>(j.n, c->d_off.p + j.lo, c->d_as.p + j.lo, c->d_ae.p + j.lo, c->wrap_len, lm,
-                                                                c->d_win_start.p + j.lo, c->d_win_len.p + j.lo, j.d_lists, c->d_kind.p + j.lo, j.d_meta);
+                                                                c->d_win_start.p + j.lo, c->d_win_len.p + j.lo, j.d_lists, c->d_kind.p + j.lo, j.d_meta,
+                                                                c->explicit_windows ? 1 : 0);
   MIAGPU_CUDA(cudaGetLastError());
   c->launches++;
   if (lm.v[0] > 0) {
@@ -877,7 +881,7 @@ static int realign_launch(miagpu_ctx* c, const RealignJob& j) {
     p.win_start = c->d_win_start.p + lo; p.win_len = c->d_win_len.p + lo;
     p.list = j.d_lists + (int64_t)b * n; p.n_list = total_pairs ? pop : meta[META_COUNT + b];
     p.n_list_ptr = j.d_meta + META_COUNT + b; p.counter = j.d_meta + META_WORK + b;
-    p.ref_codes = c->d_ref.p; p.ref_bytes = c->ref_bytes; p.prof = c->d_prof.p; p.sg5 = 1;
+    p.ref_codes = c->d_ref.p; p.ref_bytes = c->ref_bytes; p.prof = c->d_prof.p; p.sg5 = c->explicit_windows ? c->explicit_sg5 : 1;
     p.score = c->d_score.p + lo; p.as_out = c->d_as_out.p + lo; p.ae_out = c->d_ae_out.p + lo; p.abr = c->d_abr.p + lo;
     p.n_runs = c->d_nruns.p + lo; p.runs = c->d_runs.p + lo * MAX_RUNS; p.status = c->d_status.p + lo;
     int ok = 1, maxL = meta[META_MAXL + b];
@@ -979,6 +983,31 @@ extern "C" int miagpu_realign_host(miagpu_ctx* c, int64_t n, const uint8_t* base
                                    int32_t* abr, int32_t* n_runs, uint16_t* runs, uint8_t* status) {
   if (!miagpu_upload_reads(c, n, bases, offsets)) return 0;
   return realign_common(c, rc, as, ae, score, as_out, ae_out, abr, n_runs, runs, status, true);
+}
+
+// 8f4: the bare dyn_prog client sequence (ccheck.cc:571-603): pop_s1c_in_a / pop_s2c_in_a / dyn_prog / max_sg_score /
+// find_align_begin / populate_pwaln_to_begin of every resident read against ITS OWN stretch of the resident reference,
+// unmasked, no window rule.  Runs the 32-bit kernels (realign.cuh) for every read.
+extern "C" int miagpu_align_windows(miagpu_ctx* c, const uint8_t* rc, const int32_t* win_start, const int32_t* win_len, int sg5,
+                                    int32_t* score, int32_t* as_out, int32_t* ae_out, int32_t* abr, int32_t* n_runs, uint16_t* runs,
+                                    uint8_t* status) {
+  if (!c || !c->have_pssm || !c->have_ref) { set_error("miagpu_align_windows: set_pssm and set_reference first"); return 0; }
+  const int64_t n = c->n;
+  if (n && (!rc || !win_start || !win_len)) { set_error("miagpu_align_windows: rc / win_start / win_len are required"); return 0; }
+  std::vector<int32_t> win_end((size_t)n);
+  for (int64_t i = 0; i < n; i++) {
+    if (win_start[i] < 0 || win_len[i] < 1 || (int64_t)win_start[i] + win_len[i] > c->wrap_len) {
+      set_error("miagpu_align_windows: window %lld = [%d, %d + %d) leaves the reference (%d columns)", (long long)i, win_start[i],
+                win_start[i], win_len[i], c->wrap_len);
+      return 0;
+    }
+    win_end[i] = win_start[i] + win_len[i];
+  }
+  c->explicit_windows = true;
+  c->explicit_sg5 = sg5 ? 1 : 0;
+  const int ok = realign_common(c, rc, win_start, win_end.data(), score, as_out, ae_out, abr, n_runs, runs, status, false);
+  c->explicit_windows = false;
+  return ok;
 }
 
 extern "C" int miagpu_last_timing(miagpu_ctx* c, float* ms_kernels, float* ms_h2d, float* ms_d2h, int64_t* dp_cells, int32_t* launches) {
