@@ -216,10 +216,16 @@ class ResidentAssembler:
         rounds                    -> shard.ShardedRounds (or anything with .resident(...))
     """
 
-    def __init__(self, gpu, ref, sm, circular=1, k=0, soft_mask=0, cons_code=1, exchange=None):
+    def __init__(self, gpu, ref, sm, circular=1, k=0, soft_mask=0, cons_code=1, exchange=None, strand_unknown="raise"):
+        """strand_unknown: what to do with a read that scores exactly 2000 in pass 1.  The reference accepts it with
+        strand_known = 0 (mia.c:1614, 1653), never realigns it (mia_main.c:178) and keeps following its pass-1 AlnSeq pointer,
+        which from round 1 on is another read's slot -- that read is then counted twice and may inherit a dropped flag.
+        "raise" (default; every parity test runs with it) refuses such input; "drop" leaves the read out of the FSDB and counts
+        it in `strand_unknown_reads` -- a stated deviation for 10^7-read runs, where a handful of such reads do occur."""
         self.g, self.sm, self.circular, self.k, self.soft_mask, self.cons_code = gpu, sm, circular, k, soft_mask, cons_code
         self.ref0, self.x = ref, exchange
         self.split_changes = 0
+        self.strand_unknown, self.strand_unknown_reads = strand_unknown, 0
         gpu.set_pssm(sm)
 
     def _gather(self, a):
@@ -234,8 +240,12 @@ class ResidentAssembler:
         self.p1 = p
         seq_len = np.diff(off).astype(np.int32)
         keep = (p["hits"] > 0) & (p["score"] >= FIRST_ROUND_SCORE_CUTOFF)            # mia.c:1614
-        if (keep & (p["score"] == FIRST_ROUND_SCORE_CUTOFF)).any():
-            raise NotImplementedError("reads with score == 2000 keep strand_known = 0 and are never realigned (mia.c:1653)")
+        unknown = keep & (p["score"] == FIRST_ROUND_SCORE_CUTOFF)
+        if unknown.any():
+            if self.strand_unknown != "drop":
+                raise NotImplementedError("reads with score == 2000 keep strand_known = 0 and are never realigned (mia.c:1653)")
+            self.strand_unknown_reads = int(unknown.sum())
+            keep &= ~unknown
         idx = np.flatnonzero(keep)
         self._idx, self._n_all = idx, len(seq_len)
         self.seq_len, self.score = seq_len[idx], p["score"][idx].copy()
