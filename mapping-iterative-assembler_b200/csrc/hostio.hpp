@@ -371,80 +371,80 @@ extern "C" int miagpu_write_maln(const char* path, const miagpu_maln_header* hd,
   // buffers by worker threads, wave after wave, and written in order.
   std::atomic<long long> bad_read{-1};
   auto format_range = [&](size_t lo, size_t hi, Out& o) {
-  std::vector<char> colc, smp;                 // per alignment column of the read: AlnSeq.seq character
-  std::vector<int32_t> ins_at, ins_len;        // per column: read row and length of the insert in front of it
-  std::string idbuf;
-  int64_t cached = -1;
-  int front_total = 0, back_total = 0, nfront = 0;
-  for (size_t kk = lo; kk < hi; kk++) {
-    const Seg& sg = segs[order[kk]];
-    const int64_t i = sg.read;
-    const uint8_t* read = rd->bases + rd->offsets[i];
-    const int rlen = (int)(rd->offsets[i + 1] - rd->offsets[i]);
-    if (cached != i) {
-      cached = i;
-      colc.clear(); ins_at.clear(); ins_len.clear();
-      int row = rd->abr[i], pend_at = 0, pend_len = 0;
-      for (int64_t r = rd->run_off[i]; r < rd->run_off[i + 1]; r++) {
-        unsigned x = rd->packed[r];
-        int ty = (int)MIAGPU_RUN_TYPE(x), ln = (int)MIAGPU_RUN_LEN(x);
-        if (ty == MIAGPU_RUN_I) {
-          if (!pend_len) pend_at = row;
-          pend_len += ln; row += ln;
-          continue;
+    std::vector<char> colc, smp;                 // per alignment column of the read: AlnSeq.seq character
+    std::vector<int32_t> ins_at, ins_len;        // per column: read row and length of the insert in front of it
+    std::string idbuf;
+    int64_t cached = -1;
+    int front_total = 0, back_total = 0, nfront = 0;
+    for (size_t kk = lo; kk < hi; kk++) {
+      const Seg& sg = segs[order[kk]];
+      const int64_t i = sg.read;
+      const uint8_t* read = rd->bases + rd->offsets[i];
+      const int rlen = (int)(rd->offsets[i + 1] - rd->offsets[i]);
+      if (cached != i) {
+        cached = i;
+        colc.clear(); ins_at.clear(); ins_len.clear();
+        int row = rd->abr[i], pend_at = 0, pend_len = 0;
+        for (int64_t r = rd->run_off[i]; r < rd->run_off[i + 1]; r++) {
+          unsigned x = rd->packed[r];
+          int ty = (int)MIAGPU_RUN_TYPE(x), ln = (int)MIAGPU_RUN_LEN(x);
+          if (ty == MIAGPU_RUN_I) {
+            if (!pend_len) pend_at = row;
+            pend_len += ln; row += ln;
+            continue;
+          }
+          for (int q = 0; q < ln; q++) {
+            ins_at.push_back(pend_at); ins_len.push_back(pend_len); pend_len = 0;
+            if (ty == MIAGPU_RUN_M) { colc.push_back(row < rlen ? (char)read[row] : '?'); row++; }
+            else colc.push_back('-');
+          }
         }
-        for (int q = 0; q < ln; q++) {
-          ins_at.push_back(pend_at); ins_len.push_back(pend_len); pend_len = 0;
-          if (ty == MIAGPU_RUN_M) { colc.push_back(row < rlen ? (char)read[row] : '?'); row++; }
-          else colc.push_back('-');
+        if (row > rlen) { bad_read.store((long long)i); return; }
+        // asp_len of the front and back AlnSeq (fsdb.c:518-530): columns + inserted bases (deletions count as sequence)
+        int tot = (int)colc.size();
+        int s0 = rd->as[i], e0 = rd->ae[i] > L ? rd->ae[i] - L : rd->ae[i];
+        nfront = tot;
+        if (s0 > e0) { nfront = L - s0; if (nfront < 0) nfront = 0; if (nfront > tot) nfront = tot; }
+        front_total = nfront; back_total = tot - nfront;
+        for (int c = 0; c < tot; c++) (c < nfront ? front_total : back_total) += ins_len[c];
+        // smp over front then back with one running position (fsdb.c:556-616)
+        smp.resize(colc.size());
+        int act = 0;
+        for (int c = 0; c < tot; c++) {
+          act += ins_len[c];
+          int from_front = (c < nfront) ? act : front_total + act;      // fsdb.c:596: the back segment adds the front's length again
+          int from_back = front_total + back_total - act - 1;
+          smp[c] = smp_code(from_front, from_back);
+          if (colc[c] != '-') act++;
         }
       }
-      if (row > rlen) { bad_read.store((long long)i); return; }
-      // asp_len of the front and back AlnSeq (fsdb.c:518-530): columns + inserted bases (deletions count as sequence)
-      int tot = (int)colc.size();
-      int s0 = rd->as[i], e0 = rd->ae[i] > L ? rd->ae[i] - L : rd->ae[i];
-      nfront = tot;
-      if (s0 > e0) { nfront = L - s0; if (nfront < 0) nfront = 0; if (nfront > tot) nfront = tot; }
-      front_total = nfront; back_total = tot - nfront;
-      for (int c = 0; c < tot; c++) (c < nfront ? front_total : back_total) += ins_len[c];
-      // smp over front then back with one running position (fsdb.c:556-616)
-      smp.resize(colc.size());
-      int act = 0;
-      for (int c = 0; c < tot; c++) {
-        act += ins_len[c];
-        int from_front = (c < nfront) ? act : front_total + act;      // fsdb.c:596: the back segment adds the front's length again
-        int from_back = front_total + back_total - act - 1;
-        smp[c] = smp_code(from_front, from_back);
-        if (colc[c] != '-') act++;
+      // id, with split_pwaln's suffix rule (mia.c:1389-1398)
+      const char* id = rd->ids + rd->id_off[i];
+      idbuf.assign(id);
+      if (sg.seg != 'a') {
+        size_t cut = std::min<size_t>(idbuf.size(), (size_t)kMaxId - 1);
+        idbuf.resize(cut);
+        idbuf += (sg.seg == 'f') ? "_f" : "_b";
       }
+      o.s("ID "); o.s(idbuf.c_str()); o.ch('\n');
+      o.s("DESC "); if (rd->descs && rd->desc_off) o.s(rd->descs + rd->desc_off[i]); o.ch('\n');
+      o.kv("SCORE ", rd->score[i]);
+      o.kv("NUM_INPUTS ", rd->num_inputs ? rd->num_inputs[i] : 1);
+      o.kv("START ", sg.start);
+      o.kv("END ", sg.end);
+      o.kv("RC ", rd->rc[i] ? 1 : 0);
+      o.kv("TR ", (rd->trimmed && rd->trimmed[i]) ? 1 : 0);
+      o.kv("DR ", sg.dropped);
+      o.s("SEG "); o.ch(sg.seg); o.ch('\n');
+      o.s("SEQ "); o.s(colc.data() + sg.col0, (size_t)sg.ncol); o.ch('\n');
+      o.s("SMP "); o.s(smp.data() + sg.col0, (size_t)sg.ncol); o.ch('\n');
+      o.s("INS_POS");
+      for (int c = 0; c < sg.ncol; c++) {
+        int g = sg.col0 + c;
+        if (ins_len[g]) { o.ch(' '); o.i(c); o.ch(' '); o.s((const char*)read + ins_at[g], (size_t)ins_len[g]); }
+      }
+      o.ch('\n');
     }
-    // id, with split_pwaln's suffix rule (mia.c:1389-1398)
-    const char* id = rd->ids + rd->id_off[i];
-    idbuf.assign(id);
-    if (sg.seg != 'a') {
-      size_t cut = std::min<size_t>(idbuf.size(), (size_t)kMaxId - 1);
-      idbuf.resize(cut);
-      idbuf += (sg.seg == 'f') ? "_f" : "_b";
-    }
-    o.s("ID "); o.s(idbuf.c_str()); o.ch('\n');
-    o.s("DESC "); if (rd->descs && rd->desc_off) o.s(rd->descs + rd->desc_off[i]); o.ch('\n');
-    o.kv("SCORE ", rd->score[i]);
-    o.kv("NUM_INPUTS ", rd->num_inputs ? rd->num_inputs[i] : 1);
-    o.kv("START ", sg.start);
-    o.kv("END ", sg.end);
-    o.kv("RC ", rd->rc[i] ? 1 : 0);
-    o.kv("TR ", (rd->trimmed && rd->trimmed[i]) ? 1 : 0);
-    o.kv("DR ", sg.dropped);
-    o.s("SEG "); o.ch(sg.seg); o.ch('\n');
-    o.s("SEQ "); o.s(colc.data() + sg.col0, (size_t)sg.ncol); o.ch('\n');
-    o.s("SMP "); o.s(smp.data() + sg.col0, (size_t)sg.ncol); o.ch('\n');
-    o.s("INS_POS");
-    for (int c = 0; c < sg.ncol; c++) {
-      int g = sg.col0 + c;
-      if (ins_len[g]) { o.ch(' '); o.i(c); o.ch(' '); o.s((const char*)read + ins_at[g], (size_t)ins_len[g]); }
-    }
-    o.ch('\n');
-  }
   };
   const size_t total = order.size();
   unsigned hw = std::thread::hardware_concurrency();
