@@ -52,9 +52,10 @@ def fastq_text(bases, off, seed):
     return "".join(out)
 
 
-def run_session(name, ref, fq, flags, matrix):
+def run_session(name, ref, fq, flags, matrix, ref_text=None):
     with tempfile.TemporaryDirectory() as d:
-        open(os.path.join(d, "ref.fa"), "w").write(">refseq a small circle\n" + ref + "\n")
+        ref_text = ref_text or ">refseq a small circle\n" + ref + "\n"
+        open(os.path.join(d, "ref.fa"), "w").write(ref_text)
         open(os.path.join(d, "reads.fq"), "w").write(fq)
         cmd = [MIA, "-r", "ref.fa", "-f", "reads.fq", "-s", matrix, "-m", "out"] + flags
         subprocess.run(cmd, cwd=d, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
@@ -64,7 +65,8 @@ def run_session(name, ref, fq, flags, matrix):
             body = open(os.path.join(d, f"out.{i}")).read().split("\n", 1)[1]
             malns.append(body)
             i += 1
-    return dict(name=name, ref=ref, ref_id="refseq", ref_desc="a small circle", fastq=fq, flags=flags, matrix=matrix, malns=malns)
+    return dict(name=name, ref=ref, ref_id="refseq", ref_desc="a small circle", ref_text=ref_text, fastq=fq, flags=flags, matrix=matrix,
+                malns=malns)
 
 
 def reader_case(text):
@@ -117,7 +119,13 @@ def main():
     bases, off, _ = synth.make_reads(genome, 300, 30, 140, seed=15, circular=False)
     fq = fastq_text(bases, off, 16)
     out["lin_pe"] = run_session("lin_pe", ref, fq, ["-i"], "ancient.submat.solexa.pe.txt")
+    # the reference's own fixtures (test/tr1.fna, test/tf.fna: FASTA reads, lower-case reference stretch, an over-long read)
+    fx = "/root/reference/test"
+    tr1, tf = open(os.path.join(fx, "tr1.fna")).read(), open(os.path.join(fx, "tf.fna")).read()
+    for name, flags in (("tr1_tf_lin", ["-i"]), ("tr1_tf_lin_k8", ["-k", "8", "-i"]), ("tr1_tf_c", ["-c", "-i"])):
+        out[name] = run_session(name, None, tf, flags, "ancient.submat.txt", ref_text=tr1)
     cases = [reader_case(t) for t in TRICKY]
+    cases.append(reader_case(tf))
     cases.append(reader_case(out["circ_k10"]["fastq"]))
     print("reader cases:", [len(c["records"]) for c in cases])
     for k, v in out.items():

@@ -14,10 +14,12 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-@pytest.mark.parametrize("name,matrix", [("circ_k10", "ancient"), ("lin_pe", "pe")])
+@pytest.mark.parametrize("name,matrix", [("circ_k10", "ancient"), ("lin_pe", "pe"), ("tr1_tf_lin", "ancient"), ("tr1_tf_lin_k8", "ancient"),
+                                         ("tr1_tf_c", "ancient")])
 def test_c_host_writes_the_reference_maln_files(golden, name, matrix, tmp_path):
     s = json.load(gzip.open(os.path.join(HERE, "golden", "maln_session.json.gz"), "rt"))["sessions"][name]
-    (tmp_path / "ref.fa").write_text(f">{s['ref_id']} {s['ref_desc']}\n{s['ref']}\n")
+    # tr1_tf_*: the reference's own fixtures test/tr1.fna + test/tf.fna (FASTA reads, a lower-case stretch, a 236-base read)
+    (tmp_path / "ref.fa").write_text(s.get("ref_text") or f">{s['ref_id']} {s['ref_desc']}\n{s['ref']}\n")
     (tmp_path / "reads.fq").write_text(s["fastq"])
     (tmp_path / "m.txt").write_text(matrix_text(golden[matrix]))
     r = subprocess.run([HOST, "-r", "ref.fa", "-f", "reads.fq", "-s", "m.txt", "-m", "out"] + s["flags"], cwd=tmp_path, capture_output=True, text=True)

@@ -146,7 +146,7 @@ def write_from_reads(api, h, reads, path, circular):
     return api.write_maln(path, h["ref_id"], h["ref_desc"], h["seq"], circular, h["size"], h["coc"], h["gaps"], h["fpsm"], h["rpsm"], rd)
 
 
-@pytest.mark.parametrize("name", ["circ_k10", "lin_pe"])
+@pytest.mark.parametrize("name", ["circ_k10", "lin_pe", "tr1_tf_lin", "tr1_tf_c"])
 def test_write_maln_reproduces_reference_files(api, gold, name, tmp_path):
     s = gold["sessions"][name]
     circular = int("-c" in s["flags"])
