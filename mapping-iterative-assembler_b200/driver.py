@@ -355,14 +355,16 @@ class RepeatFilterAssembler:
         self.g, self.sm, self.circular, self.k, self.soft_mask, self.cons_code = gpu, sm, circular, k, soft_mask, cons_code
         self.just_outer_coords, self.ref0 = just_outer_coords, ref
         self.split_changes = 0
-        if key != "score":
-            raise NotImplementedError("-U needs FragSeq.qual_sum from the FASTQ parser (host side); pass it as key4 to miagpu_repeat_filter")
+        if key not in ("score", "qual"):
+            raise ValueError("key is 'score' (-u: sort_fsdb) or 'qual' (-U: sort_fsdb_qscore on FragSeq.qual_sum)")
+        self.key = key
         gpu.set_pssm(sm)
 
     def _filter_and_cull(self, split):
         """sort + unique flags + cull over the current FSDB; returns per-read flags for miagpu_consensus_natural"""
         g, fo = self.g, self.order
-        order, uniq = g.repeat_filter(self.rc[fo], self.as_[fo], self.ae[fo], self.score[fo], None, self.just_outer_coords, 0)
+        key4 = self.score if self.key == "score" else self.qual                     # -u: FragSeq.score, -U: FragSeq.qual_sum
+        order, uniq = g.repeat_filter(self.rc[fo], self.as_[fo], self.ae[fo], key4[fo], None, self.just_outer_coords, 0)
         # slots were numbered in the FSDB order the merges ran in (BEFORE this sort)
         nsl = 1 + split.astype(np.int64)
         first = np.zeros(len(nsl), np.int64)
@@ -383,7 +385,8 @@ class RepeatFilterAssembler:
         self.fit = fit
         return df, db
 
-    def pass1(self, bases, off):
+    def pass1(self, bases, off, qual_sum=None):
+        """qual_sum (per input read; FastxReader's `qual_sum`, read_fastq's sum(q - 33)) is the fourth sort key with key='qual'"""
         g = self.g
         g.set_reference(self.ref0, self.circular, with_rc=1)
         g.build_kmers(self.k, self.soft_mask)
@@ -395,6 +398,12 @@ class RepeatFilterAssembler:
             raise NotImplementedError("reads with score == 2000 keep strand_known = 0 and are never realigned (mia.c:1653)")
         idx = np.flatnonzero(keep)
         self.ids = idx.copy()                                                        # input index of every FSDB read
+        if self.key == "qual":
+            if qual_sum is None:
+                raise ValueError("key='qual' (-U) needs qual_sum per input read")
+            self.qual = np.ascontiguousarray(np.asarray(qual_sum)[idx], np.int32)
+        else:
+            self.qual = np.zeros(len(idx), np.int32)
         self.seq_len, self.score = seq_len[idx], p["score"][idx].copy()
         self.rc, self.as_, self.ae = p["rc"][idx].copy(), p["as_"][idx].copy(), p["ae"][idx].copy()
         split = p["start"][idx] > p["end"][idx]                                      # mia.c:1619
@@ -409,7 +418,7 @@ class RepeatFilterAssembler:
         g.compact_reads(keep_dev, rev)
         newpos = np.cumsum(ok) - 1
         self.order = newpos[self.order[ok[self.order]]]
-        for name in ("seq_len", "score", "rc", "as_", "ae", "ids"):
+        for name in ("seq_len", "score", "rc", "as_", "ae", "ids", "qual"):
             setattr(self, name, getattr(self, name)[ok])
         self.split = split[ok]
         g.set_alignment_inputs(self.rc, self.as_, self.ae)

@@ -334,6 +334,7 @@ class Ref(_AlignMixin):
         L.refh_sess_new.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, c_int_p, C.c_int, C.c_int]
         L.refh_sess_set_cut.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double]
         L.refh_sess_pass1.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, c_int_p] + [C.c_char_p] * 4
+        L.refh_sess_set_next_qual_sum.argtypes = [C.c_void_p, C.c_int]
         L.refh_sess_masks.argtypes = [C.c_void_p, c_ubyte_p, c_ubyte_p]
         L.refh_sess_end_pass1.argtypes = [C.c_void_p]
         L.refh_sess_iterate.restype = C.c_char_p
@@ -430,7 +431,8 @@ class Ref(_AlignMixin):
     def sess_set_repeat(self, s, repeat_filt=1, just_outer_coords=1):
         self.lib.refh_sess_set_repeat(s, int(repeat_filt), int(just_outer_coords))
 
-    def sess_pass1(self, s, rid, read, want_masks=False):
+    def sess_pass1(self, s, rid, read, want_masks=False, qual_sum=0):
+        self.lib.refh_sess_set_next_qual_sum(s, int(qual_sum))
         out = np.zeros(18, np.int32)
         bufs = [C.create_string_buffer(520) for _ in range(4)]
         self.lib.refh_sess_pass1(s, _b(rid), _b(read), _ip(out), *bufs)

@@ -200,7 +200,8 @@ typedef struct {
   char *last_cons, *cons;
   int hard_cut, score_cut_set;
   double slope, intercept;
-  int repeat_filt, just_outer_coords;      /* -u, -A */
+  int repeat_filt, just_outer_coords;      /* -u (1) or -U (2), -A */
+  int next_qual_sum;                       /* FragSeq.qual_sum of the next refh_sess_pass1 read (what read_fastq computes) */
 } Sess;
 
 /* mia_main.c:618-757 with the getopt results passed in */
@@ -256,10 +257,12 @@ void refh_sess_set_repeat( void* s_, int repeat_filt, int just_outer_coords ) {
 }
 static void sess_repeat_filter( Sess* s ) {            /* mia_main.c:827-834, 883-886, 938-941 */
   if ( s->repeat_filt && s->fsdb->num_fss > 0 ) {
-    sort_fsdb( s->fsdb );
+    if ( s->repeat_filt == 2 ) sort_fsdb_qscore( s->fsdb );       /* -U: mia_main.c:836-844, 887-890, 942-945 */
+    else sort_fsdb( s->fsdb );
     set_uniq_in_fsdb( s->fsdb, s->just_outer_coords, 0 );
   }
 }
+void refh_sess_set_next_qual_sum( void* s_, int q ) { ((Sess*)s_)->next_qual_sum = q; }
 void refh_sess_fs_id( void* s_, long long i, char* id ) { strcpy( id, ((Sess*)s_)->fsdb->fss[i]->id ); }
 
 /* One read through mia_main.c:759-797 (no -T, no -I).
@@ -284,7 +287,7 @@ int refh_sess_pass1( void* s_, const char* id, const char* seq, int* out,
   strncpy( fs->seq, seq, INIT_ALN_SEQ_LEN ); fs->seq[INIT_ALN_SEQ_LEN] = '\0';
   fs->seq_len = strlen( fs->seq );
   fs->qual[0] = '\0';
-  fs->qual_sum = 0;
+  fs->qual_sum = s->next_qual_sum;
   fs->trimmed = 0;
   out[0] = new_kmer_filter( fs, s->fkpa, s->rkpa, s->k > 0 ? s->k : -1, s->fw, s->rc );
   if ( out[0] ) {

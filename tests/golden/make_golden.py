@@ -68,7 +68,7 @@ def read_fixture_reads(path):
     return ids, [r[:256] for r in reads]
 
 
-def session(r, ref, reads, sm, circular, k, soft_mask, max_iter=30, repeat_filt=0, just_outer_coords=1):
+def session(r, ref, reads, sm, circular, k, soft_mask, max_iter=30, repeat_filt=0, just_outer_coords=1, qual_sums=None):
     with tempfile.NamedTemporaryFile("w", suffix=".fa", delete=False) as f:
         f.write(">ref\n" + ref + "\n")
         path = f.name
@@ -80,7 +80,7 @@ def session(r, ref, reads, sm, circular, k, soft_mask, max_iter=30, repeat_filt=
         if not rd:
             p1.append(None)
             continue
-        d = r.sess_pass1(s, "r%d" % i, rd)
+        d = r.sess_pass1(s, "r%d" % i, rd, qual_sum=0 if qual_sums is None else qual_sums[i])
         p1.append({k2: d[k2] for k2 in ("hits", "added", "score", "rc", "as_", "ae", "strand_known", "fw_score", "rc_score",
                                        "start", "end", "split", "b_start", "b_end", "f_ref", "f_frag", "b_ref", "b_frag")})
     r.sess_end_pass1(s)
@@ -97,7 +97,7 @@ def session(r, ref, reads, sm, circular, k, soft_mask, max_iter=30, repeat_filt=
             break
     os.unlink(path)
     return dict(ref=ref, reads=reads, circular=circular, k=k, soft_mask=soft_mask, pass1=p1, iters=iters, repeat_filt=repeat_filt,
-                just_outer_coords=just_outer_coords)
+                just_outer_coords=just_outer_coords, **({} if qual_sums is None else {"qual_sums": [int(q) for q in qual_sums]}))
 
 
 def main():
@@ -160,6 +160,9 @@ def main():
     reads = [reads[i] for i in order]
     sess["synth1k5_dups_c_k10_u"] = session(r, ref, reads, m["onepass"], 1, 10, 0, repeat_filt=1)
     sess["synth1k5_dups_lin_k10_uA"] = session(r, ref, reads, m["onepass"], 0, 10, 0, repeat_filt=1, just_outer_coords=0)
+    # -U: the same reads with FASTQ quality sums (read_fastq: sum(q - 33)); duplicates are decided by quality, not by score
+    qs = [int(v) for v in np.random.default_rng(35).integers(20, 41, len(reads)) * np.array([len(x) for x in reads])]
+    sess["synth1k5_dups_c_k10_U"] = session(r, ref, reads, m["onepass"], 1, 10, 0, repeat_filt=2, qual_sums=qs)
     json.dump(sess, open(os.path.join(HERE, "sessions.json"), "w"))
     # f1: the reference's sort_fsdb[_qscore] + set_uniq_in_fsdb on small FSDBs full of ties
     rng = np.random.default_rng(7)

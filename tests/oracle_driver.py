@@ -18,13 +18,13 @@ class OracleRun:
         self.iter = 0
         self.cons = None
 
-    def pass1(self, read, want_masks=False):
+    def pass1(self, read, want_masks=False, qual_sum=0):
         p = self.o.pass1(self.ctx, read, want_masks)
         if p["added"]:
             seq = self.o.revcom(read) if (p["rc"] and p["strand_known"]) else read      # fsdb.c:209-227
             end = p["b_end"] if p["split"] else p["end"]
             f, b = self.o.asm_add(self.asm, p["f_ref"] + p["b_ref"], p["f_frag"] + p["b_frag"], p["start"], end, p["rc"], p["score"])
-            self.fsdb.append(dict(rid=len(self.fsdb), unique_best=1, seq=seq, seq_len=len(read), score=p["score"], rc=p["rc"], as_=p["as_"], ae=p["ae"],
+            self.fsdb.append(dict(rid=len(self.fsdb), unique_best=1, qual_sum=int(qual_sum), seq=seq, seq_len=len(read), score=p["score"], rc=p["rc"], as_=p["as_"], ae=p["ae"],
                                   strand_known=p["strand_known"], front=f, back=-1 if b is None else b))   # mia.c:1626-1642
         return p
 
@@ -37,7 +37,8 @@ class OracleRun:
         if not self.repeat_filt or not self.fsdb:
             return None
         g = lambda k: np.array([f[k] for f in self.fsdb], np.int32)
-        order, uniq = self.o.repeat_filter(g("rc").astype(np.uint8), g("as_"), g("ae"), g("score"), None, self.just_outer_coords, 0)
+        key4 = g("qual_sum") if self.repeat_filt == 2 else g("score")                    # -U: sort_fsdb_qscore (fsdb.c:90-180, 250-253)
+        order, uniq = self.o.repeat_filter(g("rc").astype(np.uint8), g("as_"), g("ae"), key4, None, self.just_outer_coords, 0)
         for f, u in zip(self.fsdb, uniq):
             f["unique_best"] = int(u)
         self.fsdb = [self.fsdb[k] for k in order]

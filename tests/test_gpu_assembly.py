@@ -128,7 +128,7 @@ def test_sharded_assembly_to_convergence(gpu, golden, name, matrix, parts):
             g.close()
 
 
-@pytest.mark.parametrize("name", ["synth1k5_dups_c_k10_u", "synth1k5_dups_lin_k10_uA"])
+@pytest.mark.parametrize("name", ["synth1k5_dups_c_k10_u", "synth1k5_dups_lin_k10_uA", "synth1k5_dups_c_k10_U"])
 def test_repeat_filter_sessions_reproduce_reference(gpu, golden, name):
     # mia -u (and -u -A): the FSDB is re-sorted every round, duplicates are left out, sticky flags stay with FSDB positions --
     # per round: the reads in the reference's FSDB order, their unique_best flags, the consensus
@@ -136,9 +136,13 @@ def test_repeat_filter_sessions_reproduce_reference(gpu, golden, name):
     _pkg.load()
     from mia_b200 import driver
     s, bases, off = _session_inputs(name)
+    # repeat_filt 1 = -u (FragSeq.score decides between duplicates), 2 = -U (FragSeq.qual_sum, as read_fastq sums it)
     A = driver.RepeatFilterAssembler(gpu, s["ref"], golden["onepass"], s["circular"], s["k"], s["soft_mask"],
-                                     just_outer_coords=s["just_outer_coords"])
-    A.pass1(bases, off)
+                                     just_outer_coords=s["just_outer_coords"], key="qual" if s["repeat_filt"] == 2 else "score")
+    qs = None
+    if "qual_sums" in s:
+        qs = np.array([q for q, r in zip(s["qual_sums"], s["reads"]) if r], np.int32)
+    A.pass1(bases, off, qual_sum=qs)
     for it, e in enumerate(s["iters"]):
         cons, conv = A.iterate()
         fo = A.order

@@ -44,7 +44,7 @@ def _run_session(oracle, golden, name, matrix):
     for i, (rd, exp) in enumerate(zip(s["reads"], s["pass1"])):
         if exp is None:
             continue
-        p = R.pass1(rd)
+        p = R.pass1(rd, qual_sum=s["qual_sums"][i] if "qual_sums" in s else 0)
         for key, v in exp.items():
             if not exp["hits"] and key not in ("hits", "added"):
                 continue
@@ -108,6 +108,7 @@ def test_session_repeat_filter(oracle, golden):
     # -u: sort_fsdb + set_uniq_in_fsdb every round (the FSDB order itself changes), circular; -u -A, linear
     _run_session(oracle, golden, "synth1k5_dups_c_k10_u", "onepass")
     _run_session(oracle, golden, "synth1k5_dups_lin_k10_uA", "onepass")
+    _run_session(oracle, golden, "synth1k5_dups_c_k10_U", "onepass")          # -U: duplicates decided by FragSeq.qual_sum
 
 
 def test_repeat_filter_matches_reference_golden(oracle):
