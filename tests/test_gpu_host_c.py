@@ -8,7 +8,7 @@ import subprocess
 
 import pytest
 
-from test_host_c import HOST, matrix_text
+from test_host_c import HOST, ensure_host, matrix_text
 
 pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -22,6 +22,7 @@ def test_c_host_writes_the_reference_maln_files(golden, name, matrix, tmp_path):
     (tmp_path / "ref.fa").write_text(s.get("ref_text") or f">{s['ref_id']} {s['ref_desc']}\n{s['ref']}\n")
     (tmp_path / "reads.fq").write_text(s["fastq"])
     (tmp_path / "m.txt").write_text(matrix_text(golden[matrix]))
+    ensure_host()
     r = subprocess.run([HOST, "-r", "ref.fa", "-f", "reads.fq", "-s", "m.txt", "-m", "out"] + s["flags"], cwd=tmp_path, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     for it, body in enumerate(s["malns"]):
