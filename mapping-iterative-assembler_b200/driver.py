@@ -407,6 +407,7 @@ class RepeatFilterAssembler:
         self.seq_len, self.score = seq_len[idx], p["score"][idx].copy()
         self.rc, self.as_, self.ae = p["rc"][idx].copy(), p["as_"][idx].copy(), p["ae"][idx].copy()
         split = p["start"][idx] > p["end"][idx]                                      # mia.c:1619
+        self.maln_size = int(len(idx) + split.sum())                                 # culled_maln->size (mia.c:54)
         self.order = np.arange(len(idx))
         self.dropped_slot = np.zeros(2 * len(idx) + 64, np.uint8)
         self._filter_and_cull(split)                                                 # mia_main.c:827-848: only the flags survive
@@ -438,6 +439,38 @@ class RepeatFilterAssembler:
         self.split_changes += int((split != self.split).sum())
         self.split = split
         df, db = self._filter_and_cull(split)
+        self.df, self.db = df, db
         cons, self.gaps, _ = g.consensus_natural(df, db, self.cons_code)
         self.cons = cons
         return cons, cons == self.last
+
+    def write_maln(self, path, batch, ref_id, ref_desc=""):
+        """write_ma of this round's culled_maln (mia_main.c:905 / 958) under -u / -U: the reads in the FSDB order this round's
+        sort left, the non-unique ones left out (mia.c:466), AlnSeq.dropped from the slot-indexed sticky flags."""
+        from .synth import revcomp_bytes
+        g, fo = self.g, self.order
+        al = g.get_alignment()
+        tot, _, _ = g.get_runs_packed()
+        run_off, packed = np.zeros(len(self.rc) + 1, np.int64), np.zeros(max(tot, 1), np.uint16)
+        g.get_runs_packed(run_off, packed)
+        nr = np.diff(run_off)[fo]
+        new_off = np.concatenate([[0], np.cumsum(nr)]).astype(np.int64)
+        src = np.repeat(run_off[:-1][fo] - new_off[:-1], nr) + np.arange(int(new_off[-1]))
+        off, bases = np.asarray(batch["offsets"]), np.asarray(batch["bases"])
+        idb, ido, dsb, dso = batch["ids"], batch["id_off"], batch.get("descs"), batch.get("desc_off")
+        stored, ids, descs = [], [], []
+        for j in fo:                                                                 # stored orientation: fsdb.c:209-227
+            i = self.ids[j]
+            r = bases[off[i]:off[i + 1]]
+            stored.append(revcomp_bytes(r) if self.rc[j] else r)
+            ids.append(idb[ido[i]:ido[i + 1]])
+            descs.append(dsb[dso[i]:dso[i + 1]] if dsb is not None else b"\0")
+        cum = lambda xs: np.concatenate([[0], np.cumsum([len(x) for x in xs])]).astype(np.int64)
+        fpsm, rpsm = g.get_pssm()
+        if self.iter > 1:
+            ref_id, ref_desc = f"ConsAssem.{self.iter}", "iteration assembly"
+        rd = dict(bases=np.concatenate(stored) if stored else np.zeros(0, np.uint8), offsets=cum(stored), ids=b"".join(ids), id_off=cum(ids),
+                  descs=b"".join(descs), desc_off=cum(descs), rc=self.rc[fo], score=al["score"][fo], as_=al["as_out"][fo], ae=al["ae_out"][fo],
+                  abr=al["abr"][fo], run_off=new_off, packed=packed[src] if len(src) else packed[:0], unique_best=self.unique[fo],
+                  dropped_front=(self.df[fo] == 1), dropped_back=(self.db[fo] == 1))
+        return api.write_maln(path, ref_id, ref_desc, self.last, self.circular, self.maln_size, self.cons_code, self.gaps, fpsm, rpsm, rd)

@@ -119,6 +119,22 @@ def main():
     bases, off, _ = synth.make_reads(genome, 300, 30, 140, seed=15, circular=False)
     fq = fastq_text(bases, off, 16)
     out["lin_pe"] = run_session("lin_pe", ref, fq, ["-i"], "ancient.submat.solexa.pe.txt")
+    # -u / -U: PCR-style duplicates (same molecule, sometimes one base changed), qualities differ per read
+    bases, off, _ = synth.make_reads(genome, 220, 35, 75, seed=17, circular=True)
+    rng = np.random.default_rng(18)
+    rl = [bases[off[i]:off[i + 1]].copy() for i in range(220)]
+    for _ in range(130):
+        r = rl[int(rng.integers(0, 220))].copy()
+        if rng.random() < 0.4:
+            q = int(rng.integers(0, len(r)))
+            r[q] = b"ACGT"[(b"ACGT".index(bytes([r[q]])) + 1) % 4]
+        rl.append(r)
+    rl = [rl[i] for i in rng.permutation(len(rl))]
+    db = np.concatenate(rl)
+    do = np.concatenate([[0], np.cumsum([len(r) for r in rl])]).astype(np.int64)
+    fq = fastq_text(db, do, 19)
+    out["dups_c_k10_u"] = run_session("dups_c_k10_u", ref, fq, ["-c", "-k", "10", "-i", "-u"], "ancient.submat.solexa.onepass.txt")
+    out["dups_c_k10_U"] = run_session("dups_c_k10_U", ref, fq, ["-c", "-k", "10", "-i", "-U"], "ancient.submat.solexa.onepass.txt")
     # the reference's own fixtures (test/tr1.fna, test/tf.fna: FASTA reads, lower-case reference stretch, an over-long read)
     fx = "/root/reference/test"
     tr1, tf = open(os.path.join(fx, "tr1.fna")).read(), open(os.path.join(fx, "tf.fna")).read()

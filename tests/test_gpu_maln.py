@@ -41,3 +41,32 @@ def test_fastq_to_maln_files_equal_reference(gpu, golden, name, matrix, tmp_path
                 assert x == y, f"{name} iteration {it + 1}: line {ln + 2}: {x[:160]!r} != {y[:160]!r}"
             assert len(ga) == len(gb)
     assert conv and A.split_changes == 0
+
+
+@pytest.mark.parametrize("name,key", [("dups_c_k10_u", "score"), ("dups_c_k10_U", "qual")])
+def test_repeat_filter_sessions_fastq_to_maln_files_equal_reference(gpu, golden, name, key, tmp_path):
+    # mia -u / mia -U: the FSDB is re-sorted every round, duplicates (by score / by the FASTQ quality sum the reader computed) are left
+    # out of the file, AlnSeq.dropped follows the slot-indexed sticky flags -- every iteration's file byte for byte
+    import _pkg
+    _pkg.load()
+    from mia_b200 import api, driver
+    s = json.load(gzip.open(os.path.join(HERE, "golden", "maln_session.json.gz"), "rt"))["sessions"][name]
+    p = tmp_path / "reads.fq"
+    p.write_text(s["fastq"])
+    rdr = api.FastxReader(path=str(p))
+    batch = rdr.next()
+    A = driver.RepeatFilterAssembler(gpu, s["ref"], golden["onepass"], 1, 10, 0, key=key)
+    A.pass1(batch["bases"], batch["offsets"], qual_sum=batch["qual_sum"])
+    conv = False
+    for it, body in enumerate(s["malns"]):
+        assert not conv
+        _, conv = A.iterate()
+        out = str(tmp_path / f"out.{it + 1}")
+        A.write_maln(out, batch, s["ref_id"], s["ref_desc"])
+        got = open(out).read().split("\n", 1)[1]
+        if got != body:
+            ga, gb = got.split("\n"), body.split("\n")
+            for ln, (x, y) in enumerate(zip(ga, gb)):
+                assert x == y, f"{name} iteration {it + 1}: line {ln + 2}: {x[:160]!r} != {y[:160]!r}"
+            assert len(ga) == len(gb)
+    assert conv
