@@ -1,13 +1,15 @@
 /* mia_gpu.c -- a plain-C host for libmiagpu.so: the call sequence INTEGRATION.md gives a maintainer of the reference,
  * compiled and run.  It is NOT the reference's CLI (out of scope): it covers the default assembly mode only
  *
- *     mia_gpu -r ref.fa -f reads.fq -s matrix.txt -m out [-c] [-k K] [-p 1|2] [-H cut] [-F]
+ *     mia_gpu -r ref.fa -f reads.fq -s matrix.txt -m out [-c] [-k K] [-p 1|2] [-H cut] [-F] [-u | -U] [-A]
  *
  * and exists to show (and test, tests/test_gpu_host_c.py) that the C ABI alone -- no Python, no torch -- reproduces
  * the reference's `.maln` files: reader (miagpu_fastx_*), matrices (miagpu_read_pssm), pass 1, score cut, one library
  * call per round with everything resident, writer (miagpu_write_maln).  The host keeps what mia_main.c keeps: which
  * reads enter the FSDB (mia.c:1614), their strand, the convergence test (mia_main.c:909-976), the file names.
- * Reads that score exactly 2000 (strand_known = 0, mia.c:1653), -D, -u/-U, -T, -h, -C, -I are not handled here.
+ * -u / -U (the repeat filter, mia_main.c:827-844, 883-890, 938-945) run the per-phase calls instead of the one-call round, with
+ * the FSDB order and the slot-indexed sticky AlnSeq.dropped flags kept here as mia_main.c keeps them.
+ * Reads that score exactly 2000 (strand_known = 0, mia.c:1653), -D, -T, -h, -C, -I are not handled here.
  * There is no CPU fallback: without a CUDA device miagpu_create fails and so does this program. */
 #define _POSIX_C_SOURCE 199309L
 #include <stdio.h>
@@ -73,12 +75,59 @@ static void init_comp( void ) {
   for ( i = 0; a[i]; i++ ) comp[(unsigned char)a[i]] = (unsigned char)b[i];
 }
 
+/* ---- -u / -U: sort_fsdb[_qscore] + set_uniq_in_fsdb + cull_maln_from_fsdb over the current FSDB (mia_main.c:827-848, 883-891).
+ * Arrays are indexed by read (device order); order[k] = read at position k of fsdb->fss. */
+typedef struct {
+  int64_t m;
+  int joc, by_qual;
+  int32_t *len, *score, *as, *ae, *qual;
+  uint8_t *rc, *split, *unique, *df, *db, *slot;      /* slot: AlnSeq.dropped per maln slot, sticky (H10) */
+  int64_t *order, slot_cap;
+} Fsdb;
+
+static void filter_and_cull( miagpu_ctx* g, Fsdb* F ) {
+  int64_t m = F->m, k, s = 0;
+  uint8_t *rc = xmalloc( m ), *uq = xmalloc( m ), *below = xmalloc( m ), *uo = xmalloc( m );
+  int32_t *as = xmalloc( m * 4 ), *ae = xmalloc( m * 4 ), *k4 = xmalloc( m * 4 ), *lo = xmalloc( m * 4 ), *so = xmalloc( m * 4 );
+  int64_t *ord = xmalloc( m * 8 ), *first = xmalloc( m * 8 ), *neworder = xmalloc( m * 8 );
+  double slope = 0, icpt = 0;
+  for ( k = 0; k < m; k++ ) {
+    int64_t j = F->order[k];
+    rc[k] = F->rc[j]; as[k] = F->as[j]; ae[k] = F->ae[j]; k4[k] = F->by_qual ? F->qual[j] : F->score[j];
+    first[j] = s; s += 1 + F->split[j];               /* slots were numbered in the order the merges ran in: BEFORE this sort */
+  }
+  CK( miagpu_repeat_filter( g, m, rc, as, ae, k4, NULL, F->joc, 0, ord, uq ) );
+  for ( k = 0; k < m; k++ ) F->unique[F->order[k]] = uq[k];
+  for ( k = 0; k < m; k++ ) neworder[k] = F->order[ord[k]];
+  memcpy( F->order, neworder, (size_t)m * 8 );
+  for ( k = 0; k < m; k++ ) { int64_t j = F->order[k]; lo[k] = F->len[j]; so[k] = F->score[j]; uo[k] = F->unique[j]; }
+  CK( miagpu_score_cut( m, lo, so, uo, &slope, &icpt ) );                /* sums run in FSDB order */
+  CK( miagpu_cull_flags( m, F->len, F->score, NULL, 0, 1, slope, icpt, below ) );
+  if ( s + 2 > F->slot_cap ) {
+    F->slot = realloc( F->slot, (size_t)s + 66 );
+    memset( F->slot + F->slot_cap, 0, (size_t)( s + 66 - F->slot_cap ) );
+    F->slot_cap = s + 66;
+  }
+  for ( k = 0; k < m; k++ )
+    if ( below[k] && F->unique[k] ) { F->slot[first[k]] = 1; if ( F->split[k] ) F->slot[first[k] + 1] = 1; }
+  for ( k = 0; k < m; k++ ) {
+    int64_t b = first[k] + 1 < F->slot_cap ? first[k] + 1 : F->slot_cap - 1;
+    F->df[k] = F->unique[k] ? F->slot[first[k]] : 2;
+    F->db[k] = F->unique[k] ? F->slot[b] : 2;
+  }
+  free( rc ); free( uq ); free( below ); free( uo ); free( as ); free( ae ); free( k4 ); free( lo ); free( so ); free( ord ); free( first );
+  free( neworder );
+}
+
 int main( int argc, char** argv ) {
   const char *ref_fn = NULL, *frag_fn = NULL, *mat_fn = NULL, *root = "assembly.maln.iter";
-  int circular = 0, k = -1, cons_code = 1, hard_cut = 0, final_only = 0, i;
+  int circular = 0, k = -1, cons_code = 1, hard_cut = 0, final_only = 0, repeat_filt = 0, just_outer_coords = 1, i;
   for ( i = 1; i < argc; i++ ) {
     if ( !strcmp( argv[i], "-c" ) ) circular = 1;
     else if ( !strcmp( argv[i], "-F" ) ) final_only = 1;
+    else if ( !strcmp( argv[i], "-u" ) ) repeat_filt = 1;
+    else if ( !strcmp( argv[i], "-U" ) ) repeat_filt = 2;
+    else if ( !strcmp( argv[i], "-A" ) ) just_outer_coords = 0;
     else if ( !strcmp( argv[i], "-i" ) ) ;
     else if ( i + 1 < argc && !strcmp( argv[i], "-r" ) ) ref_fn = argv[++i];
     else if ( i + 1 < argc && !strcmp( argv[i], "-f" ) ) frag_fn = argv[++i];
@@ -90,7 +139,7 @@ int main( int argc, char** argv ) {
     else { fprintf( stderr, "mia_gpu: option %s is not handled by this host (see the header of host/mia_gpu.c)\n", argv[i] ); return 2; }
   }
   if ( !ref_fn || !frag_fn || !mat_fn ) {
-    fprintf( stderr, "usage: mia_gpu -r ref.fa -f reads.fa|fq -s matrix.txt [-m root] [-c] [-k K] [-p code] [-H cut] [-F]\n" );
+    fprintf( stderr, "usage: mia_gpu -r ref.fa -f reads.fa|fq -s matrix.txt [-m root] [-c] [-k K] [-p code] [-H cut] [-F] [-u|-U] [-A]\n" );
     return 2;
   }
   init_comp();
@@ -155,7 +204,17 @@ int main( int argc, char** argv ) {
   }
   /* pass-1 cull (mia_main.c:848): only its sticky flags survive */
   double slope = 0, icpt = 0;
-  if ( hard_cut > 0 ) CK( miagpu_cull_flags( m, f_len, f_score, NULL, hard_cut, 0, 0.0, 0.0, dropped ) );
+  Fsdb F;
+  memset( &F, 0, sizeof F );
+  if ( repeat_filt ) {
+    F.m = m; F.joc = just_outer_coords; F.by_qual = repeat_filt == 2;
+    F.len = f_len; F.score = f_score; F.as = f_as; F.ae = f_ae; F.rc = f_rc;
+    F.qual = xmalloc( m * 4 ); F.split = xmalloc( m ); F.unique = xmalloc( m ); F.df = xmalloc( m ); F.db = xmalloc( m );
+    F.order = xmalloc( m * 8 ); F.slot_cap = 2 * m + 64; F.slot = xmalloc( (size_t)F.slot_cap );
+    for ( j = 0; j < m; j++ ) { F.qual[j] = qual_sum[src[j]]; F.split[j] = start[src[j]] > end[src[j]]; F.order[j] = j; }
+    filter_and_cull( g, &F );
+  }
+  else if ( hard_cut > 0 ) CK( miagpu_cull_flags( m, f_len, f_score, NULL, hard_cut, 0, 0.0, 0.0, dropped ) );
   else {
     CK( miagpu_score_cut( m, f_len, f_score, NULL, &slope, &icpt ) );
     CK( miagpu_cull_flags( m, f_len, f_score, NULL, 0, 1, slope, icpt, dropped ) );
@@ -183,8 +242,17 @@ int main( int argc, char** argv ) {
     iter++;
     t1 = now_ms();
     CK( miagpu_set_reference( g, last, L, circular, 0 ) );
-    CK( miagpu_iterate_resident( g, hard_cut, 0, 0.0, 0.0, cons_code, &slope, &icpt, dropped, gaps, cons, &cons_len ) );
-    CK( miagpu_adopt_alignment( g, f_score, f_as, f_ae ) );
+    if ( repeat_filt ) {
+      CK( miagpu_realign_resident( g ) );
+      CK( miagpu_adopt_alignment( g, f_score, f_as, f_ae ) );
+      for ( j = 0; j < m; j++ ) F.split[j] = f_as[j] > ( f_ae[j] > L ? f_ae[j] - L : f_ae[j] );
+      filter_and_cull( g, &F );
+      CK( miagpu_consensus_natural( g, F.df, F.db, cons_code, gaps, NULL, cons, &cons_len ) );
+    }
+    else {
+      CK( miagpu_iterate_resident( g, hard_cut, 0, 0.0, 0.0, cons_code, &slope, &icpt, dropped, gaps, cons, &cons_len ) );
+      CK( miagpu_adopt_alignment( g, f_score, f_as, f_ae ) );
+    }
     cons[cons_len] = 0;
     converged = !strcmp( cons, last );
     t_rounds += now_ms() - t1;
@@ -206,6 +274,10 @@ int main( int argc, char** argv ) {
       rd.n = m; rd.bases = stored; rd.offsets = s_off; rd.ids = f_ids; rd.id_off = f_id_off; rd.descs = f_descs; rd.desc_off = f_desc_off;
       rd.rc = f_rc; rd.score = f_score; rd.as = f_as; rd.ae = f_ae; rd.abr = abr; rd.run_off = run_off; rd.packed = packed;
       rd.dropped_front = dropped; rd.dropped_back = dropped;
+      if ( repeat_filt ) {
+        for ( j = 0; j < m; j++ ) { F.df[j] = F.df[j] == 1; F.db[j] = F.db[j] == 1; }      /* 2 = not unique: see unique_best */
+        rd.unique_best = F.unique; rd.dropped_front = F.df; rd.dropped_back = F.db; rd.fsdb_order = F.order;
+      }
       snprintf( fn, sizeof fn, "%s.%d", root, iter );
       CK( miagpu_write_maln( fn, &hd, &rd, &n_aln ) );
       fprintf( stderr, "mia_gpu: iteration %d: %lld AlnSeqs -> %s\n", iter, (long long)n_aln, fn );

@@ -456,6 +456,8 @@ typedef struct {
   const uint8_t* unique_best;   /* nullable = all 1 */
   const uint8_t* dropped_front; /* AlnSeq.dropped of the front / only segment; nullable = 0 */
   const uint8_t* dropped_back;  /* nullable = dropped_front */
+  const int64_t* fsdb_order;    /* nullable = identity: fsdb_order[k] = index (into the arrays above) of the read at position k of
+                                   fsdb->fss, i.e. what sort_fsdb left (-u / -U); the AlnSeq list is built in this order */
 } miagpu_maln_reads;
 
 int miagpu_maln_ref_size( int ref_len, int circular );   /* mia_main.c:67 + add_ref_wrap mia.c:669-675 */

@@ -559,7 +559,7 @@ class _MalnHeader(C.Structure):
 class _MalnReads(C.Structure):
     _fields_ = [("n", C.c_int64)] + [(k, C.c_void_p) for k in
                                      ("bases", "offsets", "ids", "id_off", "descs", "desc_off", "rc", "trimmed", "num_inputs", "score", "as_",
-                                      "ae", "abr", "run_off", "packed", "unique_best", "dropped_front", "dropped_back")]
+                                      "ae", "abr", "run_off", "packed", "unique_best", "dropped_front", "dropped_back", "fsdb_order")]
 
 
 def read_pssm(path):
@@ -602,7 +602,7 @@ def write_maln(path, ref_id, ref_desc, ref_seq, circular, maln_size, cons_code, 
                     blob(r.get("descs")), a(r.get("desc_off"), np.int64), a(r["rc"], np.uint8), a(r.get("trimmed"), np.uint8),
                     a(r.get("num_inputs"), np.int32), a(r["score"], np.int32), a(r["as_"], np.int32), a(r["ae"], np.int32),
                     a(r["abr"], np.int32), a(r["run_off"], np.int64), a(r["packed"], np.uint16), a(r.get("unique_best"), np.uint8),
-                    a(r.get("dropped_front"), np.uint8), a(r.get("dropped_back"), np.uint8))
+                    a(r.get("dropped_front"), np.uint8), a(r.get("dropped_back"), np.uint8), a(r.get("fsdb_order"), np.int64))
     n_out = C.c_int64()
     if not L.miagpu_write_maln(os.fsencode(path), C.byref(hd), C.byref(rd), C.byref(n_out)):
         raise MiaGpuError(L.miagpu_last_error().decode())

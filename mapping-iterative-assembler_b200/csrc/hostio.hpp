@@ -303,7 +303,9 @@ extern "C" int miagpu_write_maln(const char* path, const miagpu_maln_header* hd,
   // ---- the AlnSeq list in FSDB order (cull_maln_from_fsdb mia.c:463-476), then sort_aln_frags
   std::vector<Seg> segs;
   segs.reserve((size_t)n + 16);
-  for (int64_t i = 0; i < n; i++) {
+  for (int64_t k = 0; k < n; k++) {
+    const int64_t i = rd->fsdb_order ? rd->fsdb_order[k] : k;                      // position k of fsdb->fss holds read i
+    if (i < 0 || i >= n) { set_error("miagpu_write_maln: fsdb_order[%lld] = %lld is not a read", (long long)k, (long long)i); return 0; }
     if (rd->unique_best && !rd->unique_best[i]) continue;
     int start = rd->as[i];
     int end = rd->ae[i] > L ? rd->ae[i] - L : rd->ae[i];                           // mia_main.c:259-263
