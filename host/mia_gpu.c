@@ -1,7 +1,7 @@
 /* mia_gpu.c -- a plain-C host for libmiagpu.so: the call sequence INTEGRATION.md gives a maintainer of the reference,
  * compiled and run.  It is NOT the reference's CLI (out of scope): it covers the default assembly mode only
  *
- *     mia_gpu -r ref.fa -f reads.fq -s matrix.txt -m out [-c] [-k K] [-p 1|2] [-H cut] [-F] [-u | -U] [-A]
+ *     mia_gpu -r ref.fa -f reads.fq -s matrix.txt -m out [-c] [-k K] [-p 1|2] [-H cut | -S slope -N icpt] [-F] [-u | -U] [-A]
  *
  * and exists to show (and test, tests/test_gpu_host_c.py) that the C ABI alone -- no Python, no torch -- reproduces
  * the reference's `.maln` files: reader (miagpu_fastx_*), matrices (miagpu_read_pssm), pass 1, score cut, one library
@@ -122,6 +122,8 @@ static void filter_and_cull( miagpu_ctx* g, Fsdb* F ) {
 int main( int argc, char** argv ) {
   const char *ref_fn = NULL, *frag_fn = NULL, *mat_fn = NULL, *root = "assembly.maln.iter";
   int circular = 0, k = -1, cons_code = 1, hard_cut = 0, final_only = 0, repeat_filt = 0, just_outer_coords = 1, i;
+  int score_cut_set = 0;
+  double user_slope = 200.0, user_icpt = 0.0;           /* DEF_S, DEF_N (params.h:36-37); -S / -N: mia_main.c:579-586 */
   for ( i = 1; i < argc; i++ ) {
     if ( !strcmp( argv[i], "-c" ) ) circular = 1;
     else if ( !strcmp( argv[i], "-F" ) ) final_only = 1;
@@ -136,8 +138,11 @@ int main( int argc, char** argv ) {
     else if ( i + 1 < argc && !strcmp( argv[i], "-k" ) ) k = atoi( argv[++i] );
     else if ( i + 1 < argc && !strcmp( argv[i], "-p" ) ) cons_code = atoi( argv[++i] );
     else if ( i + 1 < argc && !strcmp( argv[i], "-H" ) ) hard_cut = atoi( argv[++i] );
+    else if ( i + 1 < argc && !strcmp( argv[i], "-S" ) ) { user_slope = atof( argv[++i] ); score_cut_set = 1; }
+    else if ( i + 1 < argc && !strcmp( argv[i], "-N" ) ) { user_icpt = atof( argv[++i] ); score_cut_set = 1; }
     else { fprintf( stderr, "mia_gpu: option %s is not handled by this host (see the header of host/mia_gpu.c)\n", argv[i] ); return 2; }
   }
+  if ( repeat_filt && ( hard_cut > 0 || score_cut_set ) ) { fprintf( stderr, "mia_gpu: -H / -S / -N together with -u / -U are not handled by this host\n" ); return 2; }
   if ( !ref_fn || !frag_fn || !mat_fn ) {
     fprintf( stderr, "usage: mia_gpu -r ref.fa -f reads.fa|fq -s matrix.txt [-m root] [-c] [-k K] [-p code] [-H cut] [-F] [-u|-U] [-A]\n" );
     return 2;
@@ -214,7 +219,7 @@ int main( int argc, char** argv ) {
     for ( j = 0; j < m; j++ ) { F.qual[j] = qual_sum[src[j]]; F.split[j] = start[src[j]] > end[src[j]]; F.order[j] = j; }
     filter_and_cull( g, &F );
   }
-  else if ( hard_cut > 0 ) CK( miagpu_cull_flags( m, f_len, f_score, NULL, hard_cut, 0, 0.0, 0.0, dropped ) );
+  else if ( hard_cut > 0 || score_cut_set ) CK( miagpu_cull_flags( m, f_len, f_score, NULL, hard_cut, score_cut_set, user_slope, user_icpt, dropped ) );
   else {
     CK( miagpu_score_cut( m, f_len, f_score, NULL, &slope, &icpt ) );
     CK( miagpu_cull_flags( m, f_len, f_score, NULL, 0, 1, slope, icpt, dropped ) );
@@ -250,7 +255,7 @@ int main( int argc, char** argv ) {
       CK( miagpu_consensus_natural( g, F.df, F.db, cons_code, gaps, NULL, cons, &cons_len ) );
     }
     else {
-      CK( miagpu_iterate_resident( g, hard_cut, 0, 0.0, 0.0, cons_code, &slope, &icpt, dropped, gaps, cons, &cons_len ) );
+      CK( miagpu_iterate_resident( g, hard_cut, score_cut_set, user_slope, user_icpt, cons_code, &slope, &icpt, dropped, gaps, cons, &cons_len ) );
       CK( miagpu_adopt_alignment( g, f_score, f_as, f_ae ) );
     }
     cons[cons_len] = 0;

@@ -160,6 +160,7 @@ struct Seg {                  // one AlnSeq of the list
   int64_t read;
   int32_t start, end;
   int32_t col0, ncol;         // slice of the read's alignment columns
+  int32_t smp_n;              // characters of AlnSeq.smp: end - start + 1 (= ncol, except for a back segment whose read starts beyond seq_len)
   char seg;
   uint8_t dropped;
 };
@@ -319,10 +320,13 @@ extern "C" int miagpu_write_maln(const char* path, const miagpu_maln_header* hd,
       int nf = L - start;
       if (nf < 0) nf = 0;
       if (nf > ncol) nf = ncol;
-      segs.push_back({i, start, L - 1, 0, nf, 'f', (uint8_t)(df != 0)});
-      segs.push_back({i, 0, end, nf, ncol - nf, 'b', (uint8_t)(db != 0)});
+      // a read that starts beyond seq_len (as > L: the window rule can leave it there) gets a front AlnSeq of negative length and a
+      // back AlnSeq whose end - start + 1 exceeds its columns; pop_smp_from_FSDB and asp_len go by end - start + 1 (fsdb.c:518-530)
+      const int over = start > L ? start - L : 0;
+      segs.push_back({i, start, L - 1, 0, nf, nf, 'f', (uint8_t)(df != 0)});
+      segs.push_back({i, 0, end, nf, ncol - nf, ncol - nf + over, 'b', (uint8_t)(db != 0)});
     } else {
-      segs.push_back({i, start, end, 0, ncol, 'a', (uint8_t)(df != 0)});
+      segs.push_back({i, start, end, 0, ncol, ncol, 'a', (uint8_t)(df != 0)});
     }
   }
   std::vector<uint32_t> order(segs.size());
@@ -406,18 +410,25 @@ extern "C" int miagpu_write_maln(const char* path, const miagpu_maln_header* hd,
         int tot = (int)colc.size();
         int s0 = rd->as[i], e0 = rd->ae[i] > L ? rd->ae[i] - L : rd->ae[i];
         nfront = tot;
-        if (s0 > e0) { nfront = L - s0; if (nfront < 0) nfront = 0; if (nfront > tot) nfront = tot; }
-        front_total = nfront; back_total = tot - nfront;
+        int over = 0;                                                   // see the Seg list: as > L
+        front_total = tot; back_total = 0;
+        if (s0 > e0) {
+          nfront = L - s0; if (nfront < 0) nfront = 0; if (nfront > tot) nfront = tot;
+          over = s0 > L ? s0 - L : 0;
+          front_total = L - s0;                                         // end - start + 1 of the front AlnSeq: negative when as > L
+          back_total = tot - nfront + over;
+        }
         for (int c = 0; c < tot; c++) (c < nfront ? front_total : back_total) += ins_len[c];
-        // smp over front then back with one running position (fsdb.c:556-616)
-        smp.resize(colc.size());
+        // smp over front then back with one running position (fsdb.c:556-616); the `over` positions past the back AlnSeq's string
+        // are taken as the reference finds them after a fresh merge: no insert, not a '-'
+        smp.resize(colc.size() + (size_t)over);
         int act = 0;
-        for (int c = 0; c < tot; c++) {
-          act += ins_len[c];
+        for (int c = 0; c < tot + over; c++) {
+          if (c < tot) act += ins_len[c];
           int from_front = (c < nfront) ? act : front_total + act;      // fsdb.c:596: the back segment adds the front's length again
           int from_back = front_total + back_total - act - 1;
           smp[c] = smp_code(from_front, from_back);
-          if (colc[c] != '-') act++;
+          if (c >= tot || colc[c] != '-') act++;
         }
       }
       // id, with split_pwaln's suffix rule (mia.c:1389-1398)
@@ -439,7 +450,7 @@ extern "C" int miagpu_write_maln(const char* path, const miagpu_maln_header* hd,
       o.kv("DR ", sg.dropped);
       o.s("SEG "); o.ch(sg.seg); o.ch('\n');
       o.s("SEQ "); o.s(colc.data() + sg.col0, (size_t)sg.ncol); o.ch('\n');
-      o.s("SMP "); o.s(smp.data() + sg.col0, (size_t)sg.ncol); o.ch('\n');
+      o.s("SMP "); o.s(smp.data() + sg.col0, (size_t)sg.smp_n); o.ch('\n');
       o.s("INS_POS");
       for (int c = 0; c < sg.ncol; c++) {
         int g = sg.col0 + c;

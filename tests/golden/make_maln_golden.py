@@ -116,6 +116,10 @@ def main():
     bases, off, _ = synth.make_reads(genome, 400, 35, 75, seed=13, circular=True)
     fq = fastq_text(bases, off, 14)
     out["circ_k10"] = run_session("circ_k10", ref, fq, ["-c", "-k", "10", "-i"], "ancient.submat.txt")
+    # the user's score cuts (-H; -S / -N) and the second consensus rule (-p 2) on the same reads
+    out["circ_k10_H"] = run_session("circ_k10_H", ref, fq, ["-c", "-k", "10", "-i", "-H", "9000"], "ancient.submat.txt")
+    out["circ_k10_SN"] = run_session("circ_k10_SN", ref, fq, ["-c", "-k", "10", "-i", "-S", "190", "-N", "-400"], "ancient.submat.txt")
+    out["circ_k10_p2"] = run_session("circ_k10_p2", ref, fq, ["-c", "-k", "10", "-i", "-p", "2"], "ancient.submat.txt")
     bases, off, _ = synth.make_reads(genome, 300, 30, 140, seed=15, circular=False)
     fq = fastq_text(bases, off, 16)
     out["lin_pe"] = run_session("lin_pe", ref, fq, ["-i"], "ancient.submat.solexa.pe.txt")

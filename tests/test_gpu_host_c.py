@@ -15,7 +15,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 @pytest.mark.parametrize("name,matrix", [("circ_k10", "ancient"), ("lin_pe", "pe"), ("tr1_tf_lin", "ancient"), ("tr1_tf_lin_k8", "ancient"),
-                                         ("tr1_tf_c", "ancient"), ("dups_c_k10_u", "onepass"), ("dups_c_k10_U", "onepass")])
+                                         ("tr1_tf_c", "ancient"), ("dups_c_k10_u", "onepass"), ("dups_c_k10_U", "onepass"),
+                                         ("circ_k10_H", "ancient"), ("circ_k10_SN", "ancient"), ("circ_k10_p2", "ancient")])
 def test_c_host_writes_the_reference_maln_files(golden, name, matrix, tmp_path):
     s = json.load(gzip.open(os.path.join(HERE, "golden", "maln_session.json.gz"), "rt"))["sessions"][name]
     # tr1_tf_*: the reference's own fixtures test/tr1.fna + test/tf.fna (FASTA reads, a lower-case stretch, a 236-base read)
