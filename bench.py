@@ -484,7 +484,8 @@ def file_to_file(ref, orig, off, ref_sample=5000):
         out["program"] = {"reads": n, "rounds": rounds, "wall_s": t, "reads_per_s": n / t, "maln_mb": os.path.getsize(final) / 1e6,
                           "phases_ms": dict(zip(("init", "parse", "pass1", "rounds", "write", "total"), map(float, ph.groups()))) if ph else None,
                           "note": "host/mia_gpu -c -k 12 -F: process start to exit incl. CUDA context creation, FASTQ parse, pass 1, all rounds, "
-                                  "final .maln written to a tmpfs/overlay file"}
+                                  "final .maln written to a tmpfs/overlay file; context creation and first-use allocations vary run to run (0.5-3.7 s and "
+                                  "0.15-1.7 s observed), parse and write do not"}
         t_o, r_o = run([host, "-r", "ref.fa", "-f", "part.fq", "-m", "ours_part"] + flags)
         mia = os.path.join(root, "oracle", "_ref", "mia")
         if os.path.exists(mia) and r_o.returncode == 0:
