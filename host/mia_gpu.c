@@ -122,7 +122,7 @@ static void filter_and_cull( miagpu_ctx* g, Fsdb* F ) {
 int main( int argc, char** argv ) {
   const char *ref_fn = NULL, *frag_fn = NULL, *mat_fn = NULL, *root = "assembly.maln.iter";
   int circular = 0, k = -1, cons_code = 1, hard_cut = 0, final_only = 0, repeat_filt = 0, just_outer_coords = 1, i;
-  int score_cut_set = 0;
+  int score_cut_set = 0, drop_2000 = 0, n_2000 = 0;
   double user_slope = 200.0, user_icpt = 0.0;           /* DEF_S, DEF_N (params.h:36-37); -S / -N: mia_main.c:579-586 */
   for ( i = 1; i < argc; i++ ) {
     if ( !strcmp( argv[i], "-c" ) ) circular = 1;
@@ -130,6 +130,7 @@ int main( int argc, char** argv ) {
     else if ( !strcmp( argv[i], "-u" ) ) repeat_filt = 1;
     else if ( !strcmp( argv[i], "-U" ) ) repeat_filt = 2;
     else if ( !strcmp( argv[i], "-A" ) ) just_outer_coords = 0;
+    else if ( !strcmp( argv[i], "--drop-score-2000" ) ) drop_2000 = 1;   /* not a reference option: see the accept test below */
     else if ( !strcmp( argv[i], "-i" ) ) ;
     else if ( i + 1 < argc && !strcmp( argv[i], "-r" ) ) ref_fn = argv[++i];
     else if ( i + 1 < argc && !strcmp( argv[i], "-f" ) ) frag_fn = argv[++i];
@@ -184,7 +185,13 @@ int main( int argc, char** argv ) {
   for ( j = 0; j < n; j++ ) {
     keep[j] = ( hits[j] > 0 && score[j] >= FIRST_ROUND_SCORE_CUTOFF );
     if ( !keep[j] ) continue;
-    if ( score[j] == FIRST_ROUND_SCORE_CUTOFF ) { fprintf( stderr, "mia_gpu: a read scores exactly 2000 (strand_known = 0): not handled\n" ); return 3; }
+    if ( score[j] == FIRST_ROUND_SCORE_CUTOFF ) {
+      /* the reference accepts the read with strand_known = 0 (mia.c:1653), never realigns it (mia_main.c:178) and keeps following
+         its pass-1 AlnSeq pointer, which from round 1 on is another read's slot: refused, or left out on request */
+      if ( !drop_2000 ) { fprintf( stderr, "mia_gpu: a read scores exactly 2000 (strand_known = 0): not handled (--drop-score-2000 leaves such reads out)\n" ); return 3; }
+      keep[j] = 0; n_2000++;
+      continue;
+    }
     maln_size += 1 + ( start[j] > end[j] );
     src[m++] = j;
   }
@@ -231,6 +238,7 @@ int main( int argc, char** argv ) {
   CK( miagpu_set_cut_inputs( g, f_len, NULL, dropped ) );
   miagpu_fastx_close( fx );
   fprintf( stderr, "mia_gpu: %lld reads read, %lld aligned in pass 1\n", (long long)n, (long long)m );
+  if ( n_2000 ) fprintf( stderr, "mia_gpu: %d reads scoring exactly 2000 left out (--drop-score-2000)\n", n_2000 );
   t_pass1 = now_ms() - t0 - t_init - t_parse;
 
   /* ---- rounds (mia_main.c:878-976): one library call each */
