@@ -19,8 +19,8 @@ with tempfile.TemporaryDirectory() as d:
     open(os.path.join(d, "ref.fa"), "w").write(">ref synthetic\n" + ref + "\n")
     open(os.path.join(d, "m.txt"), "w").write(synth.matrix_text(bench.load_pssm()))
     open(os.path.join(d, "all.fq"), "wb").write(synth.fastq_text(orig, off))
-    for rep in range(3):
+    for rep in range(int(os.environ.get("REPS", "3"))):
         t0 = time.perf_counter()
-        r = subprocess.run([os.path.join(ROOT, "host", "mia_gpu"), "-r", "ref.fa", "-f", "all.fq", "-s", "m.txt", "-m", "out", "-c", "-k", "12", "-F"],
+        r = subprocess.run([os.path.join(ROOT, "host", "mia_gpu"), "-r", "ref.fa", "-f", "all.fq", "-s", "m.txt", "-m", "out", "-c", "-k", "12", "-F", "--drop-score-2000"],
                            cwd=d, capture_output=True, text=True)
-        print("run", rep, "wall_s %.3f" % (time.perf_counter() - t0), [l for l in r.stderr.split("\n") if "timing" in l or "convergence" in l])
+        print("run", rep, "reads", n, "wall_s %.3f" % (time.perf_counter() - t0), "fastq_mb %.0f" % (os.path.getsize(os.path.join(d, "all.fq")) / 1e6), "maln_mb", [round(os.path.getsize(os.path.join(d, f)) / 1e6) for f in os.listdir(d) if f.startswith("out.")], [l for l in r.stderr.split("\n") if "timing" in l or "convergence" in l or "left out" in l])
