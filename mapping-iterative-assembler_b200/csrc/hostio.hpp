@@ -156,6 +156,8 @@ struct Out {
   void kv(const char* k, long v) { s(k); i(v); ch('\n'); }
 };
 
+inline double wall_ms() { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec * 1e3 + t.tv_nsec * 1e-6; }
+
 struct Seg {                  // one AlnSeq of the list
   int64_t read;
   int32_t start, end;
@@ -329,13 +331,34 @@ extern "C" int miagpu_write_maln(const char* path, const miagpu_maln_header* hd,
       segs.push_back({i, start, end, 0, ncol, ncol, 'a', (uint8_t)(df != 0)});
     }
   }
+  const bool trace = getenv("MIAGPU_TRACE") != nullptr;
+  double t_a = wall_ms(), t_b, t_fmt = 0, t_wr = 0;
   std::vector<uint32_t> order(segs.size());
   for (size_t k = 0; k < order.size(); k++) order[k] = (uint32_t)k;
-  std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
-    if (segs[a].start != segs[b].start) return segs[a].start < segs[b].start;
-    return segs[a].end < segs[b].end;
-  });
+  // sort_aln_frags: stable by (start, end).  Keys are reference columns, so two stable counting passes (end, then start) do it in
+  // O(n); anything outside [0, L + 2 * 256] (cannot come out of the window rule) takes the comparison sort instead.
+  {
+    const int32_t KMAX = L + 2 * kMaxRead + 2;
+    bool small = true;
+    for (const Seg& sg : segs) if (sg.start < 0 || sg.start >= KMAX || sg.end < 0 || sg.end >= KMAX) { small = false; break; }
+    if (small && segs.size() > 4096) {
+      std::vector<uint32_t> tmp(order.size()), cnt((size_t)KMAX + 1);
+      for (int pass = 0; pass < 2; pass++) {
+        std::fill(cnt.begin(), cnt.end(), 0u);
+        for (uint32_t k : order) cnt[(size_t)(pass ? segs[k].start : segs[k].end) + 1]++;
+        for (size_t v = 1; v < cnt.size(); v++) cnt[v] += cnt[v - 1];
+        for (uint32_t k : order) tmp[cnt[(size_t)(pass ? segs[k].start : segs[k].end)]++] = k;
+        order.swap(tmp);
+      }
+    } else {
+      std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+        if (segs[a].start != segs[b].start) return segs[a].start < segs[b].start;
+        return segs[a].end < segs[b].end;
+      });
+    }
+  }
 
+  t_b = wall_ms();
   FILE* f = fopen(path, "w");
   if (!f) { set_error("miagpu_write_maln: cannot open %s for writing", path); return 0; }
   Out o(f);
@@ -461,22 +484,37 @@ extern "C" int miagpu_write_maln(const char* path, const miagpu_maln_header* hd,
   };
   const size_t total = order.size();
   unsigned hw = std::thread::hardware_concurrency();
-  size_t T = std::max<size_t>(1, std::min<size_t>({(size_t)(hw ? hw : 1), (size_t)16, (total + 1023) / 1024}));
-  if (const char* e = getenv("MIAGPU_MALN_THREADS")) T = std::max(1, atoi(e));              // tests: 1 = everything on the caller's thread
-  const size_t per = std::max<size_t>(1, std::min<size_t>(32768, (total + T - 1) / T));
+  size_t T = std::max<size_t>(1, std::min<size_t>({(size_t)(hw ? hw : 1), (size_t)32, (total + 1023) / 1024}));
+  if (const char* e = getenv("MIAGPU_MALN_THREADS")) T = std::max(1, atoi(e));              // tests: 1 = one worker
+  const size_t per = std::max<size_t>(1, std::min<size_t>(16384, (total + T - 1) / T));
   o.flush();
-  std::vector<Out> bufs;
-  for (size_t t = 0; t < T; t++) bufs.emplace_back((FILE*)nullptr);
-  for (size_t base = 0; base < total && bad_read.load() < 0; base += T * per) {
-    std::vector<std::thread> th;
+  // two sets of buffers: the workers format wave k + 1 while this thread writes wave k
+  std::vector<Out> bufs[2];
+  for (int w = 0; w < 2; w++) for (size_t t = 0; t < T; t++) bufs[w].emplace_back((FILE*)nullptr);
+  auto launch = [&](size_t base, int w, std::vector<std::thread>& th) {
     for (size_t t = 0; t < T; t++) {
       size_t lo = std::min(total, base + t * per), hi = std::min(total, lo + per);
-      bufs[t].b.clear();
-      if (lo < hi) th.emplace_back(format_range, lo, hi, std::ref(bufs[t]));
+      bufs[w][t].b.clear();
+      if (lo < hi) th.emplace_back(format_range, lo, hi, std::ref(bufs[w][t]));
     }
-    for (auto& x : th) x.join();
-    for (size_t t = 0; t < T; t++) if (!bufs[t].b.empty()) fwrite(bufs[t].b.data(), 1, bufs[t].b.size(), f);
+  };
+  std::vector<std::thread> th_cur, th_next;
+  int cur = 0;
+  if (total) launch(0, 0, th_cur);
+  for (size_t base = 0; base < total; base += T * per) {
+    const size_t next = base + T * per;
+    if (next < total && bad_read.load() < 0) launch(next, cur ^ 1, th_next);
+    const double t0 = wall_ms();
+    for (auto& x : th_cur) x.join();
+    const double t1 = wall_ms();
+    for (size_t t = 0; t < T; t++) if (!bufs[cur][t].b.empty()) fwrite(bufs[cur][t].b.data(), 1, bufs[cur][t].b.size(), f);
+    t_fmt += t1 - t0; t_wr += wall_ms() - t1;
+    th_cur.clear();
+    th_cur.swap(th_next);
+    cur ^= 1;
+    if (th_cur.empty()) break;
   }
+  if (trace) fprintf(stderr, "[miagpu trace] write_maln: sort %.1f ms, waiting for the formatters (%zu threads) %.1f ms, fwrite %.1f ms\n", t_b - t_a, T, t_fmt, t_wr);
   if (bad_read.load() >= 0) {
     fclose(f);
     set_error("miagpu_write_maln: the runs of read %lld overrun its bases", bad_read.load());
