@@ -54,6 +54,8 @@ struct Fastx {
   int format = 0;            // 0 fasta, 1 fastq (find_input_type io.c:11-25)
   bool done = false;
   int last_qual_sum = 0;     // FragSeq is reused by the caller's loop: a record without '+' keeps the previous sum
+  bool qs_set = false;       // (parallel parse) a quality line was read since this cursor started ...
+  bool used_stale = false;   // ... and whether a record took last_qual_sum from before that
   // current batch
   std::vector<uint8_t> bases;
   std::vector<int64_t> off;
@@ -108,12 +110,17 @@ struct Fastx {
     while (c != '\n' && c != -1 && sn < kMaxRead) { if (!c_space(c)) seq[sn++] = (unsigned char)c_upper(c); c = get(); }
     if (sn == kMaxRead) while (c != '\n' && c != -1) c = get();
     c = get();
-    if (c != '+') { push(id, idn, desc, dn, seq, sn, last_qual_sum); return 1; }   // io.c:121-124: accepted as it is
+    if (c != '+') {                                                                // io.c:121-124: accepted as it is
+      if (!qs_set) used_stale = true;
+      push(id, idn, desc, dn, seq, sn, last_qual_sum);
+      return 1;
+    }
     do c = get(); while (c != '\n' && c != -1);
     c = get();
     int qn = 0, qs = 0;
     while (c != '\n' && c != -1 && qn < kMaxRead) { if (!c_space(c)) { qs += c - 33; qn++; } c = get(); }
     last_qual_sum = qs;
+    qs_set = true;
     if (qn == kMaxRead) while (c != '\n' && c != -1) c = get();
     if (qn != sn) return 0;                                                        // io.c:162-166
     push(id, idn, desc, dn, seq, sn, qs);
@@ -219,11 +226,88 @@ extern "C" void miagpu_fastx_close(miagpu_fastx* h) {
 
 extern "C" int miagpu_fastx_format(miagpu_fastx* h) { return h ? h->x.format : -1; }
 
+// Speculative parallel parse of everything that is left (taken when max_reads cannot bind): the rest of the buffer is cut at guessed
+// record starts, every piece is parsed by its own cursor until it reaches or passes the next cut, and a piece is KEPT only if the
+// cursor before it stopped exactly on its cut without having ended the input and the piece did not need the previous record's
+// quality sum (a record without '+', io.c:121-124) -- i.e. only if the reference's sequential loop would have stood at that
+// byte in the same state.  The first piece that fails is parsed again, sequentially, from where the kept cursors ended.
+static void fastx_parallel(hostio::Fastx& x, size_t T) {
+  using hostio::Fastx;
+  const size_t begin = x.pos, end = x.len;
+  std::vector<size_t> cut(T + 1, end);
+  cut[0] = begin;
+  const char mark = x.format ? '@' : '>';
+  for (size_t t = 1; t < T; t++) {
+    size_t g = begin + (end - begin) / T * t;
+    if (g <= cut[t - 1]) g = cut[t - 1] + 1;
+    // a line that starts with the record mark; for FASTQ the line after next must start with '+' (a quality line may start with '@')
+    size_t p = g;
+    while (p < end) {
+      const unsigned char* nl = (const unsigned char*)memchr(x.buf + p, '\n', end - p);
+      if (!nl) { p = end; break; }
+      p = (size_t)(nl - x.buf) + 1;
+      if (p < end && x.buf[p] == (unsigned char)mark) {
+        if (!x.format) break;
+        const unsigned char* l2 = (const unsigned char*)memchr(x.buf + p, '\n', end - p);
+        const unsigned char* l3 = l2 ? (const unsigned char*)memchr(l2 + 1, '\n', end - (size_t)(l2 + 1 - x.buf)) : nullptr;
+        if (l3 && (size_t)(l3 + 1 - x.buf) < end && l3[1] == '+') break;
+      }
+    }
+    cut[t] = p;
+  }
+  std::vector<Fastx> part(T);
+  std::vector<std::thread> th;
+  for (size_t t = 0; t < T; t++) {
+    Fastx& c = part[t];
+    c.buf = x.buf; c.len = x.len; c.pos = cut[t]; c.format = x.format; c.last_qual_sum = t ? 0 : x.last_qual_sum; c.qs_set = t == 0;
+    c.clear_batch();
+    if (cut[t] >= end && t) continue;
+    th.emplace_back([&c, stop = cut[t + 1]]() {
+      while (!c.done && c.pos < stop) if (!(c.format ? c.next_fastq() : c.next_fasta())) c.done = true;
+    });
+  }
+  for (auto& t : th) t.join();
+  // keep the prefix of pieces the sequential loop would have produced
+  size_t kept = 1;
+  while (kept < T && !part[kept - 1].done && part[kept - 1].pos == cut[kept] && cut[kept] < end && !part[kept].used_stale) kept++;
+  {
+    size_t nb = x.bases.size(), ni = x.ids.size(), nd = x.descs.size(), nr = x.qual_sum.size();
+    for (size_t t = 0; t < kept; t++) { nb += part[t].bases.size(); ni += part[t].ids.size(); nd += part[t].descs.size(); nr += part[t].qual_sum.size(); }
+    x.bases.reserve(nb); x.ids.reserve(ni); x.descs.reserve(nd); x.qual_sum.reserve(nr);
+    x.off.reserve(nr + 1); x.id_off.reserve(nr + 1); x.desc_off.reserve(nr + 1);
+  }
+  for (size_t t = 0; t < kept; t++) {
+    Fastx& c = part[t];
+    const int64_t b0 = (int64_t)x.bases.size(), i0 = (int64_t)x.ids.size(), d0 = (int64_t)x.descs.size();
+    x.bases.insert(x.bases.end(), c.bases.begin(), c.bases.end());
+    x.ids.insert(x.ids.end(), c.ids.begin(), c.ids.end());
+    x.descs.insert(x.descs.end(), c.descs.begin(), c.descs.end());
+    x.qual_sum.insert(x.qual_sum.end(), c.qual_sum.begin(), c.qual_sum.end());
+    for (size_t k = 1; k < c.off.size(); k++) { x.off.push_back(c.off[k] + b0); x.id_off.push_back(c.id_off[k] + i0); x.desc_off.push_back(c.desc_off[k] + d0); }
+    x.records_total += c.records_total;
+  }
+  if (getenv("MIAGPU_TRACE")) fprintf(stderr, "[miagpu trace] fastx: %zu pieces parsed in parallel, %zu kept\n", T, kept);
+  const Fastx& last = part[kept - 1];
+  x.pos = last.pos; x.done = last.done;
+  if (last.qs_set) x.last_qual_sum = last.last_qual_sum;
+  for (size_t t = kept - 1; t > 0 && !last.qs_set; t--) if (part[t - 1].qs_set) { x.last_qual_sum = part[t - 1].last_qual_sum; break; }
+}
+
 extern "C" int miagpu_fastx_next(miagpu_fastx* h, int64_t max_reads, int64_t* n_out) {
   if (!h || !n_out || max_reads < 0) { set_error("miagpu_fastx_next: bad argument"); return 0; }
   hostio::Fastx& x = h->x;
   x.clear_batch();
   int64_t n = 0;
+  {
+    const size_t left = x.pos < x.len ? x.len - x.pos : 0;
+    size_t par_min = (size_t)8 << 20, T = std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), 16);
+    if (const char* e = getenv("MIAGPU_FASTX_PAR_MIN")) par_min = (size_t)atoll(e);        // tests: 1 = always
+    if (const char* e = getenv("MIAGPU_FASTX_THREADS")) T = (size_t)std::max(1, atoi(e));
+    if (!x.done && T > 1 && left >= par_min && left > 4 * T && (uint64_t)max_reads >= left / 6 + 1) {   // a record takes at least 6 bytes
+      fastx_parallel(x, T);
+      n = (int64_t)x.qual_sum.size();
+    }
+  }
   while (!x.done && n < max_reads) {
     int r = x.format ? x.next_fastq() : x.next_fasta();
     if (!r) { x.done = true; break; }
