@@ -210,7 +210,8 @@ int main( int argc, char** argv ) {
   char *f_ids = xmalloc( (size_t)f_id_off[m] + 1 ), *f_descs = xmalloc( (size_t)f_desc_off[m] + 1 );
   for ( j = 0; j < m; j++ ) {
     int64_t q = src[j], L = f_len[j], t;
-    for ( t = 0; t < L; t++ ) stored[s_off[j] + t] = f_rc[j] ? comp[bases[off[q] + L - 1 - t]] : bases[off[q] + t];
+    if ( !f_rc[j] ) memcpy( stored + s_off[j], bases + off[q], (size_t)L );
+    else for ( t = 0; t < L; t++ ) stored[s_off[j] + t] = comp[bases[off[q] + L - 1 - t]];
     memcpy( f_ids + f_id_off[j], ids + id_off[q], (size_t)( id_off[q + 1] - id_off[q] ) );
     memcpy( f_descs + f_desc_off[j], descs + desc_off[q], (size_t)( desc_off[q + 1] - desc_off[q] ) );
   }
