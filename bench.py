@@ -468,7 +468,10 @@ def file_to_file(ref, orig, off, ref_sample=5000):
             L.miagpu_fastx_next(h, 1 << 40, C.byref(cnt))
             t = time.perf_counter() - t0
             L.miagpu_fastx_close(h)
-        out["reader"] = {"reads": cnt.value, "file_mb": fq_bytes / 1e6, "wall_ms": t * 1e3, "mb_per_s": fq_bytes / 1e6 / t, "reads_per_s": cnt.value / t}
+        out["reader"] = {"reads": cnt.value, "file_mb": fq_bytes / 1e6, "wall_ms": t * 1e3, "mb_per_s": fq_bytes / 1e6 / t, "reads_per_s": cnt.value / t,
+                         "cursors": min(os.cpu_count() or 1, 16),
+                         "note": "miagpu_fastx_open + _next over the whole file, page cache warm; above 8 MB the file is parsed by several cursors "
+                                 "at once, pieces kept only where the one-cursor parse would have stood in the same state"}
 
         def run(cmd):
             t0 = time.perf_counter()
