@@ -248,6 +248,7 @@ int main( int argc, char** argv ) {
   int32_t* gaps = xmalloc( cons_cap * 4 );
   int64_t *run_off = xmalloc( ( m + 1 ) * 8 ), total = 0, cap = 0, n_aln = 0;
   uint16_t* packed = NULL;
+  uint8_t* st = xmalloc( m );
   int iter = 0, converged = 0;
   for ( j = 0; j < ref_len; j++ ) last[j] = (char)toupper( (unsigned char)ref[j] );      /* make_ref_upper mia.c:642-648 */
   last[ref_len] = 0;
@@ -274,7 +275,12 @@ int main( int argc, char** argv ) {
     if ( !final_only || converged || iter == MAX_ITER ) {
       miagpu_maln_header hd;
       miagpu_maln_reads rd;
-      CK( miagpu_get_alignment( g, NULL, NULL, NULL, abr, NULL, NULL ) );
+      CK( miagpu_get_alignment( g, NULL, NULL, NULL, abr, NULL, st ) );
+      for ( j = 0; j < m; j++ )
+        if ( st[j] != MIAGPU_ST_OK ) {          /* e.g. more runs than MIAGPU_MAX_RUNS: never written as if it were fine */
+          fprintf( stderr, "mia_gpu: read %lld came back with status 0x%x in iteration %d\n", (long long)src[j], st[j], iter );
+          return 4;
+        }
       CK( miagpu_get_runs_packed( g, NULL, NULL, 0, &total ) );
       if ( total > cap ) { free( packed ); cap = total + total / 4 + 16; packed = xmalloc( (size_t)cap * 2 ); }
       CK( miagpu_get_runs_packed( g, run_off, packed, cap, &total ) );

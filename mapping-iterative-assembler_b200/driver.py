@@ -307,6 +307,8 @@ class ResidentAssembler:
         from .synth import revcomp_bytes
         g = self.g
         al = g.get_alignment()
+        if (al["status"] != 0).any():
+            raise api.MiaGpuError(f"status bits set on {(al['status'] != 0).sum()} reads: not written as if they were fine")
         tot, _, _ = g.get_runs_packed()
         run_off, packed = np.zeros(len(self.rc) + 1, np.int64), np.zeros(max(tot, 1), np.uint16)
         g.get_runs_packed(run_off, packed)
@@ -450,6 +452,8 @@ class RepeatFilterAssembler:
         from .synth import revcomp_bytes
         g, fo = self.g, self.order
         al = g.get_alignment()
+        if (al["status"] != 0).any():
+            raise api.MiaGpuError(f"status bits set on {(al['status'] != 0).sum()} reads: not written as if they were fine")
         tot, _, _ = g.get_runs_packed()
         run_off, packed = np.zeros(len(self.rc) + 1, np.int64), np.zeros(max(tot, 1), np.uint16)
         g.get_runs_packed(run_off, packed)
