@@ -76,3 +76,25 @@ def test_c_host_has_no_cpu_fallback(golden, tmp_path):
     r = subprocess.run([HOST, "-r", "r.fa", "-f", "q.fq", "-s", "m.txt", "-m", "out"], cwd=tmp_path, capture_output=True, text=True)
     assert r.returncode == 1 and "no CUDA device" in r.stderr and "no CPU fallback" in r.stderr
     assert not os.path.exists(tmp_path / "out.1")
+
+
+def test_c_host_argument_errors(golden, tmp_path):
+    # what the host refuses, it refuses before touching the GPU: reference options it does not carry, missing files
+    ensure_host()
+    run = lambda *a: subprocess.run([HOST] + list(a), cwd=tmp_path, capture_output=True, text=True)
+    r = run()
+    assert r.returncode == 2 and "usage: mia_gpu" in r.stderr
+    for opt in ("-D", "-T", "-h", "-C3", "-I"):
+        r = run("-r", "r.fa", "-f", "q.fq", "-s", "m.txt", opt)
+        assert r.returncode == 2 and "not handled by this host" in r.stderr, opt
+    r = run("-r", "r.fa", "-f", "q.fq", "-s", "m.txt", "-u", "-H", "3000")
+    assert r.returncode == 2 and "-u / -U" in r.stderr
+    (tmp_path / "r.fa").write_text(">r\nACGTACGTACGTACGTACGT\n")
+    (tmp_path / "q.fq").write_text("@a\nACGTACGTAC\n+\nIIIIIIIIII\n")
+    r = run("-r", "r.fa", "-f", "q.fq", "-s", "none.txt")
+    assert r.returncode == 1 and "miagpu_read_pssm" in r.stderr and "cannot open" in r.stderr
+    (tmp_path / "m.txt").write_text(matrix_text(golden["ancient"]).replace("MIDDLE", "16"))
+    r = run("-r", "r.fa", "-f", "q.fq", "-s", "m.txt")
+    assert r.returncode == 1 and "MIDDLE" in r.stderr
+    r = run("-r", "missing.fa", "-f", "q.fq", "-s", "m.txt")
+    assert r.returncode == 1 and "cannot read reference" in r.stderr
