@@ -303,7 +303,7 @@ extern "C" int miagpu_fastx_next(miagpu_fastx* h, int64_t max_reads, int64_t* n_
     size_t par_min = (size_t)8 << 20, T = std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), 16);
     if (const char* e = getenv("MIAGPU_FASTX_PAR_MIN")) par_min = (size_t)atoll(e);        // tests: 1 = always
     if (const char* e = getenv("MIAGPU_FASTX_THREADS")) T = (size_t)std::max(1, atoi(e));
-    if (!x.done && T > 1 && left >= par_min && left > 4 * T && (uint64_t)max_reads >= left / 6 + 1) {   // a record takes at least 6 bytes
+    if (!x.done && T > 1 && left >= par_min && left > 4 * T && (uint64_t)max_reads >= left / 2 + 1) {   // cannot bind: a record takes at least 2 bytes (">\n")
       fastx_parallel(x, T);
       n = (int64_t)x.qual_sum.size();
     }
