@@ -568,6 +568,23 @@ void orc_asm_cull( orc_asm* a, long long n_reads, const int* front, const int* b
 void orc_asm_cull_u( orc_asm* a, long long n_reads, const int* front, const int* back,
                      const int* seq_len, const int* score, const unsigned char* unique_best,
                      int hard_cut, int score_cut_set, double s, double n ) {
+  orc_asm_cull_d( a, n_reads, front, back, seq_len, score, unique_best, NULL, hard_cut, score_cut_set, s, n );
+}
+
+/* find_alignable_len, mia.c:69-91: the read's length minus the N positions of ref[as, min(ae, wrap_len)), at least
+ * MIN_ALIGNABLE_LEN = 15 (params.h:38) */
+int orc_alignable_len( const char* ref_wrapped, int wrap_len, int seq_len, int as, int ae ) {
+  int n = seq_len;
+  long long end = ae;
+  if ( end > wrap_len ) end = wrap_len;
+  for ( long long i = as; i < end; i++ ) if ( ref_wrapped[i] == 'N' ) n--;
+  return n < 15 ? 15 : n;
+}
+
+/* -D: the threshold of a read takes alignable_len[r] (mia.c:460-463); the regression still runs over seq_len */
+void orc_asm_cull_d( orc_asm* a, long long n_reads, const int* front, const int* back,
+                     const int* seq_len, const int* score, const unsigned char* unique_best,
+                     const int* alignable_len, int hard_cut, int score_cut_set, double s, double n ) {
   double slope, intercept;
   if ( score_cut_set ) { slope = s; intercept = n; }
   else orc_score_cut( n_reads, seq_len, score, unique_best, &slope, &intercept );
@@ -576,7 +593,7 @@ void orc_asm_cull_u( orc_asm* a, long long n_reads, const int* front, const int*
   for ( long long r = 0; r < n_reads; r++ ) {
     if ( front[r] < 0 ) continue;
     if ( unique_best && !unique_best[r] ) continue;   /* mia.c:466: not in the culled list at all */
-    double min_score = hard_cut > 0 ? (double)hard_cut : (double)( intercept + ( slope * seq_len[r] ) );
+    double min_score = hard_cut > 0 ? (double)hard_cut : (double)( intercept + ( slope * ( alignable_len ? alignable_len[r] : seq_len[r] ) ) );
     int drop = ( score[r] < min_score );
     int ids[2] = { front[r], back[r] };
     for ( int q = 0; q < 2; q++ ) {

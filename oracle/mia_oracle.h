@@ -113,6 +113,12 @@ void orc_asm_cull_u( orc_asm* a, long long n_reads, const int* front,
                      const int* back, const int* seq_len, const int* score,
                      const unsigned char* unique_best, int hard_cut,
                      int score_cut_set, double slope, double intercept );
+/* -D (maln->distant_ref): find_alignable_len (mia.c:69-91) and the cull whose per-read threshold takes it (mia.c:460-463) */
+int  orc_alignable_len( const char* ref_wrapped, int wrap_len, int seq_len, int as, int ae );
+void orc_asm_cull_d( orc_asm* a, long long n_reads, const int* front,
+                     const int* back, const int* seq_len, const int* score,
+                     const unsigned char* unique_best, const int* alignable_len,
+                     int hard_cut, int score_cut_set, double slope, double intercept );
 /* a13: mia.c:515-603 over the culled entry list.  cons must hold
  * seq_len + sum(gaps) + 1 chars.  counts (nullable): 10 ints per base column:
  * As,Cs,Gs,Ts,gaps,cov,sA,sC,sG,sT */

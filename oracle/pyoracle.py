@@ -237,17 +237,24 @@ class Oracle(_AlignMixin):
         self.lib.orc_score_cut(len(sl), _ip(sl), _ip(sc), None, C.byref(s), C.byref(n))
         return s.value, n.value
 
-    def asm_cull(self, a, front, back, seq_len, score, hard_cut=0, score_cut_set=0, slope=200.0, intercept=0.0, unique_best=None):
+    def asm_cull(self, a, front, back, seq_len, score, hard_cut=0, score_cut_set=0, slope=200.0, intercept=0.0, unique_best=None,
+                 alignable_len=None):
+        """cull_maln_from_fsdb; alignable_len (per read, -D): the length the threshold takes (find_alignable_len)"""
         f, b = np.ascontiguousarray(front, np.int32), np.ascontiguousarray(back, np.int32)
         sl, sc = np.ascontiguousarray(seq_len, np.int32), np.ascontiguousarray(score, np.int32)
-        if unique_best is None:
-            self.lib.orc_asm_cull(a, len(sl), _ip(f), _ip(b), _ip(sl), _ip(sc), hard_cut, score_cut_set, slope, intercept)
-            return
-        uq = np.ascontiguousarray(unique_best, np.uint8)
-        fn = self.lib.orc_asm_cull_u
-        fn.argtypes = [C.c_void_p, C.c_longlong] + [C.c_void_p] * 5 + [C.c_int, C.c_int, C.c_double, C.c_double]
+        uq = None if unique_best is None else np.ascontiguousarray(unique_best, np.uint8)
+        al = None if alignable_len is None else np.ascontiguousarray(alignable_len, np.int32)
+        fn = self.lib.orc_asm_cull_d
+        fn.argtypes = [C.c_void_p, C.c_longlong] + [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_double, C.c_double]
         fn.restype = None
-        fn(a, len(sl), f.ctypes.data, b.ctypes.data, sl.ctypes.data, sc.ctypes.data, uq.ctypes.data, hard_cut, score_cut_set, slope, intercept)
+        fn(a, len(sl), f.ctypes.data, b.ctypes.data, sl.ctypes.data, sc.ctypes.data, None if uq is None else uq.ctypes.data,
+           None if al is None else al.ctypes.data, hard_cut, score_cut_set, slope, intercept)
+
+    def alignable_len(self, ref_wrapped, seq_len, as_, ae):
+        fn = self.lib.orc_alignable_len
+        fn.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        rw = _b(ref_wrapped)
+        return fn(rw, len(rw), seq_len, as_, ae)
 
     def asm_consensus(self, a, sm_fwd, sm_rc, cons_code, seq_len, max_extra=1 << 20, counts=False):
         buf = C.create_string_buffer(seq_len + max_extra + 1)

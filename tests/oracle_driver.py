@@ -17,6 +17,8 @@ class OracleRun:
         self.fsdb = []
         self.iter = 0
         self.cons = None
+        self.distant_ref = distant_ref
+        self.submat_rc = 0            # which matrix a->submat was left pointing at (H6: mia_main.c:126-137 never sets it)
 
     def pass1(self, read, want_masks=False, qual_sum=0):
         p = self.o.pass1(self.ctx, read, want_masks)
@@ -44,12 +46,18 @@ class OracleRun:
         self.fsdb = [self.fsdb[k] for k in order]
         return np.array([f["unique_best"] for f in self.fsdb], np.uint8)
 
+    def _alignable(self, ref_wrapped):
+        """-D: find_alignable_len of every read against the current (wrapped) reference (mia.c:460-463)"""
+        if not self.distant_ref:
+            return None
+        return np.array([self.o.alignable_len(ref_wrapped, f["seq_len"], f["as_"], f["ae"]) for f in self.fsdb], np.int32)
+
     def end_pass1(self):
         fr, bk, sl, sc = self._arrays()
         self.o.asm_pop_smp(self.asm, fr, bk)
         uq = self._repeat_filter()
         fr, bk, sl, sc = self._arrays()
-        self.o.asm_cull(self.asm, fr, bk, sl, sc, unique_best=uq)
+        self.o.asm_cull(self.asm, fr, bk, sl, sc, unique_best=uq, alignable_len=self._alignable(self.o.ctx_seq(self.ctx)))
         self.fsdb = [f for f in self.fsdb if f["score"] > 0]                             # clean_FSDB mia.c:400-406
         self.iter = 1
         self.last = self.cur_ref
@@ -64,20 +72,32 @@ class OracleRun:
         self.seq_len = len(ref)
         self.wrap_len = o.lib.orc_ctx_wrap_len(ctx)
         o.asm_begin_round(self.asm, self.seq_len, self.wrap_len)
+        ref_w = o.ctx_seq(ctx)
         for f in self.fsdb:
+            if self.distant_ref and not f["strand_known"] and self.iter > 1:        # mia_main.c:120-174
+                a = o.align(ref_w, f["seq"], self.smr if self.submat_rc else self.sm, 1)       # whatever matrix the last read left (H6)
+                if a["score"] > 2000:
+                    f["strand_known"], f["rc"], f["as_"], f["ae"], f["score"] = 1, 0, a["abc"], a["aec"], a["score"]
+                rcs = o.revcom(f["seq"])
+                self.submat_rc = 1                                                  # mia_main.c:151
+                a = o.align(ref_w, rcs, self.smr, 1)
+                if a["score"] > 2000 and a["score"] > f["score"]:
+                    f["strand_known"], f["rc"], f["as_"], f["ae"], f["score"], f["seq"] = 1, 1, a["abc"], a["aec"], a["score"], rcs
             if not f["strand_known"]:
                 continue
+            self.submat_rc = 1 if f["rc"] else 0                                    # mia_main.c:179-184
             r = o.realign(ctx, f["seq"], f["rc"], f["as_"], f["ae"])
             f["as_"], f["ae"], f["score"], f["unique_best"] = r["as_"], r["ae"], r["score"], 1          # mia_main.c:254
             fs, bs = o.asm_add(self.asm, r["ref_gapped"], r["read_gapped"], r["as_"], r["ae"], f["rc"], r["score"])
             f["front"] = fs
             if bs is not None:
                 f["back"] = bs          # otherwise the old back slot id stays: mia_main.c:273-276
+        al = self._alignable(ref_w)
         o.ctx_free(ctx)
         fr, bk, sl, sc = self._arrays()
         o.asm_pop_smp(self.asm, fr, bk)
         uq = self._repeat_filter()
         fr, bk, sl, sc = self._arrays()
-        o.asm_cull(self.asm, fr, bk, sl, sc, unique_best=uq)
+        o.asm_cull(self.asm, fr, bk, sl, sc, unique_best=uq, alignable_len=al)
         self.cons = o.asm_consensus(self.asm, self.sm, self.smr, self.cons_code, self.seq_len)
         return self.cons, self.cons == self.last

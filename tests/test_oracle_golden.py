@@ -5,6 +5,7 @@ import json
 import os
 
 import numpy as np
+import pytest
 
 from oracle_driver import OracleRun
 
@@ -128,3 +129,49 @@ def test_trim_matches_reference_golden(oracle):
     for i, c in enumerate(cases):
         t = oracle.trim(c["read"], c["adapter"])
         assert [t[k] for k in ("trimmed", "trim_point", "score", "abr", "abc", "aer")] == c["out"], (i, c["read"])
+
+
+# ---- round 2: the reference's FragSeq -> AlnSeq pointer behaviour (tests/golden/make_golden_r2.py)
+def _load_r2(name):
+    import gzip
+    return json.load(gzip.open(os.path.join(G, "sessions_r2.json.gz"), "rt"))[name]
+
+
+def _run_session_r2(oracle, golden, name, matrix):
+    s = _load_r2(name)
+    R = OracleRun(oracle, s["ref"], golden[matrix], s["circular"], s["k"], 0, distant_ref=s["distant_ref"])
+    for i, (rd, exp) in enumerate(zip(s["reads"], s["pass1"])):
+        p = R.pass1(rd)
+        for key, v in exp.items():
+            if not exp["hits"] and key not in ("hits", "added"):
+                continue
+            assert p[key] == v, f"{name}: pass1 read {i} field {key}"
+    R.end_pass1()
+    for it, exp in enumerate(s["iters"]):
+        cons, conv = R.iterate()
+        assert [[f["score"], f["as_"], f["ae"], f["rc"], f["strand_known"]] for f in R.fsdb] == exp["reads"], f"{name}: iteration {it} reads"
+        slots = [[x["start"], x["end"], x["dropped"], x["segment"], x["seq"], x["smp"], x["ins"]] for x in oracle.asm_entries(R.asm)]
+        assert slots == [x[1:] for x in exp["slots"]], f"{name}: iteration {it} AlnSeq list"
+        assert np.flatnonzero(oracle.asm_gaps(R.asm, R.wrap_len)).tolist() == exp["gaps"]
+        assert cons == exp["cons"], f"{name}: iteration {it} consensus"
+        assert conv == exp["converged"]
+    return R
+
+
+def test_session_reads_scoring_exactly_2000(oracle, golden):
+    # strand_known = 0 (mia.c:1653): never realigned, the pass-1 AlnSeq pointers alias other reads' slots or older content
+    R = _run_session_r2(oracle, golden, "flat_2000_c", "flat")
+    assert sum(1 for f in R.fsdb if not f["strand_known"]) == 14
+
+
+@pytest.mark.parametrize("name", ["origin305_splitflip_c", "origin303_splitflip_c"])
+def test_session_split_pattern_changes(oracle, golden, name):
+    # reads flip between wrap-split and whole: slot numbers slide under the sticky flags, back_asp goes stale (mia_main.c:268-276)
+    _run_session_r2(oracle, golden, name, "onepass")
+
+
+@pytest.mark.parametrize("name", ["synth3k_div10_c_k12_D", "synth1k_N_lin_D"])
+def test_session_distant_reference(oracle, golden, name):
+    # mia -D: accept everything with a k-mer hit, retry strand-unknown reads on both strands of the whole reference from
+    # iteration 2 on with whatever matrix the previous read left (H6), find_alignable_len in the cull
+    _run_session_r2(oracle, golden, name, "ancient")
