@@ -295,6 +295,43 @@ int miagpu_iterate_resident( miagpu_ctx* ctx, int hard_cut, int score_cut_set,
                              uint8_t* dropped, int32_t* gaps_out, char* cons_out,
                              int32_t* cons_len );
 
+/* ---- a8 / a9: the reference's FragSeq -> AlnSeq POINTER semantics in the one-call rounds.
+ * In the reference an AlnSeq is an object in maln->AlnSeqArray[k] ("slot" k) that every round re-uses for the k-th segment it
+ * merges in FSDB order (merge_pwaln_into_maln map_align.c:866-954: one slot per read, two per wrap-split read), and a FragSeq
+ * holds pointers to its slots.  Three consequences that a "every read owns its fresh AlnSeqs" model misses:
+ *   - AlnSeq.dropped is sticky per SLOT (H10: mia.c:471-478 only sets it, map_align.c:885-893 copies everything else): when
+ *     the split pattern changes, later reads slide onto slots whose flags other reads set;
+ *   - reiterate_assembly never clears back_asp (mia_main.c:273-276): a read that was wrap-split once keeps a stale pointer;
+ *   - a read whose pass-1 score is <= 2000 has strand_known = 0 (mia.c:1653; accepted at exactly 2000, or at any score under
+ *     -D, mia.c:1614) and is never realigned (mia_main.c:178): both its pass-1 pointers stay for ever.
+ * pop_smp_from_FSDB, cull_maln_from_fsdb and consensus_assembly_string follow the pointers, whatever they point at.
+ * miagpu_set_fsdb hands the state after pass 1 to the device (call it after miagpu_compact_reads, which keeps the pass-1
+ * alignments of the reads that stay, and miagpu_set_alignment_inputs); from then on miagpu_iterate_resident reproduces all of
+ * the above: slot numbers by a scan over the reads, flags per slot, stale pointers resolved into extra list entries, slot
+ * content that is no longer live kept as it was (its inserts freed, mia_main.c:80-92).
+ *   seq_len, unique_best (nullable), score     FragSeq.seq_len / unique_best / score in FSDB order
+ *   strand_known (nullable = all 1)            FragSeq.strand_known
+ *   front_slot, back_slot (-1 = NULL)          FragSeq.front_asp / back_asp as indices into the pass-1 AlnSeqArray, n_slots its
+ *                                              length (maln->num_aln_seqs after pass 1); both NULL = nothing merged yet
+ *   slot_dropped                               AlnSeq.dropped after the pass-1 cull (mia_main.c:848), n_slots flags; with
+ *                                              front_slot == NULL: one flag per READ, applied to the slots of the first round
+ *   distant_ref                                -D: miagpu_distant_retry before every round but the first; find_alignable_len
+ *                                              (mia.c:69-91) decides a read's threshold in the cull (mia.c:460-463) */
+int miagpu_set_fsdb( miagpu_ctx* ctx, const int32_t* seq_len, const uint8_t* unique_best, const int32_t* score,
+                     const uint8_t* strand_known, const int32_t* front_slot, const int32_t* back_slot, int64_t n_slots,
+                     const uint8_t* slot_dropped, int distant_ref );
+/* the state after the last round (host arrays of n, all nullable): strand_known, rc, the pointers, AlnSeq.dropped behind them */
+int miagpu_get_fsdb( miagpu_ctx* ctx, uint8_t* strand_known, uint8_t* rc, int32_t* front_slot, int32_t* back_slot,
+                     uint8_t* dropped_front, uint8_t* dropped_back, int64_t* n_slots );
+/* last round: AlnSeq slots merged, stale pointers followed, list entries they added, slot contents kept frozen so far */
+int miagpu_last_fsdb_stats( miagpu_ctx* ctx, int64_t* n_slots, int64_t* stale_pointers, int64_t* extra_entries, int64_t* frozen );
+/* -D, from iteration 2 on (mia_main.c:120-174): every strand-unknown read against the WHOLE current reference -- as it is stored,
+ * with whatever matrix the read before it left in the Alignment (H6: both variants are computed on the device, the chain over the
+ * reads is resolved on the host), then reverse-complemented with the strand-reversed matrix; a read that scores above 2000 learns
+ * its strand, as / ae / score (and is stored reverse-complemented when the reverse attempt wins).  Call after
+ * miagpu_set_reference and before miagpu_iterate_resident; does nothing in the first round or without distant_ref. */
+int miagpu_distant_retry( miagpu_ctx* ctx, int64_t* n_tried, int64_t* n_learned );
+
 /* ---- 8e. The same round with the reads sharded over `world` GPUs of one box: one context (one process) per GPU,
  * reads partitioned contiguously in FSDB order (rank 0 holds the first reads), reference, matrices and k-mer
  * tables replicated.  The library links no communication library; between the phases the caller runs ONE

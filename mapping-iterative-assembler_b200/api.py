@@ -99,6 +99,10 @@ def load_library():
     L.miagpu_maln_ref_size.argtypes = [C.c_int, C.c_int]
     L.miagpu_read_pssm.argtypes = [C.c_char_p, _i32p]
     L.miagpu_write_maln.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, _i64p]
+    L.miagpu_set_fsdb.argtypes = [C.c_void_p] + [C.c_void_p] * 6 + [C.c_int64, C.c_void_p, C.c_int]
+    L.miagpu_get_fsdb.argtypes = [C.c_void_p] + [C.c_void_p] * 6 + [_i64p]
+    L.miagpu_last_fsdb_stats.argtypes = [C.c_void_p, _i64p, _i64p, _i64p, _i64p]
+    L.miagpu_distant_retry.argtypes = [C.c_void_p, _i64p, _i64p]
     L.miagpu_stream.restype = C.c_void_p
     L.miagpu_stream.argtypes = [C.c_void_p]
     _lib = L
@@ -114,7 +118,8 @@ EXPORTS = ["miagpu_device_count", "miagpu_create", "miagpu_destroy", "miagpu_las
            "miagpu_int32_peak", "miagpu_stream", "miagpu_shard_begin", "miagpu_shard_begin_host", "miagpu_shard_cut", "miagpu_shard_finish",
            "miagpu_last_cut_stats", "miagpu_repeat_filter", "miagpu_trim", "miagpu_get_alignment",
            "miagpu_fastx_open", "miagpu_fastx_open_memory", "miagpu_fastx_format", "miagpu_fastx_next", "miagpu_fastx_batch", "miagpu_fastx_close",
-           "miagpu_maln_ref_size", "miagpu_write_maln", "miagpu_read_pssm", "miagpu_align_windows"]
+           "miagpu_maln_ref_size", "miagpu_write_maln", "miagpu_read_pssm", "miagpu_align_windows",
+           "miagpu_set_fsdb", "miagpu_get_fsdb", "miagpu_last_fsdb_stats", "miagpu_distant_retry"]
 
 
 def _ptr(a):
@@ -276,6 +281,36 @@ class MiaGpu:
     def set_cut_inputs(self, seq_len, unique_best=None, dropped=None):
         """Per-read inputs of the score cut, resident from here on (miagpu_set_cut_inputs)."""
         self._ck(self.lib.miagpu_set_cut_inputs(self.h, _ptr(np.ascontiguousarray(seq_len, np.int32)), _ptr(unique_best), _ptr(dropped)))
+
+    def set_fsdb(self, seq_len, score, unique_best=None, strand_known=None, front_slot=None, back_slot=None, n_slots=0, slot_dropped=None,
+                 distant_ref=0):
+        """The FSDB's pointer state after pass 1 (miagpu_set_fsdb): from here on iterate_resident follows the reference's
+        FragSeq -> AlnSeq pointers (slot-indexed sticky flags, stale back pointers, strand-unknown reads)."""
+        a = lambda x, dt: None if x is None else np.ascontiguousarray(x, dt)
+        sl, sc, uq, sk = a(seq_len, np.int32), a(score, np.int32), a(unique_best, np.uint8), a(strand_known, np.uint8)
+        fs, bs, sd = a(front_slot, np.int32), a(back_slot, np.int32), a(slot_dropped, np.uint8)
+        self._ck(self.lib.miagpu_set_fsdb(self.h, _ptr(sl), _ptr(uq), _ptr(sc), _ptr(sk), _ptr(fs), _ptr(bs), int(n_slots), _ptr(sd), int(distant_ref)))
+
+    def get_fsdb(self):
+        n = self.n
+        o = dict(strand_known=np.zeros(n, np.uint8), rc=np.zeros(n, np.uint8), front_slot=np.zeros(n, np.int32), back_slot=np.zeros(n, np.int32),
+                 dropped_front=np.zeros(n, np.uint8), dropped_back=np.zeros(n, np.uint8))
+        ns = C.c_int64()
+        self._ck(self.lib.miagpu_get_fsdb(self.h, *[_ptr(o[k]) for k in ("strand_known", "rc", "front_slot", "back_slot", "dropped_front",
+                                                                        "dropped_back")], C.byref(ns)))
+        o["n_slots"] = ns.value
+        return o
+
+    def last_fsdb_stats(self):
+        v = [C.c_int64() for _ in range(4)]
+        self._ck(self.lib.miagpu_last_fsdb_stats(self.h, *[C.byref(x) for x in v]))
+        return dict(n_slots=v[0].value, stale_pointers=v[1].value, extra_entries=v[2].value, frozen=v[3].value)
+
+    def distant_retry(self):
+        """-D: whole-reference attempts of the strand-unknown reads (miagpu_distant_retry) -> (tried, learned)"""
+        a, b = C.c_int64(), C.c_int64()
+        self._ck(self.lib.miagpu_distant_retry(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def reset_dropped(self):
         self._ck(self.lib.miagpu_reset_dropped(self.h))

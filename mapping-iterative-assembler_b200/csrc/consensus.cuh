@@ -35,7 +35,16 @@ struct ConsParams {
   const int32_t* ins_off;     // [seq_len+1] exclusive scan of gaps (gaps[0] forced to 0)
   int32_t* acc;               // [NPLANE][n_cols], n_cols = seq_len + ins_off[seq_len]
   int64_t n_cols;
+  // entry.read >= n_reads names a FROZEN alignment (slots.cuh): the content an earlier round left in a slot that is no longer
+  // live but still pointed at -- own bases (FZ_BASES bytes each), M / D runs only, first row 0
+  int64_t n_reads;
+  const uint8_t* fz_bases;
+  const uint16_t* fz_runs;
+  const int32_t* fz_nruns;
+  const uint8_t* fz_rc;
 };
+constexpr int FZ_BASES_STRIDE = MAX_READ;
+__device__ __forceinline__ int cons_nruns(const ConsParams& p, int rd) { return rd >= p.n_reads ? p.fz_nruns[rd - p.n_reads] : p.n_runs[rd]; }
 
 __device__ __forceinline__ int smp_depth(const miagpu_entry& e, int act) {   // fsdb.c:569-580 / 598-609
   const int dfront = e.back_formula ? e.front_len + act : act;
@@ -97,15 +106,17 @@ template <int MODE, typename Adder>
 __device__ __forceinline__ void walk_entry(const ConsParams& p, const miagpu_entry& e, int lane, const Adder& A) {
   if (e.col_count <= 0) return;
   const int rd = e.read;
-  const int nr = p.n_runs[rd];
+  const bool fz = rd >= p.n_reads;
+  const int64_t q = rd - p.n_reads;
+  const int nr = fz ? p.fz_nruns[q] : p.n_runs[rd];
   if (nr <= 0) return;
-  const uint16_t* runs = p.runs + (int64_t)rd * MAX_RUNS;
-  const uint8_t* read = p.bases + p.off[rd];
-  const int32_t* sm_strand = p.sm + (p.rc[rd] ? MIAGPU_PSSM_INTS : 0);
+  const uint16_t* runs = fz ? p.fz_runs + q * MAX_RUNS : p.runs + (int64_t)rd * MAX_RUNS;
+  const uint8_t* read = fz ? p.fz_bases + q * FZ_BASES_STRIDE : p.bases + p.off[rd];
+  const int32_t* sm_strand = p.sm + ((fz ? p.fz_rc[q] : p.rc[rd]) ? MIAGPU_PSSM_INTS : 0);
   const int cb = e.col_begin, ce = e.col_begin + e.col_count;
 
   int colpos = 0;                 // reference columns before this run
-  int rpos = p.abr[rd];           // read rows consumed before this run (absolute row)
+  int rpos = fz ? 0 : p.abr[rd];  // read rows consumed before this run (absolute row)
   const int row0 = rpos;
   int pend = 0;                   // inserted bases waiting for the next column
   for (int k = 0; k < nr; k++) {
@@ -162,7 +173,7 @@ __global__ void __launch_bounds__(256) gaps_kernel(ConsParams p) {
   bool want = false;
   if (idx < p.n_entries) {
     const int32_t rd = p.entries[idx].read;
-    want = p.entries[idx].col_count > 0 && p.n_runs[rd] > 2;
+    want = p.entries[idx].col_count > 0 && rd < p.n_reads && p.n_runs[rd] > 2;      // a frozen alignment has no inserts
   }
   unsigned m = __ballot_sync(0xffffffffu, want);
   while (m) {
@@ -208,11 +219,13 @@ __global__ void __launch_bounds__(TILE_THREADS) tile_kernel(ConsParams p, const 
     int64_t o = 0;
     if (mine) {
       e = p.entries[idx];
-      nr = p.n_runs[e.read];
-      ab = p.abr[e.read];
-      strand = p.rc[e.read] ? 1 : 0;
-      o = p.off[e.read];
-      run0 = p.runs[(int64_t)e.read * MAX_RUNS];
+      if (e.read < p.n_reads) {                              // (a frozen alignment takes the general walk: nr stays 0)
+        nr = p.n_runs[e.read];
+        ab = p.abr[e.read];
+        strand = p.rc[e.read] ? 1 : 0;
+        o = p.off[e.read];
+        run0 = p.runs[(int64_t)e.read * MAX_RUNS];
+      }
     }
     unsigned m = __ballot_sync(0xffffffffu, mine);
     while (m) {
@@ -303,11 +316,11 @@ __global__ void __launch_bounds__(256) undo_kernel(ConsParams p, int64_t n_reads
 }
 
 // start position of every entry for tile_kernel's scan (-1 = nothing to add)
-__global__ void ent_pos_kernel(int64_t n_entries, const miagpu_entry* entries, const int32_t* n_runs, int32_t* ent_pos) {
+__global__ void ent_pos_kernel(ConsParams p, int32_t* ent_pos) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_entries) return;
-  const miagpu_entry e = entries[i];
-  ent_pos[i] = (e.col_count > 0 && n_runs[e.read] > 0) ? e.ref_pos : -1;
+  if (i >= p.n_entries) return;
+  const miagpu_entry e = p.entries[i];
+  ent_pos[i] = (e.col_count > 0 && cons_nruns(p, e.read) > 0) ? e.ref_pos : -1;
 }
 
 // find_consensus (map_align.c:294-391) for every column of the padded layout.
@@ -361,8 +374,10 @@ __global__ void natural_entries_kernel(int64_t n, const int32_t* as_out, const i
       if (t == MIAGPU_RUN_I) { ins += len; if (cols < cf) fins += len; }
       else cols += len;
     }
-    const int fcols = split ? cf : cols;
-    const int fl = fcols + fins, bl = split ? (cols - fcols) + (ins - fins) : 0;
+    // a read that starts beyond seq_len (the window rule can leave it in the wrap): split_pwaln moves ALL of it to the back AlnSeq
+    // at START 0 (mia.c:1400-1422) and the front AlnSeq has the negative length asp_len computes from end - start + 1
+    const int fcols = split ? min(max(cf, 0), cols) : cols;
+    const int fl = (split && cf < 0) ? cf : fcols + fins, bl = split ? (cols + ins) - fl : 0;
     f.col_begin = 0; f.col_count = fcols; f.ref_pos = start; f.front_len = fl; f.total_len = fl + bl;
     f.dropped = dropped_front ? (dropped_front[i] != 0) : 0;
     if (split) {

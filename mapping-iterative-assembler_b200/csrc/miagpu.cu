@@ -20,6 +20,8 @@
 #include "scorecut.hpp"
 #include "scorecut.cuh"
 #include "repeat.cuh"
+#include "slots.cuh"
+#include <unordered_map>
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_radix_sort.cuh>
 
@@ -188,6 +190,30 @@ struct miagpu_ctx {
   DevBuf<char> d_called;
   int64_t n_cols = 0;
   int cons_stage = 0;                          // 0 none, 1 gaps done, 2 counts done
+  // FSDB pointer state (slots.cuh): FragSeq.front_asp / back_asp as slot indices, AlnSeq.dropped per slot
+  bool fs_on = false;                          // miagpu_set_fsdb: the one-call rounds follow the reference's pointer semantics
+  int fs_distant = 0;                          // maln->distant_ref (-D)
+  int fs_submat_rc = 0;                        // which matrix a->submat was left pointing at (H6)
+  int fs_round = 0;                            // rounds since miagpu_set_fsdb
+  int64_t fs_slot_cap = 0, fs_nslots = 0, fs_nslots_prev = 0;
+  int fs_prev_seq_len = 0;
+  bool fs_prev_valid = false, fs_prev_pass1 = false, fs_seed_read_flags = false;
+  DevBuf<uint8_t> d_known, d_slot_flag, d_slot_new, d_flip_prev;
+  DevBuf<int32_t> d_front_slot, d_back_slot, d_first, d_nsl, d_slot_owner, d_slot_owner_prev, d_ent_slot, d_stale, d_fs_cnt, d_fs_tmp, d_nprefix;
+  DevBuf<uint16_t> d_runs_prev;                // previous round's alignment: ping-pong partners of d_runs / d_nruns / d_abr / d_as_out / d_ae_out
+  DevBuf<int32_t> d_nruns_prev, d_abr_prev, d_as_prev, d_ae_prev;
+  DevBuf<uint8_t> d_fz_bases, d_fz_rc;         // frozen alignments
+  DevBuf<uint16_t> d_fz_runs;
+  DevBuf<int32_t> d_fz_nruns;
+  struct FzHost { int32_t start, cols, dels, rc; };
+  std::vector<FzHost> fz;                      // geometry of the frozen alignments
+  std::unordered_map<int64_t, int> fz_of_slot; // slot that is no longer live -> its frozen content
+  std::vector<uint8_t> h_known, h_rc;          // host mirrors (the -D chain is resolved on the host)
+  int64_t fs_n_extra = 0, fs_n_stale = 0, fs_n_ghost = 0;
+  struct FsExtra { int32_t holder, kind, slot, live_entry, frozen, front_len, total_len, act_bias, back_formula, listed; };
+  std::vector<FsExtra> fs_extra;               // this round's stale pointers, in FSDB order (front before back)
+  std::vector<int32_t> fs_patch_host;          // smp parameters the writer needs for slots whose last visitor is a stale pointer
+  miagpu_ctx* aux = nullptr;                   // scratch context of the -D attempts
   // timing of the last call
   float ms_kernels = 0, ms_h2d = 0, ms_d2h = 0;
   int64_t dp_cells = 0;
@@ -283,6 +309,12 @@ extern "C" void miagpu_destroy(miagpu_ctx* c) {
   c->rf_rc.release(); c->rf_tr.release(); c->rf_uq.release(); c->rf_tmp.release(); c->rf_as.release(); c->rf_ae.release(); c->rf_k4.release();
   c->rf_idx.release(); c->rf_idx2.release(); c->rf_key.release(); c->rf_key2.release(); c->rf_ord.release(); c->rf_bad.release();
   c->d_seqlen.release(); c->d_unique.release(); c->d_cstats.release(); c->d_ctab.release(); c->d_thr.release(); c->d_cblk.release();
+  c->d_known.release(); c->d_slot_flag.release(); c->d_slot_new.release(); c->d_flip_prev.release(); c->d_front_slot.release();
+  c->d_back_slot.release(); c->d_first.release(); c->d_nsl.release(); c->d_slot_owner.release(); c->d_slot_owner_prev.release();
+  c->d_ent_slot.release(); c->d_stale.release(); c->d_fs_cnt.release(); c->d_fs_tmp.release(); c->d_nprefix.release();
+  c->d_runs_prev.release(); c->d_nruns_prev.release(); c->d_abr_prev.release(); c->d_as_prev.release(); c->d_ae_prev.release();
+  c->d_fz_bases.release(); c->d_fz_rc.release(); c->d_fz_runs.release(); c->d_fz_nruns.release();
+  if (c->aux) miagpu_destroy(c->aux);
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -341,6 +373,7 @@ extern "C" int miagpu_get_pssm(miagpu_ctx* c, int32_t* fwd, int32_t* rev) {
 }
 
 // --------------------------------------------------------------- reference
+static int fs_upload_nprefix(miagpu_ctx* c);
 static char revcom_char(char b) {                                // map_align.c:418-431
   static const char* from = "ABCDGHKMNRSTUVWXY";
   static const char* to = "TVGHCDMKNYSAABWXR";
@@ -392,6 +425,7 @@ extern "C" int miagpu_set_reference(miagpu_ctx* c, const char* seq, int seq_len,
     MIAGPU_CUDA(cudaStreamSynchronize(c->stream));
   }
   c->have_ref = true;
+  if (c->fs_on && c->fs_distant && !fs_upload_nprefix(c)) return 0;
   return 1;
 }
 
@@ -424,6 +458,7 @@ extern "C" int miagpu_upload_reads(miagpu_ctx* c, int64_t n, const uint8_t* base
   c->n = n;
   c->total_bases = total;
   c->cut_inputs_n = -1;
+  c->fs_on = false; c->fs_prev_valid = false;
   c->max_read_len = -1;                      // computed on demand (device reduction) by the chunked kernel's launcher
   return 1;
 }
@@ -436,7 +471,8 @@ extern "C" int miagpu_upload_reads(miagpu_ctx* c, int64_t n, const uint8_t* base
 // Block-level statistics go through shared-memory counters; lanes of a warp that hit the same counter are
 // merged first (match.any + redux), so a counter sees one atomic per warp instead of up to 32.
 __global__ void classify_kernel(int64_t n, const int64_t* off, const int32_t* as, const int32_t* ae, int wrap_len, PairLmax lm,
-                                int32_t* win_start, int32_t* win_len, int32_t* lists, uint8_t* kind, int32_t* meta, int explicit_win = 0) {
+                                int32_t* win_start, int32_t* win_len, int32_t* lists, uint8_t* kind, int32_t* meta, int explicit_win = 0,
+                                const uint8_t* __restrict__ known = nullptr) {
   int lmax16 = 0;
   for (int k = 0; k < P16_NKB; k++) lmax16 = max(lmax16, lm.v[k]);
   __shared__ int s_cnt[NBUCKET], s_base[NBUCKET], s_maxL[NBUCKET], s_pop[NBUCKET];
@@ -454,7 +490,9 @@ __global__ void classify_kernel(int64_t n, const int64_t* off, const int32_t* as
   int b = -1, slot = 0, L = 0, key = -1, kb = -1;
   unsigned cells = 0;
   bool direct = false;
-  if (i < n) {
+  if (i < n && known && !known[i]) {
+    kind[i] = 15;                                       // strand unknown: not realigned (mia_main.c:178)
+  } else if (i < n) {
     L = (int)(off[i + 1] - off[i]);
     int rs = as[i] - REALIGN_BUFFER < 0 ? 0 : as[i] - REALIGN_BUFFER;
     int re = (ae[i] + REALIGN_BUFFER + 1 > wrap_len) ? wrap_len : ae[i] + REALIGN_BUFFER;
@@ -787,7 +825,7 @@ static int realign_classify(miagpu_ctx* c, const RealignJob& j, cudaStream_t st)
   MIAGPU_CUDA(cudaMemsetAsync(j.d_meta, 0, META_WORDS * sizeof(int32_t), st));
   classify_kernel<<<(unsigned)((j.n + 255) / 256), 256, 0, st>>>(j.n, c->d_off.p + j.lo, c->d_as.p + j.lo, c->d_ae.p + j.lo, c->wrap_len, lm,
                                                                 c->d_win_start.p + j.lo, c->d_win_len.p + j.lo, j.d_lists, c->d_kind.p + j.lo, j.d_meta,
-                                                                c->explicit_windows ? 1 : 0);
+                                                                c->explicit_windows ? 1 : 0, (c->fs_on && !c->explicit_windows) ? c->d_known.p + j.lo : nullptr);
   MIAGPU_CUDA(cudaGetLastError());
   c->launches++;
   if (lm.v[0] > 0) {
@@ -1056,6 +1094,7 @@ extern "C" int miagpu_set_alignment_inputs(miagpu_ctx* c, const uint8_t* rc, con
     MIAGPU_CUDA(cudaMemcpyAsync(c->d_ae.p, ae, c->n * 4, cudaMemcpyHostToDevice, c->stream));
   }
   MIAGPU_CUDA(cudaStreamSynchronize(c->stream));
+  c->h_rc.assign(rc, rc + c->n);
   return 1;
 }
 
@@ -1199,6 +1238,7 @@ static ConsParams cons_params(miagpu_ctx* c) {
   p.bases = c->d_bases.p; p.off = c->d_off.p; p.rc = c->d_rc.p; p.abr = c->d_abr.p;
   p.n_runs = c->d_nruns.p; p.runs = c->d_runs.p; p.sm = c->d_sm.p; p.seq_len = c->seq_len;
   p.gaps = c->d_gaps.p; p.ins_off = c->d_ins_off.p; p.acc = c->d_acc.p; p.n_cols = c->n_cols;
+  p.n_reads = c->n; p.fz_bases = c->d_fz_bases.p; p.fz_runs = c->d_fz_runs.p; p.fz_nruns = c->d_fz_nruns.p; p.fz_rc = c->d_fz_rc.p;
   return p;
 }
 
@@ -1222,7 +1262,7 @@ static int launch_accumulate(miagpu_ctx* c) {
   if (const char* e = getenv("MIAGPU_CONS_TILES")) tiles = atoi(e) != 0;
   if (tiles) {
     if (!c->d_ent_pos.reserve(c->n_entries + 1)) return 0;
-    ent_pos_kernel<<<(unsigned)((c->n_entries + 255) / 256), 256, 0, c->stream>>>(c->n_entries, c->d_entries.p, c->d_nruns.p, c->d_ent_pos.p);
+    ent_pos_kernel<<<(unsigned)((c->n_entries + 255) / 256), 256, 0, c->stream>>>(p, c->d_ent_pos.p);
     MIAGPU_CUDA(cudaGetLastError());
     const size_t smem = (size_t)TILE_SMEM_INTS * sizeof(int32_t);
     MIAGPU_CUDA(cudaFuncSetAttribute(tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1514,6 +1554,480 @@ extern "C" int miagpu_consensus(miagpu_ctx* c, int64_t n_entries, const miagpu_e
   return 1;
 }
 
+
+// ------------------------------------------------------------------ FSDB pointer state (slots.cuh)
+// grow a device buffer and keep what it holds (the rare paths that append to a round's entry list)
+template <typename T>
+static int grow_keep(DevBuf<T>& b, size_t need, size_t used, cudaStream_t st) {
+  if (need <= b.cap) return 1;
+  DevBuf<T> nb;
+  if (!nb.reserve(need + need / 4)) return 0;
+  if (used && b.p) MIAGPU_CUDA(cudaMemcpyAsync(nb.p, b.p, used * sizeof(T), cudaMemcpyDeviceToDevice, st));
+  MIAGPU_CUDA(cudaStreamSynchronize(st));
+  b.release();
+  b = nb;
+  return 1;
+}
+
+// -D: number of 'N' in ref[0, x) over the wrapped, upper-cased reference (find_alignable_len, mia.c:69-91)
+static int fs_upload_nprefix(miagpu_ctx* c) {
+  std::vector<int32_t> pre((size_t)c->wrap_len + 1, 0);
+  for (int i = 0; i < c->wrap_len; i++) {
+    const char ch = c->raw_wrapped[i];
+    pre[i + 1] = pre[i] + (ch == 'N' || ch == 'n');
+  }
+  if (!c->d_nprefix.reserve(pre.size())) return 0;
+  MIAGPU_CUDA(cudaMemcpyAsync(c->d_nprefix.p, pre.data(), pre.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  MIAGPU_CUDA(cudaStreamSynchronize(c->stream));
+  return 1;
+}
+
+static FsDev fs_dev(miagpu_ctx* c) {
+  FsDev f{};
+  f.known = c->d_known.p; f.front_slot = c->d_front_slot.p; f.back_slot = c->d_back_slot.p; f.slot_flag = c->d_slot_flag.p;
+  f.slot_new = c->d_slot_new.p; f.first = c->d_first.p; f.slot_owner = c->d_slot_owner.p; f.ent_slot = c->d_ent_slot.p;
+  f.stale = c->d_stale.p; f.counters = c->d_fs_cnt.p; f.stale_cap = (int32_t)std::min<size_t>(c->d_stale.cap / 3, 0x7fffffff);
+  return f;
+}
+
+static int fs_reserve_round(miagpu_ctx* c) {
+  const int64_t n = c->n;
+  const size_t slots = (size_t)c->fs_slot_cap;
+  return c->d_first.reserve(n + 2) && c->d_nsl.reserve(n + 2) && c->d_slot_owner.reserve(slots) && c->d_slot_owner_prev.reserve(slots) &&
+         c->d_ent_slot.reserve(2 * n + 2) && c->d_stale.reserve(3 * (2 * n + 16)) && c->d_fs_cnt.reserve(FS_CNT_WORDS) &&
+         c->d_runs_prev.reserve((size_t)n * MAX_RUNS) && c->d_nruns_prev.reserve(n) && c->d_abr_prev.reserve(n) && c->d_as_prev.reserve(n) &&
+         c->d_ae_prev.reserve(n) && c->d_dropf.reserve(n + 1) && c->d_dropb.reserve(n + 1);
+}
+
+// the previous round's alignment stays where it is: this round's results go to the partner buffers
+static void fs_begin_round(miagpu_ctx* c) {
+  if (c->fs_round > 0) {
+    std::swap(c->d_runs, c->d_runs_prev); std::swap(c->d_nruns, c->d_nruns_prev); std::swap(c->d_abr, c->d_abr_prev);
+    std::swap(c->d_as_out, c->d_as_prev); std::swap(c->d_ae_out, c->d_ae_prev); std::swap(c->d_slot_owner, c->d_slot_owner_prev);
+    c->fs_nslots_prev = c->fs_nslots;
+    c->fs_prev_pass1 = false; c->fs_prev_valid = true;
+  }
+  c->fs_round++;
+}
+
+// which matrix a->submat points at after the last read of a round (mia_main.c:126-184, H6): a read whose strand is known leaves
+// the matrix of its strand; a strand-unknown read is not touched at all in iteration 1 and leaves the strand-reversed matrix
+// from iteration 2 on (mia_main.c:151)
+static void fs_carry_submat(miagpu_ctx* c) {
+  if (!c->fs_distant) return;
+  for (int64_t i = c->n - 1; i >= 0; i--) {
+    if (c->h_known[i]) { c->fs_submat_rc = c->h_rc[i] ? 1 : 0; return; }
+    if (c->fs_round > 1) { c->fs_submat_rc = 1; return; }
+  }
+}
+
+// slot numbers of this round (exclusive scan of the AlnSeqs every read merges, FSDB order), natural entries, stale pointers
+static int fs_number_and_entries(miagpu_ctx* c, bool has_unique) {
+  cudaStream_t main = c->stream;
+  const int64_t n = c->n;
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  MIAGPU_CUDA(cudaMemsetAsync(c->d_fs_cnt.p, 0, FS_CNT_WORDS * sizeof(int32_t), main));
+  MIAGPU_CUDA(cudaMemsetAsync(c->d_nsl.p + n, 0, sizeof(int32_t), main));
+  fs_nsl_kernel<<<grid, 256, 0, main>>>(n, c->d_known.p, c->d_as.p, c->d_ae.p, c->d_as_out.p, c->d_ae_out.p, c->d_nruns.p, c->d_status.p, c->seq_len,
+                                        c->d_nsl.p, c->d_fs_cnt.p);
+  size_t tmp = 0;
+  MIAGPU_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, c->d_nsl.p, c->d_first.p, n + 1, main));
+  if (!c->d_cub.reserve(tmp + 16)) return 0;
+  MIAGPU_CUDA(cub::DeviceScan::ExclusiveSum(c->d_cub.p, tmp, c->d_nsl.p, c->d_first.p, n + 1, main));
+  MIAGPU_CUDA(cudaMemcpyAsync(c->d_fs_cnt.p + FS_CNT_NSLOTS, c->d_first.p + n, sizeof(int32_t), cudaMemcpyDeviceToDevice, main));
+  if (c->fs_seed_read_flags) {                       // per-read flags of miagpu_set_fsdb( slot numbers = NULL ): they belong to the slots of this numbering
+    fs_seed_flags_kernel<<<grid, 256, 0, main>>>(n, c->d_first.p, c->d_nsl.p, c->d_dropf.p, c->d_slot_flag.p);
+    c->fs_seed_read_flags = false;
+  }
+  fs_entries_kernel<<<grid, 256, 0, main>>>(n, fs_dev(c), c->d_as_out.p, c->d_ae_out.p, c->d_nruns.p, c->d_runs.p, c->seq_len,
+                                            has_unique ? c->d_unique.p : nullptr, c->d_entries.p);
+  MIAGPU_CUDA(cudaGetLastError());
+  c->launches += 4;
+  return 1;
+}
+
+// asp_len (fsdb.c:518-530) of a segment from fs_geom_kernel's record (front_len carries the negative-length quirk)
+static inline int fs_asp_len(const int32_t* g, int seg) { return seg ? g[7] - g[6] : g[6]; }
+
+// Resolve this round's stale pointers (see slots.cuh): which content each one sees, the smp parameters every touched slot ends
+// up with (the LAST pointer pop_smp_from_FSDB visits writes them), one extra list entry per stale pointer.
+static int fs_resolve(miagpu_ctx* c, int n_stale, bool has_unique) {
+  cudaStream_t st = c->stream;
+  const int64_t n = c->n;
+  if (n_stale > (int64_t)c->d_stale.cap / 3) { set_error("miagpu: %d stale AlnSeq pointers overflow the list", n_stale); return 0; }
+  if (!c->d_fs_tmp.reserve((size_t)n_stale * 8 * 4 + 64)) return 0;
+  int32_t* d_rec = c->d_fs_tmp.p;
+  fs_gather_kernel<<<(n_stale + 255) / 256, 256, 0, st>>>(n_stale, c->d_stale.p, c->d_slot_owner.p, c->fs_nslots,
+                                                          c->fs_prev_valid ? c->d_slot_owner_prev.p : nullptr, c->fs_nslots_prev, c->d_known.p, c->d_front_slot.p, d_rec);
+  MIAGPU_CUDA(cudaGetLastError());
+  std::vector<int32_t> rec((size_t)n_stale * 8);
+  MIAGPU_CUDA(cudaMemcpyAsync(rec.data(), d_rec, rec.size() * 4, cudaMemcpyDeviceToHost, st));
+  MIAGPU_CUDA(cudaStreamSynchronize(st));
+  std::vector<int> order(n_stale);
+  for (int q = 0; q < n_stale; q++) order[q] = q;
+  std::sort(order.begin(), order.end(), [&](int a, int b) {
+    return rec[8 * a] != rec[8 * b] ? rec[8 * a] < rec[8 * b] : rec[8 * a + 1] < rec[8 * b + 1];
+  });
+  // ---- content that is no longer live: frozen already, or frozen now from the previous round's results
+  std::vector<int32_t> fz_which, fz_dst;
+  std::vector<int64_t> fz_slot;
+  for (int q = 0; q < n_stale; q++) {
+    const int32_t* r = &rec[8 * q];
+    const int64_t k = r[2];
+    if (r[3] >= 0 || c->fz_of_slot.count(k)) continue;
+    if (r[4] < 0) { set_error("miagpu: read %d points at AlnSeq slot %lld, which neither this nor the previous round filled", r[0], (long long)k); return 0; }
+    c->fz_of_slot[k] = (int)(c->fz.size() + fz_which.size());
+    fz_which.push_back(r[4]); fz_dst.push_back((int32_t)(c->fz.size() + fz_which.size() - 1)); fz_slot.push_back(k);
+  }
+  if (!fz_which.empty()) {
+    const size_t m = fz_which.size(), tot = c->fz.size() + m;
+    if (!grow_keep(c->d_fz_bases, tot * FZ_BASES, c->fz.size() * FZ_BASES, st) || !grow_keep(c->d_fz_runs, tot * MAX_RUNS, c->fz.size() * MAX_RUNS, st) ||
+        !grow_keep(c->d_fz_nruns, tot, c->fz.size(), st) || !grow_keep(c->d_fz_rc, tot, c->fz.size(), st)) return 0;
+    DevBuf<int32_t> d_list;
+    if (!d_list.reserve(m * 6 + 16)) return 0;
+    MIAGPU_CUDA(cudaMemcpyAsync(d_list.p, fz_which.data(), m * 4, cudaMemcpyHostToDevice, st));
+    MIAGPU_CUDA(cudaMemcpyAsync(d_list.p + m, fz_dst.data(), m * 4, cudaMemcpyHostToDevice, st));
+    const AlnView pv{c->d_as_prev.p, c->d_ae_prev.p, c->d_nruns_prev.p, c->d_runs_prev.p, c->d_abr_prev.p, c->fs_prev_seq_len};
+    fs_freeze_kernel<<<(unsigned)((m + 127) / 128), 128, 0, st>>>((int)m, d_list.p, d_list.p + m, pv, c->d_bases.p, c->d_off.p, c->d_rc.p,
+                                                                  c->fs_prev_pass1 ? c->d_flip_prev.p : nullptr, c->d_fz_bases.p, c->d_fz_runs.p,
+                                                                  c->d_fz_nruns.p, c->d_fz_rc.p, d_list.p + 2 * m);
+    MIAGPU_CUDA(cudaGetLastError());
+    std::vector<int32_t> geo(m * 4);
+    MIAGPU_CUDA(cudaMemcpyAsync(geo.data(), d_list.p + 2 * m, m * 16, cudaMemcpyDeviceToHost, st));
+    MIAGPU_CUDA(cudaStreamSynchronize(st));
+    d_list.release();
+    for (size_t q = 0; q < m; q++) c->fz.push_back(miagpu_ctx::FzHost{geo[4 * q], geo[4 * q + 1], geo[4 * q + 2], geo[4 * q + 3]});
+  }
+  // ---- geometry of the live segments involved: the targets and the holders' own fresh front segments
+  std::vector<int32_t> want;
+  std::unordered_map<int32_t, int> at;               // 2 * read + seg -> index into geo
+  auto need = [&](int32_t e) { if (e >= 0 && !at.count(e)) { at[e] = (int)want.size(); want.push_back(e); } };
+  for (int q = 0; q < n_stale; q++) {
+    need(rec[8 * q + 3]);
+    if (rec[8 * q + 5]) need(2 * rec[8 * q]);
+  }
+  std::vector<int32_t> geo(want.size() * 8);
+  if (!want.empty()) {
+    DevBuf<int32_t> d_w;
+    if (!d_w.reserve(want.size() * 9 + 16)) return 0;
+    MIAGPU_CUDA(cudaMemcpyAsync(d_w.p, want.data(), want.size() * 4, cudaMemcpyHostToDevice, st));
+    const AlnView cv{c->d_as_out.p, c->d_ae_out.p, c->d_nruns.p, c->d_runs.p, c->d_abr.p, c->seq_len};
+    fs_geom_kernel<<<(unsigned)((want.size() + 127) / 128), 128, 0, st>>>((int)want.size(), d_w.p, cv, d_w.p + want.size());
+    MIAGPU_CUDA(cudaGetLastError());
+    MIAGPU_CUDA(cudaMemcpyAsync(geo.data(), d_w.p + want.size(), geo.size() * 4, cudaMemcpyDeviceToHost, st));
+    MIAGPU_CUDA(cudaStreamSynchronize(st));
+    d_w.release();
+  }
+  struct Content { int aln, cb, cc, ref_pos, asp, bases, rb; };
+  auto live_content = [&](int32_t e) {
+    const int32_t* g = &geo[8 * at[e]];
+    return Content{e >> 1, g[0], g[1], g[2], fs_asp_len(g, e & 1), g[1] - g[4] + g[3], g[5]};
+  };
+  auto slot_content = [&](const int32_t* r) {
+    if (r[3] >= 0) return live_content(r[3]);
+    const int fid = c->fz_of_slot[r[2]];
+    const miagpu_ctx::FzHost& z = c->fz[fid];
+    return Content{(int)(n + fid), 0, z.cols, z.start, z.cols, z.cols - z.dels, 0};      // inserts freed: mia_main.c:80-92
+  };
+  // ---- visits of pop_smp_from_FSDB (fsdb.c:542-619) by the holders of stale pointers, in FSDB order.  For a read with front
+  // content F and back content B: front_len = asp_len(F), total = asp_len(F) + asp_len(B); the running position starts at 0 in
+  // F and goes on in B; a content that begins in mid-alignment (a back segment) has consumed rb read bases before its first column.
+  struct Visit { int64_t key; int fl, total, bias, bf; };
+  std::unordered_map<int64_t, Visit> last;           // slot -> the last visit
+  auto visit = [&](int64_t slot, int64_t key, int fl, int total, int bias, int bf) {
+    auto it = last.find(slot);
+    if (it == last.end() || it->second.key < key) last[slot] = Visit{key, fl, total, bias, bf};
+  };
+  struct Ptr { int holder, kind; int64_t slot; Content ct; int32_t live_e; bool listed; };
+  std::vector<Ptr> ptrs;
+  std::unordered_map<int64_t, int32_t> live_entry;   // slot -> its natural entry
+  std::unordered_map<int, char> known_holder;
+  for (int a = 0; a < n_stale;) {
+    int b = a;
+    while (b < n_stale && rec[8 * order[b]] == rec[8 * order[a]]) b++;
+    const int i = rec[8 * order[a]];
+    const bool known = rec[8 * order[a] + 5] != 0;
+    const bool listed = !has_unique || c->h_unique.empty() || c->h_unique[i];
+    const int32_t *rf = nullptr, *rb = nullptr;
+    for (int q = a; q < b; q++) (rec[8 * order[q] + 1] ? rb : rf) = &rec[8 * order[q]];
+    Content F{}, B{};
+    int64_t slotF = rec[8 * order[a] + 6];           // front_asp: this round's own slot (known), or the stale pass-1 pointer
+    if (known) { F = live_content(2 * i); live_entry[slotF] = 2 * i; known_holder[i] = 1; }   // (a known holder is not split this round)
+    else if (rf) { F = slot_content(rf); slotF = rf[2]; }
+    else { set_error("miagpu: strand-unknown read %d has no front AlnSeq pointer", i); return 0; }
+    if (rb) B = slot_content(rb);
+    const int fl = F.asp, bl = rb ? B.asp : 0;
+    visit(slotF, 2 * (int64_t)i, fl, fl + bl, -F.rb, 0);
+    if (!known) ptrs.push_back(Ptr{i, 0, slotF, F, rf[3], listed});
+    if (rb) {
+      visit(rb[2], 2 * (int64_t)i + 1, fl, fl + bl, F.bases - B.rb, 1);
+      ptrs.push_back(Ptr{i, 1, rb[2], B, rb[3], listed});
+    }
+    a = b;
+  }
+  // the owners' own visits of the live slots that stale pointers touch (an owner that holds a stale pointer itself is done above)
+  for (int q = 0; q < n_stale; q++) {
+    const int32_t* r = &rec[8 * q];
+    if (r[3] < 0) continue;
+    live_entry[r[2]] = r[3];
+    const int j = r[3] >> 1, seg = r[3] & 1;
+    if (known_holder.count(j)) continue;
+    const int32_t* g = &geo[8 * at[r[3]]];
+    visit(r[2], 2 * (int64_t)j + seg, g[6], g[7], 0, seg);
+  }
+  // ---- every touched live slot's natural entry takes the parameters of the slot's last visit; one extra entry per stale pointer
+  // of a listed read (cull_maln_from_fsdb copies front_asp and back_asp of every unique_best read into the list, mia.c:469-476)
+  std::vector<int32_t> pat;
+  std::vector<miagpu_entry> extra;
+  c->fs_extra.clear(); c->fs_patch_host.clear();
+  for (auto& kv : last) {
+    auto le = live_entry.find(kv.first);
+    if (le == live_entry.end()) continue;
+    const Visit& v = kv.second;
+    const int32_t row[6] = {le->second, v.fl, v.total, v.bias, v.bf, -2};
+    pat.insert(pat.end(), row, row + 6);
+    c->fs_patch_host.insert(c->fs_patch_host.end(), row, row + 5);
+  }
+  int64_t n_extra = 0;
+  for (const Ptr& p : ptrs) {
+    const Visit& v = last[p.slot];
+    c->fs_extra.push_back(miagpu_ctx::FsExtra{p.holder, p.kind, (int32_t)p.slot, p.live_e, p.ct.aln >= n ? (int32_t)(p.ct.aln - n) : -1,
+                                              v.fl, v.total, v.bias, v.bf, (int32_t)p.listed});
+    if (!p.listed) continue;
+    miagpu_entry x{};
+    x.read = p.ct.aln; x.col_begin = p.ct.cb; x.col_count = p.ct.cc; x.ref_pos = p.ct.ref_pos;
+    x.front_len = v.fl; x.total_len = v.total; x.act_bias = v.bias; x.back_formula = (uint8_t)v.bf;
+    const int32_t row[6] = {(int32_t)(2 * n + n_extra), v.fl, v.total, v.bias, v.bf, (int32_t)p.slot};
+    pat.insert(pat.end(), row, row + 6);
+    extra.push_back(x);
+    n_extra++;
+  }
+  if (n_extra) {
+    if (!grow_keep(c->d_entries, (size_t)(2 * n + n_extra + 2), (size_t)(2 * n), st) ||
+        !grow_keep(c->d_ent_slot, (size_t)(2 * n + n_extra + 2), (size_t)(2 * n), st)) return 0;
+    MIAGPU_CUDA(cudaMemcpyAsync(c->d_entries.p + 2 * n, extra.data(), extra.size() * sizeof(miagpu_entry), cudaMemcpyHostToDevice, st));
+  }
+  if (!pat.empty()) {
+    DevBuf<int32_t> d_p;
+    if (!d_p.reserve(pat.size() + 16)) return 0;
+    MIAGPU_CUDA(cudaMemcpyAsync(d_p.p, pat.data(), pat.size() * 4, cudaMemcpyHostToDevice, st));
+    const int m = (int)(pat.size() / 6);
+    fs_patch_kernel<<<(m + 255) / 256, 256, 0, st>>>(m, d_p.p, c->d_entries.p, c->d_ent_slot.p, c->d_slot_flag.p);
+    MIAGPU_CUDA(cudaGetLastError());
+    MIAGPU_CUDA(cudaStreamSynchronize(st));
+    d_p.release();
+  }
+  c->n_entries = 2 * n + n_extra;
+  c->fs_n_extra = n_extra;
+  return 1;
+}
+
+// after the host has this round's counters: status of the reads, slot count, stale pointers
+static int fs_after_numbering(miagpu_ctx* c, bool has_unique, const int32_t* cnt, int32_t* total_ins) {
+  const int status = cnt[FS_CNT_STATUS];
+  c->fs_nslots = cnt[FS_CNT_NSLOTS];
+  c->fs_n_stale = cnt[FS_CNT_STALE];
+  c->fs_n_extra = 0;
+  c->fs_extra.clear(); c->fs_patch_host.clear();
+  if (status) {
+    set_error("miagpu: reads came back with status bits 0x%x (more than %d alignment runs, or a window no kernel takes): the round is not usable", status, MAX_RUNS);
+    return 0;
+  }
+  if (c->fs_nslots > c->fs_slot_cap) { set_error("miagpu: %lld AlnSeq slots, room for %lld", (long long)c->fs_nslots, (long long)c->fs_slot_cap); return 0; }
+  if (!c->fs_n_stale) return 1;
+  if (!fs_resolve(c, (int)c->fs_n_stale, has_unique)) return 0;
+  if (c->fs_n_extra && has_unique) {                 // a slot whose owner is not listed may bring inserts into the list through a stale pointer
+    ConsParams p = cons_params(c);
+    p.entries = c->d_entries.p + 2 * c->n; p.n_entries = c->fs_n_extra;
+    gaps_kernel<<<(unsigned)((c->fs_n_extra + 255) / 256), 256, 0, c->stream>>>(p);
+    size_t tmp = 0;
+    MIAGPU_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, c->d_gaps.p, c->d_ins_off.p, c->seq_len + 1, c->stream));
+    if (!c->d_cub.reserve(tmp + 16)) return 0;
+    MIAGPU_CUDA(cub::DeviceScan::ExclusiveSum(c->d_cub.p, tmp, c->d_gaps.p, c->d_ins_off.p, c->seq_len + 1, c->stream));
+    MIAGPU_CUDA(cudaMemcpyAsync(total_ins, c->d_ins_off.p + c->seq_len, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    MIAGPU_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  return 1;
+}
+
+// this round's cull through the pointers, the newly flagged slots' base columns back out of the planes, flags made sticky
+static int fs_flags_and_undo(miagpu_ctx* c, bool has_unique) {
+  cudaStream_t main = c->stream;
+  const int64_t n = c->n;
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  fs_flags_kernel<<<grid, 256, 0, main>>>(n, c->d_seqlen.p, c->d_score.p, c->d_thr.p, has_unique ? c->d_unique.p : nullptr, fs_dev(c), c->d_as_out.p,
+                                          c->d_ae_out.p, c->fs_distant ? c->d_nprefix.p : nullptr, c->wrap_len, c->d_cstats.p);
+  ConsParams p = cons_params(c);
+  fs_undo_kernel<<<(unsigned)((c->n_entries + 255) / 256), 256, 0, main>>>(p, c->d_ent_slot.p, c->d_slot_new.p, c->d_entries.p);
+  fs_commit_kernel<<<(unsigned)((c->fs_slot_cap + 255) / 256), 256, 0, main>>>(c->fs_slot_cap, c->d_slot_flag.p, c->d_slot_new.p);
+  fs_read_flags_kernel<<<grid, 256, 0, main>>>(n, c->d_front_slot.p, c->d_back_slot.p, c->d_slot_flag.p, c->d_dropf.p, c->d_dropb.p);
+  MIAGPU_CUDA(cudaGetLastError());
+  c->launches += 4;
+  return 1;
+}
+
+
+// ------------------------------------------------------------------ FSDB state: entry points
+extern "C" int miagpu_set_fsdb(miagpu_ctx* c, const int32_t* seq_len, const uint8_t* unique_best, const int32_t* score,
+                               const uint8_t* strand_known, const int32_t* front_slot, const int32_t* back_slot, int64_t n_slots,
+                               const uint8_t* slot_dropped, int distant_ref) {
+  if (!c || (c->n && (!seq_len || !score))) { set_error("miagpu_set_fsdb: seq_len and score are required"); return 0; }
+  if ((front_slot == nullptr) != (back_slot == nullptr) || n_slots < 0) { set_error("miagpu_set_fsdb: front_slot and back_slot come together"); return 0; }
+  if (!miagpu_set_cut_inputs(c, seq_len, unique_best, nullptr)) return 0;
+  const int64_t n = c->n;
+  if (c->h_rc.size() != (size_t)n) { set_error("miagpu_set_fsdb: call miagpu_set_alignment_inputs first"); return 0; }
+  cudaStream_t st = c->stream;
+  c->fs_slot_cap = std::max<int64_t>(n_slots, 2 * n) + 64;
+  if (!c->d_known.reserve(n + 1) || !c->d_front_slot.reserve(n + 1) || !c->d_back_slot.reserve(n + 1) ||
+      !c->d_slot_flag.reserve(c->fs_slot_cap) || !c->d_slot_new.reserve(c->fs_slot_cap) || !fs_reserve_round(c)) return 0;
+  c->h_known.assign((size_t)n, 1);
+  if (strand_known) for (int64_t i = 0; i < n; i++) c->h_known[i] = strand_known[i] != 0;
+  std::vector<int32_t> nat;
+  const int32_t *fs = front_slot, *bs = back_slot;
+  if (!front_slot) {                                 // no pass-1 numbering: the reads stand for themselves until the first round numbers them
+    nat.assign((size_t)2 * n, -1);
+    for (int64_t i = 0; i < n; i++) nat[i] = (int32_t)i;
+    fs = nat.data(); bs = nat.data() + n;
+    if (!n_slots) n_slots = n;
+  }
+  for (int64_t i = 0; i < n; i++)
+    if (fs[i] < 0 || fs[i] >= c->fs_slot_cap || bs[i] < -1 || bs[i] >= c->fs_slot_cap) {
+      set_error("miagpu_set_fsdb: read %lld points at slots %d / %d of %lld", (long long)i, fs[i], bs[i], (long long)n_slots);
+      return 0;
+    }
+  MIAGPU_CUDA(cudaMemsetAsync(c->d_slot_flag.p, 0, c->fs_slot_cap, st));
+  MIAGPU_CUDA(cudaMemsetAsync(c->d_slot_new.p, 0, c->fs_slot_cap, st));
+  MIAGPU_CUDA(cudaMemsetAsync(c->d_slot_owner_prev.p, 0xff, c->fs_slot_cap * sizeof(int32_t), st));
+  if (n) {
+    MIAGPU_CUDA(cudaMemcpyAsync(c->d_known.p, c->h_known.data(), n, cudaMemcpyHostToDevice, st));
+    MIAGPU_CUDA(cudaMemcpyAsync(c->d_front_slot.p, fs, n * 4, cudaMemcpyHostToDevice, st));
+    MIAGPU_CUDA(cudaMemcpyAsync(c->d_back_slot.p, bs, n * 4, cudaMemcpyHostToDevice, st));
+    MIAGPU_CUDA(cudaMemcpyAsync(c->d_score.p, score, n * 4, cudaMemcpyHostToDevice, st));
+    fs_owner_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, c->d_front_slot.p, c->d_back_slot.p, n_slots, c->d_slot_owner_prev.p);
+    MIAGPU_CUDA(cudaGetLastError());
+  }
+  c->fs_seed_read_flags = false;
+  if (slot_dropped && front_slot && n_slots) MIAGPU_CUDA(cudaMemcpyAsync(c->d_slot_flag.p, slot_dropped, n_slots, cudaMemcpyHostToDevice, st));
+  else if (slot_dropped && n) {                      // per READ: the flags go to the slots the reads take at the first numbering
+    MIAGPU_CUDA(cudaMemcpyAsync(c->d_dropf.p, slot_dropped, n, cudaMemcpyHostToDevice, st));
+    c->fs_seed_read_flags = true;
+  }
+  MIAGPU_CUDA(cudaStreamSynchronize(st));
+  c->fs_on = true; c->fs_distant = distant_ref ? 1 : 0; c->fs_submat_rc = 0; c->fs_round = 0;
+  c->fs_nslots = c->fs_nslots_prev = n_slots;
+  if (!front_slot) c->fs_prev_valid = false;         // nothing was merged before the first round
+  c->fz.clear(); c->fz_of_slot.clear(); c->fs_extra.clear(); c->fs_patch_host.clear();
+  c->fs_n_extra = c->fs_n_stale = 0;
+  if (c->fs_distant && c->have_ref && !fs_upload_nprefix(c)) return 0;
+  return 1;
+}
+
+extern "C" int miagpu_get_fsdb(miagpu_ctx* c, uint8_t* strand_known, uint8_t* rc, int32_t* front_slot, int32_t* back_slot,
+                               uint8_t* dropped_front, uint8_t* dropped_back, int64_t* n_slots) {
+  if (!c || !c->fs_on) { set_error("miagpu_get_fsdb: call miagpu_set_fsdb first"); return 0; }
+  MIAGPU_CUDA(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  const int64_t n = c->n;
+  if (n) {
+    if (dropped_front || dropped_back) {
+      fs_read_flags_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, c->d_front_slot.p, c->d_back_slot.p, c->d_slot_flag.p, c->d_dropf.p, c->d_dropb.p);
+      MIAGPU_CUDA(cudaGetLastError());
+    }
+    if (strand_known) MIAGPU_CUDA(cudaMemcpyAsync(strand_known, c->d_known.p, n, cudaMemcpyDeviceToHost, st));
+    if (rc) MIAGPU_CUDA(cudaMemcpyAsync(rc, c->d_rc.p, n, cudaMemcpyDeviceToHost, st));
+    if (front_slot) MIAGPU_CUDA(cudaMemcpyAsync(front_slot, c->d_front_slot.p, n * 4, cudaMemcpyDeviceToHost, st));
+    if (back_slot) MIAGPU_CUDA(cudaMemcpyAsync(back_slot, c->d_back_slot.p, n * 4, cudaMemcpyDeviceToHost, st));
+    if (dropped_front) MIAGPU_CUDA(cudaMemcpyAsync(dropped_front, c->d_dropf.p, n, cudaMemcpyDeviceToHost, st));
+    if (dropped_back) MIAGPU_CUDA(cudaMemcpyAsync(dropped_back, c->d_dropb.p, n, cudaMemcpyDeviceToHost, st));
+  }
+  MIAGPU_CUDA(cudaStreamSynchronize(st));
+  if (n_slots) *n_slots = c->fs_nslots;
+  return 1;
+}
+
+extern "C" int miagpu_last_fsdb_stats(miagpu_ctx* c, int64_t* n_slots, int64_t* stale_pointers, int64_t* extra_entries, int64_t* frozen) {
+  if (!c) { set_error("miagpu_last_fsdb_stats: no context"); return 0; }
+  if (n_slots) *n_slots = c->fs_nslots;
+  if (stale_pointers) *stale_pointers = c->fs_n_stale;
+  if (extra_entries) *extra_entries = c->fs_n_extra;
+  if (frozen) *frozen = (int64_t)c->fz.size();
+  return 1;
+}
+
+// -D: the strand-unknown reads' attempts against the whole current reference (mia_main.c:120-174), before the round's realign.
+extern "C" int miagpu_distant_retry(miagpu_ctx* c, int64_t* n_tried, int64_t* n_learned) {
+  if (n_tried) *n_tried = 0;
+  if (n_learned) *n_learned = 0;
+  if (!c || !c->fs_on || !c->have_ref || !c->have_pssm) { set_error("miagpu_distant_retry: set_pssm, set_reference and miagpu_set_fsdb first"); return 0; }
+  if (!c->fs_distant || c->fs_round < 1) return 1;   // iter_num > 1 only (mia_main.c:122)
+  MIAGPU_CUDA(cudaSetDevice(c->device));
+  const int64_t n = c->n;
+  std::vector<int32_t> U;
+  for (int64_t i = 0; i < n; i++) if (!c->h_known[i]) U.push_back((int32_t)i);
+  const int64_t m = (int64_t)U.size();
+  if (n_tried) *n_tried = m;
+  if (!m) return 1;
+  cudaStream_t st = c->stream;
+  if (!c->aux && !miagpu_create(&c->aux, c->device)) return 0;
+  miagpu_ctx* x = c->aux;
+  if (!miagpu_set_pssm(x, c->sm_f)) return 0;
+  if (!miagpu_set_reference(x, c->raw_wrapped.c_str(), c->seq_len, c->circular, 0)) return 0;
+  // the scratch batch: three items per read (fs_retry_reads_kernel)
+  std::vector<int64_t> off_new((size_t)3 * m + 1, 0);
+  for (int64_t q = 0; q < 3 * m; q++) off_new[q + 1] = off_new[q] + c->h_seqlen[U[q / 3]];
+  const int64_t total = off_new.back();
+  if (!x->d_bases.reserve(total + 16) || !x->d_off.reserve(3 * m + 1) || !reserve_per_read(x, 3 * m) || !c->d_fs_tmp.reserve((size_t)m * 6 + 64)) return 0;
+  MIAGPU_CUDA(cudaMemcpyAsync(x->d_off.p, off_new.data(), (3 * m + 1) * 8, cudaMemcpyHostToDevice, st));
+  MIAGPU_CUDA(cudaMemcpyAsync(c->d_fs_tmp.p, U.data(), m * 4, cudaMemcpyHostToDevice, st));
+  fs_retry_reads_kernel<<<(unsigned)((3 * m * 32 + 255) / 256), 256, 0, st>>>((int)m, c->d_fs_tmp.p, c->d_bases.p, c->d_off.p, x->d_off.p, x->d_bases.p);
+  MIAGPU_CUDA(cudaGetLastError());
+  MIAGPU_CUDA(cudaStreamSynchronize(st));
+  x->n = 3 * m; x->total_bases = total; x->cut_inputs_n = -1; x->max_read_len = -1;
+  std::vector<uint8_t> vrc((size_t)3 * m), vst((size_t)3 * m);
+  std::vector<int32_t> ws((size_t)3 * m, 0), wl((size_t)3 * m, c->wrap_len), sc((size_t)3 * m), a0((size_t)3 * m), a1((size_t)3 * m);
+  for (int64_t q = 0; q < 3 * m; q++) vrc[q] = q % 3 != 0;
+  if (!miagpu_align_windows(x, vrc.data(), ws.data(), wl.data(), 1, sc.data(), a0.data(), a1.data(), nullptr, nullptr, nullptr, vst.data())) return 0;
+  for (int64_t q = 0; q < 3 * m; q++)
+    if (vst[q] & ~(MIAGPU_ST_RUNS_OVERFLOW | MIAGPU_ST_STR_OVERFLOW)) { set_error("miagpu_distant_retry: whole-reference attempt %lld came back with status 0x%x", (long long)q, vst[q]); return 0; }
+  // the chain over the reads in FSDB order: the forward attempt runs with whatever matrix the read before left (H6)
+  std::vector<int32_t> upd;
+  int64_t learned = 0;
+  std::vector<int32_t> h_score((size_t)m);
+  {                                                  // fs->score of the strand-unknown reads (the reverse attempt must beat it)
+    std::vector<int32_t> all((size_t)n);
+    MIAGPU_CUDA(cudaMemcpyAsync(all.data(), c->d_score.p, n * 4, cudaMemcpyDeviceToHost, st));
+    MIAGPU_CUDA(cudaStreamSynchronize(st));
+    for (int64_t q = 0; q < m; q++) h_score[q] = all[U[q]];
+  }
+  for (int64_t q = 0; q < m; q++) {
+    const int32_t i = U[q];
+    int state = c->fs_submat_rc;                     // read 0: what the last read of the previous round left
+    if (i > 0) state = c->h_known[i - 1] ? (c->h_rc[i - 1] ? 1 : 0) : 1;      // (a read that stays unknown leaves the strand-reversed matrix)
+    const int64_t fwd = 3 * q + (state ? 1 : 0), rev = 3 * q + 2;
+    int known = 0, rc = 0, as = 0, ae = 0, score = h_score[q];
+    if (sc[fwd] > FIRST_ROUND_SCORE_CUTOFF) { known = 1; rc = 0; as = a0[fwd]; ae = a1[fwd]; score = sc[fwd]; }
+    if (sc[rev] > FIRST_ROUND_SCORE_CUTOFF && sc[rev] > score) { known = 1; rc = 1; as = a0[rev]; ae = a1[rev]; score = sc[rev]; }
+    if (known) {
+      c->h_known[i] = 1; c->h_rc[i] = (uint8_t)rc;
+      const int32_t row[6] = {i, rc, as, ae, score, rc};                       // strcpy( fs->seq, tmp_rc ) when the reverse attempt wins
+      upd.insert(upd.end(), row, row + 6);
+      learned++;
+    }
+  }
+  if (learned) {
+    DevBuf<int32_t> d_u;
+    if (!d_u.reserve(upd.size() + 16)) return 0;
+    MIAGPU_CUDA(cudaMemcpyAsync(d_u.p, upd.data(), upd.size() * 4, cudaMemcpyHostToDevice, st));
+    fs_apply_kernel<<<(unsigned)((learned * 32 + 255) / 256), 256, 0, st>>>((int)learned, d_u.p, c->d_known.p, c->d_rc.p, c->d_as.p, c->d_ae.p, c->d_score.p,
+                                                                           c->d_bases.p, c->d_off.p);
+    MIAGPU_CUDA(cudaGetLastError());
+    MIAGPU_CUDA(cudaStreamSynchronize(st));
+    d_u.release();
+  }
+  if (n_learned) *n_learned = learned;
+  return 1;
+}
+
 // ---------------------------------------------------- one whole round (a9..a13), score cut on the device
 struct Trace {                                       // MIAGPU_TRACE=1: host-side timeline of one iteration call on stderr
   bool on = getenv("MIAGPU_TRACE") != nullptr;
@@ -1537,6 +2051,7 @@ struct CutHost {
   int64_t tot_runs;
   int32_t total_ins;
   long long bad_after;
+  int32_t fs_cnt[FS_CNT_WORDS];
 };
 
 static int cut_reserve(miagpu_ctx* c, int64_t n) {
@@ -1606,14 +2121,19 @@ static int iterate_tail(miagpu_ctx* c, const IterTail& a, const Trace& tr) {
   c->n_entries = 2 * n;
   MIAGPU_CUDA(cudaMemsetAsync(c->d_gaps.p, 0, (c->seq_len + 2) * sizeof(int32_t), main));
   if (a.wait_old_flags) MIAGPU_CUDA(cudaStreamWaitEvent(main, c->xev[1], 0));          // the earlier rounds' flags are on the device
-  natural_entries_kernel<<<(unsigned)((n + 255) / 256), 256, 0, main>>>(n, c->d_as_out.p, c->d_ae_out.p, c->d_nruns.p, c->d_runs.p,
-                                                                        c->d_status.p, c->seq_len, c->d_dropf.p, c->d_dropf.p, c->d_entries.p,
-                                                                        has_unique ? c->d_unique.p : nullptr);
-  MIAGPU_CUDA(cudaGetLastError());
-  c->launches++;
+  if (c->fs_on) {
+    if (!fs_number_and_entries(c, has_unique)) return 0;
+  } else {
+    natural_entries_kernel<<<(unsigned)((n + 255) / 256), 256, 0, main>>>(n, c->d_as_out.p, c->d_ae_out.p, c->d_nruns.p, c->d_runs.p,
+                                                                          c->d_status.p, c->seq_len, c->d_dropf.p, c->d_dropf.p, c->d_entries.p,
+                                                                          has_unique ? c->d_unique.p : nullptr);
+    MIAGPU_CUDA(cudaGetLastError());
+    c->launches++;
+  }
   if (!launch_gaps(c)) return 0;
   MIAGPU_CUDA(cub::DeviceScan::ExclusiveSum(c->d_cub.p, tmp2, c->d_gaps.p, c->d_ins_off.p, c->seq_len + 1, main));
   MIAGPU_CUDA(cudaMemcpyAsync(&H->total_ins, c->d_ins_off.p + c->seq_len, sizeof(int32_t), cudaMemcpyDeviceToHost, main));
+  if (c->fs_on) MIAGPU_CUDA(cudaMemcpyAsync(H->fs_cnt, c->d_fs_cnt.p, sizeof(H->fs_cnt), cudaMemcpyDeviceToHost, main));
   MIAGPU_CUDA(cudaEventRecord(c->aev[6], main));
   c->launches += 2;
   tr.mark("entries + insert maxima enqueued");
@@ -1645,6 +2165,7 @@ static int iterate_tail(miagpu_ctx* c, const IterTail& a, const Trace& tr) {
   }
   // ---- column accumulation of every read that is not yet dropped (needs the insert-column layout: one short wait)
   MIAGPU_CUDA(cudaEventSynchronize(c->aev[6]));
+  if (c->fs_on && !fs_after_numbering(c, has_unique, H->fs_cnt, &H->total_ins)) { cudaStreamSynchronize(main); cudaStreamSynchronize(side); return 0; }
   const int64_t tot = H->tot_runs;
   if (a.total_runs) *a.total_runs = tot;
   if (a.packed_runs && tot > a.capacity) { cudaStreamSynchronize(main); cudaStreamSynchronize(side); set_error("miagpu_iterate: %lld runs, capacity %lld", (long long)tot, (long long)a.capacity); return 0; }
@@ -1686,16 +2207,20 @@ static int iterate_tail(miagpu_ctx* c, const IterTail& a, const Trace& tr) {
   // ---- this round's flags (cull_maln_from_fsdb, mia.c:452-470), sticky (H10); the newly dropped reads leave the base columns
   cut_thresholds(a.hard_cut, slope, intercept, H->thr);
   MIAGPU_CUDA(cudaMemcpyAsync(c->d_thr.p, H->thr, sizeof(H->thr), cudaMemcpyHostToDevice, main));
-  cut_flags_kernel<<<(unsigned)((n + 255) / 256), 256, 0, main>>>(n, c->d_seqlen.p, c->d_score.p, c->d_thr.p, c->d_dropf.p, nullptr, c->d_cstats.p,
-                                                                  has_unique ? c->d_unique.p : nullptr, c->d_newly.p);
-  undo_kernel<<<(unsigned)((n + 255) / 256), 256, 0, main>>>(cons_params(c), n, c->d_newly.p, c->d_entries.p);
-  MIAGPU_CUDA(cudaGetLastError());
-  c->launches += 2;
+  if (c->fs_on) {
+    if (!fs_flags_and_undo(c, has_unique)) return 0;
+  } else {
+    cut_flags_kernel<<<(unsigned)((n + 255) / 256), 256, 0, main>>>(n, c->d_seqlen.p, c->d_score.p, c->d_thr.p, c->d_dropf.p, nullptr, c->d_cstats.p,
+                                                                    has_unique ? c->d_unique.p : nullptr, c->d_newly.p);
+    undo_kernel<<<(unsigned)((n + 255) / 256), 256, 0, main>>>(cons_params(c), n, c->d_newly.p, c->d_entries.p);
+    MIAGPU_CUDA(cudaGetLastError());
+    c->launches += 2;
+  }
   MIAGPU_CUDA(cudaMemcpyAsync(&H->bad_after, &c->d_cstats.p->bad, sizeof(long long), cudaMemcpyDeviceToHost, main));
   MIAGPU_CUDA(cudaEventRecord(c->xev[2], main));
   if (a.dropped) {
     MIAGPU_CUDA(cudaStreamWaitEvent(down, c->xev[2], 0));
-    MIAGPU_CUDA(cudaMemcpyAsync(a.dropped, c->d_dropf.p, n, cudaMemcpyDeviceToHost, down));
+    MIAGPU_CUDA(cudaMemcpyAsync(a.dropped, c->d_dropf.p, n, cudaMemcpyDeviceToHost, down));     // fs mode: AlnSeq.dropped behind front_asp (fs_flags_and_undo)
   }
   tr.mark("flags + undo enqueued");
   c->cons_stage = 2;
@@ -1742,6 +2267,7 @@ static int host_round_front(miagpu_ctx* c, const char* who, int64_t n, const uin
   tr.mark("buffers reserved");
   realign_reset_stats(c);
   c->n = n; c->total_bases = total; c->cut_inputs_n = -1;
+  c->fs_on = false; c->fs_prev_valid = false;
   c->max_read_len = C > 1 ? MAX_READ : -1;            // chunked: the longest read is not known before the last upload
   // the side streams start after whatever the compute stream still has queued
   cut_init_kernel<<<1, 256, 0, main>>>(c->d_cstats.p);
@@ -1875,6 +2401,10 @@ extern "C" int miagpu_iterate_resident(miagpu_ctx* c, int hard_cut, int score_cu
   const bool fit = !score_cut_set && hard_cut <= 0;
   const Trace tr;
   cudaStream_t main = c->stream, down = c->s_down;
+  if (c->fs_on) {
+    if (!fs_reserve_round(c)) return 0;
+    fs_begin_round(c);
+  }
   MIAGPU_CUDA(cudaEventRecord(c->ev[1], main));
   cut_init_kernel<<<1, 256, 0, main>>>(c->d_cstats.p);
   MIAGPU_CUDA(cudaGetLastError());
@@ -1897,6 +2427,10 @@ extern "C" int miagpu_iterate_resident(miagpu_ctx* c, int hard_cut, int score_cu
   MIAGPU_CUDA(cudaEventElapsedTime(&c->ms_kernels, c->ev[1], c->ev[2]));
   c->ms_h2d = c->ms_d2h = 0;
   MIAGPU_CUDA(cudaMemcpy(&c->n_fallback, c->d_meta.p + META_NFALL, 4, cudaMemcpyDeviceToHost));
+  if (c->fs_on) {
+    c->fs_prev_seq_len = c->seq_len;                 // the geometry of this round's alignments, should the next round have to freeze one
+    fs_carry_submat(c);
+  }
   return 1;
 }
 
@@ -2718,9 +3252,22 @@ extern "C" int miagpu_compact_reads(miagpu_ctx* c, const uint8_t* keep, const ui
   } else {
     MIAGPU_CUDA(cudaMemcpyAsync(c->d_off2.p, off_new.data(), 8, cudaMemcpyHostToDevice, c->stream));
   }
+  // the pass-1 alignment of the reads that stay, in FSDB order, becomes "the previous round" of the first round: slots that
+  // pass 1 filled and no later round re-uses keep that content (slots.cuh)
+  c->fs_prev_valid = false;
+  if (m && c->d_start.cap && c->d_rc_out.cap &&
+      c->d_runs_prev.reserve((size_t)m * MAX_RUNS) && c->d_nruns_prev.reserve(m) && c->d_abr_prev.reserve(m) && c->d_as_prev.reserve(m) &&
+      c->d_ae_prev.reserve(m) && c->d_flip_prev.reserve(m)) {
+    fs_prev_from_pass1_kernel<<<(unsigned)((m + 255) / 256), 256, 0, c->stream>>>(m, c->d_src.p, c->d_dropf.p, c->d_start.p, c->d_end.p, c->d_abr.p,
+                                                                                 c->d_nruns.p, c->d_runs.p, c->d_rc_out.p, c->d_as_prev.p, c->d_ae_prev.p,
+                                                                                 c->d_abr_prev.p, c->d_nruns_prev.p, c->d_runs_prev.p, c->d_flip_prev.p);
+    MIAGPU_CUDA(cudaGetLastError());
+    c->fs_prev_valid = true; c->fs_prev_pass1 = true; c->fs_prev_seq_len = c->seq_len;
+  }
   MIAGPU_CUDA(cudaStreamSynchronize(c->stream));
   std::swap(c->d_bases, c->d_bases2);
   std::swap(c->d_off, c->d_off2);
+  c->fs_on = false;
   c->n = m; c->cut_inputs_n = -1;
   c->total_bases = off_new.back();
   c->max_read_len = maxL;

@@ -206,26 +206,29 @@ class ResidentAssembler:
     """The same loop with everything resident in HBM and one library call per round (miagpu_iterate_resident, or the
     sharded protocol when `world` > 1): the path for large read sets (BASELINE configs[2]..[4]).
 
-    Every read owns its fresh AlnSeq segments and carries one sticky dropped flag, so this equals the reference as long
-    as no read changes between wrap-split and whole from one round to the next (then the reference's slot-indexed
-    flags and never-cleared back pointers, H10 / mia_main.c:273-276, shift to OTHER reads; `Assembler` above reproduces
-    that, this class reports `split_changes` instead).
+    On one GPU the FSDB's pointer state goes to the device after pass 1 (miagpu_set_fsdb) and the rounds follow the reference's
+    FragSeq -> AlnSeq pointers there: slot-indexed sticky dropped flags (H10), never-cleared back pointers (mia_main.c:273-276),
+    reads that score exactly 2000 (strand_known = 0, mia.c:1653) and -D (`distant_ref`: mia.c:1614, mia_main.c:120-174,
+    find_alignable_len in the cull).  Sharded rounds still give every read its own fresh segments and one sticky flag and count
+    what that misses in `split_changes`.
 
     `exchange`: None for one GPU; otherwise an object with
         all_gather_host(np_array) -> concatenation over ranks in rank order
         rounds                    -> shard.ShardedRounds (or anything with .resident(...))
     """
 
-    def __init__(self, gpu, ref, sm, circular=1, k=0, soft_mask=0, cons_code=1, exchange=None, strand_unknown="raise"):
-        """strand_unknown: what to do with a read that scores exactly 2000 in pass 1.  The reference accepts it with
-        strand_known = 0 (mia.c:1614, 1653), never realigns it (mia_main.c:178) and keeps following its pass-1 AlnSeq pointer,
-        which from round 1 on is another read's slot -- that read is then counted twice and may inherit a dropped flag.
-        "raise" (default; every parity test runs with it) refuses such input; "drop" leaves the read out of the FSDB and counts
-        it in `strand_unknown_reads` -- a stated deviation for 10^7-read runs, where a handful of such reads do occur."""
+    def __init__(self, gpu, ref, sm, circular=1, k=0, soft_mask=0, cons_code=1, exchange=None, strand_unknown="raise", distant_ref=0,
+                 pointer_state=None):
+        """strand_unknown ("raise" / "drop") only matters without the pointer state (sharded rounds), which does not model reads that
+        score exactly 2000.  pointer_state: None = on unless `exchange` is given."""
         self.g, self.sm, self.circular, self.k, self.soft_mask, self.cons_code = gpu, sm, circular, k, soft_mask, cons_code
         self.ref0, self.x = ref, exchange
         self.split_changes = 0
         self.strand_unknown, self.strand_unknown_reads = strand_unknown, 0
+        self.distant_ref = int(distant_ref)
+        self.fs = (exchange is None) if pointer_state is None else bool(pointer_state)
+        if self.distant_ref and not self.fs:
+            raise NotImplementedError("-D needs the pointer state (one GPU)")
         gpu.set_pssm(sm)
 
     def _gather(self, a):
@@ -239,40 +242,66 @@ class ResidentAssembler:
         p = g.pass1(fields=("hits", "score", "rc", "as_", "ae", "start", "end"))
         self.p1 = p
         seq_len = np.diff(off).astype(np.int32)
-        keep = (p["hits"] > 0) & (p["score"] >= FIRST_ROUND_SCORE_CUTOFF)            # mia.c:1614
-        unknown = keep & (p["score"] == FIRST_ROUND_SCORE_CUTOFF)
-        if unknown.any():
+        keep = (p["hits"] > 0) & ((p["score"] >= FIRST_ROUND_SCORE_CUTOFF) | bool(self.distant_ref))   # mia.c:1614
+        unknown = keep & (p["score"] <= FIRST_ROUND_SCORE_CUTOFF)                                       # mia.c:1653
+        if not self.fs and unknown.any():
             if self.strand_unknown != "drop":
-                raise NotImplementedError("reads with score == 2000 keep strand_known = 0 and are never realigned (mia.c:1653)")
+                raise NotImplementedError("sharded rounds: reads with score == 2000 keep strand_known = 0 and are never realigned (mia.c:1653)")
             self.strand_unknown_reads = int(unknown.sum())
             keep &= ~unknown
+            unknown[:] = False
         idx = np.flatnonzero(keep)
         self._idx, self._n_all = idx, len(seq_len)
         self.seq_len, self.score = seq_len[idx], p["score"][idx].copy()
         self.rc, self.as_, self.ae = p["rc"][idx].copy(), p["as_"][idx].copy(), p["ae"][idx].copy()
+        self.strand_known = ~unknown[idx]
         self.split = p["start"][idx] > p["end"][idx]                                 # mia.c:1619
         self.maln_size = int(len(idx) + self.split.sum())                            # culled_maln->size (mia.c:54): AlnSeqs of pass 1
         if self.x is not None or not defer_cull:
             self.pass1_cull(self._gather(self.seq_len), self._gather(self.score))
         return p
 
+    def _alignable_len(self, ref_wrapped_upper, wrap_len):
+        """find_alignable_len (mia.c:69-91) of every FSDB read against the (wrapped, upper-cased) reference"""
+        isn = np.concatenate([[0], np.cumsum(np.frombuffer(ref_wrapped_upper.encode(), np.uint8) == ord("N"))])
+        a = np.clip(self.as_.astype(np.int64), 0, wrap_len)
+        e = np.clip(np.minimum(self.ae.astype(np.int64), wrap_len), a, wrap_len)
+        return np.maximum(self.seq_len - (isn[e] - isn[a]), 15).astype(np.int32)     # MIN_ALIGNABLE_LEN
+
     def pass1_cull(self, all_seq_len, all_score):
         """pass-1 cull (mia_main.c:848) with the fit over the reads of ALL ranks in FSDB order: only its dropped flags survive"""
         g, idx = self.g, self._idx
         fit = api.score_cut(all_seq_len, all_score)
-        dropped = api.cull_flags(self.seq_len, self.score, None, 0, 1, fit[0], fit[1])
+        thr_len = self.seq_len
+        if self.distant_ref:
+            ru = self.ref0.upper()
+            rw = ru + (ru[:min(256, len(ru))] if self.circular else "")
+            thr_len = self._alignable_len(rw, len(rw))
+        dropped = api.cull_flags(thr_len, self.score, None, 0, 1, fit[0], fit[1])
+        # AlnSeq slots of pass 1 in merge order (mia.c:1619-1643): one per accepted read, two when wrap-split
+        nsl = 1 + self.split.astype(np.int64)
+        first = np.cumsum(nsl) - nsl
+        n_slots = int(nsl.sum())
+        slot_dropped = np.zeros(n_slots + 1, np.uint8)
+        slot_dropped[first[dropped > 0]] = 1
+        slot_dropped[first[(dropped > 0) & self.split] + 1] = 1
         ok = self.score > 0                                                          # clean_FSDB (mia.c:400-406)
         keep_dev = np.zeros(self._n_all, np.uint8)
         keep_dev[idx[ok]] = 1
         rev = np.zeros(self._n_all, np.uint8)
-        rev[idx] = self.rc == 1                                                      # stored orientation (fsdb.c:209-227)
+        rev[idx] = (self.rc == 1) & self.strand_known                               # stored orientation (fsdb.c:209-227)
         g.compact_reads(keep_dev, rev)
         self.fsdb_idx = idx[ok]                                                      # input index of every FSDB read
-        for name in ("seq_len", "score", "rc", "as_", "ae", "split"):
+        front, back = first[ok].astype(np.int32), np.where(self.split, first + 1, -1)[ok].astype(np.int32)
+        for name in ("seq_len", "score", "rc", "as_", "ae", "split", "strand_known"):
             setattr(self, name, getattr(self, name)[ok])
         self.dropped = np.ascontiguousarray(dropped[ok], np.uint8)
         g.set_alignment_inputs(self.rc, self.as_, self.ae)
-        g.set_cut_inputs(self.seq_len, None, self.dropped)
+        if self.fs:
+            g.set_fsdb(self.seq_len, self.score, None, self.strand_known.astype(np.uint8), front, back, n_slots, slot_dropped[:n_slots],
+                       self.distant_ref)
+        else:
+            g.set_cut_inputs(self.seq_len, None, self.dropped)
         self.iter, self.cons, self.last = 0, None, self.ref0.upper()
 
     def begin_round(self):
@@ -280,6 +309,8 @@ class ResidentAssembler:
             self.last = self.cons
         self.iter += 1
         self.g.set_reference(self.last, self.circular, with_rc=0)
+        if self.distant_ref:
+            self.retried = self.g.distant_retry()                                    # mia_main.c:120-174 (iteration 2 on)
 
     def iterate(self, want_gaps=False):
         g = self.g
@@ -293,9 +324,13 @@ class ResidentAssembler:
     def end_round(self, cons, fit, gaps):
         self.fit, self.gaps = fit, gaps
         self.score, self.as_, self.ae = self.g.adopt_alignment()
+        if self.fs and not self.strand_known.all():
+            st = self.g.get_fsdb()
+            self.strand_known, self.rc = st["strand_known"].astype(bool), st["rc"]
         L = len(self.last)
-        split = self.as_ > np.where(self.ae > L, self.ae - L, self.ae)
-        self.split_changes += int((split != self.split).sum())
+        split = (self.as_ > np.where(self.ae > L, self.ae - L, self.ae)) & self.strand_known
+        if not self.fs:
+            self.split_changes += int((split != self.split).sum())
         self.split = split
         self.cons = cons
         return cons, cons == self.last

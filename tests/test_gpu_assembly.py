@@ -75,7 +75,7 @@ def _session_inputs(name):
 
 
 @pytest.mark.parametrize("name,matrix", [("synth2k_c_k10", "onepass"), ("synth3k_div10_c_k12", "ancient"), ("synth2k5_pe_long_c_k12", "pe"),
-                                         ("tr1_tf_lin", "ancient")])
+                                         ("tr1_tf_lin", "ancient"), ("tr1_tf_c", "ancient"), ("tr1_tf_c_k8_M", "ancient")])
 def test_resident_rounds_reproduce_reference_sessions(gpu, golden, name, matrix):
     # everything resident, one library call per round (score cut on the device): the reference's consensus of every round
     import _pkg
@@ -88,9 +88,49 @@ def test_resident_rounds_reproduce_reference_sessions(gpu, golden, name, matrix)
         cons, conv = A.iterate(want_gaps=True)
         got = np.stack([A.score, A.as_, A.ae, A.rc.astype(np.int32)], 1).tolist()
         assert got == e["reads"], f"{name}: iteration {it + 1} per-read score/as/ae"
+        assert np.flatnonzero(A.gaps).tolist() == [g for g in e["gaps"] if g < len(A.last)], f"{name}: iteration {it + 1} gaps"
         assert cons == e["cons"], f"{name}: iteration {it + 1} consensus"
         assert conv == e["converged"]
-    assert A.split_changes == 0
+
+
+def _load_r2(name):
+    import gzip
+    return json.load(gzip.open(os.path.join(G, "sessions_r2.json.gz"), "rt"))[name]
+
+
+@pytest.mark.parametrize("name,matrix", [("flat_2000_c", "flat"), ("origin305_splitflip_c", "onepass"), ("origin303_splitflip_c", "onepass"),
+                                         ("synth3k_div10_c_k12_D", "ancient"), ("synth1k_N_lin_D", "ancient")])
+def test_resident_rounds_follow_the_reference_pointers(gpu, golden, name, matrix):
+    # the reference's FragSeq -> AlnSeq pointer behaviour in the one-call resident rounds (tests/golden/make_golden_r2.py): reads that
+    # score exactly 2000 (strand_known = 0), split patterns that change (slot-indexed sticky flags, stale back pointers), -D
+    import _pkg
+    _pkg.load()
+    from mia_b200 import driver
+    s = _load_r2(name)
+    reads = s["reads"]
+    off = np.zeros(len(reads) + 1, np.int64)
+    np.cumsum([len(r) for r in reads], out=off[1:])
+    bases = np.frombuffer("".join(reads).encode(), np.uint8)
+    A = driver.ResidentAssembler(gpu, s["ref"], golden[matrix], s["circular"], s["k"], 0, distant_ref=s["distant_ref"])
+    p = A.pass1(bases, off)
+    for i, e in enumerate(s["pass1"]):
+        assert int(p["hits"][i]) == e["hits"], (name, i)
+        if e["hits"]:
+            got = [int(p[k][i]) for k in ("score", "rc", "as_", "ae", "start")]
+            assert got == [e[k] for k in ("score", "rc", "as_", "ae", "start")], (name, i)
+    assert A.fsdb_idx.tolist() == s["iters"][0]["ids"]
+    stale = 0
+    for it, e in enumerate(s["iters"]):
+        cons, conv = A.iterate(want_gaps=True)
+        got = np.stack([A.score, A.as_, A.ae, A.rc.astype(np.int32), A.strand_known.astype(np.int32)], 1).tolist()
+        assert got == e["reads"], f"{name}: iteration {it + 1} per-read score/as/ae/rc/strand_known"
+        st = gpu.last_fsdb_stats()
+        stale += st["stale_pointers"]
+        n_drop_exp = sum(x[3] for x in e["slots"])
+        assert np.flatnonzero(A.gaps).tolist() == [g for g in e["gaps"] if g < len(A.last)], f"{name}: iteration {it + 1} gaps"
+        assert cons == e["cons"], f"{name}: iteration {it + 1} consensus ({st}, {n_drop_exp} AlnSeqs dropped in the reference)"
+        assert conv == e["converged"]
+    assert stale > 0, "the session was made to exercise stale pointers"
 
 
 @pytest.mark.parametrize("name,matrix,parts", [("synth3k_div10_c_k12", "ancient", 2), ("synth2k5_pe_long_c_k12", "pe", 3)])
@@ -104,7 +144,7 @@ def test_sharded_assembly_to_convergence(gpu, golden, name, matrix, parts):
     n = len(off) - 1
     ctxs = [api.MiaGpu(0) for _ in range(parts)]
     try:
-        asms = [driver.ResidentAssembler(g, s["ref"], golden[matrix], s["circular"], s["k"], s["soft_mask"]) for g in ctxs]
+        asms = [driver.ResidentAssembler(g, s["ref"], golden[matrix], s["circular"], s["k"], s["soft_mask"], pointer_state=False) for g in ctxs]
         for r, a in enumerate(asms):
             lo, hi = n * r // parts, n * (r + 1) // parts
             a.pass1(np.ascontiguousarray(bases[off[lo]:off[hi]]), np.ascontiguousarray(off[lo:hi + 1] - off[lo]), defer_cull=True)
