@@ -9,7 +9,9 @@
  * reads enter the FSDB (mia.c:1614), their strand, the convergence test (mia_main.c:909-976), the file names.
  * -u / -U (the repeat filter, mia_main.c:827-844, 883-890, 938-945) run the per-phase calls instead of the one-call round, with
  * the FSDB order and the slot-indexed sticky AlnSeq.dropped flags kept here as mia_main.c keeps them.
- * Reads that score exactly 2000 (strand_known = 0, mia.c:1653), -D, -T, -h, -C, -I are not handled here.
+ * The one-call rounds follow the reference's FragSeq -> AlnSeq pointers on the device (miagpu_set_fsdb): reads that score exactly
+ * 2000 (strand_known = 0, mia.c:1653), never-cleared back pointers, slot-indexed sticky flags, and -D (mia.c:1614,
+ * mia_main.c:120-174: miagpu_distant_retry).  -T, -h, -C, -I are not handled here.
  * There is no CPU fallback: without a CUDA device miagpu_create fails and so does this program. */
 #define _POSIX_C_SOURCE 199309L
 #include <stdio.h>
@@ -122,7 +124,7 @@ static void filter_and_cull( miagpu_ctx* g, Fsdb* F ) {
 int main( int argc, char** argv ) {
   const char *ref_fn = NULL, *frag_fn = NULL, *mat_fn = NULL, *root = "assembly.maln.iter";
   int circular = 0, k = -1, cons_code = 1, hard_cut = 0, final_only = 0, repeat_filt = 0, just_outer_coords = 1, i;
-  int score_cut_set = 0, drop_2000 = 0, n_2000 = 0;
+  int score_cut_set = 0, distant_ref = 0, n_unknown = 0;
   double user_slope = 200.0, user_icpt = 0.0;           /* DEF_S, DEF_N (params.h:36-37); -S / -N: mia_main.c:579-586 */
   for ( i = 1; i < argc; i++ ) {
     if ( !strcmp( argv[i], "-c" ) ) circular = 1;
@@ -130,7 +132,7 @@ int main( int argc, char** argv ) {
     else if ( !strcmp( argv[i], "-u" ) ) repeat_filt = 1;
     else if ( !strcmp( argv[i], "-U" ) ) repeat_filt = 2;
     else if ( !strcmp( argv[i], "-A" ) ) just_outer_coords = 0;
-    else if ( !strcmp( argv[i], "--drop-score-2000" ) ) drop_2000 = 1;   /* not a reference option: see the accept test below */
+    else if ( !strcmp( argv[i], "-D" ) ) distant_ref = 1;
     else if ( !strcmp( argv[i], "-i" ) ) ;
     else if ( i + 1 < argc && !strcmp( argv[i], "-r" ) ) ref_fn = argv[++i];
     else if ( i + 1 < argc && !strcmp( argv[i], "-f" ) ) frag_fn = argv[++i];
@@ -143,7 +145,7 @@ int main( int argc, char** argv ) {
     else if ( i + 1 < argc && !strcmp( argv[i], "-N" ) ) { user_icpt = atof( argv[++i] ); score_cut_set = 1; }
     else { fprintf( stderr, "mia_gpu: option %s is not handled by this host (see the header of host/mia_gpu.c)\n", argv[i] ); return 2; }
   }
-  if ( repeat_filt && ( hard_cut > 0 || score_cut_set ) ) { fprintf( stderr, "mia_gpu: -H / -S / -N together with -u / -U are not handled by this host\n" ); return 2; }
+  if ( repeat_filt && ( hard_cut > 0 || score_cut_set || distant_ref ) ) { fprintf( stderr, "mia_gpu: -H / -S / -N / -D together with -u / -U are not handled by this host\n" ); return 2; }
   if ( !ref_fn || !frag_fn || !mat_fn ) {
     fprintf( stderr, "usage: mia_gpu -r ref.fa -f reads.fa|fq -s matrix.txt [-m root] [-c] [-k K] [-p code] [-H cut] [-F] [-u|-U] [-A]\n" );
     return 2;
@@ -179,44 +181,83 @@ int main( int argc, char** argv ) {
   uint8_t *rc = xmalloc( n ), *keep = xmalloc( n );
   CK( miagpu_pass1( g, hits, score, NULL, NULL, rc, as, ae, start, end, NULL, NULL, NULL, NULL ) );
 
-  /* sg_align's accept test (mia.c:1614), the FSDB in input order, the number of AlnSeqs pass 1 merges (mia.c:1619-1643) */
+  /* sg_align's accept test (mia.c:1614), the AlnSeq slots pass 1 merges in input order (mia.c:1619-1643), the pass-1 cull over
+     every accepted read (mia_main.c:848), then clean_FSDB (mia.c:400-406): reads that scored <= 0 (-D only) leave the FSDB */
   int64_t* src = xmalloc( n * 8 );
   int32_t maln_size = 0;
-  for ( j = 0; j < n; j++ ) {
-    keep[j] = ( hits[j] > 0 && score[j] >= FIRST_ROUND_SCORE_CUTOFF );
-    if ( !keep[j] ) continue;
-    if ( score[j] == FIRST_ROUND_SCORE_CUTOFF ) {
-      /* the reference accepts the read with strand_known = 0 (mia.c:1653), never realigns it (mia_main.c:178) and keeps following
-         its pass-1 AlnSeq pointer, which from round 1 on is another read's slot: refused, or left out on request */
-      if ( !drop_2000 ) { fprintf( stderr, "mia_gpu: a read scores exactly 2000 (strand_known = 0): not handled (--drop-score-2000 leaves such reads out)\n" ); return 3; }
-      keep[j] = 0; n_2000++;
-      continue;
+  int64_t n_acc = 0;
+  int32_t *a_len = xmalloc( n * 4 ), *a_thr = xmalloc( n * 4 ), *a_score = xmalloc( n * 4 ), *a_first = xmalloc( n * 4 );
+  uint8_t* a_below = xmalloc( n );
+  int64_t* a_src = xmalloc( n * 8 );
+  {
+    /* find_alignable_len (mia.c:69-91) against the wrapped, upper-cased input reference: -D only */
+    int wrap = circular ? ( ref_len < MIAGPU_MAX_READ ? ref_len : MIAGPU_MAX_READ ) : 0, wl = ref_len + wrap;
+    int32_t* npre = xmalloc( ( (size_t)wl + 1 ) * 4 );
+    for ( j = 0; j < wl; j++ ) npre[j + 1] = npre[j] + ( toupper( (unsigned char)ref[j % ref_len] ) == 'N' );
+    for ( j = 0; j < n; j++ ) {
+      int L = (int32_t)( off[j + 1] - off[j] ), al = L;
+      keep[j] = ( hits[j] > 0 && ( score[j] >= FIRST_ROUND_SCORE_CUTOFF || distant_ref ) );
+      if ( !keep[j] ) continue;
+      if ( distant_ref ) {
+        int64_t a = as[j], e = ae[j] > wl ? wl : ae[j];
+        if ( a >= 0 && e > a ) al -= npre[e] - npre[a];
+        if ( al < 15 ) al = 15;                                                          /* MIN_ALIGNABLE_LEN */
+      }
+      a_len[n_acc] = L; a_thr[n_acc] = al; a_score[n_acc] = score[j]; a_first[n_acc] = maln_size; a_src[n_acc] = j;
+      maln_size += 1 + ( start[j] > end[j] );
+      n_acc++;
     }
-    maln_size += 1 + ( start[j] > end[j] );
-    src[m++] = j;
+    free( npre );
+  }
+  /* pass-1 cull (mia_main.c:848): the fit over the accepted reads that score >= 2000, the threshold by (alignable) length; only
+     the sticky flags of the AlnSeq slots survive */
+  double slope = 0, icpt = 0;
+  uint8_t* slot_dropped = xmalloc( (size_t)maln_size + 2 );
+  if ( !repeat_filt ) {
+    if ( hard_cut > 0 || score_cut_set ) CK( miagpu_cull_flags( n_acc, a_thr, a_score, NULL, hard_cut, score_cut_set, user_slope, user_icpt, a_below ) );
+    else {
+      CK( miagpu_score_cut( n_acc, a_len, a_score, NULL, &slope, &icpt ) );
+      CK( miagpu_cull_flags( n_acc, a_thr, a_score, NULL, 0, 1, slope, icpt, a_below ) );
+    }
+    for ( j = 0; j < n_acc; j++ )
+      if ( a_below[j] ) {
+        slot_dropped[a_first[j]] = 1;
+        if ( start[a_src[j]] > end[a_src[j]] ) slot_dropped[a_first[j] + 1] = 1;
+      }
+  }
+  for ( j = 0; j < n_acc; j++ ) {
+    int64_t q = a_src[j];
+    if ( score[q] > 0 ) src[m++] = q; else keep[q] = 0;
   }
   int32_t *f_len = xmalloc( m * 4 ), *f_score = xmalloc( m * 4 ), *f_as = xmalloc( m * 4 ), *f_ae = xmalloc( m * 4 ), *abr = xmalloc( m * 4 );
-  uint8_t *f_rc = xmalloc( m ), *dropped = xmalloc( m );
+  uint8_t *f_rc = xmalloc( m ), *dropped = xmalloc( m ), *f_known = xmalloc( m ), *known_now = xmalloc( m ), *rc_now = xmalloc( m ), *revc = xmalloc( n );
+  int32_t *f_front = xmalloc( m * 4 ), *f_back = xmalloc( m * 4 );
   int64_t *s_off = xmalloc( ( m + 1 ) * 8 ), *f_id_off = xmalloc( ( m + 1 ) * 8 ), *f_desc_off = xmalloc( ( m + 1 ) * 8 );
   for ( j = 0; j < m; j++ ) {
     int64_t q = src[j];
     f_len[j] = (int32_t)( off[q + 1] - off[q] ); f_score[j] = score[q]; f_as[j] = as[q]; f_ae[j] = ae[q]; f_rc[j] = rc[q];
+    f_known[j] = score[q] > FIRST_ROUND_SCORE_CUTOFF;                                    /* mia.c:1653 */
+    n_unknown += !f_known[j];
     s_off[j + 1] = s_off[j] + f_len[j];
     f_id_off[j + 1] = f_id_off[j] + ( id_off[q + 1] - id_off[q] );
     f_desc_off[j + 1] = f_desc_off[j] + ( desc_off[q + 1] - desc_off[q] );
   }
+  { int64_t k = 0;                                                                        /* front_asp / back_asp as slot indices */
+    for ( j = 0; j < m; j++ ) {
+      while ( a_src[k] != src[j] ) k++;
+      f_front[j] = a_first[k];
+      f_back[j] = start[src[j]] > end[src[j]] ? a_first[k] + 1 : -1;
+    } }
   /* host copy of the FSDB: stored orientation (fsdb.c:209-227), ids, descriptions -- what the writer needs */
   uint8_t* stored = xmalloc( (size_t)s_off[m] + 1 );
   char *f_ids = xmalloc( (size_t)f_id_off[m] + 1 ), *f_descs = xmalloc( (size_t)f_desc_off[m] + 1 );
   for ( j = 0; j < m; j++ ) {
     int64_t q = src[j], L = f_len[j], t;
-    if ( !f_rc[j] ) memcpy( stored + s_off[j], bases + off[q], (size_t)L );
+    if ( !( f_rc[j] && f_known[j] ) ) memcpy( stored + s_off[j], bases + off[q], (size_t)L );   /* revcomped only when the strand is known */
     else for ( t = 0; t < L; t++ ) stored[s_off[j] + t] = comp[bases[off[q] + L - 1 - t]];
     memcpy( f_ids + f_id_off[j], ids + id_off[q], (size_t)( id_off[q + 1] - id_off[q] ) );
     memcpy( f_descs + f_desc_off[j], descs + desc_off[q], (size_t)( desc_off[q + 1] - desc_off[q] ) );
   }
-  /* pass-1 cull (mia_main.c:848): only its sticky flags survive */
-  double slope = 0, icpt = 0;
   Fsdb F;
   memset( &F, 0, sizeof F );
   if ( repeat_filt ) {
@@ -227,19 +268,19 @@ int main( int argc, char** argv ) {
     for ( j = 0; j < m; j++ ) { F.qual[j] = qual_sum[src[j]]; F.split[j] = start[src[j]] > end[src[j]]; F.order[j] = j; }
     filter_and_cull( g, &F );
   }
-  else if ( hard_cut > 0 || score_cut_set ) CK( miagpu_cull_flags( m, f_len, f_score, NULL, hard_cut, score_cut_set, user_slope, user_icpt, dropped ) );
-  else {
-    CK( miagpu_score_cut( m, f_len, f_score, NULL, &slope, &icpt ) );
-    CK( miagpu_cull_flags( m, f_len, f_score, NULL, 0, 1, slope, icpt, dropped ) );
-  }
   int64_t n_kept = 0;
-  CK( miagpu_compact_reads( g, keep, rc, &n_kept ) );
+  for ( j = 0; j < n; j++ ) revc[j] = rc[j] && score[j] > FIRST_ROUND_SCORE_CUTOFF;       /* add_virgin_fs2fsdb, fsdb.c:209-227 */
+  CK( miagpu_compact_reads( g, keep, revc, &n_kept ) );
   if ( n_kept != m ) { fprintf( stderr, "mia_gpu: compact_reads kept %lld of %lld\n", (long long)n_kept, (long long)m ); return 3; }
   CK( miagpu_set_alignment_inputs( g, f_rc, f_as, f_ae ) );
-  CK( miagpu_set_cut_inputs( g, f_len, NULL, dropped ) );
+  if ( repeat_filt ) {
+    if ( n_unknown ) { fprintf( stderr, "mia_gpu: reads that score exactly 2000 together with -u / -U are not handled by this host\n" ); return 3; }
+    CK( miagpu_set_cut_inputs( g, f_len, NULL, dropped ) );
+  }
+  else CK( miagpu_set_fsdb( g, f_len, NULL, f_score, f_known, f_front, f_back, maln_size, slot_dropped, distant_ref ) );
+  memcpy( known_now, f_known, (size_t)m );
   miagpu_fastx_close( fx );
-  fprintf( stderr, "mia_gpu: %lld reads read, %lld aligned in pass 1\n", (long long)n, (long long)m );
-  if ( n_2000 ) fprintf( stderr, "mia_gpu: %d reads scoring exactly 2000 left out (--drop-score-2000)\n", n_2000 );
+  fprintf( stderr, "mia_gpu: %lld reads read, %lld aligned in pass 1 (%d with unknown strand)\n", (long long)n, (long long)m, n_unknown );
   t_pass1 = now_ms() - t0 - t_init - t_parse;
 
   /* ---- rounds (mia_main.c:878-976): one library call each */
@@ -265,6 +306,21 @@ int main( int argc, char** argv ) {
       CK( miagpu_consensus_natural( g, F.df, F.db, cons_code, gaps, NULL, cons, &cons_len ) );
     }
     else {
+      if ( distant_ref ) {                                                              /* mia_main.c:120-174, from iteration 2 on */
+        int64_t tried = 0, learned = 0;
+        CK( miagpu_distant_retry( g, &tried, &learned ) );
+        if ( tried ) fprintf( stderr, "mia_gpu: iteration %d: %lld strand-unknown reads re-tried, %lld learned their strand\n", iter, (long long)tried, (long long)learned );
+        if ( learned ) {                                                                /* strcpy( fs->seq, tmp_rc ): the host copy follows */
+          CK( miagpu_get_fsdb( g, known_now, rc_now, NULL, NULL, NULL, NULL, NULL ) );
+          for ( j = 0; j < m; j++ )
+            if ( known_now[j] && !f_known[j] ) {
+              int64_t a = s_off[j], b = s_off[j + 1] - 1;
+              f_known[j] = 1; f_rc[j] = rc_now[j];
+              if ( rc_now[j] )
+                for ( ; a <= b; a++, b-- ) { unsigned char x = stored[a], y = stored[b]; stored[a] = comp[y]; stored[b] = comp[x]; }
+            }
+        }
+      }
       CK( miagpu_iterate_resident( g, hard_cut, score_cut_set, user_slope, user_icpt, cons_code, &slope, &icpt, dropped, gaps, cons, &cons_len ) );
       CK( miagpu_adopt_alignment( g, f_score, f_as, f_ae ) );
     }
@@ -277,7 +333,7 @@ int main( int argc, char** argv ) {
       miagpu_maln_reads rd;
       CK( miagpu_get_alignment( g, NULL, NULL, NULL, abr, NULL, st ) );
       for ( j = 0; j < m; j++ )
-        if ( st[j] != MIAGPU_ST_OK ) {          /* e.g. more runs than MIAGPU_MAX_RUNS: never written as if it were fine */
+        if ( st[j] != MIAGPU_ST_OK && f_known[j] ) {   /* e.g. more runs than MIAGPU_MAX_RUNS: never written as if it were fine */
           fprintf( stderr, "mia_gpu: read %lld came back with status 0x%x in iteration %d\n", (long long)src[j], st[j], iter );
           return 4;
         }
@@ -299,7 +355,8 @@ int main( int argc, char** argv ) {
         rd.unique_best = F.unique; rd.dropped_front = F.df; rd.dropped_back = F.db; rd.fsdb_order = F.order;
       }
       snprintf( fn, sizeof fn, "%s.%d", root, iter );
-      CK( miagpu_write_maln( fn, &hd, &rd, &n_aln ) );
+      if ( repeat_filt ) CK( miagpu_write_maln( fn, &hd, &rd, &n_aln ) );
+      else CK( miagpu_write_maln_fsdb( g, fn, &hd, &rd, &n_aln ) );
       fprintf( stderr, "mia_gpu: iteration %d: %lld AlnSeqs -> %s\n", iter, (long long)n_aln, fn );
     }
     t_write += now_ms() - t1;

@@ -501,6 +501,13 @@ int miagpu_maln_ref_size( int ref_len, int circular );   /* mia_main.c:67 + add_
 int miagpu_write_maln( const char* path, const miagpu_maln_header* hd,
                        const miagpu_maln_reads* rd, int64_t* n_alnseqs_out );
 
+/* The same for the round miagpu_iterate_resident just ran under miagpu_set_fsdb: the list follows the pointers (front_asp, then
+ * back_asp of every unique_best read in FSDB order, mia.c:463-476), so an AlnSeq that stale pointers reach is written once per
+ * pointer, with the smp codes the last visit of pop_smp_from_FSDB left and the slot's sticky dropped flag; content of slots that
+ * are no longer live is written as the earlier round left it.  rd->dropped_front / dropped_back / fsdb_order are not read. */
+int miagpu_write_maln_fsdb( miagpu_ctx* ctx, const char* path, const miagpu_maln_header* hd,
+                            const miagpu_maln_reads* rd, int64_t* n_alnseqs_out );
+
 /* ---- measurement helpers (bench.py) */
 /* per width bucket of the last realign: columns-per-lane K (0 = too wide),
  * reads, DP cells, kernel ms (CUDA events on the library's stream); MIAGPU_NBUCKET entries */

@@ -99,6 +99,7 @@ def load_library():
     L.miagpu_maln_ref_size.argtypes = [C.c_int, C.c_int]
     L.miagpu_read_pssm.argtypes = [C.c_char_p, _i32p]
     L.miagpu_write_maln.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, _i64p]
+    L.miagpu_write_maln_fsdb.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, _i64p]
     L.miagpu_set_fsdb.argtypes = [C.c_void_p] + [C.c_void_p] * 6 + [C.c_int64, C.c_void_p, C.c_int]
     L.miagpu_get_fsdb.argtypes = [C.c_void_p] + [C.c_void_p] * 6 + [_i64p]
     L.miagpu_last_fsdb_stats.argtypes = [C.c_void_p, _i64p, _i64p, _i64p, _i64p]
@@ -119,7 +120,7 @@ EXPORTS = ["miagpu_device_count", "miagpu_create", "miagpu_destroy", "miagpu_las
            "miagpu_last_cut_stats", "miagpu_repeat_filter", "miagpu_trim", "miagpu_get_alignment",
            "miagpu_fastx_open", "miagpu_fastx_open_memory", "miagpu_fastx_format", "miagpu_fastx_next", "miagpu_fastx_batch", "miagpu_fastx_close",
            "miagpu_maln_ref_size", "miagpu_write_maln", "miagpu_read_pssm", "miagpu_align_windows",
-           "miagpu_set_fsdb", "miagpu_get_fsdb", "miagpu_last_fsdb_stats", "miagpu_distant_retry"]
+           "miagpu_set_fsdb", "miagpu_get_fsdb", "miagpu_last_fsdb_stats", "miagpu_distant_retry", "miagpu_write_maln_fsdb"]
 
 
 def _ptr(a):

@@ -166,13 +166,46 @@ struct Out {
 inline double wall_ms() { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec * 1e3 + t.tv_nsec * 1e-6; }
 
 struct Seg {                  // one AlnSeq of the list
-  int64_t read;
+  int64_t read;               // the read whose alignment fills the AlnSeq (its id, description, score ...)
   int32_t start, end;
   int32_t col0, ncol;         // slice of the read's alignment columns
   int32_t smp_n;              // characters of AlnSeq.smp: end - start + 1 (= ncol, except for a back segment whose read starts beyond seq_len)
   char seg;
   uint8_t dropped;
+  // the pointer state of the one-call rounds (slots.cuh): an AlnSeq whose smp codes were written by another read's visit
+  // (pop_smp_from_FSDB follows stale pointers), and AlnSeqs whose content is an older round's (frozen) alignment
+  uint8_t ov = 0;
+  int32_t fl = 0, total = 0, bias = 0, bf = 0;
+  int32_t fz = -1, fz_score = 0, fz_rc = 0, fz_num_inputs = 1;
 };
+struct FrozenView { const uint8_t* bases; const uint16_t* runs; const int32_t* nruns; int32_t stride, max_runs; };
+int maln_emit(const char* path, const miagpu_maln_header* hd, const miagpu_maln_reads* rd, std::vector<Seg>& segs, const FrozenView* fzv,
+              int64_t* n_alnseqs_out);
+// the AlnSeq(s) read i's own alignment fills this round (mia_main.c:259-276, split_pwaln mia.c:1376-1438): returns 1 when wrap-split
+inline int natural_segs(const miagpu_maln_reads* rd, int L, int64_t i, Seg& f, Seg& b) {
+  int start = rd->as[i];
+  int end = rd->ae[i] > L ? rd->ae[i] - L : rd->ae[i];                             // mia_main.c:259-263
+  int ncol = 0;
+  for (int64_t r = rd->run_off[i]; r < rd->run_off[i + 1]; r++) {
+    unsigned x = rd->packed[r];
+    if (MIAGPU_RUN_TYPE(x) != MIAGPU_RUN_I) ncol += (int)MIAGPU_RUN_LEN(x);
+  }
+  f = Seg{}; b = Seg{};
+  f.read = b.read = i;
+  if (start > end) {                                                               // split_pwaln at seq_len
+    int nf = L - start;
+    if (nf < 0) nf = 0;
+    if (nf > ncol) nf = ncol;
+    // a read that starts beyond seq_len (as > L: the window rule can leave it there) gets a front AlnSeq of negative length and a
+    // back AlnSeq whose end - start + 1 exceeds its columns; pop_smp_from_FSDB and asp_len go by end - start + 1 (fsdb.c:518-530)
+    const int over = start > L ? start - L : 0;
+    f.start = start; f.end = L - 1; f.col0 = 0; f.ncol = nf; f.smp_n = nf; f.seg = 'f';
+    b.start = 0; b.end = end; b.col0 = nf; b.ncol = ncol - nf; b.smp_n = ncol - nf + over; b.seg = 'b';
+    return 1;
+  }
+  f.start = start; f.end = end; f.col0 = 0; f.ncol = ncol; f.smp_n = ncol; f.seg = 'a';
+  return 0;
+}
 
 inline char smp_code(int from_front, int from_back) {
   if (from_front <= kDepth) return (char)('A' + from_front);
@@ -394,27 +427,23 @@ extern "C" int miagpu_write_maln(const char* path, const miagpu_maln_header* hd,
     const int64_t i = rd->fsdb_order ? rd->fsdb_order[k] : k;                      // position k of fsdb->fss holds read i
     if (i < 0 || i >= n) { set_error("miagpu_write_maln: fsdb_order[%lld] = %lld is not a read", (long long)k, (long long)i); return 0; }
     if (rd->unique_best && !rd->unique_best[i]) continue;
-    int start = rd->as[i];
-    int end = rd->ae[i] > L ? rd->ae[i] - L : rd->ae[i];                           // mia_main.c:259-263
-    int ncol = 0;
-    for (int64_t r = rd->run_off[i]; r < rd->run_off[i + 1]; r++) {
-      unsigned x = rd->packed[r];
-      if (MIAGPU_RUN_TYPE(x) != MIAGPU_RUN_I) ncol += (int)MIAGPU_RUN_LEN(x);
-    }
     uint8_t df = rd->dropped_front ? rd->dropped_front[i] : 0, db = rd->dropped_back ? rd->dropped_back[i] : df;
-    if (start > end) {                                                             // split_pwaln at seq_len
-      int nf = L - start;
-      if (nf < 0) nf = 0;
-      if (nf > ncol) nf = ncol;
-      // a read that starts beyond seq_len (as > L: the window rule can leave it there) gets a front AlnSeq of negative length and a
-      // back AlnSeq whose end - start + 1 exceeds its columns; pop_smp_from_FSDB and asp_len go by end - start + 1 (fsdb.c:518-530)
-      const int over = start > L ? start - L : 0;
-      segs.push_back({i, start, L - 1, 0, nf, nf, 'f', (uint8_t)(df != 0)});
-      segs.push_back({i, 0, end, nf, ncol - nf, ncol - nf + over, 'b', (uint8_t)(db != 0)});
+    Seg f, b;
+    if (natural_segs(rd, L, i, f, b)) {
+      f.dropped = df != 0; b.dropped = db != 0;
+      segs.push_back(f); segs.push_back(b);
     } else {
-      segs.push_back({i, start, end, 0, ncol, ncol, 'a', (uint8_t)(df != 0)});
+      f.dropped = df != 0;
+      segs.push_back(f);
     }
   }
+  return hostio::maln_emit(path, hd, rd, segs, nullptr, n_alnseqs_out);
+}
+
+namespace hostio {
+int maln_emit(const char* path, const miagpu_maln_header* hd, const miagpu_maln_reads* rd, std::vector<Seg>& segs, const FrozenView* fzv,
+              int64_t* n_alnseqs_out) {
+  const int L = hd->ref_len;
   const bool trace = getenv("MIAGPU_TRACE") != nullptr;
   double t_a = wall_ms(), t_b, t_fmt = 0, t_wr = 0;
   std::vector<uint32_t> order(segs.size());
@@ -484,22 +513,25 @@ extern "C" int miagpu_write_maln(const char* path, const miagpu_maln_header* hd,
   // buffers by worker threads, wave after wave, and written in order.
   std::atomic<long long> bad_read{-1};
   auto format_range = [&](size_t lo, size_t hi, Out& o) {
-    std::vector<char> colc, smp;                 // per alignment column of the read: AlnSeq.seq character
-    std::vector<int32_t> ins_at, ins_len;        // per column: read row and length of the insert in front of it
+    std::vector<char> colc, smp, smp_ov;         // per alignment column of the read: AlnSeq.seq character
+    std::vector<int32_t> ins_at, ins_len, actv;  // per column: read row and length of the insert in front of it; pop_smp's running position
     std::string idbuf;
     int64_t cached = -1;
     int front_total = 0, back_total = 0, nfront = 0;
     for (size_t kk = lo; kk < hi; kk++) {
       const Seg& sg = segs[order[kk]];
       const int64_t i = sg.read;
-      const uint8_t* read = rd->bases + rd->offsets[i];
-      const int rlen = (int)(rd->offsets[i + 1] - rd->offsets[i]);
-      if (cached != i) {
-        cached = i;
+      const uint8_t* read = sg.fz >= 0 ? fzv->bases + (int64_t)sg.fz * fzv->stride : rd->bases + rd->offsets[i];
+      const int rlen = sg.fz >= 0 ? fzv->stride : (int)(rd->offsets[i + 1] - rd->offsets[i]);
+      const int64_t key = sg.fz >= 0 ? -2 - (int64_t)sg.fz : i;
+      if (cached != key) {
+        cached = key;
         colc.clear(); ins_at.clear(); ins_len.clear();
-        int row = rd->abr[i], pend_at = 0, pend_len = 0;
-        for (int64_t r = rd->run_off[i]; r < rd->run_off[i + 1]; r++) {
-          unsigned x = rd->packed[r];
+        int row = sg.fz >= 0 ? 0 : rd->abr[i], pend_at = 0, pend_len = 0;
+        const int64_t r_lo = sg.fz >= 0 ? 0 : rd->run_off[i], r_hi = sg.fz >= 0 ? fzv->nruns[sg.fz] : rd->run_off[i + 1];
+        const uint16_t* rl = sg.fz >= 0 ? fzv->runs + (int64_t)sg.fz * fzv->max_runs : rd->packed;
+        for (int64_t r = r_lo; r < r_hi; r++) {
+          unsigned x = rl[r];
           int ty = (int)MIAGPU_RUN_TYPE(x), ln = (int)MIAGPU_RUN_LEN(x);
           if (ty == MIAGPU_RUN_I) {
             if (!pend_len) pend_at = row;
@@ -515,7 +547,7 @@ extern "C" int miagpu_write_maln(const char* path, const miagpu_maln_header* hd,
         if (row > rlen) { bad_read.store((long long)i); return; }
         // asp_len of the front and back AlnSeq (fsdb.c:518-530): columns + inserted bases (deletions count as sequence)
         int tot = (int)colc.size();
-        int s0 = rd->as[i], e0 = rd->ae[i] > L ? rd->ae[i] - L : rd->ae[i];
+        int s0 = sg.fz >= 0 ? 0 : rd->as[i], e0 = sg.fz >= 0 ? tot : (rd->ae[i] > L ? rd->ae[i] - L : rd->ae[i]);
         nfront = tot;
         int over = 0;                                                   // see the Seg list: as > L
         front_total = tot; back_total = 0;
@@ -529,14 +561,25 @@ extern "C" int miagpu_write_maln(const char* path, const miagpu_maln_header* hd,
         // smp over front then back with one running position (fsdb.c:556-616); the `over` positions past the back AlnSeq's string
         // are taken as the reference finds them after a fresh merge: no insert, not a '-'
         smp.resize(colc.size() + (size_t)over);
+        actv.resize(colc.size() + (size_t)over);
         int act = 0;
         for (int c = 0; c < tot + over; c++) {
           if (c < tot) act += ins_len[c];
+          actv[c] = act;
           int from_front = (c < nfront) ? act : front_total + act;      // fsdb.c:596: the back segment adds the front's length again
           int from_back = front_total + back_total - act - 1;
           smp[c] = smp_code(from_front, from_back);
           if (c >= tot || colc[c] != '-') act++;
         }
+      }
+      const char* smp_of = smp.data() + sg.col0;
+      if (sg.ov) {                                   // the codes another read's visit left in this AlnSeq (fsdb.c:563-614 through a stale pointer)
+        smp_ov.resize((size_t)sg.smp_n);
+        for (int c = 0; c < sg.smp_n; c++) {
+          const int a = sg.bias + actv[std::min<size_t>((size_t)sg.col0 + c, actv.size() - 1)];
+          smp_ov[c] = smp_code(sg.bf ? sg.fl + a : a, sg.total - a - 1);
+        }
+        smp_of = smp_ov.data();
       }
       // id, with split_pwaln's suffix rule (mia.c:1389-1398)
       const char* id = rd->ids + rd->id_off[i];
@@ -548,16 +591,16 @@ extern "C" int miagpu_write_maln(const char* path, const miagpu_maln_header* hd,
       }
       o.s("ID "); o.s(idbuf.c_str()); o.ch('\n');
       o.s("DESC "); if (rd->descs && rd->desc_off) o.s(rd->descs + rd->desc_off[i]); o.ch('\n');
-      o.kv("SCORE ", rd->score[i]);
-      o.kv("NUM_INPUTS ", rd->num_inputs ? rd->num_inputs[i] : 1);
+      o.kv("SCORE ", sg.fz >= 0 ? sg.fz_score : rd->score[i]);
+      o.kv("NUM_INPUTS ", sg.fz >= 0 ? sg.fz_num_inputs : rd->num_inputs ? rd->num_inputs[i] : 1);
       o.kv("START ", sg.start);
       o.kv("END ", sg.end);
-      o.kv("RC ", rd->rc[i] ? 1 : 0);
+      o.kv("RC ", (sg.fz >= 0 ? sg.fz_rc : rd->rc[i]) ? 1 : 0);
       o.kv("TR ", (rd->trimmed && rd->trimmed[i]) ? 1 : 0);
       o.kv("DR ", sg.dropped);
       o.s("SEG "); o.ch(sg.seg); o.ch('\n');
       o.s("SEQ "); o.s(colc.data() + sg.col0, (size_t)sg.ncol); o.ch('\n');
-      o.s("SMP "); o.s(smp.data() + sg.col0, (size_t)sg.smp_n); o.ch('\n');
+      o.s("SMP "); o.s(smp_of, (size_t)sg.smp_n); o.ch('\n');
       o.s("INS_POS");
       for (int c = 0; c < sg.ncol; c++) {
         int g = sg.col0 + c;
@@ -611,3 +654,4 @@ extern "C" int miagpu_write_maln(const char* path, const miagpu_maln_header* hd,
   if (n_alnseqs_out) *n_alnseqs_out = (int64_t)segs.size();
   return 1;
 }
+}  // namespace hostio

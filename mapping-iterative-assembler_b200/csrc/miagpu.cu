@@ -201,11 +201,11 @@ struct miagpu_ctx {
   DevBuf<uint8_t> d_known, d_slot_flag, d_slot_new, d_flip_prev;
   DevBuf<int32_t> d_front_slot, d_back_slot, d_first, d_nsl, d_slot_owner, d_slot_owner_prev, d_ent_slot, d_stale, d_fs_cnt, d_fs_tmp, d_nprefix;
   DevBuf<uint16_t> d_runs_prev;                // previous round's alignment: ping-pong partners of d_runs / d_nruns / d_abr / d_as_out / d_ae_out
-  DevBuf<int32_t> d_nruns_prev, d_abr_prev, d_as_prev, d_ae_prev;
+  DevBuf<int32_t> d_nruns_prev, d_abr_prev, d_as_prev, d_ae_prev, d_score_prev;
   DevBuf<uint8_t> d_fz_bases, d_fz_rc;         // frozen alignments
   DevBuf<uint16_t> d_fz_runs;
   DevBuf<int32_t> d_fz_nruns;
-  struct FzHost { int32_t start, cols, dels, rc; };
+  struct FzHost { int32_t start, cols, dels, rc, score, seg, read, num_inputs; };
   std::vector<FzHost> fz;                      // geometry of the frozen alignments
   std::unordered_map<int64_t, int> fz_of_slot; // slot that is no longer live -> its frozen content
   std::vector<uint8_t> h_known, h_rc;          // host mirrors (the -D chain is resolved on the host)
@@ -312,7 +312,7 @@ extern "C" void miagpu_destroy(miagpu_ctx* c) {
   c->d_known.release(); c->d_slot_flag.release(); c->d_slot_new.release(); c->d_flip_prev.release(); c->d_front_slot.release();
   c->d_back_slot.release(); c->d_first.release(); c->d_nsl.release(); c->d_slot_owner.release(); c->d_slot_owner_prev.release();
   c->d_ent_slot.release(); c->d_stale.release(); c->d_fs_cnt.release(); c->d_fs_tmp.release(); c->d_nprefix.release();
-  c->d_runs_prev.release(); c->d_nruns_prev.release(); c->d_abr_prev.release(); c->d_as_prev.release(); c->d_ae_prev.release();
+  c->d_runs_prev.release(); c->d_nruns_prev.release(); c->d_abr_prev.release(); c->d_as_prev.release(); c->d_ae_prev.release(); c->d_score_prev.release();
   c->d_fz_bases.release(); c->d_fz_rc.release(); c->d_fz_runs.release(); c->d_fz_nruns.release();
   if (c->aux) miagpu_destroy(c->aux);
   cudaStreamDestroy(c->stream);
@@ -1596,7 +1596,7 @@ static int fs_reserve_round(miagpu_ctx* c) {
   return c->d_first.reserve(n + 2) && c->d_nsl.reserve(n + 2) && c->d_slot_owner.reserve(slots) && c->d_slot_owner_prev.reserve(slots) &&
          c->d_ent_slot.reserve(2 * n + 2) && c->d_stale.reserve(3 * (2 * n + 16)) && c->d_fs_cnt.reserve(FS_CNT_WORDS) &&
          c->d_runs_prev.reserve((size_t)n * MAX_RUNS) && c->d_nruns_prev.reserve(n) && c->d_abr_prev.reserve(n) && c->d_as_prev.reserve(n) &&
-         c->d_ae_prev.reserve(n) && c->d_dropf.reserve(n + 1) && c->d_dropb.reserve(n + 1);
+         c->d_ae_prev.reserve(n) && c->d_score_prev.reserve(n + 1) && c->d_dropf.reserve(n + 1) && c->d_dropb.reserve(n + 1);
 }
 
 // the previous round's alignment stays where it is: this round's results go to the partner buffers
@@ -1607,6 +1607,7 @@ static void fs_begin_round(miagpu_ctx* c) {
     c->fs_nslots_prev = c->fs_nslots;
     c->fs_prev_pass1 = false; c->fs_prev_valid = true;
   }
+  if (c->n) cudaMemcpyAsync(c->d_score_prev.p, c->d_score.p, c->n * sizeof(int32_t), cudaMemcpyDeviceToDevice, c->stream);   // AlnSeq.score of the slots as they are
   c->fs_round++;
 }
 
@@ -1684,19 +1685,23 @@ static int fs_resolve(miagpu_ctx* c, int n_stale, bool has_unique) {
     if (!grow_keep(c->d_fz_bases, tot * FZ_BASES, c->fz.size() * FZ_BASES, st) || !grow_keep(c->d_fz_runs, tot * MAX_RUNS, c->fz.size() * MAX_RUNS, st) ||
         !grow_keep(c->d_fz_nruns, tot, c->fz.size(), st) || !grow_keep(c->d_fz_rc, tot, c->fz.size(), st)) return 0;
     DevBuf<int32_t> d_list;
-    if (!d_list.reserve(m * 6 + 16)) return 0;
+    if (!d_list.reserve(m * 10 + 16)) return 0;
     MIAGPU_CUDA(cudaMemcpyAsync(d_list.p, fz_which.data(), m * 4, cudaMemcpyHostToDevice, st));
     MIAGPU_CUDA(cudaMemcpyAsync(d_list.p + m, fz_dst.data(), m * 4, cudaMemcpyHostToDevice, st));
     const AlnView pv{c->d_as_prev.p, c->d_ae_prev.p, c->d_nruns_prev.p, c->d_runs_prev.p, c->d_abr_prev.p, c->fs_prev_seq_len};
     fs_freeze_kernel<<<(unsigned)((m + 127) / 128), 128, 0, st>>>((int)m, d_list.p, d_list.p + m, pv, c->d_bases.p, c->d_off.p, c->d_rc.p,
-                                                                  c->fs_prev_pass1 ? c->d_flip_prev.p : nullptr, c->d_fz_bases.p, c->d_fz_runs.p,
-                                                                  c->d_fz_nruns.p, c->d_fz_rc.p, d_list.p + 2 * m);
+                                                                  c->fs_prev_pass1 ? c->d_flip_prev.p : nullptr, c->d_score_prev.p, c->d_fz_bases.p,
+                                                                  c->d_fz_runs.p, c->d_fz_nruns.p, c->d_fz_rc.p, d_list.p + 2 * m);
     MIAGPU_CUDA(cudaGetLastError());
-    std::vector<int32_t> geo(m * 4);
-    MIAGPU_CUDA(cudaMemcpyAsync(geo.data(), d_list.p + 2 * m, m * 16, cudaMemcpyDeviceToHost, st));
+    std::vector<int32_t> geo(m * 8);
+    MIAGPU_CUDA(cudaMemcpyAsync(geo.data(), d_list.p + 2 * m, m * 32, cudaMemcpyDeviceToHost, st));
     MIAGPU_CUDA(cudaStreamSynchronize(st));
     d_list.release();
-    for (size_t q = 0; q < m; q++) c->fz.push_back(miagpu_ctx::FzHost{geo[4 * q], geo[4 * q + 1], geo[4 * q + 2], geo[4 * q + 3]});
+    for (size_t q = 0; q < m; q++) {
+      const int32_t* g = &geo[8 * q];
+      // AlnSeq.num_inputs of a pass-1 AlnSeq is what sg_align leaves in the PWAlnFrag: nothing (mia.c:1558-1573 never sets it) = 0
+      c->fz.push_back(miagpu_ctx::FzHost{g[0], g[1], g[2], g[3], g[4], g[5], g[6], c->fs_prev_pass1 ? 0 : 1});
+    }
   }
   // ---- geometry of the live segments involved: the targets and the holders' own fresh front segments
   std::vector<int32_t> want;
@@ -3278,3 +3283,82 @@ extern "C" int miagpu_compact_reads(miagpu_ctx* c, const uint8_t* keep, const ui
 
 // host-side formats either side of the path: FASTA / FASTQ reader, .maln writer
 #include "hostio.hpp"
+
+// write_ma of the round miagpu_iterate_resident just ran under miagpu_set_fsdb: the culled list follows the pointers
+// (cull_maln_from_fsdb mia.c:463-476: front_asp, then back_asp of every unique_best read in FSDB order), so an AlnSeq that stale
+// pointers reach appears once per pointer, with the smp codes of the last visit (fsdb.c:542-619) and the slot's sticky dropped flag.
+// rd as for miagpu_write_maln (dropped_front / dropped_back / fsdb_order are not read: the slot flags come from the device).
+extern "C" int miagpu_write_maln_fsdb(miagpu_ctx* c, const char* path, const miagpu_maln_header* hd, const miagpu_maln_reads* rd,
+                                      int64_t* n_alnseqs_out) {
+  using namespace hostio;
+  if (!c || !c->fs_on || !path || !hd || !rd) { set_error("miagpu_write_maln_fsdb: call miagpu_set_fsdb and a round first"); return 0; }
+  const int64_t n = c->n;
+  if (rd->n != n || (n && (!rd->bases || !rd->offsets || !rd->rc || !rd->score || !rd->as || !rd->ae || !rd->abr || !rd->run_off || !rd->packed ||
+                           !rd->ids || !rd->id_off))) { set_error("miagpu_write_maln_fsdb: incomplete read arrays"); return 0; }
+  MIAGPU_CUDA(cudaSetDevice(c->device));
+  std::vector<int32_t> front((size_t)n), back((size_t)n);
+  std::vector<uint8_t> known((size_t)n), flag((size_t)c->fs_slot_cap);
+  MIAGPU_CUDA(cudaMemcpy(flag.data(), c->d_slot_flag.p, flag.size(), cudaMemcpyDeviceToHost));
+  if (n) {
+    MIAGPU_CUDA(cudaMemcpy(front.data(), c->d_front_slot.p, n * 4, cudaMemcpyDeviceToHost));
+    MIAGPU_CUDA(cudaMemcpy(back.data(), c->d_back_slot.p, n * 4, cudaMemcpyDeviceToHost));
+    MIAGPU_CUDA(cudaMemcpy(known.data(), c->d_known.p, n, cudaMemcpyDeviceToHost));
+  }
+  const size_t nfz = c->fz.size();
+  std::vector<uint8_t> fzb(nfz * FZ_BASES + 1);
+  std::vector<uint16_t> fzr(nfz * MAX_RUNS + 1);
+  std::vector<int32_t> fzn(nfz + 1);
+  if (nfz) {
+    MIAGPU_CUDA(cudaMemcpy(fzb.data(), c->d_fz_bases.p, nfz * FZ_BASES, cudaMemcpyDeviceToHost));
+    MIAGPU_CUDA(cudaMemcpy(fzr.data(), c->d_fz_runs.p, nfz * MAX_RUNS * 2, cudaMemcpyDeviceToHost));
+    MIAGPU_CUDA(cudaMemcpy(fzn.data(), c->d_fz_nruns.p, nfz * 4, cudaMemcpyDeviceToHost));
+  }
+  const FrozenView fzv{fzb.data(), fzr.data(), fzn.data(), FZ_BASES, MAX_RUNS};
+  std::unordered_map<int32_t, const int32_t*> ov;                              // natural entry -> parameters of its slot's last visit
+  for (size_t q = 0; q + 5 <= c->fs_patch_host.size(); q += 5) ov[c->fs_patch_host[q]] = &c->fs_patch_host[q];
+  std::unordered_map<int64_t, const miagpu_ctx::FsExtra*> stale;                // 2 * holder + kind -> what the pointer sees
+  for (const auto& x : c->fs_extra) stale[2 * (int64_t)x.holder + x.kind] = &x;
+  const int L = hd->ref_len;
+  auto with_params = [](Seg& sg, int fl, int total, int bias, int bf) { sg.ov = 1; sg.fl = fl; sg.total = total; sg.bias = bias; sg.bf = bf; };
+  std::vector<Seg> segs;
+  segs.reserve((size_t)n + 16);
+  for (int64_t i = 0; i < n; i++) {
+    if (rd->unique_best && !rd->unique_best[i]) continue;
+    Seg f, b;
+    bool split = false;
+    if (known[i]) {
+      split = natural_segs(rd, L, i, f, b) != 0;
+      f.dropped = flag[front[i]];
+      auto it = ov.find((int32_t)(2 * i));
+      if (it != ov.end()) with_params(f, it->second[1], it->second[2], it->second[3], it->second[4]);
+      segs.push_back(f);
+      if (split) {
+        b.dropped = flag[back[i]];
+        it = ov.find((int32_t)(2 * i + 1));
+        if (it != ov.end()) with_params(b, it->second[1], it->second[2], it->second[3], it->second[4]);
+        segs.push_back(b);
+      }
+    }
+    for (int kind = known[i] ? 1 : 0; kind < 2; kind++) {
+      if (kind == 1 && (split || back[i] < 0)) continue;
+      auto it = stale.find(2 * i + kind);
+      if (it == stale.end()) { set_error("miagpu_write_maln_fsdb: the pointer of read %lld was not resolved by the last round", (long long)i); return 0; }
+      const miagpu_ctx::FsExtra& x = *it->second;
+      Seg sg;
+      if (x.frozen >= 0) {
+        const miagpu_ctx::FzHost& z = c->fz[x.frozen];
+        sg.read = z.read; sg.start = z.start; sg.end = z.start + z.cols - 1; sg.col0 = 0; sg.ncol = z.cols; sg.smp_n = z.cols; sg.seg = (char)z.seg;
+        sg.fz = x.frozen; sg.fz_score = z.score; sg.fz_rc = z.rc; sg.fz_num_inputs = z.num_inputs;
+      } else {
+        Seg of, ob;
+        const int64_t j = x.live_entry >> 1;
+        natural_segs(rd, L, j, of, ob);
+        sg = (x.live_entry & 1) ? ob : of;
+      }
+      sg.dropped = flag[x.slot];
+      with_params(sg, x.front_len, x.total_len, x.act_bias, x.back_formula);
+      segs.push_back(sg);
+    }
+  }
+  return maln_emit(path, hd, rd, segs, &fzv, n_alnseqs_out);
+}

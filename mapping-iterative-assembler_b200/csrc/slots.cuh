@@ -184,8 +184,8 @@ __global__ void fs_geom_kernel(int m, const int32_t* __restrict__ which, AlnView
 // reverse-complemented while they are copied.  dst[q] = index of the frozen alignment that receives list item q.
 __global__ void fs_freeze_kernel(int m, const int32_t* __restrict__ which, const int32_t* __restrict__ dst, AlnView v,
                                  const uint8_t* __restrict__ bases, const int64_t* __restrict__ off, const uint8_t* __restrict__ rc,
-                                 const uint8_t* __restrict__ flip, uint8_t* fz_bases, uint16_t* fz_runs, int32_t* fz_nruns, uint8_t* fz_rc,
-                                 int32_t* geo) {
+                                 const uint8_t* __restrict__ flip, const int32_t* __restrict__ score_prev, uint8_t* fz_bases, uint16_t* fz_runs,
+                                 int32_t* fz_nruns, uint8_t* fz_rc, int32_t* geo) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= m) return;
   const int e = which[q], j = e >> 1, seg = e & 1, d = dst[q];
@@ -223,11 +223,14 @@ __global__ void fs_freeze_kernel(int m, const int32_t* __restrict__ which, const
   }
   fz_nruns[d] = no;
   fz_rc[d] = rc[j];
-  int32_t* o = geo + 4 * q;
+  int32_t* o = geo + 8 * q;
   o[0] = seg ? 0 : v.as_out[j];                      // AlnSeq.start
   o[1] = ce - cb;                                    // columns
   o[2] = dels;
   o[3] = rc[j];
+  o[4] = score_prev ? score_prev[j] : 0;             // AlnSeq.score
+  o[5] = g.split ? (seg ? 'b' : 'f') : 'a';          // AlnSeq.segment
+  o[6] = j; o[7] = 0;
 }
 
 // patches of the host's resolution: pat[6 * q ..] = entry, front_len, total_len, act_bias, back_formula, slot (ent_slot; -2 = keep)

@@ -34,3 +34,23 @@ def test_c_host_writes_the_reference_maln_files(golden, name, matrix, tmp_path):
             assert len(got) == len(body)
     assert not os.path.exists(tmp_path / f"out.{len(s['malns']) + 1}")
     assert "Assembly convergence" in r.stderr
+
+
+@pytest.mark.parametrize("name", ["flat_2000_c", "origin305_splitflip_c", "synth3k_div10_c_k12_D", "synth1k_N_lin_D"])
+def test_c_host_follows_the_reference_pointers(golden, name, tmp_path):
+    # tests/golden/make_maln_golden_r2.py: reads that score exactly 2000 (strand_known = 0), split patterns that change, -D.  The
+    # reference's `.maln` files list an AlnSeq once per FragSeq pointer that reaches it -- stale pointers included.
+    s = json.load(gzip.open(os.path.join(HERE, "golden", "maln_session_r2.json.gz"), "rt"))[name]
+    (tmp_path / "ref.fa").write_text(s["ref_text"])
+    (tmp_path / "reads.fq").write_text(s["fastq"])
+    (tmp_path / "m.txt").write_text(matrix_text(golden[s["matrix"]]))
+    ensure_host()
+    r = subprocess.run([HOST, "-r", "ref.fa", "-f", "reads.fq", "-s", "m.txt", "-m", "out"] + s["flags"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    for it, body in enumerate(s["malns"]):
+        got = open(tmp_path / f"out.{it + 1}").read().split("\n", 1)[1]
+        if got != body:
+            for ln, (x, y) in enumerate(zip(got.split("\n"), body.split("\n"))):
+                assert x == y, f"{name} iteration {it + 1}: line {ln + 2}: {x[:160]!r} != {y[:160]!r}"
+            assert len(got) == len(body)
+    assert not os.path.exists(tmp_path / f"out.{len(s['malns']) + 1}")

@@ -84,10 +84,12 @@ def test_c_host_argument_errors(golden, tmp_path):
     run = lambda *a: subprocess.run([HOST] + list(a), cwd=tmp_path, capture_output=True, text=True)
     r = run()
     assert r.returncode == 2 and "usage: mia_gpu" in r.stderr
-    for opt in ("-D", "-T", "-h", "-C3", "-I"):
+    for opt in ("-T", "-h", "-C3", "-I"):
         r = run("-r", "r.fa", "-f", "q.fq", "-s", "m.txt", opt)
         assert r.returncode == 2 and "not handled by this host" in r.stderr, opt
     r = run("-r", "r.fa", "-f", "q.fq", "-s", "m.txt", "-u", "-H", "3000")
+    assert r.returncode == 2 and "-u / -U" in r.stderr
+    r = run("-r", "r.fa", "-f", "q.fq", "-s", "m.txt", "-u", "-D")
     assert r.returncode == 2 and "-u / -U" in r.stderr
     (tmp_path / "r.fa").write_text(">r\nACGTACGTACGTACGTACGT\n")
     (tmp_path / "q.fq").write_text("@a\nACGTACGTAC\n+\nIIIIIIIIII\n")
