@@ -295,6 +295,11 @@ int main( int argc, char** argv ) {
   last[ref_len] = 0;
   while ( !converged && iter < MAX_ITER ) {
     int32_t cons_len = 0, L = (int32_t)strlen( last );
+    if ( (size_t)L * 4 + 4096 > cons_cap ) {            /* the consensus grew: seq_len + sum(gaps) + 1 characters come back */
+      cons_cap = (size_t)L * 4 + 4096;
+      last = realloc( last, cons_cap ); cons = realloc( cons, cons_cap ); gaps = realloc( gaps, cons_cap * 4 );
+      if ( !last || !cons || !gaps ) { fprintf( stderr, "mia_gpu: out of memory\n" ); return 1; }
+    }
     iter++;
     t1 = now_ms();
     CK( miagpu_set_reference( g, last, L, circular, 0 ) );

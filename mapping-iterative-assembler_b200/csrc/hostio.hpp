@@ -544,7 +544,7 @@ int maln_emit(const char* path, const miagpu_maln_header* hd, const miagpu_maln_
             else colc.push_back('-');
           }
         }
-        if (row > rlen) { bad_read.store((long long)i); return; }
+        if (row > rlen || (sg.fz < 0 && rd->abr[i] < 0)) { bad_read.store((long long)i); return; }
         // asp_len of the front and back AlnSeq (fsdb.c:518-530): columns + inserted bases (deletions count as sequence)
         int tot = (int)colc.size();
         int s0 = sg.fz >= 0 ? 0 : rd->as[i], e0 = sg.fz >= 0 ? tot : (rd->ae[i] > L ? rd->ae[i] - L : rd->ae[i]);
@@ -644,13 +644,14 @@ int maln_emit(const char* path, const miagpu_maln_header* hd, const miagpu_maln_
   if (trace) fprintf(stderr, "[miagpu trace] write_maln: sort %.1f ms, waiting for the formatters (%zu threads) %.1f ms, fwrite %.1f ms\n", t_b - t_a, T, t_fmt, t_wr);
   if (bad_read.load() >= 0) {
     fclose(f);
+    unlink(path);                                    // no partial file
     set_error("miagpu_write_maln: the runs of read %lld overrun its bases", bad_read.load());
     return 0;
   }
   o.flush();
   bool ok = !ferror(f);
   if (fclose(f) != 0) ok = false;
-  if (!ok) { set_error("miagpu_write_maln: write to %s failed", path); return 0; }
+  if (!ok) { unlink(path); set_error("miagpu_write_maln: write to %s failed", path); return 0; }
   if (n_alnseqs_out) *n_alnseqs_out = (int64_t)segs.size();
   return 1;
 }

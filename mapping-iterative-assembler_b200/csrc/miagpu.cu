@@ -620,6 +620,16 @@ __global__ void pair_scatter_kernel(int64_t n, const int64_t* off, const uint8_t
   }
 }
 
+// OR of the per-read status bytes of a round (reads the consensus would silently leave out: more than MAX_RUNS runs, a window
+// no kernel takes): the one-call rounds fail instead
+__global__ void status_or_kernel(int64_t n, const uint8_t* __restrict__ status, const int32_t* __restrict__ n_runs, int32_t* out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int st = 0;
+  if (i < n) st = status[i] | (n_runs[i] <= 0 ? MIAGPU_ST_RUNS_OVERFLOW : 0);
+  st = __reduce_or_sync(0xffffffffu, st);
+  if ((threadIdx.x & 31) == 0 && st) atomicOr(out, st);
+}
+
 __global__ void flag_big_kernel(const int32_t* list, int n_list, int32_t* score, int32_t* n_runs, uint8_t* status) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_list) { int rd = list[i]; score[rd] = INT_MIN; n_runs[rd] = -1; status[rd] = 0x80; }
@@ -1282,8 +1292,14 @@ extern "C" int miagpu_accumulate_gaps(miagpu_ctx* c, int64_t n_entries, const mi
   if (!c || !c->have_ref || !c->have_pssm) { set_error("miagpu_accumulate_gaps: set_pssm / set_reference / realign first"); return 0; }
   if (n_entries < 0 || (n_entries && !entries)) { set_error("miagpu_accumulate_gaps: bad entries"); return 0; }
   MIAGPU_CUDA(cudaSetDevice(c->device));
-  for (int64_t i = 0; i < n_entries; i++)
-    if (entries[i].read < 0 || entries[i].read >= c->n) { set_error("miagpu_accumulate_gaps: entry %lld names read %d of %lld", (long long)i, entries[i].read, (long long)c->n); return 0; }
+  for (int64_t i = 0; i < n_entries; i++) {
+    const miagpu_entry& e = entries[i];
+    if (e.read < 0 || e.read >= c->n) { set_error("miagpu_accumulate_gaps: entry %lld names read %d of %lld", (long long)i, e.read, (long long)c->n); return 0; }
+    if (e.ref_pos < 0 || e.col_begin < 0 || e.col_count < 0 || e.col_count > 2 * MAX_READ || e.col_begin > 2 * MAX_READ) {
+      set_error("miagpu_accumulate_gaps: entry %lld has ref_pos %d, columns [%d, +%d)", (long long)i, e.ref_pos, e.col_begin, e.col_count);
+      return 0;
+    }
+  }
   c->launches = 0;
   if (!c->d_entries.reserve(n_entries) || !c->d_gaps.reserve(c->seq_len + 2) || !c->d_ins_off.reserve(c->seq_len + 2)) return 0;
   MIAGPU_CUDA(cudaEventRecord(c->ev[0], c->stream));
@@ -2061,7 +2077,7 @@ struct CutHost {
 
 static int cut_reserve(miagpu_ctx* c, int64_t n) {
   const int64_t nb = (n + CUT_BLOCK - 1) / CUT_BLOCK;
-  if (!c->d_cstats.reserve(1) || !c->d_ctab.reserve(1) || !c->d_thr.reserve(MAX_READ + 1) || !c->d_cblk.reserve(nb + 1)) return 0;
+  if (!c->d_cstats.reserve(1) || !c->d_ctab.reserve(1) || !c->d_thr.reserve(MAX_READ + 1) || !c->d_cblk.reserve(nb + 1) || !c->d_fs_cnt.reserve(FS_CNT_WORDS)) return 0;
   if (!c->h_cut) MIAGPU_CUDA(cudaMallocHost(&c->h_cut, sizeof(CutHost)));
   if (c->h_cblk_cap < nb) {
     if (c->h_cblk) cudaFreeHost(c->h_cblk);
@@ -2129,16 +2145,18 @@ static int iterate_tail(miagpu_ctx* c, const IterTail& a, const Trace& tr) {
   if (c->fs_on) {
     if (!fs_number_and_entries(c, has_unique)) return 0;
   } else {
+    MIAGPU_CUDA(cudaMemsetAsync(c->d_fs_cnt.p, 0, FS_CNT_WORDS * sizeof(int32_t), main));
+    status_or_kernel<<<(unsigned)((n + 255) / 256), 256, 0, main>>>(n, c->d_status.p, c->d_nruns.p, c->d_fs_cnt.p + FS_CNT_STATUS);
     natural_entries_kernel<<<(unsigned)((n + 255) / 256), 256, 0, main>>>(n, c->d_as_out.p, c->d_ae_out.p, c->d_nruns.p, c->d_runs.p,
                                                                           c->d_status.p, c->seq_len, c->d_dropf.p, c->d_dropf.p, c->d_entries.p,
                                                                           has_unique ? c->d_unique.p : nullptr);
     MIAGPU_CUDA(cudaGetLastError());
-    c->launches++;
+    c->launches += 2;
   }
   if (!launch_gaps(c)) return 0;
   MIAGPU_CUDA(cub::DeviceScan::ExclusiveSum(c->d_cub.p, tmp2, c->d_gaps.p, c->d_ins_off.p, c->seq_len + 1, main));
   MIAGPU_CUDA(cudaMemcpyAsync(&H->total_ins, c->d_ins_off.p + c->seq_len, sizeof(int32_t), cudaMemcpyDeviceToHost, main));
-  if (c->fs_on) MIAGPU_CUDA(cudaMemcpyAsync(H->fs_cnt, c->d_fs_cnt.p, sizeof(H->fs_cnt), cudaMemcpyDeviceToHost, main));
+  MIAGPU_CUDA(cudaMemcpyAsync(H->fs_cnt, c->d_fs_cnt.p, sizeof(H->fs_cnt), cudaMemcpyDeviceToHost, main));
   MIAGPU_CUDA(cudaEventRecord(c->aev[6], main));
   c->launches += 2;
   tr.mark("entries + insert maxima enqueued");
@@ -2171,6 +2189,11 @@ static int iterate_tail(miagpu_ctx* c, const IterTail& a, const Trace& tr) {
   // ---- column accumulation of every read that is not yet dropped (needs the insert-column layout: one short wait)
   MIAGPU_CUDA(cudaEventSynchronize(c->aev[6]));
   if (c->fs_on && !fs_after_numbering(c, has_unique, H->fs_cnt, &H->total_ins)) { cudaStreamSynchronize(main); cudaStreamSynchronize(side); return 0; }
+  if (!c->fs_on && H->fs_cnt[FS_CNT_STATUS]) {       // never a consensus that silently lacks reads
+    cudaStreamSynchronize(main); cudaStreamSynchronize(side);
+    set_error("miagpu: reads came back with status bits 0x%x (more than %d alignment runs, or a window no kernel takes): the round is not usable", H->fs_cnt[FS_CNT_STATUS], MAX_RUNS);
+    return 0;
+  }
   const int64_t tot = H->tot_runs;
   if (a.total_runs) *a.total_runs = tot;
   if (a.packed_runs && tot > a.capacity) { cudaStreamSynchronize(main); cudaStreamSynchronize(side); set_error("miagpu_iterate: %lld runs, capacity %lld", (long long)tot, (long long)a.capacity); return 0; }
@@ -2481,7 +2504,9 @@ static int shard_after_dp(miagpu_ctx* c, bool stats_done, bool has_unique, void*
   MIAGPU_CUDA(cudaGetLastError());
   c->launches += 2;
   c->n_entries = 2 * n;
+  MIAGPU_CUDA(cudaMemsetAsync(c->d_fs_cnt.p, 0, FS_CNT_WORDS * sizeof(int32_t), main));
   if (n) {
+    status_or_kernel<<<(unsigned)((n + 255) / 256), 256, 0, main>>>(n, c->d_status.p, c->d_nruns.p, c->d_fs_cnt.p + FS_CNT_STATUS);
     natural_entries_kernel<<<(unsigned)((n + 255) / 256), 256, 0, main>>>(n, c->d_as_out.p, c->d_ae_out.p, c->d_nruns.p, c->d_runs.p,
                                                                           c->d_status.p, c->seq_len, nullptr, nullptr, c->d_entries.p,
                                                                           has_unique ? c->d_unique.p : nullptr);
@@ -2594,7 +2619,12 @@ extern "C" int miagpu_shard_cut(miagpu_ctx* c, double* slope_out, double* interc
       c->launches += 2;
     }
   }
+  MIAGPU_CUDA(cudaMemcpyAsync(H->fs_cnt, c->d_fs_cnt.p, sizeof(H->fs_cnt), cudaMemcpyDeviceToHost, main));
   MIAGPU_CUDA(cudaStreamSynchronize(main));
+  if (H->fs_cnt[FS_CNT_STATUS]) {
+    set_error("miagpu_shard_cut: local reads came back with status bits 0x%x (more than %d alignment runs, or a window no kernel takes)", H->fs_cnt[FS_CNT_STATUS], MAX_RUNS);
+    return 0;
+  }
   double slope = c->sh_slope, intercept = c->sh_icpt;
   if (fit) {
     if (S.cnt <= 0) { set_error("miagpu_shard_cut: no read of any rank scores >= %d: nothing to fit", FIRST_ROUND_SCORE_CUTOFF); return 0; }

@@ -60,9 +60,13 @@ def natural_entries(as_out, ae_out, n_runs, runs, seq_len, dropped_front=None, d
     if dropped_front is not None:
         ent["dropped"][f] = np.asarray(dropped_front)[idx]
     for i in np.flatnonzero(split):
-        cf = seq_len - int(as_out[i])
-        fi = _front_ins(runs[i], int(n_runs[i]), cf)
-        fl, bl = cf + fi, (int(cols[i]) - cf) + (int(ins[i]) - fi)
+        cf_raw = seq_len - int(as_out[i])
+        # a read that starts beyond seq_len: split_pwaln moves ALL of it to the back AlnSeq at START 0 (mia.c:1400-1422); the front
+        # AlnSeq keeps the negative length asp_len computes from end - start + 1 (fsdb.c:522-523)
+        cf = min(max(cf_raw, 0), int(cols[i]))
+        fi = _front_ins(runs[i], int(n_runs[i]), cf_raw)
+        fl = cf_raw if cf_raw < 0 else cf + fi
+        bl = (int(cols[i]) + int(ins[i])) - fl
         a, b = first[i], first[i] + 1
         ent["col_count"][a] = cf
         ent["front_len"][a] = fl
