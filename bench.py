@@ -45,13 +45,13 @@ def load_pssm(name="onepass"):
     return np.load(os.path.join(ROOT, "tests", "golden", "pssm.npz"))[name]
 
 
-def make_workload(n_reads, seed, ref=None):
+def make_workload(n_reads, seed, ref=None, divergence=0.005, indel_rate=0.0, min_len=35, max_len=75):
     import _pkg
     _pkg.load()
     from mia_b200 import synth
     ref = ref or synth.random_reference(REF_LEN, seed=1)
-    genome = synth.diverge(ref, 0.005, seed=2)
-    bases, off, truth = synth.make_reads(genome, n_reads, 35, 75, seed=seed)
+    genome = synth.diverge(ref, divergence, seed=2, indel_rate=indel_rate)
+    bases, off, truth = synth.make_reads(genome, n_reads, min_len, max_len, seed=seed)
     rc = truth["strand"].astype(np.uint8)
     # stored orientation: reverse-strand reads are kept reverse-complemented (fsdb.c:209-227)
     comp = np.zeros(256, np.uint8)
@@ -61,7 +61,7 @@ def make_workload(n_reads, seed, ref=None):
     pos = np.arange(len(bases)) - off[rid]
     src = np.where(rc[rid] == 1, off[rid] + (off[rid + 1] - off[rid]) - 1 - pos, np.arange(len(bases)))
     stored = np.where(rc[rid] == 1, comp[bases[src]], bases)
-    as_ = truth["start"].astype(np.int32)
+    as_ = np.minimum(truth["start"], len(ref) - 1).astype(np.int32)      # (a sample with indels is a little longer / shorter than the reference)
     ae = (as_ + truth["length"] - 1).astype(np.int32)
     return ref, np.ascontiguousarray(stored, np.uint8), off, rc, as_, ae
 
@@ -242,6 +242,11 @@ def run_ours(args):
         t = torch.tensor([total_ms, e2e_total], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms, e2e_total = t.tolist()
+    cut_stats = g.last_cut_stats()
+    parity = None
+    if not args.no_parity:
+        parity = parity_block(g, args, world, rank, local, ref, bases, off, rc, as_, ae, sm, cons)
+        g.set_reference(ref, circular=1, with_rc=0)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -260,19 +265,23 @@ def run_ours(args):
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     # algorithmic bytes of the dominant realign launch: read bases + offset(8) + rc/as/ae(9) in,
     # score/as/ae/abr/n_runs/status(21) + one run word(2) out, per read
-    # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture, scaled by DP cells to this launch
-    traffic, traffic_src = None, None
+    # DRAM traffic and SASS warp instructions of the dominant kernel: from the committed ncu capture of THIS round's build
+    # (profiles/r02_kernels.json, written by profiles/summarize.py from the .ncu-rep), per read / per cell of the captured launch
+    traffic, traffic_src, ipc, ipc_src = None, None, None, None
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        ent = next((v for k, v in tj.items() if dom["kernel"].split("<")[0] == k.split("<")[0]), None)
+        kj = json.load(open(os.path.join(ROOT, "profiles", "r02_kernels.json")))
+        ent = kj.get(dom["kernel"]) or next((v for k, v in kj.items() if k.split("<")[0] == dom["kernel"].split("<")[0]), None)
         if ent:
-            traffic = ent["dram_bytes_per_launch"] / ent["cells_per_launch"] * dom["cells"]
-            traffic_src = ent["source"]
+            traffic = ent["dram_bytes_per_launch"] / ent["reads_per_launch"] * dom["reads"]
+            ipc = ent["warp_inst_per_launch"] / ent["cells_per_launch"]
+            traffic_src = ipc_src = ent["source"]
     except Exception:
         pass
     frac_reads = dom["reads"] / n
     alg_bytes = frac_reads * (len(bases) + n * (8 + 9 + 21 + 2))
     dom_s = dom["ms"] * 1e-3
+    clk = (clocks or {}).get("sm_mhz") or 1965.0
+    issue_peak = 4 * 148 * clk / 1e3                    # G warp instructions / s: 4 schedulers x 148 SMs x SM clock under load
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
@@ -289,28 +298,34 @@ def run_ours(args):
                                       round(float(np.max(e2e_times)) * 1e3, 3)]},
         "gpu_launches": launches["n"],
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "achieved": alg_bytes / dom_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": alg_bytes / dom_s / 1e9 / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
-                     "kernel": dom["kernel"], "kernel_ms": dom["ms"], "kernel_share_of_step": dom["ms"] / ms_per_step,
-                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst)" if peaks else "fallback 6650 GB/s",
-                     "note": "integer-issue bound, not HBM bound: see roofline_int32"},
-        "roofline_int32": {"bound": "int32 issue", "achieved": INT_OPS_PER_CELL * dom["cells"] / dom_s / 1e12,
+        # the bound of the dominant kernel is the issue slot (max-plus recurrence in 16x2 SIMD: no dense contraction, ~0.01 B per cell):
+        # SASS warp instructions per cell (ncu smsp__inst_executed.sum / cells of the captured launch) x cells/s of the launch timed
+        # here, against 4 schedulers x 148 SMs x the SM clock sampled under load
+        "roofline": {"bound": "issue", "achieved": None if ipc is None else ipc * dom["cells"] / dom_s / 1e9, "peak": issue_peak,
+                     "unit": "G warp-inst/s", "frac": None if ipc is None else ipc * dom["cells"] / dom_s / 1e9 / issue_peak,
+                     "traffic": traffic, "traffic_algorithmic": alg_bytes, "warp_inst_per_cell": ipc, "source": ipc_src,
+                     "kernel": dom["kernel"], "kernel_ms": dom["ms"], "kernel_reads": dom["reads"], "kernel_gcups": dom["cells"] / dom_s / 1e9,
+                     "kernel_share_of_step": dom["ms"] / ms_per_step, "sm_mhz": clk,
+                     "peak_source": "4 x 148 x SM clock (nvidia-smi median during the timed region)"},
+        "roofline_hbm": {"bound": "hbm", "achieved": alg_bytes / dom_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": alg_bytes / dom_s / 1e9 / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst)" if peaks else "fallback 6650 GB/s",
+                         "note": "reported to show that HBM is NOT the limiter"},
+        "roofline_int32": {"bound": "int32 ops", "achieved": INT_OPS_PER_CELL * dom["cells"] / dom_s / 1e12,
                            "peak": int_peak / 1e12, "unit": "Tops/s", "frac": INT_OPS_PER_CELL * dom["cells"] / dom_s / int_peak,
-                           "ops_per_cell": INT_OPS_PER_CELL, "kernel_gcups": dom["cells"] / dom_s / 1e9,
-                           "peak_source": "miagpu_int32_peak micro-benchmark, same run"},
-        # the pair kernels compute two 16-bit cells per 32-bit SIMD op, so the 15-ops-per-cell figure can exceed the INT32 peak;
-        # what bounds them is the issue slot: SASS warp instructions per cell (ncu smsp__inst_executed.sum / cells of the
-        # committed capture profiles/r01c_ncu_pair16_full.md) x cells/s against 4 schedulers x 148 SMs x SM clock
-        "roofline_issue": (lambda ipc, clk: {"bound": "issue slots", "warp_inst_per_cell": ipc, "achieved": ipc * dom["cells"] / dom_s / 1e9,
-                                             "peak": 4 * 148 * clk / 1e3, "unit": "G warp-inst/s",
-                                             "frac": ipc * dom["cells"] / dom_s / 1e9 / (4 * 148 * clk / 1e3),
-                                             "source": "905,288,115 inst / 3.19e9 cells, ncu --set full of pair16_kernel<10,16> (profiles/)"})(
-            905288115 / 3189673284, (clocks or {}).get("sm_mhz") or 1965.0) if dom["kernel"].startswith("pair16") else None,
+                           "ops_per_cell": INT_OPS_PER_CELL,
+                           "peak_source": "miagpu_int32_peak micro-benchmark (32-bit IADD3 / IMNMX / SEL), same run",
+                           "note": "the pair kernels do TWO 16-bit cells per 32-bit SIMD operation, so SURVEY 8d's 15-ops-per-cell figure can "
+                                   "exceed the 32-bit peak (frac > 1): not a roofline, kept for comparison with the 32-bit kernels"},
         "buckets": pbuckets + buckets,
         "pair16": {"reads_handed_to_32bit_kernels": n_fallback, "max_read_len": lmax16},
         "consensus_matches_e2e": bool(cons == cons_e2e),
-        "score_cut": g.last_cut_stats(),
+        "score_cut": cut_stats,
+        "parity": parity,
     }
+    # ---- the other read shapes of BASELINE.json (indel-bearing divergent reads, 30-140 bp merged pairs), with their own parity checks
+    if world == 1 and not args.no_shapes:
+        line["shapes"] = shaped_rounds(g, args, flush, lib_stream)
     # ---- the same round on R-mt (the reference's mt311 consensus, real composition and low-complexity stretches)
     if world == 1 and not args.no_rmt:
         line["r_mt"] = rmt_numbers(g, args, flush, lib_stream)
@@ -326,6 +341,104 @@ def run_ours(args):
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def parity_block(g, args, world, rank, local, ref, bases, off, rc, as_, ae, sm, cons_full):
+    """Untimed: ties what was just measured to the CPU checker (oracle/_ref = the unmodified reference where it was built).
+    (1) the first `--parity-reads` reads of rank 0's workload through one resident round on ONE GPU: every read's score / as /
+    ae / abr / gapped strings and the round's consensus against the checker; (2) N > 1: every rank holds the same consensus
+    after the timed sharded round, and the sharded round over that common prefix (each rank its contiguous slice) gives the
+    consensus of the one-GPU round of (1)."""
+    import hashlib
+    import torch
+    import torch.distributed as dist
+    import gpu_checks
+    from mia_b200 import shard
+    P = min(args.parity_reads, len(off) - 1)
+    out = {}
+    # rank 0's workload is a function of its seed: every rank regenerates its prefix
+    if rank == 0:
+        r0 = (ref, bases, off, rc, as_, ae)
+    else:
+        r0 = make_workload(args.reads, seed=1000)
+    _, b0, o0, rc0, as0, ae0 = r0
+    pb, po = np.ascontiguousarray(b0[: o0[P]]), np.ascontiguousarray(o0[: P + 1])
+    if world > 1:
+        h = int(hashlib.md5(cons_full.encode()).hexdigest()[:15], 16)
+        t = torch.tensor([h], dtype=torch.int64, device="cuda")
+        allh = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allh, t)
+        out["ranks_hold_one_consensus"] = bool(all(int(x) == h for x in allh))
+        # the sharded round over the common prefix
+        lo, hi = P * rank // world, P * (rank + 1) // world
+        g.set_reference(ref, circular=1, with_rc=0)
+        g.upload_reads(np.ascontiguousarray(pb[po[lo]:po[hi]]), np.ascontiguousarray(po[lo:hi + 1] - po[lo]))
+        g.set_alignment_inputs(rc0[lo:hi], as0[lo:hi], ae0[lo:hi])
+        g.set_cut_inputs(np.diff(po[lo:hi + 1]).astype(np.int32))
+        Sp = shard.ShardedRounds(g, local, world, rank, -(-P // world))
+        cons_sh = Sp.resident()[0]
+        hs = int(hashlib.md5(cons_sh.encode()).hexdigest()[:15], 16)
+        t = torch.tensor([hs], dtype=torch.int64, device="cuda")
+        dist.all_gather(allh, t)
+        out["sharded_prefix_ranks_agree"] = bool(all(int(x) == hs for x in allh))
+    if rank == 0:
+        t0 = time.perf_counter()
+        res = gpu_checks.round_parity(g, ref, pb, po, rc0[:P], as0[:P], ae0[:P], sm)
+        cons_1 = res.pop("consensus")
+        out.update(res)
+        if world > 1:
+            out["sharded_equals_single_gpu"] = bool(cons_sh == cons_1)
+        out["wall_s"] = round(time.perf_counter() - t0, 1)
+    return out
+
+
+def shaped_rounds(g, args, flush, lib_stream):
+    """The resident round on the other BASELINE read shapes, 1 GPU, beside the headline (same timing rules): configs[3] -- reads of
+    a sample 10 % + 0.5 % indels away from the reference they are realigned to (the first rounds of a divergent-seed assembly:
+    about every fourth read carries a gap) -- and configs[2] -- merged paired-end reads, 30-140 bp, ancient.submat.solexa.pe.
+    Each with its own parity check of a prefix against the CPU checker."""
+    import torch
+    import gpu_checks
+    res = {}
+    for tag, kw, mat in (("c4_divergent_indels", dict(divergence=0.10, indel_rate=0.005), "ancient"),
+                         ("c3_merged_pe_30_140", dict(divergence=0.005, indel_rate=0.0005, min_len=30, max_len=140), "pe")):
+        n = args.reads
+        sm = load_pssm(mat)
+        ref, bases, off, rc, as_, ae = make_workload(n, seed=3000, **kw)
+        g.set_pssm(sm)
+        g.set_reference(ref, circular=1, with_rc=0)
+        g.upload_reads(bases, off)
+        g.set_alignment_inputs(rc, as_, ae)
+        g.set_cut_inputs(np.diff(off).astype(np.int32))
+        for _ in range(3):
+            g.reset_dropped()
+            g.iterate_resident()
+        steps = max(3, args.steps // 2)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for k in range(steps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            ev[k][0].record(lib_stream)
+            g.reset_dropped()
+            g.iterate_resident()
+            ev[k][1].record(lib_stream)
+            torch.cuda.synchronize()
+        ms = float(sum(a.elapsed_time(b) for a, b in ev)) / steps
+        g.realign_resident()
+        g.realign_resident()
+        cells = g.last_timing()["dp_cells"]
+        pb, n_fallback, lmax16 = g.last_pair_buckets()
+        b32 = g.last_buckets()
+        al = g.get_alignment()
+        P = min(args.parity_reads // 4, n)
+        par = gpu_checks.round_parity(g, ref, np.ascontiguousarray(bases[: off[P]]), np.ascontiguousarray(off[: P + 1]), rc[:P], as_[:P], ae[:P], sm)
+        par.pop("consensus")
+        res[tag] = {"reads": n, "matrix": mat, "ms_per_step": ms, "value": n / (ms * 1e-3), "gcups": cells / (ms * 1e-3) / 1e9,
+                    "gapped_fraction": float((al["n_runs"] > 1).mean()), "reads_in_16bit_kernels": int(sum(b["reads"] for b in pb)),
+                    "fallback_fraction": n_fallback / n, "reads_handed_to_32bit_kernels": n_fallback, "max_read_len_16bit": lmax16,
+                    "ms_16bit_kernels": float(sum(b["ms"] for b in pb)), "ms_32bit_kernels": float(sum(b["ms"] for b in b32)), "parity": par}
+    g.set_pssm(load_pssm("onepass"))
+    return res
 
 
 def rmt_numbers(g, args, flush, lib_stream):
@@ -427,9 +540,13 @@ def pass1_numbers(g, ref, stored, off, rc, args, only_k12=False):
         g.pass1()                                   # warm-up
         out = g.pass1()
         t = g.last_timing()
-        nominal = t["dp_cells"]
+        nominal, effective = g.last_pass1_cells()
         res[tag] = {"reads": m, "kernel_ms": t["ms_kernels"], "reads_per_s": m / (t["ms_kernels"] * 1e-3),
+                    "nominal_cells": nominal, "effective_cells": effective,
+                    # GCUPS on nominal cells for unmasked runs, on EFFECTIVE cells (L x unmasked columns) for -k runs; both printed
+                    "gcups": (effective if k > 0 else nominal) / (t["ms_kernels"] * 1e-3) / 1e9,
                     "nominal_gcups": nominal / (t["ms_kernels"] * 1e-3) / 1e9,
+                    "effective_gcups": effective / (t["ms_kernels"] * 1e-3) / 1e9,
                     "accepted": int((out["score"] >= 2000).sum()), "rc_fraction": float(out["rc"].mean()),
                     "skipped_by_filter": int(((out["status"] & 2) != 0).sum()),
                     "reads_windowed_pair_kernels": g.last_pass1_stats()[0], "reads_general_kernel": g.last_pass1_stats()[1]}
@@ -534,14 +651,16 @@ def _ref_worker(q, ref, bases, off, rc, as_, ae, sm, smr, lo, hi, steps, warmup)
     from oracle.pyoracle import Ref
     r = Ref()
     wrap = ref + ref[:256]
-    o = off[lo:hi + 1] - off[lo]
-    b = bases[off[lo]:off[hi]]
+    o = np.ascontiguousarray(off[lo:hi + 1] - off[lo])
+    b = np.ascontiguousarray(bases[off[lo]:off[hi]])
     ws, wl = windows(off[lo:hi + 1], as_[lo:hi], ae[lo:hi], len(wrap))
+    rcs = np.ascontiguousarray(rc[lo:hi])
+    m = max(1, (hi - lo) // 8)                           # a warm-up pass takes an eighth of the shard: every array cut to it
     for _ in range(warmup):
-        r.time_realign(wrap, b, o, ws[: max(1, (hi - lo) // 8)], wl, rc[lo:hi], sm, smr)
+        r.time_realign(wrap, b, np.ascontiguousarray(o[: m + 1]), ws[:m].copy(), wl[:m].copy(), rcs[:m].copy(), sm, smr)
     ts, cells = [], 0
     for _ in range(steps):
-        t, cells, _ = r.time_realign(wrap, b, o, ws, wl, rc[lo:hi], sm, smr)
+        t, cells, _ = r.time_realign(wrap, b, o, ws, wl, rcs, sm, smr)
         ts.append(t)
     q.put((ts, cells))
 
@@ -552,10 +671,11 @@ def run_reference(args):
     if rank != 0:
         return
     import multiprocessing as mp
-    from oracle.pyoracle import Oracle, have_ref
+    from oracle.pyoracle import Oracle, Ref, have_ref
     if not have_ref():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libmia_ref.so missing (reference sources not on this box)"}))
         return
+    Ref()                                                # the parent maps oracle/_ref/libmia_ref.so too (the workers are forked from it)
     cores = os.cpu_count() or 1
     per_core = args.ref_reads_per_core
     n = cores * per_core
@@ -564,7 +684,7 @@ def run_reference(args):
     smr = Oracle().revcom_pssm(sm)
     q = mp.Queue()
     procs = [mp.Process(target=_ref_worker, args=(q, ref, bases, off, rc, as_, ae, sm, smr, i * per_core, (i + 1) * per_core,
-                                                  args.steps, min(args.warmup, 1))) for i in range(cores)]
+                                                  args.steps, args.warmup)) for i in range(cores)]
     t0 = time.perf_counter()
     for p in procs:
         p.start()
@@ -578,7 +698,7 @@ def run_reference(args):
     value = n / (ms * 1e-3)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int32", "data": "synthetic",
         "config": {"workload": "BASELINE configs[1] (same generator), bounded sample per step", "reads_per_step": n,
                    "ref_len": REF_LEN},
@@ -602,6 +722,9 @@ def main():
     ap.add_argument("--no-pass1", action="store_true")
     ap.add_argument("--no-rmt", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-shapes", action="store_true")
+    ap.add_argument("--parity-reads", type=int, default=20000, help="prefix of rank 0's workload checked against the CPU reference")
     ap.add_argument("--pass1-unmasked-reads", type=int, default=1000000)
     args = ap.parse_args()
     if args.impl == "reference":

@@ -119,6 +119,10 @@ int miagpu_pass1( miagpu_ctx* ctx, int32_t* hits, int32_t* score,
  * csrc/pass1.cuh), reads the general chunked kernel took, reads without a hit. */
 int miagpu_last_pass1_stats( miagpu_ctx* ctx, int64_t* fast_reads,
                              int64_t* general_reads, int64_t* skipped_reads );
+/* DP cells of the last miagpu_pass1: nominal = 2 * L * len1 per read (what the reference visits), effective = L * the
+ * columns new_kmer_filter unmasks, summed over both strands (a strand with >= 128 hits, or with more than 12 separate stretches,
+ * counts whole); equal without the filter */
+int miagpu_last_pass1_cells( miagpu_ctx* ctx, int64_t* nominal, int64_t* effective );
 /* per read of the last miagpu_pass1: 0 no k-mer hit, 1 finished by the pair kernels, 2 general kernel
  * (decided while seeding), 3 general kernel (the winning job's path was not a plain diagonal) */
 int miagpu_last_pass1_route( miagpu_ctx* ctx, uint8_t* route );

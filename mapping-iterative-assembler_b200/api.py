@@ -53,6 +53,7 @@ def load_library():
     L.miagpu_pass1.argtypes = [C.c_void_p] + [C.c_void_p] * 13
     L.miagpu_last_pass1_stats.argtypes = [C.c_void_p, _i64p, _i64p, _i64p]
     L.miagpu_last_pass1_route.argtypes = [C.c_void_p, C.c_void_p]
+    L.miagpu_last_pass1_cells.argtypes = [C.c_void_p, _i64p, _i64p]
     L.miagpu_compact_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, _i64p]
     L.miagpu_realign.argtypes = [C.c_void_p] + [C.c_void_p] * 10
     L.miagpu_get_runs_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, _i64p]
@@ -120,7 +121,7 @@ EXPORTS = ["miagpu_device_count", "miagpu_create", "miagpu_destroy", "miagpu_las
            "miagpu_last_cut_stats", "miagpu_repeat_filter", "miagpu_trim", "miagpu_get_alignment",
            "miagpu_fastx_open", "miagpu_fastx_open_memory", "miagpu_fastx_format", "miagpu_fastx_next", "miagpu_fastx_batch", "miagpu_fastx_close",
            "miagpu_maln_ref_size", "miagpu_write_maln", "miagpu_read_pssm", "miagpu_align_windows",
-           "miagpu_set_fsdb", "miagpu_get_fsdb", "miagpu_last_fsdb_stats", "miagpu_distant_retry", "miagpu_write_maln_fsdb"]
+           "miagpu_set_fsdb", "miagpu_get_fsdb", "miagpu_last_fsdb_stats", "miagpu_distant_retry", "miagpu_write_maln_fsdb", "miagpu_last_pass1_cells"]
 
 
 def _ptr(a):
@@ -200,6 +201,12 @@ class MiaGpu:
         f, g, k = C.c_int64(), C.c_int64(), C.c_int64()
         self._ck(self.lib.miagpu_last_pass1_stats(self.h, C.byref(f), C.byref(g), C.byref(k)))
         return f.value, g.value, k.value
+
+    def last_pass1_cells(self):
+        """(nominal, effective) DP cells of the last pass 1"""
+        a, b = C.c_int64(), C.c_int64()
+        self._ck(self.lib.miagpu_last_pass1_cells(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def last_pass1_route(self):
         r = np.zeros(self.n, np.uint8)

@@ -177,7 +177,7 @@ struct miagpu_ctx {
   DevBuf<uint8_t> d_jkind, d_jstatus, d_route;
   DevBuf<int32_t> d_jws, d_jwl, d_jscore, d_jabc, d_jaec, d_jabr, d_p1list, d_p1meta, d_jpairs, d_jread, d_jfirst;
   DevBuf<uint16_t> d_jcount;
-  int64_t p1_fast = 0, p1_general = 0, p1_skipped = 0;
+  int64_t p1_fast = 0, p1_general = 0, p1_skipped = 0, p1_eff = 0, dp_cells_p1 = 0;
   DevBuf<uint16_t> d_packed;
   DevBuf<int64_t> d_off2;
   DevBuf<int32_t> d_src;
@@ -932,6 +932,7 @@ static int realign_launch(miagpu_ctx* c, const RealignJob& j) {
     p.ref_codes = c->d_ref.p; p.ref_bytes = c->ref_bytes; p.prof = c->d_prof.p; p.sg5 = c->explicit_windows ? c->explicit_sg5 : 1;
     p.score = c->d_score.p + lo; p.as_out = c->d_as_out.p + lo; p.ae_out = c->d_ae_out.p + lo; p.abr = c->d_abr.p + lo;
     p.n_runs = c->d_nruns.p + lo; p.runs = c->d_runs.p + lo * MAX_RUNS; p.status = c->d_status.p + lo;
+    p.cells_done = j.timed ? reinterpret_cast<unsigned long long*>(j.d_meta + META_CELLS32) + b : nullptr;
     int ok = 1, maxL = meta[META_MAXL + b];
     switch (BUCKET_K[b]) {
       case 2: ok = launch_bucket<2>(c, p, maxL); break;
@@ -976,9 +977,12 @@ static int realign_bucket_times(miagpu_ctx* c) {
   MIAGPU_CUDA(cudaMemcpyAsync(meta, c->d_meta.p, sizeof(meta), cudaMemcpyDeviceToHost, c->stream));
   MIAGPU_CUDA(cudaStreamSynchronize(c->stream));
   c->n_fallback = meta[META_NFALL];
+  int64_t cells32[NBUCKET];
+  memcpy(cells32, meta + META_CELLS32, sizeof(cells32));
   for (int b = 0; b < NBUCKET; b++)
     if (c->bucket_reads[b]) {
       c->bucket_reads[b] = meta[META_COUNT + b];
+      if (b != NBUCKET - 1) c->bucket_cells[b] = cells32[b];               // what the 32-bit kernel of this bucket computed, not the class's total
       MIAGPU_CUDA(cudaEventElapsedTime(&c->bucket_ms[b], c->bev[2 * b], c->bev[2 * b + 1]));
     }
   for (int kb = 0; kb < P16_NKB; kb++)
@@ -3220,6 +3224,9 @@ extern "C" int miagpu_pass1(miagpu_ctx* c, int32_t* hits, int32_t* score, int32_
   }
   const int len1 = c->circular ? c->wrap_len : c->seq_len;
   c->dp_cells = 2 * (int64_t)len1 * c->total_bases;                        // nominal cells
+  c->dp_cells_p1 = c->dp_cells;
+  c->p1_eff = c->dp_cells;                                                 // without the filter every cell is computed
+  if (fast) memcpy(&c->p1_eff, c->h_meta + P1_EFF, sizeof(int64_t));
   return 1;
 }
 
@@ -3228,6 +3235,13 @@ extern "C" int miagpu_last_pass1_route(miagpu_ctx* c, uint8_t* route) {
   if (c->p1_fast + c->p1_skipped == 0 && c->p1_general == c->n) { memset(route, 2, c->n); return 1; }   // the fast path was off
   MIAGPU_CUDA(cudaSetDevice(c->device));
   MIAGPU_CUDA(cudaMemcpy(route, c->d_route.p, c->n, cudaMemcpyDeviceToHost));
+  return 1;
+}
+
+extern "C" int miagpu_last_pass1_cells(miagpu_ctx* c, int64_t* nominal, int64_t* effective) {
+  if (!c) { set_error("miagpu_last_pass1_cells: bad argument"); return 0; }
+  if (nominal) *nominal = c->dp_cells_p1;
+  if (effective) *effective = c->p1_eff;
   return 1;
 }
 

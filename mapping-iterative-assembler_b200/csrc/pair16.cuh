@@ -89,8 +89,9 @@ constexpr int META_PREADS = 120;     // [12] eligible reads per pair class
 constexpr int META_PCELLS = 132;     // [12] int64 cells of the eligible reads
 constexpr int META_MAXLEN = 156;     // scratch of max_len_kernel
 constexpr int META_NFALL = 157;      // reads handed from the pair kernels to the 32-bit kernels
-constexpr int META_P1 = 158;         // [6]  pass-1 counters (pass1.cuh)
-constexpr int META_HOST = 168;       // words copied to the host after classification
+constexpr int META_P1 = 158;         // [8]  pass-1 counters (pass1.cuh)
+constexpr int META_CELLS32 = 168;    // [10] int64 DP cells the 32-bit kernels actually computed, per width bucket
+constexpr int META_HOST = 192;       // words copied to the host after classification
 constexpr int P16_KEYS = P16_NKB * (P16_MAXL + 1);
 constexpr int META_KEYS = 1792;      // room per key table
 constexpr int META_HIST = 256;       // [P16_KEYS] eligible reads per (pair class, read length)

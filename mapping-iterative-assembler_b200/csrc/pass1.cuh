@@ -38,6 +38,7 @@ constexpr int P1_WORK = META_P1 + 3;      // work-fetch counter of the general k
 
 constexpr int P1_WORK2 = META_P1 + 5;       // work-fetch counter of the general kernel's second launch (reads the merge handed over)
 constexpr int P1_NJOBS = META_P1 + 4;       // jobs allocated (may exceed the capacity: reads that did not fit go to the general kernel)
+constexpr int P1_EFF = META_P1 + 6;         // [2] int64: effective DP cells = sum over strands of L x unmasked columns
 constexpr int P1_JPS = 12;           // stretches per strand that become jobs
 constexpr int P1_MAXD = 128;         // diagonals kept per strand: KMER_SATURATE hits unmask the whole strand anyway
 
@@ -159,6 +160,8 @@ __global__ void __launch_bounds__(256) p1_seed_kernel(P1SeedParams p) {
   __shared__ uint32_t s_code[8][17], s_valid[8][9];
   __shared__ int s_need[8];
   __shared__ long long s_first[8];
+  __shared__ unsigned long long s_eff;
+  if (threadIdx.x == 0) s_eff = 0;
   for (int i = threadIdx.x; i < P16_KEYS; i += blockDim.x) s_hist[i] = 0;
   if (threadIdx.x < P16_NKB) { s_preads[threadIdx.x] = 0; s_pcells[threadIdx.x] = 0; }
   if (threadIdx.x < 3) s_counts[threadIdx.x] = 0;
@@ -184,6 +187,18 @@ __global__ void __launch_bounds__(256) p1_seed_kernel(P1SeedParams p) {
     }
     const int total = st[0].hits + st[1].hits;
     if (live && lane == 0) p.hits[rd] = odd ? 0 : total;
+    if (live && lane == 0 && !odd && total > 0) {                         // effective cells: L x the columns new_kmer_filter unmasks
+      unsigned long long eff = 0;
+      for (int s = 0; s < 2; s++) {
+        if (!st[s].hits) continue;
+        if (st[s].hits >= KMER_SATURATE || st[s].n > P1_JPS) { eff += (unsigned long long)L * p.len1; continue; }   // (> 12 stretches: counted whole)
+        for (int t = 0; t < st[s].n; t++) {
+          const int a = max(st[s].lo[t] - ALIGN_MASK_BUFFER, 0), z = min(st[s].hi[t] + L + ALIGN_MASK_BUFFER - s, p.len1 - 1);
+          if (z >= a) eff += (unsigned long long)L * (z - a + 1);
+        }
+      }
+      atomicAdd(&s_eff, eff);
+    }
     bool fast = live && !odd && total > 0;
     // masked columns needed between two stretches so that no column-gap candidate crosses (see the header)
     const int need = (L - 1) * (max(p.pssm_max, 0) + GEP) + GEP;
@@ -253,6 +268,7 @@ __global__ void __launch_bounds__(256) p1_seed_kernel(P1SeedParams p) {
     atomicAdd(reinterpret_cast<unsigned long long*>(p.meta + META_PCELLS) + threadIdx.x, s_pcells[threadIdx.x]);
   }
   if (threadIdx.x == 0 && s_counts[0]) atomicAdd(&p.meta[P1_NSKIPPED], s_counts[0]);
+  if (threadIdx.x == 0 && s_eff) atomicAdd(reinterpret_cast<unsigned long long*>(p.meta + P1_EFF), s_eff);
 }
 
 struct P1MergeParams {

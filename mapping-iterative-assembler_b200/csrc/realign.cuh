@@ -64,6 +64,7 @@ struct RealignParams {
   // maximum of the LAST COLUMN in row order; as_out / ae_out are matrix columns (abc, aec), aer_out the end row
   int32_t shared_rows;
   int32_t* aer_out;
+  unsigned long long* cells_done;   // nullable: DP cells of the reads this launch computed (measurement)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -351,6 +352,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) realign_kernel(RealignPa
         for (int a = 0, b = nrun - 1; a < b; a++, b--) {     // runs were produced 3'->5'
           uint16_t x = my_runs[a]; my_runs[a] = my_runs[b]; my_runs[b] = x;
         }
+      if (p.cells_done) atomicAdd(p.cells_done, (unsigned long long)L * (unsigned long long)len1);
       p.score[rd] = score;
       p.as_out[rd] = TRIM ? col : col + ws;       // mia_main.c:250-255
       p.ae_out[rd] = TRIM ? aec : aec + ws;

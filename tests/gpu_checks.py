@@ -172,3 +172,67 @@ def check_pass1(gpu, oracle, ref, reads, sm, circular=1, k=0, soft_mask=0):
             bad.append((i, "strings", rg, fg, o["f_ref"] + o["b_ref"], o["f_frag"] + o["b_frag"]))
     oracle.ctx_free(ctx)
     return bad, out
+
+
+# ---------------------------------------------------------------- parity of a whole one-call round on a prefix of a workload
+class Checker:
+    """The CPU side of a parity check: the unmodified reference (oracle/_ref) where it was built, else the oracle restatement.
+    Per read it runs the reference's own call sequence on the window reiterate_assembly would cut (mia_main.c:190-235)."""
+
+    def __init__(self):
+        from oracle.pyoracle import Oracle, Ref, have_ref
+        self.o = Oracle()
+        self.r = Ref() if have_ref() else None
+        self.kind = "oracle/_ref (unmodified reference)" if self.r else "oracle (restatement)"
+
+    def realign(self, wrap, read, rc, as_, ae, sm, smr):
+        L, W = len(read), len(wrap)
+        rs = max(0, as_ - 50)
+        re = W if ae + 51 > W else ae + 50
+        if rs + L > re:
+            rs, re = 0, W
+        a = (self.r or self.o).align(wrap[rs:re], read, smr if rc else sm, 1)
+        return dict(score=a["score"], as_=a["abc"] + rs, ae=a["aec"] + rs, abr=a["abr"], ref_gapped=a["ref_gapped"], read_gapped=a["read_gapped"])
+
+
+def round_parity(gpu, ref, bases, off, rc, as_, ae, sm, circular=1, checker=None, want_consensus=True):
+    """One resident one-call round (miagpu_iterate_resident under miagpu_set_fsdb) over the given reads against the CPU checker:
+    every read's score / as / ae / abr / gapped strings, and the round's consensus after the checker's own score cut.
+    -> dict(reads, per_read_equal, n_diff, first_diff, gapped_reads, consensus_equal, checker)"""
+    from mia_b200 import api
+    ck = checker or Checker()
+    o = ck.o
+    n = len(off) - 1
+    seq_len = np.diff(off).astype(np.int32)
+    gpu.set_pssm(sm)
+    gpu.set_reference(ref, circular=circular, with_rc=0)
+    gpu.upload_reads(bases, off)
+    gpu.set_alignment_inputs(rc, as_, ae)
+    gpu.set_fsdb(seq_len, np.full(n, 2001, np.int32))
+    cons, fit, _ = gpu.iterate_resident()
+    al = gpu.get_alignment()
+    tot, _, _ = gpu.get_runs_packed()
+    run_off, packed = np.zeros(n + 1, np.int64), np.zeros(max(tot, 1), np.uint16)
+    gpu.get_runs_packed(run_off, packed)
+    wrap = ref + (ref[:min(256, len(ref))] if circular else "")
+    smr = o.revcom_pssm(sm)
+    res, bad, gapped = [], [], 0
+    for i in range(n):
+        read = bases[off[i]:off[i + 1]].tobytes().decode()
+        e = ck.realign(wrap, read, int(rc[i]), int(as_[i]), int(ae[i]), sm, smr)
+        res.append(e)
+        runs = packed[run_off[i]:run_off[i + 1]]
+        gapped += len(runs) > 1
+        rg, fg = api.expand_runs(wrap, read, int(al["as_out"][i]), int(al["abr"][i]), runs, len(runs))
+        got = (int(al["score"][i]), int(al["as_out"][i]), int(al["ae_out"][i]), int(al["abr"][i]), rg, fg)
+        exp = (e["score"], e["as_"], e["ae"], e["abr"], e["ref_gapped"], e["read_gapped"])
+        if got != exp:
+            bad.append((i, got[:4], exp[:4]))
+    out = dict(reads=n, per_read_equal=not bad, n_diff=len(bad), first_diff=str(bad[0]) if bad else None, gapped_reads=int(gapped),
+               checker=ck.kind)
+    if want_consensus:
+        ocons, _, _, _ = oracle_round(o, ref, bases, off, rc, res, sm, circular)
+        out["consensus_equal"] = bool(ocons == cons)
+        out["consensus_len"] = len(cons)
+    out["consensus"] = cons
+    return out
