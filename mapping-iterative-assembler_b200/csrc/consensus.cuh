@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(256) gaps_kernel(ConsParams p) {
 // memory only for the read bases.
 constexpr int TILE_THREADS = 512;
 constexpr int TILE_SMEM_INTS = NPLANE * TILE_COLS + (TILE_COLS + 1) + 2 * MIAGPU_PSSM_INTS;
-__global__ void __launch_bounds__(TILE_THREADS) tile_kernel(ConsParams p, const int32_t* __restrict__ ent_pos) {
+__global__ void __launch_bounds__(TILE_THREADS) tile_kernel(ConsParams p, const int32_t* __restrict__ bin_list, const int32_t* __restrict__ bin_start) {
   extern __shared__ int32_t s_acc[];                       // [NPLANE][TILE_COLS]
   int32_t* s_ins = s_acc + NPLANE * TILE_COLS;             // ins_off[t0 + i], i <= TILE_COLS
   int32_t* s_sm = s_ins + TILE_COLS + 1;
@@ -207,13 +207,15 @@ __global__ void __launch_bounds__(TILE_THREADS) tile_kernel(ConsParams p, const 
   for (int i = threadIdx.x; i < 2 * MIAGPU_PSSM_INTS; i += blockDim.x) s_sm[i] = p.sm[i];
   __syncthreads();
   const TileAdder A{s_acc, c0, p.acc, p.n_cols};
-  const int64_t per = (p.n_entries + gridDim.x - 1) / gridDim.x;
-  const int64_t lo = per * blockIdx.x, hi = min(lo + per, p.n_entries);
+  // the entries that start inside this tile were binned (ent_bin_*_kernel): slice blockIdx.x of the tile's list
+  const int64_t b0 = bin_start[blockIdx.y], b1 = bin_start[blockIdx.y + 1];
+  const int64_t per = (b1 - b0 + gridDim.x - 1) / gridDim.x;
+  const int64_t lo = b0 + per * blockIdx.x, hi = min(lo + per, b1);
+  (void)t1;
   for (int64_t base = lo + warp * 32; base < hi; base += nwarps * 32) {
-    const int64_t idx = base + lane;
-    int pos0 = -1;
-    if (idx < hi) pos0 = ent_pos[idx];
-    const bool mine = pos0 >= t0 && pos0 < t1;
+    const int64_t at = base + lane;
+    const bool mine = at < hi;
+    const int64_t idx = mine ? bin_list[at] : 0;
     miagpu_entry e{};
     int nr = 0, ab = 0, strand = 0, run0 = 0;
     int64_t o = 0;
@@ -234,7 +236,7 @@ __global__ void __launch_bounds__(TILE_THREADS) tile_kernel(ConsParams p, const 
       const int b_nr = __shfl_sync(0xffffffffu, nr, b);
       const int b_run0 = __shfl_sync(0xffffffffu, run0, b);
       if (b_nr != 1 || (b_run0 >> 14) != MIAGPU_RUN_M) {   // gaps in the alignment: the general walk
-        const miagpu_entry eb = p.entries[base + b];
+        const miagpu_entry eb = p.entries[__shfl_sync(0xffffffffu, idx, b)];
         walk_entry<1>(p, eb, lane, A);
         continue;
       }
@@ -315,12 +317,52 @@ __global__ void __launch_bounds__(256) undo_kernel(ConsParams p, int64_t n_reads
   }
 }
 
-// start position of every entry for tile_kernel's scan (-1 = nothing to add)
-__global__ void ent_pos_kernel(ConsParams p, int32_t* ent_pos) {
+// Entries binned by the tile their first column lies in (a counting sort in two kernels; the order inside a bin does not
+// matter: integer sums).  ent_bin_count_kernel: tile of every entry (-1 = nothing to add) + entries per tile;
+// ent_bin_scan_kernel: bin starts + cursors; ent_bin_scatter_kernel: entry indices into their bins.
+constexpr int MAX_TILES = 64;
+__global__ void __launch_bounds__(256) ent_bin_count_kernel(ConsParams p, int32_t* ent_tile, int32_t* counts) {
+  __shared__ int s_cnt[MAX_TILES];
+  if (threadIdx.x < MAX_TILES) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= p.n_entries) return;
-  const miagpu_entry e = p.entries[i];
-  ent_pos[i] = (e.col_count > 0 && cons_nruns(p, e.read) > 0) ? e.ref_pos : -1;
+  int t = -1;
+  if (i < p.n_entries) {
+    const miagpu_entry e = p.entries[i];
+    if (e.col_count > 0 && cons_nruns(p, e.read) > 0 && e.ref_pos >= 0 && e.ref_pos < p.seq_len) t = e.ref_pos / TILE_POS;
+    ent_tile[i] = t;
+  }
+  const unsigned peers = __match_any_sync(0xffffffffu, t);
+  if (t >= 0 && (peers & ((1u << (threadIdx.x & 31)) - 1)) == 0) atomicAdd(&s_cnt[t], __popc(peers));
+  __syncthreads();
+  if (threadIdx.x < MAX_TILES && s_cnt[threadIdx.x]) atomicAdd(&counts[threadIdx.x], s_cnt[threadIdx.x]);
+}
+__global__ void ent_bin_scan_kernel(int n_tiles, const int32_t* counts, int32_t* bin_start, int32_t* cursor) {
+  if (threadIdx.x != 0) return;
+  int run = 0;
+  for (int t = 0; t < n_tiles; t++) { bin_start[t] = run; cursor[t] = run; run += counts[t]; }
+  bin_start[n_tiles] = run;
+}
+__global__ void __launch_bounds__(256) ent_bin_scatter_kernel(int64_t n_entries, const int32_t* __restrict__ ent_tile, int32_t* cursor, int32_t* bin_list) {
+  __shared__ int s_cnt[MAX_TILES], s_base[MAX_TILES];
+  if (threadIdx.x < MAX_TILES) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = i < n_entries ? ent_tile[i] : -1;
+  const int lane = threadIdx.x & 31;
+  const unsigned peers = __match_any_sync(0xffffffffu, t);
+  int slot = 0;
+  if (t >= 0) {
+    const int leader = __ffs(peers) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(&s_cnt[t], __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    slot = base + __popc(peers & ((1u << lane) - 1));
+  }
+  __syncthreads();
+  if (threadIdx.x < MAX_TILES) s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd(&cursor[threadIdx.x], s_cnt[threadIdx.x]) : 0;
+  __syncthreads();
+  if (t >= 0) bin_list[s_base[t] + slot] = (int32_t)i;
 }
 
 // find_consensus (map_align.c:294-391) for every column of the padded layout.

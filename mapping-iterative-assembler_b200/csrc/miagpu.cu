@@ -1272,18 +1272,24 @@ static int launch_accumulate(miagpu_ctx* c) {
   if (!c->n_entries) return 1;
   ConsParams p = cons_params(c);
   const int n_tiles = (c->seq_len + TILE_POS - 1) / TILE_POS;
-  bool tiles = n_tiles <= 64 && c->n_entries >= 4096;
+  bool tiles = n_tiles <= MAX_TILES && c->n_entries >= 4096;
   if (const char* e = getenv("MIAGPU_CONS_TILES")) tiles = atoi(e) != 0;
   if (tiles) {
-    if (!c->d_ent_pos.reserve(c->n_entries + 1)) return 0;
-    ent_pos_kernel<<<(unsigned)((c->n_entries + 255) / 256), 256, 0, c->stream>>>(p, c->d_ent_pos.p);
+    // d_ent_pos: [n_entries] tile of every entry | [n_entries] the bins | counts[64] | starts[65] | cursors[64]
+    const int64_t ne = c->n_entries;
+    if (!c->d_ent_pos.reserve(2 * ne + 3 * MAX_TILES + 8)) return 0;
+    int32_t *ent_tile = c->d_ent_pos.p, *bin_list = ent_tile + ne, *counts = bin_list + ne, *starts = counts + MAX_TILES, *cursor = starts + MAX_TILES + 1;
+    MIAGPU_CUDA(cudaMemsetAsync(counts, 0, MAX_TILES * sizeof(int32_t), c->stream));
+    ent_bin_count_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, c->stream>>>(p, ent_tile, counts);
+    ent_bin_scan_kernel<<<1, 32, 0, c->stream>>>(n_tiles, counts, starts, cursor);
+    ent_bin_scatter_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, c->stream>>>(ne, ent_tile, cursor, bin_list);
     MIAGPU_CUDA(cudaGetLastError());
     const size_t smem = (size_t)TILE_SMEM_INTS * sizeof(int32_t);
     MIAGPU_CUDA(cudaFuncSetAttribute(tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int slices = std::max(1, (2 * c->num_sms + n_tiles - 1) / n_tiles);
-    tile_kernel<<<dim3(slices, n_tiles), TILE_THREADS, smem, c->stream>>>(p, c->d_ent_pos.p);
+    tile_kernel<<<dim3(slices, n_tiles), TILE_THREADS, smem, c->stream>>>(p, bin_list, starts);
     MIAGPU_CUDA(cudaGetLastError());
-    c->launches += 2;
+    c->launches += 4;
   } else {
     entry_kernel<1><<<(unsigned)((c->n_entries * 32 + 255) / 256), 256, 0, c->stream>>>(p);
     MIAGPU_CUDA(cudaGetLastError());

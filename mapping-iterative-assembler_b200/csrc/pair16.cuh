@@ -42,6 +42,16 @@
 //    row means the alignment is one M run from (abr, abc) = (L-1-n, aec-n), n = min(L-1, aec).
 //    Otherwise (gap, start-new cell on the path, jump stored as trace 0) the read is appended to the
 //    32-bit kernel's list.  No trace matrix, no band, no scratch memory.
+//
+// 5. Reads beyond the 16-bit frame (RB = true).  In the frame of 2. a cell on a good path gains up to max(sm) + GEP per row, so
+//    a read of more than ~130 rows runs out of the 16-bit range.  The RB variant starts the frame near the TOP of the range and
+//    subtracts D = 8 * (max(sm) + GEP) from all state every 8 rows (saturating), so that exact values never rise above their
+//    start (+ a bounded fluctuation: within 8 rows, and the GEP*K a path regains each time it crosses into the next lane) while a
+//    real read sinks by (max(sm) - its entries) per row.  The start-new level and every cell are clamped from below at the
+//    levels the frame of 2. guarantees, so no operation wraps; a clamped value is too HIGH (poisoned), and so is everything
+//    derived from it -- but never above clamp level + fluctuation.  If the end cell lies above that bound, every cell of its path
+//    does too (values do not rise along a path beyond the fluctuation), none of them was poisoned, and every poisoned candidate
+//    they met was strictly lower: score, end cell and verdict are exact.  Otherwise the read goes to the 32-bit kernel.
 #pragma once
 #include "common.cuh"
 #include "realign.cuh"
@@ -49,7 +59,7 @@
 
 namespace miagpu {
 
-constexpr int P16_MAXL = 144;                       // rows the shared row-offset arrays hold
+constexpr int P16_MAXL = MAX_READ;                  // rows the shared row-offset arrays hold
 constexpr int PROF16_N = 2 * NMAT * 5 * PROF_ROW_INTS;   // int16 entries
 constexpr int P16_NKB = 12;                         // width classes: 128 / 144 / 160 / 176 / 192 / 208 / 224 / 256 columns (K = columns / 16),
                                                     // then the narrow classes of pass-1 jobs: 64 / 80 / 96 / 112 (K = 4 .. 7)
@@ -127,7 +137,24 @@ struct Pair16Params {
   uint32_t gep2;                 // K2(2*GEP), passed as data so that ptxas keeps this add an IMAD (FMA pipe) instead of folding it into a VIADD
   int32_t strand_stride;         // JOB kernels: bytes between the forward and the reverse-complement codes in ref_codes
   const int32_t* job_read;       // JOB kernels: read of a job, bit 31 = reverse strand
+  // RB kernels (see 5. in the header): OFF of the high frame, the amount subtracted every P16_RB_ROWS rows, the lowest end value that is exact
+  int32_t rb_off, rb_d, rb_thresh;
 };
+
+constexpr int P16_RB_ROWS = 8;
+// parameters of the RB frame for K columns per lane and the largest matrix entry; feasible = a real read has room to sink
+struct RbFrame { int off, d, thresh, room; };
+__host__ __device__ inline RbFrame p16_rb_frame(int K, int max_entry) {
+  const int mx = max_entry > 0 ? max_entry : 0;
+  const int G = P16_RB_ROWS * (mx + 2 * GEP) + GEP * K;                          // fluctuation of an exact value above its long-run level
+  RbFrame f;
+  f.d = P16_RB_ROWS * (mx + GEP);
+  f.off = mx + GEP * (K - 1) + G + 64 - 32767;                                   // row 0 starts at most G + 64 below the top
+  const int clamp_cell = -(GOP + 3 * GEP) - (32768 - 2 * GOP - GEP - PSSM_ABS_LIMIT - GEP * K - 32) + 2 * GEP + PSSM_ABS_LIMIT;   // p16_off(K), see below
+  f.thresh = clamp_cell + 2 * G + 2 * GOP;                                       // unbiased; above it nothing is poisoned
+  f.room = (-f.off) - f.thresh;                                                  // how far a read may sink below the top of row 0
+  return f;
+}
 
 constexpr uint8_t P16_ST_GENERAL = 0x40;   // JOB kernels: the alignment is not one plain diagonal, the general kernel takes the read
 
@@ -197,7 +224,7 @@ __host__ __device__ constexpr int p16_smem_fixed() {
 #ifndef P16_SIX_BLOCKS_K
 #define P16_SIX_BLOCKS_K 7
 #endif
-template <int K, int G, bool JOB>
+template <int K, int G, bool JOB, bool RB = false>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, (K <= 5 ? 8 : K <= P16_SIX_BLOCKS_K ? 6 : K <= 12 ? 5 : 4)) pair16_kernel(Pair16Params p) {
   static_assert(K >= 4 && ((G == 16 && K <= 16) || (G == 8 && K <= 24)), "columns per lane / lanes per pair");
   constexpr int NP = 32 / G;                         // pairs per warp
@@ -239,14 +266,19 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, (K <= 5 ? 8 : K <= P16_S
   const uint32_t prof_base = smem_u32(s_prof);
   const uint32_t tab_addr = smem_u32(tab);
 
-  constexpr int OFF = p16_off(K);
+  constexpr int OFFN = p16_off(K);
+  const int OFF = RB ? p.rb_off : OFFN;              // (a compile-time constant without RB)
   constexpr int CONV = GEP * K;                      // frame shift per lane of distance
   constexpr int SENT = -32768 + GOP;                 // "-infinity" that survives one -GOP
   const int n_items = *p.n_items;
   const uint32_t gep2 = p.gep2;
   const uint32_t keep = sub ? 0xffffffffu : 0u;      // lane masks for the group's first lane (one LOP3 instead of a select)
   const uint32_t sentm = sub ? 0u : B2(SENT);
-  uint32_t ncmp0m = sub ? 0u : B2(-(GOP + 3 * GEP) - OFF);
+  uint32_t ncmp0m = sub ? 0u : B2(-(GOP + 3 * GEP) - OFFN);
+  // RB: the start-new level N(r) in the frame, sinking with the frame but never below the level of the low frame; the cells' clamp
+  constexpr uint32_t RB_NMIN = B2(-(GOP + 3 * GEP) - OFFN), RB_CELLMIN = B2(-(GOP + 3 * GEP) - OFFN + 2 * GEP - PSSM_ABS_LIMIT);
+  const uint32_t rb_d2 = RB ? K2(p.rb_d) : 0u;
+  uint32_t cur_n = 0;
 
   // table entries this lane builds every row: e = sub + G*t -> (a, b) = (e / 5, e % 5)
   uint32_t eoa[NE], eob[NE];
@@ -283,11 +315,19 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, (K <= 5 ? 8 : K <= P16_S
     const int wsA = p.win_start[rdA], wsB = p.win_start[rdB];
     const int lenA = p.win_len[rdA], lenB = p.win_len[rdB];
     const int sA = JOB ? 0 : (p.rc[rdA] ? 1 : 0), sB = JOB ? 0 : (p.rc[rdB] ? 1 : 0);
+    bool mlA = false, mlB = false;
     if (JOB) {                                        // first column: column 0 of the matrix, or a column with a masked left neighbour
-      const bool mlA = wsA - (jrA < 0 ? p.strand_stride : 0) > 0, mlB = wsB - (jrB < 0 ? p.strand_stride : 0) > 0;
-      const uint32_t real = B2(-(GOP + 3 * GEP) - OFF), cut = B2(SENT);
-      ncmp0m = sub ? 0u : (((mlA ? cut : real) & 0xffffu) | ((mlB ? cut : real) & 0xffff0000u));
+      mlA = wsA - (jrA < 0 ? p.strand_stride : 0) > 0; mlB = wsB - (jrB < 0 ? p.strand_stride : 0) > 0;
+      const uint32_t real = B2(-(GOP + 3 * GEP) - OFFN), cut = B2(SENT);
+      if (!RB) ncmp0m = sub ? 0u : (((mlA ? cut : real) & 0xffffu) | ((mlB ? cut : real) & 0xffff0000u));
     }
+    int rb_shift = 0;                                 // RB: what has been subtracted from the frame so far
+    auto rb_ncmp0 = [&]() {                           // RB: column 0's operand follows the start-new level
+      if (!JOB) { ncmp0m = sub ? 0u : cur_n; return; }
+      const uint32_t cut = B2(SENT);
+      ncmp0m = sub ? 0u : (((mlA ? cut : cur_n) & 0xffffu) | ((mlB ? cut : cur_n) & 0xffff0000u));
+    };
+    if (RB) { cur_n = ((uint32_t)(-(GOP + 3 * GEP) - OFF + 32768) & 0xffffu) * 0x10001u; rb_ncmp0(); }
 
     __syncwarp();
     for (int r = sub; r < L; r += G) {
@@ -315,7 +355,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, (K <= 5 ? 8 : K <= P16_S
 #pragma unroll
       for (int j = 0; j < K; j++) {
         const uint2 e = lds_entry<0>(comb[j]);
-        W[j] = B2(GEP * j - OFF) + e.x + e.y;         // biased seed + entries: 32-bit adds, as in cell_pair
+        if (RB) W[j] = ((uint32_t)(GEP * j - OFF + 32768) & 0xffffu) * 0x10001u + e.x + e.y;
+        else W[j] = B2(GEP * j - OFFN) + e.x + e.y;   // biased seed + entries: 32-bit adds, as in cell_pair
         Rg[j] = B2(-32768);
         acc[j] = 0;
       }
@@ -357,7 +398,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, (K <= 5 ? 8 : K <= P16_S
       for (int j = 2; j < K; j++) Q[j] = __viaddmax_u16x2(W[j - 2], K2(-GOP), Q[j - 1]);
 #pragma unroll
       for (int j = 0; j < K; j++) {
-        const uint32_t ncmpj = B2(-(GOP + 3 * GEP) - OFF) + K2(GEP * j);     // NCMP_j: compile-time after unrolling
+        const uint32_t ncmpj = (RB ? cur_n : B2(-(GOP + 3 * GEP) - OFFN)) + K2(GEP * j);     // NCMP_j: compile-time after unrolling (without RB)
         uint32_t D, ad;
         if (j > 0) { D = W[j - 1]; ad = acc[j - 1]; }
         else { D = and_or(l1c, keep, ncmp0m); ad = ain; }   // column 0: S = sub + N, never start-new (mia.c:805-822)
@@ -370,6 +411,17 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, (K <= 5 ? 8 : K <= P16_S
         else accn[j] = ad | (bp ^ D);
       }
       __syncwarp();
+    };
+    // RB: every P16_RB_ROWS rows the frame sinks by rb_d (see 5. in the header); cells and the start-new level keep the low frame's floors
+    auto rebase = [&](uint32_t (&W)[K]) {
+#pragma unroll
+      for (int j = 0; j < K; j++) {
+        W[j] = __vmaxu2(__vsubus2(W[j], rb_d2), RB_CELLMIN);
+        Rg[j] = __vsubus2(Rg[j], rb_d2);
+      }
+      cur_n = __vmaxu2(__vsubus2(cur_n, rb_d2), RB_NMIN);
+      rb_shift += p.rb_d;
+      rb_ncmp0();
     };
     // The same row, updated IN PLACE (G = 8: twice the columns per lane, no room for a second register set): the column-gap
     // chain and the diagonal operand read row r-1's cells just before they are overwritten, two rotating registers deep.
@@ -425,6 +477,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, (K <= 5 ? 8 : K <= P16_S
       uint32_t W1[K], acc1[K];
       int r = 1;
       for (; r + 1 < L; r += 2) {
+        if (RB && (r & (P16_RB_ROWS - 1)) == 1 && r > 1) rebase(W);
         dp_row(r, std::integral_constant<int, 1>{}, W, acc, W1, acc1);
         dp_row(r + 1, std::integral_constant<int, 0>{}, W1, acc1, W, acc);
       }
@@ -452,12 +505,14 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, (K <= 5 ? 8 : K <= P16_S
       }
       best = __reduce_max_sync(gmask, best);
       const int aec = KEY_IDX_MASK - (best & KEY_IDX_MASK);
-      const int score = (best >> 9) + OFF - GEP * (L - 1);
+      const int score = (best >> 9) + OFF - GEP * (L - 1) + rb_shift;
       bool bad = false;
 #pragma unroll
       for (int j = 0; j < K; j++)
         if (sub * K + j == aec) bad = (h ? (acc[j] >> 16) : (acc[j] & 0xffffu)) != 0;
-      const bool ok = !__any_sync(gmask, bad);
+      // RB: an end value at or below the poison bound may have met clamped cells: the 32-bit kernel takes the read
+      const bool sunk = RB && (best >> 9) + GEP * (aec % K) <= p.rb_thresh;
+      const bool ok = !__any_sync(gmask, bad) && !sunk;
       const int nsteps = min(L - 1, aec);
       if (JOB) {
         if (sub == 0 && live) {
