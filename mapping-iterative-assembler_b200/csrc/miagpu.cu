@@ -478,10 +478,10 @@ __global__ void classify_kernel(int64_t n, const int64_t* off, const int32_t* as
   __shared__ int s_cnt[NBUCKET], s_base[NBUCKET], s_maxL[NBUCKET], s_pop[NBUCKET];
   __shared__ unsigned long long s_cells[NBUCKET];
   __shared__ int s_hist[P16_KEYS];
-  __shared__ int s_preads[P16_NKB];
+  __shared__ int s_preads[P16_NKB], s_pmaxl[P16_NKB];
   __shared__ unsigned long long s_pcells[P16_NKB];
   if (threadIdx.x < NBUCKET) { s_cnt[threadIdx.x] = 0; s_maxL[threadIdx.x] = 0; s_pop[threadIdx.x] = 0; s_cells[threadIdx.x] = 0; }
-  if (threadIdx.x < P16_NKB) { s_preads[threadIdx.x] = 0; s_pcells[threadIdx.x] = 0; }
+  if (threadIdx.x < P16_NKB) { s_preads[threadIdx.x] = 0; s_pcells[threadIdx.x] = 0; s_pmaxl[threadIdx.x] = 0; }
   if (lmax16 > 0) for (int i = threadIdx.x; i < P16_KEYS; i += blockDim.x) s_hist[i] = 0;
   __syncthreads();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -528,7 +528,8 @@ __global__ void classify_kernel(int64_t n, const int64_t* off, const int32_t* as
     if (key >= 0 && (pk & lt) == 0) atomicAdd(&s_hist[key], __popc(pk));
     const unsigned pc = __match_any_sync(0xffffffffu, kb);
     const unsigned long long cs = (unsigned long long)__reduce_add_sync(pc, cells & 0xffffu) + ((unsigned long long)__reduce_add_sync(pc, cells >> 16) << 16);
-    if (kb >= 0 && (pc & lt) == 0) { atomicAdd(&s_preads[kb], __popc(pc)); atomicAdd(&s_pcells[kb], cs); }
+    const int mxl = __reduce_max_sync(pc, L);
+    if (kb >= 0 && (pc & lt) == 0) { atomicAdd(&s_preads[kb], __popc(pc)); atomicAdd(&s_pcells[kb], cs); atomicMax(&s_pmaxl[kb], mxl); }
   }
   // reads that go straight to a 32-bit list take consecutive slots
   {
@@ -550,6 +551,7 @@ __global__ void classify_kernel(int64_t n, const int64_t* off, const int32_t* as
   if (threadIdx.x < P16_NKB && s_preads[threadIdx.x]) {
     atomicAdd(&meta[META_PREADS + threadIdx.x], s_preads[threadIdx.x]);
     atomicAdd(reinterpret_cast<unsigned long long*>(meta + META_PCELLS) + threadIdx.x, s_pcells[threadIdx.x]);
+    atomicMax(&meta[META_PMAXL + threadIdx.x], s_pmaxl[threadIdx.x]);
   }
   if (lmax16 > 0)
     for (int k = threadIdx.x; k < P16_KEYS; k += blockDim.x)
@@ -744,17 +746,18 @@ static int launch_bucket(miagpu_ctx* c, RealignParams p, int maxL) {
   return 1;
 }
 
-template <int K, int G, bool JOB = false>
+template <int K, int G, bool JOB = false, bool RB = false>
 static int launch_pair16(miagpu_ctx* c, Pair16Params p, int n_pairs, int maxL) {
   bool ref_in_smem = p.ref_bytes <= 160 * 1024;
   size_t smem = p16_smem_fixed<G>() + (ref_in_smem ? p.ref_bytes : 0);
   static size_t cached_smem = ~(size_t)0;
   static int cached_per_sm = 0;
   if (cached_smem != smem) {
-    MIAGPU_CUDA(cudaFuncSetAttribute((pair16_kernel<K, G, JOB>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MIAGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cached_per_sm, (pair16_kernel<K, G, JOB>), WARPS_PER_BLOCK * 32, smem));
+    MIAGPU_CUDA(cudaFuncSetAttribute((pair16_kernel<K, G, JOB, RB>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MIAGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cached_per_sm, (pair16_kernel<K, G, JOB, RB>), WARPS_PER_BLOCK * 32, smem));
     cached_smem = smem;
   }
+  if (RB) { const RbFrame f = p16_rb_frame(K, c->pssm_max); p.rb_off = f.off; p.rb_d = f.d; p.rb_thresh = f.thresh; }
   int per_sm = cached_per_sm;
   if (per_sm < 1) { set_error("pair16_kernel<%d,%d> does not fit on an SM (smem %zu)", K, G, smem); return 0; }
   int cap = 8;
@@ -765,7 +768,7 @@ static int launch_pair16(miagpu_ctx* c, Pair16Params p, int n_pairs, int maxL) {
   (void)maxL;
   p.ref_in_smem = ref_in_smem;
   p.gep2 = K2(2 * GEP);
-  pair16_kernel<K, G, JOB><<<blocks, WARPS_PER_BLOCK * 32, smem, c->launch_stream>>>(p);
+  pair16_kernel<K, G, JOB, RB><<<blocks, WARPS_PER_BLOCK * 32, smem, c->launch_stream>>>(p);
   MIAGPU_CUDA(cudaGetLastError());
   c->launches++;
   return 1;
@@ -811,12 +814,26 @@ static PairNp realign_np() {
   for (int kb = 0; kb < P16_NKB; kb++) r.v[kb] = 32 / realign_g(kb);
   return r;
 }
-static PairLmax pair_lmax(miagpu_ctx* c) {
+// longest read every pair class takes in the low frame (pair16.cuh 2.)
+static PairLmax pair_lmax_low(miagpu_ctx* c) {
   int lmax16 = c->lmax16;
   if (const char* e = getenv("MIAGPU_PAIR16")) if (atoi(e) == 0) lmax16 = 0;
   c->pair_g = 16;                                    // lanes per pair of the pass-1 job kernels
   PairLmax lm{};
   for (int kb = 0; kb < P16_NKB; kb++) lm.v[kb] = lmax16 > 0 ? std::min(p16_lmax(P16_COLS[kb] / realign_g(kb), c->pssm_max), P16_MAXL) : 0;
+  return lm;
+}
+// does the class have an RB instantiation (pair16.cuh 5.) with room for real reads under the current matrices?
+static bool pair_rb_class(miagpu_ctx* c, int kb, bool job) {
+  if (const char* e = getenv("MIAGPU_PAIR_RB")) if (atoi(e) == 0) return false;
+  if (realign_g(kb) != 16 || kb >= P16_NKB_WIDE || (job && kb < 2)) return false;      // JOB: K = 10 .. 16 only (a stretch is about L + 20 columns)
+  return p16_rb_frame(P16_COLS[kb] / 16, c->pssm_max).room >= 16384;
+}
+// longest read every pair class takes at all: the RB frame holds any read of the class's width
+static PairLmax pair_lmax(miagpu_ctx* c, bool job = false) {
+  PairLmax lm = pair_lmax_low(c);
+  for (int kb = 0; kb < P16_NKB; kb++)
+    if (lm.v[kb] > 0 && pair_rb_class(c, kb, job)) lm.v[kb] = P16_MAXL;
   return lm;
 }
 
@@ -853,6 +870,7 @@ static int realign_launch(miagpu_ctx* c, const RealignJob& j) {
   if (n == 0) return 1;
   const int32_t* meta = j.h_meta;
   const PairNp npk = realign_np();
+  const PairLmax lm_low = pair_lmax_low(c);
   const bool concurrent = !j.timed && !getenv("MIAGPU_SERIAL_LAUNCH");
   int rr = 0;
   int64_t cells[NBUCKET], pcells[P16_NKB];
@@ -895,7 +913,16 @@ static int realign_launch(miagpu_ctx* c, const RealignJob& j) {
       p.lists = j.d_lists; p.list_counts = j.d_meta + META_COUNT; p.n_reads = n; p.n_fallback = j.d_meta + META_NFALL;
       const int maxL = P16_MAXL;
       int ok = 1;
-      switch (realign_g(kb) == 8 ? 100 + kb : kb) {
+      const bool rb = meta[META_PMAXL + kb] > lm_low.v[kb];         // a read of the class is beyond the low frame: the whole class takes the RB frame
+      switch (realign_g(kb) == 8 ? 100 + kb : rb ? 200 + kb : kb) {
+        case 200: ok = launch_pair16<8, 16, false, true>(c, p, ni, maxL); break;
+        case 201: ok = launch_pair16<9, 16, false, true>(c, p, ni, maxL); break;
+        case 202: ok = launch_pair16<10, 16, false, true>(c, p, ni, maxL); break;
+        case 203: ok = launch_pair16<11, 16, false, true>(c, p, ni, maxL); break;
+        case 204: ok = launch_pair16<12, 16, false, true>(c, p, ni, maxL); break;
+        case 205: ok = launch_pair16<13, 16, false, true>(c, p, ni, maxL); break;
+        case 206: ok = launch_pair16<14, 16, false, true>(c, p, ni, maxL); break;
+        case 207: ok = launch_pair16<16, 16, false, true>(c, p, ni, maxL); break;
         case 100: ok = launch_pair16<16, 8>(c, p, ni, maxL); break;
         case 101: ok = launch_pair16<18, 8>(c, p, ni, maxL); break;
         case 102: ok = launch_pair16<20, 8>(c, p, ni, maxL); break;
@@ -2987,6 +3014,7 @@ extern "C" int miagpu_build_kmers(miagpu_ctx* c, int k, int soft_mask) {
 // Pass 1 with the k-mer filter on (pass1.cuh): seed every read, run the strands' separate stretches through the pair
 // kernels, merge, and leave the rest to the general kernel.
 static int pass1_fast(miagpu_ctx* c, const PairLmax& lm) {
+  const PairLmax lm_low = pair_lmax_low(c);
   const int64_t n = c->n, nj = 10 * n + 4096;          // job capacity; reads whose jobs do not fit go to the general kernel
   const int np = 32 / c->pair_g;
   if (n > 0x7fffffffLL / 8) { set_error("miagpu_pass1: at most %d reads per batch", 0x7fffffff / 8); return 0; }
@@ -3057,7 +3085,14 @@ static int pass1_fast(miagpu_ctx* c, const PairLmax& lm) {
       p.score = c->d_jscore.p; p.as_out = c->d_jabc.p; p.ae_out = c->d_jaec.p; p.abr = c->d_jabr.p; p.status = c->d_jstatus.p;
       p.n_reads = nj;
       int ok = 1;
-      switch (kb) {
+      const bool rb = c->h_meta[META_PMAXL + kb] > lm_low.v[kb];
+      switch (rb ? 200 + kb : kb) {
+        case 202: ok = launch_pair16<10, 16, true, true>(c, p, ni, P16_MAXL); break;
+        case 203: ok = launch_pair16<11, 16, true, true>(c, p, ni, P16_MAXL); break;
+        case 204: ok = launch_pair16<12, 16, true, true>(c, p, ni, P16_MAXL); break;
+        case 205: ok = launch_pair16<13, 16, true, true>(c, p, ni, P16_MAXL); break;
+        case 206: ok = launch_pair16<14, 16, true, true>(c, p, ni, P16_MAXL); break;
+        case 207: ok = launch_pair16<16, 16, true, true>(c, p, ni, P16_MAXL); break;
         case 0: ok = launch_pair16<8, 16, true>(c, p, ni, P16_MAXL); break;
         case 1: ok = launch_pair16<9, 16, true>(c, p, ni, P16_MAXL); break;
         case 2: ok = launch_pair16<10, 16, true>(c, p, ni, P16_MAXL); break;
@@ -3193,7 +3228,7 @@ extern "C" int miagpu_pass1(miagpu_ctx* c, int32_t* hits, int32_t* score, int32_
       !c->d_end.reserve(n + 1) || !c->d_rc_out.reserve(n + 1)) return 0;
   MIAGPU_CUDA(cudaMemsetAsync(c->d_meta.p, 0, 128 * sizeof(int32_t), c->stream));
   MIAGPU_CUDA(cudaEventRecord(c->ev[1], c->stream));
-  const PairLmax lm = pair_lmax(c);
+  const PairLmax lm = c->kmer_k > 0 ? pair_lmax(c, true) : pair_lmax_low(c);      // (the whole-strand sweep has no RB frame)
   bool fast = c->kmer_k > 0 && lm.v[0] > 0 && n > 0;
   if (const char* e = getenv("MIAGPU_PASS1_FAST")) fast = fast && atoi(e) != 0;
   bool sweep = c->kmer_k <= 0 && lm.v[SW_CLASS] > 0 && n > 0;

@@ -101,9 +101,10 @@ constexpr int META_MAXLEN = 156;     // scratch of max_len_kernel
 constexpr int META_NFALL = 157;      // reads handed from the pair kernels to the 32-bit kernels
 constexpr int META_P1 = 158;         // [8]  pass-1 counters (pass1.cuh)
 constexpr int META_CELLS32 = 168;    // [10] int64 DP cells the 32-bit kernels actually computed, per width bucket
-constexpr int META_HOST = 192;       // words copied to the host after classification
+constexpr int META_PMAXL = 192;      // [12] longest eligible read per pair class (decides between the low and the RB frame)
+constexpr int META_HOST = 208;       // words copied to the host after classification
 constexpr int P16_KEYS = P16_NKB * (P16_MAXL + 1);
-constexpr int META_KEYS = 1792;      // room per key table
+constexpr int META_KEYS = 3200;      // room per key table
 constexpr int META_HIST = 256;       // [P16_KEYS] eligible reads per (pair class, read length)
 constexpr int META_PSTART = META_HIST + META_KEYS;    // [P16_KEYS] first pair of the key
 constexpr int META_CURSOR = META_PSTART + META_KEYS;  // [P16_KEYS] scatter cursors
@@ -157,6 +158,7 @@ __host__ __device__ inline RbFrame p16_rb_frame(int K, int max_entry) {
 }
 
 constexpr uint8_t P16_ST_GENERAL = 0x40;   // JOB kernels: the alignment is not one plain diagonal, the general kernel takes the read
+constexpr uint8_t P16_ST_SUNK = 0x20;      // JOB + RB kernels: the job's end value lies in the poisoned range, its score is only an upper bound
 
 // packed constants: B2(v) = the cell value v in both halves (biased), K2(k) = the addend k in both halves
 __host__ __device__ constexpr uint32_t B2(int v) { return ((uint32_t)(v + 32768) & 0xffffu) * 0x10001u; }
@@ -517,8 +519,10 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, (K <= 5 ? 8 : K <= P16_S
       if (JOB) {
         if (sub == 0 && live) {
           const int lo = ws - ((h ? jrB : jrA) < 0 ? p.strand_stride : 0);
-          p.score[rd] = score;                          // exact whatever the path looks like: a losing job needs no more
-          if (ok) {
+          p.score[rd] = score;                          // exact whatever the path looks like (unless sunk): a losing job needs no more
+          if (sunk) {
+            p.status[rd] = P16_ST_SUNK;                 // sg_align reports both strands' scores: the general kernel computes this read
+          } else if (ok) {
             p.as_out[rd] = aec - nsteps + lo;           // abc
             p.ae_out[rd] = aec + lo;                    // aec
             p.abr[rd] = L - 1 - nsteps;

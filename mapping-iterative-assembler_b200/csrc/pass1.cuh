@@ -152,7 +152,7 @@ struct P1SeedParams {
 
 __global__ void __launch_bounds__(256) p1_seed_kernel(P1SeedParams p) {
   __shared__ int s_hist[P16_KEYS];
-  __shared__ int s_preads[P16_NKB];
+  __shared__ int s_preads[P16_NKB], s_pmaxl[P16_NKB];
   __shared__ unsigned long long s_pcells[P16_NKB];
   __shared__ int s_counts[3];
   __shared__ int s_diag[8][2][P1_MAXD];
@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(256) p1_seed_kernel(P1SeedParams p) {
   __shared__ unsigned long long s_eff;
   if (threadIdx.x == 0) s_eff = 0;
   for (int i = threadIdx.x; i < P16_KEYS; i += blockDim.x) s_hist[i] = 0;
-  if (threadIdx.x < P16_NKB) { s_preads[threadIdx.x] = 0; s_pcells[threadIdx.x] = 0; }
+  if (threadIdx.x < P16_NKB) { s_preads[threadIdx.x] = 0; s_pcells[threadIdx.x] = 0; s_pmaxl[threadIdx.x] = 0; }
   if (threadIdx.x < 3) s_counts[threadIdx.x] = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -256,6 +256,7 @@ __global__ void __launch_bounds__(256) p1_seed_kernel(P1SeedParams p) {
           p.jread[job] = (int32_t)((uint32_t)rd | ((uint32_t)s << 31));
           atomicAdd(&s_hist[kb * (P16_MAXL + 1) + L], 1);
           atomicAdd(&s_preads[kb], 1);
+          atomicMax(&s_pmaxl[kb], L);
           atomicAdd(&s_pcells[kb], (unsigned long long)L * wl);
         }
     }
@@ -266,6 +267,7 @@ __global__ void __launch_bounds__(256) p1_seed_kernel(P1SeedParams p) {
   if (threadIdx.x < P16_NKB && s_preads[threadIdx.x]) {
     atomicAdd(&p.meta[META_PREADS + threadIdx.x], s_preads[threadIdx.x]);
     atomicAdd(reinterpret_cast<unsigned long long*>(p.meta + META_PCELLS) + threadIdx.x, s_pcells[threadIdx.x]);
+    atomicMax(&p.meta[META_PMAXL + threadIdx.x], s_pmaxl[threadIdx.x]);
   }
   if (threadIdx.x == 0 && s_counts[0]) atomicAdd(&p.meta[P1_NSKIPPED], s_counts[0]);
   if (threadIdx.x == 0 && s_eff) atomicAdd(reinterpret_cast<unsigned long long*>(p.meta + P1_EFF), s_eff);
@@ -294,12 +296,15 @@ __global__ void p1_merge_kernel(P1MergeParams p) {
   int64_t bj[2] = {-1, -1};
   int64_t j0 = p.jfirst[rd];
   const int cnt[2] = {p.jcount[rd] & 0xff, p.jcount[rd] >> 8};
+  bool sunk = false;                                // a job whose score is only an upper bound (pair16.cuh 5.): both strands' scores are outputs
   for (int s = 0; s < 2; s++)
-    for (int t = 0; t < cnt[s]; t++, j0++)          // stretches in column order: the first maximum wins (mia.c:1278-1302)
+    for (int t = 0; t < cnt[s]; t++, j0++) {        // stretches in column order: the first maximum wins (mia.c:1278-1302)
+      sunk |= (p.jstatus[j0] & P16_ST_SUNK) != 0;
       if (p.jscore[j0] > best[s]) { best[s] = p.jscore[j0]; bj[s] = j0; }
+    }
   const int s = !(best[0] > best[1]) ? 1 : 0;       // forward only if strictly better (mia.c:1549-1554)
   const int64_t j = bj[s];
-  if (j < 0 || p.jstatus[j] != MIAGPU_ST_OK) {      // the winner's path is not one plain diagonal: the general kernel traces it
+  if (j < 0 || sunk || p.jstatus[j] != MIAGPU_ST_OK) {      // the winner's path is not one plain diagonal: the general kernel traces it
     p.general_list[atomicAdd(p.meta + P1_NGENERAL, 1)] = (int32_t)rd;
     p.route[rd] = 3;
     return;

@@ -87,3 +87,22 @@ def test_pair16_eight_lane_variant_equals_default(gpu, monkeypatch):
     nr = np.maximum(a["n_runs"], 0)
     m = np.arange(a["runs"].shape[1])[None, :] < nr[:, None]
     assert (np.where(m, a["runs"], 0) == np.where(m, z["runs"], 0)).all()
+
+
+@pytest.mark.parametrize("matrix,div,indel", [("pe", 0.01, 0.001), ("onepass", 0.12, 0.006), ("ancient", 0.30, 0.01)])
+def test_pair16_rebased_frame_takes_long_reads(gpu, monkeypatch, matrix, div, indel):
+    # reads of 100-156 bases are beyond the low 16-bit frame (~130 rows): the RB variant (pair16.cuh 5.) takes them -- exact against the
+    # 32-bit kernel field for field, including reads that diverge so much that they sink to the poison bound and are handed over
+    case = gpu_checks.make_case(16000, 6000, seed=301, divergence=div, indel_rate=indel, min_len=100, max_len=156)
+    sm = gpu_checks.load_pssm(matrix)
+    a, taken, handed, _ = _realign(gpu, case, sm, True)
+    b, taken0, _, _ = _realign(gpu, case, sm, False)
+    monkeypatch.setenv("MIAGPU_PAIR_RB", "0")
+    _, taken_low, _, _ = _realign(gpu, case, sm, True)
+    monkeypatch.delenv("MIAGPU_PAIR_RB")
+    assert taken0 == 0 and taken > 15000 and taken_low < 9000, (taken, taken_low)
+    for k in ("score", "as_out", "ae_out", "abr", "n_runs", "status"):
+        assert (a[k] == b[k]).all(), (k, np.flatnonzero(a[k] != b[k])[:5], a[k][a[k] != b[k]][:5], b[k][a[k] != b[k]][:5])
+    nr = np.maximum(a["n_runs"], 0)
+    mask = np.arange(a["runs"].shape[1])[None, :] < nr[:, None]
+    assert (a["runs"][mask] == b["runs"][mask]).all()

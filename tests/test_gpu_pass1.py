@@ -207,3 +207,20 @@ def test_unmasked_sweep16_edge_reads_vs_oracle(gpu, oracle, circular, matrix):
     assert not bad, f"{len(bad)} reads differ; first {bad[0]}"
     fast, general, skipped = gpu.last_pass1_stats()
     assert fast > 100, (fast, general, skipped)
+
+
+def test_pass1_long_reads_take_the_windowed_fast_path(gpu, oracle, monkeypatch):
+    # merged-pair lengths (BASELINE configs[2]: 30-140 bp, here up to 200): stretches of reads beyond the low 16-bit frame run in
+    # the RB frame of the pair kernels (pair16.cuh 5.) instead of the general chunked kernel -- exact against the oracle, and
+    # field for field against the general kernel
+    ref, reads = _reads(2500, 6000, seed=411, min_len=90, max_len=200, divergence=0.02, indel_rate=0.002)
+    sm = gpu_checks.load_pssm("pe")
+    bad, a = gpu_checks.check_pass1(gpu, oracle, ref, reads, sm, 1, 12)
+    assert not bad, f"{len(bad)} reads differ; first {bad[0]}"
+    fast, general, skipped = gpu.last_pass1_stats()
+    assert fast > 1500, (fast, general, skipped)       # the rest: stretches wider than 256 columns (reads beyond ~230 bases), gapped winners
+    monkeypatch.setenv("MIAGPU_PAIR_RB", "0")
+    z = gpu.pass1()
+    assert gpu.last_pass1_stats()[0] < fast
+    for k in ("hits", "score", "fw_score", "rc_score", "rc", "as_", "ae", "start", "end", "abr", "n_runs", "status"):
+        assert (a[k] == z[k]).all(), (k, int((a[k] != z[k]).sum()))
