@@ -336,31 +336,36 @@ int miagpu_last_fsdb_stats( miagpu_ctx* ctx, int64_t* n_slots, int64_t* stale_po
  * miagpu_set_reference and before miagpu_iterate_resident; does nothing in the first round or without distant_ref. */
 int miagpu_distant_retry( miagpu_ctx* ctx, int64_t* n_tried, int64_t* n_learned );
 
-/* ---- 8e. The same round with the reads sharded over `world` GPUs of one box: one context (one process) per GPU,
- * reads partitioned contiguously in FSDB order (rank 0 holds the first reads), reference, matrices and k-mer
- * tables replicated.  The library links no communication library; between the phases the caller runs ONE
- * collective each, on miagpu_stream(), over device buffers the library hands out (ncclAllGather /
- * ncclAllReduce in C, torch.distributed in bench.py; INTEGRATION.md shows both):
+/* ---- 8e. The same round with the reads sharded over `world` GPUs of one box: one context per GPU (one process per GPU, or one
+ * host thread per GPU: host/mia_gpu.c), reads partitioned contiguously in FSDB order (rank 0 holds the first reads), reference,
+ * matrices and k-mer tables replicated.  The library links no communication library; between the phases the caller runs ONE
+ * collective each, on miagpu_stream(), over device buffers the library hands out (ncclAllReduce / ncclAllGather in C,
+ * torch.distributed in bench.py; INTEGRATION.md shows both):
  *
  *   miagpu_shard_begin       realign the resident local reads (inputs as for miagpu_iterate_resident); or
  *   miagpu_shard_begin_host  the same for a local batch in host memory (arguments as for miagpu_iterate_host)
- *        -> all-gather  gather_send (gather_words uint32) into gather_recv (world * gather_words, rank order)
- *        -> all-reduce  MAX, int32, max_words words at max_buf
- *   miagpu_shard_cut         find_fsdb_score_cut over the reads of ALL ranks in rank order (fsdb.c:269-383: every
- *                            rank evaluates the same two exact chains and gets the same slope / intercept, bit for
- *                            bit what one GPU computes over the concatenated reads), cull flags of the local reads
- *                            (mia.c:452-470, sticky as in H10), insert-column layout, column accumulation
- *        -> all-reduce  SUM, int32, sum_words words at sum_buf
- *   miagpu_shard_finish      base calling (identical on every rank) and downloads: dropped[n] = the local reads'
- *                            sticky flags, packed_runs / total_runs as in miagpu_get_runs_packed, gaps_out /
- *                            cons_out / cons_len as in miagpu_consensus.  All nullable.
+ *        -> all-reduce  MAX, int32, max_words words at max_buf: per-position insert maxima, best score per read length, and one
+ *                       header row per rank with that rank's integer sums (zero elsewhere: the MAX gathers them)
+ *   miagpu_shard_fit         this rank's part of find_fsdb_score_cut (fsdb.c:269-383): xbar / ybar from the sums of all ranks, then
+ *                            the two chains over the LOCAL reads as block records (integer increments per 512 reads in the binade
+ *                            the running sum is predicted to be in, with a proof per block), plus the keys of the few blocks that
+ *                            may have to be added read by read; beside it the column accumulation of the local reads
+ *        -> all-gather  gather_send (gather_words uint32) into gather_recv (world * gather_words, rank order): about 50 bytes per
+ *                       512 reads.  gather_words = 0 (the cut was given: -H / -S -N): nothing to gather
+ *   miagpu_shard_cut         every rank stitches the same chains from the records of ALL ranks in rank order = FSDB order and gets the
+ *                            same slope / intercept, bit for bit what one GPU computes over the concatenated reads; cull flags of
+ *                            the local reads (mia.c:452-470, sticky as in H10), the newly dropped reads leave the base columns
+ *        -> all-reduce  SUM, int32, sum_words words at sum_buf (the column planes)
+ *   miagpu_shard_finish      base calling (identical on every rank) and downloads: dropped[n] = the local reads' sticky flags,
+ *                            packed_runs / total_runs as in miagpu_get_runs_packed, gaps_out / cons_out / cons_len as in
+ *                            miagpu_consensus.  All nullable.
  *
- * n_max = the largest local read count of any rank (the same value on every rank).  hard_cut / score_cut_set /
- * slope / intercept as in miagpu_cull_flags.  world = 1 needs no collectives (gather_recv must still receive a
- * copy of gather_send) and equals miagpu_iterate_resident / miagpu_iterate_host. */
+ * n_max = the largest local read count of any rank (the same value on every rank).  hard_cut / score_cut_set / slope / intercept
+ * as in miagpu_cull_flags.  world = 1 needs no collectives (gather_recv must still receive a copy of gather_send) and equals
+ * miagpu_iterate_resident / miagpu_iterate_host.  Sharded rounds give every read its own AlnSeqs and one sticky flag
+ * (miagpu_set_cut_inputs); the pointer state of miagpu_set_fsdb is a one-GPU feature. */
 int miagpu_shard_begin( miagpu_ctx* ctx, int world, int rank, int64_t n_max, int hard_cut,
                         int score_cut_set, double slope, double intercept,
-                        void** gather_send, void** gather_recv, int64_t* gather_words,
                         void** max_buf, int64_t* max_words );
 int miagpu_shard_begin_host( miagpu_ctx* ctx, int world, int rank, int64_t n_max, int64_t n,
                              const uint8_t* bases, const int64_t* offsets, const uint8_t* rc,
@@ -368,9 +373,8 @@ int miagpu_shard_begin_host( miagpu_ctx* ctx, int world, int rank, int64_t n_max
                              int32_t* as_out, int32_t* ae_out, int32_t* abr, int32_t* n_runs,
                              uint8_t* status, const int32_t* seq_len, const uint8_t* unique_best,
                              const uint8_t* dropped, int hard_cut, int score_cut_set,
-                             double slope, double intercept, void** gather_send,
-                             void** gather_recv, int64_t* gather_words, void** max_buf,
-                             int64_t* max_words );
+                             double slope, double intercept, void** max_buf, int64_t* max_words );
+int miagpu_shard_fit( miagpu_ctx* ctx, void** gather_send, void** gather_recv, int64_t* gather_words );
 int miagpu_shard_cut( miagpu_ctx* ctx, double* slope_out, double* intercept_out,
                       void** sum_buf, int64_t* sum_words );
 int miagpu_shard_finish( miagpu_ctx* ctx, int cons_code, uint8_t* dropped,

@@ -77,9 +77,10 @@ def load_library():
     L.miagpu_iterate_host.argtypes = ([C.c_void_p, C.c_int64] + [C.c_void_p] * 12 + [C.c_int64, _i64p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                       C.c_double, C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_char_p, _i32p])
     _vpp = C.POINTER(C.c_void_p)
-    L.miagpu_shard_begin.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_double, _vpp, _vpp, _i64p, _vpp, _i64p]
+    L.miagpu_shard_begin.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_double, _vpp, _i64p]
     L.miagpu_shard_begin_host.argtypes = ([C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int64] + [C.c_void_p] * 14 +
-                                          [C.c_int, C.c_int, C.c_double, C.c_double, _vpp, _vpp, _i64p, _vpp, _i64p])
+                                          [C.c_int, C.c_int, C.c_double, C.c_double, _vpp, _i64p])
+    L.miagpu_shard_fit.argtypes = [C.c_void_p, _vpp, _vpp, _i64p]
     L.miagpu_shard_cut.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), _vpp, _i64p]
     L.miagpu_shard_finish.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, _i64p, C.c_void_p, C.c_char_p, _i32p]
     L.miagpu_last_cut_stats.argtypes = [C.c_void_p, _i64p, _i64p]
@@ -117,7 +118,7 @@ EXPORTS = ["miagpu_device_count", "miagpu_create", "miagpu_destroy", "miagpu_las
            "miagpu_consensus", "miagpu_accumulate_gaps", "miagpu_accumulate_counts", "miagpu_call", "miagpu_consensus_natural", "miagpu_accumulate_gaps_natural",
            "miagpu_score_cut", "miagpu_cull_flags",
            "miagpu_set_alignment_inputs", "miagpu_realign_resident", "miagpu_adopt_alignment", "miagpu_set_cut_inputs", "miagpu_reset_dropped", "miagpu_iterate_resident", "miagpu_last_buckets", "miagpu_last_pair_buckets", "miagpu_last_timing",
-           "miagpu_int32_peak", "miagpu_stream", "miagpu_shard_begin", "miagpu_shard_begin_host", "miagpu_shard_cut", "miagpu_shard_finish",
+           "miagpu_int32_peak", "miagpu_stream", "miagpu_shard_begin", "miagpu_shard_begin_host", "miagpu_shard_fit", "miagpu_shard_cut", "miagpu_shard_finish",
            "miagpu_last_cut_stats", "miagpu_repeat_filter", "miagpu_trim", "miagpu_get_alignment",
            "miagpu_fastx_open", "miagpu_fastx_open_memory", "miagpu_fastx_format", "miagpu_fastx_next", "miagpu_fastx_batch", "miagpu_fastx_close",
            "miagpu_maln_ref_size", "miagpu_write_maln", "miagpu_read_pssm", "miagpu_align_windows",
@@ -338,27 +339,30 @@ class MiaGpu:
 
     # -- sharded rounds: three phases with one collective after each of the first two (see shard.py)
     def shard_begin(self, world, rank, n_max, hard_cut=0, score_cut=None):
-        """-> dict(send=(ptr, words), recv=(ptr, world * words), max=(ptr, words)): device buffers to all-gather / MAX-reduce"""
-        gs, gr, mb = C.c_void_p(), C.c_void_p(), C.c_void_p()
-        gw, mw = C.c_int64(), C.c_int64()
+        """-> (ptr, words) of the device buffer to MAX-reduce (insert maxima, best scores, the ranks' header rows)"""
+        mb, mw = C.c_void_p(), C.c_int64()
         slope, icpt = score_cut if score_cut is not None else (0.0, 0.0)
         self._ck(self.lib.miagpu_shard_begin(self.h, world, rank, n_max, hard_cut, 0 if score_cut is None else 1, slope, icpt,
-                                             C.byref(gs), C.byref(gr), C.byref(gw), C.byref(mb), C.byref(mw)))
-        return dict(send=(gs.value, gw.value), recv=(gr.value, world * gw.value), max=(mb.value, mw.value))
+                                             C.byref(mb), C.byref(mw)))
+        return mb.value, mw.value
 
     def shard_begin_host(self, world, rank, n_max, bases, offsets, rc, as_, ae, seq_len, dropped, out, unique_best=None, hard_cut=0,
                          score_cut=None):
         n = len(offsets) - 1
-        gs, gr, mb = C.c_void_p(), C.c_void_p(), C.c_void_p()
-        gw, mw = C.c_int64(), C.c_int64()
+        mb, mw = C.c_void_p(), C.c_int64()
         slope, icpt = score_cut if score_cut is not None else (0.0, 0.0)
         self._ck(self.lib.miagpu_shard_begin_host(self.h, world, rank, n_max, n, _ptr(bases), _ptr(offsets), _ptr(rc), _ptr(as_), _ptr(ae),
                                                   _ptr(out["score"]), _ptr(out["as_out"]), _ptr(out["ae_out"]), _ptr(out["abr"]),
                                                   _ptr(out["n_runs"]), _ptr(out["status"]), _ptr(seq_len), _ptr(unique_best), _ptr(dropped),
-                                                  hard_cut, 0 if score_cut is None else 1, slope, icpt,
-                                                  C.byref(gs), C.byref(gr), C.byref(gw), C.byref(mb), C.byref(mw)))
+                                                  hard_cut, 0 if score_cut is None else 1, slope, icpt, C.byref(mb), C.byref(mw)))
         self.n = n
-        return dict(send=(gs.value, gw.value), recv=(gr.value, world * gw.value), max=(mb.value, mw.value))
+        return mb.value, mw.value
+
+    def shard_fit(self):
+        """-> dict(send=(ptr, words), recv=(ptr, world * words)) of the block records to all-gather (words = 0: nothing to gather)"""
+        gs, gr, gw = C.c_void_p(), C.c_void_p(), C.c_int64()
+        self._ck(self.lib.miagpu_shard_fit(self.h, C.byref(gs), C.byref(gr), C.byref(gw)))
+        return dict(send=(gs.value, gw.value), recv=(gr.value, gw.value))
 
     def shard_cut(self):
         """-> ((slope, intercept), (ptr, words) of the column planes to SUM-reduce)"""

@@ -160,6 +160,10 @@ struct miagpu_ctx {
   bool sh_fit = false, sh_host = false, sh_want_packed = false, sh_has_unique = false;
   double sh_slope = 0, sh_icpt = 0;
   DevBuf<uint32_t> d_sh_send, d_sh_recv, d_sh_pf;
+  DevBuf<ShardPrep> d_sh_prep;
+  int64_t sh_nb = 0;
+  uint32_t* h_sh_recv = nullptr;                // pinned: what the all-gather of the block records brought
+  size_t h_sh_cap = 0;
   DevBuf<int32_t> d_sh_pfid;
   uint32_t* h_sh_pf = nullptr;                  // pinned: SHARD_PF_SLOTS blocks of keys
   int32_t* h_sh_pfid = nullptr;                 // pinned: count + block ids
@@ -301,6 +305,8 @@ extern "C" void miagpu_destroy(miagpu_ctx* c) {
   if (c->h_cblk) cudaFreeHost(c->h_cblk);
   if (c->h_score) cudaFreeHost(c->h_score);
   if (c->h_call) cudaFreeHost(c->h_call);
+  if (c->h_sh_recv) cudaFreeHost(c->h_sh_recv);
+  c->d_sh_prep.release();
   if (c->h_sh_pf) cudaFreeHost(c->h_sh_pf);
   if (c->h_sh_pfid) cudaFreeHost(c->h_sh_pfid);
   c->d_sh_send.release(); c->d_sh_recv.release(); c->d_sh_pf.release(); c->d_sh_pfid.release();
@@ -2110,6 +2116,7 @@ struct CutHost {
   int32_t total_ins;
   long long bad_after;
   int32_t fs_cnt[FS_CNT_WORDS];
+  ShardPrep prep;
 };
 
 static int cut_reserve(miagpu_ctx* c, int64_t n) {
@@ -2517,45 +2524,47 @@ extern "C" int miagpu_iterate_resident(miagpu_ctx* c, int hard_cut, int score_cu
 // Integer sums and maxima commute and the chains are evaluated exactly: the results are bit-identical to a
 // single-GPU round over the concatenated reads for any number of ranks.
 static int shard_reserve(miagpu_ctx* c, int world, int64_t n_max) {
-  const int64_t stride = (n_max + SHARD_HDR_WORDS + CUT_BLOCK - 1) / CUT_BLOCK * CUT_BLOCK;
-  c->sh_stride = stride;
-  const int64_t nb = (int64_t)world * stride / CUT_BLOCK;
-  if (!c->d_sh_send.reserve(stride) || !c->d_sh_recv.reserve((size_t)world * stride) || !c->d_sh_pf.reserve((size_t)SHARD_PF_SLOTS * CUT_BLOCK) ||
-      !c->d_sh_pfid.reserve(SHARD_PF_SLOTS + 8) || !cut_reserve(c, nb * CUT_BLOCK)) return 0;
-  if (!c->h_sh_pf) MIAGPU_CUDA(cudaMallocHost(&c->h_sh_pf, sizeof(uint32_t) * SHARD_PF_SLOTS * CUT_BLOCK));
-  if (!c->h_sh_pfid) MIAGPU_CUDA(cudaMallocHost(&c->h_sh_pfid, sizeof(int32_t) * (SHARD_PF_SLOTS + 8)));
+  const int64_t nb = (n_max + CUT_BLOCK - 1) / CUT_BLOCK;                    // chain blocks per rank (the same on every rank)
+  // what a rank sends in the all-gather: nb block records | count + SHARD_PF_SLOTS block ids | SHARD_PF_SLOTS blocks of keys
+  const int64_t words = (nb * (int64_t)sizeof(ShardBlockRec) + 3) / 4 + (SHARD_PF_SLOTS + 8) + (int64_t)SHARD_PF_SLOTS * CUT_BLOCK;
+  c->sh_stride = (words + 3) / 4 * 4;
+  c->sh_nb = nb;
+  if (!c->d_sh_send.reserve(c->sh_stride) || !c->d_sh_recv.reserve((size_t)world * c->sh_stride) || !c->d_sh_prep.reserve(1) || !cut_reserve(c, nb * CUT_BLOCK)) return 0;
+  const size_t need = (size_t)world * c->sh_stride * sizeof(uint32_t);
+  if (c->h_sh_cap < need) {
+    if (c->h_sh_recv) cudaFreeHost(c->h_sh_recv);
+    c->h_sh_recv = nullptr; c->h_sh_cap = 0;
+    MIAGPU_CUDA(cudaMallocHost(&c->h_sh_recv, need + need / 8));
+    c->h_sh_cap = need + need / 8;
+  }
   return 1;
 }
 
-// after the DP: what this rank contributes to the collectives, and the flag-independent part of the consensus
-static int shard_after_dp(miagpu_ctx* c, bool stats_done, bool has_unique, void** gather_send, void** gather_recv, int64_t* gather_words,
-                          void** max_buf, int64_t* max_words) {
+// after the DP: this rank's header row + insert maxima + best scores for the all-reduce(MAX), and the flag-independent part of the consensus
+static int shard_after_dp(miagpu_ctx* c, bool stats_done, bool has_unique, void** max_buf, int64_t* max_words) {
   cudaStream_t main = c->stream;
-  const int64_t n = c->n, stride = c->sh_stride;
+  const int64_t n = c->n;
   c->sh_has_unique = has_unique;
   if (!stats_done && !cut_launch_stats(c, 0, n, has_unique)) return 0;
-  shard_pack_kernel<<<(unsigned)((stride + 255) / 256), 256, 0, main>>>(n, stride, c->d_seqlen.p, c->d_score.p, has_unique ? c->d_unique.p : nullptr,
-                                                                       c->d_sh_send.p);
   MIAGPU_CUDA(cudaMemsetAsync(c->d_gaps.p, 0, (c->seq_len + 2) * sizeof(int32_t), main));
-  shard_hdr_kernel<<<1, 256, 0, main>>>(c->d_cstats.p, c->d_sh_send.p, stride, c->d_gaps.p + c->seq_len + 2);
+  int32_t* best = c->d_gaps.p + c->seq_len + 2;
+  int32_t* hdr = best + MAX_READ + 1;
+  shard_hdr2_kernel<<<1, 256, 0, main>>>(c->d_cstats.p, best, hdr, c->sh_world, c->sh_rank, (int)n);
   MIAGPU_CUDA(cudaGetLastError());
-  c->launches += 2;
+  c->launches++;
   c->n_entries = 2 * n;
   MIAGPU_CUDA(cudaMemsetAsync(c->d_fs_cnt.p, 0, FS_CNT_WORDS * sizeof(int32_t), main));
   if (n) {
     status_or_kernel<<<(unsigned)((n + 255) / 256), 256, 0, main>>>(n, c->d_status.p, c->d_nruns.p, c->d_fs_cnt.p + FS_CNT_STATUS);
     natural_entries_kernel<<<(unsigned)((n + 255) / 256), 256, 0, main>>>(n, c->d_as_out.p, c->d_ae_out.p, c->d_nruns.p, c->d_runs.p,
-                                                                          c->d_status.p, c->seq_len, nullptr, nullptr, c->d_entries.p,
+                                                                          c->d_status.p, c->seq_len, c->d_dropf.p, c->d_dropf.p, c->d_entries.p,
                                                                           has_unique ? c->d_unique.p : nullptr);
     MIAGPU_CUDA(cudaGetLastError());
-    c->launches++;
+    c->launches += 2;
     if (!launch_gaps(c)) return 0;
   }
-  if (gather_send) *gather_send = c->d_sh_send.p;
-  if (gather_recv) *gather_recv = c->d_sh_recv.p;
-  if (gather_words) *gather_words = stride;
   if (max_buf) *max_buf = c->d_gaps.p;
-  if (max_words) *max_words = c->seq_len + 2 + MAX_READ + 1;
+  if (max_words) *max_words = c->seq_len + 2 + MAX_READ + 1 + (int64_t)c->sh_world * SHARD_HDR2;
   c->sh_phase = 1;
   return 1;
 }
@@ -2563,19 +2572,24 @@ static int shard_after_dp(miagpu_ctx* c, bool stats_done, bool has_unique, void*
 static int shard_args(miagpu_ctx* c, const char* who, int world, int rank, int64_t n_max, int64_t n) {
   if (!c || !c->have_pssm || !c->have_ref) { set_error("%s: set_pssm and set_reference first", who); return 0; }
   if (world < 1 || rank < 0 || rank >= world || n_max < n || n_max < 1) { set_error("%s: bad world / rank / n_max (n_max must be the largest read count of any rank)", who); return 0; }
-  if ((int64_t)world * (n_max + SHARD_HDR_WORDS + CUT_BLOCK) > 0x7fffffffLL * 64) { set_error("%s: too many reads", who); return 0; }
+  if ((int64_t)world * (n_max + CUT_BLOCK) > 0x7fffffffLL * 64) { set_error("%s: too many reads", who); return 0; }
   return 1;
 }
 
+static int shard_reserve_common(miagpu_ctx* c, int world, int64_t n_max) {
+  const int64_t n = c->n;
+  return c->d_entries.reserve(2 * n + 2) && c->d_gaps.reserve(c->seq_len + 2 + MAX_READ + 8 + (size_t)world * SHARD_HDR2) &&
+         c->d_ins_off.reserve(c->seq_len + 2) && c->d_off2.reserve(2 * (n + 2)) && c->d_seqlen.reserve(n + 1) && c->d_score.reserve(n + 1) &&
+         c->d_newly.reserve(n + 1) && shard_reserve(c, world, n_max);
+}
+
 extern "C" int miagpu_shard_begin(miagpu_ctx* c, int world, int rank, int64_t n_max, int hard_cut, int score_cut_set, double slope,
-                                  double intercept, void** gather_send, void** gather_recv, int64_t* gather_words, void** max_buf,
-                                  int64_t* max_words) {
+                                  double intercept, void** max_buf, int64_t* max_words) {
   if (!shard_args(c, "miagpu_shard_begin", world, rank, n_max, c ? c->n : 0)) return 0;
   if (c->cut_inputs_n != c->n) { set_error("miagpu_shard_begin: upload reads, alignment inputs and cut inputs first"); return 0; }
+  if (c->fs_on) { set_error("miagpu_shard_begin: the pointer state of miagpu_set_fsdb is not available in sharded rounds"); return 0; }
   MIAGPU_CUDA(cudaSetDevice(c->device));
-  const int64_t n = c->n;
-  if (!c->d_entries.reserve(2 * n + 2) || !c->d_gaps.reserve(c->seq_len + 2 + MAX_READ + 8) || !c->d_ins_off.reserve(c->seq_len + 2) ||
-      !c->d_off2.reserve(2 * (n + 2)) || !c->d_seqlen.reserve(n + 1) || !c->d_score.reserve(n + 1) || !shard_reserve(c, world, n_max)) return 0;
+  if (!shard_reserve_common(c, world, n_max)) return 0;
   c->sh_world = world; c->sh_rank = rank; c->sh_nmax = n_max; c->sh_hard_cut = hard_cut; c->sh_cut_set = score_cut_set;
   c->sh_slope = slope; c->sh_icpt = intercept; c->sh_fit = !score_cut_set && hard_cut <= 0; c->sh_host = false; c->sh_want_packed = false;
   c->sh_phase = 0;
@@ -2584,15 +2598,14 @@ extern "C" int miagpu_shard_begin(miagpu_ctx* c, int world, int rank, int64_t n_
   MIAGPU_CUDA(cudaGetLastError());
   if (!realign_device(c, false)) return 0;
   MIAGPU_CUDA(cudaEventRecord(c->ev[2], c->stream));
-  return shard_after_dp(c, false, !c->h_unique.empty(), gather_send, gather_recv, gather_words, max_buf, max_words);
+  return shard_after_dp(c, false, !c->h_unique.empty(), max_buf, max_words);
 }
 
 extern "C" int miagpu_shard_begin_host(miagpu_ctx* c, int world, int rank, int64_t n_max, int64_t n, const uint8_t* bases,
                                        const int64_t* offsets, const uint8_t* rc, const int32_t* as, const int32_t* ae, int32_t* score,
                                        int32_t* as_out, int32_t* ae_out, int32_t* abr, int32_t* n_runs, uint8_t* status,
                                        const int32_t* seq_len, const uint8_t* unique_best, const uint8_t* dropped, int hard_cut,
-                                       int score_cut_set, double slope, double intercept, void** gather_send, void** gather_recv,
-                                       int64_t* gather_words, void** max_buf, int64_t* max_words) {
+                                       int score_cut_set, double slope, double intercept, void** max_buf, int64_t* max_words) {
   if (!shard_args(c, "miagpu_shard_begin_host", world, rank, n_max, n)) return 0;
   const Trace tr;
   int C = 1;
@@ -2602,137 +2615,164 @@ extern "C" int miagpu_shard_begin_host(miagpu_ctx* c, int world, int rank, int64
     if (c->s_up) { cudaStreamSynchronize(c->s_down); cudaStreamSynchronize(c->s_up); }
     return 0;
   }
-  if (!shard_reserve(c, world, n_max)) return 0;
+  if (!shard_reserve_common(c, world, n_max)) return 0;
   c->sh_world = world; c->sh_rank = rank; c->sh_nmax = n_max; c->sh_hard_cut = hard_cut; c->sh_cut_set = score_cut_set;
   c->sh_slope = slope; c->sh_icpt = intercept; c->sh_fit = !score_cut_set && hard_cut <= 0; c->sh_host = true; c->sh_chunks = C;
-  return shard_after_dp(c, true, unique_best != nullptr, gather_send, gather_recv, gather_words, max_buf, max_words);
+  // the flags of earlier rounds arrive on the upload stream: the entries (which take them) wait for them
+  MIAGPU_CUDA(cudaStreamWaitEvent(c->stream, c->xev[1], 0));
+  return shard_after_dp(c, true, unique_best != nullptr, max_buf, max_words);
 }
 
-extern "C" int miagpu_shard_cut(miagpu_ctx* c, double* slope_out, double* intercept_out, void** sum_buf, int64_t* sum_words) {
-  if (!c || c->sh_phase != 1) { set_error("miagpu_shard_cut: call miagpu_shard_begin first"); return 0; }
+// After the all-reduce(MAX): this rank's part of the regression -- the sums of all ranks, the tables, the block records of the local
+// reads (scorecut.cuh) -- into gather_send for the all-gather; beside it (side stream) the column accumulation of the local reads
+// with the flags of earlier rounds, laid out by the reduced insert maxima.  *gather_words = 0: nothing to gather (the cut is given).
+extern "C" int miagpu_shard_fit(miagpu_ctx* c, void** gather_send, void** gather_recv, int64_t* gather_words) {
+  if (!c || c->sh_phase != 1) { set_error("miagpu_shard_fit: call miagpu_shard_begin first"); return 0; }
   MIAGPU_CUDA(cudaSetDevice(c->device));
-  cudaStream_t main = c->stream;
-  const int64_t n = c->n, stride = c->sh_stride;
-  const int world = c->sh_world;
-  const int64_t ntot = (int64_t)world * stride, nb = ntot / CUT_BLOCK;
-  const bool fit = c->sh_fit;
+  cudaStream_t main = c->stream, side = c->s_aux[2];
+  const int64_t n = c->n, nb = c->sh_nb;
   CutHost* H = c->h_cut;
+  int32_t* best = c->d_gaps.p + c->seq_len + 2;
+  int32_t* hdr = best + MAX_READ + 1;
   // insert-column layout from the reduced maxima
   size_t tmp = 0;
   MIAGPU_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, c->d_gaps.p, c->d_ins_off.p, c->seq_len + 1, main));
   if (!c->d_cub.reserve(tmp + 16)) return 0;
-  if (fit) {
-    shard_merge_kernel<<<1, 256, 0, main>>>(world, stride, c->d_sh_recv.p, c->d_gaps.p + c->seq_len + 2, c->d_cstats.p, c->d_sh_pfid.p);
-    MIAGPU_CUDA(cudaGetLastError());
-    MIAGPU_CUDA(cudaMemcpyAsync(&H->stats, c->d_cstats.p, sizeof(CutStatsDev), cudaMemcpyDeviceToHost, main));
-    MIAGPU_CUDA(cudaEventRecord(c->xev[0], main));
-    c->launches++;
-  }
   MIAGPU_CUDA(cub::DeviceScan::ExclusiveSum(c->d_cub.p, tmp, c->d_gaps.p, c->d_ins_off.p, c->seq_len + 1, main));
   MIAGPU_CUDA(cudaMemcpyAsync(&H->total_ins, c->d_ins_off.p + c->seq_len, sizeof(int32_t), cudaMemcpyDeviceToHost, main));
-  c->launches += 2;
-  CutSums S;
-  CutFit F;
-  if (fit) {
-    MIAGPU_CUDA(cudaEventSynchronize(c->xev[0]));
-    S.sx = H->stats.sx; S.sy = H->stats.sy; S.cnt = H->stats.cnt; S.bad = H->stats.bad == LLONG_MAX ? -1 : H->stats.bad;
-    memcpy(S.best, H->stats.best, sizeof(S.best));
-    if (S.bad >= 0) { cudaStreamSynchronize(main); set_error("miagpu_shard_cut: seq_len of local read %lld out of range", (long long)S.bad); return 0; }
-    if (S.cnt > 0) {
-      cut_fit_tables(S, F);
-      H->tab.ybar = F.ybar;
-      memcpy(H->tab.dx, F.dx_of, sizeof(F.dx_of));
-      memcpy(H->tab.dx2, F.dx2_of, sizeof(F.dx2_of));
-      MIAGPU_CUDA(cudaMemcpyAsync(c->d_ctab.p, &H->tab, sizeof(CutTables), cudaMemcpyHostToDevice, main));
-      CutSrc src{};
-      src.keys = c->d_sh_recv.p; src.n_max = c->sh_nmax; src.stride = stride;
-      cut_approx_kernel<true><<<(unsigned)nb, CUT_THREADS, 0, main>>>(ntot, src, c->d_ctab.p, c->d_cblk.p);
-      cut_prefix_kernel<<<1, CUT_PREFIX_THREADS, 0, main>>>(nb, c->d_cblk.p);
-      cut_exact_kernel<true><<<(unsigned)nb, CUT_THREADS, 0, main>>>(ntot, src, c->d_ctab.p, c->d_cblk.p, c->d_sh_pf.p, c->d_sh_pfid.p);
-      MIAGPU_CUDA(cudaGetLastError());
-      MIAGPU_CUDA(cudaMemcpyAsync(c->h_cblk, c->d_cblk.p, sizeof(CutBlockDev) * nb, cudaMemcpyDeviceToHost, main));
-      MIAGPU_CUDA(cudaMemcpyAsync(c->h_sh_pfid, c->d_sh_pfid.p, sizeof(int32_t) * (SHARD_PF_SLOTS + 1), cudaMemcpyDeviceToHost, main));
-      MIAGPU_CUDA(cudaMemcpyAsync(c->h_sh_pf, c->d_sh_pf.p, sizeof(uint32_t) * SHARD_PF_SLOTS * CUT_BLOCK, cudaMemcpyDeviceToHost, main));
-      c->launches += 2;
-    }
-  }
   MIAGPU_CUDA(cudaMemcpyAsync(H->fs_cnt, c->d_fs_cnt.p, sizeof(H->fs_cnt), cudaMemcpyDeviceToHost, main));
-  MIAGPU_CUDA(cudaStreamSynchronize(main));
+  MIAGPU_CUDA(cudaEventRecord(c->aev[6], main));
+  c->launches += 2;
+  if (c->sh_fit) {
+    uint32_t* send = c->d_sh_send.p;
+    ShardBlockRec* recs = reinterpret_cast<ShardBlockRec*>(send);
+    int32_t* pf_ids = reinterpret_cast<int32_t*>(send + (nb * sizeof(ShardBlockRec) + 3) / 4);
+    uint32_t* pf_keys = reinterpret_cast<uint32_t*>(pf_ids + SHARD_PF_SLOTS + 8);
+    shard_prep_kernel<<<1, 256, 0, main>>>(c->sh_world, c->sh_rank, hdr, best, c->d_cstats.p, c->d_ctab.p, c->d_sh_prep.p, pf_ids);
+    CutSrc src{};
+    src.seq_len = c->d_seqlen.p; src.score = c->d_score.p; src.unique_best = c->sh_has_unique ? c->d_unique.p : nullptr;
+    cut_approx_kernel<false><<<(unsigned)nb, CUT_THREADS, 0, main>>>(n, src, c->d_ctab.p, c->d_cblk.p);
+    cut_prefix_kernel<<<1, CUT_PREFIX_THREADS, 0, main>>>(nb, c->d_cblk.p, c->d_sh_prep.p->start);
+    cut_exact_kernel<false><<<(unsigned)nb, CUT_THREADS, 0, main>>>(n, src, c->d_ctab.p, c->d_cblk.p, pf_keys, pf_ids);
+    shard_records_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, main>>>(nb, c->d_cblk.p, recs);
+    MIAGPU_CUDA(cudaGetLastError());
+    c->launches += 5;
+  }
+  // the column planes: sized on the host from the layout (one short wait), accumulated beside the regression
+  MIAGPU_CUDA(cudaEventSynchronize(c->aev[6]));
   if (H->fs_cnt[FS_CNT_STATUS]) {
-    set_error("miagpu_shard_cut: local reads came back with status bits 0x%x (more than %d alignment runs, or a window no kernel takes)", H->fs_cnt[FS_CNT_STATUS], MAX_RUNS);
+    cudaStreamSynchronize(main);
+    set_error("miagpu_shard_fit: local reads came back with status bits 0x%x (more than %d alignment runs, or a window no kernel takes)", H->fs_cnt[FS_CNT_STATUS], MAX_RUNS);
     return 0;
   }
+  c->n_cols = (int64_t)c->seq_len + H->total_ins;
+  // the planes are followed by nothing yet: the caller all-reduces exactly n_cols * NPLANE words
+  if (!c->d_acc.reserve(c->n_cols * NPLANE) || !c->d_called.reserve(c->n_cols + 16)) return 0;
+  MIAGPU_CUDA(cudaStreamWaitEvent(side, c->aev[6], 0));
+  MIAGPU_CUDA(cudaMemsetAsync(c->d_acc.p, 0, c->n_cols * NPLANE * sizeof(int32_t), side));
+  cudaStream_t keep = c->stream;
+  c->stream = side;                                    // launch_accumulate puts its kernels on c->stream
+  const int ok = launch_accumulate(c);
+  c->stream = keep;
+  if (!ok) return 0;
+  MIAGPU_CUDA(cudaEventRecord(c->aev[7], side));
+  if (gather_send) *gather_send = c->d_sh_send.p;
+  if (gather_recv) *gather_recv = c->d_sh_recv.p;
+  if (gather_words) *gather_words = c->sh_fit ? c->sh_stride : 0;
+  c->sh_phase = 2;
+  return 1;
+}
+
+extern "C" int miagpu_shard_cut(miagpu_ctx* c, double* slope_out, double* intercept_out, void** sum_buf, int64_t* sum_words) {
+  if (!c || c->sh_phase != 2) { set_error("miagpu_shard_cut: call miagpu_shard_fit first"); return 0; }
+  MIAGPU_CUDA(cudaSetDevice(c->device));
+  cudaStream_t main = c->stream;
+  const int64_t n = c->n, stride = c->sh_stride, nb = c->sh_nb;
+  const int world = c->sh_world;
+  const bool fit = c->sh_fit;
+  CutHost* H = c->h_cut;
   double slope = c->sh_slope, intercept = c->sh_icpt;
   if (fit) {
+    MIAGPU_CUDA(cudaMemcpyAsync(c->h_sh_recv, c->d_sh_recv.p, (size_t)world * stride * sizeof(uint32_t), cudaMemcpyDeviceToHost, main));
+    MIAGPU_CUDA(cudaMemcpyAsync(&H->prep, c->d_sh_prep.p, sizeof(ShardPrep), cudaMemcpyDeviceToHost, main));
+    MIAGPU_CUDA(cudaMemcpyAsync(&H->stats, c->d_cstats.p, sizeof(CutStatsDev), cudaMemcpyDeviceToHost, main));
+    MIAGPU_CUDA(cudaStreamSynchronize(main));
+    CutSums S;
+    CutFit F;
+    S.sx = H->prep.sx; S.sy = H->prep.sy; S.cnt = H->prep.cnt; S.bad = H->stats.bad == LLONG_MAX ? -1 : H->stats.bad;
+    memcpy(S.best, H->stats.best, sizeof(S.best));
+    if (S.bad >= 0) { set_error("miagpu_shard_cut: seq_len of local read %lld out of range", (long long)S.bad); return 0; }
     if (S.cnt <= 0) { set_error("miagpu_shard_cut: no read of any rank scores >= %d: nothing to fit", FIRST_ROUND_SCORE_CUTOFF); return 0; }
-    std::vector<ChainBlock> bxy(nb), bxx(nb);
-    for (int64_t b = 0; b < nb; b++) {
-      const CutBlockDev& B = c->h_cblk[b];
-      bxy[b] = ChainBlock{B.approx[0], B.T[0], B.A[0], B.e[0], B.ok[0] != 0};
-      bxx[b] = ChainBlock{B.approx[1], B.T[1], B.A[1], B.e[1], B.ok[1] != 0};
+    cut_fit_tables(S, F);
+    const int64_t nbt = (int64_t)world * nb;
+    std::vector<ChainBlock> bxy(nbt), bxx(nbt);
+    auto rank_words = [&](int r) { return c->h_sh_recv + (size_t)r * stride; };
+    for (int r = 0; r < world; r++) {
+      const ShardBlockRec* recs = reinterpret_cast<const ShardBlockRec*>(rank_words(r));
+      for (int64_t b = 0; b < nb; b++) {
+        const ShardBlockRec& B = recs[b];
+        bxy[r * nb + b] = ChainBlock{0.0, B.T[0], B.A[0], B.e[0], B.ok[0] != 0};
+        bxx[r * nb + b] = ChainBlock{0.0, B.T[1], B.A[1], B.e[1], B.ok[1] != 0};
+      }
     }
-    // keys of a block the stitch cannot prove: prefetched with the records, else fetched now
-    const int npf = std::min<int>(c->h_sh_pfid[0], SHARD_PF_SLOTS);
-    std::vector<std::pair<int64_t, std::vector<uint32_t>>> fetched;
-    int64_t n_fetched = 0;
-    int fetch_failed = 0;
-    auto block_keys = [&](int64_t b) -> const uint32_t* {
+    // keys of a block the stitch cannot prove: they came with the records of the rank that owns the block
+    int missing = 0;
+    auto block_keys = [&](int64_t gb) -> const uint32_t* {
+      const int r = (int)(gb / nb);
+      const int64_t b = gb % nb;
+      const int32_t* pf_ids = reinterpret_cast<const int32_t*>(rank_words(r) + (nb * sizeof(ShardBlockRec) + 3) / 4);
+      const uint32_t* pf_keys = reinterpret_cast<const uint32_t*>(pf_ids + SHARD_PF_SLOTS + 8);
+      const int npf = std::min<int>(pf_ids[0], SHARD_PF_SLOTS);
       for (int k = 0; k < npf; k++)
-        if (c->h_sh_pfid[1 + k] == b) return c->h_sh_pf + (size_t)k * CUT_BLOCK;
-      for (auto& f : fetched)
-        if (f.first == b) return f.second.data();
-      fetched.emplace_back(b, std::vector<uint32_t>(CUT_BLOCK));
-      if (cudaMemcpy(fetched.back().second.data(), c->d_sh_recv.p + b * CUT_BLOCK, sizeof(uint32_t) * CUT_BLOCK, cudaMemcpyDeviceToHost) != cudaSuccess) fetch_failed = 1;
-      const int64_t l0 = b * CUT_BLOCK % stride;
-      for (int k = 0; k < CUT_BLOCK; k++)
-        if (l0 + k >= c->sh_nmax) fetched.back().second[k] = CUT_KEY_UNUSED;
-      n_fetched++;
-      return fetched.back().second.data();
+        if (pf_ids[1 + k] == b) return pf_keys + (size_t)k * CUT_BLOCK;
+      missing++;
+      return nullptr;
     };
     int64_t ser0 = 0, ser1 = 0;
-    const double ssxy = chain_stitch_blocks(bxy.data(), nb, [&](int64_t b, double Sum) {
+    const double ssxy = chain_stitch_blocks(bxy.data(), nbt, [&](int64_t b, double Sum) {
       const uint32_t* k = block_keys(b);
+      if (!k) return Sum;
       for (int i = 0; i < CUT_BLOCK; i++) Sum += k[i] == CUT_KEY_UNUSED ? 0.0 : F.dx_of[k[i] & 511] * ((double)(int)(k[i] >> 9) - F.ybar);
       return Sum;
     }, &ser0);
-    const double ssxx = chain_stitch_blocks(bxx.data(), nb, [&](int64_t b, double Sum) {
+    const double ssxx = chain_stitch_blocks(bxx.data(), nbt, [&](int64_t b, double Sum) {
       const uint32_t* k = block_keys(b);
+      if (!k) return Sum;
       for (int i = 0; i < CUT_BLOCK; i++) Sum += k[i] == CUT_KEY_UNUSED ? 0.0 : F.dx2_of[k[i] & 511];
       return Sum;
     }, &ser1);
-    if (fetch_failed) { set_error("miagpu_shard_cut: device copy failed"); return 0; }
+    if (missing) {
+      set_error("miagpu_shard_cut: %d blocks of the regression's chains could not be proven and their keys did not travel (more than %d such blocks on one rank)", missing, SHARD_PF_SLOTS);
+      return 0;
+    }
     c->cut_serial_blocks = ser0 + ser1;
-    c->sh_fetched = n_fetched;
+    c->sh_fetched = 0;
     cut_fit_slope(S, F, ssxy, ssxx, &slope, &intercept);
   }
   if (slope_out) *slope_out = slope;
   if (intercept_out) *intercept_out = intercept;
   c->sh_slope = slope; c->sh_icpt = intercept;
-  // ---- flags of the local reads (cull_maln_from_fsdb, mia.c:452-470), sticky (H10)
+  // ---- flags of the local reads (cull_maln_from_fsdb, mia.c:452-470), sticky (H10); the reads this round drops leave the base columns
   cut_thresholds(c->sh_hard_cut, slope, intercept, H->thr);
   MIAGPU_CUDA(cudaMemcpyAsync(c->d_thr.p, H->thr, sizeof(H->thr), cudaMemcpyHostToDevice, main));
-  if (c->sh_host) MIAGPU_CUDA(cudaStreamWaitEvent(main, c->xev[1], 0));
+  MIAGPU_CUDA(cudaStreamWaitEvent(main, c->aev[7], 0));                                // the accumulation of shard_fit
   if (n) {
-    cut_flags_kernel<<<(unsigned)((n + 255) / 256), 256, 0, main>>>(n, c->d_seqlen.p, c->d_score.p, c->d_thr.p, c->d_dropf.p, c->d_entries.p, c->d_cstats.p,
-                                                                    c->sh_has_unique ? c->d_unique.p : nullptr);
+    cut_flags_kernel<<<(unsigned)((n + 255) / 256), 256, 0, main>>>(n, c->d_seqlen.p, c->d_score.p, c->d_thr.p, c->d_dropf.p, nullptr, c->d_cstats.p,
+                                                                    c->sh_has_unique ? c->d_unique.p : nullptr, c->d_newly.p);
+    undo_kernel<<<(unsigned)((n + 255) / 256), 256, 0, main>>>(cons_params(c), n, c->d_newly.p, c->d_entries.p);
     MIAGPU_CUDA(cudaGetLastError());
-    c->launches++;
+    c->launches += 2;
   }
   MIAGPU_CUDA(cudaEventRecord(c->xev[2], main));
-  // ---- column accumulation of the local reads into planes laid out by the reduced insert maxima
-  c->n_cols = (int64_t)c->seq_len + H->total_ins;
-  if (!c->d_acc.reserve(c->n_cols * NPLANE) || !c->d_called.reserve(c->n_cols + 16)) return 0;
-  MIAGPU_CUDA(cudaMemsetAsync(c->d_acc.p, 0, c->n_cols * NPLANE * sizeof(int32_t), main));
-  if (!launch_accumulate(c)) return 0;
   if (sum_buf) *sum_buf = c->d_acc.p;
   if (sum_words) *sum_words = c->n_cols * NPLANE;
-  c->sh_phase = 2;
+  c->sh_phase = 3;
   return 1;
 }
 
 extern "C" int miagpu_shard_finish(miagpu_ctx* c, int cons_code, uint8_t* dropped, uint16_t* packed_runs, int64_t capacity,
                                    int64_t* total_runs, int32_t* gaps_out, char* cons_out, int32_t* cons_len) {
-  if (!c || c->sh_phase != 2) { set_error("miagpu_shard_finish: call miagpu_shard_cut first"); return 0; }
+  if (!c || c->sh_phase != 3) { set_error("miagpu_shard_finish: call miagpu_shard_cut first"); return 0; }
   MIAGPU_CUDA(cudaSetDevice(c->device));
   cudaStream_t down = c->s_down;
   const int64_t n = c->n;

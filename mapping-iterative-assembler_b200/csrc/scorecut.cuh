@@ -26,6 +26,7 @@ struct CutStatsDev {
   long long sx, sy, cnt, bad;                        // bad = smallest index whose seq_len is outside [0, MAX_READ] (LLONG_MAX = none)
   int best[MAX_READ + 1];
   int pad;
+  long long sxx, sxy;                                // sum len^2, sum len * score over the reads the fit uses (sharded rounds: where a rank's chain starts)
 };
 struct CutTables {                                   // host-made, the same doubles the reference forms per read
   double ybar;
@@ -40,7 +41,7 @@ struct CutBlockDev {                                 // chain 0 = ssxy, chain 1 
 
 __global__ void cut_init_kernel(CutStatsDev* st) {
   const int t = threadIdx.x;
-  if (t == 0) { st->sx = 0; st->sy = 0; st->cnt = 0; st->bad = LLONG_MAX; st->pad = 0; }
+  if (t == 0) { st->sx = 0; st->sy = 0; st->cnt = 0; st->bad = LLONG_MAX; st->pad = 0; st->sxx = 0; st->sxy = 0; }
   for (int l = t; l <= MAX_READ; l += blockDim.x) st->best[l] = INT_MIN;
 }
 
@@ -60,31 +61,35 @@ __global__ void __launch_bounds__(CUT_THREADS) cut_stats_kernel(int64_t lo, int6
                                                                 const int32_t* __restrict__ score, const uint8_t* __restrict__ unique_best,
                                                                 CutStatsDev* st) {
   __shared__ int s_best[MAX_READ + 1];
-  __shared__ long long s_sum[3];
+  __shared__ long long s_sum[5];
   for (int l = threadIdx.x; l <= MAX_READ; l += blockDim.x) s_best[l] = INT_MIN;
-  if (threadIdx.x < 3) s_sum[threadIdx.x] = 0;
+  if (threadIdx.x < 5) s_sum[threadIdx.x] = 0;
   __syncthreads();
-  long long sx = 0, sy = 0, cnt = 0;
+  long long sx = 0, sy = 0, cnt = 0, sxx = 0, sxy = 0;
   for (int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (int64_t)gridDim.x * blockDim.x) {
     const int l = seq_len[i];
     if (l < 0 || l > MAX_READ) { atomicMin(&st->bad, (long long)i); continue; }
     const int sc = score[i];
     if ((!unique_best || unique_best[i]) && sc >= FIRST_ROUND_SCORE_CUTOFF) {
-      sx += l; sy += sc; cnt++;
+      sx += l; sy += sc; cnt++; sxx += (long long)l * l; sxy += (long long)l * sc;
       if (sc > s_best[l]) atomicMax(&s_best[l], sc);
     }
   }
-  sx = warp_sum_ll(sx); sy = warp_sum_ll(sy); cnt = warp_sum_ll(cnt);
+  sx = warp_sum_ll(sx); sy = warp_sum_ll(sy); cnt = warp_sum_ll(cnt); sxx = warp_sum_ll(sxx); sxy = warp_sum_ll(sxy);
   if ((threadIdx.x & 31) == 0 && cnt) {
     atomicAdd((unsigned long long*)&s_sum[0], (unsigned long long)sx);
     atomicAdd((unsigned long long*)&s_sum[1], (unsigned long long)sy);
     atomicAdd((unsigned long long*)&s_sum[2], (unsigned long long)cnt);
+    atomicAdd((unsigned long long*)&s_sum[3], (unsigned long long)sxx);
+    atomicAdd((unsigned long long*)&s_sum[4], (unsigned long long)sxy);
   }
   __syncthreads();
   if (threadIdx.x == 0 && s_sum[2]) {
     atomicAdd((unsigned long long*)&st->sx, (unsigned long long)s_sum[0]);
     atomicAdd((unsigned long long*)&st->sy, (unsigned long long)s_sum[1]);
     atomicAdd((unsigned long long*)&st->cnt, (unsigned long long)s_sum[2]);
+    atomicAdd((unsigned long long*)&st->sxx, (unsigned long long)s_sum[3]);
+    atomicAdd((unsigned long long*)&st->sxy, (unsigned long long)s_sum[4]);
   }
   for (int l = threadIdx.x; l <= MAX_READ; l += blockDim.x)
     if (s_best[l] != INT_MIN) atomicMax(&st->best[l], s_best[l]);
@@ -96,7 +101,7 @@ __global__ void __launch_bounds__(CUT_THREADS) cut_stats_kernel(int64_t lo, int6
 // (padding and the rank's header) count as unused reads: a 0.0 addend leaves a rounded chain unchanged.
 constexpr uint32_t CUT_KEY_UNUSED = 0xffffffffu;
 constexpr int SHARD_HDR_WORDS = 8;                   // tail of a rank's stride: sum len, sum score, count (int64 each), 2 spare
-constexpr int SHARD_PF_SLOTS = 256;                  // chain blocks whose keys travel to the host with the block records
+constexpr int SHARD_PF_SLOTS = 48;                   // chain blocks (per rank) whose keys travel with the block records
 
 struct CutSrc {
   const int32_t* seq_len; const int32_t* score; const uint8_t* unique_best;       // KEYS = false
@@ -161,7 +166,7 @@ __global__ void __launch_bounds__(CUT_THREADS) cut_approx_kernel(int64_t n, CutS
 
 // exclusive prefix of the blocks' plain sums: one block, a contiguous run of chain blocks per thread
 constexpr int CUT_PREFIX_THREADS = 1024;
-__global__ void __launch_bounds__(CUT_PREFIX_THREADS) cut_prefix_kernel(int64_t nb, CutBlockDev* blk) {
+__global__ void __launch_bounds__(CUT_PREFIX_THREADS) cut_prefix_kernel(int64_t nb, CutBlockDev* blk, const double* __restrict__ start = nullptr) {
   __shared__ double s_tot[2][CUT_PREFIX_THREADS];
   const int t = threadIdx.x;
   const int64_t per = (nb + CUT_PREFIX_THREADS - 1) / CUT_PREFIX_THREADS;
@@ -177,6 +182,7 @@ __global__ void __launch_bounds__(CUT_PREFIX_THREADS) cut_prefix_kernel(int64_t 
     __syncthreads();
   }
   double r0 = s_tot[0][t] - a0, r1 = s_tot[1][t] - a1;
+  if (start) { r0 += start[0]; r1 += start[1]; }        // sharded rounds: where this rank's part of the chains begins (predicted)
   for (int64_t j = lo; j < hi; j++) {
     blk[j].run[0] = r0; blk[j].run[1] = r1;
     r0 += blk[j].approx[0]; r1 += blk[j].approx[1];
@@ -246,7 +252,7 @@ __global__ void __launch_bounds__(CUT_THREADS) cut_exact_kernel(int64_t n, CutSr
     blk[b].e[ch] = ch ? e[1] : e[0];
     blk[b].ok[ch] = (ch ? valid[1] : valid[0]) && !s_bad[ch] && Ac < 4503599627370496.0;   // 2^52: all partial integer sums exact
   }
-  if (KEYS && pf_keys) {
+  if (pf_keys) {
     if (threadIdx.x == 0) {
       bool suspect = false;
 #pragma unroll
@@ -264,12 +270,78 @@ __global__ void __launch_bounds__(CUT_THREADS) cut_exact_kernel(int64_t n, CutSr
     if (slot >= 0)
       for (int k = threadIdx.x; k < CUT_BLOCK; k += CUT_THREADS) {
         const int64_t i = i0 + k;
-        pf_keys[(size_t)slot * CUT_BLOCK + k] = (i < n && l0 + k < src.n_max) ? src.keys[i] : CUT_KEY_UNUSED;
+        uint32_t key = CUT_KEY_UNUSED;
+        if (KEYS) { if (i < n && l0 + k < src.n_max) key = src.keys[i]; }
+        else if (i < n) key = cut_key(src.seq_len[i], src.score[i], !src.unique_best || src.unique_best[i]);
+        pf_keys[(size_t)slot * CUT_BLOCK + k] = key;
       }
   }
 }
 
-// ---- sharded rounds: what a rank contributes to the all-gather / all-reduce(MAX), and the merge of what came back
+// ---- sharded rounds, protocol of round 2: every rank evaluates ITS OWN part of the two chains.
+//   all-reduce MAX of [insert maxima | best score per length | world x SHARD_HDR2 header words]: a rank writes its integer sums
+//       into its own header row (30-bit pieces, everything else zero), so the MAX is a gather
+//   shard_prep_kernel: the sums of all ranks -> xbar, ybar and the tables (the same doubles the host forms), and where this
+//       rank's part of either chain starts: sum over the ranks before it of  sum(len - xbar)^2  and  sum(len - xbar)(score - ybar)
+//       expanded in the ranks' integer sums -- a PREDICTION of the running sums (it only has to name the binade; the stitch checks)
+//   cut_approx / cut_prefix / cut_exact over the rank's own reads -> block records + the keys of the blocks the stitch may have to
+//       add read by read -> all-gather (about 50 B per 512 reads instead of 4 B per read)
+//   host: chain_stitch_blocks over all ranks' records in rank order
+constexpr int SHARD_HDR2 = 16;                       // header words per rank: 5 sums x 2 pieces of 30 bits, local read count
+__device__ __forceinline__ void put60(int32_t* dst, long long v) { dst[0] = (int32_t)(v & 0x3fffffff); dst[1] = (int32_t)((v >> 30) & 0x3fffffff); }
+__device__ __forceinline__ long long get60(const int32_t* src) { return (long long)src[0] | ((long long)src[1] << 30); }
+__global__ void shard_hdr2_kernel(const CutStatsDev* st, int32_t* max_best, int32_t* hdr, int world, int rank, int n_local) {
+  const int t = threadIdx.x;
+  for (int i = t; i < world * SHARD_HDR2; i += blockDim.x) hdr[i] = 0;
+  for (int l = t; l <= MAX_READ; l += blockDim.x) max_best[l] = max(st->best[l], 0);     // (no read of that length: INT_MIN -> 0; scores that count are >= 2000)
+  __syncthreads();
+  if (t == 0) {
+    int32_t* h = hdr + rank * SHARD_HDR2;
+    put60(h, st->sx); put60(h + 2, st->sy); put60(h + 4, st->cnt); put60(h + 6, st->sxx); put60(h + 8, st->sxy);
+    h[10] = n_local;
+  }
+}
+struct ShardPrep { double start[2]; long long sx, sy, cnt; };
+__global__ void shard_prep_kernel(int world, int rank, const int32_t* __restrict__ hdr, const int32_t* __restrict__ max_best, CutStatsDev* st,
+                                  CutTables* tab, ShardPrep* out, int32_t* pf_ids) {
+  __shared__ double s_xbar, s_ybar;
+  const int t = threadIdx.x;
+  if (t == 0) {
+    long long sx = 0, sy = 0, cnt = 0;
+    for (int r = 0; r < world; r++) { const int32_t* h = hdr + r * SHARD_HDR2; sx += get60(h); sy += get60(h + 2); cnt += get60(h + 4); }
+    st->sx = sx; st->sy = sy; st->cnt = cnt;
+    out->sx = sx; out->sy = sy; out->cnt = cnt;
+    const double xbar = cnt > 0 ? __ddiv_rn((double)sx, (double)cnt) : 0.0, ybar = cnt > 0 ? __ddiv_rn((double)sy, (double)cnt) : 0.0;
+    s_xbar = xbar; s_ybar = ybar;
+    tab->ybar = ybar;
+    double a = 0, b = 0;                             // predicted running sums where this rank's reads begin
+    for (int r = 0; r < rank; r++) {
+      const int32_t* h = hdr + r * SHARD_HDR2;
+      const double x = (double)get60(h), y = (double)get60(h + 2), c = (double)get60(h + 4), xx = (double)get60(h + 6), xy = (double)get60(h + 8);
+      a += xy - xbar * y - ybar * x + c * xbar * ybar;
+      b += xx - 2.0 * xbar * x + c * xbar * xbar;
+    }
+    out->start[0] = a; out->start[1] = b;
+    pf_ids[0] = 0;
+  }
+  __syncthreads();
+  for (int l = t; l <= MAX_READ; l += blockDim.x) {
+    const double dx = __dsub_rn((double)l, s_xbar);
+    tab->dx[l] = dx; tab->dx2[l] = __dmul_rn(dx, dx);
+    st->best[l] = max_best[l] > 0 ? max_best[l] : INT_MIN;
+  }
+}
+// what travels: per block T, A (2 chains), e, ok
+struct ShardBlockRec { double T[2], A[2]; int e[2], ok[2]; };
+__global__ void shard_records_kernel(int64_t nb, const CutBlockDev* __restrict__ blk, ShardBlockRec* out) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  ShardBlockRec r;
+  for (int ch = 0; ch < 2; ch++) { r.T[ch] = blk[b].T[ch]; r.A[ch] = blk[b].A[ch]; r.e[ch] = blk[b].e[ch]; r.ok[ch] = blk[b].ok[ch]; }
+  out[b] = r;
+}
+
+// ---- sharded rounds (round-1 protocol, kept for reference): what a rank contributes to the all-gather / all-reduce(MAX), and the merge of what came back
 __global__ void shard_pack_kernel(int64_t n, int64_t stride, const int32_t* __restrict__ seq_len, const int32_t* __restrict__ score,
                                   const uint8_t* __restrict__ unique_best, uint32_t* send) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

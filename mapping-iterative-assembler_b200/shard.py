@@ -1,7 +1,8 @@
 """Sharded rounds: reads partitioned over the GPUs of one box, one process and one
 libmiagpu context per GPU, consensus replicated.  The library has no communication dependency; this
-module runs the three collectives of a round (all-gather of the regression keys, all-reduce MAX of
-the insert maxima + per-length best scores, all-reduce SUM of the column planes) with
+module runs the three collectives of a round (all-reduce MAX of the insert maxima + per-length best
+scores + the ranks' integer sums, all-gather of the regression's block records, all-reduce SUM of the
+column planes) with
 torch.distributed / NCCL on the library's own stream, so that a round is one stream-ordered
 sequence without host synchronisation between the DP and the collectives.  A C host makes the same
 calls with ncclAllGather / ncclAllReduce.
@@ -33,18 +34,27 @@ class ShardedRounds:
         self.stream = torch.cuda.ExternalStream(gpu.lib.miagpu_stream(gpu.h), device=self.device)
 
     # the collectives, ordered on the library's stream
-    def _after_begin(self, b):
+    def _after_begin(self, mb):
         import torch
         import torch.distributed as dist
-        send = dev_tensor(b["send"][0], b["send"][1], self.device)
-        recv = dev_tensor(b["recv"][0], b["recv"][1], self.device)
-        mx = dev_tensor(b["max"][0], b["max"][1], self.device)
+        if self.world > 1:
+            mx = dev_tensor(mb[0], mb[1], self.device)
+            with torch.cuda.stream(self.stream):
+                dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=self.group)
+
+    def _after_fit(self, f):
+        import torch
+        import torch.distributed as dist
+        words = f["send"][1]
+        if not words:
+            return
+        send = dev_tensor(f["send"][0], words, self.device)
+        recv = dev_tensor(f["recv"][0], words * self.world, self.device)
         with torch.cuda.stream(self.stream):
             if self.world == 1:
                 recv.copy_(send)
             else:
                 dist.all_gather_into_tensor(recv, send, group=self.group)
-                dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=self.group)
 
     def _after_cut(self, sb):
         import torch
@@ -54,23 +64,25 @@ class ShardedRounds:
             with torch.cuda.stream(self.stream):
                 dist.all_reduce(planes, op=dist.ReduceOp.SUM, group=self.group)
 
-    def resident(self, cons_code=1, hard_cut=0, score_cut=None, dropped=None, want_gaps=False):
-        """miagpu_iterate_resident for a shard: -> (consensus, (slope, intercept), gaps)"""
-        b = self.g.shard_begin(self.world, self.rank, self.n_max, hard_cut, score_cut)
-        self._after_begin(b)
+    def _round(self):
+        self._after_fit(self.g.shard_fit())
         fit, sb = self.g.shard_cut()
         self._after_cut(sb)
+        return fit
+
+    def resident(self, cons_code=1, hard_cut=0, score_cut=None, dropped=None, want_gaps=False):
+        """miagpu_iterate_resident for a shard: -> (consensus, (slope, intercept), gaps)"""
+        self._after_begin(self.g.shard_begin(self.world, self.rank, self.n_max, hard_cut, score_cut))
+        fit = self._round()
         cons, gaps, _ = self.g.shard_finish(cons_code, dropped, None, want_gaps)
         return cons, fit, gaps
 
     def host(self, bases, offsets, rc, as_, ae, seq_len, dropped, out, packed=None, cons_code=1, unique_best=None, hard_cut=0,
              score_cut=None, want_gaps=False):
         """miagpu_iterate_host for a shard: -> (consensus, (slope, intercept), total_runs, gaps); dropped updated in place"""
-        b = self.g.shard_begin_host(self.world, self.rank, self.n_max, bases, offsets, rc, as_, ae, seq_len, dropped, out, unique_best,
-                                    hard_cut, score_cut)
-        self._after_begin(b)
-        fit, sb = self.g.shard_cut()
-        self._after_cut(sb)
+        self._after_begin(self.g.shard_begin_host(self.world, self.rank, self.n_max, bases, offsets, rc, as_, ae, seq_len, dropped, out,
+                                                  unique_best, hard_cut, score_cut))
+        fit = self._round()
         cons, gaps, tot = self.g.shard_finish(cons_code, dropped, packed, want_gaps, want_total_runs=True)
         return cons, fit, tot, gaps
 
@@ -87,17 +99,23 @@ class LocalShards:
         import torch
         torch.cuda.synchronize(self.device)
 
-    def _exchange_begin(self, bs):
+    def _exchange_begin(self, mbs):
         import torch
         self._sync()
-        sends = [dev_tensor(b["send"][0], b["send"][1], self.device) for b in bs]
-        allk = torch.cat(sends)
-        for b in bs:
-            dev_tensor(b["recv"][0], b["recv"][1], self.device).copy_(allk)
-        mx = [dev_tensor(b["max"][0], b["max"][1], self.device) for b in bs]
+        mx = [dev_tensor(mb[0], mb[1], self.device) for mb in mbs]
         m = torch.stack(mx).max(0).values
         for t in mx:
             t.copy_(m)
+        self._sync()
+
+    def _exchange_fit(self, fs):
+        import torch
+        self._sync()
+        if fs[0]["send"][1]:
+            sends = [dev_tensor(f["send"][0], f["send"][1], self.device) for f in fs]
+            allk = torch.cat(sends)
+            for f in fs:
+                dev_tensor(f["recv"][0], f["send"][1] * self.world, self.device).copy_(allk)
         self._sync()
 
     def _exchange_cut(self, sbs):
@@ -109,12 +127,16 @@ class LocalShards:
             t.copy_(total)
         self._sync()
 
-    def resident(self, n_max, cons_code=1, hard_cut=0, score_cut=None, dropped=None, want_gaps=False):
-        """dropped: list of uint8 arrays (one per shard) or None.  -> list of (consensus, fit, gaps) per shard"""
-        bs = [g.shard_begin(self.world, r, n_max, hard_cut, score_cut) for r, g in enumerate(self.gpus)]
-        self._exchange_begin(bs)
+    def _round(self):
+        self._exchange_fit([g.shard_fit() for g in self.gpus])
         cuts = [g.shard_cut() for g in self.gpus]
         self._exchange_cut([c[1] for c in cuts])
+        return cuts
+
+    def resident(self, n_max, cons_code=1, hard_cut=0, score_cut=None, dropped=None, want_gaps=False):
+        """dropped: list of uint8 arrays (one per shard) or None.  -> list of (consensus, fit, gaps) per shard"""
+        self._exchange_begin([g.shard_begin(self.world, r, n_max, hard_cut, score_cut) for r, g in enumerate(self.gpus)])
+        cuts = self._round()
         res = []
         for r, g in enumerate(self.gpus):
             cons, gaps, _ = g.shard_finish(cons_code, None if dropped is None else dropped[r], None, want_gaps)
@@ -123,11 +145,9 @@ class LocalShards:
 
     def host(self, n_max, shards, cons_code=1, hard_cut=0, score_cut=None, want_gaps=False):
         """shards: list of dicts(bases, off, rc, as_, ae, seq_len, dropped, out, packed=None, unique_best=None)"""
-        bs = [g.shard_begin_host(self.world, r, n_max, s["bases"], s["off"], s["rc"], s["as_"], s["ae"], s["seq_len"], s["dropped"], s["out"],
-                                 s.get("unique_best"), hard_cut, score_cut) for r, (g, s) in enumerate(zip(self.gpus, shards))]
-        self._exchange_begin(bs)
-        cuts = [g.shard_cut() for g in self.gpus]
-        self._exchange_cut([c[1] for c in cuts])
+        self._exchange_begin([g.shard_begin_host(self.world, r, n_max, s["bases"], s["off"], s["rc"], s["as_"], s["ae"], s["seq_len"], s["dropped"],
+                                                 s["out"], s.get("unique_best"), hard_cut, score_cut) for r, (g, s) in enumerate(zip(self.gpus, shards))])
+        cuts = self._round()
         res = []
         for r, (g, s) in enumerate(zip(self.gpus, shards)):
             cons, gaps, tot = g.shard_finish(cons_code, s["dropped"], s.get("packed"), want_gaps, want_total_runs=True)
