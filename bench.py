@@ -9,8 +9,9 @@ configs[1]: 1 M synthetic 35-75 bp aDNA-damaged reads vs a 16,569 bp circular re
 ancient.submat.solexa.onepass, single iteration.  The step also holds the iteration's score cut
 (cull_maln_from_fsdb / find_fsdb_score_cut, mia.c:418-479, fsdb.c:269-383) between the two, at every N.
 Reads shard across ranks (weak scaling: 1 M reads per GPU, consensus replicated; per round one
-all-gather of the regression keys, one all-reduce MAX of the insert maxima and one all-reduce SUM of
-the column planes over NCCL, enqueued on the library's stream: mia_b200/shard.py).
+all-reduce MAX (insert maxima, best scores, the ranks' integer sums), one all-gather of the regression's
+block records (~50 B per 512 reads) and one all-reduce SUM of the column planes over NCCL, enqueued on
+the library's stream: mia_b200/shard.py).
 
   value : reads/s, whole job, inputs resident in HBM, device time (CUDA events on the
           library's stream), max over ranks.
@@ -117,6 +118,29 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this process to the CPUs next to its GPU (sysfs local_cpulist of the GPU's PCI function), so that the pinned host buffers
+    of the end-to-end arm are first touched on the GPU's own NUMA node: with one process per GPU on a two-socket host half of the
+    uploads otherwise cross the socket interconnect.  Returns the CPU list, or None when the information is not there."""
+    try:
+        bdf = subprocess.run(["nvidia-smi", "-i", str(index), "--query-gpu=pci.bus_id", "--format=csv,noheader"], capture_output=True,
+                             text=True, timeout=10).stdout.strip().lower()
+        if bdf.startswith("00000000:"):
+            bdf = bdf[4:]
+        cpus = open(f"/sys/bus/pci/devices/{bdf}/local_cpulist").read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            a, _, b = part.partition("-")
+            ids.update(range(int(a), int(b or a) + 1))
+        ids &= os.sched_getaffinity(0)
+        if ids:
+            os.sched_setaffinity(0, ids)
+            return cpus
+    except Exception:
+        pass
+    return None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -130,6 +154,7 @@ def run_ours(args):
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None       # before any pinned buffer is allocated (first touch decides the node)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n = args.reads
@@ -148,7 +173,7 @@ def run_ours(args):
 
     def step_resident():
         """the whole round on resident inputs: realign, score cut, consensus (N > 1: the sharded protocol,
-        all-gather + 2 all-reduces over NCCL on the library's stream; same work per read at every N)"""
+        2 all-reduces + 1 small all-gather over NCCL on the library's stream; same work per read at every N)"""
         g.reset_dropped()                               # every timed step starts from the same state
         cons = g.iterate_resident()[0] if world == 1 else S.resident()[0]
         launches["n"] += g.last_timing()["launches"]
@@ -289,8 +314,9 @@ def run_ours(args):
         "config": {"workload": "BASELINE configs[1]: 1M synthetic 35-75 bp aDNA-damaged reads per GPU vs 16,569 bp circular "
                                "R-rand reference, ancient.submat.solexa.onepass, single iteration (realign + score cut + consensus)",
                    "reads_per_gpu": n, "ref_len": REF_LEN, "l2": "256 MiB buffer written between timed steps",
-                   "parallelism": f"reads sharded x{world}, consensus replicated; per round 1 all-gather (regression keys, 4 B/read) + "
-                                  f"all-reduce MAX (insert maxima) + all-reduce SUM (column planes) over NCCL on the library stream"},
+                   "host_cpus_of_rank0": numa,
+                   "parallelism": f"reads sharded x{world}, consensus replicated; per round all-reduce MAX (insert maxima + the ranks' sums) + "
+                                  f"all-gather (regression block records, ~50 B per 512 reads) + all-reduce SUM (column planes) over NCCL on the library stream"},
         "gcups": gcups, "dp_cells_per_step": world * cells,
         "e2e": {"value": world * n / (e2e_total / args.steps), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_total / args.steps * 1e3,

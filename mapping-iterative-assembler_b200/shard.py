@@ -18,10 +18,20 @@ class _Raw:
         self.__cuda_array_interface__ = {"shape": (count,), "typestr": typestr, "data": (ptr, False), "version": 3}
 
 
+_views = {}
+
+
 def dev_tensor(ptr, words, device, typestr="<i4"):
-    """torch view of `words` 32-bit words of device memory owned by the library"""
+    """torch view of `words` 32-bit words of device memory owned by the library (views are cached: a round hands out the same
+    buffers again and again, and building a view costs tens of microseconds on the round's critical path)"""
     import torch
-    return torch.as_tensor(_Raw(ptr, words, typestr), device=device)
+    key = (ptr, words, str(device), typestr)
+    t = _views.get(key)
+    if t is None:
+        if len(_views) > 256:
+            _views.clear()
+        t = _views[key] = torch.as_tensor(_Raw(ptr, words, typestr), device=device)
+    return t
 
 
 class ShardedRounds:
