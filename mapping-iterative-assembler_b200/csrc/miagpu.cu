@@ -69,6 +69,7 @@ static const int P16_G_REALIGN[P16_NKB] = {8, 8, 8, 8, 16, 16, 16, 16, 16, 16, 1
 struct PairNp { int v[P16_NKB]; };                           // pairs per work item (= per warp) of every class
 
 constexpr int MAX_CHUNKS = 16;
+constexpr int MAX_DEVICES = 64;
 
 }  // namespace miagpu
 
@@ -725,12 +726,16 @@ static int launch_bucket(miagpu_ctx* c, RealignParams p, int maxL) {
   using TL = TraceLayout<K>;
   bool ref_in_smem = c->ref_bytes <= 160 * 1024;
   size_t smem = PROF_INTS * 4 + WARPS_PER_BLOCK * MAX_READ * 2 + (ref_in_smem ? c->ref_bytes : 0);
-  static size_t cached_smem = ~(size_t)0;            // per instantiation: the attribute / occupancy calls cost more than the launch
-  static int cached_per_sm = 0;
-  if (cached_smem != smem) {
+  // per instantiation AND per device (function attributes belong to a device; several contexts of one process may drive several GPUs):
+  // the attribute / occupancy calls cost more than the launch
+  static size_t cached_smem_d[MAX_DEVICES];
+  static int cached_per_sm_d[MAX_DEVICES];
+  size_t& cached_smem = cached_smem_d[c->device % MAX_DEVICES];
+  int& cached_per_sm = cached_per_sm_d[c->device % MAX_DEVICES];
+  if (cached_smem != smem + 1) {
     MIAGPU_CUDA(cudaFuncSetAttribute(realign_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     MIAGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cached_per_sm, realign_kernel<K>, WARPS_PER_BLOCK * 32, smem));
-    cached_smem = smem;
+    cached_smem = smem + 1;
   }
   int per_sm = cached_per_sm;
   if (per_sm < 1) { set_error("realign_kernel<%d> does not fit on an SM (smem %zu)", K, smem); return 0; }
@@ -756,12 +761,14 @@ template <int K, int G, bool JOB = false, bool RB = false>
 static int launch_pair16(miagpu_ctx* c, Pair16Params p, int n_pairs, int maxL) {
   bool ref_in_smem = p.ref_bytes <= 160 * 1024;
   size_t smem = p16_smem_fixed<G>() + (ref_in_smem ? p.ref_bytes : 0);
-  static size_t cached_smem = ~(size_t)0;
-  static int cached_per_sm = 0;
-  if (cached_smem != smem) {
+  static size_t cached_smem_d[MAX_DEVICES];
+  static int cached_per_sm_d[MAX_DEVICES];
+  size_t& cached_smem = cached_smem_d[c->device % MAX_DEVICES];
+  int& cached_per_sm = cached_per_sm_d[c->device % MAX_DEVICES];
+  if (cached_smem != smem + 1) {
     MIAGPU_CUDA(cudaFuncSetAttribute((pair16_kernel<K, G, JOB, RB>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     MIAGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cached_per_sm, (pair16_kernel<K, G, JOB, RB>), WARPS_PER_BLOCK * 32, smem));
-    cached_smem = smem;
+    cached_smem = smem + 1;
   }
   if (RB) { const RbFrame f = p16_rb_frame(K, c->pssm_max); p.rb_off = f.off; p.rb_d = f.d; p.rb_thresh = f.thresh; }
   int per_sm = cached_per_sm;
@@ -3225,8 +3232,9 @@ static int pass1_sweep(miagpu_ctx* c, const PairLmax& lm) {
     sp.gep2 = K2(2 * GEP);
     sp.jscore = c->d_jscore.p; sp.jabc = c->d_jabc.p; sp.jaec = c->d_jaec.p; sp.jabr = c->d_jabr.p; sp.jstatus = c->d_jstatus.p;
     const size_t smem = sw_smem();
-    static int per_sm = -1;
-    if (per_sm < 0) {
+    static int per_sm_d[MAX_DEVICES];
+    int& per_sm = per_sm_d[c->device % MAX_DEVICES];
+    if (per_sm <= 0) {
       MIAGPU_CUDA(cudaFuncSetAttribute(sweep16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       MIAGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep16_kernel, WARPS_PER_BLOCK * 32, smem));
     }

@@ -54,3 +54,34 @@ def test_c_host_follows_the_reference_pointers(golden, name, tmp_path):
                 assert x == y, f"{name} iteration {it + 1}: line {ln + 2}: {x[:160]!r} != {y[:160]!r}"
             assert len(got) == len(body)
     assert not os.path.exists(tmp_path / f"out.{len(s['malns']) + 1}")
+
+
+@pytest.mark.parametrize("gpus", [1, 2, 4])
+@pytest.mark.parametrize("name,matrix", [("circ_k10", "ancient"), ("lin_pe", "pe"), ("circ_k10_SN", "ancient")])
+def test_c_host_for_the_gpus_of_one_box(golden, name, matrix, gpus, tmp_path):
+    # host/mia_gpu_mg.c: one process, one context + one thread per GPU, NCCL between them (ncclCommInitAll), the sharded protocol of
+    # include/miagpu.h -> the `.maln` files the unmodified reference binary wrote.  -g 1 runs the same code on a one-GPU box.
+    import _pkg
+    _pkg.load()
+    from mia_b200 import api
+    if api.load_library().miagpu_device_count() < gpus:
+        pytest.skip(f"needs {gpus} GPUs")
+    s = json.load(gzip.open(os.path.join(HERE, "golden", "maln_session.json.gz"), "rt"))["sessions"][name]
+    (tmp_path / "ref.fa").write_text(s.get("ref_text") or f">{s['ref_id']} {s['ref_desc']}\n{s['ref']}\n")
+    (tmp_path / "reads.fq").write_text(s["fastq"])
+    (tmp_path / "m.txt").write_text(matrix_text(golden[matrix]))
+    ensure_host()
+    mg = os.path.join(os.path.dirname(HOST), "mia_gpu_mg")
+    if not os.path.exists(mg):
+        pytest.skip("host/mia_gpu_mg not built (needs nccl.h / libnccl at build time)")
+    r = subprocess.run([mg, "-g", str(gpus), "-r", "ref.fa", "-f", "reads.fq", "-s", "m.txt", "-m", "out"] + s["flags"], cwd=tmp_path,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    for it, body in enumerate(s["malns"]):
+        got = open(tmp_path / f"out.{it + 1}").read().split("\n", 1)[1]
+        if got != body:
+            for ln, (x, y) in enumerate(zip(got.split("\n"), body.split("\n"))):
+                assert x == y, f"{name} -g {gpus} iteration {it + 1}: line {ln + 2}: {x[:160]!r} != {y[:160]!r}"
+            assert len(got) == len(body)
+    assert not os.path.exists(tmp_path / f"out.{len(s['malns']) + 1}")
+    assert "Assembly convergence" in r.stderr
