@@ -236,3 +236,69 @@ def round_parity(gpu, ref, bases, off, rc, as_, ae, sm, circular=1, checker=None
         out["consensus_len"] = len(cons)
     out["consensus"] = cons
     return out
+
+
+def assembly_parity(gpu, ref, reads, sm, circular=1, k=12, distant_ref=0, max_iter=30):
+    """A whole assembly (pass 1 with the k-mer filter, rounds until the consensus stops changing) of `reads` (list of str) through
+    driver.ResidentAssembler on one GPU against the same assembly by the CPU checker -- the unmodified reference's own main loop
+    (oracle/ref_harness.c: refh_sess_*) where oracle/_ref was built, else the oracle restatement (tests/oracle_driver.py): pass-1
+    results of every read, per round every read's score / as / ae / rc / strand_known and the consensus.
+    -> dict(reads, fsdb, rounds, pass1_equal, rounds_equal, consensus_equal, converged_equal, checker, first_diff)"""
+    import tempfile
+    from mia_b200 import driver
+    from oracle.pyoracle import Oracle, Ref, have_ref
+    n = len(reads)
+    off = np.zeros(n + 1, np.int64)
+    np.cumsum([len(r) for r in reads], out=off[1:])
+    bases = np.frombuffer("".join(reads).encode(), np.uint8)
+    A = driver.ResidentAssembler(gpu, ref, sm, circular, k, 0, distant_ref=distant_ref)
+    p = A.pass1(bases, off)
+    first_diff = None
+    exp_iters = []
+    if have_ref():
+        r = Ref()
+        kind = "oracle/_ref (the unmodified reference's main loop)"
+        with tempfile.NamedTemporaryFile("w", suffix=".fa", delete=False) as f:
+            f.write(">ref\n" + ref + "\n")
+            path = f.name
+        s = r.sess_new(path, circular, sm, k=k, soft_mask=0, distant_ref=distant_ref)
+        p1 = [r.sess_pass1(s, "r%d" % i, rd) for i, rd in enumerate(reads)]
+        r.sess_end_pass1(s)
+        for _ in range(max_iter):
+            cons, conv = r.sess_iterate(s, sort=0)
+            exp_iters.append((cons, conv, [[x["score"], x["as_"], x["ae"], x["rc"], x["strand_known"]] for x in r.sess_reads(s)]))
+            if conv:
+                break
+        os.unlink(path)
+    else:
+        from oracle_driver import OracleRun
+        o = Oracle()
+        kind = "oracle (restatement)"
+        R = OracleRun(o, ref, sm, circular, k, 0, distant_ref=distant_ref)
+        p1 = [R.pass1(rd) for rd in reads]
+        R.end_pass1()
+        for _ in range(max_iter):
+            cons, conv = R.iterate()
+            exp_iters.append((cons, conv, [[f["score"], f["as_"], f["ae"], f["rc"], f["strand_known"]] for f in R.fsdb]))
+            if conv:
+                break
+    pass1_equal = True
+    for i, e in enumerate(p1):
+        got = [int(p["hits"][i])] + ([int(p[k2][i]) for k2 in ("score", "rc", "as_", "ae")] if e["hits"] else [])
+        exp = [e["hits"]] + ([e[k2] for k2 in ("score", "rc", "as_", "ae")] if e["hits"] else [])
+        if got != exp:
+            pass1_equal = False
+            first_diff = first_diff or f"pass 1 read {i}: {got} != {exp}"
+    rounds_equal = cons_equal = conv_equal = True
+    for it, (cons, conv, rd) in enumerate(exp_iters):
+        gc, gconv = A.iterate()
+        got = np.stack([A.score, A.as_, A.ae, A.rc.astype(np.int32), A.strand_known.astype(np.int32)], 1).tolist()
+        if got != rd:
+            rounds_equal = False
+            first_diff = first_diff or f"round {it + 1}: per-read results differ"
+        if gc != cons:
+            cons_equal = False
+            first_diff = first_diff or f"round {it + 1}: consensus differs"
+        conv_equal &= gconv == conv
+    return dict(reads=n, fsdb=len(A.seq_len), rounds=len(exp_iters), pass1_equal=pass1_equal, rounds_equal=rounds_equal, consensus_equal=cons_equal,
+                converged_equal=bool(conv_equal), checker=kind, first_diff=first_diff)
