@@ -2700,10 +2700,21 @@ extern "C" int miagpu_shard_cut(miagpu_ctx* c, double* slope_out, double* interc
   CutHost* H = c->h_cut;
   double slope = c->sh_slope, intercept = c->sh_icpt;
   if (fit) {
-    MIAGPU_CUDA(cudaMemcpyAsync(c->h_sh_recv, c->d_sh_recv.p, (size_t)world * stride * sizeof(uint32_t), cudaMemcpyDeviceToHost, main));
+    // every rank's records, ids and the first SHARD_PF_FIRST key blocks in one strided copy; the other key blocks only if a rank used them
+    const size_t pitch = (size_t)stride * sizeof(uint32_t);
+    const size_t ids_at = ((size_t)nb * sizeof(ShardBlockRec) + 3) / 4 * 4;
+    const size_t first = ids_at + (size_t)(SHARD_PF_SLOTS + 8) * 4 + (size_t)SHARD_PF_FIRST * CUT_BLOCK * 4;
+    MIAGPU_CUDA(cudaMemcpy2DAsync(c->h_sh_recv, pitch, c->d_sh_recv.p, pitch, first, world, cudaMemcpyDeviceToHost, main));
     MIAGPU_CUDA(cudaMemcpyAsync(&H->prep, c->d_sh_prep.p, sizeof(ShardPrep), cudaMemcpyDeviceToHost, main));
     MIAGPU_CUDA(cudaMemcpyAsync(&H->stats, c->d_cstats.p, sizeof(CutStatsDev), cudaMemcpyDeviceToHost, main));
     MIAGPU_CUDA(cudaStreamSynchronize(main));
+    int most = 0;
+    for (int r = 0; r < world; r++) most = std::max(most, *reinterpret_cast<const int32_t*>(reinterpret_cast<const char*>(c->h_sh_recv) + r * pitch + ids_at));
+    if (most > SHARD_PF_FIRST) {
+      MIAGPU_CUDA(cudaMemcpy2DAsync(reinterpret_cast<char*>(c->h_sh_recv) + first, pitch, reinterpret_cast<const char*>(c->d_sh_recv.p) + first, pitch,
+                                    pitch - first, world, cudaMemcpyDeviceToHost, main));
+      MIAGPU_CUDA(cudaStreamSynchronize(main));
+    }
     CutSums S;
     CutFit F;
     S.sx = H->prep.sx; S.sy = H->prep.sy; S.cnt = H->prep.cnt; S.bad = H->stats.bad == LLONG_MAX ? -1 : H->stats.bad;
@@ -2724,7 +2735,8 @@ extern "C" int miagpu_shard_cut(miagpu_ctx* c, double* slope_out, double* interc
     }
     // keys of a block the stitch cannot prove: they came with the records of the rank that owns the block
     int missing = 0;
-    auto block_keys = [&](int64_t gb) -> const uint32_t* {
+    char first_missing[200] = "";
+    auto block_keys = [&](int64_t gb, double Sum, const ChainBlock& B, int chain) -> const uint32_t* {
       const int r = (int)(gb / nb);
       const int64_t b = gb % nb;
       const int32_t* pf_ids = reinterpret_cast<const int32_t*>(rank_words(r) + (nb * sizeof(ShardBlockRec) + 3) / 4);
@@ -2732,24 +2744,26 @@ extern "C" int miagpu_shard_cut(miagpu_ctx* c, double* slope_out, double* interc
       const int npf = std::min<int>(pf_ids[0], SHARD_PF_SLOTS);
       for (int k = 0; k < npf; k++)
         if (pf_ids[1 + k] == b) return pf_keys + (size_t)k * CUT_BLOCK;
-      missing++;
+      if (!missing++)
+        snprintf(first_missing, sizeof first_missing, "first: rank %d block %lld chain %d, running sum %.17g, record e=%d ok=%d T=%g A=%g, %d blocks of that rank sent keys",
+                 r, (long long)b, chain, Sum, B.e, (int)B.ok, B.T, B.A, pf_ids[0]);
       return nullptr;
     };
     int64_t ser0 = 0, ser1 = 0;
     const double ssxy = chain_stitch_blocks(bxy.data(), nbt, [&](int64_t b, double Sum) {
-      const uint32_t* k = block_keys(b);
+      const uint32_t* k = block_keys(b, Sum, bxy[b], 0);
       if (!k) return Sum;
       for (int i = 0; i < CUT_BLOCK; i++) Sum += k[i] == CUT_KEY_UNUSED ? 0.0 : F.dx_of[k[i] & 511] * ((double)(int)(k[i] >> 9) - F.ybar);
       return Sum;
     }, &ser0);
     const double ssxx = chain_stitch_blocks(bxx.data(), nbt, [&](int64_t b, double Sum) {
-      const uint32_t* k = block_keys(b);
+      const uint32_t* k = block_keys(b, Sum, bxx[b], 1);
       if (!k) return Sum;
       for (int i = 0; i < CUT_BLOCK; i++) Sum += k[i] == CUT_KEY_UNUSED ? 0.0 : F.dx2_of[k[i] & 511];
       return Sum;
     }, &ser1);
     if (missing) {
-      set_error("miagpu_shard_cut: %d blocks of the regression's chains could not be proven and their keys did not travel (more than %d such blocks on one rank)", missing, SHARD_PF_SLOTS);
+      set_error("miagpu_shard_cut: %d blocks of the regression's chains could not be proven and their keys did not travel (at most %d blocks per rank send keys; %s)", missing, SHARD_PF_SLOTS, first_missing);
       return 0;
     }
     c->cut_serial_blocks = ser0 + ser1;

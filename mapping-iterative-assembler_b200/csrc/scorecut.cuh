@@ -101,7 +101,8 @@ __global__ void __launch_bounds__(CUT_THREADS) cut_stats_kernel(int64_t lo, int6
 // (padding and the rank's header) count as unused reads: a 0.0 addend leaves a rounded chain unchanged.
 constexpr uint32_t CUT_KEY_UNUSED = 0xffffffffu;
 constexpr int SHARD_HDR_WORDS = 8;                   // tail of a rank's stride: sum len, sum score, count (int64 each), 2 spare
-constexpr int SHARD_PF_SLOTS = 48;                   // chain blocks (per rank) whose keys travel with the block records
+constexpr int SHARD_PF_SLOTS = 96;                   // chain blocks (per rank) whose keys travel with the block records
+constexpr int SHARD_PF_FIRST = 48;                   // ... of which the first ones come to the host with the records (the rest only when a rank used them)
 
 struct CutSrc {
   const int32_t* seq_len; const int32_t* score; const uint8_t* unique_best;       // KEYS = false

@@ -49,6 +49,7 @@ def main():
     ap.add_argument("--reads", type=int, default=10_000_000)
     ap.add_argument("--prefix", type=int, default=10_000)
     ap.add_argument("--distant", action="store_true")
+    ap.add_argument("--parity-only", action="store_true", help="only the prefix check of the data set --reads names (one GPU)")
     args = ap.parse_args()
     sh = SHAPES[args.shape]
     world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
@@ -60,6 +61,18 @@ def main():
     ref = synth.random_reference(sh["ref_len"], seed=1 if sh["ref_len"] < 100000 else 321)
     genome = synth.diverge(ref, sh["div"], seed=3, indel_rate=sh["indel"])
     per = args.reads // PIECES
+    if args.parity_only:
+        t0 = time.perf_counter()
+        sm = gpu_checks.load_pssm(sh["matrix"])
+        b0, o0 = synth.make_reads(genome, per, sh["lens"][0], sh["lens"][1], seed=1000, circular=bool(sh["circular"]))[:2]
+        P = min(args.prefix, per)
+        reads = [synth.read_str(b0, o0, i) for i in range(P)]
+        gp = api.MiaGpu(local)
+        par = gpu_checks.assembly_parity(gp, ref, reads, sm, sh["circular"], sh["k"], int(args.distant))
+        gp.close()
+        par["wall_s"] = round(time.perf_counter() - t0, 1)
+        print(json.dumps(dict(config=sh["name"] + (" -D" if args.distant else ""), data_set_reads=per * PIECES, prefix_parity=par)))
+        return
     t0 = time.perf_counter()
     mine = range(rank * PIECES // world, (rank + 1) * PIECES // world)
     parts = [synth.make_reads(genome, per, sh["lens"][0], sh["lens"][1], seed=1000 + p, circular=bool(sh["circular"]))[:2] for p in mine]
