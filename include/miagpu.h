@@ -124,7 +124,9 @@ int miagpu_last_pass1_stats( miagpu_ctx* ctx, int64_t* fast_reads,
  * counts whole); equal without the filter */
 int miagpu_last_pass1_cells( miagpu_ctx* ctx, int64_t* nominal, int64_t* effective );
 /* per read of the last miagpu_pass1: 0 no k-mer hit, 1 finished by the pair kernels, 2 general kernel
- * (decided while seeding), 3 general kernel (the winning job's path was not a plain diagonal) */
+ * (decided while seeding), 3 general kernel (a job of the read left the 16-bit frame), 4 pair kernels for the scores +
+ * the windowed 32-bit kernel for the winning stretch's trace (the winner's path was not a plain diagonal; counted with 1
+ * in miagpu_last_pass1_stats) */
 int miagpu_last_pass1_route( miagpu_ctx* ctx, uint8_t* route );
 
 /* After pass 1 the host tells the device which resident reads to keep and in

@@ -108,6 +108,8 @@ struct miagpu_ctx {
   DevBuf<uint16_t> d_runs;
   DevBuf<int32_t> d_meta;                      // META_* layout below
   DevBuf<uint32_t> d_scratch[4];               // trace scratch of the 32-bit kernels, one per launch stream
+  DevBuf<int32_t> d_p1trace;                   // pass 1: winning jobs the 32-bit JOB kernels trace
+  int p1_traced = 0;
   cudaStream_t s_aux[4] = {};                  // [0] = stream; [1..3] side streams of the concurrent DP launches
   cudaEvent_t aev[8] = {};                     // fork / join events of those
   cudaStream_t launch_stream = nullptr;        // where launch_bucket / launch_pair16 / launch_strip put their kernel
@@ -279,7 +281,7 @@ extern "C" void miagpu_destroy(miagpu_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   c->d_jkind.release(); c->d_jstatus.release(); c->d_route.release(); c->d_jws.release(); c->d_jwl.release(); c->d_jscore.release();
-  c->d_jabc.release(); c->d_jaec.release(); c->d_jabr.release(); c->d_p1list.release(); c->d_p1meta.release(); c->d_jpairs.release();
+  c->d_jabc.release(); c->d_jaec.release(); c->d_jabr.release(); c->d_p1list.release(); c->d_p1trace.release(); c->d_p1meta.release(); c->d_jpairs.release();
   c->d_jread.release(); c->d_jfirst.release(); c->d_jcount.release();
   c->d_prof.release(); c->d_ref.release(); c->d_rcref.release(); c->d_ref2.release(); c->d_bases.release(); c->d_off.release();
   c->d_rc.release(); c->d_status.release(); c->d_as.release(); c->d_ae.release(); c->d_score.release();
@@ -752,6 +754,36 @@ static int launch_bucket(miagpu_ctx* c, RealignParams p, int maxL) {
   p.scratch_words_per_warp = words;
   p.ref_in_smem = ref_in_smem;
   realign_kernel<K><<<blocks, WARPS_PER_BLOCK * 32, smem, c->launch_stream>>>(p);
+  MIAGPU_CUDA(cudaGetLastError());
+  c->launches++;
+  return 1;
+}
+
+// pass 1: the winning jobs whose path is not one plain diagonal, stretch by stretch with a trace (realign.cuh, JOB)
+template <int K>
+static int launch_p1_trace(miagpu_ctx* c, RealignParams p, int maxL) {
+  using TL = TraceLayout<K>;
+  const bool ref_in_smem = p.ref_bytes <= 160 * 1024;
+  const size_t smem = PROF_INTS * 4 + WARPS_PER_BLOCK * MAX_READ * 2 + (ref_in_smem ? p.ref_bytes : 0);
+  static size_t cached_smem_d[MAX_DEVICES];
+  static int cached_per_sm_d[MAX_DEVICES];
+  size_t& cached_smem = cached_smem_d[c->device % MAX_DEVICES];
+  int& cached_per_sm = cached_per_sm_d[c->device % MAX_DEVICES];
+  if (cached_smem != smem + 1) {
+    MIAGPU_CUDA(cudaFuncSetAttribute((realign_kernel<K, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MIAGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cached_per_sm, (realign_kernel<K, false, true>), WARPS_PER_BLOCK * 32, smem));
+    cached_smem = smem + 1;
+  }
+  if (cached_per_sm < 1) { set_error("realign_kernel<%d, JOB> does not fit on an SM (smem %zu)", K, smem); return 0; }
+  const int blocks = std::min(c->num_sms * std::min(cached_per_sm, 8), (p.n_list + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+  if (blocks < 1) return 1;
+  const int64_t words = (int64_t)std::max(maxL - 1, 1) * TL::ROW_WORDS;
+  DevBuf<uint32_t>& scratch = c->d_scratch[c->launch_slot];
+  if (!scratch.reserve((size_t)words * blocks * WARPS_PER_BLOCK)) return 0;
+  p.scratch = scratch.p;
+  p.scratch_words_per_warp = words;
+  p.ref_in_smem = ref_in_smem;
+  realign_kernel<K, false, true><<<blocks, WARPS_PER_BLOCK * 32, smem, c->launch_stream>>>(p);
   MIAGPU_CUDA(cudaGetLastError());
   c->launches++;
   return 1;
@@ -3082,7 +3114,7 @@ static int pass1_fast(miagpu_ctx* c, const PairLmax& lm) {
   if (!c->d_jread.reserve(nj + 1) || !c->d_jfirst.reserve(n + 1) || !c->d_jcount.reserve(n + 1)) return 0;
   if (!c->d_jkind.reserve(nj + 1) || !c->d_jstatus.reserve(nj + 1) || !c->d_route.reserve(n + 1) || !c->d_jws.reserve(nj + 1) ||
       !c->d_jwl.reserve(nj + 1) || !c->d_jscore.reserve(nj + 1) || !c->d_jabc.reserve(nj + 1) || !c->d_jaec.reserve(nj + 1) ||
-      !c->d_jabr.reserve(nj + 1) || !c->d_p1list.reserve(n + 1) || !c->d_p1meta.reserve(META_WORDS) ||
+      !c->d_jabr.reserve(nj + 1) || !c->d_p1list.reserve(n + 1) || !c->d_p1trace.reserve(n + 1) || !c->d_p1meta.reserve(META_WORDS) ||
       !c->d_jpairs.reserve(nj + 4 * P16_KEYS + 64)) return 0;
   cudaStream_t st = c->stream;
   int32_t* meta = c->d_p1meta.p;
@@ -3183,6 +3215,7 @@ static int pass1_fast(miagpu_ctx* c, const PairLmax& lm) {
   mp.score = c->d_score.p; mp.fw_score = c->d_fw.p; mp.rc_score = c->d_rcs.p; mp.as_out = c->d_as_out.p; mp.ae_out = c->d_ae_out.p;
   mp.start = c->d_start.p; mp.end = c->d_end.p; mp.abr = c->d_abr.p; mp.n_runs = c->d_nruns.p; mp.rc_out = c->d_rc_out.p;
   mp.runs = c->d_runs.p; mp.status = c->d_status.p;
+  mp.trace_list = getenv("MIAGPU_P1_NO_TRACE") ? nullptr : c->d_p1trace.p;
   p1_merge_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(mp);
   MIAGPU_CUDA(cudaGetLastError());
   MIAGPU_CUDA(cudaEventRecord(c->p1ev[2], st));
@@ -3192,6 +3225,38 @@ static int pass1_fast(miagpu_ctx* c, const PairLmax& lm) {
   MIAGPU_CUDA(cudaStreamSynchronize(st));
   const int n_general = c->h_meta[P1_NGENERAL];
   c->p1_general = n_general; c->p1_fast = c->h_meta[P1_NFAST]; c->p1_skipped = c->h_meta[P1_NSKIPPED];
+  c->p1_traced = c->h_meta[P1_NTRACE];
+  if (c->p1_traced) {
+    if (!ensure_max_read_len(c)) return 0;
+    const int maxL = std::min(std::max(c->max_read_len, 2), MAX_READ);
+    // gapped winners (reads with an indel against the reference, or a mismatch close to an end that a gap buys out): their stretch
+    // alone, 32-bit with a trace, three widths; every launch walks the whole list and takes its own widths
+    RealignParams p{};
+    p.bases = c->d_bases.p; p.off = c->d_off.p; p.rc = nullptr; p.win_start = c->d_jws.p; p.win_len = c->d_jwl.p;
+    p.list = c->d_p1trace.p; p.n_list = c->p1_traced; p.n_list_ptr = nullptr;
+    p.ref_codes = c->d_ref2.p; p.ref_bytes = 2 * c->ref_bytes; p.prof = c->d_prof.p; p.sg5 = 1;
+    p.score = c->d_score.p; p.as_out = c->d_as_out.p; p.ae_out = c->d_ae_out.p; p.abr = c->d_abr.p; p.n_runs = c->d_nruns.p;
+    p.runs = c->d_runs.p; p.status = c->d_status.p; p.start = c->d_start.p; p.end = c->d_end.p;
+    p.job_read = c->d_jread.p; p.strand_stride = c->ref_bytes; p.seq_len = c->seq_len;
+    cudaStream_t lanes3[3] = {c->s_aux[2], c->s_aux[3], st};
+    MIAGPU_CUDA(cudaEventRecord(c->aev[2], st));
+    int ok = 1;
+    for (int t = 0; t < 3 && ok; t++) {
+      c->launch_stream = lanes3[t];
+      c->launch_slot = 1 + t;                          // scratch 0 may still serve the general kernel's first launch
+      if (lanes3[t] != st) MIAGPU_CUDA(cudaStreamWaitEvent(lanes3[t], c->aev[2], 0));
+      p.counter = meta + P1_TWORK + t;
+      p.job_wl_lo = t == 0 ? 0 : t == 1 ? 64 : 128;
+      p.job_wl_hi = t == 0 ? 64 : t == 1 ? 128 : 256;
+      ok = t == 0 ? launch_p1_trace<2>(c, p, maxL) : t == 1 ? launch_p1_trace<4>(c, p, maxL) : launch_p1_trace<8>(c, p, maxL);
+    }
+    c->launch_stream = st; c->launch_slot = 0;
+    if (!ok) return 0;
+    for (int i = 2; i < 4; i++) {
+      MIAGPU_CUDA(cudaEventRecord(c->aev[1 + i], c->s_aux[i]));
+      MIAGPU_CUDA(cudaStreamWaitEvent(st, c->aev[1 + i], 0));
+    }
+  }
   if (n_general0) MIAGPU_CUDA(cudaStreamWaitEvent(st, c->aev[1], 0));      // the two general launches share their scratch
   if (n_general > n_general0 &&
       !launch_strip(c, 0, c->d_p1list.p + n_general0, n_general - n_general0, meta + P1_WORK2, 0, nullptr)) return 0;

@@ -39,6 +39,8 @@ constexpr int P1_WORK = META_P1 + 3;      // work-fetch counter of the general k
 constexpr int P1_WORK2 = META_P1 + 5;       // work-fetch counter of the general kernel's second launch (reads the merge handed over)
 constexpr int P1_NJOBS = META_P1 + 4;       // jobs allocated (may exceed the capacity: reads that did not fit go to the general kernel)
 constexpr int P1_EFF = META_P1 + 6;         // [2] int64: effective DP cells = sum over strands of L x unmasked columns
+constexpr int P1_NTRACE = META_COUNT;       // winning jobs whose path is not one plain diagonal: traced by realign_kernel<K, false, true> (list fill counter)
+constexpr int P1_TWORK = META_WORK;         // [3] work-fetch counters of those launches (the pass-1 meta block has no 32-bit work lists of its own)
 constexpr int P1_JPS = 12;           // stretches per strand that become jobs
 constexpr int P1_MAXD = 128;         // diagonals kept per strand: KMER_SATURATE hits unmask the whole strand anyway
 
@@ -282,6 +284,7 @@ struct P1MergeParams {
   const uint8_t* jkind; const uint8_t* jstatus;
   const int32_t* jscore; const int32_t* jabc; const int32_t* jaec; const int32_t* jabr;
   int32_t* general_list;
+  int32_t* trace_list;           // nullable (whole-strand jobs of sweep16.cuh: no window to trace in); else the winning jobs the 32-bit JOB kernels trace
   int32_t* meta;
   int32_t *score, *fw_score, *rc_score, *as_out, *ae_out, *start, *end, *abr, *n_runs;
   uint8_t* rc_out;
@@ -304,7 +307,17 @@ __global__ void p1_merge_kernel(P1MergeParams p) {
     }
   const int s = !(best[0] > best[1]) ? 1 : 0;       // forward only if strictly better (mia.c:1549-1554)
   const int64_t j = bj[s];
-  if (j < 0 || sunk || p.jstatus[j] != MIAGPU_ST_OK) {      // the winner's path is not one plain diagonal: the general kernel traces it
+  if (j >= 0 && !sunk && p.jstatus[j] == P16_ST_GENERAL && p.trace_list) {
+    // every job's score is exact, so the winner is known; only its path is not: the 32-bit kernel runs the winner's stretch with a trace
+    p.trace_list[atomicAdd(p.meta + P1_NTRACE, 1)] = (int32_t)j;
+    atomicAdd(p.meta + P1_NFAST, 1);
+    p.route[rd] = 4;
+    p.rc_out[rd] = (uint8_t)s;
+    p.fw_score[rd] = best[0]; p.rc_score[rd] = best[1];
+    p.score[rd] = best[s];
+    return;
+  }
+  if (j < 0 || sunk || p.jstatus[j] != MIAGPU_ST_OK) {      // a sunk job, or no window to trace in: the general kernel computes the read
     p.general_list[atomicAdd(p.meta + P1_NGENERAL, 1)] = (int32_t)rd;
     p.route[rd] = 3;
     return;

@@ -65,6 +65,15 @@ struct RealignParams {
   int32_t shared_rows;
   int32_t* aer_out;
   unsigned long long* cells_done;   // nullable: DP cells of the reads this launch computed (measurement)
+  // JOB (pass 1 with the k-mer filter, pass1.cuh): a work item names a JOB -- the read job_read[job] & 0x7fffffff against one stretch
+  // of unmasked columns of the strand bit 31 names (win_start / win_len indexed by job, in the two-strand code array) -- whose 16-bit
+  // run found a winning path that is not one plain diagonal.  Forward matrix on both strands (H5); a stretch that does not begin at
+  // the strand's column 0 starts a new alignment in its first column (pair16.cuh, JOB).  Outputs are sg_align's (mia.c:1568-1610),
+  // per read.  An instantiation takes the jobs with job_wl_lo < win_len <= job_wl_hi and leaves the others to its siblings.
+  const int32_t* job_read;
+  int32_t strand_stride, job_wl_lo, job_wl_hi, seq_len;
+  int32_t* start;
+  int32_t* end;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -118,8 +127,9 @@ struct TraceLayout {
 constexpr int WARPS_PER_BLOCK = 4;
 
 // dynamic shared memory: [prof PROF_INTS ints][rowoff WARPS*256 u16][ref codes]
-template <int K, bool TRIM = false>
+template <int K, bool TRIM = false, bool JOB = false>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) realign_kernel(RealignParams p) {
+  static_assert(!(TRIM && JOB), "one mode at a time");
   static_assert(K >= 2 && K <= 16, "columns per lane");
   using TL = TraceLayout<K>;
   extern __shared__ __align__(16) uint8_t smem[];
@@ -177,12 +187,17 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) realign_kernel(RealignPa
     if (lane == 0) item = atomicAdd(p.counter, 1);
     item = __shfl_sync(0xffffffffu, item, 0);
     if (item >= n_list) break;
-    const int rd = TRIM ? item : p.list[item];
+    const int job = JOB ? p.list[item] : 0;
+    const int jr = JOB ? p.job_read[job] : 0;
+    const int rd = JOB ? (jr & 0x7fffffff) : TRIM ? item : p.list[item];
+    const int ws = p.win_start[JOB ? job : rd];
+    const int len1 = p.win_len[JOB ? job : rd];
+    if (JOB && !(len1 > p.job_wl_lo && len1 <= p.job_wl_hi)) continue;       // a sibling instantiation's job (warp-uniform)
     const int64_t o0 = TRIM ? 0 : p.off[rd];
     const int L = TRIM ? p.shared_rows : (int)(p.off[rd + 1] - o0);
-    const int ws = p.win_start[rd];
-    const int len1 = p.win_len[rd];
-    const int strand = TRIM ? 0 : (p.rc[rd] ? 1 : 0);
+    const int strand = (TRIM || JOB) ? 0 : (p.rc[rd] ? 1 : 0);
+    const int jlo = JOB ? ws - (jr < 0 ? p.strand_stride : 0) : 0;            // the stretch's first column in strand coordinates
+    const bool masked_left = JOB && jlo > 0;
     // TRIM: the lane / register that hold the last column, its running first maximum over the rows
     const int lcl = TRIM ? (len1 - 1) / K : 0, lcj = TRIM ? (len1 - 1) - lcl * K : 0;
     int lc_best = INT_MIN, lc_row = 0;
@@ -236,6 +251,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) realign_kernel(RealignPa
 #pragma unroll
       for (int j = 2; j < K; j++) cand[j] = Sp[j - 2] + candP[j - 2];
       int D = lane ? l1 : NdKey;         // column 0: S = sub + N, trace 0 (mia.c:805-822)
+      if (JOB && masked_left && lane == 0) D = NEG_KEY;     // masked left neighbour: nothing to continue, the cell starts new (S = N)
 
       // lane total, then exclusive warp max-scan = best_gap_col state entering this lane
       int t = cand[0];
@@ -353,13 +369,34 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) realign_kernel(RealignPa
           uint16_t x = my_runs[a]; my_runs[a] = my_runs[b]; my_runs[b] = x;
         }
       if (p.cells_done) atomicAdd(p.cells_done, (unsigned long long)L * (unsigned long long)len1);
-      p.score[rd] = score;
-      p.as_out[rd] = TRIM ? col : col + ws;       // mia_main.c:250-255
-      p.ae_out[rd] = TRIM ? aec : aec + ws;
-      p.abr[rd] = row;
-      if (TRIM) p.aer_out[rd] = aer;
-      if (p.n_runs) p.n_runs[rd] = nrun;
-      p.status[rd] = st;
+      if (JOB) {
+        // sg_align's coordinates (mia.c:1568-1610); runs go out in forward-reference orientation (strip.cuh does the same)
+        const int s = jr < 0 ? 1 : 0;
+        const int abc = col + jlo, aes = aec + jlo;
+        int start = abc, end = aes;
+        if (s == 1) {                                        // c2rcc, mia.c:26-30; revcom_PWAF reverses the columns
+          start = p.seq_len - (aes % p.seq_len) - 1;
+          end = p.seq_len - (abc % p.seq_len) - 1;
+          if (my_runs && nrun > 0)
+            for (int a = 0, b = nrun - 1; a < b; a++, b--) { uint16_t x = my_runs[a]; my_runs[a] = my_runs[b]; my_runs[b] = x; }   // undo the reversal above
+        }
+        int as = start, ae = end;
+        if (as > ae) ae = p.seq_len + as;                    // mia.c:1600-1604
+        if (end > p.seq_len) end -= p.seq_len;               // mia.c:1606-1610
+        if (score != p.score[rd]) st |= MIAGPU_ST_UNSUPPORTED;   // the 16-bit job's score is exact: anything else is a bug, not a result
+        p.as_out[rd] = as; p.ae_out[rd] = ae; p.start[rd] = start; p.end[rd] = end;
+        p.abr[rd] = s == 1 ? 0 : row;
+        p.n_runs[rd] = nrun;
+        p.status[rd] = st;
+      } else {
+        p.score[rd] = score;
+        p.as_out[rd] = TRIM ? col : col + ws;       // mia_main.c:250-255
+        p.ae_out[rd] = TRIM ? aec : aec + ws;
+        p.abr[rd] = row;
+        if (TRIM) p.aer_out[rd] = aer;
+        if (p.n_runs) p.n_runs[rd] = nrun;
+        p.status[rd] = st;
+      }
     }
   }
 }

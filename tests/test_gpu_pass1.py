@@ -67,7 +67,36 @@ def test_pass1_fast_path_linear_short_k(gpu, oracle):
     bad, out = gpu_checks.check_pass1(gpu, oracle, ref, reads, gpu_checks.load_pssm("ancient"), 0, 10)
     assert not bad, f"{len(bad)} reads differ; first {bad[0]}"
     fast, general, skipped = gpu.last_pass1_stats()
-    assert fast > 500 and general > 0, (fast, general, skipped)
+    route = gpu.last_pass1_route()
+    # 3 % divergence + indels: gapped winners; their stretches are traced by the windowed 32-bit kernel (route 4), not the general one
+    assert fast > 500 and int((route == 4).sum()) > 50, (fast, general, skipped, np.bincount(route).tolist())
+
+
+def test_pass1_traced_winners_equal_general_kernel(gpu, monkeypatch):
+    # size-independent property: gapped winners traced in their own stretch (realign_kernel<K, false, true>) come out exactly as the
+    # general chunked kernel computes them over the whole masked strands
+    import _pkg
+    _pkg.load()
+    from mia_b200 import synth
+    ref = synth.random_reference(16569, seed=1)
+    g = synth.diverge(ref, 0.08, seed=2, indel_rate=0.006)
+    b, off, _ = synth.make_reads(g, 40000, 30, 140, seed=78)
+    gpu.set_pssm(gpu_checks.load_pssm("ancient"))
+    gpu.set_reference(ref, circular=1, with_rc=1)
+    gpu.build_kmers(10)
+    gpu.upload_reads(b, off)
+    a = gpu.pass1()
+    route = gpu.last_pass1_route()
+    assert int((route == 4).sum()) > 4000, np.bincount(route).tolist()
+    assert not (a["status"][route == 4] != 0).any()
+    monkeypatch.setenv("MIAGPU_P1_NO_TRACE", "1")
+    z = gpu.pass1()
+    assert int((gpu.last_pass1_route() == 4).sum()) == 0
+    for k in ("hits", "score", "fw_score", "rc_score", "rc", "as_", "ae", "start", "end", "abr", "n_runs", "status"):
+        assert (a[k] == z[k]).all(), (k, int((a[k] != z[k]).sum()), np.flatnonzero(a[k] != z[k])[:5].tolist())
+    nr = np.maximum(a["n_runs"], 0)
+    m = np.arange(a["runs"].shape[1])[None, :] < nr[:, None]
+    assert (np.where(m, a["runs"], 0) == np.where(m, z["runs"], 0)).all()
 
 
 def test_pass1_fast_equals_general_large(gpu, monkeypatch):
