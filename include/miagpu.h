@@ -123,6 +123,16 @@ int miagpu_last_pass1_stats( miagpu_ctx* ctx, int64_t* fast_reads,
  * columns new_kmer_filter unmasks, summed over both strands (a strand with >= 128 hits, or with more than 12 separate stretches,
  * counts whole); equal without the filter */
 int miagpu_last_pass1_cells( miagpu_ctx* ctx, int64_t* nominal, int64_t* effective );
+/* ---- f4. mia -h (hp_special, mia_main.c:424, 497; init_alignment( ..., hp_special ) mia.c:988-1028): from now on
+ * dyn_prog's two homopolymer-discounted gap candidates (mia.c:882-905, hp_discount_penalty mia.c:1096-1134,
+ * pop_hpl_and_hps mia.c:1193-1234) take part in every alignment of this context: pass 1 (homopolymers of the whole
+ * strands, mia_main.c:735-739), the rounds (of the read's window, mia_main.c:221-224), the -D attempts
+ * (mia_main.c:132-134, 158-160).  They all run in the chunked 32-bit kernel; the 16-bit kernels do not carry the
+ * candidates.  The reads' raw bytes are compared with the reference's bases (mia.c:886): the reference may hold
+ * A C G T N only (anything else is refused at the first alignment).  miagpu_trim and miagpu_align_windows with
+ * sg5 = 0 refuse a context in this mode. */
+int miagpu_set_homopolymer( miagpu_ctx* ctx, int on );
+
 /* per read of the last miagpu_pass1: 0 no k-mer hit, 1 finished by the pair kernels, 2 general kernel
  * (decided while seeding), 3 general kernel (a job of the read left the 16-bit frame), 4 pair kernels for the scores +
  * the windowed 32-bit kernel for the winning stretch's trace (the winner's path was not a plain diagonal; counted with 1

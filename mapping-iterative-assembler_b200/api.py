@@ -52,6 +52,7 @@ def load_library():
     L.miagpu_upload_reads.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     L.miagpu_pass1.argtypes = [C.c_void_p] + [C.c_void_p] * 13
     L.miagpu_last_pass1_stats.argtypes = [C.c_void_p, _i64p, _i64p, _i64p]
+    L.miagpu_set_homopolymer.argtypes = [C.c_void_p, C.c_int]
     L.miagpu_last_pass1_route.argtypes = [C.c_void_p, C.c_void_p]
     L.miagpu_last_pass1_cells.argtypes = [C.c_void_p, _i64p, _i64p]
     L.miagpu_compact_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, _i64p]
@@ -122,7 +123,7 @@ EXPORTS = ["miagpu_device_count", "miagpu_create", "miagpu_destroy", "miagpu_las
            "miagpu_last_cut_stats", "miagpu_repeat_filter", "miagpu_trim", "miagpu_get_alignment",
            "miagpu_fastx_open", "miagpu_fastx_open_memory", "miagpu_fastx_format", "miagpu_fastx_next", "miagpu_fastx_batch", "miagpu_fastx_close",
            "miagpu_maln_ref_size", "miagpu_write_maln", "miagpu_read_pssm", "miagpu_align_windows",
-           "miagpu_set_fsdb", "miagpu_get_fsdb", "miagpu_last_fsdb_stats", "miagpu_distant_retry", "miagpu_write_maln_fsdb", "miagpu_last_pass1_cells"]
+           "miagpu_set_fsdb", "miagpu_get_fsdb", "miagpu_last_fsdb_stats", "miagpu_distant_retry", "miagpu_write_maln_fsdb", "miagpu_last_pass1_cells", "miagpu_set_homopolymer"]
 
 
 def _ptr(a):
@@ -196,6 +197,10 @@ class MiaGpu:
         self._ck(self.lib.miagpu_pass1(self.h, *[_ptr(o[k]) for k in ("hits", "score", "fw_score", "rc_score", "rc", "as_", "ae",
                                                                      "start", "end", "abr", "n_runs", "runs", "status")]))
         return {k: v for k, v in o.items() if v is not None}
+
+    def set_homopolymer(self, on=True):
+        """mia -h: the homopolymer-discounted gap candidates in every alignment of this context"""
+        self._ck(self.lib.miagpu_set_homopolymer(self.h, int(bool(on))))
 
     def last_pass1_stats(self):
         """(reads finished by the windowed pair kernels, reads the general kernel took, reads without a k-mer hit)"""

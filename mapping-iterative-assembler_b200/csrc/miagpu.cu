@@ -110,6 +110,10 @@ struct miagpu_ctx {
   DevBuf<uint32_t> d_scratch[4];               // trace scratch of the 32-bit kernels, one per launch stream
   DevBuf<int32_t> d_p1trace;                   // pass 1: winning jobs the 32-bit JOB kernels trace
   int p1_traced = 0;
+  // mia -h (miagpu_set_homopolymer): every DP runs in the chunked kernel with the two homopolymer-discounted gap candidates
+  bool hp = false, hps_valid = false;
+  DevBuf<int32_t> d_hps[2];                    // start of the homopolymer of every (wrapped) strand column
+  DevBuf<int32_t> d_ckh;                       // one more checkpoint value per row and processed chunk (strip.cuh)
   cudaStream_t s_aux[4] = {};                  // [0] = stream; [1..3] side streams of the concurrent DP launches
   cudaEvent_t aev[8] = {};                     // fork / join events of those
   cudaStream_t launch_stream = nullptr;        // where launch_bucket / launch_pair16 / launch_strip put their kernel
@@ -434,7 +438,44 @@ extern "C" int miagpu_set_reference(miagpu_ctx* c, const char* seq, int seq_len,
     MIAGPU_CUDA(cudaStreamSynchronize(c->stream));
   }
   c->have_ref = true;
+  c->hps_valid = false;
   if (c->fs_on && c->fs_distant && !fs_upload_nprefix(c)) return 0;
+  return 1;
+}
+
+// mia -h: hp_special (mia_main.c:424, 497).  From now on dyn_prog's two homopolymer-discounted gap candidates (mia.c:882-905) take part
+// in every alignment of this context: pass 1 (homopolymers of the whole strands, mia_main.c:735-739), the rounds (of the read's window,
+// mia_main.c:221-224), the -D attempts (mia_main.c:132-134, 158-160).  All of them run in the chunked 32-bit kernel (strip.cuh); the
+// 16-bit kernels do not carry the candidates.  miagpu_trim and explicit windows with sg5 = 0 refuse a context in this mode.
+extern "C" int miagpu_set_homopolymer(miagpu_ctx* c, int on) {
+  if (!c) { set_error("miagpu_set_homopolymer: no context"); return 0; }
+  c->hp = on != 0;
+  return 1;
+}
+
+// pop_hpl_and_hps (mia.c:1193-1234) over the upper-cased wrapped strands: only the starts are needed (hp_discount_penalty ignores
+// the column homopolymer's length).  The kernel compares the read's raw byte with the reference base it knows as a code 0..4, so a
+// reference with other letters than A C G T N cannot be served exactly and is refused.
+static int ensure_hps(miagpu_ctx* c) {
+  if (c->hps_valid) return 1;
+  const int len1 = c->wrap_len;
+  std::vector<int32_t> h(len1);
+  for (int s = 0; s < (c->with_rc ? 2 : 1); s++) {
+    const std::string& t = s ? c->raw_rc_wrapped : c->raw_wrapped;
+    int start = 0;
+    for (int i = 0; i < len1; i++) {
+      const char b = (char)toupper((unsigned char)t[i]);
+      if (b != 'A' && b != 'C' && b != 'G' && b != 'T' && b != 'N') {
+        set_error("homopolymer mode: reference base '%c' at %d: only A C G T N can be compared with the reads on the device", t[i], i);
+        return 0;
+      }
+      if (i > 0 && b != (char)toupper((unsigned char)t[i - 1])) start = i;
+      h[i] = start;
+    }
+    if (!c->d_hps[s].reserve(len1 + 1)) return 0;
+    MIAGPU_CUDA(cudaMemcpy(c->d_hps[s].p, h.data(), (size_t)len1 * 4, cudaMemcpyHostToDevice));
+  }
+  c->hps_valid = true;
   return 1;
 }
 
@@ -680,19 +721,23 @@ static int launch_strip(miagpu_ctx* c, int mode, const int32_t* list, int n_list
   // few reads: a team of warps per read (strip_team_kernel), else a warp per read
   bool team = total <= (int64_t)2 * c->num_sms * 4;
   if (const char* e = getenv("MIAGPU_STRIP_TEAM")) team = atoi(e) != 0;
+  const bool hp = c->hp;
+  if (hp) { team = false; if (!ensure_hps(c)) return 0; }          // the team schedule does not carry the homopolymer checkpoints
   const size_t smem = team ? PROF_INTS * 4 + MAX_READ * 2 + (size_t)((n_chunks + 3) & ~3) * 4 + (size_t)2 * TEAM_WARPS * Lmax * 16
-                           : PROF_INTS * 4 + WARPS_PER_BLOCK * MAX_READ * 2;
+                           : PROF_INTS * 4 + WARPS_PER_BLOCK * MAX_READ * 2 + (hp ? WARPS_PER_BLOCK * STRIP_HP_SMEM_PER_WARP : 0);
   if (team && smem > 200 * 1024) team = false;
   int per_sm = 0;
   if (team) {
     if (smem > 40 * 1024) MIAGPU_CUDA(cudaFuncSetAttribute(strip_team_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // + static
     MIAGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, strip_team_kernel, TEAM_WARPS * 32, smem));
+  } else if (hp) {
+    MIAGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, strip_kernel<true>, WARPS_PER_BLOCK * 32, smem));
   } else {
-    MIAGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, strip_kernel, WARPS_PER_BLOCK * 32, smem));
+    MIAGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, strip_kernel<false>, WARPS_PER_BLOCK * 32, smem));
   }
   if (per_sm < 1) { set_error("strip_kernel does not fit on an SM (team %d, %zu bytes of shared memory, Lmax %d, %d chunks)", (int)team, smem, Lmax, n_chunks); return 0; }
   // per-warp (per-team) scratch: keep the total under ~6 GB
-  const size_t per_warp = (size_t)2 * mask_words * 4 + (size_t)2 * (n_chunks + 1) * Lmax * 16 + (size_t)2 * n_chunks * 4 + (size_t)Lmax * CW * 4;
+  const size_t per_warp = (size_t)2 * mask_words * 4 + (size_t)2 * (n_chunks + 1) * Lmax * (hp ? 20 : 16) + (size_t)2 * n_chunks * 4 + (size_t)Lmax * CW * 4;
   const int units_per_block = team ? 1 : WARPS_PER_BLOCK;
   per_sm = std::min(per_sm, 4);
   while (per_sm > 1 && per_warp * c->num_sms * per_sm * units_per_block > ((size_t)6 << 30)) per_sm--;
@@ -700,6 +745,7 @@ static int launch_strip(miagpu_ctx* c, int mode, const int32_t* list, int n_list
   const size_t warps = (size_t)blocks * units_per_block;
   if (!c->d_smask.reserve(warps * 2 * mask_words) || !c->d_ckpt.reserve(warps * 2 * (n_chunks + 1) * Lmax) ||
       !c->d_chunk_ids.reserve(warps * 2 * n_chunks) || !c->d_strace.reserve(warps * Lmax * CW)) return 0;
+  if (hp && !c->d_ckh.reserve(warps * 2 * (n_chunks + 1) * Lmax)) return 0;
   StripParams p{};
   p.bases = c->d_bases.p; p.off = c->d_off.p; p.n = c->n; p.counter = counter; p.mode = mode;
   p.list = list; p.n_list = n_list; p.n_list_ptr = n_list_ptr; p.rc_in = c->d_rc.p;
@@ -712,12 +758,15 @@ static int launch_strip(miagpu_ctx* c, int mode, const int32_t* list, int n_list
   p.hits = mode == 0 ? c->d_hits.p : nullptr; p.score = c->d_score.p; p.fw_score = c->d_fw.p; p.rc_score = c->d_rcs.p;
   p.as_out = c->d_as_out.p; p.ae_out = c->d_ae_out.p; p.start = c->d_start.p; p.end = c->d_end.p; p.abr = c->d_abr.p;
   p.n_runs = c->d_nruns.p; p.rc_out = c->d_rc_out.p; p.runs = c->d_runs.p; p.status = c->d_status.p;
-  if (mode == 1 && lo) {                       // a chunk of the batch: list entries count from read `lo`
+  p.win_start = c->d_win_start.p; p.win_len = c->d_win_len.p;
+  p.hps[0] = c->d_hps[0].p; p.hps[1] = c->with_rc ? c->d_hps[1].p : c->d_hps[0].p; p.ckh = c->d_ckh.p;
+  if (mode >= 1 && lo) {                       // a chunk of the batch: list entries count from read `lo`
     p.off += lo; p.rc_in += lo; p.score += lo; p.as_out += lo; p.ae_out += lo; p.abr += lo; p.n_runs += lo;
-    p.runs += lo * MAX_RUNS; p.status += lo;
+    p.runs += lo * MAX_RUNS; p.status += lo; p.win_start += lo; p.win_len += lo;
   }
   if (team) strip_team_kernel<<<blocks, TEAM_WARPS * 32, smem, c->launch_stream>>>(p);
-  else strip_kernel<<<blocks, WARPS_PER_BLOCK * 32, smem, c->launch_stream>>>(p);
+  else if (hp) strip_kernel<true><<<blocks, WARPS_PER_BLOCK * 32, smem, c->launch_stream>>>(p);
+  else strip_kernel<false><<<blocks, WARPS_PER_BLOCK * 32, smem, c->launch_stream>>>(p);
   MIAGPU_CUDA(cudaGetLastError());
   c->launches++;
   return 1;
@@ -893,7 +942,8 @@ static void realign_reset_stats(miagpu_ctx* c) {
 // window rule + width classes + pair layout of one job on stream st; the meta block is copied to j.h_meta
 static int realign_classify(miagpu_ctx* c, const RealignJob& j, cudaStream_t st) {
   if (j.n == 0) return 1;
-  const PairLmax lm = pair_lmax(c);
+  PairLmax lm = pair_lmax(c);
+  if (c->hp) for (int kb = 0; kb < P16_NKB; kb++) lm.v[kb] = 0;      // mia -h: no read is pair-eligible
   MIAGPU_CUDA(cudaMemsetAsync(j.d_meta, 0, META_WORDS * sizeof(int32_t), st));
   classify_kernel<<<(unsigned)((j.n + 255) / 256), 256, 0, st>>>(j.n, c->d_off.p + j.lo, c->d_as.p + j.lo, c->d_ae.p + j.lo, c->wrap_len, lm,
                                                                 c->d_win_start.p + j.lo, c->d_win_len.p + j.lo, j.d_lists, c->d_kind.p + j.lo, j.d_meta,
@@ -916,7 +966,7 @@ static int realign_launch(miagpu_ctx* c, const RealignJob& j) {
   const int32_t* meta = j.h_meta;
   const PairNp npk = realign_np();
   const PairLmax lm_low = pair_lmax_low(c);
-  const bool concurrent = !j.timed && !getenv("MIAGPU_SERIAL_LAUNCH");
+  const bool concurrent = !j.timed && !getenv("MIAGPU_SERIAL_LAUNCH") && !c->hp;     // the chunked kernel's launches share their scratch
   int rr = 0;
   int64_t cells[NBUCKET], pcells[P16_NKB];
   memcpy(cells, meta + META_CELLS, sizeof(cells));
@@ -1006,6 +1056,14 @@ static int realign_launch(miagpu_ctx* c, const RealignJob& j) {
     p.n_runs = c->d_nruns.p + lo; p.runs = c->d_runs.p + lo * MAX_RUNS; p.status = c->d_status.p + lo;
     p.cells_done = j.timed ? reinterpret_cast<unsigned long long*>(j.d_meta + META_CELLS32) + b : nullptr;
     int ok = 1, maxL = meta[META_MAXL + b];
+    if (c->hp) {                                      // mia -h: the chunked kernel, the read's window as the matrix (the widest class: the whole reference)
+      if (c->explicit_windows && !c->explicit_sg5) { set_error("homopolymer mode: explicit windows need sg5 = 1"); return 0; }
+      ok = launch_strip(c, 2, p.list, meta[META_COUNT + b], j.d_meta + META_WORK + b, lo);
+      if (!ok) return 0;
+      if (j.timed) MIAGPU_CUDA(cudaEventRecord(c->bev[2 * b + 1], c->stream));
+      if (j.timed) c->bucket_reads[b] = -1;
+      continue;
+    }
     switch (BUCKET_K[b]) {
       case 2: ok = launch_bucket<2>(c, p, maxL); break;
       case 4: ok = launch_bucket<4>(c, p, maxL); break;
@@ -1017,7 +1075,7 @@ static int realign_launch(miagpu_ctx* c, const RealignJob& j) {
       case 12: ok = launch_bucket<12>(c, p, maxL); break;
       case 16: ok = launch_bucket<16>(c, p, maxL); break;
       default:
-        ok = launch_strip(c, 1, p.list, meta[META_COUNT + b], j.d_meta + META_WORK + b, lo);   // too wide for either kernel: never pair-eligible
+        ok = launch_strip(c, 2, p.list, meta[META_COUNT + b], j.d_meta + META_WORK + b, lo);   // too wide for either kernel (its window, or the whole reference, as the matrix): never pair-eligible
     }
     if (!ok) return 0;
     if (j.timed) MIAGPU_CUDA(cudaEventRecord(c->bev[2 * b + 1], c->stream));
@@ -2075,6 +2133,7 @@ extern "C" int miagpu_distant_retry(miagpu_ctx* c, int64_t* n_tried, int64_t* n_
   miagpu_ctx* x = c->aux;
   if (!miagpu_set_pssm(x, c->sm_f)) return 0;
   if (!miagpu_set_reference(x, c->raw_wrapped.c_str(), c->seq_len, c->circular, 0)) return 0;
+  x->hp = c->hp;                                     // mia_main.c:132-134, 158-160
   // the scratch batch: three items per read (fs_retry_reads_kernel)
   std::vector<int64_t> off_new((size_t)3 * m + 1, 0);
   for (int64_t q = 0; q < 3 * m; q++) off_new[q + 1] = off_new[q] + c->h_seqlen[U[q / 3]];
@@ -2904,6 +2963,7 @@ extern "C" int miagpu_trim(miagpu_ctx* c, int64_t n, const uint8_t* bases, const
     return 0;
   }
   if (n == 0) return 1;
+  if (c->hp) { set_error("miagpu_trim: adapter trimming with the homopolymer discount (mia -T -h) is not built"); return 0; }
   if (n > 0x7fffffffLL || offsets[n] > 0x7fffffffLL) { set_error("miagpu_trim: batch too large"); return 0; }
   MIAGPU_CUDA(cudaSetDevice(c->device));
   cudaStream_t st = c->stream;
@@ -3356,9 +3416,9 @@ extern "C" int miagpu_pass1(miagpu_ctx* c, int32_t* hits, int32_t* score, int32_
   MIAGPU_CUDA(cudaMemsetAsync(c->d_meta.p, 0, 128 * sizeof(int32_t), c->stream));
   MIAGPU_CUDA(cudaEventRecord(c->ev[1], c->stream));
   const PairLmax lm = c->kmer_k > 0 ? pair_lmax(c, true) : pair_lmax_low(c);      // (the whole-strand sweep has no RB frame)
-  bool fast = c->kmer_k > 0 && lm.v[0] > 0 && n > 0;
+  bool fast = c->kmer_k > 0 && lm.v[0] > 0 && n > 0 && !c->hp;             // mia -h: the chunked kernel only
   if (const char* e = getenv("MIAGPU_PASS1_FAST")) fast = fast && atoi(e) != 0;
-  bool sweep = c->kmer_k <= 0 && lm.v[SW_CLASS] > 0 && n > 0;
+  bool sweep = c->kmer_k <= 0 && lm.v[SW_CLASS] > 0 && n > 0 && !c->hp;
   if (const char* e = getenv("MIAGPU_PASS1_FAST")) sweep = sweep && atoi(e) != 0;
   c->p1_fast = c->p1_general = c->p1_skipped = 0;
   c->p1ev_valid = fast || sweep;

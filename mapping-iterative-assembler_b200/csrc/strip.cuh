@@ -40,8 +40,15 @@ struct StripParams {
   int64_t n;
   int32_t* counter;
   // mode 0: pass 1 (both strands, forward matrix, k-mer masks).  mode 1: single strand, unmasked,
-  // explicit work list + per-read strand matrix (wide realign)
+  // explicit work list + per-read strand matrix (wide realign).  mode 2: like 1, but the matrix columns are the read's own
+  // window [win_start, win_start + win_len) of the forward strand (the rounds of mia -h, which only this kernel computes)
   int32_t mode;
+  const int32_t* win_start;
+  const int32_t* win_len;
+  // mia -h (strip_kernel<true>): start of the homopolymer every strand column belongs to (pop_hpl_and_hps over the whole wrapped
+  // strand, mia_main.c:735-739; a window clips it, mia_main.c:221-224), and one more checkpoint value per row and processed chunk
+  const int32_t* hps[2];
+  int32_t* ckh;                       // [warp][2][(max_chunks+1)][Lmax]
   const int32_t* list;
   int32_t n_list;
   const int32_t* n_list_ptr;          // nullable: the list's length on the device (mode 0 with a list)
@@ -67,6 +74,34 @@ struct StripParams {
   uint8_t* status;
 };
 
+// mia -h.  The two extra candidates of a cell (mia.c:882-905) need, beyond what a row-parallel sweep holds anyway:
+//   column candidate (rows where a read homopolymer starts): S[r-1][hs-1], hs = start of the column's reference homopolymer --
+//       any earlier column: the chunk's previous row is kept in shared memory (srow); for the homopolymer that crosses the chunk's
+//       left edge the value comes from the previous processed chunk, which recorded that one column for every row (ckh);
+//   row candidate (rows inside a read homopolymer that started at row rs): S[rs-1][c-1] -- a snapshot of row rs-1 taken when the
+//       homopolymer starts (registers HS), shifted by one column.
+// hp_discount_penalty(gap_len, ., hprl) = GEP * gap_len + trunc(GOP * f(hprl)) (mia.c:1096-1134; the row candidate passes the
+// COLUMN distance, which is 0 there).
+struct HpRow {
+  const uint8_t* rch;                 // per row: the read's raw byte as 0..4 (exactly 'A','C','G','T','N') times 4, 28 for anything else
+  const uint16_t* hprs;               // per row: first row of its homopolymer (raw bytes compared, mia.c:1193-1234)
+  const int32_t* hpg;                 // per row: trunc(GOP * f(length of its homopolymer))
+  int32_t* srow;                      // CW ints of the warp: the chunk's previous row
+};
+struct HpChunk {
+  HpRow row;
+  const int32_t* hps;                 // indexed by matrix column (already offset by the window start), absolute strand columns
+  int32_t clip;                       // absolute strand column of matrix column 0
+  const int32_t* ckh_in;              // per row: S[row][hs(c0) - 1], valid when in_valid
+  int32_t* ckh_out;                   // per row: S[row][hs(c0 + CW) - 1] for the next processed chunk (nullable)
+  bool in_valid;
+};
+__device__ __forceinline__ int hp_gop_part(int len) {      // trunc(GOP * f): 1000 x {1, .5, .33, .25, .2, .17, .14, .13, .11, .10}, exact in double
+  return len <= 1 ? GOP : len == 2 ? 500 : len == 3 ? 330 : len == 4 ? 250 : len == 5 ? 200 : len == 6 ? 170 : len == 7 ? 140 : len == 8 ? 130
+       : len == 9 ? 110 : 100;
+}
+static_assert(GOP == 1000, "hp_gop_part spells out trunc(GOP * f) for GOP = 1000");
+
 struct PV { int v, i; };
 __device__ __forceinline__ PV pv_better(PV a, PV b) { return (b.v > a.v) ? b : a; }   // strict '>' keeps the earlier
 
@@ -77,13 +112,38 @@ __device__ __forceinline__ PV pv_better(PV a, PV b) { return (b.v > a.v) ? b : a
 // ahead: row r waits until *flag_prev > r (that warp has written its row r candidate state and its row r-1 scores) and
 // announces its own progress through *flag_mine.  The hand-over goes through shared memory (ring_in = that warp's
 // per-row {S1, S2, PV, PI}, ring_out = mine); the global checkpoints are still written, for the traceback.
-template <bool TRACE, bool PIPE = false>
+template <bool TRACE, bool PIPE = false, bool HP = false>
 __device__ void strip_chunk(const int L, const int len1, const int c0, const uint8_t* __restrict__ ref, const uint32_t* __restrict__ mask,
                             const uint16_t* rowoff, const uint32_t prof_base, const int4* ck_in, const bool adjacent, const bool have_in,
                             int4* ck_out, int32_t* trace, int& best, int& best_col, volatile int* flag_prev = nullptr,
-                            volatile int* flag_mine = nullptr, volatile int* ring_in = nullptr, volatile int* ring_out = nullptr) {
+                            volatile int* flag_mine = nullptr, volatile int* ring_in = nullptr, volatile int* ring_out = nullptr,
+                            const HpChunk* hp = nullptr) {
+  static_assert(!(PIPE && HP), "the team schedule does not carry the homopolymer checkpoints");
   const int lane = threadIdx.x & 31;
   const int cbase = c0 + lane * SK;
+  int hsj[SK], HS[SK], HS0 = HIM;                   // HP: homopolymer start per column (matrix columns); snapshot of row rs-1
+  int tb = -1;                                      // HP: the column the next processed chunk needs from this one, -1 none
+  if (HP) {
+#pragma unroll
+    for (int j = 0; j < SK; j++) {
+      const int c = cbase + j;
+      hsj[j] = c < len1 ? max(hp->hps[c], hp->clip) - hp->clip : c;
+      HS[j] = HIM;
+    }
+    if (c0 + CW < len1) tb = max(hp->hps[c0 + CW], hp->clip) - hp->clip - 1;
+  }
+  auto put_ckh = [&](const int r, const int (&Srow)[SK]) {
+    if (!HP || !hp->ckh_out || tb < 0) return;
+    if (tb >= c0) {
+      const int tl = (tb - c0) / SK, tj = (tb - c0) - tl * SK;
+      if (lane == tl) {
+        int v = Srow[0];
+#pragma unroll
+        for (int j = 1; j < SK; j++) if (j == tj) v = Srow[j];
+        hp->ckh_out[r] = v;
+      }
+    } else if (lane == 0) hp->ckh_out[r] = hp->in_valid ? hp->ckh_in[r] : HIM;     // one homopolymer covers the whole chunk
+  };
   int code4[SK];
   bool mb[SK];
   {
@@ -107,6 +167,13 @@ __device__ void strip_chunk(const int L, const int len1, const int c0, const uin
   if (ck_out && lane == 31) {
     ck_out[0] = make_int4(Sp[SK - 1], Sp[SK - 2], 0, 0);
     if (PIPE) { ring_out[0] = Sp[SK - 1]; ring_out[1] = Sp[SK - 2]; }
+  }
+  if (HP) {
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < SK; j++) hp->row.srow[lane * SK + j] = Sp[j];
+    put_ckh(0, Sp);
+    __syncwarp();
   }
   for (int r = 1; r < L; r++) {
     const uint32_t pa = prof_base + rowoff[r];
@@ -166,6 +233,17 @@ __device__ void strip_chunk(const int L, const int len1, const int c0, const uin
 
     int D = l1;
     int tr[SK];
+    int rs = 0, pg = 0, rcl = 28;
+    bool rstart = false;
+    if (HP) {
+      rs = hp->row.hprs[r]; pg = hp->row.hpg[r]; rcl = hp->row.rch[r];
+      rstart = rs == r;
+      if (rstart) {                                                      // a read homopolymer starts: keep row r-1 (HS0: the column left of this lane)
+#pragma unroll
+        for (int j = 0; j < SK; j++) HS[j] = Sp[j];
+        HS0 = l1;
+      }
+    }
 #pragma unroll
     for (int j = 0; j < SK; j++) {
       const int c = cbase + j;
@@ -178,10 +256,25 @@ __device__ void strip_chunk(const int L, const int len1, const int c0, const uin
         } else {
           const int Gc = c >= 2 ? P.v - (GOP - GEP) - GEP * c : HIM;     // mia.c:838-850
           const int Gr = r >= 2 ? RV[j] - (GOP - GEP) - GEP * r : HIM;   // mia.c:856-868
-          if (N > D && N > Gc && N > Gr) { S = N; trace_v = c; }         // mia.c:910-918
-          else if (D >= Gc && D >= Gr) { S = sub + D; trace_v = 0; }
-          else if (Gc >= Gr) { S = sub + Gc; trace_v = P.i; }
-          else { S = sub + Gr; trace_v = -RI[j]; }
+          int hc = HIM, hr = HIM;                                        // mia.c:882-905
+          if (HP && code4[j] == rcl) {                                   // seq1[col] == seq2[row]
+            const int hs = hsj[j];
+            if (rstart) {
+              if (hs != c && hs > 0) {
+                const int src = hs - 1;
+                const int v = src >= c0 ? hp->row.srow[src - c0] : (hp->in_valid ? hp->ckh_in[r - 1] : HIM);
+                hc = v - (GEP * (c - hs) + pg);
+              }
+            } else if (rs > 0 && hs == c) {
+              hr = (j ? HS[j - 1] : HS0) - pg;                           // gap_len = col - hpcs[col] = 0, as written
+            }
+          }
+          if (N > D && N > Gc && N > Gr && N > hc && N > hr) { S = N; trace_v = c; }         // mia.c:910-918
+          else if (D >= Gc && D >= Gr && D >= hc && D >= hr) { S = sub + D; trace_v = 0; }
+          else if (Gc >= Gr && Gc >= hc && Gc >= hr) { S = sub + Gc; trace_v = P.i; }
+          else if (Gr >= hc && Gr >= hr) { S = sub + Gr; trace_v = -RI[j]; }
+          else if (hc >= hr) { S = sub + hc; trace_v = hsj[j] - 1; }                         // mia.c:950-955
+          else { S = sub + hr; trace_v = -(rs - 1); }                                        // mia.c:956-961
           // row r-1 joins best_gap_row[c-1] (used from row r+1 on)
           const int cv = D + GEP * (r - 1);
           if (cv > RV[j]) { RV[j] = cv; RI[j] = r - 1; }
@@ -199,6 +292,13 @@ __device__ void strip_chunk(const int L, const int len1, const int c0, const uin
       int4* trow = reinterpret_cast<int4*>(trace + (int64_t)r * CW + lane * SK);
       trow[0] = make_int4(tr[0], tr[1], tr[2], tr[3]);
       trow[1] = make_int4(tr[4], tr[5], tr[6], tr[7]);
+    }
+    if (HP) {
+      __syncwarp();                                                      // every lane has read row r-1
+#pragma unroll
+      for (int j = 0; j < SK; j++) hp->row.srow[lane * SK + j] = Sp[j];
+      put_ckh(r, Sp);
+      __syncwarp();
     }
   }
   // max_sg_score over this chunk's columns (mia.c:1293-1299): strict '>' in column order
@@ -255,12 +355,31 @@ __device__ int seed_strand(const KmerTable& kt, const int k, const uint8_t* read
   return hits;
 }
 
+// mia -h: what processed chunk q of a strand takes from / leaves to its neighbours (uniform over the warp)
+__device__ __forceinline__ HpChunk hp_chunk(const StripParams& p, const HpRow& row, const int s, const int ws, const int len1, const int32_t* ids,
+                                            const int q, int32_t* ckh, const bool want_out) {
+  HpChunk h;
+  h.row = row; h.hps = p.hps[s] + ws; h.clip = ws;
+  const int c0 = ids[q] * CW;
+  const int hs0 = max(h.hps[c0], ws) - ws;
+  h.in_valid = false;
+  if (q > 0 && hs0 < c0) {                            // the first column's homopolymer began before the chunk: did the previous processed chunk record it?
+    const int pb = (ids[q - 1] + 1) * CW;             // that chunk recorded column hs(pb) - 1
+    h.in_valid = pb < len1 && max(h.hps[pb], ws) - ws == hs0;
+  }
+  h.ckh_in = ckh + (int64_t)q * p.Lmax;
+  h.ckh_out = want_out ? ckh + (int64_t)(q + 1) * p.Lmax : nullptr;
+  return h;
+}
+
 // One warp: strand pick, traceback (re-running the chunks the path crosses from their checkpoints) and the outputs of read rd.
+// len1 / ws: the matrix columns of this read (the whole strand, or its window in mode 2).
+template <bool HP = false>
 __device__ void strip_finish(const StripParams& p, const int rd, const int L, const int nstrand, const bool masked, const int (&best)[2],
                              const int (&bcol)[2], const int (&nch)[2], const uint32_t* mask0, const int32_t* ids0, const int4* ck0,
-                             int32_t* trace, const uint16_t* rowoff, const uint32_t prof_base) {
+                             int32_t* trace, const uint16_t* rowoff, const uint32_t prof_base, const int len1, const int ws = 0,
+                             const HpRow* hprow = nullptr, int32_t* ckh0 = nullptr) {
   const int lane = threadIdx.x & 31;
-  const int len1 = p.len1;
   // ---- strand pick: fw only if strictly better (mia.c:1549-1554)
   const int s = (nstrand == 2 && !(best[0] > best[1])) ? 1 : 0;
   const int score = best[s];
@@ -291,8 +410,14 @@ __device__ void strip_finish(const StripParams& p, const int rd, const int L, co
       if (q < 0) { lost = true; break; }                               // cannot happen: the path only visits unmasked cells
       int dummy_b = INT_MIN, dummy_c = 0;
       __syncwarp();
-      strip_chunk<true>(L, len1, ch * CW, p.ref_codes[s], mask, rowoff, prof_base, ck + (int64_t)q * p.Lmax,
-                        q > 0 && ids[q - 1] == ch - 1, q > 0, nullptr, trace, dummy_b, dummy_c);
+      if (HP) {
+        const HpChunk h = hp_chunk(p, *hprow, s, ws, len1, ids, q, ckh0 + (int64_t)s * (p.max_chunks + 1) * p.Lmax, false);
+        strip_chunk<true, false, true>(L, len1, ch * CW, p.ref_codes[s] + ws, mask, rowoff, prof_base, ck + (int64_t)q * p.Lmax,
+                                       q > 0 && ids[q - 1] == ch - 1, q > 0, nullptr, trace, dummy_b, dummy_c, nullptr, nullptr, nullptr, nullptr, &h);
+      } else {
+        strip_chunk<true>(L, len1, ch * CW, p.ref_codes[s] + ws, mask, rowoff, prof_base, ck + (int64_t)q * p.Lmax,
+                          q > 0 && ids[q - 1] == ch - 1, q > 0, nullptr, trace, dummy_b, dummy_c);
+      }
       __syncwarp();
       loaded = ch;
     }
@@ -327,7 +452,7 @@ __device__ void strip_finish(const StripParams& p, const int rd, const int L, co
       p.abr[rd] = s == 1 ? 0 : abr;                                     // row of the returned runs' first base in the STORED orientation
     } else {
       for (int a = 0, b = nrun - 1; a < b; a++, b--) { uint16_t x = my_runs[a]; my_runs[a] = my_runs[b]; my_runs[b] = x; }
-      p.as_out[rd] = abc; p.ae_out[rd] = aec;                           // window starts at 0: mia_main.c:209-212, 250-255
+      p.as_out[rd] = abc + ws; p.ae_out[rd] = aec + ws;                 // mia_main.c:250-255 (ws = 0 for the whole reference, 209-212)
       p.abr[rd] = abr;
     }
     p.score[rd] = score;
@@ -336,7 +461,9 @@ __device__ void strip_finish(const StripParams& p, const int rd, const int L, co
   }
 }
 
-// dynamic smem: [prof PROF_INTS ints][rowoff WARPS*256 u16]
+// dynamic smem: [prof PROF_INTS ints][rowoff WARPS*256 u16]; HP: + per warp [srow CW ints][hpg 256 ints][hprs 256 u16][rch 256 u8]
+constexpr int STRIP_HP_SMEM_PER_WARP = CW * 4 + MAX_READ * 4 + MAX_READ * 2 + MAX_READ;
+template <bool HP = false>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) strip_kernel(StripParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   int32_t* s_prof = reinterpret_cast<int32_t*>(smem);
@@ -345,14 +472,22 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) strip_kernel(StripParams
   for (int i = tid; i < PROF_INTS; i += blockDim.x) s_prof[i] = p.prof[i];
   __syncthreads();
   uint16_t* rowoff = s_rowoff + warp * MAX_READ;
+  HpRow hprow{};
+  if (HP) {
+    uint8_t* base = smem + PROF_INTS * 4 + WARPS_PER_BLOCK * MAX_READ * 2 + (size_t)warp * STRIP_HP_SMEM_PER_WARP;
+    hprow.srow = reinterpret_cast<int32_t*>(base);
+    hprow.hpg = reinterpret_cast<int32_t*>(base + CW * 4);
+    hprow.hprs = reinterpret_cast<uint16_t*>(base + CW * 4 + MAX_READ * 4);
+    hprow.rch = base + CW * 4 + MAX_READ * 4 + MAX_READ * 2;
+  }
   const uint32_t prof_base = smem_u32(s_prof);
   const int64_t gw = (int64_t)blockIdx.x * WARPS_PER_BLOCK + warp;
   uint32_t* mask0 = p.mask + gw * 2 * p.mask_words;
   int4* ck0 = p.ckpt + gw * 2 * (int64_t)(p.max_chunks + 1) * p.Lmax;
   int32_t* ids0 = p.chunk_ids + gw * 2 * p.max_chunks;
   int32_t* trace = p.trace + gw * (int64_t)p.Lmax * CW;
+  int32_t* ckh0 = HP ? p.ckh + gw * 2 * (int64_t)(p.max_chunks + 1) * p.Lmax : nullptr;
   const int total = p.n_list_ptr ? *p.n_list_ptr : (p.mode == 0 && !p.list) ? (int)p.n : p.n_list;
-  const int len1 = p.len1;
 
   for (;;) {
     int item = 0;
@@ -363,6 +498,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) strip_kernel(StripParams
     const int64_t o0 = p.off[rd];
     const int L = (int)(p.off[rd + 1] - o0);
     const uint8_t* read = p.bases + o0;
+    const int ws = p.mode == 2 ? p.win_start[rd] : 0;                    // the matrix columns: the whole strand, or the read's window
+    const int len1 = p.mode == 2 ? p.win_len[rd] : p.len1;
     if (L <= 0 || L > MAX_READ) {
       if (lane == 0) { p.status[rd] = MIAGPU_ST_UNSUPPORTED; p.n_runs[rd] = -1; p.score[rd] = INT_MIN; if (p.hits) p.hits[rd] = 0; }
       continue;
@@ -371,6 +508,25 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) strip_kernel(StripParams
     const int mat = p.mode == 0 ? 0 : (p.rc_in[rd] ? 1 : 0);             // pass 1 scores BOTH strands with the forward matrix (H5)
     __syncwarp();
     for (int r = lane; r < L; r += 32) rowoff[r] = (uint16_t)(prof_row_index(mat, sm_depth(r, L), base_code(read[r])) * 4);
+    if (HP) {                                                            // pop_hpl_and_hps over the read (mia.c:1527-1531 / mia_main.c:222)
+      uint8_t* rch = const_cast<uint8_t*>(hprow.rch);
+      uint16_t* hprs = const_cast<uint16_t*>(hprow.hprs);
+      int32_t* hpg = const_cast<int32_t*>(hprow.hpg);
+      for (int r = lane; r < L; r += 32) {
+        const uint8_t b = read[r];
+        rch[r] = (uint8_t)(b == 'A' ? 0 : b == 'C' ? 4 : b == 'G' ? 8 : b == 'T' ? 12 : b == 'N' ? 16 : 28);
+      }
+      if (lane == 0) {
+        int start = 0;
+        for (int r = 1; r <= L; r++)
+          if (r == L || read[r] != read[r - 1]) {
+            const int g = hp_gop_part(r - start);
+            for (int q = start; q < r; q++) { hprs[q] = (uint16_t)start; hpg[q] = g; }
+            start = r;
+          }
+      }
+      __syncwarp();
+    }
     // ---- k-mer filter
     int hits[2] = {1, 0};
     const bool masked = p.mode == 0 && p.k > 0;
@@ -416,13 +572,19 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) strip_kernel(StripParams
       int prev = -2;
       for (int q = 0; q < n; q++) {
         const int ch = ids[q];
-        strip_chunk<false>(L, len1, ch * CW, p.ref_codes[s], mask, rowoff, prof_base, ck + (int64_t)q * p.Lmax, prev == ch - 1, q > 0,
-                           ck + (int64_t)(q + 1) * p.Lmax, nullptr, best[s], bcol[s]);
+        if (HP) {
+          const HpChunk h = hp_chunk(p, hprow, s, ws, len1, ids, q, ckh0 + (int64_t)s * (p.max_chunks + 1) * p.Lmax, true);
+          strip_chunk<false, false, true>(L, len1, ch * CW, p.ref_codes[s] + ws, mask, rowoff, prof_base, ck + (int64_t)q * p.Lmax, prev == ch - 1,
+                                          q > 0, ck + (int64_t)(q + 1) * p.Lmax, nullptr, best[s], bcol[s], nullptr, nullptr, nullptr, nullptr, &h);
+        } else {
+          strip_chunk<false>(L, len1, ch * CW, p.ref_codes[s] + ws, mask, rowoff, prof_base, ck + (int64_t)q * p.Lmax, prev == ch - 1, q > 0,
+                             ck + (int64_t)(q + 1) * p.Lmax, nullptr, best[s], bcol[s]);
+        }
         prev = ch;
         __syncwarp();
       }
     }
-    strip_finish(p, rd, L, nstrand, masked, best, bcol, nch, mask0, ids0, ck0, trace, rowoff, prof_base);
+    strip_finish<HP>(p, rd, L, nstrand, masked, best, bcol, nch, mask0, ids0, ck0, trace, rowoff, prof_base, len1, ws, &hprow, ckh0);
   }
 }
 
@@ -452,8 +614,6 @@ __global__ void __launch_bounds__(TEAM_WARPS * 32) strip_team_kernel(StripParams
   int32_t* ids0 = p.chunk_ids + gw * 2 * p.max_chunks;
   int32_t* trace = p.trace + gw * (int64_t)p.Lmax * CW;
   const int total = p.n_list_ptr ? *p.n_list_ptr : (p.mode == 0 && !p.list) ? (int)p.n : p.n_list;
-  const int len1 = p.len1;
-  const int n_chunks_all = (len1 + CW - 1) / CW;
 
   for (;;) {
     __syncthreads();
@@ -465,6 +625,9 @@ __global__ void __launch_bounds__(TEAM_WARPS * 32) strip_team_kernel(StripParams
     const int64_t o0 = p.off[rd];
     const int L = (int)(p.off[rd + 1] - o0);
     const uint8_t* read = p.bases + o0;
+    const int ws = p.mode == 2 ? p.win_start[rd] : 0;                    // the matrix columns: the whole strand, or the read's window
+    const int len1 = p.mode == 2 ? p.win_len[rd] : p.len1;
+    const int n_chunks_all = (len1 + CW - 1) / CW;
     if (L <= 0 || L > MAX_READ) {
       if (tid == 0) { p.status[rd] = MIAGPU_ST_UNSUPPORTED; p.n_runs[rd] = -1; p.score[rd] = INT_MIN; if (p.hits) p.hits[rd] = 0; }
       continue;
@@ -519,7 +682,7 @@ __global__ void __launch_bounds__(TEAM_WARPS * 32) strip_team_kernel(StripParams
       int wb = INT_MIN, wc = 0x7fffffff;
       for (int q = warp; q < n; q += TEAM_WARPS) {
         const int ch = ids[q];
-        strip_chunk<false, true>(L, len1, ch * CW, p.ref_codes[s], mask, rowoff, prof_base, ck + (int64_t)q * p.Lmax,
+        strip_chunk<false, true>(L, len1, ch * CW, p.ref_codes[s] + ws, mask, rowoff, prof_base, ck + (int64_t)q * p.Lmax,
                                  q > 0 && ids[q - 1] == ch - 1, q > 0, ck + (int64_t)(q + 1) * p.Lmax, nullptr, wb, wc,
                                  q > 0 ? s_flag + (q - 1) : nullptr, s_flag + q,
                                  s_ring + (size_t)((((q - 1) / TEAM_WARPS) & 1) * TEAM_WARPS + (q + TEAM_WARPS - 1) % TEAM_WARPS) * p.Lmax * 4,
@@ -535,7 +698,7 @@ __global__ void __launch_bounds__(TEAM_WARPS * 32) strip_team_kernel(StripParams
       best[s] = b; bcol[s] = bc;
       __syncthreads();
     }
-    if (warp == 0) strip_finish(p, rd, L, nstrand, masked, best, bcol, nch, mask0, ids0, ck0, trace, rowoff, prof_base);
+    if (warp == 0) strip_finish(p, rd, L, nstrand, masked, best, bcol, nch, mask0, ids0, ck0, trace, rowoff, prof_base, len1, ws);
   }
 }
 

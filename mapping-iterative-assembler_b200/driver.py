@@ -218,9 +218,10 @@ class ResidentAssembler:
     """
 
     def __init__(self, gpu, ref, sm, circular=1, k=0, soft_mask=0, cons_code=1, exchange=None, strand_unknown="raise", distant_ref=0,
-                 pointer_state=None):
+                 pointer_state=None, hp=0):
         """strand_unknown ("raise" / "drop") only matters without the pointer state (sharded rounds), which does not model reads that
-        score exactly 2000.  pointer_state: None = on unless `exchange` is given."""
+        score exactly 2000.  pointer_state: None = on unless `exchange` is given.  hp: mia -h (miagpu_set_homopolymer; the caller's
+        context keeps the mode until it is switched off)."""
         self.g, self.sm, self.circular, self.k, self.soft_mask, self.cons_code = gpu, sm, circular, k, soft_mask, cons_code
         self.ref0, self.x = ref, exchange
         self.split_changes = 0
@@ -230,6 +231,7 @@ class ResidentAssembler:
         if self.distant_ref and not self.fs:
             raise NotImplementedError("-D needs the pointer state (one GPU)")
         gpu.set_pssm(sm)
+        gpu.set_homopolymer(hp)
 
     def _gather(self, a):
         return a if self.x is None else self.x.all_gather_host(a)

@@ -102,11 +102,48 @@ char orc_revcom_char( char b ) {                      /* map_align.c:418-431 */
 static int *g_S = NULL, *g_T = NULL;
 static size_t g_cells = 0;
 
+/* pop_hpl_and_hps, mia.c:1193-1234: per position the length and the start of its homopolymer (raw characters compared) */
+void orc_hp_runs( const char* seq, int len, int* hpl, int* hps ) {
+  int start = 0;
+  for ( int i = 0; i < len; i++ ) {
+    if ( i > 0 && seq[i] != seq[i-1] ) {
+      for ( int j = start; j < i; j++ ) hpl[j] = i - start;
+      start = i;
+    }
+    hps[i] = start;
+  }
+  for ( int j = start; j < len; j++ ) hpl[j] = len - start;
+}
+/* hp_discount_penalty, mia.c:1096-1134: int penalty = GEP * gap_len, then `penalty += GOP * f` in double, truncated on the
+   way back into the int; the first length is not used */
+int orc_hp_penalty( int gap_len, int hplen2 ) {
+  static const double f[11] = { 0.10, 1.0, 0.5, 0.33, 0.25, 0.2, 0.17, 0.14, 0.13, 0.11, 0.10 };
+  int penalty = ORC_GEP * gap_len;
+  if ( hplen2 == 1 ) { penalty += ORC_GOP; return penalty; }
+  double fac = ( hplen2 >= 2 && hplen2 <= 10 ) ? f[hplen2] : 0.10;
+  penalty = (int)( (double)penalty + ORC_GOP * fac );
+  return penalty;
+}
+
 int orc_align( const char* seq1, int len1, const char* seq2, int len2,
                const unsigned char* mask, const int* sm, int sg5,
                int* out5, char* ref_gapped, char* read_gapped,
                int* score_mat, int* trace_mat ) {
+  return orc_align_hp( seq1, len1, seq2, len2, mask, sm, sg5, 0, out5, ref_gapped, read_gapped, score_mat, trace_mat );
+}
+
+/* hp != 0: mia -h, the two homopolymer-discounted gap candidates of mia.c:882-905 and their place in the cascade (910-964) */
+int orc_align_hp( const char* seq1, int len1, const char* seq2, int len2,
+                  const unsigned char* mask, const int* sm, int sg5, int hp,
+                  int* out5, char* ref_gapped, char* read_gapped,
+                  int* score_mat, int* trace_mat ) {
   if ( len1 <= 0 || len2 <= 0 || len2 > ORC_MAX_READ ) return 0;
+  int *hpcl = NULL, *hpcs = NULL, hprl[ORC_MAX_READ], hprs[ORC_MAX_READ];
+  if ( hp ) {
+    hpcl = (int*)malloc( sizeof(int) * len1 ); hpcs = (int*)malloc( sizeof(int) * len1 );
+    orc_hp_runs( seq1, len1, hpcl, hpcs );
+    orc_hp_runs( seq2, len2, hprl, hprs );
+  }
   size_t need = (size_t)len1 * len2;
   if ( need > g_cells ) {
     free( g_S ); free( g_T );
@@ -155,10 +192,19 @@ int orc_align( const char* seq1, int len1, const char* seq2, int len2,
         gr = (long long)S[(size_t)br*len1 + c-1] - ( ORC_GOP + (long long)ORC_GEP * ( r - br - 1 ) );
       }
       long long dg = Sp[c-1];
-      if ( start_new > dg && start_new > gc && start_new > gr ) { Sr[c] = start_new; Tr[c] = c; }   /* mia.c:910-918 */
-      else if ( dg >= gc && dg >= gr ) { Sr[c] = (int)( sub + dg ); Tr[c] = 0; }                   /* 922-929 */
-      else if ( gc >= gr )             { Sr[c] = (int)( sub + gc ); Tr[c] = bgc; }                 /* 933-939 */
-      else                             { Sr[c] = (int)( sub + gr ); Tr[c] = -RI[c-1]; }            /* 942-948 */
+      long long hc = ORC_HIM, hr = ORC_HIM;           /* mia.c:882-905 */
+      if ( hp && seq1[c] == seq2[r] ) {
+        if ( hprs[r] == r && hpcs[c] != c && hpcs[c] > 0 )
+          hc = (long long)Sp[hpcs[c]-1] - orc_hp_penalty( c - hpcs[c], hprl[r] );
+        if ( hpcs[c] == c && hprs[r] != r && hprs[r] > 0 )
+          hr = (long long)S[(size_t)( hprs[r] - 1 ) * len1 + c-1] - orc_hp_penalty( c - hpcs[c], hprl[r] );   /* the COLUMN distance, as written: 0 here */
+      }
+      if ( start_new > dg && start_new > gc && start_new > gr && start_new > hc && start_new > hr ) { Sr[c] = start_new; Tr[c] = c; }   /* mia.c:910-918 */
+      else if ( dg >= gc && dg >= gr && dg >= hc && dg >= hr ) { Sr[c] = (int)( sub + dg ); Tr[c] = 0; }   /* 922-929 */
+      else if ( gc >= gr && gc >= hc && gc >= hr ) { Sr[c] = (int)( sub + gc ); Tr[c] = bgc; }             /* 933-939 */
+      else if ( gr >= hc && gr >= hr ) { Sr[c] = (int)( sub + gr ); Tr[c] = -RI[c-1]; }                    /* 942-948 */
+      else if ( hc >= hr ) { Sr[c] = (int)( sub + hc ); Tr[c] = hpcs[c] - 1; }                             /* 950-955 */
+      else                 { Sr[c] = (int)( sub + hr ); Tr[c] = -( hprs[r] - 1 ); }                        /* 956-961 */
     }
     /* mia.c:975-979 writes the sg3 penalty to column len1, outside the matrix: no effect */
   }
@@ -187,7 +233,7 @@ int orc_align( const char* seq1, int len1, const char* seq2, int len2,
   if ( read_gapped ) strcpy( read_gapped, fas + fi );
   if ( score_mat ) memcpy( score_mat, S, need * sizeof(int) );
   if ( trace_mat ) memcpy( trace_mat, T, need * sizeof(int) );
-  free( c1 ); free( RI );
+  free( c1 ); free( RI ); free( hpcl ); free( hpcs );
   return ok;
 }
 
@@ -297,7 +343,7 @@ unsigned orc_kmer_filter( const orc_kmer* f, const orc_kmer* r, int k,
 /* ------------------------------------------------------------- context */
 struct orc_ctx {
   char *seq, *rcseq;           /* upper-cased, wrapped, NUL-terminated */
-  int seq_len, wrap_len, circular, k, distant_ref;
+  int seq_len, wrap_len, circular, k, distant_ref, hp;
   orc_kmer *fk, *rk;
   int smf[ORC_PSSM_INTS], smr[ORC_PSSM_INTS];
 };
@@ -327,6 +373,8 @@ orc_ctx* orc_ctx_new( const char* seq, int seq_len, int circular, int with_rc,
   orc_revcom_pssm( c->smf, c->smr );
   return c;
 }
+
+void orc_ctx_set_hp( orc_ctx* c, int hp ) { c->hp = hp; }    /* mia -h: init_alignment( ..., hp_special ), mia_main.c:683-690 */
 
 void orc_ctx_free( orc_ctx* c ) {
   if ( !c ) return;
@@ -369,8 +417,8 @@ int orc_pass1( const orc_ctx* c, const char* read, int L, int* out,
     int of[5], orc[5];
     char fr[ORC_ALN_STR], ff[ORC_ALN_STR], rr[ORC_ALN_STR], rf[ORC_ALN_STR];
     /* both strands with the FORWARD matrix, sg5 = 1: mia_main.c:788-789, mia.c:1535-1542 */
-    orc_align( c->seq,   len1, read, L, mf, c->smf, 1, of,  fr, ff, NULL, NULL );
-    orc_align( c->rcseq, len1, read, L, mr, c->smf, 1, orc, rr, rf, NULL, NULL );
+    orc_align_hp( c->seq,   len1, read, L, mf, c->smf, 1, c->hp, of,  fr, ff, NULL, NULL );   /* hp arrays over the whole strands: mia_main.c:735-739 */
+    orc_align_hp( c->rcseq, len1, read, L, mr, c->smf, 1, c->hp, orc, rr, rf, NULL, NULL );
     int rc = !( of[0] > orc[0] );                     /* tie -> rc, mia.c:1549-1554 */
     const int* b = rc ? orc : of;
     strcpy( f_ref, rc ? rr : fr ); strcpy( f_frag, rc ? rf : ff );
@@ -409,8 +457,8 @@ int orc_realign( const orc_ctx* c, const char* read, int L, int rc,
   int ref_end = ( ae + 50 + 1 > c->wrap_len ) ? c->wrap_len : ae + 50; /* 197-203 */
   if ( ref_start + L > ref_end ) { ref_start = 0; ref_end = c->wrap_len; }   /* 209-212 */
   int o[5];
-  if ( !orc_align( c->seq + ref_start, ref_end - ref_start, read, L, NULL,
-                   rc ? c->smr : c->smf, 1, o, ref_gapped, read_gapped, NULL, NULL ) ) return 0;
+  if ( !orc_align_hp( c->seq + ref_start, ref_end - ref_start, read, L, NULL,
+                      rc ? c->smr : c->smf, 1, c->hp, o, ref_gapped, read_gapped, NULL, NULL ) ) return 0;   /* hp arrays over the window: mia_main.c:221-224 */
   out[0] = o[0]; out[1] = o[2] + ref_start; out[2] = o[4] + ref_start;       /* 250-257 */
   out[3] = o[1]; out[4] = o[2]; out[5] = o[3]; out[6] = o[4]; out[7] = ref_start;
   return 1;

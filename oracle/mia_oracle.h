@@ -45,6 +45,14 @@ int orc_align( const char* seq1, int len1, const char* seq2, int len2,
                const unsigned char* mask, const int* sm, int sg5,
                int* out5, char* ref_gapped, char* read_gapped,
                int* score_mat, int* trace_mat );
+/* the same with mia -h (hp != 0): the homopolymer-discounted gap candidates of mia.c:882-905, hp_discount_penalty
+ * (mia.c:1096-1134) and pop_hpl_and_hps (mia.c:1193-1234) over seq1 and seq2 as given */
+int orc_align_hp( const char* seq1, int len1, const char* seq2, int len2,
+                  const unsigned char* mask, const int* sm, int sg5, int hp,
+                  int* out5, char* ref_gapped, char* read_gapped,
+                  int* score_mat, int* trace_mat );
+void orc_hp_runs( const char* seq, int len, int* hpl, int* hps );
+int  orc_hp_penalty( int gap_len, int hplen2 );
 
 /* ---- a2+a3: k-mer table and filter (kmer.c:18-168, 239-331) */
 typedef struct orc_kmer orc_kmer;
@@ -60,6 +68,7 @@ typedef struct orc_ctx orc_ctx;
 /* seq is the raw reference (case preserved for -M); k<=0 => no k-mer filter */
 orc_ctx* orc_ctx_new( const char* seq, int seq_len, int circular, int with_rc,
                       int k, int soft_mask, const int* sm_fwd, int distant_ref );
+void     orc_ctx_set_hp( orc_ctx* c, int hp );   /* mia -h for orc_pass1 / orc_realign of this context */
 void     orc_ctx_free( orc_ctx* c );
 int      orc_ctx_wrap_len( const orc_ctx* c );
 const char* orc_ctx_seq( const orc_ctx* c );      /* upper-cased, wrapped */

@@ -140,7 +140,8 @@ class Oracle(_AlignMixin):
         return "".join(self.lib.orc_revcom_char(_b(ch)).decode() for ch in reversed(s))
 
     # -- a5..a7
-    def align(self, seq1, seq2, sm, sg5=1, mask=None, matrices=False):
+    def align(self, seq1, seq2, sm, sg5=1, mask=None, matrices=False, hp=0):
+        """hp: mia -h (homopolymer-discounted gap candidates, mia.c:882-905)"""
         seq1, seq2 = _b(seq1), _b(seq2)
         out5 = np.zeros(5, np.int32)
         rg, fg = C.create_string_buffer(520), C.create_string_buffer(520)
@@ -150,10 +151,10 @@ class Oracle(_AlignMixin):
         if matrices:
             S = np.zeros((len(seq2), len(seq1)), np.int32)
             T = np.zeros((len(seq2), len(seq1)), np.int32)
-        self.lib.orc_align.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, c_ubyte_p, c_int_p, C.c_int, c_int_p,
-                                       C.c_char_p, C.c_char_p, c_int_p, c_int_p]
-        ok = self.lib.orc_align(seq1, len(seq1), seq2, len(seq2), m, _ip(sm), sg5, _ip(out5), rg, fg,
-                                None if S is None else _ip(S), None if T is None else _ip(T))
+        self.lib.orc_align_hp.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, c_ubyte_p, c_int_p, C.c_int, C.c_int, c_int_p,
+                                          C.c_char_p, C.c_char_p, c_int_p, c_int_p]
+        ok = self.lib.orc_align_hp(seq1, len(seq1), seq2, len(seq2), m, _ip(sm), sg5, int(hp), _ip(out5), rg, fg,
+                                   None if S is None else _ip(S), None if T is None else _ip(T))
         res = self._res(out5, rg, fg)
         res["ok"] = ok
         if matrices:
@@ -180,10 +181,14 @@ class Oracle(_AlignMixin):
         return hits, mf, mr
 
     # -- context / pass 1 / realign
-    def ctx_new(self, seq, circular, sm_fwd, with_rc=1, k=0, soft_mask=0, distant_ref=0):
+    def ctx_new(self, seq, circular, sm_fwd, with_rc=1, k=0, soft_mask=0, distant_ref=0, hp=0):
         seq = _b(seq)
         sm = np.ascontiguousarray(sm_fwd, np.int32)
-        return self.lib.orc_ctx_new(seq, len(seq), circular, with_rc, k, soft_mask, _ip(sm), distant_ref)
+        c = self.lib.orc_ctx_new(seq, len(seq), circular, with_rc, k, soft_mask, _ip(sm), distant_ref)
+        if hp:
+            self.lib.orc_ctx_set_hp.argtypes = [C.c_void_p, C.c_int]
+            self.lib.orc_ctx_set_hp(c, 1)
+        return c
 
     def ctx_free(self, c):
         self.lib.orc_ctx_free(c)
@@ -381,7 +386,12 @@ class Ref(_AlignMixin):
     def sm_depth(self, row, length):
         return self.lib.refh_find_sm_depth(row, length)
 
-    def align(self, seq1, seq2, sm, sg5=1, mask=None, matrices=False):
+    def set_hp(self, on):
+        """mia -h for the alignments / sessions made from now on (refh_set_hp)"""
+        self.lib.refh_set_hp(int(bool(on)))
+
+    def align(self, seq1, seq2, sm, sg5=1, mask=None, matrices=False, hp=0):
+        self.set_hp(hp)
         seq1, seq2 = _b(seq1), _b(seq2)
         out5 = np.zeros(5, np.int32)
         rg, fg = C.create_string_buffer(520), C.create_string_buffer(520)
@@ -428,7 +438,8 @@ class Ref(_AlignMixin):
         return hits, mf, mr
 
     # session = mia_main.c main() with in-memory reads
-    def sess_new(self, ref_fasta_path, circular, sm, k=0, soft_mask=0, distant_ref=0, cons_code=1):
+    def sess_new(self, ref_fasta_path, circular, sm, k=0, soft_mask=0, distant_ref=0, cons_code=1, hp=0):
+        self.set_hp(hp)
         s = self.lib.refh_sess_new(_b(ref_fasta_path), circular, k, soft_mask, _ip(np.ascontiguousarray(sm, np.int32)),
                                    distant_ref, cons_code)
         if not s:

@@ -53,6 +53,9 @@ int refh_find_sm_depth( int row, int len ) { return find_sm_depth( row, len ); }
 /* ------------------------------------------------------------- alignment */
 static AlignmentP g_al = NULL;
 static int g_al_cols = 0;
+static int g_hp = 0, g_al_hp = 0;
+/* mia -h (hp_special, mia_main.c:424, 497): the alignments refh_align and refh_sess_new make from now on carry it */
+void refh_set_hp( int on ) { g_hp = on ? 1 : 0; }
 
 /* out5 = score, abr, abc, aer, aec.  score_mat / trace_mat (nullable) get the
    full len2 x len1 matrices, row-major.  Returns 1, or 0 on alloc failure. */
@@ -63,10 +66,11 @@ int refh_align( const char* seq1, int len1, const char* seq2, int len2,
   PWAlnFrag pw;
   PSSMP sm = pssm_from_flat( sm775 );
   int r, c;
-  if ( g_al == NULL || g_al_cols < len1 + 1 ) {
+  if ( g_al == NULL || g_al_cols < len1 + 1 || g_al_hp != g_hp ) {
     if ( g_al ) free_alignment( g_al );
     g_al_cols = len1 + 2 * INIT_ALN_SEQ_LEN;
-    g_al = init_alignment( INIT_ALN_SEQ_LEN, g_al_cols, 0, 0 );
+    g_al = init_alignment( INIT_ALN_SEQ_LEN, g_al_cols, 0, g_hp );
+    g_al_hp = g_hp;
     if ( g_al == NULL ) return 0;
   }
   g_al->seq1 = seq1;
@@ -80,6 +84,10 @@ int refh_align( const char* seq1, int len1, const char* seq2, int len2,
   else        memset( g_al->align_mask, 1, len1 );
   pop_s1c_in_a( g_al );
   pop_s2c_in_a( g_al );
+  if ( g_al->hp ) {                                   /* mia_main.c:221-224 */
+    pop_hpl_and_hps( g_al->seq2, g_al->len2, g_al->hprl, g_al->hprs );
+    pop_hpl_and_hps( g_al->seq1, g_al->len1, g_al->hpcl, g_al->hpcs );
+  }
   dyn_prog( g_al );
   out5[0] = max_sg_score( g_al );
   find_align_begin( g_al );
@@ -229,14 +237,18 @@ void* refh_sess_new( const char* ref_fasta, int circular, int k, int soft_mask,
   }
   make_ref_upper( s->maln->ref );
   s->fs = (FragSeqP)calloc( 1, sizeof(FragSeq) );
-  s->fw = init_alignment( INIT_ALN_SEQ_LEN, s->maln->ref->wrap_seq_len + 2*INIT_ALN_SEQ_LEN, 0, 0 );
-  s->rc = init_alignment( INIT_ALN_SEQ_LEN, s->maln->ref->wrap_seq_len + 2*INIT_ALN_SEQ_LEN, 1, 0 );
+  s->fw = init_alignment( INIT_ALN_SEQ_LEN, s->maln->ref->wrap_seq_len + 2*INIT_ALN_SEQ_LEN, 0, g_hp );
+  s->rc = init_alignment( INIT_ALN_SEQ_LEN, s->maln->ref->wrap_seq_len + 2*INIT_ALN_SEQ_LEN, 1, g_hp );
   s->fw->seq1 = s->maln->ref->seq;
   s->rc->seq1 = s->maln->ref->rcseq;
   s->fw->len1 = circular ? s->maln->ref->wrap_seq_len : s->maln->ref->seq_len;
   s->rc->len1 = s->fw->len1;
   pop_s1c_in_a( s->fw );
   pop_s1c_in_a( s->rc );
+  if ( g_hp ) {                                       /* mia_main.c:735-739 */
+    pop_hpl_and_hps( s->fw->seq1, s->fw->len1, s->fw->hpcl, s->fw->hpcs );
+    pop_hpl_and_hps( s->rc->seq1, s->rc->len1, s->rc->hpcl, s->rc->hpcs );
+  }
   s->front = (PWAlnFragP)calloc( 1, sizeof(PWAlnFrag) );
   s->back  = (PWAlnFragP)calloc( 1, sizeof(PWAlnFrag) );
   s->slope = DEF_S; s->intercept = DEF_N;

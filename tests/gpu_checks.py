@@ -31,13 +31,17 @@ def make_case(n_reads, ref_len, seed, divergence=0.02, indel_rate=0.004, min_len
     return ref, out, off, rc, as_, ae
 
 
-def check_realign(gpu, oracle, ref, bases, off, rc, as_, ae, sm, circular=1, sample=None):
-    """GPU realign vs oracle realign, read by read: score, as, ae, abr, gapped strings."""
+def check_realign(gpu, oracle, ref, bases, off, rc, as_, ae, sm, circular=1, sample=None, hp=0):
+    """GPU realign vs oracle realign, read by read: score, as, ae, abr, gapped strings.  hp: mia -h on both sides."""
     from mia_b200 import api
     gpu.set_pssm(sm)
     gpu.set_reference(ref, circular=circular, with_rc=0)
-    out = gpu.realign_host(bases, off, rc, as_, ae)
-    ctx = oracle.ctx_new(ref, circular, sm, with_rc=0, k=0)
+    gpu.set_homopolymer(hp)
+    try:
+        out = gpu.realign_host(bases, off, rc, as_, ae)
+    finally:
+        gpu.set_homopolymer(0)
+    ctx = oracle.ctx_new(ref, circular, sm, with_rc=0, k=0, hp=hp)
     wref = oracle.ctx_seq(ctx)
     n = len(off) - 1
     idx = range(n) if sample is None else sample
@@ -136,8 +140,8 @@ def check_consensus(gpu, oracle, ref, bases, off, rc, as_, ae, sm, circular=1, c
     return problems, dict(n_split=int(split.sum()), n_ins_cols=int(ggaps.sum()), cons_len=len(gcons))
 
 
-def check_pass1(gpu, oracle, ref, reads, sm, circular=1, k=0, soft_mask=0):
-    """GPU pass 1 (k-mer filter + both-strand DP + strand pick + traceback + coordinates) vs oracle."""
+def check_pass1(gpu, oracle, ref, reads, sm, circular=1, k=0, soft_mask=0, hp=0):
+    """GPU pass 1 (k-mer filter + both-strand DP + strand pick + traceback + coordinates) vs oracle.  hp: mia -h on both sides."""
     import numpy as np
     from mia_b200 import api
     gpu.set_pssm(sm)
@@ -147,8 +151,12 @@ def check_pass1(gpu, oracle, ref, reads, sm, circular=1, k=0, soft_mask=0):
     np.cumsum([len(r) for r in reads], out=off[1:])
     bases = np.frombuffer("".join(reads).encode(), np.uint8)
     gpu.upload_reads(bases, off)
-    out = gpu.pass1()
-    ctx = oracle.ctx_new(ref, circular, sm, with_rc=1, k=k, soft_mask=soft_mask)
+    gpu.set_homopolymer(hp)
+    try:
+        out = gpu.pass1()
+    finally:
+        gpu.set_homopolymer(0)
+    ctx = oracle.ctx_new(ref, circular, sm, with_rc=1, k=k, soft_mask=soft_mask, hp=hp)
     wref = oracle.ctx_seq(ctx)
     bad = []
     for i, rd in enumerate(reads):
@@ -164,6 +172,12 @@ def check_pass1(gpu, oracle, ref, reads, sm, circular=1, k=0, soft_mask=0):
         exp = (o["score"], o["fw_score"], o["rc_score"], o["rc"], o["as_"], o["ae"], o["start"], o["end"] if not o["split"] else o["b_end"])
         if got != exp:
             bad.append((i, got, exp))
+            continue
+        if int(out["status"][i]) & 1:                     # more than MIAGPU_MAX_RUNS runs: reported, the strings cannot be compared
+            n_gap_runs = sum(1 for x, y in zip(" " + o["f_ref"] + o["b_ref"], o["f_ref"] + o["b_ref"]) if y == "-" and x != "-") + \
+                sum(1 for x, y in zip(" " + o["f_frag"] + o["b_frag"], o["f_frag"] + o["b_frag"]) if y == "-" and x != "-")
+            if 2 * n_gap_runs + 1 <= 24:
+                bad.append((i, "runs overflow reported for an alignment of", 2 * n_gap_runs + 1, "runs"))
             continue
         # gapped strings in forward-reference orientation: the stored read is revcomp'd for rc
         stored = oracle.revcom(rd) if o["rc"] else rd
@@ -238,7 +252,7 @@ def round_parity(gpu, ref, bases, off, rc, as_, ae, sm, circular=1, checker=None
     return out
 
 
-def assembly_parity(gpu, ref, reads, sm, circular=1, k=12, distant_ref=0, max_iter=30):
+def assembly_parity(gpu, ref, reads, sm, circular=1, k=12, distant_ref=0, max_iter=30, hp=0):
     """A whole assembly (pass 1 with the k-mer filter, rounds until the consensus stops changing) of `reads` (list of str) through
     driver.ResidentAssembler on one GPU against the same assembly by the CPU checker -- the unmodified reference's own main loop
     (oracle/ref_harness.c: refh_sess_*) where oracle/_ref was built, else the oracle restatement (tests/oracle_driver.py): pass-1
@@ -251,7 +265,7 @@ def assembly_parity(gpu, ref, reads, sm, circular=1, k=12, distant_ref=0, max_it
     off = np.zeros(n + 1, np.int64)
     np.cumsum([len(r) for r in reads], out=off[1:])
     bases = np.frombuffer("".join(reads).encode(), np.uint8)
-    A = driver.ResidentAssembler(gpu, ref, sm, circular, k, 0, distant_ref=distant_ref)
+    A = driver.ResidentAssembler(gpu, ref, sm, circular, k, 0, distant_ref=distant_ref, hp=hp)
     p = A.pass1(bases, off)
     first_diff = None
     exp_iters = []
@@ -261,7 +275,8 @@ def assembly_parity(gpu, ref, reads, sm, circular=1, k=12, distant_ref=0, max_it
         with tempfile.NamedTemporaryFile("w", suffix=".fa", delete=False) as f:
             f.write(">ref\n" + ref + "\n")
             path = f.name
-        s = r.sess_new(path, circular, sm, k=k, soft_mask=0, distant_ref=distant_ref)
+        s = r.sess_new(path, circular, sm, k=k, soft_mask=0, distant_ref=distant_ref, hp=hp)
+        r.set_hp(0)
         p1 = [r.sess_pass1(s, "r%d" % i, rd) for i, rd in enumerate(reads)]
         r.sess_end_pass1(s)
         for _ in range(max_iter):
@@ -274,7 +289,7 @@ def assembly_parity(gpu, ref, reads, sm, circular=1, k=12, distant_ref=0, max_it
         from oracle_driver import OracleRun
         o = Oracle()
         kind = "oracle (restatement)"
-        R = OracleRun(o, ref, sm, circular, k, 0, distant_ref=distant_ref)
+        R = OracleRun(o, ref, sm, circular, k, 0, distant_ref=distant_ref, hp=hp)
         p1 = [R.pass1(rd) for rd in reads]
         R.end_pass1()
         for _ in range(max_iter):
@@ -300,5 +315,7 @@ def assembly_parity(gpu, ref, reads, sm, circular=1, k=12, distant_ref=0, max_it
             cons_equal = False
             first_diff = first_diff or f"round {it + 1}: consensus differs"
         conv_equal &= gconv == conv
+    if hp:
+        gpu.set_homopolymer(0)
     return dict(reads=n, fsdb=len(A.seq_len), rounds=len(exp_iters), pass1_equal=pass1_equal, rounds_equal=rounds_equal, consensus_equal=cons_equal,
                 converged_equal=bool(conv_equal), checker=kind, first_diff=first_diff)

@@ -4,11 +4,12 @@ import numpy as np
 
 
 class OracleRun:
-    def __init__(self, o, ref_raw, sm, circular=1, k=0, soft_mask=0, cons_code=1, distant_ref=0, repeat_filt=0, just_outer_coords=1):
+    def __init__(self, o, ref_raw, sm, circular=1, k=0, soft_mask=0, cons_code=1, distant_ref=0, repeat_filt=0, just_outer_coords=1, hp=0):
         self.o, self.sm, self.circular, self.cons_code = o, np.ascontiguousarray(sm, np.int32), circular, cons_code
         self.repeat_filt, self.just_outer_coords = repeat_filt, just_outer_coords
         self.smr = o.revcom_pssm(self.sm)
-        self.ctx = o.ctx_new(ref_raw, circular, self.sm, with_rc=1, k=k, soft_mask=soft_mask, distant_ref=distant_ref)
+        self.hp = hp                  # mia -h
+        self.ctx = o.ctx_new(ref_raw, circular, self.sm, with_rc=1, k=k, soft_mask=soft_mask, distant_ref=distant_ref, hp=hp)
         self.seq_len = len(ref_raw)
         self.wrap_len = o.lib.orc_ctx_wrap_len(self.ctx)
         self.cur_ref = o.ctx_seq(self.ctx)[: self.seq_len]
@@ -68,19 +69,19 @@ class OracleRun:
             self.iter += 1
             self.last = self.cons
         ref = self.last
-        ctx = o.ctx_new(ref, self.circular, self.sm, with_rc=0, k=0)
+        ctx = o.ctx_new(ref, self.circular, self.sm, with_rc=0, k=0, hp=self.hp)
         self.seq_len = len(ref)
         self.wrap_len = o.lib.orc_ctx_wrap_len(ctx)
         o.asm_begin_round(self.asm, self.seq_len, self.wrap_len)
         ref_w = o.ctx_seq(ctx)
         for f in self.fsdb:
             if self.distant_ref and not f["strand_known"] and self.iter > 1:        # mia_main.c:120-174
-                a = o.align(ref_w, f["seq"], self.smr if self.submat_rc else self.sm, 1)       # whatever matrix the last read left (H6)
+                a = o.align(ref_w, f["seq"], self.smr if self.submat_rc else self.sm, 1, hp=self.hp)       # whatever matrix the last read left (H6)
                 if a["score"] > 2000:
                     f["strand_known"], f["rc"], f["as_"], f["ae"], f["score"] = 1, 0, a["abc"], a["aec"], a["score"]
                 rcs = o.revcom(f["seq"])
                 self.submat_rc = 1                                                  # mia_main.c:151
-                a = o.align(ref_w, rcs, self.smr, 1)
+                a = o.align(ref_w, rcs, self.smr, 1, hp=self.hp)
                 if a["score"] > 2000 and a["score"] > f["score"]:
                     f["strand_known"], f["rc"], f["as_"], f["ae"], f["score"], f["seq"] = 1, 1, a["abc"], a["aec"], a["score"], rcs
             if not f["strand_known"]:

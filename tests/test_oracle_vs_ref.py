@@ -50,6 +50,71 @@ def test_align_fuzz_full_matrices(oracle, ref, golden):
         assert (a["S"] == b["S"]).all() and (a["T"] == b["T"]).all(), it
 
 
+def _fuzz_hp(rng):
+    # homopolymer-rich sequences: runs of 1-9 equal bases, the read a copy with run lengths changed here and there
+    runs = [(rng.choice("ACGT"), max(1, int(rng.expovariate(0.45)))) for _ in range(rng.randint(4, 45))]
+    ref = "".join(b * min(n, 9) for b, n in runs)
+    a = rng.randint(0, max(0, len(runs) - 3))
+    sub = runs[a:a + rng.randint(2, 25)]
+    rd = []
+    for b, n in sub:
+        x = rng.random()
+        if x < 0.25:
+            n = max(1, n + rng.choice((-2, -1, 1, 2)))
+        elif x < 0.30:
+            b = rng.choice("ACGT")
+        rd.append(b * min(n, 9))
+    rd = "".join(rd)[:250] or "A"
+    mask = None
+    if rng.random() < 0.3:
+        mask = np.zeros(len(ref), np.uint8)
+        for _ in range(rng.randint(1, 3)):
+            s = rng.randint(0, len(ref) - 1)
+            mask[s:min(len(ref), s + rng.randint(1, 90))] = 1
+    return ref, rd, mask
+
+
+def test_align_fuzz_homopolymer_discount(oracle, ref, golden):
+    # mia -h: the two extra gap candidates (mia.c:882-905), their place in the cascade, hp_discount_penalty's truncation
+    rng = random.Random(431)
+    mats = [golden["flat"], golden["ancient"], golden["ancient_rc"], golden["onepass"]]
+    used = 0
+    for it in range(1200):
+        s1, s2, mask = _fuzz_hp(rng) if it % 4 else _fuzz(rng)
+        sm, sg5 = rng.choice(mats), rng.randint(0, 1)
+        a = ref.align(s1, s2, sm, sg5, mask, matrices=True, hp=1)
+        b = oracle.align(s1, s2, sm, sg5, mask, matrices=True, hp=1)
+        for k in ("score", "abr", "abc", "aer", "aec", "ref_gapped", "read_gapped"):
+            assert a[k] == b[k], (it, k)
+        assert (a["S"] == b["S"]).all() and (a["T"] == b["T"]).all(), it
+        used += int((a["S"] != oracle.align(s1, s2, sm, sg5, mask, matrices=True)["S"]).any())
+    ref.set_hp(0)
+    assert used > 300, used              # the discount changed the matrix in that many cases: the candidates are exercised
+
+
+def test_session_homopolymer_discount(oracle, ref, golden):
+    import _pkg
+    _pkg.load()
+    from mia_b200 import synth
+    refseq = _hp_reference(2200, 7)
+    g = synth.diverge(refseq, 0.02, seed=3, indel_rate=0.01)
+    b, off, _ = synth.make_reads(g, 260, 35, 90, seed=4)
+    reads = [synth.read_str(b, off, i) for i in range(260)]
+    try:
+        _session_compare(oracle, ref, refseq, reads, golden["onepass"], 1, 10, hp=1)
+        _session_compare(oracle, ref, refseq, reads[:100], golden["ancient"], 0, 0, hp=1)
+    finally:
+        ref.set_hp(0)
+
+
+def _hp_reference(n, seed):
+    rng = random.Random(seed)
+    out = []
+    while sum(len(x) for x in out) < n:
+        out.append(rng.choice("ACGT") * min(9, max(1, int(rng.expovariate(0.5)))))
+    return "".join(out)[:n]
+
+
 def test_kmer_table_and_filter(oracle, ref):
     import _pkg
     _pkg.load()
@@ -75,12 +140,12 @@ def test_kmer_table_and_filter(oracle, ref):
         oracle.kmer_free(fo)
 
 
-def _session_compare(oracle, ref, refseq, reads, sm, circular, k, soft_mask=0):
+def _session_compare(oracle, ref, refseq, reads, sm, circular, k, soft_mask=0, hp=0):
     with tempfile.NamedTemporaryFile("w", suffix=".fa", delete=False) as f:
         f.write(">ref\n" + refseq + "\n")
         path = f.name
-    s = ref.sess_new(path, circular, sm, k=k, soft_mask=soft_mask)
-    R = OracleRun(oracle, refseq, sm, circular, k, soft_mask)
+    s = ref.sess_new(path, circular, sm, k=k, soft_mask=soft_mask, hp=hp)
+    R = OracleRun(oracle, refseq, sm, circular, k, soft_mask, hp=hp)
     for i, rd in enumerate(reads):
         a, b = ref.sess_pass1(s, "r%d" % i, rd), R.pass1(rd)
         for key in a:
