@@ -1,7 +1,7 @@
 /* mia_gpu.c -- a plain-C host for libmiagpu.so: the call sequence INTEGRATION.md gives a maintainer of the reference,
  * compiled and run.  It is NOT the reference's CLI (out of scope): it covers the default assembly mode only
  *
- *     mia_gpu -r ref.fa -f reads.fq -s matrix.txt -m out [-c] [-k K] [-p 1|2] [-H cut | -S slope -N icpt] [-F] [-u | -U] [-A]
+ *     mia_gpu -r ref.fa -f reads.fq -s matrix.txt -m out [-c] [-k K] [-p 1|2] [-H cut | -S slope -N icpt] [-F] [-u | -U] [-A] [-D] [-h]
  *
  * and exists to show (and test, tests/test_gpu_host_c.py) that the C ABI alone -- no Python, no torch -- reproduces
  * the reference's `.maln` files: reader (miagpu_fastx_*), matrices (miagpu_read_pssm), pass 1, score cut, one library
@@ -11,7 +11,8 @@
  * the FSDB order and the slot-indexed sticky AlnSeq.dropped flags kept here as mia_main.c keeps them.
  * The one-call rounds follow the reference's FragSeq -> AlnSeq pointers on the device (miagpu_set_fsdb): reads that score exactly
  * 2000 (strand_known = 0, mia.c:1653), never-cleared back pointers, slot-indexed sticky flags, and -D (mia.c:1614,
- * mia_main.c:120-174: miagpu_distant_retry).  -T, -h, -C, -I are not handled here.
+ * mia_main.c:120-174: miagpu_distant_retry).  -h (mia_main.c:497: the homopolymer discount in every alignment) is
+ * miagpu_set_homopolymer.  -T, -C, -I are not handled here.
  * There is no CPU fallback: without a CUDA device miagpu_create fails and so does this program. */
 #define _POSIX_C_SOURCE 199309L
 #include <stdio.h>
@@ -124,7 +125,7 @@ static void filter_and_cull( miagpu_ctx* g, Fsdb* F ) {
 int main( int argc, char** argv ) {
   const char *ref_fn = NULL, *frag_fn = NULL, *mat_fn = NULL, *root = "assembly.maln.iter";
   int circular = 0, k = -1, cons_code = 1, hard_cut = 0, final_only = 0, repeat_filt = 0, just_outer_coords = 1, i;
-  int score_cut_set = 0, distant_ref = 0, n_unknown = 0;
+  int score_cut_set = 0, distant_ref = 0, n_unknown = 0, hp_special = 0;
   double user_slope = 200.0, user_icpt = 0.0;           /* DEF_S, DEF_N (params.h:36-37); -S / -N: mia_main.c:579-586 */
   for ( i = 1; i < argc; i++ ) {
     if ( !strcmp( argv[i], "-c" ) ) circular = 1;
@@ -133,6 +134,7 @@ int main( int argc, char** argv ) {
     else if ( !strcmp( argv[i], "-U" ) ) repeat_filt = 2;
     else if ( !strcmp( argv[i], "-A" ) ) just_outer_coords = 0;
     else if ( !strcmp( argv[i], "-D" ) ) distant_ref = 1;
+    else if ( !strcmp( argv[i], "-h" ) ) hp_special = 1;
     else if ( !strcmp( argv[i], "-i" ) ) ;
     else if ( i + 1 < argc && !strcmp( argv[i], "-r" ) ) ref_fn = argv[++i];
     else if ( i + 1 < argc && !strcmp( argv[i], "-f" ) ) frag_fn = argv[++i];
@@ -161,6 +163,7 @@ int main( int argc, char** argv ) {
   double t0 = now_ms(), t_init, t_parse, t_pass1, t_rounds = 0, t_write = 0, t1;
   CK( miagpu_read_pssm( mat_fn, fwd ) );
   CK( miagpu_create( &g, 0 ) );
+  CK( miagpu_set_homopolymer( g, hp_special ) );
   CK( miagpu_set_pssm( g, fwd ) );
   CK( miagpu_get_pssm( g, fpsm, rpsm ) );
   CK( miagpu_set_reference( g, ref, ref_len, circular, 1 ) );

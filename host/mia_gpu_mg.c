@@ -68,7 +68,7 @@ static char* read_reference( const char* fn, char* id, char* desc, int* len_out 
 
 /* ---- what all threads share */
 typedef struct {
-  int world, circular, k, cons_code, hard_cut, score_cut_set, final_only;
+  int world, circular, k, cons_code, hard_cut, score_cut_set, final_only, hp_special;
   double user_slope, user_icpt;
   const char *root, *ref_id, *ref_desc;
   char* ref; int ref_len;
@@ -118,6 +118,7 @@ static void* worker( void* arg_ ) {
   miagpu_ctx* g = NULL;
   int64_t j;
   CK( S, miagpu_create( &g, rank ) );
+  CK( S, miagpu_set_homopolymer( g, S->hp_special ) );
   CK( S, miagpu_set_pssm( g, S->fwd ) );
   CK( S, miagpu_set_reference( g, S->ref, S->ref_len, S->circular, 1 ) );
   CK( S, miagpu_build_kmers( g, S->k, 0 ) );
@@ -284,6 +285,7 @@ int main( int argc, char** argv ) {
   for ( i = 1; i < argc; i++ ) {
     if ( !strcmp( argv[i], "-c" ) ) S.circular = 1;
     else if ( !strcmp( argv[i], "-F" ) ) S.final_only = 1;
+    else if ( !strcmp( argv[i], "-h" ) ) S.hp_special = 1;
     else if ( !strcmp( argv[i], "-i" ) ) ;
     else if ( i + 1 < argc && !strcmp( argv[i], "-g" ) ) ngpu = atoi( argv[++i] );
     else if ( i + 1 < argc && !strcmp( argv[i], "-r" ) ) ref_fn = argv[++i];

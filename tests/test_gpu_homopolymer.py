@@ -1,57 +1,13 @@
 """GPU: mia -h -- the homopolymer-discounted gap candidates (mia.c:882-905) in pass 1, in the rounds and in whole assemblies,
 against the oracle (pinned to the unmodified reference with -h in tests/test_oracle_vs_ref.py) and against the reference's own
 main loop where oracle/_ref is present."""
-import random
-
 import numpy as np
 import pytest
 
 import gpu_checks
+from hp_data import hp_reference, hp_reads
 
 pytestmark = pytest.mark.gpu
-
-
-def hp_reference(n, seed, long_runs_at=()):
-    rng = random.Random(seed)
-    out = []
-    while sum(len(x) for x in out) < n:
-        out.append(rng.choice("ACGT") * min(9, max(1, int(rng.expovariate(0.5)))))
-    s = list("".join(out)[:n])
-    for pos, length, base in long_runs_at:            # homopolymers laid across the chunked kernel's 256-column boundaries
-        s[pos:pos + length] = base * length
-    return "".join(s[:n])
-
-
-def hp_reads(ref, n, seed, lo=30, hi=120, circular=False):
-    """reads copied from the reference with homopolymer lengths changed here and there, a few substitutions, both strands"""
-    rng = random.Random(seed)
-    comp = {"A": "T", "C": "G", "G": "C", "T": "A", "N": "N"}
-    reads, starts = [], []
-    for _ in range(n):
-        L = rng.randint(lo, hi)
-        p = rng.randint(0, len(ref) - 1 if circular else len(ref) - L)
-        src = (ref + ref)[p:p + L]
-        runs, i = [], 0
-        while i < len(src):
-            j = i
-            while j < len(src) and src[j] == src[i]:
-                j += 1
-            runs.append((src[i], j - i))
-            i = j
-        rd = []
-        for b, k in runs:
-            x = rng.random()
-            if x < 0.09:
-                k = max(1, k + rng.choice((-2, -1, 1, 1, 2)))
-            elif x < 0.11:
-                b = rng.choice("ACGT")
-            rd.append(b * k)
-        rd = "".join(rd)[:250]
-        if rng.random() < 0.5:
-            rd = "".join(comp[c] for c in reversed(rd))
-        reads.append(rd)
-        starts.append(p)
-    return reads, starts
 
 
 @pytest.mark.parametrize("circular,k,matrix", [(0, 0, "ancient"), (1, 10, "onepass"), (0, 12, "pe")])
@@ -103,6 +59,38 @@ def test_assembly_homopolymer_discount(gpu, circular, k, distant):
     reads, _ = hp_reads(sample, 400, 41, lo=35, hi=110 if not distant else 80, circular=bool(circular))
     par = gpu_checks.assembly_parity(gpu, ref, reads, gpu_checks.load_pssm("onepass" if not distant else "ancient"), circular, k, distant, hp=1)
     assert par["pass1_equal"] and par["rounds_equal"] and par["consensus_equal"] and par["converged_equal"], par
+
+
+@pytest.mark.parametrize("name", ["hp2k_c_k10_h", "hp2k_lin_k12_hD"])
+def test_reference_sessions_with_homopolymer_discount(gpu, golden, name):
+    # the committed sessions of the unmodified reference with -h (tests/golden/make_golden_hp.py) through driver.ResidentAssembler:
+    # per round every read's score / as / ae / rc / strand_known and the consensus
+    import gzip
+    import json
+    import os
+    import _pkg
+    _pkg.load()
+    from mia_b200 import driver
+    s = json.load(gzip.open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hp.json.gz"), "rt"))["sessions"][name]
+    reads = s["reads"]
+    off = np.zeros(len(reads) + 1, np.int64)
+    np.cumsum([len(r) for r in reads], out=off[1:])
+    bases = np.frombuffer("".join(reads).encode(), np.uint8)
+    try:
+        A = driver.ResidentAssembler(gpu, s["ref"], golden[s["matrix"]], s["circular"], s["k"], 0, distant_ref=s["distant_ref"], hp=1)
+        p = A.pass1(bases, off)
+        for i, e in enumerate(s["pass1"]):
+            assert int(p["hits"][i]) == e["hits"]
+            if e["hits"]:
+                assert [int(p[k2][i]) for k2 in ("score", "rc", "as_", "ae")] == [e[k2] for k2 in ("score", "rc", "as_", "ae")], i
+        for it, e in enumerate(s["iters"]):
+            cons, conv = A.iterate()
+            got = np.stack([A.score, A.as_, A.ae, A.rc.astype(np.int32), A.strand_known.astype(np.int32)], 1).tolist()
+            assert got == e["reads"], f"{name}: iteration {it + 1} per-read results"
+            assert cons == e["cons"], f"{name}: iteration {it + 1} consensus"
+            assert conv == e["converged"]
+    finally:
+        gpu.set_homopolymer(0)
 
 
 def test_homopolymer_mode_refusals(gpu):

@@ -56,6 +56,26 @@ def test_c_host_follows_the_reference_pointers(golden, name, tmp_path):
     assert not os.path.exists(tmp_path / f"out.{len(s['malns']) + 1}")
 
 
+@pytest.mark.parametrize("name", ["hp2k_c_k10_h", "hp2k_lin_k12_hD"])
+def test_c_host_homopolymer_discount(golden, name, tmp_path):
+    # mia -h / mia -h -D (tests/golden/make_golden_hp.py): FASTQ -> device -> the `.maln` files of the unmodified reference binary
+    s = json.load(gzip.open(os.path.join(HERE, "golden", "hp.json.gz"), "rt"))["sessions"][name]
+    (tmp_path / "ref.fa").write_text(s["ref_text"])
+    (tmp_path / "reads.fq").write_text(s["fastq"])
+    (tmp_path / "m.txt").write_text(matrix_text(golden[s["matrix"]]))
+    ensure_host()
+    r = subprocess.run([HOST, "-r", "ref.fa", "-f", "reads.fq", "-s", "m.txt", "-m", "out"] + s["flags"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    for it, body in enumerate(s["malns"]):
+        got = open(tmp_path / f"out.{it + 1}").read().split("\n", 1)[1]
+        if got != body:
+            for ln, (x, y) in enumerate(zip(got.split("\n"), body.split("\n"))):
+                assert x == y, f"{name} iteration {it + 1}: line {ln + 2}: {x[:160]!r} != {y[:160]!r}"
+            assert len(got) == len(body)
+    if s["complete"]:
+        assert not os.path.exists(tmp_path / f"out.{len(s['malns']) + 1}")
+
+
 @pytest.mark.parametrize("gpus", [1, 2, 4])
 @pytest.mark.parametrize("name,matrix", [("circ_k10", "ancient"), ("lin_pe", "pe"), ("circ_k10_SN", "ancient")])
 def test_c_host_for_the_gpus_of_one_box(golden, name, matrix, gpus, tmp_path):

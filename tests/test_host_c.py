@@ -84,7 +84,7 @@ def test_c_host_argument_errors(golden, tmp_path):
     run = lambda *a: subprocess.run([HOST] + list(a), cwd=tmp_path, capture_output=True, text=True)
     r = run()
     assert r.returncode == 2 and "usage: mia_gpu" in r.stderr
-    for opt in ("-T", "-h", "-C3", "-I"):
+    for opt in ("-T", "-C3", "-I"):
         r = run("-r", "r.fa", "-f", "q.fq", "-s", "m.txt", opt)
         assert r.returncode == 2 and "not handled by this host" in r.stderr, opt
     r = run("-r", "r.fa", "-f", "q.fq", "-s", "m.txt", "-u", "-H", "3000")

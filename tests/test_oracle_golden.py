@@ -175,3 +175,37 @@ def test_session_distant_reference(oracle, golden, name):
     # mia -D: accept everything with a k-mer hit, retry strand-unknown reads on both strands of the whole reference from
     # iteration 2 on with whatever matrix the previous read left (H6), find_alignable_len in the cull
     _run_session_r2(oracle, golden, name, "ancient")
+
+
+# ---- mia -h: the homopolymer-discounted gap candidates (tests/golden/make_golden_hp.py)
+def _load_hp():
+    import gzip
+    return json.load(gzip.open(os.path.join(G, "hp.json.gz"), "rt"))
+
+
+def test_align_homopolymer_discount_matches_reference_golden(oracle, golden):
+    mats = {"flat": golden["flat"], "onepass": golden["onepass"], "ancient": golden["ancient"]}
+    for i, c in enumerate(_load_hp()["align"]):
+        a = oracle.align(c["ref"], c["read"], mats[c["matrix"]], c["sg5"], None, hp=1)
+        assert [a["score"], a["abr"], a["abc"], a["aer"], a["aec"], a["ref_gapped"], a["read_gapped"]] == c["out"], i
+
+
+@pytest.mark.parametrize("name", ["hp2k_c_k10_h", "hp2k_lin_k12_hD"])
+def test_session_homopolymer_discount(oracle, golden, name):
+    # mia -h and mia -h -D as whole sessions: pass 1 with the homopolymers of the whole strands, the rounds with those of the windows
+    s = _load_hp()["sessions"][name]
+    R = OracleRun(oracle, s["ref"], golden[s["matrix"]], s["circular"], s["k"], 0, distant_ref=s["distant_ref"], hp=1)
+    for i, (rd, exp) in enumerate(zip(s["reads"], s["pass1"])):
+        p = R.pass1(rd)
+        for key, v in exp.items():
+            if not exp["hits"] and key not in ("hits", "added"):
+                continue
+            assert p[key] == v, f"{name}: pass1 read {i} field {key}"
+    R.end_pass1()
+    for it, exp in enumerate(s["iters"]):
+        cons, conv = R.iterate()
+        assert [[f["score"], f["as_"], f["ae"], f["rc"], f["strand_known"]] for f in R.fsdb] == exp["reads"], f"{name}: iteration {it} reads"
+        slots = [[x["start"], x["end"], x["dropped"], x["segment"], x["seq"], x["smp"], x["ins"]] for x in oracle.asm_entries(R.asm)]
+        assert slots == [x[1:] for x in exp["slots"]], f"{name}: iteration {it} AlnSeq list"
+        assert cons == exp["cons"], f"{name}: iteration {it} consensus"
+        assert conv == exp["converged"]
