@@ -109,7 +109,9 @@ struct miagpu_ctx {
   DevBuf<int32_t> d_meta;                      // META_* layout below
   DevBuf<uint32_t> d_scratch[4];               // trace scratch of the 32-bit kernels, one per launch stream
   DevBuf<int32_t> d_p1trace;                   // pass 1: winning jobs the 32-bit JOB kernels trace
-  int p1_traced = 0;
+  DevBuf<int32_t> d_sw_jobs, d_sw_layout, d_sw_pairs;   // pass 1: whole-strand jobs of sweep16_kernel, their work items
+  DevBuf<int32_t> d_p1sunk;                    // pass 1: jobs that left the 16-bit frame
+  int p1_traced = 0, p1_swept = 0;
   // mia -h (miagpu_set_homopolymer): every DP runs in the chunked kernel with the two homopolymer-discounted gap candidates
   bool hp = false, hps_valid = false;
   DevBuf<int32_t> d_hps[2];                    // start of the homopolymer of every (wrapped) strand column
@@ -285,7 +287,7 @@ extern "C" void miagpu_destroy(miagpu_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   c->d_jkind.release(); c->d_jstatus.release(); c->d_route.release(); c->d_jws.release(); c->d_jwl.release(); c->d_jscore.release();
-  c->d_jabc.release(); c->d_jaec.release(); c->d_jabr.release(); c->d_p1list.release(); c->d_p1trace.release(); c->d_p1meta.release(); c->d_jpairs.release();
+  c->d_jabc.release(); c->d_jaec.release(); c->d_jabr.release(); c->d_p1list.release(); c->d_p1trace.release(); c->d_sw_jobs.release(); c->d_sw_layout.release(); c->d_sw_pairs.release(); c->d_p1sunk.release(); c->d_p1meta.release(); c->d_jpairs.release();
   c->d_jread.release(); c->d_jfirst.release(); c->d_jcount.release();
   c->d_prof.release(); c->d_ref.release(); c->d_rcref.release(); c->d_ref2.release(); c->d_bases.release(); c->d_off.release();
   c->d_rc.release(); c->d_status.release(); c->d_as.release(); c->d_ae.release(); c->d_score.release();
@@ -3166,6 +3168,55 @@ extern "C" int miagpu_build_kmers(miagpu_ctx* c, int k, int soft_mask) {
 
 // Pass 1 with the k-mer filter on (pass1.cuh): seed every read, run the strands' separate stretches through the pair
 // kernels, merge, and leave the rest to the general kernel.
+// longest read sweep16_kernel takes: the whole frame with the re-based variant when the matrices leave it room
+static int sweep_lmax(miagpu_ctx* c, const PairLmax& lm_low) {
+  bool rb = p16_rb_frame(SW_K, c->pssm_max).room >= 16384;
+  if (const char* e = getenv("MIAGPU_PAIR_RB")) if (atoi(e) == 0) rb = false;
+  return lm_low.v[SW_CLASS] > 0 ? (rb ? P16_MAXL : lm_low.v[SW_CLASS]) : 0;
+}
+
+// Whole-strand 16-bit sweeps of m jobs (jobs: device list, nullptr = jobs 0 .. m-1; d_jread names their reads and strands): work
+// items by read length, the plain frame for the reads it holds, the re-based frame for the longer ones.  On c->launch_stream.
+static int launch_sweep(miagpu_ctx* c, const int32_t* jobs, int64_t m, int lmax_low) {
+  if (m <= 0) return 1;
+  cudaStream_t st = c->launch_stream;
+  const int len1 = c->circular ? c->wrap_len : c->seq_len;
+  if (!c->d_sw_layout.reserve(SW_LAYOUT_WORDS) || !c->d_sw_pairs.reserve((size_t)m + 4 * (MAX_READ + 2) + 8)) return 0;
+  int32_t *cnt = c->d_sw_layout.p, *start = cnt + (MAX_READ + 2), *cursor = start + (MAX_READ + 2), *n_items = cursor + (MAX_READ + 2), *work = n_items + 2;
+  MIAGPU_CUDA(cudaMemsetAsync(cnt, 0, SW_LAYOUT_WORDS * sizeof(int32_t), st));
+  MIAGPU_CUDA(cudaMemsetAsync(c->d_sw_pairs.p, 0xff, ((size_t)m + 4 * (MAX_READ + 2) + 8) * sizeof(int32_t), st));
+  sw_hist_kernel<<<(unsigned)std::min<int64_t>(2 * c->num_sms, (m + 255) / 256), 256, 0, st>>>(m, jobs, c->d_jread.p, c->d_off.p, cnt);
+  sw_layout_kernel<<<1, 32, 0, st>>>(cnt, start, cursor, lmax_low, n_items);
+  sw_scatter_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(m, jobs, c->d_jread.p, c->d_off.p, cursor, c->d_sw_pairs.p);
+  MIAGPU_CUDA(cudaGetLastError());
+  Sweep16Params sp{};
+  sp.bases = c->d_bases.p; sp.off = c->d_off.p; sp.pairs = c->d_sw_pairs.p; sp.job_read = c->d_jread.p;
+  sp.ref2 = c->d_ref2.p; sp.strand_stride = c->ref_bytes; sp.len1 = len1; sp.prof16 = c->d_prof16.p; sp.gep2 = K2(2 * GEP);
+  sp.jscore = c->d_jscore.p; sp.jabc = c->d_jabc.p; sp.jaec = c->d_jaec.p; sp.jabr = c->d_jabr.p; sp.jstatus = c->d_jstatus.p;
+  const RbFrame f = p16_rb_frame(SW_K, c->pssm_max);
+  sp.rb_off = f.off; sp.rb_d = f.d; sp.rb_thresh = f.thresh;
+  const size_t smem = sw_smem();
+  static int per_sm_d[MAX_DEVICES][2];
+  int* per_sm = per_sm_d[c->device % MAX_DEVICES];
+  if (per_sm[0] <= 0) {
+    MIAGPU_CUDA(cudaFuncSetAttribute(sweep16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MIAGPU_CUDA(cudaFuncSetAttribute(sweep16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MIAGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[0], sweep16_kernel<false>, WARPS_PER_BLOCK * 32, smem));
+    MIAGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], sweep16_kernel<true>, WARPS_PER_BLOCK * 32, smem));
+  }
+  if (per_sm[0] < 1 || per_sm[1] < 1) { set_error("sweep16_kernel does not fit on an SM (smem %zu)", smem); return 0; }
+  const int64_t items_max = m / 4 + (MAX_READ + 2);                         // every length's run is padded to whole items
+  const int blocks0 = (int)std::min<int64_t>((int64_t)c->num_sms * per_sm[0], (items_max + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+  const int blocks1 = (int)std::min<int64_t>((int64_t)c->num_sms * per_sm[1], (items_max + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+  sp.n_items = n_items; sp.first_item = nullptr; sp.counter = work;
+  sweep16_kernel<false><<<blocks0, WARPS_PER_BLOCK * 32, smem, st>>>(sp);
+  sp.n_items = n_items + 1; sp.first_item = n_items; sp.counter = work + 1;
+  sweep16_kernel<true><<<blocks1, WARPS_PER_BLOCK * 32, smem, st>>>(sp);
+  MIAGPU_CUDA(cudaGetLastError());
+  c->launches += 5;
+  return 1;
+}
+
 static int pass1_fast(miagpu_ctx* c, const PairLmax& lm) {
   const PairLmax lm_low = pair_lmax_low(c);
   const int64_t n = c->n, nj = 10 * n + 4096;          // job capacity; reads whose jobs do not fit go to the general kernel
@@ -3174,7 +3225,7 @@ static int pass1_fast(miagpu_ctx* c, const PairLmax& lm) {
   if (!c->d_jread.reserve(nj + 1) || !c->d_jfirst.reserve(n + 1) || !c->d_jcount.reserve(n + 1)) return 0;
   if (!c->d_jkind.reserve(nj + 1) || !c->d_jstatus.reserve(nj + 1) || !c->d_route.reserve(n + 1) || !c->d_jws.reserve(nj + 1) ||
       !c->d_jwl.reserve(nj + 1) || !c->d_jscore.reserve(nj + 1) || !c->d_jabc.reserve(nj + 1) || !c->d_jaec.reserve(nj + 1) ||
-      !c->d_jabr.reserve(nj + 1) || !c->d_p1list.reserve(n + 1) || !c->d_p1trace.reserve(n + 1) || !c->d_p1meta.reserve(META_WORDS) ||
+      !c->d_jabr.reserve(nj + 1) || !c->d_p1list.reserve(n + 1) || !c->d_p1trace.reserve(n + 1) || !c->d_sw_jobs.reserve(2 * n + 1) || !c->d_p1sunk.reserve(nj + 1) || !c->d_p1meta.reserve(META_WORDS) ||
       !c->d_jpairs.reserve(nj + 4 * P16_KEYS + 64)) return 0;
   cudaStream_t st = c->stream;
   int32_t* meta = c->d_p1meta.p;
@@ -3185,6 +3236,7 @@ static int pass1_fast(miagpu_ctx* c, const PairLmax& lm) {
   sp.bases = c->d_bases.p; sp.off = c->d_off.p; sp.n = n; sp.k = c->kmer_k; sp.len1 = len1; sp.strand_stride = c->ref_bytes; sp.pssm_max = c->pssm_max;
   for (int t = 0; t < 2; t++) sp.kt[t] = KmerTable{c->d_kb[t].p, c->d_kk[t].p, c->d_kp[t].p, c->kmer_shift[t]};
   sp.lm = lm;
+  sp.sw_lmax = getenv("MIAGPU_P1_NO_SWEEP") ? 0 : sweep_lmax(c, lm_low); sp.sw_jobs = c->d_sw_jobs.p;
   sp.job_cap = nj; sp.jread = c->d_jread.p; sp.jfirst = c->d_jfirst.p; sp.jcount = c->d_jcount.p;
   sp.jkind = c->d_jkind.p; sp.jws = c->d_jws.p; sp.jwl = c->d_jwl.p; sp.hits = c->d_hits.p; sp.route = c->d_route.p;
   sp.general_list = c->d_p1list.p; sp.score = c->d_score.p; sp.n_runs = c->d_nruns.p; sp.status = c->d_status.p; sp.meta = meta;
@@ -3203,11 +3255,17 @@ static int pass1_fast(miagpu_ctx* c, const PairLmax& lm) {
   // The reads the seeding already sent to the general kernel (saturated strands above all: a whole strand on one
   // warp, milliseconds per read) start first, on a side stream, and run beside the pair kernels.
   const int n_general0 = c->h_meta[P1_NGENERAL];
-  if (n_general0) {
+  const int n_sweep = c->h_meta[P1_NSWEEP];
+  c->p1_swept = n_sweep;
+  if (n_general0 || n_sweep) {
     MIAGPU_CUDA(cudaEventRecord(c->aev[0], st));
     MIAGPU_CUDA(cudaStreamWaitEvent(c->s_aux[1], c->aev[0], 0));
     c->launch_stream = c->s_aux[1];
-    const int ok = launch_strip(c, 0, c->d_p1list.p, n_general0, meta + P1_WORK, 0, nullptr);
+    // the strands the filter saturated (error-free reads of 128 + k - 1 bases and more): whole-strand sweeps in 16 bits, two jobs per
+    // half-warp; the merge below needs their scores
+    int ok = launch_sweep(c, c->d_sw_jobs.p, n_sweep, lm_low.v[SW_CLASS]);
+    if (ok && n_sweep) MIAGPU_CUDA(cudaEventRecord(c->aev[5], c->s_aux[1]));
+    if (ok && n_general0) ok = launch_strip(c, 0, c->d_p1list.p, n_general0, meta + P1_WORK, 0, nullptr);
     c->launch_stream = st;
     if (!ok) return 0;
     MIAGPU_CUDA(cudaEventRecord(c->aev[1], c->s_aux[1]));
@@ -3237,6 +3295,7 @@ static int pass1_fast(miagpu_ctx* c, const PairLmax& lm) {
       p.ref_codes = c->d_ref2.p; p.ref_bytes = 2 * c->ref_bytes; p.strand_stride = c->ref_bytes; p.prof16 = c->d_prof16.p; p.job_read = c->d_jread.p;
       p.score = c->d_jscore.p; p.as_out = c->d_jabc.p; p.ae_out = c->d_jaec.p; p.abr = c->d_jabr.p; p.status = c->d_jstatus.p;
       p.n_reads = nj;
+      p.sunk_list = c->d_p1sunk.p; p.sunk_count = meta + P1_NSUNK;
       int ok = 1;
       const bool rb = c->h_meta[META_PMAXL + kb] > lm_low.v[kb];
       switch (rb ? 200 + kb : kb) {
@@ -3268,6 +3327,29 @@ static int pass1_fast(miagpu_ctx* c, const PairLmax& lm) {
       MIAGPU_CUDA(cudaStreamWaitEvent(st, c->aev[1 + i], 0));
     }
   }
+  if (total_pairs && !getenv("MIAGPU_P1_NO_SUNK32")) {
+    // jobs whose alignment left the 16-bit frame (a chance stretch of a long read sinks fast): exact scores from the 32-bit JOB
+    // kernel, so that the merge sees no job it cannot use; the list's length stays on the device (usually a per cent of the reads)
+    if (!ensure_max_read_len(c)) return 0;
+    const int maxL = std::min(std::max(c->max_read_len, 2), MAX_READ);
+    RealignParams p{};
+    p.bases = c->d_bases.p; p.off = c->d_off.p; p.rc = nullptr; p.win_start = c->d_jws.p; p.win_len = c->d_jwl.p;
+    p.list = c->d_p1sunk.p; p.n_list = 2 * WARPS_PER_BLOCK * c->num_sms; p.n_list_ptr = meta + P1_NSUNK;
+    p.ref_codes = c->d_ref2.p; p.ref_bytes = 2 * c->ref_bytes; p.prof = c->d_prof.p; p.sg5 = 1;
+    p.score = c->d_score.p; p.status = c->d_status.p;
+    p.job_read = c->d_jread.p; p.strand_stride = c->ref_bytes; p.seq_len = c->seq_len;
+    p.job_score = c->d_jscore.p; p.job_abc = c->d_jabc.p; p.job_aec = c->d_jaec.p; p.job_abr = c->d_jabr.p; p.job_status = c->d_jstatus.p;
+    for (int t = 0; t < 3; t++) {
+      c->launch_slot = 1 + t;
+      p.counter = meta + P1_SWORK + t;
+      p.job_wl_lo = t == 0 ? 0 : t == 1 ? 64 : 128;
+      p.job_wl_hi = t == 0 ? 64 : t == 1 ? 128 : 256;
+      const int ok = t == 0 ? launch_p1_trace<2>(c, p, maxL) : t == 1 ? launch_p1_trace<4>(c, p, maxL) : launch_p1_trace<8>(c, p, maxL);
+      if (!ok) { c->launch_slot = 0; return 0; }
+    }
+    c->launch_slot = 0;
+  }
+  if (n_sweep) MIAGPU_CUDA(cudaStreamWaitEvent(st, c->aev[5], 0));
   MIAGPU_CUDA(cudaEventRecord(c->p1ev[1], st));
   P1MergeParams mp{};
   mp.n = n; mp.off = c->d_off.p; mp.seq_len = c->seq_len; mp.route = c->d_route.p; mp.jfirst = c->d_jfirst.p; mp.jcount = c->d_jcount.p; mp.jkind = c->d_jkind.p; mp.jstatus = c->d_jstatus.p;
@@ -3330,29 +3412,25 @@ static int pass1_sweep(miagpu_ctx* c, const PairLmax& lm) {
   if (n > 0x3fffffffLL) { set_error("miagpu_pass1: at most %d reads per batch", 0x3fffffff); return 0; }
   if (!c->d_jfirst.reserve(n + 1) || !c->d_jcount.reserve(n + 1) || !c->d_jkind.reserve(nj + 1) || !c->d_jstatus.reserve(nj + 1) ||
       !c->d_route.reserve(n + 1) || !c->d_jscore.reserve(nj + 1) || !c->d_jabc.reserve(nj + 1) || !c->d_jaec.reserve(nj + 1) ||
-      !c->d_jabr.reserve(nj + 1) || !c->d_p1list.reserve(n + 1) || !c->d_p1meta.reserve(META_WORDS) || !c->d_kind.reserve(n + 1) ||
-      !c->d_jpairs.reserve(n + 4 * P16_KEYS + 64)) return 0;
+      !c->d_jabr.reserve(nj + 1) || !c->d_p1list.reserve(n + 1) || !c->d_p1meta.reserve(META_WORDS) || !c->d_jread.reserve(nj + 1) ||
+      !c->d_sw_jobs.reserve(nj + 1)) return 0;
   cudaStream_t st = c->stream;
   int32_t* meta = c->d_p1meta.p;
-  const int len1 = c->circular ? c->wrap_len : c->seq_len;
   MIAGPU_CUDA(cudaMemsetAsync(meta, 0, META_WORDS * sizeof(int32_t), st));
+  const int lmax_low = lm.v[SW_CLASS];
   SweepPrepParams pp{};
-  pp.n = n; pp.off = c->d_off.p; pp.lmax = lm.v[SW_CLASS]; pp.kind = c->d_kind.p; pp.route = c->d_route.p; pp.jfirst = c->d_jfirst.p;
-  pp.jcount = c->d_jcount.p; pp.jkind = c->d_jkind.p; pp.hits = c->d_hits.p; pp.general_list = c->d_p1list.p; pp.meta = meta;
+  pp.n = n; pp.off = c->d_off.p; pp.lmax = sweep_lmax(c, lm); pp.route = c->d_route.p; pp.jfirst = c->d_jfirst.p;
+  pp.jcount = c->d_jcount.p; pp.jkind = c->d_jkind.p; pp.job_read = c->d_jread.p; pp.sw_jobs = c->d_sw_jobs.p; pp.hits = c->d_hits.p;
+  pp.general_list = c->d_p1list.p; pp.meta = meta;
   sweep_prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pp, P1_NGENERAL);
-  MIAGPU_CUDA(cudaGetLastError());
-  PairNp np1; for (int kb = 0; kb < P16_NKB; kb++) np1.v[kb] = 1;
-  pair_layout_kernel<<<1, LAYOUT_THREADS, 0, st>>>(meta, np1);
   MIAGPU_CUDA(cudaGetLastError());
   MIAGPU_CUDA(cudaEventRecord(c->p1ev[0], st));
   MIAGPU_CUDA(cudaMemcpyAsync(c->h_meta, meta, sizeof(int32_t) * META_HOST, cudaMemcpyDeviceToHost, st));
   MIAGPU_CUDA(cudaStreamSynchronize(st));
-  c->launches += 2;
-  int n_pairs = 0, base = 0;
-  for (int kb = 0; kb < P16_NKB; kb++) { if (kb < SW_CLASS) base += c->h_meta[META_NPAIRS + kb]; n_pairs += c->h_meta[META_NPAIRS + kb]; }
-  const int n_items = c->h_meta[META_NPAIRS + SW_CLASS];
+  c->launches += 1;
+  const int64_t n_sweep_reads = c->h_meta[META_PREADS + SW_CLASS];
   const int n_general0 = c->h_meta[P1_NGENERAL];
-  if (n_general0) {                                   // reads beyond the 16-bit frame: the general kernel, beside the sweep
+  if (n_general0) {                                   // reads no 16-bit frame holds: the general kernel, beside the sweep
     MIAGPU_CUDA(cudaEventRecord(c->aev[0], st));
     MIAGPU_CUDA(cudaStreamWaitEvent(c->s_aux[1], c->aev[0], 0));
     c->launch_stream = c->s_aux[1];
@@ -3361,28 +3439,8 @@ static int pass1_sweep(miagpu_ctx* c, const PairLmax& lm) {
     if (!ok) return 0;
     MIAGPU_CUDA(cudaEventRecord(c->aev[1], c->s_aux[1]));
   }
-  if (n_items) {
-    MIAGPU_CUDA(cudaMemsetAsync(c->d_jpairs.p, 0xff, (size_t)2 * n_pairs * sizeof(int32_t), st));
-    pair_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, c->d_off.p, c->d_kind.p, meta, c->d_jpairs.p);
-    MIAGPU_CUDA(cudaGetLastError());
-    Sweep16Params sp{};
-    sp.bases = c->d_bases.p; sp.off = c->d_off.p; sp.pairs = c->d_jpairs.p + 2 * (int64_t)base; sp.n_items = meta + META_NPAIRS + SW_CLASS;
-    sp.counter = meta + META_PWORK + SW_CLASS; sp.ref_fw = c->d_ref.p; sp.ref_rc = c->d_rcref.p; sp.len1 = len1; sp.prof16 = c->d_prof16.p;
-    sp.gep2 = K2(2 * GEP);
-    sp.jscore = c->d_jscore.p; sp.jabc = c->d_jabc.p; sp.jaec = c->d_jaec.p; sp.jabr = c->d_jabr.p; sp.jstatus = c->d_jstatus.p;
-    const size_t smem = sw_smem();
-    static int per_sm_d[MAX_DEVICES];
-    int& per_sm = per_sm_d[c->device % MAX_DEVICES];
-    if (per_sm <= 0) {
-      MIAGPU_CUDA(cudaFuncSetAttribute(sweep16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      MIAGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep16_kernel, WARPS_PER_BLOCK * 32, smem));
-    }
-    if (per_sm < 1) { set_error("sweep16_kernel does not fit on an SM (smem %zu)", smem); return 0; }
-    const int blocks = std::min(c->num_sms * per_sm, (n_items + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
-    sweep16_kernel<<<blocks, WARPS_PER_BLOCK * 32, smem, st>>>(sp);
-    MIAGPU_CUDA(cudaGetLastError());
-    c->launches += 2;
-  }
+  c->launch_stream = st;
+  if (!launch_sweep(c, c->d_sw_jobs.p, 2 * n_sweep_reads, lmax_low)) return 0;
   MIAGPU_CUDA(cudaEventRecord(c->p1ev[1], st));
   P1MergeParams mp{};
   mp.n = n; mp.off = c->d_off.p; mp.seq_len = c->seq_len; mp.route = c->d_route.p; mp.jfirst = c->d_jfirst.p; mp.jcount = c->d_jcount.p;

@@ -135,6 +135,8 @@ struct Pair16Params {
   int32_t* list_counts;          // their fill counters
   int64_t n_reads;
   int32_t* n_fallback;           // statistics
+  int32_t* sunk_list;            // JOB + RB kernels: jobs whose end value lies in the poisoned range (list + fill counter): the 32-bit
+  int32_t* sunk_count;           // JOB kernel computes them exactly before the merge
   uint32_t gep2;                 // K2(2*GEP), passed as data so that ptxas keeps this add an IMAD (FMA pipe) instead of folding it into a VIADD
   int32_t strand_stride;         // JOB kernels: bytes between the forward and the reverse-complement codes in ref_codes
   const int32_t* job_read;       // JOB kernels: read of a job, bit 31 = reverse strand
@@ -521,7 +523,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, (K <= 5 ? 8 : K <= P16_S
           const int lo = ws - ((h ? jrB : jrA) < 0 ? p.strand_stride : 0);
           p.score[rd] = score;                          // exact whatever the path looks like (unless sunk): a losing job needs no more
           if (sunk) {
-            p.status[rd] = P16_ST_SUNK;                 // sg_align reports both strands' scores: the general kernel computes this read
+            p.status[rd] = P16_ST_SUNK;                 // sg_align reports both strands' scores: the 32-bit JOB kernel computes this job
+            if (p.sunk_list) p.sunk_list[atomicAdd(p.sunk_count, 1)] = rd;
           } else if (ok) {
             p.as_out[rd] = aec - nsteps + lo;           // abc
             p.ae_out[rd] = aec + lo;                    // aec

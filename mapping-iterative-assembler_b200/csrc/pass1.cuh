@@ -41,6 +41,10 @@ constexpr int P1_NJOBS = META_P1 + 4;       // jobs allocated (may exceed the ca
 constexpr int P1_EFF = META_P1 + 6;         // [2] int64: effective DP cells = sum over strands of L x unmasked columns
 constexpr int P1_NTRACE = META_COUNT;       // winning jobs whose path is not one plain diagonal: traced by realign_kernel<K, false, true> (list fill counter)
 constexpr int P1_TWORK = META_WORK;         // [3] work-fetch counters of those launches (the pass-1 meta block has no 32-bit work lists of its own)
+constexpr int P1_NSWEEP = META_COUNT + 1;   // strands the filter saturated: whole-strand jobs of sweep16_kernel (list fill counter)
+constexpr int P1_NSUNK = META_COUNT + 2;    // jobs that left the 16-bit frame (pair16.cuh 5.): computed by the 32-bit JOB kernel before the merge (list fill counter)
+constexpr int P1_SWORK = META_WORK + 3;     // [3] work-fetch counters of those launches
+constexpr uint8_t P1_KIND_SWEEP = 1;        // jkind of such a job (a pair-class job has 16 + class, 0 = no job)
 constexpr int P1_JPS = 12;           // stretches per strand that become jobs
 constexpr int P1_MAXD = 128;         // diagonals kept per strand: KMER_SATURATE hits unmask the whole strand anyway
 
@@ -136,6 +140,8 @@ struct P1SeedParams {
   int32_t k, len1, strand_stride, pssm_max;
   KmerTable kt[2];
   PairLmax lm;
+  int32_t sw_lmax;               // longest read sweep16_kernel takes (0: saturated strands go to the general kernel)
+  int32_t* sw_jobs;              // jobs of the saturated strands
   // per job (zeroed jkind: a slot nobody filled is no job)
   int64_t job_cap;
   uint8_t* jkind;                // 16 + pair class, 0 = no job
@@ -204,9 +210,15 @@ __global__ void __launch_bounds__(256) p1_seed_kernel(P1SeedParams p) {
     bool fast = live && !odd && total > 0;
     // masked columns needed between two stretches so that no column-gap candidate crosses (see the header)
     const int need = (L - 1) * (max(p.pssm_max, 0) + GEP) + GEP;
+    bool sat[2] = {false, false};
     for (int s = 0; s < 2 && fast; s++) {
       if (!st[s].hits) continue;
-      if (st[s].hits >= KMER_SATURATE || st[s].n > P1_JPS) { fast = false; break; }
+      if (st[s].hits >= KMER_SATURATE) {                                   // kmer.c:283-285: the whole strand is unmasked -> one whole-strand job
+        if (L > p.sw_lmax) { fast = false; break; }
+        sat[s] = true; st[s].n = 1;
+        continue;
+      }
+      if (st[s].n > P1_JPS) { fast = false; break; }
       const int span = L + 2 * ALIGN_MASK_BUFFER - s;                    // last column of a hit's interval minus its first
       int prev_z = -1;
       for (int t = 0; t < st[s].n; t++) {
@@ -250,6 +262,14 @@ __global__ void __launch_bounds__(256) p1_seed_kernel(P1SeedParams p) {
       int64_t job = first;
       for (int s = 0; s < 2; s++)
         for (int t = 0; t < st[s].n; t++, job++) {
+          if (sat[s]) {
+            p.jkind[job] = P1_KIND_SWEEP;
+            p.jws[job] = s * p.strand_stride;
+            p.jwl[job] = p.len1;
+            p.jread[job] = (int32_t)((uint32_t)rd | ((uint32_t)s << 31));
+            p.sw_jobs[atomicAdd(p.meta + P1_NSWEEP, 1)] = (int32_t)job;
+            continue;
+          }
           const int a = st[s].lo[t], wl = st[s].hi[t] - a + 1;
           const int kb = p16_job_class(wl);
           p.jkind[job] = (uint8_t)(16 + kb);
@@ -307,7 +327,7 @@ __global__ void p1_merge_kernel(P1MergeParams p) {
     }
   const int s = !(best[0] > best[1]) ? 1 : 0;       // forward only if strictly better (mia.c:1549-1554)
   const int64_t j = bj[s];
-  if (j >= 0 && !sunk && p.jstatus[j] == P16_ST_GENERAL && p.trace_list) {
+  if (j >= 0 && !sunk && p.jstatus[j] == P16_ST_GENERAL && p.trace_list && p.jkind[j] != P1_KIND_SWEEP) {
     // every job's score is exact, so the winner is known; only its path is not: the 32-bit kernel runs the winner's stretch with a trace
     p.trace_list[atomicAdd(p.meta + P1_NTRACE, 1)] = (int32_t)j;
     atomicAdd(p.meta + P1_NFAST, 1);

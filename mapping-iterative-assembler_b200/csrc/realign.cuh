@@ -74,6 +74,11 @@ struct RealignParams {
   int32_t strand_stride, job_wl_lo, job_wl_hi, seq_len;
   int32_t* start;
   int32_t* end;
+  // JOB, per-job outputs instead (job_score != nullptr): jobs the 16-bit kernels could not finish exactly (pair16.cuh 5., "sunk")
+  // are computed here before the merge looks at them -- score, abc / aec in strand coordinates, abr, and whether the path is one
+  // plain diagonal (status MIAGPU_ST_OK) or not (0x40: the merge has the winner traced)
+  int32_t* job_score; int32_t* job_abc; int32_t* job_aec; int32_t* job_abr;
+  uint8_t* job_status;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -322,7 +327,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) realign_kernel(RealignPa
     // ---- find_align_begin + populate_pwaln_to_begin, executed uniformly by the warp
     __syncwarp();   // trace stores of all lanes visible (same warp, global memory)
     int row = aer, col = aec, nrun = 0, curM = 0, ncols = 0;
-    uint16_t* my_runs = p.runs ? p.runs + (int64_t)rd * MAX_RUNS : nullptr;
+    uint16_t* my_runs = (p.runs && !(JOB && p.job_score)) ? p.runs + (int64_t)rd * MAX_RUNS : nullptr;
     const uint16_t* t16 = reinterpret_cast<const uint16_t*>(trace);
     auto push = [&](int type, int len) {
       if (my_runs && nrun < MAX_RUNS && lane == 0) my_runs[nrun] = (uint16_t)((type << 14) | len);
@@ -369,7 +374,11 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) realign_kernel(RealignPa
           uint16_t x = my_runs[a]; my_runs[a] = my_runs[b]; my_runs[b] = x;
         }
       if (p.cells_done) atomicAdd(p.cells_done, (unsigned long long)L * (unsigned long long)len1);
-      if (JOB) {
+      if (JOB && p.job_score) {
+        p.job_score[job] = score;
+        p.job_abc[job] = col + jlo; p.job_aec[job] = aec + jlo; p.job_abr[job] = row;
+        p.job_status[job] = (nrun == 1 && st == MIAGPU_ST_OK) ? MIAGPU_ST_OK : 0x40;
+      } else if (JOB) {
         // sg_align's coordinates (mia.c:1568-1610); runs go out in forward-reference orientation (strip.cuh does the same)
         const int s = jr < 0 ? 1 : 0;
         const int abc = col + jlo, aes = aec + jlo;

@@ -31,32 +31,41 @@ constexpr int SW_CLASS = 7;                         // the pair class whose fram
 struct Sweep16Params {
   const uint8_t* bases;
   const int64_t* off;
-  const int32_t* pairs;          // [n_items][2] reads of equal length; -1 = empty second slot
+  const int32_t* pairs;          // [n_items][2 half-warps][2] JOBS whose reads have one length; -1 = empty slot
   const int32_t* n_items;
+  const int32_t* first_item;     // nullable: the launch's items begin at *first_item (the re-based launch follows the plain one's)
   int32_t* counter;
-  const uint8_t* ref_fw;         // codes of the wrapped forward strand
-  const uint8_t* ref_rc;         // codes of the wrapped reverse-complement strand
+  const int32_t* job_read;       // job -> read, bit 31 = reverse-complement strand
+  const uint8_t* ref2;           // codes of the wrapped forward strand, then (strand_stride bytes on) of the reverse-complement strand
+  int32_t strand_stride;
   int32_t len1;
   const int16_t* prof16;
   uint32_t gep2;
-  // per job (2 * read + strand), the layout p1_merge_kernel reads
+  int32_t rb_off, rb_d, rb_thresh;   // RB: the re-based frame of pair16.cuh 5. (K = 16)
+  // per job, the layout p1_merge_kernel reads
   int32_t* jscore; int32_t* jabc; int32_t* jaec; int32_t* jabr;
   uint8_t* jstatus;
 };
 
-// dynamic shared memory: [prof16][rowoff WARPS*2*P16_MAXL u16][tab WARPS*2*2*P16_TAB_WORDS u32][ring WARPS*2*2*P16_MAXL*4 u32]
+// dynamic shared memory: [prof16][rowoff WARPS*2*2*P16_MAXL u16][tab WARPS*2*2*P16_TAB_WORDS u32][ring WARPS*2*2*P16_MAXL*4 u32]
 __host__ __device__ constexpr int sw_smem() {
-  return (PROF16_N + 8) * 2 + WARPS_PER_BLOCK * 2 * P16_MAXL * 2 + WARPS_PER_BLOCK * 2 * 2 * P16_TAB_WORDS * 4 +
+  return (PROF16_N + 8) * 2 + WARPS_PER_BLOCK * 2 * 2 * P16_MAXL * 2 + WARPS_PER_BLOCK * 2 * 2 * P16_TAB_WORDS * 4 +
          WARPS_PER_BLOCK * 2 * 2 * P16_MAXL * 16;
 }
 
+// A half-warp (16 lanes x 16 columns) carries TWO jobs in the halves of its registers: job A in the low half, job B in the high
+// half -- (read, strand) pairs whose reads have one length.  Without the k-mer filter they are the two strands of one read; with
+// it they are the strands the filter saturated (kmer.c:283-285: the whole strand is unmasked) of any two reads of one length.
+// RB: the re-based frame (pair16.cuh 5.) for reads beyond the plain one; every chunk goes through the same re-basings, so what a
+// chunk hands to the next stays in step: the last two cells of row r-1 are re-based by the consumer when row r begins with one.
+template <bool RB>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) sweep16_kernel(Sweep16Params p) {
   constexpr int K = SW_K, G = SW_G;
   constexpr int NE = (25 + G - 1) / G;
   extern __shared__ __align__(16) uint8_t smem[];
   int16_t* s_prof = reinterpret_cast<int16_t*>(smem);
   constexpr int PROF_BYTES = (PROF16_N + 8) * 2;
-  constexpr int ROWOFF_BYTES = WARPS_PER_BLOCK * 2 * P16_MAXL * 2;
+  constexpr int ROWOFF_BYTES = WARPS_PER_BLOCK * 2 * 2 * P16_MAXL * 2;
   constexpr int TAB_BYTES = WARPS_PER_BLOCK * 2 * 2 * P16_TAB_WORDS * 4;
   uint16_t* s_rowoff = reinterpret_cast<uint16_t*>(smem + PROF_BYTES);
   uint32_t* s_tab = reinterpret_cast<uint32_t*>(smem + PROF_BYTES + ROWOFF_BYTES);
@@ -68,16 +77,21 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) sweep16_kernel(Sweep1
   for (int i = tid; i < PROF16_N + 8; i += blockDim.x) s_prof[i] = p.prof16[i];
   __syncthreads();
 
-  uint16_t* row = s_rowoff + (warp * 2 + hw) * P16_MAXL;
+  uint16_t* rowA = s_rowoff + ((warp * 2 + hw) * 2 + 0) * P16_MAXL;
+  uint16_t* rowB = s_rowoff + ((warp * 2 + hw) * 2 + 1) * P16_MAXL;
   uint32_t* tab = s_tab + (warp * 2 + hw) * 2 * P16_TAB_WORDS;
   uint4* ring = s_ring + (size_t)(warp * 2 + hw) * 2 * P16_MAXL;      // two buffers of P16_MAXL rows: {l2, l1, acc, scan total}
   const uint32_t prof_base = smem_u32(s_prof);
   const uint32_t tab_addr = smem_u32(tab);
 
-  constexpr int OFF = p16_off(K);
+  constexpr int OFFN = p16_off(K);
+  const int OFF = RB ? p.rb_off : OFFN;
   constexpr int CONV = GEP * K;
   constexpr int SENT = -32768 + GOP;
+  constexpr uint32_t RB_NMIN = B2(-(GOP + 3 * GEP) - OFFN), RB_CELLMIN = B2(-(GOP + 3 * GEP) - OFFN + 2 * GEP - PSSM_ABS_LIMIT);
+  const uint32_t rb_d2 = RB ? K2(p.rb_d) : 0u;
   const int n_items = *p.n_items;
+  const int32_t* pairs = p.pairs + (p.first_item ? 4 * (int64_t)*p.first_item : 0);
   const uint32_t gep2 = p.gep2;
   const int len1 = p.len1;
 
@@ -88,12 +102,12 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) sweep16_kernel(Sweep1
     eoa[t] = (e / 5) * 2;
     eob[t] = (e % 5) * 2;
   }
-  // both halves use the read's own row: entry (a, b) = { sub(r, a), sub(r, b) << 16 }
+  // entry (a, b) = { sub_A(r, a), sub_B(r, b) << 16 }
   auto build_table = [&](int r, uint32_t* dst) {
-    const uint32_t pr = prof_base + row[r];
+    const uint32_t pa = prof_base + rowA[r], pb = prof_base + rowB[r];
 #pragma unroll
     for (int t = 0; t < NE; t++) {
-      const uint2 v = make_uint2((uint32_t)lds_s16(pr + eoa[t]), lds_u16(pr + eob[t]) << 16);
+      const uint2 v = make_uint2((uint32_t)lds_s16(pa + eoa[t]), lds_u16(pb + eob[t]) << 16);
       if (sub + G * t < 25) reinterpret_cast<uint2*>(dst)[sub + G * t] = v;
     }
   };
@@ -103,33 +117,45 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) sweep16_kernel(Sweep1
     if (lane == 0) item = atomicAdd(p.counter, 1);
     item = __shfl_sync(0xffffffffu, item, 0);
     if (item >= n_items) break;
-    int rd = p.pairs[2 * item + hw];
-    const bool live = rd >= 0;                       // an empty slot recomputes the item's first read and writes nothing
-    if (!live) rd = p.pairs[2 * item];
-    const int64_t o = p.off[rd];
-    const int L = (int)(p.off[rd + 1] - o);          // the same for both reads of the item
+    int jobA = pairs[4 * item + 2 * hw], jobB = pairs[4 * item + 2 * hw + 1];
+    const bool liveA = jobA >= 0;                    // an empty half-warp recomputes the item's first job and writes nothing
+    if (!liveA) jobA = pairs[4 * item];
+    const bool liveB = liveA && jobB >= 0;           // an empty B slot rides along as a copy of A
+    if (!liveB) jobB = jobA;
+    const int jrA = p.job_read[jobA], jrB = p.job_read[jobB];
+    const int rdA = jrA & 0x7fffffff, rdB = jrB & 0x7fffffff;
+    const uint8_t* refA = p.ref2 + (jrA < 0 ? p.strand_stride : 0);
+    const uint8_t* refB = p.ref2 + (jrB < 0 ? p.strand_stride : 0);
+    const int64_t oA = p.off[rdA], oB = p.off[rdB];
+    const int L = (int)(p.off[rdA + 1] - oA);        // the same for every read of the item
     __syncwarp();
-    for (int r = sub; r < L; r += G) row[r] = (uint16_t)(prof_row_index(0, sm_depth(r, L), base_code(p.bases[o + r])) * 2);
+    for (int r = sub; r < L; r += G) {
+      const int d = sm_depth(r, L);
+      rowA[r] = (uint16_t)(prof_row_index(0, d, base_code(p.bases[oA + r])) * 2);
+      rowB[r] = (uint16_t)(prof_row_index(0, d, base_code(p.bases[oB + r])) * 2);
+    }
     __syncwarp();
 
-    int bestv[2] = {INT_MIN, INT_MIN}, bestc[2] = {0, 0};
-    bool bestbad[2] = {false, false};
+    int bestv[2] = {INT_MIN, INT_MIN}, bestc[2] = {0, 0}, rb_shift = 0;
+    bool bestbad[2] = {false, false}, bestsunk[2] = {false, false};
     int cur = 0;                                     // ring buffer the current chunk WRITES; it reads the other one
     for (int c0 = 0; c0 < len1; c0 += SW_CW, cur ^= 1) {
       const bool first = c0 == 0;
       uint4* rin = ring + (cur ^ 1) * P16_MAXL;
       uint4* rout = ring + cur * P16_MAXL;
-      // lane masks of the read's first lane: in the first chunk it has no left neighbour (one LOP3 instead of a select)
+      // lane masks of the group's first lane: in the first chunk it has no left neighbour (one LOP3 instead of a select)
       const bool edge = sub == 0 && first;
       const uint32_t keep = edge ? 0u : 0xffffffffu;
       const uint32_t sentm = edge ? B2(SENT) : 0u;
-      const uint32_t ncmp0m = edge ? B2(-(GOP + 3 * GEP) - OFF) : 0u;
+      uint32_t cur_n = RB ? ((uint32_t)(-(GOP + 3 * GEP) - OFF + 32768) & 0xffffu) * 0x10001u : B2(-(GOP + 3 * GEP) - OFFN);
+      uint32_t ncmp0m = edge ? cur_n : 0u;
+      rb_shift = 0;
       uint32_t comb[K];
 #pragma unroll
       for (int j = 0; j < K; j++) {
         const int c = c0 + sub * K + j;
         int a = 4, b = 4;
-        if (c < len1) { a = __ldg(p.ref_fw + c); b = __ldg(p.ref_rc + c); }
+        if (c < len1) { a = __ldg(refA + c); b = __ldg(refB + c); }
         comb[j] = tab_addr + (uint32_t)(a * 5 + b) * 8;
       }
       __syncwarp();
@@ -141,7 +167,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) sweep16_kernel(Sweep1
 #pragma unroll
       for (int j = 0; j < K; j++) {
         const uint2 e = lds_entry<0>(comb[j]);
-        W[j] = B2(GEP * j - OFF) + e.x + e.y;
+        if (RB) W[j] = ((uint32_t)(GEP * j - OFF + 32768) & 0xffffu) * 0x10001u + e.x + e.y;
+        else W[j] = B2(GEP * j - OFFN) + e.x + e.y;
         Rg[j] = B2(-32768);
         acc[j] = 0;
       }
@@ -158,6 +185,10 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) sweep16_kernel(Sweep1
         if (sub == 0 && !first) {                                    // the previous chunk's last lane is this lane's left neighbour
           const uint4 a = rin[r - 1], b = rin[r];
           l2 = a.x; l1 = a.y; ain = a.z; qin = b.w;
+          if (RB && (r & (P16_RB_ROWS - 1)) == 1 && r > 1) {         // row r begins with a re-basing: row r-1's cells follow it
+            l2 = __vmaxu2(__vsubus2(l2, rb_d2), RB_CELLMIN);
+            l1 = __vmaxu2(__vsubus2(l1, rb_d2), RB_CELLMIN);
+          }
         }
         l2 = and_or(__vadd2(l2, K2(-CONV)), keep, sentm);
         const uint32_t l1c = __vadd2(l1, K2(-CONV));
@@ -187,7 +218,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) sweep16_kernel(Sweep1
         for (int j = 2; j < K; j++) Q[j] = __viaddmax_u16x2(W[j - 2], K2(-GOP), Q[j - 1]);
 #pragma unroll
         for (int j = 0; j < K; j++) {
-          const uint32_t ncmpj = B2(-(GOP + 3 * GEP) - OFF) + K2(GEP * j);
+          const uint32_t ncmpj = (RB ? cur_n : B2(-(GOP + 3 * GEP) - OFFN)) + K2(GEP * j);
           uint32_t D, ad;
           if (j > 0) { D = W[j - 1]; ad = acc[j - 1]; }
           else { D = and_or(l1c, keep, ncmp0m); ad = ain; }          // matrix column 0: S = sub + N, never start-new (mia.c:805-822)
@@ -203,14 +234,26 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) sweep16_kernel(Sweep1
         }
         __syncwarp();
       };
+      auto rebase = [&](uint32_t (&W)[K]) {                          // pair16.cuh 5.
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+          W[j] = __vmaxu2(__vsubus2(W[j], rb_d2), RB_CELLMIN);
+          Rg[j] = __vsubus2(Rg[j], rb_d2);
+        }
+        cur_n = __vmaxu2(__vsubus2(cur_n, rb_d2), RB_NMIN);
+        rb_shift += p.rb_d;
+        ncmp0m = edge ? cur_n : 0u;
+      };
       {
         uint32_t W1[K], acc1[K];
         int r = 1;
         for (; r + 1 < L; r += 2) {
+          if (RB && (r & (P16_RB_ROWS - 1)) == 1 && r > 1) rebase(W);
           dp_row(r, std::integral_constant<int, 1>{}, W, acc, W1, acc1);
           dp_row(r + 1, std::integral_constant<int, 0>{}, W1, acc1, W, acc);
         }
         if (r < L) {
+          if (RB && (r & (P16_RB_ROWS - 1)) == 1 && r > 1) rebase(W);
           dp_row(r, std::integral_constant<int, 1>{}, W, acc, W1, acc1);
 #pragma unroll
           for (int j = 0; j < K; j++) { W[j] = W1[j]; acc[j] = acc1[j]; }
@@ -235,24 +278,66 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) sweep16_kernel(Sweep1
         for (int j = 0; j < K; j++)
           if (sub * K + j == cl) bad = (h ? (acc[j] >> 16) : (acc[j] & 0xffffu)) != 0;
         bad = __any_sync(gmask, bad);
-        if (best != INT_MIN && v > bestv[h]) { bestv[h] = v; bestc[h] = c0 + cl; bestbad[h] = bad; }
+        if (best != INT_MIN && v > bestv[h]) {
+          bestv[h] = v; bestc[h] = c0 + cl; bestbad[h] = bad;
+          bestsunk[h] = RB && v + GEP * (cl % K) <= p.rb_thresh;      // an end value in the poisoned range: only an upper bound
+        }
       }
       __syncwarp();
     }
-    if (sub == 0 && live) {
+    if (sub == 0 && liveA) {
 #pragma unroll
       for (int h = 0; h < 2; h++) {
-        const int64_t j = 2 * (int64_t)rd + h;
+        if (h && !liveB) continue;
+        const int64_t j = h ? jobB : jobA;
         const int aec = bestc[h];
         const int nsteps = min(L - 1, aec);
-        p.jscore[j] = bestv[h] + OFF - GEP * (L - 1);
+        p.jscore[j] = bestv[h] + OFF - GEP * (L - 1) + rb_shift;
         p.jaec[j] = aec;
         p.jabc[j] = aec - nsteps;
         p.jabr[j] = L - 1 - nsteps;
-        p.jstatus[j] = bestbad[h] ? P16_ST_GENERAL : MIAGPU_ST_OK;
+        p.jstatus[j] = bestsunk[h] ? P16_ST_SUNK : bestbad[h] ? P16_ST_GENERAL : MIAGPU_ST_OK;
       }
     }
   }
+}
+
+// ---- work items of the sweep: jobs grouped by read length, four to an item (two per half-warp, two half-warps that must run
+// the same number of rows).  A counting sort over the lengths; every length's run is padded with -1 to a multiple of four.
+//   cnt[0 .. 256] jobs per length | start[0 .. 257] first slot of a length (start[257] = all slots) | cursor[0 .. 256]
+constexpr int SW_LAYOUT_WORDS = 3 * (MAX_READ + 2) + 4;      // + n_items[2], work counters[2]
+__global__ void __launch_bounds__(256) sw_hist_kernel(int64_t m, const int32_t* __restrict__ jobs, const int32_t* __restrict__ job_read,
+                                                      const int64_t* __restrict__ off, int32_t* cnt) {
+  __shared__ int s_cnt[MAX_READ + 1];
+  for (int l = threadIdx.x; l <= MAX_READ; l += blockDim.x) s_cnt[l] = 0;
+  __syncthreads();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+    const int rd = job_read[jobs ? jobs[i] : (int32_t)i] & 0x7fffffff;
+    atomicAdd(&s_cnt[min((int)(off[rd + 1] - off[rd]), MAX_READ)], 1);
+  }
+  __syncthreads();
+  for (int l = threadIdx.x; l <= MAX_READ; l += blockDim.x) if (s_cnt[l]) atomicAdd(cnt + l, s_cnt[l]);
+}
+// n_items[0] = items whose reads are at most lmax_low long (the plain frame), n_items[1] = the others (the re-based frame)
+__global__ void sw_layout_kernel(const int32_t* cnt, int32_t* start, int32_t* cursor, int lmax_low, int32_t* n_items) {
+  if (threadIdx.x != 0) return;
+  int run = 0, low = 0;
+  for (int l = 0; l <= MAX_READ; l++) {
+    start[l] = run; cursor[l] = run;
+    run += (cnt[l] + 3) & ~3;
+    if (l == lmax_low) low = run;
+  }
+  start[MAX_READ + 1] = run;
+  n_items[0] = low / 4;
+  n_items[1] = (run - low) / 4;
+}
+__global__ void __launch_bounds__(256) sw_scatter_kernel(int64_t m, const int32_t* __restrict__ jobs, const int32_t* __restrict__ job_read,
+                                                         const int64_t* __restrict__ off, int32_t* cursor, int32_t* out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const int job = jobs ? jobs[i] : (int32_t)i;
+  const int rd = job_read[job] & 0x7fffffff;
+  out[atomicAdd(cursor + min((int)(off[rd + 1] - off[rd]), MAX_READ), 1)] = job;
 }
 
 // every read becomes two "jobs" (forward strand, reverse-complement strand) of the sweep; reads the 16-bit frame does
@@ -261,7 +346,7 @@ struct SweepPrepParams {
   int64_t n;
   const int64_t* off;
   int lmax;
-  uint8_t* kind; uint8_t* route; int32_t* jfirst; uint16_t* jcount; uint8_t* jkind; int32_t* hits;
+  uint8_t* route; int32_t* jfirst; uint16_t* jcount; uint8_t* jkind; int32_t* job_read; int32_t* sw_jobs; int32_t* hits;
   int32_t* general_list; int32_t* meta;
 };
 __global__ void sweep_prep_kernel(SweepPrepParams p, int p1_ngeneral) {
@@ -269,16 +354,17 @@ __global__ void sweep_prep_kernel(SweepPrepParams p, int p1_ngeneral) {
   if (rd >= p.n) return;
   const int L = (int)(p.off[rd + 1] - p.off[rd]);
   p.hits[rd] = 1;
+  p.job_read[2 * rd] = (int32_t)rd;
+  p.job_read[2 * rd + 1] = (int32_t)((uint32_t)rd | 0x80000000u);
   if (L >= 1 && L <= p.lmax) {
-    p.kind[rd] = (uint8_t)(16 + SW_CLASS);
     p.route[rd] = 1;
     p.jfirst[rd] = (int32_t)(2 * rd);
     p.jcount[rd] = 0x0101;
     p.jkind[2 * rd] = p.jkind[2 * rd + 1] = (uint8_t)(16 + SW_CLASS);
-    atomicAdd(&p.meta[META_HIST + SW_CLASS * (P16_MAXL + 1) + L], 1);
-    atomicAdd(&p.meta[META_PREADS + SW_CLASS], 1);
+    const int slot = atomicAdd(&p.meta[META_PREADS + SW_CLASS], 1);
+    p.sw_jobs[2 * slot] = (int32_t)(2 * rd);
+    p.sw_jobs[2 * slot + 1] = (int32_t)(2 * rd + 1);
   } else {
-    p.kind[rd] = 0;
     p.route[rd] = 2;
     p.jcount[rd] = 0;
     p.general_list[atomicAdd(p.meta + p1_ngeneral, 1)] = (int32_t)rd;

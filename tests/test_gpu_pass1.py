@@ -124,6 +124,32 @@ def test_pass1_fast_equals_general_large(gpu, monkeypatch):
     assert (np.where(m, a["runs"], 0) == np.where(m, z["runs"], 0)).all()
 
 
+def test_pass1_saturated_strands_take_the_16bit_sweep(gpu, monkeypatch):
+    # reads with >= 128 k-mer hits on a strand (kmer.c:283-285: the whole strand is unmasked): whole-strand jobs of sweep16_kernel
+    # in the re-based frame, two reads per half-warp, the other strand's stretches as windowed jobs -- equal to the general kernel
+    import _pkg
+    _pkg.load()
+    from mia_b200 import synth
+    ref = synth.random_reference(16569, seed=1)
+    g = synth.diverge(ref, 0.004, seed=2, indel_rate=0.0005)
+    b, off, _ = synth.make_reads(g, 30000, 120, 200, seed=79)
+    gpu.set_pssm(gpu_checks.load_pssm("pe"))
+    gpu.set_reference(ref, circular=1, with_rc=1)
+    gpu.build_kmers(12)
+    gpu.upload_reads(b, off)
+    a = gpu.pass1()
+    fast, general, skipped = gpu.last_pass1_stats()
+    assert (a["hits"] >= 128).sum() > 10000 and general < 3000, (int((a["hits"] >= 128).sum()), fast, general, skipped)
+    monkeypatch.setenv("MIAGPU_P1_NO_SWEEP", "1")
+    z = gpu.pass1()
+    assert gpu.last_pass1_stats()[1] > 10000
+    for k in ("hits", "score", "fw_score", "rc_score", "rc", "as_", "ae", "start", "end", "abr", "n_runs", "status"):
+        assert (a[k] == z[k]).all(), (k, int((a[k] != z[k]).sum()), np.flatnonzero(a[k] != z[k])[:5].tolist())
+    nr = np.maximum(a["n_runs"], 0)
+    m = np.arange(a["runs"].shape[1])[None, :] < nr[:, None]
+    assert (np.where(m, a["runs"], 0) == np.where(m, z["runs"], 0)).all()
+
+
 @pytest.mark.parametrize("circular,k", [(0, 10), (1, 12)])
 def test_pass1_multi_stretch_repeats_and_ties(gpu, oracle, circular, k):
     # exact and near-exact repeats far apart: several stretches per strand with equal / competing scores -> every
