@@ -459,7 +459,23 @@ def shaped_rounds(g, args, flush, lib_stream):
         P = min(args.parity_reads // 4, n)
         par = gpu_checks.round_parity(g, ref, np.ascontiguousarray(bases[: off[P]]), np.ascontiguousarray(off[: P + 1]), rc[:P], as_[:P], ae[:P], sm)
         par.pop("consensus")
-        res[tag] = {"reads": n, "matrix": mat, "ms_per_step": ms, "value": n / (ms * 1e-3), "gcups": cells / (ms * 1e-3) / 1e9,
+        # pass 1 (k = 12) on the same reads: what the read shape does to the k-mer-filtered first pass
+        p1 = None
+        if not args.no_pass1:
+            g.set_reference(ref, circular=1, with_rc=1)
+            g.build_kmers(12)
+            p1_ms = []
+            for _ in range(3):
+                flush.zero_()
+                torch.cuda.synchronize()
+                g.pass1(fields=("score",))
+                p1_ms.append(g.last_timing()["ms_kernels"])
+            fastp, generalp, skippedp = g.last_pass1_stats()
+            nominal, effective = g.last_pass1_cells()
+            p1 = {"k": 12, "ms": float(min(p1_ms[1:])), "reads_per_s": n / (min(p1_ms[1:]) * 1e-3), "windowed_16bit": int(fastp), "general_kernel": int(generalp),
+                  "no_kmer_hit": int(skippedp), "effective_gcups": effective / (min(p1_ms[1:]) * 1e-3) / 1e9}
+            g.set_reference(ref, circular=1, with_rc=0)
+        res[tag] = {"reads": n, "matrix": mat, "ms_per_step": ms, "value": n / (ms * 1e-3), "gcups": cells / (ms * 1e-3) / 1e9, "pass1": p1,
                     "gapped_fraction": float((al["n_runs"] > 1).mean()), "reads_in_16bit_kernels": int(sum(b["reads"] for b in pb)),
                     "fallback_fraction": n_fallback / n, "reads_handed_to_32bit_kernels": n_fallback, "max_read_len_16bit": lmax16,
                     "ms_16bit_kernels": float(sum(b["ms"] for b in pb)), "ms_32bit_kernels": float(sum(b["ms"] for b in b32)), "parity": par}
