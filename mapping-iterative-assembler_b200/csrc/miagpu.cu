@@ -3177,7 +3177,8 @@ static int sweep_lmax(miagpu_ctx* c, const PairLmax& lm_low) {
 
 // Whole-strand 16-bit sweeps of m jobs (jobs: device list, nullptr = jobs 0 .. m-1; d_jread names their reads and strands): work
 // items by read length, the plain frame for the reads it holds, the re-based frame for the longer ones.  On c->launch_stream.
-static int launch_sweep(miagpu_ctx* c, const int32_t* jobs, int64_t m, int lmax_low) {
+// same_read: the list holds reads; a half-warp takes both strands of one (pass 1 without the filter).
+static int launch_sweep(miagpu_ctx* c, const int32_t* jobs, int64_t m, int lmax_low, bool same_read = false) {
   if (m <= 0) return 1;
   cudaStream_t st = c->launch_stream;
   const int len1 = c->circular ? c->wrap_len : c->seq_len;
@@ -3185,9 +3186,11 @@ static int launch_sweep(miagpu_ctx* c, const int32_t* jobs, int64_t m, int lmax_
   int32_t *cnt = c->d_sw_layout.p, *start = cnt + (MAX_READ + 2), *cursor = start + (MAX_READ + 2), *n_items = cursor + (MAX_READ + 2), *work = n_items + 2;
   MIAGPU_CUDA(cudaMemsetAsync(cnt, 0, SW_LAYOUT_WORDS * sizeof(int32_t), st));
   MIAGPU_CUDA(cudaMemsetAsync(c->d_sw_pairs.p, 0xff, ((size_t)m + 4 * (MAX_READ + 2) + 8) * sizeof(int32_t), st));
-  sw_hist_kernel<<<(unsigned)std::min<int64_t>(2 * c->num_sms, (m + 255) / 256), 256, 0, st>>>(m, jobs, c->d_jread.p, c->d_off.p, cnt);
-  sw_layout_kernel<<<1, 32, 0, st>>>(cnt, start, cursor, lmax_low, n_items);
-  sw_scatter_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(m, jobs, c->d_jread.p, c->d_off.p, cursor, c->d_sw_pairs.p);
+  const int32_t* jr = same_read ? nullptr : c->d_jread.p;
+  const int per_item = same_read ? 2 : 4;
+  sw_hist_kernel<<<(unsigned)std::min<int64_t>(2 * c->num_sms, (m + 255) / 256), 256, 0, st>>>(m, jobs, jr, c->d_off.p, cnt);
+  sw_layout_kernel<<<1, 32, 0, st>>>(cnt, start, cursor, lmax_low, n_items, per_item);
+  sw_scatter_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(m, jobs, jr, c->d_off.p, cursor, c->d_sw_pairs.p);
   MIAGPU_CUDA(cudaGetLastError());
   Sweep16Params sp{};
   sp.bases = c->d_bases.p; sp.off = c->d_off.p; sp.pairs = c->d_sw_pairs.p; sp.job_read = c->d_jread.p;
@@ -3195,23 +3198,33 @@ static int launch_sweep(miagpu_ctx* c, const int32_t* jobs, int64_t m, int lmax_
   sp.jscore = c->d_jscore.p; sp.jabc = c->d_jabc.p; sp.jaec = c->d_jaec.p; sp.jabr = c->d_jabr.p; sp.jstatus = c->d_jstatus.p;
   const RbFrame f = p16_rb_frame(SW_K, c->pssm_max);
   sp.rb_off = f.off; sp.rb_d = f.d; sp.rb_thresh = f.thresh;
-  const size_t smem = sw_smem();
-  static int per_sm_d[MAX_DEVICES][2];
+  // shared memory follows the longest read (the hand-over rings are the bulk of it): short reads leave room for four blocks per SM
+  if (!ensure_max_read_len(c)) return 0;
+  const int rows_cap = std::min((std::max(c->max_read_len, 8) + 7) & ~7, P16_MAXL);
+  sp.rows_cap = rows_cap;
+  const size_t smem = sw_smem(rows_cap);
+  static int per_sm_d[MAX_DEVICES][2], cached_rows_d[MAX_DEVICES];
   int* per_sm = per_sm_d[c->device % MAX_DEVICES];
-  if (per_sm[0] <= 0) {
-    MIAGPU_CUDA(cudaFuncSetAttribute(sweep16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MIAGPU_CUDA(cudaFuncSetAttribute(sweep16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MIAGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[0], sweep16_kernel<false>, WARPS_PER_BLOCK * 32, smem));
-    MIAGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], sweep16_kernel<true>, WARPS_PER_BLOCK * 32, smem));
+  int& cached_rows = cached_rows_d[c->device % MAX_DEVICES];
+  if (cached_rows != rows_cap) {
+    MIAGPU_CUDA(cudaFuncSetAttribute((sweep16_kernel<false, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MIAGPU_CUDA(cudaFuncSetAttribute((sweep16_kernel<true, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MIAGPU_CUDA(cudaFuncSetAttribute((sweep16_kernel<false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MIAGPU_CUDA(cudaFuncSetAttribute((sweep16_kernel<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MIAGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[0], (sweep16_kernel<false, false>), WARPS_PER_BLOCK * 32, smem));
+    MIAGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], (sweep16_kernel<true, false>), WARPS_PER_BLOCK * 32, smem));
+    cached_rows = rows_cap;
   }
   if (per_sm[0] < 1 || per_sm[1] < 1) { set_error("sweep16_kernel does not fit on an SM (smem %zu)", smem); return 0; }
-  const int64_t items_max = m / 4 + (MAX_READ + 2);                         // every length's run is padded to whole items
+  const int64_t items_max = m / per_item + (MAX_READ + 2);                  // every length's run is padded to whole items
   const int blocks0 = (int)std::min<int64_t>((int64_t)c->num_sms * per_sm[0], (items_max + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
   const int blocks1 = (int)std::min<int64_t>((int64_t)c->num_sms * per_sm[1], (items_max + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
   sp.n_items = n_items; sp.first_item = nullptr; sp.counter = work;
-  sweep16_kernel<false><<<blocks0, WARPS_PER_BLOCK * 32, smem, st>>>(sp);
+  if (same_read) sweep16_kernel<false, true><<<blocks0, WARPS_PER_BLOCK * 32, smem, st>>>(sp);
+  else sweep16_kernel<false, false><<<blocks0, WARPS_PER_BLOCK * 32, smem, st>>>(sp);
   sp.n_items = n_items + 1; sp.first_item = n_items; sp.counter = work + 1;
-  sweep16_kernel<true><<<blocks1, WARPS_PER_BLOCK * 32, smem, st>>>(sp);
+  if (same_read) sweep16_kernel<true, true><<<blocks1, WARPS_PER_BLOCK * 32, smem, st>>>(sp);
+  else sweep16_kernel<true, false><<<blocks1, WARPS_PER_BLOCK * 32, smem, st>>>(sp);
   MIAGPU_CUDA(cudaGetLastError());
   c->launches += 5;
   return 1;
@@ -3440,7 +3453,7 @@ static int pass1_sweep(miagpu_ctx* c, const PairLmax& lm) {
     MIAGPU_CUDA(cudaEventRecord(c->aev[1], c->s_aux[1]));
   }
   c->launch_stream = st;
-  if (!launch_sweep(c, c->d_sw_jobs.p, 2 * n_sweep_reads, lmax_low)) return 0;
+  if (!launch_sweep(c, c->d_sw_jobs.p, n_sweep_reads, lmax_low, true)) return 0;
   MIAGPU_CUDA(cudaEventRecord(c->p1ev[1], st));
   P1MergeParams mp{};
   mp.n = n; mp.off = c->d_off.p; mp.seq_len = c->seq_len; mp.route = c->d_route.p; mp.jfirst = c->d_jfirst.p; mp.jcount = c->d_jcount.p;

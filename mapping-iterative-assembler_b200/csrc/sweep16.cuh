@@ -39,6 +39,8 @@ struct Sweep16Params {
   const uint8_t* ref2;           // codes of the wrapped forward strand, then (strand_stride bytes on) of the reverse-complement strand
   int32_t strand_stride;
   int32_t len1;
+  int32_t rows_cap;              // rows the per-job arrays in shared memory hold (>= the longest read of the launch): sized per launch,
+                                 // because the hand-over rings decide how many blocks an SM takes
   const int16_t* prof16;
   uint32_t gep2;
   int32_t rb_off, rb_d, rb_thresh;   // RB: the re-based frame of pair16.cuh 5. (K = 16)
@@ -47,10 +49,10 @@ struct Sweep16Params {
   uint8_t* jstatus;
 };
 
-// dynamic shared memory: [prof16][rowoff WARPS*2*2*P16_MAXL u16][tab WARPS*2*2*P16_TAB_WORDS u32][ring WARPS*2*2*P16_MAXL*4 u32]
-__host__ __device__ constexpr int sw_smem() {
-  return (PROF16_N + 8) * 2 + WARPS_PER_BLOCK * 2 * 2 * P16_MAXL * 2 + WARPS_PER_BLOCK * 2 * 2 * P16_TAB_WORDS * 4 +
-         WARPS_PER_BLOCK * 2 * 2 * P16_MAXL * 16;
+// dynamic shared memory: [prof16][rowoff WARPS*2*2*rows_cap u16][tab WARPS*2*2*P16_TAB_WORDS u32][ring WARPS*2*2*rows_cap*4 u32]
+__host__ __device__ constexpr int sw_smem(int rows_cap) {
+  return (PROF16_N + 8) * 2 + WARPS_PER_BLOCK * 2 * 2 * rows_cap * 2 + WARPS_PER_BLOCK * 2 * 2 * P16_TAB_WORDS * 4 +
+         WARPS_PER_BLOCK * 2 * 2 * rows_cap * 16;
 }
 
 // A half-warp (16 lanes x 16 columns) carries TWO jobs in the halves of its registers: job A in the low half, job B in the high
@@ -58,14 +60,18 @@ __host__ __device__ constexpr int sw_smem() {
 // it they are the strands the filter saturated (kmer.c:283-285: the whole strand is unmasked) of any two reads of one length.
 // RB: the re-based frame (pair16.cuh 5.) for reads beyond the plain one; every chunk goes through the same re-basings, so what a
 // chunk hands to the next stays in step: the last two cells of row r-1 are re-based by the consumer when row r begins with one.
-template <bool RB>
+// SAME: the two jobs of a half-warp are the two strands of ONE read (pass 1 without the filter): `pairs` holds reads, two per
+// item, job = 2 * read + strand; one row array, one table row -- the kernel of round 1, kept because the general pairing costs it
+// eight more registers' worth of spills.
+template <bool RB, bool SAME = false>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) sweep16_kernel(Sweep16Params p) {
   constexpr int K = SW_K, G = SW_G;
   constexpr int NE = (25 + G - 1) / G;
   extern __shared__ __align__(16) uint8_t smem[];
   int16_t* s_prof = reinterpret_cast<int16_t*>(smem);
   constexpr int PROF_BYTES = (PROF16_N + 8) * 2;
-  constexpr int ROWOFF_BYTES = WARPS_PER_BLOCK * 2 * 2 * P16_MAXL * 2;
+  const int RC = p.rows_cap;                           // a multiple of 8: the sections stay 16-byte aligned
+  const int ROWOFF_BYTES = WARPS_PER_BLOCK * 2 * 2 * RC * 2;
   constexpr int TAB_BYTES = WARPS_PER_BLOCK * 2 * 2 * P16_TAB_WORDS * 4;
   uint16_t* s_rowoff = reinterpret_cast<uint16_t*>(smem + PROF_BYTES);
   uint32_t* s_tab = reinterpret_cast<uint32_t*>(smem + PROF_BYTES + ROWOFF_BYTES);
@@ -77,10 +83,9 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) sweep16_kernel(Sweep1
   for (int i = tid; i < PROF16_N + 8; i += blockDim.x) s_prof[i] = p.prof16[i];
   __syncthreads();
 
-  uint16_t* rowA = s_rowoff + ((warp * 2 + hw) * 2 + 0) * P16_MAXL;
-  uint16_t* rowB = s_rowoff + ((warp * 2 + hw) * 2 + 1) * P16_MAXL;
+  uint16_t* rowA = s_rowoff + ((warp * 2 + hw) * 2 + 0) * RC;            // job B's rows: rowA + RC
   uint32_t* tab = s_tab + (warp * 2 + hw) * 2 * P16_TAB_WORDS;
-  uint4* ring = s_ring + (size_t)(warp * 2 + hw) * 2 * P16_MAXL;      // two buffers of P16_MAXL rows: {l2, l1, acc, scan total}
+  uint4* ring = s_ring + (size_t)(warp * 2 + hw) * 2 * RC;            // two buffers of RC rows: {l2, l1, acc, scan total}
   const uint32_t prof_base = smem_u32(s_prof);
   const uint32_t tab_addr = smem_u32(tab);
 
@@ -91,7 +96,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) sweep16_kernel(Sweep1
   constexpr uint32_t RB_NMIN = B2(-(GOP + 3 * GEP) - OFFN), RB_CELLMIN = B2(-(GOP + 3 * GEP) - OFFN + 2 * GEP - PSSM_ABS_LIMIT);
   const uint32_t rb_d2 = RB ? K2(p.rb_d) : 0u;
   const int n_items = *p.n_items;
-  const int32_t* pairs = p.pairs + (p.first_item ? 4 * (int64_t)*p.first_item : 0);
+
   const uint32_t gep2 = p.gep2;
   const int len1 = p.len1;
 
@@ -104,7 +109,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) sweep16_kernel(Sweep1
   }
   // entry (a, b) = { sub_A(r, a), sub_B(r, b) << 16 }
   auto build_table = [&](int r, uint32_t* dst) {
-    const uint32_t pa = prof_base + rowA[r], pb = prof_base + rowB[r];
+    const uint32_t pa = prof_base + rowA[r], pb = SAME ? pa : prof_base + rowA[RC + r];
 #pragma unroll
     for (int t = 0; t < NE; t++) {
       const uint2 v = make_uint2((uint32_t)lds_s16(pa + eoa[t]), lds_u16(pb + eob[t]) << 16);
@@ -117,32 +122,43 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) sweep16_kernel(Sweep1
     if (lane == 0) item = atomicAdd(p.counter, 1);
     item = __shfl_sync(0xffffffffu, item, 0);
     if (item >= n_items) break;
-    int jobA = pairs[4 * item + 2 * hw], jobB = pairs[4 * item + 2 * hw + 1];
-    const bool liveA = jobA >= 0;                    // an empty half-warp recomputes the item's first job and writes nothing
-    if (!liveA) jobA = pairs[4 * item];
-    const bool liveB = liveA && jobB >= 0;           // an empty B slot rides along as a copy of A
-    if (!liveB) jobB = jobA;
-    const int jrA = p.job_read[jobA], jrB = p.job_read[jobB];
-    const int rdA = jrA & 0x7fffffff, rdB = jrB & 0x7fffffff;
-    const uint8_t* refA = p.ref2 + (jrA < 0 ? p.strand_stride : 0);
-    const uint8_t* refB = p.ref2 + (jrB < 0 ? p.strand_stride : 0);
-    const int64_t oA = p.off[rdA], oB = p.off[rdB];
-    const int L = (int)(p.off[rdA + 1] - oA);        // the same for every read of the item
-    __syncwarp();
-    for (int r = sub; r < L; r += G) {
-      const int d = sm_depth(r, L);
-      rowA[r] = (uint16_t)(prof_row_index(0, d, base_code(p.bases[oA + r])) * 2);
-      rowB[r] = (uint16_t)(prof_row_index(0, d, base_code(p.bases[oB + r])) * 2);
+    if (p.first_item) item += *p.first_item;
+    // (the jobs are read again at the end instead of being kept in registers through the sweep)
+    int soA = 0, soB = 0, L;                         // strand offsets into ref2; rows
+    if (SAME) {
+      int rd = p.pairs[2 * (int64_t)item + hw];
+      if (rd < 0) rd = p.pairs[2 * (int64_t)item];   // an empty slot recomputes the item's first read and writes nothing
+      const int64_t o = p.off[rd];
+      L = (int)(p.off[rd + 1] - o);
+      __syncwarp();
+      for (int r = sub; r < L; r += G) rowA[r] = (uint16_t)(prof_row_index(0, sm_depth(r, L), base_code(p.bases[o + r])) * 2);
+      __syncwarp();
+    } else {
+      int jobA = p.pairs[4 * (int64_t)item + 2 * hw], jobB = p.pairs[4 * (int64_t)item + 2 * hw + 1];
+      if (jobA < 0) jobA = p.pairs[4 * (int64_t)item];     // an empty half-warp recomputes the item's first job and writes nothing
+      if (jobB < 0) jobB = jobA;                           // an empty B slot rides along as a copy of A
+      const int jrA = p.job_read[jobA], jrB = p.job_read[jobB];
+      const int rdA = jrA & 0x7fffffff, rdB = jrB & 0x7fffffff;
+      soA = jrA < 0 ? p.strand_stride : 0;
+      soB = jrB < 0 ? p.strand_stride : 0;
+      const int64_t oA = p.off[rdA], oB = p.off[rdB];
+      L = (int)(p.off[rdA + 1] - oA);                // the same for every read of the item
+      __syncwarp();
+      for (int r = sub; r < L; r += G) {
+        const int d = sm_depth(r, L);
+        rowA[r] = (uint16_t)(prof_row_index(0, d, base_code(p.bases[oA + r])) * 2);
+        rowA[RC + r] = (uint16_t)(prof_row_index(0, d, base_code(p.bases[oB + r])) * 2);
+      }
+      __syncwarp();
     }
-    __syncwarp();
 
     int bestv[2] = {INT_MIN, INT_MIN}, bestc[2] = {0, 0}, rb_shift = 0;
     bool bestbad[2] = {false, false}, bestsunk[2] = {false, false};
     int cur = 0;                                     // ring buffer the current chunk WRITES; it reads the other one
     for (int c0 = 0; c0 < len1; c0 += SW_CW, cur ^= 1) {
       const bool first = c0 == 0;
-      uint4* rin = ring + (cur ^ 1) * P16_MAXL;
-      uint4* rout = ring + cur * P16_MAXL;
+      uint4* rin = ring + (cur ^ 1) * RC;
+      uint4* rout = ring + cur * RC;
       // lane masks of the group's first lane: in the first chunk it has no left neighbour (one LOP3 instead of a select)
       const bool edge = sub == 0 && first;
       const uint32_t keep = edge ? 0u : 0xffffffffu;
@@ -155,7 +171,10 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) sweep16_kernel(Sweep1
       for (int j = 0; j < K; j++) {
         const int c = c0 + sub * K + j;
         int a = 4, b = 4;
-        if (c < len1) { a = __ldg(refA + c); b = __ldg(refB + c); }
+        if (c < len1) {
+          if (SAME) { a = __ldg(p.ref2 + c); b = __ldg(p.ref2 + p.strand_stride + c); }
+          else { a = __ldg(p.ref2 + soA + c); b = __ldg(p.ref2 + soB + c); }
+        }
         comb[j] = tab_addr + (uint32_t)(a * 5 + b) * 8;
       }
       __syncwarp();
@@ -285,10 +304,13 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) sweep16_kernel(Sweep1
       }
       __syncwarp();
     }
-    if (sub == 0 && liveA) {
+    int jobA, jobB;
+    if (SAME) { const int rd = p.pairs[2 * (int64_t)item + hw]; jobA = rd < 0 ? -1 : 2 * rd; jobB = 2 * rd + 1; }
+    else { jobA = p.pairs[4 * (int64_t)item + 2 * hw]; jobB = p.pairs[4 * (int64_t)item + 2 * hw + 1]; }
+    if (sub == 0 && jobA >= 0) {
 #pragma unroll
       for (int h = 0; h < 2; h++) {
-        if (h && !liveB) continue;
+        if (h && jobB < 0) continue;
         const int64_t j = h ? jobB : jobA;
         const int aec = bestc[h];
         const int nsteps = min(L - 1, aec);
@@ -306,37 +328,40 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) sweep16_kernel(Sweep1
 // the same number of rows).  A counting sort over the lengths; every length's run is padded with -1 to a multiple of four.
 //   cnt[0 .. 256] jobs per length | start[0 .. 257] first slot of a length (start[257] = all slots) | cursor[0 .. 256]
 constexpr int SW_LAYOUT_WORDS = 3 * (MAX_READ + 2) + 4;      // + n_items[2], work counters[2]
+// (job_read == nullptr: the list holds reads, not jobs)
 __global__ void __launch_bounds__(256) sw_hist_kernel(int64_t m, const int32_t* __restrict__ jobs, const int32_t* __restrict__ job_read,
                                                       const int64_t* __restrict__ off, int32_t* cnt) {
   __shared__ int s_cnt[MAX_READ + 1];
   for (int l = threadIdx.x; l <= MAX_READ; l += blockDim.x) s_cnt[l] = 0;
   __syncthreads();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
-    const int rd = job_read[jobs ? jobs[i] : (int32_t)i] & 0x7fffffff;
+    const int e = jobs ? jobs[i] : (int32_t)i;
+    const int rd = job_read ? job_read[e] & 0x7fffffff : e;
     atomicAdd(&s_cnt[min((int)(off[rd + 1] - off[rd]), MAX_READ)], 1);
   }
   __syncthreads();
   for (int l = threadIdx.x; l <= MAX_READ; l += blockDim.x) if (s_cnt[l]) atomicAdd(cnt + l, s_cnt[l]);
 }
 // n_items[0] = items whose reads are at most lmax_low long (the plain frame), n_items[1] = the others (the re-based frame)
-__global__ void sw_layout_kernel(const int32_t* cnt, int32_t* start, int32_t* cursor, int lmax_low, int32_t* n_items) {
+// per_item: list entries per work item (4 jobs, or 2 reads)
+__global__ void sw_layout_kernel(const int32_t* cnt, int32_t* start, int32_t* cursor, int lmax_low, int32_t* n_items, int per_item) {
   if (threadIdx.x != 0) return;
   int run = 0, low = 0;
   for (int l = 0; l <= MAX_READ; l++) {
     start[l] = run; cursor[l] = run;
-    run += (cnt[l] + 3) & ~3;
+    run += (cnt[l] + per_item - 1) / per_item * per_item;
     if (l == lmax_low) low = run;
   }
   start[MAX_READ + 1] = run;
-  n_items[0] = low / 4;
-  n_items[1] = (run - low) / 4;
+  n_items[0] = low / per_item;
+  n_items[1] = (run - low) / per_item;
 }
 __global__ void __launch_bounds__(256) sw_scatter_kernel(int64_t m, const int32_t* __restrict__ jobs, const int32_t* __restrict__ job_read,
                                                          const int64_t* __restrict__ off, int32_t* cursor, int32_t* out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
   const int job = jobs ? jobs[i] : (int32_t)i;
-  const int rd = job_read[job] & 0x7fffffff;
+  const int rd = job_read ? job_read[job] & 0x7fffffff : job;
   out[atomicAdd(cursor + min((int)(off[rd + 1] - off[rd]), MAX_READ), 1)] = job;
 }
 
@@ -361,9 +386,7 @@ __global__ void sweep_prep_kernel(SweepPrepParams p, int p1_ngeneral) {
     p.jfirst[rd] = (int32_t)(2 * rd);
     p.jcount[rd] = 0x0101;
     p.jkind[2 * rd] = p.jkind[2 * rd + 1] = (uint8_t)(16 + SW_CLASS);
-    const int slot = atomicAdd(&p.meta[META_PREADS + SW_CLASS], 1);
-    p.sw_jobs[2 * slot] = (int32_t)(2 * rd);
-    p.sw_jobs[2 * slot + 1] = (int32_t)(2 * rd + 1);
+    p.sw_jobs[atomicAdd(&p.meta[META_PREADS + SW_CLASS], 1)] = (int32_t)rd;      // the sweep's list holds READS here (SAME kernels)
   } else {
     p.route[rd] = 2;
     p.jcount[rd] = 0;
