@@ -392,6 +392,16 @@ int miagpu_shard_cut( miagpu_ctx* ctx, double* slope_out, double* intercept_out,
 int miagpu_shard_finish( miagpu_ctx* ctx, int cons_code, uint8_t* dropped,
                          uint16_t* packed_runs, int64_t capacity, int64_t* total_runs,
                          int32_t* gaps_out, char* cons_out, int32_t* cons_len );
+
+/* Pointer state (miagpu_set_fsdb) in sharded rounds.  Slot numbers run over the reads of ALL ranks in FSDB order: a rank passes
+ * miagpu_set_fsdb the GLOBAL slot numbers of its reads' pass-1 pointers, the global slot count and the flags of all slots.  A
+ * round numbers its slots from the ranks' slot counts (they travel in the header rows of the MAX all-reduce), follows the local
+ * reads' pointers as a one-GPU round does, and refuses a stale pointer whose slot a read of another rank owns this round (or
+ * whose last content lives on another rank): such a pointer sits within a few reads of a shard boundary.  AlnSeq.dropped lives in
+ * the slots, and the slots a rank's reads take drift from round to round, so every rank keeps the flags of all slots: after
+ * miagpu_shard_finish the caller MAX-reduces this buffer (one byte per slot) over the ranks, before the next miagpu_shard_begin.
+ * *bytes = 0: no pointer state, nothing to do.  -D and the repeat filter are not available in sharded rounds. */
+int miagpu_shard_flags( miagpu_ctx* ctx, void** flag_buf, int64_t* bytes );
 /* chain blocks of the last round's regression that were summed read by read on the host, and how many of
  * those needed an extra device fetch (sharded rounds prefetch the likely ones with the block records) */
 int miagpu_last_cut_stats( miagpu_ctx* ctx, int64_t* serial_blocks, int64_t* fetched_blocks );

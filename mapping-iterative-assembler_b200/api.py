@@ -123,7 +123,7 @@ EXPORTS = ["miagpu_device_count", "miagpu_create", "miagpu_destroy", "miagpu_las
            "miagpu_last_cut_stats", "miagpu_repeat_filter", "miagpu_trim", "miagpu_get_alignment",
            "miagpu_fastx_open", "miagpu_fastx_open_memory", "miagpu_fastx_format", "miagpu_fastx_next", "miagpu_fastx_batch", "miagpu_fastx_close",
            "miagpu_maln_ref_size", "miagpu_write_maln", "miagpu_read_pssm", "miagpu_align_windows",
-           "miagpu_set_fsdb", "miagpu_get_fsdb", "miagpu_last_fsdb_stats", "miagpu_distant_retry", "miagpu_write_maln_fsdb", "miagpu_last_pass1_cells", "miagpu_set_homopolymer"]
+           "miagpu_set_fsdb", "miagpu_get_fsdb", "miagpu_last_fsdb_stats", "miagpu_distant_retry", "miagpu_write_maln_fsdb", "miagpu_last_pass1_cells", "miagpu_set_homopolymer", "miagpu_shard_flags"]
 
 
 def _ptr(a):
@@ -386,6 +386,13 @@ class MiaGpu:
         self._ck(self.lib.miagpu_shard_finish(self.h, cons_code, _ptr(dropped), _ptr(packed), cap, C.byref(tot) if want_tot else None,
                                               _ptr(gaps), self._consbuf, C.byref(cl)))
         return self._consbuf.value.decode(), gaps, (tot.value if want_tot else None)
+
+    def shard_flags(self):
+        """-> (ptr, bytes) of the slot flags to MAX-reduce over the ranks after shard_finish (bytes = 0: no pointer state)"""
+        b, n = C.c_void_p(), C.c_int64()
+        self.lib.miagpu_shard_flags.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), _i64p]
+        self._ck(self.lib.miagpu_shard_flags(self.h, C.byref(b), C.byref(n)))
+        return b.value, n.value
 
     def last_cut_stats(self):
         a, b = C.c_int64(), C.c_int64()

@@ -396,13 +396,15 @@ __global__ void call_kernel(const int32_t* acc, int64_t n_cols, int cons_code, c
 // dropped_back, or unique[i] == 0, leaves its entries empty.
 __global__ void natural_entries_kernel(int64_t n, const int32_t* as_out, const int32_t* ae_out, const int32_t* n_runs,
                                        const uint16_t* runs, const uint8_t* status, int seq_len, const uint8_t* dropped_front,
-                                       const uint8_t* dropped_back, miagpu_entry* out, const uint8_t* unique = nullptr) {
+                                       const uint8_t* dropped_back, miagpu_entry* out, const uint8_t* unique = nullptr,
+                                       const uint8_t* known = nullptr) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   miagpu_entry f{}, b{};
   f.read = b.read = (int32_t)i;
   const int nr = n_runs[i];
-  const bool absent = (unique && !unique[i]) || (dropped_front && dropped_front[i] == 2);
+  // (known: a strand-unknown read merges no AlnSeq of its own, mia_main.c:178)
+  const bool absent = (unique && !unique[i]) || (dropped_front && dropped_front[i] == 2) || (known && !known[i]);
   if (nr > 0 && !(status[i] & MIAGPU_ST_UNSUPPORTED) && !absent) {
     const int start = as_out[i];
     int end = ae_out[i];

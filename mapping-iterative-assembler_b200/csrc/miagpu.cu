@@ -209,6 +209,7 @@ struct miagpu_ctx {
   int fs_submat_rc = 0;                        // which matrix a->submat was left pointing at (H6)
   int fs_round = 0;                            // rounds since miagpu_set_fsdb
   int64_t fs_slot_cap = 0, fs_nslots = 0, fs_nslots_prev = 0;
+  bool fs_sharded = false;                     // the round in flight numbers its slots over all ranks (miagpu_shard_*)
   int fs_prev_seq_len = 0;
   bool fs_prev_valid = false, fs_prev_pass1 = false, fs_seed_read_flags = false;
   DevBuf<uint8_t> d_known, d_slot_flag, d_slot_new, d_flip_prev;
@@ -1745,6 +1746,7 @@ static FsDev fs_dev(miagpu_ctx* c) {
   f.known = c->d_known.p; f.front_slot = c->d_front_slot.p; f.back_slot = c->d_back_slot.p; f.slot_flag = c->d_slot_flag.p;
   f.slot_new = c->d_slot_new.p; f.first = c->d_first.p; f.slot_owner = c->d_slot_owner.p; f.ent_slot = c->d_ent_slot.p;
   f.stale = c->d_stale.p; f.counters = c->d_fs_cnt.p; f.stale_cap = (int32_t)std::min<size_t>(c->d_stale.cap / 3, 0x7fffffff);
+  f.slot_base = c->fs_sharded ? c->d_fs_cnt.p + FS_CNT_BASE : nullptr;
   return f;
 }
 
@@ -1780,8 +1782,12 @@ static void fs_carry_submat(miagpu_ctx* c) {
   }
 }
 
-// slot numbers of this round (exclusive scan of the AlnSeqs every read merges, FSDB order), natural entries, stale pointers
-static int fs_number_and_entries(miagpu_ctx* c, bool has_unique) {
+static int fs_number(miagpu_ctx* c);
+static int fs_entries(miagpu_ctx* c, bool has_unique);
+static int fs_number_and_entries(miagpu_ctx* c, bool has_unique) { return fs_number(c) && fs_entries(c, has_unique); }
+
+// slot numbers of this round: exclusive scan of the AlnSeqs every read merges, FSDB order (sharded rounds: of this rank's reads)
+static int fs_number(miagpu_ctx* c) {
   cudaStream_t main = c->stream;
   const int64_t n = c->n;
   const unsigned grid = (unsigned)((n + 255) / 256);
@@ -1794,6 +1800,16 @@ static int fs_number_and_entries(miagpu_ctx* c, bool has_unique) {
   if (!c->d_cub.reserve(tmp + 16)) return 0;
   MIAGPU_CUDA(cub::DeviceScan::ExclusiveSum(c->d_cub.p, tmp, c->d_nsl.p, c->d_first.p, n + 1, main));
   MIAGPU_CUDA(cudaMemcpyAsync(c->d_fs_cnt.p + FS_CNT_NSLOTS, c->d_first.p + n, sizeof(int32_t), cudaMemcpyDeviceToDevice, main));
+  MIAGPU_CUDA(cudaGetLastError());
+  c->launches += 3;
+  return 1;
+}
+
+// natural entries with the flags of their slots, slot owners, this round's pointers, the list of stale pointers
+static int fs_entries(miagpu_ctx* c, bool has_unique) {
+  cudaStream_t main = c->stream;
+  const int64_t n = c->n;
+  const unsigned grid = (unsigned)((n + 255) / 256);
   if (c->fs_seed_read_flags) {                       // per-read flags of miagpu_set_fsdb( slot numbers = NULL ): they belong to the slots of this numbering
     fs_seed_flags_kernel<<<grid, 256, 0, main>>>(n, c->d_first.p, c->d_nsl.p, c->d_dropf.p, c->d_slot_flag.p);
     c->fs_seed_read_flags = false;
@@ -1801,7 +1817,7 @@ static int fs_number_and_entries(miagpu_ctx* c, bool has_unique) {
   fs_entries_kernel<<<grid, 256, 0, main>>>(n, fs_dev(c), c->d_as_out.p, c->d_ae_out.p, c->d_nruns.p, c->d_runs.p, c->seq_len,
                                             has_unique ? c->d_unique.p : nullptr, c->d_entries.p);
   MIAGPU_CUDA(cudaGetLastError());
-  c->launches += 4;
+  c->launches += 1;
   return 1;
 }
 
@@ -1833,8 +1849,17 @@ static int fs_resolve(miagpu_ctx* c, int n_stale, bool has_unique) {
   for (int q = 0; q < n_stale; q++) {
     const int32_t* r = &rec[8 * q];
     const int64_t k = r[2];
+    if (r[3] < 0 && r[7] && c->fs_sharded) {
+      set_error("miagpu: sharded rounds: local read %d holds a stale pointer to AlnSeq slot %lld, which a read of another rank owns this round "
+                "(a pointer that crosses a shard boundary is not served)", r[0], (long long)k);
+      return 0;
+    }
     if (r[3] >= 0 || c->fz_of_slot.count(k)) continue;
-    if (r[4] < 0) { set_error("miagpu: read %d points at AlnSeq slot %lld, which neither this nor the previous round filled", r[0], (long long)k); return 0; }
+    if (r[4] < 0) {
+      set_error("miagpu: read %d points at AlnSeq slot %lld, which neither this nor the previous round filled%s", r[0], (long long)k,
+                c->fs_sharded ? " on this rank (sharded rounds: its last content lives on another rank)" : "");
+      return 0;
+    }
     c->fz_of_slot[k] = (int)(c->fz.size() + fz_which.size());
     fz_which.push_back(r[4]); fz_dst.push_back((int32_t)(c->fz.size() + fz_which.size() - 1)); fz_slot.push_back(k);
   }
@@ -1988,7 +2013,7 @@ static int fs_resolve(miagpu_ctx* c, int n_stale, bool has_unique) {
 // after the host has this round's counters: status of the reads, slot count, stale pointers
 static int fs_after_numbering(miagpu_ctx* c, bool has_unique, const int32_t* cnt, int32_t* total_ins) {
   const int status = cnt[FS_CNT_STATUS];
-  c->fs_nslots = cnt[FS_CNT_NSLOTS];
+  c->fs_nslots = c->fs_sharded ? cnt[FS_CNT_TOTAL] : cnt[FS_CNT_NSLOTS];
   c->fs_n_stale = cnt[FS_CNT_STALE];
   c->fs_n_extra = 0;
   c->fs_extra.clear(); c->fs_patch_host.clear();
@@ -2040,7 +2065,7 @@ extern "C" int miagpu_set_fsdb(miagpu_ctx* c, const int32_t* seq_len, const uint
   const int64_t n = c->n;
   if (c->h_rc.size() != (size_t)n) { set_error("miagpu_set_fsdb: call miagpu_set_alignment_inputs first"); return 0; }
   cudaStream_t st = c->stream;
-  c->fs_slot_cap = std::max<int64_t>(n_slots, 2 * n) + 64;
+  c->fs_slot_cap = std::max<int64_t>(2 * n_slots, 2 * n) + 64;     // (sharded rounds: n_slots counts the slots of ALL ranks; a round takes at most two per read)
   if (!c->d_known.reserve(n + 1) || !c->d_front_slot.reserve(n + 1) || !c->d_back_slot.reserve(n + 1) ||
       !c->d_slot_flag.reserve(c->fs_slot_cap) || !c->d_slot_new.reserve(c->fs_slot_cap) || !fs_reserve_round(c)) return 0;
   c->h_known.assign((size_t)n, 1);
@@ -2076,7 +2101,7 @@ extern "C" int miagpu_set_fsdb(miagpu_ctx* c, const int32_t* seq_len, const uint
     c->fs_seed_read_flags = true;
   }
   MIAGPU_CUDA(cudaStreamSynchronize(st));
-  c->fs_on = true; c->fs_distant = distant_ref ? 1 : 0; c->fs_submat_rc = 0; c->fs_round = 0;
+  c->fs_on = true; c->fs_distant = distant_ref ? 1 : 0; c->fs_submat_rc = 0; c->fs_round = 0; c->fs_sharded = false;
   c->fs_nslots = c->fs_nslots_prev = n_slots;
   if (!front_slot) c->fs_prev_valid = false;         // nothing was merged before the first round
   c->fz.clear(); c->fz_of_slot.clear(); c->fs_extra.clear(); c->fs_patch_host.clear();
@@ -2575,6 +2600,7 @@ extern "C" int miagpu_iterate_resident(miagpu_ctx* c, int hard_cut, int score_cu
   cudaStream_t main = c->stream, down = c->s_down;
   if (c->fs_on) {
     if (!fs_reserve_round(c)) return 0;
+    c->fs_sharded = false;
     fs_begin_round(c);
   }
   MIAGPU_CUDA(cudaEventRecord(c->ev[1], main));
@@ -2649,20 +2675,32 @@ static int shard_after_dp(miagpu_ctx* c, bool stats_done, bool has_unique, void*
   MIAGPU_CUDA(cudaMemsetAsync(c->d_gaps.p, 0, (c->seq_len + 2) * sizeof(int32_t), main));
   int32_t* best = c->d_gaps.p + c->seq_len + 2;
   int32_t* hdr = best + MAX_READ + 1;
-  shard_hdr2_kernel<<<1, 256, 0, main>>>(c->d_cstats.p, best, hdr, c->sh_world, c->sh_rank, (int)n);
+  c->n_entries = 2 * n;
+  if (c->fs_on) {
+    // pointer state: this rank's slot count goes out with the header; the slots can only be numbered (and the entries take their
+    // flags) once every rank's count is back -- miagpu_shard_fit.  The insert maxima need the entries' geometry only.
+    if (!fs_number(c)) return 0;
+    if (n) {
+      natural_entries_kernel<<<(unsigned)((n + 255) / 256), 256, 0, main>>>(n, c->d_as_out.p, c->d_ae_out.p, c->d_nruns.p, c->d_runs.p,
+                                                                            c->d_status.p, c->seq_len, nullptr, nullptr, c->d_entries.p, nullptr, c->d_known.p);
+      MIAGPU_CUDA(cudaGetLastError());
+      c->launches++;
+    }
+  } else {
+    MIAGPU_CUDA(cudaMemsetAsync(c->d_fs_cnt.p, 0, FS_CNT_WORDS * sizeof(int32_t), main));
+  }
+  shard_hdr2_kernel<<<1, 256, 0, main>>>(c->d_cstats.p, best, hdr, c->sh_world, c->sh_rank, (int)n, c->fs_on ? c->d_fs_cnt.p + FS_CNT_NSLOTS : nullptr);
   MIAGPU_CUDA(cudaGetLastError());
   c->launches++;
-  c->n_entries = 2 * n;
-  MIAGPU_CUDA(cudaMemsetAsync(c->d_fs_cnt.p, 0, FS_CNT_WORDS * sizeof(int32_t), main));
-  if (n) {
+  if (n && !c->fs_on) {
     status_or_kernel<<<(unsigned)((n + 255) / 256), 256, 0, main>>>(n, c->d_status.p, c->d_nruns.p, c->d_fs_cnt.p + FS_CNT_STATUS);
     natural_entries_kernel<<<(unsigned)((n + 255) / 256), 256, 0, main>>>(n, c->d_as_out.p, c->d_ae_out.p, c->d_nruns.p, c->d_runs.p,
                                                                           c->d_status.p, c->seq_len, c->d_dropf.p, c->d_dropf.p, c->d_entries.p,
                                                                           has_unique ? c->d_unique.p : nullptr);
     MIAGPU_CUDA(cudaGetLastError());
     c->launches += 2;
-    if (!launch_gaps(c)) return 0;
   }
+  if (n && !launch_gaps(c)) return 0;
   if (max_buf) *max_buf = c->d_gaps.p;
   if (max_words) *max_words = c->seq_len + 2 + MAX_READ + 1 + (int64_t)c->sh_world * SHARD_HDR2;
   c->sh_phase = 1;
@@ -2687,9 +2725,14 @@ extern "C" int miagpu_shard_begin(miagpu_ctx* c, int world, int rank, int64_t n_
                                   double intercept, void** max_buf, int64_t* max_words) {
   if (!shard_args(c, "miagpu_shard_begin", world, rank, n_max, c ? c->n : 0)) return 0;
   if (c->cut_inputs_n != c->n) { set_error("miagpu_shard_begin: upload reads, alignment inputs and cut inputs first"); return 0; }
-  if (c->fs_on) { set_error("miagpu_shard_begin: the pointer state of miagpu_set_fsdb is not available in sharded rounds"); return 0; }
+  if (c->fs_on && (c->fs_distant || !c->h_unique.empty())) { set_error("miagpu_shard_begin: the pointer state in sharded rounds goes without -D and without the repeat filter"); return 0; }
   MIAGPU_CUDA(cudaSetDevice(c->device));
   if (!shard_reserve_common(c, world, n_max)) return 0;
+  if (c->fs_on) {
+    if (!fs_reserve_round(c)) return 0;
+    c->fs_sharded = true;
+    fs_begin_round(c);
+  }
   c->sh_world = world; c->sh_rank = rank; c->sh_nmax = n_max; c->sh_hard_cut = hard_cut; c->sh_cut_set = score_cut_set;
   c->sh_slope = slope; c->sh_icpt = intercept; c->sh_fit = !score_cut_set && hard_cut <= 0; c->sh_host = false; c->sh_want_packed = false;
   c->sh_phase = 0;
@@ -2707,6 +2750,7 @@ extern "C" int miagpu_shard_begin_host(miagpu_ctx* c, int world, int rank, int64
                                        const int32_t* seq_len, const uint8_t* unique_best, const uint8_t* dropped, int hard_cut,
                                        int score_cut_set, double slope, double intercept, void** max_buf, int64_t* max_words) {
   if (!shard_args(c, "miagpu_shard_begin_host", world, rank, n_max, n)) return 0;
+  if (c->fs_on) { set_error("miagpu_shard_begin_host: the pointer state goes with resident reads (miagpu_shard_begin)"); return 0; }
   const Trace tr;
   int C = 1;
   c->sh_phase = 0;
@@ -2734,6 +2778,14 @@ extern "C" int miagpu_shard_fit(miagpu_ctx* c, void** gather_send, void** gather
   CutHost* H = c->h_cut;
   int32_t* best = c->d_gaps.p + c->seq_len + 2;
   int32_t* hdr = best + MAX_READ + 1;
+  if (c->fs_on) {
+    // every rank's slot count is back: global slot numbers (the ranks' reads one after the other), entries with the flags of their
+    // slots, owners of the local slots (-1: another rank's), this round's pointers and the list of stale ones
+    fs_base_kernel<<<1, 32, 0, main>>>(c->sh_world, c->sh_rank, hdr, SHARD_HDR2, c->d_fs_cnt.p);
+    MIAGPU_CUDA(cudaMemsetAsync(c->d_slot_owner.p, 0xff, (size_t)c->fs_slot_cap * sizeof(int32_t), main));
+    if (!fs_entries(c, false)) return 0;
+    c->launches += 2;
+  }
   // insert-column layout from the reduced maxima
   size_t tmp = 0;
   MIAGPU_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, c->d_gaps.p, c->d_ins_off.p, c->seq_len + 1, main));
@@ -2765,6 +2817,8 @@ extern "C" int miagpu_shard_fit(miagpu_ctx* c, void** gather_send, void** gather
     set_error("miagpu_shard_fit: local reads came back with status bits 0x%x (more than %d alignment runs, or a window no kernel takes)", H->fs_cnt[FS_CNT_STATUS], MAX_RUNS);
     return 0;
   }
+  // pointer state: stale pointers -> extra entries / patched smp parameters / frozen content, all of it local to this rank
+  if (c->fs_on && !fs_after_numbering(c, false, H->fs_cnt, &H->total_ins)) { cudaStreamSynchronize(main); return 0; }
   c->n_cols = (int64_t)c->seq_len + H->total_ins;
   // the planes are followed by nothing yet: the caller all-reduces exactly n_cols * NPLANE words
   if (!c->d_acc.reserve(c->n_cols * NPLANE) || !c->d_called.reserve(c->n_cols + 16)) return 0;
@@ -2870,7 +2924,9 @@ extern "C" int miagpu_shard_cut(miagpu_ctx* c, double* slope_out, double* interc
   cut_thresholds(c->sh_hard_cut, slope, intercept, H->thr);
   MIAGPU_CUDA(cudaMemcpyAsync(c->d_thr.p, H->thr, sizeof(H->thr), cudaMemcpyHostToDevice, main));
   MIAGPU_CUDA(cudaStreamWaitEvent(main, c->aev[7], 0));                                // the accumulation of shard_fit
-  if (n) {
+  if (n && c->fs_on) {
+    if (!fs_flags_and_undo(c, false)) return 0;      // through the pointers; every slot a local pointer reaches is local (miagpu_shard_fit)
+  } else if (n) {
     cut_flags_kernel<<<(unsigned)((n + 255) / 256), 256, 0, main>>>(n, c->d_seqlen.p, c->d_score.p, c->d_thr.p, c->d_dropf.p, nullptr, c->d_cstats.p,
                                                                     c->sh_has_unique ? c->d_unique.p : nullptr, c->d_newly.p);
     undo_kernel<<<(unsigned)((n + 255) / 256), 256, 0, main>>>(cons_params(c), n, c->d_newly.p, c->d_entries.p);
@@ -2916,6 +2972,18 @@ extern "C" int miagpu_shard_finish(miagpu_ctx* c, int cons_code, uint8_t* droppe
   c->ms_kernels = ms_dp;
   c->ms_h2d = c->ms_d2h = 0;
   MIAGPU_CUDA(cudaMemcpy(&c->n_fallback, c->d_meta.p + META_NFALL, 4, cudaMemcpyDeviceToHost));
+  if (c->fs_on) c->fs_prev_seq_len = c->seq_len;     // the geometry of this round's alignments, should the next round have to freeze one
+  return 1;
+}
+
+// Pointer state in sharded rounds: AlnSeq.dropped lives in the slots, slot numbers run over the reads of all ranks, and the slots a
+// rank's reads take drift from round to round -- so every rank keeps the flags of ALL slots.  After miagpu_shard_cut the flags this
+// round set are in this buffer (one byte per slot); the caller MAX-reduces it over the ranks before the next miagpu_shard_begin.
+// *bytes = 0: the context has no pointer state, nothing to do.
+extern "C" int miagpu_shard_flags(miagpu_ctx* c, void** flag_buf, int64_t* bytes) {
+  if (!c) { set_error("miagpu_shard_flags: no context"); return 0; }
+  if (flag_buf) *flag_buf = c->fs_on ? c->d_slot_flag.p : nullptr;
+  if (bytes) *bytes = c->fs_on ? c->fs_slot_cap : 0;
   return 1;
 }
 

@@ -291,7 +291,8 @@ __global__ void __launch_bounds__(CUT_THREADS) cut_exact_kernel(int64_t n, CutSr
 constexpr int SHARD_HDR2 = 16;                       // header words per rank: 5 sums x 2 pieces of 30 bits, local read count
 __device__ __forceinline__ void put60(int32_t* dst, long long v) { dst[0] = (int32_t)(v & 0x3fffffff); dst[1] = (int32_t)((v >> 30) & 0x3fffffff); }
 __device__ __forceinline__ long long get60(const int32_t* src) { return (long long)src[0] | ((long long)src[1] << 30); }
-__global__ void shard_hdr2_kernel(const CutStatsDev* st, int32_t* max_best, int32_t* hdr, int world, int rank, int n_local) {
+__global__ void shard_hdr2_kernel(const CutStatsDev* st, int32_t* max_best, int32_t* hdr, int world, int rank, int n_local,
+                                  const int32_t* n_slots_local = nullptr) {
   const int t = threadIdx.x;
   for (int i = t; i < world * SHARD_HDR2; i += blockDim.x) hdr[i] = 0;
   for (int l = t; l <= MAX_READ; l += blockDim.x) max_best[l] = max(st->best[l], 0);     // (no read of that length: INT_MIN -> 0; scores that count are >= 2000)
@@ -300,6 +301,7 @@ __global__ void shard_hdr2_kernel(const CutStatsDev* st, int32_t* max_best, int3
     int32_t* h = hdr + rank * SHARD_HDR2;
     put60(h, st->sx); put60(h + 2, st->sy); put60(h + 4, st->cnt); put60(h + 6, st->sxx); put60(h + 8, st->sxy);
     h[10] = n_local;
+    h[11] = n_slots_local ? *n_slots_local : 0;          // pointer state: AlnSeq slots this rank's reads take this round (slots.cuh)
   }
 }
 struct ShardPrep { double start[2]; long long sx, sy, cnt; };

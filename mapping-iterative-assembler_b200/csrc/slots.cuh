@@ -27,6 +27,7 @@
 namespace miagpu {
 
 constexpr int FS_CNT_STALE = 0, FS_CNT_STATUS = 1, FS_CNT_NSLOTS = 2, FS_CNT_WORDS = 8;
+constexpr int FS_CNT_BASE = 3, FS_CNT_TOTAL = 4;   // sharded rounds: first slot of this rank's reads, slots of all ranks (this round)
 constexpr int FZ_BASES = MAX_READ;                  // bytes of bases per frozen alignment
 
 struct FsDev {
@@ -41,6 +42,8 @@ struct FsDev {
   int32_t* stale;              // [stale_cap][3]: read, kind (0 front_asp, 1 back_asp), slot
   int32_t* counters;           // FS_CNT_*
   int32_t stale_cap;
+  const int32_t* slot_base;    // nullable; sharded rounds: *slot_base = the slot of this rank's first AlnSeq (slot numbers are global:
+                               // the ranks' reads one after the other in FSDB order)
 };
 
 // Columns / inserted bases / deletions of an alignment and of its part in front of the wrap point
@@ -117,7 +120,7 @@ __global__ void fs_entries_kernel(int64_t n, FsDev f, const int32_t* __restrict_
   };
   if (!f.known || f.known[i]) {
     const int nr = n_runs[i];
-    const int s0 = f.first[i];
+    const int s0 = f.first[i] + (f.slot_base ? *f.slot_base : 0);
     const SegGeom g = seg_geom(as_out[i], ae_out[i], seq_len, runs + i * MAX_RUNS, nr > 0 ? nr : 0);
     seg_entries((int)i, as_out[i], g, ef, eb);
     f.front_slot[i] = s0;
@@ -154,7 +157,8 @@ __global__ void fs_gather_kernel(int n_stale, const int32_t* __restrict__ stale,
   rec[8 * q + 3] = (k >= 0 && k < n_slots) ? slot_owner[k] : -1;
   rec[8 * q + 4] = (k >= 0 && k < n_slots_prev && slot_owner_prev) ? slot_owner_prev[k] : -1;
   rec[8 * q + 5] = (!known || known[i]) ? 1 : 0;
-  rec[8 * q + 6] = front_slot[i]; rec[8 * q + 7] = 0;
+  rec[8 * q + 6] = front_slot[i];
+  rec[8 * q + 7] = (k >= 0 && k < n_slots) ? 1 : 0;      // live this round (sharded rounds: possibly on another rank, then rec[3] = -1)
 }
 
 // Geometry of the segments of a list of alignments (2 * read + seg), from the current or the previous round's results:
@@ -299,6 +303,14 @@ __global__ void fs_read_flags_kernel(int64_t n, const int32_t* __restrict__ fron
   const int kf = front_slot[i], kb = back_slot[i];
   if (dropped_front) dropped_front[i] = kf >= 0 ? slot_flag[kf] : 0;
   if (dropped_back) dropped_back[i] = kb >= 0 ? slot_flag[kb] : 0;
+}
+
+// sharded rounds: the ranks' slot counts of this round came back in the header rows of the MAX all-reduce (word 11 of a row)
+__global__ void fs_base_kernel(int world, int rank, const int32_t* __restrict__ hdr, int hdr_stride, int32_t* counters) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int base = 0, total = 0;
+  for (int r = 0; r < world; r++) { const int v = hdr[r * hdr_stride + 11]; if (r < rank) base += v; total += v; }
+  counters[FS_CNT_BASE] = base; counters[FS_CNT_TOTAL] = total;
 }
 
 // legacy per-read flags (miagpu_set_cut_inputs) become the flags of the slots the reads take at the first numbering

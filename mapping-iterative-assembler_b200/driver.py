@@ -259,8 +259,12 @@ class ResidentAssembler:
         self.strand_known = ~unknown[idx]
         self.split = p["start"][idx] > p["end"][idx]                                 # mia.c:1619
         self.maln_size = int(len(idx) + self.split.sum())                            # culled_maln->size (mia.c:54): AlnSeqs of pass 1
-        if self.x is not None or not defer_cull:
-            self.pass1_cull(self._gather(self.seq_len), self._gather(self.score))
+        if self.x is not None:
+            counts = self._gather(np.array([len(self.seq_len)], np.int64))            # reads per rank, in rank order
+            lo = int(counts[: self.x.rank].sum()) if self.fs else 0
+            self.pass1_cull(self._gather(self.seq_len), self._gather(self.score), self._gather(self.split.astype(np.uint8)) if self.fs else None, lo)
+        elif not defer_cull:
+            self.pass1_cull(self.seq_len, self.score)
         return p
 
     def _alignable_len(self, ref_wrapped_upper, wrap_len):
@@ -270,8 +274,10 @@ class ResidentAssembler:
         e = np.clip(np.minimum(self.ae.astype(np.int64), wrap_len), a, wrap_len)
         return np.maximum(self.seq_len - (isn[e] - isn[a]), 15).astype(np.int32)     # MIN_ALIGNABLE_LEN
 
-    def pass1_cull(self, all_seq_len, all_score):
-        """pass-1 cull (mia_main.c:848) with the fit over the reads of ALL ranks in FSDB order: only its dropped flags survive"""
+    def pass1_cull(self, all_seq_len, all_score, all_split=None, lo=0):
+        """pass-1 cull (mia_main.c:848) with the fit over the reads of ALL ranks in FSDB order: only its dropped flags survive.
+        all_split / lo (pointer state over several shards): the wrap-split flags of all ranks' reads and where this shard's reads
+        begin among them -- AlnSeq slots are numbered over all reads, every shard keeps the flags of all slots."""
         g, idx = self.g, self._idx
         fit = api.score_cut(all_seq_len, all_score)
         thr_len = self.seq_len
@@ -281,12 +287,23 @@ class ResidentAssembler:
             thr_len = self._alignable_len(rw, len(rw))
         dropped = api.cull_flags(thr_len, self.score, None, 0, 1, fit[0], fit[1])
         # AlnSeq slots of pass 1 in merge order (mia.c:1619-1643): one per accepted read, two when wrap-split
-        nsl = 1 + self.split.astype(np.int64)
-        first = np.cumsum(nsl) - nsl
-        n_slots = int(nsl.sum())
-        slot_dropped = np.zeros(n_slots + 1, np.uint8)
-        slot_dropped[first[dropped > 0]] = 1
-        slot_dropped[first[(dropped > 0) & self.split] + 1] = 1
+        if all_split is None:
+            nsl = 1 + self.split.astype(np.int64)
+            first = np.cumsum(nsl) - nsl
+            n_slots = int(nsl.sum())
+            slot_dropped = np.zeros(n_slots + 1, np.uint8)
+            slot_dropped[first[dropped > 0]] = 1
+            slot_dropped[first[(dropped > 0) & self.split] + 1] = 1
+        else:
+            asp = np.asarray(all_split).astype(bool)
+            ansl = 1 + asp.astype(np.int64)
+            afirst = np.cumsum(ansl) - ansl
+            n_slots = int(ansl.sum())
+            adrop = api.cull_flags(np.asarray(all_seq_len, np.int32), np.asarray(all_score, np.int32), None, 0, 1, fit[0], fit[1])
+            slot_dropped = np.zeros(n_slots + 1, np.uint8)
+            slot_dropped[afirst[adrop > 0]] = 1
+            slot_dropped[afirst[(adrop > 0) & asp] + 1] = 1
+            first = afirst[lo: lo + len(self.seq_len)]
         ok = self.score > 0                                                          # clean_FSDB (mia.c:400-406)
         keep_dev = np.zeros(self._n_all, np.uint8)
         keep_dev[idx[ok]] = 1

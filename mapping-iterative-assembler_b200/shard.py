@@ -80,11 +80,22 @@ class ShardedRounds:
         self._after_cut(sb)
         return fit
 
+    def _after_finish(self):
+        """pointer state: the slot flags of all ranks (MAX), before the next round begins"""
+        import torch
+        import torch.distributed as dist
+        ptr, nbytes = self.g.shard_flags()
+        if nbytes and self.world > 1:
+            fl = dev_tensor(ptr, nbytes, self.device, "|u1")
+            with torch.cuda.stream(self.stream):
+                dist.all_reduce(fl, op=dist.ReduceOp.MAX, group=self.group)
+
     def resident(self, cons_code=1, hard_cut=0, score_cut=None, dropped=None, want_gaps=False):
         """miagpu_iterate_resident for a shard: -> (consensus, (slope, intercept), gaps)"""
         self._after_begin(self.g.shard_begin(self.world, self.rank, self.n_max, hard_cut, score_cut))
         fit = self._round()
         cons, gaps, _ = self.g.shard_finish(cons_code, dropped, None, want_gaps)
+        self._after_finish()
         return cons, fit, gaps
 
     def host(self, bases, offsets, rc, as_, ae, seq_len, dropped, out, packed=None, cons_code=1, unique_best=None, hard_cut=0,
@@ -143,6 +154,18 @@ class LocalShards:
         self._exchange_cut([c[1] for c in cuts])
         return cuts
 
+    def _exchange_flags(self):
+        import torch
+        fl = [g.shard_flags() for g in self.gpus]
+        if not fl[0][1]:
+            return
+        self._sync()
+        ts = [dev_tensor(p, n, self.device, "|u1") for p, n in fl]
+        m = torch.stack(ts).max(0).values
+        for t in ts:
+            t.copy_(m)
+        self._sync()
+
     def resident(self, n_max, cons_code=1, hard_cut=0, score_cut=None, dropped=None, want_gaps=False):
         """dropped: list of uint8 arrays (one per shard) or None.  -> list of (consensus, fit, gaps) per shard"""
         self._exchange_begin([g.shard_begin(self.world, r, n_max, hard_cut, score_cut) for r, g in enumerate(self.gpus)])
@@ -151,6 +174,7 @@ class LocalShards:
         for r, g in enumerate(self.gpus):
             cons, gaps, _ = g.shard_finish(cons_code, None if dropped is None else dropped[r], None, want_gaps)
             res.append((cons, cuts[r][0], gaps))
+        self._exchange_flags()
         return res
 
     def host(self, n_max, shards, cons_code=1, hard_cut=0, score_cut=None, want_gaps=False):

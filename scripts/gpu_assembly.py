@@ -49,6 +49,7 @@ def main():
     ap.add_argument("--reads", type=int, default=10_000_000)
     ap.add_argument("--prefix", type=int, default=10_000)
     ap.add_argument("--distant", action="store_true")
+    ap.add_argument("--legacy-shards", action="store_true", help="sharded rounds without the pointer state (round-1 behaviour: reads scoring exactly 2000 left out, split changes counted)")
     ap.add_argument("--parity-only", action="store_true", help="only the prefix check of the data set --reads names (one GPU)")
     args = ap.parse_args()
     sh = SHAPES[args.shape]
@@ -83,6 +84,7 @@ def main():
 
     class Exchange:
         rounds = None
+        rank = int(os.environ.get("RANK", "0"))
 
         @staticmethod
         def all_gather_host(a):
@@ -106,7 +108,7 @@ def main():
 
     g = api.MiaGpu(local)
     mk = lambda gg, x=None: driver.ResidentAssembler(gg, ref, sm, circular=sh["circular"], k=sh["k"], exchange=x, strand_unknown="drop",
-                                                     distant_ref=int(args.distant))
+                                                     distant_ref=int(args.distant), pointer_state=None if (x is None or args.legacy_shards) else True)
     W = mk(g)                                          # load every kernel once on a small prefix: the timed calls show steady cost
     m = min(20000, len(off) - 1)
     W.pass1(np.ascontiguousarray(bases[: off[m]]), np.ascontiguousarray(off[: m + 1]))
@@ -126,6 +128,10 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         n_fsdb, n_unknown, n_max = int(t[0]), int(t[1]), int(mx[0])
+        if A.fs:
+            u = torch.tensor([int((~A.strand_known).sum())], device="cuda", dtype=torch.int64)
+            dist.all_reduce(u)
+            n_unknown = int(u[0])
         Exchange.rounds = shard.ShardedRounds(g, local, world, rank, n_max)
     else:
         n_fsdb, n_unknown = n_local, int((~A.strand_known).sum())
@@ -176,8 +182,8 @@ def main():
                    reads_per_s_whole_assembly=per * PIECES / total_s,
                    reads_per_s_per_round=per * PIECES / (sum(r["ms"] for r in rounds) / len(rounds) / 1e3),
                    all_ranks_same_consensus=same, consensus_equals_sample_genome=(cons == genome), identity_to_sample_genome=ident,
-                   split_changes_not_modelled=int(A.split_changes), reads_scoring_exactly_2000_left_out=n_unknown if world > 1 else 0,
-                   strand_unknown_reads=n_unknown if world == 1 else 0,
+                   pointer_state=bool(A.fs), split_changes_not_modelled=int(A.split_changes),
+                   reads_scoring_exactly_2000_left_out=n_unknown if not A.fs else 0, strand_unknown_reads=n_unknown if A.fs else 0,
                    pass1_route_rank0=dict(zip(("pair_kernels", "general_kernel", "no_kmer_hit"), p1_route)), **extra)
         if args.prefix > 0:                            # the first reads of the data set as an assembly of their own, against the CPU checker
             t0 = time.perf_counter()

@@ -133,6 +133,63 @@ def test_resident_rounds_follow_the_reference_pointers(gpu, golden, name, matrix
     assert stale > 0, "the session was made to exercise stale pointers"
 
 
+@pytest.mark.parametrize("name,matrix,parts", [("flat_2000_c", "flat", 2), ("origin305_splitflip_c", "onepass", 2), ("origin303_splitflip_c", "onepass", 3),
+                                               ("origin305_splitflip_c", "onepass", 3)])
+def test_sharded_rounds_follow_the_reference_pointers(gpu, golden, name, matrix, parts):
+    # the pointer state with the reads on several shards (contexts of one process, collectives emulated by device copies): global slot
+    # numbers, slot flags replicated, stale pointers resolved on the shard that holds them -- the reference's rounds, read by read.
+    # A stale pointer that crosses a shard boundary is refused (miagpu.h): the test moves the boundaries until none does.
+    import _pkg
+    _pkg.load()
+    from mia_b200 import api, driver, shard
+    s = _load_r2(name)
+    reads = s["reads"]
+    n = len(reads)
+    off = np.zeros(n + 1, np.int64)
+    np.cumsum([len(r) for r in reads], out=off[1:])
+    bases = np.frombuffer("".join(reads).encode(), np.uint8)
+    refused, done = [], False
+    for shift in (0.0, 0.07, -0.07, 0.13, -0.13, 0.21):
+        cuts = [0] + [int(n * (r / parts + shift / parts)) for r in range(1, parts)] + [n]
+        ctxs = [api.MiaGpu(0) for _ in range(parts)]
+        try:
+            asms = [driver.ResidentAssembler(g, s["ref"], golden[matrix], s["circular"], s["k"], 0, pointer_state=True) for g in ctxs]
+            for r, a in enumerate(asms):
+                lo, hi = cuts[r], cuts[r + 1]
+                a.pass1(np.ascontiguousarray(bases[off[lo]:off[hi]]), np.ascontiguousarray(off[lo:hi + 1] - off[lo]), defer_cull=True)
+            all_sl = np.concatenate([a.seq_len for a in asms])
+            all_sc = np.concatenate([a.score for a in asms])
+            all_sp = np.concatenate([a.split for a in asms]).astype(np.uint8)
+            los = np.concatenate([[0], np.cumsum([len(a.seq_len) for a in asms])])
+            for r, a in enumerate(asms):
+                a.pass1_cull(all_sl, all_sc, all_sp, int(los[r]))
+            L = shard.LocalShards(ctxs)
+            stale = 0
+            for it, e in enumerate(s["iters"]):
+                for a in asms:
+                    a.begin_round()
+                res = L.resident(max(len(a.seq_len) for a in asms), dropped=[a.dropped for a in asms])
+                outs = [a.end_round(*r) for a, r in zip(asms, res)]
+                stale += sum(g.last_fsdb_stats()["stale_pointers"] for g in ctxs)
+                for cons, conv in outs:
+                    assert cons == e["cons"], f"{name}: iteration {it + 1} consensus (cuts {cuts})"
+                    assert conv == e["converged"]
+                got = np.concatenate([np.stack([a.score, a.as_, a.ae, a.rc.astype(np.int32), a.strand_known.astype(np.int32)], 1) for a in asms]).tolist()
+                assert got == e["reads"], f"{name}: iteration {it + 1} per-read results (cuts {cuts})"
+            assert stale > 0, "the session was made to exercise stale pointers"
+            done = True
+        except api.MiaGpuError as ex:
+            if "another rank" not in str(ex):
+                raise
+            refused.append((cuts, str(ex)[:120]))
+        finally:
+            for g in ctxs:
+                g.close()
+        if done:
+            break
+    assert done, f"every sharding was refused: {refused}"
+
+
 @pytest.mark.parametrize("name,matrix,parts", [("synth3k_div10_c_k12", "ancient", 2), ("synth2k5_pe_long_c_k12", "pe", 3)])
 def test_sharded_assembly_to_convergence(gpu, golden, name, matrix, parts):
     # BASELINE configs[2] / [3] in small: pass 1 and every round with the reads sharded (contexts of one process, collectives
