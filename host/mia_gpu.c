@@ -305,6 +305,7 @@ int main( int argc, char** argv ) {
     }
     iter++;
     t1 = now_ms();
+    CK( miagpu_set_cons_capacity( g, (int64_t)cons_cap ) );
     CK( miagpu_set_reference( g, last, L, circular, 0 ) );
     if ( repeat_filt ) {
       CK( miagpu_realign_resident( g ) );

@@ -119,6 +119,7 @@ static void* worker( void* arg_ ) {
   int64_t j;
   CK( S, miagpu_create( &g, rank ) );
   CK( S, miagpu_set_homopolymer( g, S->hp_special ) );
+  CK( S, miagpu_set_cons_capacity( g, (int64_t)S->cons_cap ) );      /* what the cons buffers of this program hold */
   CK( S, miagpu_set_pssm( g, S->fwd ) );
   CK( S, miagpu_set_reference( g, S->ref, S->ref_len, S->circular, 1 ) );
   CK( S, miagpu_build_kmers( g, S->k, 0 ) );

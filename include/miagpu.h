@@ -217,7 +217,9 @@ typedef struct {
 /* Accumulate + call in one step (single GPU).  Outputs are host arrays, any may
  * be NULL: gaps_out[seq_len] = ref->gaps for positions < seq_len;
  * counts_out[seq_len*10] = BaseCounts of every base column (MIAGPU_COUNTS_PER_COL
- * order); cons_out must hold seq_len + sum(gaps) + 1 chars; *cons_len its strlen. */
+ * order); cons_out receives at most seq_len + sum(gaps) + 1 chars and must hold
+ * seq_len * 4 + 4096 bytes unless miagpu_set_cons_capacity said otherwise: a consensus
+ * that does not fit fails the call (nothing is written); *cons_len its strlen. */
 int miagpu_consensus( miagpu_ctx* ctx, int64_t n_entries,
                       const miagpu_entry* entries, int cons_code,
                       int32_t* gaps_out, int32_t* counts_out, char* cons_out,
@@ -239,6 +241,12 @@ int miagpu_accumulate_counts( miagpu_ctx* ctx, void** dev_counts,
                               int64_t* n_counts );
 int miagpu_call( miagpu_ctx* ctx, int cons_code, int32_t* gaps_out,
                  int32_t* counts_out, char* cons_out, int32_t* cons_len );
+/* Size in bytes of the buffer the caller passes as cons_out to the calls of this context
+ * (0 = the default, seq_len * 4 + 4096).  The reference sizes its consensus string from
+ * the gaps it has just counted (consensus_assembly_string, mia.c:527-533); a caller of
+ * this library allocates before the gaps are known, so it announces its buffer and a
+ * longer consensus fails the call rather than overrunning it. */
+int miagpu_set_cons_capacity( miagpu_ctx* ctx, int64_t bytes );
 
 /* The same with the entry list built ON THE DEVICE from the resident alignments:
  * every read contributes its own fresh segment(s) (no stale AlnSeq pointers to

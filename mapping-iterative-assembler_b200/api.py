@@ -53,6 +53,7 @@ def load_library():
     L.miagpu_pass1.argtypes = [C.c_void_p] + [C.c_void_p] * 13
     L.miagpu_last_pass1_stats.argtypes = [C.c_void_p, _i64p, _i64p, _i64p]
     L.miagpu_set_homopolymer.argtypes = [C.c_void_p, C.c_int]
+    L.miagpu_set_cons_capacity.argtypes = [C.c_void_p, C.c_int64]
     L.miagpu_last_pass1_route.argtypes = [C.c_void_p, C.c_void_p]
     L.miagpu_last_pass1_cells.argtypes = [C.c_void_p, _i64p, _i64p]
     L.miagpu_compact_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, _i64p]
@@ -123,7 +124,7 @@ EXPORTS = ["miagpu_device_count", "miagpu_create", "miagpu_destroy", "miagpu_las
            "miagpu_last_cut_stats", "miagpu_repeat_filter", "miagpu_trim", "miagpu_get_alignment",
            "miagpu_fastx_open", "miagpu_fastx_open_memory", "miagpu_fastx_format", "miagpu_fastx_next", "miagpu_fastx_batch", "miagpu_fastx_close",
            "miagpu_maln_ref_size", "miagpu_write_maln", "miagpu_read_pssm", "miagpu_align_windows",
-           "miagpu_set_fsdb", "miagpu_get_fsdb", "miagpu_last_fsdb_stats", "miagpu_distant_retry", "miagpu_write_maln_fsdb", "miagpu_last_pass1_cells", "miagpu_set_homopolymer", "miagpu_shard_flags"]
+           "miagpu_set_fsdb", "miagpu_get_fsdb", "miagpu_last_fsdb_stats", "miagpu_distant_retry", "miagpu_write_maln_fsdb", "miagpu_last_pass1_cells", "miagpu_set_homopolymer", "miagpu_shard_flags", "miagpu_set_cons_capacity"]
 
 
 def _ptr(a):

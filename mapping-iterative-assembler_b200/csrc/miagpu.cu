@@ -94,6 +94,7 @@ struct miagpu_ctx {
   bool have_ref = false;
   std::string raw_wrapped, raw_rc_wrapped;     // case preserved (k-mer soft mask)
   int seq_len = 0, wrap_len = 0, circular = 0, with_rc = 0;
+  int64_t cons_capacity = 0;                         // bytes behind the caller's cons_out (0 = the header's default)
   bool explicit_windows = false;   // miagpu_align_windows: d_as / d_ae hold [start, end) of every read's window, no window rule
   int explicit_sg5 = 1;
   DevBuf<uint8_t> d_ref, d_rcref, d_ref2;      // codes 0..4, padded to 16 B; d_ref2 = both strands back to back
@@ -1004,6 +1005,7 @@ static int realign_launch(miagpu_ctx* c, const RealignJob& j) {
       if (j.timed) MIAGPU_CUDA(cudaEventRecord(c->pev[2 * kb], c->stream));
       Pair16Params p{};
       p.bases = c->d_bases.p; p.off = c->d_off.p + lo; p.rc = c->d_rc.p + lo; p.win_start = c->d_win_start.p + lo; p.win_len = c->d_win_len.p + lo;
+      p.win_len_narrow = getenv("MIAGPU_NO_NARROW") ? nullptr : c->d_win_len.p + lo;
       p.pairs = j.d_pairs + 2 * (int64_t)base; p.n_items = j.d_meta + META_NPAIRS + kb; p.counter = j.d_meta + META_PWORK + kb;
       p.ref_codes = c->d_ref.p; p.ref_bytes = c->ref_bytes; p.prof16 = c->d_prof16.p;
       p.score = c->d_score.p + lo; p.as_out = c->d_as_out.p + lo; p.ae_out = c->d_ae_out.p + lo; p.abr = c->d_abr.p + lo;
@@ -1043,8 +1045,20 @@ static int realign_launch(miagpu_ctx* c, const RealignJob& j) {
 
   // ---- 32-bit kernels over the direct lists plus whatever the pair kernels appended
   if (concurrent && !fork_streams(c, 4)) return 0;
+  // A read the pair kernels hand over arrives with the window cut at its end cell (pair16.cuh), i.e. in its own bucket or a narrower
+  // one: the bound of a list's final length and of its longest read take in the pair-eligible reads of every wider bucket.
+  int pop_ub[NBUCKET], maxL_ub[NBUCKET];
+  {
+    int wider = 0, widerL = 0;                        // pair-eligible reads of the buckets >= b, their longest read
+    for (int b = NBUCKET - 1; b >= 0; b--) {
+      const int elig = total_pairs && b != NBUCKET - 1 ? meta[META_POP + b] - meta[META_COUNT + b] : 0;
+      if (elig > 0) { wider += elig; widerL = std::max(widerL, meta[META_MAXL + b]); }
+      pop_ub[b] = meta[META_COUNT + b] + (b != NBUCKET - 1 ? wider : 0);
+      maxL_ub[b] = std::max(meta[META_MAXL + b], b != NBUCKET - 1 ? widerL : 0);
+    }
+  }
   for (int b = 0; b < NBUCKET; b++) {
-    const int pop = meta[META_POP + b];               // upper bound of the final list length
+    const int pop = pop_ub[b];                        // upper bound of the final list length
     if (!pop) continue;
     if (!total_pairs && !meta[META_COUNT + b]) continue;
     pick_stream(c, concurrent, rr);
@@ -1058,7 +1072,7 @@ static int realign_launch(miagpu_ctx* c, const RealignJob& j) {
     p.score = c->d_score.p + lo; p.as_out = c->d_as_out.p + lo; p.ae_out = c->d_ae_out.p + lo; p.abr = c->d_abr.p + lo;
     p.n_runs = c->d_nruns.p + lo; p.runs = c->d_runs.p + lo * MAX_RUNS; p.status = c->d_status.p + lo;
     p.cells_done = j.timed ? reinterpret_cast<unsigned long long*>(j.d_meta + META_CELLS32) + b : nullptr;
-    int ok = 1, maxL = meta[META_MAXL + b];
+    int ok = 1, maxL = maxL_ub[b];
     if (c->hp) {                                      // mia -h: the chunked kernel, the read's window as the matrix (the widest class: the whole reference)
       if (c->explicit_windows && !c->explicit_sg5) { set_error("homopolymer mode: explicit windows need sg5 = 1"); return 0; }
       ok = launch_strip(c, 2, p.list, meta[META_COUNT + b], j.d_meta + META_WORK + b, lo);
@@ -1529,11 +1543,25 @@ extern "C" int miagpu_call(miagpu_ctx* c, int cons_code, int32_t* gaps_out, int3
     for (int pos = 0; pos < c->seq_len; pos++)
       for (int pl = 0; pl < NPLANE; pl++) counts_out[(int64_t)pos * NPLANE + pl] = acc[(int64_t)pl * nc + pos + ins_off[pos + 1]];
   // consensus string: columns in layout order, gap calls dropped (mia.c:562-570, 600-601)
-  int32_t n = 0;
+  int64_t n = 0;
+  for (int64_t i = 0; i < nc; i++) n += called[i] != '-' && called[i] != ' ';
+  // the caller's buffer: seq_len * 4 + 4096 bytes by contract (miagpu.h), or what miagpu_set_cons_capacity announced
+  const int64_t cap = c->cons_capacity > 0 ? c->cons_capacity : (int64_t)c->seq_len * 4 + 4096;
+  if (cons_out && n + 1 > cap) {
+    set_error("miagpu_call: the consensus has %lld characters, cons_out holds %lld (miagpu_set_cons_capacity announces a larger buffer)", (long long)n, (long long)cap);
+    return 0;
+  }
+  n = 0;
   for (int64_t i = 0; i < nc; i++)
     if (called[i] != '-' && called[i] != ' ') { if (cons_out) cons_out[n] = called[i]; n++; }
   if (cons_out) cons_out[n] = 0;
-  if (cons_len) *cons_len = n;
+  if (cons_len) *cons_len = (int32_t)n;
+  return 1;
+}
+
+extern "C" int miagpu_set_cons_capacity(miagpu_ctx* c, int64_t bytes) {
+  if (!c || bytes < 0) { set_error("miagpu_set_cons_capacity: bad argument"); return 0; }
+  c->cons_capacity = bytes;                          // 0 = back to the contract's seq_len * 4 + 4096
   return 1;
 }
 

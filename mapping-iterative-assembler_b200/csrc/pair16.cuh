@@ -117,6 +117,7 @@ struct Pair16Params {
   const uint8_t* rc;
   const int32_t* win_start;
   const int32_t* win_len;
+  int32_t* win_len_narrow;       // realign windows only (null = off): a read handed to the 32-bit kernels keeps the columns up to its end cell
   const int32_t* pairs;          // [n_items][32/G][2] read ids; -1 = empty slot (a work item's first slot is never empty)
   const int32_t* n_items;        // device counter (layout kernel wrote it)
   int32_t* counter;
@@ -544,7 +545,12 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, (K <= 5 ? 8 : K <= P16_S
           p.runs[(int64_t)rd * MAX_RUNS] = (uint16_t)((MIAGPU_RUN_M << 14) | (nsteps + 1));
           p.status[rd] = MIAGPU_ST_OK;
         } else {
-          const int b = bucket32_of(len1);
+          // dyn_prog's candidates of a cell all come from lower columns (mia.c:838-871), so the columns to the right of the end cell
+          // -- exact here unless sunk -- can reach neither its value nor its path, and being the FIRST maximum of the last row
+          // (mia.c:1278-1302) it stays the only one of the narrower window: the 32-bit kernel sweeps [ws, ws + aec] alone
+          int wl = len1;
+          if (p.win_len_narrow && !sunk) { wl = aec + 1; p.win_len_narrow[rd] = wl; }
+          const int b = bucket32_of(wl);
           const int slot = atomicAdd(p.list_counts + b, 1);
           p.lists[(int64_t)b * p.n_reads + slot] = rd;
           atomicAdd(p.n_fallback, 1);

@@ -23,3 +23,23 @@ def test_consensus_low_coverage_linear(gpu, oracle):
     problems, _ = gpu_checks.check_consensus(gpu, oracle, ref, bases, off, rc, as_, ae, gpu_checks.load_pssm("ancient"),
                                              circular=0, drop_frac=0.3)
     assert not problems, problems
+
+
+def test_consensus_that_does_not_fit_the_callers_buffer_fails(gpu):
+    # the reference sizes its consensus string from the gaps it has counted (mia.c:527-533); a caller of the library
+    # announces its buffer (miagpu_set_cons_capacity) and a longer consensus fails the call instead of overrunning it
+    from mia_b200 import api
+    ref, bases, off, rc, as_, ae = gpu_checks.make_case(300, 1200, seed=71)
+    gpu.set_pssm(gpu_checks.load_pssm("onepass"))
+    gpu.set_reference(ref, circular=1, with_rc=0)
+    gpu.realign_host(bases, off, rc, as_, ae)
+    cons, _, _ = gpu.consensus_natural()
+    assert len(cons) > 1000
+    assert gpu.lib.miagpu_set_cons_capacity(gpu.h, len(cons))          # one byte short of the string + its terminator
+    try:
+        with pytest.raises(api.MiaGpuError, match="cons_out holds"):
+            gpu.consensus_natural()
+        assert gpu.lib.miagpu_set_cons_capacity(gpu.h, len(cons) + 1)
+        assert gpu.consensus_natural()[0] == cons
+    finally:
+        assert gpu.lib.miagpu_set_cons_capacity(gpu.h, 0)
