@@ -355,6 +355,18 @@ int miagpu_last_fsdb_stats( miagpu_ctx* ctx, int64_t* n_slots, int64_t* stale_po
  * its strand, as / ae / score (and is stored reverse-complemented when the reverse attempt wins).  Call after
  * miagpu_set_reference and before miagpu_iterate_resident; does nothing in the first round or without distant_ref. */
 int miagpu_distant_retry( miagpu_ctx* ctx, int64_t* n_tried, int64_t* n_learned );
+/* The same in two steps, for reads sharded over several contexts (miagpu_shard_*): the matrix the forward attempt of a shard's
+ * FIRST read runs with is the one the LAST read of the shard before it left (H6 does not stop at a shard boundary).
+ *   _begin  the attempts of the local strand-unknown reads on the device; state_after[s] (two ints) = the matrix the last local
+ *           read leaves -- 0 forward, 1 strand-reversed -- if the first one is entered with s: the identity for a shard without
+ *           reads, a constant as soon as one local read's strand is known.  In the first round nothing is tried (iter_num > 1,
+ *           mia_main.c:122) and state_after describes the untouched reads.
+ *   the caller all-gathers the ranks' state_after pairs (two ints per rank) and folds them in rank order, starting from what
+ *   the last round left (0 before the first round)
+ *   _end    the local chain entered with state_in, the reads that learned their strand updated on the device.
+ * miagpu_distant_retry = _begin + _end with the state this context carried over from its own previous round. */
+int miagpu_distant_retry_begin( miagpu_ctx* ctx, int64_t* n_tried, int32_t* state_after );
+int miagpu_distant_retry_end( miagpu_ctx* ctx, int state_in, int64_t* n_learned );
 
 /* ---- 8e. The same round with the reads sharded over `world` GPUs of one box: one context per GPU (one process per GPU, or one
  * host thread per GPU: host/mia_gpu.c), reads partitioned contiguously in FSDB order (rank 0 holds the first reads), reference,

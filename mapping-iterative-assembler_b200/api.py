@@ -108,6 +108,8 @@ def load_library():
     L.miagpu_get_fsdb.argtypes = [C.c_void_p] + [C.c_void_p] * 6 + [_i64p]
     L.miagpu_last_fsdb_stats.argtypes = [C.c_void_p, _i64p, _i64p, _i64p, _i64p]
     L.miagpu_distant_retry.argtypes = [C.c_void_p, _i64p, _i64p]
+    L.miagpu_distant_retry_begin.argtypes = [C.c_void_p, _i64p, _i32p]
+    L.miagpu_distant_retry_end.argtypes = [C.c_void_p, C.c_int, _i64p]
     L.miagpu_stream.restype = C.c_void_p
     L.miagpu_stream.argtypes = [C.c_void_p]
     _lib = L
@@ -124,7 +126,8 @@ EXPORTS = ["miagpu_device_count", "miagpu_create", "miagpu_destroy", "miagpu_las
            "miagpu_last_cut_stats", "miagpu_repeat_filter", "miagpu_trim", "miagpu_get_alignment",
            "miagpu_fastx_open", "miagpu_fastx_open_memory", "miagpu_fastx_format", "miagpu_fastx_next", "miagpu_fastx_batch", "miagpu_fastx_close",
            "miagpu_maln_ref_size", "miagpu_write_maln", "miagpu_read_pssm", "miagpu_align_windows",
-           "miagpu_set_fsdb", "miagpu_get_fsdb", "miagpu_last_fsdb_stats", "miagpu_distant_retry", "miagpu_write_maln_fsdb", "miagpu_last_pass1_cells", "miagpu_set_homopolymer", "miagpu_shard_flags", "miagpu_set_cons_capacity"]
+           "miagpu_set_fsdb", "miagpu_get_fsdb", "miagpu_last_fsdb_stats", "miagpu_distant_retry", "miagpu_write_maln_fsdb", "miagpu_last_pass1_cells", "miagpu_set_homopolymer", "miagpu_shard_flags", "miagpu_set_cons_capacity",
+           "miagpu_distant_retry_begin", "miagpu_distant_retry_end"]
 
 
 def _ptr(a):
@@ -326,6 +329,19 @@ class MiaGpu:
         a, b = C.c_int64(), C.c_int64()
         self._ck(self.lib.miagpu_distant_retry(self.h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def distant_retry_begin(self):
+        """-D over several shards, step 1 (miagpu_distant_retry_begin) -> (tried, [state after the last local read if the first
+        is entered with the forward matrix, ... with the strand-reversed one])"""
+        a, st = C.c_int64(), (C.c_int32 * 2)()
+        self._ck(self.lib.miagpu_distant_retry_begin(self.h, C.byref(a), st))
+        return a.value, [int(st[0]), int(st[1])]
+
+    def distant_retry_end(self, state_in):
+        """step 2: the local chain entered with state_in -> learned"""
+        b = C.c_int64()
+        self._ck(self.lib.miagpu_distant_retry_end(self.h, int(state_in), C.byref(b)))
+        return b.value
 
     def reset_dropped(self):
         self._ck(self.lib.miagpu_reset_dropped(self.h))

@@ -208,6 +208,8 @@ struct miagpu_ctx {
   bool fs_on = false;                          // miagpu_set_fsdb: the one-call rounds follow the reference's pointer semantics
   int fs_distant = 0;                          // maln->distant_ref (-D)
   int fs_submat_rc = 0;                        // which matrix a->submat was left pointing at (H6)
+  std::vector<int32_t> dr_U, dr_sc, dr_a0, dr_a1, dr_score;   // miagpu_distant_retry_begin -> _end: the strand-unknown reads, their three attempts, fs->score
+  bool dr_ready = false;
   int fs_round = 0;                            // rounds since miagpu_set_fsdb
   int64_t fs_slot_cap = 0, fs_nslots = 0, fs_nslots_prev = 0;
   bool fs_sharded = false;                     // the round in flight numbers its slots over all ranks (miagpu_shard_*)
@@ -2171,66 +2173,112 @@ extern "C" int miagpu_last_fsdb_stats(miagpu_ctx* c, int64_t* n_slots, int64_t* 
 }
 
 // -D: the strand-unknown reads' attempts against the whole current reference (mia_main.c:120-174), before the round's realign.
-extern "C" int miagpu_distant_retry(miagpu_ctx* c, int64_t* n_tried, int64_t* n_learned) {
+// -D in two steps, so that shards can pass the matrix state (H6) from one to the next between them:
+//   _begin  the whole-reference attempts of the local strand-unknown reads on the device (three per read: as stored with either
+//           matrix, reverse-complemented with the strand-reversed one); state_after[s] = which matrix the LAST local read leaves
+//           in the Alignment when the first one is entered with s (0 = forward, 1 = strand-reversed) -- the identity for a shard
+//           without reads, a constant as soon as one read's strand was known before;
+//   _end    the chain over the local reads in FSDB order entered with state_in, results applied.
+// In the first round (iter_num == 1, mia_main.c:122) nothing is tried: a strand-unknown read is not touched and leaves the matrix alone.
+static int distant_after(const miagpu_ctx* c, int s) {
+  for (int64_t i = c->n - 1; i >= 0; i--) {
+    if (c->h_known[i]) return c->h_rc[i] ? 1 : 0;
+    if (c->fs_round >= 1) return 1;                    // tried and still unknown: the reverse attempt's matrix stays (mia_main.c:151)
+  }
+  return s;
+}
+// one pass of the chain; apply = false: only the state after the last local read is wanted (h_known / h_rc are put back)
+static int distant_chain(miagpu_ctx* c, int state_in, bool apply, std::vector<int32_t>* upd, int64_t* learned) {
+  const std::vector<int32_t>& U = c->dr_U;
+  const int64_t m = (int64_t)U.size();
+  std::vector<uint8_t> sk, sr;
+  if (!apply) { sk = c->h_known; sr = c->h_rc; }
+  for (int64_t q = 0; q < m; q++) {
+    const int32_t i = U[q];
+    int state = state_in;                              // read 0: what the read before it (the previous round's last, or the previous shard's) left
+    if (i > 0) state = c->h_known[i - 1] ? (c->h_rc[i - 1] ? 1 : 0) : 1;      // (a read that stays unknown leaves the strand-reversed matrix)
+    const int64_t fwd = 3 * q + (state ? 1 : 0), rev = 3 * q + 2;
+    int known = 0, rc = 0, as = 0, ae = 0, score = c->dr_score[q];
+    if (c->dr_sc[fwd] > FIRST_ROUND_SCORE_CUTOFF) { known = 1; rc = 0; as = c->dr_a0[fwd]; ae = c->dr_a1[fwd]; score = c->dr_sc[fwd]; }
+    if (c->dr_sc[rev] > FIRST_ROUND_SCORE_CUTOFF && c->dr_sc[rev] > score) { known = 1; rc = 1; as = c->dr_a0[rev]; ae = c->dr_a1[rev]; score = c->dr_sc[rev]; }
+    if (known) {
+      c->h_known[i] = 1; c->h_rc[i] = (uint8_t)rc;
+      if (upd) {
+        const int32_t row[6] = {i, rc, as, ae, score, rc};                     // strcpy( fs->seq, tmp_rc ) when the reverse attempt wins
+        upd->insert(upd->end(), row, row + 6);
+      }
+      if (learned) ++*learned;
+    }
+  }
+  const int after = distant_after(c, state_in);
+  if (!apply) { c->h_known = sk; c->h_rc = sr; }
+  return after;
+}
+
+extern "C" int miagpu_distant_retry_begin(miagpu_ctx* c, int64_t* n_tried, int32_t* state_after) {
   if (n_tried) *n_tried = 0;
-  if (n_learned) *n_learned = 0;
   if (!c || !c->fs_on || !c->have_ref || !c->have_pssm) { set_error("miagpu_distant_retry: set_pssm, set_reference and miagpu_set_fsdb first"); return 0; }
-  if (!c->fs_distant || c->fs_round < 1) return 1;   // iter_num > 1 only (mia_main.c:122)
+  c->dr_U.clear(); c->dr_sc.clear(); c->dr_a0.clear(); c->dr_a1.clear(); c->dr_score.clear();
+  c->dr_ready = true;
+  if (!c->fs_distant) { if (state_after) { state_after[0] = 0; state_after[1] = 1; } return 1; }
+  if (c->fs_round < 1) {                               // iter_num > 1 only (mia_main.c:122)
+    if (state_after) { state_after[0] = distant_after(c, 0); state_after[1] = distant_after(c, 1); }
+    return 1;
+  }
   MIAGPU_CUDA(cudaSetDevice(c->device));
   const int64_t n = c->n;
-  std::vector<int32_t> U;
+  std::vector<int32_t>& U = c->dr_U;
   for (int64_t i = 0; i < n; i++) if (!c->h_known[i]) U.push_back((int32_t)i);
   const int64_t m = (int64_t)U.size();
   if (n_tried) *n_tried = m;
-  if (!m) return 1;
-  cudaStream_t st = c->stream;
-  if (!c->aux && !miagpu_create(&c->aux, c->device)) return 0;
-  miagpu_ctx* x = c->aux;
-  if (!miagpu_set_pssm(x, c->sm_f)) return 0;
-  if (!miagpu_set_reference(x, c->raw_wrapped.c_str(), c->seq_len, c->circular, 0)) return 0;
-  x->hp = c->hp;                                     // mia_main.c:132-134, 158-160
-  // the scratch batch: three items per read (fs_retry_reads_kernel)
-  std::vector<int64_t> off_new((size_t)3 * m + 1, 0);
-  for (int64_t q = 0; q < 3 * m; q++) off_new[q + 1] = off_new[q] + c->h_seqlen[U[q / 3]];
-  const int64_t total = off_new.back();
-  if (!x->d_bases.reserve(total + 16) || !x->d_off.reserve(3 * m + 1) || !reserve_per_read(x, 3 * m) || !c->d_fs_tmp.reserve((size_t)m * 6 + 64)) return 0;
-  MIAGPU_CUDA(cudaMemcpyAsync(x->d_off.p, off_new.data(), (3 * m + 1) * 8, cudaMemcpyHostToDevice, st));
-  MIAGPU_CUDA(cudaMemcpyAsync(c->d_fs_tmp.p, U.data(), m * 4, cudaMemcpyHostToDevice, st));
-  fs_retry_reads_kernel<<<(unsigned)((3 * m * 32 + 255) / 256), 256, 0, st>>>((int)m, c->d_fs_tmp.p, c->d_bases.p, c->d_off.p, x->d_off.p, x->d_bases.p);
-  MIAGPU_CUDA(cudaGetLastError());
-  MIAGPU_CUDA(cudaStreamSynchronize(st));
-  x->n = 3 * m; x->total_bases = total; x->cut_inputs_n = -1; x->max_read_len = -1;
-  std::vector<uint8_t> vrc((size_t)3 * m), vst((size_t)3 * m);
-  std::vector<int32_t> ws((size_t)3 * m, 0), wl((size_t)3 * m, c->wrap_len), sc((size_t)3 * m), a0((size_t)3 * m), a1((size_t)3 * m);
-  for (int64_t q = 0; q < 3 * m; q++) vrc[q] = q % 3 != 0;
-  if (!miagpu_align_windows(x, vrc.data(), ws.data(), wl.data(), 1, sc.data(), a0.data(), a1.data(), nullptr, nullptr, nullptr, vst.data())) return 0;
-  for (int64_t q = 0; q < 3 * m; q++)
-    if (vst[q] & ~(MIAGPU_ST_RUNS_OVERFLOW | MIAGPU_ST_STR_OVERFLOW)) { set_error("miagpu_distant_retry: whole-reference attempt %lld came back with status 0x%x", (long long)q, vst[q]); return 0; }
-  // the chain over the reads in FSDB order: the forward attempt runs with whatever matrix the read before left (H6)
-  std::vector<int32_t> upd;
-  int64_t learned = 0;
-  std::vector<int32_t> h_score((size_t)m);
-  {                                                  // fs->score of the strand-unknown reads (the reverse attempt must beat it)
+  if (m) {
+    cudaStream_t st = c->stream;
+    if (!c->aux && !miagpu_create(&c->aux, c->device)) return 0;
+    miagpu_ctx* x = c->aux;
+    if (!miagpu_set_pssm(x, c->sm_f)) return 0;
+    if (!miagpu_set_reference(x, c->raw_wrapped.c_str(), c->seq_len, c->circular, 0)) return 0;
+    x->hp = c->hp;                                     // mia_main.c:132-134, 158-160
+    // the scratch batch: three items per read (fs_retry_reads_kernel)
+    std::vector<int64_t> off_new((size_t)3 * m + 1, 0);
+    for (int64_t q = 0; q < 3 * m; q++) off_new[q + 1] = off_new[q] + c->h_seqlen[U[q / 3]];
+    const int64_t total = off_new.back();
+    if (!x->d_bases.reserve(total + 16) || !x->d_off.reserve(3 * m + 1) || !reserve_per_read(x, 3 * m) || !c->d_fs_tmp.reserve((size_t)m * 6 + 64)) return 0;
+    MIAGPU_CUDA(cudaMemcpyAsync(x->d_off.p, off_new.data(), (3 * m + 1) * 8, cudaMemcpyHostToDevice, st));
+    MIAGPU_CUDA(cudaMemcpyAsync(c->d_fs_tmp.p, U.data(), m * 4, cudaMemcpyHostToDevice, st));
+    fs_retry_reads_kernel<<<(unsigned)((3 * m * 32 + 255) / 256), 256, 0, st>>>((int)m, c->d_fs_tmp.p, c->d_bases.p, c->d_off.p, x->d_off.p, x->d_bases.p);
+    MIAGPU_CUDA(cudaGetLastError());
+    MIAGPU_CUDA(cudaStreamSynchronize(st));
+    x->n = 3 * m; x->total_bases = total; x->cut_inputs_n = -1; x->max_read_len = -1;
+    std::vector<uint8_t> vrc((size_t)3 * m), vst((size_t)3 * m);
+    std::vector<int32_t> ws((size_t)3 * m, 0), wl((size_t)3 * m, c->wrap_len);
+    c->dr_sc.resize((size_t)3 * m); c->dr_a0.resize((size_t)3 * m); c->dr_a1.resize((size_t)3 * m);
+    for (int64_t q = 0; q < 3 * m; q++) vrc[q] = q % 3 != 0;
+    if (!miagpu_align_windows(x, vrc.data(), ws.data(), wl.data(), 1, c->dr_sc.data(), c->dr_a0.data(), c->dr_a1.data(), nullptr, nullptr, nullptr, vst.data())) return 0;
+    for (int64_t q = 0; q < 3 * m; q++)
+      if (vst[q] & ~(MIAGPU_ST_RUNS_OVERFLOW | MIAGPU_ST_STR_OVERFLOW)) { set_error("miagpu_distant_retry: whole-reference attempt %lld came back with status 0x%x", (long long)q, vst[q]); return 0; }
+    // fs->score of the strand-unknown reads (the reverse attempt must beat it)
     std::vector<int32_t> all((size_t)n);
     MIAGPU_CUDA(cudaMemcpyAsync(all.data(), c->d_score.p, n * 4, cudaMemcpyDeviceToHost, st));
     MIAGPU_CUDA(cudaStreamSynchronize(st));
-    for (int64_t q = 0; q < m; q++) h_score[q] = all[U[q]];
+    c->dr_score.resize((size_t)m);
+    for (int64_t q = 0; q < m; q++) c->dr_score[q] = all[U[q]];
   }
-  for (int64_t q = 0; q < m; q++) {
-    const int32_t i = U[q];
-    int state = c->fs_submat_rc;                     // read 0: what the last read of the previous round left
-    if (i > 0) state = c->h_known[i - 1] ? (c->h_rc[i - 1] ? 1 : 0) : 1;      // (a read that stays unknown leaves the strand-reversed matrix)
-    const int64_t fwd = 3 * q + (state ? 1 : 0), rev = 3 * q + 2;
-    int known = 0, rc = 0, as = 0, ae = 0, score = h_score[q];
-    if (sc[fwd] > FIRST_ROUND_SCORE_CUTOFF) { known = 1; rc = 0; as = a0[fwd]; ae = a1[fwd]; score = sc[fwd]; }
-    if (sc[rev] > FIRST_ROUND_SCORE_CUTOFF && sc[rev] > score) { known = 1; rc = 1; as = a0[rev]; ae = a1[rev]; score = sc[rev]; }
-    if (known) {
-      c->h_known[i] = 1; c->h_rc[i] = (uint8_t)rc;
-      const int32_t row[6] = {i, rc, as, ae, score, rc};                       // strcpy( fs->seq, tmp_rc ) when the reverse attempt wins
-      upd.insert(upd.end(), row, row + 6);
-      learned++;
-    }
-  }
+  if (state_after)
+    for (int s = 0; s < 2; s++) state_after[s] = distant_chain(c, s, false, nullptr, nullptr);
+  return 1;
+}
+
+extern "C" int miagpu_distant_retry_end(miagpu_ctx* c, int state_in, int64_t* n_learned) {
+  if (n_learned) *n_learned = 0;
+  if (!c || !c->fs_on || !c->dr_ready) { set_error("miagpu_distant_retry_end: call miagpu_distant_retry_begin first"); return 0; }
+  c->dr_ready = false;
+  if (state_in != 0 && state_in != 1) { set_error("miagpu_distant_retry_end: state_in is 0 (forward matrix) or 1 (strand-reversed)"); return 0; }
+  if (c->dr_U.empty()) return 1;
+  MIAGPU_CUDA(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  std::vector<int32_t> upd;
+  int64_t learned = 0;
+  distant_chain(c, state_in, true, &upd, &learned);    // the chain over the reads in FSDB order: the forward attempt runs with whatever matrix the read before left (H6)
   if (learned) {
     DevBuf<int32_t> d_u;
     if (!d_u.reserve(upd.size() + 16)) return 0;
@@ -2241,8 +2289,18 @@ extern "C" int miagpu_distant_retry(miagpu_ctx* c, int64_t* n_tried, int64_t* n_
     MIAGPU_CUDA(cudaStreamSynchronize(st));
     d_u.release();
   }
+  c->dr_U.clear();
   if (n_learned) *n_learned = learned;
   return 1;
+}
+
+// one GPU: the chain is entered with what the last read of the previous round left (fs_carry_submat)
+extern "C" int miagpu_distant_retry(miagpu_ctx* c, int64_t* n_tried, int64_t* n_learned) {
+  if (n_tried) *n_tried = 0;
+  if (n_learned) *n_learned = 0;
+  if (!c || !c->fs_on || !c->have_ref || !c->have_pssm) { set_error("miagpu_distant_retry: set_pssm, set_reference and miagpu_set_fsdb first"); return 0; }
+  if (!c->fs_distant || c->fs_round < 1) return 1;   // iter_num > 1 only (mia_main.c:122)
+  return miagpu_distant_retry_begin(c, n_tried, nullptr) && miagpu_distant_retry_end(c, c->fs_submat_rc, n_learned);
 }
 
 // ---------------------------------------------------- one whole round (a9..a13), score cut on the device
@@ -2753,7 +2811,7 @@ extern "C" int miagpu_shard_begin(miagpu_ctx* c, int world, int rank, int64_t n_
                                   double intercept, void** max_buf, int64_t* max_words) {
   if (!shard_args(c, "miagpu_shard_begin", world, rank, n_max, c ? c->n : 0)) return 0;
   if (c->cut_inputs_n != c->n) { set_error("miagpu_shard_begin: upload reads, alignment inputs and cut inputs first"); return 0; }
-  if (c->fs_on && (c->fs_distant || !c->h_unique.empty())) { set_error("miagpu_shard_begin: the pointer state in sharded rounds goes without -D and without the repeat filter"); return 0; }
+  if (c->fs_on && !c->h_unique.empty()) { set_error("miagpu_shard_begin: the pointer state in sharded rounds goes without the repeat filter"); return 0; }
   MIAGPU_CUDA(cudaSetDevice(c->device));
   if (!shard_reserve_common(c, world, n_max)) return 0;
   if (c->fs_on) {

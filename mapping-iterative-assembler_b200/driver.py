@@ -209,8 +209,9 @@ class ResidentAssembler:
     On one GPU the FSDB's pointer state goes to the device after pass 1 (miagpu_set_fsdb) and the rounds follow the reference's
     FragSeq -> AlnSeq pointers there: slot-indexed sticky dropped flags (H10), never-cleared back pointers (mia_main.c:273-276),
     reads that score exactly 2000 (strand_known = 0, mia.c:1653) and -D (`distant_ref`: mia.c:1614, mia_main.c:120-174,
-    find_alignable_len in the cull).  Sharded rounds still give every read its own fresh segments and one sticky flag and count
-    what that misses in `split_changes`.
+    find_alignable_len in the cull).  Sharded rounds do the same with `pointer_state=True` (global slot numbers, slot flags
+    replicated, the -D chain passed from shard to shard: `retry_begin` / `retry_end`); without it every read gets its own
+    fresh segments and one sticky flag, and what that misses is counted in `split_changes`.
 
     `exchange`: None for one GPU; otherwise an object with
         all_gather_host(np_array) -> concatenation over ranks in rank order
@@ -229,7 +230,9 @@ class ResidentAssembler:
         self.distant_ref = int(distant_ref)
         self.fs = (exchange is None) if pointer_state is None else bool(pointer_state)
         if self.distant_ref and not self.fs:
-            raise NotImplementedError("-D needs the pointer state (one GPU)")
+            raise NotImplementedError("-D needs the pointer state (pointer_state=True)")
+        self.matrix_state = 0                                                        # H6 over shards: which matrix the last read of the last shard left
+        self._manual_retry = False                                                   # True: the caller drives retry_begin / retry_end (shards without an exchange object)
         gpu.set_pssm(sm)
         gpu.set_homopolymer(hp)
 
@@ -262,7 +265,8 @@ class ResidentAssembler:
         if self.x is not None:
             counts = self._gather(np.array([len(self.seq_len)], np.int64))            # reads per rank, in rank order
             lo = int(counts[: self.x.rank].sum()) if self.fs else 0
-            self.pass1_cull(self._gather(self.seq_len), self._gather(self.score), self._gather(self.split.astype(np.uint8)) if self.fs else None, lo)
+            self.pass1_cull(self._gather(self.seq_len), self._gather(self.score), self._gather(self.split.astype(np.uint8)) if self.fs else None, lo,
+                            self._gather(self.cull_len()) if self.fs and self.distant_ref else None)
         elif not defer_cull:
             self.pass1_cull(self.seq_len, self.score)
         return p
@@ -274,17 +278,22 @@ class ResidentAssembler:
         e = np.clip(np.minimum(self.ae.astype(np.int64), wrap_len), a, wrap_len)
         return np.maximum(self.seq_len - (isn[e] - isn[a]), 15).astype(np.int32)     # MIN_ALIGNABLE_LEN
 
-    def pass1_cull(self, all_seq_len, all_score, all_split=None, lo=0):
+    def cull_len(self):
+        """the length that picks a read's threshold in the pass-1 cull (mia.c:460-463): seq_len, or find_alignable_len under -D"""
+        if not self.distant_ref:
+            return self.seq_len
+        ru = self.ref0.upper()
+        rw = ru + (ru[:min(256, len(ru))] if self.circular else "")
+        return self._alignable_len(rw, len(rw))
+
+    def pass1_cull(self, all_seq_len, all_score, all_split=None, lo=0, all_cull_len=None):
         """pass-1 cull (mia_main.c:848) with the fit over the reads of ALL ranks in FSDB order: only its dropped flags survive.
         all_split / lo (pointer state over several shards): the wrap-split flags of all ranks' reads and where this shard's reads
-        begin among them -- AlnSeq slots are numbered over all reads, every shard keeps the flags of all slots."""
+        begin among them -- AlnSeq slots are numbered over all reads, every shard keeps the flags of all slots; all_cull_len: the
+        ranks' cull_len() under -D."""
         g, idx = self.g, self._idx
         fit = api.score_cut(all_seq_len, all_score)
-        thr_len = self.seq_len
-        if self.distant_ref:
-            ru = self.ref0.upper()
-            rw = ru + (ru[:min(256, len(ru))] if self.circular else "")
-            thr_len = self._alignable_len(rw, len(rw))
+        thr_len = self.cull_len()
         dropped = api.cull_flags(thr_len, self.score, None, 0, 1, fit[0], fit[1])
         # AlnSeq slots of pass 1 in merge order (mia.c:1619-1643): one per accepted read, two when wrap-split
         if all_split is None:
@@ -299,7 +308,9 @@ class ResidentAssembler:
             ansl = 1 + asp.astype(np.int64)
             afirst = np.cumsum(ansl) - ansl
             n_slots = int(ansl.sum())
-            adrop = api.cull_flags(np.asarray(all_seq_len, np.int32), np.asarray(all_score, np.int32), None, 0, 1, fit[0], fit[1])
+            if self.distant_ref and all_cull_len is None:
+                raise ValueError("-D over several shards: pass1_cull needs the cull_len() of all ranks")
+            adrop = api.cull_flags(np.asarray(all_seq_len if all_cull_len is None else all_cull_len, np.int32), np.asarray(all_score, np.int32), None, 0, 1, fit[0], fit[1])
             slot_dropped = np.zeros(n_slots + 1, np.uint8)
             slot_dropped[afirst[adrop > 0]] = 1
             slot_dropped[afirst[(adrop > 0) & asp] + 1] = 1
@@ -328,8 +339,27 @@ class ResidentAssembler:
             self.last = self.cons
         self.iter += 1
         self.g.set_reference(self.last, self.circular, with_rc=0)
-        if self.distant_ref:
+        if self.distant_ref and self.x is not None:                                  # mia_main.c:120-174 over shards: the matrix state crosses their boundaries (H6)
+            after = self._gather(np.array(self.retry_begin(), np.int32)).reshape(-1, 2)
+            self.retry_end(after, self.x.rank)
+        elif self.distant_ref and not self._manual_retry:
             self.retried = self.g.distant_retry()                                    # mia_main.c:120-174 (iteration 2 on)
+
+    def retry_begin(self):
+        """-D over shards, step 1: the local attempts -> [state after this shard if entered with 0, ... with 1]"""
+        self._tried, after = self.g.distant_retry_begin()
+        return after
+
+    def retry_end(self, all_after, rank):
+        """step 2: all_after = the retry_begin() results of all shards in rank order; enters the local chain with what the shards
+        before this one leave, and keeps what the last shard leaves for the next round"""
+        s = self.matrix_state
+        for r in range(rank):
+            s = int(all_after[r][s])
+        self.retried = (self._tried, self.g.distant_retry_end(s))
+        for r in range(rank, len(all_after)):
+            s = int(all_after[r][s])
+        self.matrix_state = s
 
     def iterate(self, want_gaps=False):
         g = self.g
