@@ -394,8 +394,8 @@ int miagpu_distant_retry_end( miagpu_ctx* ctx, int state_in, int64_t* n_learned 
  *
  * n_max = the largest local read count of any rank (the same value on every rank).  hard_cut / score_cut_set / slope / intercept
  * as in miagpu_cull_flags.  world = 1 needs no collectives (gather_recv must still receive a copy of gather_send) and equals
- * miagpu_iterate_resident / miagpu_iterate_host.  Sharded rounds give every read its own AlnSeqs and one sticky flag
- * (miagpu_set_cut_inputs); the pointer state of miagpu_set_fsdb is a one-GPU feature. */
+ * miagpu_iterate_resident / miagpu_iterate_host.  With miagpu_set_cut_inputs a sharded round gives every read its own AlnSeqs
+ * and one sticky flag; with miagpu_set_fsdb it follows the reference's pointers (see miagpu_shard_flags below). */
 int miagpu_shard_begin( miagpu_ctx* ctx, int world, int rank, int64_t n_max, int hard_cut,
                         int score_cut_set, double slope, double intercept,
                         void** max_buf, int64_t* max_words );
@@ -417,10 +417,13 @@ int miagpu_shard_finish( miagpu_ctx* ctx, int cons_code, uint8_t* dropped,
  * miagpu_set_fsdb the GLOBAL slot numbers of its reads' pass-1 pointers, the global slot count and the flags of all slots.  A
  * round numbers its slots from the ranks' slot counts (they travel in the header rows of the MAX all-reduce), follows the local
  * reads' pointers as a one-GPU round does, and refuses a stale pointer whose slot a read of another rank owns this round (or
- * whose last content lives on another rank): such a pointer sits within a few reads of a shard boundary.  AlnSeq.dropped lives in
+ * whose last content lives on another rank): without -D such a pointer sits within a few reads of a shard boundary; under -D the
+ * stale pass-1 pointers of strand-unknown reads reach as far as there are such reads before them, so large -D runs belong on one
+ * GPU (BASELINE configs[3], 2 M reads: 1.8 s, profiles/r02_c4_distant.md).  AlnSeq.dropped lives in
  * the slots, and the slots a rank's reads take drift from round to round, so every rank keeps the flags of all slots: after
  * miagpu_shard_finish the caller MAX-reduces this buffer (one byte per slot) over the ranks, before the next miagpu_shard_begin.
- * *bytes = 0: no pointer state, nothing to do.  -D and the repeat filter are not available in sharded rounds. */
+ * *bytes = 0: no pointer state, nothing to do.  -D: miagpu_distant_retry_begin / _end before miagpu_shard_begin.  The repeat
+ * filter is not available in sharded rounds. */
 int miagpu_shard_flags( miagpu_ctx* ctx, void** flag_buf, int64_t* bytes );
 /* chain blocks of the last round's regression that were summed read by read on the host, and how many of
  * those needed an extra device fetch (sharded rounds prefetch the likely ones with the block records) */

@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmiagpu.so")
+LIB_PATH = os.environ.get("MIAGPU_LIB") or os.path.join(HERE, "libmiagpu.so")      # MIAGPU_LIB: a differently built libmiagpu.so (kernel experiments)
 MAX_RUNS = 24
 RUN_M, RUN_I, RUN_D = 0, 1, 2
 

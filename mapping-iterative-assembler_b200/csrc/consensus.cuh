@@ -195,68 +195,66 @@ __global__ void __launch_bounds__(256) gaps_kernel(ConsParams p) {
 // memory only for the read bases.
 constexpr int TILE_THREADS = 512;
 constexpr int TILE_SMEM_INTS = NPLANE * TILE_COLS + (TILE_COLS + 1) + 2 * MIAGPU_PSSM_INTS;
-__global__ void __launch_bounds__(TILE_THREADS) tile_kernel(ConsParams p, const int32_t* __restrict__ bin_list, const int32_t* __restrict__ bin_start) {
+// What tile_kernel needs of a binned entry, 32 bytes, written in bin order by ent_bin_scatter_kernel so that a warp reads 32 of them
+// in one contiguous kilobyte: no per-read look-ups (n_runs, runs, abr, rc, off) while the tile is walked.
+//   a = { byte offset of read row `abr` in p.bases (lo, hi), ref_pos, col_begin | hi_col << 16 }
+//   b = { front_len | total_len << 16 (signed halves), act_bias (signed low half) | flags << 16, entry index, 0 }
+// flags: 1 dropped, 2 back_formula, 4 reverse strand, 8 FAST = the alignment is one M run (everything above is valid); without
+// FAST only the entry index counts and the warp takes the general walk.  hi_col = min(run length, col_begin + col_count).
+struct TileRec { uint4 a, b; };
+constexpr uint32_t TR_DROPPED = 1, TR_BACKF = 2, TR_STRAND = 4, TR_FAST = 8;
+
+__global__ void __launch_bounds__(TILE_THREADS) tile_kernel(ConsParams p, const TileRec* __restrict__ recs, const int32_t* __restrict__ bin_start) {
   extern __shared__ int32_t s_acc[];                       // [NPLANE][TILE_COLS]
   int32_t* s_ins = s_acc + NPLANE * TILE_COLS;             // ins_off[t0 + i], i <= TILE_COLS
   int32_t* s_sm = s_ins + TILE_COLS + 1;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  const int t0 = blockIdx.y * TILE_POS, t1 = min(t0 + TILE_POS, p.seq_len);
+  const int t0 = blockIdx.y * TILE_POS;
   const int64_t c0 = (int64_t)t0 + p.ins_off[t0];
   for (int i = threadIdx.x; i < NPLANE * TILE_COLS; i += blockDim.x) s_acc[i] = 0;
   for (int i = threadIdx.x; i <= TILE_COLS; i += blockDim.x) s_ins[i] = p.ins_off[min(t0 + i, p.seq_len)];
   for (int i = threadIdx.x; i < 2 * MIAGPU_PSSM_INTS; i += blockDim.x) s_sm[i] = p.sm[i];
   __syncthreads();
   const TileAdder A{s_acc, c0, p.acc, p.n_cols};
-  // the entries that start inside this tile were binned (ent_bin_*_kernel): slice blockIdx.x of the tile's list
+  // the entries that start inside this tile were binned (ent_bin_*_kernel): slice blockIdx.x of the tile's records
   const int64_t b0 = bin_start[blockIdx.y], b1 = bin_start[blockIdx.y + 1];
   const int64_t per = (b1 - b0 + gridDim.x - 1) / gridDim.x;
   const int64_t lo = b0 + per * blockIdx.x, hi = min(lo + per, b1);
-  (void)t1;
+  const int ins0 = s_ins[0];
   for (int64_t base = lo + warp * 32; base < hi; base += nwarps * 32) {
     const int64_t at = base + lane;
     const bool mine = at < hi;
-    const int64_t idx = mine ? bin_list[at] : 0;
-    miagpu_entry e{};
-    int nr = 0, ab = 0, strand = 0, run0 = 0;
-    int64_t o = 0;
-    if (mine) {
-      e = p.entries[idx];
-      if (e.read < p.n_reads) {                              // (a frozen alignment takes the general walk: nr stays 0)
-        nr = p.n_runs[e.read];
-        ab = p.abr[e.read];
-        strand = p.rc[e.read] ? 1 : 0;
-        o = p.off[e.read];
-        run0 = p.runs[(int64_t)e.read * MAX_RUNS];
-      }
+    TileRec r{};
+    if (mine) { r.a = __ldg(&recs[at].a); r.b = __ldg(&recs[at].b); }
+    if (mine && ((r.b.y >> 16) & TR_FAST)) {               // the 32 entries' bases on their way into L2 while the warp walks them one by one
+      const uint8_t* q = p.bases + (((int64_t)r.a.y << 32) | r.a.x);
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(q + (r.a.w & 0xffffu)));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(q + (r.a.w >> 16) - 1));
     }
     unsigned m = __ballot_sync(0xffffffffu, mine);
     while (m) {
       const int b = __ffs(m) - 1;
       m &= m - 1;
-      const int b_nr = __shfl_sync(0xffffffffu, nr, b);
-      const int b_run0 = __shfl_sync(0xffffffffu, run0, b);
-      if (b_nr != 1 || (b_run0 >> 14) != MIAGPU_RUN_M) {   // gaps in the alignment: the general walk
-        const miagpu_entry eb = p.entries[__shfl_sync(0xffffffffu, idx, b)];
+      const uint32_t bf = __shfl_sync(0xffffffffu, r.b.y, b);
+      const uint32_t flags = bf >> 16;
+      if (!(flags & TR_FAST)) {                            // gaps in the alignment, or a frozen one: the general walk
+        const miagpu_entry eb = p.entries[__shfl_sync(0xffffffffu, r.b.z, b)];
         walk_entry<1>(p, eb, lane, A);
         continue;
       }
-      const int cb = __shfl_sync(0xffffffffu, e.col_begin, b), cc = __shfl_sync(0xffffffffu, e.col_count, b);
-      const int rp = __shfl_sync(0xffffffffu, e.ref_pos, b), fl = __shfl_sync(0xffffffffu, e.front_len, b);
-      const int tl = __shfl_sync(0xffffffffu, e.total_len, b), bias = __shfl_sync(0xffffffffu, e.act_bias, b);
-      const int flags = __shfl_sync(0xffffffffu, (int)e.dropped | ((int)e.back_formula << 8), b);
-      const int b_ab = __shfl_sync(0xffffffffu, ab, b), b_strand = __shfl_sync(0xffffffffu, strand, b);
-      const int64_t b_o = __shfl_sync(0xffffffffu, o, b);
-      const int len = b_run0 & 0x3fff;
-      const bool dropped = flags & 0xff, backf = (flags >> 8) != 0;
-      const int32_t* sms = s_sm + b_strand * MIAGPU_PSSM_INTS;
-      const uint8_t* read = p.bases + b_o + b_ab;
-      const int hi_col = min(len, cb + cc);
+      const uint32_t alo = __shfl_sync(0xffffffffu, r.a.x, b), ahi = __shfl_sync(0xffffffffu, r.a.y, b);
+      const int rp = (int)__shfl_sync(0xffffffffu, r.a.z, b);
+      const uint32_t ch = __shfl_sync(0xffffffffu, r.a.w, b), ft = __shfl_sync(0xffffffffu, r.b.x, b);
+      const int cb = (int)(ch & 0xffffu), hi_col = (int)(ch >> 16);
+      const int fl = (int)(int16_t)(ft & 0xffffu), tl = (int)(int16_t)(ft >> 16), bias = (int)(int16_t)(bf & 0xffffu);
+      const bool dropped = flags & TR_DROPPED, backf = flags & TR_BACKF;
+      const int32_t* sms = s_sm + ((flags & TR_STRAND) ? MIAGPU_PSSM_INTS : 0);
+      const uint8_t* read = p.bases + (((int64_t)ahi << 32) | alo);
       // the entry's last column inside the shared window => all of them are (positions and insert offsets grow together)
       const int d_last = min(rp + (hi_col - 1 - cb), p.seq_len - 1) - t0;
-      const bool inside = hi_col > cb && d_last >= 0 && d_last < TILE_COLS && d_last + (s_ins[min(d_last + 1, TILE_COLS)] - s_ins[0]) < TILE_COLS;
+      const bool inside = hi_col > cb && d_last >= 0 && d_last < TILE_COLS && d_last + (s_ins[min(d_last + 1, TILE_COLS)] - ins0) < TILE_COLS;
       if (inside) {
         const LocalAdder LA{s_acc};
-        const int ins0 = s_ins[0];
         for (int i = cb + lane; i < hi_col; i += 32) {
           const int pos = rp + (i - cb);
           if (pos >= p.seq_len) continue;
@@ -343,26 +341,44 @@ __global__ void ent_bin_scan_kernel(int n_tiles, const int32_t* counts, int32_t*
   for (int t = 0; t < n_tiles; t++) { bin_start[t] = run; cursor[t] = run; run += counts[t]; }
   bin_start[n_tiles] = run;
 }
-__global__ void __launch_bounds__(256) ent_bin_scatter_kernel(int64_t n_entries, const int32_t* __restrict__ ent_tile, int32_t* cursor, int32_t* bin_list) {
+__global__ void __launch_bounds__(256) ent_bin_scatter_kernel(ConsParams p, const int32_t* __restrict__ ent_tile, int32_t* cursor, TileRec* recs) {
   __shared__ int s_cnt[MAX_TILES], s_base[MAX_TILES];
   if (threadIdx.x < MAX_TILES) s_cnt[threadIdx.x] = 0;
   __syncthreads();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int t = i < n_entries ? ent_tile[i] : -1;
+  const int t = i < p.n_entries ? ent_tile[i] : -1;
   const int lane = threadIdx.x & 31;
   const unsigned peers = __match_any_sync(0xffffffffu, t);
   int slot = 0;
+  TileRec r{};
   if (t >= 0) {
     const int leader = __ffs(peers) - 1;
     int base = 0;
     if (lane == leader) base = atomicAdd(&s_cnt[t], __popc(peers));
     base = __shfl_sync(peers, base, leader);
     slot = base + __popc(peers & ((1u << lane) - 1));
+    // the record (entries come in read order here: the per-read look-ups are next to each other)
+    const miagpu_entry e = p.entries[i];
+    r.b.z = (uint32_t)i;
+    if (e.read < p.n_reads && p.n_runs[e.read] == 1) {
+      const int run0 = p.runs[(int64_t)e.read * MAX_RUNS];
+      const int len = run0 & 0x3fff;
+      const bool fits = e.front_len >= -32768 && e.front_len <= 32767 && e.total_len >= -32768 && e.total_len <= 32767 &&
+                        e.act_bias >= -32768 && e.act_bias <= 32767 && e.col_begin <= 0xffff;
+      if ((run0 >> 14) == MIAGPU_RUN_M && fits) {
+        const int64_t addr = p.off[e.read] + p.abr[e.read];
+        const int hi_col = min(len, e.col_begin + e.col_count);
+        const uint32_t flags = TR_FAST | (e.dropped ? TR_DROPPED : 0u) | (e.back_formula ? TR_BACKF : 0u) | (p.rc[e.read] ? TR_STRAND : 0u);
+        r.a = make_uint4((uint32_t)addr, (uint32_t)(addr >> 32), (uint32_t)e.ref_pos, (uint32_t)e.col_begin | ((uint32_t)hi_col << 16));
+        r.b.x = ((uint32_t)e.front_len & 0xffffu) | ((uint32_t)e.total_len << 16);
+        r.b.y = ((uint32_t)e.act_bias & 0xffffu) | (flags << 16);
+      }
+    }
   }
   __syncthreads();
   if (threadIdx.x < MAX_TILES) s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd(&cursor[threadIdx.x], s_cnt[threadIdx.x]) : 0;
   __syncthreads();
-  if (t >= 0) bin_list[s_base[t] + slot] = (int32_t)i;
+  if (t >= 0) { recs[s_base[t] + slot].a = r.a; recs[s_base[t] + slot].b = r.b; }
 }
 
 // find_consensus (map_align.c:294-391) for every column of the padded layout.

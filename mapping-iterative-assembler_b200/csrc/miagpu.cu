@@ -1424,19 +1424,20 @@ static int launch_accumulate(miagpu_ctx* c) {
   bool tiles = n_tiles <= MAX_TILES && c->n_entries >= 4096;
   if (const char* e = getenv("MIAGPU_CONS_TILES")) tiles = atoi(e) != 0;
   if (tiles) {
-    // d_ent_pos: [n_entries] tile of every entry | [n_entries] the bins | counts[64] | starts[65] | cursors[64]
+    // d_ent_pos: the records in bin order (TileRec, 8 words each) | [n_entries] tile of every entry | counts[64] | starts[65] | cursors[64]
     const int64_t ne = c->n_entries;
-    if (!c->d_ent_pos.reserve(2 * ne + 3 * MAX_TILES + 8)) return 0;
-    int32_t *ent_tile = c->d_ent_pos.p, *bin_list = ent_tile + ne, *counts = bin_list + ne, *starts = counts + MAX_TILES, *cursor = starts + MAX_TILES + 1;
+    if (!c->d_ent_pos.reserve(9 * ne + 3 * MAX_TILES + 16)) return 0;
+    TileRec* recs = reinterpret_cast<TileRec*>(c->d_ent_pos.p);
+    int32_t *ent_tile = c->d_ent_pos.p + 8 * ne, *counts = ent_tile + ne, *starts = counts + MAX_TILES, *cursor = starts + MAX_TILES + 1;
     MIAGPU_CUDA(cudaMemsetAsync(counts, 0, MAX_TILES * sizeof(int32_t), c->stream));
     ent_bin_count_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, c->stream>>>(p, ent_tile, counts);
     ent_bin_scan_kernel<<<1, 32, 0, c->stream>>>(n_tiles, counts, starts, cursor);
-    ent_bin_scatter_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, c->stream>>>(ne, ent_tile, cursor, bin_list);
+    ent_bin_scatter_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, c->stream>>>(p, ent_tile, cursor, recs);
     MIAGPU_CUDA(cudaGetLastError());
     const size_t smem = (size_t)TILE_SMEM_INTS * sizeof(int32_t);
     MIAGPU_CUDA(cudaFuncSetAttribute(tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int slices = std::max(1, (2 * c->num_sms + n_tiles - 1) / n_tiles);
-    tile_kernel<<<dim3(slices, n_tiles), TILE_THREADS, smem, c->stream>>>(p, bin_list, starts);
+    tile_kernel<<<dim3(slices, n_tiles), TILE_THREADS, smem, c->stream>>>(p, recs, starts);
     MIAGPU_CUDA(cudaGetLastError());
     c->launches += 4;
   } else {
