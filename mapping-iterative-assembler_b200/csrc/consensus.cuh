@@ -102,8 +102,26 @@ __device__ __forceinline__ void add_base_dev(const Adder& A, Col col, int ch_cod
 //         column never counts)
 // MODE 1: base columns + insert columns
 // MODE 2: base columns only (what AlnSeq.dropped decides, mia.c:571-579; insert columns count dropped reads too)
-template <int MODE, typename Adder>
-__device__ __forceinline__ void walk_entry(const ConsParams& p, const miagpu_entry& e, int lane, const Adder& A) {
+// Where the columns of a reference position lie.  GlobalLay: the padded layout of the whole alignment, straight from ins_off / gaps.
+// TileLay: the same for an entry that lies wholly inside a tile's shared window -- columns relative to the window, insert offsets
+// and lengths from the tile's copy of ins_off (gaps[pos] = ins_off[pos + 1] - ins_off[pos] for pos > 0, the only positions asked).
+struct GlobalLay {
+  const int32_t* ins_off;
+  const int32_t* gaps;
+  __device__ __forceinline__ int64_t col(int pos) const { return (int64_t)pos + ins_off[pos + 1]; }    // the base column sits after its insert columns
+  __device__ __forceinline__ int64_t icol(int pos) const { return (int64_t)pos + ins_off[pos]; }
+  __device__ __forceinline__ int gap(int pos) const { return gaps[pos]; }
+};
+struct TileLay {
+  const int32_t* s_ins;     // ins_off[t0 + i]
+  int t0, ins0;
+  __device__ __forceinline__ int col(int pos) const { return pos - t0 + s_ins[pos - t0 + 1] - ins0; }
+  __device__ __forceinline__ int icol(int pos) const { return pos - t0 + s_ins[pos - t0] - ins0; }
+  __device__ __forceinline__ int gap(int pos) const { return s_ins[pos - t0 + 1] - s_ins[pos - t0]; }
+};
+
+template <int MODE, typename Adder, typename Lay>
+__device__ __forceinline__ void walk_entry(const ConsParams& p, const miagpu_entry& e, int lane, const Adder& A, const Lay& Y, const int32_t* sm) {
   if (e.col_count <= 0) return;
   const int rd = e.read;
   const bool fz = rd >= p.n_reads;
@@ -112,7 +130,7 @@ __device__ __forceinline__ void walk_entry(const ConsParams& p, const miagpu_ent
   if (nr <= 0) return;
   const uint16_t* runs = fz ? p.fz_runs + q * MAX_RUNS : p.runs + (int64_t)rd * MAX_RUNS;
   const uint8_t* read = fz ? p.fz_bases + q * FZ_BASES_STRIDE : p.bases + p.off[rd];
-  const int32_t* sm_strand = p.sm + ((fz ? p.fz_rc[q] : p.rc[rd]) ? MIAGPU_PSSM_INTS : 0);
+  const int32_t* sm_strand = sm + ((fz ? p.fz_rc[q] : p.rc[rd]) ? MIAGPU_PSSM_INTS : 0);
   const int cb = e.col_begin, ce = e.col_begin + e.col_count;
 
   int colpos = 0;                 // reference columns before this run
@@ -138,13 +156,13 @@ __device__ __forceinline__ void walk_entry(const ConsParams& p, const miagpu_ent
         const int depth = smp_depth(e, act);
         if (!e.dropped) {
           const int ch = isM ? base_code(read[row]) : 5;
-          add_base_dev(A, pos + p.ins_off[pos + 1], ch, sm_strand, depth);   // base column sits after its insert columns
+          add_base_dev(A, Y.col(pos), ch, sm_strand, depth);
         }
         if (MODE == 2) continue;
-        const int g = (i > cb && pos > 0) ? p.gaps[pos] : 0; // find_ins_cons: start < pos <= end, dropped NOT checked
+        const int g = (i > cb && pos > 0) ? Y.gap(pos) : 0;  // find_ins_cons: start < pos <= end, dropped NOT checked
         for (int j = 0; j < g; j++) {
           const int ch = j < q ? base_code(read[row - q + j]) : 5;
-          add_base_dev(A, pos + p.ins_off[pos] + j, ch, sm_strand, depth);
+          add_base_dev(A, Y.icol(pos) + j, ch, sm_strand, depth);
         }
       }
     }
@@ -152,6 +170,11 @@ __device__ __forceinline__ void walk_entry(const ConsParams& p, const miagpu_ent
     if (type == MIAGPU_RUN_M) rpos += len;
     pend = 0;
   }
+}
+
+template <int MODE, typename Adder>
+__device__ __forceinline__ void walk_entry(const ConsParams& p, const miagpu_entry& e, int lane, const Adder& A) {
+  walk_entry<MODE>(p, e, lane, A, GlobalLay{p.ins_off, p.gaps}, p.sm);
 }
 
 // MODE 0 / 1 over the whole entry list, accumulators in global memory: one warp per entry.
@@ -237,14 +260,25 @@ __global__ void __launch_bounds__(TILE_THREADS) tile_kernel(ConsParams p, const 
       m &= m - 1;
       const uint32_t bf = __shfl_sync(0xffffffffu, r.b.y, b);
       const uint32_t flags = bf >> 16;
+      const int rp = (int)__shfl_sync(0xffffffffu, r.a.z, b);
+      const uint32_t ch = __shfl_sync(0xffffffffu, r.a.w, b);
+      if (flags & TR_DROPPED) {
+        // a dropped entry only counts in insert columns (mia.c:571-579): none between its first and last position => nothing to add
+        const int df = rp - t0, dl = min(rp + (int)(ch >> 16) - (int)(ch & 0xffffu) - 1, p.seq_len - 1) - t0;
+        if (dl < TILE_COLS && dl >= df && s_ins[dl + 1] == s_ins[df]) continue;
+      }
       if (!(flags & TR_FAST)) {                            // gaps in the alignment, or a frozen one: the general walk
         const miagpu_entry eb = p.entries[__shfl_sync(0xffffffffu, r.b.z, b)];
-        walk_entry<1>(p, eb, lane, A);
+        // wholly inside the shared window (its last position and that position's columns): layout, scores and sums from shared memory
+        const int dl = min(eb.ref_pos + eb.col_count - 1, p.seq_len - 1) - t0;
+        if (dl >= 0 && dl < TILE_COLS && dl + (s_ins[min(dl + 1, TILE_COLS)] - ins0) < TILE_COLS)
+          walk_entry<1>(p, eb, lane, LocalAdder{s_acc}, TileLay{s_ins, t0, ins0}, s_sm);
+        else
+          walk_entry<1>(p, eb, lane, A);
         continue;
       }
       const uint32_t alo = __shfl_sync(0xffffffffu, r.a.x, b), ahi = __shfl_sync(0xffffffffu, r.a.y, b);
-      const int rp = (int)__shfl_sync(0xffffffffu, r.a.z, b);
-      const uint32_t ch = __shfl_sync(0xffffffffu, r.a.w, b), ft = __shfl_sync(0xffffffffu, r.b.x, b);
+      const uint32_t ft = __shfl_sync(0xffffffffu, r.b.x, b);
       const int cb = (int)(ch & 0xffffu), hi_col = (int)(ch >> 16);
       const int fl = (int)(int16_t)(ft & 0xffffu), tl = (int)(int16_t)(ft >> 16), bias = (int)(int16_t)(bf & 0xffffu);
       const bool dropped = flags & TR_DROPPED, backf = flags & TR_BACKF;
@@ -360,6 +394,9 @@ __global__ void __launch_bounds__(256) ent_bin_scatter_kernel(ConsParams p, cons
     // the record (entries come in read order here: the per-read look-ups are next to each other)
     const miagpu_entry e = p.entries[i];
     r.b.z = (uint32_t)i;
+    r.a.z = (uint32_t)e.ref_pos;                           // every record: where the entry lies and whether it is dropped (tile_kernel skips
+    r.a.w = (uint32_t)min(e.col_begin, 0xffff) | ((uint32_t)min(e.col_begin + e.col_count, 0xffff) << 16);   // dropped entries without insert columns)
+    r.b.y = (e.dropped ? TR_DROPPED : 0u) << 16;
     if (e.read < p.n_reads && p.n_runs[e.read] == 1) {
       const int run0 = p.runs[(int64_t)e.read * MAX_RUNS];
       const int len = run0 & 0x3fff;

@@ -94,6 +94,7 @@ struct miagpu_ctx {
   bool have_ref = false;
   std::string raw_wrapped, raw_rc_wrapped;     // case preserved (k-mer soft mask)
   int seq_len = 0, wrap_len = 0, circular = 0, with_rc = 0;
+  int64_t cut_prev_newly = -1;                       // reads the previous one-call round's cut dropped (-1: unknown)
   int64_t cons_capacity = 0;                         // bytes behind the caller's cons_out (0 = the header's default)
   bool explicit_windows = false;   // miagpu_align_windows: d_as / d_ae hold [start, end) of every read's window, no window rule
   int explicit_sg5 = 1;
@@ -2327,6 +2328,7 @@ struct CutHost {
   int64_t tot_runs;
   int32_t total_ins;
   long long bad_after;
+  int32_t newly_dropped;
   int32_t fs_cnt[FS_CNT_WORDS];
   ShardPrep prep;
 };
@@ -2457,7 +2459,13 @@ static int iterate_tail(miagpu_ctx* c, const IterTail& a, const Trace& tr) {
   c->n_cols = (int64_t)c->seq_len + H->total_ins;
   if (!c->d_acc.reserve(c->n_cols * NPLANE) || !c->d_called.reserve(c->n_cols + 16)) return 0;
   MIAGPU_CUDA(cudaMemsetAsync(c->d_acc.p, 0, c->n_cols * NPLANE * sizeof(int32_t), main));
-  if (!launch_accumulate(c)) return 0;
+  // Normally the columns of every read not yet dropped are accumulated while the host stitches the chains, and the few reads this
+  // round's cut drops are taken back out afterwards.  When the previous round dropped more than an eighth of the reads (the first
+  // rounds on a divergent seed: mia.c:452-470 cuts most of them), the same is likely now: wait for the cut, flag the entries,
+  // and accumulate once.  Integer sums: the planes are the same either way.
+  // (a cut the caller gave -- -H / -S -N -- is known at once: flags first, always)
+  const bool cut_first = !c->fs_on && (!fit || (c->cut_prev_newly >= 0 && c->cut_prev_newly * 8 > n)) && !getenv("MIAGPU_NO_CUT_FIRST");
+  if (!cut_first && !launch_accumulate(c)) return 0;
   if (a.packed_runs) {
     pack_runs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, main>>>(n, c->d_nruns.p, offs, c->d_runs.p, c->d_packed.p);
     MIAGPU_CUDA(cudaEventRecord(c->xev[3], main));
@@ -2493,6 +2501,12 @@ static int iterate_tail(miagpu_ctx* c, const IterTail& a, const Trace& tr) {
   MIAGPU_CUDA(cudaMemcpyAsync(c->d_thr.p, H->thr, sizeof(H->thr), cudaMemcpyHostToDevice, main));
   if (c->fs_on) {
     if (!fs_flags_and_undo(c, has_unique)) return 0;
+  } else if (cut_first) {                              // the entries take this round's flags, then one accumulation
+    cut_flags_kernel<<<(unsigned)((n + 255) / 256), 256, 0, main>>>(n, c->d_seqlen.p, c->d_score.p, c->d_thr.p, c->d_dropf.p, c->d_entries.p, c->d_cstats.p,
+                                                                    has_unique ? c->d_unique.p : nullptr, c->d_newly.p);
+    MIAGPU_CUDA(cudaGetLastError());
+    c->launches += 1;
+    if (!launch_accumulate(c)) return 0;
   } else {
     cut_flags_kernel<<<(unsigned)((n + 255) / 256), 256, 0, main>>>(n, c->d_seqlen.p, c->d_score.p, c->d_thr.p, c->d_dropf.p, nullptr, c->d_cstats.p,
                                                                     has_unique ? c->d_unique.p : nullptr, c->d_newly.p);
@@ -2500,6 +2514,7 @@ static int iterate_tail(miagpu_ctx* c, const IterTail& a, const Trace& tr) {
     MIAGPU_CUDA(cudaGetLastError());
     c->launches += 2;
   }
+  MIAGPU_CUDA(cudaMemcpyAsync(&H->newly_dropped, &c->d_cstats.p->pad, sizeof(int32_t), cudaMemcpyDeviceToHost, main));
   MIAGPU_CUDA(cudaMemcpyAsync(&H->bad_after, &c->d_cstats.p->bad, sizeof(long long), cudaMemcpyDeviceToHost, main));
   MIAGPU_CUDA(cudaEventRecord(c->xev[2], main));
   if (a.dropped) {
@@ -2513,6 +2528,7 @@ static int iterate_tail(miagpu_ctx* c, const IterTail& a, const Trace& tr) {
   c->launches = launches + 1;
   tr.mark("consensus called and downloaded");
   if (H->bad_after != LLONG_MAX) { set_error("miagpu_cull_flags: seq_len[%lld] = %d out of range", H->bad_after, a.h_seq_len[H->bad_after]); return 0; }
+  c->cut_prev_newly = c->fs_on ? -1 : H->newly_dropped;
   MIAGPU_CUDA(cudaStreamSynchronize(down));
   tr.mark("download stream drained");
   return 1;

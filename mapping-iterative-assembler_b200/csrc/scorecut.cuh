@@ -25,7 +25,7 @@ constexpr int CUT_PER_THREAD = CUT_BLOCK / CUT_THREADS;
 struct CutStatsDev {
   long long sx, sy, cnt, bad;                        // bad = smallest index whose seq_len is outside [0, MAX_READ] (LLONG_MAX = none)
   int best[MAX_READ + 1];
-  int pad;
+  int pad;                                           // reads newly dropped by cut_flags_kernel (reset by cut_init_kernel)
   long long sxx, sxy;                                // sum len^2, sum len * score over the reads the fit uses (sharded rounds: where a rank's chain starts)
 };
 struct CutTables {                                   // host-made, the same doubles the reference forms per read
@@ -390,6 +390,10 @@ __global__ void cut_flags_kernel(int64_t n, const int32_t* __restrict__ seq_len,
   if (newly) newly[i] = s & !old;
   sticky[i] = s;
   if (entries) { entries[2 * i].dropped = s; entries[2 * i + 1].dropped = s; }
+  // how many reads this round's cut dropped (st->pad): the next round decides by it whether to accumulate before the cut is known
+  const bool nw = s & !old;
+  const unsigned act = __activemask(), m = __ballot_sync(act, nw);
+  if (nw && (threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(&st->pad, __popc(m));
 }
 
 }  // namespace miagpu

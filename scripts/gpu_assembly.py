@@ -3,7 +3,7 @@ consensus stops changing, on one GPU (plain python) or with the reads sharded ov
 
     --shape c3   configs[2]: merged paired-end reads 30-140 bp, ancient.submat.solexa.pe, 16,569 bp circle, k = 12
     --shape c4   configs[3]: reads of a sample 10 % + 0.5 % indels away from the 16,569 bp seed reference, ancient.submat, k = 12
-                 (--distant: mia -D, one GPU only)
+                 (--distant: mia -D; over several GPUs only while no stale pointer crosses a shard boundary)
     --shape c5   configs[4]: 1 Mb linear reference, 35-75 bp reads, ancient.submat.solexa.onepass, k = 14
 
 The data set does not depend on the number of GPUs (8 seeded pieces; rank r of W takes pieces [8r/W, 8(r+1)/W)), so the md5 of every
