@@ -464,6 +464,7 @@ def shaped_rounds(g, args, flush, lib_stream):
         if not args.no_pass1:
             g.set_reference(ref, circular=1, with_rc=1)
             g.build_kmers(12)
+            g.upload_reads(bases, off)                 # (the parity check above left its prefix on the device)
             p1_ms = []
             for _ in range(3):
                 flush.zero_()
