@@ -226,6 +226,9 @@ __host__ __device__ constexpr int p16_smem_fixed() {
 #ifndef P16_INPLACE
 #define P16_INPLACE 0
 #endif
+#ifndef P16_SCAN4
+#define P16_SCAN4 0
+#endif
 #ifndef P16_SIX_BLOCKS_K
 #define P16_SIX_BLOCKS_K 7
 #endif
@@ -368,6 +371,37 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, (K <= 5 ? 8 : K <= P16_S
       __syncwarp();
     }
 
+    // Exclusive prefix over the group's lanes of the lane totals X (each in its own lane's frame): q of lane i = max over the lanes
+    // l < i of X_l - CONV * (i - l), clamped so that nothing wraps (a clamped value ends at the bottom of the range, below every
+    // start-new level).  P16_SCAN4 = 0: four doubling steps + the shift by one lane = five dependent shuffles.  P16_SCAN4 = 1
+    // (16 lanes): the shift first, then windows of four lanes (three independent shuffles) and four windows (three more): three
+    // dependent shuffle latencies instead of five for six more instructions per row.  The scan's shuffles are where a warp waits
+    // (profiles/r02j_ncu_pair16_full.md: 28 % of the not-issued samples sit on the instruction behind each of them), yet the
+    // shorter chain measures SLOWER (K = 11: 1.365 -> 1.384 ms, K = 10: 1.156 -> 1.170 ms; bit-identical results): the other
+    // warps fill those waits already, what counts is the number of ALU-pipe instructions.  Kept as an option, off.
+    auto lane_prefix = [&](uint32_t X) -> uint32_t {
+      if (P16_SCAN4 && G == 16) {
+        uint32_t s = __shfl_up_sync(0xffffffffu, X, 1, G);
+        s = __vadd2(__vmaxu2(s, B2(-32768 + CONV)), K2(-CONV)) & keep;          // s_i = X_(i-1) in lane i's frame; the first lane: bottom
+        const uint32_t a1 = __shfl_up_sync(0xffffffffu, s, 1, G), a2 = __shfl_up_sync(0xffffffffu, s, 2, G), a3 = __shfl_up_sync(0xffffffffu, s, 3, G);
+        uint32_t w = __viaddmax_u16x2(__vmaxu2(a1, B2(-32768 + CONV)), K2(-CONV), s);    // lanes < d get their own s back: max(s, max(s,cl)-dec) = s
+        w = __viaddmax_u16x2(__vmaxu2(a2, B2(-32768 + 2 * CONV)), K2(-2 * CONV), w);
+        w = __viaddmax_u16x2(__vmaxu2(a3, B2(-32768 + 3 * CONV)), K2(-3 * CONV), w);     // w_i covers s_(i-3) .. s_i
+        const uint32_t b1 = __shfl_up_sync(0xffffffffu, w, 4, G), b2 = __shfl_up_sync(0xffffffffu, w, 8, G), b3 = __shfl_up_sync(0xffffffffu, w, 12, G);
+        uint32_t q = __viaddmax_u16x2(__vmaxu2(b1, B2(-32768 + 4 * CONV)), K2(-4 * CONV), w);
+        q = __viaddmax_u16x2(__vmaxu2(b2, B2(-32768 + 8 * CONV)), K2(-8 * CONV), q);
+        q = __viaddmax_u16x2(__vmaxu2(b3, B2(-32768 + 12 * CONV)), K2(-12 * CONV), q);
+        return q;
+      }
+      // inclusive cross-lane scan, converting by CONV per lane, clamped so nothing wraps
+#pragma unroll
+      for (int d = 1; d < G; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, X, d, G);
+        X = __viaddmax_u16x2(__vmaxu2(y, B2(-32768 + CONV * d)), K2(-CONV * d), X);    // lanes < d get their own X back: max(X, max(X,cl)-dec) = X
+      }
+      const uint32_t q = __shfl_up_sync(0xffffffffu, X, 1, G);
+      return __vadd2(__vmaxu2(q, B2(-32768 + CONV)), K2(-CONV)) & keep;         // B2(-32768) = 0
+    };
     // One DP row: row r-1 in W / acc -> row r in Wn / accn (Rg in place).  PAR = r & 1 selects the table buffer at
     // compile time (an immediate offset of the LDS), so the row loop below is unrolled by two and ping-pongs
     // between two register sets (no moves at the back edge).
@@ -387,14 +421,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, (K <= 5 ? 8 : K <= P16_S
       for (int j = 1; j + 1 < K - 2; j += 2) X = __vimax3_u16x2(X, W[j], W[j + 1]);
       if ((K - 3) & 1) X = __vmaxu2(X, W[K - 3]);
       X = __vadd2(X, K2(-GOP));
-      // inclusive cross-lane scan, converting by CONV per lane, clamped so nothing wraps
-#pragma unroll
-      for (int d = 1; d < G; d <<= 1) {
-        const uint32_t y = __shfl_up_sync(0xffffffffu, X, d, G);
-        X = __viaddmax_u16x2(__vmaxu2(y, B2(-32768 + CONV * d)), K2(-CONV * d), X);    // lanes < d get their own X back: max(X, max(X,cl)-dec) = X
-      }
-      uint32_t q = __shfl_up_sync(0xffffffffu, X, 1, G);
-      q = __vadd2(__vmaxu2(q, B2(-32768 + CONV)), K2(-CONV)) & keep;      // B2(-32768) = 0
+      const uint32_t q = lane_prefix(X);
       // column-gap chain (mia.c:838-850): Q[j] = max over columns <= c-2 of V - GOP
       uint32_t Q[K];
       Q[0] = __viaddmax_u16x2(l2, K2(-GOP), q);
@@ -445,13 +472,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, (K <= 5 ? 8 : K <= P16_S
       for (int j = 1; j + 1 < K - 2; j += 2) X = __vimax3_u16x2(X, W[j], W[j + 1]);
       if ((K - 3) & 1) X = __vmaxu2(X, W[K - 3]);
       X = __vadd2(X, K2(-GOP));
-#pragma unroll
-      for (int d = 1; d < G; d <<= 1) {
-        const uint32_t y = __shfl_up_sync(0xffffffffu, X, d, G);
-        X = __viaddmax_u16x2(__vmaxu2(y, B2(-32768 + CONV * d)), K2(-CONV * d), X);
-      }
-      uint32_t q = __shfl_up_sync(0xffffffffu, X, 1, G);
-      q = __vadd2(__vmaxu2(q, B2(-32768 + CONV)), K2(-CONV)) & keep;
+      uint32_t q = lane_prefix(X);
       uint32_t o2 = l2, o1 = l1, oa = ain;            // row r-1: cells j-2, j-1 and the verdict carry of cell j-1
 #pragma unroll
       for (int j = 0; j < K; j++) {
