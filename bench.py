@@ -332,7 +332,12 @@ def run_ours(args):
                      "traffic": traffic, "traffic_algorithmic": alg_bytes, "warp_inst_per_cell": ipc, "source": ipc_src,
                      "kernel": dom["kernel"], "kernel_ms": dom["ms"], "kernel_reads": dom["reads"], "kernel_gcups": dom["cells"] / dom_s / 1e9,
                      "kernel_share_of_step": dom["ms"] / ms_per_step, "sm_mhz": clk,
-                     "peak_source": "4 x 148 x SM clock (nvidia-smi median during the timed region)"},
+                     "peak_source": "4 x 148 x SM clock (nvidia-smi median during the timed region)",
+                     # the tighter view of the same bound: 84 of the row loop's 164 SASS instructions (K = 11) are ALU-pipe instructions
+                     # (VIMNMX* / VIADDMNMX / LOP3 .U16x2), and that pipe takes one warp instruction per two cycles and scheduler
+                     "alu_pipe": None if ipc is None else {"share_of_instructions": 84 / 164, "peak": issue_peak / 2, "unit": "G warp-inst/s",
+                                                           "frac": ipc * (84 / 164) * dom["cells"] / dom_s / 1e9 / (issue_peak / 2),
+                                                           "source": "cuobjdump -sass of pair16_kernel<11,16> (DESIGN 4.2); ncu sm__inst_executed_pipe_alu 63 % (profiles/r02j_ncu_pair16_full.md)"}},
         "roofline_hbm": {"bound": "hbm", "achieved": alg_bytes / dom_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                          "frac": alg_bytes / dom_s / 1e9 / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst)" if peaks else "fallback 6650 GB/s",
