@@ -54,3 +54,43 @@ def test_natural_entries_match_oracle_slots(oracle):
         bl = len(slots[a + 1]["seq"]) + ins(slots[a + 1])
         assert ent[a]["front_len"] == fl and ent[a]["total_len"] == fl + bl == ent[a + 1]["total_len"]
         assert ent[a + 1]["col_begin"] == len(slots[a]["seq"])
+
+
+def test_distant_retry_state_is_folded_over_shards_in_rank_order():
+    # -D over shards (driver.ResidentAssembler.retry_begin / retry_end): the matrix the first forward attempt of a shard runs with is
+    # what the last read of the shard before it left (mia_main.c:120-174, H6).  Every shard reports the state it leaves as a function
+    # of the state it is entered with; the fold over the ranks must hand every shard its true entry state and keep the last shard's
+    # exit state for the next round -- checked against walking the shards one after the other.
+    import _pkg
+    _pkg.load()
+    from mia_b200 import driver
+    rng = np.random.default_rng(5)
+
+    class StubGpu:
+        def __init__(self, after):
+            self.after, self.entered = after, None
+
+        def distant_retry_begin(self):
+            return 7, list(self.after)
+
+        def distant_retry_end(self, state_in):
+            self.entered = state_in
+            return 3
+
+    for _ in range(200):
+        world = int(rng.integers(1, 7))
+        # identity (a shard without reads, or with strand-unknown reads only in round 1), constant 0 / 1, or the swap a chain cannot
+        # produce but the fold must still treat as a function
+        afters = [[(0, 1), (0, 0), (1, 1), (1, 0)][int(rng.integers(0, 4))] for _ in range(world)]
+        carried = int(rng.integers(0, 2))
+        want_in, s = [], carried
+        for r in range(world):
+            want_in.append(s)
+            s = afters[r][s]
+        for rank in range(world):
+            A = object.__new__(driver.ResidentAssembler)
+            A.g, A.matrix_state = StubGpu(afters[rank]), carried
+            assert A.retry_begin() == list(afters[rank])
+            A.retry_end(np.array(afters, np.int32), rank)
+            assert A.g.entered == want_in[rank]
+            assert A.matrix_state == s and A.retried == (7, 3)
