@@ -46,6 +46,18 @@ struct ConsParams {
 constexpr int FZ_BASES_STRIDE = MAX_READ;
 __device__ __forceinline__ int cons_nruns(const ConsParams& p, int rd) { return rd >= p.n_reads ? p.fz_nruns[rd - p.n_reads] : p.n_runs[rd]; }
 
+// an entry as two 16-byte loads (the struct's own alignment is 4: the compiler would load it word by word); entry arrays are
+// cudaMalloc'ed and 32 bytes per element
+__device__ __forceinline__ miagpu_entry load_entry(const miagpu_entry* p) {
+  static_assert(sizeof(miagpu_entry) == 32, "miagpu_entry is eight 32-bit words");
+  const uint4 a = *reinterpret_cast<const uint4*>(p), b = *(reinterpret_cast<const uint4*>(p) + 1);
+  miagpu_entry e;
+  e.read = (int32_t)a.x; e.col_begin = (int32_t)a.y; e.col_count = (int32_t)a.z; e.ref_pos = (int32_t)a.w;
+  e.front_len = (int32_t)b.x; e.total_len = (int32_t)b.y; e.act_bias = (int32_t)b.z;
+  e.dropped = (uint8_t)(b.w & 0xffu); e.back_formula = (uint8_t)((b.w >> 8) & 0xffu); e.reserved[0] = e.reserved[1] = 0;
+  return e;
+}
+
 __device__ __forceinline__ int smp_depth(const miagpu_entry& e, int act) {   // fsdb.c:569-580 / 598-609
   const int dfront = e.back_formula ? e.front_len + act : act;
   const int dback = e.total_len - act - 1;
@@ -183,7 +195,7 @@ __global__ void __launch_bounds__(256) entry_kernel(ConsParams p) {
   const int lane = threadIdx.x & 31;
   const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (w >= p.n_entries) return;
-  const miagpu_entry e = p.entries[w];
+  const miagpu_entry e = load_entry(p.entries + w);
   walk_entry<MODE>(p, e, lane, GlobalAdder{p.acc, p.n_cols});
 }
 
@@ -202,7 +214,7 @@ __global__ void __launch_bounds__(256) gaps_kernel(ConsParams p) {
   while (m) {
     const int b = __ffs(m) - 1;
     m &= m - 1;
-    const miagpu_entry e = p.entries[w0 + b];
+    const miagpu_entry e = load_entry(p.entries + w0 + b);
     walk_entry<0>(p, e, lane, GlobalAdder{p.acc, p.n_cols});
   }
 }
@@ -268,7 +280,7 @@ __global__ void __launch_bounds__(TILE_THREADS) tile_kernel(ConsParams p, const 
         if (dl < TILE_COLS && dl >= df && s_ins[dl + 1] == s_ins[df]) continue;
       }
       if (!(flags & TR_FAST)) {                            // gaps in the alignment, or a frozen one: the general walk
-        const miagpu_entry eb = p.entries[__shfl_sync(0xffffffffu, r.b.z, b)];
+        const miagpu_entry eb = load_entry(p.entries + __shfl_sync(0xffffffffu, r.b.z, b));
         // wholly inside the shared window (its last position and that position's columns): layout, scores and sums from shared memory
         const int dl = min(eb.ref_pos + eb.col_count - 1, p.seq_len - 1) - t0;
         if (dl >= 0 && dl < TILE_COLS && dl + (s_ins[min(dl + 1, TILE_COLS)] - ins0) < TILE_COLS)
@@ -340,7 +352,7 @@ __global__ void __launch_bounds__(256) undo_kernel(ConsParams p, int64_t n_reads
     m &= m - 1;
     for (int h = 0; h < 2; h++) {
       const int64_t idx = 2 * (w0 + b) + h;
-      const miagpu_entry e = entries[idx];
+      const miagpu_entry e = load_entry(entries + idx);
       if (e.dropped) continue;
       walk_entry<2>(p, e, lane, NegGlobalAdder{p.acc, p.n_cols});
       __syncwarp();
@@ -360,8 +372,9 @@ __global__ void __launch_bounds__(256) ent_bin_count_kernel(ConsParams p, int32_
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int t = -1;
   if (i < p.n_entries) {
-    const miagpu_entry e = p.entries[i];
-    if (e.col_count > 0 && cons_nruns(p, e.read) > 0 && e.ref_pos >= 0 && e.ref_pos < p.seq_len) t = e.ref_pos / TILE_POS;
+    const uint4 a = *reinterpret_cast<const uint4*>(p.entries + i);        // read, col_begin, col_count, ref_pos
+    const int e_read = (int)a.x, e_cols = (int)a.z, e_pos = (int)a.w;
+    if (e_cols > 0 && cons_nruns(p, e_read) > 0 && e_pos >= 0 && e_pos < p.seq_len) t = e_pos / TILE_POS;
     ent_tile[i] = t;
   }
   const unsigned peers = __match_any_sync(0xffffffffu, t);
@@ -392,7 +405,7 @@ __global__ void __launch_bounds__(256) ent_bin_scatter_kernel(ConsParams p, cons
     base = __shfl_sync(peers, base, leader);
     slot = base + __popc(peers & ((1u << lane) - 1));
     // the record (entries come in read order here: the per-read look-ups are next to each other)
-    const miagpu_entry e = p.entries[i];
+    const miagpu_entry e = load_entry(p.entries + i);
     r.b.z = (uint32_t)i;
     r.a.z = (uint32_t)e.ref_pos;                           // every record: where the entry lies and whether it is dropped (tile_kernel skips
     r.a.w = (uint32_t)min(e.col_begin, 0xffff) | ((uint32_t)min(e.col_begin + e.col_count, 0xffff) << 16);   // dropped entries without insert columns)
@@ -483,8 +496,13 @@ __global__ void natural_entries_kernel(int64_t n, const int32_t* as_out, const i
       b.dropped = dropped_back ? (dropped_back[i] != 0) : f.dropped;
     }
   }
-  out[2 * i] = f;
-  out[2 * i + 1] = b;
+  // two 16-byte stores per entry (the struct's own alignment is 4: the compiler would store it word by word)
+  static_assert(sizeof(miagpu_entry) == 32, "miagpu_entry is eight 32-bit words");
+  uint4* q = reinterpret_cast<uint4*>(out + 2 * i);
+  q[0] = make_uint4((uint32_t)f.read, (uint32_t)f.col_begin, (uint32_t)f.col_count, (uint32_t)f.ref_pos);
+  q[1] = make_uint4((uint32_t)f.front_len, (uint32_t)f.total_len, (uint32_t)f.act_bias, (uint32_t)f.dropped | ((uint32_t)f.back_formula << 8));
+  q[2] = make_uint4((uint32_t)b.read, (uint32_t)b.col_begin, (uint32_t)b.col_count, (uint32_t)b.ref_pos);
+  q[3] = make_uint4((uint32_t)b.front_len, (uint32_t)b.total_len, (uint32_t)b.act_bias, (uint32_t)b.dropped | ((uint32_t)b.back_formula << 8));
 }
 
 // gaps[0] is ignored by the consensus (mia.c:557 "ref_pos > 0"); force it to 0 so the scan
