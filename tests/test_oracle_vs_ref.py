@@ -243,3 +243,38 @@ def test_trim_oracle_equals_reference(oracle, ref):
             rd = rd[: len(rd) // 2] + "N" + rd[len(rd) // 2 + 1:]
         rd = rd or "A"
         assert oracle.trim(rd, ad) == ref.trim(rd, ad), (t, rd, ad)
+
+
+def test_columns_right_of_the_end_cell_do_not_matter(oracle, ref):
+    # What the 16-bit kernels rely on when they hand a gapped read to the 32-bit kernels with its window cut at the end cell
+    # (pair16.cuh): every candidate of a dyn_prog cell comes from a lower column (mia.c:838-871) and max_sg_score takes the FIRST
+    # maximum of the last row (mia.c:1278-1302), so the alignment against window[0 .. aec] equals the alignment against the whole
+    # window -- checked here on the unmodified reference itself and on the oracle, reads with indels, every matrix, both sg5.
+    import numpy as np
+    import gpu_checks
+    rng = np.random.default_rng(11)
+    n_gapped = 0
+    for t in range(300):
+        sm = gpu_checks.load_pssm(["onepass", "ancient", "pe", "flat"][t % 4])
+        L = int(rng.integers(20, 90))
+        W = L + int(rng.integers(20, 130))
+        window = "".join("ACGT"[i] for i in rng.integers(0, 4, W))
+        s0 = int(rng.integers(0, W - L + 1))
+        read = list(window[s0:s0 + L])
+        for _ in range(int(rng.integers(0, 4))):                       # a few substitutions, an insert or a deletion
+            read[int(rng.integers(0, len(read)))] = "ACGT"[int(rng.integers(0, 4))]
+        if t % 3 == 0 and len(read) > 12:
+            p = int(rng.integers(4, len(read) - 4))
+            read[p:p] = list("ACGT"[int(rng.integers(0, 4))] * int(rng.integers(1, 4)))
+        elif t % 3 == 1 and len(read) > 16:
+            p = int(rng.integers(4, len(read) - 8))
+            del read[p:p + int(rng.integers(1, 4))]
+        read = "".join(read)
+        for checker in (ref, oracle):
+            for sg5 in (1, 0):
+                full = checker.align(window, read, sm, sg5=sg5)
+                cut = checker.align(window[: full["aec"] + 1], read, sm, sg5=sg5)
+                for k in ("score", "abr", "abc", "aer", "aec", "ref_gapped", "read_gapped"):
+                    assert cut[k] == full[k], (t, sg5, k, cut[k], full[k])
+        n_gapped += "-" in full["ref_gapped"] or "-" in full["read_gapped"]
+    assert n_gapped > 60
