@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(256) gaps_kernel(ConsParams p) {
 // flagged entries one by one; the common alignment -- a single M run -- takes a loop that touches global
 // memory only for the read bases.
 constexpr int TILE_THREADS = 512;
-constexpr int TILE_SMEM_INTS = NPLANE * TILE_COLS + (TILE_COLS + 1) + 2 * MIAGPU_PSSM_INTS;
+constexpr int TILE_SMEM_INTS = NPLANE * TILE_COLS + (TILE_COLS + 1) + 2 * MIAGPU_PSSM_INTS + 64 + 32;   // + base-code table (256 bytes) + a sink word per lane
 // What tile_kernel needs of a binned entry, 32 bytes, written in bin order by ent_bin_scatter_kernel so that a warp reads 32 of them
 // in one contiguous kilobyte: no per-read look-ups (n_runs, runs, abr, rc, off) while the tile is walked.
 //   a = { byte offset of read row `abr` in p.bases (lo, hi), ref_pos, col_begin | hi_col << 16 }
@@ -243,12 +243,15 @@ __global__ void __launch_bounds__(TILE_THREADS) tile_kernel(ConsParams p, const 
   extern __shared__ int32_t s_acc[];                       // [NPLANE][TILE_COLS]
   int32_t* s_ins = s_acc + NPLANE * TILE_COLS;             // ins_off[t0 + i], i <= TILE_COLS
   int32_t* s_sm = s_ins + TILE_COLS + 1;
+  uint8_t* s_code = reinterpret_cast<uint8_t*>(s_sm + 2 * MIAGPU_PSSM_INTS);   // base_code() of every byte value: one LDS instead of four compares
+  int32_t* s_sink = s_sm + 2 * MIAGPU_PSSM_INTS + 64;                          // where the count of an N goes (no base plane of its own)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int t0 = blockIdx.y * TILE_POS;
   const int64_t c0 = (int64_t)t0 + p.ins_off[t0];
   for (int i = threadIdx.x; i < NPLANE * TILE_COLS; i += blockDim.x) s_acc[i] = 0;
   for (int i = threadIdx.x; i <= TILE_COLS; i += blockDim.x) s_ins[i] = p.ins_off[min(t0 + i, p.seq_len)];
   for (int i = threadIdx.x; i < 2 * MIAGPU_PSSM_INTS; i += blockDim.x) s_sm[i] = p.sm[i];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_code[i] = (uint8_t)base_code((uint8_t)i);
   __syncthreads();
   const TileAdder A{s_acc, c0, p.acc, p.n_cols};
   // the entries that start inside this tile were binned (ent_bin_*_kernel): slice blockIdx.x of the tile's records
@@ -309,7 +312,15 @@ __global__ void __launch_bounds__(TILE_THREADS) tile_kernel(ConsParams p, const 
           const int depth = dfront <= PSSM_DEPTH ? dfront : (dback < PSSM_DEPTH ? 2 * PSSM_DEPTH - dback : PSSM_DEPTH);
           const int d = pos - t0;
           const int io0 = s_ins[d] - ins0, io1 = s_ins[d + 1] - ins0;
-          if (!dropped) add_base_dev(LA, d + io1, base_code(read[i]), sms, depth);
+          if (!dropped) {                                    // add_base_dev for a base (never '-'), without its branches
+            const int ch = s_code[read[i]], col = d + io1;
+            int32_t* cell = s_acc + col;
+            atomicAdd(cell + PL_COV * TILE_COLS, 1);
+            atomicAdd(ch < 4 ? cell + ch * TILE_COLS : s_sink + lane, 1);
+            const int32_t* m = sms + depth * 25 + ch;        // sm[depth][X][b]
+#pragma unroll
+            for (int x = 0; x < 4; x++) atomicAdd(cell + (PL_SCORE + x) * TILE_COLS, m[x * 5]);
+          }
           if (i > cb && pos > 0)                             // find_ins_cons: start < pos <= end, dropped NOT checked
             for (int j = io0; j < io1; j++) add_base_dev(LA, d + j, 5, sms, depth);
         }
